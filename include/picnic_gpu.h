@@ -1,0 +1,200 @@
+/*
+ * picnic_gpu.h -- C ABI of the B200 particle engine behind PICNIC's species and
+ * scattering interfaces.
+ *
+ * The reference has no FFI for this path: its seams are the C++
+ * classes PicChargedSpecies / PicSpeciesInterface / Scattering, plus the Fortran
+ * array ABI of the per-particle kernels (CHF_FRA1 = pointer + inclusive lo/hi
+ * bounds, column-major, ghosts included; src/particle_tools/MeshInterpF_F.H:8-44).
+ * Each entry point below names the reference method it replaces; the C++ shim in
+ * picnic_b200/host/ forwards the same-named methods to these calls.
+ *
+ * Conventions
+ *   - plain C, opaque handles, no exceptions, no exit(): every call returns 0 on
+ *     success and <0 on error (text via pgpu_last_error()).  PGPU_ERR_SEGMENTS is
+ *     the reference's Fortran STOP "particle crossing more cell than allowed"
+ *     (MeshInterpChargeConservingF.ChF:1018-1021,1555-1558).
+ *   - all pointers are HOST pointers borrowed for the duration of the call;
+ *     the library owns every device allocation.
+ *   - grid arrays: one component, column-major, inclusive lo/hi per direction in
+ *     GLOBAL cell/node indices, ghosts included (Chombo FArrayBox layout).
+ *   - particle arrays: SoA, component-major (x[d*n+p], v[c*n+p]).
+ *   - one caller thread per device; calls that return data synchronise.
+ *   - there is NO CPU fallback: if no CUDA device is usable pgpu_init fails.
+ */
+#ifndef PICNIC_GPU_H
+#define PICNIC_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgpu_grid_s *pgpu_grid_t;
+typedef struct pgpu_species_s *pgpu_species_t;
+
+enum { PGPU_CIC = 0, PGPU_TSC = 1, PGPU_CC0 = 2, PGPU_CC1 = 3 }; /* InterpType */
+enum { PGPU_EX = 0, PGPU_EY, PGPU_EZ, PGPU_BX, PGPU_BY, PGPU_BZ, PGPU_NFIELD };
+enum { PGPU_JX = 0, PGPU_JY, PGPU_JZ };
+enum { PGPU_BC_NONE = 0, PGPU_BC_PERIODIC = 1, PGPU_BC_SYMMETRY = 2 };
+enum {
+  PGPU_OK = 0,
+  PGPU_ERR_ARG = -1,
+  PGPU_ERR_CUDA = -2,
+  PGPU_ERR_SEGMENTS = -3, /* CC1: num_segments > ghosts+1 */
+  PGPU_ERR_BOUNDS = -4,   /* a particle stencil left the ghosted arrays */
+  PGPU_ERR_STATE = -5,
+  PGPU_ERR_COMM = -6
+};
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int pgpu_init(int device);
+int pgpu_finalize(void);
+const char *pgpu_last_error(void);
+int pgpu_abi_version(void);
+/* Run all kernels on this cudaStream_t (0 = the library's own stream). */
+int pgpu_set_stream(void *cuda_stream);
+int pgpu_synchronize(void);
+/* 0: fast arithmetic (FMA contraction, reciprocal multiplies, guarded floors);
+ * 1: reference operation order (no contraction, true divides).  Cell/node indices
+ * are bit-exact in both modes. */
+int pgpu_set_exact_math(int on);
+/* Deposit algorithm: 0 = global fp64 RED atomics, 1 = shared-memory tile
+ * accumulators with one flush per tile (needs a cell-sorted species). */
+int pgpu_set_deposit_mode(int mode);
+
+/* ---- grid: DomainGrid + the box owned by this device ----------------------- */
+typedef struct {
+  int D;               /* SpaceDim (1 or 2) */
+  int ncell[2];        /* grid.num_cells (global) */
+  double xmin[2];      /* DomainGrid::getXmin */
+  double dx[2];        /* DomainGrid::getdX */
+  int nghost;          /* grid.num_ghosts */
+  int periodic[2];     /* grid.is_periodic */
+  int box_lo[2];       /* cells owned by this device, inclusive, global indices */
+  int box_hi[2];
+  double volume_scale; /* DomainGrid::getVolumeScale */
+} pgpu_grid_desc;
+
+int pgpu_grid_create(const pgpu_grid_desc *desc, pgpu_grid_t *out);
+int pgpu_grid_destroy(pgpu_grid_t g);
+/* Upload one E/B component (EMFields E on edges/nodes, B on faces/cells) for the
+ * whole ghosted box: what PicChargedSpecies::interpolateFieldsToParticles reads
+ * (PicChargedSpecies.cpp:3814-3917).  lo/hi must equal the box's ghosted bounds
+ * for that centring. */
+int pgpu_fields_set(pgpu_grid_t g, int comp, const double *data, const int *lo, const int *hi);
+/* Bounds of component `comp` (PGPU_EX..BZ; J uses the E bounds) */
+int pgpu_field_bounds(pgpu_grid_t g, int comp, int *lo, int *hi);
+/* Total current of all species: PicSpeciesInterface::m_currentDensity[_virtual] */
+int pgpu_current_zero(pgpu_grid_t g);                         /* SpaceUtils::zero, PicSpeciesInterface.cpp:831-834 */
+int pgpu_current_add_species(pgpu_grid_t g, pgpu_species_t s);/* FArrayBox::plus, :841-855 */
+/* Ghost ADD-exchange of the total J, then ghost refresh: the exchange part of
+ * PicSpeciesInterface::finalizeSettingJ (:766-772).  Single device: periodic fold. */
+int pgpu_current_finalize(pgpu_grid_t g);
+int pgpu_current_get(pgpu_grid_t g, int comp, double *data, const int *lo, const int *hi);
+
+/* ---- species: PicChargedSpecies ------------------------------------------- */
+typedef struct {
+  double mass;         /* m_mass   (units of me) */
+  double charge;       /* m_charge (units of |qe|) */
+  double fnorm_const;  /* m_fnorm_const, PicChargedSpecies.cpp:1953-1958 */
+  double cvac_norm;    /* m_cvac_norm,   PicChargedSpecies.cpp:1960 */
+  int interp_N;        /* m_interpRhoToGrid (CIC|TSC) */
+  int interp_J;        /* m_interpJToGrid */
+  int interp_E;        /* m_interpEToParts */
+  double rtol;         /* pic_species.rtol_particles */
+  int iter_max;        /* pic_species.iter_max_particles */
+  int order_swap;      /* pic_species.part_order_swap */
+  int bc_check_lo[2];  /* interp_bc_check -> m_bc_check_lo/hi */
+  int bc_check_hi[2];
+  int motion;          /* m_motion */
+  int forces;          /* m_forces */
+} pgpu_species_desc;
+
+int pgpu_species_create(pgpu_grid_t g, const pgpu_species_desc *desc, pgpu_species_t *out);
+int pgpu_species_destroy(pgpu_species_t s);
+/* Replace the particle set (PicChargedSpecies::initialize / partData() sync). */
+int pgpu_species_upload(pgpu_species_t s, long n, const double *x, const double *xold,
+                        const double *v, const double *vold, const double *w,
+                        const uint64_t *id);
+/* Any output pointer may be NULL. */
+int pgpu_species_download(pgpu_species_t s, double *x, double *xold, double *v,
+                          double *vold, double *w, uint64_t *id);
+long pgpu_species_count(pgpu_species_t s);            /* numParticles() */
+
+/* push: same-named PicChargedSpecies methods */
+int pgpu_advance_positions_explicit(pgpu_species_t s, double full_dt, int half_step); /* :463-504 */
+int pgpu_advance_positions_implicit(pgpu_species_t s, double full_dt);               /* :506-561 */
+int pgpu_advance_positions_2nd_half(pgpu_species_t s);                               /* :997-1025 */
+int pgpu_interpolate_fields_to_particles(pgpu_species_t s);                          /* :3814-3917 */
+int pgpu_advance_velocities(pgpu_species_t s, double full_dt, int half_step);        /* :1116-1134 */
+int pgpu_advance_velocities_2nd_half(pgpu_species_t s);                              /* :1136-1244 */
+int pgpu_average_velocities(pgpu_species_t s);                                       /* :1202-1226 */
+int pgpu_update_old_particle_positions(pgpu_species_t s);                            /* :1821-1845 */
+int pgpu_update_old_particle_velocities(pgpu_species_t s);                           /* :1847-1867 */
+int pgpu_reset_particles(pgpu_species_t s);                                          /* :1791-1819 */
+/* Ep/Bp of the last pgpu_interpolate_fields_to_particles (test/diagnostic hook) */
+int pgpu_species_download_fields(pgpu_species_t s, double *Ep, double *Bp);
+
+typedef struct {
+  long num_parts_its;   /* m_num_parts_its increment  (:1646) */
+  long num_apply_its;   /* m_num_apply_its increment  (:1654,1671) */
+  long num_unconverged; /* particles left at the iteration cap (:1680) */
+} pgpu_picard_stats;
+/* advanceParticles (:1594-1612) */
+int pgpu_advance_particles(pgpu_species_t s, double dt);
+/* advanceParticlesIteratively (:1614-1716).  deposit_J != 0 fuses this species'
+ * setCurrentDensity(dt,false) (:3184-3253) into the same kernel. */
+int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_J,
+                                       pgpu_picard_stats *stats);
+
+/* deposit */
+int pgpu_set_current_density(pgpu_species_t s, double dt, int from_explicit_solver); /* :3184-3253 */
+int pgpu_species_current_get(pgpu_species_t s, int comp, double *data, const int *lo, const int *hi);
+/* setChargeDensityOnNodes (:3134-3182, stag = 1,1), setChargeDensity (:3049-3086,
+ * stag = 0,0) and one face direction (:3088-3132): deposit, x charge/volume_scale,
+ * ghost add-exchange.  Result returned in data (bounds for that centring). */
+int pgpu_set_charge_density(pgpu_species_t s, const int *stag, double *data, const int *lo, const int *hi);
+
+/* cell sort + cell moments: binTheParticles (:1913-1947), set*DensityFromBinFab
+ * (:2881-3047), PicSpeciesInterface::setDebyeLength (PicSpeciesInterface.cpp:1627-1721) */
+int pgpu_bin_particles(pgpu_species_t s);
+int pgpu_species_cell_index(pgpu_species_t s, int *cell /* [D][n] */);
+int pgpu_species_cell_offsets(pgpu_species_t s, long *offsets /* ncell+1 */);
+int pgpu_set_moments_from_bins(pgpu_species_t s);
+int pgpu_species_moments_get(pgpu_species_t s, double *dens, double *mom, double *ene);
+int pgpu_debye_length(pgpu_grid_t g, pgpu_species_t *species, int nspecies, double *LDe_or_null);
+
+/* boundary conditions + ownership: applyBCs (:1080-1114) for periodic / symmetry
+ * (PicChargedSpeciesBC.cpp:738-765, 808-870).  bc_lo/bc_hi[d] = PGPU_BC_*. */
+int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi);
+
+/* reductions: setStableDt (:1869-1911), globalMoments (:4067-4130) */
+int pgpu_stable_dt(pgpu_species_t s, double *dt_out);
+int pgpu_global_moments(pgpu_species_t s, double *out /* [w, wux,wuy,wuz, wuu_x,wuu_y,wuu_z] */);
+
+/* ---- collisions: Scattering subclasses ------------------------------------- */
+/* TakizukaAbe::applyScattering (TakizukaAbe.cpp:240-536).  Species must be binned
+ * and have number densities set.  sA == sB selects self-scattering.  The Philox
+ * counter is keyed by (seed, step, cell, pair). */
+int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt_sec,
+                    uint64_t seed, uint64_t step, long *npairs);
+/* TakizukaAbe::computeDeltaU (:538-578) for explicit random numbers (test hook). */
+int pgpu_ta_delta_u(long n, const double *vp1, const double *den1, const double *vp2,
+                    const double *den2, double b90_fact, double Clog, double dt_sec,
+                    const double *gauss, const double *u_theta, const double *u_phi,
+                    double *dU);
+
+/* ---- instrumentation ---------------------------------------------------------- */
+/* CUDA-event timing of the library's own kernels on the launch stream. */
+int pgpu_profile_enable(int on);
+int pgpu_profile_reset(void);
+/* total milliseconds and launch count of kernels whose name starts with prefix */
+int pgpu_profile_query(const char *prefix, double *ms, long *launches);
+long pgpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,243 @@
+"""ctypes front-end of the CPU oracle (liboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module (see oracle/picnic_oracle.h).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+CIC, TSC, CC0, CC1 = 0, 1, 2, 3
+
+# component centring (1 = nodal, 0 = cell centred) per direction, SURVEY App. A
+E_STAG = {1: [(0,), (1,), (1,)], 2: [(0, 1), (1, 0), (1, 1)]}
+B_STAG = {1: [(1,), (0,), (0,)], 2: [(1, 0), (0, 1), (0, 0)]}
+
+
+class Geom(C.Structure):
+    _fields_ = [("D", C.c_int), ("le", C.c_double * 2), ("re", C.c_double * 2),
+                ("dx", C.c_double * 2), ("ghosts", C.c_int),
+                ("bc_lo", C.c_int * 2), ("bc_hi", C.c_int * 2)]
+
+
+class CFab(C.Structure):
+    _fields_ = [("p", C.POINTER(C.c_double)), ("lo", C.c_int * 2), ("hi", C.c_int * 2)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_ta_b90_fact.restype = C.c_double
+        dbl = C.c_double
+        _LIB.orc_boris.argtypes = [C.c_long] + [C.c_void_p] * 4 + [dbl, dbl, C.c_int]
+        _LIB.orc_advance_positions_explicit.argtypes = [C.c_int, C.c_long] + [C.c_void_p] * 3 + [dbl]
+        _LIB.orc_advance_positions_implicit.argtypes = [C.c_int, C.c_long] + [C.c_void_p] * 3 + [dbl]
+        _LIB.orc_advance_positions_2nd_half.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_void_p]
+        _LIB.orc_advance_velocities_2nd_half.argtypes = [C.c_long, C.c_void_p, C.c_void_p]
+        _LIB.orc_average_velocities.argtypes = [C.c_long, C.c_void_p, C.c_void_p]
+        _LIB.orc_gather.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 6
+        _LIB.orc_deposit_current.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 4 + [dbl, C.c_void_p]
+        _LIB.orc_deposit_rho.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 4
+        _LIB.orc_scale_fab.argtypes = [C.c_void_p, C.c_int, dbl]
+        _LIB.orc_advance_particles.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 6 + [dbl, dbl, C.c_int]
+        _LIB.orc_advance_particles_iteratively.argtypes = (
+            [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 6 + [dbl, dbl, dbl, C.c_int] + [C.c_void_p] * 3)
+        _LIB.orc_fold_periodic.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        _LIB.orc_bin.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+        _LIB.orc_cell_moments.argtypes = [C.c_void_p, C.c_long] + [C.c_void_p] * 3 + [dbl, dbl] + [C.c_void_p] * 5
+        _LIB.orc_debye_accumulate.argtypes = [C.c_long] + [C.c_void_p] * 3 + [dbl, dbl, C.c_void_p]
+        _LIB.orc_debye_finish.argtypes = [C.c_long, C.c_void_p]
+        _LIB.orc_bc_periodic.argtypes = [C.c_long, C.c_void_p, C.c_void_p, dbl, dbl]
+        _LIB.orc_bc_symmetry.argtypes = [C.c_long] + [C.c_void_p] * 4 + [dbl, dbl, C.c_int, C.c_int]
+        _LIB.orc_rng_seed.argtypes = [C.c_uint64]
+        _LIB.orc_scatter_delta_u.argtypes = [dbl] * 7 + [C.c_void_p]
+        _LIB.orc_ta_delta_u.argtypes = [C.c_void_p, dbl, C.c_void_p, dbl, dbl, dbl, dbl, dbl, dbl, dbl, C.c_void_p]
+        _LIB.orc_ta_b90_fact.argtypes = [dbl] * 4
+        _LIB.orc_ta_self.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, dbl, dbl, dbl, dbl, C.c_void_p]
+        _LIB.orc_ta_inter.argtypes = ([C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, dbl, dbl,
+                                       C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, dbl, dbl, dbl, dbl, C.c_void_p])
+    return _LIB
+
+
+def _ptr(a):
+    assert a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Fab:
+    """One component in Chombo FArrayBox layout: column-major, inclusive bounds."""
+
+    def __init__(self, lo, hi, data=None):
+        self.lo = tuple(int(v) for v in lo)
+        self.hi = tuple(int(v) for v in hi)
+        shape = tuple(h - l + 1 for l, h in zip(self.lo, self.hi))
+        self.a = np.zeros(shape, dtype=np.float64, order="F") if data is None else np.asfortranarray(data, dtype=np.float64)
+        assert self.a.shape == shape
+
+    def c(self):
+        f = CFab()
+        f.p = self.a.ctypes.data_as(C.POINTER(C.c_double))
+        for d in range(2):
+            f.lo[d] = self.lo[d] if d < len(self.lo) else 0
+            f.hi[d] = self.hi[d] if d < len(self.hi) else 0
+        return f
+
+    def copy(self):
+        return Fab(self.lo, self.hi, self.a.copy(order="F"))
+
+
+def fab_for(box_lo, box_hi, nghost, stag):
+    lo = [l - nghost for l in box_lo]
+    hi = [h + nghost + s for h, s in zip(box_hi, stag)]
+    return Fab(lo, hi)
+
+
+def make_geom(D, le, re, dx, ghosts, bc_lo=None, bc_hi=None):
+    g = Geom()
+    g.D = D
+    for d in range(D):
+        g.le[d], g.re[d], g.dx[d] = le[d], re[d], dx[d]
+        g.bc_lo[d] = 0 if bc_lo is None else bc_lo[d]
+        g.bc_hi[d] = 0 if bc_hi is None else bc_hi[d]
+    if D == 1:
+        g.le[1], g.re[1], g.dx[1] = 0.0, 1.0, 1.0
+    g.ghosts = ghosts
+    return g
+
+
+def _fabs3(fabs):
+    arr = (CFab * 3)()
+    for i, f in enumerate(fabs):
+        arr[i] = f.c()
+    return arr
+
+
+def gather(g, interp, x, xold, E, B):
+    n = x.shape[1]
+    Ep = np.zeros((3, n))
+    Bp = np.zeros((3, n))
+    rc = lib().orc_gather(C.byref(g), interp, n, _ptr(x), _ptr(xold), _fabs3(E), _fabs3(B), _ptr(Ep), _ptr(Bp))
+    return rc, Ep, Bp
+
+
+def boris(v, vold, Ep, Bp, fnorm, cnormDt, by_half):
+    out = np.empty_like(v)
+    lib().orc_boris(v.shape[1], _ptr(out), _ptr(vold), _ptr(Ep), _ptr(Bp), fnorm, cnormDt, int(by_half))
+    return out
+
+
+def deposit_current(g, interp, x, xold, v, w, cnormDt, J):
+    n = x.shape[1]
+    return lib().orc_deposit_current(C.byref(g), interp, n, _ptr(x), _ptr(xold), _ptr(v), _ptr(w), cnormDt, _fabs3(J))
+
+
+def deposit_rho(g, interp, x, w, stag, rho):
+    st = (C.c_int * 2)(*(list(stag) + [0])[:2])
+    f = rho.c()
+    lib().orc_deposit_rho(C.byref(g), interp, x.shape[1], _ptr(x), _ptr(w), st, C.byref(f))
+
+
+def scale_fab(f, D, s):
+    cf = f.c()
+    lib().orc_scale_fab(C.byref(cf), D, s)
+
+
+def fold_periodic(f, D, stag, valid_lo, valid_hi, periodic):
+    cf = f.c()
+    i2 = lambda v: (C.c_int * 2)(*(list(v) + [0])[:2])
+    lib().orc_fold_periodic(C.byref(cf), D, i2(stag), i2(valid_lo), i2(valid_hi), i2(periodic))
+
+
+def advance_particles(g, interpE, x, xold, v, vold, E, B, fnorm, cnormDt, order_swap):
+    n = x.shape[1]
+    return lib().orc_advance_particles(C.byref(g), interpE, n, _ptr(x), _ptr(xold), _ptr(v), _ptr(vold),
+                                       _fabs3(E), _fabs3(B), fnorm, cnormDt, int(order_swap))
+
+
+def advance_particles_iteratively(g, interpE, x, xold, v, vold, E, B, fnorm, cnormDt, rtol, iter_max):
+    n = x.shape[1]
+    apply_its = C.c_long(0)
+    unconv = C.c_long(0)
+    its = np.zeros(n, dtype=np.int32)
+    rc = lib().orc_advance_particles_iteratively(
+        C.byref(g), interpE, n, _ptr(x), _ptr(xold), _ptr(v), _ptr(vold), _fabs3(E), _fabs3(B),
+        fnorm, cnormDt, rtol, iter_max, C.byref(apply_its), C.byref(unconv), _ptr(its))
+    return rc, apply_its.value, unconv.value, its
+
+
+def bin_cells(g, x):
+    n = x.shape[1]
+    cell = np.zeros((g.D, n), dtype=np.int32)
+    lib().orc_bin(C.byref(g), n, _ptr(x), _ptr(cell))
+    return cell
+
+
+def cell_moments(g, x, v, w, mass, volume_scale, lo, hi):
+    n = x.shape[1]
+    shape = [h - l + 1 for l, h in zip(lo, hi)]
+    ncell = int(np.prod(shape))
+    dens = np.zeros(ncell)
+    mom = np.zeros((3, ncell))
+    ene = np.zeros((3, ncell))
+    i2 = lambda v_: (C.c_int * 2)(*(list(v_) + [0])[:2])
+    lib().orc_cell_moments(C.byref(g), n, _ptr(x), _ptr(v), _ptr(w), mass, volume_scale, i2(lo), i2(hi),
+                           _ptr(dens), _ptr(mom), _ptr(ene))
+    return dens, mom, ene
+
+
+def debye_length(species_moments):
+    """species_moments: list of (dens, mom, ene, mass, charge)."""
+    ncell = species_moments[0][0].size
+    acc = np.zeros(ncell)
+    for dens, mom, ene, mass, charge in species_moments:
+        lib().orc_debye_accumulate(ncell, _ptr(dens), _ptr(mom), _ptr(ene), mass, charge, _ptr(acc))
+    lib().orc_debye_finish(ncell, _ptr(acc))
+    return acc
+
+
+def scatter_delta_u(u, costh, sinth, cosphi, sinphi):
+    dU = np.zeros(3)
+    lib().orc_scatter_delta_u(u[0], u[1], u[2], costh, sinth, cosphi, sinphi, _ptr(dU))
+    return dU
+
+
+def ta_delta_u(vp1, den1, vp2, den2, b90_fact, Clog, dt_sec, gauss, u_theta, u_phi):
+    dU = np.zeros(3)
+    a = np.ascontiguousarray(vp1, dtype=np.float64)
+    b = np.ascontiguousarray(vp2, dtype=np.float64)
+    lib().orc_ta_delta_u(_ptr(a), den1, _ptr(b), den2, b90_fact, Clog, dt_sec, gauss, u_theta, u_phi, _ptr(dU))
+    return dU
+
+
+def ta_b90_fact(q1, q2, m1, m2):
+    return lib().orc_ta_b90_fact(q1, q2, m1, m2)
+
+
+def ta_self(cell_start, v, dens, mass, charge, Clog, dt_sec):
+    npairs = C.c_long(0)
+    cs = np.ascontiguousarray(cell_start, dtype=np.int64)
+    lib().orc_ta_self(cs.size - 1, _ptr(cs), _ptr(v), v.shape[1], _ptr(dens), mass, charge, Clog, dt_sec, C.byref(npairs))
+    return npairs.value
+
+
+def ta_inter(cs1, v1, dens1, m1, q1, cs2, v2, dens2, m2, q2, Clog, dt_sec):
+    npairs = C.c_long(0)
+    cs1 = np.ascontiguousarray(cs1, dtype=np.int64)
+    cs2 = np.ascontiguousarray(cs2, dtype=np.int64)
+    lib().orc_ta_inter(cs1.size - 1, _ptr(cs1), _ptr(v1), v1.shape[1], _ptr(dens1), m1, q1,
+                       _ptr(cs2), _ptr(v2), v2.shape[1], _ptr(dens2), m2, q2, Clog, dt_sec, C.byref(npairs))
+    return npairs.value

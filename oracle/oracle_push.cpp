@@ -1,0 +1,294 @@
+/*
+ * oracle_push.cpp -- TEST INFRASTRUCTURE ONLY (see picnic_oracle.h).
+ *
+ * CPU restatement of the particle advance loops of
+ *   src/species/pic/PicSpeciesUtils.cpp:8-101            (Boris, PLANAR)
+ *   src/species/pic/charged/PicChargedSpecies.cpp        (position updates,
+ *       stepNormTransfer, advanceParticles[Iteratively], binning, moments, BCs)
+ *   src/species/pic/PicSpeciesInterface.cpp:1627-1721    (Debye length)
+ * Non-relativistic build (RELATIVISTIC_PARTICLES undefined), planar push.
+ */
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "picnic_oracle.h"
+
+namespace {
+/* src/core/PicnicConstants.H:13-51 */
+const double kPI = M_PI;
+const double kTWOPI = 2.0 * M_PI;
+const double kFOURPI = 4.0 * M_PI;
+const double kCVAC = 2.99792458e+08;
+const double kMU0 = kFOURPI * 1.0e-7;
+const double kEP0 = 1.0 / kCVAC / kCVAC / kMU0;
+const double kME = 9.10938370e-31;
+const double kQE = 1.60217663e-19;
+const double kH = 6.62607015e-34;
+const double kHBAR = kH / kTWOPI;
+const double kEV_PER_JOULE = 1.0 / kQE;
+}  // namespace
+
+/* PicSpeciesUtils::applyForces (PicSpeciesUtils.cpp:8-101), dirp = {0,1,2}. */
+extern "C" void orc_boris(long n, double *v, const double *vold, const double *Ep,
+                          const double *Bp, double fnorm, double cnormDt,
+                          int byHalfDt) {
+  const double alpha = fnorm * cnormDt / 2.0;
+  for (long p = 0; p < n; ++p) {
+    const double vm0 = vold[p] + alpha * Ep[p];
+    const double vm1 = vold[n + p] + alpha * Ep[n + p];
+    const double vm2 = vold[2 * n + p] + alpha * Ep[2 * n + p];
+    const double bp0 = alpha * Bp[p];
+    const double bp1 = alpha * Bp[n + p];
+    const double bp2 = alpha * Bp[2 * n + p];
+    const double denom = 1.0 + bp0 * bp0 + bp1 * bp1 + bp2 * bp2;
+    const double vpr0 = vm0 + vm1 * bp2 - vm2 * bp1;
+    const double vpr1 = vm1 + vm2 * bp0 - vm0 * bp2;
+    const double vpr2 = vm2 + vm0 * bp1 - vm1 * bp0;
+    double up0 = vm0 + (vpr1 * bp2 - vpr2 * bp1) / denom;
+    double up1 = vm1 + (vpr2 * bp0 - vpr0 * bp2) / denom;
+    double up2 = vm2 + (vpr0 * bp1 - vpr1 * bp0) / denom;
+    if (!byHalfDt) {
+      up0 = 2.0 * up0 - vold[p];
+      up1 = 2.0 * up1 - vold[n + p];
+      up2 = 2.0 * up2 - vold[2 * n + p];
+    }
+    v[p] = up0;
+    v[n + p] = up1;
+    v[2 * n + p] = up2;
+  }
+}
+
+/* PicChargedSpecies::advancePositionsExplicit (PicChargedSpecies.cpp:483-504) */
+extern "C" void orc_advance_positions_explicit(int D, long n, double *x,
+                                               const double *xold,
+                                               const double *v, double cnormDt) {
+  for (long p = 0; p < n; ++p)
+    for (int d = 0; d < D; ++d) x[d * n + p] = xold[d * n + p] + v[d * n + p] * cnormDt;
+}
+
+/* PicChargedSpecies::advancePositionsImplicit (PicChargedSpecies.cpp:523-561) */
+extern "C" void orc_advance_positions_implicit(int D, long n, double *x,
+                                               const double *xold,
+                                               const double *v, double cnormDt) {
+  const double cnormHalfDt = cnormDt * 0.5;
+  for (long p = 0; p < n; ++p)
+    for (int d = 0; d < D; ++d) x[d * n + p] = xold[d * n + p] + v[d * n + p] * cnormHalfDt;
+}
+
+/* PicChargedSpecies::advancePositions_2ndHalf (PicChargedSpecies.cpp:1015-1025) */
+extern "C" void orc_advance_positions_2nd_half(int D, long n, double *x,
+                                               const double *xold) {
+  for (long i = 0; i < (long)D * n; ++i) x[i] = 2.0 * x[i] - xold[i];
+}
+
+/* PicChargedSpecies::advanceVelocities_2ndHalf (PicChargedSpecies.cpp:1228-1244) */
+extern "C" void orc_advance_velocities_2nd_half(long n, double *v,
+                                                const double *vold) {
+  for (long i = 0; i < 3 * n; ++i) v[i] = 2.0 * v[i] - vold[i];
+}
+
+/* PicChargedSpecies::averageVelocities (PicChargedSpecies.cpp:1202-1226) */
+extern "C" void orc_average_velocities(long n, double *v, const double *vold) {
+  for (long i = 0; i < 3 * n; ++i) v[i] = (v[i] + vold[i]) / 2.0;
+}
+
+/* PicChargedSpecies::advanceParticles (PicChargedSpecies.cpp:1594-1612) */
+extern "C" int orc_advance_particles(const orc_geom *g, int interpE, long n,
+                                     double *x, const double *xold, double *v,
+                                     const double *vold, const orc_fab *E,
+                                     const orc_fab *B, double fnorm,
+                                     double cnormDt, int order_swap) {
+  std::vector<double> Ep(3 * n), Bp(3 * n);
+  if (order_swap) orc_advance_positions_implicit(g->D, n, x, xold, v, cnormDt);
+  const int rc = orc_gather(g, interpE, n, x, xold, E, B, Ep.data(), Bp.data());
+  orc_boris(n, v, vold, Ep.data(), Bp.data(), fnorm, cnormDt, 1);
+  if (!order_swap) orc_advance_positions_implicit(g->D, n, x, xold, v, cnormDt);
+  return rc;
+}
+
+/* stepNormTransfer (PicChargedSpecies.cpp:658-733) for one particle.
+ * Returns true if the particle is converged; updates xbar as the reference does. */
+static bool step_norm(const orc_geom *g, long n, long p, double *x,
+                      const double *xold, const double *v, double cnormDt,
+                      double rtol, bool reverse) {
+  const double cnormHalfDt = 0.5 * cnormDt;
+  double dxp[2] = {0.0, 0.0};
+  double rel_diff_max = 0.0;
+  for (int d = 0; d < g->D; ++d) {
+    const double dxp0 = x[d * n + p] - xold[d * n + p];
+    dxp[d] = v[d * n + p] * cnormHalfDt;
+    const double rel_diff_dir = std::fabs(dxp0 - dxp[d]) / g->dx[d];
+    rel_diff_max = std::max(rel_diff_max, rel_diff_dir);
+  }
+  if (reverse) {
+    if (rel_diff_max < rtol) return true;
+    for (int d = 0; d < g->D; ++d) x[d * n + p] = xold[d * n + p] + dxp[d];
+    return false;
+  }
+  for (int d = 0; d < g->D; ++d) x[d * n + p] = xold[d * n + p] + dxp[d];
+  return !(rel_diff_max >= rtol);
+}
+
+/* PicChargedSpecies::advanceParticlesIteratively (PicChargedSpecies.cpp:1614-1716).
+ * The linked-list transfers are restated as an "active" index list; particles
+ * are independent, so list order has no effect on per-particle results. */
+extern "C" int orc_advance_particles_iteratively(
+    const orc_geom *g, int interpE, long n, double *x, const double *xold,
+    double *v, const double *vold, const orc_fab *E, const orc_fab *B,
+    double fnorm, double cnormDt, double rtol, int iter_max, long *num_apply_its,
+    long *num_unconverged, int *its_out) {
+  int rc = 0;
+  long apply_its = 0;
+  std::vector<double> Ep(3 * n), Bp(3 * n);
+  if (orc_gather(g, interpE, n, x, xold, E, B, Ep.data(), Bp.data())) rc = -1;
+  orc_boris(n, v, vold, Ep.data(), Bp.data(), fnorm, cnormDt, 1);
+  apply_its += n;
+  std::vector<long> temp;
+  for (long p = 0; p < n; ++p) {
+    if (its_out) its_out[p] = 1;
+    if (!step_norm(g, n, p, x, xold, v, cnormDt, rtol, false)) temp.push_back(p);
+  }
+  int iter = 1;
+  double xp[2], xpo[2], vo[3], vn[3], ep[3], bp[3];
+  while (!temp.empty()) {
+    std::vector<long> still;
+    for (long p : temp) {
+      /* single-particle gather + Boris through the same array routines */
+      for (int d = 0; d < g->D; ++d) {
+        xp[d] = x[d * n + p];
+        xpo[d] = xold[d * n + p];
+      }
+      for (int c = 0; c < 3; ++c) vo[c] = vold[c * n + p];
+      if (orc_gather(g, interpE, 1, xp, xpo, E, B, ep, bp)) rc = -1;
+      orc_boris(1, vn, vo, ep, bp, fnorm, cnormDt, 1);
+      for (int c = 0; c < 3; ++c) v[c * n + p] = vn[c];
+      if (its_out) its_out[p] += 1;
+    }
+    apply_its += (long)temp.size();
+    for (long p : temp)
+      if (!step_norm(g, n, p, x, xold, v, cnormDt, rtol, true)) still.push_back(p);
+    temp.swap(still);
+    if (temp.empty()) break;
+    if (iter >= iter_max) break;
+    iter += 1;
+  }
+  if (num_apply_its) *num_apply_its = apply_its;
+  if (num_unconverged) *num_unconverged = (long)temp.size();
+  return rc;
+}
+
+/* BinFab::locateBin (BinFabImplem.H:582-594): (int)floor((x-origin)/dx). */
+extern "C" void orc_bin(const orc_geom *g, long n, const double *x, int *cell) {
+  for (long p = 0; p < n; ++p)
+    for (int d = 0; d < g->D; ++d) {
+      double t = x[d * n + p];
+      t -= g->le[d];
+      t /= g->dx[d];
+      cell[d * n + p] = (int)std::floor(t);
+    }
+}
+
+/* set{Number,Momentum,Energy}DensityFromBinFab (PicChargedSpecies.cpp:2881-3047),
+ * cartesian (Jacobian == 1).  Sums run over the particles of a cell in the
+ * order they appear in the input arrays. */
+extern "C" void orc_cell_moments(const orc_geom *g, long n, const double *x,
+                                 const double *v, const double *w, double mass,
+                                 double volume_scale, const int *lo, const int *hi,
+                                 double *dens, double *mom, double *ene) {
+  const int D = g->D;
+  const int n0 = hi[0] - lo[0] + 1;
+  const int n1 = (D == 2) ? hi[1] - lo[1] + 1 : 1;
+  const long ncell = (long)n0 * n1;
+  const double dV_mapped = (D == 1) ? g->dx[0] : g->dx[0] * g->dx[1];
+  const double dV_phys = dV_mapped * volume_scale;
+  std::fill(dens, dens + ncell, 0.0);
+  std::fill(mom, mom + 3 * ncell, 0.0);
+  std::fill(ene, ene + 3 * ncell, 0.0);
+  std::vector<int> cell((size_t)D * n);
+  orc_bin(g, n, x, cell.data());
+  for (long p = 0; p < n; ++p) {
+    const int i = cell[p] - lo[0];
+    const int j = (D == 2) ? cell[n + p] - lo[1] : 0;
+    if (i < 0 || i >= n0 || j < 0 || j >= n1) continue;
+    const long c = i + (long)j * n0;
+    const double wp = w[p];
+    dens[c] += wp;
+    for (int k = 0; k < 3; ++k) {
+      const double up = v[k * n + p];
+      mom[k * ncell + c] += wp * up;
+      ene[k * ncell + c] += wp * up * up;
+    }
+  }
+  const double kn = 1.0 / dV_phys, km = mass / dV_phys, ke = 0.5 * mass / dV_phys;
+  for (long c = 0; c < ncell; ++c) dens[c] *= kn;
+  for (long c = 0; c < 3 * ncell; ++c) {
+    mom[c] *= km;
+    ene[c] *= ke;
+  }
+}
+
+/* PicSpeciesInterface::setDebyeLength (PicSpeciesInterface.cpp:1627-1721) */
+extern "C" void orc_debye_accumulate(long ncell, const double *dens,
+                                     const double *mom, const double *ene,
+                                     double mass, double charge, double *sum_inv) {
+  const double mcSq_eV = kME * kCVAC * kCVAC * kEV_PER_JOULE;
+  const double Aconst = kEP0 / kQE / (charge * charge);
+  for (long c = 0; c < ncell; ++c) {
+    const double N = dens[c];
+    if (N == 0.0) continue;
+    const double R = 1.0 / std::cbrt(4.0 / 3.0 * kPI * N);
+    const double rho = N * mass;
+    const double rhoUx = mom[c], rhoUy = mom[ncell + c], rhoUz = mom[2 * ncell + c];
+    const double meanE = (rhoUx * rhoUx + rhoUy * rhoUy + rhoUz * rhoUz) / rho / 2.0;
+    const double EF_eV = kHBAR * kHBAR / (2.0 * kME * mass) *
+                         std::pow(3.0 * kPI * kPI * N, 2.0 / 3.0) * kEV_PER_JOULE;
+    double rhoE = 0.0;
+    for (int dir = 0; dir < 3; ++dir) rhoE += ene[dir * ncell + c];
+    double T_eV = 2.0 / 3.0 * (rhoE - meanE) / N * mcSq_eV;
+    T_eV = std::max(T_eV, 0.01);
+    const double LDe_sq = std::max(Aconst * (T_eV + 2.0 / 3.0 * EF_eV) / N, R * R);
+    sum_inv[c] += 1.0 / LDe_sq;
+  }
+}
+
+extern "C" void orc_debye_finish(long ncell, double *a) {
+  for (long c = 0; c < ncell; ++c) a[c] = 1.0 / std::sqrt(a[c]);
+}
+
+/* PicChargedSpeciesBC::enforcePeriodic (PicChargedSpeciesBC.cpp:738-765) */
+extern "C" void orc_bc_periodic(long n, double *x, double *xold, double left,
+                                double right) {
+  const double Lbox = right - left;
+  for (long p = 0; p < n; ++p) {
+    if (x[p] < left) {
+      x[p] = x[p] + Lbox;
+      xold[p] = xold[p] + Lbox;
+    }
+    if (x[p] >= right) {
+      x[p] = x[p] - Lbox;
+      xold[p] = xold[p] - Lbox;
+    }
+  }
+}
+
+/* PicChargedSpeciesBC::symmetry_Lo / symmetry_Hi (PicChargedSpeciesBC.cpp:808-870) */
+extern "C" void orc_bc_symmetry(long n, double *x, double *xold, double *v,
+                                double *vold, double left, double right,
+                                int do_lo, int do_hi) {
+  for (long p = 0; p < n; ++p) {
+    if (do_lo && x[p] <= left) {
+      x[p] = 2. * left - x[p];
+      v[p] = -v[p];
+      xold[p] = 2. * left - xold[p];
+      vold[p] = -vold[p];
+    }
+    if (do_hi && x[p] >= right) {
+      x[p] = 2. * right - x[p];
+      v[p] = -v[p];
+      xold[p] = 2. * right - xold[p];
+      vold[p] = -vold[p];
+      if (x[p] == right) x[p] = 0.999999999 * right;
+    }
+  }
+}

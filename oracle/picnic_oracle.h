@@ -1,0 +1,153 @@
+/*
+ * picnic_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Scalar CPU restatement of the arithmetic of PICNIC's per-particle hot path
+ * (push, gather, deposit, binary collisions).  It exists to check the CUDA path
+ * in picnic_b200/ and to provide the CPU baseline leg of bench.py.  Nothing in
+ * the product path may include, link or call it.
+ *
+ * PARITY STATUS: "parity unpinned".  The reference ships no golden vectors for
+ * this path and cannot be built here (Chombo,
+ * gfortran, MPI and HDF5 are absent), so this restatement is pinned only by
+ * reading the reference source and by the reference-derived invariants tested in
+ * tests/test_oracle_invariants.py (charge continuity of CC0/CC1, gather/deposit
+ * adjointness, Boris energy identity, analytic gyration, pair conservation).
+ *
+ * Every function cites the reference file:line it restates (paths relative to
+ * the PICNIC source tree).  Operation order follows the reference so that the
+ * oracle is bit-faithful when compiled with -O2 -ffp-contract=off.
+ *
+ * Array conventions
+ *   particles : SoA, component-major: x[d*n + p], v[c*n + p]
+ *   grids     : Chombo FArrayBox layout = column-major with inclusive lo/hi
+ *               bounds per direction, ghosts included: a(i,j) =
+ *               p[(i-lo0) + (j-lo1)*(hi0-lo0+1)].  For D==1 lo[1]=hi[1]=0.
+ */
+#ifndef PICNIC_ORACLE_H
+#define PICNIC_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_CIC = 0, ORC_TSC = 1, ORC_CC0 = 2, ORC_CC1 = 3 };
+
+typedef struct {
+  int D;           /* SpaceDim: 1 or 2 */
+  double le[2];    /* m_domainLeftEdge  (DomainGrid::getXmin) */
+  double re[2];    /* m_domainRightEdge (DomainGrid::getXmax) */
+  double dx[2];    /* mesh spacing */
+  int ghosts;      /* grid.num_ghosts (CC1 segment limit) */
+  int bc_lo[2];    /* m_bc_check_lo (interp_bc_check) */
+  int bc_hi[2];    /* m_bc_check_hi */
+} orc_geom;
+
+typedef struct {
+  double *p;       /* first element (lo0,lo1) of ONE component */
+  int lo[2];
+  int hi[2];
+} orc_fab;
+
+/* ---- push ------------------------------------------------------------- */
+void orc_boris(long n, double *v, const double *vold, const double *Ep,
+               const double *Bp, double fnorm, double cnormDt, int byHalfDt);
+void orc_advance_positions_explicit(int D, long n, double *x, const double *xold,
+                                    const double *v, double cnormDt);
+void orc_advance_positions_implicit(int D, long n, double *x, const double *xold,
+                                    const double *v, double cnormDt);
+void orc_advance_positions_2nd_half(int D, long n, double *x, const double *xold);
+void orc_advance_velocities_2nd_half(long n, double *v, const double *vold);
+void orc_average_velocities(long n, double *v, const double *vold);
+
+/* ---- gather / deposit --------------------------------------------------- */
+/* E[0..2],B[0..2] = the six component arrays in the order the reference passes
+ * them to MeshInterp::interpolateEMfieldsToPart.  Returns 0, or -1 if a CC1
+ * particle needs more than ghosts+1 segments (reference: Fortran STOP). */
+int orc_gather(const orc_geom *g, int interp, long n, const double *x,
+               const double *xold, const orc_fab *E, const orc_fab *B,
+               double *Ep, double *Bp);
+/* Accumulates into J[0..2] (caller zeroes them); no charge/volume_scale factor. */
+int orc_deposit_current(const orc_geom *g, int interp, long n, const double *x,
+                        const double *xold, const double *v, const double *w,
+                        double cnormDt, orc_fab *J);
+/* interp: ORC_CIC or ORC_TSC.  stag[d]=1 nodal, 0 cell-centred in d. */
+void orc_deposit_rho(const orc_geom *g, int interp, long n, const double *x,
+                     const double *w, const int *stag, orc_fab *rho);
+void orc_scale_fab(orc_fab *f, int D, double s);
+
+/* ---- implicit advance --------------------------------------------------- */
+int orc_advance_particles(const orc_geom *g, int interpE, long n, double *x,
+                          const double *xold, double *v, const double *vold,
+                          const orc_fab *E, const orc_fab *B, double fnorm,
+                          double cnormDt, int order_swap);
+/* Picard loop.  its_out (optional, may be NULL) receives the number of
+ * gather+Boris applications per particle; num_apply_its / num_unconverged are
+ * the reference's m_num_apply_its increment and the length of the temp list
+ * left over at the iteration cap. */
+int orc_advance_particles_iteratively(const orc_geom *g, int interpE, long n,
+                                      double *x, const double *xold, double *v,
+                                      const double *vold, const orc_fab *E,
+                                      const orc_fab *B, double fnorm,
+                                      double cnormDt, double rtol, int iter_max,
+                                      long *num_apply_its, long *num_unconverged,
+                                      int *its_out);
+
+/* ---- ghost handling of a deposited field (periodic, one box) -------------- */
+/* Adds every ghost entry onto its periodic image inside the valid region
+ * (valid cells lo..hi; nodal directions own nodes lo..hi+1 with node hi+1 the
+ * periodic image of node lo), then refreshes ghosts and the duplicated
+ * boundary node with the summed values. */
+void orc_fold_periodic(orc_fab *f, int D, const int *stag, const int *valid_lo,
+                       const int *valid_hi, const int *periodic);
+
+/* ---- binning and cell moments --------------------------------------------- */
+void orc_bin(const orc_geom *g, long n, const double *x, int *cell_ijk);
+/* dens[ncell], mom[3*ncell], ene[3*ncell] over the cell box lo..hi (column
+ * major); kernel factors follow set{Number,Momentum,Energy}DensityFromBinFab. */
+void orc_cell_moments(const orc_geom *g, long n, const double *x,
+                      const double *v, const double *w, double mass,
+                      double volume_scale, const int *lo, const int *hi,
+                      double *dens, double *mom, double *ene);
+/* Accumulate 1/LDe^2 of one species into sum_inv (caller zeroes), then call
+ * orc_debye_finish. */
+void orc_debye_accumulate(long ncell, const double *dens, const double *mom,
+                          const double *ene, double mass, double charge,
+                          double *sum_inv);
+void orc_debye_finish(long ncell, double *sum_inv_to_LDe);
+
+/* ---- boundary conditions --------------------------------------------------- */
+void orc_bc_periodic(long n, double *x_dir, double *xold_dir, double left,
+                     double right);
+void orc_bc_symmetry(long n, double *x_dir, double *xold_dir, double *v_dir,
+                     double *vold_dir, double left, double right, int do_lo,
+                     int do_hi);
+
+/* ---- collisions ------------------------------------------------------------ */
+void orc_rng_seed(uint64_t seed);
+/* ScatteringUtils::computeDeltaU with explicit angles */
+void orc_scatter_delta_u(double ux, double uy, double uz, double costh,
+                         double sinth, double cosphi, double sinphi,
+                         double *dU);
+/* TakizukaAbe::computeDeltaU with explicit random numbers: gauss ~ N(0,1),
+ * u_theta, u_phi ~ U[0,1). */
+void orc_ta_delta_u(const double *vp1, double den1, const double *vp2,
+                    double den2, double b90_fact, double Clog, double dt_sec,
+                    double gauss, double u_theta, double u_phi, double *dU);
+double orc_ta_b90_fact(double charge1, double charge2, double mass1, double mass2);
+/* Whole-box TA scattering on cell-binned particles.  cell_start[ncell+1] are
+ * offsets into the (cell-sorted) particle arrays of each species. */
+void orc_ta_self(long ncell, const long *cell_start, double *v, long n,
+                 const double *dens, double mass, double charge, double Clog,
+                 double dt_sec, long *npairs);
+void orc_ta_inter(long ncell, const long *cell_start1, double *v1, long n1,
+                  const double *dens1, double mass1, double charge1,
+                  const long *cell_start2, double *v2, long n2,
+                  const double *dens2, double mass2, double charge2, double Clog,
+                  double dt_sec, long *npairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,352 @@
+"""ctypes binding of the C ABI (include/picnic_gpu.h) -- used by tests/ and bench.py.
+
+This is the same boundary the C++ shim (picnic_b200/host/) calls.  There is no CPU
+fallback: if libpicnic_gpu.so is missing, or no CUDA device is usable, every entry
+point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpicnic_gpu.so")
+
+CIC, TSC, CC0, CC1 = 0, 1, 2, 3
+BC_NONE, BC_PERIODIC, BC_SYMMETRY = 0, 1, 2
+ERR_SEGMENTS, ERR_BOUNDS = -3, -4
+
+
+class PgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("D", C.c_int), ("ncell", C.c_int * 2), ("xmin", C.c_double * 2), ("dx", C.c_double * 2),
+                ("nghost", C.c_int), ("periodic", C.c_int * 2), ("box_lo", C.c_int * 2),
+                ("box_hi", C.c_int * 2), ("volume_scale", C.c_double)]
+
+
+class SpeciesDesc(C.Structure):
+    _fields_ = [("mass", C.c_double), ("charge", C.c_double), ("fnorm_const", C.c_double),
+                ("cvac_norm", C.c_double), ("interp_N", C.c_int), ("interp_J", C.c_int),
+                ("interp_E", C.c_int), ("rtol", C.c_double), ("iter_max", C.c_int),
+                ("order_swap", C.c_int), ("bc_check_lo", C.c_int * 2), ("bc_check_hi", C.c_int * 2),
+                ("motion", C.c_int), ("forces", C.c_int)]
+
+
+class PicardStats(C.Structure):
+    _fields_ = [("num_parts_its", C.c_long), ("num_apply_its", C.c_long), ("num_unconverged", C.c_long)]
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raise if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("picnic_b200: %s is missing -- run `python -m picnic_b200.build` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.pgpu_last_error.restype = C.c_char_p
+    lib.pgpu_species_count.restype = C.c_long
+    lib.pgpu_launch_count.restype = C.c_long
+    vp, dbl, i32, lng = C.c_void_p, C.c_double, C.c_int, C.c_long
+    sig = {
+        "pgpu_init": [i32], "pgpu_finalize": [], "pgpu_set_stream": [vp], "pgpu_synchronize": [],
+        "pgpu_set_exact_math": [i32], "pgpu_set_deposit_mode": [i32],
+        "pgpu_grid_create": [vp, vp], "pgpu_grid_destroy": [vp],
+        "pgpu_fields_set": [vp, i32, vp, vp, vp], "pgpu_field_bounds": [vp, i32, vp, vp],
+        "pgpu_current_zero": [vp], "pgpu_current_add_species": [vp, vp], "pgpu_current_finalize": [vp],
+        "pgpu_current_get": [vp, i32, vp, vp, vp],
+        "pgpu_species_create": [vp, vp, vp], "pgpu_species_destroy": [vp],
+        "pgpu_species_upload": [vp, lng, vp, vp, vp, vp, vp, vp],
+        "pgpu_species_download": [vp, vp, vp, vp, vp, vp, vp],
+        "pgpu_species_count": [vp],
+        "pgpu_advance_positions_explicit": [vp, dbl, i32], "pgpu_advance_positions_implicit": [vp, dbl],
+        "pgpu_advance_positions_2nd_half": [vp], "pgpu_interpolate_fields_to_particles": [vp],
+        "pgpu_advance_velocities": [vp, dbl, i32], "pgpu_advance_velocities_2nd_half": [vp],
+        "pgpu_average_velocities": [vp], "pgpu_update_old_particle_positions": [vp],
+        "pgpu_update_old_particle_velocities": [vp], "pgpu_reset_particles": [vp],
+        "pgpu_species_download_fields": [vp, vp, vp],
+        "pgpu_advance_particles": [vp, dbl], "pgpu_advance_particles_iteratively": [vp, dbl, i32, vp],
+        "pgpu_set_current_density": [vp, dbl, i32], "pgpu_species_current_get": [vp, i32, vp, vp, vp],
+        "pgpu_set_charge_density": [vp, vp, vp, vp, vp],
+        "pgpu_bin_particles": [vp], "pgpu_species_cell_index": [vp, vp],
+        "pgpu_species_cell_offsets": [vp, vp], "pgpu_set_moments_from_bins": [vp],
+        "pgpu_species_moments_get": [vp, vp, vp, vp], "pgpu_debye_length": [vp, vp, i32, vp],
+        "pgpu_apply_bcs": [vp, vp, vp], "pgpu_stable_dt": [vp, vp], "pgpu_global_moments": [vp, vp],
+        "pgpu_collide_ta": [vp, vp, dbl, dbl, C.c_uint64, C.c_uint64, vp],
+        "pgpu_ta_delta_u": [lng, vp, vp, vp, vp, dbl, dbl, dbl, vp, vp, vp, vp],
+        "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
+        "pgpu_launch_count": [], "pgpu_abi_version": [], "pgpu_last_error": [],
+    }
+    for name, args in sig.items():
+        getattr(lib, name).argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PgpuError(rc, load().pgpu_last_error().decode())
+
+
+def init(device=0):
+    check(load().pgpu_init(device))
+
+
+def finalize():
+    load().pgpu_finalize()
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i2(v):
+    return (C.c_int * 2)(*(list(v) + [0, 0])[:2])
+
+
+class Grid:
+    def __init__(self, D, ncell, xmin, dx, nghost, periodic, box_lo=None, box_hi=None, volume_scale=1.0):
+        d = GridDesc()
+        d.D = D
+        box_lo = [0] * D if box_lo is None else box_lo
+        box_hi = [n - 1 for n in ncell] if box_hi is None else box_hi
+        for k in range(D):
+            d.ncell[k], d.xmin[k], d.dx[k] = ncell[k], xmin[k], dx[k]
+            d.periodic[k], d.box_lo[k], d.box_hi[k] = int(periodic[k]), box_lo[k], box_hi[k]
+        d.nghost = nghost
+        d.volume_scale = volume_scale
+        self.desc = d
+        self.D = D
+        self.h = C.c_void_p()
+        check(load().pgpu_grid_create(C.byref(d), C.byref(self.h)))
+
+    def field_bounds(self, comp):
+        lo, hi = (C.c_int * 2)(), (C.c_int * 2)()
+        check(load().pgpu_field_bounds(self.h, comp, lo, hi))
+        return tuple(lo[:self.D]), tuple(hi[:self.D])
+
+    def set_field(self, comp, arr, lo, hi):
+        a = np.asfortranarray(arr, dtype=np.float64)
+        check(load().pgpu_fields_set(self.h, comp, _p(a), _i2(lo), _i2(hi)))
+        self._keep = a  # async H2D: keep the host buffer alive until the next sync
+
+    def set_fields(self, E, B):
+        keep = []
+        for c, (lo, hi, a) in enumerate(list(E) + list(B)):
+            a = np.asfortranarray(a, dtype=np.float64)
+            keep.append(a)
+            check(load().pgpu_fields_set(self.h, c, _p(a), _i2(lo), _i2(hi)))
+        check(load().pgpu_synchronize())
+
+    def current_zero(self):
+        check(load().pgpu_current_zero(self.h))
+
+    def current_add(self, sp):
+        check(load().pgpu_current_add_species(self.h, sp.h))
+
+    def current_finalize(self):
+        check(load().pgpu_current_finalize(self.h))
+
+    def current_get(self, comp):
+        lo, hi = self.field_bounds(comp)
+        shape = tuple(h - l + 1 for l, h in zip(lo, hi))
+        out = np.zeros(shape, order="F")
+        check(load().pgpu_current_get(self.h, comp, _p(out), _i2(lo), _i2(hi)))
+        return out
+
+    def debye_length(self, species):
+        arr = (C.c_void_p * len(species))(*[s.h for s in species])
+        nbox = [self.desc.box_hi[k] - self.desc.box_lo[k] + 1 for k in range(self.D)]
+        out = np.zeros(int(np.prod(nbox)))
+        check(load().pgpu_debye_length(self.h, arr, len(species), _p(out)))
+        return out
+
+    def destroy(self):
+        if self.h:
+            load().pgpu_grid_destroy(self.h)
+            self.h = None
+
+
+class Species:
+    def __init__(self, grid, mass, charge, fnorm_const, cvac_norm, interp_N=TSC, interp_J=CC1, interp_E=CC1,
+                 rtol=1e-12, iter_max=21, order_swap=0, bc_check_lo=(0, 0), bc_check_hi=(0, 0),
+                 motion=1, forces=1):
+        d = SpeciesDesc()
+        d.mass, d.charge, d.fnorm_const, d.cvac_norm = mass, charge, fnorm_const, cvac_norm
+        d.interp_N, d.interp_J, d.interp_E = interp_N, interp_J, interp_E
+        d.rtol, d.iter_max, d.order_swap = rtol, iter_max, int(order_swap)
+        for k in range(2):
+            d.bc_check_lo[k] = bc_check_lo[k] if k < len(bc_check_lo) else 0
+            d.bc_check_hi[k] = bc_check_hi[k] if k < len(bc_check_hi) else 0
+        d.motion, d.forces = int(motion), int(forces)
+        self.desc = d
+        self.grid = grid
+        self.D = grid.D
+        self.h = C.c_void_p()
+        check(load().pgpu_species_create(grid.h, C.byref(d), C.byref(self.h)))
+
+    @property
+    def n(self):
+        return load().pgpu_species_count(self.h)
+
+    def upload(self, x, v, w, xold=None, vold=None, ids=None):
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        x, v, w, xold, vold = c(x), c(v), c(w), c(xold), c(vold)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+        n = w.size
+        assert x.shape == (self.D, n) and v.shape == (3, n)
+        check(load().pgpu_species_upload(self.h, n, _p(x), _p(xold), _p(v), _p(vold), _p(w), _p(ids)))
+
+    def download(self):
+        n = self.n
+        out = {"x": np.zeros((self.D, n)), "xold": np.zeros((self.D, n)), "v": np.zeros((3, n)),
+               "vold": np.zeros((3, n)), "w": np.zeros(n), "id": np.zeros(n, dtype=np.uint64)}
+        check(load().pgpu_species_download(self.h, _p(out["x"]), _p(out["xold"]), _p(out["v"]),
+                                           _p(out["vold"]), _p(out["w"]), _p(out["id"])))
+        return out
+
+    def advance_positions_explicit(self, dt, half=False):
+        check(load().pgpu_advance_positions_explicit(self.h, dt, int(half)))
+
+    def advance_positions_implicit(self, dt):
+        check(load().pgpu_advance_positions_implicit(self.h, dt))
+
+    def advance_positions_2nd_half(self):
+        check(load().pgpu_advance_positions_2nd_half(self.h))
+
+    def interpolate_fields(self):
+        check(load().pgpu_interpolate_fields_to_particles(self.h))
+
+    def particle_fields(self):
+        n = self.n
+        Ep, Bp = np.zeros((3, n)), np.zeros((3, n))
+        check(load().pgpu_species_download_fields(self.h, _p(Ep), _p(Bp)))
+        return Ep, Bp
+
+    def advance_velocities(self, dt, half):
+        check(load().pgpu_advance_velocities(self.h, dt, int(half)))
+
+    def advance_velocities_2nd_half(self):
+        check(load().pgpu_advance_velocities_2nd_half(self.h))
+
+    def average_velocities(self):
+        check(load().pgpu_average_velocities(self.h))
+
+    def update_old_positions(self):
+        check(load().pgpu_update_old_particle_positions(self.h))
+
+    def update_old_velocities(self):
+        check(load().pgpu_update_old_particle_velocities(self.h))
+
+    def reset_particles(self):
+        check(load().pgpu_reset_particles(self.h))
+
+    def advance_particles(self, dt):
+        check(load().pgpu_advance_particles(self.h, dt))
+        check(load().pgpu_synchronize())
+
+    def advance_iteratively(self, dt, deposit=False, stats=True):
+        st = PicardStats()
+        check(load().pgpu_advance_particles_iteratively(self.h, dt, int(deposit), C.byref(st) if stats else None))
+        return st if stats else None
+
+    def set_current_density(self, dt, from_explicit=False):
+        check(load().pgpu_set_current_density(self.h, dt, int(from_explicit)))
+
+    def current_get(self, comp):
+        lo, hi = self.grid.field_bounds(comp)
+        shape = tuple(h - l + 1 for l, h in zip(lo, hi))
+        out = np.zeros(shape, order="F")
+        check(load().pgpu_species_current_get(self.h, comp, _p(out), _i2(lo), _i2(hi)))
+        return out
+
+    def charge_density(self, stag):
+        g = self.grid.desc
+        lo = [g.box_lo[k] - g.nghost for k in range(self.D)]
+        hi = [g.box_hi[k] + g.nghost + stag[k] for k in range(self.D)]
+        out = np.zeros(tuple(h - l + 1 for l, h in zip(lo, hi)), order="F")
+        check(load().pgpu_set_charge_density(self.h, _i2(stag), _p(out), _i2(lo), _i2(hi)))
+        return out, lo, hi
+
+    def bin_particles(self):
+        check(load().pgpu_bin_particles(self.h))
+
+    def cell_index(self):
+        out = np.zeros((self.D, self.n), dtype=np.int32)
+        check(load().pgpu_species_cell_index(self.h, _p(out)))
+        return out
+
+    def cell_offsets(self):
+        g = self.grid.desc
+        ncell = int(np.prod([g.box_hi[k] - g.box_lo[k] + 1 for k in range(self.D)]))
+        out = np.zeros(ncell + 1, dtype=np.int64)
+        check(load().pgpu_species_cell_offsets(self.h, _p(out)))
+        return out
+
+    def set_moments(self):
+        check(load().pgpu_set_moments_from_bins(self.h))
+
+    def moments(self):
+        g = self.grid.desc
+        ncell = int(np.prod([g.box_hi[k] - g.box_lo[k] + 1 for k in range(self.D)]))
+        dens, mom, ene = np.zeros(ncell), np.zeros((3, ncell)), np.zeros((3, ncell))
+        check(load().pgpu_species_moments_get(self.h, _p(dens), _p(mom), _p(ene)))
+        return dens, mom, ene
+
+    def apply_bcs(self, bc_lo, bc_hi):
+        check(load().pgpu_apply_bcs(self.h, _i2(bc_lo), _i2(bc_hi)))
+
+    def stable_dt(self):
+        out = C.c_double(0)
+        check(load().pgpu_stable_dt(self.h, C.byref(out)))
+        return out.value
+
+    def global_moments(self):
+        out = np.zeros(7)
+        check(load().pgpu_global_moments(self.h, _p(out)))
+        return out
+
+    def destroy(self):
+        if self.h:
+            load().pgpu_species_destroy(self.h)
+            self.h = None
+
+
+def collide_ta(sA, sB, Clog, dt_sec, seed, step, count=True):
+    np_ = C.c_long(0)
+    check(load().pgpu_collide_ta(sA.h, sB.h, Clog, dt_sec, seed, step, C.byref(np_) if count else None))
+    return np_.value
+
+
+def ta_delta_u(vp1, den1, vp2, den2, b90_fact, Clog, dt_sec, gauss, u_theta, u_phi):
+    n = den1.size
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    out = np.zeros((3, n))
+    args = [c(vp1), c(den1), c(vp2), c(den2)]
+    rnd = [c(gauss), c(u_theta), c(u_phi)]
+    check(load().pgpu_ta_delta_u(n, _p(args[0]), _p(args[1]), _p(args[2]), _p(args[3]), b90_fact, Clog, dt_sec,
+                                 _p(rnd[0]), _p(rnd[1]), _p(rnd[2]), _p(out)))
+    return out
+
+
+def profile_enable(on=True):
+    load().pgpu_profile_enable(int(on))
+
+
+def profile_reset():
+    load().pgpu_profile_reset()
+
+
+def profile_query(prefix=""):
+    ms, k = C.c_double(0), C.c_long(0)
+    load().pgpu_profile_query(prefix.encode(), C.byref(ms), C.byref(k))
+    return ms.value, k.value

@@ -1,0 +1,817 @@
+// pgpu_api.cu -- C ABI (include/picnic_gpu.h): lifecycle, grid and species state,
+// the streaming per-particle passes, grid-side helpers of the deposit, reductions.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "pgpu_internal.h"
+
+namespace pgpu {
+
+static char g_err[512] = "";
+static Context g_ctx;
+Context &ctx() { return g_ctx; }
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return PGPU_ERR_CUDA;
+}
+
+KTimer::KTimer(const char *n) : name(n) {
+  Context &c = ctx();
+  c.launches += 1;
+  if (c.profile) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, c.stream);
+  }
+}
+KTimer::~KTimer() {
+  Context &c = ctx();
+  if (a) {
+    cudaEventRecord(b, c.stream);
+    c.recs.push_back(Context::Rec{std::string(name), a, b});
+  }
+}
+
+static void profile_drain() {
+  Context &c = ctx();
+  for (auto &r : c.recs) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    auto &e = c.prof[r.name];
+    e.first += ms;
+    e.second += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  c.recs.clear();
+}
+
+GeoAny species_geo(const pgpu_species_s *s) {
+  GeoAny g = s->grid->geo;
+  for (int d = 0; d < 2; ++d) {
+    g.bc_lo[d] = s->desc.bc_check_lo[d];
+    g.bc_hi[d] = s->desc.bc_check_hi[d];
+  }
+  return g;
+}
+FieldSet grid_fields(const pgpu_grid_s *g) {
+  FieldSet F;
+  for (int c = 0; c < 6; ++c) F.f[c] = g->field[c].view();
+  return F;
+}
+CurrentSet species_current(const pgpu_species_s *s) {
+  CurrentSet J;
+  for (int c = 0; c < 3; ++c) J.j[c] = s->J[c].view();
+  return J;
+}
+
+// centring of the six field components: 1 = nodal
+static void comp_stag(int D, int comp, int *stag) {
+  static const int e1[3][2] = {{0, 0}, {1, 0}, {1, 0}};
+  static const int b1[3][2] = {{1, 0}, {0, 0}, {0, 0}};
+  static const int e2[3][2] = {{0, 1}, {1, 0}, {1, 1}};
+  static const int b2[3][2] = {{1, 0}, {0, 1}, {0, 0}};
+  const int(*t)[2] = (D == 1) ? (comp < 3 ? e1 : b1) : (comp < 3 ? e2 : b2);
+  stag[0] = t[comp % 3][0];
+  stag[1] = t[comp % 3][1];
+}
+
+static int alloc_fab(const pgpu_grid_desc &d, const int *stag, DeviceFab *f) {
+  for (int k = 0; k < 2; ++k) {
+    if (k < d.D) {
+      f->lo[k] = d.box_lo[k] - d.nghost;
+      f->hi[k] = d.box_hi[k] + d.nghost + stag[k];
+    } else {
+      f->lo[k] = f->hi[k] = 0;
+    }
+    f->stag[k] = (k < d.D) ? stag[k] : 0;
+  }
+  f->n0 = f->hi[0] - f->lo[0] + 1;
+  f->n1 = f->hi[1] - f->lo[1] + 1;
+  PGPU_CUDA(cudaMalloc(&f->p, f->size() * sizeof(double)));
+  PGPU_CUDA(cudaMemsetAsync(f->p, 0, f->size() * sizeof(double), ctx().stream));
+  return 0;
+}
+
+// read back and clear the device counters (synchronises)
+static int fetch_counters(Counters *out) {
+  Context &c = ctx();
+  PGPU_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c.stream));
+  PGPU_CUDA(cudaMemsetAsync(c.d_counters, 0, sizeof(Counters), c.stream));
+  PGPU_CUDA(cudaStreamSynchronize(c.stream));
+  *out = *c.h_counters;
+  return 0;
+}
+static int check_err_bits(unsigned err) {
+  if (err & ERRBIT_SEGMENTS) {
+    set_error("particle crossing more cells than allowed: num_segments > ghosts+1 "
+              "(decrease the time step or increase grid.num_ghosts)");
+    ctx().sticky_error = PGPU_ERR_SEGMENTS;
+    return PGPU_ERR_SEGMENTS;
+  }
+  if (err & ERRBIT_BOUNDS) {
+    set_error("a particle stencil left the ghosted field arrays");
+    ctx().sticky_error = PGPU_ERR_BOUNDS;
+    return PGPU_ERR_BOUNDS;
+  }
+  return 0;
+}
+
+// ---- small streaming kernels --------------------------------------------------------
+// out = a*in1 + b*in2 evaluated as the reference writes it (no contraction):
+// mode 0: out = in2 + in1*a          (xp = xpold + up*cnormDt)
+// mode 1: out = 2*in1 - in2          (2nd-half updates)
+// mode 2: out = (in1 + in2)/2        (averageVelocities)
+__global__ void k_stream(double *out, const double *in1, const double *in2, long n, double a, int mode) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double u = in1[i], v = in2[i];
+  double r;
+  if (mode == 0) r = __dadd_rn(v, __dmul_rn(u, a));
+  else if (mode == 1) r = __dsub_rn(__dmul_rn(2.0, u), v);
+  else r = __ddiv_rn(__dadd_rn(u, v), 2.0);
+  out[i] = r;
+}
+
+__global__ void k_boris_stored(PartPtrs p, long n, double alpha, int byHalfDt, int exact) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double uo[3], E[3], B[3], u[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uo[c] = p.vold[c][i];
+    E[c] = p.Ep[c][i];
+    B[c] = p.Bp[c][i];
+  }
+  if (exact) boris<true>(uo, E, B, alpha, byHalfDt != 0, u);
+  else boris<false>(uo, E, B, alpha, byHalfDt != 0, u);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) p.v[c][i] = u[c];
+}
+
+__global__ void k_scale(double *a, long n, double s) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = __dmul_rn(a[i], s);
+}
+__global__ void k_add(double *a, const double *b, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = __dadd_rn(a[i], b[i]);
+}
+
+// Periodic ghost fold of one direction: pass 0 adds every non-owned entry onto its
+// owned image (atomics: several images can map to one entry), pass 1 refreshes the
+// images.  Owned index range in direction `dir` is own_lo..own_hi (cells; for nodal
+// data node own_hi+1 is the image of node own_lo).
+__global__ void k_fold(FabView f, int dir, int own_lo, int own_hi, int pass) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)f.n0 * f.n1;
+  if (t >= total) return;
+  const int a = (int)(t % f.n0), b = (int)(t / f.n0);
+  const int idx = (dir == 0) ? a + f.lo0 : b + f.lo1;
+  if (idx >= own_lo && idx <= own_hi) return;
+  const int N = own_hi - own_lo + 1;
+  int im = idx;
+  while (im < own_lo) im += N;
+  while (im > own_hi) im -= N;
+  const long src = (dir == 0) ? (long)(im - f.lo0) + (long)b * f.n0 : (long)a + (long)(im - f.lo1) * f.n0;
+  if (pass == 0) atomicAdd(f.p + src, f.p[t]);
+  else f.p[t] = f.p[src];
+}
+
+static inline unsigned nb(long n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+int scale_fab(const DeviceFab &f, double s) {
+  KTimer t("fab_scale");
+  k_scale<<<nb((long)f.size()), 256, 0, ctx().stream>>>(f.p, (long)f.size(), s);
+  return 0;
+}
+
+int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f) {
+  Context &c = ctx();
+  const FabView v = f.view();
+  const long total = (long)f.size();
+  for (int dir = 0; dir < g->desc.D; ++dir) {
+    if (!g->desc.periodic[dir]) continue;
+    // only a box spanning the whole periodic direction folds onto itself
+    if (g->desc.box_lo[dir] != 0 || g->desc.box_hi[dir] != g->desc.ncell[dir] - 1) continue;
+    for (int pass = 0; pass < 2; ++pass) {
+      KTimer t("fold_periodic");
+      k_fold<<<nb(total), 256, 0, c.stream>>>(v, dir, g->desc.box_lo[dir], g->desc.box_hi[dir], pass);
+    }
+  }
+  return 0;
+}
+
+int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi) {
+  for (int d = 0; d < D; ++d)
+    if (lo[d] != f.lo[d] || hi[d] != f.hi[d]) {
+      set_error("array bounds [%d:%d] in dir %d do not match the device box [%d:%d]", lo[d], hi[d], d,
+                f.lo[d], f.hi[d]);
+      return PGPU_ERR_ARG;
+    }
+  Context &c = ctx();
+  PGPU_CUDA(cudaMemcpyAsync(data, f.p, f.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  PGPU_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+static int ensure_capacity(pgpu_species_s *s, long n) {
+  if ((size_t)n <= s->cap) return 0;
+  const size_t cap = (size_t)(n + n / 16 + 1024);
+  const int D = s->grid->desc.D;
+  auto re = [&](double *&p) -> int {
+    if (p) cudaFree(p);
+    p = nullptr;
+    PGPU_CUDA(cudaMalloc(&p, cap * sizeof(double)));
+    return 0;
+  };
+  for (int d = 0; d < D; ++d) {
+    if (re(s->x[d])) return PGPU_ERR_CUDA;
+    if (re(s->xold[d])) return PGPU_ERR_CUDA;
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (re(s->v[c])) return PGPU_ERR_CUDA;
+    if (re(s->vold[c])) return PGPU_ERR_CUDA;
+  }
+  if (re(s->w)) return PGPU_ERR_CUDA;
+  if (re(s->tmp)) return PGPU_ERR_CUDA;
+  if (s->id) cudaFree(s->id);
+  PGPU_CUDA(cudaMalloc(&s->id, cap * sizeof(uint64_t)));
+  for (int c = 0; c < 3; ++c) {  // Ep/Bp are allocated lazily
+    if (s->Ep[c]) cudaFree(s->Ep[c]);
+    if (s->Bp[c]) cudaFree(s->Bp[c]);
+    s->Ep[c] = s->Bp[c] = nullptr;
+  }
+  if (s->cell_key) cudaFree(s->cell_key);
+  if (s->perm) cudaFree(s->perm);
+  PGPU_CUDA(cudaMalloc(&s->cell_key, cap * sizeof(int)));
+  PGPU_CUDA(cudaMalloc(&s->perm, cap * sizeof(int)));
+  s->cap = cap;
+  return 0;
+}
+
+static int ensure_epbp(pgpu_species_s *s) {
+  for (int c = 0; c < 3; ++c) {
+    if (!s->Ep[c]) PGPU_CUDA(cudaMalloc(&s->Ep[c], s->cap * sizeof(double)));
+    if (!s->Bp[c]) PGPU_CUDA(cudaMalloc(&s->Bp[c], s->cap * sizeof(double)));
+  }
+  return 0;
+}
+
+}  // namespace pgpu
+
+using namespace pgpu;
+
+#define NEED_INIT()                                        \
+  do {                                                     \
+    if (!ctx().inited) {                                   \
+      set_error("pgpu_init has not been called");          \
+      return PGPU_ERR_STATE;                               \
+    }                                                      \
+  } while (0)
+
+extern "C" {
+
+const char *pgpu_last_error(void) { return g_err; }
+int pgpu_abi_version(void) { return 1; }
+
+int pgpu_init(int device) {
+  Context &c = ctx();
+  if (c.inited) return 0;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return PGPU_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("device %d out of range (0..%d)", device, ndev - 1);
+    return PGPU_ERR_ARG;
+  }
+  PGPU_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return PGPU_ERR_CUDA;
+  }
+  c.sm_count = prop.multiProcessorCount;
+  c.device = device;
+  PGPU_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  c.own_stream = true;
+  PGPU_CUDA(cudaMalloc(&c.d_counters, sizeof(Counters)));
+  PGPU_CUDA(cudaMemset(c.d_counters, 0, sizeof(Counters)));
+  PGPU_CUDA(cudaMallocHost(&c.h_counters, sizeof(Counters)));
+  c.inited = true;
+  c.sticky_error = 0;
+  return 0;
+}
+
+int pgpu_finalize(void) {
+  Context &c = ctx();
+  if (!c.inited) return 0;
+  cudaStreamSynchronize(c.stream);
+  profile_drain();
+  if (c.own_stream) cudaStreamDestroy(c.stream);
+  cudaFree(c.d_counters);
+  cudaFreeHost(c.h_counters);
+  c = Context();
+  return 0;
+}
+
+int pgpu_set_stream(void *cuda_stream) {
+  NEED_INIT();
+  Context &c = ctx();
+  cudaStreamSynchronize(c.stream);
+  if (cuda_stream == nullptr) {
+    if (!c.own_stream) {
+      PGPU_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+      c.own_stream = true;
+    }
+  } else {
+    if (c.own_stream) cudaStreamDestroy(c.stream);
+    c.stream = (cudaStream_t)cuda_stream;
+    c.own_stream = false;
+  }
+  return 0;
+}
+
+int pgpu_synchronize(void) {
+  NEED_INIT();
+  Context &c = ctx();
+  Counters k;
+  if (fetch_counters(&k)) return PGPU_ERR_CUDA;
+  int rc = check_err_bits(k.err);
+  if (rc) return rc;
+  PGPU_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pgpu_set_exact_math(int on) {
+  ctx().exact = on != 0;
+  return 0;
+}
+int pgpu_set_deposit_mode(int mode) {
+  if (mode < 0 || mode > 1) return PGPU_ERR_ARG;
+  ctx().deposit_mode = mode;
+  return 0;
+}
+
+// ---- grid -------------------------------------------------------------------------
+int pgpu_grid_create(const pgpu_grid_desc *d, pgpu_grid_t *out) {
+  NEED_INIT();
+  if (!d || !out || (d->D != 1 && d->D != 2) || d->nghost < 1) {
+    set_error("bad grid descriptor");
+    return PGPU_ERR_ARG;
+  }
+  for (int k = 0; k < d->D; ++k)
+    if (d->dx[k] <= 0 || d->box_hi[k] < d->box_lo[k] || d->box_lo[k] < 0 || d->box_hi[k] >= d->ncell[k]) {
+      set_error("bad grid descriptor in direction %d", k);
+      return PGPU_ERR_ARG;
+    }
+  pgpu_grid_s *g = new pgpu_grid_s();
+  g->desc = *d;
+  g->geo.D = d->D;
+  for (int k = 0; k < 2; ++k) {
+    const bool on = k < d->D;
+    g->geo.le[k] = on ? d->xmin[k] : 0.0;
+    g->geo.dx[k] = on ? d->dx[k] : 1.0;
+    g->geo.rdx[k] = 1.0 / g->geo.dx[k];
+    // DomainGrid Xmax = Xmin + ncell*dX in exact arithmetic; decks give X_max directly
+    g->geo.re[k] = on ? d->xmin[k] + d->ncell[k] * d->dx[k] : 1.0;
+    g->geo.bc_lo[k] = g->geo.bc_hi[k] = 0;
+    g->nbox[k] = on ? d->box_hi[k] - d->box_lo[k] + 1 : 1;
+  }
+  g->geo.ghosts = d->nghost;
+  g->ncell_box = (long)g->nbox[0] * g->nbox[1];
+  for (int c = 0; c < 6; ++c) {
+    int stag[2];
+    comp_stag(d->D, c, stag);
+    if (alloc_fab(*d, stag, &g->field[c])) return PGPU_ERR_CUDA;
+  }
+  for (int c = 0; c < 3; ++c) {
+    int stag[2];
+    comp_stag(d->D, c, stag);
+    if (alloc_fab(*d, stag, &g->jtot[c])) return PGPU_ERR_CUDA;
+  }
+  PGPU_CUDA(cudaMalloc(&g->debye, g->ncell_box * sizeof(double)));
+  *out = g;
+  return 0;
+}
+
+int pgpu_grid_destroy(pgpu_grid_t g) {
+  if (!g) return 0;
+  cudaStreamSynchronize(ctx().stream);
+  for (int c = 0; c < 6; ++c) cudaFree(g->field[c].p);
+  for (int c = 0; c < 3; ++c) cudaFree(g->jtot[c].p);
+  if (g->scratch_rho.p) cudaFree(g->scratch_rho.p);
+  cudaFree(g->debye);
+  delete g;
+  return 0;
+}
+
+int pgpu_field_bounds(pgpu_grid_t g, int comp, int *lo, int *hi) {
+  if (!g || comp < 0 || comp >= 6) return PGPU_ERR_ARG;
+  for (int d = 0; d < 2; ++d) {
+    lo[d] = g->field[comp].lo[d];
+    hi[d] = g->field[comp].hi[d];
+  }
+  return 0;
+}
+
+int pgpu_fields_set(pgpu_grid_t g, int comp, const double *data, const int *lo, const int *hi) {
+  NEED_INIT();
+  if (!g || comp < 0 || comp >= 6 || !data) return PGPU_ERR_ARG;
+  const DeviceFab &f = g->field[comp];
+  for (int d = 0; d < g->desc.D; ++d)
+    if (lo[d] != f.lo[d] || hi[d] != f.hi[d]) {
+      set_error("field %d: bounds [%d:%d] in dir %d do not match the device box [%d:%d]", comp, lo[d], hi[d],
+                d, f.lo[d], f.hi[d]);
+      return PGPU_ERR_ARG;
+    }
+  PGPU_CUDA(cudaMemcpyAsync(f.p, data, f.size() * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+  return 0;
+}
+
+int pgpu_current_zero(pgpu_grid_t g) {
+  NEED_INIT();
+  for (int c = 0; c < 3; ++c)
+    PGPU_CUDA(cudaMemsetAsync(g->jtot[c].p, 0, g->jtot[c].size() * sizeof(double), ctx().stream));
+  return 0;
+}
+
+int pgpu_current_add_species(pgpu_grid_t g, pgpu_species_t s) {
+  NEED_INIT();
+  for (int c = 0; c < 3; ++c) {
+    KTimer t("current_add");
+    k_add<<<nb((long)g->jtot[c].size()), 256, 0, ctx().stream>>>(g->jtot[c].p, s->J[c].p, (long)g->jtot[c].size());
+  }
+  return 0;
+}
+
+int pgpu_current_finalize(pgpu_grid_t g) {
+  NEED_INIT();
+  for (int c = 0; c < 3; ++c)
+    if (fold_periodic(g, g->jtot[c])) return PGPU_ERR_CUDA;
+  return 0;
+}
+
+int pgpu_current_get(pgpu_grid_t g, int comp, double *data, const int *lo, const int *hi) {
+  NEED_INIT();
+  if (!g || comp < 0 || comp >= 3) return PGPU_ERR_ARG;
+  return copy_fab_to_host(g->jtot[comp], g->desc.D, data, lo, hi);
+}
+
+// ---- species ----------------------------------------------------------------------
+int pgpu_species_create(pgpu_grid_t g, const pgpu_species_desc *d, pgpu_species_t *out) {
+  NEED_INIT();
+  if (!g || !d || !out) return PGPU_ERR_ARG;
+  if (d->interp_E < 0 || d->interp_E > 3 || d->interp_J < 0 || d->interp_J > 3 || d->interp_N < 0 ||
+      d->interp_N > 1) {
+    set_error("bad interpolation type (interp_N must be CIC or TSC)");
+    return PGPU_ERR_ARG;
+  }
+  pgpu_species_s *s = new pgpu_species_s();
+  s->grid = g;
+  s->desc = *d;
+  for (int c = 0; c < 3; ++c) {
+    int stag[2];
+    comp_stag(g->desc.D, c, stag);
+    if (alloc_fab(g->desc, stag, &s->J[c])) return PGPU_ERR_CUDA;
+  }
+  PGPU_CUDA(cudaMalloc(&s->cell_count, (g->ncell_box + 2) * sizeof(int)));
+  PGPU_CUDA(cudaMalloc(&s->cell_start, (g->ncell_box + 2) * sizeof(int)));
+  PGPU_CUDA(cudaMalloc(&s->dens, g->ncell_box * sizeof(double)));
+  PGPU_CUDA(cudaMalloc(&s->mom, 3 * g->ncell_box * sizeof(double)));
+  PGPU_CUDA(cudaMalloc(&s->ene, 3 * g->ncell_box * sizeof(double)));
+  *out = s;
+  return 0;
+}
+
+int pgpu_species_destroy(pgpu_species_t s) {
+  if (!s) return 0;
+  cudaStreamSynchronize(ctx().stream);
+  for (int d = 0; d < 2; ++d) {
+    cudaFree(s->x[d]);
+    cudaFree(s->xold[d]);
+  }
+  for (int c = 0; c < 3; ++c) {
+    cudaFree(s->v[c]);
+    cudaFree(s->vold[c]);
+    cudaFree(s->Ep[c]);
+    cudaFree(s->Bp[c]);
+    cudaFree(s->J[c].p);
+  }
+  cudaFree(s->w);
+  cudaFree(s->id);
+  cudaFree(s->tmp);
+  cudaFree(s->cell_key);
+  cudaFree(s->perm);
+  cudaFree(s->cell_count);
+  cudaFree(s->cell_start);
+  cudaFree(s->dens);
+  cudaFree(s->mom);
+  cudaFree(s->ene);
+  delete s;
+  return 0;
+}
+
+long pgpu_species_count(pgpu_species_t s) { return s ? s->n : -1; }
+
+int pgpu_species_upload(pgpu_species_t s, long n, const double *x, const double *xold, const double *v,
+                        const double *vold, const double *w, const uint64_t *id) {
+  NEED_INIT();
+  if (!s || n < 0 || (n > 0 && (!x || !v || !w))) return PGPU_ERR_ARG;
+  if (ensure_capacity(s, n)) return PGPU_ERR_CUDA;
+  const int D = s->grid->desc.D;
+  cudaStream_t st = ctx().stream;
+  const size_t nb8 = (size_t)n * sizeof(double);
+  for (int d = 0; d < D; ++d) {
+    PGPU_CUDA(cudaMemcpyAsync(s->x[d], x + (size_t)d * n, nb8, cudaMemcpyHostToDevice, st));
+    PGPU_CUDA(cudaMemcpyAsync(s->xold[d], (xold ? xold : x) + (size_t)d * n, nb8, cudaMemcpyHostToDevice, st));
+  }
+  for (int c = 0; c < 3; ++c) {
+    PGPU_CUDA(cudaMemcpyAsync(s->v[c], v + (size_t)c * n, nb8, cudaMemcpyHostToDevice, st));
+    PGPU_CUDA(cudaMemcpyAsync(s->vold[c], (vold ? vold : v) + (size_t)c * n, nb8, cudaMemcpyHostToDevice, st));
+  }
+  PGPU_CUDA(cudaMemcpyAsync(s->w, w, nb8, cudaMemcpyHostToDevice, st));
+  if (id) PGPU_CUDA(cudaMemcpyAsync(s->id, id, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  else PGPU_CUDA(cudaMemsetAsync(s->id, 0, (size_t)n * sizeof(uint64_t), st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  s->n = n;
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_species_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
+                          uint64_t *id) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  const int D = s->grid->desc.D;
+  const long n = s->n;
+  cudaStream_t st = ctx().stream;
+  const size_t nb8 = (size_t)n * sizeof(double);
+  for (int d = 0; d < D; ++d) {
+    if (x) PGPU_CUDA(cudaMemcpyAsync(x + (size_t)d * n, s->x[d], nb8, cudaMemcpyDeviceToHost, st));
+    if (xold) PGPU_CUDA(cudaMemcpyAsync(xold + (size_t)d * n, s->xold[d], nb8, cudaMemcpyDeviceToHost, st));
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (v) PGPU_CUDA(cudaMemcpyAsync(v + (size_t)c * n, s->v[c], nb8, cudaMemcpyDeviceToHost, st));
+    if (vold) PGPU_CUDA(cudaMemcpyAsync(vold + (size_t)c * n, s->vold[c], nb8, cudaMemcpyDeviceToHost, st));
+  }
+  if (w) PGPU_CUDA(cudaMemcpyAsync(w, s->w, nb8, cudaMemcpyDeviceToHost, st));
+  if (id) PGPU_CUDA(cudaMemcpyAsync(id, s->id, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pgpu_species_download_fields(pgpu_species_t s, double *Ep, double *Bp) {
+  NEED_INIT();
+  if (!s || !s->Ep[0]) {
+    set_error("no particle fields stored; call pgpu_interpolate_fields_to_particles first");
+    return PGPU_ERR_STATE;
+  }
+  const long n = s->n;
+  cudaStream_t st = ctx().stream;
+  for (int c = 0; c < 3; ++c) {
+    if (Ep) PGPU_CUDA(cudaMemcpyAsync(Ep + (size_t)c * n, s->Ep[c], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (Bp) PGPU_CUDA(cudaMemcpyAsync(Bp + (size_t)c * n, s->Bp[c], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- streaming passes ---------------------------------------------------------------
+static int stream_pass(const char *name, double *out, const double *a, const double *b, long n, double s,
+                       int mode) {
+  if (n == 0) return 0;
+  KTimer t(name);
+  k_stream<<<nb(n), 256, 0, ctx().stream>>>(out, a, b, n, s, mode);
+  return 0;
+}
+
+int pgpu_advance_positions_explicit(pgpu_species_t s, double full_dt, int half_step) {
+  NEED_INIT();
+  if (!s->desc.motion) return 0;
+  const double cnormDt = s->desc.cvac_norm * full_dt;
+  const double dt_factor = half_step ? 0.5 : 1.0;
+  for (int d = 0; d < s->grid->desc.D; ++d)
+    stream_pass("advance_positions", s->x[d], s->v[d], s->xold[d], s->n, cnormDt * dt_factor, 0);
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_advance_positions_implicit(pgpu_species_t s, double full_dt) {
+  NEED_INIT();
+  if (!s->desc.motion) return 0;
+  const double cnormDt = s->desc.cvac_norm * full_dt;
+  const double cnormHalfDt = cnormDt * 0.5;
+  for (int d = 0; d < s->grid->desc.D; ++d)
+    stream_pass("advance_positions", s->x[d], s->v[d], s->xold[d], s->n, cnormHalfDt, 0);
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_advance_positions_2nd_half(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s->desc.motion) return 0;
+  for (int d = 0; d < s->grid->desc.D; ++d)
+    stream_pass("second_half", s->x[d], s->x[d], s->xold[d], s->n, 0.0, 1);
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_advance_velocities_2nd_half(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s->desc.forces) return 0;
+  for (int c = 0; c < 3; ++c) stream_pass("second_half", s->v[c], s->v[c], s->vold[c], s->n, 0.0, 1);
+  return 0;
+}
+
+int pgpu_average_velocities(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s->desc.forces) return 0;
+  for (int c = 0; c < 3; ++c) stream_pass("average_velocities", s->v[c], s->v[c], s->vold[c], s->n, 0.0, 2);
+  return 0;
+}
+
+int pgpu_update_old_particle_positions(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s->desc.motion) return 0;
+  for (int d = 0; d < s->grid->desc.D; ++d)
+    PGPU_CUDA(cudaMemcpyAsync(s->xold[d], s->x[d], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+  return 0;
+}
+
+int pgpu_update_old_particle_velocities(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s->desc.forces) return 0;
+  for (int c = 0; c < 3; ++c)
+    PGPU_CUDA(cudaMemcpyAsync(s->vold[c], s->v[c], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+  return 0;
+}
+
+int pgpu_reset_particles(pgpu_species_t s) {
+  NEED_INIT();
+  for (int d = 0; d < s->grid->desc.D; ++d)
+    PGPU_CUDA(cudaMemcpyAsync(s->x[d], s->xold[d], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+  for (int c = 0; c < 3; ++c)
+    PGPU_CUDA(cudaMemcpyAsync(s->v[c], s->vold[c], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_interpolate_fields_to_particles(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s->desc.forces || s->desc.charge == 0.0) return 0;
+  if (ensure_epbp(s)) return PGPU_ERR_CUDA;
+  int rc = launch_gather(s);
+  if (rc) return rc;
+  return pgpu_synchronize();
+}
+
+int pgpu_advance_velocities(pgpu_species_t s, double full_dt, int half_step) {
+  NEED_INIT();
+  if (!s->desc.forces) return 0;
+  if (!s->Ep[0]) {
+    set_error("advanceVelocities needs particle fields: call pgpu_interpolate_fields_to_particles first");
+    return PGPU_ERR_STATE;
+  }
+  if (s->n == 0) return 0;
+  const double cnormDt = full_dt * s->desc.cvac_norm;
+  const double alpha = s->desc.fnorm_const * cnormDt / 2.0;
+  KTimer t("boris");
+  k_boris_stored<<<nb(s->n), 256, 0, ctx().stream>>>(s->ptrs(), s->n, alpha, half_step, ctx().exact ? 1 : 0);
+  return 0;
+}
+
+static AdvanceParams make_params(pgpu_species_t s, double dt, bool iterative) {
+  AdvanceParams p;
+  p.cnormDt = dt * s->desc.cvac_norm;
+  p.alpha = s->desc.fnorm_const * p.cnormDt / 2.0;
+  p.rtol = s->desc.rtol;
+  p.iter_max = iterative ? s->desc.iter_max : -1;
+  p.order_swap = s->desc.order_swap;
+  const GeoAny &g = s->grid->geo;
+  p.volume = (g.D == 1) ? g.dx[0] : g.dx[0] * g.dx[1];
+  p.rvolume = 1.0 / p.volume;
+  return p;
+}
+
+int pgpu_advance_particles(pgpu_species_t s, double dt) {
+  NEED_INIT();
+  if (!s->desc.motion || !s->desc.forces || s->desc.charge == 0.0) {
+    // degenerate switches: compose the reference sequence from the separate passes
+    if (s->desc.order_swap) pgpu_advance_positions_implicit(s, dt);
+    if (s->desc.forces && s->desc.charge != 0.0) {
+      int rc = pgpu_interpolate_fields_to_particles(s);
+      if (rc) return rc;
+      pgpu_advance_velocities(s, dt, 1);
+    }
+    if (!s->desc.order_swap) pgpu_advance_positions_implicit(s, dt);
+    return 0;
+  }
+  s->binned = false;
+  return launch_advance(s, make_params(s, dt, false), false);
+}
+
+static int scale_species_current(pgpu_species_t s) {
+  const double f = s->desc.charge / s->grid->desc.volume_scale;
+  for (int c = 0; c < 3; ++c) {
+    KTimer t("current_scale");
+    k_scale<<<nb((long)s->J[c].size()), 256, 0, ctx().stream>>>(s->J[c].p, (long)s->J[c].size(), f);
+  }
+  return 0;
+}
+
+int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_J, pgpu_picard_stats *stats) {
+  NEED_INIT();
+  const bool iterative = !(s->desc.iter_max == 0 || !s->desc.motion || !s->desc.forces || s->desc.charge == 0.0);
+  int rc = 0;
+  if (!iterative && (!s->desc.motion || !s->desc.forces || s->desc.charge == 0.0)) {
+    rc = pgpu_advance_particles(s, dt);
+    if (rc) return rc;
+    if (deposit_J && s->desc.charge != 0.0) rc = pgpu_set_current_density(s, dt, 0);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    return rc;
+  }
+  s->binned = false;
+  const bool fuse = deposit_J && s->desc.interp_J == s->desc.interp_E && !ctx().exact;
+  if (deposit_J)
+    for (int c = 0; c < 3; ++c)
+      PGPU_CUDA(cudaMemsetAsync(s->J[c].p, 0, s->J[c].size() * sizeof(double), ctx().stream));
+  rc = launch_advance(s, make_params(s, dt, iterative), fuse);
+  if (rc) return rc;
+  if (deposit_J) {
+    if (!fuse) {
+      rc = launch_deposit_current(s, dt * s->desc.cvac_norm);
+      if (rc) return rc;
+    }
+    scale_species_current(s);
+  }
+  if (stats) {
+    Counters k;
+    if (fetch_counters(&k)) return PGPU_ERR_CUDA;
+    stats->num_parts_its = iterative ? s->n : 0;
+    stats->num_apply_its = iterative ? (long)k.apply_its : 0;
+    stats->num_unconverged = (long)k.unconverged;
+    return check_err_bits(k.err);
+  }
+  return 0;
+}
+
+int pgpu_set_current_density(pgpu_species_t s, double dt, int /*from_explicit_solver*/) {
+  NEED_INIT();
+  for (int c = 0; c < 3; ++c)
+    PGPU_CUDA(cudaMemsetAsync(s->J[c].p, 0, s->J[c].size() * sizeof(double), ctx().stream));
+  int rc = launch_deposit_current(s, dt * s->desc.cvac_norm);
+  if (rc) return rc;
+  return scale_species_current(s);
+}
+
+int pgpu_species_current_get(pgpu_species_t s, int comp, double *data, const int *lo, const int *hi) {
+  NEED_INIT();
+  if (!s || comp < 0 || comp >= 3) return PGPU_ERR_ARG;
+  int rc = copy_fab_to_host(s->J[comp], s->grid->desc.D, data, lo, hi);
+  if (rc) return rc;
+  return pgpu_synchronize();
+}
+
+// ---- instrumentation ------------------------------------------------------------------
+int pgpu_profile_enable(int on) {
+  ctx().profile = on != 0;
+  return 0;
+}
+int pgpu_profile_reset(void) {
+  profile_drain();
+  ctx().prof.clear();
+  ctx().launches = 0;
+  return 0;
+}
+int pgpu_profile_query(const char *prefix, double *ms, long *launches) {
+  profile_drain();
+  double t = 0;
+  long k = 0;
+  const size_t len = prefix ? strlen(prefix) : 0;
+  for (auto &e : ctx().prof)
+    if (len == 0 || e.first.compare(0, len, prefix) == 0) {
+      t += e.second.first;
+      k += e.second.second;
+    }
+  if (ms) *ms = t;
+  if (launches) *launches = k;
+  return 0;
+}
+long pgpu_launch_count(void) { return ctx().launches; }
+
+}  // extern "C"

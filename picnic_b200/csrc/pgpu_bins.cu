@@ -1,0 +1,587 @@
+// pgpu_bins.cu -- cell sort (binTheParticles), cell moments, Debye length, charge
+// deposit, boundary conditions and the particle reductions.
+//
+// The reference rebuilds per-cell linked lists of particle pointers every scatter
+// call (PicChargedSpecies::binTheParticles, PicChargedSpecies.cpp:1913-1947 +
+// BinFab::locateBin, BinFabImplem.H:582-594).  Here the same cell index is the key
+// of a counting sort that physically reorders the SoA arrays, so that the particles
+// of a cell are contiguous (warp-contiguous for the collision and moment kernels)
+// and the gather/deposit kernels see cell-coherent warps.
+#include <cstring>
+
+#include "pgpu_internal.h"
+
+namespace pgpu {
+
+static inline unsigned nb(long n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+struct BoxInfo {
+  int D;
+  double le[2], dx[2];
+  int lo[2], n[2];
+  int ncell;
+};
+
+static BoxInfo box_info(const pgpu_grid_s *g) {
+  BoxInfo b;
+  b.D = g->desc.D;
+  for (int d = 0; d < 2; ++d) {
+    b.le[d] = g->geo.le[d];
+    b.dx[d] = g->geo.dx[d];
+    b.lo[d] = (d < b.D) ? g->desc.box_lo[d] : 0;
+    b.n[d] = g->nbox[d];
+  }
+  b.ncell = (int)g->ncell_box;
+  return b;
+}
+
+// BinFab::locateBin: thisPos -= origin; thisPos /= dx; (int)floor(thisPos)
+__device__ __forceinline__ int locate_bin(double x, double le, double dx) {
+  return __double2int_rd(__ddiv_rn(__dsub_rn(x, le), dx));
+}
+
+__global__ void k_cell_key(const double *x0, const double *x1, long n, BoxInfo b, int *key, int *count) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c0 = locate_bin(x0[i], b.le[0], b.dx[0]) - b.lo[0];
+  int c1 = (b.D == 2) ? locate_bin(x1[i], b.le[1], b.dx[1]) - b.lo[1] : 0;
+  int k = b.ncell;  // outcast bin
+  if (c0 >= 0 && c0 < b.n[0] && c1 >= 0 && c1 < b.n[1]) k = c0 + c1 * b.n[0];
+  key[i] = k;
+  if (count) atomicAdd(count + k, 1);
+}
+
+__global__ void k_cell_ijk(const double *x0, const double *x1, long n, BoxInfo b, int *out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = locate_bin(x0[i], b.le[0], b.dx[0]);
+  if (b.D == 2) out[n + i] = locate_bin(x1[i], b.le[1], b.dx[1]);
+}
+
+// exclusive scan of `in[0..n)` into `out[0..n]` (out[n] = total); single block, any n
+__global__ void k_exclusive_scan(const int *in, int *out, int n) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < n) ? in[i] : 0;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane == 31) warp_sums[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+      int ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += t;
+      }
+      warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const int prefix = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
+    if (i < n) out[i] = prefix;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = prefix + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry;
+}
+
+// slot claim: perm[cell_start[k] + (running count)] = i   (order inside a cell arbitrary)
+__global__ void k_claim_slots(const int *key, long n, const int *cell_start, int *fill, int *perm) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = key[i];
+  const int slot = cell_start[k] + atomicAdd(fill + k, 1);
+  perm[slot] = (int)i;
+}
+
+// make the order inside each cell deterministic (ascending source index = stable sort):
+// one warp per cell, rank sort
+__global__ void k_sort_within_cells(const int *cell_start, int ncell_plus, const int *perm_in, int *perm_out) {
+  const int warp = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp >= ncell_plus) return;
+  const int s = cell_start[warp], e = cell_start[warp + 1];
+  for (int k = s + lane; k < e; k += 32) {
+    const int mine = perm_in[k];
+    int rank = 0;
+    for (int j = s; j < e; ++j) rank += (perm_in[j] < mine) ? 1 : 0;
+    perm_out[s + rank] = mine;
+  }
+}
+
+template <class T>
+__global__ void k_permute(T *out, const T *in, const int *perm, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[perm[i]];
+}
+
+// set{Number,Momentum,Energy}DensityFromBinFab (PicChargedSpecies.cpp:2881-3047):
+// one warp per cell over the cell-sorted arrays
+__global__ void k_cell_moments(const int *cell_start, int ncell, const double *w, const double *v0,
+                               const double *v1, const double *v2, double kn, double km, double ke,
+                               double *dens, double *mom, double *ene) {
+  const int cell = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (cell >= ncell) return;
+  const int s = cell_start[cell], e = cell_start[cell + 1];
+  double a[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int k = s + lane; k < e; k += 32) {
+    const double wp = w[k], u0 = v0[k], u1 = v1[k], u2 = v2[k];
+    a[0] += wp;
+    a[1] += wp * u0;
+    a[2] += wp * u1;
+    a[3] += wp * u2;
+    a[4] += wp * u0 * u0;
+    a[5] += wp * u1 * u1;
+    a[6] += wp * u2 * u2;
+  }
+#pragma unroll
+  for (int q = 0; q < 7; ++q)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+  if (lane == 0) {
+    dens[cell] = a[0] * kn;
+    for (int q = 0; q < 3; ++q) {
+      mom[q * ncell + cell] = a[1 + q] * km;
+      ene[q * ncell + cell] = a[4 + q] * ke;
+    }
+  }
+}
+
+// PicSpeciesInterface::setDebyeLength (PicSpeciesInterface.cpp:1627-1721), one species
+__global__ void k_debye_accumulate(int ncell, const double *dens, const double *mom, const double *ene,
+                                   double mass, double charge, double *sum_inv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const double PI = 3.14159265358979323846, CVAC = 2.99792458e+08, ME = 9.10938370e-31, QE = 1.60217663e-19;
+  const double MU0 = 4.0 * PI * 1.0e-7, EP0 = 1.0 / CVAC / CVAC / MU0;
+  const double HBAR = 6.62607015e-34 / (2.0 * PI);
+  const double EV_PER_JOULE = 1.0 / QE;
+  const double mcSq_eV = ME * CVAC * CVAC * EV_PER_JOULE;
+  const double Aconst = EP0 / QE / (charge * charge);
+  const double N = dens[c];
+  if (N == 0.0) return;
+  const double R = 1.0 / cbrt(4.0 / 3.0 * PI * N);
+  const double rho = N * mass;
+  const double ux = mom[c], uy = mom[ncell + c], uz = mom[2 * ncell + c];
+  const double meanE = (ux * ux + uy * uy + uz * uz) / rho / 2.0;
+  const double EF_eV = HBAR * HBAR / (2.0 * ME * mass) * pow(3.0 * PI * PI * N, 2.0 / 3.0) * EV_PER_JOULE;
+  double rhoE = 0.0;
+  for (int dir = 0; dir < 3; ++dir) rhoE += ene[dir * ncell + c];
+  double T_eV = 2.0 / 3.0 * (rhoE - meanE) / N * mcSq_eV;
+  T_eV = fmax(T_eV, 0.01);
+  const double LDe_sq = fmax(Aconst * (T_eV + 2.0 / 3.0 * EF_eV) / N, R * R);
+  sum_inv[c] += 1.0 / LDe_sq;
+}
+__global__ void k_debye_finish(int ncell, double *a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncell) a[c] = 1.0 / sqrt(a[c]);
+}
+
+// MeshInterp::deposit -> cic_deposit / tsc_deposit (MeshInterpF.ChF:206-255, 739-800)
+template <int D, bool X>
+__global__ void k_deposit_rho(const double *x0, const double *x1, const double *w, long n, Geo<D> g,
+                              int interp, int stag0, int stag1, FabView rho, double volume, Counters *cnt) {
+  typedef M<X> m;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned err = 0;
+  if (i < n) {
+    const double xp[2] = {x0[i], D == 2 ? x1[i] : 0.0};
+    const int stag[2] = {stag0, stag1};
+    const double particle_rho = __ddiv_rn(w[i], volume);
+    const int npt = (interp == TSC) ? 3 : 2;
+    int index[D];
+    double wt[D][3];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      // off = 0.5*dx*(1-stag)
+      const double off = m::mul(m::mul(0.5, g.dx[d]), __dsub_rn(1.0, (double)stag[d]));
+      double a = __dsub_rn(__dsub_rn(xp[d], g.le[d]), (interp == TSC) ? 0.5 * g.dx[d] : off);
+      if (interp == TSC) a = __dsub_rn(a, off);
+      index[d] = floor_div<X>(a, g.dx[d], g.rdx[d]);
+      for (int q = 0; q < npt; ++q) {
+        const double l = m::add(m::sub(m::add(m::mul((double)(index[d] + q), g.dx[d]), off), xp[d]), g.le[d]);
+        const double r = fabs(m::div(l, g.dx[d], g.rdx[d]));
+        wt[d][q] = (interp == TSC) ? tsc_w<X>(r) : m::sub(1.0, r);
+      }
+    }
+    for (int q0 = 0; q0 < npt; ++q0) {
+      const int ii = index[0] + q0;
+      const unsigned a = (unsigned)(ii - rho.lo0);
+      if (D == 1) {
+        if (a < (unsigned)rho.n0) atomicAdd(rho.p + a, m::mul(particle_rho, wt[0][q0]));
+        else err |= ERRBIT_BOUNDS;
+      } else {
+        for (int q1 = 0; q1 < npt; ++q1) {
+          const unsigned b = (unsigned)(index[D - 1] + q1 - rho.lo1);
+          if (a < (unsigned)rho.n0 && b < (unsigned)rho.n1)
+            atomicAdd(rho.p + (a + (size_t)b * rho.n0), m::mul(particle_rho, m::mul(wt[0][q0], wt[D - 1][q1])));
+          else err |= ERRBIT_BOUNDS;
+        }
+      }
+    }
+  }
+  err = __reduce_or_sync(0xffffffffu, err);
+  if ((threadIdx.x & 31) == 0 && err) atomicOr(&cnt->err, err);
+}
+
+// PicChargedSpeciesBC::enforcePeriodic (PicChargedSpeciesBC.cpp:738-765)
+__global__ void k_bc_periodic(double *x, double *xold, long n, double left, double right) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double Lbox = __dsub_rn(right, left);
+  double xp = x[i], xo = xold[i];
+  bool ch = false;
+  if (xp < left) {
+    xp = __dadd_rn(xp, Lbox);
+    xo = __dadd_rn(xo, Lbox);
+    ch = true;
+  }
+  if (xp >= right) {
+    xp = __dsub_rn(xp, Lbox);
+    xo = __dsub_rn(xo, Lbox);
+    ch = true;
+  }
+  if (ch) {
+    x[i] = xp;
+    xold[i] = xo;
+  }
+}
+
+// PicChargedSpeciesBC::symmetry_Lo / symmetry_Hi (PicChargedSpeciesBC.cpp:808-870)
+__global__ void k_bc_symmetry(double *x, double *xold, double *v, double *vold, long n, double left,
+                              double right, int do_lo, int do_hi) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double xp = x[i], xo = xold[i], vp = v[i], vo = vold[i];
+  bool ch = false;
+  if (do_lo && xp <= left) {
+    xp = __dsub_rn(__dmul_rn(2., left), xp);
+    vp = -vp;
+    xo = __dsub_rn(__dmul_rn(2., left), xo);
+    vo = -vo;
+    ch = true;
+  }
+  if (do_hi && xp >= right) {
+    xp = __dsub_rn(__dmul_rn(2., right), xp);
+    vp = -vp;
+    xo = __dsub_rn(__dmul_rn(2., right), xo);
+    vo = -vo;
+    if (xp == right) xp = __dmul_rn(0.999999999, right);
+    ch = true;
+  }
+  if (ch) {
+    x[i] = xp;
+    xold[i] = xo;
+    v[i] = vp;
+    vold[i] = vo;
+  }
+}
+
+// block reduction helpers for the global reductions
+__global__ void k_max_dtinv(const double *v0, const double *v1, long n, int D, double dx0, double dx1,
+                            unsigned long long *out_bits) {
+  double mx = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    mx = fmax(mx, __ddiv_rn(fabs(v0[i]), dx0));
+    if (D == 2) mx = fmax(mx, __ddiv_rn(fabs(v1[i]), dx1));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  // non-negative doubles order like their bit patterns
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(mx));
+}
+
+__global__ void k_global_moments(const double *w, const double *v0, const double *v1, const double *v2,
+                                 long n, double *out7) {
+  double a[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double wp = w[i], u0 = v0[i], u1 = v1[i], u2 = v2[i];
+    a[0] += wp;
+    a[1] += wp * u0;
+    a[2] += wp * u1;
+    a[3] += wp * u2;
+    a[4] += wp * u0 * u0;
+    a[5] += wp * u1 * u1;
+    a[6] += wp * u2 * u2;
+  }
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out7 + q, a[q]);
+  }
+}
+
+}  // namespace pgpu
+
+using namespace pgpu;
+
+#define NEED_INIT()                               \
+  do {                                            \
+    if (!ctx().inited) {                          \
+      set_error("pgpu_init has not been called"); \
+      return PGPU_ERR_STATE;                      \
+    }                                             \
+  } while (0)
+
+template <class T>
+static void permute_array(T *&arr, T *&tmp, const int *perm, long n) {
+  k_permute<T><<<nb(n), 256, 0, ctx().stream>>>(tmp, arr, perm, n);
+  T *t = arr;
+  arr = tmp;
+  tmp = t;
+}
+
+extern "C" {
+
+int pgpu_bin_particles(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  Context &c = ctx();
+  const pgpu_grid_s *g = s->grid;
+  const BoxInfo b = box_info(g);
+  const long n = s->n;
+  const int nbins = b.ncell + 1;  // + outcast bin
+  PGPU_CUDA(cudaMemsetAsync(s->cell_count, 0, (nbins + 1) * sizeof(int), c.stream));
+  if (n > 0) {
+    KTimer t("bin_key");
+    k_cell_key<<<nb(n), 256, 0, c.stream>>>(s->x[0], s->x[1], n, b, s->cell_key, s->cell_count);
+  }
+  {
+    KTimer t("bin_scan");
+    k_exclusive_scan<<<1, 1024, 0, c.stream>>>(s->cell_count, s->cell_start, nbins);
+  }
+  if (n > 0) {
+    PGPU_CUDA(cudaMemsetAsync(s->cell_count, 0, (nbins + 1) * sizeof(int), c.stream));
+    int *perm_raw = reinterpret_cast<int *>(s->tmp);  // tmp holds >= n doubles
+    {
+      KTimer t("bin_claim");
+      k_claim_slots<<<nb(n), 256, 0, c.stream>>>(s->cell_key, n, s->cell_start, s->cell_count, perm_raw);
+    }
+    {
+      KTimer t("bin_order");
+      k_sort_within_cells<<<nb((long)nbins * 32), 256, 0, c.stream>>>(s->cell_start, nbins, perm_raw, s->perm);
+    }
+    KTimer t("bin_permute");
+    const int D = g->desc.D;
+    for (int d = 0; d < D; ++d) {
+      permute_array(s->x[d], s->tmp, s->perm, n);
+      permute_array(s->xold[d], s->tmp, s->perm, n);
+    }
+    for (int q = 0; q < 3; ++q) {
+      permute_array(s->v[q], s->tmp, s->perm, n);
+      permute_array(s->vold[q], s->tmp, s->perm, n);
+    }
+    permute_array(s->w, s->tmp, s->perm, n);
+    double *idd = reinterpret_cast<double *>(s->id);
+    permute_array(idd, s->tmp, s->perm, n);
+    s->id = reinterpret_cast<uint64_t *>(idd);
+  }
+  s->binned = true;
+  return 0;
+}
+
+int pgpu_species_cell_index(pgpu_species_t s, int *cell) {
+  NEED_INIT();
+  if (!s || !cell) return PGPU_ERR_ARG;
+  const long n = s->n;
+  if (n == 0) return 0;
+  const int D = s->grid->desc.D;
+  int *d_out = nullptr;
+  PGPU_CUDA(cudaMalloc(&d_out, (size_t)D * n * sizeof(int)));
+  k_cell_ijk<<<nb(n), 256, 0, ctx().stream>>>(s->x[0], s->x[1], n, box_info(s->grid), d_out);
+  PGPU_CUDA(cudaMemcpyAsync(cell, d_out, (size_t)D * n * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+  PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
+  cudaFree(d_out);
+  return 0;
+}
+
+int pgpu_species_cell_offsets(pgpu_species_t s, long *offsets) {
+  NEED_INIT();
+  if (!s || !offsets) return PGPU_ERR_ARG;
+  if (!s->binned) {
+    set_error("species is not binned; call pgpu_bin_particles first");
+    return PGPU_ERR_STATE;
+  }
+  const long nc = s->grid->ncell_box + 2;
+  std::vector<int> h(nc);
+  PGPU_CUDA(cudaMemcpyAsync(h.data(), s->cell_start, nc * sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+  PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (long i = 0; i < nc - 1; ++i) offsets[i] = h[i];
+  return 0;
+}
+
+int pgpu_set_moments_from_bins(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s->binned) {
+    set_error("species is not binned; call pgpu_bin_particles first");
+    return PGPU_ERR_STATE;
+  }
+  const pgpu_grid_s *g = s->grid;
+  const double dV_mapped = (g->desc.D == 1) ? g->geo.dx[0] : g->geo.dx[0] * g->geo.dx[1];
+  const double dV_phys = dV_mapped * g->desc.volume_scale;
+  const int ncell = (int)g->ncell_box;
+  KTimer t("cell_moments");
+  k_cell_moments<<<nb((long)ncell * 32), 256, 0, ctx().stream>>>(
+      s->cell_start, ncell, s->w, s->v[0], s->v[1], s->v[2], 1.0 / dV_phys, s->desc.mass / dV_phys,
+      0.5 * s->desc.mass / dV_phys, s->dens, s->mom, s->ene);
+  return 0;
+}
+
+int pgpu_species_moments_get(pgpu_species_t s, double *dens, double *mom, double *ene) {
+  NEED_INIT();
+  const long nc = s->grid->ncell_box;
+  cudaStream_t st = ctx().stream;
+  if (dens) PGPU_CUDA(cudaMemcpyAsync(dens, s->dens, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (mom) PGPU_CUDA(cudaMemcpyAsync(mom, s->mom, 3 * nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (ene) PGPU_CUDA(cudaMemcpyAsync(ene, s->ene, 3 * nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pgpu_debye_length(pgpu_grid_t g, pgpu_species_t *species, int nspecies, double *LDe) {
+  NEED_INIT();
+  const int nc = (int)g->ncell_box;
+  cudaStream_t st = ctx().stream;
+  PGPU_CUDA(cudaMemsetAsync(g->debye, 0, nc * sizeof(double), st));
+  for (int k = 0; k < nspecies; ++k) {
+    pgpu_species_t s = species[k];
+    if (s->desc.charge == 0.0) continue;
+    KTimer t("debye");
+    k_debye_accumulate<<<nb(nc), 256, 0, st>>>(nc, s->dens, s->mom, s->ene, s->desc.mass, s->desc.charge, g->debye);
+  }
+  {
+    KTimer t("debye");
+    k_debye_finish<<<nb(nc), 256, 0, st>>>(nc, g->debye);
+  }
+  if (LDe) {
+    PGPU_CUDA(cudaMemcpyAsync(LDe, g->debye, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PGPU_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+int pgpu_set_charge_density(pgpu_species_t s, const int *stag, double *data, const int *lo, const int *hi) {
+  NEED_INIT();
+  pgpu_grid_s *g = s->grid;
+  const int D = g->desc.D;
+  Context &c = ctx();
+  DeviceFab f;
+  int st2[2] = {stag[0], D == 2 ? stag[1] : 0};
+  for (int k = 0; k < 2; ++k) {
+    if (k < D) {
+      f.lo[k] = g->desc.box_lo[k] - g->desc.nghost;
+      f.hi[k] = g->desc.box_hi[k] + g->desc.nghost + st2[k];
+    }
+    f.stag[k] = st2[k];
+  }
+  f.n0 = f.hi[0] - f.lo[0] + 1;
+  f.n1 = f.hi[1] - f.lo[1] + 1;
+  for (int k = 0; k < D; ++k)
+    if (lo[k] != f.lo[k] || hi[k] != f.hi[k]) {
+      set_error("charge density bounds do not match the ghosted box for this centring");
+      return PGPU_ERR_ARG;
+    }
+  // scratch sized for the all-nodal array, the largest centring
+  if (!g->scratch_rho.p) {
+    size_t mx = (size_t)(g->nbox[0] + 2 * g->desc.nghost + 1) * (size_t)(D == 2 ? g->nbox[1] + 2 * g->desc.nghost + 1 : 1);
+    PGPU_CUDA(cudaMalloc(&g->scratch_rho.p, mx * sizeof(double)));
+  }
+  f.p = g->scratch_rho.p;
+  PGPU_CUDA(cudaMemsetAsync(f.p, 0, f.size() * sizeof(double), c.stream));
+  const GeoAny ga = species_geo(s);
+  const double volume = (D == 1) ? ga.dx[0] : ga.dx[0] * ga.dx[1];
+  if (s->n > 0) {
+    KTimer t("deposit_rho");
+    if (D == 1) {
+      if (c.exact)
+        k_deposit_rho<1, true><<<nb(s->n), 256, 0, c.stream>>>(s->x[0], s->x[1], s->w, s->n, make_geo<1>(ga), s->desc.interp_N, st2[0], st2[1], f.view(), volume, c.d_counters);
+      else
+        k_deposit_rho<1, false><<<nb(s->n), 256, 0, c.stream>>>(s->x[0], s->x[1], s->w, s->n, make_geo<1>(ga), s->desc.interp_N, st2[0], st2[1], f.view(), volume, c.d_counters);
+    } else {
+      if (c.exact)
+        k_deposit_rho<2, true><<<nb(s->n), 256, 0, c.stream>>>(s->x[0], s->x[1], s->w, s->n, make_geo<2>(ga), s->desc.interp_N, st2[0], st2[1], f.view(), volume, c.d_counters);
+      else
+        k_deposit_rho<2, false><<<nb(s->n), 256, 0, c.stream>>>(s->x[0], s->x[1], s->w, s->n, make_geo<2>(ga), s->desc.interp_N, st2[0], st2[1], f.view(), volume, c.d_counters);
+    }
+  }
+  // this_rho.mult(m_charge/volume_scale); ghost add-exchange; (cartesian Jacobian == 1)
+  scale_fab(f, s->desc.charge / g->desc.volume_scale);
+  if (fold_periodic(g, f)) return PGPU_ERR_CUDA;
+  int rc = copy_fab_to_host(f, D, data, lo, hi);
+  if (rc) return rc;
+  return pgpu_synchronize();
+}
+
+int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi) {
+  NEED_INIT();
+  if (!s->desc.motion) return 0;
+  const pgpu_grid_s *g = s->grid;
+  const long n = s->n;
+  if (n == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  for (int d = 0; d < g->desc.D; ++d) {
+    const double left = g->geo.le[d], right = g->geo.re[d];
+    if (bc_lo[d] == PGPU_BC_PERIODIC || bc_hi[d] == PGPU_BC_PERIODIC) {
+      KTimer t("bc_periodic");
+      k_bc_periodic<<<nb(n), 256, 0, st>>>(s->x[d], s->xold[d], n, left, right);
+    }
+    const int do_lo = bc_lo[d] == PGPU_BC_SYMMETRY, do_hi = bc_hi[d] == PGPU_BC_SYMMETRY;
+    if (do_lo || do_hi) {
+      KTimer t("bc_symmetry");
+      k_bc_symmetry<<<nb(n), 256, 0, st>>>(s->x[d], s->xold[d], s->v[d], s->vold[d], n, left, right, do_lo, do_hi);
+    }
+  }
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_stable_dt(pgpu_species_t s, double *dt_out) {
+  NEED_INIT();
+  Context &c = ctx();
+  unsigned long long *d_bits = &c.d_counters->maxbits;  // zero between calls
+  Counters k;
+  if (s->n > 0) {
+    KTimer t("stable_dt");
+    k_max_dtinv<<<c.sm_count * 4, 256, 0, c.stream>>>(s->v[0], s->v[1], s->n, s->grid->desc.D, s->grid->geo.dx[0],
+                                                       s->grid->geo.dx[1], d_bits);
+  }
+  PGPU_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c.stream));
+  PGPU_CUDA(cudaMemsetAsync(&c.d_counters->maxbits, 0, sizeof(unsigned long long), c.stream));
+  PGPU_CUDA(cudaStreamSynchronize(c.stream));
+  k = *c.h_counters;
+  double maxDtinv;
+  memcpy(&maxDtinv, &k.maxbits, sizeof(double));
+  // local_stable_dt = 1.0/maxDtinv/m_cvac_norm (PicChargedSpecies.cpp:1904)
+  *dt_out = 1.0 / maxDtinv / s->desc.cvac_norm;
+  return 0;
+}
+
+int pgpu_global_moments(pgpu_species_t s, double *out) {
+  NEED_INIT();
+  Context &c = ctx();
+  double *d_out = nullptr;
+  PGPU_CUDA(cudaMalloc(&d_out, 7 * sizeof(double)));
+  PGPU_CUDA(cudaMemsetAsync(d_out, 0, 7 * sizeof(double), c.stream));
+  if (s->n > 0) {
+    KTimer t("global_moments");
+    k_global_moments<<<c.sm_count * 4, 256, 0, c.stream>>>(s->w, s->v[0], s->v[1], s->v[2], s->n, d_out);
+  }
+  PGPU_CUDA(cudaMemcpyAsync(out, d_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  PGPU_CUDA(cudaStreamSynchronize(c.stream));
+  cudaFree(d_out);
+  return 0;
+}
+
+}  // extern "C"

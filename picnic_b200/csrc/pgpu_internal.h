@@ -1,0 +1,183 @@
+// pgpu_internal.h -- host-side state of the particle engine and the launchers that
+// the translation units share.  Not part of the public ABI (include/picnic_gpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/picnic_gpu.h"
+#include "pgpu_device.cuh"
+
+namespace pgpu {
+
+// ---- kernel argument bundles (passed by value) ---------------------------------
+struct GeoAny {  // runtime-D geometry; converted to Geo<D> by the launchers
+  int D;
+  double le[2], re[2], dx[2], rdx[2];
+  int ghosts;
+  int bc_lo[2], bc_hi[2];
+};
+template <int D>
+inline Geo<D> make_geo(const GeoAny &a) {
+  Geo<D> g;
+  for (int d = 0; d < D; ++d) {
+    g.le[d] = a.le[d];
+    g.re[d] = a.re[d];
+    g.dx[d] = a.dx[d];
+    g.rdx[d] = a.rdx[d];
+    g.bc_lo[d] = a.bc_lo[d];
+    g.bc_hi[d] = a.bc_hi[d];
+  }
+  g.ghosts = a.ghosts;
+  return g;
+}
+
+struct FieldSet {  // Ex,Ey,Ez,Bx,By,Bz in the order MeshInterp receives them
+  FabView f[6];
+};
+struct CurrentSet {
+  FabView j[3];
+};
+struct PartPtrs {
+  double *x[2], *xold[2], *v[3], *vold[3], *w;
+  double *Ep[3], *Bp[3];
+};
+
+struct AdvanceParams {
+  double alpha;     // fnorm*cnormDt/2
+  double cnormDt;
+  double rtol;
+  int iter_max;     // <0 : single pass (advanceParticles)
+  int order_swap;
+  double volume;    // cell volume prod(dx) (deposit)
+  double rvolume;   // 1/volume
+};
+
+struct Counters {          // device-resident, 64-bit
+  unsigned long long apply_its;
+  unsigned long long unconverged;
+  unsigned long long npairs;    // collision pairs of the last collide call
+  unsigned long long maxbits;   // bit pattern of a non-negative double maximum
+  unsigned int err;        // ERRBIT_*
+  unsigned int pad;
+};
+
+// ---- device array with capacity ---------------------------------------------------
+struct DArr {
+  double *p = nullptr;
+  size_t cap = 0;
+};
+
+struct DeviceFab {
+  double *p = nullptr;
+  int lo[2] = {0, 0}, hi[2] = {0, 0};
+  int n0 = 1, n1 = 1;
+  int stag[2] = {0, 0};
+  size_t size() const { return (size_t)n0 * n1; }
+  FabView view() const { return FabView{p, lo[0], lo[1], n0, n1}; }
+};
+
+struct Context {
+  int device = -1;
+  bool inited = false;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool exact = false;
+  int deposit_mode = 0;
+  Counters *d_counters = nullptr;
+  Counters *h_counters = nullptr;  // pinned
+  int sticky_error = 0;
+  int sm_count = 148;
+  // profiling
+  bool profile = false;
+  struct Rec {
+    std::string name;
+    cudaEvent_t a, b;
+  };
+  std::vector<Rec> recs;
+  std::map<std::string, std::pair<double, long>> prof;
+  long launches = 0;
+};
+Context &ctx();
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+#define PGPU_CUDA(x)                                     \
+  do {                                                   \
+    cudaError_t e__ = (x);                               \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #x);   \
+  } while (0)
+
+// scoped kernel timer: records events around a launch when profiling is on
+struct KTimer {
+  const char *name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  explicit KTimer(const char *n);
+  ~KTimer();
+};
+
+}  // namespace pgpu
+
+struct pgpu_grid_s {
+  pgpu_grid_desc desc;
+  pgpu::GeoAny geo;  // bc flags are per species; copied in at launch
+  pgpu::DeviceFab field[6];
+  pgpu::DeviceFab jtot[3];
+  pgpu::DeviceFab scratch_rho;  // reused by set_charge_density
+  double *debye = nullptr;      // [ncell_box]
+  long ncell_box = 0;
+  int nbox[2] = {1, 1};
+};
+
+struct pgpu_species_s {
+  pgpu_grid_t grid = nullptr;
+  pgpu_species_desc desc;
+  long n = 0;
+  size_t cap = 0;
+  double *x[2] = {nullptr, nullptr}, *xold[2] = {nullptr, nullptr};
+  double *v[3] = {nullptr, nullptr, nullptr}, *vold[3] = {nullptr, nullptr, nullptr};
+  double *w = nullptr;
+  uint64_t *id = nullptr;
+  double *Ep[3] = {nullptr, nullptr, nullptr}, *Bp[3] = {nullptr, nullptr, nullptr};
+  double *tmp = nullptr;  // permutation scratch (one array)
+  pgpu::DeviceFab J[3];
+  // binning
+  int *cell_key = nullptr;     // [n] linear cell id inside the box (or ncell_box for outcasts)
+  int *perm = nullptr;         // [n]
+  int *cell_count = nullptr;   // [ncell_box+1]
+  int *cell_start = nullptr;   // [ncell_box+2]
+  bool binned = false;
+  double *dens = nullptr, *mom = nullptr, *ene = nullptr;  // [ncell],[3 ncell],[3 ncell]
+  pgpu::PartPtrs ptrs() const {
+    pgpu::PartPtrs p;
+    for (int d = 0; d < 2; ++d) {
+      p.x[d] = x[d];
+      p.xold[d] = xold[d];
+    }
+    for (int c = 0; c < 3; ++c) {
+      p.v[c] = v[c];
+      p.vold[c] = vold[c];
+      p.Ep[c] = Ep[c];
+      p.Bp[c] = Bp[c];
+    }
+    p.w = w;
+    return p;
+  }
+};
+
+namespace pgpu {
+GeoAny species_geo(const pgpu_species_s *s);
+FieldSet grid_fields(const pgpu_grid_s *g);
+CurrentSet species_current(const pgpu_species_s *s);
+
+int scale_fab(const DeviceFab &f, double s);
+int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f);
+int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi);
+
+// launchers implemented in the kernel translation units
+int launch_gather(pgpu_species_s *s);
+int launch_deposit_current(pgpu_species_s *s, double cnormDt);
+int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);
+}  // namespace pgpu

@@ -1,0 +1,320 @@
+// pgpu_push.cu -- gather, deposit and the fused implicit advance kernels.
+//
+// One thread per particle, SoA arrays, coalesced 8-byte loads.  The fused kernel
+// keeps a particle in registers through every particle-Picard pass
+// (PicChargedSpecies::advanceParticlesIteratively, PicChargedSpecies.cpp:1614-1716)
+// and, when asked, deposits its current before retiring it
+// (PicChargedSpecies::setCurrentDensity, :3184-3253), so the compulsory HBM traffic
+// is one read of (x_old, u_old, xbar, w) and one write of (xbar, ubar).
+#include "pgpu_internal.h"
+
+namespace pgpu {
+
+template <int D, bool X>
+struct GatherOp {
+  const FieldSet &F;
+  double acc[6];
+  bool oob;
+  __device__ __forceinline__ GatherOp(const FieldSet &f) : F(f), oob(false) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[c] = 0.0;
+  }
+  __device__ __forceinline__ void operator()(int c, int i, int j, double w) {
+    const FabView &f = F.f[c];
+    const unsigned a = (unsigned)(i - f.lo0);
+    const unsigned b = (D == 2) ? (unsigned)(j - f.lo1) : 0u;
+    if (a < (unsigned)f.n0 && b < (unsigned)f.n1) {
+      const double val = __ldg(f.p + (a + (size_t)b * f.n0));
+      acc[c] = M<X>::mad(w, val, acc[c]);
+    } else {
+      oob = true;
+    }
+  }
+};
+
+// deposit straight into HBM/L2 with native fp64 reductions (RED.E.ADD.F64)
+template <int D, bool X>
+struct DepositOpGlobal {
+  const CurrentSet &J;
+  double val[3];  // v_c * (w/volume)
+  bool oob;
+  __device__ __forceinline__ DepositOpGlobal(const CurrentSet &j) : J(j), oob(false) {}
+  __device__ __forceinline__ void operator()(int c, int i, int j, double w) {
+    const FabView &f = J.j[c];
+    const unsigned a = (unsigned)(i - f.lo0);
+    const unsigned b = (D == 2) ? (unsigned)(j - f.lo1) : 0u;
+    if (a < (unsigned)f.n0 && b < (unsigned)f.n1) {
+      atomicAdd(f.p + (a + (size_t)b * f.n0), M<X>::mul(val[c], w));
+    } else {
+      oob = true;
+    }
+  }
+};
+
+__device__ __forceinline__ void flush_counters(Counters *cnt, unsigned apply, unsigned unconv,
+                                               unsigned err) {
+  apply = __reduce_add_sync(0xffffffffu, apply);
+  unconv = __reduce_add_sync(0xffffffffu, unconv);
+  err = __reduce_or_sync(0xffffffffu, err);
+  if ((threadIdx.x & 31) == 0) {
+    if (apply) atomicAdd(&cnt->apply_its, (unsigned long long)apply);
+    if (unconv) atomicAdd(&cnt->unconverged, (unsigned long long)unconv);
+    if (err) atomicOr(&cnt->err, err);
+  }
+}
+
+// ---- interpolateFieldsToParticles: store Ep,Bp ------------------------------------
+template <int D, int IE, bool X>
+__global__ void __launch_bounds__(256)
+k_gather(PartPtrs p, long n, Geo<D> g, FieldSet F, Counters *cnt) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned err = 0;
+  if (i < n) {
+    double xp[D], xo[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      xp[d] = p.x[d][i];
+      xo[d] = p.xold[d][i];
+    }
+    GatherOp<D, X> op(F);
+    if (!gather_visit<D, IE, X>(g, xp, xo, op)) err |= ERRBIT_SEGMENTS;
+    if (op.oob) err |= ERRBIT_BOUNDS;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      p.Ep[c][i] = op.acc[c];
+      p.Bp[c][i] = op.acc[3 + c];
+    }
+  }
+  flush_counters(cnt, 0, 0, err);
+}
+
+// ---- setCurrentDensity: deposit only ------------------------------------------------
+template <int D, int IJ, bool X>
+__global__ void __launch_bounds__(256)
+k_deposit(PartPtrs p, long n, Geo<D> g, CurrentSet J, double volume, double rvolume, Counters *cnt) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned err = 0;
+  if (i < n) {
+    double xp[D], xo[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      xp[d] = p.x[d][i];
+      xo[d] = p.xold[d][i];
+    }
+    const double rhop = X ? __ddiv_rn(p.w[i], volume) : p.w[i] * rvolume;
+    DepositOpGlobal<D, X> op(J);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) op.val[c] = M<X>::mul(p.v[c][i], rhop);
+    if (!deposit_visit<D, IJ, X>(g, xp, xo, op)) err |= ERRBIT_SEGMENTS;
+    if (op.oob) err |= ERRBIT_BOUNDS;
+  }
+  flush_counters(cnt, 0, 0, err);
+}
+
+// ---- advanceParticles / advanceParticlesIteratively (+ optional fused deposit) ------
+template <int D, int IE, bool X, bool DEP>
+__global__ void __launch_bounds__(256)
+k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams prm, Counters *cnt) {
+  typedef M<X> m;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned err = 0, apply = 0, unconv = 0;
+  if (i < n) {
+    double xb[D], xo[D], uo[3], ub[3];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      xb[d] = p.x[d][i];
+      xo[d] = p.xold[d][i];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uo[c] = p.vold[c][i];
+      ub[c] = uo[c];  // only survives if the first gather fails
+    }
+    const double hdt = m::mul(prm.cnormDt, 0.5);  // cnormHalfDt
+
+    if (prm.iter_max < 0) {
+      // advanceParticles (PicChargedSpecies.cpp:1594-1612)
+      if (prm.order_swap) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) xb[d] = m::mad(p.v[d][i], hdt, xo[d]);
+      }
+      GatherOp<D, X> op(F);
+      if (!gather_visit<D, IE, X>(g, xb, xo, op)) err |= ERRBIT_SEGMENTS;
+      if (op.oob) err |= ERRBIT_BOUNDS;
+      boris<X>(uo, op.acc, op.acc + 3, prm.alpha, true, ub);
+      apply = 1;
+      if (!prm.order_swap) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) xb[d] = m::mad(ub[d], hdt, xo[d]);
+      }
+    } else {
+      // advanceParticlesIteratively (:1614-1716) with stepNormTransfer (:658-733)
+      bool converged = false;
+      int iter = 0;  // 0 = the initial, non-reverse pass
+      while (true) {
+        GatherOp<D, X> op(F);
+        if (!gather_visit<D, IE, X>(g, xb, xo, op)) {
+          err |= ERRBIT_SEGMENTS;
+          break;  // the reference aborts here (Fortran STOP)
+        }
+        if (op.oob) {
+          err |= ERRBIT_BOUNDS;
+          break;
+        }
+        boris<X>(uo, op.acc, op.acc + 3, prm.alpha, true, ub);
+        apply += 1;
+        double dxp[D];
+        double rel_diff_max = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const double dxp0 = m::sub(xb[d], xo[d]);
+          dxp[d] = m::mul(ub[d], hdt);
+          const double rel = __ddiv_rn(fabs(m::sub(dxp0, dxp[d])), g.dx[d]);
+          rel_diff_max = fmax(rel_diff_max, rel);
+        }
+        if (iter == 0) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) xb[d] = m::add(xo[d], dxp[d]);
+          converged = !(rel_diff_max >= prm.rtol);
+        } else {
+          if (rel_diff_max < prm.rtol) converged = true;
+          else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) xb[d] = m::add(xo[d], dxp[d]);
+          }
+        }
+        if (converged) break;
+        if (iter >= prm.iter_max) {
+          // iter counts reverse passes done; cap reached (:1678-1693)
+          unconv = 1;
+          break;
+        }
+        iter += 1;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) p.x[d][i] = xb[d];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p.v[c][i] = ub[c];
+
+    if (DEP && !(err & (ERRBIT_SEGMENTS | ERRBIT_BOUNDS))) {
+      const double rhop = X ? __ddiv_rn(p.w[i], prm.volume) : p.w[i] * prm.rvolume;
+      DepositOpGlobal<D, X> dop(J);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dop.val[c] = m::mul(ub[c], rhop);
+      if (!deposit_visit<D, IE, X>(g, xb, xo, dop)) err |= ERRBIT_SEGMENTS;
+      if (dop.oob) err |= ERRBIT_BOUNDS;
+    }
+  }
+  flush_counters(cnt, apply, unconv, err);
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+static inline unsigned nblocks(long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+template <int D, int IE>
+static int launch_gather_t(pgpu_species_s *s) {
+  Context &c = ctx();
+  const Geo<D> g = make_geo<D>(species_geo(s));
+  const FieldSet F = grid_fields(s->grid);
+  KTimer t("gather");
+  if (c.exact)
+    k_gather<D, IE, true><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, c.d_counters);
+  else
+    k_gather<D, IE, false><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, c.d_counters);
+  return 0;
+}
+
+template <int D>
+static int launch_gather_d(pgpu_species_s *s) {
+  switch (s->desc.interp_E) {
+    case CIC: return launch_gather_t<D, CIC>(s);
+    case TSC: return launch_gather_t<D, TSC>(s);
+    case CC0: return launch_gather_t<D, CC0>(s);
+    case CC1: return launch_gather_t<D, CC1>(s);
+  }
+  return PGPU_ERR_ARG;
+}
+
+int launch_gather(pgpu_species_s *s) {
+  if (s->n == 0) return 0;
+  return s->grid->desc.D == 1 ? launch_gather_d<1>(s) : launch_gather_d<2>(s);
+}
+
+template <int D, int IJ>
+static int launch_deposit_t(pgpu_species_s *s) {
+  Context &c = ctx();
+  const GeoAny ga = species_geo(s);
+  const Geo<D> g = make_geo<D>(ga);
+  const CurrentSet J = species_current(s);
+  const double volume = (D == 1) ? ga.dx[0] : ga.dx[0] * ga.dx[1];
+  KTimer t("deposit_current");
+  if (c.exact)
+    k_deposit<D, IJ, true><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, J, volume,
+                                                                      1.0 / volume, c.d_counters);
+  else
+    k_deposit<D, IJ, false><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, J, volume,
+                                                                       1.0 / volume, c.d_counters);
+  return 0;
+}
+
+template <int D>
+static int launch_deposit_d(pgpu_species_s *s) {
+  switch (s->desc.interp_J) {
+    case CIC: return launch_deposit_t<D, CIC>(s);
+    case TSC: return launch_deposit_t<D, TSC>(s);
+    case CC0: return launch_deposit_t<D, CC0>(s);
+    case CC1: return launch_deposit_t<D, CC1>(s);
+  }
+  return PGPU_ERR_ARG;
+}
+
+int launch_deposit_current(pgpu_species_s *s, double /*cnormDt*/) {
+  if (s->n == 0) return 0;
+  return s->grid->desc.D == 1 ? launch_deposit_d<1>(s) : launch_deposit_d<2>(s);
+}
+
+template <int D, int IE>
+static int launch_advance_t(pgpu_species_s *s, const AdvanceParams &prm, bool fuse) {
+  Context &c = ctx();
+  const Geo<D> g = make_geo<D>(species_geo(s));
+  const FieldSet F = grid_fields(s->grid);
+  const CurrentSet J = species_current(s);
+  const unsigned nb = nblocks(s->n, 256);
+  if (fuse) {
+    // the fused deposit exists in fast arithmetic only; exact mode runs the two
+    // kernels back to back (the API never asks for exact+fused)
+    if (c.exact) return PGPU_ERR_STATE;
+    KTimer t("advance_deposit_fused");
+    k_advance<D, IE, false, true><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, c.d_counters);
+  } else {
+    KTimer t("advance");
+    if (c.exact)
+      k_advance<D, IE, true, false><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, c.d_counters);
+    else
+      k_advance<D, IE, false, false><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, c.d_counters);
+  }
+  return 0;
+}
+
+template <int D>
+static int launch_advance_d(pgpu_species_s *s, const AdvanceParams &prm, bool fuse) {
+  switch (s->desc.interp_E) {
+    case CIC: return launch_advance_t<D, CIC>(s, prm, fuse);
+    case TSC: return launch_advance_t<D, TSC>(s, prm, fuse);
+    case CC0: return launch_advance_t<D, CC0>(s, prm, fuse);
+    case CC1: return launch_advance_t<D, CC1>(s, prm, fuse);
+  }
+  return PGPU_ERR_ARG;
+}
+
+// fuse_deposit requires interp_J == interp_E (the fused kernel reuses one visitor type)
+int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit) {
+  if (s->n == 0) return 0;
+  return s->grid->desc.D == 1 ? launch_advance_d<1>(s, prm, fuse_deposit)
+                              : launch_advance_d<2>(s, prm, fuse_deposit);
+}
+
+}  // namespace pgpu

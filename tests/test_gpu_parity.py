@@ -1,0 +1,367 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs.  Tolerances (BASELINE.json north_star): push and deposit within
+1e-12 relative, particle-to-cell indexing bit-exact.  In `exact` arithmetic mode the
+kernels follow the reference's operation order and must agree to round-off of the
+atomics' summation order only."""
+import numpy as np
+import pytest
+
+from common import INTERPS, Problem, make_gpu, orc, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_FAST = 1e-12
+TOL_EXACT_PUSH = 1e-15   # no summation-order freedom: identical operation order
+TOL_EXACT_DEP = 2e-14    # atomics reorder the per-node sums
+
+
+def _prob(D, seed=11, n=4000, max_disp=1.2, nghost=4):
+    if D == 1:
+        return Problem(1, (24,), (0.25,), (0.5,), nghost, n, seed=seed, max_disp=max_disp)
+    return Problem(2, (12, 10), (0.25, 0.3), (0.5, -1.0), nghost, n, seed=seed, max_disp=max_disp)
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("interp", ["CIC", "TSC", "CC0", "CC1"])
+@pytest.mark.parametrize("D", [1, 2])
+def test_gather(pgpu, D, interp, exact):
+    prob = _prob(D)
+    pgpu.load().pgpu_set_exact_math(exact)
+    grid, sp = make_gpu(pgpu, prob, INTERPS[interp])
+    sp.interpolate_fields()
+    Ep, Bp = sp.particle_fields()
+    rc, Ep0, Bp0 = orc.gather(prob.geom, INTERPS[interp], prob.x, prob.xold, prob.E, prob.B)
+    assert rc == 0
+    tol = TOL_EXACT_PUSH if exact else TOL_FAST
+    assert rel_err(Ep, Ep0) <= tol
+    assert rel_err(Bp, Bp0) <= tol
+    sp.destroy(); grid.destroy()
+    pgpu.load().pgpu_set_exact_math(0)
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("interp", ["CIC", "TSC", "CC0", "CC1"])
+@pytest.mark.parametrize("D", [1, 2])
+def test_deposit_current(pgpu, D, interp, exact):
+    prob = _prob(D, seed=12)
+    pgpu.load().pgpu_set_exact_math(exact)
+    charge, vs = -1.0, 2.5
+    grid, sp = make_gpu(pgpu, prob, INTERPS[interp], charge=charge, volume_scale=vs)
+    sp.set_current_density(0.1)
+    J0 = prob.new_J()
+    assert orc.deposit_current(prob.geom, INTERPS[interp], prob.x, prob.xold, prob.v, prob.w, 0.1, J0) == 0
+    tol = TOL_EXACT_DEP if exact else TOL_FAST
+    for c in range(3):
+        orc.scale_fab(J0[c], D, charge / vs)
+        J = sp.current_get(c)
+        # norm-wise: thermal sums cancel, compare against the component's scale
+        assert rel_err(J, J0[c].a) <= tol, (c, interp)
+    # total = species (one species), then ghost add-exchange
+    grid.current_zero(); grid.current_add(sp); grid.current_finalize()
+    for c in range(3):
+        orc.fold_periodic(J0[c], D, orc.E_STAG[D][c], prob.box_lo, prob.box_hi, (1,) * D)
+        assert rel_err(grid.current_get(c), J0[c].a) <= tol
+    sp.destroy(); grid.destroy()
+    pgpu.load().pgpu_set_exact_math(0)
+
+
+def test_cell_index_bit_exact(pgpu):
+    """floor((x-le)/dx) with a true divide, on and next to cell faces (both modes)."""
+    D, ncell, dx, xmin = 2, (37, 29), (0.1, 0.3), (0.7, -2.1)
+    rng = np.random.default_rng(5)
+    faces0 = xmin[0] + np.arange(ncell[0]) * dx[0]
+    faces1 = xmin[1] + np.arange(ncell[1]) * dx[1]
+    xs, ys = [], []
+    for f0 in faces0:
+        for k in (-2, -1, 0, 1, 2):
+            v = f0
+            for _ in range(abs(k)):
+                v = np.nextafter(v, np.inf if k > 0 else -np.inf)
+            xs.append(v)
+    xs = np.array(xs)
+    ys = rng.choice(faces1, size=xs.size) + rng.choice([0.0, 1e-17, -1e-17, 4e-17], size=xs.size)
+    x = np.ascontiguousarray(np.stack([xs, ys]))
+    n = x.shape[1]
+    prob = Problem(D, ncell, dx, xmin, 3, n, seed=1)
+    prob.x = x; prob.xold = x.copy()
+    grid, sp = make_gpu(pgpu, prob, INTERPS["CIC"])
+    got = sp.cell_index()
+    want = orc.bin_cells(prob.geom, x)
+    assert np.array_equal(got, want)
+    sp.destroy(); grid.destroy()
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("D", [1, 2])
+def test_deposit_indices_on_cell_faces(pgpu, D, exact):
+    """Particles exactly on faces / half-faces: the touched nodes must be identical, so the
+    deposited arrays must have the same support."""
+    ncell, dx, xmin = ((16,), (0.1,), (0.3,)) if D == 1 else ((8, 8), (0.1, 0.3), (0.3, -0.6))
+    n = 600
+    prob = Problem(D, ncell, dx, xmin, 4, n, seed=3, max_disp=0.9)
+    rng = np.random.default_rng(7)
+    for d in range(D):
+        k = rng.integers(0, 2 * ncell[d], size=n)
+        prob.xold[d] = xmin[d] + k * (0.5 * dx[d])          # faces and cell centres
+        prob.x[d] = prob.xold[d] + rng.integers(-1, 2, size=n) * (0.25 * dx[d])
+    pgpu.load().pgpu_set_exact_math(exact)
+    for interp in ("CIC", "TSC", "CC0", "CC1"):
+        grid, sp = make_gpu(pgpu, prob, INTERPS[interp], charge=1.0)
+        sp.set_current_density(0.1)
+        J0 = prob.new_J()
+        assert orc.deposit_current(prob.geom, INTERPS[interp], prob.x, prob.xold, prob.v, prob.w, 0.1, J0) == 0
+        for c in range(3):
+            J = sp.current_get(c)
+            assert rel_err(J, J0[c].a) <= (TOL_EXACT_DEP if exact else TOL_FAST)
+            # same support up to exact zeros
+            assert np.array_equal(np.abs(J) > 1e-300, np.abs(J0[c].a) > 1e-300), (interp, c)
+        sp.destroy(); grid.destroy()
+    pgpu.load().pgpu_set_exact_math(0)
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("swap", [0, 1])
+@pytest.mark.parametrize("D", [1, 2])
+def test_advance_particles_single_pass(pgpu, D, swap, exact):
+    prob = _prob(D, seed=13, max_disp=0.6)
+    pgpu.load().pgpu_set_exact_math(exact)
+    fnorm, cvac, dt = -0.8, 0.9986, 0.4
+    grid, sp = make_gpu(pgpu, prob, INTERPS["CC1"], iter_max=0, order_swap=swap, fnorm=fnorm, cvac_norm=cvac)
+    st = sp.advance_iteratively(dt, deposit=False)   # iter_max == 0 -> advanceParticles
+    got = sp.download()
+    x, v = prob.x.copy(), prob.v.copy()
+    assert orc.advance_particles(prob.geom, orc.CC1, x, prob.xold, v, prob.vold, prob.E, prob.B, fnorm, dt * cvac, swap) == 0
+    tol = TOL_EXACT_PUSH if exact else TOL_FAST
+    assert rel_err(got["v"], v) <= tol
+    assert np.max(np.abs(got["x"] - x) / np.array(prob.dx)[:, None]) <= tol * 10
+    sp.destroy(); grid.destroy()
+    pgpu.load().pgpu_set_exact_math(0)
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("interp", ["CIC", "TSC", "CC0", "CC1"])
+@pytest.mark.parametrize("D", [1, 2])
+def test_advance_iteratively(pgpu, D, interp, exact):
+    prob = Problem(D, (24,) if D == 1 else (12, 10), (0.25,) if D == 1 else (0.25, 0.3), (0.5,) * D, 4, 3000,
+                   seed=14, max_disp=0.5, E0=0.3, B0=0.8)
+    pgpu.load().pgpu_set_exact_math(exact)
+    fnorm, cvac, dt, rtol, itmax = -0.7, 0.9986, 0.5, 1e-12, 25
+    grid, sp = make_gpu(pgpu, prob, INTERPS[interp], rtol=rtol, iter_max=itmax, fnorm=fnorm, cvac_norm=cvac)
+    st = sp.advance_iteratively(dt, deposit=False)
+    got = sp.download()
+    x, v = prob.x.copy(), prob.v.copy()
+    rc, apply_its, unconv, its = orc.advance_particles_iteratively(
+        prob.geom, INTERPS[interp], x, prob.xold, v, prob.vold, prob.E, prob.B, fnorm, dt * cvac, rtol, itmax)
+    assert rc == 0
+    assert st.num_parts_its == prob.n
+    tol = TOL_EXACT_PUSH if exact else TOL_FAST
+    if exact:
+        assert st.num_apply_its == apply_its and st.num_unconverged == unconv
+    else:
+        # a convergence test decided within round-off of rtol may take one more/less pass
+        assert abs(st.num_apply_its - apply_its) <= max(3, prob.n // 100)
+    # positions: error relative to the cell size (the convergence measure of stepNorm)
+    assert np.max(np.abs(got["x"] - x) / np.array(prob.dx)[:, None]) <= (tol if exact else 4 * rtol)
+    assert rel_err(got["v"], v) <= (tol if exact else 1e-11)
+    sp.destroy(); grid.destroy()
+    pgpu.load().pgpu_set_exact_math(0)
+
+
+@pytest.mark.parametrize("interp", ["CIC", "TSC", "CC0", "CC1"])
+@pytest.mark.parametrize("D", [1, 2])
+def test_fused_advance_deposit_matches_unfused(pgpu, D, interp):
+    prob = Problem(D, (24,) if D == 1 else (12, 10), (0.25,) if D == 1 else (0.25, 0.3), (0.5,) * D, 4, 3000,
+                   seed=15, max_disp=0.5, E0=0.3, B0=0.8)
+    fnorm, cvac, dt = -0.7, 0.9986, 0.5
+    grid, sp = make_gpu(pgpu, prob, INTERPS[interp], fnorm=fnorm, cvac_norm=cvac, charge=-1.0, volume_scale=3.0)
+    sp.advance_iteratively(dt, deposit=True)
+    fused = [sp.current_get(c) for c in range(3)]
+    got = sp.download()
+    # oracle: advance, then deposit with the converged (xbar, ubar)
+    x, v = prob.x.copy(), prob.v.copy()
+    orc.advance_particles_iteratively(prob.geom, INTERPS[interp], x, prob.xold, v, prob.vold, prob.E, prob.B,
+                                      fnorm, dt * cvac, 1e-12, 21)
+    J0 = prob.new_J()
+    orc.deposit_current(prob.geom, INTERPS[interp], x, prob.xold, v, prob.w, dt * cvac, J0)
+    for c in range(3):
+        orc.scale_fab(J0[c], D, -1.0 / 3.0)
+        assert rel_err(fused[c], J0[c].a) <= 1e-11
+    # and the separate deposit kernel on the device state gives the same field
+    sp.set_current_density(dt)
+    for c in range(3):
+        assert rel_err(sp.current_get(c), fused[c]) <= 1e-13
+    sp.destroy(); grid.destroy()
+
+
+def test_cc1_segment_limit_error(pgpu):
+    prob = Problem(1, (16,), (0.25,), (0.0,), 2, 64, seed=5, max_disp=3.9)
+    grid, sp = make_gpu(pgpu, prob, INTERPS["CC1"])
+    with pytest.raises(pgpu.PgpuError) as e:
+        sp.interpolate_fields()
+    assert e.value.code == pgpu.ERR_SEGMENTS
+    sp.destroy(); grid.destroy()
+
+
+@pytest.mark.parametrize("interp_N", [0, 1])
+@pytest.mark.parametrize("D", [1, 2])
+def test_charge_density(pgpu, D, interp_N):
+    prob = _prob(D, seed=16)
+    for exact in (1, 0):
+        pgpu.load().pgpu_set_exact_math(exact)
+        grid, sp = make_gpu(pgpu, prob, INTERPS["CC1"], charge=-1.0, volume_scale=2.0, interp_N=interp_N)
+        for stag in ([1] * D, [0] * D, [1] + [0] * (D - 1)):
+            rho, lo, hi = sp.charge_density(stag)
+            ref = orc.fab_for(prob.box_lo, prob.box_hi, prob.nghost, stag)
+            orc.deposit_rho(prob.geom, interp_N, prob.x, prob.w, stag, ref)
+            orc.scale_fab(ref, D, -1.0 / 2.0)
+            orc.fold_periodic(ref, D, stag, prob.box_lo, prob.box_hi, (1,) * D)
+            assert rel_err(rho, ref.a) <= (TOL_EXACT_DEP if exact else TOL_FAST)
+        sp.destroy(); grid.destroy()
+    pgpu.load().pgpu_set_exact_math(0)
+
+
+def test_streaming_passes(pgpu):
+    prob = _prob(2, seed=17)
+    cvac, dt = 0.9986, 0.3
+    grid, sp = make_gpu(pgpu, prob, INTERPS["CIC"], cvac_norm=cvac)
+    n, D = prob.n, 2
+    x = np.empty_like(prob.x)
+    sp.advance_positions_explicit(dt, half=True)
+    orc.lib().orc_advance_positions_explicit(D, n, x.ctypes.data, prob.xold.ctypes.data, prob.v.ctypes.data, cvac * dt * 0.5)
+    assert np.array_equal(sp.download()["x"], x)
+    sp.advance_positions_implicit(dt)
+    orc.lib().orc_advance_positions_implicit(D, n, x.ctypes.data, prob.xold.ctypes.data, prob.v.ctypes.data, cvac * dt)
+    assert np.array_equal(sp.download()["x"], x)
+    sp.advance_positions_2nd_half(); sp.advance_velocities_2nd_half()
+    v = prob.v.copy()
+    orc.lib().orc_advance_positions_2nd_half(D, n, x.ctypes.data, prob.xold.ctypes.data)
+    orc.lib().orc_advance_velocities_2nd_half(n, v.ctypes.data, prob.vold.ctypes.data)
+    got = sp.download()
+    assert np.array_equal(got["x"], x) and np.array_equal(got["v"], v)
+    sp.average_velocities()
+    orc.lib().orc_average_velocities(n, v.ctypes.data, prob.vold.ctypes.data)
+    assert np.array_equal(sp.download()["v"], v)
+    sp.update_old_positions(); sp.update_old_velocities()
+    got = sp.download()
+    assert np.array_equal(got["xold"], got["x"]) and np.array_equal(got["vold"], got["v"])
+    sp.destroy(); grid.destroy()
+
+
+def test_explicit_boris_from_stored_fields(pgpu):
+    prob = _prob(2, seed=18)
+    fnorm, cvac, dt = 1.3, 0.9986, 0.2
+    for exact in (1, 0):
+        pgpu.load().pgpu_set_exact_math(exact)
+        grid, sp = make_gpu(pgpu, prob, INTERPS["TSC"], fnorm=fnorm, cvac_norm=cvac)
+        sp.interpolate_fields()
+        sp.advance_velocities(dt, half=False)
+        rc, Ep, Bp = orc.gather(prob.geom, orc.TSC, prob.x, prob.xold, prob.E, prob.B)
+        v = orc.boris(prob.v.copy(), prob.vold, Ep, Bp, fnorm, dt * cvac, False)
+        assert rel_err(sp.download()["v"], v) <= (TOL_EXACT_PUSH if exact else TOL_FAST)
+        sp.destroy(); grid.destroy()
+    pgpu.load().pgpu_set_exact_math(0)
+
+
+@pytest.mark.parametrize("D", [1, 2])
+def test_bin_sort_and_moments(pgpu, D):
+    prob = _prob(D, seed=19, n=5000)
+    # leave some cells empty and make the occupancy ragged
+    keep = (prob.x[0] - prob.xmin[0]) / prob.dx[0] % 4 > 0.8
+    prob.x = np.ascontiguousarray(prob.x[:, keep]); prob.xold = prob.x.copy()
+    prob.v = np.ascontiguousarray(prob.v[:, keep]); prob.vold = np.ascontiguousarray(prob.vold[:, keep])
+    prob.w = np.ascontiguousarray(prob.w[keep]); prob.n = prob.w.size
+    # keep the particles inside the box (bins cover owned cells only)
+    for d in range(D):
+        prob.x[d] = np.clip(prob.x[d], prob.xmin[d], np.nextafter(prob.xmax[d], -np.inf))
+    mass, vs = 1836.15, 1.5e-25
+    grid, sp = make_gpu(pgpu, prob, INTERPS["CIC"], mass=mass, charge=1.0, volume_scale=vs)
+    sp.bin_particles()
+    got = sp.download()
+    offs = sp.cell_offsets()
+    cells = orc.bin_cells(prob.geom, got["x"])
+    lin = cells[0] if D == 1 else cells[0] + cells[1] * prob.ncell[0]
+    assert np.all(np.diff(lin) >= 0)                                   # sorted by cell
+    counts = np.bincount(lin, minlength=int(np.prod(prob.ncell)))
+    assert np.array_equal(np.diff(offs), counts)                        # offsets
+    assert offs[-1] == prob.n
+    # a permutation of the input, stable inside each cell (ids ascending)
+    order = got["id"].astype(np.int64)
+    assert np.array_equal(np.sort(order), np.arange(prob.n))
+    assert np.array_equal(got["x"], prob.x[:, order]) and np.array_equal(got["w"], prob.w[order])
+    for c in np.nonzero(counts > 1)[0][:50]:
+        assert np.all(np.diff(order[offs[c]:offs[c + 1]]) > 0)
+    sp.set_moments()
+    dens, mom, ene = sp.moments()
+    d0, m0, e0 = orc.cell_moments(prob.geom, prob.x, prob.v, prob.w, mass, vs, prob.box_lo, prob.box_hi)
+    assert rel_err(dens, d0) <= 1e-13 and rel_err(mom, m0) <= 1e-12 and rel_err(ene, e0) <= 1e-13
+    assert np.array_equal(dens == 0.0, d0 == 0.0)
+    sp.destroy(); grid.destroy()
+
+
+def test_debye_length(pgpu):
+    d = __import__("picnic_b200.decks", fromlist=["x"])
+    deck = d.deck_c2(ncell=8, ppc=4)
+    rng = np.random.default_rng(3)
+    prob = Problem(2, deck.ncell, deck.dx, deck.xmin, 2, 10, seed=1)
+    grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, 2, (1, 1), volume_scale=deck.volume_scale)
+    sps, moms = [], []
+    for sdef in deck.species:
+        p = d.load_species(deck, sdef, (0, 0), (7, 7), rng)
+        sp = pgpu.Species(grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm)
+        sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
+        sp.bin_particles(); sp.set_moments()
+        sps.append(sp)
+        d0, m0, e0 = orc.cell_moments(prob.geom, p["x"], p["v"], p["w"], sdef.mass, deck.volume_scale, (0, 0), (7, 7))
+        moms.append((d0, m0, e0, sdef.mass, sdef.charge))
+    got = grid.debye_length(sps)
+    want = orc.debye_length(moms)
+    assert rel_err(got, want) <= 1e-12
+    assert np.all(got > 0) and np.all(np.isfinite(got))
+    for sp in sps:
+        sp.destroy()
+    grid.destroy()
+
+
+def test_boundary_conditions(pgpu):
+    prob = _prob(2, seed=21, n=3000, max_disp=2.5)   # many particles leave the domain
+    grid, sp = make_gpu(pgpu, prob, INTERPS["CIC"])
+    sp.apply_bcs((pgpu.BC_PERIODIC, pgpu.BC_SYMMETRY), (pgpu.BC_PERIODIC, pgpu.BC_SYMMETRY))
+    got = sp.download()
+    x, xo, v, vo = prob.x.copy(), prob.xold.copy(), prob.v.copy(), prob.vold.copy()
+    L = orc.lib()
+    n = prob.n
+    L.orc_bc_periodic(n, x[0].ctypes.data, xo[0].ctypes.data, prob.xmin[0], prob.xmax[0])
+    L.orc_bc_symmetry(n, x[1].ctypes.data, xo[1].ctypes.data, v[1].ctypes.data, vo[1].ctypes.data,
+                      prob.xmin[1], prob.xmax[1], 1, 1)
+    for k, a in (("x", x), ("xold", xo), ("v", v), ("vold", vo)):
+        assert np.array_equal(got[k], a), k
+    assert np.any(got["x"] != prob.x)
+    sp.destroy(); grid.destroy()
+
+
+def test_reductions(pgpu):
+    prob = _prob(2, seed=22)
+    cvac = 0.9986
+    grid, sp = make_gpu(pgpu, prob, INTERPS["CIC"], cvac_norm=cvac)
+    dt = sp.stable_dt()
+    want = 1.0 / np.max(np.abs(prob.v[:2]) / np.array(prob.dx)[:, None]) / cvac
+    assert abs(dt - want) / want < 1e-15
+    gm = sp.global_moments()
+    w, v = prob.w, prob.v
+    want = np.array([w.sum()] + [(w * v[k]).sum() for k in range(3)] + [(w * v[k] ** 2).sum() for k in range(3)])
+    assert np.max(np.abs(gm - want) / np.abs(want).max()) < 1e-13
+    sp.destroy(); grid.destroy()
+
+
+def test_empty_species(pgpu):
+    prob = _prob(2, seed=23, n=8)
+    grid, sp = make_gpu(pgpu, prob, INTERPS["CC1"])
+    z = np.zeros((2, 0)); z3 = np.zeros((3, 0))
+    sp.upload(z, z3, np.zeros(0))
+    assert sp.n == 0
+    st = sp.advance_iteratively(0.1, deposit=True)
+    assert st.num_apply_its == 0
+    sp.bin_particles(); sp.set_moments()
+    assert np.all(sp.moments()[0] == 0.0)
+    assert np.all(sp.current_get(0) == 0.0)
+    sp.destroy(); grid.destroy()
