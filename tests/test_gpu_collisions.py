@@ -43,8 +43,12 @@ def test_ta_delta_u_matches_oracle(pgpu):
                      for i in range(n)], axis=1)
     u = np.linalg.norm(v1 - v2, axis=0)
     assert np.max(np.abs(got - want) / u) < 1e-13
-    # |u + dU| == |u|
-    assert np.max(np.abs(np.linalg.norm(v1 - v2 + got, axis=0) - u) / u) < 1e-13
+    # |u + dU| == |u|.  Reference quirk kept on purpose (ScatteringUtils.H:95-99): the
+    # u_perp == 0 branch uses u = |u| where the rotation needs the signed uz, so an
+    # exactly anti-aligned pair (uz < 0) does not conserve |u|; those are excluded here.
+    keep = ~((np.hypot(v1[0] - v2[0], v1[1] - v2[1]) == 0.0) & (v1[2] - v2[2] < 0.0))
+    assert keep.sum() >= n - 5
+    assert np.max((np.abs(np.linalg.norm(v1 - v2 + got, axis=0) - u) / u)[keep]) < 1e-13
 
 
 def _ragged_cells(rng, ncell, counts_choice):

@@ -113,8 +113,15 @@ def test_deposit_indices_on_cell_faces(pgpu, D, exact):
         for c in range(3):
             J = sp.current_get(c)
             assert rel_err(J, J0[c].a) <= (TOL_EXACT_DEP if exact else TOL_FAST)
-            # same support up to exact zeros
-            assert np.array_equal(np.abs(J) > 1e-300, np.abs(J0[c].a) > 1e-300), (interp, c)
+            if exact:
+                # same support up to exact zeros
+                assert np.array_equal(np.abs(J) > 1e-300, np.abs(J0[c].a) > 1e-300), (interp, c)
+            else:
+                # fast arithmetic may turn an exactly-zero weight (particle on a face) into
+                # ~1 ulp: the touched nodes are the same, the support agrees above round-off
+                thr = 1e-10 * np.max(np.abs(J0[c].a))
+                assert not np.any((np.abs(J) > thr) & (np.abs(J0[c].a) <= 1e-300)), (interp, c)
+                assert not np.any((np.abs(J0[c].a) > thr) & (np.abs(J) <= 1e-300)), (interp, c)
         sp.destroy(); grid.destroy()
     pgpu.load().pgpu_set_exact_math(0)
 
@@ -270,9 +277,11 @@ def test_bin_sort_and_moments(pgpu, D):
     prob.x = np.ascontiguousarray(prob.x[:, keep]); prob.xold = prob.x.copy()
     prob.v = np.ascontiguousarray(prob.v[:, keep]); prob.vold = np.ascontiguousarray(prob.vold[:, keep])
     prob.w = np.ascontiguousarray(prob.w[keep]); prob.n = prob.w.size
-    # keep the particles inside the box (bins cover owned cells only)
+    # keep the particles inside the box (bins cover owned cells only).  nextafter(xmax)
+    # is NOT enough: floor((x-le)/dx) rounds up to ncell there (that particle is an
+    # outcast in the reference too), so stay a hair further in.
     for d in range(D):
-        prob.x[d] = np.clip(prob.x[d], prob.xmin[d], np.nextafter(prob.xmax[d], -np.inf))
+        prob.x[d] = np.clip(prob.x[d], prob.xmin[d], prob.xmax[d] - 1e-9 * prob.dx[d])
     mass, vs = 1836.15, 1.5e-25
     grid, sp = make_gpu(pgpu, prob, INTERPS["CIC"], mass=mass, charge=1.0, volume_scale=vs)
     sp.bin_particles()
