@@ -1,0 +1,501 @@
+#!/usr/bin/env python
+"""bench.py -- particle-advances/s of the implicit push + deposit hot path.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE
+JSON line (rank 0).  Under torchrun (N > 1) every rank owns one box of a periodic domain
+tiled N boxes wide (weak scaling: the per-GPU box is fixed), with the ghost-J add-exchange
+between neighbouring boxes over NCCL.
+
+Workload (config.workload): BASELINE.json configs[2] "C3" -- 2D implicit energy-conserving
+PIC, 512x512 cells, 2 species x 100 particles per cell (5.24e7 particles), CC1 gather and
+deposit, rtol_particles = 1e-12, iter_max_particles = 21 -- the configuration the
+north-star target (push+deposit vs HBM roofline on one B200) is quoted on.
+
+One STEP = the particle side of one implicit time step under a Picard outer loop with
+`n_outer` nonlinear function evaluations (PICTimeIntegrator_EM_ThetaImplicit.cpp:193-364):
+    updateOldParticlePositions/Velocities
+    n_outer x preRHSOp:  [E,B of that iteration] -> per species advanceParticlesIteratively
+                         + setCurrentDensity (fused), sum over species, ghost add-exchange
+    advanceVelocities_2ndHalf, advancePositions_2ndHalf, applyBCs (periodic)
+    binTheParticles (cell sort) every `sort_every` steps
+Units per step = particles x n_outer particle-advances.  Fields are smooth
+analytic modes; outer iteration j sees the field scaled by (1 + eps_j), eps = 0, 1e-3, 1e-6,
+which mimics the shrinking field updates of a converging Picard loop so that the particle
+Picard loop does real work in every evaluation (mean passes k is reported).
+
+`value`  : device-resident: the three field sets are already in HBM (field slots).
+`e2e`    : the same step driven through the reference-facing C ABI with HOST buffers: every
+           preRHSOp uploads E,B (6 components) from pinned host memory and reads the summed
+           J (3 components) back to pinned host memory, inside the timed region.
+`--impl reference`: the CPU oracle (the restatement of the reference algorithm; the
+           reference itself needs Chombo/gfortran/MPI and cannot be built) on all
+           host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from picnic_b200 import decks  # noqa: E402
+
+BYTES_PER_ADVANCE_2D = 88.0   # (2D+7)*8 B, compulsory SoA traffic of one advance
+EPS_OUTER = (0.0, 1.0e-3, 1.0e-6, 1.0e-9)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ncell", type=int, default=512, help="cells per direction of the per-GPU box")
+    ap.add_argument("--ppc", type=int, default=10, help="particles per cell per direction per species")
+    ap.add_argument("--n-outer", type=int, default=3)
+    ap.add_argument("--sort-every", type=int, default=1)
+    ap.add_argument("--dt", type=float, default=0.1)
+    ap.add_argument("--iter-max", type=int, default=21)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="particles per species in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------
+def box_layout(world):
+    """Tile `world` equal square boxes (System.cpp:181-185) as px x py."""
+    px = 1
+    while px * px < world:
+        px *= 2
+    py = world // px
+    assert px * py == world, "world size must be a power of two"
+    return px, py
+
+
+def make_deck(args, world):
+    px, py = box_layout(world)
+    d = decks.deck_c3(ncell=args.ncell, ppc=args.ppc, dt=args.dt, iter_max=args.iter_max)
+    d.ncell = (args.ncell * px, args.ncell * py)
+    return d, (px, py)
+
+
+def rank_box(args, rank, layout):
+    px, _ = layout
+    bi, bj = rank % px, rank // px
+    lo = (bi * args.ncell, bj * args.ncell)
+    hi = (lo[0] + args.ncell - 1, lo[1] + args.ncell - 1)
+    return lo, hi
+
+
+def field_amplitudes(deck):
+    """E0, B0 such that omega_pe*dt ~ omega_ce*dt ~ 0.1-like kicks: a thermal electron's
+    velocity changes by ~10 % per step from E and rotates by ~0.1 rad from B."""
+    sp = deck.species[0]
+    fn = abs(sp.fnorm_const(deck.units))
+    vth = np.sqrt(decks.QE / decks.ME * sp.temperature_eV[0] / sp.mass) / decks.CVAC
+    alpha = fn * deck.cnorm_dt / 2.0
+    return 0.05 * vth / alpha, 0.05 / alpha
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# the GPU arm
+# ------------------------------------------------------------------------------------------
+class Engine:
+    """The particle side of the implicit step, driven through the C ABI (capi)."""
+
+    def __init__(self, args, rank, world, device):
+        import torch
+        from picnic_b200 import capi
+        self.torch, self.capi, self.args, self.rank, self.world = torch, capi, args, rank, world
+        capi.load()
+        capi.init(device)
+        self.deck, self.layout = make_deck(args, world)
+        deck = self.deck
+        self.lo, self.hi = rank_box(args, rank, self.layout)
+        self.grid = capi.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), box_lo=self.lo,
+                              box_hi=self.hi, volume_scale=deck.volume_scale)
+        E0, B0 = field_amplitudes(deck)
+        E, B = decks.analytic_fields(deck, self.lo, self.hi, E0=E0, B0=B0)
+        self.n_outer = args.n_outer
+        # pinned host copies of the field sets of each outer iteration + pinned J read-back
+        self.host_fields = []
+        for j in range(self.n_outer):
+            comps = []
+            for (lo, hi, a) in list(E) + list(B):
+                t = torch.empty(a.size, dtype=torch.float64).pin_memory()
+                h = t.numpy().reshape(a.shape, order="F")
+                h[...] = a * (1.0 + EPS_OUTER[j % len(EPS_OUTER)])
+                comps.append((lo, hi, h, t))
+            self.host_fields.append(comps)
+        self.host_J = []
+        for c in range(3):
+            lo, hi = self.grid.field_bounds(c)
+            shape = tuple(h - l + 1 for l, h in zip(lo, hi))
+            t = torch.empty(int(np.prod(shape)), dtype=torch.float64).pin_memory()
+            self.host_J.append((lo, hi, t.numpy().reshape(shape, order="F"), t))
+        for j in range(self.n_outer):           # resident field slots for the device-timed arm
+            self.grid.fields_select(j)
+            self._upload_fields(j)
+        self.grid.fields_select(0)
+        capi.check(capi.load().pgpu_synchronize())
+        rng = np.random.default_rng(deck.seed + 1000 * rank)
+        self.species = []
+        self.n_particles = 0
+        for sdef in deck.species:
+            p = decks.load_species(deck, sdef, self.lo, self.hi, rng)
+            sp = capi.Species(self.grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm,
+                              interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E,
+                              rtol=deck.rtol, iter_max=deck.iter_max)
+            sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
+            sp.bin_particles()
+            self.species.append(sp)
+            self.n_particles += sp.n
+            del p
+        self.h2d = sum(h.nbytes for (_, _, h, _) in self.host_fields[0]) * self.n_outer
+        self.d2h = sum(h.nbytes for (_, _, h, _) in self.host_J) * self.n_outer
+        self.step_no = 0
+        self.halo = None
+        if world > 1:
+            from picnic_b200 import halo
+            self.halo = halo.HaloExchange(self.grid, self.deck, self.lo, self.hi, rank, self.layout)
+
+    def _upload_fields(self, j):
+        lib, capi = self.capi.load(), self.capi
+        for c, (lo, hi, h, _) in enumerate(self.host_fields[j]):
+            capi.check(lib.pgpu_fields_set(self.grid.h, c, h.ctypes.data, capi._i2(lo), capi._i2(hi)))
+
+    def pre_rhs_op(self, j, host_io):
+        """PicSpeciesInterface::preRHSOp (PicSpeciesInterface.cpp:899-994) for outer iteration j."""
+        capi, lib = self.capi, self.capi.load()
+        if host_io:
+            self._upload_fields(j)                  # async H2D from pinned memory on the engine stream
+        else:
+            self.grid.fields_select(j)
+        self.grid.current_zero()
+        for sp in self.species:
+            capi.check(lib.pgpu_advance_particles_iteratively(sp.h, self.deck.dt, 1, None))
+            self.grid.current_add(sp)
+        if self.halo is not None:
+            self.halo.add_exchange()
+        self.grid.current_finalize()
+        if host_io:
+            for c, (lo, hi, h, _) in enumerate(self.host_J):
+                capi.check(lib.pgpu_current_get(self.grid.h, c, h.ctypes.data, capi._i2(lo), capi._i2(hi)))
+
+    def step(self, host_io=False):
+        for sp in self.species:
+            sp.update_old_positions()
+            sp.update_old_velocities()
+        if host_io:
+            self.grid.fields_select(0)
+        for j in range(self.n_outer):
+            self.pre_rhs_op(j, host_io)
+        for sp in self.species:
+            sp.advance_velocities_2nd_half()
+            sp.advance_positions_2nd_half()
+            sp.apply_bcs((1, 1), (1, 1))
+        self.step_no += 1
+        if self.args.sort_every > 0 and self.step_no % self.args.sort_every == 0:
+            for sp in self.species:
+                sp.bin_particles()
+
+    def sync(self):
+        self.capi.check(self.capi.load().pgpu_synchronize())
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from picnic_b200 import capi
+    eng = Engine(args, rank, world, local)
+    # run the library on a torch stream so that torch.cuda.Event brackets its kernels
+    stream = torch.cuda.Stream(device=local)
+    capi.check(capi.load().pgpu_set_stream(stream.cuda_stream))
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def region(nsteps, host_io, profile=False):
+        barrier()
+        if profile:
+            capi.profile_reset()
+            capi.profile_enable(True)
+            capi.picard_totals(reset=True)
+        launches0 = capi.load().pgpu_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(nsteps):
+            eng.step(host_io)
+        e1.record(stream)
+        barrier()
+        if profile:
+            capi.profile_enable(False)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, capi.load().pgpu_launch_count() - launches0
+
+    # warm-up (>= 3 steps), then the timed region.  The particle arrays (5 GB per GPU) are far
+    # larger than the 126 MB L2, so every pass streams from HBM; no explicit flush is needed.
+    region(max(args.warmup, 1), False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = region(args.steps, False, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = {}
+    for name in ("advance_deposit_fused", "advance", "deposit_current", "bin_", "second_half", "fold_periodic",
+                 "current_add", "current_scale", "bc_periodic"):
+        prof[name] = capi.profile_query(name)
+    adv, app, unconv = capi.picard_totals(reset=True)
+    k_mean = app / max(adv, 1)
+
+    n_total = eng.n_particles * world
+    units = float(n_total) * args.n_outer * args.steps
+    value = units / (ms * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        region(1, True)
+        ms_e, _ = region(args.steps, True)
+        e2e = {"value": units / (ms_e * 1e-3), "unit": "particle-advances/s",
+               "h2d_bytes_per_step": int(eng.h2d), "d2h_bytes_per_step": int(eng.d2h),
+               "ms_per_step": ms_e / args.steps}
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        k_ms, k_n = prof["advance_deposit_fused"]
+        if k_n == 0:
+            k_ms, k_n = prof["advance"]
+        per_launch_units = eng.n_particles / len(eng.species)
+        achieved = (BYTES_PER_ADVANCE_2D * per_launch_units) / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
+        out = {
+            "metric": "particle-advances/s (implicit push + deposit)", "value": value, "unit": "particle-advances/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3: 2D implicit energy-conserving PIC, %dx%d cells per GPU box, 2 species x %d ppc, "
+                                   "CC1 gather/deposit, Picard particle loop (rtol 1e-12, iter_max %d), %d nonlinear "
+                                   "evaluations per step" % (args.ncell, args.ncell, args.ppc ** 2, args.iter_max,
+                                                             args.n_outer),
+                       "particles_per_gpu": eng.n_particles, "boxes": "%dx%d" % eng.layout, "dt": args.dt,
+                       "n_outer": args.n_outer, "sort_every": args.sort_every,
+                       "mean_picard_passes": round(k_mean, 3), "unconverged_particles": int(unconv),
+                       "l2_policy": "inputs (%.1f GB particle SoA per GPU) exceed the 126 MB L2; no flush needed"
+                                    % (eng.n_particles * 96 / 1e9)},
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "k_advance (fused gather+Boris+Picard+deposit)",
+                         "bytes_per_unit": BYTES_PER_ADVANCE_2D, "units_per_launch": per_launch_units,
+                         "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms,
+                         "peak_source": peak_src},
+            "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, steps=1)
+    for sp in eng.species:
+        sp.destroy()
+    eng.grid.destroy()
+    capi.finalize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------
+# the CPU arm: the oracle (restatement of the reference algorithm) on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_sample_problem(args, nthreads):
+    """A bounded sample of the C3 workload: a strip of the same box (full 512 cells wide, a few
+    rows), same ppc, same fields, same dt -- particle density and field sampling are identical."""
+    from oracle import oracle as orc
+    deck, _ = make_deck(args, 1)
+    target = args.cpu_sample or 1000000 * max(nthreads, 1)          # particles per species
+    rows = max(1, min(args.ncell, int(round(target / (args.ncell * args.ppc ** 2)))))
+    E0, B0 = field_amplitudes(deck)
+    lo, hi = (0, 0), (args.ncell - 1, args.ncell - 1)
+    E, B = decks.analytic_fields(deck, lo, hi, E0=E0, B0=B0)
+    geom = orc.make_geom(2, deck.xmin, deck.xmax, deck.dx, deck.nghost)
+    Ef = [orc.Fab(l, h, a) for (l, h, a) in E]
+    Bf = [orc.Fab(l, h, a) for (l, h, a) in B]
+    rng = np.random.default_rng(deck.seed)
+    row0 = args.ncell // 2 - rows // 2
+    parts = [decks.load_species(deck, s, (0, row0), (args.ncell - 1, row0 + rows - 1), rng) for s in deck.species]
+    return orc, deck, geom, Ef, Bf, parts, rows
+
+
+def cpu_step(orc, deck, geom, Ef, Bf, parts, args, nthreads, pool):
+    """Same step as Engine.step on the sample; threads own contiguous particle slices and
+    private J arrays (the reference's MPI ranks own boxes the same way)."""
+    n_adv = 0
+    lo, hi = (0, 0), (args.ncell - 1, args.ncell - 1)
+
+    def work(sdef, sl):
+        x, xold, v, vold, w = sl
+        fn = sdef.fnorm_const(deck.units)
+        J = [orc.fab_for(lo, hi, deck.nghost, s) for s in orc.E_STAG[2]]
+        for j in range(args.n_outer):
+            # (the eps-scaled field sets only change k slightly; the CPU arm reuses one set)
+            rc, _, _, _ = orc.advance_particles_iteratively(geom, deck.interp_E, x, xold, v, vold, Ef, Bf, fn,
+                                                            deck.cnorm_dt, deck.rtol, deck.iter_max)
+            assert rc == 0
+            for f in J:
+                f.a[...] = 0.0
+            orc.deposit_current(geom, deck.interp_J, x, xold, v, w, deck.cnorm_dt, J)
+        orc.lib().orc_advance_velocities_2nd_half(v.shape[1], orc._ptr(v), orc._ptr(vold))
+        orc.lib().orc_advance_positions_2nd_half(2, x.shape[1], orc._ptr(x), orc._ptr(xold))
+        xold[...] = x
+        vold[...] = v
+        return x.shape[1] * args.n_outer
+
+    futs = []
+    for sdef, p in zip(deck.species, parts):
+        for sl in p["slices"]:
+            futs.append(pool.submit(work, sdef, sl))
+    for f in futs:
+        n_adv += f.result()
+    return n_adv
+
+
+def cpu_arm(args, steps, warmup):
+    import concurrent.futures as cf
+    nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    orc, deck, geom, Ef, Bf, parts, rows = cpu_sample_problem(args, nthreads)
+    for p in parts:
+        n = p["w"].size
+        edges = np.linspace(0, n, nthreads + 1).astype(np.int64)
+        p["slices"] = []
+        for a, b in zip(edges[:-1], edges[1:]):
+            x = np.ascontiguousarray(p["x"][:, a:b]); v = np.ascontiguousarray(p["v"][:, a:b])
+            p["slices"].append((x, x.copy(), v, v.copy(), np.ascontiguousarray(p["w"][a:b])))
+    n_sample = sum(p["w"].size for p in parts)
+    with cf.ThreadPoolExecutor(max_workers=nthreads) as pool:
+        for _ in range(warmup):
+            cpu_step(orc, deck, geom, Ef, Bf, parts, args, nthreads, pool)
+        t0 = time.perf_counter()
+        units = 0
+        for _ in range(steps):
+            units += cpu_step(orc, deck, geom, Ef, Bf, parts, args, nthreads, pool)
+        dt = time.perf_counter() - t0
+    return {"value": units / dt, "unit": "particle-advances/s", "cores": nthreads, "kind": "port",
+            "sample": "%d rows x %d cells x 2 species x %d ppc = %d particles of the C3 box, %d step(s) x %d "
+                      "evaluations, oracle (g++ -O2 -ffp-contract=off) on %d threads"
+                      % (rows, args.ncell, args.ppc ** 2, n_sample, steps, args.n_outer, nthreads),
+            "seconds": dt}, dt / max(steps, 1)
+
+
+def cpu_baseline(args, steps=1):
+    res, _ = cpu_arm(args, steps=steps, warmup=0)
+    return res
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    res, sec_per_step = cpu_arm(args, steps=steps, warmup=min(args.warmup, 1))
+    out = {"impl": "reference", "metric": "particle-advances/s (implicit push + deposit)", "value": res["value"],
+           "unit": "particle-advances/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+           "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C3 (bounded sample): " + res["sample"]},
+           "cpu_baseline": res,
+           "e2e": {"value": res["value"], "unit": "particle-advances/s", "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": 0},
+           "gpu_launches": 0,
+           "note": "reference = CPU oracle port of the reference algorithm; the reference binary needs "
+                   "Chombo + gfortran + MPI + HDF5 and cannot be built (DESIGN.md)"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -25,6 +25,7 @@
 #ifndef PICNIC_GPU_H
 #define PICNIC_GPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -84,6 +85,15 @@ int pgpu_grid_destroy(pgpu_grid_t g);
  * (PicChargedSpecies.cpp:3814-3917).  lo/hi must equal the box's ghosted bounds
  * for that centring. */
 int pgpu_fields_set(pgpu_grid_t g, int comp, const double *data, const int *lo, const int *hi);
+/* Up to 4 resident field sets per grid: pgpu_fields_set writes the selected slot and
+ * the particle kernels read it.  Lets the host shim double-buffer the E/B upload of
+ * the next nonlinear iteration (preRHSOp, PicSpeciesInterface.cpp:899-994) behind the
+ * particle work of the current one.  Slot 0 is selected at creation. */
+int pgpu_fields_select(pgpu_grid_t g, int slot);
+/* Page-lock a caller-owned host array (e.g. a Chombo FArrayBox dataPtr) so that the
+ * H2D/D2H copies of pgpu_fields_set / pgpu_current_get run at full PCIe/C2C rate. */
+int pgpu_host_register(void *ptr, size_t bytes);
+int pgpu_host_unregister(void *ptr);
 /* Bounds of component `comp` (PGPU_EX..BZ; J uses the E bounds) */
 int pgpu_field_bounds(pgpu_grid_t g, int comp, int *lo, int *hi);
 /* Total current of all species: PicSpeciesInterface::m_currentDensity[_virtual] */
@@ -193,6 +203,10 @@ int pgpu_profile_reset(void);
 /* total milliseconds and launch count of kernels whose name starts with prefix */
 int pgpu_profile_query(const char *prefix, double *ms, long *launches);
 long pgpu_launch_count(void);
+/* Running totals over pgpu_advance_particles_iteratively calls since the last reset:
+ * particles advanced, Boris applications (m_num_apply_its) and particles left
+ * unconverged -- picardParams / avg_picard_its (PicChargedSpecies.cpp:4280-4337). */
+int pgpu_picard_totals(long *advances, long *apply_its, long *unconverged, int reset);
 
 #ifdef __cplusplus
 }

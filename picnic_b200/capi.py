@@ -61,7 +61,8 @@ def load():
         "pgpu_init": [i32], "pgpu_finalize": [], "pgpu_set_stream": [vp], "pgpu_synchronize": [],
         "pgpu_set_exact_math": [i32], "pgpu_set_deposit_mode": [i32],
         "pgpu_grid_create": [vp, vp], "pgpu_grid_destroy": [vp],
-        "pgpu_fields_set": [vp, i32, vp, vp, vp], "pgpu_field_bounds": [vp, i32, vp, vp],
+        "pgpu_fields_set": [vp, i32, vp, vp, vp], "pgpu_fields_select": [vp, i32],
+        "pgpu_host_register": [vp, C.c_size_t], "pgpu_host_unregister": [vp], "pgpu_field_bounds": [vp, i32, vp, vp],
         "pgpu_current_zero": [vp], "pgpu_current_add_species": [vp, vp], "pgpu_current_finalize": [vp],
         "pgpu_current_get": [vp, i32, vp, vp, vp],
         "pgpu_species_create": [vp, vp, vp], "pgpu_species_destroy": [vp],
@@ -84,7 +85,7 @@ def load():
         "pgpu_collide_ta": [vp, vp, dbl, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_ta_delta_u": [lng, vp, vp, vp, vp, dbl, dbl, dbl, vp, vp, vp, vp],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
-        "pgpu_launch_count": [], "pgpu_abi_version": [], "pgpu_last_error": [],
+        "pgpu_launch_count": [], "pgpu_picard_totals": [vp, vp, vp, i32], "pgpu_abi_version": [], "pgpu_last_error": [],
     }
     for name, args in sig.items():
         getattr(lib, name).argtypes = args
@@ -146,6 +147,9 @@ class Grid:
             keep.append(a)
             check(load().pgpu_fields_set(self.h, c, _p(a), _i2(lo), _i2(hi)))
         check(load().pgpu_synchronize())
+
+    def fields_select(self, slot):
+        check(load().pgpu_fields_select(self.h, slot))
 
     def current_zero(self):
         check(load().pgpu_current_zero(self.h))
@@ -350,3 +354,9 @@ def profile_query(prefix=""):
     ms, k = C.c_double(0), C.c_long(0)
     load().pgpu_profile_query(prefix.encode(), C.byref(ms), C.byref(k))
     return ms.value, k.value
+
+
+def picard_totals(reset=True):
+    a, b, u = C.c_long(0), C.c_long(0), C.c_long(0)
+    check(load().pgpu_picard_totals(C.byref(a), C.byref(b), C.byref(u), int(reset)))
+    return a.value, b.value, u.value

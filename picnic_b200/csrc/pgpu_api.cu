@@ -109,6 +109,8 @@ static int fetch_counters(Counters *out) {
   PGPU_CUDA(cudaMemsetAsync(c.d_counters, 0, sizeof(Counters), c.stream));
   PGPU_CUDA(cudaStreamSynchronize(c.stream));
   *out = *c.h_counters;
+  c.total_apply_its += (long)out->apply_its;
+  c.total_unconverged += (long)out->unconverged;
   return 0;
 }
 static int check_err_bits(unsigned err) {
@@ -398,6 +400,7 @@ int pgpu_grid_create(const pgpu_grid_desc *d, pgpu_grid_t *out) {
     int stag[2];
     comp_stag(d->D, c, stag);
     if (alloc_fab(*d, stag, &g->field[c])) return PGPU_ERR_CUDA;
+    g->field_slot[0][c] = g->field[c];
   }
   for (int c = 0; c < 3; ++c) {
     int stag[2];
@@ -412,7 +415,9 @@ int pgpu_grid_create(const pgpu_grid_desc *d, pgpu_grid_t *out) {
 int pgpu_grid_destroy(pgpu_grid_t g) {
   if (!g) return 0;
   cudaStreamSynchronize(ctx().stream);
-  for (int c = 0; c < 6; ++c) cudaFree(g->field[c].p);
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < 6; ++c)
+      if (g->field_slot[k][c].p) cudaFree(g->field_slot[k][c].p);
   for (int c = 0; c < 3; ++c) cudaFree(g->jtot[c].p);
   if (g->scratch_rho.p) cudaFree(g->scratch_rho.p);
   cudaFree(g->debye);
@@ -440,6 +445,32 @@ int pgpu_fields_set(pgpu_grid_t g, int comp, const double *data, const int *lo, 
       return PGPU_ERR_ARG;
     }
   PGPU_CUDA(cudaMemcpyAsync(f.p, data, f.size() * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+  return 0;
+}
+
+int pgpu_fields_select(pgpu_grid_t g, int slot) {
+  NEED_INIT();
+  if (!g || slot < 0 || slot >= 4) return PGPU_ERR_ARG;
+  for (int c = 0; c < 6; ++c) {
+    if (!g->field_slot[slot][c].p) {
+      int stag[2];
+      comp_stag(g->desc.D, c, stag);
+      if (alloc_fab(g->desc, stag, &g->field_slot[slot][c])) return PGPU_ERR_CUDA;
+    }
+    g->field[c] = g->field_slot[slot][c];
+  }
+  g->cur_slot = slot;
+  return 0;
+}
+
+int pgpu_host_register(void *ptr, size_t bytes) {
+  NEED_INIT();
+  PGPU_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int pgpu_host_unregister(void *ptr) {
+  NEED_INIT();
+  PGPU_CUDA(cudaHostUnregister(ptr));
   return 0;
 }
 
@@ -746,6 +777,7 @@ int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_
     return rc;
   }
   s->binned = false;
+  ctx().total_advances += s->n;
   const bool fuse = deposit_J && s->desc.interp_J == s->desc.interp_E && !ctx().exact;
   if (deposit_J)
     for (int c = 0; c < 3; ++c)
@@ -788,6 +820,18 @@ int pgpu_species_current_get(pgpu_species_t s, int comp, double *data, const int
 }
 
 // ---- instrumentation ------------------------------------------------------------------
+int pgpu_picard_totals(long *advances, long *apply_its, long *unconverged, int reset) {
+  NEED_INIT();
+  Counters k;
+  if (fetch_counters(&k)) return PGPU_ERR_CUDA;
+  Context &c = ctx();
+  if (advances) *advances = c.total_advances;
+  if (apply_its) *apply_its = c.total_apply_its;
+  if (unconverged) *unconverged = c.total_unconverged;
+  if (reset) c.total_advances = c.total_apply_its = c.total_unconverged = 0;
+  return check_err_bits(k.err);
+}
+
 int pgpu_profile_enable(int on) {
   ctx().profile = on != 0;
   return 0;

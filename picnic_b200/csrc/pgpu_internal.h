@@ -100,6 +100,8 @@ struct Context {
   std::vector<Rec> recs;
   std::map<std::string, std::pair<double, long>> prof;
   long launches = 0;
+  // running totals since the last pgpu_picard_totals(reset): advances launched, passes applied
+  long total_advances = 0, total_apply_its = 0, total_unconverged = 0;
 };
 Context &ctx();
 void set_error(const char *fmt, ...);
@@ -123,7 +125,9 @@ struct KTimer {
 struct pgpu_grid_s {
   pgpu_grid_desc desc;
   pgpu::GeoAny geo;  // bc flags are per species; copied in at launch
-  pgpu::DeviceFab field[6];
+  pgpu::DeviceFab field[6];             // the selected slot (aliases field_slot[cur_slot])
+  pgpu::DeviceFab field_slot[4][6];     // resident field sets (slot 0 always allocated)
+  int cur_slot = 0;
   pgpu::DeviceFab jtot[3];
   pgpu::DeviceFab scratch_rho;  // reused by set_charge_density
   double *debye = nullptr;      // [ncell_box]
