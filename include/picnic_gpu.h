@@ -61,8 +61,11 @@ int pgpu_synchronize(void);
  * 1: reference operation order (no contraction, true divides).  Cell/node indices
  * are bit-exact in both modes. */
 int pgpu_set_exact_math(int on);
-/* Deposit algorithm: 0 = global fp64 RED atomics, 1 = shared-memory tile
- * accumulators with one flush per tile (needs a cell-sorted species). */
+/* Deposit/advance algorithm: 1 (default) = 2D CC1 species take the specialised fused
+ * kernel (single-segment closed forms, per-warp shared-memory run sums, one fp64 RED
+ * per node and run; fastest on a cell-sorted species, correct on any order), with the
+ * generic visitor kernel for the particles it defers; 0 = generic kernel only (one
+ * global fp64 RED per particle and node).  Exact-math mode always uses the generic one. */
 int pgpu_set_deposit_mode(int mode);
 
 /* ---- grid: DomainGrid + the box owned by this device ----------------------- */

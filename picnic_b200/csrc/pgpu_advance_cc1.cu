@@ -1,0 +1,456 @@
+// pgpu_advance_cc1.cu -- the headline kernel: fused implicit advance + current deposit
+// for 2D CC1/CC1 species (PicChargedSpecies::advanceParticlesIteratively,
+// PicChargedSpecies.cpp:1614-1716, + setCurrentDensity, :3184-3253, with the CC1 shape
+// of MeshInterpChargeConservingF.ChF:1482-2013).
+//
+// Design (DESIGN.md "k_advance_cc1"):
+//  * One thread per particle, SoA, coalesced loads; the particle stays in registers for
+//    all particle-Picard passes, so HBM sees one read of (x_old, u_old, xbar, w) and one
+//    write of (xbar, ubar).
+//  * FAST PATH = the orbit x_old -> x_new = 2 xbar - x_old stays inside one cell of the
+//    half-shifted ("dual") grid that CC1 segments on, which is the case for all but the
+//    few percent of particles that cross a dual-cell face in a step.  Then CC1 has one
+//    segment with seg_factor == 1 exactly, all node indices are fixed by x_old, and the
+//    weights reduce to closed forms in the normalised offsets d = xi - (i0+1), |d| <= 1/2:
+//        W_0 = ((1/2-d_o)^2 + (1/2-d_n)^2)/4,  W_2 = ((1/2+d_o)^2 + (1/2+d_n)^2)/4,
+//        W_1 = 1 - W_0 - W_2,   delta = dbar + 1/2          
+//    The in-plane E stencil (12 values) and Bz (4 values) are loaded once per particle.
+//    The same-cell test |d_n| < 1/2 is decided in normalised coordinates with a 1e-9 guard
+//    band; inside the band the reference's own floor((x-le-dx/2)/dx) (true divide) decides,
+//    so the segment count is the reference's.
+//  * Particles that leave the fast path (a face crossing in any pass, or a stencil that
+//    touches the array edge) are NOT written: their indices are appended to a deferred
+//    list and the generic visitor kernel (pgpu_push.cu) redoes them from their untouched
+//    state.  No CPU fallback is involved; both kernels are device code.
+//  * DEPOSIT without per-particle atomics: a particle's 21 contributions (Jx 2x3, Jy 3x2,
+//    Jz 3x3 nodes relative to its dual cell) go to a per-warp shared-memory matrix
+//    [21][33]; lanes 0..20 then sum one row each over every run of consecutive lanes with
+//    the same dual cell (the particle arrays are cell sorted, so runs are long) and issue
+//    ONE fp64 RED per (node, run) -- ~1.5 REDs per particle instead of 22.
+#include "pgpu_internal.h"
+
+namespace pgpu {
+
+namespace {
+
+constexpr int NSLOT = 21;
+constexpr int ROWPAD = 33;
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr double BAND = 1.0e-9;
+
+struct FastArgs {
+  const double *xo[2];
+  double *xb[2];
+  const double *uo[3];
+  double *ub[3];
+  const double *w;
+  long n;
+  double le[2], dx[2], rdx[2], hdx[2];
+  int i_lo[2], i_hi[2];     // dual-cell index range whose whole stencil is inside every array
+  const double *F[6];       // origin-shifted: F[c][i + j*fn0[c]] is component c at global (i,j)
+  int fn0[6];
+  double *J[3];             // origin-shifted likewise
+  int jn0[3];
+  double alpha, hdt, rtol, rvolume;
+  int iter_max;
+  int *list;                // deferred particle indices
+  unsigned *list_count;
+  Counters *cnt;
+};
+
+__device__ __forceinline__ double rcp_fast(double a) { return 1.0 / a; }
+
+template <bool DEP>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) k_advance_cc1_2d(const FastArgs A) {
+  __shared__ double sbuf[DEP ? WARPS_PER_BLOCK * NSLOT * ROWPAD : 1];
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool active = i < A.n;
+  unsigned apply = 0, unconv = 0;
+  bool fast = active;
+  bool defer = false;
+
+  double xo[2] = {0, 0}, xb[2] = {0, 0}, uo[3] = {0, 0, 0}, ub[3] = {0, 0, 0}, wp = 0.0;
+  if (active) {
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      xo[d] = A.xo[d][i];
+      xb[d] = A.xb[d][i];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) uo[c] = A.uo[c][i];
+    wp = A.w[i];
+  }
+
+  // dual cell of x_old (bit-exact index_old of the reference) and normalised offset
+  int i0[2] = {0, 0};
+  double dO[2] = {0, 0};
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double xr = __dsub_rn(xo[d], A.le[d]);
+    i0[d] = floor_div_fast(__dsub_rn(xr, A.hdx[d]), A.dx[d], A.rdx[d]);
+    dO[d] = fma(xr, A.rdx[d], -(double)(i0[d] + 1));
+    if (i0[d] < A.i_lo[d] || i0[d] > A.i_hi[d]) fast = false;
+  }
+  if (active && !fast) defer = true;
+
+  double dB[2] = {0, 0};   // normalised offset of xbar (valid when the last check passed)
+  if (fast) {
+    // ---- per-particle loads: in-plane E stencil and Bz ------------------------------
+    const int bEx = i0[0] + i0[1] * A.fn0[0];
+    const int bEy = i0[0] + i0[1] * A.fn0[1];
+    const int bBz = i0[0] + i0[1] * A.fn0[5];
+    double ex[3], dex[3], ey[3], dey[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double v0 = __ldg(A.F[0] + bEx + b * A.fn0[0]);
+      const double v1 = __ldg(A.F[0] + bEx + b * A.fn0[0] + 1);
+      ex[b] = v0;
+      dex[b] = v1 - v0;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double v0 = __ldg(A.F[1] + bEy + a);
+      const double v1 = __ldg(A.F[1] + bEy + a + A.fn0[1]);
+      ey[a] = v0;
+      dey[a] = v1 - v0;
+    }
+    double bz0, bz1, bz2, bz3;
+    {
+      const double v00 = __ldg(A.F[5] + bBz), v10 = __ldg(A.F[5] + bBz + 1);
+      const double v01 = __ldg(A.F[5] + bBz + A.fn0[5]), v11 = __ldg(A.F[5] + bBz + A.fn0[5] + 1);
+      bz0 = v00;
+      bz1 = v10 - v00;
+      bz2 = v01 - v00;
+      bz3 = (v11 - v01) - bz1;
+    }
+    const int bEz = i0[0] + i0[1] * A.fn0[2];
+    const int bBx = i0[0] + i0[1] * A.fn0[3];
+    const int bBy = i0[0] + i0[1] * A.fn0[4];
+    double pO[2][2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const double a = 0.5 - dO[d], b = 0.5 + dO[d];
+      pO[d][0] = a * a;
+      pO[d][1] = b * b;
+    }
+
+    // ---- particle-Picard loop (stepNormTransfer semantics, :658-733) ---------------
+    bool converged = false;
+    int iter = 0;
+    while (true) {
+      double dxp0[2], dN[2];
+      bool same = true;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        dxp0[d] = xb[d] - xo[d];
+        dB[d] = fma(dxp0[d], A.rdx[d], dO[d]);
+        dN[d] = fma(2.0, dB[d], -dO[d]);
+        if (!(fabs(dN[d]) < 0.5 - BAND)) {
+          // guard band: let the reference's floor decide (and catch real crossings)
+          const double xn = fma(2.0, xb[d], -xo[d]);
+          const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
+          if (in != i0[d]) same = false;
+        }
+      }
+      if (!same) {
+        defer = true;
+        break;
+      }
+      const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
+      double Wx[3], Wy[3];
+      {
+        const double a0 = 0.5 - dN[0], b0 = 0.5 + dN[0];
+        Wx[0] = 0.25 * fma(a0, a0, pO[0][0]);
+        Wx[2] = 0.25 * fma(b0, b0, pO[0][1]);
+        Wx[1] = (1.0 - Wx[0]) - Wx[2];
+        const double a1 = 0.5 - dN[1], b1 = 0.5 + dN[1];
+        Wy[0] = 0.25 * fma(a1, a1, pO[1][0]);
+        Wy[2] = 0.25 * fma(b1, b1, pO[1][1]);
+        Wy[1] = (1.0 - Wy[0]) - Wy[2];
+      }
+      double E[3], B[3];
+      E[0] = Wy[0] * fma(del0, dex[0], ex[0]);
+      E[0] = fma(Wy[1], fma(del0, dex[1], ex[1]), E[0]);
+      E[0] = fma(Wy[2], fma(del0, dex[2], ex[2]), E[0]);
+      E[1] = Wx[0] * fma(del1, dey[0], ey[0]);
+      E[1] = fma(Wx[1], fma(del1, dey[1], ey[1]), E[1]);
+      E[1] = fma(Wx[2], fma(del1, dey[2], ey[2]), E[1]);
+      // nodal CIC at xbar: node pair (i0+s, i0+s+1), fraction f
+      const int sx = del0 >= 0.5 ? 1 : 0, sy = del1 >= 0.5 ? 1 : 0;
+      const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
+      {
+        const double *p = A.F[2] + bEz + sx + sy * A.fn0[2];
+        const double v00 = __ldg(p), v10 = __ldg(p + 1);
+        const double v01 = __ldg(p + A.fn0[2]), v11 = __ldg(p + A.fn0[2] + 1);
+        const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
+        E[2] = fma(fy, t1 - t0, t0);
+      }
+      {  // Bx: nodal in x, cell-centred in y
+        const double *p = A.F[3] + bBx + sx;
+        const double v00 = __ldg(p), v10 = __ldg(p + 1);
+        const double v01 = __ldg(p + A.fn0[3]), v11 = __ldg(p + A.fn0[3] + 1);
+        const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
+        B[0] = fma(del1, t1 - t0, t0);
+      }
+      {  // By: cell-centred in x, nodal in y
+        const double *p = A.F[4] + bBy + sy * A.fn0[4];
+        const double v00 = __ldg(p), v10 = __ldg(p + 1);
+        const double v01 = __ldg(p + A.fn0[4]), v11 = __ldg(p + A.fn0[4] + 1);
+        const double t0 = fma(del0, v10 - v00, v00), t1 = fma(del0, v11 - v01, v01);
+        B[1] = fma(fy, t1 - t0, t0);
+      }
+      B[2] = fma(del1, fma(del0, bz3, bz2), fma(del0, bz1, bz0));
+
+      // Boris half step (PicSpeciesUtils.cpp:8-101)
+      {
+        const double vm0 = fma(A.alpha, E[0], uo[0]), vm1 = fma(A.alpha, E[1], uo[1]),
+                     vm2 = fma(A.alpha, E[2], uo[2]);
+        const double b0 = A.alpha * B[0], b1 = A.alpha * B[1], b2 = A.alpha * B[2];
+        const double den = fma(b2, b2, fma(b1, b1, fma(b0, b0, 1.0)));
+        const double p0 = fma(vm1, b2, vm0) - vm2 * b1;
+        const double p1 = fma(vm2, b0, vm1) - vm0 * b2;
+        const double p2 = fma(vm0, b1, vm2) - vm1 * b0;
+        const double rden = rcp_fast(den);
+        ub[0] = fma(fma(p1, b2, -(p2 * b1)), rden, vm0);
+        ub[1] = fma(fma(p2, b0, -(p0 * b2)), rden, vm1);
+        ub[2] = fma(fma(p0, b1, -(p1 * b0)), rden, vm2);
+      }
+      apply += 1;
+      if (A.iter_max < 0) {  // advanceParticles (:1594-1612), part_order_swap == false
+        xb[0] = fma(ub[0], A.hdt, xo[0]);
+        xb[1] = fma(ub[1], A.hdt, xo[1]);
+        converged = false;   // xbar moved: re-check the cell before depositing
+        break;
+      }
+      const double dxp_0 = ub[0] * A.hdt, dxp_1 = ub[1] * A.hdt;
+      const double rel = fmax(fabs(dxp0[0] - dxp_0) * A.rdx[0], fabs(dxp0[1] - dxp_1) * A.rdx[1]);
+      if (iter == 0) {
+        xb[0] = xo[0] + dxp_0;
+        xb[1] = xo[1] + dxp_1;
+        if (!(rel >= A.rtol)) {
+          converged = false;  // position was updated after the gather
+          break;
+        }
+      } else {
+        if (rel < A.rtol) {
+          converged = true;   // reverse pass: xbar is the one the weights were built from
+          break;
+        }
+        xb[0] = xo[0] + dxp_0;
+        xb[1] = xo[1] + dxp_1;
+      }
+      if (iter >= A.iter_max) {
+        unconv = 1;
+        break;
+      }
+      iter += 1;
+    }
+
+    if (!defer && !converged) {
+      // xbar changed after the last gather: the orbit must still be single-segment
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const double dxp0 = xb[d] - xo[d];
+        dB[d] = fma(dxp0, A.rdx[d], dO[d]);
+        const double dN = fma(2.0, dB[d], -dO[d]);
+        if (!(fabs(dN) < 0.5 - BAND)) {
+          const double xn = fma(2.0, xb[d], -xo[d]);
+          const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
+          if (in != i0[d]) defer = true;
+        }
+      }
+    }
+    if (!defer) {
+      A.xb[0][i] = xb[0];
+      A.xb[1][i] = xb[1];
+      A.ub[0][i] = ub[0];
+      A.ub[1][i] = ub[1];
+      A.ub[2][i] = ub[2];
+    } else {
+      apply = 0;
+      unconv = 0;
+    }
+  }
+
+  // ---- deferred list (warp-aggregated append) ------------------------------------------
+  {
+    const unsigned m = __ballot_sync(0xffffffffu, defer);
+    if (m) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(A.list_count, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (defer) A.list[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+    }
+  }
+
+  // ---- deposit: per-warp transposition + run sums ----------------------------------------
+  if (DEP) {
+    const bool dep = fast && !defer;
+    double *buf = sbuf + (threadIdx.x >> 5) * (NSLOT * ROWPAD);
+    unsigned key = 0xffffffffu;
+    if (dep) {
+      key = ((unsigned)(i0[1] + 32768) << 16) | (unsigned)(i0[0] + 32768);
+      const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
+      const double dN0 = fma(2.0, dB[0], -dO[0]), dN1 = fma(2.0, dB[1], -dO[1]);
+      double Wx[3], Wy[3];
+      {
+        const double a0 = 0.5 - dN0, b0 = 0.5 + dN0, c0 = 0.5 - dO[0], e0 = 0.5 + dO[0];
+        Wx[0] = 0.25 * fma(a0, a0, c0 * c0);
+        Wx[2] = 0.25 * fma(b0, b0, e0 * e0);
+        Wx[1] = (1.0 - Wx[0]) - Wx[2];
+        const double a1 = 0.5 - dN1, b1 = 0.5 + dN1, c1 = 0.5 - dO[1], e1 = 0.5 + dO[1];
+        Wy[0] = 0.25 * fma(a1, a1, c1 * c1);
+        Wy[2] = 0.25 * fma(b1, b1, e1 * e1);
+        Wy[1] = (1.0 - Wy[0]) - Wy[2];
+      }
+      const double rhop = wp * A.rvolume;
+      const double jx = ub[0] * rhop, jy = ub[1] * rhop, jz = ub[2] * rhop;
+      // Jx(i0+a, j0+b), a<2, b<3  -> rows 0..5 (row = a + 2 b)
+      const double jx1 = jx * del0, jx0 = jx - jx1;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        buf[(0 + 2 * b) * ROWPAD + lane] = jx0 * Wy[b];
+        buf[(1 + 2 * b) * ROWPAD + lane] = jx1 * Wy[b];
+      }
+      // Jy(i0+a, j0+b), a<3, b<2  -> rows 6..11 (row = 6 + a + 3 b)
+      const double jy1 = jy * del1, jy0 = jy - jy1;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        buf[(6 + a) * ROWPAD + lane] = jy0 * Wx[a];
+        buf[(9 + a) * ROWPAD + lane] = jy1 * Wx[a];
+      }
+      // Jz nodal CIC at xbar over nodes i0..i0+2 x j0..j0+2 -> rows 12..20 (row = 12 + a + 3 b)
+      double nx[3], ny[3];
+      if (del0 >= 0.5) { nx[0] = 0.0; nx[1] = 1.5 - del0; nx[2] = del0 - 0.5; }
+      else             { nx[0] = 0.5 - del0; nx[1] = del0 + 0.5; nx[2] = 0.0; }
+      if (del1 >= 0.5) { ny[0] = 0.0; ny[1] = 1.5 - del1; ny[2] = del1 - 0.5; }
+      else             { ny[0] = 0.5 - del1; ny[1] = del1 + 0.5; ny[2] = 0.0; }
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const double t = jz * ny[b];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) buf[(12 + a + 3 * b) * ROWPAD + lane] = t * nx[a];
+      }
+    }
+    __syncwarp();
+    // runs of equal keys across the warp
+    const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (prev != key);
+    unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned valid = __ballot_sync(0xffffffffu, key != 0xffffffffu);
+    if (valid) {
+      // row owner: which array / node offset this lane sums
+      int comp = 0, da = 0, db = 0;
+      if (lane < 6) { comp = 0; da = lane & 1; db = lane >> 1; }
+      else if (lane < 12) { comp = 1; da = (lane - 6) % 3; db = (lane - 6) / 3; }
+      else if (lane < NSLOT) { comp = 2; da = (lane - 12) % 3; db = (lane - 12) / 3; }
+      const int jn0 = A.jn0[comp];
+      double *jp = A.J[comp] + da + db * jn0;
+      const double *row = buf + lane * ROWPAD;
+      while (heads) {
+        const int s = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const int e = heads ? (__ffs(heads) - 1) : 32;
+        const unsigned k = __shfl_sync(0xffffffffu, key, s);
+        if (k != 0xffffffffu && lane < NSLOT) {
+          double sum = row[s];
+          for (int c = s + 1; c < e; ++c) sum += row[c];
+          const int ci = (int)(k & 0xffffu) - 32768, cj = (int)(k >> 16) - 32768;
+          atomicAdd(jp + ci + cj * jn0, sum);
+        }
+      }
+    }
+  }
+
+  // ---- counters ----------------------------------------------------------------------------
+  apply = __reduce_add_sync(0xffffffffu, apply);
+  unconv = __reduce_add_sync(0xffffffffu, unconv);
+  if (lane == 0) {
+    if (apply) atomicAdd(&A.cnt->apply_its, (unsigned long long)apply);
+    if (unconv) atomicAdd(&A.cnt->unconverged, (unsigned long long)unconv);
+  }
+}
+
+}  // namespace
+
+// Returns 1 if the fast kernel was launched (deferred particles are then in s->defer_list),
+// 0 if this species/configuration is not eligible, <0 on error.
+int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit) {
+  Context &c = ctx();
+  const pgpu_grid_s *g = s->grid;
+  if (c.exact || g->desc.D != 2 || s->desc.interp_E != CC1) return 0;
+  if (deposit && s->desc.interp_J != CC1) return 0;
+  if (prm.iter_max < 0 && prm.order_swap) return 0;
+  for (int d = 0; d < 2; ++d)
+    if (s->desc.bc_check_lo[d] || s->desc.bc_check_hi[d]) return 0;
+  if (g->nbox[0] + 2 * g->desc.nghost >= 32768 || g->nbox[1] + 2 * g->desc.nghost >= 32768) return 0;
+  if (s->n == 0) return 1;
+  if (!s->defer_list || s->defer_cap < (size_t)s->n) {
+    if (s->defer_list) cudaFree(s->defer_list);
+    if (!s->defer_count) PGPU_CUDA(cudaMalloc(&s->defer_count, sizeof(unsigned)));
+    PGPU_CUDA(cudaMalloc(&s->defer_list, s->cap * sizeof(int)));
+    s->defer_cap = s->cap;
+  }
+  PGPU_CUDA(cudaMemsetAsync(s->defer_count, 0, sizeof(unsigned), c.stream));
+
+  FastArgs A;
+  for (int d = 0; d < 2; ++d) {
+    A.xo[d] = s->xold[d];
+    A.xb[d] = s->x[d];
+    A.le[d] = g->geo.le[d];
+    A.dx[d] = g->geo.dx[d];
+    A.rdx[d] = g->geo.rdx[d];
+    A.hdx[d] = 0.5 * g->geo.dx[d];
+  }
+  for (int k = 0; k < 3; ++k) {
+    A.uo[k] = s->vold[k];
+    A.ub[k] = s->v[k];
+  }
+  A.w = s->w;
+  A.n = s->n;
+  // dual-cell range whose stencil (i0..i0+2 in either direction) lies inside all nine arrays
+  int lo[2] = {-(1 << 30), -(1 << 30)}, hi[2] = {1 << 30, 1 << 30};
+  auto clamp = [&](const DeviceFab &f) {
+    for (int d = 0; d < 2; ++d) {
+      lo[d] = lo[d] > f.lo[d] ? lo[d] : f.lo[d];
+      hi[d] = hi[d] < f.hi[d] - 2 ? hi[d] : f.hi[d] - 2;
+    }
+  };
+  for (int k = 0; k < 6; ++k) {
+    const DeviceFab &f = g->field[k];
+    clamp(f);
+    A.F[k] = f.p - f.lo[0] - (long)f.lo[1] * f.n0;
+    A.fn0[k] = f.n0;
+  }
+  for (int k = 0; k < 3; ++k) {
+    const DeviceFab &f = s->J[k];
+    clamp(f);
+    A.J[k] = f.p - f.lo[0] - (long)f.lo[1] * f.n0;
+    A.jn0[k] = f.n0;
+  }
+  for (int d = 0; d < 2; ++d) {
+    A.i_lo[d] = lo[d];
+    A.i_hi[d] = hi[d];
+  }
+  A.alpha = prm.alpha;
+  A.hdt = prm.cnormDt * 0.5;
+  A.rtol = prm.rtol;
+  A.rvolume = prm.rvolume;
+  A.iter_max = prm.iter_max;
+  A.list = s->defer_list;
+  A.list_count = s->defer_count;
+  A.cnt = c.d_counters;
+  const int bs = WARPS_PER_BLOCK * 32;
+  const unsigned nb = (unsigned)((s->n + bs - 1) / bs);
+  if (deposit) {
+    KTimer t("advance_cc1_fused");
+    k_advance_cc1_2d<true><<<nb, bs, 0, c.stream>>>(A);
+  } else {
+    KTimer t("advance_cc1");
+    k_advance_cc1_2d<false><<<nb, bs, 0, c.stream>>>(A);
+  }
+  return 1;
+}
+
+}  // namespace pgpu

@@ -366,6 +366,7 @@ int pgpu_set_exact_math(int on) {
 int pgpu_set_deposit_mode(int mode) {
   if (mode < 0 || mode > 1) return PGPU_ERR_ARG;
   ctx().deposit_mode = mode;
+  ctx().use_fast_cc1 = mode == 1;
   return 0;
 }
 
@@ -547,6 +548,8 @@ int pgpu_species_destroy(pgpu_species_t s) {
   cudaFree(s->id);
   cudaFree(s->tmp);
   cudaFree(s->cell_key);
+  cudaFree(s->defer_list);
+  cudaFree(s->defer_count);
   cudaFree(s->perm);
   cudaFree(s->cell_count);
   cudaFree(s->cell_start);

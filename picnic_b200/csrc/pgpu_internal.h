@@ -86,7 +86,8 @@ struct Context {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   bool exact = false;
-  int deposit_mode = 0;
+  int deposit_mode = 1;
+  bool use_fast_cc1 = true;  // pgpu_set_deposit_mode(0) turns the specialised CC1 kernel off
   Counters *d_counters = nullptr;
   Counters *h_counters = nullptr;  // pinned
   int sticky_error = 0;
@@ -153,6 +154,9 @@ struct pgpu_species_s {
   int *cell_count = nullptr;   // [ncell_box+1]
   int *cell_start = nullptr;   // [ncell_box+2]
   bool binned = false;
+  int *defer_list = nullptr;        // particles the CC1 fast kernel left to the generic one
+  unsigned *defer_count = nullptr;
+  size_t defer_cap = 0;
   double *dens = nullptr, *mom = nullptr, *ene = nullptr;  // [ncell],[3 ncell],[3 ncell]
   pgpu::PartPtrs ptrs() const {
     pgpu::PartPtrs p;
@@ -184,4 +188,5 @@ int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, con
 int launch_gather(pgpu_species_s *s);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);
+int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit);
 }  // namespace pgpu

@@ -114,11 +114,17 @@ k_deposit(PartPtrs p, long n, Geo<D> g, CurrentSet J, double volume, double rvol
 // ---- advanceParticles / advanceParticlesIteratively (+ optional fused deposit) ------
 template <int D, int IE, bool X, bool DEP>
 __global__ void __launch_bounds__(256)
-k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams prm, Counters *cnt) {
+k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams prm, Counters *cnt,
+          const int *list, const unsigned *list_count) {
   typedef M<X> m;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  // list == nullptr: thread t handles particle t (the grid covers n).  Otherwise the
+  // particles to do are list[0 .. *list_count) -- the ones the CC1 fast kernel deferred
+  // (pgpu_advance_cc1.cu) -- walked with a grid stride.
+  const long total = list ? (long)*list_count : n;
+  const long stride = (long)gridDim.x * blockDim.x;
   unsigned err = 0, apply = 0, unconv = 0;
-  if (i < n) {
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long i = list ? (long)list[t] : t;
     double xb[D], xo[D], uo[3], ub[3];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -142,7 +148,7 @@ k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
       if (!gather_visit<D, IE, X>(g, xb, xo, op)) err |= ERRBIT_SEGMENTS;
       if (op.oob) err |= ERRBIT_BOUNDS;
       boris<X>(uo, op.acc, op.acc + 3, prm.alpha, true, ub);
-      apply = 1;
+      apply += 1;
       if (!prm.order_swap) {
 #pragma unroll
         for (int d = 0; d < D; ++d) xb[d] = m::mad(ub[d], hdt, xo[d]);
@@ -186,7 +192,7 @@ k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
         if (converged) break;
         if (iter >= prm.iter_max) {
           // iter counts reverse passes done; cap reached (:1678-1693)
-          unconv = 1;
+          unconv += 1;
           break;
         }
         iter += 1;
@@ -277,44 +283,55 @@ int launch_deposit_current(pgpu_species_s *s, double /*cnormDt*/) {
 }
 
 template <int D, int IE>
-static int launch_advance_t(pgpu_species_s *s, const AdvanceParams &prm, bool fuse) {
+static int launch_advance_t(pgpu_species_s *s, const AdvanceParams &prm, bool fuse, bool deferred) {
   Context &c = ctx();
   const Geo<D> g = make_geo<D>(species_geo(s));
   const FieldSet F = grid_fields(s->grid);
   const CurrentSet J = species_current(s);
-  const unsigned nb = nblocks(s->n, 256);
+  // deferred list: its length lives on the device, so walk it with a fixed grid
+  const unsigned nb = deferred ? (unsigned)(c.sm_count * 4) : nblocks(s->n, 256);
+  const int *list = deferred ? s->defer_list : nullptr;
+  const unsigned *cnt = deferred ? s->defer_count : nullptr;
   if (fuse) {
     // the fused deposit exists in fast arithmetic only; exact mode runs the two
     // kernels back to back (the API never asks for exact+fused)
     if (c.exact) return PGPU_ERR_STATE;
-    KTimer t("advance_deposit_fused");
-    k_advance<D, IE, false, true><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, c.d_counters);
+    KTimer t(deferred ? "advance_deferred" : "advance_deposit_fused");
+    k_advance<D, IE, false, true><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, c.d_counters, list, cnt);
   } else {
-    KTimer t("advance");
+    KTimer t(deferred ? "advance_deferred" : "advance");
     if (c.exact)
-      k_advance<D, IE, true, false><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, c.d_counters);
+      k_advance<D, IE, true, false><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, c.d_counters, list, cnt);
     else
-      k_advance<D, IE, false, false><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, c.d_counters);
+      k_advance<D, IE, false, false><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, c.d_counters, list, cnt);
   }
   return 0;
 }
 
 template <int D>
-static int launch_advance_d(pgpu_species_s *s, const AdvanceParams &prm, bool fuse) {
+static int launch_advance_d(pgpu_species_s *s, const AdvanceParams &prm, bool fuse, bool deferred) {
   switch (s->desc.interp_E) {
-    case CIC: return launch_advance_t<D, CIC>(s, prm, fuse);
-    case TSC: return launch_advance_t<D, TSC>(s, prm, fuse);
-    case CC0: return launch_advance_t<D, CC0>(s, prm, fuse);
-    case CC1: return launch_advance_t<D, CC1>(s, prm, fuse);
+    case CIC: return launch_advance_t<D, CIC>(s, prm, fuse, deferred);
+    case TSC: return launch_advance_t<D, TSC>(s, prm, fuse, deferred);
+    case CC0: return launch_advance_t<D, CC0>(s, prm, fuse, deferred);
+    case CC1: return launch_advance_t<D, CC1>(s, prm, fuse, deferred);
   }
   return PGPU_ERR_ARG;
 }
 
-// fuse_deposit requires interp_J == interp_E (the fused kernel reuses one visitor type)
+// fuse_deposit requires interp_J == interp_E (the fused kernel reuses one visitor type).
+// 2D CC1 species in fast arithmetic take the specialised kernel (pgpu_advance_cc1.cu)
+// first; this generic visitor kernel then handles only the particles it deferred.
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit) {
   if (s->n == 0) return 0;
-  return s->grid->desc.D == 1 ? launch_advance_d<1>(s, prm, fuse_deposit)
-                              : launch_advance_d<2>(s, prm, fuse_deposit);
+  bool deferred = false;
+  if (ctx().use_fast_cc1) {
+    const int fr = launch_advance_cc1_fast(s, prm, fuse_deposit);
+    if (fr < 0) return fr;
+    deferred = fr == 1;
+  }
+  return s->grid->desc.D == 1 ? launch_advance_d<1>(s, prm, fuse_deposit, deferred)
+                              : launch_advance_d<2>(s, prm, fuse_deposit, deferred);
 }
 
 }  // namespace pgpu
