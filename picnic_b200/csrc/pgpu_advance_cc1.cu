@@ -4,7 +4,7 @@
 // of MeshInterpChargeConservingF.ChF:1482-2013).
 //
 // Design (DESIGN.md "k_advance_cc1"):
-//  * One thread per particle, SoA, coalesced loads; the particle stays in registers for
+//  * SoA arrays, coalesced 128-bit loads; a particle stays in registers for
 //    all particle-Picard passes, so HBM sees one read of (x_old, u_old, xbar, w) and one
 //    write of (xbar, ubar).
 //  * FAST PATH = the orbit x_old -> x_new = 2 xbar - x_old stays inside one cell of the
@@ -22,11 +22,13 @@
 //    touches the array edge) are NOT written: their indices are appended to a deferred
 //    list and the generic visitor kernel (pgpu_push.cu) redoes them from their untouched
 //    state.  No CPU fallback is involved; both kernels are device code.
-//  * DEPOSIT without per-particle atomics: a particle's 21 contributions (Jx 2x3, Jy 3x2,
-//    Jz 3x3 nodes relative to its dual cell) go to a per-warp shared-memory matrix
-//    [21][33]; lanes 0..20 then sum one row each over every run of consecutive lanes with
-//    the same dual cell (the particle arrays are cell sorted, so runs are long) and issue
-//    ONE fp64 RED per (node, run) -- ~1.5 REDs per particle instead of 22.
+//  * DEPOSIT without per-particle atomics: a thread owns 2*PAIRS consecutive particles
+//    (128-bit loads/stores) and adds their 21 contributions (Jx 2x3, Jy 3x2, Jz 3x3 nodes
+//    relative to the dual cell) in registers while the dual cell stays the same -- the
+//    cell sort orders particles by (cell, half-cell quadrant), so it nearly always does.
+//    A warp then runs a segmented shuffle reduction over runs of lanes with equal dual
+//    cells and issues ONE fp64 RED per (node, run): ~1 RED per particle instead of 22.
+//    Correct for any particle order; only the number of REDs depends on the order.
 #include "pgpu_internal.h"
 
 namespace pgpu {
@@ -34,9 +36,9 @@ namespace pgpu {
 namespace {
 
 constexpr int NSLOT = 21;
-constexpr int ROWPAD = 33;
-constexpr int WARPS_PER_BLOCK = 8;
+constexpr int BLOCK = 128;
 constexpr double BAND = 1.0e-9;
+constexpr unsigned NOKEY = 0xffffffffu;
 
 struct FastArgs {
   const double *xo[2];
@@ -58,308 +60,411 @@ struct FastArgs {
   Counters *cnt;
 };
 
-__device__ __forceinline__ double rcp_fast(double a) { return 1.0 / a; }
-
+// One particle through all its particle-Picard passes on the single-segment fast path.
+// Returns false (and leaves xb/ub untouched in memory terms: the caller does not store)
+// when the particle has to be redone by the generic kernel.  On success c[0..20] holds
+// its current contributions relative to its dual cell `key`.
 template <bool DEP>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) k_advance_cc1_2d(const FastArgs A) {
-  __shared__ double sbuf[DEP ? WARPS_PER_BLOCK * NSLOT * ROWPAD : 1];
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const bool active = i < A.n;
-  unsigned apply = 0, unconv = 0;
-  bool fast = active;
-  bool defer = false;
-
-  double xo[2] = {0, 0}, xb[2] = {0, 0}, uo[3] = {0, 0, 0}, ub[3] = {0, 0, 0}, wp = 0.0;
-  if (active) {
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      xo[d] = A.xo[d][i];
-      xb[d] = A.xb[d][i];
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) uo[c] = A.uo[c][i];
-    wp = A.w[i];
-  }
-
+__device__ __forceinline__ bool advance_one(const FastArgs &A, const double (&xo)[2], double (&xb)[2],
+                                            const double (&uo)[3], double (&ub)[3], double wp,
+                                            unsigned &apply, unsigned &unconv, unsigned &key,
+                                            double (&c)[NSLOT]) {
   // dual cell of x_old (bit-exact index_old of the reference) and normalised offset
-  int i0[2] = {0, 0};
-  double dO[2] = {0, 0};
+  int i0[2];
+  double dO[2];
+  bool ok = true;
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
     const double xr = __dsub_rn(xo[d], A.le[d]);
     i0[d] = floor_div_fast(__dsub_rn(xr, A.hdx[d]), A.dx[d], A.rdx[d]);
     dO[d] = fma(xr, A.rdx[d], -(double)(i0[d] + 1));
-    if (i0[d] < A.i_lo[d] || i0[d] > A.i_hi[d]) fast = false;
+    if (i0[d] < A.i_lo[d] || i0[d] > A.i_hi[d]) ok = false;
   }
-  if (active && !fast) defer = true;
+  if (!ok) return false;
 
-  double dB[2] = {0, 0};   // normalised offset of xbar (valid when the last check passed)
-  if (fast) {
-    // ---- per-particle loads: in-plane E stencil and Bz ------------------------------
-    const int bEx = i0[0] + i0[1] * A.fn0[0];
-    const int bEy = i0[0] + i0[1] * A.fn0[1];
-    const int bBz = i0[0] + i0[1] * A.fn0[5];
-    double ex[3], dex[3], ey[3], dey[3];
+  // ---- per-particle loads: in-plane E stencil and Bz ----------------------------------
+  double ex[3], dex[3], ey[3], dey[3];
+  {
+    const double *p = A.F[0] + (i0[0] + i0[1] * A.fn0[0]);
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-      const double v0 = __ldg(A.F[0] + bEx + b * A.fn0[0]);
-      const double v1 = __ldg(A.F[0] + bEx + b * A.fn0[0] + 1);
+      const double v0 = __ldg(p + b * A.fn0[0]);
+      const double v1 = __ldg(p + b * A.fn0[0] + 1);
       ex[b] = v0;
       dex[b] = v1 - v0;
     }
+  }
+  {
+    const double *p = A.F[1] + (i0[0] + i0[1] * A.fn0[1]);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const double v0 = __ldg(A.F[1] + bEy + a);
-      const double v1 = __ldg(A.F[1] + bEy + a + A.fn0[1]);
+      const double v0 = __ldg(p + a);
+      const double v1 = __ldg(p + a + A.fn0[1]);
       ey[a] = v0;
       dey[a] = v1 - v0;
     }
-    double bz0, bz1, bz2, bz3;
-    {
-      const double v00 = __ldg(A.F[5] + bBz), v10 = __ldg(A.F[5] + bBz + 1);
-      const double v01 = __ldg(A.F[5] + bBz + A.fn0[5]), v11 = __ldg(A.F[5] + bBz + A.fn0[5] + 1);
-      bz0 = v00;
-      bz1 = v10 - v00;
-      bz2 = v01 - v00;
-      bz3 = (v11 - v01) - bz1;
-    }
-    const int bEz = i0[0] + i0[1] * A.fn0[2];
-    const int bBx = i0[0] + i0[1] * A.fn0[3];
-    const int bBy = i0[0] + i0[1] * A.fn0[4];
-    double pO[2][2];
+  }
+  double bz0, bz1, bz2, bz3;
+  {
+    const double *p = A.F[5] + (i0[0] + i0[1] * A.fn0[5]);
+    const double v00 = __ldg(p), v10 = __ldg(p + 1);
+    const double v01 = __ldg(p + A.fn0[5]), v11 = __ldg(p + A.fn0[5] + 1);
+    bz0 = v00;
+    bz1 = v10 - v00;
+    bz2 = v01 - v00;
+    bz3 = (v11 - v01) - bz1;
+  }
+  const double *pEz = A.F[2] + (i0[0] + i0[1] * A.fn0[2]);
+  const double *pBx = A.F[3] + (i0[0] + i0[1] * A.fn0[3]);
+  const double *pBy = A.F[4] + (i0[0] + i0[1] * A.fn0[4]);
+  double pO[2][2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double a = 0.5 - dO[d], b = 0.5 + dO[d];
+    pO[d][0] = a * a;
+    pO[d][1] = b * b;
+  }
+
+  // ---- particle-Picard loop (stepNormTransfer semantics, :658-733) -----------------------
+  double dB[2];
+  bool recheck = true;   // xbar moved after the last gather
+  int iter = 0;
+  unsigned napply = 0, nunconv = 0;
+  while (true) {
+    double dxp0[2], dN[2];
+    bool same = true;
 #pragma unroll
     for (int d = 0; d < 2; ++d) {
-      const double a = 0.5 - dO[d], b = 0.5 + dO[d];
-      pO[d][0] = a * a;
-      pO[d][1] = b * b;
+      dxp0[d] = xb[d] - xo[d];
+      dB[d] = fma(dxp0[d], A.rdx[d], dO[d]);
+      dN[d] = fma(2.0, dB[d], -dO[d]);
+      if (!(fabs(dN[d]) < 0.5 - BAND)) {
+        // guard band: let the reference's floor decide (and catch real crossings)
+        const double xn = fma(2.0, xb[d], -xo[d]);
+        const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
+        if (in != i0[d]) same = false;
+      }
     }
+    if (!same) return false;
+    const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
+    double Wx[3], Wy[3];
+    {
+      const double a0 = 0.5 - dN[0], b0 = 0.5 + dN[0];
+      Wx[0] = 0.25 * fma(a0, a0, pO[0][0]);
+      Wx[2] = 0.25 * fma(b0, b0, pO[0][1]);
+      Wx[1] = (1.0 - Wx[0]) - Wx[2];
+      const double a1 = 0.5 - dN[1], b1 = 0.5 + dN[1];
+      Wy[0] = 0.25 * fma(a1, a1, pO[1][0]);
+      Wy[2] = 0.25 * fma(b1, b1, pO[1][1]);
+      Wy[1] = (1.0 - Wy[0]) - Wy[2];
+    }
+    double E[3], B[3];
+    E[0] = Wy[0] * fma(del0, dex[0], ex[0]);
+    E[0] = fma(Wy[1], fma(del0, dex[1], ex[1]), E[0]);
+    E[0] = fma(Wy[2], fma(del0, dex[2], ex[2]), E[0]);
+    E[1] = Wx[0] * fma(del1, dey[0], ey[0]);
+    E[1] = fma(Wx[1], fma(del1, dey[1], ey[1]), E[1]);
+    E[1] = fma(Wx[2], fma(del1, dey[2], ey[2]), E[1]);
+    // nodal CIC at xbar: node pair (i0+s, i0+s+1), fraction f
+    const int sx = del0 >= 0.5 ? 1 : 0, sy = del1 >= 0.5 ? 1 : 0;
+    const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
+    {
+      const double *p = pEz + (sx + sy * A.fn0[2]);
+      const double v00 = __ldg(p), v10 = __ldg(p + 1);
+      const double v01 = __ldg(p + A.fn0[2]), v11 = __ldg(p + A.fn0[2] + 1);
+      const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
+      E[2] = fma(fy, t1 - t0, t0);
+    }
+    {  // Bx: nodal in x, cell-centred in y
+      const double *p = pBx + sx;
+      const double v00 = __ldg(p), v10 = __ldg(p + 1);
+      const double v01 = __ldg(p + A.fn0[3]), v11 = __ldg(p + A.fn0[3] + 1);
+      const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
+      B[0] = fma(del1, t1 - t0, t0);
+    }
+    {  // By: cell-centred in x, nodal in y
+      const double *p = pBy + sy * A.fn0[4];
+      const double v00 = __ldg(p), v10 = __ldg(p + 1);
+      const double v01 = __ldg(p + A.fn0[4]), v11 = __ldg(p + A.fn0[4] + 1);
+      const double t0 = fma(del0, v10 - v00, v00), t1 = fma(del0, v11 - v01, v01);
+      B[1] = fma(fy, t1 - t0, t0);
+    }
+    B[2] = fma(del1, fma(del0, bz3, bz2), fma(del0, bz1, bz0));
 
-    // ---- particle-Picard loop (stepNormTransfer semantics, :658-733) ---------------
-    bool converged = false;
-    int iter = 0;
-    while (true) {
-      double dxp0[2], dN[2];
-      bool same = true;
+    // Boris half step (PicSpeciesUtils.cpp:8-101)
+    {
+      const double vm0 = fma(A.alpha, E[0], uo[0]), vm1 = fma(A.alpha, E[1], uo[1]),
+                   vm2 = fma(A.alpha, E[2], uo[2]);
+      const double b0 = A.alpha * B[0], b1 = A.alpha * B[1], b2 = A.alpha * B[2];
+      const double den = fma(b2, b2, fma(b1, b1, fma(b0, b0, 1.0)));
+      const double p0 = fma(vm1, b2, vm0) - vm2 * b1;
+      const double p1 = fma(vm2, b0, vm1) - vm0 * b2;
+      const double p2 = fma(vm0, b1, vm2) - vm1 * b0;
+      const double rden = 1.0 / den;
+      ub[0] = fma(fma(p1, b2, -(p2 * b1)), rden, vm0);
+      ub[1] = fma(fma(p2, b0, -(p0 * b2)), rden, vm1);
+      ub[2] = fma(fma(p0, b1, -(p1 * b0)), rden, vm2);
+    }
+    napply += 1;
+    if (A.iter_max < 0) {  // advanceParticles (:1594-1612), part_order_swap == false
+      xb[0] = fma(ub[0], A.hdt, xo[0]);
+      xb[1] = fma(ub[1], A.hdt, xo[1]);
+      break;
+    }
+    const double dxp_0 = ub[0] * A.hdt, dxp_1 = ub[1] * A.hdt;
+    const double rel = fmax(fabs(dxp0[0] - dxp_0) * A.rdx[0], fabs(dxp0[1] - dxp_1) * A.rdx[1]);
+    if (iter == 0) {
+      xb[0] = xo[0] + dxp_0;
+      xb[1] = xo[1] + dxp_1;
+      if (!(rel >= A.rtol)) break;
+    } else {
+      if (rel < A.rtol) {
+        recheck = false;   // reverse pass: xbar is the one the weights were built from
+        break;
+      }
+      xb[0] = xo[0] + dxp_0;
+      xb[1] = xo[1] + dxp_1;
+    }
+    if (iter >= A.iter_max) {
+      nunconv = 1;
+      break;
+    }
+    iter += 1;
+  }
+
+  if (recheck) {
+    // xbar changed after the last gather: the orbit must still be single-segment
 #pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        dxp0[d] = xb[d] - xo[d];
-        dB[d] = fma(dxp0[d], A.rdx[d], dO[d]);
-        dN[d] = fma(2.0, dB[d], -dO[d]);
-        if (!(fabs(dN[d]) < 0.5 - BAND)) {
-          // guard band: let the reference's floor decide (and catch real crossings)
-          const double xn = fma(2.0, xb[d], -xo[d]);
-          const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
-          if (in != i0[d]) same = false;
-        }
+    for (int d = 0; d < 2; ++d) {
+      const double dxp0 = xb[d] - xo[d];
+      dB[d] = fma(dxp0, A.rdx[d], dO[d]);
+      const double dN = fma(2.0, dB[d], -dO[d]);
+      if (!(fabs(dN) < 0.5 - BAND)) {
+        const double xn = fma(2.0, xb[d], -xo[d]);
+        const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
+        if (in != i0[d]) ok = false;
       }
-      if (!same) {
-        defer = true;
-        break;
-      }
-      const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
-      double Wx[3], Wy[3];
-      {
-        const double a0 = 0.5 - dN[0], b0 = 0.5 + dN[0];
-        Wx[0] = 0.25 * fma(a0, a0, pO[0][0]);
-        Wx[2] = 0.25 * fma(b0, b0, pO[0][1]);
-        Wx[1] = (1.0 - Wx[0]) - Wx[2];
-        const double a1 = 0.5 - dN[1], b1 = 0.5 + dN[1];
-        Wy[0] = 0.25 * fma(a1, a1, pO[1][0]);
-        Wy[2] = 0.25 * fma(b1, b1, pO[1][1]);
-        Wy[1] = (1.0 - Wy[0]) - Wy[2];
-      }
-      double E[3], B[3];
-      E[0] = Wy[0] * fma(del0, dex[0], ex[0]);
-      E[0] = fma(Wy[1], fma(del0, dex[1], ex[1]), E[0]);
-      E[0] = fma(Wy[2], fma(del0, dex[2], ex[2]), E[0]);
-      E[1] = Wx[0] * fma(del1, dey[0], ey[0]);
-      E[1] = fma(Wx[1], fma(del1, dey[1], ey[1]), E[1]);
-      E[1] = fma(Wx[2], fma(del1, dey[2], ey[2]), E[1]);
-      // nodal CIC at xbar: node pair (i0+s, i0+s+1), fraction f
-      const int sx = del0 >= 0.5 ? 1 : 0, sy = del1 >= 0.5 ? 1 : 0;
-      const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
-      {
-        const double *p = A.F[2] + bEz + sx + sy * A.fn0[2];
-        const double v00 = __ldg(p), v10 = __ldg(p + 1);
-        const double v01 = __ldg(p + A.fn0[2]), v11 = __ldg(p + A.fn0[2] + 1);
-        const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
-        E[2] = fma(fy, t1 - t0, t0);
-      }
-      {  // Bx: nodal in x, cell-centred in y
-        const double *p = A.F[3] + bBx + sx;
-        const double v00 = __ldg(p), v10 = __ldg(p + 1);
-        const double v01 = __ldg(p + A.fn0[3]), v11 = __ldg(p + A.fn0[3] + 1);
-        const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
-        B[0] = fma(del1, t1 - t0, t0);
-      }
-      {  // By: cell-centred in x, nodal in y
-        const double *p = A.F[4] + bBy + sy * A.fn0[4];
-        const double v00 = __ldg(p), v10 = __ldg(p + 1);
-        const double v01 = __ldg(p + A.fn0[4]), v11 = __ldg(p + A.fn0[4] + 1);
-        const double t0 = fma(del0, v10 - v00, v00), t1 = fma(del0, v11 - v01, v01);
-        B[1] = fma(fy, t1 - t0, t0);
-      }
-      B[2] = fma(del1, fma(del0, bz3, bz2), fma(del0, bz1, bz0));
+    }
+    if (!ok) return false;
+  }
+  apply += napply;
+  unconv += nunconv;
 
-      // Boris half step (PicSpeciesUtils.cpp:8-101)
-      {
-        const double vm0 = fma(A.alpha, E[0], uo[0]), vm1 = fma(A.alpha, E[1], uo[1]),
-                     vm2 = fma(A.alpha, E[2], uo[2]);
-        const double b0 = A.alpha * B[0], b1 = A.alpha * B[1], b2 = A.alpha * B[2];
-        const double den = fma(b2, b2, fma(b1, b1, fma(b0, b0, 1.0)));
-        const double p0 = fma(vm1, b2, vm0) - vm2 * b1;
-        const double p1 = fma(vm2, b0, vm1) - vm0 * b2;
-        const double p2 = fma(vm0, b1, vm2) - vm1 * b0;
-        const double rden = rcp_fast(den);
-        ub[0] = fma(fma(p1, b2, -(p2 * b1)), rden, vm0);
-        ub[1] = fma(fma(p2, b0, -(p0 * b2)), rden, vm1);
-        ub[2] = fma(fma(p0, b1, -(p1 * b0)), rden, vm2);
-      }
-      apply += 1;
-      if (A.iter_max < 0) {  // advanceParticles (:1594-1612), part_order_swap == false
-        xb[0] = fma(ub[0], A.hdt, xo[0]);
-        xb[1] = fma(ub[1], A.hdt, xo[1]);
-        converged = false;   // xbar moved: re-check the cell before depositing
-        break;
-      }
-      const double dxp_0 = ub[0] * A.hdt, dxp_1 = ub[1] * A.hdt;
-      const double rel = fmax(fabs(dxp0[0] - dxp_0) * A.rdx[0], fabs(dxp0[1] - dxp_1) * A.rdx[1]);
-      if (iter == 0) {
-        xb[0] = xo[0] + dxp_0;
-        xb[1] = xo[1] + dxp_1;
-        if (!(rel >= A.rtol)) {
-          converged = false;  // position was updated after the gather
-          break;
+  if (DEP) {
+    key = ((unsigned)(i0[1] + 32768) << 16) | (unsigned)(i0[0] + 32768);
+    const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
+    const double dN0 = fma(2.0, dB[0], -dO[0]), dN1 = fma(2.0, dB[1], -dO[1]);
+    double Wx[3], Wy[3];
+    {
+      const double a0 = 0.5 - dN0, b0 = 0.5 + dN0;
+      Wx[0] = 0.25 * fma(a0, a0, pO[0][0]);
+      Wx[2] = 0.25 * fma(b0, b0, pO[0][1]);
+      Wx[1] = (1.0 - Wx[0]) - Wx[2];
+      const double a1 = 0.5 - dN1, b1 = 0.5 + dN1;
+      Wy[0] = 0.25 * fma(a1, a1, pO[1][0]);
+      Wy[2] = 0.25 * fma(b1, b1, pO[1][1]);
+      Wy[1] = (1.0 - Wy[0]) - Wy[2];
+    }
+    const double rhop = wp * A.rvolume;
+    const double jx = ub[0] * rhop, jy = ub[1] * rhop, jz = ub[2] * rhop;
+    // Jx(i0+a, j0+b), a<2, b<3  -> slot a + 2 b
+    const double jx1 = jx * del0, jx0 = jx - jx1;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      c[0 + 2 * b] = jx0 * Wy[b];
+      c[1 + 2 * b] = jx1 * Wy[b];
+    }
+    // Jy(i0+a, j0+b), a<3, b<2  -> slot 6 + a + 3 b
+    const double jy1 = jy * del1, jy0 = jy - jy1;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      c[6 + a] = jy0 * Wx[a];
+      c[9 + a] = jy1 * Wx[a];
+    }
+    // Jz nodal CIC at xbar over nodes i0..i0+2 x j0..j0+2 -> slot 12 + a + 3 b
+    double nx[3], ny[3];
+    if (del0 >= 0.5) { nx[0] = 0.0; nx[1] = 1.5 - del0; nx[2] = del0 - 0.5; }
+    else             { nx[0] = 0.5 - del0; nx[1] = del0 + 0.5; nx[2] = 0.0; }
+    if (del1 >= 0.5) { ny[0] = 0.0; ny[1] = 1.5 - del1; ny[2] = del1 - 0.5; }
+    else             { ny[0] = 0.5 - del1; ny[1] = del1 + 0.5; ny[2] = 0.0; }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double t = jz * ny[b];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) c[12 + a + 3 * b] = t * nx[a];
+    }
+  }
+  return true;
+}
+
+// 21 fp64 REDs of one accumulator set into the J arrays at dual cell `key`
+__device__ __forceinline__ void flush_direct(const FastArgs &A, unsigned key, const double (&acc)[NSLOT]) {
+  const int ci = (int)(key & 0xffffu) - 32768, cj = (int)(key >> 16) - 32768;
+  {
+    double *p = A.J[0] + (ci + cj * A.jn0[0]);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      atomicAdd(p + b * A.jn0[0], acc[2 * b]);
+      atomicAdd(p + b * A.jn0[0] + 1, acc[2 * b + 1]);
+    }
+  }
+  {
+    double *p = A.J[1] + (ci + cj * A.jn0[1]);
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) atomicAdd(p + a + b * A.jn0[1], acc[6 + a + 3 * b]);
+  }
+  {
+    double *p = A.J[2] + (ci + cj * A.jn0[2]);
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) atomicAdd(p + a + b * A.jn0[2], acc[12 + a + 3 * b]);
+  }
+}
+
+// PAIRS x 2 consecutive particles per thread (128-bit loads/stores), processed one after the
+// other; their contributions accumulate in registers while the dual cell stays the same.
+template <bool DEP, int PAIRS>
+__global__ void __launch_bounds__(BLOCK, 3) k_advance_cc1_2d(const FastArgs A) {
+  constexpr int P = 2 * PAIRS;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long base = t * P;
+  const int lane = threadIdx.x & 31;
+  unsigned apply = 0, unconv = 0;
+  unsigned acc_key = NOKEY;
+  double acc[NSLOT];
+#pragma unroll
+  for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
+  unsigned defer_mask = 0;
+
+#pragma unroll 1
+  for (int pr = 0; pr < PAIRS; ++pr) {
+    const long i = base + 2 * pr;
+    if (i >= A.n) break;
+    const bool two = i + 1 < A.n;
+    double2 xo0, xo1, xb0, xb1, u0, u1, u2, w2;
+    if (two) {
+      xo0 = *reinterpret_cast<const double2 *>(A.xo[0] + i);
+      xo1 = *reinterpret_cast<const double2 *>(A.xo[1] + i);
+      xb0 = *reinterpret_cast<const double2 *>(A.xb[0] + i);
+      xb1 = *reinterpret_cast<const double2 *>(A.xb[1] + i);
+      u0 = *reinterpret_cast<const double2 *>(A.uo[0] + i);
+      u1 = *reinterpret_cast<const double2 *>(A.uo[1] + i);
+      u2 = *reinterpret_cast<const double2 *>(A.uo[2] + i);
+      w2 = *reinterpret_cast<const double2 *>(A.w + i);
+    } else {
+      xo0 = make_double2(A.xo[0][i], 0.0);
+      xo1 = make_double2(A.xo[1][i], 0.0);
+      xb0 = make_double2(A.xb[0][i], 0.0);
+      xb1 = make_double2(A.xb[1][i], 0.0);
+      u0 = make_double2(A.uo[0][i], 0.0);
+      u1 = make_double2(A.uo[1][i], 0.0);
+      u2 = make_double2(A.uo[2][i], 0.0);
+      w2 = make_double2(A.w[i], 0.0);
+    }
+    double2 ob0 = xb0, ob1 = xb1, ov0 = u0, ov1 = u1, ov2 = u2;   // outputs (xbar, ubar)
+    bool okA = false, okB = false;
+    {
+      const double xo[2] = {xo0.x, xo1.x};
+      double xb[2] = {xb0.x, xb1.x};
+      const double uo[3] = {u0.x, u1.x, u2.x};
+      double ub[3] = {0.0, 0.0, 0.0};
+      unsigned key = NOKEY;
+      double c[NSLOT];
+      okA = advance_one<DEP>(A, xo, xb, uo, ub, w2.x, apply, unconv, key, c);
+      if (okA) {
+        ob0.x = xb[0]; ob1.x = xb[1]; ov0.x = ub[0]; ov1.x = ub[1]; ov2.x = ub[2];
+        if (DEP) {
+          if (key != acc_key) {
+            if (acc_key != NOKEY) flush_direct(A, acc_key, acc);
+            acc_key = key;
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) acc[j] = c[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) acc[j] += c[j];
+          }
         }
       } else {
-        if (rel < A.rtol) {
-          converged = true;   // reverse pass: xbar is the one the weights were built from
-          break;
-        }
-        xb[0] = xo[0] + dxp_0;
-        xb[1] = xo[1] + dxp_1;
+        defer_mask |= 1u << (2 * pr);
       }
-      if (iter >= A.iter_max) {
-        unconv = 1;
-        break;
-      }
-      iter += 1;
     }
-
-    if (!defer && !converged) {
-      // xbar changed after the last gather: the orbit must still be single-segment
+    if (two) {
+      const double xo[2] = {xo0.y, xo1.y};
+      double xb[2] = {xb0.y, xb1.y};
+      const double uo[3] = {u0.y, u1.y, u2.y};
+      double ub[3] = {0.0, 0.0, 0.0};
+      unsigned key = NOKEY;
+      double c[NSLOT];
+      okB = advance_one<DEP>(A, xo, xb, uo, ub, w2.y, apply, unconv, key, c);
+      if (okB) {
+        ob0.y = xb[0]; ob1.y = xb[1]; ov0.y = ub[0]; ov1.y = ub[1]; ov2.y = ub[2];
+        if (DEP) {
+          if (key != acc_key) {
+            if (acc_key != NOKEY) flush_direct(A, acc_key, acc);
+            acc_key = key;
 #pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        const double dxp0 = xb[d] - xo[d];
-        dB[d] = fma(dxp0, A.rdx[d], dO[d]);
-        const double dN = fma(2.0, dB[d], -dO[d]);
-        if (!(fabs(dN) < 0.5 - BAND)) {
-          const double xn = fma(2.0, xb[d], -xo[d]);
-          const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
-          if (in != i0[d]) defer = true;
+            for (int j = 0; j < NSLOT; ++j) acc[j] = c[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) acc[j] += c[j];
+          }
         }
+      } else {
+        defer_mask |= 1u << (2 * pr + 1);
       }
     }
-    if (!defer) {
-      A.xb[0][i] = xb[0];
-      A.xb[1][i] = xb[1];
-      A.ub[0][i] = ub[0];
-      A.ub[1][i] = ub[1];
-      A.ub[2][i] = ub[2];
+    // a deferred particle keeps its stored (xbar, ubar): the generic kernel restarts from them
+    if (two && okA && okB) {
+      *reinterpret_cast<double2 *>(A.xb[0] + i) = ob0;
+      *reinterpret_cast<double2 *>(A.xb[1] + i) = ob1;
+      *reinterpret_cast<double2 *>(A.ub[0] + i) = ov0;
+      *reinterpret_cast<double2 *>(A.ub[1] + i) = ov1;
+      *reinterpret_cast<double2 *>(A.ub[2] + i) = ov2;
     } else {
-      apply = 0;
-      unconv = 0;
+      if (okA) {
+        A.xb[0][i] = ob0.x; A.xb[1][i] = ob1.x;
+        A.ub[0][i] = ov0.x; A.ub[1][i] = ov1.x; A.ub[2][i] = ov2.x;
+      }
+      if (okB) {
+        A.xb[0][i + 1] = ob0.y; A.xb[1][i + 1] = ob1.y;
+        A.ub[0][i + 1] = ov0.y; A.ub[1][i + 1] = ov1.y; A.ub[2][i + 1] = ov2.y;
+      }
     }
   }
 
-  // ---- deferred list (warp-aggregated append) ------------------------------------------
-  {
-    const unsigned m = __ballot_sync(0xffffffffu, defer);
-    if (m) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(A.list_count, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (defer) A.list[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
-    }
+  // ---- deferred list ---------------------------------------------------------------------
+  if (defer_mask) {
+    unsigned slot = atomicAdd(A.list_count, (unsigned)__popc(defer_mask));
+#pragma unroll
+    for (int q = 0; q < P; ++q)
+      if (defer_mask & (1u << q)) A.list[slot++] = (int)(base + q);
   }
 
-  // ---- deposit: per-warp transposition + run sums ----------------------------------------
+  // ---- deposit: segmented warp reduction over runs of equal dual cells, one RED per node
+  //      and run (the particle arrays are cell sorted, so a warp holds a handful of runs)
   if (DEP) {
-    const bool dep = fast && !defer;
-    double *buf = sbuf + (threadIdx.x >> 5) * (NSLOT * ROWPAD);
-    unsigned key = 0xffffffffu;
-    if (dep) {
-      key = ((unsigned)(i0[1] + 32768) << 16) | (unsigned)(i0[0] + 32768);
-      const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
-      const double dN0 = fma(2.0, dB[0], -dO[0]), dN1 = fma(2.0, dB[1], -dO[1]);
-      double Wx[3], Wy[3];
-      {
-        const double a0 = 0.5 - dN0, b0 = 0.5 + dN0, c0 = 0.5 - dO[0], e0 = 0.5 + dO[0];
-        Wx[0] = 0.25 * fma(a0, a0, c0 * c0);
-        Wx[2] = 0.25 * fma(b0, b0, e0 * e0);
-        Wx[1] = (1.0 - Wx[0]) - Wx[2];
-        const double a1 = 0.5 - dN1, b1 = 0.5 + dN1, c1 = 0.5 - dO[1], e1 = 0.5 + dO[1];
-        Wy[0] = 0.25 * fma(a1, a1, c1 * c1);
-        Wy[2] = 0.25 * fma(b1, b1, e1 * e1);
-        Wy[1] = (1.0 - Wy[0]) - Wy[2];
-      }
-      const double rhop = wp * A.rvolume;
-      const double jx = ub[0] * rhop, jy = ub[1] * rhop, jz = ub[2] * rhop;
-      // Jx(i0+a, j0+b), a<2, b<3  -> rows 0..5 (row = a + 2 b)
-      const double jx1 = jx * del0, jx0 = jx - jx1;
+    const unsigned any = __ballot_sync(0xffffffffu, acc_key != NOKEY);
+    if (any) {
+      // runs = maximal stretches of consecutive lanes with the same key (any particle order
+      // is handled: a key that reappears later simply forms another run)
+      const unsigned prev = __shfl_up_sync(0xffffffffu, acc_key, 1);
+      const bool head = (lane == 0) || (prev != acc_key);
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      const unsigned above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+      const int run_end = above ? (__ffs(above) - 1) : 32;
 #pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        buf[(0 + 2 * b) * ROWPAD + lane] = jx0 * Wy[b];
-        buf[(1 + 2 * b) * ROWPAD + lane] = jx1 * Wy[b];
-      }
-      // Jy(i0+a, j0+b), a<3, b<2  -> rows 6..11 (row = 6 + a + 3 b)
-      const double jy1 = jy * del1, jy0 = jy - jy1;
+      for (int off = 1; off < 32; off <<= 1) {
+        const bool take = lane + off < run_end;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        buf[(6 + a) * ROWPAD + lane] = jy0 * Wx[a];
-        buf[(9 + a) * ROWPAD + lane] = jy1 * Wx[a];
-      }
-      // Jz nodal CIC at xbar over nodes i0..i0+2 x j0..j0+2 -> rows 12..20 (row = 12 + a + 3 b)
-      double nx[3], ny[3];
-      if (del0 >= 0.5) { nx[0] = 0.0; nx[1] = 1.5 - del0; nx[2] = del0 - 0.5; }
-      else             { nx[0] = 0.5 - del0; nx[1] = del0 + 0.5; nx[2] = 0.0; }
-      if (del1 >= 0.5) { ny[0] = 0.0; ny[1] = 1.5 - del1; ny[2] = del1 - 0.5; }
-      else             { ny[0] = 0.5 - del1; ny[1] = del1 + 0.5; ny[2] = 0.0; }
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        const double t = jz * ny[b];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) buf[(12 + a + 3 * b) * ROWPAD + lane] = t * nx[a];
-      }
-    }
-    __syncwarp();
-    // runs of equal keys across the warp
-    const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = (lane == 0) || (prev != key);
-    unsigned heads = __ballot_sync(0xffffffffu, head);
-    const unsigned valid = __ballot_sync(0xffffffffu, key != 0xffffffffu);
-    if (valid) {
-      // row owner: which array / node offset this lane sums
-      int comp = 0, da = 0, db = 0;
-      if (lane < 6) { comp = 0; da = lane & 1; db = lane >> 1; }
-      else if (lane < 12) { comp = 1; da = (lane - 6) % 3; db = (lane - 6) / 3; }
-      else if (lane < NSLOT) { comp = 2; da = (lane - 12) % 3; db = (lane - 12) / 3; }
-      const int jn0 = A.jn0[comp];
-      double *jp = A.J[comp] + da + db * jn0;
-      const double *row = buf + lane * ROWPAD;
-      while (heads) {
-        const int s = __ffs(heads) - 1;
-        heads &= heads - 1;
-        const int e = heads ? (__ffs(heads) - 1) : 32;
-        const unsigned k = __shfl_sync(0xffffffffu, key, s);
-        if (k != 0xffffffffu && lane < NSLOT) {
-          double sum = row[s];
-          for (int c = s + 1; c < e; ++c) sum += row[c];
-          const int ci = (int)(k & 0xffffu) - 32768, cj = (int)(k >> 16) - 32768;
-          atomicAdd(jp + ci + cj * jn0, sum);
+        for (int j = 0; j < NSLOT; ++j) {
+          const double v = __shfl_down_sync(0xffffffffu, acc[j], off);
+          acc[j] += take ? v : 0.0;
         }
       }
+      if (head && acc_key != NOKEY) flush_direct(A, acc_key, acc);
     }
   }
 
@@ -441,14 +546,18 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   A.list = s->defer_list;
   A.list_count = s->defer_count;
   A.cnt = c.d_counters;
-  const int bs = WARPS_PER_BLOCK * 32;
-  const unsigned nb = (unsigned)((s->n + bs - 1) / bs);
+  const int pairs = c.cc1_pairs;
+  const long per_block = (long)BLOCK * 2 * pairs;
+  const unsigned nb = (unsigned)((s->n + per_block - 1) / per_block);
+  KTimer t(deposit ? "advance_cc1_fused" : "advance_cc1");
   if (deposit) {
-    KTimer t("advance_cc1_fused");
-    k_advance_cc1_2d<true><<<nb, bs, 0, c.stream>>>(A);
+    if (pairs == 1) k_advance_cc1_2d<true, 1><<<nb, BLOCK, 0, c.stream>>>(A);
+    else if (pairs == 2) k_advance_cc1_2d<true, 2><<<nb, BLOCK, 0, c.stream>>>(A);
+    else k_advance_cc1_2d<true, 4><<<nb, BLOCK, 0, c.stream>>>(A);
   } else {
-    KTimer t("advance_cc1");
-    k_advance_cc1_2d<false><<<nb, bs, 0, c.stream>>>(A);
+    if (pairs == 1) k_advance_cc1_2d<false, 1><<<nb, BLOCK, 0, c.stream>>>(A);
+    else if (pairs == 2) k_advance_cc1_2d<false, 2><<<nb, BLOCK, 0, c.stream>>>(A);
+    else k_advance_cc1_2d<false, 4><<<nb, BLOCK, 0, c.stream>>>(A);
   }
   return 1;
 }

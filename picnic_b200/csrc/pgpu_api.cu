@@ -2,6 +2,7 @@
 // the streaming per-particle passes, grid-side helpers of the deposit, reductions.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "pgpu_internal.h"
@@ -316,6 +317,10 @@ int pgpu_init(int device) {
   PGPU_CUDA(cudaMallocHost(&c.h_counters, sizeof(Counters)));
   c.inited = true;
   c.sticky_error = 0;
+  if (const char *e = getenv("PGPU_CC1_PAIRS")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) c.cc1_pairs = v;
+  }
   return 0;
 }
 
@@ -548,6 +553,9 @@ int pgpu_species_destroy(pgpu_species_t s) {
   cudaFree(s->id);
   cudaFree(s->tmp);
   cudaFree(s->cell_key);
+  cudaFree(s->key_sorted);
+  cudaFree(s->cub_tmp);
+  for (int k = 0; k < 4; ++k) cudaFree(s->spare[k]);
   cudaFree(s->defer_list);
   cudaFree(s->defer_count);
   cudaFree(s->perm);

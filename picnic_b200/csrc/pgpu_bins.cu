@@ -7,7 +7,10 @@
 // of a counting sort that physically reorders the SoA arrays, so that the particles
 // of a cell are contiguous (warp-contiguous for the collision and moment kernels)
 // and the gather/deposit kernels see cell-coherent warps.
+#include <algorithm>
 #include <cstring>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "pgpu_internal.h"
 
@@ -40,15 +43,29 @@ __device__ __forceinline__ int locate_bin(double x, double le, double dx) {
   return __double2int_rd(__ddiv_rn(__dsub_rn(x, le), dx));
 }
 
-__global__ void k_cell_key(const double *x0, const double *x1, long n, BoxInfo b, int *key, int *count) {
+// Sort key = 4*cell + quadrant.  `cell` is the reference's bin (locate_bin); the quadrant
+// says which half of the cell the particle sits in per direction, i.e. which cell of the
+// half-shifted grid that the CC1 deposit segments on -- particles of one cell stay
+// contiguous (what the collision and moment kernels need) and, inside the cell, particles
+// that deposit onto the same node set are contiguous too (what pgpu_advance_cc1.cu sums
+// over).  Outcasts (outside the box) get the last key.
+__global__ void k_cell_key(const double *x0, const double *x1, long n, BoxInfo b, int *key, int *iota) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int c0 = locate_bin(x0[i], b.le[0], b.dx[0]) - b.lo[0];
-  int c1 = (b.D == 2) ? locate_bin(x1[i], b.le[1], b.dx[1]) - b.lo[1] : 0;
-  int k = b.ncell;  // outcast bin
-  if (c0 >= 0 && c0 < b.n[0] && c1 >= 0 && c1 < b.n[1]) k = c0 + c1 * b.n[0];
+  const double xa = x0[i];
+  const int g0 = locate_bin(xa, b.le[0], b.dx[0]);
+  int q = (__dsub_rn(xa, b.le[0]) - ((double)g0 + 0.5) * b.dx[0]) >= 0.0 ? 1 : 0;
+  int c0 = g0 - b.lo[0], c1 = 0;
+  if (b.D == 2) {
+    const double xc = x1[i];
+    const int g1 = locate_bin(xc, b.le[1], b.dx[1]);
+    q |= (__dsub_rn(xc, b.le[1]) - ((double)g1 + 0.5) * b.dx[1]) >= 0.0 ? 2 : 0;
+    c1 = g1 - b.lo[1];
+  }
+  int k = 4 * b.ncell;  // outcast bin
+  if (c0 >= 0 && c0 < b.n[0] && c1 >= 0 && c1 < b.n[1]) k = 4 * (c0 + c1 * b.n[0]) + q;
   key[i] = k;
-  if (count) atomicAdd(count + k, 1);
+  iota[i] = (int)i;
 }
 
 __global__ void k_cell_ijk(const double *x0, const double *x1, long n, BoxInfo b, int *out) {
@@ -58,71 +75,30 @@ __global__ void k_cell_ijk(const double *x0, const double *x1, long n, BoxInfo b
   if (b.D == 2) out[n + i] = locate_bin(x1[i], b.le[1], b.dx[1]);
 }
 
-// exclusive scan of `in[0..n)` into `out[0..n]` (out[n] = total); single block, any n
-__global__ void k_exclusive_scan(const int *in, int *out, int n) {
-  __shared__ int warp_sums[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int base = 0; base < n; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const int v = (i < n) ? in[i] : 0;
-    int s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
-    }
-    if (lane == 31) warp_sums[wid] = s;
-    __syncthreads();
-    if (wid == 0) {
-      int ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, ws, o);
-        if (lane >= o) ws += t;
-      }
-      warp_sums[lane] = ws;
-    }
-    __syncthreads();
-    const int prefix = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
-    if (i < n) out[i] = prefix;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry = prefix + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[n] = carry;
+// cell_start[c] = first sorted position whose cell is >= c, for c = 0..nbins (nbins = ncell+1
+// bins incl. the outcast bin; cell_start[nbins] = n).  One thread per sorted position fills
+// the entries of every cell that begins at its position (empty cells included).
+__global__ void k_cell_starts(const int *sorted_key, long n, int nbins, int *cell_start) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const int cur = (i < n) ? (sorted_key[i] >> 2) : nbins;
+  const int prev = (i > 0) ? (sorted_key[i - 1] >> 2) : -1;
+  for (int c = prev + 1; c <= cur; ++c) cell_start[c] = (int)i;
 }
 
-// slot claim: perm[cell_start[k] + (running count)] = i   (order inside a cell arbitrary)
-__global__ void k_claim_slots(const int *key, long n, const int *cell_start, int *fill, int *perm) {
+// out[a][i] = in[a][perm[i]] for up to 4 arrays per launch (perm is read once per particle)
+struct PermuteSet {
+  const double *in[4];
+  double *out[4];
+  int count;
+};
+__global__ void k_permute(PermuteSet ps, const int *perm, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int k = key[i];
-  const int slot = cell_start[k] + atomicAdd(fill + k, 1);
-  perm[slot] = (int)i;
-}
-
-// make the order inside each cell deterministic (ascending source index = stable sort):
-// one warp per cell, rank sort
-__global__ void k_sort_within_cells(const int *cell_start, int ncell_plus, const int *perm_in, int *perm_out) {
-  const int warp = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (warp >= ncell_plus) return;
-  const int s = cell_start[warp], e = cell_start[warp + 1];
-  for (int k = s + lane; k < e; k += 32) {
-    const int mine = perm_in[k];
-    int rank = 0;
-    for (int j = s; j < e; ++j) rank += (perm_in[j] < mine) ? 1 : 0;
-    perm_out[s + rank] = mine;
-  }
-}
-
-template <class T>
-__global__ void k_permute(T *out, const T *in, const int *perm, long n) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[perm[i]];
+  const int src = perm[i];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    if (a < ps.count) ps.out[a][i] = ps.in[a][src];
 }
 
 // set{Number,Momentum,Energy}DensityFromBinFab (PicChargedSpecies.cpp:2881-3047):
@@ -335,14 +311,6 @@ using namespace pgpu;
     }                                             \
   } while (0)
 
-template <class T>
-static void permute_array(T *&arr, T *&tmp, const int *perm, long n) {
-  k_permute<T><<<nb(n), 256, 0, ctx().stream>>>(tmp, arr, perm, n);
-  T *t = arr;
-  arr = tmp;
-  tmp = t;
-}
-
 extern "C" {
 
 int pgpu_bin_particles(pgpu_species_t s) {
@@ -353,40 +321,68 @@ int pgpu_bin_particles(pgpu_species_t s) {
   const BoxInfo b = box_info(g);
   const long n = s->n;
   const int nbins = b.ncell + 1;  // + outcast bin
-  PGPU_CUDA(cudaMemsetAsync(s->cell_count, 0, (nbins + 1) * sizeof(int), c.stream));
-  if (n > 0) {
+  if (n == 0) {
+    PGPU_CUDA(cudaMemsetAsync(s->cell_start, 0, (nbins + 1) * sizeof(int), c.stream));
+    s->binned = true;
+    return 0;
+  }
+  // scratch: sorted keys + the pool of spare particle arrays the gather writes into
+  if (s->sort_cap < s->cap) {
+    if (s->key_sorted) cudaFree(s->key_sorted);
+    for (double *&p : s->spare)
+      if (p) { cudaFree(p); p = nullptr; }
+    PGPU_CUDA(cudaMalloc(&s->key_sorted, s->cap * sizeof(int)));
+    for (int k = 0; k < 4; ++k) PGPU_CUDA(cudaMalloc(&s->spare[k], s->cap * sizeof(double)));
+    s->sort_cap = s->cap;
+  }
+  int *iota = reinterpret_cast<int *>(s->tmp);  // tmp holds >= n doubles
+  {
     KTimer t("bin_key");
-    k_cell_key<<<nb(n), 256, 0, c.stream>>>(s->x[0], s->x[1], n, b, s->cell_key, s->cell_count);
+    k_cell_key<<<nb(n), 256, 0, c.stream>>>(s->x[0], s->x[1], n, b, s->cell_key, iota);
+  }
+  int nbits = 1;
+  while ((1L << nbits) <= 4L * b.ncell) ++nbits;
+  {
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, s->cell_key, s->key_sorted, iota, s->perm, (int)n, 0, nbits,
+                                    c.stream);
+    if (need > s->cub_bytes) {
+      if (s->cub_tmp) cudaFree(s->cub_tmp);
+      PGPU_CUDA(cudaMalloc(&s->cub_tmp, need));
+      s->cub_bytes = need;
+    }
+    KTimer t("bin_sort");
+    PGPU_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_tmp, need, s->cell_key, s->key_sorted, iota, s->perm, (int)n, 0,
+                                              nbits, c.stream));
   }
   {
-    KTimer t("bin_scan");
-    k_exclusive_scan<<<1, 1024, 0, c.stream>>>(s->cell_count, s->cell_start, nbins);
+    KTimer t("bin_starts");
+    k_cell_starts<<<nb(n + 1), 256, 0, c.stream>>>(s->key_sorted, n, nbins, s->cell_start);
   }
-  if (n > 0) {
-    PGPU_CUDA(cudaMemsetAsync(s->cell_count, 0, (nbins + 1) * sizeof(int), c.stream));
-    int *perm_raw = reinterpret_cast<int *>(s->tmp);  // tmp holds >= n doubles
-    {
-      KTimer t("bin_claim");
-      k_claim_slots<<<nb(n), 256, 0, c.stream>>>(s->cell_key, n, s->cell_start, s->cell_count, perm_raw);
-    }
-    {
-      KTimer t("bin_order");
-      k_sort_within_cells<<<nb((long)nbins * 32), 256, 0, c.stream>>>(s->cell_start, nbins, perm_raw, s->perm);
+  // gather every particle array into the sorted order, four arrays per launch; the old
+  // arrays become the next spares
+  std::vector<double **> arrs;
+  const int D = g->desc.D;
+  for (int d = 0; d < D; ++d) arrs.push_back(&s->x[d]);
+  for (int q = 0; q < 3; ++q) arrs.push_back(&s->v[q]);
+  arrs.push_back(&s->w);
+  arrs.push_back(reinterpret_cast<double **>(&s->id));
+  for (int d = 0; d < D; ++d) arrs.push_back(&s->xold[d]);
+  for (int q = 0; q < 3; ++q) arrs.push_back(&s->vold[q]);
+  for (size_t a0 = 0; a0 < arrs.size(); a0 += 4) {
+    PermuteSet ps;
+    ps.count = (int)std::min<size_t>(4, arrs.size() - a0);
+    for (int a = 0; a < ps.count; ++a) {
+      ps.in[a] = *arrs[a0 + a];
+      ps.out[a] = s->spare[a];
     }
     KTimer t("bin_permute");
-    const int D = g->desc.D;
-    for (int d = 0; d < D; ++d) {
-      permute_array(s->x[d], s->tmp, s->perm, n);
-      permute_array(s->xold[d], s->tmp, s->perm, n);
+    k_permute<<<nb(n), 256, 0, c.stream>>>(ps, s->perm, n);
+    for (int a = 0; a < ps.count; ++a) {
+      double *old = *arrs[a0 + a];
+      *arrs[a0 + a] = s->spare[a];
+      s->spare[a] = old;
     }
-    for (int q = 0; q < 3; ++q) {
-      permute_array(s->v[q], s->tmp, s->perm, n);
-      permute_array(s->vold[q], s->tmp, s->perm, n);
-    }
-    permute_array(s->w, s->tmp, s->perm, n);
-    double *idd = reinterpret_cast<double *>(s->id);
-    permute_array(idd, s->tmp, s->perm, n);
-    s->id = reinterpret_cast<uint64_t *>(idd);
   }
   s->binned = true;
   return 0;

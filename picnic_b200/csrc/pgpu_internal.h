@@ -87,6 +87,7 @@ struct Context {
   bool own_stream = false;
   bool exact = false;
   int deposit_mode = 1;
+  int cc1_pairs = 2;         // particle pairs per thread of the CC1 kernel (1, 2 or 4); env PGPU_CC1_PAIRS
   bool use_fast_cc1 = true;  // pgpu_set_deposit_mode(0) turns the specialised CC1 kernel off
   Counters *d_counters = nullptr;
   Counters *h_counters = nullptr;  // pinned
@@ -154,6 +155,11 @@ struct pgpu_species_s {
   int *cell_count = nullptr;   // [ncell_box+1]
   int *cell_start = nullptr;   // [ncell_box+2]
   bool binned = false;
+  int *key_sorted = nullptr;        // [n] sorted (4*cell+quadrant) keys of the last bin
+  double *spare[4] = {nullptr, nullptr, nullptr, nullptr};  // gather targets of the cell sort
+  size_t sort_cap = 0;
+  void *cub_tmp = nullptr;
+  size_t cub_bytes = 0;
   int *defer_list = nullptr;        // particles the CC1 fast kernel left to the generic one
   unsigned *defer_count = nullptr;
   size_t defer_cap = 0;
