@@ -29,6 +29,8 @@
 //    A warp then runs a segmented shuffle reduction over runs of lanes with equal dual
 //    cells and issues ONE fp64 RED per (node, run): ~1 RED per particle instead of 22.
 //    Correct for any particle order; only the number of REDs depends on the order.
+#include <algorithm>
+
 #include "pgpu_internal.h"
 
 namespace pgpu {
@@ -326,8 +328,8 @@ __device__ __forceinline__ void flush_direct(const FastArgs &A, unsigned key, co
 
 // PAIRS x 2 consecutive particles per thread (128-bit loads/stores), processed one after the
 // other; their contributions accumulate in registers while the dual cell stays the same.
-template <bool DEP, int PAIRS>
-__global__ void __launch_bounds__(BLOCK, 3) k_advance_cc1_2d(const FastArgs A) {
+template <bool DEP, int PAIRS, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d(const FastArgs A) {
   constexpr int P = 2 * PAIRS;
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long base = t * P;
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_advance_cc1_2d(const FastArgs A) {
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) {
           const double v = __shfl_down_sync(0xffffffffu, acc[j], off);
-          acc[j] += take ? v : 0.0;
+          if (take) acc[j] += v;
         }
       }
       if (head && acc_key != NOKEY) flush_direct(A, acc_key, acc);
@@ -469,6 +471,597 @@ __global__ void __launch_bounds__(BLOCK, 3) k_advance_cc1_2d(const FastArgs A) {
   }
 
   // ---- counters ----------------------------------------------------------------------------
+  apply = __reduce_add_sync(0xffffffffu, apply);
+  unconv = __reduce_add_sync(0xffffffffu, unconv);
+  if (lane == 0) {
+    if (apply) atomicAdd(&A.cnt->apply_its, (unsigned long long)apply);
+    if (unconv) atomicAdd(&A.cnt->unconverged, (unsigned long long)unconv);
+  }
+}
+
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UBLKCP, SYNCS) ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (contiguous bytes, 16-byte aligned and sized), completion on mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk copy, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int TP = 4;                 // consecutive particles per thread
+constexpr int TILE = BLOCK * TP;      // particles per tile
+constexpr int NIN = 8;                // xo0 xo1 xb0 xb1 uo0 uo1 uo2 w
+constexpr int STAGES = 2;
+constexpr size_t TMA_SMEM = (size_t)STAGES * NIN * TILE * sizeof(double) + 64;
+
+// Persistent, double-buffered version: each block walks tiles of TILE consecutive particles.
+// One thread issues eight 1D TMA bulk copies per tile (the SoA slices of that tile) into a
+// shared-memory stage and arms an mbarrier; while the block computes tile k the copies of
+// tile k+1 are in flight, so no warp ever waits on HBM latency and the particle data never
+// occupies registers before it is used.  Results (xbar in place, ubar over the u_old slots)
+// leave through TMA bulk stores.  Thread t owns particles 4t..4t+3 of the tile (visited in a
+// lane-rotated order so that the 8-byte shared loads are bank-conflict free).
+template <bool DEP>
+__global__ void __launch_bounds__(BLOCK, 3) k_advance_cc1_2d_tma(const FastArgs A, int ntiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *sm = reinterpret_cast<double *>(smem_raw);                       // [STAGES][NIN][TILE]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + STAGES * NIN * TILE);  // [STAGES]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const double *src[NIN] = {A.xo[0], A.xo[1], A.xb[0], A.xb[1], A.uo[0], A.uo[1], A.uo[2], A.w};
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue_load = [&](int tile, int stage) {
+    mbar_expect_tx(&bars[stage], NIN * TILE * (unsigned)sizeof(double));
+    const long off = (long)tile * TILE;
+#pragma unroll
+    for (int a = 0; a < NIN; ++a)
+      bulk_g2s(sm + ((size_t)stage * NIN + a) * TILE, src[a] + off, TILE * (unsigned)sizeof(double), &bars[stage]);
+  };
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) issue_load(tile, 0);
+
+  unsigned apply = 0, unconv = 0;
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const int stage = it & 1;
+    const unsigned parity = (it >> 1) & 1;
+    if (tid == 0) {
+      const int next = tile + gridDim.x;
+      if (next < ntiles) {
+        bulk_wait_read0();   // the stores that read the other stage have drained
+        issue_load(next, stage ^ 1);
+      }
+    }
+    mbar_wait(&bars[stage], parity);
+    double *st = sm + (size_t)stage * NIN * TILE;
+    const long tbase = (long)tile * TILE;
+    const int nvalid = (A.n - tbase) < TILE ? (int)(A.n - tbase) : TILE;
+
+    unsigned acc_key = NOKEY;
+    double acc[NSLOT];
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
+    unsigned defer_mask = 0;
+#pragma unroll 1
+    for (int qq = 0; qq < TP; ++qq) {
+      const int q = (qq + (lane >> 2)) & (TP - 1);
+      const int k = tid * TP + q;
+      if (k >= nvalid) continue;
+      const double xo[2] = {st[0 * TILE + k], st[1 * TILE + k]};
+      double xb[2] = {st[2 * TILE + k], st[3 * TILE + k]};
+      const double uo[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
+      const double wp = st[7 * TILE + k];
+      double ub[3] = {0.0, 0.0, 0.0};
+      unsigned key = NOKEY;
+      double c[NSLOT];
+      if (advance_one<DEP>(A, xo, xb, uo, ub, wp, apply, unconv, key, c)) {
+        st[2 * TILE + k] = xb[0];
+        st[3 * TILE + k] = xb[1];
+        st[4 * TILE + k] = ub[0];
+        st[5 * TILE + k] = ub[1];
+        st[6 * TILE + k] = ub[2];
+        if (DEP) {
+          if (key != acc_key) {
+            if (acc_key != NOKEY) flush_direct(A, acc_key, acc);
+            acc_key = key;
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) acc[j] = c[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) acc[j] += c[j];
+          }
+        }
+      } else {
+        // deferred: xbar stays as stored (the generic kernel restarts from it); the ubar slot
+        // keeps u_old, which that kernel overwrites
+        defer_mask |= 1u << q;
+      }
+    }
+    // results -> global
+    if (nvalid == TILE) {
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) bulk_s2g(A.xb[a] + tbase, st + (2 + a) * TILE, TILE * (unsigned)sizeof(double));
+#pragma unroll
+        for (int a = 0; a < 3; ++a) bulk_s2g(A.ub[a] + tbase, st + (4 + a) * TILE, TILE * (unsigned)sizeof(double));
+        bulk_commit();
+      }
+    } else {
+      // ragged last tile: plain stores of the valid particles only
+#pragma unroll 1
+      for (int q = 0; q < TP; ++q) {
+        const int k = tid * TP + q;
+        if (k < nvalid && !(defer_mask & (1u << q))) {
+          A.xb[0][tbase + k] = st[2 * TILE + k];
+          A.xb[1][tbase + k] = st[3 * TILE + k];
+          A.ub[0][tbase + k] = st[4 * TILE + k];
+          A.ub[1][tbase + k] = st[5 * TILE + k];
+          A.ub[2][tbase + k] = st[6 * TILE + k];
+        }
+      }
+      __syncthreads();
+    }
+    if (defer_mask) {
+      unsigned slot = atomicAdd(A.list_count, (unsigned)__popc(defer_mask));
+#pragma unroll
+      for (int q = 0; q < TP; ++q)
+        if (defer_mask & (1u << q)) A.list[slot++] = (int)(tbase + tid * TP + q);
+    }
+    if (DEP) {
+      const unsigned any = __ballot_sync(0xffffffffu, acc_key != NOKEY);
+      if (any) {
+        const unsigned prev = __shfl_up_sync(0xffffffffu, acc_key, 1);
+        const bool head = (lane == 0) || (prev != acc_key);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const unsigned above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+        const int run_end = above ? (__ffs(above) - 1) : 32;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const bool take = lane + off < run_end;
+#pragma unroll
+          for (int j = 0; j < NSLOT; ++j) {
+            const double v = __shfl_down_sync(0xffffffffu, acc[j], off);
+            if (take) acc[j] += v;
+          }
+        }
+        if (head && acc_key != NOKEY) flush_direct(A, acc_key, acc);
+      }
+    }
+  }
+  if (tid == 0) bulk_wait0();   // all bulk stores complete before the block retires
+
+  apply = __reduce_add_sync(0xffffffffu, apply);
+  unconv = __reduce_add_sync(0xffffffffu, unconv);
+  if (lane == 0) {
+    if (apply) atomicAdd(&A.cnt->apply_its, (unsigned long long)apply);
+    if (unconv) atomicAdd(&A.cnt->unconverged, (unsigned long long)unconv);
+  }
+}
+
+
+// =============================================================================================
+// Two-phase tile kernel.  Phase 1 pushes the tile's particles (all particle-Picard passes) and
+// leaves (xbar, ubar) in the shared-memory tile; phase 2 re-reads them and builds the current
+// contributions.  Splitting the phases keeps the 21 register accumulators out of the Picard
+// loop's live range, which is what lets four blocks (16 warps) share an SM.
+// =============================================================================================
+struct CellRef {
+  int i0[2];
+  double dO[2];
+};
+
+__device__ __forceinline__ bool locate_dual(const FastArgs &A, const double (&xo)[2], CellRef &r) {
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double xr = __dsub_rn(xo[d], A.le[d]);
+    r.i0[d] = floor_div_fast(__dsub_rn(xr, A.hdx[d]), A.dx[d], A.rdx[d]);
+    r.dO[d] = fma(xr, A.rdx[d], -(double)(r.i0[d] + 1));
+    if (r.i0[d] < A.i_lo[d] || r.i0[d] > A.i_hi[d]) ok = false;
+  }
+  return ok;
+}
+
+// normalised offsets of xbar and x_new; false if the orbit leaves the dual cell of x_old
+__device__ __forceinline__ bool orbit_offsets(const FastArgs &A, const CellRef &r, const double (&xo)[2],
+                                              const double (&xb)[2], double (&dxp0)[2], double (&dB)[2],
+                                              double (&dN)[2]) {
+  bool same = true;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    dxp0[d] = xb[d] - xo[d];
+    dB[d] = fma(dxp0[d], A.rdx[d], r.dO[d]);
+    dN[d] = fma(2.0, dB[d], -r.dO[d]);
+    if (!(fabs(dN[d]) < 0.5 - BAND)) {
+      // guard band: let the reference's floor decide (and catch real crossings)
+      const double xn = fma(2.0, xb[d], -xo[d]);
+      const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
+      if (in != r.i0[d]) same = false;
+    }
+  }
+  return same;
+}
+
+// Phase 1: returns false if the particle must be redone by the generic kernel.
+__device__ __forceinline__ bool push_one(const FastArgs &A, const double (&xo)[2], double (&xb)[2],
+                                         const double (&uo)[3], double (&ub)[3], unsigned &apply,
+                                         unsigned &unconv) {
+  CellRef r;
+  if (!locate_dual(A, xo, r)) return false;
+  const int(&i0)[2] = r.i0;
+  const double(&dO)[2] = r.dO;
+  double ex[3], dex[3], ey[3], dey[3];
+  {
+    const double *p = A.F[0] + (i0[0] + i0[1] * A.fn0[0]);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double v0 = __ldg(p + b * A.fn0[0]);
+      const double v1 = __ldg(p + b * A.fn0[0] + 1);
+      ex[b] = v0;
+      dex[b] = v1 - v0;
+    }
+  }
+  {
+    const double *p = A.F[1] + (i0[0] + i0[1] * A.fn0[1]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double v0 = __ldg(p + a);
+      const double v1 = __ldg(p + a + A.fn0[1]);
+      ey[a] = v0;
+      dey[a] = v1 - v0;
+    }
+  }
+  double bz0, bz1, bz2, bz3;
+  {
+    const double *p = A.F[5] + (i0[0] + i0[1] * A.fn0[5]);
+    const double v00 = __ldg(p), v10 = __ldg(p + 1);
+    const double v01 = __ldg(p + A.fn0[5]), v11 = __ldg(p + A.fn0[5] + 1);
+    bz0 = v00;
+    bz1 = v10 - v00;
+    bz2 = v01 - v00;
+    bz3 = (v11 - v01) - bz1;
+  }
+  const int oEz = i0[0] + i0[1] * A.fn0[2];
+  const int oBx = i0[0] + i0[1] * A.fn0[3];
+  const int oBy = i0[0] + i0[1] * A.fn0[4];
+  double pO[2][2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double a = 0.5 - dO[d], b = 0.5 + dO[d];
+    pO[d][0] = a * a;
+    pO[d][1] = b * b;
+  }
+
+  int iter = 0;
+  bool done = false;
+  unsigned napply = 0, nunconv = 0;
+  while (true) {
+    double dxp0[2], dB[2], dN[2];
+    if (!orbit_offsets(A, r, xo, xb, dxp0, dB, dN)) return false;
+    if (done) break;
+    const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
+    double Wx[3], Wy[3];
+    {
+      const double a0 = 0.5 - dN[0], b0 = 0.5 + dN[0];
+      Wx[0] = 0.25 * fma(a0, a0, pO[0][0]);
+      Wx[2] = 0.25 * fma(b0, b0, pO[0][1]);
+      Wx[1] = (1.0 - Wx[0]) - Wx[2];
+      const double a1 = 0.5 - dN[1], b1 = 0.5 + dN[1];
+      Wy[0] = 0.25 * fma(a1, a1, pO[1][0]);
+      Wy[2] = 0.25 * fma(b1, b1, pO[1][1]);
+      Wy[1] = (1.0 - Wy[0]) - Wy[2];
+    }
+    double E[3], B[3];
+    E[0] = Wy[0] * fma(del0, dex[0], ex[0]);
+    E[0] = fma(Wy[1], fma(del0, dex[1], ex[1]), E[0]);
+    E[0] = fma(Wy[2], fma(del0, dex[2], ex[2]), E[0]);
+    E[1] = Wx[0] * fma(del1, dey[0], ey[0]);
+    E[1] = fma(Wx[1], fma(del1, dey[1], ey[1]), E[1]);
+    E[1] = fma(Wx[2], fma(del1, dey[2], ey[2]), E[1]);
+    const int sx = del0 >= 0.5 ? 1 : 0, sy = del1 >= 0.5 ? 1 : 0;
+    const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
+    {
+      const double *p = A.F[2] + (oEz + sx + sy * A.fn0[2]);
+      const double v00 = __ldg(p), v10 = __ldg(p + 1);
+      const double v01 = __ldg(p + A.fn0[2]), v11 = __ldg(p + A.fn0[2] + 1);
+      const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
+      E[2] = fma(fy, t1 - t0, t0);
+    }
+    {
+      const double *p = A.F[3] + (oBx + sx);
+      const double v00 = __ldg(p), v10 = __ldg(p + 1);
+      const double v01 = __ldg(p + A.fn0[3]), v11 = __ldg(p + A.fn0[3] + 1);
+      const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
+      B[0] = fma(del1, t1 - t0, t0);
+    }
+    {
+      const double *p = A.F[4] + (oBy + sy * A.fn0[4]);
+      const double v00 = __ldg(p), v10 = __ldg(p + 1);
+      const double v01 = __ldg(p + A.fn0[4]), v11 = __ldg(p + A.fn0[4] + 1);
+      const double t0 = fma(del0, v10 - v00, v00), t1 = fma(del0, v11 - v01, v01);
+      B[1] = fma(fy, t1 - t0, t0);
+    }
+    B[2] = fma(del1, fma(del0, bz3, bz2), fma(del0, bz1, bz0));
+    {
+      const double vm0 = fma(A.alpha, E[0], uo[0]), vm1 = fma(A.alpha, E[1], uo[1]),
+                   vm2 = fma(A.alpha, E[2], uo[2]);
+      const double b0 = A.alpha * B[0], b1 = A.alpha * B[1], b2 = A.alpha * B[2];
+      const double den = fma(b2, b2, fma(b1, b1, fma(b0, b0, 1.0)));
+      const double p0 = fma(vm1, b2, vm0) - vm2 * b1;
+      const double p1 = fma(vm2, b0, vm1) - vm0 * b2;
+      const double p2 = fma(vm0, b1, vm2) - vm1 * b0;
+      const double rden = 1.0 / den;
+      ub[0] = fma(fma(p1, b2, -(p2 * b1)), rden, vm0);
+      ub[1] = fma(fma(p2, b0, -(p0 * b2)), rden, vm1);
+      ub[2] = fma(fma(p0, b1, -(p1 * b0)), rden, vm2);
+    }
+    napply += 1;
+    if (A.iter_max < 0) {  // advanceParticles (:1594-1612), part_order_swap == false
+      xb[0] = fma(ub[0], A.hdt, xo[0]);
+      xb[1] = fma(ub[1], A.hdt, xo[1]);
+      done = true;
+      continue;
+    }
+    const double dxp_0 = ub[0] * A.hdt, dxp_1 = ub[1] * A.hdt;
+    const double rel = fmax(fabs(dxp0[0] - dxp_0) * A.rdx[0], fabs(dxp0[1] - dxp_1) * A.rdx[1]);
+    if (iter == 0) {
+      xb[0] = xo[0] + dxp_0;
+      xb[1] = xo[1] + dxp_1;
+      if (!(rel >= A.rtol)) done = true;
+    } else {
+      if (rel < A.rtol) break;  // reverse pass: xbar unchanged, its orbit was checked above
+      xb[0] = xo[0] + dxp_0;
+      xb[1] = xo[1] + dxp_1;
+    }
+    if (!done && iter >= A.iter_max) {
+      nunconv = 1;
+      done = true;
+    }
+    iter += 1;
+  }
+  apply += napply;
+  unconv += nunconv;
+  return true;
+}
+
+// Phase 2: the 21 node contributions of a pushed, single-segment particle.
+__device__ __forceinline__ void deposit_one(const FastArgs &A, const double (&xo)[2], const double (&xb)[2],
+                                            const double (&ub)[3], double wp, unsigned &key,
+                                            double (&c)[NSLOT]) {
+  CellRef r;
+  locate_dual(A, xo, r);
+  key = ((unsigned)(r.i0[1] + 32768) << 16) | (unsigned)(r.i0[0] + 32768);
+  double dB[2], dN[2], Wx[3], Wy[3];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    dB[d] = fma(xb[d] - xo[d], A.rdx[d], r.dO[d]);
+    dN[d] = fma(2.0, dB[d], -r.dO[d]);
+  }
+  {
+    const double a0 = 0.5 - dN[0], b0 = 0.5 + dN[0], c0 = 0.5 - r.dO[0], e0 = 0.5 + r.dO[0];
+    Wx[0] = 0.25 * fma(a0, a0, c0 * c0);
+    Wx[2] = 0.25 * fma(b0, b0, e0 * e0);
+    Wx[1] = (1.0 - Wx[0]) - Wx[2];
+    const double a1 = 0.5 - dN[1], b1 = 0.5 + dN[1], c1 = 0.5 - r.dO[1], e1 = 0.5 + r.dO[1];
+    Wy[0] = 0.25 * fma(a1, a1, c1 * c1);
+    Wy[2] = 0.25 * fma(b1, b1, e1 * e1);
+    Wy[1] = (1.0 - Wy[0]) - Wy[2];
+  }
+  const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
+  const double rhop = wp * A.rvolume;
+  const double jx = ub[0] * rhop, jy = ub[1] * rhop, jz = ub[2] * rhop;
+  const double jx1 = jx * del0, jx0 = jx - jx1;
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    c[0 + 2 * b] = jx0 * Wy[b];
+    c[1 + 2 * b] = jx1 * Wy[b];
+  }
+  const double jy1 = jy * del1, jy0 = jy - jy1;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    c[6 + a] = jy0 * Wx[a];
+    c[9 + a] = jy1 * Wx[a];
+  }
+  double nx[3], ny[3];
+  if (del0 >= 0.5) { nx[0] = 0.0; nx[1] = 1.5 - del0; nx[2] = del0 - 0.5; }
+  else             { nx[0] = 0.5 - del0; nx[1] = del0 + 0.5; nx[2] = 0.0; }
+  if (del1 >= 0.5) { ny[0] = 0.0; ny[1] = 1.5 - del1; ny[2] = del1 - 0.5; }
+  else             { ny[0] = 0.5 - del1; ny[1] = del1 + 0.5; ny[2] = 0.0; }
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const double t = jz * ny[b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c[12 + a + 3 * b] = t * nx[a];
+  }
+}
+
+constexpr size_t TILE2_SMEM = (size_t)NIN * TILE * sizeof(double) + 64;
+
+template <bool DEP, int RSTEPS>
+__global__ void __launch_bounds__(BLOCK, 4) k_advance_cc1_2d_tile(const FastArgs A, int ntiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *st = reinterpret_cast<double *>(smem_raw);                 // [NIN][TILE]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(st + NIN * TILE);
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  unsigned apply = 0, unconv = 0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const long tbase = (long)tile * TILE;
+    if (tid == 0) {
+      bulk_wait_read0();   // the previous tile's stores have finished reading the buffer
+      mbar_expect_tx(bar, NIN * TILE * (unsigned)sizeof(double));
+      constexpr unsigned BYTES = TILE * (unsigned)sizeof(double);
+      bulk_g2s(st + 0 * TILE, A.xo[0] + tbase, BYTES, bar);
+      bulk_g2s(st + 1 * TILE, A.xo[1] + tbase, BYTES, bar);
+      bulk_g2s(st + 2 * TILE, A.xb[0] + tbase, BYTES, bar);
+      bulk_g2s(st + 3 * TILE, A.xb[1] + tbase, BYTES, bar);
+      bulk_g2s(st + 4 * TILE, A.uo[0] + tbase, BYTES, bar);
+      bulk_g2s(st + 5 * TILE, A.uo[1] + tbase, BYTES, bar);
+      bulk_g2s(st + 6 * TILE, A.uo[2] + tbase, BYTES, bar);
+      bulk_g2s(st + 7 * TILE, A.w + tbase, BYTES, bar);
+    }
+    mbar_wait(bar, (unsigned)(it & 1));
+    const int nvalid = (A.n - tbase) < TILE ? (int)(A.n - tbase) : TILE;
+
+    // ---- phase 1: push ------------------------------------------------------------------
+    unsigned defer_mask = 0;
+#pragma unroll 1
+    for (int qq = 0; qq < TP; ++qq) {
+      const int q = (qq + (lane >> 2)) & (TP - 1);
+      const int k = tid * TP + q;
+      if (k >= nvalid) {
+        defer_mask |= 16u << q;   // not a particle
+        continue;
+      }
+      const double xo[2] = {st[0 * TILE + k], st[1 * TILE + k]};
+      double xb[2] = {st[2 * TILE + k], st[3 * TILE + k]};
+      const double uo[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
+      double ub[3] = {0.0, 0.0, 0.0};
+      if (push_one(A, xo, xb, uo, ub, apply, unconv)) {
+        st[2 * TILE + k] = xb[0];
+        st[3 * TILE + k] = xb[1];
+        st[4 * TILE + k] = ub[0];
+        st[5 * TILE + k] = ub[1];
+        st[6 * TILE + k] = ub[2];
+      } else {
+        // deferred: xbar stays as stored (the generic kernel restarts from it); the ubar slot
+        // keeps u_old, which that kernel overwrites
+        defer_mask |= 1u << q;
+      }
+    }
+
+    // ---- phase 2: deposit ---------------------------------------------------------------
+    if (DEP) {
+      unsigned acc_key = NOKEY;
+      double acc[NSLOT];
+#pragma unroll
+      for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
+#pragma unroll 1
+      for (int qq = 0; qq < TP; ++qq) {
+        const int q = (qq + (lane >> 2)) & (TP - 1);
+        if (defer_mask & (17u << q)) continue;
+        const int k = tid * TP + q;
+        const double xo[2] = {st[0 * TILE + k], st[1 * TILE + k]};
+        const double xb[2] = {st[2 * TILE + k], st[3 * TILE + k]};
+        const double ub[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
+        const double wp = st[7 * TILE + k];
+        unsigned key;
+        double c[NSLOT];
+        deposit_one(A, xo, xb, ub, wp, key, c);
+        if (key != acc_key) {
+          if (acc_key != NOKEY) flush_direct(A, acc_key, acc);
+          acc_key = key;
+#pragma unroll
+          for (int j = 0; j < NSLOT; ++j) acc[j] = c[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < NSLOT; ++j) acc[j] += c[j];
+        }
+      }
+      const unsigned any = __ballot_sync(0xffffffffu, acc_key != NOKEY);
+      if (any) {
+        const unsigned prev = __shfl_up_sync(0xffffffffu, acc_key, 1);
+        const bool head = (lane == 0) || (prev != acc_key);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const unsigned above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+        const int run_end = above ? (__ffs(above) - 1) : 32;
+        const int run_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+        for (int sidx = 0; sidx < RSTEPS; ++sidx) {
+          const int off = 1 << sidx;
+          const bool take = lane + off < run_end;
+#pragma unroll
+          for (int j = 0; j < NSLOT; ++j) {
+            const double v = __shfl_down_sync(0xffffffffu, acc[j], off);
+            if (take) acc[j] += v;
+          }
+        }
+        // after RSTEPS steps lane l holds the sum over [l, min(l + 2^RSTEPS, run_end))
+        if (acc_key != NOKEY && (((lane - run_start) & ((1 << RSTEPS) - 1)) == 0)) flush_direct(A, acc_key, acc);
+      }
+    }
+
+    // ---- results -> global ----------------------------------------------------------------
+    defer_mask &= 15u;
+    if (nvalid == TILE) {
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        constexpr unsigned BYTES = TILE * (unsigned)sizeof(double);
+        bulk_s2g(A.xb[0] + tbase, st + 2 * TILE, BYTES);
+        bulk_s2g(A.xb[1] + tbase, st + 3 * TILE, BYTES);
+        bulk_s2g(A.ub[0] + tbase, st + 4 * TILE, BYTES);
+        bulk_s2g(A.ub[1] + tbase, st + 5 * TILE, BYTES);
+        bulk_s2g(A.ub[2] + tbase, st + 6 * TILE, BYTES);
+        bulk_commit();
+      }
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < TP; ++q) {
+        const int k = tid * TP + q;
+        if (k < nvalid && !(defer_mask & (1u << q))) {
+          A.xb[0][tbase + k] = st[2 * TILE + k];
+          A.xb[1][tbase + k] = st[3 * TILE + k];
+          A.ub[0][tbase + k] = st[4 * TILE + k];
+          A.ub[1][tbase + k] = st[5 * TILE + k];
+          A.ub[2][tbase + k] = st[6 * TILE + k];
+        }
+      }
+      __syncthreads();
+    }
+    if (defer_mask) {
+      unsigned slot = atomicAdd(A.list_count, (unsigned)__popc(defer_mask));
+#pragma unroll
+      for (int q = 0; q < TP; ++q)
+        if (defer_mask & (1u << q)) A.list[slot++] = (int)(tbase + tid * TP + q);
+    }
+  }
+  if (tid == 0) bulk_wait0();
+
   apply = __reduce_add_sync(0xffffffffu, apply);
   unconv = __reduce_add_sync(0xffffffffu, unconv);
   if (lane == 0) {
@@ -546,18 +1139,56 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   A.list = s->defer_list;
   A.list_count = s->defer_count;
   A.cnt = c.d_counters;
+  KTimer t(deposit ? "advance_cc1_fused" : "advance_cc1");
+  const bool tile_ok = s->cap >= (size_t)(((s->n + TILE - 1) / TILE) * TILE);
+  if (c.cc1_tma == 2 && tile_ok) {
+    const int ntiles = (int)((s->n + TILE - 1) / TILE);
+    const int grid = std::min(ntiles, c.sm_count * 4 * c.cc1_waves);
+#define PGPU_TILE_LAUNCH(DEPV, RS)                                                                        \
+  do {                                                                                                    \
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tile<DEPV, RS>,                                       \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE2_SMEM));       \
+    k_advance_cc1_2d_tile<DEPV, RS><<<grid, BLOCK, TILE2_SMEM, c.stream>>>(A, ntiles);                    \
+  } while (0)
+    if (!deposit) PGPU_TILE_LAUNCH(false, 0);
+    else if (c.cc1_rsteps == 0) PGPU_TILE_LAUNCH(true, 0);
+    else if (c.cc1_rsteps == 1) PGPU_TILE_LAUNCH(true, 1);
+    else if (c.cc1_rsteps == 2) PGPU_TILE_LAUNCH(true, 2);
+    else if (c.cc1_rsteps == 3) PGPU_TILE_LAUNCH(true, 3);
+    else if (c.cc1_rsteps == 4) PGPU_TILE_LAUNCH(true, 4);
+    else PGPU_TILE_LAUNCH(true, 5);
+    return 1;
+  }
+  if (c.cc1_tma == 1 && tile_ok) {
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)TMA_SMEM));
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)TMA_SMEM));
+    const int ntiles = (int)((s->n + TILE - 1) / TILE);
+    const int grid = std::min(ntiles, c.sm_count * 3);
+    if (deposit) k_advance_cc1_2d_tma<true><<<grid, BLOCK, TMA_SMEM, c.stream>>>(A, ntiles);
+    else k_advance_cc1_2d_tma<false><<<grid, BLOCK, TMA_SMEM, c.stream>>>(A, ntiles);
+    return 1;
+  }
   const int pairs = c.cc1_pairs;
   const long per_block = (long)BLOCK * 2 * pairs;
   const unsigned nb = (unsigned)((s->n + per_block - 1) / per_block);
-  KTimer t(deposit ? "advance_cc1_fused" : "advance_cc1");
+  const int minb = c.cc1_minblocks;
+#define PGPU_LAUNCH_CC1(DEPV, PV, MB) k_advance_cc1_2d<DEPV, PV, MB><<<nb, BLOCK, 0, c.stream>>>(A)
+#define PGPU_PICK_MB(DEPV, PV)                            \
+  do {                                                    \
+    if (minb == 4) PGPU_LAUNCH_CC1(DEPV, PV, 4);          \
+    else if (minb == 5) PGPU_LAUNCH_CC1(DEPV, PV, 5);     \
+    else PGPU_LAUNCH_CC1(DEPV, PV, 3);                    \
+  } while (0)
   if (deposit) {
-    if (pairs == 1) k_advance_cc1_2d<true, 1><<<nb, BLOCK, 0, c.stream>>>(A);
-    else if (pairs == 2) k_advance_cc1_2d<true, 2><<<nb, BLOCK, 0, c.stream>>>(A);
-    else k_advance_cc1_2d<true, 4><<<nb, BLOCK, 0, c.stream>>>(A);
+    if (pairs == 1) PGPU_PICK_MB(true, 1);
+    else if (pairs == 2) PGPU_PICK_MB(true, 2);
+    else PGPU_PICK_MB(true, 4);
   } else {
-    if (pairs == 1) k_advance_cc1_2d<false, 1><<<nb, BLOCK, 0, c.stream>>>(A);
-    else if (pairs == 2) k_advance_cc1_2d<false, 2><<<nb, BLOCK, 0, c.stream>>>(A);
-    else k_advance_cc1_2d<false, 4><<<nb, BLOCK, 0, c.stream>>>(A);
+    if (pairs == 1) PGPU_PICK_MB(false, 1);
+    else if (pairs == 2) PGPU_PICK_MB(false, 2);
+    else PGPU_PICK_MB(false, 4);
   }
   return 1;
 }

@@ -317,6 +317,10 @@ int pgpu_init(int device) {
   PGPU_CUDA(cudaMallocHost(&c.h_counters, sizeof(Counters)));
   c.inited = true;
   c.sticky_error = 0;
+  if (const char *e = getenv("PGPU_CC1_MINB")) c.cc1_minblocks = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_TMA")) c.cc1_tma = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_RSTEPS")) c.cc1_rsteps = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_WAVES")) c.cc1_waves = atoi(e) > 0 ? atoi(e) : 1;
   if (const char *e = getenv("PGPU_CC1_PAIRS")) {
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) c.cc1_pairs = v;

@@ -87,6 +87,10 @@ struct Context {
   bool own_stream = false;
   bool exact = false;
   int deposit_mode = 1;
+  int cc1_tma = 2;           // CC1 kernel: 2 = two-phase TMA tile kernel, 1 = double-buffered TMA, 0 = direct loads (env PGPU_CC1_TMA)
+  int cc1_rsteps = 3;        // shuffle-reduction steps before the REDs (env PGPU_CC1_RSTEPS)
+  int cc1_waves = 64;        // tile kernel grid = min(tiles, SMs*4*waves) (env PGPU_CC1_WAVES)
+  int cc1_minblocks = 3;     // register cap of the direct CC1 kernel: 3, 4 or 5 blocks of 128 per SM
   int cc1_pairs = 2;         // particle pairs per thread of the CC1 kernel (1, 2 or 4); env PGPU_CC1_PAIRS
   bool use_fast_cc1 = true;  // pgpu_set_deposit_mode(0) turns the specialised CC1 kernel off
   Counters *d_counters = nullptr;
