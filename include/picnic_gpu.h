@@ -183,6 +183,11 @@ int pgpu_debye_length(pgpu_grid_t g, pgpu_species_t *species, int nspecies, doub
  * (PicChargedSpeciesBC.cpp:738-765, 808-870).  bc_lo/bc_hi[d] = PGPU_BC_*. */
 int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi);
 
+/* advanceVelocities_2ndHalf + advancePositions_2ndHalf + applyBCs in one pass over the
+ * particles: the tail of every implicit step (PICTimeIntegrator_EM_ThetaImplicit.cpp:311-319).
+ * Bit-identical to the three separate calls; falls back to them for symmetry walls. */
+int pgpu_finish_implicit_step(pgpu_species_t s, const int *bc_lo, const int *bc_hi);
+
 /* reductions: setStableDt (:1869-1911), globalMoments (:4067-4130) */
 int pgpu_stable_dt(pgpu_species_t s, double *dt_out);
 int pgpu_global_moments(pgpu_species_t s, double *out /* [w, wux,wuy,wuz, wuu_x,wuu_y,wuu_z] */);

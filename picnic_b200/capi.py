@@ -81,7 +81,7 @@ def load():
         "pgpu_bin_particles": [vp], "pgpu_species_cell_index": [vp, vp],
         "pgpu_species_cell_offsets": [vp, vp], "pgpu_set_moments_from_bins": [vp],
         "pgpu_species_moments_get": [vp, vp, vp, vp], "pgpu_debye_length": [vp, vp, i32, vp],
-        "pgpu_apply_bcs": [vp, vp, vp], "pgpu_stable_dt": [vp, vp], "pgpu_global_moments": [vp, vp],
+        "pgpu_apply_bcs": [vp, vp, vp], "pgpu_finish_implicit_step": [vp, vp, vp], "pgpu_stable_dt": [vp, vp], "pgpu_global_moments": [vp, vp],
         "pgpu_collide_ta": [vp, vp, dbl, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_ta_delta_u": [lng, vp, vp, vp, vp, dbl, dbl, dbl, vp, vp, vp, vp],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
@@ -308,6 +308,9 @@ class Species:
 
     def apply_bcs(self, bc_lo, bc_hi):
         check(load().pgpu_apply_bcs(self.h, _i2(bc_lo), _i2(bc_hi)))
+
+    def finish_implicit_step(self, bc_lo, bc_hi):
+        check(load().pgpu_finish_implicit_step(self.h, _i2(bc_lo), _i2(bc_hi)))
 
     def stable_dt(self):
         out = C.c_double(0)

@@ -558,6 +558,7 @@ int pgpu_species_destroy(pgpu_species_t s) {
   cudaFree(s->tmp);
   cudaFree(s->cell_key);
   cudaFree(s->key_sorted);
+  cudaFree(s->old_perm);
   cudaFree(s->cub_tmp);
   for (int k = 0; k < 4; ++k) cudaFree(s->spare[k]);
   cudaFree(s->defer_list);
@@ -596,6 +597,7 @@ int pgpu_species_upload(pgpu_species_t s, long n, const double *x, const double 
   PGPU_CUDA(cudaStreamSynchronize(st));
   s->n = n;
   s->binned = false;
+  s->pos_old_pending = s->vel_old_pending = false;
   return 0;
 }
 
@@ -603,6 +605,7 @@ int pgpu_species_download(pgpu_species_t s, double *x, double *xold, double *v, 
                           uint64_t *id) {
   NEED_INIT();
   if (!s) return PGPU_ERR_ARG;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   const int D = s->grid->desc.D;
   const long n = s->n;
   cudaStream_t st = ctx().stream;
@@ -649,6 +652,7 @@ static int stream_pass(const char *name, double *out, const double *a, const dou
 int pgpu_advance_positions_explicit(pgpu_species_t s, double full_dt, int half_step) {
   NEED_INIT();
   if (!s->desc.motion) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   const double cnormDt = s->desc.cvac_norm * full_dt;
   const double dt_factor = half_step ? 0.5 : 1.0;
   for (int d = 0; d < s->grid->desc.D; ++d)
@@ -660,6 +664,7 @@ int pgpu_advance_positions_explicit(pgpu_species_t s, double full_dt, int half_s
 int pgpu_advance_positions_implicit(pgpu_species_t s, double full_dt) {
   NEED_INIT();
   if (!s->desc.motion) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   const double cnormDt = s->desc.cvac_norm * full_dt;
   const double cnormHalfDt = cnormDt * 0.5;
   for (int d = 0; d < s->grid->desc.D; ++d)
@@ -671,6 +676,7 @@ int pgpu_advance_positions_implicit(pgpu_species_t s, double full_dt) {
 int pgpu_advance_positions_2nd_half(pgpu_species_t s) {
   NEED_INIT();
   if (!s->desc.motion) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   for (int d = 0; d < s->grid->desc.D; ++d)
     stream_pass("second_half", s->x[d], s->x[d], s->xold[d], s->n, 0.0, 1);
   s->binned = false;
@@ -680,6 +686,7 @@ int pgpu_advance_positions_2nd_half(pgpu_species_t s) {
 int pgpu_advance_velocities_2nd_half(pgpu_species_t s) {
   NEED_INIT();
   if (!s->desc.forces) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   for (int c = 0; c < 3; ++c) stream_pass("second_half", s->v[c], s->v[c], s->vold[c], s->n, 0.0, 1);
   return 0;
 }
@@ -687,6 +694,7 @@ int pgpu_advance_velocities_2nd_half(pgpu_species_t s) {
 int pgpu_average_velocities(pgpu_species_t s) {
   NEED_INIT();
   if (!s->desc.forces) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   for (int c = 0; c < 3; ++c) stream_pass("average_velocities", s->v[c], s->v[c], s->vold[c], s->n, 0.0, 2);
   return 0;
 }
@@ -694,6 +702,7 @@ int pgpu_average_velocities(pgpu_species_t s) {
 int pgpu_update_old_particle_positions(pgpu_species_t s) {
   NEED_INIT();
   if (!s->desc.motion) return 0;
+  s->pos_old_pending = false;   // every xold entry is overwritten: a pending gather is moot
   for (int d = 0; d < s->grid->desc.D; ++d)
     PGPU_CUDA(cudaMemcpyAsync(s->xold[d], s->x[d], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
   return 0;
@@ -702,6 +711,7 @@ int pgpu_update_old_particle_positions(pgpu_species_t s) {
 int pgpu_update_old_particle_velocities(pgpu_species_t s) {
   NEED_INIT();
   if (!s->desc.forces) return 0;
+  s->vel_old_pending = false;
   for (int c = 0; c < 3; ++c)
     PGPU_CUDA(cudaMemcpyAsync(s->vold[c], s->v[c], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
   return 0;
@@ -709,6 +719,7 @@ int pgpu_update_old_particle_velocities(pgpu_species_t s) {
 
 int pgpu_reset_particles(pgpu_species_t s) {
   NEED_INIT();
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   for (int d = 0; d < s->grid->desc.D; ++d)
     PGPU_CUDA(cudaMemcpyAsync(s->x[d], s->xold[d], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
   for (int c = 0; c < 3; ++c)
@@ -734,6 +745,7 @@ int pgpu_advance_velocities(pgpu_species_t s, double full_dt, int half_step) {
     return PGPU_ERR_STATE;
   }
   if (s->n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   const double cnormDt = full_dt * s->desc.cvac_norm;
   const double alpha = s->desc.fnorm_const * cnormDt / 2.0;
   KTimer t("boris");

@@ -211,6 +211,51 @@ __global__ void k_deposit_rho(const double *x0, const double *x1, const double *
   if ((threadIdx.x & 31) == 0 && err) atomicOr(&cnt->err, err);
 }
 
+// advanceVelocities_2ndHalf + advancePositions_2ndHalf + periodic applyBCs in one pass
+// (PicChargedSpecies.cpp:1136-1244, 997-1025; PicChargedSpeciesBC.cpp:738-765): the three
+// calls always follow each other at the end of an implicit step
+// (PICTimeIntegrator_EM_ThetaImplicit.cpp:311-319).  Same arithmetic as the separate kernels.
+struct FinishArgs {
+  double *x[2], *xold[2], *v[3];
+  const double *vold[3];
+  long n;
+  int D, motion, forces;
+  int periodic[2];
+  double left[2], right[2];
+};
+__global__ void k_finish_step(FinishArgs a) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  if (a.forces) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a.v[c][i] = __dsub_rn(__dmul_rn(2.0, a.v[c][i]), a.vold[c][i]);
+  }
+  if (a.motion) {
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      if (d >= a.D) break;
+      double xo = a.xold[d][i];
+      double xp = __dsub_rn(__dmul_rn(2.0, a.x[d][i]), xo);
+      bool ch = false;
+      if (a.periodic[d]) {
+        const double Lbox = __dsub_rn(a.right[d], a.left[d]);
+        if (xp < a.left[d]) {
+          xp = __dadd_rn(xp, Lbox);
+          xo = __dadd_rn(xo, Lbox);
+          ch = true;
+        }
+        if (xp >= a.right[d]) {
+          xp = __dsub_rn(xp, Lbox);
+          xo = __dsub_rn(xo, Lbox);
+          ch = true;
+        }
+      }
+      a.x[d][i] = xp;
+      if (ch) a.xold[d][i] = xo;
+    }
+  }
+}
+
 // PicChargedSpeciesBC::enforcePeriodic (PicChargedSpeciesBC.cpp:738-765)
 __global__ void k_bc_periodic(double *x, double *xold, long n, double left, double right) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,6 +356,41 @@ using namespace pgpu;
     }                                             \
   } while (0)
 
+namespace pgpu {
+// out-of-place gather of a list of particle arrays through the spare pool
+static int gather_arrays(pgpu_species_s *s, std::vector<double **> &arrs, const int *perm) {
+  const long n = s->n;
+  for (size_t a0 = 0; a0 < arrs.size(); a0 += 4) {
+    PermuteSet ps;
+    ps.count = (int)std::min<size_t>(4, arrs.size() - a0);
+    for (int a = 0; a < ps.count; ++a) {
+      ps.in[a] = *arrs[a0 + a];
+      ps.out[a] = s->spare[a];
+    }
+    KTimer t("bin_permute");
+    k_permute<<<nb(n), 256, 0, ctx().stream>>>(ps, perm, n);
+    for (int a = 0; a < ps.count; ++a) {
+      double *old = *arrs[a0 + a];
+      *arrs[a0 + a] = s->spare[a];
+      s->spare[a] = old;
+    }
+  }
+  return 0;
+}
+
+int materialize_old(pgpu_species_s *s) {
+  if (!s->pos_old_pending && !s->vel_old_pending) return 0;
+  std::vector<double **> arrs;
+  if (s->pos_old_pending)
+    for (int d = 0; d < s->grid->desc.D; ++d) arrs.push_back(&s->xold[d]);
+  if (s->vel_old_pending)
+    for (int q = 0; q < 3; ++q) arrs.push_back(&s->vold[q]);
+  s->pos_old_pending = s->vel_old_pending = false;
+  if (s->n == 0) return 0;
+  return gather_arrays(s, arrs, s->old_perm);
+}
+}  // namespace pgpu
+
 extern "C" {
 
 int pgpu_bin_particles(pgpu_species_t s) {
@@ -359,31 +439,23 @@ int pgpu_bin_particles(pgpu_species_t s) {
     KTimer t("bin_starts");
     k_cell_starts<<<nb(n + 1), 256, 0, c.stream>>>(s->key_sorted, n, nbins, s->cell_start);
   }
-  // gather every particle array into the sorted order, four arrays per launch; the old
-  // arrays become the next spares
+  // gather the particle arrays into the sorted order, four arrays per launch (the old arrays
+  // become the next spares); xold / vold are gathered lazily (materialize_old)
+  if (materialize_old(s)) return PGPU_ERR_CUDA;   // a still-pending gather of an earlier sort
   std::vector<double **> arrs;
   const int D = g->desc.D;
   for (int d = 0; d < D; ++d) arrs.push_back(&s->x[d]);
   for (int q = 0; q < 3; ++q) arrs.push_back(&s->v[q]);
   arrs.push_back(&s->w);
   arrs.push_back(reinterpret_cast<double **>(&s->id));
-  for (int d = 0; d < D; ++d) arrs.push_back(&s->xold[d]);
-  for (int q = 0; q < 3; ++q) arrs.push_back(&s->vold[q]);
-  for (size_t a0 = 0; a0 < arrs.size(); a0 += 4) {
-    PermuteSet ps;
-    ps.count = (int)std::min<size_t>(4, arrs.size() - a0);
-    for (int a = 0; a < ps.count; ++a) {
-      ps.in[a] = *arrs[a0 + a];
-      ps.out[a] = s->spare[a];
-    }
-    KTimer t("bin_permute");
-    k_permute<<<nb(n), 256, 0, c.stream>>>(ps, s->perm, n);
-    for (int a = 0; a < ps.count; ++a) {
-      double *old = *arrs[a0 + a];
-      *arrs[a0 + a] = s->spare[a];
-      s->spare[a] = old;
-    }
+  if (gather_arrays(s, arrs, s->perm)) return PGPU_ERR_CUDA;
+  if (!s->old_perm || s->old_perm_cap < s->cap) {
+    if (s->old_perm) cudaFree(s->old_perm);
+    PGPU_CUDA(cudaMalloc(&s->old_perm, s->cap * sizeof(int)));
+    s->old_perm_cap = s->cap;
   }
+  std::swap(s->perm, s->old_perm);
+  s->pos_old_pending = s->vel_old_pending = true;
   s->binned = true;
   return 0;
 }
@@ -526,6 +598,7 @@ int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi) {
   const pgpu_grid_s *g = s->grid;
   const long n = s->n;
   if (n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   cudaStream_t st = ctx().stream;
   for (int d = 0; d < g->desc.D; ++d) {
     const double left = g->geo.le[d], right = g->geo.re[d];
@@ -539,6 +612,45 @@ int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi) {
       k_bc_symmetry<<<nb(n), 256, 0, st>>>(s->x[d], s->xold[d], s->v[d], s->vold[d], n, left, right, do_lo, do_hi);
     }
   }
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_finish_implicit_step(pgpu_species_t s, const int *bc_lo, const int *bc_hi) {
+  NEED_INIT();
+  if (!s || !bc_lo || !bc_hi) return PGPU_ERR_ARG;
+  const pgpu_grid_s *g = s->grid;
+  bool fusable = true;
+  for (int d = 0; d < g->desc.D; ++d) {
+    if (bc_lo[d] == PGPU_BC_SYMMETRY || bc_hi[d] == PGPU_BC_SYMMETRY) fusable = false;
+    if ((bc_lo[d] == PGPU_BC_PERIODIC) != (bc_hi[d] == PGPU_BC_PERIODIC)) fusable = false;
+  }
+  if (!fusable) {
+    int rc = pgpu_advance_velocities_2nd_half(s);
+    if (!rc) rc = pgpu_advance_positions_2nd_half(s);
+    if (!rc) rc = pgpu_apply_bcs(s, bc_lo, bc_hi);
+    return rc;
+  }
+  if (s->n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  FinishArgs a;
+  for (int d = 0; d < 2; ++d) {
+    a.x[d] = s->x[d];
+    a.xold[d] = s->xold[d];
+    a.periodic[d] = d < g->desc.D && bc_lo[d] == PGPU_BC_PERIODIC;
+    a.left[d] = g->geo.le[d];
+    a.right[d] = g->geo.re[d];
+  }
+  for (int c = 0; c < 3; ++c) {
+    a.v[c] = s->v[c];
+    a.vold[c] = s->vold[c];
+  }
+  a.n = s->n;
+  a.D = g->desc.D;
+  a.motion = s->desc.motion;
+  a.forces = s->desc.forces;
+  KTimer t("finish_step");
+  k_finish_step<<<nb(s->n), 256, 0, ctx().stream>>>(a);
   s->binned = false;
   return 0;
 }

@@ -159,6 +159,12 @@ struct pgpu_species_s {
   int *cell_count = nullptr;   // [ncell_box+1]
   int *cell_start = nullptr;   // [ncell_box+2]
   bool binned = false;
+  // lazy permutation of the *old* arrays: the cell sort gathers x, v, w, id at once and leaves
+  // xold / vold in the previous order until somebody reads them (materialize_old); an
+  // updateOldParticle* call in between simply overwrites them and drops the pending gather
+  int *old_perm = nullptr;
+  size_t old_perm_cap = 0;
+  bool pos_old_pending = false, vel_old_pending = false;
   int *key_sorted = nullptr;        // [n] sorted (4*cell+quadrant) keys of the last bin
   double *spare[4] = {nullptr, nullptr, nullptr, nullptr};  // gather targets of the cell sort
   size_t sort_cap = 0;
@@ -195,6 +201,7 @@ int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f);
 int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi);
 
 // launchers implemented in the kernel translation units
+int materialize_old(pgpu_species_s *s);
 int launch_gather(pgpu_species_s *s);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);

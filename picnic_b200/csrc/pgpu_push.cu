@@ -246,6 +246,7 @@ static int launch_gather_d(pgpu_species_s *s) {
 
 int launch_gather(pgpu_species_s *s) {
   if (s->n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   return s->grid->desc.D == 1 ? launch_gather_d<1>(s) : launch_gather_d<2>(s);
 }
 
@@ -279,6 +280,7 @@ static int launch_deposit_d(pgpu_species_s *s) {
 
 int launch_deposit_current(pgpu_species_s *s, double /*cnormDt*/) {
   if (s->n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   return s->grid->desc.D == 1 ? launch_deposit_d<1>(s) : launch_deposit_d<2>(s);
 }
 
@@ -324,6 +326,7 @@ static int launch_advance_d(pgpu_species_s *s, const AdvanceParams &prm, bool fu
 // first; this generic visitor kernel then handles only the particles it deferred.
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit) {
   if (s->n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   bool deferred = false;
   if (ctx().use_fast_cc1) {
     const int fr = launch_advance_cc1_fast(s, prm, fuse_deposit);
