@@ -60,244 +60,12 @@ struct FastArgs {
   int *list;                // deferred particle indices
   unsigned *list_count;
   Counters *cnt;
+  // coefficient tables of the selected field slot (k_build_tables)
+  const double *tdual, *tnode;
+  int tlo[2], tn0;
+  double tol[2];            // rtol * dx
+  const int4 *tile_box;     // per tile: dual-cell window (i, j, columns, rows) staged in shared memory
 };
-
-// One particle through all its particle-Picard passes on the single-segment fast path.
-// Returns false (and leaves xb/ub untouched in memory terms: the caller does not store)
-// when the particle has to be redone by the generic kernel.  On success c[0..20] holds
-// its current contributions relative to its dual cell `key`.
-template <bool DEP>
-__device__ __forceinline__ bool advance_one(const FastArgs &A, const double (&xo)[2], double (&xb)[2],
-                                            const double (&uo)[3], double (&ub)[3], double wp,
-                                            unsigned &apply, unsigned &unconv, unsigned &key,
-                                            double (&c)[NSLOT]) {
-  // dual cell of x_old (bit-exact index_old of the reference) and normalised offset
-  int i0[2];
-  double dO[2];
-  bool ok = true;
-#pragma unroll
-  for (int d = 0; d < 2; ++d) {
-    const double xr = __dsub_rn(xo[d], A.le[d]);
-    i0[d] = floor_div_fast(__dsub_rn(xr, A.hdx[d]), A.dx[d], A.rdx[d]);
-    dO[d] = fma(xr, A.rdx[d], -(double)(i0[d] + 1));
-    if (i0[d] < A.i_lo[d] || i0[d] > A.i_hi[d]) ok = false;
-  }
-  if (!ok) return false;
-
-  // ---- per-particle loads: in-plane E stencil and Bz ----------------------------------
-  double ex[3], dex[3], ey[3], dey[3];
-  {
-    const double *p = A.F[0] + (i0[0] + i0[1] * A.fn0[0]);
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const double v0 = __ldg(p + b * A.fn0[0]);
-      const double v1 = __ldg(p + b * A.fn0[0] + 1);
-      ex[b] = v0;
-      dex[b] = v1 - v0;
-    }
-  }
-  {
-    const double *p = A.F[1] + (i0[0] + i0[1] * A.fn0[1]);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const double v0 = __ldg(p + a);
-      const double v1 = __ldg(p + a + A.fn0[1]);
-      ey[a] = v0;
-      dey[a] = v1 - v0;
-    }
-  }
-  double bz0, bz1, bz2, bz3;
-  {
-    const double *p = A.F[5] + (i0[0] + i0[1] * A.fn0[5]);
-    const double v00 = __ldg(p), v10 = __ldg(p + 1);
-    const double v01 = __ldg(p + A.fn0[5]), v11 = __ldg(p + A.fn0[5] + 1);
-    bz0 = v00;
-    bz1 = v10 - v00;
-    bz2 = v01 - v00;
-    bz3 = (v11 - v01) - bz1;
-  }
-  const double *pEz = A.F[2] + (i0[0] + i0[1] * A.fn0[2]);
-  const double *pBx = A.F[3] + (i0[0] + i0[1] * A.fn0[3]);
-  const double *pBy = A.F[4] + (i0[0] + i0[1] * A.fn0[4]);
-  double pO[2][2];
-#pragma unroll
-  for (int d = 0; d < 2; ++d) {
-    const double a = 0.5 - dO[d], b = 0.5 + dO[d];
-    pO[d][0] = a * a;
-    pO[d][1] = b * b;
-  }
-
-  // ---- particle-Picard loop (stepNormTransfer semantics, :658-733) -----------------------
-  double dB[2];
-  bool recheck = true;   // xbar moved after the last gather
-  int iter = 0;
-  unsigned napply = 0, nunconv = 0;
-  while (true) {
-    double dxp0[2], dN[2];
-    bool same = true;
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      dxp0[d] = xb[d] - xo[d];
-      dB[d] = fma(dxp0[d], A.rdx[d], dO[d]);
-      dN[d] = fma(2.0, dB[d], -dO[d]);
-      if (!(fabs(dN[d]) < 0.5 - BAND)) {
-        // guard band: let the reference's floor decide (and catch real crossings)
-        const double xn = fma(2.0, xb[d], -xo[d]);
-        const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
-        if (in != i0[d]) same = false;
-      }
-    }
-    if (!same) return false;
-    const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
-    double Wx[3], Wy[3];
-    {
-      const double a0 = 0.5 - dN[0], b0 = 0.5 + dN[0];
-      Wx[0] = 0.25 * fma(a0, a0, pO[0][0]);
-      Wx[2] = 0.25 * fma(b0, b0, pO[0][1]);
-      Wx[1] = (1.0 - Wx[0]) - Wx[2];
-      const double a1 = 0.5 - dN[1], b1 = 0.5 + dN[1];
-      Wy[0] = 0.25 * fma(a1, a1, pO[1][0]);
-      Wy[2] = 0.25 * fma(b1, b1, pO[1][1]);
-      Wy[1] = (1.0 - Wy[0]) - Wy[2];
-    }
-    double E[3], B[3];
-    E[0] = Wy[0] * fma(del0, dex[0], ex[0]);
-    E[0] = fma(Wy[1], fma(del0, dex[1], ex[1]), E[0]);
-    E[0] = fma(Wy[2], fma(del0, dex[2], ex[2]), E[0]);
-    E[1] = Wx[0] * fma(del1, dey[0], ey[0]);
-    E[1] = fma(Wx[1], fma(del1, dey[1], ey[1]), E[1]);
-    E[1] = fma(Wx[2], fma(del1, dey[2], ey[2]), E[1]);
-    // nodal CIC at xbar: node pair (i0+s, i0+s+1), fraction f
-    const int sx = del0 >= 0.5 ? 1 : 0, sy = del1 >= 0.5 ? 1 : 0;
-    const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
-    {
-      const double *p = pEz + (sx + sy * A.fn0[2]);
-      const double v00 = __ldg(p), v10 = __ldg(p + 1);
-      const double v01 = __ldg(p + A.fn0[2]), v11 = __ldg(p + A.fn0[2] + 1);
-      const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
-      E[2] = fma(fy, t1 - t0, t0);
-    }
-    {  // Bx: nodal in x, cell-centred in y
-      const double *p = pBx + sx;
-      const double v00 = __ldg(p), v10 = __ldg(p + 1);
-      const double v01 = __ldg(p + A.fn0[3]), v11 = __ldg(p + A.fn0[3] + 1);
-      const double t0 = fma(fx, v10 - v00, v00), t1 = fma(fx, v11 - v01, v01);
-      B[0] = fma(del1, t1 - t0, t0);
-    }
-    {  // By: cell-centred in x, nodal in y
-      const double *p = pBy + sy * A.fn0[4];
-      const double v00 = __ldg(p), v10 = __ldg(p + 1);
-      const double v01 = __ldg(p + A.fn0[4]), v11 = __ldg(p + A.fn0[4] + 1);
-      const double t0 = fma(del0, v10 - v00, v00), t1 = fma(del0, v11 - v01, v01);
-      B[1] = fma(fy, t1 - t0, t0);
-    }
-    B[2] = fma(del1, fma(del0, bz3, bz2), fma(del0, bz1, bz0));
-
-    // Boris half step (PicSpeciesUtils.cpp:8-101)
-    {
-      const double vm0 = fma(A.alpha, E[0], uo[0]), vm1 = fma(A.alpha, E[1], uo[1]),
-                   vm2 = fma(A.alpha, E[2], uo[2]);
-      const double b0 = A.alpha * B[0], b1 = A.alpha * B[1], b2 = A.alpha * B[2];
-      const double den = fma(b2, b2, fma(b1, b1, fma(b0, b0, 1.0)));
-      const double p0 = fma(vm1, b2, vm0) - vm2 * b1;
-      const double p1 = fma(vm2, b0, vm1) - vm0 * b2;
-      const double p2 = fma(vm0, b1, vm2) - vm1 * b0;
-      const double rden = 1.0 / den;
-      ub[0] = fma(fma(p1, b2, -(p2 * b1)), rden, vm0);
-      ub[1] = fma(fma(p2, b0, -(p0 * b2)), rden, vm1);
-      ub[2] = fma(fma(p0, b1, -(p1 * b0)), rden, vm2);
-    }
-    napply += 1;
-    if (A.iter_max < 0) {  // advanceParticles (:1594-1612), part_order_swap == false
-      xb[0] = fma(ub[0], A.hdt, xo[0]);
-      xb[1] = fma(ub[1], A.hdt, xo[1]);
-      break;
-    }
-    const double dxp_0 = ub[0] * A.hdt, dxp_1 = ub[1] * A.hdt;
-    const double rel = fmax(fabs(dxp0[0] - dxp_0) * A.rdx[0], fabs(dxp0[1] - dxp_1) * A.rdx[1]);
-    if (iter == 0) {
-      xb[0] = xo[0] + dxp_0;
-      xb[1] = xo[1] + dxp_1;
-      if (!(rel >= A.rtol)) break;
-    } else {
-      if (rel < A.rtol) {
-        recheck = false;   // reverse pass: xbar is the one the weights were built from
-        break;
-      }
-      xb[0] = xo[0] + dxp_0;
-      xb[1] = xo[1] + dxp_1;
-    }
-    if (iter >= A.iter_max) {
-      nunconv = 1;
-      break;
-    }
-    iter += 1;
-  }
-
-  if (recheck) {
-    // xbar changed after the last gather: the orbit must still be single-segment
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const double dxp0 = xb[d] - xo[d];
-      dB[d] = fma(dxp0, A.rdx[d], dO[d]);
-      const double dN = fma(2.0, dB[d], -dO[d]);
-      if (!(fabs(dN) < 0.5 - BAND)) {
-        const double xn = fma(2.0, xb[d], -xo[d]);
-        const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
-        if (in != i0[d]) ok = false;
-      }
-    }
-    if (!ok) return false;
-  }
-  apply += napply;
-  unconv += nunconv;
-
-  if (DEP) {
-    key = ((unsigned)(i0[1] + 32768) << 16) | (unsigned)(i0[0] + 32768);
-    const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
-    const double dN0 = fma(2.0, dB[0], -dO[0]), dN1 = fma(2.0, dB[1], -dO[1]);
-    double Wx[3], Wy[3];
-    {
-      const double a0 = 0.5 - dN0, b0 = 0.5 + dN0;
-      Wx[0] = 0.25 * fma(a0, a0, pO[0][0]);
-      Wx[2] = 0.25 * fma(b0, b0, pO[0][1]);
-      Wx[1] = (1.0 - Wx[0]) - Wx[2];
-      const double a1 = 0.5 - dN1, b1 = 0.5 + dN1;
-      Wy[0] = 0.25 * fma(a1, a1, pO[1][0]);
-      Wy[2] = 0.25 * fma(b1, b1, pO[1][1]);
-      Wy[1] = (1.0 - Wy[0]) - Wy[2];
-    }
-    const double rhop = wp * A.rvolume;
-    const double jx = ub[0] * rhop, jy = ub[1] * rhop, jz = ub[2] * rhop;
-    // Jx(i0+a, j0+b), a<2, b<3  -> slot a + 2 b
-    const double jx1 = jx * del0, jx0 = jx - jx1;
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      c[0 + 2 * b] = jx0 * Wy[b];
-      c[1 + 2 * b] = jx1 * Wy[b];
-    }
-    // Jy(i0+a, j0+b), a<3, b<2  -> slot 6 + a + 3 b
-    const double jy1 = jy * del1, jy0 = jy - jy1;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      c[6 + a] = jy0 * Wx[a];
-      c[9 + a] = jy1 * Wx[a];
-    }
-    // Jz nodal CIC at xbar over nodes i0..i0+2 x j0..j0+2 -> slot 12 + a + 3 b
-    double nx[3], ny[3];
-    if (del0 >= 0.5) { nx[0] = 0.0; nx[1] = 1.5 - del0; nx[2] = del0 - 0.5; }
-    else             { nx[0] = 0.5 - del0; nx[1] = del0 + 0.5; nx[2] = 0.0; }
-    if (del1 >= 0.5) { ny[0] = 0.0; ny[1] = 1.5 - del1; ny[2] = del1 - 0.5; }
-    else             { ny[0] = 0.5 - del1; ny[1] = del1 + 0.5; ny[2] = 0.0; }
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const double t = jz * ny[b];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) c[12 + a + 3 * b] = t * nx[a];
-    }
-  }
-  return true;
-}
 
 // 21 fp64 REDs of one accumulator set into the J arrays at dual cell `key`
 __device__ __forceinline__ void flush_direct(const FastArgs &A, unsigned key, const double (&acc)[NSLOT]) {
@@ -325,160 +93,6 @@ __device__ __forceinline__ void flush_direct(const FastArgs &A, unsigned key, co
       for (int a = 0; a < 3; ++a) atomicAdd(p + a + b * A.jn0[2], acc[12 + a + 3 * b]);
   }
 }
-
-// PAIRS x 2 consecutive particles per thread (128-bit loads/stores), processed one after the
-// other; their contributions accumulate in registers while the dual cell stays the same.
-template <bool DEP, int PAIRS, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d(const FastArgs A) {
-  constexpr int P = 2 * PAIRS;
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long base = t * P;
-  const int lane = threadIdx.x & 31;
-  unsigned apply = 0, unconv = 0;
-  unsigned acc_key = NOKEY;
-  double acc[NSLOT];
-#pragma unroll
-  for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
-  unsigned defer_mask = 0;
-
-#pragma unroll 1
-  for (int pr = 0; pr < PAIRS; ++pr) {
-    const long i = base + 2 * pr;
-    if (i >= A.n) break;
-    const bool two = i + 1 < A.n;
-    double2 xo0, xo1, xb0, xb1, u0, u1, u2, w2;
-    if (two) {
-      xo0 = *reinterpret_cast<const double2 *>(A.xo[0] + i);
-      xo1 = *reinterpret_cast<const double2 *>(A.xo[1] + i);
-      xb0 = *reinterpret_cast<const double2 *>(A.xb[0] + i);
-      xb1 = *reinterpret_cast<const double2 *>(A.xb[1] + i);
-      u0 = *reinterpret_cast<const double2 *>(A.uo[0] + i);
-      u1 = *reinterpret_cast<const double2 *>(A.uo[1] + i);
-      u2 = *reinterpret_cast<const double2 *>(A.uo[2] + i);
-      w2 = *reinterpret_cast<const double2 *>(A.w + i);
-    } else {
-      xo0 = make_double2(A.xo[0][i], 0.0);
-      xo1 = make_double2(A.xo[1][i], 0.0);
-      xb0 = make_double2(A.xb[0][i], 0.0);
-      xb1 = make_double2(A.xb[1][i], 0.0);
-      u0 = make_double2(A.uo[0][i], 0.0);
-      u1 = make_double2(A.uo[1][i], 0.0);
-      u2 = make_double2(A.uo[2][i], 0.0);
-      w2 = make_double2(A.w[i], 0.0);
-    }
-    double2 ob0 = xb0, ob1 = xb1, ov0 = u0, ov1 = u1, ov2 = u2;   // outputs (xbar, ubar)
-    bool okA = false, okB = false;
-    {
-      const double xo[2] = {xo0.x, xo1.x};
-      double xb[2] = {xb0.x, xb1.x};
-      const double uo[3] = {u0.x, u1.x, u2.x};
-      double ub[3] = {0.0, 0.0, 0.0};
-      unsigned key = NOKEY;
-      double c[NSLOT];
-      okA = advance_one<DEP>(A, xo, xb, uo, ub, w2.x, apply, unconv, key, c);
-      if (okA) {
-        ob0.x = xb[0]; ob1.x = xb[1]; ov0.x = ub[0]; ov1.x = ub[1]; ov2.x = ub[2];
-        if (DEP) {
-          if (key != acc_key) {
-            if (acc_key != NOKEY) flush_direct(A, acc_key, acc);
-            acc_key = key;
-#pragma unroll
-            for (int j = 0; j < NSLOT; ++j) acc[j] = c[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < NSLOT; ++j) acc[j] += c[j];
-          }
-        }
-      } else {
-        defer_mask |= 1u << (2 * pr);
-      }
-    }
-    if (two) {
-      const double xo[2] = {xo0.y, xo1.y};
-      double xb[2] = {xb0.y, xb1.y};
-      const double uo[3] = {u0.y, u1.y, u2.y};
-      double ub[3] = {0.0, 0.0, 0.0};
-      unsigned key = NOKEY;
-      double c[NSLOT];
-      okB = advance_one<DEP>(A, xo, xb, uo, ub, w2.y, apply, unconv, key, c);
-      if (okB) {
-        ob0.y = xb[0]; ob1.y = xb[1]; ov0.y = ub[0]; ov1.y = ub[1]; ov2.y = ub[2];
-        if (DEP) {
-          if (key != acc_key) {
-            if (acc_key != NOKEY) flush_direct(A, acc_key, acc);
-            acc_key = key;
-#pragma unroll
-            for (int j = 0; j < NSLOT; ++j) acc[j] = c[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < NSLOT; ++j) acc[j] += c[j];
-          }
-        }
-      } else {
-        defer_mask |= 1u << (2 * pr + 1);
-      }
-    }
-    // a deferred particle keeps its stored (xbar, ubar): the generic kernel restarts from them
-    if (two && okA && okB) {
-      *reinterpret_cast<double2 *>(A.xb[0] + i) = ob0;
-      *reinterpret_cast<double2 *>(A.xb[1] + i) = ob1;
-      *reinterpret_cast<double2 *>(A.ub[0] + i) = ov0;
-      *reinterpret_cast<double2 *>(A.ub[1] + i) = ov1;
-      *reinterpret_cast<double2 *>(A.ub[2] + i) = ov2;
-    } else {
-      if (okA) {
-        A.xb[0][i] = ob0.x; A.xb[1][i] = ob1.x;
-        A.ub[0][i] = ov0.x; A.ub[1][i] = ov1.x; A.ub[2][i] = ov2.x;
-      }
-      if (okB) {
-        A.xb[0][i + 1] = ob0.y; A.xb[1][i + 1] = ob1.y;
-        A.ub[0][i + 1] = ov0.y; A.ub[1][i + 1] = ov1.y; A.ub[2][i + 1] = ov2.y;
-      }
-    }
-  }
-
-  // ---- deferred list ---------------------------------------------------------------------
-  if (defer_mask) {
-    unsigned slot = atomicAdd(A.list_count, (unsigned)__popc(defer_mask));
-#pragma unroll
-    for (int q = 0; q < P; ++q)
-      if (defer_mask & (1u << q)) A.list[slot++] = (int)(base + q);
-  }
-
-  // ---- deposit: segmented warp reduction over runs of equal dual cells, one RED per node
-  //      and run (the particle arrays are cell sorted, so a warp holds a handful of runs)
-  if (DEP) {
-    const unsigned any = __ballot_sync(0xffffffffu, acc_key != NOKEY);
-    if (any) {
-      // runs = maximal stretches of consecutive lanes with the same key (any particle order
-      // is handled: a key that reappears later simply forms another run)
-      const unsigned prev = __shfl_up_sync(0xffffffffu, acc_key, 1);
-      const bool head = (lane == 0) || (prev != acc_key);
-      const unsigned heads = __ballot_sync(0xffffffffu, head);
-      const unsigned above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
-      const int run_end = above ? (__ffs(above) - 1) : 32;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const bool take = lane + off < run_end;
-#pragma unroll
-        for (int j = 0; j < NSLOT; ++j) {
-          const double v = __shfl_down_sync(0xffffffffu, acc[j], off);
-          if (take) acc[j] += v;
-        }
-      }
-      if (head && acc_key != NOKEY) flush_direct(A, acc_key, acc);
-    }
-  }
-
-  // ---- counters ----------------------------------------------------------------------------
-  apply = __reduce_add_sync(0xffffffffu, apply);
-  unconv = __reduce_add_sync(0xffffffffu, unconv);
-  if (lane == 0) {
-    if (apply) atomicAdd(&A.cnt->apply_its, (unsigned long long)apply);
-    if (unconv) atomicAdd(&A.cnt->unconverged, (unsigned long long)unconv);
-  }
-}
-
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UBLKCP, SYNCS) ---------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -514,6 +128,9 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
                "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void l2_prefetch(const void *src_gmem, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -522,159 +139,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 constexpr int TP = 4;                 // consecutive particles per thread
 constexpr int TILE = BLOCK * TP;      // particles per tile
 constexpr int NIN = 8;                // xo0 xo1 xb0 xb1 uo0 uo1 uo2 w
-constexpr int STAGES = 2;
-constexpr size_t TMA_SMEM = (size_t)STAGES * NIN * TILE * sizeof(double) + 64;
-
-// Persistent, double-buffered version: each block walks tiles of TILE consecutive particles.
-// One thread issues eight 1D TMA bulk copies per tile (the SoA slices of that tile) into a
-// shared-memory stage and arms an mbarrier; while the block computes tile k the copies of
-// tile k+1 are in flight, so no warp ever waits on HBM latency and the particle data never
-// occupies registers before it is used.  Results (xbar in place, ubar over the u_old slots)
-// leave through TMA bulk stores.  Thread t owns particles 4t..4t+3 of the tile (visited in a
-// lane-rotated order so that the 8-byte shared loads are bank-conflict free).
-template <bool DEP>
-__global__ void __launch_bounds__(BLOCK, 3) k_advance_cc1_2d_tma(const FastArgs A, int ntiles) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *sm = reinterpret_cast<double *>(smem_raw);                       // [STAGES][NIN][TILE]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + STAGES * NIN * TILE);  // [STAGES]
-  const int tid = threadIdx.x, lane = tid & 31;
-  const double *src[NIN] = {A.xo[0], A.xo[1], A.xb[0], A.xb[1], A.uo[0], A.uo[1], A.uo[2], A.w};
-
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  auto issue_load = [&](int tile, int stage) {
-    mbar_expect_tx(&bars[stage], NIN * TILE * (unsigned)sizeof(double));
-    const long off = (long)tile * TILE;
-#pragma unroll
-    for (int a = 0; a < NIN; ++a)
-      bulk_g2s(sm + ((size_t)stage * NIN + a) * TILE, src[a] + off, TILE * (unsigned)sizeof(double), &bars[stage]);
-  };
-  int tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) issue_load(tile, 0);
-
-  unsigned apply = 0, unconv = 0;
-  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
-    const int stage = it & 1;
-    const unsigned parity = (it >> 1) & 1;
-    if (tid == 0) {
-      const int next = tile + gridDim.x;
-      if (next < ntiles) {
-        bulk_wait_read0();   // the stores that read the other stage have drained
-        issue_load(next, stage ^ 1);
-      }
-    }
-    mbar_wait(&bars[stage], parity);
-    double *st = sm + (size_t)stage * NIN * TILE;
-    const long tbase = (long)tile * TILE;
-    const int nvalid = (A.n - tbase) < TILE ? (int)(A.n - tbase) : TILE;
-
-    unsigned acc_key = NOKEY;
-    double acc[NSLOT];
-#pragma unroll
-    for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
-    unsigned defer_mask = 0;
-#pragma unroll 1
-    for (int qq = 0; qq < TP; ++qq) {
-      const int q = (qq + (lane >> 2)) & (TP - 1);
-      const int k = tid * TP + q;
-      if (k >= nvalid) continue;
-      const double xo[2] = {st[0 * TILE + k], st[1 * TILE + k]};
-      double xb[2] = {st[2 * TILE + k], st[3 * TILE + k]};
-      const double uo[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
-      const double wp = st[7 * TILE + k];
-      double ub[3] = {0.0, 0.0, 0.0};
-      unsigned key = NOKEY;
-      double c[NSLOT];
-      if (advance_one<DEP>(A, xo, xb, uo, ub, wp, apply, unconv, key, c)) {
-        st[2 * TILE + k] = xb[0];
-        st[3 * TILE + k] = xb[1];
-        st[4 * TILE + k] = ub[0];
-        st[5 * TILE + k] = ub[1];
-        st[6 * TILE + k] = ub[2];
-        if (DEP) {
-          if (key != acc_key) {
-            if (acc_key != NOKEY) flush_direct(A, acc_key, acc);
-            acc_key = key;
-#pragma unroll
-            for (int j = 0; j < NSLOT; ++j) acc[j] = c[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < NSLOT; ++j) acc[j] += c[j];
-          }
-        }
-      } else {
-        // deferred: xbar stays as stored (the generic kernel restarts from it); the ubar slot
-        // keeps u_old, which that kernel overwrites
-        defer_mask |= 1u << q;
-      }
-    }
-    // results -> global
-    if (nvalid == TILE) {
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-#pragma unroll
-        for (int a = 0; a < 2; ++a) bulk_s2g(A.xb[a] + tbase, st + (2 + a) * TILE, TILE * (unsigned)sizeof(double));
-#pragma unroll
-        for (int a = 0; a < 3; ++a) bulk_s2g(A.ub[a] + tbase, st + (4 + a) * TILE, TILE * (unsigned)sizeof(double));
-        bulk_commit();
-      }
-    } else {
-      // ragged last tile: plain stores of the valid particles only
-#pragma unroll 1
-      for (int q = 0; q < TP; ++q) {
-        const int k = tid * TP + q;
-        if (k < nvalid && !(defer_mask & (1u << q))) {
-          A.xb[0][tbase + k] = st[2 * TILE + k];
-          A.xb[1][tbase + k] = st[3 * TILE + k];
-          A.ub[0][tbase + k] = st[4 * TILE + k];
-          A.ub[1][tbase + k] = st[5 * TILE + k];
-          A.ub[2][tbase + k] = st[6 * TILE + k];
-        }
-      }
-      __syncthreads();
-    }
-    if (defer_mask) {
-      unsigned slot = atomicAdd(A.list_count, (unsigned)__popc(defer_mask));
-#pragma unroll
-      for (int q = 0; q < TP; ++q)
-        if (defer_mask & (1u << q)) A.list[slot++] = (int)(tbase + tid * TP + q);
-    }
-    if (DEP) {
-      const unsigned any = __ballot_sync(0xffffffffu, acc_key != NOKEY);
-      if (any) {
-        const unsigned prev = __shfl_up_sync(0xffffffffu, acc_key, 1);
-        const bool head = (lane == 0) || (prev != acc_key);
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        const unsigned above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
-        const int run_end = above ? (__ffs(above) - 1) : 32;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const bool take = lane + off < run_end;
-#pragma unroll
-          for (int j = 0; j < NSLOT; ++j) {
-            const double v = __shfl_down_sync(0xffffffffu, acc[j], off);
-            if (take) acc[j] += v;
-          }
-        }
-        if (head && acc_key != NOKEY) flush_direct(A, acc_key, acc);
-      }
-    }
-  }
-  if (tid == 0) bulk_wait0();   // all bulk stores complete before the block retires
-
-  apply = __reduce_add_sync(0xffffffffu, apply);
-  unconv = __reduce_add_sync(0xffffffffu, unconv);
-  if (lane == 0) {
-    if (apply) atomicAdd(&A.cnt->apply_its, (unsigned long long)apply);
-    if (unconv) atomicAdd(&A.cnt->unconverged, (unsigned long long)unconv);
-  }
-}
-
 
 // =============================================================================================
 // Two-phase tile kernel.  Phase 1 pushes the tile's particles (all particle-Picard passes) and
@@ -1070,6 +534,559 @@ __global__ void __launch_bounds__(BLOCK, 4) k_advance_cc1_2d_tile(const FastArgs
   }
 }
 
+// =============================================================================================
+// Table-driven two-phase tile kernel (the default).
+//
+// All particles of a dual cell read the same stencil, so the stencil algebra that does not
+// depend on the particle is hoisted out of the particle loop into per-cell coefficient tables,
+// rebuilt by k_build_tables whenever the E/B arrays of a field slot change (one thread per
+// cell; the tables of a 512^2 box are 59 MB and stay L2 resident while the sorted particles
+// stream past):
+//   dual record (16 doubles, one per dual cell (i0,j0)):
+//     in-plane E as  E0 = g1 + W0'*G0 + W2'*G2,  g1 = e1 + del0*d1, Gk = Pk + del0*Qk,
+//     with W' = 4 W (the 1/4 of the CC1 weights is folded into P,Q) and W1 = 1 - W0 - W2
+//     eliminated:  [e1 d1 P0 Q0 P2 Q2] for Ex, the same six for Ey, and the four bilinear
+//     coefficients of Bz.
+//   node record (12 doubles, one per index pair (i,j)): bilinear coefficients
+//     c0 + fx c1 + fy c2 + fx fy c3 of Ez over nodes (i..i+1, j..j+1), of Bx (nodal in x,
+//     centred in y) and of By (centred in x, nodal in y).
+// A particle-Picard pass is then 78 fp64 instructions and six 128-bit loads.  Phase 1 leaves
+// the dual-cell key and the normalised offsets (d_old, d_bar) in the shared-memory tile, so the
+// deposit phase does not locate the particle again.
+// =============================================================================================
+constexpr int TD = 16, TN = 12;
+
+struct TabArgs {
+  const double *F[6];   // origin-shifted like FastArgs::F
+  int fn0[6];
+  int lo[2], n0, n1;    // records for indices lo .. lo+n-1 in either direction
+  double *dual, *node;
+};
+
+__global__ void __launch_bounds__(128) k_build_tables(const TabArgs T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T.n0 * T.n1) return;
+  const int i = T.lo[0] + t % T.n0, j = T.lo[1] + t / T.n0;
+  auto at = [&](int c, int a, int b) { return __ldg(T.F[c] + ((i + a) + (long)(j + b) * T.fn0[c])); };
+  auto bilinear = [&](int c, double *o) {
+    const double v00 = at(c, 0, 0), v10 = at(c, 1, 0), v01 = at(c, 0, 1), v11 = at(c, 1, 1);
+    o[0] = v00;
+    o[1] = v10 - v00;
+    o[2] = v01 - v00;
+    o[3] = (v11 - v01) - (v10 - v00);
+  };
+  double rec[TD];
+  bilinear(2, rec);        // Ez
+  bilinear(3, rec + 4);    // Bx
+  bilinear(4, rec + 8);    // By
+  double2 *dn = reinterpret_cast<double2 *>(T.node + (size_t)t * TN);
+#pragma unroll
+  for (int k = 0; k < TN / 2; ++k) dn[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+  // the dual record needs one more row/column of Ex, Ey: only for true dual cells
+  if (t % T.n0 == T.n0 - 1 || t / T.n0 == T.n1 - 1) return;
+  {
+    // Ex(i+a, j+b), a<2, b<3: value at a=0 and x-difference per row b
+    double e[3], d[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      e[b] = at(0, 0, b);
+      d[b] = at(0, 1, b) - e[b];
+    }
+    rec[0] = e[1];
+    rec[1] = d[1];
+    rec[2] = 0.25 * (e[0] - e[1]);
+    rec[3] = 0.25 * (d[0] - d[1]);
+    rec[4] = 0.25 * (e[2] - e[1]);
+    rec[5] = 0.25 * (d[2] - d[1]);
+  }
+  {
+    // Ey(i+a, j+b), a<3, b<2: value at b=0 and y-difference per column a
+    double e[3], d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      e[a] = at(1, a, 0);
+      d[a] = at(1, a, 1) - e[a];
+    }
+    rec[6] = e[1];
+    rec[7] = d[1];
+    rec[8] = 0.25 * (e[0] - e[1]);
+    rec[9] = 0.25 * (d[0] - d[1]);
+    rec[10] = 0.25 * (e[2] - e[1]);
+    rec[11] = 0.25 * (d[2] - d[1]);
+  }
+  bilinear(5, rec + 12);   // Bz
+  double2 *dd = reinterpret_cast<double2 *>(T.dual + (size_t)t * TD);
+#pragma unroll
+  for (int k = 0; k < TD / 2; ++k) dd[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+}
+
+__device__ __forceinline__ unsigned hi_abs(double x) { return (unsigned)__double2hiint(x) & 0x7fffffffu; }
+// hi word of the doubles in [0.5 - 2^-22, 0.5): |x| with a smaller hi word is < 0.5 - 2.3e-7
+constexpr unsigned HI_HALF_BAND = 0x3fdfffffu;
+
+// 1/den for den >= 1: MUFU.RCP64H seed + two Newton steps (full double precision, no
+// special-case branch; den = 1 + |b|^2 is never 0, inf or denormal for finite fields)
+__device__ __forceinline__ double rcp_ge1(double den) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  double e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// 128-bit load through a generic pointer (the table window lives in shared memory, or in
+// global memory for particles outside the window)
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+
+struct TabWindow {
+  const double *dual, *node;   // record (i0, j0) of the window origin
+  int i, j, ncol, nrow;        // dual-cell window
+  int drow, nrow_stride;       // doubles between rows of the dual / node records
+};
+
+// Phase 1 with the coefficient tables.  On success key/dO/dB describe the final orbit.
+__device__ __forceinline__ bool push_tab(const FastArgs &A, const TabWindow &Wn, const double (&xo)[2],
+                                         double (&xb)[2], const double (&uo)[3], double (&ub)[3],
+                                         unsigned &key, double (&dO)[2], double (&dB)[2], unsigned &apply,
+                                         unsigned &unconv) {
+  int i0[2];
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double xr = __dsub_rn(xo[d], A.le[d]);
+    i0[d] = floor_div_fast(__dsub_rn(xr, A.hdx[d]), A.dx[d], A.rdx[d]);
+    dO[d] = fma(xr, A.rdx[d], -(double)(i0[d] + 1));
+    if (i0[d] < A.i_lo[d] || i0[d] > A.i_hi[d]) ok = false;
+  }
+  if (!ok) return false;
+  key = ((unsigned)(i0[1] + 32768) << 16) | (unsigned)(i0[0] + 32768);
+  const double *td, *tn;
+  int nrow;
+  {
+    const unsigned wi = (unsigned)(i0[0] - Wn.i), wj = (unsigned)(i0[1] - Wn.j);
+    if (wi < (unsigned)Wn.ncol && wj < (unsigned)Wn.nrow) {
+      td = Wn.dual + (wi * TD + wj * Wn.drow);
+      tn = Wn.node + (wi * TN + wj * Wn.nrow_stride);
+      nrow = Wn.nrow_stride;
+    } else {
+      const int cidx = (i0[0] - A.tlo[0]) + (i0[1] - A.tlo[1]) * A.tn0;
+      td = A.tdual + (size_t)cidx * TD;
+      tn = A.tnode + (size_t)cidx * TN;
+      nrow = A.tn0 * TN;
+    }
+  }
+  const double2 x01 = ld2(td), x23 = ld2(td + 2), x45 = ld2(td + 4);      // Ex: e1 d1 | P0 Q0 | P2 Q2
+  const double2 y01 = ld2(td + 6), y23 = ld2(td + 8), y45 = ld2(td + 10);  // Ey
+  const double2 z01 = ld2(td + 12), z23 = ld2(td + 14);                     // Bz c0 c1 | c2 c3
+  double pO[2][2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double a = 0.5 - dO[d], b = 0.5 + dO[d];
+    pO[d][0] = a * a;
+    pO[d][1] = b * b;
+  }
+
+  int iter = 0;
+  bool done = false;
+  unsigned napply = 0, nunconv = 0;
+  while (true) {
+    double dxp0[2], dN[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      dxp0[d] = xb[d] - xo[d];
+      dB[d] = fma(dxp0[d], A.rdx[d], dO[d]);
+      dN[d] = fma(2.0, dB[d], -dO[d]);
+    }
+    if (!(hi_abs(dN[0]) < HI_HALF_BAND && hi_abs(dN[1]) < HI_HALF_BAND)) {
+      // near (or past) a dual-cell face: the reference's own floor decides
+      bool same = true;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const double xn = fma(2.0, xb[d], -xo[d]);
+        const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
+        if (in != i0[d]) same = false;
+      }
+      if (!same) return false;
+    }
+    if (done) break;
+    const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
+    double E[3], B[3];
+    {
+      const double a0 = 0.5 - dN[0], b0 = 0.5 + dN[0], a1 = 0.5 - dN[1], b1 = 0.5 + dN[1];
+      const double Wx0 = fma(a0, a0, pO[0][0]), Wx2 = fma(b0, b0, pO[0][1]);   // 4 W
+      const double Wy0 = fma(a1, a1, pO[1][0]), Wy2 = fma(b1, b1, pO[1][1]);
+      E[0] = fma(Wy0, fma(del0, x23.y, x23.x), fma(Wy2, fma(del0, x45.y, x45.x), fma(del0, x01.y, x01.x)));
+      E[1] = fma(Wx0, fma(del1, y23.y, y23.x), fma(Wx2, fma(del1, y45.y, y45.x), fma(del1, y01.y, y01.x)));
+    }
+    {
+      // nodal CIC at xbar: node pair (i0+s, i0+s+1), fraction f
+      const bool sx = del0 >= 0.5, sy = del1 >= 0.5;
+      const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
+      const int ox = sx ? TN : 0, oy = sy ? nrow : 0;
+      const double2 ez01 = ld2(tn + ox + oy), ez23 = ld2(tn + ox + oy + 2);
+      const double2 bx01 = ld2(tn + ox + 4), bx23 = ld2(tn + ox + 6);
+      const double2 by01 = ld2(tn + oy + 8), by23 = ld2(tn + oy + 10);
+      E[2] = fma(fy, fma(fx, ez23.y, ez23.x), fma(fx, ez01.y, ez01.x));
+      B[0] = fma(del1, fma(fx, bx23.y, bx23.x), fma(fx, bx01.y, bx01.x));
+      B[1] = fma(fy, fma(del0, by23.y, by23.x), fma(del0, by01.y, by01.x));
+      B[2] = fma(del1, fma(del0, z23.y, z23.x), fma(del0, z01.y, z01.x));
+    }
+    // Boris half step (PicSpeciesUtils.cpp:8-101)
+    {
+      const double vm0 = fma(A.alpha, E[0], uo[0]), vm1 = fma(A.alpha, E[1], uo[1]),
+                   vm2 = fma(A.alpha, E[2], uo[2]);
+      const double b0 = A.alpha * B[0], b1 = A.alpha * B[1], b2 = A.alpha * B[2];
+      const double den = fma(b2, b2, fma(b1, b1, fma(b0, b0, 1.0)));
+      const double p0 = fma(-vm2, b1, fma(vm1, b2, vm0));
+      const double p1 = fma(-vm0, b2, fma(vm2, b0, vm1));
+      const double p2 = fma(-vm1, b0, fma(vm0, b1, vm2));
+      const double rden = rcp_ge1(den);
+      const double r0 = b0 * rden, r1 = b1 * rden, r2 = b2 * rden;
+      ub[0] = fma(-p2, r1, fma(p1, r2, vm0));
+      ub[1] = fma(-p0, r2, fma(p2, r0, vm1));
+      ub[2] = fma(-p1, r0, fma(p0, r1, vm2));
+    }
+    napply += 1;
+    if (A.iter_max < 0) {  // advanceParticles (:1594-1612), part_order_swap == false
+      xb[0] = fma(ub[0], A.hdt, xo[0]);
+      xb[1] = fma(ub[1], A.hdt, xo[1]);
+      done = true;
+      continue;
+    }
+    // stepNormTransfer (:658-733): |dxp0 - dxp| / dX against rtol, as |dxp0 - dxp| against rtol*dX
+    const double dxp_0 = ub[0] * A.hdt, dxp_1 = ub[1] * A.hdt;
+    const double e0 = fabs(dxp0[0] - dxp_0), e1 = fabs(dxp0[1] - dxp_1);
+    if (iter == 0) {
+      xb[0] = xo[0] + dxp_0;
+      xb[1] = xo[1] + dxp_1;
+      if (!(e0 >= A.tol[0]) && !(e1 >= A.tol[1])) done = true;
+    } else {
+      if (e0 < A.tol[0] && e1 < A.tol[1]) break;  // reverse pass: xbar unchanged, its orbit was checked above
+      xb[0] = xo[0] + dxp_0;
+      xb[1] = xo[1] + dxp_1;
+    }
+    if (!done && iter >= A.iter_max) {
+      nunconv = 1;
+      done = true;
+    }
+    iter += 1;
+  }
+  apply += napply;
+  unconv += nunconv;
+  return true;
+}
+
+// Phase 2: add the 21 node contributions of one pushed particle into acc (FMA form).
+__device__ __forceinline__ void deposit_tab(const FastArgs &A, const double (&dO)[2], const double (&dB)[2],
+                                            const double (&ub)[3], double wp, double (&acc)[NSLOT]) {
+  double W[2][3], n[2][3], del[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double dN = fma(2.0, dB[d], -dO[d]);
+    const double a = 0.5 - dN, b = 0.5 + dN, c = 0.5 - dO[d], e = 0.5 + dO[d];
+    W[d][0] = 0.25 * fma(a, a, c * c);
+    W[d][2] = 0.25 * fma(b, b, e * e);
+    W[d][1] = (1.0 - W[d][0]) - W[d][2];
+    del[d] = dB[d] + 0.5;
+    // nodal CIC at xbar over the three nodes of the dual cell
+    const bool s = del[d] >= 0.5;
+    const double lo = 0.5 - del[d], hi = del[d] - 0.5;     // one of them is the (positive) end weight
+    n[d][0] = s ? 0.0 : lo;
+    n[d][2] = s ? hi : 0.0;
+    n[d][1] = s ? 1.0 - hi : 1.0 - lo;
+  }
+  const double rhop = wp * A.rvolume;
+  const double jx = ub[0] * rhop, jy = ub[1] * rhop, jz = ub[2] * rhop;
+  // Jx(i0+a, j0+b), a<2, b<3  -> slot a + 2 b
+  const double jx1 = jx * del[0], jx0 = jx - jx1;
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    acc[0 + 2 * b] = fma(jx0, W[1][b], acc[0 + 2 * b]);
+    acc[1 + 2 * b] = fma(jx1, W[1][b], acc[1 + 2 * b]);
+  }
+  // Jy(i0+a, j0+b), a<3, b<2  -> slot 6 + a + 3 b
+  const double jy1 = jy * del[1], jy0 = jy - jy1;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    acc[6 + a] = fma(jy0, W[0][a], acc[6 + a]);
+    acc[9 + a] = fma(jy1, W[0][a], acc[9 + a]);
+  }
+  // Jz nodal CIC over nodes i0..i0+2 x j0..j0+2 -> slot 12 + a + 3 b
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const double t = jz * n[1][b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) acc[12 + a + 3 * b] = fma(t, n[0][a], acc[12 + a + 3 * b]);
+  }
+}
+
+constexpr int NTAB = 8;    // xo0->dO0 xo1->dO1 xb0 xb1 u0 u1 u2 w
+constexpr int WMAX = 16;   // widest dual-cell window staged in shared memory (2 rows; node records: 3 rows, +1 column)
+constexpr int SDUAL = 2 * WMAX * TD, SNODE = 3 * (WMAX + 1) * TN;
+constexpr size_t TAB_SMEM =
+    (size_t)(NTAB * TILE + SDUAL + SNODE) * sizeof(double) + TILE * sizeof(unsigned) + 64;
+
+// Window of a tile = the dual cells its particles can sit in if the tile is cell sorted: the
+// cells of its first and last particle bound the rest.  Particles outside the window (unsorted
+// input, or moved since the sort) read the tables from global memory instead -- any order is
+// correct, the sorted one is fast.
+__global__ void k_tile_boxes(const FastArgs A, int ntiles, int4 *box) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const long first = (long)t * TILE;
+  const long last = (first + TILE <= A.n ? first + TILE : A.n) - 1;
+  int c[2][2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const long p = e ? last : first;
+#pragma unroll
+    for (int d = 0; d < 2; ++d)   // primal cell (BinFab::locateBin)
+      c[e][d] = __double2int_rd(__ddiv_rn(__dsub_rn(A.xo[d][p], A.le[d]), A.dx[d]));
+  }
+  int4 b = make_int4(0, 0, 0, 0);
+  if (c[0][1] == c[1][1] && c[1][0] >= c[0][0]) {
+    // dual columns i-1 .. i_last, dual rows j-1 .. j, clipped to the table
+    const int i0 = max(c[0][0] - 1, A.i_lo[0]), i1 = min(c[1][0], A.i_hi[0]);
+    const int j0 = max(c[0][1] - 1, A.i_lo[1]), j1 = min(c[0][1], A.i_hi[1]);
+    if (i1 >= i0 && j1 >= j0 && i1 - i0 + 1 <= WMAX) b = make_int4(i0, j0, i1 - i0 + 1, j1 - j0 + 1);
+  }
+  box[t] = b;
+}
+
+template <bool DEP, int RSTEPS, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastArgs A, int ntiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *st = reinterpret_cast<double *>(smem_raw);                 // [NTAB][TILE]
+  double *sdual = st + NTAB * TILE;                                   // [2][WMAX][TD]
+  double *snode = sdual + SDUAL;                                      // [3][WMAX+1][TN]
+  unsigned *skey = reinterpret_cast<unsigned *>(snode + SNODE);      // [TILE]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(skey + TILE);
+  __shared__ int4 sbox;
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  // window of this block's next tile, fetched one tile ahead by the issuing lanes
+  int nbx = 0, nby = 0, nbz = 0, nbw = 0;
+  auto fetch_box = [&](int t) {
+    const int4 b = __ldg(A.tile_box + t);
+    nbx = b.x;
+    nby = b.y;
+    nbz = b.z;
+    nbw = b.w;
+  };
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (lane == 0 && (int)blockIdx.x < ntiles) fetch_box(blockIdx.x);
+  __syncthreads();
+
+  unsigned apply = 0, unconv = 0;
+  int it = 0;
+#ifdef PGPU_CLOCKS
+  long long ck[6] = {0, 0, 0, 0, 0, 0}, c0, c1;
+#define CK(i) do { c1 = clock64(); ck[i] += c1 - c0; c0 = c1; } while (0)
+  c0 = clock64();
+#else
+#define CK(i)
+#endif
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const long tbase = (long)tile * TILE;
+    if (lane == 0) {
+      // lane 0 of each warp issues a share of the tile's bulk copies (a bulk copy is issued by one
+      // thread; four threads in four warps issue in parallel): warp w loads particle arrays 2w and
+      // 2w+1 -- the ones it stored for the previous tile -- plus rows of the table window
+      const int wp = tid >> 5;
+      if (wp) bulk_wait_read0();   // this thread's stores of the previous tile have read their buffers
+      if (tid == 0) CK(0);
+      const int4 box = make_int4(nbx, nby, nbz, nbw);
+      const unsigned dbytes = (unsigned)box.z * TD * (unsigned)sizeof(double);
+      const unsigned nbytes = (unsigned)(box.z + 1) * TN * (unsigned)sizeof(double);
+      constexpr unsigned BYTES = TILE * (unsigned)sizeof(double);
+      const size_t c0 = (size_t)(box.x - A.tlo[0]) + (size_t)(box.y - A.tlo[1]) * A.tn0;
+      if (wp == 0) {
+        sbox = box;
+        const unsigned tabbytes = box.z ? box.w * dbytes + (box.w + 1) * nbytes : 0u;
+        mbar_expect_tx(bar, NIN * TILE * (unsigned)sizeof(double) + tabbytes);
+        bulk_g2s(st + 0 * TILE, A.xo[0] + tbase, BYTES, bar);
+        bulk_g2s(st + 1 * TILE, A.xo[1] + tbase, BYTES, bar);
+        if (box.z) {
+          for (int r = 0; r < box.w; ++r)
+            bulk_g2s(sdual + r * (WMAX * TD), A.tdual + (c0 + (size_t)r * A.tn0) * TD, dbytes, bar);
+        }
+      } else {
+        if (wp == 1) {
+          bulk_g2s(st + 2 * TILE, A.xb[0] + tbase, BYTES, bar);
+          bulk_g2s(st + 3 * TILE, A.xb[1] + tbase, BYTES, bar);
+        } else if (wp == 2) {
+          bulk_g2s(st + 4 * TILE, A.uo[0] + tbase, BYTES, bar);
+          bulk_g2s(st + 5 * TILE, A.uo[1] + tbase, BYTES, bar);
+        } else {
+          bulk_g2s(st + 6 * TILE, A.uo[2] + tbase, BYTES, bar);
+          bulk_g2s(st + 7 * TILE, A.w + tbase, BYTES, bar);
+        }
+        const int r = wp - 1;   // node-record row of the window
+        if (box.z && r <= box.w)
+          bulk_g2s(snode + r * ((WMAX + 1) * TN), A.tnode + (c0 + (size_t)r * A.tn0) * TN, nbytes, bar);
+      }
+      if (tile + (int)gridDim.x < ntiles) fetch_box(tile + gridDim.x);
+    }
+    if (tid == 0) CK(1);
+    __syncthreads();       // sbox written (and the previous tile's shared-memory reads are over)
+    mbar_wait(bar, (unsigned)(it & 1));
+    if (tid == 0) CK(2);
+    const int nvalid = (A.n - tbase) < TILE ? (int)(A.n - tbase) : TILE;
+    TabWindow Wn;
+    {
+      const int4 box = sbox;
+      Wn.dual = sdual;
+      Wn.node = snode;
+      Wn.i = box.x;
+      Wn.j = box.y;
+      Wn.ncol = box.z;
+      Wn.nrow = box.w;
+      Wn.drow = WMAX * TD;
+      Wn.nrow_stride = (WMAX + 1) * TN;
+    }
+
+    // ---- phase 1: push ------------------------------------------------------------------
+    unsigned defer_mask = 0;
+#pragma unroll 1
+    for (int qq = 0; qq < TP; ++qq) {
+      const int q = (qq + (lane >> 2)) & (TP - 1);
+      const int k = tid * TP + q;
+      unsigned key = NOKEY;
+      if (k < nvalid) {
+        const double xo[2] = {st[0 * TILE + k], st[1 * TILE + k]};
+        double xb[2] = {st[2 * TILE + k], st[3 * TILE + k]};
+        const double uo[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
+        double ub[3] = {0.0, 0.0, 0.0}, dO[2], dB[2];
+        if (push_tab(A, Wn, xo, xb, uo, ub, key, dO, dB, apply, unconv)) {
+          st[0 * TILE + k] = dO[0];
+          st[1 * TILE + k] = dO[1];
+          st[2 * TILE + k] = xb[0];
+          st[3 * TILE + k] = xb[1];
+          st[4 * TILE + k] = ub[0];
+          st[5 * TILE + k] = ub[1];
+          st[6 * TILE + k] = ub[2];
+        } else {
+          // deferred: xbar stays as stored (the generic kernel restarts from it); the ubar slot
+          // keeps u_old, which that kernel overwrites
+          key = NOKEY;
+          defer_mask |= 1u << q;
+        }
+      }
+      skey[k] = key;
+    }
+
+    if (tid == 0) CK(3);
+    // ---- phase 2: deposit (same thread -> particle map: no block barrier needed) ---------
+    if (DEP) {
+      unsigned acc_key = NOKEY;
+      double acc[NSLOT];
+#pragma unroll
+      for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
+#pragma unroll 1
+      for (int qq = 0; qq < TP; ++qq) {
+        const int q = (qq + (lane >> 2)) & (TP - 1);
+        const int k = tid * TP + q;
+        const unsigned key = skey[k];
+        if (key == NOKEY) continue;
+        if (key != acc_key) {
+          if (acc_key != NOKEY) {
+            flush_direct(A, acc_key, acc);
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
+          }
+          acc_key = key;
+        }
+        const double dO[2] = {st[0 * TILE + k], st[1 * TILE + k]};
+        // d_bar from xbar and the dual-cell index (the same value as phase 1's up to rounding)
+        const double dB[2] = {
+            fma(st[2 * TILE + k] - A.le[0], A.rdx[0], -(double)((int)(key & 0xffffu) - 32767)),
+            fma(st[3 * TILE + k] - A.le[1], A.rdx[1], -(double)((int)(key >> 16) - 32767))};
+        const double ub[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
+        deposit_tab(A, dO, dB, ub, st[7 * TILE + k], acc);
+      }
+      const unsigned any = __ballot_sync(0xffffffffu, acc_key != NOKEY);
+      if (any) {
+        // runs = maximal stretches of consecutive lanes with the same key (any particle order
+        // is handled: a key that reappears later simply forms another run)
+        const unsigned prev = __shfl_up_sync(0xffffffffu, acc_key, 1);
+        const bool head = (lane == 0) || (prev != acc_key);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const unsigned above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+        const int run_end = above ? (__ffs(above) - 1) : 32;
+        const int run_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+        for (int sidx = 0; sidx < RSTEPS; ++sidx) {
+          const int off = 1 << sidx;
+          const double take = (lane + off < run_end) ? 1.0 : 0.0;
+#pragma unroll
+          for (int j = 0; j < NSLOT; ++j) acc[j] = fma(__shfl_down_sync(0xffffffffu, acc[j], off), take, acc[j]);
+        }
+        // after RSTEPS steps lane l holds the sum over [l, min(l + 2^RSTEPS, run_end))
+        if (acc_key != NOKEY && (((lane - run_start) & ((1 << RSTEPS) - 1)) == 0)) flush_direct(A, acc_key, acc);
+      }
+    }
+
+    if (tid == 0) CK(4);
+    // ---- results -> global ----------------------------------------------------------------
+    if (nvalid == TILE) {
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) CK(5);
+      if (lane == 0 && tid) {
+        constexpr unsigned BYTES = TILE * (unsigned)sizeof(double);
+        const int wp = tid >> 5;
+        if (wp == 1) {
+          bulk_s2g(A.xb[0] + tbase, st + 2 * TILE, BYTES);
+          bulk_s2g(A.xb[1] + tbase, st + 3 * TILE, BYTES);
+        } else if (wp == 2) {
+          bulk_s2g(A.ub[0] + tbase, st + 4 * TILE, BYTES);
+          bulk_s2g(A.ub[1] + tbase, st + 5 * TILE, BYTES);
+        } else {
+          bulk_s2g(A.ub[2] + tbase, st + 6 * TILE, BYTES);
+        }
+        bulk_commit();
+      }
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < TP; ++q) {
+        const int k = tid * TP + q;
+        if (k < nvalid && !(defer_mask & (1u << q))) {
+          A.xb[0][tbase + k] = st[2 * TILE + k];
+          A.xb[1][tbase + k] = st[3 * TILE + k];
+          A.ub[0][tbase + k] = st[4 * TILE + k];
+          A.ub[1][tbase + k] = st[5 * TILE + k];
+          A.ub[2][tbase + k] = st[6 * TILE + k];
+        }
+      }
+      __syncthreads();
+    }
+    if (defer_mask) {
+      unsigned slot = atomicAdd(A.list_count, (unsigned)__popc(defer_mask));
+#pragma unroll
+      for (int q = 0; q < TP; ++q)
+        if (defer_mask & (1u << q)) A.list[slot++] = (int)(tbase + tid * TP + q);
+    }
+  }
+  if (lane == 0 && tid) bulk_wait0();
+#ifdef PGPU_CLOCKS
+  if (tid == 0 && (blockIdx.x % 97) == 5 && blockIdx.x < 600)
+    printf("#blk %d tiles %d cycles/tile: wait_read %lld issue %lld mbar %lld phase1 %lld phase2 %lld endsync %lld\n",
+           blockIdx.x, it, ck[0] / it, ck[1] / it, ck[2] / it, ck[3] / it, ck[4] / it, ck[5] / it);
+#endif
+
+  apply = __reduce_add_sync(0xffffffffu, apply);
+  unconv = __reduce_add_sync(0xffffffffu, unconv);
+  if (lane == 0) {
+    if (apply) atomicAdd(&A.cnt->apply_its, (unsigned long long)apply);
+    if (unconv) atomicAdd(&A.cnt->unconverged, (unsigned long long)unconv);
+  }
+}
+
 }  // namespace
 
 // Returns 1 if the fast kernel was launched (deferred particles are then in s->defer_list),
@@ -1139,57 +1156,97 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   A.list = s->defer_list;
   A.list_count = s->defer_count;
   A.cnt = c.d_counters;
-  KTimer t(deposit ? "advance_cc1_fused" : "advance_cc1");
+  A.tdual = A.tnode = nullptr;
   const bool tile_ok = s->cap >= (size_t)(((s->n + TILE - 1) / TILE) * TILE);
-  if (c.cc1_tma == 2 && tile_ok) {
-    const int ntiles = (int)((s->n + TILE - 1) / TILE);
-    const int grid = std::min(ntiles, c.sm_count * 4 * c.cc1_waves);
+  if (!tile_ok) return 0;
+  const int ntiles = (int)((s->n + TILE - 1) / TILE);
+  const int grid = std::min(ntiles, c.sm_count * 4 * c.cc1_waves);
+  if (c.cc1_tma == 3) {
+    // coefficient tables of the selected field slot, rebuilt when its E/B arrays changed
+    pgpu_grid_s *gm = s->grid;
+    const int slot = gm->cur_slot;
+    const int n0 = hi[0] - lo[0] + 2, n1 = hi[1] - lo[1] + 2;   // dual range + 1 (node records)
+    if (n0 < 2 || n1 < 2) return 0;
+    const size_t ncell = (size_t)n0 * n1;
+    if (gm->tab_cells != ncell) {
+      for (int k = 0; k < 4; ++k) {
+        if (gm->tab_dual[k]) cudaFree(gm->tab_dual[k]);
+        if (gm->tab_node[k]) cudaFree(gm->tab_node[k]);
+        gm->tab_dual[k] = gm->tab_node[k] = nullptr;
+        gm->tab_dirty[k] = true;
+      }
+      gm->tab_cells = ncell;
+    }
+    if (!gm->tab_dual[slot]) {
+      PGPU_CUDA(cudaMalloc(&gm->tab_dual[slot], ncell * TD * sizeof(double)));
+      PGPU_CUDA(cudaMalloc(&gm->tab_node[slot], ncell * TN * sizeof(double)));
+      gm->tab_dirty[slot] = true;
+    }
+    if (gm->tab_dirty[slot]) {
+      TabArgs T;
+      for (int k = 0; k < 6; ++k) {
+        T.F[k] = A.F[k];
+        T.fn0[k] = A.fn0[k];
+      }
+      T.lo[0] = lo[0];
+      T.lo[1] = lo[1];
+      T.n0 = n0;
+      T.n1 = n1;
+      T.dual = gm->tab_dual[slot];
+      T.node = gm->tab_node[slot];
+      KTimer t("build_tables");
+      k_build_tables<<<(unsigned)((ncell + 127) / 128), 128, 0, c.stream>>>(T);
+      gm->tab_dirty[slot] = false;
+    }
+    A.tdual = gm->tab_dual[slot];
+    A.tnode = gm->tab_node[slot];
+    A.tlo[0] = lo[0];
+    A.tlo[1] = lo[1];
+    A.tn0 = n0;
+    A.tol[0] = prm.rtol * A.dx[0];
+    A.tol[1] = prm.rtol * A.dx[1];
+    if (s->tile_box_cap < (size_t)ntiles) {
+      if (s->tile_box) cudaFree(s->tile_box);
+      s->tile_box_cap = (size_t)(s->cap + TILE - 1) / TILE;
+      PGPU_CUDA(cudaMalloc(&s->tile_box, s->tile_box_cap * sizeof(int4)));
+    }
+    A.tile_box = (const int4 *)s->tile_box;
+    {
+      KTimer t("tile_boxes");
+      k_tile_boxes<<<(unsigned)((ntiles + 127) / 128), 128, 0, c.stream>>>(A, ntiles, (int4 *)s->tile_box);
+    }
+    KTimer t(deposit ? "advance_cc1_fused" : "advance_cc1");
+#define PGPU_TAB_LAUNCH(DEPV, RS, MB)                                                                     \
+  do {                                                                                                    \
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tab<DEPV, RS, MB>,                                    \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM));        \
+    k_advance_cc1_2d_tab<DEPV, RS, MB><<<gridm, BLOCK, TAB_SMEM, c.stream>>>(A, ntiles);                  \
+  } while (0)
+    const int mb = c.cc1_minblocks == 5 ? 5 : 4;
+    const int gridm = std::min(ntiles, c.sm_count * mb * c.cc1_waves);
+    if (!deposit) {
+      if (mb == 4) PGPU_TAB_LAUNCH(false, 0, 4);
+      else PGPU_TAB_LAUNCH(false, 0, 5);
+    } else if (c.cc1_rsteps <= 2) {
+      if (mb == 4) PGPU_TAB_LAUNCH(true, 2, 4);
+      else PGPU_TAB_LAUNCH(true, 2, 5);
+    } else {
+      if (mb == 4) PGPU_TAB_LAUNCH(true, 3, 4);
+      else PGPU_TAB_LAUNCH(true, 3, 5);
+    }
+    return 1;
+  }
+  KTimer t(deposit ? "advance_cc1_fused" : "advance_cc1");
 #define PGPU_TILE_LAUNCH(DEPV, RS)                                                                        \
   do {                                                                                                    \
     PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tile<DEPV, RS>,                                       \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE2_SMEM));       \
     k_advance_cc1_2d_tile<DEPV, RS><<<grid, BLOCK, TILE2_SMEM, c.stream>>>(A, ntiles);                    \
   } while (0)
-    if (!deposit) PGPU_TILE_LAUNCH(false, 0);
-    else if (c.cc1_rsteps == 0) PGPU_TILE_LAUNCH(true, 0);
-    else if (c.cc1_rsteps == 1) PGPU_TILE_LAUNCH(true, 1);
-    else if (c.cc1_rsteps == 2) PGPU_TILE_LAUNCH(true, 2);
-    else if (c.cc1_rsteps == 3) PGPU_TILE_LAUNCH(true, 3);
-    else if (c.cc1_rsteps == 4) PGPU_TILE_LAUNCH(true, 4);
-    else PGPU_TILE_LAUNCH(true, 5);
-    return 1;
-  }
-  if (c.cc1_tma == 1 && tile_ok) {
-    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)TMA_SMEM));
-    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)TMA_SMEM));
-    const int ntiles = (int)((s->n + TILE - 1) / TILE);
-    const int grid = std::min(ntiles, c.sm_count * 3);
-    if (deposit) k_advance_cc1_2d_tma<true><<<grid, BLOCK, TMA_SMEM, c.stream>>>(A, ntiles);
-    else k_advance_cc1_2d_tma<false><<<grid, BLOCK, TMA_SMEM, c.stream>>>(A, ntiles);
-    return 1;
-  }
-  const int pairs = c.cc1_pairs;
-  const long per_block = (long)BLOCK * 2 * pairs;
-  const unsigned nb = (unsigned)((s->n + per_block - 1) / per_block);
-  const int minb = c.cc1_minblocks;
-#define PGPU_LAUNCH_CC1(DEPV, PV, MB) k_advance_cc1_2d<DEPV, PV, MB><<<nb, BLOCK, 0, c.stream>>>(A)
-#define PGPU_PICK_MB(DEPV, PV)                            \
-  do {                                                    \
-    if (minb == 4) PGPU_LAUNCH_CC1(DEPV, PV, 4);          \
-    else if (minb == 5) PGPU_LAUNCH_CC1(DEPV, PV, 5);     \
-    else PGPU_LAUNCH_CC1(DEPV, PV, 3);                    \
-  } while (0)
-  if (deposit) {
-    if (pairs == 1) PGPU_PICK_MB(true, 1);
-    else if (pairs == 2) PGPU_PICK_MB(true, 2);
-    else PGPU_PICK_MB(true, 4);
-  } else {
-    if (pairs == 1) PGPU_PICK_MB(false, 1);
-    else if (pairs == 2) PGPU_PICK_MB(false, 2);
-    else PGPU_PICK_MB(false, 4);
-  }
+  if (!deposit) PGPU_TILE_LAUNCH(false, 0);
+  else if (c.cc1_rsteps <= 2) PGPU_TILE_LAUNCH(true, 2);
+  else if (c.cc1_rsteps == 3) PGPU_TILE_LAUNCH(true, 3);
+  else PGPU_TILE_LAUNCH(true, 4);
   return 1;
 }
 

@@ -317,14 +317,10 @@ int pgpu_init(int device) {
   PGPU_CUDA(cudaMallocHost(&c.h_counters, sizeof(Counters)));
   c.inited = true;
   c.sticky_error = 0;
-  if (const char *e = getenv("PGPU_CC1_MINB")) c.cc1_minblocks = atoi(e);
   if (const char *e = getenv("PGPU_CC1_TMA")) c.cc1_tma = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_MINB")) c.cc1_minblocks = atoi(e);
   if (const char *e = getenv("PGPU_CC1_RSTEPS")) c.cc1_rsteps = atoi(e);
   if (const char *e = getenv("PGPU_CC1_WAVES")) c.cc1_waves = atoi(e) > 0 ? atoi(e) : 1;
-  if (const char *e = getenv("PGPU_CC1_PAIRS")) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) c.cc1_pairs = v;
-  }
   return 0;
 }
 
@@ -429,6 +425,10 @@ int pgpu_grid_destroy(pgpu_grid_t g) {
     for (int c = 0; c < 6; ++c)
       if (g->field_slot[k][c].p) cudaFree(g->field_slot[k][c].p);
   for (int c = 0; c < 3; ++c) cudaFree(g->jtot[c].p);
+  for (int k = 0; k < 4; ++k) {
+    if (g->tab_dual[k]) cudaFree(g->tab_dual[k]);
+    if (g->tab_node[k]) cudaFree(g->tab_node[k]);
+  }
   if (g->scratch_rho.p) cudaFree(g->scratch_rho.p);
   cudaFree(g->debye);
   delete g;
@@ -455,6 +455,7 @@ int pgpu_fields_set(pgpu_grid_t g, int comp, const double *data, const int *lo, 
       return PGPU_ERR_ARG;
     }
   PGPU_CUDA(cudaMemcpyAsync(f.p, data, f.size() * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+  g->tab_dirty[g->cur_slot] = true;
   return 0;
 }
 
@@ -562,6 +563,7 @@ int pgpu_species_destroy(pgpu_species_t s) {
   cudaFree(s->cub_tmp);
   for (int k = 0; k < 4; ++k) cudaFree(s->spare[k]);
   cudaFree(s->defer_list);
+  cudaFree(s->tile_box);
   cudaFree(s->defer_count);
   cudaFree(s->perm);
   cudaFree(s->cell_count);

@@ -87,11 +87,10 @@ struct Context {
   bool own_stream = false;
   bool exact = false;
   int deposit_mode = 1;
-  int cc1_tma = 2;           // CC1 kernel: 2 = two-phase TMA tile kernel, 1 = double-buffered TMA, 0 = direct loads (env PGPU_CC1_TMA)
-  int cc1_rsteps = 3;        // shuffle-reduction steps before the REDs (env PGPU_CC1_RSTEPS)
+  int cc1_tma = 3;           // CC1 kernel: 3 = table-driven two-phase TMA tile kernel, 2 = the same reading the raw field arrays (env PGPU_CC1_TMA)
+  int cc1_rsteps = 3;        // shuffle-reduction steps before the REDs: 2, 3 or 4 (env PGPU_CC1_RSTEPS)
+  int cc1_minblocks = 4;     // blocks of 128 threads per SM the table kernel is compiled for: 4 (128 regs) or 5 (96 regs); env PGPU_CC1_MINB
   int cc1_waves = 64;        // tile kernel grid = min(tiles, SMs*4*waves) (env PGPU_CC1_WAVES)
-  int cc1_minblocks = 3;     // register cap of the direct CC1 kernel: 3, 4 or 5 blocks of 128 per SM
-  int cc1_pairs = 2;         // particle pairs per thread of the CC1 kernel (1, 2 or 4); env PGPU_CC1_PAIRS
   bool use_fast_cc1 = true;  // pgpu_set_deposit_mode(0) turns the specialised CC1 kernel off
   Counters *d_counters = nullptr;
   Counters *h_counters = nullptr;  // pinned
@@ -134,6 +133,11 @@ struct pgpu_grid_s {
   pgpu::DeviceFab field[6];             // the selected slot (aliases field_slot[cur_slot])
   pgpu::DeviceFab field_slot[4][6];     // resident field sets (slot 0 always allocated)
   int cur_slot = 0;
+  // per-cell coefficient tables of each field slot for the 2D CC1 kernel (pgpu_advance_cc1.cu)
+  double *tab_dual[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *tab_node[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool tab_dirty[4] = {true, true, true, true};
+  size_t tab_cells = 0;
   pgpu::DeviceFab jtot[3];
   pgpu::DeviceFab scratch_rho;  // reused by set_charge_density
   double *debye = nullptr;      // [ncell_box]
@@ -173,6 +177,8 @@ struct pgpu_species_s {
   int *defer_list = nullptr;        // particles the CC1 fast kernel left to the generic one
   unsigned *defer_count = nullptr;
   size_t defer_cap = 0;
+  void *tile_box = nullptr;         // int4 per particle tile: table window of the CC1 kernel
+  size_t tile_box_cap = 0;
   double *dens = nullptr, *mom = nullptr, *ene = nullptr;  // [ncell],[3 ncell],[3 ncell]
   pgpu::PartPtrs ptrs() const {
     pgpu::PartPtrs p;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: tools/bench_env_sweep.sh "VAR=a VAR2=b" "VAR=c" ...  -- one short bench per env setting
 for cfg in "$@"; do
-  env $cfg python bench.py --steps 5 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err
+  env $cfg python bench.py --steps 5 --warmup 2 --no-cpu-baseline --no-e2e 2> gpurun_out/b.err | grep -v '^#' > gpurun_out/b.json
   python - "$cfg" <<'PY'
 import json, sys
 try:
