@@ -149,6 +149,10 @@ int pgpu_update_old_particle_velocities(pgpu_species_t s);                      
 int pgpu_reset_particles(pgpu_species_t s);                                          /* :1791-1819 */
 /* Ep/Bp of the last pgpu_interpolate_fields_to_particles (test/diagnostic hook) */
 int pgpu_species_download_fields(pgpu_species_t s, double *Ep, double *Bp);
+/* Set Ep/Bp directly: JustinsParticle::setElectricField / setMagneticField
+ * (JustinsParticle.H:127-151); lets pgpu_advance_velocities be driven -- and checked against
+ * the reference's PicSpeciesUtils::applyForces -- without a gather. */
+int pgpu_species_upload_fields(pgpu_species_t s, const double *Ep, const double *Bp);
 
 typedef struct {
   long num_parts_its;   /* m_num_parts_its increment  (:1646) */
@@ -203,6 +207,11 @@ int pgpu_ta_delta_u(long n, const double *vp1, const double *den1, const double 
                     const double *den2, double b90_fact, double Clog, double dt_sec,
                     const double *gauss, const double *u_theta, const double *u_phi,
                     double *dU);
+
+/* ScatteringUtils::computeDeltaU (ScatteringUtils.H:84-111) for explicit angles (test hook):
+ * u[3n] relative velocities (component-major), one angle set per pair, dU[3n] out. */
+int pgpu_scatter_delta_u(long n, const double *u, const double *costh, const double *sinth,
+                         const double *cosphi, const double *sinphi, double *dU);
 
 /* ---- instrumentation ---------------------------------------------------------- */
 /* CUDA-event timing of the library's own kernels on the launch stream. */

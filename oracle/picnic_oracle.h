@@ -6,12 +6,21 @@
  * in picnic_b200/ and to provide the CPU baseline leg of bench.py.  Nothing in
  * the product path may include, link or call it.
  *
- * PARITY STATUS: "parity unpinned".  The reference ships no golden vectors for
- * this path and cannot be built here (Chombo,
- * gfortran, MPI and HDF5 are absent), so this restatement is pinned only by
- * reading the reference source and by the reference-derived invariants tested in
- * tests/test_oracle_invariants.py (charge continuity of CC0/CC1, gather/deposit
- * adjointness, Boris energy identity, analytic gyration, pair conservation).
+ * PARITY STATUS
+ *   pinned   : orc_boris, orc_scatter_delta_u -- bit-equal to the reference's own
+ *              PicSpeciesUtils::applyForces / ScatteringUtils::computeDeltaU compiled
+ *              from /root/reference behind oracle/chombo_mock (oracle/ref_build.sh ->
+ *              oracle/_ref), vectors committed in tests/golden/ref_pins.npz
+ *              (tests/test_ref_pin.py).
+ *   "parity unpinned": everything else (CIC/TSC/CC0/CC1 gather and deposit, the
+ *              Picard loop, binning, moments, TA/Coulomb/Elastic pairing).  The
+ *              reference ships no golden vectors for this path (SURVEY.md section
+ *              4 / 8c) and those parts cannot be built here (Chombo proper, chfpp,
+ *              gfortran, MPI and HDF5 are absent), so they are pinned only by
+ *              reading the reference source and by the reference-derived invariants
+ *              tested in tests/test_oracle_invariants.py (charge continuity of
+ *              CC0/CC1, gather/deposit adjointness, Boris energy identity, analytic
+ *              gyration, pair conservation).
  *
  * Every function cites the reference file:line it restates (paths relative to
  * the PICNIC source tree).  Operation order follows the reference so that the

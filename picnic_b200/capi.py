@@ -74,7 +74,8 @@ def load():
         "pgpu_advance_velocities": [vp, dbl, i32], "pgpu_advance_velocities_2nd_half": [vp],
         "pgpu_average_velocities": [vp], "pgpu_update_old_particle_positions": [vp],
         "pgpu_update_old_particle_velocities": [vp], "pgpu_reset_particles": [vp],
-        "pgpu_species_download_fields": [vp, vp, vp],
+        "pgpu_species_download_fields": [vp, vp, vp], "pgpu_species_upload_fields": [vp, vp, vp],
+        "pgpu_scatter_delta_u": [lng, vp, vp, vp, vp, vp, vp],
         "pgpu_advance_particles": [vp, dbl], "pgpu_advance_particles_iteratively": [vp, dbl, i32, vp],
         "pgpu_set_current_density": [vp, dbl, i32], "pgpu_species_current_get": [vp, i32, vp, vp, vp],
         "pgpu_set_charge_density": [vp, vp, vp, vp, vp],
@@ -236,6 +237,10 @@ class Species:
         check(load().pgpu_species_download_fields(self.h, _p(Ep), _p(Bp)))
         return Ep, Bp
 
+    def set_particle_fields(self, Ep, Bp):
+        Ep, Bp = np.ascontiguousarray(Ep, dtype=np.float64), np.ascontiguousarray(Bp, dtype=np.float64)
+        check(load().pgpu_species_upload_fields(self.h, _p(Ep), _p(Bp)))
+
     def advance_velocities(self, dt, half):
         check(load().pgpu_advance_velocities(self.h, dt, int(half)))
 
@@ -342,6 +347,16 @@ def ta_delta_u(vp1, den1, vp2, den2, b90_fact, Clog, dt_sec, gauss, u_theta, u_p
     rnd = [c(gauss), c(u_theta), c(u_phi)]
     check(load().pgpu_ta_delta_u(n, _p(args[0]), _p(args[1]), _p(args[2]), _p(args[3]), b90_fact, Clog, dt_sec,
                                  _p(rnd[0]), _p(rnd[1]), _p(rnd[2]), _p(out)))
+    return out
+
+
+def scatter_delta_u(u, costh, sinth, cosphi, sinphi):
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    u = c(u)
+    n = u.shape[1]
+    a = [c(costh), c(sinth), c(cosphi), c(sinphi)]
+    out = np.zeros((3, n))
+    check(load().pgpu_scatter_delta_u(n, _p(u), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(out)))
     return out
 
 

@@ -642,6 +642,20 @@ int pgpu_species_download_fields(pgpu_species_t s, double *Ep, double *Bp) {
   return 0;
 }
 
+int pgpu_species_upload_fields(pgpu_species_t s, const double *Ep, const double *Bp) {
+  NEED_INIT();
+  if (!s || !Ep || !Bp) return PGPU_ERR_ARG;
+  if (ensure_epbp(s)) return PGPU_ERR_CUDA;
+  const long n = s->n;
+  cudaStream_t st = ctx().stream;
+  for (int c = 0; c < 3; ++c) {
+    PGPU_CUDA(cudaMemcpyAsync(s->Ep[c], Ep + (size_t)c * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    PGPU_CUDA(cudaMemcpyAsync(s->Bp[c], Bp + (size_t)c * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // ---- streaming passes ---------------------------------------------------------------
 static int stream_pass(const char *name, double *out, const double *a, const double *b, long n, double s,
                        int mode) {

@@ -97,6 +97,17 @@ __global__ void k_ta_delta_u(long n, const double *vp1, const double *den1, cons
   dU[2 * n + i] = d[2];
 }
 
+__global__ void k_scatter_delta_u(long n, const double *u, const double *ct, const double *st, const double *cp,
+                                  const double *sp, double *dU) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d[3];
+  scatter_delta_u(u[i], u[n + i], u[2 * n + i], ct[i], st[i], cp[i], sp[i], d);
+  dU[i] = d[0];
+  dU[n + i] = d[1];
+  dU[2 * n + i] = d[2];
+}
+
 struct TAParams {
   double b90_fact, Clog, dt_sec;
   double f1, f2;  // mu/m1, mu/m2
@@ -262,6 +273,31 @@ int pgpu_ta_delta_u(long n, const double *vp1, const double *den1, const double 
     k_ta_delta_u<<<nb(n), 256, 0, st>>>(n, d_v1, d_d1, d_v2, d_d2, b90_fact, Clog, dt_sec, d_g, d_t, d_p, d_o);
   }
   PGPU_CUDA(cudaMemcpyAsync(dU, d_o, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d);
+  return 0;
+}
+
+int pgpu_scatter_delta_u(long n, const double *u, const double *costh, const double *sinth, const double *cosphi,
+                         const double *sinphi, double *dU) {
+  if (!ctx().inited) {
+    set_error("pgpu_init has not been called");
+    return PGPU_ERR_STATE;
+  }
+  cudaStream_t st = ctx().stream;
+  double *d = nullptr;
+  const size_t N = (size_t)n;
+  PGPU_CUDA(cudaMalloc(&d, 10 * N * sizeof(double)));   // u[3n] ct st cp sp dU[3n]
+  PGPU_CUDA(cudaMemcpyAsync(d, u, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(d + 3 * N, costh, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(d + 4 * N, sinth, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(d + 5 * N, cosphi, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(d + 6 * N, sinphi, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  {
+    KTimer t("scatter_delta_u");
+    k_scatter_delta_u<<<nb(n), 256, 0, st>>>(n, d, d + 3 * N, d + 4 * N, d + 5 * N, d + 6 * N, d + 7 * N);
+  }
+  PGPU_CUDA(cudaMemcpyAsync(dU, d + 7 * N, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
   PGPU_CUDA(cudaStreamSynchronize(st));
   cudaFree(d);
   return 0;
