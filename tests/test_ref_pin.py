@@ -47,7 +47,7 @@ def test_oracle_delta_u_bit_equals_reference():
     # u is along +z there) does not preserve |u| -- a reference quirk the oracle and the CUDA code keep
     u = GOLD["in_u"]
     quirk = (u[0] == 0.0) & (u[1] == 0.0) & (u[2] < 0.0)
-    assert quirk.sum() == 3
+    assert quirk.sum() >= 1 and (~quirk & (u[0] == 0.0) & (u[1] == 0.0)).sum() >= 1
     d = GOLD["out_rotate"] - (u.T + GOLD["out_delta_u"])
     assert np.abs(d[~quirk]).max() <= 4e-16 * np.abs(u).max()
 
