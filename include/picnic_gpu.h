@@ -192,6 +192,27 @@ int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi);
  * Bit-identical to the three separate calls; falls back to them for symmetry walls. */
 int pgpu_finish_implicit_step(pgpu_species_t s, const int *bc_lo, const int *bc_hi);
 
+/* ---- multi-box exchanges (one box per device) ----------------------------
+ * The collectives are issued by the host plumbing on DEVICE buffers (suffix _d = device
+ * pointer); these calls move data between those buffers and the library's arrays. */
+enum { PGPU_FAB_JTOTAL = 0, PGPU_FAB_FIELD = 1 };
+/* Copy the index box lo..hi (global indices, inclusive) of a grid array into / out of a
+ * contiguous column-major device buffer; add != 0 accumulates: the two halves of the ghost
+ * ADD-exchange of PicSpeciesInterface::finalizeSettingJ (PicSpeciesInterface.cpp:766-772). */
+int pgpu_fab_pack_d(pgpu_grid_t g, int kind, int comp, const int *lo, const int *hi, double *buf_d);
+int pgpu_fab_unpack_d(pgpu_grid_t g, int kind, int comp, const int *lo, const int *hi, const double *buf_d,
+                      int add);
+/* Particle migration = ParticleData::gatherOutcast + remapOutcast (ParticleDataI.H:405-547).
+ * mark: counts[(d0+1)+3*(d1+1)] = particles now owned by the neighbour box in direction
+ * (d0,d1) (counts[4] = 0), counts[9] = particles outside the decomposition.  pack: writes the
+ * leavers' wire records (pgpu_wire_doubles() doubles each: x[D] xold[D] v[3] vold[3] w id),
+ * grouped by direction code in ascending order, to buf_d and removes them from the species.
+ * append: adds n_add records received from neighbours. */
+int pgpu_wire_doubles(pgpu_grid_t g);
+int pgpu_species_mark_leavers(pgpu_species_t s, long *counts /* [10] */);
+int pgpu_species_pack_leavers_d(pgpu_species_t s, double *buf_d);
+int pgpu_species_append_d(pgpu_species_t s, long n_add, const double *buf_d);
+
 /* reductions: setStableDt (:1869-1911), globalMoments (:4067-4130) */
 int pgpu_stable_dt(pgpu_species_t s, double *dt_out);
 int pgpu_global_moments(pgpu_species_t s, double *out /* [w, wux,wuy,wuz, wuu_x,wuu_y,wuu_z] */);

@@ -262,6 +262,53 @@ static int ensure_capacity(pgpu_species_s *s, long n) {
   return 0;
 }
 
+// Capacity for n particles, keeping the first s->n of every array (arrivals of a migration).
+int grow_capacity(pgpu_species_s *s, long n) {
+  if ((size_t)n <= s->cap) return 0;
+  const size_t cap = (size_t)(n + n / 16 + 1024);
+  const int D = s->grid->desc.D;
+  cudaStream_t st = ctx().stream;
+  auto re = [&](double *&p) -> int {
+    double *q = nullptr;
+    PGPU_CUDA(cudaMalloc(&q, cap * sizeof(double)));
+    if (p) {
+      PGPU_CUDA(cudaMemcpyAsync(q, p, s->n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      PGPU_CUDA(cudaStreamSynchronize(st));
+      cudaFree(p);
+    }
+    p = q;
+    return 0;
+  };
+  for (int d = 0; d < D; ++d) {
+    if (re(s->x[d])) return PGPU_ERR_CUDA;
+    if (re(s->xold[d])) return PGPU_ERR_CUDA;
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (re(s->v[c])) return PGPU_ERR_CUDA;
+    if (re(s->vold[c])) return PGPU_ERR_CUDA;
+  }
+  if (re(s->w)) return PGPU_ERR_CUDA;
+  {
+    double *idp = reinterpret_cast<double *>(s->id);
+    if (re(idp)) return PGPU_ERR_CUDA;
+    s->id = reinterpret_cast<uint64_t *>(idp);
+  }
+  if (s->tmp) cudaFree(s->tmp);
+  PGPU_CUDA(cudaMalloc(&s->tmp, cap * sizeof(double)));
+  for (int c = 0; c < 3; ++c) {
+    if (s->Ep[c]) cudaFree(s->Ep[c]);
+    if (s->Bp[c]) cudaFree(s->Bp[c]);
+    s->Ep[c] = s->Bp[c] = nullptr;
+  }
+  if (s->cell_key) cudaFree(s->cell_key);
+  if (s->perm) cudaFree(s->perm);
+  PGPU_CUDA(cudaMalloc(&s->cell_key, cap * sizeof(int)));
+  PGPU_CUDA(cudaMalloc(&s->perm, cap * sizeof(int)));
+  s->cap = cap;
+  s->binned = false;
+  return 0;
+}
+
 static int ensure_epbp(pgpu_species_s *s) {
   for (int c = 0; c < 3; ++c) {
     if (!s->Ep[c]) PGPU_CUDA(cudaMalloc(&s->Ep[c], s->cap * sizeof(double)));
@@ -564,6 +611,8 @@ int pgpu_species_destroy(pgpu_species_t s) {
   for (int k = 0; k < 4; ++k) cudaFree(s->spare[k]);
   cudaFree(s->defer_list);
   cudaFree(s->tile_box);
+  cudaFree(s->mig);
+  cudaFree(s->mig_list);
   cudaFree(s->defer_count);
   cudaFree(s->perm);
   cudaFree(s->cell_count);

@@ -1,0 +1,316 @@
+// pgpu_exchange.cu -- device side of the multi-box exchanges.
+//
+// One process per GPU owns one Chombo box.  The collectives themselves are issued by the host
+// plumbing (picnic_b200/halo.py: torch.distributed, NCCL over NVLink) on DEVICE buffers; this
+// file provides what has to touch the particle and grid arrays:
+//   * pack / unpack(+add) of an index box of a grid array  -- the ghost ADD-exchange of J
+//     (LevelData::exchange with an add op in PicSpeciesInterface::finalizeSettingJ,
+//     PicSpeciesInterface.cpp:766-772) and the ghost refresh that follows;
+//   * outgoing-particle migration: ParticleData::gatherOutcast / remapOutcast
+//     (src/particle_tools/ParticleDataI.H:405-547): a particle belongs to the box whose cells
+//     contain it, box index = floor((x - origin) / (dx * boxSize)) per direction.  Leavers are
+//     packed into wire records, the holes they leave are filled from the tail of the arrays,
+//     and arrivals are appended.
+#include "pgpu_internal.h"
+
+namespace pgpu {
+
+static inline unsigned nb(long n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---- grid arrays ------------------------------------------------------------------------
+__global__ void k_fab_pack(FabView f, int lo0, int lo1, int m0, int m1, double *buf) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)m0 * m1) return;
+  const int a = (int)(t % m0), b = (int)(t / m0);
+  buf[t] = f.p[(long)(lo0 + a - f.lo0) + (long)(lo1 + b - f.lo1) * f.n0];
+}
+__global__ void k_fab_unpack(FabView f, int lo0, int lo1, int m0, int m1, const double *buf, int add) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)m0 * m1) return;
+  const int a = (int)(t % m0), b = (int)(t / m0);
+  double *p = f.p + ((long)(lo0 + a - f.lo0) + (long)(lo1 + b - f.lo1) * f.n0);
+  *p = add ? __dadd_rn(*p, buf[t]) : buf[t];
+}
+
+static const DeviceFab *pick_fab(pgpu_grid_t g, int kind, int comp) {
+  if (!g) return nullptr;
+  if (kind == PGPU_FAB_JTOTAL && comp >= 0 && comp < 3) return &g->jtot[comp];
+  if (kind == PGPU_FAB_FIELD && comp >= 0 && comp < 6) return &g->field[comp];
+  return nullptr;
+}
+
+static int check_box(const DeviceFab &f, int D, const int *lo, const int *hi, int *m) {
+  m[0] = m[1] = 1;
+  for (int d = 0; d < D; ++d) {
+    if (lo[d] < f.lo[d] || hi[d] > f.hi[d] || hi[d] < lo[d]) {
+      set_error("index box [%d:%d] in dir %d is not inside the device array [%d:%d]", lo[d], hi[d], d, f.lo[d],
+                f.hi[d]);
+      return PGPU_ERR_ARG;
+    }
+    m[d] = hi[d] - lo[d] + 1;
+  }
+  return 0;
+}
+
+// ---- migration --------------------------------------------------------------------------
+struct MigGeo {
+  int D;
+  double le[2], boxlen[2];   // origin, dx * boxSize
+  int my[2], nbx[2];         // this box's coordinate and the number of boxes per direction
+  int periodic[2];
+};
+
+// direction code of the owning box relative to this one: (d0+1) + 3 (d1+1), 4 = stays;
+// 9 = left the decomposition (a host boundary condition has to deal with it)
+__device__ __forceinline__ int owner_code(const MigGeo &G, double x0, double x1) {
+  int code = 0, mul = 1;
+  const double xs[2] = {x0, x1};
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    int diff = 0;
+    if (d < G.D) {
+      const int b = __double2int_rd(__ddiv_rn(__dsub_rn(xs[d], G.le[d]), G.boxlen[d]));
+      diff = b - G.my[d];
+      if (G.periodic[d]) {
+        if (diff > 1) diff -= G.nbx[d];
+        if (diff < -1) diff += G.nbx[d];
+      }
+      if (b < 0 || b >= G.nbx[d] || diff < -1 || diff > 1) return 9;
+    }
+    code += (diff + 1) * mul;
+    mul *= 3;
+  }
+  return code;
+}
+
+struct MigCounters {
+  unsigned count[10];   // per code; [9] = lost
+  unsigned nleave;      // list length
+  unsigned nhole, nmove;
+  unsigned cursor[9];
+};
+
+__global__ void k_mark_leavers(const double *x0, const double *x1, long n, MigGeo G, int *dead, int *list,
+                               MigCounters *mc) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int code = owner_code(G, x0[i], G.D == 2 ? x1[i] : 0.0);
+  dead[i] = code == 4 ? 0 : 1 + code;
+  if (code != 4) {
+    atomicAdd(&mc->count[code], 1u);
+    const unsigned slot = atomicAdd(&mc->nleave, 1u);
+    list[slot] = (int)i;
+  }
+}
+
+struct WirePtrs {
+  double *x[2], *xold[2], *v[3], *vold[3], *w;
+  uint64_t *id;
+  int D;
+};
+__device__ __forceinline__ int wire_len(int D) { return 2 * D + 8; }
+
+__device__ __forceinline__ void wire_out(const WirePtrs &P, long i, double *r) {
+  int k = 0;
+  for (int d = 0; d < P.D; ++d) r[k++] = P.x[d][i];
+  for (int d = 0; d < P.D; ++d) r[k++] = P.xold[d][i];
+  for (int c = 0; c < 3; ++c) r[k++] = P.v[c][i];
+  for (int c = 0; c < 3; ++c) r[k++] = P.vold[c][i];
+  r[k++] = P.w[i];
+  r[k++] = __longlong_as_double((long long)P.id[i]);
+}
+__device__ __forceinline__ void wire_in(const WirePtrs &P, long i, const double *r) {
+  int k = 0;
+  for (int d = 0; d < P.D; ++d) P.x[d][i] = r[k++];
+  for (int d = 0; d < P.D; ++d) P.xold[d][i] = r[k++];
+  for (int c = 0; c < 3; ++c) P.v[c][i] = r[k++];
+  for (int c = 0; c < 3; ++c) P.vold[c][i] = r[k++];
+  P.w[i] = r[k++];
+  P.id[i] = (uint64_t)__double_as_longlong(r[k++]);
+}
+
+// records grouped by direction code: offset[code] + running cursor
+__global__ void k_pack_leavers(WirePtrs P, const int *list, const int *dead, MigCounters *mc, const unsigned *offset,
+                               double *buf, long new_n, int *holes) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= mc->nleave) return;
+  const long i = list[t];
+  const int code = dead[i] - 1;
+  if (code < 9) {
+    const unsigned pos = offset[code] + atomicAdd(&mc->cursor[code], 1u);
+    wire_out(P, i, buf + (size_t)pos * wire_len(P.D));
+  }
+  if (i < new_n) holes[atomicAdd(&mc->nhole, 1u)] = (int)i;
+}
+__global__ void k_list_movers(const int *dead, long new_n, long n, MigCounters *mc, int *movers) {
+  const long i = new_n + (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!dead[i]) movers[atomicAdd(&mc->nmove, 1u)] = (int)i;
+}
+__global__ void k_fill_holes(WirePtrs P, const int *holes, const int *movers, const MigCounters *mc) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= mc->nhole) return;
+  const long dst = holes[t], src = movers[t];
+  for (int d = 0; d < P.D; ++d) {
+    P.x[d][dst] = P.x[d][src];
+    P.xold[d][dst] = P.xold[d][src];
+  }
+  for (int c = 0; c < 3; ++c) {
+    P.v[c][dst] = P.v[c][src];
+    P.vold[c][dst] = P.vold[c][src];
+  }
+  P.w[dst] = P.w[src];
+  P.id[dst] = P.id[src];
+}
+__global__ void k_append(WirePtrs P, long n0, long nadd, const double *buf) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nadd) return;
+  wire_in(P, n0 + t, buf + (size_t)t * wire_len(P.D));
+}
+
+static WirePtrs wire_ptrs(pgpu_species_s *s) {
+  WirePtrs P;
+  P.D = s->grid->desc.D;
+  for (int d = 0; d < 2; ++d) {
+    P.x[d] = s->x[d];
+    P.xold[d] = s->xold[d];
+  }
+  for (int c = 0; c < 3; ++c) {
+    P.v[c] = s->v[c];
+    P.vold[c] = s->vold[c];
+  }
+  P.w = s->w;
+  P.id = s->id;
+  return P;
+}
+
+}  // namespace pgpu
+
+using namespace pgpu;
+
+extern "C" {
+
+int pgpu_fab_pack_d(pgpu_grid_t g, int kind, int comp, const int *lo, const int *hi, double *buf_d) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  const DeviceFab *f = pick_fab(g, kind, comp);
+  if (!f || !buf_d) return PGPU_ERR_ARG;
+  int m[2];
+  if (check_box(*f, g->desc.D, lo, hi, m)) return PGPU_ERR_ARG;
+  KTimer t("halo_pack");
+  k_fab_pack<<<nb((long)m[0] * m[1]), 256, 0, ctx().stream>>>(f->view(), lo[0], g->desc.D == 2 ? lo[1] : 0, m[0], m[1],
+                                                             buf_d);
+  return 0;
+}
+
+int pgpu_fab_unpack_d(pgpu_grid_t g, int kind, int comp, const int *lo, const int *hi, const double *buf_d, int add) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  const DeviceFab *f = pick_fab(g, kind, comp);
+  if (!f || !buf_d) return PGPU_ERR_ARG;
+  int m[2];
+  if (check_box(*f, g->desc.D, lo, hi, m)) return PGPU_ERR_ARG;
+  KTimer t("halo_unpack");
+  k_fab_unpack<<<nb((long)m[0] * m[1]), 256, 0, ctx().stream>>>(f->view(), lo[0], g->desc.D == 2 ? lo[1] : 0, m[0],
+                                                               m[1], buf_d, add);
+  return 0;
+}
+
+int pgpu_wire_doubles(pgpu_grid_t g) { return g ? 2 * g->desc.D + 8 : 0; }
+
+int pgpu_species_mark_leavers(pgpu_species_t s, long *counts) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!s || !counts) return PGPU_ERR_ARG;
+  Context &c = ctx();
+  const pgpu_grid_s *g = s->grid;
+  for (int k = 0; k < 10; ++k) counts[k] = 0;
+  if (!s->mig) PGPU_CUDA(cudaMalloc(&s->mig, sizeof(MigCounters) + 16 * sizeof(unsigned)));
+  PGPU_CUDA(cudaMemsetAsync(s->mig, 0, sizeof(MigCounters) + 16 * sizeof(unsigned), c.stream));
+  s->mig_marked = false;
+  if (s->n == 0) {
+    s->mig_marked = true;
+    s->mig_leave = 0;
+    return 0;
+  }
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  MigGeo G;
+  G.D = g->desc.D;
+  for (int d = 0; d < 2; ++d) {
+    const bool on = d < G.D;
+    G.le[d] = g->geo.le[d];
+    G.boxlen[d] = on ? g->geo.dx[d] * g->nbox[d] : 1.0;
+    G.my[d] = on ? g->desc.box_lo[d] / g->nbox[d] : 0;
+    G.nbx[d] = on ? g->desc.ncell[d] / g->nbox[d] : 1;
+    G.periodic[d] = on ? g->desc.periodic[d] : 0;
+    if (on && (g->desc.box_lo[d] % g->nbox[d] || g->desc.ncell[d] % g->nbox[d])) {
+      set_error("migration needs the square equal-box decomposition of System.cpp:169-245");
+      return PGPU_ERR_ARG;
+    }
+  }
+  {
+    KTimer t("mig_mark");
+    k_mark_leavers<<<nb(s->n), 256, 0, c.stream>>>(s->x[0], s->x[1], s->n, G, s->cell_key, s->perm,
+                                                  (MigCounters *)s->mig);
+  }
+  MigCounters h;
+  PGPU_CUDA(cudaMemcpyAsync(&h, s->mig, sizeof(MigCounters), cudaMemcpyDeviceToHost, c.stream));
+  PGPU_CUDA(cudaStreamSynchronize(c.stream));
+  for (int k = 0; k < 10; ++k) counts[k] = h.count[k];
+  s->mig_leave = h.nleave;
+  for (int k = 0; k < 10; ++k) s->mig_count[k] = h.count[k];
+  s->mig_marked = true;
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_species_pack_leavers_d(pgpu_species_t s, double *buf_d) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!s || !s->mig_marked) {
+    set_error("pgpu_species_pack_leavers_d needs pgpu_species_mark_leavers first");
+    return PGPU_ERR_STATE;
+  }
+  Context &c = ctx();
+  const long L = s->mig_leave;
+  s->mig_marked = false;
+  if (L == 0) return 0;
+  if (!buf_d) return PGPU_ERR_ARG;
+  unsigned off[16] = {0};
+  for (int k = 1; k < 10; ++k) off[k] = off[k - 1] + (k - 1 == 4 ? 0u : (unsigned)s->mig_count[k - 1]);
+  unsigned *d_off = (unsigned *)((char *)s->mig + sizeof(MigCounters));
+  PGPU_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, c.stream));
+  const long new_n = s->n - L;
+  // scratch: holes and movers lists live in the second half of the key array / spare ints
+  if (s->mig_list_cap < (size_t)(2 * L)) {
+    if (s->mig_list) cudaFree(s->mig_list);
+    s->mig_list_cap = (size_t)(2 * L + 1024);
+    PGPU_CUDA(cudaMalloc(&s->mig_list, s->mig_list_cap * sizeof(int)));
+  }
+  int *holes = s->mig_list, *movers = s->mig_list + L;
+  const WirePtrs P = wire_ptrs(s);
+  {
+    KTimer t("mig_pack");
+    k_pack_leavers<<<nb(L), 256, 0, c.stream>>>(P, s->perm, s->cell_key, (MigCounters *)s->mig, d_off, buf_d, new_n,
+                                               holes);
+    k_list_movers<<<nb(L), 256, 0, c.stream>>>(s->cell_key, new_n, s->n, (MigCounters *)s->mig, movers);
+    k_fill_holes<<<nb(L), 256, 0, c.stream>>>(P, holes, movers, (const MigCounters *)s->mig);
+  }
+  s->n = new_n;
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_species_append_d(pgpu_species_t s, long n_add, const double *buf_d) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!s || n_add < 0) return PGPU_ERR_ARG;
+  if (n_add == 0) return 0;
+  if (!buf_d) return PGPU_ERR_ARG;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  if (grow_capacity(s, s->n + n_add)) return PGPU_ERR_CUDA;
+  {
+    KTimer t("mig_append");
+    k_append<<<nb(n_add), 256, 0, ctx().stream>>>(wire_ptrs(s), s->n, n_add, buf_d);
+  }
+  s->n += n_add;
+  s->binned = false;
+  return 0;
+}
+
+}  // extern "C"

@@ -177,6 +177,12 @@ struct pgpu_species_s {
   int *defer_list = nullptr;        // particles the CC1 fast kernel left to the generic one
   unsigned *defer_count = nullptr;
   size_t defer_cap = 0;
+  // migration scratch (pgpu_exchange.cu)
+  void *mig = nullptr;
+  bool mig_marked = false;
+  long mig_leave = 0, mig_count[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int *mig_list = nullptr;
+  size_t mig_list_cap = 0;
   void *tile_box = nullptr;         // int4 per particle tile: table window of the CC1 kernel
   size_t tile_box_cap = 0;
   double *dens = nullptr, *mom = nullptr, *ene = nullptr;  // [ncell],[3 ncell],[3 ncell]
@@ -208,6 +214,7 @@ int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, con
 
 // launchers implemented in the kernel translation units
 int materialize_old(pgpu_species_s *s);
+int grow_capacity(pgpu_species_s *s, long n);   // keeps the particles (pgpu_api.cu)
 int launch_gather(pgpu_species_s *s);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);

@@ -1,0 +1,328 @@
+"""Multi-box exchanges of the particle engine: one process per GPU, one Chombo box per process.
+
+What the reference does with MPI inside Chombo -- `LevelData::exchange` with an add op on the
+ghost cells of J (PicSpeciesInterface::finalizeSettingJ, PicSpeciesInterface.cpp:766-772) and
+`ParticleData::remapOutcast` (ParticleDataI.H:405-547) -- is done here with point-to-point
+messages between the boxes of the square equal-box decomposition (System.cpp:169-245), on DEVICE
+buffers over NCCL/NVLink (`torch.distributed`; gloo on CPU in the tests).  The arithmetic on the
+library's arrays stays in the CUDA library (pgpu_fab_pack_d / pgpu_fab_unpack_d /
+pgpu_species_mark_leavers / _pack_leavers_d / _append_d); this module only computes index boxes
+and moves buffers.  Collisions and moments are cell-local and need no exchange.
+
+The add-exchange runs direction by direction over the full transverse extent of the arrays
+(ghosts included), so corners need no diagonal messages: after the pass in direction d every
+index that two boxes share in d holds the sum of both, and the later directions carry those
+sums on.  Directions in which the box spans the whole periodic domain are folded locally by
+`pgpu_current_finalize`.
+"""
+import numpy as np
+
+STAG_J = {1: [(0,), (1,), (1,)], 2: [(0, 1), (1, 0), (1, 1)]}   # Jx, Jy, Jz centring (1 = nodal)
+
+
+class BoxLayout:
+    """px x py equal boxes of nbox cells tiling a domain of ncell cells; rank = bi + bj*px."""
+
+    def __init__(self, D, ncell, nbox, nghost, periodic):
+        self.D, self.ncell, self.nbox, self.nghost = D, tuple(ncell), tuple(nbox), nghost
+        self.periodic = tuple(int(p) for p in periodic)
+        self.nb = tuple(nc // nb for nc, nb in zip(ncell, nbox))
+        for nc, nb in zip(ncell, nbox):
+            assert nc % nb == 0, "boxes must tile the domain"
+        for d in range(D):
+            assert self.nb[d] == 1 or nbox[d] >= 2 * nghost + 1, "box narrower than its ghost overlap"
+        self.world = int(np.prod(self.nb))
+
+    def coords(self, rank):
+        return (rank % self.nb[0],) if self.D == 1 else (rank % self.nb[0], rank // self.nb[0])
+
+    def rank_of(self, c):
+        return c[0] if self.D == 1 else c[0] + c[1] * self.nb[0]
+
+    def box(self, rank):
+        c = self.coords(rank)
+        lo = tuple(ci * nb for ci, nb in zip(c, self.nbox))
+        hi = tuple(l + nb - 1 for l, nb in zip(lo, self.nbox))
+        return lo, hi
+
+    def neighbor(self, rank, d, side):
+        """Rank of the neighbour box in direction d (side -1 / +1), or None at a wall."""
+        c = list(self.coords(rank))
+        c[d] += side
+        if c[d] < 0 or c[d] >= self.nb[d]:
+            if not self.periodic[d]:
+                return None
+            c[d] %= self.nb[d]
+        return self.rank_of(c)
+
+    def neighbor_code(self, rank, code):
+        """Rank that owns direction code (d0+1) + 3 (d1+1) of `rank` (migration)."""
+        off = (code % 3 - 1, code // 3 - 1)
+        c = list(self.coords(rank))
+        for d in range(self.D):
+            c[d] += off[d]
+            if c[d] < 0 or c[d] >= self.nb[d]:
+                if not self.periodic[d]:
+                    return None
+                c[d] %= self.nb[d]
+        return self.rank_of(c)
+
+    def array_bounds(self, rank, stag):
+        lo, hi = self.box(rank)
+        g = self.nghost
+        return (tuple(l - g for l in lo), tuple(h + g + s for h, s in zip(hi, stag)))
+
+    def overlap(self, rank, stag, d, side):
+        """Index box (in this rank's global indices) shared with the neighbour in direction d:
+        2*nghost + stag[d] layers around the common face, full extent elsewhere."""
+        alo, ahi = self.array_bounds(rank, stag)
+        lo, hi = list(alo), list(ahi)
+        blo, bhi = self.box(rank)
+        g = self.nghost
+        if side > 0:
+            lo[d], hi[d] = bhi[d] + 1 - g, bhi[d] + g + stag[d]
+        else:
+            lo[d], hi[d] = blo[d] - g, blo[d] - 1 + g + stag[d]
+        return tuple(lo), tuple(hi)
+
+
+# ------------------------------------------------------------------------------------------------
+# communicators
+# ------------------------------------------------------------------------------------------------
+class DistComm:
+    """torch.distributed point-to-point (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, rank, world, stream=None):
+        """stream: the torch CUDA stream the library runs on (pgpu_set_stream).  Collectives are
+        enqueued relative to it, so pack -> send and recv -> unpack order on the device without
+        a host synchronisation."""
+        import contextlib
+        import torch
+        import torch.distributed as dist
+        self.dist, self.rank, self.world, self.torch = dist, rank, world, torch
+        self.ctx = (lambda: torch.cuda.stream(stream)) if stream is not None else contextlib.nullcontext
+        self.reqs = []
+
+    def post(self, sends, recvs):
+        ops = [self.dist.P2POp(self.dist.isend, t, peer, tag=tag) for (peer, tag, t) in sends]
+        ops += [self.dist.P2POp(self.dist.irecv, t, peer, tag=tag) for (peer, tag, t) in recvs]
+        with self.ctx():
+            self.reqs = self.dist.batch_isend_irecv(ops) if ops else []
+
+    def wait(self):
+        with self.ctx():
+            for r in self.reqs:
+                r.wait()
+        self.reqs = []
+
+    def all_gather(self, t):
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        with self.ctx():
+            self.dist.all_gather(out, t)
+        return out
+
+
+class LoopComm:
+    """All boxes in ONE process (tests, and several boxes per GPU): a mailbox keyed by
+    (source, destination, tag).  Call post() for every box before wait() for any."""
+
+    def __init__(self, world):
+        self.world, self.box, self.gathered = world, {}, {}
+
+    def view(self, rank):
+        return _LoopView(self, rank)
+
+
+class _LoopView:
+    def __init__(self, hub, rank):
+        self.hub, self.rank, self.world = hub, rank, hub.world
+        self.recvs = []
+
+    def post(self, sends, recvs):
+        for (peer, tag, t) in sends:
+            self.hub.box[(self.rank, peer, tag)] = t.clone()
+        self.recvs = recvs
+
+    def wait(self):
+        for (peer, tag, t) in self.recvs:
+            t.copy_(self.hub.box.pop((peer, self.rank, tag)))
+        self.recvs = []
+
+    def all_gather_post(self, t):
+        self.hub.gathered[self.rank] = t.clone()
+
+    def all_gather_collect(self):
+        return [self.hub.gathered[r] for r in range(self.world)]
+
+
+# ------------------------------------------------------------------------------------------------
+# ghost add-exchange of the total current
+# ------------------------------------------------------------------------------------------------
+class CapiGridBackend:
+    """Device buffers <-> the library's total-J arrays through the C ABI."""
+
+    def __init__(self, grid, device, on_torch_stream=False):
+        """on_torch_stream: the library runs on the torch stream the communicator enqueues on
+        (no host synchronisation between pack and send)."""
+        import torch
+        from . import capi
+        self.torch, self.capi, self.grid, self.device = torch, capi, grid, device
+        self.on_torch_stream = on_torch_stream
+
+    def new_buffer(self, count):
+        return self.torch.empty(count, dtype=self.torch.float64, device=self.device)
+
+    def pack(self, comp, lo, hi, buf):
+        c = self.capi
+        c.check(c.load().pgpu_fab_pack_d(self.grid.h, 0, comp, c._i2(lo), c._i2(hi), buf.data_ptr()))
+
+    def unpack_add(self, comp, lo, hi, buf):
+        c = self.capi
+        c.check(c.load().pgpu_fab_unpack_d(self.grid.h, 0, comp, c._i2(lo), c._i2(hi), buf.data_ptr(), 1))
+
+    def sync(self):
+        if not self.on_torch_stream:   # the library runs on its own stream; collectives on torch's
+            self.capi.check(self.capi.load().pgpu_synchronize())
+
+
+class HaloExchange:
+    """Ghost ADD-exchange of Jx, Jy, Jz between neighbouring boxes, direction by direction."""
+
+    def __init__(self, layout, rank, comm, backend):
+        self.layout, self.rank, self.comm, self.be = layout, rank, comm, backend
+        self.plan = []   # per direction: list of (peer, send_tag, recv_tag, comp, lo, hi, sendbuf, recvbuf)
+        D = layout.D
+        for d in range(D):
+            if layout.nb[d] == 1:
+                continue          # spans the domain: folded locally (pgpu_current_finalize)
+            msgs = []
+            for side in (-1, +1):
+                peer = layout.neighbor(rank, d, side)
+                if peer is None:
+                    continue
+                for comp, stag in enumerate(STAG_J[D]):
+                    lo, hi = layout.overlap(rank, stag, d, side)
+                    count = int(np.prod([h - l + 1 for l, h in zip(lo, hi)]))
+                    # my +side message is the peer's -side message: tag by (receiver's side, comp)
+                    send_tag = 16 * d + 4 * (0 if side > 0 else 1) + comp
+                    recv_tag = 16 * d + 4 * (1 if side > 0 else 0) + comp
+                    msgs.append((peer, send_tag, recv_tag, comp, lo, hi, self.be.new_buffer(count),
+                                 self.be.new_buffer(count)))
+            self.plan.append(msgs)
+        self.bytes_per_exchange = sum(2 * 8 * m[6].numel() for msgs in self.plan for m in msgs)
+
+    def n_phases(self):
+        return len(self.plan)
+
+    def begin(self, phase):
+        msgs = self.plan[phase]
+        for (_, _, _, comp, lo, hi, sb, _) in msgs:
+            self.be.pack(comp, lo, hi, sb)
+        self.be.sync()
+        self.comm.post([(m[0], m[1], m[6]) for m in msgs], [(m[0], m[2], m[7]) for m in msgs])
+
+    def end(self, phase):
+        self.comm.wait()
+        for (_, _, _, comp, lo, hi, _, rb) in self.plan[phase]:
+            self.be.unpack_add(comp, lo, hi, rb)
+
+    def add_exchange(self):
+        """One process per box: the whole exchange (every rank calls this collectively)."""
+        for ph in range(self.n_phases()):
+            self.begin(ph)
+            self.end(ph)
+
+
+# ------------------------------------------------------------------------------------------------
+# particle migration
+# ------------------------------------------------------------------------------------------------
+class CapiSpeciesBackend:
+    def __init__(self, species, device, on_torch_stream=False):
+        import torch
+        from . import capi
+        self.torch, self.capi, self.sp, self.device = torch, capi, species, device
+        self.nw = capi.load().pgpu_wire_doubles(species.grid.h)
+        self.on_torch_stream = on_torch_stream
+
+    def mark_leavers(self):
+        import ctypes
+        cnt = (ctypes.c_long * 10)()
+        self.capi.check(self.capi.load().pgpu_species_mark_leavers(self.sp.h, cnt))
+        return np.array(list(cnt), dtype=np.int64)
+
+    def new_buffer(self, nrec):
+        return self.torch.empty(max(nrec, 1) * self.nw, dtype=self.torch.float64, device=self.device)
+
+    def pack_leavers(self, buf):
+        self.capi.check(self.capi.load().pgpu_species_pack_leavers_d(self.sp.h, buf.data_ptr()))
+
+    def append(self, nrec, buf):
+        self.capi.check(self.capi.load().pgpu_species_append_d(self.sp.h, int(nrec), buf.data_ptr()))
+
+    def sync(self):
+        if not self.on_torch_stream:
+            self.capi.check(self.capi.load().pgpu_synchronize())
+
+
+class Migration:
+    """Outgoing particles to the owning neighbour box, once per step after applyBCs."""
+
+    def __init__(self, layout, rank, comm, backend):
+        self.layout, self.rank, self.comm, self.be = layout, rank, comm, backend
+        self.sendbuf = None
+        self.counts = None
+        self.lost = 0
+
+    def begin_counts(self):
+        import torch
+        c = self.be.mark_leavers()
+        self.lost = int(c[9])
+        self.counts = c[:9].copy()
+        self.counts[4] = 0
+        t = torch.as_tensor(self.counts).to(self.be.device if hasattr(self.be, "device") else "cpu")
+        return t
+
+    def begin_payload(self, all_counts):
+        """all_counts[r] = the 9 per-direction leaver counts of rank r."""
+        lay, me, nw = self.layout, self.rank, self.be.nw
+        total = int(self.counts.sum())
+        self.sendbuf = self.be.new_buffer(total)
+        self.be.pack_leavers(self.sendbuf)
+        self.be.sync()
+        sends, recvs, self.arrivals = [], [], []
+        off = 0
+        for code in range(9):
+            n = int(self.counts[code])
+            if n == 0:
+                continue
+            peer = lay.neighbor_code(me, code)
+            assert peer is not None and peer != me, "leaver without an owner box"
+            sends.append((peer, code, self.sendbuf[off * nw:(off + n) * nw]))
+            off += n
+        for r in range(lay.world):
+            if r == me:
+                continue
+            cr = [int(v) for v in all_counts[r]]
+            for code in range(9):
+                if cr[code] and lay.neighbor_code(r, code) == me:
+                    buf = self.be.new_buffer(cr[code])
+                    recvs.append((r, code, buf[:cr[code] * nw]))
+                    self.arrivals.append((cr[code], buf))
+        self.comm.post(sends, recvs)
+
+    def end(self):
+        self.comm.wait()
+        n_in = 0
+        for (n, buf) in self.arrivals:
+            self.be.append(n, buf)
+            n_in += n
+        self.be.sync()
+        self.sendbuf, self.arrivals = None, []
+        return n_in
+
+    def migrate(self):
+        """One process per box: the whole migration (collective)."""
+        t = self.begin_counts()
+        allc = [x.cpu().numpy() for x in self.comm.all_gather(t)]
+        self.begin_payload(allc)
+        return self.end()
