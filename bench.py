@@ -54,7 +54,7 @@ EPS_OUTER = (0.0, 1.0e-3, 1.0e-6, 1.0e-9)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ncell", type=int, default=512, help="cells per direction of the per-GPU box")
@@ -120,7 +120,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -160,12 +160,10 @@ class ClockSampler:
 class Engine:
     """The particle side of the implicit step, driven through the C ABI (capi)."""
 
-    def __init__(self, args, rank, world, device):
+    def __init__(self, args, rank, world, device, stream=None):
         import torch
         from picnic_b200 import capi
         self.torch, self.capi, self.args, self.rank, self.world = torch, capi, args, rank, world
-        capi.load()
-        capi.init(device)
         self.deck, self.layout = make_deck(args, world)
         deck = self.deck
         self.lo, self.hi = rank_box(args, rank, self.layout)
@@ -211,10 +209,19 @@ class Engine:
         self.h2d = sum(h.nbytes for (_, _, h, _) in self.host_fields[0]) * self.n_outer
         self.d2h = sum(h.nbytes for (_, _, h, _) in self.host_J) * self.n_outer
         self.step_no = 0
-        self.halo = None
+        self.halo, self.migration = None, []
         if world > 1:
+            # one box per GPU: ghost add-exchange of J after every deposit and particle migration
+            # once per step, on device buffers over NCCL (picnic_b200/halo.py)
             from picnic_b200 import halo
-            self.halo = halo.HaloExchange(self.grid, self.deck, self.lo, self.hi, rank, self.layout)
+            dev = torch.device("cuda", device)
+            lay = halo.BoxLayout(2, deck.ncell, (args.ncell, args.ncell), deck.nghost, (1, 1))
+            assert lay.world == world and lay.box(rank) == (tuple(self.lo), tuple(self.hi))
+            comm = halo.DistComm(rank, world, stream=stream)
+            self.halo = halo.HaloExchange(lay, rank, comm, halo.CapiGridBackend(self.grid, dev, on_torch_stream=True))
+            self.migration = [halo.Migration(lay, rank, comm, halo.CapiSpeciesBackend(sp, dev, on_torch_stream=True))
+                              for sp in self.species]
+        self.migrated = 0
 
     def _upload_fields(self, j):
         lib, capi = self.capi.load(), self.capi
@@ -249,6 +256,9 @@ class Engine:
             self.pre_rhs_op(j, host_io)
         for sp in self.species:
             sp.finish_implicit_step((1, 1), (1, 1))   # 2nd-half v, 2nd-half x, periodic applyBCs
+        if self.migration:                             # remapOutcast: leavers to the owning box
+            from picnic_b200 import halo
+            self.migrated += halo.migrate_all(self.migration)
         self.step_no += 1
         if self.args.sort_every > 0 and self.step_no % self.args.sort_every == 0:
             for sp in self.species:
@@ -273,10 +283,13 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from picnic_b200 import capi
-    eng = Engine(args, rank, world, local)
-    # run the library on a torch stream so that torch.cuda.Event brackets its kernels
+    capi.load()
+    capi.init(local)
+    # run the library on a torch stream so that torch.cuda.Event brackets its kernels and the
+    # NCCL exchanges order against them without host synchronisation
     stream = torch.cuda.Stream(device=local)
     capi.check(capi.load().pgpu_set_stream(stream.cuda_stream))
+    eng = Engine(args, rank, world, local, stream=stream)
 
     def barrier():
         eng.sync()
@@ -317,11 +330,12 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     prof = {}
     for name in ("advance_cc1_fused", "advance_deferred", "advance_deposit_fused", "advance", "deposit_current", "bin_", "finish_step", "second_half", "fold_periodic",
-                 "current_add", "current_scale", "bc_periodic"):
+                 "current_add", "current_scale", "bc_periodic", "halo_", "mig_", "build_tables", "tile_boxes"):
         prof[name] = capi.profile_query(name)
     adv, app, unconv = capi.picard_totals(reset=True)
     k_mean = app / max(adv, 1)
 
+    # weak scaling: every rank loads the same number of particles and migration conserves the sum
     n_total = eng.n_particles * world
     units = float(n_total) * args.n_outer * args.steps
     value = units / (ms * 1e-3)
@@ -333,6 +347,14 @@ def run_ours(args):
         e2e = {"value": units / (ms_e * 1e-3), "unit": "particle-advances/s",
                "h2d_bytes_per_step": int(eng.h2d), "d2h_bytes_per_step": int(eng.d2h),
                "ms_per_step": ms_e / args.steps}
+
+    # migration must conserve the particles of the whole domain
+    n_now = sum(sp.n for sp in eng.species)
+    if world > 1:
+        t = torch.tensor([n_now], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        n_now = int(t.item())
+    assert n_now == n_total, "particles lost in migration: %d != %d" % (n_now, n_total)
 
     out = None
     if rank == 0:
@@ -360,6 +382,9 @@ def run_ours(args):
                                                              args.n_outer),
                        "particles_per_gpu": eng.n_particles, "boxes": "%dx%d" % eng.layout, "dt": args.dt,
                        "n_outer": args.n_outer, "sort_every": args.sort_every,
+                       "exchange": (None if world == 1 else
+                                    {"ghost_J_bytes_per_evaluation": eng.halo.bytes_per_exchange,
+                                     "migrated_particles_rank0": int(eng.migrated)}),
                        "mean_picard_passes": round(k_mean, 3), "unconverged_particles": int(unconv),
                        "l2_policy": "inputs (%.1f GB particle SoA per GPU) exceed the 126 MB L2; no flush needed"
                                     % (eng.n_particles * 96 / 1e9)},

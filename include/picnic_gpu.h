@@ -210,6 +210,11 @@ int pgpu_fab_unpack_d(pgpu_grid_t g, int kind, int comp, const int *lo, const in
  * append: adds n_add records received from neighbours. */
 int pgpu_wire_doubles(pgpu_grid_t g);
 int pgpu_species_mark_leavers(pgpu_species_t s, long *counts /* [10] */);
+/* The same without a host synchronisation: the counts go to a device int64[10] (so that they
+ * can be all-gathered on the device and read back once for all boxes and species); the caller
+ * hands this box's counts back with _set_leaver_counts before packing. */
+int pgpu_species_mark_leavers_d(pgpu_species_t s, long long *counts_d);
+int pgpu_species_set_leaver_counts(pgpu_species_t s, const long *counts /* [10] */);
 int pgpu_species_pack_leavers_d(pgpu_species_t s, double *buf_d);
 int pgpu_species_append_d(pgpu_species_t s, long n_add, const double *buf_d);
 

@@ -78,6 +78,7 @@ def load():
         "pgpu_scatter_delta_u": [lng, vp, vp, vp, vp, vp, vp],
         "pgpu_fab_pack_d": [vp, i32, i32, vp, vp, vp], "pgpu_fab_unpack_d": [vp, i32, i32, vp, vp, vp, i32],
         "pgpu_wire_doubles": [vp], "pgpu_species_mark_leavers": [vp, vp],
+        "pgpu_species_mark_leavers_d": [vp, vp], "pgpu_species_set_leaver_counts": [vp, vp],
         "pgpu_species_pack_leavers_d": [vp, vp], "pgpu_species_append_d": [vp, lng, vp],
         "pgpu_advance_particles": [vp, dbl], "pgpu_advance_particles_iteratively": [vp, dbl, i32, vp],
         "pgpu_set_current_density": [vp, dbl, i32], "pgpu_species_current_get": [vp, i32, vp, vp, vp],

@@ -216,18 +216,21 @@ int pgpu_fab_unpack_d(pgpu_grid_t g, int kind, int comp, const int *lo, const in
 
 int pgpu_wire_doubles(pgpu_grid_t g) { return g ? 2 * g->desc.D + 8 : 0; }
 
-int pgpu_species_mark_leavers(pgpu_species_t s, long *counts) {
-  if (!ctx().inited) return PGPU_ERR_STATE;
-  if (!s || !counts) return PGPU_ERR_ARG;
+__global__ void k_counts_out(const MigCounters *mc, long long *out) {
+  if (threadIdx.x < 10) out[threadIdx.x] = (long long)mc->count[threadIdx.x];
+}
+
+// Launches the marking pass; no synchronisation.  counts_d (optional): device int64[10].
+static int mark_leavers_launch(pgpu_species_s *s, long long *counts_d) {
   Context &c = ctx();
   const pgpu_grid_s *g = s->grid;
-  for (int k = 0; k < 10; ++k) counts[k] = 0;
   if (!s->mig) PGPU_CUDA(cudaMalloc(&s->mig, sizeof(MigCounters) + 16 * sizeof(unsigned)));
   PGPU_CUDA(cudaMemsetAsync(s->mig, 0, sizeof(MigCounters) + 16 * sizeof(unsigned), c.stream));
   s->mig_marked = false;
+  s->mig_leave = 0;
+  for (int k = 0; k < 10; ++k) s->mig_count[k] = 0;
   if (s->n == 0) {
-    s->mig_marked = true;
-    s->mig_leave = 0;
+    if (counts_d) k_counts_out<<<1, 32, 0, c.stream>>>((const MigCounters *)s->mig, counts_d);
     return 0;
   }
   if (materialize_old(s)) return PGPU_ERR_CUDA;
@@ -249,15 +252,45 @@ int pgpu_species_mark_leavers(pgpu_species_t s, long *counts) {
     KTimer t("mig_mark");
     k_mark_leavers<<<nb(s->n), 256, 0, c.stream>>>(s->x[0], s->x[1], s->n, G, s->cell_key, s->perm,
                                                   (MigCounters *)s->mig);
+    if (counts_d) k_counts_out<<<1, 32, 0, c.stream>>>((const MigCounters *)s->mig, counts_d);
   }
-  MigCounters h;
-  PGPU_CUDA(cudaMemcpyAsync(&h, s->mig, sizeof(MigCounters), cudaMemcpyDeviceToHost, c.stream));
-  PGPU_CUDA(cudaStreamSynchronize(c.stream));
-  for (int k = 0; k < 10; ++k) counts[k] = h.count[k];
-  s->mig_leave = h.nleave;
-  for (int k = 0; k < 10; ++k) s->mig_count[k] = h.count[k];
-  s->mig_marked = true;
   s->binned = false;
+  return 0;
+}
+
+int pgpu_species_mark_leavers(pgpu_species_t s, long *counts) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!s || !counts) return PGPU_ERR_ARG;
+  Context &c = ctx();
+  for (int k = 0; k < 10; ++k) counts[k] = 0;
+  const int rc = mark_leavers_launch(s, nullptr);
+  if (rc) return rc;
+  if (s->n) {
+    MigCounters h;
+    PGPU_CUDA(cudaMemcpyAsync(&h, s->mig, sizeof(MigCounters), cudaMemcpyDeviceToHost, c.stream));
+    PGPU_CUDA(cudaStreamSynchronize(c.stream));
+    for (int k = 0; k < 10; ++k) counts[k] = s->mig_count[k] = h.count[k];
+    s->mig_leave = h.nleave;
+  }
+  s->mig_marked = true;
+  return 0;
+}
+
+int pgpu_species_mark_leavers_d(pgpu_species_t s, long long *counts_d) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!s || !counts_d) return PGPU_ERR_ARG;
+  return mark_leavers_launch(s, counts_d);
+}
+
+int pgpu_species_set_leaver_counts(pgpu_species_t s, const long *counts) {
+  if (!s || !counts) return PGPU_ERR_ARG;
+  long tot = 0;
+  for (int k = 0; k < 10; ++k) {
+    s->mig_count[k] = counts[k];
+    tot += counts[k];
+  }
+  s->mig_leave = tot;
+  s->mig_marked = true;
   return 0;
 }
 

@@ -116,10 +116,12 @@ class DistComm:
         self.reqs = []
 
     def all_gather(self, t):
-        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        """Host copies of every rank's tensor (the read-back happens on the communicator's stream)."""
         with self.ctx():
+            t = t.clone()
+            out = [self.torch.empty_like(t) for _ in range(self.world)]
             self.dist.all_gather(out, t)
-        return out
+            return [o.cpu() for o in out]
 
 
 class LoopComm:
@@ -250,6 +252,15 @@ class CapiSpeciesBackend:
         self.capi.check(self.capi.load().pgpu_species_mark_leavers(self.sp.h, cnt))
         return np.array(list(cnt), dtype=np.int64)
 
+    def mark_leavers_device(self, counts_d):
+        """No host synchronisation: counts land in the device int64[10] tensor counts_d."""
+        self.capi.check(self.capi.load().pgpu_species_mark_leavers_d(self.sp.h, counts_d.data_ptr()))
+
+    def set_leaver_counts(self, counts):
+        import ctypes
+        cnt = (ctypes.c_long * 10)(*[int(v) for v in counts])
+        self.capi.check(self.capi.load().pgpu_species_set_leaver_counts(self.sp.h, cnt))
+
     def new_buffer(self, nrec):
         return self.torch.empty(max(nrec, 1) * self.nw, dtype=self.torch.float64, device=self.device)
 
@@ -279,8 +290,10 @@ class Migration:
         self.lost = int(c[9])
         self.counts = c[:9].copy()
         self.counts[4] = 0
-        t = torch.as_tensor(self.counts).to(self.be.device if hasattr(self.be, "device") else "cpu")
-        return t
+        return torch.as_tensor(self.counts)
+
+    def counts_on_device(self, t):
+        return t.to(self.be.device)
 
     def begin_payload(self, all_counts):
         """all_counts[r] = the 9 per-direction leaver counts of rank r."""
@@ -320,9 +333,40 @@ class Migration:
         self.sendbuf, self.arrivals = None, []
         return n_in
 
+    def use_counts(self, c10):
+        """Counts of this box obtained elsewhere (migrate_all's single device all-gather)."""
+        c10 = np.asarray(c10, dtype=np.int64)
+        self.lost = int(c10[9])
+        self.counts = c10[:9].copy()
+        self.counts[4] = 0
+        full = np.zeros(10, dtype=np.int64)
+        full[:9] = self.counts
+        full[9] = self.lost           # removed from the species, not sent anywhere
+        self.be.set_leaver_counts(full)
+
     def migrate(self):
         """One process per box: the whole migration (collective)."""
-        t = self.begin_counts()
-        allc = [x.cpu().numpy() for x in self.comm.all_gather(t)]
+        t = self.counts_on_device(self.begin_counts())
+        allc = [x.numpy() for x in self.comm.all_gather(t)]
         self.begin_payload(allc)
         return self.end()
+
+
+def migrate_all(migrations):
+    """Migration of several species of one box with ONE host synchronisation: every species is
+    marked on the device, the count vectors of all species and boxes are all-gathered on the
+    device and read back once, then the payloads move species by species."""
+    if not migrations:
+        return 0
+    m0 = migrations[0]
+    torch = m0.be.torch
+    dev_counts = torch.zeros((len(migrations), 10), dtype=torch.int64, device=m0.be.device)
+    for k, m in enumerate(migrations):
+        m.be.mark_leavers_device(dev_counts[k])
+    allc = [x.numpy() for x in m0.comm.all_gather(dev_counts)]        # [rank][species, 10]
+    n_in = 0
+    for k, m in enumerate(migrations):
+        m.use_counts(allc[m.rank][k])
+        m.begin_payload([allc[r][k][:9] for r in range(m.layout.world)])
+        n_in += m.end()
+    return n_in

@@ -99,7 +99,7 @@ def test_migration_on_device(pgpu):
         s.apply_bcs((1, 1), (1, 1))                       # periodic wrap of x and xold
         grids.append(g); sps.append(s)
         migs.append(halo.Migration(lay, r, hub.view(r), halo.CapiSpeciesBackend(s, dev)))
-    counts = [m.begin_counts().cpu().numpy() for m in migs]
+    counts = [m.begin_counts().numpy() for m in migs]
     moved = sum(int(c.sum()) for c in counts)
     assert moved > 200 and all(m.lost == 0 for m in migs)
     for m in migs:
