@@ -127,6 +127,8 @@ typedef struct {
 
 int pgpu_species_create(pgpu_grid_t g, const pgpu_species_desc *desc, pgpu_species_t *out);
 int pgpu_species_destroy(pgpu_species_t s);
+/* PicChargedSpecies::setParticleSolverParams (PicChargedSpecies.H:125-141) */
+int pgpu_species_set_solver_params(pgpu_species_t s, int order_swap, int iter_max, double rtol);
 /* Replace the particle set (PicChargedSpecies::initialize / partData() sync). */
 int pgpu_species_upload(pgpu_species_t s, long n, const double *x, const double *xold,
                         const double *v, const double *vold, const double *w,

@@ -66,6 +66,7 @@ def load():
         "pgpu_current_zero": [vp], "pgpu_current_add_species": [vp, vp], "pgpu_current_finalize": [vp],
         "pgpu_current_get": [vp, i32, vp, vp, vp],
         "pgpu_species_create": [vp, vp, vp], "pgpu_species_destroy": [vp],
+        "pgpu_species_set_solver_params": [vp, i32, i32, dbl],
         "pgpu_species_upload": [vp, lng, vp, vp, vp, vp, vp, vp],
         "pgpu_species_download": [vp, vp, vp, vp, vp, vp, vp],
         "pgpu_species_count": [vp],

@@ -587,6 +587,14 @@ int pgpu_species_create(pgpu_grid_t g, const pgpu_species_desc *d, pgpu_species_
   return 0;
 }
 
+int pgpu_species_set_solver_params(pgpu_species_t s, int order_swap, int iter_max, double rtol) {
+  if (!s || iter_max < 0 || !(rtol > 0.0)) return PGPU_ERR_ARG;
+  s->desc.order_swap = order_swap ? 1 : 0;
+  s->desc.iter_max = iter_max;
+  s->desc.rtol = rtol;
+  return 0;
+}
+
 int pgpu_species_destroy(pgpu_species_t s) {
   if (!s) return 0;
   cudaStreamSynchronize(ctx().stream);
