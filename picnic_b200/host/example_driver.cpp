@@ -24,7 +24,7 @@ int main(int argc, char **argv) {
   FILE *f = std::fopen(argv[1], "rb");
   if (!f) fatal("example_driver: cannot open problem file");
   int hdr[8];   // D, ncell0, ncell1, nghost, n, n_outer, iter_max, pad
-  double par[8];   // xmin0 xmin1 dx0 dx1 dt rtol fnorm cvac_norm
+  double par[10];  // xmin0 xmin1 dx0 dx1 dt rtol fnorm cvac_norm volume_scale pad
   rd(f, hdr, sizeof(hdr));
   rd(f, par, sizeof(par));
   const int D = hdr[0], ncell[2] = {hdr[1], hdr[2]}, nghost = hdr[3], n_outer = hdr[5];
@@ -34,7 +34,7 @@ int main(int argc, char **argv) {
 
   initialize(0);
   {
-    Mesh mesh(D, ncell, xmin, dx, nghost, periodic, lo, hi, 1.0);
+    Mesh mesh(D, ncell, xmin, dx, nghost, periodic, lo, hi, par[8]);
     // fields: six components with the bounds the mesh reports
     std::vector<std::vector<double>> F(6);
     FabRef R[6];

@@ -29,7 +29,7 @@ def test_host_shim_builds_and_fails_loudly_without_device(driver, tmp_path):
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is present")
     p = tmp_path / "p.bin"
-    p.write_bytes(struct.pack("8i", 2, 8, 8, 2, 0, 1, 0, 0) + struct.pack("8d", 0, 0, 1, 1, 0.1, 1e-12, 1, 1))
+    p.write_bytes(struct.pack("8i", 2, 8, 8, 2, 0, 1, 0, 0) + struct.pack("10d", 0, 0, 1, 1, 0.1, 1e-12, 1, 1, 1, 0))
     r = subprocess.run([driver, str(p), str(tmp_path / "r.bin")], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
@@ -47,8 +47,8 @@ def test_example_driver_matches_oracle(driver, tmp_path):
     prob = tmp_path / "p.bin"
     with open(prob, "wb") as f:
         f.write(struct.pack("8i", 2, 16, 16, deck.nghost, n, n_outer, deck.iter_max, 0))
-        f.write(struct.pack("8d", deck.xmin[0], deck.xmin[1], deck.dx[0], deck.dx[1], deck.dt, deck.rtol, fn,
-                            deck.units.cvac_norm))
+        f.write(struct.pack("10d", deck.xmin[0], deck.xmin[1], deck.dx[0], deck.dx[1], deck.dt, deck.rtol, fn,
+                            deck.units.cvac_norm, deck.volume_scale, 0.0))
         for (_, _, a) in list(E) + list(B):
             f.write(np.asfortranarray(a).tobytes(order="F"))
         f.write(np.ascontiguousarray(p["x"]).tobytes())
