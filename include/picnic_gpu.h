@@ -236,6 +236,40 @@ int pgpu_ta_delta_u(long n, const double *vp1, const double *den1, const double 
                     const double *gauss, const double *u_theta, const double *u_phi,
                     double *dU);
 
+/* Coulomb::applyScattering, PROBABILISTIC weight method (Coulomb.cpp:358-592, 919-1180): weighted
+ * particles, lighter-weight particle always scatters, heavier with probability wmin/wmax; pairing
+ * O(N) or all pairs (NxN / cells below NxN_Nthresh); sigma limited by the atomic spacing; b_max =
+ * the Debye length set by pgpu_debye_length.  Species must be binned with moments set. */
+enum { PGPU_ANG_TAKIZUKA = 0, PGPU_ANG_NANBU = 1, PGPU_ANG_BOBYLEV = 2, PGPU_ANG_ISOTROPIC = 5 };
+typedef struct {
+  double Clog;            /* coulomb_logarithm; 0 = per pair from b_max / b_min (Coulomb.cpp:1664-1672) */
+  int angular_scattering; /* PGPU_ANG_*  (NANBU_FAS*, large-angle events: not implemented -> PGPU_ERR_ARG) */
+  int NxN;                /* Coulomb.NxN */
+  int NxN_Nthresh;        /* Coulomb.NxN_Nthresh (11) */
+  int num_subcycles;      /* Coulomb.num_subcycles (1) */
+} pgpu_coulomb_params;
+int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm, double dt_sec,
+                         uint64_t seed, uint64_t step, long *npairs);
+/* Coulomb::GalileanScatter + SetPolarScattering for explicit random numbers (test hook); per pair:
+ * EF_norm, den12, bmax, sigma_max, gauss (N(0,1)), u_polar, u_phi (U[0,1)); outputs dU[3n], s12[n]. */
+int pgpu_coulomb_delta_u(long n, const double *vp1, const double *vp2, double charge1, double charge2,
+                         double mass1, double mass2, const pgpu_coulomb_params *prm, double dt_sec,
+                         const double *EF_norm, const double *den12, const double *bmax, const double *sigma_max,
+                         const double *gauss, const double *u_polar, const double *u_phi, double *dU, double *s12);
+
+/* Elastic::electronImpact (Elastic.cpp:225-388), PROBABILISTIC weights: every particle of sA picks a
+ * random partner of sB in its cell; sigma constant (ntab = 0) or tabulated (E [eV] ascending, Q, xi)
+ * with the reference's interpolation; angular 0 = ISOTROPIC (Q = momentum-transfer), 1 = OKHRIMOVSKYY. */
+typedef struct {
+  double const_sigma;     /* [m^2] */
+  int ntab;
+  const double *E, *Q, *xi;   /* host arrays of length ntab */
+  int angular_scattering;
+  int use_loglog_interp;
+} pgpu_elastic_params;
+int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elastic_params *prm, double dt_sec,
+                         uint64_t seed, uint64_t step, long *ncollisions);
+
 /* ScatteringUtils::computeDeltaU (ScatteringUtils.H:84-111) for explicit angles (test hook):
  * u[3n] relative velocities (component-major), one angle set per pair, dU[3n] out. */
 int pgpu_scatter_delta_u(long n, const double *u, const double *costh, const double *sinth,

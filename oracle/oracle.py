@@ -241,3 +241,85 @@ def ta_inter(cs1, v1, dens1, m1, q1, cs2, v2, dens2, m2, q2, Clog, dt_sec):
     lib().orc_ta_inter(cs1.size - 1, _ptr(cs1), _ptr(v1), v1.shape[1], _ptr(dens1), m1, q1,
                        _ptr(cs2), _ptr(v2), v2.shape[1], _ptr(dens2), m2, q2, Clog, dt_sec, C.byref(npairs))
     return npairs.value
+
+
+# ---- Coulomb (PROBABILISTIC) and Elastic ------------------------------------------------------
+_COUL_SET = False
+
+
+def _coul_sigs():
+    global _COUL_SET
+    if _COUL_SET:
+        return
+    L, dbl, vp, i32, lng = lib(), C.c_double, C.c_void_p, C.c_int, C.c_long
+    L.orc_nanbu_costh_sinth.argtypes = [dbl, dbl, vp, vp]
+    L.orc_coulomb_delta_u.argtypes = [vp, vp, dbl, dbl, dbl, dbl, dbl, dbl, i32, dbl, dbl, dbl, dbl, dbl, dbl, dbl, vp, vp]
+    L.orc_coulomb_delta_u.restype = i32
+    L.orc_coulomb_intra.argtypes = [lng, vp, vp, vp, lng, vp, vp, dbl, dbl, dbl, dbl, i32, i32, i32, dbl, vp]
+    L.orc_coulomb_inter.argtypes = ([lng, vp, vp, vp, lng, vp, dbl, dbl, vp, vp, vp, lng, vp, dbl, dbl, vp, dbl, dbl,
+                                     i32, i32, i32, dbl, vp])
+    L.orc_elastic_sigma.argtypes = [dbl, dbl, dbl, i32, vp, vp, vp, i32, i32, vp]
+    L.orc_elastic_sigma.restype = dbl
+    L.orc_elastic.argtypes = [lng, vp, vp, vp, lng, dbl, vp, vp, vp, lng, vp, dbl, dbl, i32, vp, vp, vp, i32, i32, dbl, vp]
+    _COUL_SET = True
+
+
+def nanbu_costh_sinth(s12, U):
+    _coul_sigs()
+    c, s = C.c_double(0), C.c_double(0)
+    lib().orc_nanbu_costh_sinth(s12, U, C.byref(c), C.byref(s))
+    return c.value, s.value
+
+
+def coulomb_delta_u(vp1, vp2, q1, q2, m1, m2, EF_norm, Clog, angular, den12, bmax, sigma_max, dt_sec, gauss, upol, uphi):
+    _coul_sigs()
+    a, b = np.ascontiguousarray(vp1, dtype=np.float64), np.ascontiguousarray(vp2, dtype=np.float64)
+    dU, s12 = np.zeros(3), C.c_double(0)
+    lib().orc_coulomb_delta_u(_ptr(a), _ptr(b), q1, q2, m1, m2, EF_norm, Clog, angular, den12, bmax, sigma_max, dt_sec,
+                              gauss, upol, uphi, _ptr(dU), C.byref(s12))
+    return dU, s12.value
+
+
+def coulomb_intra(cell_start, v, w, dens, LDe, cellV_SI, mass, charge, Clog, angular, NxN, NxN_Nthresh, dt_sec):
+    _coul_sigs()
+    npairs = C.c_long(0)
+    cs = np.ascontiguousarray(cell_start, dtype=np.int64)
+    lib().orc_coulomb_intra(cs.size - 1, _ptr(cs), _ptr(v), _ptr(w), v.shape[1], _ptr(dens), _ptr(LDe), cellV_SI, mass,
+                            charge, Clog, angular, int(NxN), NxN_Nthresh, dt_sec, C.byref(npairs))
+    return npairs.value
+
+
+def coulomb_inter(cs1, v1, w1, dens1, m1, q1, cs2, v2, w2, dens2, m2, q2, LDe, cellV_SI, Clog, angular, NxN,
+                  NxN_Nthresh, dt_sec):
+    _coul_sigs()
+    npairs = C.c_long(0)
+    cs1 = np.ascontiguousarray(cs1, dtype=np.int64)
+    cs2 = np.ascontiguousarray(cs2, dtype=np.int64)
+    lib().orc_coulomb_inter(cs1.size - 1, _ptr(cs1), _ptr(v1), _ptr(w1), v1.shape[1], _ptr(dens1), m1, q1, _ptr(cs2),
+                            _ptr(v2), _ptr(w2), v2.shape[1], _ptr(dens2), m2, q2, _ptr(LDe), cellV_SI, Clog, angular,
+                            int(NxN), NxN_Nthresh, dt_sec, C.byref(npairs))
+    return npairs.value
+
+
+def elastic_sigma(g12, mu, const_sigma=0.0, E=None, Q=None, XI=None, angular=0, loglog=False):
+    _coul_sigs()
+    xi = C.c_double(0)
+    n = 0 if E is None else len(E)
+    arr = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (E, Q, XI)]
+    s = lib().orc_elastic_sigma(g12, mu, const_sigma, n, *[None if a is None else _ptr(a) for a in arr], angular,
+                                int(loglog), C.byref(xi))
+    return s, xi.value
+
+
+def elastic(cs1, v1, w1, m1, cs2, v2, w2, dens2, m2, dt_sec, const_sigma=0.0, E=None, Q=None, XI=None, angular=0,
+            loglog=False):
+    _coul_sigs()
+    ncoll = C.c_long(0)
+    cs1 = np.ascontiguousarray(cs1, dtype=np.int64)
+    cs2 = np.ascontiguousarray(cs2, dtype=np.int64)
+    n = 0 if E is None else len(E)
+    arr = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (E, Q, XI)]
+    lib().orc_elastic(cs1.size - 1, _ptr(cs1), _ptr(v1), _ptr(w1), v1.shape[1], m1, _ptr(cs2), _ptr(v2), _ptr(w2),
+                      v2.shape[1], _ptr(dens2), m2, const_sigma, n, *[None if a is None else _ptr(a) for a in arr],
+                      angular, int(loglog), dt_sec, C.byref(ncoll))
+    return ncoll.value

@@ -14,6 +14,7 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <random>
 #include <vector>
 
@@ -219,4 +220,356 @@ extern "C" void orc_ta_inter(long ncell, const long *cell_start1, double *v1,
     }
   }
   if (npairs_out) *npairs_out = npairs;
+}
+
+/* =====================================================================================
+ * Coulomb, PROBABILISTIC weight method (src/scattering/Coulomb.cpp:14-77, 400-592,
+ * 919-1180, 1642-1692, 1795-1903; Coulomb.H:339-363) and Elastic::electronImpact
+ * (src/scattering/Elastic.cpp:225-476).  Non-relativistic build (Galilean scatter).
+ * ===================================================================================== */
+namespace {
+const double kHBAR = 6.62607015e-34 / (2.0 * M_PI);   /* PicnicConstants.H:31,34: H/TWOPI */
+
+struct CoulombConsts {
+  double mass1, mass2, mu, b90_fact, bqm_fact, EF_fact;
+};
+CoulombConsts coulomb_consts(double charge1, double charge2, double mass1, double mass2) {
+  CoulombConsts k;
+  k.mass1 = mass1;
+  k.mass2 = mass2;
+  k.mu = mass1 * mass2 / (mass1 + mass2);
+  const double qocSq = kQE * kQE / (kCVAC * kCVAC);
+  const double b90_codeToPhys = qocSq / (kTWOPI * kEP0 * kME);
+  k.b90_fact = std::abs(charge1 * charge2) * b90_codeToPhys;
+  k.bqm_fact = kHBAR / (2.0 * kME * kCVAC);
+  k.EF_fact = 0.0;
+  if (mass1 == 1.0 || mass2 == 1.0)
+    k.EF_fact = kHBAR * kHBAR / (2.0 * kME * k.mu) * std::pow(3.0 * kPI * kPI, 2.0 / 3.0) / (kME * kCVAC * kCVAC);
+  return k;
+}
+}  // namespace
+
+/* Coulomb::setNANBUcosthsinth (Coulomb.H:339-363) with the uniform draw made explicit */
+extern "C" void orc_nanbu_costh_sinth(double s12, double U, double *costh, double *sinth) {
+  double A12, c;
+  if (s12 < 0.1466) {
+    A12 = 1.0 / (s12 * (1.0 - s12 / 2.0 + s12 * s12 / 6.0));
+    c = 1.0 + 1.0 / A12 * std::log(1.0 - U * (1.0 - std::exp(-2.0 * A12)));
+  } else if (s12 < 3.0) {
+    const double s12sq = s12 * s12, s12cu = s12 * s12sq;
+    A12 = 1.0 / (0.0056958 + 0.9560202 * s12 - 0.508139 * s12sq + 0.47913906 * s12cu - 0.12788975 * s12sq * s12sq +
+                 0.02389567 * s12cu * s12sq);
+    c = 1.0 + 1.0 / A12 * std::log(1.0 - U * (1.0 - std::exp(-2.0 * A12)));
+  } else if (s12 < 6.0) {
+    A12 = 3.0 * std::exp(-s12);
+    c = 1.0 + 1.0 / A12 * std::log(1.0 - U * (1.0 - std::exp(-2.0 * A12)));
+  } else {
+    c = 2.0 * U - 1.0;
+  }
+  *costh = c;
+  *sinth = std::sqrt(1.0 - c * c);
+}
+
+/* Coulomb::GalileanScatter + SetPolarScattering (TAKIZUKA=0, NANBU=1, BOBYLEV=2, ISOTROPIC=5)
+ * with explicit draws: r_polar = |randn| for TAKIZUKA's small-angle branch, else a uniform;
+ * u_phi uniform.  Returns 0 and leaves dU = 0 when the reference returns early (Appendix B:
+ * the reference then uses an uninitialised deltaU; treated as zero). */
+extern "C" int orc_coulomb_delta_u(const double *vp1, const double *vp2, double charge1, double charge2,
+                                   double mass1, double mass2, double EF_norm, double Clog_in, int angular,
+                                   double den12, double bmax, double sigma_max, double dt_sec, double gauss,
+                                   double u_polar, double u_phi, double *dU, double *s12_out) {
+  const CoulombConsts k = coulomb_consts(charge1, charge2, mass1, mass2);
+  dU[0] = dU[1] = dU[2] = 0.0;
+  const double ux = vp1[0] - vp2[0], uy = vp1[1] - vp2[1], uz = vp1[2] - vp2[2];
+  const double u = sqrt(ux * ux + uy * uy + uz * uz);
+  if (u <= std::numeric_limits<double>::min()) return 0;
+  const double vsum = std::sqrt(vp1[0] * vp1[0] + vp1[1] * vp1[1] + vp1[2] * vp1[2]) +
+                      std::sqrt(vp2[0] * vp2[0] + vp2[1] * vp2[1] + vp2[2] * vp2[2]);
+  if (u <= 1.0e-14 * vsum) return 0;
+  double b0 = k.b90_fact / (k.mu * u * u + 2.0 * EF_norm);
+  const double bmin_qm = k.bqm_fact / (k.mu * u + std::sqrt(2.0 * EF_norm * k.mu));
+  double Clog = Clog_in;
+  if (Clog == 0.0 && u > 0.0) {
+    Clog = 0.5 * std::log((b0 * b0 / 4.0 + bmax * bmax) / (b0 * b0 / 4.0 + bmin_qm * bmin_qm));
+    Clog = std::max(2.0, Clog);
+  }
+  b0 = k.b90_fact / (k.mu * u * u);
+  double sigma_eff = kPI * b0 * b0 * Clog;
+  sigma_eff = std::min(sigma_eff, sigma_max);
+  const double s12 = sigma_eff * den12 * u * kCVAC * dt_sec;
+  if (s12_out) *s12_out = s12;
+  double costh = 1.0, sinth = 0.0;
+  switch (angular) {
+    case 0:
+      if (s12 < 2.0) {
+        const double delta = sqrt(s12 / 2.0) * std::abs(gauss);
+        const double deltasq = delta * delta;
+        sinth = 2.0 * delta / (1.0 + deltasq);
+        costh = 1.0 - 2.0 * deltasq / (1.0 + deltasq);
+      } else {
+        const double theta = kPI * u_polar;
+        costh = std::cos(theta);
+        sinth = std::sin(theta);
+      }
+      break;
+    case 1:
+      orc_nanbu_costh_sinth(s12, u_polar, &costh, &sinth);
+      break;
+    case 2:
+      costh = 1.0 - std::min(s12, 2.0);
+      sinth = std::sin(std::acos(costh));
+      break;
+    default: {
+      const double theta = kPI * u_polar;
+      costh = std::cos(theta);
+      sinth = std::sin(theta);
+    }
+  }
+  const double phi = kTWOPI * u_phi;
+  orc_scatter_delta_u(ux, uy, uz, costh, sinth, std::cos(phi), std::sin(phi), dU);
+  return 1;
+}
+
+namespace {
+/* one pair with the reference's draw order: polar draw(s) inside SetPolarScattering, then phi,
+ * then the weight-rejection uniform (only for unequal weights) */
+struct PairCtx {
+  double charge1, charge2, mass1, mass2, EF_norm, Clog;
+  int angular;
+  double bmax, sigma_max, dt_sec;
+};
+void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2, double den12, double f1,
+                  double f2) {
+  /* replicate which draws GalileanScatter makes: decide the branch from s12 first */
+  double dU[3], s12 = 0.0;
+  double probe[3];
+  const int live = orc_coulomb_delta_u(b1, b2, c.charge1, c.charge2, c.mass1, c.mass2, c.EF_norm, c.Clog, 2,
+                                       den12, c.bmax, c.sigma_max, c.dt_sec, 0.0, 0.0, 0.0, probe, &s12);
+  if (live) {
+    double gauss = 0.0, upol = 0.0;
+    if (c.angular == 0) {
+      if (s12 < 2.0) gauss = mu_randn();
+      else upol = mu_rand();
+    } else if (c.angular != 2) {
+      upol = mu_rand();
+    }
+    const double uphi = mu_rand();
+    orc_coulomb_delta_u(b1, b2, c.charge1, c.charge2, c.mass1, c.mass2, c.EF_norm, c.Clog, c.angular, den12,
+                        c.bmax, c.sigma_max, c.dt_sec, gauss, upol, uphi, dU, nullptr);
+  } else {
+    dU[0] = dU[1] = dU[2] = 0.0;
+  }
+  if ((float)w1 == (float)w2) {
+    for (int n = 0; n < 3; n++) b1[n] += f1 * dU[n];
+    for (int n = 0; n < 3; n++) b2[n] -= f2 * dU[n];
+  } else if ((float)w1 < (float)w2) {
+    for (int n = 0; n < 3; n++) b1[n] += f1 * dU[n];
+    if (mu_rand() < w1 / w2)
+      for (int n = 0; n < 3; n++) b2[n] -= f2 * dU[n];
+  } else {
+    if (mu_rand() < w2 / w1)
+      for (int n = 0; n < 3; n++) b1[n] += f1 * dU[n];
+    for (int n = 0; n < 3; n++) b2[n] -= f2 * dU[n];
+  }
+}
+}  // namespace
+
+/* Coulomb::applyIntraScattering_PROB (Coulomb.cpp:400-592), enforce_conservations = false */
+extern "C" void orc_coulomb_intra(long ncell, const long *cell_start, double *v, const double *w, long n,
+                                  const double *dens, const double *LDe, double cellV_SI, double mass, double charge,
+                                  double Clog, int angular, int NxN_in, int NxN_Nthresh, double dt_sec,
+                                  long *npairs_out) {
+  const CoulombConsts k = coulomb_consts(charge, charge, mass, mass);
+  long npairs = 0;
+  std::vector<long> idx;
+  for (long c = 0; c < ncell; ++c) {
+    const double numDen = dens[c];
+    if (numDen == 0.0) continue;
+    const double atomic_spacing = 1.0 / std::cbrt(4.0 / 3.0 * kPI * numDen);
+    PairCtx ctx = {charge, charge, mass, mass, k.EF_fact * std::pow(numDen, 2.0 / 3.0), Clog, angular,
+                   LDe[c], 1.0 / (numDen * atomic_spacing), dt_sec};
+    const long numCell = cell_start[c + 1] - cell_start[c];
+    if (numCell < 2) continue;
+    bool NxN = NxN_in != 0;
+    if (numCell < NxN_Nthresh) NxN = true;
+    bool odd_NxN = false;
+    if (!NxN && numCell % 2 == 1) odd_NxN = true;
+    const long Naa = numCell - 1;
+    idx.resize(numCell);
+    for (long q = 0; q < numCell; ++q) idx[q] = cell_start[c] + q;
+    std::shuffle(idx.begin(), idx.end(), global_rand_gen);
+    const long p1_max = numCell - 2;
+    for (long p1 = 0; p1 <= p1_max; p1++) {
+      long p2_max = p1 + 1;
+      if (NxN) p2_max = numCell - 1;
+      else if (odd_NxN) p2_max = 2;
+      for (long p2 = p1 + 1; p2 <= p2_max; p2++) {
+        const long i1 = idx[p1], i2 = idx[p2];
+        const double wpMax = std::max(w[i1], w[i2]);
+        double den12;
+        if (NxN) den12 = wpMax / cellV_SI;
+        else if (odd_NxN) den12 = wpMax * Naa / cellV_SI / 2.0;
+        else den12 = wpMax * Naa / cellV_SI;
+        double a[3] = {v[i1], v[n + i1], v[2 * n + i1]}, b[3] = {v[i2], v[n + i2], v[2 * n + i2]};
+        coulomb_pair(ctx, a, w[i1], b, w[i2], den12, 0.5, 0.5);
+        for (int q = 0; q < 3; ++q) {
+          v[q * n + i1] = a[q];
+          v[q * n + i2] = b[q];
+        }
+        ++npairs;
+      }
+      if (odd_NxN && p1 == 1) odd_NxN = false;
+      if (!odd_NxN && !NxN) ++p1;
+    }
+  }
+  if (npairs_out) *npairs_out = npairs;
+}
+
+/* Coulomb::applyInterScattering_PROB (Coulomb.cpp:919-1180), enforce_conservations = false */
+extern "C" void orc_coulomb_inter(long ncell, const long *cs1, double *v1, const double *w1, long n1,
+                                  const double *dens1, double mass1, double charge1, const long *cs2, double *v2,
+                                  const double *w2, long n2, const double *dens2, double mass2, double charge2,
+                                  const double *LDe, double cellV_SI, double Clog, int angular, int NxN_in,
+                                  int NxN_Nthresh, double dt_sec, long *npairs_out) {
+  const CoulombConsts k = coulomb_consts(charge1, charge2, mass1, mass2);
+  long npairs = 0;
+  std::vector<long> idx1, idx2;
+  for (long c = 0; c < ncell; ++c) {
+    const double numDen1 = dens1[c], numDen2 = dens2[c];
+    if (numDen1 * numDen2 == 0.0) continue;
+    const double minn = std::min(numDen1, numDen2), maxn = std::max(numDen1, numDen2);
+    const double atomic_spacing = 1.0 / std::cbrt(4.0 / 3.0 * kPI * minn);
+    PairCtx ctx = {charge1, charge2, mass1, mass2, k.EF_fact * std::pow(maxn, 2.0 / 3.0), Clog, angular,
+                   LDe[c], 1.0 / (minn * atomic_spacing), dt_sec};
+    const long numCell1 = cs1[c + 1] - cs1[c], numCell2 = cs2[c + 1] - cs2[c];
+    if (numCell1 * numCell2 < 2) continue;
+    const long Nmin = std::min(numCell1, numCell2), Nmax = std::max(numCell1, numCell2);
+    bool NxN = NxN_in != 0;
+    if (Nmin < NxN_Nthresh) NxN = true;
+    idx1.resize(numCell1);
+    for (long q = 0; q < numCell1; ++q) idx1[q] = cs1[c] + q;
+    std::shuffle(idx1.begin(), idx1.end(), global_rand_gen);
+    idx2.resize(numCell2);
+    for (long q = 0; q < numCell2; ++q) idx2[q] = cs2[c] + q;
+    std::shuffle(idx2.begin(), idx2.end(), global_rand_gen);
+    for (long p = 0; p < Nmax; p++) {
+      long p1, p2, pmin_start;
+      if (Nmin == numCell1) {
+        p1 = p % numCell1;
+        p2 = p;
+        pmin_start = p1;
+      } else {
+        p1 = p;
+        p2 = p % numCell2;
+        pmin_start = p2;
+      }
+      long pmin_end = pmin_start;
+      if (NxN) {
+        pmin_start = 0;
+        pmin_end = Nmin - 1;
+      }
+      for (long pmin = pmin_start; pmin <= pmin_end; pmin++) {
+        if (NxN) {
+          if (Nmin == numCell1) p1 = pmin;
+          else p2 = pmin;
+        }
+        const long i1 = idx1[p1], i2 = idx2[p2];
+        const double wpMax = std::max(w1[i1], w2[i2]);
+        const double den12 = NxN ? wpMax / cellV_SI : wpMax * Nmin / cellV_SI;
+        double a[3] = {v1[i1], v1[n1 + i1], v1[2 * n1 + i1]}, b[3] = {v2[i2], v2[n2 + i2], v2[2 * n2 + i2]};
+        coulomb_pair(ctx, a, w1[i1], b, w2[i2], den12, k.mu / mass1, k.mu / mass2);
+        for (int q = 0; q < 3; ++q) {
+          v1[q * n1 + i1] = a[q];
+          v2[q * n2 + i2] = b[q];
+        }
+        ++npairs;
+      }
+    }
+  }
+  if (npairs_out) *npairs_out = npairs;
+}
+
+/* Elastic::getSigma / getTextSigma (Elastic.cpp:390-476): const sigma (ntab == 0) or a table
+ * (E [eV] ascending, Q, xi) with the reference's interpolation; angular: 0 ISOTROPIC (Q = Qelm),
+ * 1 OKHRIMOVSKYY (Q = Qela).  The interpolation formulas, including which end they weight, are
+ * the reference's (MathUtils::linearInterp, ScatteringUtils::semilogInterp/loglogInterp). */
+extern "C" double orc_elastic_sigma(double g12, double mu, double const_sigma, int ntab, const double *E,
+                                    const double *Q, const double *XI, int angular, int loglog, double *xi_out) {
+  *xi_out = 0.0;
+  if (ntab == 0) return const_sigma;
+  const double mcSq = kME * kCVAC * kCVAC / kQE;
+  const double KE = mu * mcSq * g12 * g12 / 2.0;
+  double sigma = 0.0, xi = 0.0;
+  auto lin = [&](const double *Y, int i) {   /* MathUtils::linearInterp (MathUtils.cpp:134-148) */
+    return (Y[i + 1] * (KE - E[i]) + Y[i] * (E[i + 1] - KE)) / (E[i + 1] - E[i]);
+  };
+  auto loglogI = [&](const double *Y, int i) {
+    const double l0 = log10(KE), lu = log10(E[i]), ld = log10(E[i + 1]);
+    return pow(10.0, (log10(Y[i + 1]) * (l0 - ld) + log10(Y[i]) * (lu - l0)) / (lu - ld));
+  };
+  auto semilogI = [&](const double *Y, int i) {
+    const double l0 = log10(KE), lu = log10(E[i]), ld = log10(E[i + 1]);
+    return (Y[i + 1] * (l0 - ld) + Y[i] * (lu - l0)) / (lu - ld);
+  };
+  if (KE >= E[ntab - 1]) {
+    if (angular == 0) sigma = Q[ntab - 1] * log(KE) / log(E[ntab - 1]) * E[ntab - 1] / KE;
+    else {
+      sigma = Q[ntab - 1] * E[ntab - 1] / KE;
+      xi = XI[ntab - 1];
+    }
+  } else {
+    int index = ntab / 2;
+    while (KE < E[index]) index--;
+    while (KE > E[index + 1]) index++;
+    if (loglog && Q[index] * E[index] > 0.0) sigma = loglogI(Q, index);
+    else sigma = lin(Q, index);
+    if (angular == 1) {
+      if (E[index] * KE > 0.0) xi = semilogI(XI, index);
+      else xi = lin(XI, index);
+    }
+  }
+  *xi_out = xi;
+  return sigma;
+}
+
+/* Elastic::electronImpact (Elastic.cpp:225-388), PROBABILISTIC weight method */
+extern "C" void orc_elastic(long ncell, const long *cs1, double *v1, const double *w1, long n1, double mass1,
+                            const long *cs2, double *v2, const double *w2, long n2, const double *dens2,
+                            double mass2, double const_sigma, int ntab, const double *E, const double *Q,
+                            const double *XI, int angular, int loglog, double dt_sec, long *ncoll_out) {
+  const double mu = mass1 * mass2 / (mass1 + mass2);
+  long ncoll = 0;
+  for (long c = 0; c < ncell; ++c) {
+    const long numCell1 = cs1[c + 1] - cs1[c], numCell2 = cs2[c + 1] - cs2[c];
+    if (numCell1 < 1 || numCell2 < 1) continue;
+    for (long q = 0; q < numCell1; ++q) {
+      const long i1 = cs1[c] + q;
+      std::uniform_int_distribution<> pick(0, (int)numCell2 - 1);   /* MathUtils::randInt */
+      const long i2 = cs2[c] + pick(global_rand_gen);
+      double a[3] = {v1[i1], v1[n1 + i1], v1[2 * n1 + i1]}, b[3] = {v2[i2], v2[n2 + i2], v2[2 * n2 + i2]};
+      double g12 = 0.0;
+      for (int d = 0; d < 3; ++d) g12 += pow(a[d] - b[d], 2);
+      g12 = sqrt(g12);
+      double xi;
+      const double sigma = orc_elastic_sigma(g12, mu, const_sigma, ntab, E, Q, XI, angular, loglog, &xi);
+      if (sigma == 0.0) continue;
+      const double arg = g12 * kCVAC * sigma * dens2[c] * dt_sec;
+      const double q12 = 1.0 - exp(-arg);
+      if (mu_rand() <= q12) {
+        ++ncoll;
+        const double phi = kTWOPI * mu_rand();
+        const double R = mu_rand();
+        const double costh = 1.0 - 2.0 * R * (1.0 - xi) / (1.0 + xi * (1.0 - 2.0 * R));
+        const double sinth = sqrt(1.0 - costh * costh);
+        double dU[3];
+        orc_scatter_delta_u(a[0] - b[0], a[1] - b[1], a[2] - b[2], costh, sinth, cos(phi), sin(phi), dU);
+        const double r2 = mu_rand();
+        if (r2 <= w2[i2] / w1[i1])
+          for (int d = 0; d < 3; ++d) v1[d * n1 + i1] = a[d] + mu / mass1 * dU[d];
+        if (r2 <= w1[i1] / w2[i2])
+          for (int d = 0; d < 3; ++d) v2[d * n2 + i2] = b[d] - mu / mass2 * dU[d];
+      }
+    }
+  }
+  if (ncoll_out) *ncoll_out = ncoll;
 }

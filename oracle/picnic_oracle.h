@@ -156,6 +156,29 @@ void orc_ta_inter(long ncell, const long *cell_start1, double *v1, long n1,
                   const double *dens2, double mass2, double charge2, double Clog,
                   double dt_sec, long *npairs);
 
+/* Coulomb (PROBABILISTIC, Galilean) and Elastic: see oracle_scatter.cpp */
+void orc_nanbu_costh_sinth(double s12, double U, double *costh, double *sinth);
+int orc_coulomb_delta_u(const double *vp1, const double *vp2, double charge1, double charge2,
+                        double mass1, double mass2, double EF_norm, double Clog_in, int angular,
+                        double den12, double bmax, double sigma_max, double dt_sec, double gauss,
+                        double u_polar, double u_phi, double *dU, double *s12_out);
+void orc_coulomb_intra(long ncell, const long *cell_start, double *v, const double *w, long n,
+                       const double *dens, const double *LDe, double cellV_SI, double mass,
+                       double charge, double Clog, int angular, int NxN, int NxN_Nthresh,
+                       double dt_sec, long *npairs);
+void orc_coulomb_inter(long ncell, const long *cs1, double *v1, const double *w1, long n1,
+                       const double *dens1, double mass1, double charge1, const long *cs2,
+                       double *v2, const double *w2, long n2, const double *dens2, double mass2,
+                       double charge2, const double *LDe, double cellV_SI, double Clog,
+                       int angular, int NxN, int NxN_Nthresh, double dt_sec, long *npairs);
+double orc_elastic_sigma(double g12, double mu, double const_sigma, int ntab, const double *E,
+                         const double *Q, const double *XI, int angular, int loglog,
+                         double *xi_out);
+void orc_elastic(long ncell, const long *cs1, double *v1, const double *w1, long n1, double mass1,
+                 const long *cs2, double *v2, const double *w2, long n2, const double *dens2,
+                 double mass2, double const_sigma, int ntab, const double *E, const double *Q,
+                 const double *XI, int angular, int loglog, double dt_sec, long *ncoll);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,16 @@ class SpeciesDesc(C.Structure):
                 ("motion", C.c_int), ("forces", C.c_int)]
 
 
+class CoulombParams(C.Structure):
+    _fields_ = [("Clog", C.c_double), ("angular_scattering", C.c_int), ("NxN", C.c_int), ("NxN_Nthresh", C.c_int),
+                ("num_subcycles", C.c_int)]
+
+
+class ElasticParams(C.Structure):
+    _fields_ = [("const_sigma", C.c_double), ("ntab", C.c_int), ("E", C.c_void_p), ("Q", C.c_void_p),
+                ("xi", C.c_void_p), ("angular_scattering", C.c_int), ("use_loglog_interp", C.c_int)]
+
+
 class PicardStats(C.Structure):
     _fields_ = [("num_parts_its", C.c_long), ("num_apply_its", C.c_long), ("num_unconverged", C.c_long)]
 
@@ -90,6 +100,9 @@ def load():
         "pgpu_apply_bcs": [vp, vp, vp], "pgpu_finish_implicit_step": [vp, vp, vp], "pgpu_stable_dt": [vp, vp], "pgpu_global_moments": [vp, vp],
         "pgpu_collide_ta": [vp, vp, dbl, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_ta_delta_u": [lng, vp, vp, vp, vp, dbl, dbl, dbl, vp, vp, vp, vp],
+        "pgpu_collide_coulomb": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
+        "pgpu_coulomb_delta_u": [lng, vp, vp, dbl, dbl, dbl, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "pgpu_collide_elastic": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
         "pgpu_launch_count": [], "pgpu_picard_totals": [vp, vp, vp, i32], "pgpu_abi_version": [], "pgpu_last_error": [],
     }
@@ -353,6 +366,35 @@ def ta_delta_u(vp1, den1, vp2, den2, b90_fact, Clog, dt_sec, gauss, u_theta, u_p
     check(load().pgpu_ta_delta_u(n, _p(args[0]), _p(args[1]), _p(args[2]), _p(args[3]), b90_fact, Clog, dt_sec,
                                  _p(rnd[0]), _p(rnd[1]), _p(rnd[2]), _p(out)))
     return out
+
+
+def collide_coulomb(sA, sB, Clog, dt_sec, seed, step, angular=0, NxN=False, NxN_Nthresh=11, num_subcycles=1,
+                    count=True):
+    prm = CoulombParams(Clog, angular, int(NxN), NxN_Nthresh, num_subcycles)
+    np_ = C.c_long(0)
+    check(load().pgpu_collide_coulomb(sA.h, sB.h, C.byref(prm), dt_sec, seed, step, C.byref(np_) if count else None))
+    return np_.value
+
+
+def coulomb_delta_u(vp1, vp2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, den12, bmax, sigma_max, gauss, upol, uphi):
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    n = np.asarray(den12).size
+    prm = CoulombParams(Clog, angular, 0, 11, 1)
+    a = [c(vp1), c(vp2), c(EF_norm), c(den12), c(bmax), c(sigma_max), c(gauss), c(upol), c(uphi)]
+    dU, s12 = np.zeros((3, n)), np.zeros(n)
+    check(load().pgpu_coulomb_delta_u(n, _p(a[0]), _p(a[1]), q1, q2, m1, m2, C.byref(prm), dt_sec, *[_p(x) for x in a[2:]],
+                                      _p(dU), _p(s12)))
+    return dU, s12
+
+
+def collide_elastic(sA, sB, dt_sec, seed, step, const_sigma=0.0, E=None, Q=None, xi=None, angular=0, loglog=False,
+                    count=True):
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    E, Q, xi = c(E), c(Q), c(xi)
+    prm = ElasticParams(const_sigma, 0 if E is None else E.size, _p(E), _p(Q), _p(xi), angular, int(loglog))
+    nc = C.c_long(0)
+    check(load().pgpu_collide_elastic(sA.h, sB.h, C.byref(prm), dt_sec, seed, step, C.byref(nc) if count else None))
+    return nc.value
 
 
 def scatter_delta_u(u, costh, sinth, cosphi, sinphi):

@@ -241,6 +241,411 @@ k_ta_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, do
   if (lane == 0) atomicAdd(npairs, (unsigned long long)pMax);
 }
 
+
+// =============================================================================================
+// Coulomb, PROBABILISTIC weight method (src/scattering/Coulomb.cpp:400-592, 919-1180,
+// 1642-1692, 1795-1903; Coulomb.H:339-363), non-relativistic (Galilean) build.
+// One warp per cell.  Pairs that share a particle are ordered by construction:
+//  * O(N) pairing: disjoint neighbour pairs of the shuffled list, one lane each;
+//  * NxN pairing (small cells, or Coulomb.NxN = true): a round-robin tournament -- every round
+//    is a set of disjoint pairs done by the lanes in parallel, rounds are separated by a warp
+//    barrier.  The reference visits the same pairs in lexicographic order; the order of
+//    independent random kicks is statistically irrelevant.
+//  * inter-species: a lane owns one particle of the shorter list and walks its partners.
+// =============================================================================================
+enum { STREAM_WEIGHT = 0x5754u, STREAM_ELA = 0x454cu };
+enum { ANG_TAKIZUKA = 0, ANG_NANBU = 1, ANG_BOBYLEV = 2, ANG_ISOTROPIC = 5 };
+
+struct CoulParams {
+  double b90_fact, bqm_fact, EF_fact, mu, f1, f2, Clog, dt_sec, cellV_SI;
+  int angular, NxN, NxN_Nthresh;
+  unsigned seed_lo, seed_hi, step_lo, step_hi;
+  int box_lo0, box_lo1, nbox0, ncell_glob0;
+};
+__device__ __forceinline__ unsigned global_cell(const CoulParams &P, int cell) {
+  const int i = cell % P.nbox0 + P.box_lo0, j = cell / P.nbox0 + P.box_lo1;
+  return (unsigned)(i + j * P.ncell_glob0);
+}
+
+// Coulomb::setNANBUcosthsinth (Coulomb.H:339-363)
+__device__ __forceinline__ void nanbu_costh_sinth(double s12, double U, double &costh, double &sinth) {
+  double A12, c;
+  if (s12 < 0.1466) {
+    A12 = 1.0 / (s12 * (1.0 - s12 / 2.0 + s12 * s12 / 6.0));
+    c = 1.0 + 1.0 / A12 * log(1.0 - U * (1.0 - exp(-2.0 * A12)));
+  } else if (s12 < 3.0) {
+    const double s12sq = s12 * s12, s12cu = s12 * s12sq;
+    A12 = 1.0 / (0.0056958 + 0.9560202 * s12 - 0.508139 * s12sq + 0.47913906 * s12cu - 0.12788975 * s12sq * s12sq +
+                 0.02389567 * s12cu * s12sq);
+    c = 1.0 + 1.0 / A12 * log(1.0 - U * (1.0 - exp(-2.0 * A12)));
+  } else if (s12 < 6.0) {
+    A12 = 3.0 * exp(-s12);
+    c = 1.0 + 1.0 / A12 * log(1.0 - U * (1.0 - exp(-2.0 * A12)));
+  } else {
+    c = 2.0 * U - 1.0;
+  }
+  costh = c;
+  sinth = sqrt(1.0 - c * c);
+}
+
+// Coulomb::GalileanScatter (:1642-1692) + SetPolarScattering (:1795-1903) with explicit draws.
+// false (dU = 0) where the reference returns early.
+__device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const double *vp1, const double *vp2,
+                                                double EF_norm, double den12, double bmax, double sigma_max,
+                                                double gauss, double upol, double uphi, double *dU, double *s12o) {
+  const double PI = 3.14159265358979323846, CVAC = 2.99792458e+08;
+  dU[0] = dU[1] = dU[2] = 0.0;
+  const double ux = vp1[0] - vp2[0], uy = vp1[1] - vp2[1], uz = vp1[2] - vp2[2];
+  const double u = sqrt(ux * ux + uy * uy + uz * uz);
+  if (u <= 2.2250738585072014e-308) return false;
+  const double vsum = sqrt(vp1[0] * vp1[0] + vp1[1] * vp1[1] + vp1[2] * vp1[2]) +
+                      sqrt(vp2[0] * vp2[0] + vp2[1] * vp2[1] + vp2[2] * vp2[2]);
+  if (u <= 1.0e-14 * vsum) return false;
+  double b0 = P.b90_fact / (P.mu * u * u + 2.0 * EF_norm);
+  const double bmin_qm = P.bqm_fact / (P.mu * u + sqrt(2.0 * EF_norm * P.mu));
+  double Clog = P.Clog;
+  if (Clog == 0.0) {
+    Clog = 0.5 * log((b0 * b0 / 4.0 + bmax * bmax) / (b0 * b0 / 4.0 + bmin_qm * bmin_qm));
+    Clog = fmax(2.0, Clog);
+  }
+  b0 = P.b90_fact / (P.mu * u * u);
+  double sigma_eff = PI * b0 * b0 * Clog;
+  sigma_eff = fmin(sigma_eff, sigma_max);
+  const double s12 = sigma_eff * den12 * u * CVAC * P.dt_sec;
+  if (s12o) *s12o = s12;
+  double costh = 1.0, sinth = 0.0;
+  switch (P.angular) {
+    case ANG_TAKIZUKA:
+      if (s12 < 2.0) {
+        const double delta = sqrt(s12 / 2.0) * fabs(gauss);
+        const double deltasq = delta * delta;
+        sinth = 2.0 * delta / (1.0 + deltasq);
+        costh = 1.0 - 2.0 * deltasq / (1.0 + deltasq);
+      } else {
+        sincos(PI * upol, &sinth, &costh);
+      }
+      break;
+    case ANG_NANBU:
+      nanbu_costh_sinth(s12, upol, costh, sinth);
+      break;
+    case ANG_BOBYLEV:
+      costh = 1.0 - fmin(s12, 2.0);
+      sinth = sin(acos(costh));
+      break;
+    default:
+      sincos(PI * upol, &sinth, &costh);
+  }
+  double sinphi, cosphi;
+  sincos(2.0 * PI * uphi, &sinphi, &cosphi);
+  scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
+  return true;
+}
+
+__global__ void k_coulomb_delta_u(long n, CoulParams P, const double *vp1, const double *vp2, const double *EF,
+                                  const double *den12, const double *bmax, const double *smax, const double *gauss,
+                                  const double *upol, const double *uphi, double *dU, double *s12) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a[3] = {vp1[i], vp1[n + i], vp1[2 * n + i]}, b[3] = {vp2[i], vp2[n + i], vp2[2 * n + i]};
+  double d[3], s = 0.0;
+  coulomb_delta_u(P, a, b, EF[i], den12[i], bmax[i], smax[i], gauss[i], upol[i], uphi[i], d, &s);
+  dU[i] = d[0];
+  dU[n + i] = d[1];
+  dU[2 * n + i] = d[2];
+  s12[i] = s;
+}
+
+struct CellCtx {
+  double EF_norm, bmax, sigma_max;
+  unsigned gcell;
+};
+
+// one pair: draws from Philox(cell, pair), weight rejection as Coulomb.cpp:561-584 / 1149-1172
+__device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx &C, double *a0, double *a1, double *a2,
+                                             const double *wa, int pa, double *b0, double *b1, double *b2,
+                                             const double *wb, int pb, double den_fact, unsigned pair_id,
+                                             unsigned salt) {
+  u4 c;
+  c.x = pair_id;
+  c.y = C.gcell;
+  c.z = P.step_lo;
+  c.w = P.step_hi ^ (STREAM_PAIR << 16) ^ salt;
+  const u4 r = philox4x32_10(c, P.seed_lo, P.seed_hi);
+  const double TWOPI = 6.28318530717958647692;
+  const double gauss = sqrt(-2.0 * log(u01(r.x))) * cos(TWOPI * u01(r.y));
+  const double w1 = wa[pa], w2 = wb[pb];
+  const double den12 = fmax(w1, w2) * den_fact;
+  double va[3] = {a0[pa], a1[pa], a2[pa]}, vb[3] = {b0[pb], b1[pb], b2[pb]}, dU[3];
+  coulomb_delta_u(P, va, vb, C.EF_norm, den12, C.bmax, C.sigma_max, gauss, u01(r.z), u01(r.w), dU, nullptr);
+  bool s1 = true, s2 = true;
+  if ((float)w1 != (float)w2) {
+    c.w = P.step_hi ^ (STREAM_WEIGHT << 16) ^ salt;
+    const double ur = u01(philox4x32_10(c, P.seed_lo, P.seed_hi).x);
+    if ((float)w1 < (float)w2) s2 = ur < w1 / w2;
+    else s1 = ur < w2 / w1;
+  }
+  if (s1) {
+    a0[pa] = va[0] + P.f1 * dU[0];
+    a1[pa] = va[1] + P.f1 * dU[1];
+    a2[pa] = va[2] + P.f1 * dU[2];
+  }
+  if (s2) {
+    b0[pb] = vb[0] - P.f2 * dU[0];
+    b1[pb] = vb[1] - P.f2 * dU[1];
+    b2[pb] = vb[2] - P.f2 * dU[2];
+  }
+}
+
+__device__ __forceinline__ void ta_from_coul(const CoulParams &P, TAParams &T) {
+  T.seed_lo = P.seed_lo;
+  T.seed_hi = P.seed_hi;
+  T.step_lo = P.step_lo;
+  T.step_hi = P.step_hi;
+}
+
+// Coulomb::applyIntraScattering_PROB (:400-592)
+__global__ void __launch_bounds__(256)
+k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double *v2, const double *w,
+                const uint64_t *id, const double *dens, const double *LDe, CoulParams P, unsigned *key, int *order,
+                unsigned long long *npairs) {
+  const int cell = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (cell >= ncell) return;
+  const double numDen = dens[cell];
+  const int s = cell_start[cell], n = cell_start[cell + 1] - s;
+  if (numDen == 0.0 || n < 2) return;
+  const double PI = 3.14159265358979323846;
+  CellCtx C;
+  C.EF_norm = P.EF_fact * pow(numDen, 2.0 / 3.0);
+  C.bmax = LDe[cell];
+  C.sigma_max = 1.0 / (numDen * (1.0 / cbrt(4.0 / 3.0 * PI * numDen)));
+  C.gcell = global_cell(P, cell);
+  TAParams T;
+  ta_from_coul(P, T);
+  warp_shuffle_order(s, n, id, T, 4u, key, order, lane);
+  const bool NxN = P.NxN || n < P.NxN_Nthresh;
+  const double Naa = (double)(n - 1);
+  unsigned long long mine = 0;
+  if (NxN) {
+    // round-robin tournament over M = n (+1 if odd) players: M-1 rounds of M/2 disjoint pairs
+    const int M = n + (n & 1), R = M - 1;
+    const double den_fact = 1.0 / P.cellV_SI;
+    for (int r = 0; r < R; ++r) {
+      for (int i = lane; i < M / 2; i += 32) {
+        int pa = (i == 0) ? M - 1 : (r + i) % R;
+        int pb = (i == 0) ? r : (r - i + R) % R;
+        if (pa < n && pb < n) {
+          if (pa > pb) {
+            const int t = pa;
+            pa = pb;
+            pb = t;
+          }
+          coulomb_pair(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], den_fact,
+                       (unsigned)(pa * 65536 + pb), 0u);
+          ++mine;
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    const int pstart = (n & 1) ? 3 : 0;
+    if (pstart == 3 && lane == 0) {
+      // odd cell: (0,1), (0,2), (1,2) with half the density (:468-470, 536-538)
+      const int p1[3] = {0, 0, 1}, p2[3] = {1, 2, 2};
+      for (int q = 0; q < 3; ++q) {
+        coulomb_pair(P, C, v0, v1, v2, w, s + order[s + p1[q]], v0, v1, v2, w, s + order[s + p2[q]],
+                     Naa / P.cellV_SI / 2.0, (unsigned)(p1[q] * 65536 + p2[q]), 1u);
+        ++mine;
+      }
+    }
+    const int nmain = (n - pstart) / 2;
+    for (int q = lane; q < nmain; q += 32) {
+      const int pa = pstart + 2 * q, pb = pa + 1;
+      coulomb_pair(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], Naa / P.cellV_SI,
+                   (unsigned)(pa * 65536 + pb), 0u);
+      ++mine;
+    }
+  }
+  mine = __reduce_add_sync(0xffffffffu, (unsigned)mine);
+  if (lane == 0) atomicAdd(npairs, mine);
+}
+
+// Coulomb::applyInterScattering_PROB (:919-1180)
+__global__ void __launch_bounds__(256)
+k_coulomb_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, double *a2, const double *wa,
+                const uint64_t *id1, const double *dens1, double *b0, double *b1, double *b2, const double *wb,
+                const uint64_t *id2, const double *dens2, const double *LDe, CoulParams P, unsigned *key1, int *order1,
+                unsigned *key2, int *order2, unsigned long long *npairs) {
+  const int cell = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (cell >= ncell) return;
+  const double numDen1 = dens1[cell], numDen2 = dens2[cell];
+  if (numDen1 * numDen2 == 0.0) return;
+  const int s1 = cs1[cell], n1 = cs1[cell + 1] - s1;
+  const int s2 = cs2[cell], n2 = cs2[cell + 1] - s2;
+  if ((long)n1 * n2 < 2) return;
+  const double PI = 3.14159265358979323846;
+  const double minn = fmin(numDen1, numDen2), maxn = fmax(numDen1, numDen2);
+  CellCtx C;
+  C.EF_norm = P.EF_fact * pow(maxn, 2.0 / 3.0);
+  C.bmax = LDe[cell];
+  C.sigma_max = 1.0 / (minn * (1.0 / cbrt(4.0 / 3.0 * PI * minn)));
+  C.gcell = global_cell(P, cell);
+  TAParams T;
+  ta_from_coul(P, T);
+  warp_shuffle_order(s1, n1, id1, T, 5u, key1, order1, lane);
+  warp_shuffle_order(s2, n2, id2, T, 6u, key2, order2, lane);
+  const int Nmin = min(n1, n2), Nmax = max(n1, n2);
+  const bool first_short = (Nmin == n1);
+  const bool NxN = P.NxN || Nmin < P.NxN_Nthresh;
+  unsigned long long mine = 0;
+  if (NxN) {
+    // all Nmin x Nmax pairs: chunks of Nmin long-list particles, Latin-square rounds inside a chunk
+    const double den_fact = 1.0 / P.cellV_SI;
+    for (int cb = 0; cb < Nmax; cb += Nmin) {
+      const int nc = min(Nmin, Nmax - cb);
+      for (int rr = 0; rr < Nmin; ++rr) {
+        for (int t = lane; t < nc; t += 32) {
+          const int pl = cb + t, ps = (t + rr) % Nmin;
+          const int i1 = s1 + order1[s1 + (first_short ? ps : pl)];
+          const int i2 = s2 + order2[s2 + (first_short ? pl : ps)];
+          coulomb_pair(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)(pl * 65536 + ps), 2u);
+          ++mine;
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const double den_fact = (double)Nmin / P.cellV_SI;
+    for (int r = lane; r < Nmin; r += 32) {
+      for (int p = r; p < Nmax; p += Nmin) {
+        const int i1 = s1 + order1[s1 + (first_short ? r : p)];
+        const int i2 = s2 + order2[s2 + (first_short ? p : r)];
+        coulomb_pair(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)p, 2u);
+        ++mine;
+      }
+    }
+  }
+  mine = __reduce_add_sync(0xffffffffu, (unsigned)mine);
+  if (lane == 0) atomicAdd(npairs, mine);
+}
+
+// =============================================================================================
+// Elastic::electronImpact (src/scattering/Elastic.cpp:225-388), PROBABILISTIC weights.
+// Every species-1 particle of a cell picks a random species-2 partner; lanes that picked the
+// same partner in one batch go one after the other (__match_any_sync), as the reference's
+// sequential loop would.
+// =============================================================================================
+struct ElaParams {
+  double mu, f1, f2, const_sigma, dt_sec, mcSq;
+  int ntab, angular, loglog;
+  const double *E, *Q, *XI;
+  unsigned seed_lo, seed_hi, step_lo, step_hi;
+};
+
+// Elastic::getSigma / getTextSigma (:390-476) incl. the reference's interpolation formulas
+__device__ __forceinline__ double elastic_sigma(const ElaParams &P, double g12, double &xi) {
+  xi = 0.0;
+  if (P.ntab == 0) return P.const_sigma;
+  const double KE = P.mu * P.mcSq * g12 * g12 / 2.0;
+  const double *E = P.E, *Q = P.Q, *XI = P.XI;
+  const int N = P.ntab;
+  double sigma = 0.0;
+  if (KE >= E[N - 1]) {
+    if (P.angular == 0) sigma = Q[N - 1] * log(KE) / log(E[N - 1]) * E[N - 1] / KE;
+    else {
+      sigma = Q[N - 1] * E[N - 1] / KE;
+      xi = XI[N - 1];
+    }
+    return sigma;
+  }
+  int i = N / 2;
+  while (KE < E[i]) i--;
+  while (KE > E[i + 1]) i++;
+  const double l0 = log10(KE), lu = log10(E[i]), ld = log10(E[i + 1]);
+  if (P.loglog && Q[i] * E[i] > 0.0) sigma = pow(10.0, (log10(Q[i + 1]) * (l0 - ld) + log10(Q[i]) * (lu - l0)) / (lu - ld));
+  else sigma = (Q[i + 1] * (KE - E[i]) + Q[i] * (E[i + 1] - KE)) / (E[i + 1] - E[i]);
+  if (P.angular == 1) {
+    if (E[i] * KE > 0.0) xi = (XI[i + 1] * (l0 - ld) + XI[i] * (lu - l0)) / (lu - ld);
+    else xi = (XI[i + 1] * (KE - E[i]) + XI[i] * (E[i + 1] - KE)) / (E[i + 1] - E[i]);
+  }
+  return sigma;
+}
+
+__global__ void __launch_bounds__(256)
+k_elastic(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, double *a2, const double *wa,
+          const uint64_t *id1, double *b0, double *b1, double *b2, const double *wb, const double *dens2, ElaParams P,
+          unsigned long long *ncoll) {
+  const int cell = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (cell >= ncell) return;
+  const int s1 = cs1[cell], n1 = cs1[cell + 1] - s1;
+  const int s2 = cs2[cell], n2 = cs2[cell + 1] - s2;
+  if (n1 < 1 || n2 < 1) return;
+  const double numDen2 = dens2[cell];
+  const double TWOPI = 6.28318530717958647692, CVAC = 2.99792458e+08;
+  unsigned mine = 0;
+  for (int base = 0; base < n1; base += 32) {
+    const int q = base + lane;
+    const bool have = q < n1;
+    int i1 = 0, i2 = -1 - lane;   // distinct dummies for idle lanes
+    u4 r0, r1;
+    if (have) {
+      i1 = s1 + q;
+      const uint64_t pid = id1[i1];
+      u4 c;
+      c.x = (unsigned)pid;
+      c.y = (unsigned)(pid >> 32);
+      c.z = P.step_lo;
+      c.w = P.step_hi ^ (STREAM_ELA << 16);
+      r0 = philox4x32_10(c, P.seed_lo, P.seed_hi);
+      c.w ^= 1u;
+      r1 = philox4x32_10(c, P.seed_lo, P.seed_hi);
+      i2 = s2 + min(n2 - 1, (int)(u01(r0.x) * n2));     // MathUtils::randInt(0, n2-1)
+    }
+    bool pending = have;
+    while (__any_sync(0xffffffffu, pending)) {
+      const unsigned same = __match_any_sync(0xffffffffu, pending ? i2 : -1 - lane);
+      const bool turn = pending && (__ffs(same) - 1 == lane);
+      if (turn) {
+        const double va[3] = {a0[i1], a1[i1], a2[i1]}, vb[3] = {b0[i2], b1[i2], b2[i2]};
+        const double ux = va[0] - vb[0], uy = va[1] - vb[1], uz = va[2] - vb[2];
+        const double g12 = sqrt(ux * ux + uy * uy + uz * uz);
+        double xi;
+        const double sigma = elastic_sigma(P, g12, xi);
+        if (sigma != 0.0) {
+          const double q12 = 1.0 - exp(-(g12 * CVAC * sigma * numDen2 * P.dt_sec));
+          if (u01(r0.y) <= q12) {
+            ++mine;
+            double sinphi, cosphi;
+            sincos(TWOPI * u01(r0.z), &sinphi, &cosphi);
+            const double R = u01(r0.w);
+            const double costh = 1.0 - 2.0 * R * (1.0 - xi) / (1.0 + xi * (1.0 - 2.0 * R));   // getScatteringCos
+            const double sinth = sqrt(1.0 - costh * costh);
+            double dU[3];
+            scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
+            const double r2 = u01(r1.x), w1 = wa[i1], w2 = wb[i2];
+            if (r2 <= w2 / w1) {
+              a0[i1] = va[0] + P.f1 * dU[0];
+              a1[i1] = va[1] + P.f1 * dU[1];
+              a2[i1] = va[2] + P.f1 * dU[2];
+            }
+            if (r2 <= w1 / w2) {
+              b0[i2] = vb[0] - P.f2 * dU[0];
+              b1[i2] = vb[1] - P.f2 * dU[1];
+              b2[i2] = vb[2] - P.f2 * dU[2];
+            }
+          }
+        }
+        pending = false;
+      }
+      __syncwarp();
+    }
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0 && mine) atomicAdd(ncoll, (unsigned long long)mine);
+}
+
 }  // namespace pgpu
 
 using namespace pgpu;
@@ -301,6 +706,195 @@ int pgpu_scatter_delta_u(long n, const double *u, const double *costh, const dou
   PGPU_CUDA(cudaStreamSynchronize(st));
   cudaFree(d);
   return 0;
+}
+
+
+static int coulomb_consts(double charge1, double charge2, double mass1, double mass2, const pgpu_coulomb_params *prm,
+                          double dt_sec, CoulParams *P) {
+  if (!prm) return PGPU_ERR_ARG;
+  const int a = prm->angular_scattering;
+  if (a != PGPU_ANG_TAKIZUKA && a != PGPU_ANG_NANBU && a != PGPU_ANG_BOBYLEV && a != PGPU_ANG_ISOTROPIC) {
+    set_error("Coulomb: angular_scattering %d is not implemented (TAKIZUKA, NANBU, BOBYLEV, ISOTROPIC are)", a);
+    return PGPU_ERR_ARG;
+  }
+  if (charge1 == 0.0 || charge2 == 0.0) {
+    set_error("Coulomb: neutral species");
+    return PGPU_ERR_ARG;
+  }
+  const double PI = 3.14159265358979323846, CVAC = 2.99792458e+08, ME = 9.10938370e-31, QE = 1.60217663e-19;
+  const double MU0 = 4.0 * PI * 1.0e-7, EP0 = 1.0 / CVAC / CVAC / MU0, HBAR = 6.62607015e-34 / (2.0 * PI);
+  P->mu = mass1 * mass2 / (mass1 + mass2);
+  const double qocSq = QE * QE / (CVAC * CVAC);
+  P->b90_fact = fabs(charge1 * charge2) * qocSq / (2.0 * PI * EP0 * ME);     // Coulomb.cpp:47-50
+  P->bqm_fact = HBAR / (2.0 * ME * CVAC);
+  P->EF_fact = 0.0;
+  if (mass1 == 1.0 || mass2 == 1.0)
+    P->EF_fact = HBAR * HBAR / (2.0 * ME * P->mu) * pow(3.0 * PI * PI, 2.0 / 3.0) / (ME * CVAC * CVAC);
+  P->f1 = P->mu / mass1;
+  P->f2 = P->mu / mass2;
+  P->Clog = prm->Clog;
+  P->dt_sec = dt_sec;
+  P->angular = a;
+  P->NxN = prm->NxN ? 1 : 0;
+  P->NxN_Nthresh = prm->NxN_Nthresh;
+  P->cellV_SI = 1.0;
+  P->seed_lo = P->seed_hi = P->step_lo = P->step_hi = 0;
+  P->box_lo0 = P->box_lo1 = 0;
+  P->nbox0 = P->ncell_glob0 = 1;
+  return 0;
+}
+
+int pgpu_coulomb_delta_u(long n, const double *vp1, const double *vp2, double charge1, double charge2, double mass1,
+                         double mass2, const pgpu_coulomb_params *prm, double dt_sec, const double *EF_norm,
+                         const double *den12, const double *bmax, const double *sigma_max, const double *gauss,
+                         const double *u_polar, const double *u_phi, double *dU, double *s12) {
+  if (!ctx().inited) {
+    set_error("pgpu_init has not been called");
+    return PGPU_ERR_STATE;
+  }
+  CoulParams P;
+  const int rc = coulomb_consts(charge1, charge2, mass1, mass2, prm, dt_sec, &P);
+  if (rc) return rc;
+  cudaStream_t st = ctx().stream;
+  const size_t N = (size_t)n;
+  double *d = nullptr;
+  PGPU_CUDA(cudaMalloc(&d, 17 * N * sizeof(double)));   // v1[3] v2[3] EF den bmax smax g up uphi dU[3] s12
+  const double *src[9] = {vp1, vp2, EF_norm, den12, bmax, sigma_max, gauss, u_polar, u_phi};
+  const size_t len[9] = {3 * N, 3 * N, N, N, N, N, N, N, N};
+  size_t off[10] = {0};
+  for (int k = 0; k < 9; ++k) {
+    PGPU_CUDA(cudaMemcpyAsync(d + off[k], src[k], len[k] * sizeof(double), cudaMemcpyHostToDevice, st));
+    off[k + 1] = off[k] + len[k];
+  }
+  {
+    KTimer t("coulomb_delta_u");
+    k_coulomb_delta_u<<<nb(n), 256, 0, st>>>(n, P, d + off[0], d + off[1], d + off[2], d + off[3], d + off[4],
+                                             d + off[5], d + off[6], d + off[7], d + off[8], d + off[9],
+                                             d + off[9] + 3 * N);
+  }
+  PGPU_CUDA(cudaMemcpyAsync(dU, d + off[9], 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaMemcpyAsync(s12, d + off[9] + 3 * N, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d);
+  return 0;
+}
+
+static int fetch_pairs(long *out) {
+  Context &c = ctx();
+  if (out) {
+    PGPU_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c.stream));
+    PGPU_CUDA(cudaMemsetAsync(&c.d_counters->npairs, 0, sizeof(unsigned long long), c.stream));
+    PGPU_CUDA(cudaStreamSynchronize(c.stream));
+    *out = (long)c.h_counters->npairs;
+  } else {
+    PGPU_CUDA(cudaMemsetAsync(&c.d_counters->npairs, 0, sizeof(unsigned long long), c.stream));
+  }
+  return 0;
+}
+
+static int need_binned(pgpu_species_t sA, pgpu_species_t sB) {
+  if (!ctx().inited) {
+    set_error("pgpu_init has not been called");
+    return PGPU_ERR_STATE;
+  }
+  if (!sA || !sB || sA->grid != sB->grid) return PGPU_ERR_ARG;
+  if (!sA->binned || !sB->binned) {
+    set_error("collisions need binned species: call pgpu_bin_particles + pgpu_set_moments_from_bins first");
+    return PGPU_ERR_STATE;
+  }
+  return 0;
+}
+
+int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm, double dt_sec,
+                         uint64_t seed, uint64_t step, long *npairs_out) {
+  int rc = need_binned(sA, sB);
+  if (rc) return rc;
+  Context &c = ctx();
+  const pgpu_grid_s *g = sA->grid;
+  CoulParams P;
+  rc = coulomb_consts(sA->desc.charge, sB->desc.charge, sA->desc.mass, sB->desc.mass, prm, dt_sec, &P);
+  if (rc) return rc;
+  const int nsub = prm->num_subcycles > 0 ? prm->num_subcycles : 1;
+  P.dt_sec = dt_sec / (double)nsub;                                   // Coulomb.cpp:371
+  const double dV = (g->desc.D == 1) ? g->geo.dx[0] : g->geo.dx[0] * g->geo.dx[1];
+  P.cellV_SI = dV * g->desc.volume_scale;
+  P.seed_lo = (unsigned)seed;
+  P.seed_hi = (unsigned)(seed >> 32);
+  P.step_lo = (unsigned)step;
+  P.box_lo0 = g->desc.box_lo[0];
+  P.box_lo1 = (g->desc.D == 2) ? g->desc.box_lo[1] : 0;
+  P.nbox0 = g->nbox[0];
+  P.ncell_glob0 = g->desc.ncell[0];
+  const int ncell = (int)g->ncell_box;
+  unsigned long long *d_np = &c.d_counters->npairs;
+  for (int sub = 0; sub < nsub; ++sub) {
+    P.step_hi = ((unsigned)(step >> 32) & 0xffu) | ((unsigned)sub << 8);
+    if (sA == sB) {
+      KTimer t("collide_coulomb_intra");
+      k_coulomb_intra<<<nb((long)ncell * 32), 256, 0, c.stream>>>(sA->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2],
+                                                                  sA->w, sA->id, sA->dens, g->debye, P,
+                                                                  (unsigned *)sA->cell_key, sA->perm, d_np);
+    } else {
+      KTimer t("collide_coulomb_inter");
+      k_coulomb_inter<<<nb((long)ncell * 32), 256, 0, c.stream>>>(
+          sA->cell_start, sB->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->w, sA->id, sA->dens, sB->v[0],
+          sB->v[1], sB->v[2], sB->w, sB->id, sB->dens, g->debye, P, (unsigned *)sA->cell_key, sA->perm,
+          (unsigned *)sB->cell_key, sB->perm, d_np);
+    }
+  }
+  return fetch_pairs(npairs_out);
+}
+
+int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elastic_params *prm, double dt_sec,
+                         uint64_t seed, uint64_t step, long *ncoll_out) {
+  int rc = need_binned(sA, sB);
+  if (rc) return rc;
+  if (!prm || sA == sB || (prm->ntab && (!prm->E || !prm->Q || prm->ntab < 2))) return PGPU_ERR_ARG;
+  if (prm->ntab && prm->angular_scattering == 1 && !prm->xi) return PGPU_ERR_ARG;
+  Context &c = ctx();
+  const pgpu_grid_s *g = sA->grid;
+  const double CVAC = 2.99792458e+08, ME = 9.10938370e-31, QE = 1.60217663e-19;
+  ElaParams P;
+  const double m1 = sA->desc.mass, m2 = sB->desc.mass;
+  P.mu = m1 * m2 / (m1 + m2);
+  P.f1 = P.mu / m1;
+  P.f2 = P.mu / m2;
+  P.const_sigma = prm->const_sigma;
+  P.dt_sec = dt_sec;
+  P.mcSq = ME * CVAC * CVAC / QE;
+  P.ntab = prm->ntab;
+  P.angular = prm->angular_scattering;
+  P.loglog = prm->use_loglog_interp;
+  P.E = P.Q = P.XI = nullptr;
+  double *d_tab = nullptr;
+  if (prm->ntab) {
+    const size_t N = (size_t)prm->ntab;
+    PGPU_CUDA(cudaMalloc(&d_tab, 3 * N * sizeof(double)));
+    PGPU_CUDA(cudaMemcpyAsync(d_tab, prm->E, N * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    PGPU_CUDA(cudaMemcpyAsync(d_tab + N, prm->Q, N * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    if (prm->xi) PGPU_CUDA(cudaMemcpyAsync(d_tab + 2 * N, prm->xi, N * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    else PGPU_CUDA(cudaMemsetAsync(d_tab + 2 * N, 0, N * sizeof(double), c.stream));
+    P.E = d_tab;
+    P.Q = d_tab + N;
+    P.XI = d_tab + 2 * N;
+  }
+  P.seed_lo = (unsigned)seed;
+  P.seed_hi = (unsigned)(seed >> 32);
+  P.step_lo = (unsigned)step;
+  P.step_hi = (unsigned)(step >> 32) & 0xffffu;
+  const int ncell = (int)g->ncell_box;
+  {
+    KTimer t("collide_elastic");
+    k_elastic<<<nb((long)ncell * 32), 256, 0, c.stream>>>(sA->cell_start, sB->cell_start, ncell, sA->v[0], sA->v[1],
+                                                          sA->v[2], sA->w, sA->id, sB->v[0], sB->v[1], sB->v[2], sB->w,
+                                                          sB->dens, P, &c.d_counters->npairs);
+  }
+  rc = fetch_pairs(ncoll_out);
+  if (d_tab) {
+    cudaStreamSynchronize(c.stream);
+    cudaFree(d_tab);
+  }
+  return rc;
 }
 
 int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt_sec, uint64_t seed,

@@ -214,4 +214,61 @@ void TakizukaAbe::printParameters() const {
   std::cout << "  Coulomb Logarithm = " << m_Clog << std::endl;
 }
 
+Coulomb::Coulomb(int a_sp1, int a_sp2, Real a_Clog, AngularScattering a_angular, bool a_NxN, int a_NxN_Nthresh,
+                 int a_num_subcycles)
+    : m_sp1(a_sp1), m_sp2(a_sp2), m_scatter_dt(DBL_MAX), m_npairs(0) {
+  m_prm.Clog = a_Clog;
+  m_prm.angular_scattering = a_angular;
+  m_prm.NxN = a_NxN ? 1 : 0;
+  m_prm.NxN_Nthresh = a_NxN_Nthresh;
+  m_prm.num_subcycles = a_num_subcycles;
+  if (a_Clog != 0.0 && a_Clog < 2.0) fatal("Coulomb: coulomb_logarithm must be 0 (computed) or >= 2");   // Coulomb.H:224
+}
+void Coulomb::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real a_dt_sec) const {
+  PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
+  if (a->numParticles() == 0 || b->numParticles() == 0) return;
+  long np = 0;
+  check(pgpu_collide_coulomb(a->handle(), b->handle(), &m_prm, a_dt_sec, s_seed, s_step, &np), "Coulomb::applyScattering");
+  m_npairs = np;
+}
+void Coulomb::printParameters() const {
+  std::cout << " Coulomb scattering parameters:" << std::endl;
+  std::cout << "  species A = " << m_sp1 << ", species B = " << m_sp2 << std::endl;
+  std::cout << "  Coulomb Logarithm = " << m_prm.Clog << (m_prm.Clog == 0.0 ? " (computed per pair)" : "") << std::endl;
+  std::cout << "  angular scattering = " << m_prm.angular_scattering << ", weight method = PROBABILISTIC" << std::endl;
+  std::cout << "  NxN pairings = " << (m_prm.NxN ? "true" : "false") << ", NxN Nthresh = " << m_prm.NxN_Nthresh << std::endl;
+}
+
+Elastic::Elastic(int a_sp1, int a_sp2, Real a_const_sigma)
+    : m_sp1(a_sp1), m_sp2(a_sp2), m_const_sigma(a_const_sigma), m_okhrimovskyy(false), m_loglog(false), m_ncoll(0) {}
+Elastic::Elastic(int a_sp1, int a_sp2, const std::vector<Real> &a_E_eV, const std::vector<Real> &a_Q,
+                 const std::vector<Real> &a_xi, bool a_okhrimovskyy, bool a_use_loglog_interp)
+    : m_sp1(a_sp1), m_sp2(a_sp2), m_const_sigma(0.0), m_E(a_E_eV), m_Q(a_Q), m_xi(a_xi),
+      m_okhrimovskyy(a_okhrimovskyy), m_loglog(a_use_loglog_interp), m_ncoll(0) {
+  if (m_E.size() < 2 || m_Q.size() != m_E.size() || (a_okhrimovskyy && m_xi.size() != m_E.size()))
+    fatal("Elastic: cross-section table columns differ in length");
+}
+void Elastic::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real a_dt_sec) const {
+  PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
+  if (a->numParticles() == 0 || b->numParticles() == 0) return;
+  pgpu_elastic_params prm;
+  prm.const_sigma = m_const_sigma;
+  prm.ntab = (int)m_E.size();
+  prm.E = m_E.empty() ? nullptr : m_E.data();
+  prm.Q = m_Q.empty() ? nullptr : m_Q.data();
+  prm.xi = m_xi.empty() ? nullptr : m_xi.data();
+  prm.angular_scattering = m_okhrimovskyy ? 1 : 0;
+  prm.use_loglog_interp = m_loglog ? 1 : 0;
+  long nc = 0;
+  check(pgpu_collide_elastic(a->handle(), b->handle(), &prm, a_dt_sec, s_seed, s_step, &nc), "Elastic::applyScattering");
+  m_ncoll = nc;
+}
+void Elastic::printParameters() const {
+  std::cout << " Elastic scattering parameters:" << std::endl;
+  std::cout << "  species A = " << m_sp1 << ", species B = " << m_sp2 << std::endl;
+  if (m_E.empty()) std::cout << "  constant cross section = " << m_const_sigma << " m^2" << std::endl;
+  else std::cout << "  tabulated cross section, " << m_E.size() << " rows, "
+                 << (m_okhrimovskyy ? "OKHRIMOVSKYY" : "ISOTROPIC") << std::endl;
+}
+
 }  // namespace picnic_gpu

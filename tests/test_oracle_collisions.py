@@ -1,0 +1,137 @@
+"""CPU checks of the Coulomb / Elastic restatement in the oracle (reference-derived properties):
+Nanbu's A(s) fit reproduces <cos theta> = exp(-s) (Nanbu 1997; the relation the reference quotes in
+Coulomb.H:343-344), equal-weight Coulomb pairs conserve momentum and energy, the pair counts are the
+reference's (NxN below NxN_Nthresh, odd-N triple), the weighted rejection conserves momentum and
+energy on average, and the elastic cross-section lookup interpolates as the reference writes it."""
+import numpy as np
+import pytest
+
+from common import orc
+
+DT_SEC = 0.1 * 1.77e-17
+
+
+def test_nanbu_mean_cosine():
+    U = (np.arange(20000) + 0.5) / 20000
+    for s in (0.01, 0.1, 0.3, 1.0, 2.5, 4.0, 8.0):
+        c = np.array([orc.nanbu_costh_sinth(s, u)[0] for u in U])
+        assert np.all(np.abs(c) <= 1.0 + 1e-12)
+        assert abs(c.mean() - np.exp(-s)) < (0.012 if s < 6 else 1e-3), s      # s >= 6: isotropic
+
+
+def _cells(rng, counts):
+    cs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    n = int(cs[-1])
+    v = rng.standard_normal((3, n)) * 0.02
+    return cs, v
+
+
+@pytest.mark.parametrize("angular", [0, 1, 2, 5])
+def test_coulomb_intra_equal_weights_conserve_and_count(angular):
+    rng = np.random.default_rng(3)
+    counts = np.array([0, 1, 2, 3, 5, 10, 11, 12, 13, 40, 41])
+    cs, v = _cells(rng, counts)
+    n = v.shape[1]
+    w = np.full(n, 2.0e27)
+    cellV = 1.0e-3
+    dens = counts * 2.0e27 / cellV
+    LDe = np.full(counts.size, 1.0e-9)
+    v0 = v.copy()
+    orc.lib().orc_rng_seed(5)
+    npairs = orc.coulomb_intra(cs, v, w, dens, LDe, cellV, 1.0, -1.0, 0.0, angular, False, 11, DT_SEC)
+
+    def expect(c):
+        if c < 2:
+            return 0
+        if c < 11:
+            return c * (c - 1) // 2
+        return c // 2 if c % 2 == 0 else (c - 3) // 2 + 3
+    assert npairs == sum(expect(c) for c in counts)
+    for k, c in enumerate(counts):
+        a, b = cs[k], cs[k + 1]
+        if c < 2:
+            assert np.array_equal(v[:, a:b], v0[:, a:b])
+            continue
+        assert np.max(np.abs(v[:, a:b].sum(axis=1) - v0[:, a:b].sum(axis=1))) < 1e-15 * c
+        assert abs((v[:, a:b] ** 2).sum() - (v0[:, a:b] ** 2).sum()) / (v0[:, a:b] ** 2).sum() < 1e-13
+
+
+def test_coulomb_inter_weighted_conserves_on_average():
+    """Unequal weights: the lighter-weight particle always scatters, the heavier with probability
+    wmin/wmax, so momentum and energy are conserved in expectation (Coulomb.cpp:1149-1172)."""
+    rng = np.random.default_rng(8)
+    ncell, n1c, n2c = 400, 24, 16
+    cs1 = np.arange(ncell + 1, dtype=np.int64) * n1c
+    cs2 = np.arange(ncell + 1, dtype=np.int64) * n2c
+    v1 = rng.standard_normal((3, ncell * n1c)) * 0.02
+    v2 = rng.standard_normal((3, ncell * n2c)) * 0.0008
+    v1[0] += 0.01
+    w1 = np.where(rng.random(ncell * n1c) < 0.5, 1.0e27, 3.0e27)
+    w2 = np.where(rng.random(ncell * n2c) < 0.5, 2.0e27, 0.5e27)
+    cellV = 1.0e-3
+    dens1 = np.add.reduceat(w1, cs1[:-1]) / cellV
+    dens2 = np.add.reduceat(w2, cs2[:-1]) / cellV
+    LDe = np.full(ncell, 5.0e-10)
+    m1, m2 = 1.0, 1836.15
+    P0 = m1 * (w1 * v1).sum(axis=1) + m2 * (w2 * v2).sum(axis=1)
+    K0 = m1 * (w1 * v1 ** 2).sum() + m2 * (w2 * v2 ** 2).sum()
+    dp_e0 = m1 * (w1 * v1[0]).sum()
+    orc.lib().orc_rng_seed(2)
+    npairs = orc.coulomb_inter(cs1, v1, w1, dens1, m1, -1.0, cs2, v2, w2, dens2, m2, 1.0, LDe, cellV, 10.0, 1, False, 11,
+                               40 * DT_SEC)
+    assert npairs == ncell * max(n1c, n2c)
+    P1 = m1 * (w1 * v1).sum(axis=1) + m2 * (w2 * v2).sum(axis=1)
+    K1 = m1 * (w1 * v1 ** 2).sum() + m2 * (w2 * v2 ** 2).sum()
+    exchanged = abs(m1 * (w1 * v1[0]).sum() - dp_e0)
+    assert exchanged > 0.02 * abs(dp_e0)                       # the drift really slowed down
+    assert abs(P1[0] - P0[0]) < 0.2 * exchanged                # ... and the ions took it, on average
+    assert abs(K1 - K0) / K0 < 0.02
+
+
+def test_elastic_sigma_lookup():
+    E = np.array([0.01, 0.1, 1.0, 10.0, 100.0])
+    Q = np.array([1.0e-19, 2.0e-19, 5.0e-20, 2.0e-20, 1.0e-20])
+    XI = np.array([0.0, 0.1, 0.3, 0.6, 0.9])
+    mu = 1.0 * 7294.3 / (1.0 + 7294.3)
+    mcSq = 9.10938370e-31 * 2.99792458e+08 ** 2 / 1.60217663e-19
+    beta = lambda KE: np.sqrt(2.0 * KE / (mu * mcSq))
+    # constant cross section
+    assert orc.elastic_sigma(0.01, mu, const_sigma=3e-20) == (3e-20, 0.0)
+    # linear interpolation inside the table, at the exact form of MathUtils::linearInterp
+    s, xi = orc.elastic_sigma(beta(0.55), mu, E=E, Q=Q, XI=XI, angular=0)
+    assert abs(s - (Q[2] * (0.55 - 0.1) + Q[1] * (1.0 - 0.55)) / 0.9) < 1e-30 and xi == 0.0
+    # above the table: SigM ~ ln(E)/E (ISOTROPIC), SigT ~ 1/E with the last xi (OKHRIMOVSKYY)
+    s, _ = orc.elastic_sigma(beta(400.0), mu, E=E, Q=Q, XI=XI, angular=0)
+    assert abs(s - Q[-1] * np.log(400.0) / np.log(100.0) * 100.0 / 400.0) < 1e-32
+    s, xi = orc.elastic_sigma(beta(400.0), mu, E=E, Q=Q, XI=XI, angular=1)
+    assert abs(s - Q[-1] * 100.0 / 400.0) < 1e-32 and xi == XI[-1]
+    # the reference's log interpolations weight the FAR node (ScatteringUtils.cpp:104-145): kept as is
+    s, xi = orc.elastic_sigma(beta(0.1 * 1.0000001), mu, E=E, Q=Q, XI=XI, angular=1, loglog=True)
+    assert abs(s - Q[2]) / Q[2] < 1e-5 and abs(xi - XI[2]) < 1e-5
+
+
+def test_elastic_probability_and_conservation():
+    rng = np.random.default_rng(4)
+    ncell, n1c, n2c = 300, 20, 10
+    cs1 = np.arange(ncell + 1, dtype=np.int64) * n1c
+    cs2 = np.arange(ncell + 1, dtype=np.int64) * n2c
+    v1 = rng.standard_normal((3, ncell * n1c)) * 0.02
+    v2 = rng.standard_normal((3, ncell * n2c)) * 0.0002
+    w1 = np.full(ncell * n1c, 1.0e20)
+    w2 = np.full(ncell * n2c, 1.0e20)
+    dens2 = np.full(ncell, 1.0e22)
+    m1, m2 = 1.0, 7294.3
+    sigma = 1.0e-19
+    v10, v20 = v1.copy(), v2.copy()
+    orc.lib().orc_rng_seed(9)
+    dt = 2.0e-12
+    ncoll = orc.elastic(cs1, v1, w1, m1, cs2, v2, w2, dens2, m2, dt, const_sigma=sigma)
+    g = np.linalg.norm(v10, axis=0)          # partners are ~at rest
+    expect = (1.0 - np.exp(-g * 2.99792458e8 * sigma * 1.0e22 * dt)).sum()
+    assert abs(ncoll - expect) < 4.0 * np.sqrt(expect)
+    P0 = m1 * v10.sum(axis=1) + m2 * v20.sum(axis=1)
+    P1 = m1 * v1.sum(axis=1) + m2 * v2.sum(axis=1)
+    assert np.max(np.abs(P1 - P0)) < 1e-12 * (m1 * np.abs(v10).sum())
+    K0 = m1 * (v10 ** 2).sum() + m2 * (v20 ** 2).sum()
+    K1 = m1 * (v1 ** 2).sum() + m2 * (v2 ** 2).sum()
+    assert abs(K1 - K0) / K0 < 1e-12
