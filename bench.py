@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles per species in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-collisions", action="store_true", help="skip the secondary C2 collision-pairs/s leg")
     return ap.parse_args()
 
 
@@ -268,6 +269,82 @@ class Engine:
         self.capi.check(self.capi.load().pgpu_synchronize())
 
 
+def collisions_leg(args, torch, capi, stream, peak):
+    """Secondary line item: collision-pairs/s on BASELINE.json configs[1] "C2" -- 2D 256x256 cells,
+    64 particles per cell per species, electrons (150 eV) + protons (50 eV), Takizuka-Abe binary
+    Coulomb collisions (Clog = 3): e-e, i-i and e-i every step, preceded by prepForScatter (cell
+    sort + cell moments of both species, PicSpeciesInterface.cpp:1593-1625).  pairs/step =
+    (32 + 32 + 64) per cell.  Device-resident; the C ABI has no per-step host traffic here."""
+    deck = decks.deck_c2()
+    lo, hi = (0, 0), (deck.ncell[0] - 1, deck.ncell[1] - 1)
+    grid = capi.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), volume_scale=deck.volume_scale)
+    rng = np.random.default_rng(deck.seed)
+    sps = []
+    for sdef in deck.species:
+        p = decks.load_species(deck, sdef, lo, hi, rng)
+        sp = capi.Species(grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm,
+                          interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E)
+        sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
+        sps.append(sp)
+    dt_sec = deck.dt * deck.units.time
+    state = {"step": 0}
+
+    def one_step(prep):
+        if prep:
+            for sp in sps:
+                sp.bin_particles()
+                sp.set_moments()
+        n = 0
+        for (a, b) in ((0, 0), (1, 1), (0, 1)):
+            capi.check(capi.load().pgpu_collide_ta(sps[a].h, sps[b].h, 3.0, dt_sec, 1983, state["step"], None))
+        state["step"] += 1
+
+    def timed(nsteps, prep):
+        capi.check(capi.load().pgpu_synchronize())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(nsteps):
+            one_step(prep)
+        e1.record(stream)
+        capi.check(capi.load().pgpu_synchronize())
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    one_step(True)
+    # pair count of one step (counted once, outside the timed region: the count read-back synchronises)
+    pairs = 0
+    for (a, b) in ((0, 0), (1, 1), (0, 1)):
+        pairs += capi.collide_ta(sps[a], sps[b], 3.0, dt_sec, 1983, 10 ** 6)
+    nsteps = max(args.steps, 5)
+    timed(max(args.warmup, 3), True)
+    capi.profile_reset()
+    capi.profile_enable(True)
+    ms_full = timed(nsteps, True)
+    capi.profile_enable(False)
+    k_self, n_self = capi.profile_query("collide_ta_self")
+    k_inter, n_inter = capi.profile_query("collide_ta_inter")
+    ms_k = timed(nsteps, False)
+    n_total = sum(sp.n for sp in sps)
+    for sp in sps:
+        sp.destroy()
+    grid.destroy()
+    kern_ms = (k_self + k_inter) / nsteps
+    achieved = 96.0 * pairs / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+    return {"metric": "collision-pairs/s (Takizuka-Abe, intra-cell)", "unit": "collision-pairs/s",
+            "value": pairs * nsteps / (ms_full * 1e-3),
+            "value_kernels_only": pairs * nsteps / (ms_k * 1e-3),
+            "workload": "C2: 2D %dx%d cells, 64 ppc/species, e-e + i-i + e-i TA (Clog 3) per step; `value` includes "
+                        "prepForScatter (cell sort + cell moments of both species) every step"
+                        % (deck.ncell[0], deck.ncell[1]),
+            "particles": n_total, "pairs_per_step": pairs, "steps": nsteps,
+            "ms_per_step": ms_full / nsteps, "ms_per_step_kernels_only": ms_k / nsteps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "bytes_per_unit": 96.0,
+                         "kernel": "collide_ta_self + collide_ta_inter (3 launches per step)",
+                         "kernel_ms_per_step": kern_ms}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -330,7 +407,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     prof = {}
     for name in ("advance_cc1_fused", "advance_deferred", "advance_deposit_fused", "advance", "deposit_current", "bin_", "finish_step", "second_half", "fold_periodic",
-                 "current_add", "current_scale", "bc_periodic", "halo_", "mig_", "build_tables", "tile_boxes"):
+                 "current_add", "current_scale", "bc_periodic", "halo_", "mig_", "build_tables", "tile_boxes",
+                 "bin_key", "bin_sort", "bin_permute", "bin_starts"):
         prof[name] = capi.profile_query(name)
     adv, app, unconv = capi.picard_totals(reset=True)
     k_mean = app / max(adv, 1)
@@ -403,6 +481,8 @@ def run_ours(args):
     for sp in eng.species:
         sp.destroy()
     eng.grid.destroy()
+    if rank == 0 and world == 1 and not args.no_collisions:
+        out["collisions"] = collisions_leg(args, torch, capi, stream, out["roofline"]["peak"])
     capi.finalize()
     if world > 1:
         dist.barrier()

@@ -10,6 +10,9 @@ rep, rx, idx, lib, fsub = sys.argv[1:6]
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", "::regex:%s:%s" % (rx, idx)],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
+if len(rows) < 3:   # some ncu versions reject the kernel-id filter on imported reports: take the first kernel
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
 hdr = rows[1]
 ia, isrc, iex, ismp = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 ins = []
