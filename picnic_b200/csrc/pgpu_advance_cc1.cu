@@ -554,7 +554,12 @@ __global__ void __launch_bounds__(BLOCK, 4) k_advance_cc1_2d_tile(const FastArgs
 // the dual-cell key and the normalised offsets (d_old, d_bar) in the shared-memory tile, so the
 // deposit phase does not locate the particle again.
 // =============================================================================================
-constexpr int TD = 16, TN = 12;
+// The dual record is padded to 18 doubles (144 B) and the rows of the shared-memory window are
+// offset by another 64 B: with a 128 B stride the same word of two neighbouring records falls
+// into the same banks, and the 128-bit record loads of a warp that straddles two or three dual
+// cells (the usual case) then replay -- ncu: 8.5 wavefronts per load instead of ~3.  The node
+// record (96 B) does not need it.
+constexpr int TD = 18, TN = 12, TDU = 16;   // stride / stride / doubles used of the dual record
 
 struct TabArgs {
   const double *F[6];   // origin-shifted like FastArgs::F
@@ -575,7 +580,7 @@ __global__ void __launch_bounds__(128) k_build_tables(const TabArgs T) {
     o[2] = v01 - v00;
     o[3] = (v11 - v01) - (v10 - v00);
   };
-  double rec[TD];
+  double rec[TDU];
   bilinear(2, rec);        // Ez
   bilinear(3, rec + 4);    // Bx
   bilinear(4, rec + 8);    // By
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(128) k_build_tables(const TabArgs T) {
   bilinear(5, rec + 12);   // Bz
   double2 *dd = reinterpret_cast<double2 *>(T.dual + (size_t)t * TD);
 #pragma unroll
-  for (int k = 0; k < TD / 2; ++k) dd[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
+  for (int k = 0; k < TDU / 2; ++k) dd[k] = make_double2(rec[2 * k], rec[2 * k + 1]);
 }
 
 __device__ __forceinline__ unsigned hi_abs(double x) { return (unsigned)__double2hiint(x) & 0x7fffffffu; }
@@ -647,7 +652,15 @@ struct TabWindow {
 };
 
 // Phase 1 with the coefficient tables.  On success key/dO/dB describe the final orbit.
-__device__ __forceinline__ bool push_tab(const FastArgs &A, const TabWindow &Wn, const double (&xo)[2],
+// Dual record of the last particle this thread pushed: the cell sort makes a thread's consecutive
+// particles share their dual cell nearly always, so the eight 128-bit record loads are skipped
+// unless the key changes (they were 1/4 of the kernel's shared-memory wavefronts).
+struct DualRec {
+  unsigned key;
+  double2 x01, x23, x45, y01, y23, y45, z01, z23;
+};
+
+__device__ __forceinline__ bool push_tab(const FastArgs &A, const TabWindow &Wn, DualRec &R, const double (&xo)[2],
                                          double (&xb)[2], const double (&uo)[3], double (&ub)[3],
                                          unsigned &key, double (&dO)[2], double (&dB)[2], unsigned &apply,
                                          unsigned &unconv) {
@@ -677,9 +690,14 @@ __device__ __forceinline__ bool push_tab(const FastArgs &A, const TabWindow &Wn,
       nrow = A.tn0 * TN;
     }
   }
-  const double2 x01 = ld2(td), x23 = ld2(td + 2), x45 = ld2(td + 4);      // Ex: e1 d1 | P0 Q0 | P2 Q2
-  const double2 y01 = ld2(td + 6), y23 = ld2(td + 8), y45 = ld2(td + 10);  // Ey
-  const double2 z01 = ld2(td + 12), z23 = ld2(td + 14);                     // Bz c0 c1 | c2 c3
+  if (key != R.key) {
+    R.key = key;
+    R.x01 = ld2(td), R.x23 = ld2(td + 2), R.x45 = ld2(td + 4);       // Ex: e1 d1 | P0 Q0 | P2 Q2
+    R.y01 = ld2(td + 6), R.y23 = ld2(td + 8), R.y45 = ld2(td + 10);   // Ey
+    R.z01 = ld2(td + 12), R.z23 = ld2(td + 14);                        // Bz c0 c1 | c2 c3
+  }
+  const double2 x01 = R.x01, x23 = R.x23, x45 = R.x45, y01 = R.y01, y23 = R.y23, y45 = R.y45, z01 = R.z01,
+                z23 = R.z23;
   double pO[2][2];
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
@@ -824,7 +842,8 @@ __device__ __forceinline__ void deposit_tab(const FastArgs &A, const double (&dO
 
 constexpr int NTAB = 8;    // xo0->dO0 xo1->dO1 xb0 xb1 u0 u1 u2 w
 constexpr int WMAX = 16;   // widest dual-cell window staged in shared memory (2 rows; node records: 3 rows, +1 column)
-constexpr int SDUAL = 2 * WMAX * TD, SNODE = 3 * (WMAX + 1) * TN;
+constexpr int DROW = WMAX * TD + 8;   // doubles between the two rows of the staged dual records
+constexpr int SDUAL = 2 * DROW, SNODE = 3 * (WMAX + 1) * TN;
 constexpr size_t TAB_SMEM =
     (size_t)(NTAB * TILE + SDUAL + SNODE) * sizeof(double) + TILE * sizeof(unsigned) + 64;
 
@@ -913,7 +932,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
         bulk_g2s(st + 1 * TILE, A.xo[1] + tbase, BYTES, bar);
         if (box.z) {
           for (int r = 0; r < box.w; ++r)
-            bulk_g2s(sdual + r * (WMAX * TD), A.tdual + (c0 + (size_t)r * A.tn0) * TD, dbytes, bar);
+            bulk_g2s(sdual + r * DROW, A.tdual + (c0 + (size_t)r * A.tn0) * TD, dbytes, bar);
         }
       } else {
         if (wp == 1) {
@@ -946,12 +965,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
       Wn.j = box.y;
       Wn.ncol = box.z;
       Wn.nrow = box.w;
-      Wn.drow = WMAX * TD;
+      Wn.drow = DROW;
       Wn.nrow_stride = (WMAX + 1) * TN;
     }
 
     // ---- phase 1: push ------------------------------------------------------------------
     unsigned defer_mask = 0;
+    DualRec R;
+    R.key = NOKEY;   // the window is restaged per tile, so the cached record does not outlive it
 #pragma unroll 1
     for (int qq = 0; qq < TP; ++qq) {
       const int q = (qq + (lane >> 2)) & (TP - 1);
@@ -962,7 +983,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
         double xb[2] = {st[2 * TILE + k], st[3 * TILE + k]};
         const double uo[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
         double ub[3] = {0.0, 0.0, 0.0}, dO[2], dB[2];
-        if (push_tab(A, Wn, xo, xb, uo, ub, key, dO, dB, apply, unconv)) {
+        if (push_tab(A, Wn, R, xo, xb, uo, ub, key, dO, dB, apply, unconv)) {
           st[0 * TILE + k] = dO[0];
           st[1 * TILE + k] = dO[1];
           st[2 * TILE + k] = xb[0];
