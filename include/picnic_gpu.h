@@ -270,6 +270,18 @@ typedef struct {
 int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elastic_params *prm, double dt_sec,
                          uint64_t seed, uint64_t step, long *ncollisions);
 
+/* Scattering::setMeanFreeTime (Scattering.H:60): nu_max = box maximum of the per-cell collision
+ * frequency [Hz]; the model's m_scatter_dt is 1/nu_max (the caller min-reduces the dt over ranks as
+ * ScatteringInterface.cpp:324-345 does).  TakizukaAbe::setIntraMFT/setInterMFT (TakizukaAbe.cpp:80-238),
+ * Coulomb::setIntraMFT/setInterMFT (Coulomb.cpp:108-356; needs pgpu_debye_length),
+ * Elastic::setInterMFT (Elastic.cpp:146-202, incl. its use of species 1's moments for both species).
+ * Species need pgpu_set_moments_from_bins.  nu_max = 0 when no cell holds both species. */
+int pgpu_scatter_nu_max_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double *nu_max);
+int pgpu_scatter_nu_max_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm,
+                                double *nu_max);
+int pgpu_scatter_nu_max_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elastic_params *prm,
+                                double *nu_max);
+
 /* ScatteringUtils::computeDeltaU (ScatteringUtils.H:84-111) for explicit angles (test hook):
  * u[3n] relative velocities (component-major), one angle set per pair, dU[3n] out. */
 int pgpu_scatter_delta_u(long n, const double *u, const double *costh, const double *sinth,

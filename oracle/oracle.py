@@ -261,6 +261,14 @@ def _coul_sigs():
     L.orc_elastic_sigma.argtypes = [dbl, dbl, dbl, i32, vp, vp, vp, i32, i32, vp]
     L.orc_elastic_sigma.restype = dbl
     L.orc_elastic.argtypes = [lng, vp, vp, vp, lng, dbl, vp, vp, vp, lng, vp, dbl, dbl, i32, vp, vp, vp, i32, i32, dbl, vp]
+    L.orc_gammainc_3half.restype = dbl
+    L.orc_gammainc_3half.argtypes = [dbl]
+    L.orc_ta_nu_max.restype = dbl
+    L.orc_ta_nu_max.argtypes = [lng, vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, i32]
+    L.orc_coulomb_nu_max.restype = dbl
+    L.orc_coulomb_nu_max.argtypes = [lng, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, i32]
+    L.orc_elastic_nu_max.restype = dbl
+    L.orc_elastic_nu_max.argtypes = [lng, vp, vp, vp, vp, dbl, dbl, dbl, i32, vp, vp, vp, i32, i32]
     _COUL_SET = True
 
 
@@ -323,3 +331,35 @@ def elastic(cs1, v1, w1, m1, cs2, v2, w2, dens2, m2, dt_sec, const_sigma=0.0, E=
                       v2.shape[1], _ptr(dens2), m2, const_sigma, n, *[None if a is None else _ptr(a) for a in arr],
                       angular, int(loglog), dt_sec, C.byref(ncoll))
     return ncoll.value
+
+
+def ta_nu_max(m1, m2, q1, q2, mass1, mass2, Clog, intra):
+    """TakizukaAbe::setMeanFreeTime: m = (dens[ncell], mom[3, ncell], ene[3, ncell]) per species."""
+    _coul_sigs()
+    d1, _, e1 = [np.ascontiguousarray(a, dtype=np.float64) for a in m1]
+    d2, _, e2 = [np.ascontiguousarray(a, dtype=np.float64) for a in m2]
+    return lib().orc_ta_nu_max(d1.size, _ptr(d1), _ptr(e1), _ptr(d2), _ptr(e2), q1, q2, mass1, mass2, Clog, int(intra))
+
+
+def coulomb_nu_max(LDe, m1, m2, q1, q2, mass1, mass2, Clog, intra):
+    _coul_sigs()
+    LDe = np.ascontiguousarray(LDe, dtype=np.float64)
+    d1, p1, e1 = [np.ascontiguousarray(a, dtype=np.float64) for a in m1]
+    d2, p2, e2 = [np.ascontiguousarray(a, dtype=np.float64) for a in m2]
+    return lib().orc_coulomb_nu_max(d1.size, _ptr(LDe), _ptr(d1), _ptr(p1), _ptr(e1), _ptr(d2), _ptr(p2), _ptr(e2),
+                                    q1, q2, mass1, mass2, Clog, int(intra))
+
+
+def elastic_nu_max(m1, m2, mass1, mass2, const_sigma=0.0, E=None, Q=None, XI=None, angular=0, loglog=False):
+    _coul_sigs()
+    d1, _, e1 = [np.ascontiguousarray(a, dtype=np.float64) for a in m1]
+    d2, _, e2 = [np.ascontiguousarray(a, dtype=np.float64) for a in m2]
+    n = 0 if E is None else len(E)
+    arr = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (E, Q, XI)]
+    return lib().orc_elastic_nu_max(d1.size, _ptr(d1), _ptr(e1), _ptr(d2), _ptr(e2), mass1, mass2, const_sigma, n,
+                                    *[None if a is None else _ptr(a) for a in arr], angular, int(loglog))
+
+
+def gammainc_3half(x):
+    _coul_sigs()
+    return lib().orc_gammainc_3half(float(x))

@@ -573,3 +573,180 @@ extern "C" void orc_elastic(long ncell, const long *cs1, double *v1, const doubl
   }
   if (ncoll_out) *ncoll_out = ncoll;
 }
+
+/* =====================================================================================
+ * Scattering::setMeanFreeTime -- the per-cell collision frequency whose box maximum sets
+ * m_scatter_dt = 1/nu_max (the MPI MAX over ranks is commented out in the reference, the
+ * caller min-reduces the resulting dt: ScatteringInterface.cpp:324-345).  Inputs are the
+ * cell moments of set{Number,Momentum,Energy}DensityFromBinFab: dens[c], mom[k*ncell+c],
+ * ene[k*ncell+c], and the Debye length LDe[c].  Returned: nu_max [Hz] (0 if no cell counts).
+ * ===================================================================================== */
+namespace {
+/* MathUtils::gammainc (MathUtils.cpp:65-95): Taylor series for a = 3/2, x < 10 */
+double mu_gammainc_3half(double x) {
+  double soln = std::tgamma(1.5);
+  if (x < 10.0) {
+    const int pmax = 41;
+    double coef, sign = -1.0, factorial = 1;
+    soln = 0.0;
+    for (int p = 1; p < pmax; p++) {
+      coef = 0.5 + p;
+      if (p > 1) factorial = factorial * (p - 1);
+      sign = -sign;
+      soln = soln + sign * pow(x, coef) / coef / factorial;
+    }
+  }
+  return soln;
+}
+const double kEV_PER_JOULE = 1.0 / kQE;
+const double kM3_PER_CM3 = 1.0 / 1.0e+06;
+}  // namespace
+
+extern "C" double orc_gammainc_3half(double x) { return mu_gammainc_3half(x); }
+
+/* TakizukaAbe::setIntraMFT / setInterMFT (TakizukaAbe.cpp:80-238) */
+extern "C" double orc_ta_nu_max(long ncell, const double *dens1, const double *ene1, const double *dens2,
+                                const double *ene2, double charge1, double charge2, double mass1, double mass2,
+                                double Clog, int intra) {
+  const double cvacSq = kCVAC * kCVAC;
+  double box_nuMax = 0.0;
+  if (intra) {
+    for (long c = 0; c < ncell; ++c) {
+      const double numberDensity = dens1[c];
+      if (numberDensity == 0.0) continue;
+      double energyDensity = 0.0;
+      for (int dir = 0; dir < 3; dir++) energyDensity = energyDensity + ene1[dir * ncell + c];
+      double Teff_eV = kME * 2.0 / 3.0 * energyDensity / numberDensity * cvacSq;
+      Teff_eV = kEV_PER_JOULE * Teff_eV;
+      double tau = 3.44e5 * pow(Teff_eV, 1.5) / (numberDensity * kM3_PER_CM3) / Clog;
+      tau = tau * sqrt(mass1 / 2.0) / pow(charge1 * charge2, 2);
+      box_nuMax = std::max(box_nuMax, 1.0 / tau);
+    }
+    return box_nuMax;
+  }
+  const double factor = pow(kQE * charge1 * kQE * charge2 / kEP0, 2) / kFOURPI;
+  for (long c = 0; c < ncell; ++c) {
+    const double numberDensity1 = dens1[c], numberDensity2 = dens2[c];
+    if (numberDensity1 * numberDensity2 == 0.0) continue;
+    double energyDensity1 = 0.0, energyDensity2 = 0.0;
+    for (int dir = 0; dir < 3; dir++) {
+      energyDensity1 = energyDensity1 + ene1[dir * ncell + c];
+      energyDensity2 = energyDensity2 + ene2[dir * ncell + c];
+    }
+    const double energy1 = kME * energyDensity1 / numberDensity1 * cvacSq;
+    const double energy2 = kME * energyDensity2 / numberDensity2 * cvacSq;
+    const double Teff1_eV = kEV_PER_JOULE * 2.0 / 3.0 * energy1;
+    const double Teff2_eV = kEV_PER_JOULE * 2.0 / 3.0 * energy2;
+    const double VT1 = sqrt(kQE * Teff1_eV / (kME * mass1));
+    const double VT2 = sqrt(kQE * Teff2_eV / (kME * mass2));
+    const double x12 = (Teff1_eV / mass1) / (Teff2_eV / mass2);
+    const double x21 = 1. / x12;
+    const double psi12 = 2.0 / sqrt(kPI) * mu_gammainc_3half(x12);
+    const double psi21 = 2.0 / sqrt(kPI) * mu_gammainc_3half(x21);
+    const double nu012 = factor * Clog * numberDensity2 / (pow(energy1, 2)) * VT1;
+    const double nu021 = factor * Clog * numberDensity1 / (pow(energy2, 2)) * VT2;
+    const double nu12 = (1.0 + mass1 / mass2) * psi12 * nu012;
+    const double nu21 = (1.0 + mass2 / mass1) * psi21 * nu021;
+    box_nuMax = std::max(box_nuMax, nu12);
+    box_nuMax = std::max(box_nuMax, nu21);
+  }
+  return box_nuMax;
+}
+
+/* Coulomb::setIntraMFT / setInterMFT (Coulomb.cpp:108-356) */
+extern "C" double orc_coulomb_nu_max(long ncell, const double *LDe, const double *dens1, const double *mom1,
+                                     const double *ene1, const double *dens2, const double *mom2,
+                                     const double *ene2, double charge1, double charge2, double mass1,
+                                     double mass2, double Clog_in, int intra) {
+  const CoulombConsts k = coulomb_consts(charge1, charge2, mass1, mass2);
+  const double cvacSq = kCVAC * kCVAC;
+  const double mcSq_eV = kME * kEV_PER_JOULE * cvacSq;
+  double box_nuMax = 0.0;
+  for (long c = 0; c < ncell; ++c) {
+    double g12sq, numFreq, sigma_max, EF_norm;
+    const double bmax = LDe[c];
+    if (intra) {
+      const double numDen = dens1[c];
+      if (numDen == 0.0) continue;
+      const double rho = mass1 * numDen;
+      const double atomic_spacing = 1.0 / std::cbrt(4.0 / 3.0 * kPI * numDen);
+      sigma_max = 1.0 / (numDen * atomic_spacing);
+      EF_norm = k.EF_fact * std::pow(numDen, 2.0 / 3.0);
+      const double rhoUx = mom1[c], rhoUy = mom1[ncell + c], rhoUz = mom1[2 * ncell + c];
+      const double meanE = (rhoUx * rhoUx + rhoUy * rhoUy + rhoUz * rhoUz) / rho / 2.0;
+      double eneDen = 0.0;
+      for (int dir = 0; dir < 3; dir++) eneDen += ene1[dir * ncell + c];
+      double T_eV = 2.0 / 3.0 * (eneDen - meanE) / numDen * mcSq_eV;
+      T_eV = std::max(T_eV, 0.01);
+      g12sq = 6.0 * kQE / kME * T_eV / mass1;
+      numFreq = numDen;
+    } else {
+      const double numDen1 = dens1[c], numDen2 = dens2[c];
+      if (numDen1 * numDen2 == 0.0) continue;
+      const double rho1 = mass1 * numDen1, rho2 = mass2 * numDen2;
+      const double minn = std::min(numDen1, numDen2);
+      const double atomic_spacing = 1.0 / std::cbrt(4.0 / 3.0 * kPI * minn);
+      sigma_max = 1.0 / (minn * atomic_spacing);
+      const double maxn = std::max(numDen1, numDen2);
+      EF_norm = k.EF_fact * std::pow(maxn, 2.0 / 3.0);
+      const double rhoUx1 = mom1[c], rhoUy1 = mom1[ncell + c], rhoUz1 = mom1[2 * ncell + c];
+      const double meanE1 = (rhoUx1 * rhoUx1 + rhoUy1 * rhoUy1 + rhoUz1 * rhoUz1) / rho1 / 2.0;
+      const double rhoUx2 = mom2[c], rhoUy2 = mom2[ncell + c], rhoUz2 = mom2[2 * ncell + c];
+      const double meanE2 = (rhoUx2 * rhoUx2 + rhoUy2 * rhoUy2 + rhoUz2 * rhoUz2) / rho2 / 2.0;
+      double eneDen1 = 0.0, eneDen2 = 0.0;
+      for (int dir = 0; dir < 3; dir++) eneDen1 += ene1[dir * ncell + c];
+      for (int dir = 0; dir < 3; dir++) eneDen2 += ene2[dir * ncell + c];
+      double T1_eV = 2.0 / 3.0 * (eneDen1 - meanE1) / numDen1 * mcSq_eV;
+      double T2_eV = 2.0 / 3.0 * (eneDen2 - meanE2) / numDen2 * mcSq_eV;
+      T1_eV = std::max(T1_eV, 0.01);
+      T2_eV = std::max(T2_eV, 0.01);
+      const double VT1 = std::sqrt(kQE * T1_eV / (kME * mass1));
+      const double VT2 = std::sqrt(kQE * T2_eV / (kME * mass2));
+      g12sq = (3.0 * VT1 * VT1 + 3.0 * VT2 * VT2);
+      g12sq += std::pow((rhoUx1 / rho1 - rhoUx2 / rho2), 2) * cvacSq;
+      g12sq += std::pow((rhoUy1 / rho1 - rhoUy2 / rho2), 2) * cvacSq;
+      g12sq += std::pow((rhoUz1 / rho1 - rhoUz2 / rho2), 2) * cvacSq;
+      numFreq = maxn;
+    }
+    const double g12sq_norm = g12sq / cvacSq;
+    const double b90 = k.b90_fact / (k.mu * g12sq_norm + 2.0 * EF_norm);
+    double Clog = Clog_in;
+    if (Clog == 0.0 && g12sq > 0.0) { /* Lee and More 1984 Eqs 20-22 */
+      const double bmin_qm = k.bqm_fact / (k.mu * std::sqrt(g12sq_norm));
+      const double bmin = std::max(b90 / 2.0, bmin_qm);
+      Clog = 0.5 * std::log(1.0 + bmax * bmax / bmin / bmin);
+      Clog = std::max(2.0, Clog);
+    }
+    double sigma90 = 8.0 / kPI * b90 * b90 * Clog;
+    sigma90 = std::min(sigma90, sigma_max);
+    const double nu90 = sqrt(g12sq) * numFreq * sigma90;
+    box_nuMax = std::max(box_nuMax, nu90);
+  }
+  return box_nuMax;
+}
+
+/* Elastic::setInterMFT (Elastic.cpp:146-202).  Reference quirk kept by the caller: setMeanFreeTime
+ * hands species 1's moments in for BOTH species (Elastic.cpp:130-131) while m_mass2 stays species 2's. */
+extern "C" double orc_elastic_nu_max(long ncell, const double *dens1, const double *ene1, const double *dens2,
+                                     const double *ene2, double mass1, double mass2, double const_sigma, int ntab,
+                                     const double *E, const double *Q, const double *XI, int angular, int loglog) {
+  const double mu = mass1 * mass2 / (mass1 + mass2);
+  double box_nuMax = 0.0;
+  for (long c = 0; c < ncell; ++c) {
+    const double n1 = dens1[c], n2 = dens2[c];
+    if (n1 * n2 == 0.0) continue;
+    double b1 = 0.0, b2 = 0.0;
+    for (int dir = 0; dir < 3; dir++) {
+      b1 += 2.0 * ene1[dir * ncell + c];
+      b2 += 2.0 * ene2[dir * ncell + c];
+    }
+    b1 /= n1 * mass1;
+    b2 /= n2 * mass2;
+    const double g12 = sqrt(b1 + b2);
+    double xi;
+    const double sigma = orc_elastic_sigma(g12, mu, const_sigma, ntab, E, Q, XI, angular, loglog, &xi);
+    const double local_nuMax = n2 * sigma * g12 * kCVAC;
+    box_nuMax = std::max(box_nuMax, local_nuMax);
+  }
+  return box_nuMax;
+}

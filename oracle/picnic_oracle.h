@@ -179,6 +179,21 @@ void orc_elastic(long ncell, const long *cs1, double *v1, const double *w1, long
                  double mass2, double const_sigma, int ntab, const double *E, const double *Q,
                  const double *XI, int angular, int loglog, double dt_sec, long *ncoll);
 
+
+/* Scattering::setMeanFreeTime: box maximum of the per-cell collision frequency [Hz]
+ * (TakizukaAbe.cpp:55-238, Coulomb.cpp:79-356, Elastic.cpp:122-202, MathUtils.cpp:65-95) */
+double orc_gammainc_3half(double x);
+double orc_ta_nu_max(long ncell, const double *dens1, const double *ene1, const double *dens2,
+                     const double *ene2, double charge1, double charge2, double mass1, double mass2,
+                     double Clog, int intra);
+double orc_coulomb_nu_max(long ncell, const double *LDe, const double *dens1, const double *mom1,
+                          const double *ene1, const double *dens2, const double *mom2,
+                          const double *ene2, double charge1, double charge2, double mass1,
+                          double mass2, double Clog, int intra);
+double orc_elastic_nu_max(long ncell, const double *dens1, const double *ene1, const double *dens2,
+                          const double *ene2, double mass1, double mass2, double const_sigma, int ntab,
+                          const double *E, const double *Q, const double *XI, int angular, int loglog);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,8 @@ def load():
         "pgpu_collide_coulomb": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_coulomb_delta_u": [lng, vp, vp, dbl, dbl, dbl, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "pgpu_collide_elastic": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
+        "pgpu_scatter_nu_max_ta": [vp, vp, dbl, vp], "pgpu_scatter_nu_max_coulomb": [vp, vp, vp, vp],
+        "pgpu_scatter_nu_max_elastic": [vp, vp, vp, vp],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
         "pgpu_launch_count": [], "pgpu_picard_totals": [vp, vp, vp, i32], "pgpu_abi_version": [], "pgpu_last_error": [],
     }
@@ -395,6 +397,29 @@ def collide_elastic(sA, sB, dt_sec, seed, step, const_sigma=0.0, E=None, Q=None,
     nc = C.c_long(0)
     check(load().pgpu_collide_elastic(sA.h, sB.h, C.byref(prm), dt_sec, seed, step, C.byref(nc) if count else None))
     return nc.value
+
+
+def nu_max_ta(sA, sB, Clog):
+    """TakizukaAbe::setMeanFreeTime: box maximum of the collision frequency [Hz] (scatter dt = 1/nu_max)."""
+    out = C.c_double(0.0)
+    check(load().pgpu_scatter_nu_max_ta(sA.h, sB.h, Clog, C.byref(out)))
+    return out.value
+
+
+def nu_max_coulomb(sA, sB, Clog, angular=0):
+    prm = CoulombParams(Clog, angular, 0, 11, 1)
+    out = C.c_double(0.0)
+    check(load().pgpu_scatter_nu_max_coulomb(sA.h, sB.h, C.byref(prm), C.byref(out)))
+    return out.value
+
+
+def nu_max_elastic(sA, sB, const_sigma=0.0, E=None, Q=None, xi=None, angular=0, loglog=False):
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    E, Q, xi = c(E), c(Q), c(xi)
+    prm = ElasticParams(const_sigma, 0 if E is None else E.size, _p(E), _p(Q), _p(xi), angular, int(loglog))
+    out = C.c_double(0.0)
+    check(load().pgpu_scatter_nu_max_elastic(sA.h, sB.h, C.byref(prm), C.byref(out)))
+    return out.value
 
 
 def scatter_delta_u(u, costh, sinth, cosphi, sinphi):

@@ -646,6 +646,189 @@ k_elastic(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, dou
   if (lane == 0 && mine) atomicAdd(ncoll, (unsigned long long)mine);
 }
 
+
+// ---- Scattering::setMeanFreeTime: box maximum of the per-cell collision frequency -----------
+// (TakizukaAbe.cpp:80-238, Coulomb.cpp:108-356, Elastic.cpp:146-202).  One thread per cell; the
+// maximum of the non-negative frequencies is taken on their bit patterns.
+__device__ __forceinline__ void max_bits(unsigned long long *out, double v) {
+  if (!(v > 0.0)) return;   // also drops NaN (a cell with zero temperature)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
+}
+
+// MathUtils::gammainc (MathUtils.cpp:65-95), a = 3/2
+__device__ double gammainc_3half(double x) {
+  double soln = 0.88622692545275801365;   // tgamma(1.5)
+  if (x < 10.0) {
+    double sign = -1.0, factorial = 1.0;
+    soln = 0.0;
+    for (int p = 1; p < 41; p++) {
+      const double coef = 0.5 + p;
+      if (p > 1) factorial = factorial * (p - 1);
+      sign = -sign;
+      soln = soln + sign * pow(x, coef) / coef / factorial;
+    }
+  }
+  return soln;
+}
+
+struct NuConsts {
+  double CVAC, ME, QE, EP0, PI;
+};
+__device__ __forceinline__ NuConsts nu_consts() {
+  NuConsts k;
+  k.PI = 3.14159265358979323846;
+  k.CVAC = 2.99792458e+08;
+  k.ME = 9.10938370e-31;
+  k.QE = 1.60217663e-19;
+  k.EP0 = 1.0 / k.CVAC / k.CVAC / (4.0 * k.PI * 1.0e-7);
+  return k;
+}
+
+__global__ void k_nu_max_ta(int ncell, const double *dens1, const double *ene1, const double *dens2,
+                            const double *ene2, double charge1, double charge2, double mass1, double mass2,
+                            double Clog, int intra, unsigned long long *out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const NuConsts k = nu_consts();
+  const double cvacSq = k.CVAC * k.CVAC, EV_PER_JOULE = 1.0 / k.QE;
+  double nu = 0.0;
+  if (c < ncell) {
+    if (intra) {
+      const double n = dens1[c];
+      if (n != 0.0) {
+        double e = 0.0;
+        for (int d = 0; d < 3; ++d) e = e + ene1[(size_t)d * ncell + c];
+        double T = k.ME * 2.0 / 3.0 * e / n * cvacSq;
+        T = EV_PER_JOULE * T;
+        double tau = 3.44e5 * pow(T, 1.5) / (n * (1.0 / 1.0e+06)) / Clog;
+        tau = tau * sqrt(mass1 / 2.0) / pow(charge1 * charge2, 2.0);
+        nu = 1.0 / tau;
+      }
+    } else {
+      const double n1 = dens1[c], n2 = dens2[c];
+      if (n1 * n2 != 0.0) {
+        const double q = k.QE * charge1 * k.QE * charge2 / k.EP0;
+        const double factor = q * q / (4.0 * k.PI);
+        double e1 = 0.0, e2 = 0.0;
+        for (int d = 0; d < 3; ++d) {
+          e1 = e1 + ene1[(size_t)d * ncell + c];
+          e2 = e2 + ene2[(size_t)d * ncell + c];
+        }
+        const double energy1 = k.ME * e1 / n1 * cvacSq, energy2 = k.ME * e2 / n2 * cvacSq;
+        const double T1 = EV_PER_JOULE * 2.0 / 3.0 * energy1, T2 = EV_PER_JOULE * 2.0 / 3.0 * energy2;
+        const double VT1 = sqrt(k.QE * T1 / (k.ME * mass1)), VT2 = sqrt(k.QE * T2 / (k.ME * mass2));
+        const double x12 = (T1 / mass1) / (T2 / mass2), x21 = 1. / x12;
+        const double psi12 = 2.0 / sqrt(k.PI) * gammainc_3half(x12);
+        const double psi21 = 2.0 / sqrt(k.PI) * gammainc_3half(x21);
+        const double nu012 = factor * Clog * n2 / (energy1 * energy1) * VT1;
+        const double nu021 = factor * Clog * n1 / (energy2 * energy2) * VT2;
+        nu = fmax((1.0 + mass1 / mass2) * psi12 * nu012, (1.0 + mass2 / mass1) * psi21 * nu021);
+      }
+    }
+  }
+  max_bits(out, nu);
+}
+
+__global__ void k_nu_max_coulomb(int ncell, const double *LDe, const double *dens1, const double *mom1,
+                                 const double *ene1, const double *dens2, const double *mom2, const double *ene2,
+                                 double mass1, double mass2, CoulParams P, int intra, unsigned long long *out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const NuConsts k = nu_consts();
+  const double cvacSq = k.CVAC * k.CVAC, mcSq_eV = k.ME * (1.0 / k.QE) * cvacSq;
+  double nu = 0.0;
+  if (c < ncell) {
+    bool live = false;
+    double g12sq = 0.0, nfreq = 0.0, sigma_max = 0.0, EF_norm = 0.0;
+    const size_t N = (size_t)ncell;
+    if (intra) {
+      const double n = dens1[c];
+      if (n != 0.0) {
+        live = true;
+        const double rho = mass1 * n;
+        const double spacing = 1.0 / cbrt(4.0 / 3.0 * k.PI * n);
+        sigma_max = 1.0 / (n * spacing);
+        EF_norm = P.EF_fact * pow(n, 2.0 / 3.0);
+        const double ux = mom1[c], uy = mom1[N + c], uz = mom1[2 * N + c];
+        const double meanE = (ux * ux + uy * uy + uz * uz) / rho / 2.0;
+        double e = 0.0;
+        for (int d = 0; d < 3; ++d) e += ene1[d * N + c];
+        double T = 2.0 / 3.0 * (e - meanE) / n * mcSq_eV;
+        T = fmax(T, 0.01);
+        g12sq = 6.0 * k.QE / k.ME * T / mass1;
+        nfreq = n;
+      }
+    } else {
+      const double n1 = dens1[c], n2 = dens2[c];
+      if (n1 * n2 != 0.0) {
+        live = true;
+        const double rho1 = mass1 * n1, rho2 = mass2 * n2;
+        const double minn = fmin(n1, n2), maxn = fmax(n1, n2);
+        const double spacing = 1.0 / cbrt(4.0 / 3.0 * k.PI * minn);
+        sigma_max = 1.0 / (minn * spacing);
+        EF_norm = P.EF_fact * pow(maxn, 2.0 / 3.0);
+        const double ux1 = mom1[c], uy1 = mom1[N + c], uz1 = mom1[2 * N + c];
+        const double ux2 = mom2[c], uy2 = mom2[N + c], uz2 = mom2[2 * N + c];
+        const double meanE1 = (ux1 * ux1 + uy1 * uy1 + uz1 * uz1) / rho1 / 2.0;
+        const double meanE2 = (ux2 * ux2 + uy2 * uy2 + uz2 * uz2) / rho2 / 2.0;
+        double e1 = 0.0, e2 = 0.0;
+        for (int d = 0; d < 3; ++d) e1 += ene1[d * N + c];
+        for (int d = 0; d < 3; ++d) e2 += ene2[d * N + c];
+        double T1 = 2.0 / 3.0 * (e1 - meanE1) / n1 * mcSq_eV, T2 = 2.0 / 3.0 * (e2 - meanE2) / n2 * mcSq_eV;
+        T1 = fmax(T1, 0.01);
+        T2 = fmax(T2, 0.01);
+        const double VT1 = sqrt(k.QE * T1 / (k.ME * mass1)), VT2 = sqrt(k.QE * T2 / (k.ME * mass2));
+        g12sq = (3.0 * VT1 * VT1 + 3.0 * VT2 * VT2);
+        const double dx = ux1 / rho1 - ux2 / rho2, dy = uy1 / rho1 - uy2 / rho2, dz = uz1 / rho1 - uz2 / rho2;
+        g12sq += dx * dx * cvacSq;
+        g12sq += dy * dy * cvacSq;
+        g12sq += dz * dz * cvacSq;
+        nfreq = maxn;
+      }
+    }
+    if (live) {
+      const double g12sq_norm = g12sq / cvacSq;
+      const double b90 = P.b90_fact / (P.mu * g12sq_norm + 2.0 * EF_norm);
+      double Clog = P.Clog;
+      if (Clog == 0.0 && g12sq > 0.0) {
+        const double bmax = LDe[c];
+        const double bmin_qm = P.bqm_fact / (P.mu * sqrt(g12sq_norm));
+        const double bmin = fmax(b90 / 2.0, bmin_qm);
+        Clog = 0.5 * log(1.0 + bmax * bmax / bmin / bmin);
+        Clog = fmax(2.0, Clog);
+      }
+      double sigma90 = 8.0 / k.PI * b90 * b90 * Clog;
+      sigma90 = fmin(sigma90, sigma_max);
+      nu = sqrt(g12sq) * nfreq * sigma90;
+    }
+  }
+  max_bits(out, nu);
+}
+
+__global__ void k_nu_max_elastic(int ncell, const double *dens1, const double *ene1, const double *dens2,
+                                 const double *ene2, double mass1, double mass2, ElaParams P,
+                                 unsigned long long *out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double nu = 0.0;
+  if (c < ncell) {
+    const double n1 = dens1[c], n2 = dens2[c];
+    if (n1 * n2 != 0.0) {
+      const size_t N = (size_t)ncell;
+      double b1 = 0.0, b2 = 0.0;
+      for (int d = 0; d < 3; ++d) {
+        b1 += 2.0 * ene1[d * N + c];
+        b2 += 2.0 * ene2[d * N + c];
+      }
+      b1 /= n1 * mass1;
+      b2 /= n2 * mass2;
+      const double g12 = sqrt(b1 + b2);
+      double xi;
+      const double sigma = elastic_sigma(P, g12, xi);
+      nu = n2 * sigma * g12 * 2.99792458e+08;
+    }
+  }
+  max_bits(out, nu);
+}
 }  // namespace pgpu
 
 using namespace pgpu;
@@ -954,6 +1137,115 @@ int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt
     PGPU_CUDA(cudaMemsetAsync(&c.d_counters->npairs, 0, sizeof(unsigned long long), c.stream));
   }
   return 0;
+}
+
+
+// ---- Scattering::setMeanFreeTime ---------------------------------------------------------------
+static int need_moments(pgpu_species_t sA, pgpu_species_t sB) {
+  if (!ctx().inited) {
+    set_error("pgpu_init has not been called");
+    return PGPU_ERR_STATE;
+  }
+  if (!sA || !sB || sA->grid != sB->grid) return PGPU_ERR_ARG;
+  if (!sA->dens || !sB->dens) {
+    set_error("setMeanFreeTime needs the cell moments: call pgpu_set_moments_from_bins first");
+    return PGPU_ERR_STATE;
+  }
+  return 0;
+}
+
+static int fetch_nu_max(double *nu_max) {
+  Context &c = ctx();
+  PGPU_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c.stream));
+  PGPU_CUDA(cudaMemsetAsync(&c.d_counters->maxbits, 0, sizeof(unsigned long long), c.stream));
+  PGPU_CUDA(cudaStreamSynchronize(c.stream));
+  memcpy(nu_max, &c.h_counters->maxbits, sizeof(double));
+  return 0;
+}
+
+int pgpu_scatter_nu_max_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double *nu_max) {
+  int rc = need_moments(sA, sB);
+  if (rc) return rc;
+  if (!nu_max) return PGPU_ERR_ARG;
+  Context &c = ctx();
+  const int ncell = (int)sA->grid->ncell_box;
+  {
+    KTimer t("nu_max");
+    k_nu_max_ta<<<nb(ncell), 256, 0, c.stream>>>(ncell, sA->dens, sA->ene, sB->dens, sB->ene, sA->desc.charge,
+                                                 sB->desc.charge, sA->desc.mass, sB->desc.mass, Clog, sA == sB,
+                                                 &c.d_counters->maxbits);
+  }
+  return fetch_nu_max(nu_max);
+}
+
+int pgpu_scatter_nu_max_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm,
+                                double *nu_max) {
+  int rc = need_moments(sA, sB);
+  if (rc) return rc;
+  if (!nu_max || !prm) return PGPU_ERR_ARG;
+  Context &c = ctx();
+  const pgpu_grid_s *g = sA->grid;
+  if (!g->debye) {
+    set_error("Coulomb::setMeanFreeTime needs the Debye length: call pgpu_debye_length first");
+    return PGPU_ERR_STATE;
+  }
+  CoulParams P;
+  rc = coulomb_consts(sA->desc.charge, sB->desc.charge, sA->desc.mass, sB->desc.mass, prm, 0.0, &P);
+  if (rc) return rc;
+  const int ncell = (int)g->ncell_box;
+  {
+    KTimer t("nu_max");
+    k_nu_max_coulomb<<<nb(ncell), 256, 0, c.stream>>>(ncell, g->debye, sA->dens, sA->mom, sA->ene, sB->dens, sB->mom,
+                                                      sB->ene, sA->desc.mass, sB->desc.mass, P, sA == sB,
+                                                      &c.d_counters->maxbits);
+  }
+  return fetch_nu_max(nu_max);
+}
+
+int pgpu_scatter_nu_max_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elastic_params *prm,
+                                double *nu_max) {
+  int rc = need_moments(sA, sB);
+  if (rc) return rc;
+  if (!nu_max || !prm || (prm->ntab && (!prm->E || !prm->Q || prm->ntab < 2))) return PGPU_ERR_ARG;
+  if (prm->ntab && prm->angular_scattering == 1 && !prm->xi) return PGPU_ERR_ARG;
+  Context &c = ctx();
+  const double CVAC = 2.99792458e+08, ME = 9.10938370e-31, QE = 1.60217663e-19;
+  ElaParams P;
+  const double m1 = sA->desc.mass, m2 = sB->desc.mass;
+  P.mu = m1 * m2 / (m1 + m2);
+  P.f1 = P.mu / m1;
+  P.f2 = P.mu / m2;
+  P.const_sigma = prm->const_sigma;
+  P.dt_sec = 0.0;
+  P.mcSq = ME * CVAC * CVAC / QE;
+  P.ntab = prm->ntab;
+  P.angular = prm->angular_scattering;
+  P.loglog = prm->use_loglog_interp;
+  P.E = P.Q = P.XI = nullptr;
+  P.seed_lo = P.seed_hi = P.step_lo = P.step_hi = 0;
+  double *d_tab = nullptr;
+  if (prm->ntab) {
+    const size_t N = (size_t)prm->ntab;
+    PGPU_CUDA(cudaMalloc(&d_tab, 3 * N * sizeof(double)));
+    PGPU_CUDA(cudaMemcpyAsync(d_tab, prm->E, N * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    PGPU_CUDA(cudaMemcpyAsync(d_tab + N, prm->Q, N * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    if (prm->xi) PGPU_CUDA(cudaMemcpyAsync(d_tab + 2 * N, prm->xi, N * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    else PGPU_CUDA(cudaMemsetAsync(d_tab + 2 * N, 0, N * sizeof(double), c.stream));
+    P.E = d_tab;
+    P.Q = d_tab + N;
+    P.XI = d_tab + 2 * N;
+  }
+  const int ncell = (int)sA->grid->ncell_box;
+  {
+    // Reference quirk kept: Elastic::setMeanFreeTime reads species 1's moments
+    // for BOTH species (Elastic.cpp:130-131); the masses are the two species' own.
+    KTimer t("nu_max");
+    k_nu_max_elastic<<<nb(ncell), 256, 0, c.stream>>>(ncell, sA->dens, sA->ene, sA->dens, sA->ene, m1, m2, P,
+                                                      &c.d_counters->maxbits);
+  }
+  rc = fetch_nu_max(nu_max);   // synchronises
+  if (d_tab) cudaFree(d_tab);
+  return rc;
 }
 
 }  // extern "C"

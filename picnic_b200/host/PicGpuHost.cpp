@@ -195,10 +195,13 @@ TakizukaAbe::TakizukaAbe(int a_sp1, int a_sp2, Real a_Clog)
   // TakizukaAbe.H:50 asserts Clog >= 3 (assert off in OPT builds); report instead of ignoring
   if (a_Clog < 3.0) std::cerr << "picnic_gpu::TakizukaAbe: coulomb_logarithm " << a_Clog << " < 3" << std::endl;
 }
-void TakizukaAbe::setMeanFreeTime(const std::vector<PicChargedSpecies *> &) const {
-  // nu_max per cell -> scatter dt (TakizukaAbe.cpp:55-238) only limits the time step the host
-  // chooses; the binary collisions themselves do not need it.  Left at DBL_MAX = no limit.
-  m_scatter_dt = DBL_MAX;
+void TakizukaAbe::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {
+  // m_scatter_dt = 1/nu_max over the cells of this box (TakizukaAbe.cpp:55-238); needs the cell
+  // moments of prepForScatter.  nu_max == 0 (no cell holds both species) leaves the dt unlimited.
+  double nu = 0.0;
+  check(pgpu_scatter_nu_max_ta(a_species[m_sp1]->handle(), a_species[m_sp2]->handle(), m_Clog, &nu),
+        "TakizukaAbe::setMeanFreeTime");
+  m_scatter_dt = nu > 0.0 ? 1.0 / nu : DBL_MAX;
 }
 void TakizukaAbe::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real a_dt_sec) const {
   PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
@@ -224,6 +227,13 @@ Coulomb::Coulomb(int a_sp1, int a_sp2, Real a_Clog, AngularScattering a_angular,
   m_prm.num_subcycles = a_num_subcycles;
   if (a_Clog != 0.0 && a_Clog < 2.0) fatal("Coulomb: coulomb_logarithm must be 0 (computed) or >= 2");   // Coulomb.H:224
 }
+void Coulomb::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {
+  // Coulomb.cpp:79-356; needs Mesh::setDebyeLength and the cell moments
+  double nu = 0.0;
+  check(pgpu_scatter_nu_max_coulomb(a_species[m_sp1]->handle(), a_species[m_sp2]->handle(), &m_prm, &nu),
+        "Coulomb::setMeanFreeTime");
+  m_scatter_dt = nu > 0.0 ? 1.0 / nu : DBL_MAX;
+}
 void Coulomb::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real a_dt_sec) const {
   PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
   if (a->numParticles() == 0 || b->numParticles() == 0) return;
@@ -240,17 +250,15 @@ void Coulomb::printParameters() const {
 }
 
 Elastic::Elastic(int a_sp1, int a_sp2, Real a_const_sigma)
-    : m_sp1(a_sp1), m_sp2(a_sp2), m_const_sigma(a_const_sigma), m_okhrimovskyy(false), m_loglog(false), m_ncoll(0) {}
+    : m_sp1(a_sp1), m_sp2(a_sp2), m_const_sigma(a_const_sigma), m_okhrimovskyy(false), m_loglog(false), m_scatter_dt(DBL_MAX), m_ncoll(0) {}
 Elastic::Elastic(int a_sp1, int a_sp2, const std::vector<Real> &a_E_eV, const std::vector<Real> &a_Q,
                  const std::vector<Real> &a_xi, bool a_okhrimovskyy, bool a_use_loglog_interp)
     : m_sp1(a_sp1), m_sp2(a_sp2), m_const_sigma(0.0), m_E(a_E_eV), m_Q(a_Q), m_xi(a_xi),
-      m_okhrimovskyy(a_okhrimovskyy), m_loglog(a_use_loglog_interp), m_ncoll(0) {
+      m_okhrimovskyy(a_okhrimovskyy), m_loglog(a_use_loglog_interp), m_scatter_dt(DBL_MAX), m_ncoll(0) {
   if (m_E.size() < 2 || m_Q.size() != m_E.size() || (a_okhrimovskyy && m_xi.size() != m_E.size()))
     fatal("Elastic: cross-section table columns differ in length");
 }
-void Elastic::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real a_dt_sec) const {
-  PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
-  if (a->numParticles() == 0 || b->numParticles() == 0) return;
+pgpu_elastic_params Elastic::params() const {
   pgpu_elastic_params prm;
   prm.const_sigma = m_const_sigma;
   prm.ntab = (int)m_E.size();
@@ -259,6 +267,20 @@ void Elastic::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real 
   prm.xi = m_xi.empty() ? nullptr : m_xi.data();
   prm.angular_scattering = m_okhrimovskyy ? 1 : 0;
   prm.use_loglog_interp = m_loglog ? 1 : 0;
+  return prm;
+}
+void Elastic::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {
+  // Elastic.cpp:122-202
+  const pgpu_elastic_params prm = params();
+  double nu = 0.0;
+  check(pgpu_scatter_nu_max_elastic(a_species[m_sp1]->handle(), a_species[m_sp2]->handle(), &prm, &nu),
+        "Elastic::setMeanFreeTime");
+  m_scatter_dt = nu > 0.0 ? 1.0 / nu : DBL_MAX;
+}
+void Elastic::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real a_dt_sec) const {
+  PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
+  if (a->numParticles() == 0 || b->numParticles() == 0) return;
+  const pgpu_elastic_params prm = params();
   long nc = 0;
   check(pgpu_collide_elastic(a->handle(), b->handle(), &prm, a_dt_sec, s_seed, s_step, &nc), "Elastic::applyScattering");
   m_ncoll = nc;

@@ -96,6 +96,18 @@ int main(int argc, char **argv) {
     std::fclose(g);
     std::printf("example_driver: n=%ld apply_its=%llu unconverged=%llu\n", n, (unsigned long long)apply_its,
                 (unsigned long long)sp.numUnconverged());
+
+    // ---- collisions: ScatteringInterface::applyScattering for one self-scattering model ------
+    // prepForScatter (bin + cell moments), Scattering::setMeanFreeTime -> scatterDt, applyScattering;
+    // done after the result file is written so that the step above stays checkable on its own
+    sp.binTheParticles();
+    sp.setNumberDensityFromBinFab();
+    std::vector<PicChargedSpecies *> all(1, &sp);
+    TakizukaAbe ta(0, 0, 3.0);
+    ta.setMeanFreeTime(all);
+    Scattering::setRandomState(1983, 0);
+    ta.applyScattering(all, dt * 1.77e-17);
+    std::printf("example_driver: TA scatterDt=%.17g pairs=%ld\n", ta.scatterDt(), ta.lastPairCount());
   }
   finalize();
   return 0;

@@ -294,3 +294,42 @@ def test_elastic_table_lookup_matches_oracle_statistics(pgpu):
     # forward-peaked scattering randomises the electron directions at the same rate
     f = lambda v0, v: float(np.mean(np.sum(v0 * v, axis=0) / (np.linalg.norm(v0, axis=0) * np.linalg.norm(v, axis=0))))
     assert abs(f(be["v"], ae["v"]) - f(be["v"], v1)) < 0.02
+
+
+def test_mean_free_time_matches_oracle(pgpu):
+    """Scattering::setMeanFreeTime for TA, Coulomb (fixed and computed Clog) and Elastic (constant and
+    tabulated sigma), intra and inter species, on ragged cells with empty ones."""
+    rng = np.random.default_rng(71)
+    ncell = 96
+    xe, _ = _ragged_cells(rng, ncell, [0, 3, 9, 20, 33])
+    xi, _ = _ragged_cells(rng, ncell, [0, 2, 7, 16, 40])
+    deck = decks.Deck(D=1, ncell=(ncell,), dx=(0.25,), xmin=(0.0,), nghost=2)
+    se, si = decks.electron_proton((1,))
+    grid = pgpu.Grid(1, (ncell,), (0.0,), (0.25,), 2, (1,), volume_scale=deck.volume_scale)
+    ve = rng.standard_normal((3, xe.shape[1])) * 0.02 + 1e-3
+    vi = rng.standard_normal((3, xi.shape[1])) * 0.0005
+    we = rng.uniform(0.5, 1.5, xe.shape[1]) * 1e28
+    wi = rng.uniform(0.5, 1.5, xi.shape[1]) * 1e28
+    spe = _species_on_grid(pgpu, grid, deck, se, xe, ve, we)
+    spi = _species_on_grid(pgpu, grid, deck, si, xi, vi, wi)
+    LDe = grid.debye_length([spe, spi])
+    me, mi = spe.moments(), spi.moments()
+    rel = lambda a, b: abs(a - b) / abs(b)
+    for (sa, sb, ma, mb, da, db, intra) in ((spe, spe, me, me, se, se, True), (spi, spi, mi, mi, si, si, True),
+                                            (spe, spi, me, mi, se, si, False)):
+        got = pgpu.nu_max_ta(sa, sb, 3.0)
+        want = orc.ta_nu_max(ma, mb, da.charge, db.charge, da.mass, db.mass, 3.0, intra)
+        assert want > 0 and rel(got, want) < 1e-11
+        for Clog in (10.0, 0.0):
+            got = pgpu.nu_max_coulomb(sa, sb, Clog)
+            want = orc.coulomb_nu_max(LDe, ma, mb, da.charge, db.charge, da.mass, db.mass, Clog, intra)
+            assert want > 0 and rel(got, want) < 1e-11
+    # Elastic: the reference reads species 1's moments for both species (Elastic.cpp:130-131)
+    E = np.array([0.01, 0.1, 1.0, 10.0, 100.0, 1000.0])
+    Q = np.array([5.0e-20, 6.0e-20, 7.0e-20, 4.0e-20, 1.0e-20, 2.0e-21])
+    XI = np.array([0.0, 0.05, 0.2, 0.5, 0.8, 0.95])
+    got = pgpu.nu_max_elastic(spe, spi, const_sigma=6e-20)
+    assert rel(got, orc.elastic_nu_max(me, me, se.mass, si.mass, const_sigma=6e-20)) < 1e-12
+    got = pgpu.nu_max_elastic(spe, spi, E=E, Q=Q, xi=XI, angular=1, loglog=True)
+    assert rel(got, orc.elastic_nu_max(me, me, se.mass, si.mass, E=E, Q=Q, XI=XI, angular=1, loglog=True)) < 1e-11
+    spe.destroy(); spi.destroy(); grid.destroy()

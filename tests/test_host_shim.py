@@ -88,3 +88,15 @@ def test_example_driver_matches_oracle(driver, tmp_path):
     assert np.array_equal(ids[k], np.arange(n, dtype=np.uint64))
     assert np.max(np.abs(gx[:, k] - xw)) <= 1e-11 * deck.dx[0]
     assert np.max(np.abs(gv[:, k] - v)) <= 1e-11 * np.max(np.abs(v))
+    # the collision tail of the driver: TakizukaAbe::setMeanFreeTime on the end-of-step particles
+    line = [l for l in r.stdout.splitlines() if "TA scatterDt" in l][0]
+    dt_scatter = float(line.split("scatterDt=")[1].split()[0])
+    cells = np.floor((xw - np.array(deck.xmin)[:, None]) / np.array(deck.dx)[:, None]).astype(int)
+    cid = cells[0] + 16 * cells[1]
+    dV = deck.dx[0] * deck.dx[1] * deck.volume_scale
+    dens = np.bincount(cid, weights=p["w"], minlength=256) / dV
+    ene = np.stack([np.bincount(cid, weights=0.5 * sdef.mass * p["w"] * v[k_] ** 2, minlength=256) / dV for k_ in range(3)])
+    nu = orc.ta_nu_max((dens, np.zeros((3, 256)), ene), (dens, np.zeros((3, 256)), ene), sdef.charge, sdef.charge,
+                       sdef.mass, sdef.mass, 3.0, True)
+    assert abs(dt_scatter * nu - 1.0) < 1e-9
+    assert int(line.split("pairs=")[1]) == sum((c // 2 if c % 2 == 0 else (c - 3) // 2 + 3) for c in np.bincount(cid, minlength=256) if c >= 2)
