@@ -651,10 +651,10 @@ k_elastic(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, dou
 // (TakizukaAbe.cpp:80-238, Coulomb.cpp:108-356, Elastic.cpp:146-202).  One thread per cell; the
 // maximum of the non-negative frequencies is taken on their bit patterns.
 __device__ __forceinline__ void max_bits(unsigned long long *out, double v) {
-  if (!(v > 0.0)) return;   // also drops NaN (a cell with zero temperature)
+  if (!(v > 0.0)) v = 0.0;   // also drops NaN (a cell with zero temperature); every lane takes part
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
 }
 
 // MathUtils::gammainc (MathUtils.cpp:65-95), a = 3/2
