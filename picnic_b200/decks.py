@@ -212,5 +212,8 @@ def deck_c3(ncell=512, ppc=10, dt=3.0, iter_max=21):
 def deck_c4(ncell=250000, ppc=200):
     """C4: 1D shock stand-in, 2 species x ncell x 200 ppc (periodic for timing)."""
     d = Deck(D=1, ncell=(ncell,), dx=(0.25,), xmin=(0.0,), nghost=3, dt=3.0)
+    # positions reach 6e4 code units, where one ulp is 3e-11 dx: the step-norm test |dxp0 - dxp|/dx
+    # cannot resolve the 1e-12 of the small decks (the reference's long 1D decks use 1e-8 .. 1e-10)
+    d.rtol = 1.0e-8
     d.species = electron_proton((ppc,))
     return d

@@ -188,12 +188,14 @@ class CapiGridBackend:
 
 
 class HaloExchange:
-    """Ghost ADD-exchange of Jx, Jy, Jz between neighbouring boxes, direction by direction."""
+    """Ghost ADD-exchange of Jx, Jy, Jz between neighbouring boxes, direction by direction.  The three
+    components that go to one neighbour travel in ONE message (one send and one receive per side and
+    direction: the cost of these KB-scale exchanges is per message, not per byte)."""
 
     def __init__(self, layout, rank, comm, backend):
         self.layout, self.rank, self.comm, self.be = layout, rank, comm, backend
-        self.plan = []   # per direction: list of (peer, send_tag, recv_tag, comp, lo, hi, sendbuf, recvbuf)
-        D = layout.D
+        self.plan = []   # per direction: list of (peer, send_tag, recv_tag, parts, sendbuf, recvbuf)
+        D = layout.D     # parts = [(comp, lo, hi, offset, count)] inside the side's buffer
         for d in range(D):
             if layout.nb[d] == 1:
                 continue          # spans the domain: folded locally (pgpu_current_finalize)
@@ -202,31 +204,35 @@ class HaloExchange:
                 peer = layout.neighbor(rank, d, side)
                 if peer is None:
                     continue
+                parts, off = [], 0
                 for comp, stag in enumerate(STAG_J[D]):
                     lo, hi = layout.overlap(rank, stag, d, side)
                     count = int(np.prod([h - l + 1 for l, h in zip(lo, hi)]))
-                    # my +side message is the peer's -side message: tag by (receiver's side, comp)
-                    send_tag = 16 * d + 4 * (0 if side > 0 else 1) + comp
-                    recv_tag = 16 * d + 4 * (1 if side > 0 else 0) + comp
-                    msgs.append((peer, send_tag, recv_tag, comp, lo, hi, self.be.new_buffer(count),
-                                 self.be.new_buffer(count)))
+                    parts.append((comp, lo, hi, off, count))
+                    off += count
+                # my +side message is the peer's -side message: tag by the receiver's side
+                send_tag = 16 * d + 4 * (0 if side > 0 else 1)
+                recv_tag = 16 * d + 4 * (1 if side > 0 else 0)
+                msgs.append((peer, send_tag, recv_tag, parts, self.be.new_buffer(off), self.be.new_buffer(off)))
             self.plan.append(msgs)
-        self.bytes_per_exchange = sum(2 * 8 * m[6].numel() for msgs in self.plan for m in msgs)
+        self.bytes_per_exchange = sum(2 * 8 * m[4].numel() for msgs in self.plan for m in msgs)
 
     def n_phases(self):
         return len(self.plan)
 
     def begin(self, phase):
         msgs = self.plan[phase]
-        for (_, _, _, comp, lo, hi, sb, _) in msgs:
-            self.be.pack(comp, lo, hi, sb)
+        for (_, _, _, parts, sb, _) in msgs:
+            for (comp, lo, hi, off, count) in parts:
+                self.be.pack(comp, lo, hi, sb[off:off + count])
         self.be.sync()
-        self.comm.post([(m[0], m[1], m[6]) for m in msgs], [(m[0], m[2], m[7]) for m in msgs])
+        self.comm.post([(m[0], m[1], m[4]) for m in msgs], [(m[0], m[2], m[5]) for m in msgs])
 
     def end(self, phase):
         self.comm.wait()
-        for (_, _, _, comp, lo, hi, _, rb) in self.plan[phase]:
-            self.be.unpack_add(comp, lo, hi, rb)
+        for (_, _, _, parts, _, rb) in self.plan[phase]:
+            for (comp, lo, hi, off, count) in parts:
+                self.be.unpack_add(comp, lo, hi, rb[off:off + count])
 
     def add_exchange(self):
         """One process per box: the whole exchange (every rank calls this collectively)."""

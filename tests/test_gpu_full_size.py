@@ -1,0 +1,173 @@
+"""Parity at BASELINE.json's FULL sizes through size-independent properties (the oracle needs minutes
+per million particles, so at these sizes the checks are the invariants the reference's schemes are
+built on -- SURVEY.md 8c -- which the oracle satisfies at small size in test_oracle_invariants.py):
+  C3  2D 512x512 cells, 2 species x 100 ppc (5.24e7 particles): CC1 discrete charge continuity of
+      the fused advance+deposit, gather/deposit adjointness (sum J.E dV = sum w ubar.E_p), cell-sort
+      idempotence and conservation of the particle multiset;
+  C2  2D 256x256 cells, 64 ppc/species, Takizuka-Abe: exact pair counts, total momentum and energy of
+      the whole plasma conserved to round-off, cell-locality (per-cell particle count unchanged);
+  C4  1D 250 000 cells x 200 ppc x 2 species = 1e8 particles: 1D CC1 charge continuity and weighted
+      Coulomb (NANBU) momentum/energy conservation for equal weights."""
+import numpy as np
+import pytest
+
+from picnic_b200 import decks
+
+pytestmark = pytest.mark.gpu
+
+
+def _upload(pgpu, grid, deck, sdef, lo, hi, rng, **kw):
+    p = decks.load_species(deck, sdef, lo, hi, rng)
+    sp = pgpu.Species(grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm,
+                      interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E, rtol=deck.rtol,
+                      iter_max=deck.iter_max, **kw)
+    sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
+    n, w0 = p["w"].size, float(p["w"][0])
+    del p
+    return sp, n, w0
+
+
+def test_c3_full_size_charge_continuity_and_adjointness(pgpu):
+    deck = decks.deck_c3()                                    # 512 x 512, 10 x 10 ppc, dt = 0.1 in bench units
+    deck.dt = 0.1
+    n0 = deck.ncell[0]
+    lo, hi = (0, 0), (n0 - 1, n0 - 1)
+    E, B = decks.analytic_fields(deck, lo, hi, E0=3.0e7, B0=5.0e8)
+    grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), volume_scale=deck.volume_scale)
+    grid.set_fields(E, B)
+    rng = np.random.default_rng(11)
+    g = deck.nghost
+    dV = deck.dx[0] * deck.dx[1] * deck.volume_scale
+    for sdef in deck.species:
+        sp, n, w0 = _upload(pgpu, grid, deck, sdef, lo, hi, rng)
+        assert n == n0 * n0 * 100
+        m0 = sp.global_moments()
+        sp.bin_particles()
+        off = sp.cell_offsets()
+        assert np.all(np.diff(off) == 100)                    # every cell keeps its 100 particles
+        sp.bin_particles()                                    # idempotent: same cells, same multiset
+        assert np.array_equal(sp.cell_offsets(), off)
+        m1 = sp.global_moments()
+        assert np.all(np.abs(m1 - m0) <= 1e-12 * np.abs(m0) + 1e-300)
+        rho_old, _, _ = sp.charge_density((1, 1))
+        st = sp.advance_iteratively(deck.dt, deposit=True)
+        assert st.num_unconverged == 0
+        # ---- adjointness: sum_grid J.E dV = q sum_p w ubar.E_p (the energy-conservation identity) ----
+        sp.interpolate_fields()                               # E_p at xbar with the same CC1 weights
+        Ep, _ = sp.particle_fields()
+        got = sp.download()
+        terms = got["w"] * np.sum(got["v"] * Ep, axis=0)
+        work_p = sdef.charge * float(np.sum(terms))
+        scale = abs(sdef.charge) * float(np.sum(np.abs(terms)))
+        grid.current_zero(); grid.current_add(sp)
+        work_g = 0.0
+        for c in range(3):
+            Jc = sp.current_get(c)                            # before the periodic fold: ghosts hold their share
+            work_g += float(np.sum(Jc * E[c][2])) * dV
+        assert abs(work_g - work_p) <= 1e-12 * scale
+        del got, Ep, terms
+        # ---- continuity: (rho_new - rho_old) + dt div J = 0 on every owned node -----------------------
+        grid.current_finalize()
+        Jx, Jy = grid.current_get(0), grid.current_get(1)
+        sp.advance_positions_2nd_half()
+        rho_new, _, _ = sp.charge_density((1, 1))
+        jx = Jx[g - 1:g + n0, g:g + n0]
+        jy = Jy[g:g + n0, g - 1:g + n0]
+        div = (jx[1:, :] - jx[:-1, :]) / deck.dx[0] + (jy[:, 1:] - jy[:, :-1]) / deck.dx[1]
+        resid = (rho_new - rho_old)[g:g + n0, g:g + n0] + deck.cnorm_dt * div
+        assert np.max(np.abs(resid)) <= 1e-11 * np.max(np.abs(rho_old))
+        sp.destroy()
+    grid.destroy()
+
+
+def test_c2_full_size_takizuka_abe_conservation(pgpu):
+    deck = decks.deck_c2()                                    # 256 x 256, 8 x 8 ppc per species
+    n0 = deck.ncell[0]
+    lo, hi = (0, 0), (n0 - 1, n0 - 1)
+    grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), volume_scale=deck.volume_scale)
+    rng = np.random.default_rng(12)
+    sps = [_upload(pgpu, grid, deck, sdef, lo, hi, rng)[0] for sdef in deck.species]
+    for sp in sps:
+        sp.bin_particles()
+        sp.set_moments()
+    ncell = n0 * n0
+    dt_sec = deck.dt * deck.units.time
+    mass = [s.mass for s in deck.species]
+
+    def totals():
+        m = [sp.global_moments() for sp in sps]               # [w, w u (3), w u^2 (3)] per species
+        P = sum(mk * mm[1:4] for mk, mm in zip(mass, m))
+        K = sum(mk * mm[4:7].sum() for mk, mm in zip(mass, m))
+        return P, K, m
+
+    P0, K0, m0 = totals()
+    pscale = sum(mk * np.sqrt(mm[0] * mm[4:7].sum()) for mk, mm in zip(mass, m0))   # ~ sum m w |u|
+    pairs = 0
+    for step in range(3):
+        for (a, b) in ((0, 0), (1, 1), (0, 1)):
+            pairs += pgpu.collide_ta(sps[a], sps[b], 3.0, dt_sec, 1983, step)
+    assert pairs == 3 * (32 + 32 + 64) * ncell                # N even: N/2 self pairs; inter: max(N1, N2)
+    P1, K1, m1 = totals()
+    assert np.max(np.abs(P1 - P0)) <= 1e-12 * pscale
+    assert abs(K1 - K0) <= 1e-12 * K0
+    # energy moved between the species (Te = 150 eV -> Ti = 50 eV) and collisions are cell local
+    Ke0, Ke1 = mass[0] * m0[0][4:7].sum(), mass[0] * m1[0][4:7].sum()
+    assert Ke1 < Ke0
+    for sp in sps:
+        assert np.all(np.diff(sp.cell_offsets()) == 64)
+        sp.destroy()
+    grid.destroy()
+
+
+def test_c4_full_size_1d_continuity_and_coulomb(pgpu):
+    deck = decks.deck_c4()                                    # 1D, 250 000 cells x 200 ppc x 2 species
+    deck.dt = 0.1
+    n0 = deck.ncell[0]
+    lo, hi = (0,), (n0 - 1,)
+    E, B = decks.analytic_fields(deck, lo, hi, E0=3.0e7, B0=5.0e8)
+    grid = pgpu.Grid(1, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1,), volume_scale=deck.volume_scale)
+    grid.set_fields(E, B)
+    rng = np.random.default_rng(13)
+    g = deck.nghost
+    sps = []
+    for sdef in deck.species:
+        sp, n, _ = _upload(pgpu, grid, deck, sdef, lo, hi, rng)
+        assert n == n0 * 200
+        rho_old, _, _ = sp.charge_density((1,))
+        st = sp.advance_iteratively(deck.dt, deposit=True)
+        assert st.num_unconverged == 0
+        grid.current_zero(); grid.current_add(sp); grid.current_finalize()
+        Jx = grid.current_get(0)
+        sp.advance_positions_2nd_half()
+        rho_new, _, _ = sp.charge_density((1,))
+        jx = Jx[g - 1:g + n0]                                 # cells -1 .. n0-1 around nodes 0 .. n0-1
+        resid = (rho_new - rho_old)[g:g + n0] + deck.cnorm_dt * (jx[1:] - jx[:-1]) / deck.dx[0]
+        # round-off floor: a position near x = n0 dx carries ulp(x)/dx = eps n0 of a cell in its shape weights
+        assert np.max(np.abs(resid)) <= 4.0 * np.finfo(float).eps * n0 * np.max(np.abs(rho_old))
+        sp.apply_bcs((1,), (1,))
+        sps.append(sp)
+    for sp in sps:
+        sp.bin_particles()
+        sp.set_moments()
+    grid.debye_length(sps)
+    mass = [s.mass for s in deck.species]
+    mom = lambda: ([sp.global_moments() for sp in sps])
+    m0 = mom()
+    pairs = 0
+    for (a, b) in ((0, 0), (1, 1), (0, 1)):
+        pairs += pgpu.collide_coulomb(sps[a], sps[b], 10.0, deck.dt * deck.units.time, 1983, 0, angular=1)
+    # O(N) pairing on ~200 particles per cell (a few crossed a cell face in the advance above):
+    # N even -> N/2 pairs, N odd -> (N-3)/2 + 3; inter-species max(N1, N2)   (Coulomb.cpp:468-592, 1088-1180)
+    cnt = [np.diff(sp.cell_offsets()) for sp in sps]
+    assert min(c.min() for c in cnt) >= 11
+    intra = lambda c: int(np.sum(np.where(c % 2 == 0, c // 2, (c - 3) // 2 + 3)))
+    assert pairs == intra(cnt[0]) + intra(cnt[1]) + int(np.sum(np.maximum(cnt[0], cnt[1])))
+    m1 = mom()
+    P0 = sum(mk * mm[1:4] for mk, mm in zip(mass, m0)); P1 = sum(mk * mm[1:4] for mk, mm in zip(mass, m1))
+    K0 = sum(mk * mm[4:7].sum() for mk, mm in zip(mass, m0)); K1 = sum(mk * mm[4:7].sum() for mk, mm in zip(mass, m1))
+    pscale = sum(mk * np.sqrt(mm[0] * mm[4:7].sum()) for mk, mm in zip(mass, m0))
+    assert np.max(np.abs(P1 - P0)) <= 1e-12 * pscale          # equal weights: every pair conserves exactly
+    assert abs(K1 - K0) <= 1e-12 * K0
+    for sp in sps:
+        sp.destroy()
+    grid.destroy()
