@@ -452,6 +452,15 @@ def run_ours(args):
             k_name = "advance_deposit_fused"
             k_ms, k_n = prof[k_name]
         per_launch_units = eng.n_particles / len(eng.species)
+        # DRAM bytes of one launch of the headline kernel from the committed `ncu --set full` capture
+        # (dram__bytes_read.sum + dram__bytes_write.sum); only quoted for the launch size it was taken at
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["advance_cc1_fused"]
+            if int(tr["particles_per_launch"]) == int(per_launch_units):
+                traffic = float(tr["dram_bytes_per_launch"])
+        except Exception:
+            pass
         achieved = (BYTES_PER_ADVANCE_2D * per_launch_units) / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
         out = {
             "metric": "particle-advances/s (implicit push + deposit)", "value": value, "unit": "particle-advances/s",
@@ -471,7 +480,7 @@ def run_ours(args):
                                     % (eng.n_particles * 96 / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "kernel": k_name + " (fused gather + Boris + particle-Picard + deposit)",
                          "bytes_per_unit": BYTES_PER_ADVANCE_2D, "units_per_launch": per_launch_units,
                          "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms,

@@ -65,6 +65,7 @@ struct FastArgs {
   int tlo[2], tn0;
   double tol[2];            // rtol * dx
   const int4 *tile_box;     // per tile: dual-cell window (i, j, columns, rows) staged in shared memory
+  int prefetch;             // persistent grid: pull the block's next tile into L2 while this one is computed
 };
 
 // 21 fp64 REDs of one accumulator set into the J arrays at dual cell `key`
@@ -949,7 +950,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
         if (box.z && r <= box.w)
           bulk_g2s(snode + r * ((WMAX + 1) * TN), A.tnode + (c0 + (size_t)r * A.tn0) * TN, nbytes, bar);
       }
-      if (tile + (int)gridDim.x < ntiles) fetch_box(tile + gridDim.x);
+      if (tile + (int)gridDim.x < ntiles) {
+        fetch_box(tile + gridDim.x);
+        if (A.prefetch) {
+          const long nb = tbase + (long)gridDim.x * TILE;
+          if (wp == 0) { l2_prefetch(A.xo[0] + nb, BYTES); l2_prefetch(A.xo[1] + nb, BYTES); }
+          else if (wp == 1) { l2_prefetch(A.xb[0] + nb, BYTES); l2_prefetch(A.xb[1] + nb, BYTES); }
+          else if (wp == 2) { l2_prefetch(A.uo[0] + nb, BYTES); l2_prefetch(A.uo[1] + nb, BYTES); }
+          else { l2_prefetch(A.uo[2] + nb, BYTES); l2_prefetch(A.w + nb, BYTES); }
+        }
+      }
     }
     if (tid == 0) CK(1);
     __syncthreads();       // sbox written (and the previous tile's shared-memory reads are over)
@@ -1178,6 +1188,7 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   A.list_count = s->defer_count;
   A.cnt = c.d_counters;
   A.tdual = A.tnode = nullptr;
+  A.prefetch = c.cc1_prefetch;
   const bool tile_ok = s->cap >= (size_t)(((s->n + TILE - 1) / TILE) * TILE);
   if (!tile_ok) return 0;
   const int ntiles = (int)((s->n + TILE - 1) / TILE);

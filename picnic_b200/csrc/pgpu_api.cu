@@ -366,6 +366,7 @@ int pgpu_init(int device) {
   c.sticky_error = 0;
   if (const char *e = getenv("PGPU_CC1_TMA")) c.cc1_tma = atoi(e);
   if (const char *e = getenv("PGPU_CC1_MINB")) c.cc1_minblocks = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_PREFETCH")) c.cc1_prefetch = atoi(e);
   if (const char *e = getenv("PGPU_CC1_RSTEPS")) c.cc1_rsteps = atoi(e);
   if (const char *e = getenv("PGPU_CC1_WAVES")) c.cc1_waves = atoi(e) > 0 ? atoi(e) : 1;
   return 0;
