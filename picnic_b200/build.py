@@ -25,9 +25,9 @@ def _needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(src):
-    obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+def _compile(src, tag="", defines=()):
+    obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
+    cmd = ["nvcc"] + NVCC_FLAGS + list(defines) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -48,5 +48,22 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_variant(tag, defines):
+    """A/B experiments: the same sources with extra -D flags into libpicnic_gpu_<tag>.so, picked up by
+    capi.load() when PGPU_LIB=<tag> (kernel tuning only; the product library is libpicnic_gpu.so)."""
+    out = os.path.join(HERE, "libpicnic_gpu_%s.so" % tag)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(lambda f: _compile(f, "_" + tag, defines), SOURCES))
+    r = subprocess.run(["nvcc", "-shared", "-o", out] + objs + ["-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    print("built", out)
+    return out
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        build_variant(sys.argv[i + 1], sys.argv[i + 2:])
+    else:
+        build(force="--force" in sys.argv, verbose=True)

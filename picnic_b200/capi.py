@@ -59,6 +59,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("PGPU_LIB"):      # kernel A/B experiments (picnic_b200/build.py --variant)
+        LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libpicnic_gpu_%s.so" % os.environ["PGPU_LIB"])
     if not os.path.exists(LIB_PATH):
         raise ImportError("picnic_b200: %s is missing -- run `python -m picnic_b200.build` "
                           "(there is no CPU fallback)" % LIB_PATH)

@@ -45,6 +45,7 @@ constexpr unsigned NOKEY = 0xffffffffu;
 struct FastArgs {
   const double *xo[2];
   double *xb[2];
+  double *xbo[2];           // where xbar is written: xb, or the stale xold arrays when xold is aliased to x (tab kernel)
   const double *uo[3];
   double *ub[3];
   const double *w;
@@ -68,30 +69,30 @@ struct FastArgs {
   int prefetch;             // persistent grid: pull the block's next tile into L2 while this one is computed
 };
 
-// 21 fp64 REDs of one accumulator set into the J arrays at dual cell `key`
+// 21 fp64 REDs of one accumulator set into the J arrays at dual cell `key` (one pointer per grid row:
+// the rest are immediate offsets)
 __device__ __forceinline__ void flush_direct(const FastArgs &A, unsigned key, const double (&acc)[NSLOT]) {
   const int ci = (int)(key & 0xffffu) - 32768, cj = (int)(key >> 16) - 32768;
   {
-    double *p = A.J[0] + (ci + cj * A.jn0[0]);
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      atomicAdd(p + b * A.jn0[0], acc[2 * b]);
-      atomicAdd(p + b * A.jn0[0] + 1, acc[2 * b + 1]);
-    }
+    double *p0 = A.J[0] + (ci + cj * A.jn0[0]);
+    double *p1 = p0 + A.jn0[0];
+    double *p2 = p1 + A.jn0[0];
+    atomicAdd(p0, acc[0]), atomicAdd(p0 + 1, acc[1]);
+    atomicAdd(p1, acc[2]), atomicAdd(p1 + 1, acc[3]);
+    atomicAdd(p2, acc[4]), atomicAdd(p2 + 1, acc[5]);
   }
   {
-    double *p = A.J[1] + (ci + cj * A.jn0[1]);
+    double *p0 = A.J[1] + (ci + cj * A.jn0[1]);
+    double *p1 = p0 + A.jn0[1];
 #pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int a = 0; a < 3; ++a) atomicAdd(p + a + b * A.jn0[1], acc[6 + a + 3 * b]);
+    for (int a = 0; a < 3; ++a) atomicAdd(p0 + a, acc[6 + a]), atomicAdd(p1 + a, acc[9 + a]);
   }
   {
-    double *p = A.J[2] + (ci + cj * A.jn0[2]);
+    double *p0 = A.J[2] + (ci + cj * A.jn0[2]);
+    double *p1 = p0 + A.jn0[2];
+    double *p2 = p1 + A.jn0[2];
 #pragma unroll
-    for (int b = 0; b < 3; ++b)
-#pragma unroll
-      for (int a = 0; a < 3; ++a) atomicAdd(p + a + b * A.jn0[2], acc[12 + a + 3 * b]);
+    for (int a = 0; a < 3; ++a) atomicAdd(p0 + a, acc[12 + a]), atomicAdd(p1 + a, acc[15 + a]), atomicAdd(p2 + a, acc[18 + a]);
   }
 }
 
@@ -646,6 +647,11 @@ __device__ __forceinline__ double rcp_ge1(double den) {
 // global memory for particles outside the window)
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 
+
+#ifndef PGPU_TAB_LDGSTS
+#define PGPU_TAB_LDGSTS 0
+#endif
+
 struct TabWindow {
   const double *dual, *node;   // record (i0, j0) of the window origin
   int i, j, ncol, nrow;        // dual-cell window
@@ -905,7 +911,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
   unsigned apply = 0, unconv = 0;
   int it = 0;
 #ifdef PGPU_CLOCKS
-  long long ck[6] = {0, 0, 0, 0, 0, 0}, c0, c1;
+  long long ck[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c0, c1;
 #define CK(i) do { c1 = clock64(); ck[i] += c1 - c0; c0 = c1; } while (0)
   c0 = clock64();
 #else
@@ -920,36 +926,48 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
       const int wp = tid >> 5;
       if (wp) bulk_wait_read0();   // this thread's stores of the previous tile have read their buffers
       if (tid == 0) CK(0);
+      constexpr unsigned BYTES = TILE * (unsigned)sizeof(double);
+#if !PGPU_TAB_LDGSTS
+      // the particle arrays first: their addresses do not depend on the tile's window
+      if (wp == 0) {
+        bulk_g2s(st + 0 * TILE, A.xo[0] + tbase, BYTES, bar);
+        bulk_g2s(st + 1 * TILE, A.xo[1] + tbase, BYTES, bar);
+      } else if (wp == 1) {
+        bulk_g2s(st + 2 * TILE, A.xb[0] + tbase, BYTES, bar);
+        bulk_g2s(st + 3 * TILE, A.xb[1] + tbase, BYTES, bar);
+      } else if (wp == 2) {
+        bulk_g2s(st + 4 * TILE, A.uo[0] + tbase, BYTES, bar);
+        bulk_g2s(st + 5 * TILE, A.uo[1] + tbase, BYTES, bar);
+      } else {
+        bulk_g2s(st + 6 * TILE, A.uo[2] + tbase, BYTES, bar);
+        bulk_g2s(st + 7 * TILE, A.w + tbase, BYTES, bar);
+      }
+#endif
+      if (tid == 0) CK(6);
       const int4 box = make_int4(nbx, nby, nbz, nbw);
       const unsigned dbytes = (unsigned)box.z * TD * (unsigned)sizeof(double);
       const unsigned nbytes = (unsigned)(box.z + 1) * TN * (unsigned)sizeof(double);
-      constexpr unsigned BYTES = TILE * (unsigned)sizeof(double);
-      const size_t c0 = (size_t)(box.x - A.tlo[0]) + (size_t)(box.y - A.tlo[1]) * A.tn0;
+      const size_t cw0 = (size_t)(box.x - A.tlo[0]) + (size_t)(box.y - A.tlo[1]) * A.tn0;
       if (wp == 0) {
         sbox = box;
-        const unsigned tabbytes = box.z ? box.w * dbytes + (box.w + 1) * nbytes : 0u;
-        mbar_expect_tx(bar, NIN * TILE * (unsigned)sizeof(double) + tabbytes);
-        bulk_g2s(st + 0 * TILE, A.xo[0] + tbase, BYTES, bar);
-        bulk_g2s(st + 1 * TILE, A.xo[1] + tbase, BYTES, bar);
         if (box.z) {
           for (int r = 0; r < box.w; ++r)
-            bulk_g2s(sdual + r * DROW, A.tdual + (c0 + (size_t)r * A.tn0) * TD, dbytes, bar);
+            bulk_g2s(sdual + r * DROW, A.tdual + (cw0 + (size_t)r * A.tn0) * TD, dbytes, bar);
         }
+        // the one arrival of the phase, posted after this thread's copies (a copy that completes first only
+        // drives the transaction count negative for a while; the phase cannot end before this arrival)
+        const unsigned tabbytes = box.z ? box.w * dbytes + (box.w + 1) * nbytes : 0u;
+#if PGPU_TAB_LDGSTS
+        mbar_expect_tx(bar, tabbytes);
+#else
+        mbar_expect_tx(bar, NIN * TILE * (unsigned)sizeof(double) + tabbytes);
+#endif
       } else {
-        if (wp == 1) {
-          bulk_g2s(st + 2 * TILE, A.xb[0] + tbase, BYTES, bar);
-          bulk_g2s(st + 3 * TILE, A.xb[1] + tbase, BYTES, bar);
-        } else if (wp == 2) {
-          bulk_g2s(st + 4 * TILE, A.uo[0] + tbase, BYTES, bar);
-          bulk_g2s(st + 5 * TILE, A.uo[1] + tbase, BYTES, bar);
-        } else {
-          bulk_g2s(st + 6 * TILE, A.uo[2] + tbase, BYTES, bar);
-          bulk_g2s(st + 7 * TILE, A.w + tbase, BYTES, bar);
-        }
         const int r = wp - 1;   // node-record row of the window
         if (box.z && r <= box.w)
-          bulk_g2s(snode + r * ((WMAX + 1) * TN), A.tnode + (c0 + (size_t)r * A.tn0) * TN, nbytes, bar);
+          bulk_g2s(snode + r * ((WMAX + 1) * TN), A.tnode + (cw0 + (size_t)r * A.tn0) * TN, nbytes, bar);
       }
+      if (tid == 0) CK(7);
       if (tile + (int)gridDim.x < ntiles) {
         fetch_box(tile + gridDim.x);
         if (A.prefetch) {
@@ -963,6 +981,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
     }
     if (tid == 0) CK(1);
     __syncthreads();       // sbox written (and the previous tile's shared-memory reads are over)
+#if PGPU_TAB_LDGSTS
+    {
+      // every thread copies 16 particle-array chunks of 16 bytes (LDGSTS) instead of eight 4 KB bulk copies
+      const double *src[NIN] = {A.xo[0], A.xo[1], A.xb[0], A.xb[1], A.uo[0], A.uo[1], A.uo[2], A.w};
+#pragma unroll
+      for (int a = 0; a < NIN; ++a)
+#pragma unroll
+        for (int h = 0; h < TILE / (2 * BLOCK); ++h) {
+          const int c2 = 2 * (tid + h * BLOCK);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st + a * TILE + c2)),
+                       "l"(src[a] + tbase + c2)
+                       : "memory");
+        }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+#endif
     mbar_wait(bar, (unsigned)(it & 1));
     if (tid == 0) CK(2);
     const int nvalid = (A.n - tbase) < TILE ? (int)(A.n - tbase) : TILE;
@@ -1072,8 +1108,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
         constexpr unsigned BYTES = TILE * (unsigned)sizeof(double);
         const int wp = tid >> 5;
         if (wp == 1) {
-          bulk_s2g(A.xb[0] + tbase, st + 2 * TILE, BYTES);
-          bulk_s2g(A.xb[1] + tbase, st + 3 * TILE, BYTES);
+          bulk_s2g(A.xbo[0] + tbase, st + 2 * TILE, BYTES);
+          bulk_s2g(A.xbo[1] + tbase, st + 3 * TILE, BYTES);
         } else if (wp == 2) {
           bulk_s2g(A.ub[0] + tbase, st + 4 * TILE, BYTES);
           bulk_s2g(A.ub[1] + tbase, st + 5 * TILE, BYTES);
@@ -1083,12 +1119,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
         bulk_commit();
       }
     } else {
+      // ragged last tile; like the bulk stores above this also writes the deferred particles' slots
+      // (stored xbar, u_old) -- needed when the outputs are not the arrays the inputs came from
 #pragma unroll 1
       for (int q = 0; q < TP; ++q) {
         const int k = tid * TP + q;
-        if (k < nvalid && !(defer_mask & (1u << q))) {
-          A.xb[0][tbase + k] = st[2 * TILE + k];
-          A.xb[1][tbase + k] = st[3 * TILE + k];
+        if (k < nvalid) {
+          A.xbo[0][tbase + k] = st[2 * TILE + k];
+          A.xbo[1][tbase + k] = st[3 * TILE + k];
           A.ub[0][tbase + k] = st[4 * TILE + k];
           A.ub[1][tbase + k] = st[5 * TILE + k];
           A.ub[2][tbase + k] = st[6 * TILE + k];
@@ -1106,8 +1144,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
   if (lane == 0 && tid) bulk_wait0();
 #ifdef PGPU_CLOCKS
   if (tid == 0 && (blockIdx.x % 97) == 5 && blockIdx.x < 600)
-    printf("#blk %d tiles %d cycles/tile: wait_read %lld issue %lld mbar %lld phase1 %lld phase2 %lld endsync %lld\n",
-           blockIdx.x, it, ck[0] / it, ck[1] / it, ck[2] / it, ck[3] / it, ck[4] / it, ck[5] / it);
+    printf("#blk %d tiles %d cycles/tile: wait_read %lld issue %lld (particle copies %lld, window copies %lld) mbar %lld phase1 %lld "
+           "phase2 %lld endsync %lld\n",
+           blockIdx.x, it, ck[0] / it, (ck[6] + ck[7] + ck[1]) / it, ck[6] / it, ck[7] / it, ck[2] / it, ck[3] / it, ck[4] / it,
+           ck[5] / it);
 #endif
 
   apply = __reduce_add_sync(0xffffffffu, apply);
@@ -1141,17 +1181,22 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   PGPU_CUDA(cudaMemsetAsync(s->defer_count, 0, sizeof(unsigned), c.stream));
 
   FastArgs A;
+  // updateOldParticle* recorded as an alias (xold == x, vold == v): the table kernel reads the old state
+  // from x / v and writes xbar / ubar into the stale old arrays; the pointers are swapped after the launch
+  if (c.cc1_tma != 3 && materialize_old(s)) return PGPU_ERR_CUDA;
+  const bool xa = s->xold_alias, va = s->vold_alias;
   for (int d = 0; d < 2; ++d) {
-    A.xo[d] = s->xold[d];
+    A.xo[d] = xa ? s->x[d] : s->xold[d];
     A.xb[d] = s->x[d];
+    A.xbo[d] = xa ? s->xold[d] : s->x[d];
     A.le[d] = g->geo.le[d];
     A.dx[d] = g->geo.dx[d];
     A.rdx[d] = g->geo.rdx[d];
     A.hdx[d] = 0.5 * g->geo.dx[d];
   }
   for (int k = 0; k < 3; ++k) {
-    A.uo[k] = s->vold[k];
-    A.ub[k] = s->v[k];
+    A.uo[k] = va ? s->v[k] : s->vold[k];
+    A.ub[k] = va ? s->vold[k] : s->v[k];
   }
   A.w = s->w;
   A.n = s->n;
@@ -1254,7 +1299,7 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM));        \
     k_advance_cc1_2d_tab<DEPV, RS, MB><<<gridm, BLOCK, TAB_SMEM, c.stream>>>(A, ntiles);                  \
   } while (0)
-    const int mb = c.cc1_minblocks == 5 ? 5 : 4;
+    const int mb = c.cc1_minblocks == 5 ? 5 : (c.cc1_minblocks == 3 ? 3 : 4);
     const int gridm = std::min(ntiles, c.sm_count * mb * c.cc1_waves);
     if (!deposit) {
       if (mb == 4) PGPU_TAB_LAUNCH(false, 0, 4);
@@ -1264,8 +1309,14 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
       else PGPU_TAB_LAUNCH(true, 2, 5);
     } else {
       if (mb == 4) PGPU_TAB_LAUNCH(true, 3, 4);
+      else if (mb == 3) PGPU_TAB_LAUNCH(true, 3, 3);
       else PGPU_TAB_LAUNCH(true, 3, 5);
     }
+    if (xa)
+      for (int d = 0; d < 2; ++d) std::swap(s->x[d], s->xold[d]);
+    if (va)
+      for (int k = 0; k < 3; ++k) std::swap(s->v[k], s->vold[k]);
+    s->xold_alias = s->vold_alias = false;
     return 1;
   }
   KTimer t(deposit ? "advance_cc1_fused" : "advance_cc1");

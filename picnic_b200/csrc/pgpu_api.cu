@@ -265,6 +265,7 @@ static int ensure_capacity(pgpu_species_s *s, long n) {
 // Capacity for n particles, keeping the first s->n of every array (arrivals of a migration).
 int grow_capacity(pgpu_species_s *s, long n) {
   if ((size_t)n <= s->cap) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
   const size_t cap = (size_t)(n + n / 16 + 1024);
   const int D = s->grid->desc.D;
   cudaStream_t st = ctx().stream;
@@ -658,6 +659,7 @@ int pgpu_species_upload(pgpu_species_t s, long n, const double *x, const double 
   s->n = n;
   s->binned = false;
   s->pos_old_pending = s->vel_old_pending = false;
+  s->xold_alias = s->vold_alias = false;
   return 0;
 }
 
@@ -777,8 +779,7 @@ int pgpu_update_old_particle_positions(pgpu_species_t s) {
   NEED_INIT();
   if (!s->desc.motion) return 0;
   s->pos_old_pending = false;   // every xold entry is overwritten: a pending gather is moot
-  for (int d = 0; d < s->grid->desc.D; ++d)
-    PGPU_CUDA(cudaMemcpyAsync(s->xold[d], s->x[d], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+  s->xold_alias = true;         // the copy itself is deferred (materialize_old) or never happens (CC1 tile kernel)
   return 0;
 }
 
@@ -786,8 +787,7 @@ int pgpu_update_old_particle_velocities(pgpu_species_t s) {
   NEED_INIT();
   if (!s->desc.forces) return 0;
   s->vel_old_pending = false;
-  for (int c = 0; c < 3; ++c)
-    PGPU_CUDA(cudaMemcpyAsync(s->vold[c], s->v[c], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+  s->vold_alias = true;
   return 0;
 }
 

@@ -985,6 +985,8 @@ static int need_binned(pgpu_species_t sA, pgpu_species_t sB) {
     set_error("collisions need binned species: call pgpu_bin_particles + pgpu_set_moments_from_bins first");
     return PGPU_ERR_STATE;
   }
+  // collisions write v: a deferred vold = v copy has to happen first
+  if (materialize_old(sA) || materialize_old(sB)) return PGPU_ERR_CUDA;
   return 0;
 }
 
@@ -1091,6 +1093,7 @@ int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt
     set_error("collisions need binned species: call pgpu_bin_particles + pgpu_set_moments_from_bins first");
     return PGPU_ERR_STATE;
   }
+  if (materialize_old(sA) || materialize_old(sB)) return PGPU_ERR_CUDA;
   Context &c = ctx();
   const pgpu_grid_s *g = sA->grid;
   // m_mu, m_b90_fact (TakizukaAbe.cpp:39-49); long double as in TakizukaAbe.H:137-139

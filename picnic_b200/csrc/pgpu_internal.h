@@ -170,6 +170,11 @@ struct pgpu_species_s {
   int *old_perm = nullptr;
   size_t old_perm_cap = 0;
   bool pos_old_pending = false, vel_old_pending = false;
+  // updateOldParticlePositions/Velocities without the copy: "xold == x" ("vold == v") is only recorded.
+  // The CC1 tile kernel consumes the flag (reads the old state from x / v, writes xbar / ubar into the
+  // stale old arrays, then the array pointers are swapped); everybody else gets the copy from
+  // materialize_old before touching either array
+  bool xold_alias = false, vold_alias = false;
   int *key_sorted = nullptr;        // [n] sorted (4*cell+quadrant) keys of the last bin
   double *spare[4] = {nullptr, nullptr, nullptr, nullptr};  // gather targets of the cell sort
   size_t sort_cap = 0;
@@ -214,7 +219,7 @@ int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f);
 int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi);
 
 // launchers implemented in the kernel translation units
-int materialize_old(pgpu_species_s *s);
+int materialize_old(pgpu_species_s *s, bool keep_alias = false);
 int grow_capacity(pgpu_species_s *s, long n);   // keeps the particles (pgpu_api.cu)
 int launch_gather(pgpu_species_s *s);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);

@@ -326,13 +326,14 @@ static int launch_advance_d(pgpu_species_s *s, const AdvanceParams &prm, bool fu
 // first; this generic visitor kernel then handles only the particles it deferred.
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit) {
   if (s->n == 0) return 0;
-  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  if (materialize_old(s, true)) return PGPU_ERR_CUDA;   // pending gathers; an aliased old group is left to the CC1 kernel
   bool deferred = false;
   if (ctx().use_fast_cc1) {
     const int fr = launch_advance_cc1_fast(s, prm, fuse_deposit);
     if (fr < 0) return fr;
     deferred = fr == 1;
   }
+  if (materialize_old(s)) return PGPU_ERR_CUDA;         // no-op if the CC1 kernel consumed the alias
   return s->grid->desc.D == 1 ? launch_advance_d<1>(s, prm, fuse_deposit, deferred)
                               : launch_advance_d<2>(s, prm, fuse_deposit, deferred);
 }

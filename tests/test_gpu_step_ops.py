@@ -91,3 +91,60 @@ def test_finish_implicit_step_equals_separate_calls(pgpu, D):
     b = sp.download(); sp.destroy(); grid.destroy()
     for name in ("x", "xold", "v", "vold"):
         assert np.array_equal(a[name], b[name]), name
+
+
+@pytest.mark.parametrize("user", ["download", "advance", "advance_twice", "advance_pos_only", "sort_advance",
+                                  "second_half", "collide", "generic_kernel", "ragged"])
+def test_update_old_without_copy(pgpu, user):
+    """updateOldParticlePositions/Velocities (PicChargedSpecies.cpp:1821-1867) only record "old == new";
+    the CC1 tile kernel consumes the alias (out-of-place write + pointer swap), every other user gets
+    the copy first.  Whatever runs next must behave as if the copy had been made."""
+    n = 5000 if user != "ragged" else 512 * 3 + 77
+    prob = _prob(seed=41, n=n)
+    _inside(prob)
+    interp = INTERPS["CC1"] if user != "generic_kernel" else INTERPS["CC0"]
+    grid, sp = make_gpu(pgpu, prob, interp, fnorm=-0.7, cvac_norm=0.9986)
+    if user == "sort_advance":
+        sp.bin_particles()
+    if user != "advance_pos_only":
+        sp.update_old_velocities()
+    sp.update_old_positions()
+    xold = prob.x.copy()
+    vold = prob.v.copy() if user != "advance_pos_only" else prob.vold.copy()
+    if user == "sort_advance":
+        sp.bin_particles()                       # alias survives a sort
+    if user == "download":
+        got = sp.download(); o = got["id"].astype(np.int64)
+        assert np.array_equal(got["xold"], xold[:, o]) and np.array_equal(got["vold"], vold[:, o])
+        assert np.array_equal(got["x"], prob.x[:, o]) and np.array_equal(got["v"], prob.v[:, o])
+    elif user == "second_half":
+        sp.advance_positions_2nd_half(); sp.advance_velocities_2nd_half()
+        got = sp.download()
+        assert np.array_equal(got["x"], prob.x) and np.array_equal(got["v"], prob.v)   # 2x - x
+        assert np.array_equal(got["xold"], xold) and np.array_equal(got["vold"], vold)
+    elif user == "collide":
+        sp.bin_particles(); sp.set_moments()
+        pgpu.collide_ta(sp, sp, 3.0, 1e-18, 7, 0)
+        got = sp.download(); o = got["id"].astype(np.int64)
+        assert np.array_equal(got["vold"], vold[:, o])           # the copy happened before v changed
+        assert not np.array_equal(got["v"], prob.v[:, o])
+    else:
+        ie = orc.CC1 if user != "generic_kernel" else orc.CC0
+        reps = 2 if user == "advance_twice" else 1
+        x, v = prob.x.copy(), prob.v.copy()
+        for _ in range(reps):
+            sp.advance_iteratively(0.5, deposit=True)
+            rc, _, _, _ = orc.advance_particles_iteratively(prob.geom, ie, x, xold, v, vold, prob.E, prob.B,
+                                                            -0.7, 0.5 * 0.9986, 1e-12, 21)
+            assert rc == 0
+        J = [sp.current_get(c) for c in range(3)]
+        J0 = prob.new_J()
+        orc.deposit_current(prob.geom, ie, x, xold, v, prob.w, 0.5 * 0.9986, J0)
+        got = sp.download(); o = got["id"].astype(np.int64)
+        assert np.array_equal(got["xold"], xold[:, o]) and np.array_equal(got["vold"], vold[:, o])
+        assert np.max(np.abs(got["x"] - x[:, o]) / np.array(prob.dx)[:, None]) <= 4e-12
+        assert np.max(np.abs(got["v"] - v[:, o])) / np.max(np.abs(v)) <= 1e-11
+        for c in range(3):
+            ref = J0[c].a * (-1.0)               # charge / volume_scale
+            assert np.max(np.abs(J[c] - ref)) <= 1e-11 * np.max(np.abs(ref))
+    sp.destroy(); grid.destroy()
