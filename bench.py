@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--sort-every", type=int, default=4,
                     help="cell-sort period in steps (the reference never sorts a collisionless deck; the sort only "
                          "keeps the fused kernel on its fast path: measured 11.6 / 10.5 / 9.9 / 9.5 ms per step at 1/2/4/8)")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="ghost-J add-exchange between boxes: the library's peer-memory kernels (default) or "
+                         "pack + NCCL send/recv + unpack-add")
     ap.add_argument("--dt", type=float, default=0.1)
     ap.add_argument("--iter-max", type=int, default=21)
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles per species in the CPU sample (0 = auto)")
@@ -222,15 +225,42 @@ class Engine:
             lay = halo.BoxLayout(2, deck.ncell, (args.ncell, args.ncell), deck.nghost, (1, 1))
             assert lay.world == world and lay.box(rank) == (tuple(self.lo), tuple(self.hi))
             comm = halo.DistComm(rank, world, stream=stream)
-            self.halo = halo.HaloExchange(lay, rank, comm, halo.CapiGridBackend(self.grid, dev, on_torch_stream=True))
+            if args.halo == "peer":
+                # ghost-J exchange by the library's own kernels over peer memory (NVLink): CUDA IPC inboxes
+                self.halo = halo.PeerHaloExchange(lay, rank, self.grid)
+                self.halo.connect_ipc(comm)
+            else:
+                self.halo = halo.HaloExchange(lay, rank, comm,
+                                              halo.CapiGridBackend(self.grid, dev, on_torch_stream=True))
             self.migration = [halo.Migration(lay, rank, comm, halo.CapiSpeciesBackend(sp, dev, on_torch_stream=True))
                               for sp in self.species]
         self.migrated = 0
+        self.sections, self.stream = None, stream
 
     def _upload_fields(self, j):
         lib, capi = self.capi.load(), self.capi
         for c, (lo, hi, h, _) in enumerate(self.host_fields[j]):
             capi.check(lib.pgpu_fields_set(self.grid.h, c, h.ctypes.data, capi._i2(lo), capi._i2(hi)))
+
+    # device-side section timers: pairs of events on the engine stream, resolved after the region
+    def _mark(self, name):
+        if self.sections is None:
+            return
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.stream)
+        self.sections.append((name, ev))
+
+    def sections_begin(self):
+        self.sections = []
+        self._mark("start")
+
+    def sections_end(self):
+        """{section: total ms} of everything recorded since sections_begin (call after a synchronize)."""
+        out, marks = {}, self.sections
+        self.sections = None
+        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
 
     def pre_rhs_op(self, j, host_io):
         """PicSpeciesInterface::preRHSOp (PicSpeciesInterface.cpp:899-994) for outer iteration j."""
@@ -240,15 +270,19 @@ class Engine:
         else:
             self.grid.fields_select(j)
         self.grid.current_zero()
+        self._mark("fields_in")
         for sp in self.species:
             capi.check(lib.pgpu_advance_particles_iteratively(sp.h, self.deck.dt, 1, None))
             self.grid.current_add(sp)
+        self._mark("advance_deposit")
         if self.halo is not None:
             self.halo.add_exchange()
+            self._mark("ghost_J_exchange")
         self.grid.current_finalize()
         if host_io:
             for c, (lo, hi, h, _) in enumerate(self.host_J):
                 capi.check(lib.pgpu_current_get(self.grid.h, c, h.ctypes.data, capi._i2(lo), capi._i2(hi)))
+        self._mark("J_out")
 
     def step(self, host_io=False):
         for sp in self.species:
@@ -260,13 +294,16 @@ class Engine:
             self.pre_rhs_op(j, host_io)
         for sp in self.species:
             sp.finish_implicit_step((1, 1), (1, 1))   # 2nd-half v, 2nd-half x, periodic applyBCs
+        self._mark("finish_step")
         if self.migration:                             # remapOutcast: leavers to the owning box
             from picnic_b200 import halo
             self.migrated += halo.migrate_all(self.migration)
+            self._mark("migration")
         self.step_no += 1
         if self.args.sort_every > 0 and self.step_no % self.args.sort_every == 0:
             for sp in self.species:
                 sp.bin_particles()
+            self._mark("cell_sort")
 
     def sync(self):
         self.capi.check(self.capi.load().pgpu_synchronize())
@@ -387,12 +424,15 @@ def run_ours(args):
         launches0 = capi.load().pgpu_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        if profile:
+            eng.sections_begin()
         for _ in range(nsteps):
             eng.step(host_io)
         e1.record(stream)
         barrier()
         if profile:
             capi.profile_enable(False)
+            region.sections = {k: round(v / nsteps, 4) for k, v in eng.sections_end().items()}
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -473,7 +513,9 @@ def run_ours(args):
                        "particles_per_gpu": eng.n_particles, "boxes": "%dx%d" % eng.layout, "dt": args.dt,
                        "n_outer": args.n_outer, "sort_every": args.sort_every,
                        "exchange": (None if world == 1 else
-                                    {"ghost_J_bytes_per_evaluation": eng.halo.bytes_per_exchange,
+                                    {"ghost_J": "peer-memory kernels over NVLink (CUDA IPC inboxes)" if args.halo == "peer"
+                                                else "pack + NCCL send/recv + unpack-add",
+                                     "ghost_J_bytes_per_evaluation": eng.halo.bytes_per_exchange,
                                      "migrated_particles_rank0": int(eng.migrated)}),
                        "mean_picard_passes": round(k_mean, 3), "unconverged_particles": int(unconv),
                        "l2_policy": "inputs (%.1f GB particle SoA per GPU) exceed the 126 MB L2; no flush needed"
@@ -486,6 +528,7 @@ def run_ours(args):
                          "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms,
                          "peak_source": peak_src},
             "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]},
+            "section_ms_per_step": getattr(region, "sections", None),   # rank 0, CUDA events between the phases of a step
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

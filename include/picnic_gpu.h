@@ -220,6 +220,35 @@ int pgpu_species_set_leaver_counts(pgpu_species_t s, const long *counts /* [10] 
 int pgpu_species_pack_leavers_d(pgpu_species_t s, double *buf_d);
 int pgpu_species_append_d(pgpu_species_t s, long n_add, const double *buf_d);
 
+/* Ghost ADD-exchange of the total J over peer memory (NVLink/NVSwitch), no collective library on the
+ * data path: LevelData::exchange with an add op in finalizeSettingJ (PicSpeciesInterface.cpp:766-772).
+ * A plan is a list of messages; message = the index boxes (global indices, inclusive) of Jx, Jy, Jz that
+ * this box shares with one neighbour in one phase (direction).  The same boxes are sent (this box's
+ * copy goes into the neighbour's inbox) and received (the neighbour's copy, delivered into inbox area
+ * recv_area of this box, is added).  Inboxes are device buffers of the owning process: same-process
+ * peers pass pgpu_halo_inbox() pointers around, other processes the 64-byte CUDA IPC handle.
+ * One exchange = pgpu_halo_begin, then for every phase pgpu_halo_send followed by pgpu_halo_recv_add
+ * (all boxes of a process send before any receives).  Collective; nothing synchronises with the host. */
+typedef struct pgpu_halo_s *pgpu_halo_t;
+typedef struct {
+  int phase;         /* 0 .. 7, executed in ascending order */
+  int recv_area;     /* 0 .. nmsg-1, unique: where the neighbour's copy of these boxes lands */
+  int lo[3][2], hi[3][2];
+} pgpu_halo_msg;
+int pgpu_halo_create(pgpu_grid_t g, int nmsg, const pgpu_halo_msg *msgs, pgpu_halo_t *out);
+int pgpu_halo_destroy(pgpu_halo_t h);
+int pgpu_halo_phases(pgpu_halo_t h);
+/* inbox area of message msg: offset in doubles behind the flag block, and its length */
+int pgpu_halo_area_offset(pgpu_halo_t h, int msg, long *offset_doubles, long *count);
+int pgpu_halo_inbox(pgpu_halo_t h, void **inbox_d, size_t *bytes);
+int pgpu_halo_ipc_handle(pgpu_halo_t h, void *handle64);
+int pgpu_halo_ipc_open(pgpu_halo_t h, const void *handle64, void **inbox_d);
+/* message msg is delivered into area peer_area (at peer_area_offset doubles) of the inbox peer_inbox_d */
+int pgpu_halo_connect(pgpu_halo_t h, int msg, void *peer_inbox_d, int peer_area, long peer_area_offset);
+int pgpu_halo_begin(pgpu_halo_t h);
+int pgpu_halo_send(pgpu_halo_t h, int phase);
+int pgpu_halo_recv_add(pgpu_halo_t h, int phase);
+
 /* reductions: setStableDt (:1869-1911), globalMoments (:4067-4130) */
 int pgpu_stable_dt(pgpu_species_t s, double *dt_out);
 int pgpu_global_moments(pgpu_species_t s, double *out /* [w, wux,wuy,wuz, wuu_x,wuu_y,wuu_z] */);

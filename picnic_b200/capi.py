@@ -108,6 +108,11 @@ def load():
         "pgpu_collide_elastic": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_scatter_nu_max_ta": [vp, vp, dbl, vp], "pgpu_scatter_nu_max_coulomb": [vp, vp, vp, vp],
         "pgpu_scatter_nu_max_elastic": [vp, vp, vp, vp],
+        "pgpu_halo_create": [vp, i32, vp, vp], "pgpu_halo_destroy": [vp], "pgpu_halo_phases": [vp],
+        "pgpu_halo_area_offset": [vp, i32, vp, vp], "pgpu_halo_inbox": [vp, vp, vp],
+        "pgpu_halo_ipc_handle": [vp, vp], "pgpu_halo_ipc_open": [vp, vp, vp],
+        "pgpu_halo_connect": [vp, i32, vp, i32, lng], "pgpu_halo_begin": [vp], "pgpu_halo_send": [vp, i32],
+        "pgpu_halo_recv_add": [vp, i32],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
         "pgpu_launch_count": [], "pgpu_picard_totals": [vp, vp, vp, i32], "pgpu_abi_version": [], "pgpu_last_error": [],
     }
@@ -115,6 +120,11 @@ def load():
         getattr(lib, name).argtypes = args
     _lib = lib
     return lib
+
+
+class HaloMsg(C.Structure):
+    """pgpu_halo_msg"""
+    _fields_ = [("phase", C.c_int), ("recv_area", C.c_int), ("lo", (C.c_int * 2) * 3), ("hi", (C.c_int * 2) * 3)]
 
 
 def check(rc):

@@ -241,6 +241,123 @@ class HaloExchange:
             self.end(ph)
 
 
+class PeerHaloExchange:
+    """The same direction-by-direction plan as HaloExchange, executed by the library over peer memory
+    (pgpu_halo_*, csrc/pgpu_halo_p2p.cu): per direction one kernel stores this box's overlap strips into
+    the neighbours' inboxes over NVLink and stamps their arrival flags, a second one waits for this box's
+    own flags and adds what arrived.  No NCCL call and no host synchronisation on the data path; the
+    only collective is the one-off exchange of the CUDA IPC handles of the inboxes (connect_*)."""
+
+    def __init__(self, layout, rank, grid):
+        from . import capi
+        self.capi, self.layout, self.rank, self.grid = capi, layout, rank, grid
+        D = layout.D
+        self.msgs = []          # (phase, side, peer)
+        recs = []
+        phase = 0
+        for d in range(D):
+            if layout.nb[d] == 1:
+                continue
+            for side in (-1, +1):
+                peer = layout.neighbor(rank, d, side)
+                if peer is None:
+                    continue
+                m = capi.HaloMsg()
+                m.phase, m.recv_area = phase, len(recs)
+                for comp, stag in enumerate(STAG_J[D]):
+                    lo, hi = layout.overlap(rank, stag, d, side)
+                    for k in range(D):
+                        m.lo[comp][k], m.hi[comp][k] = lo[k], hi[k]
+                recs.append(m)
+                self.msgs.append((phase, side, peer))
+            phase += 1
+        arr = (capi.HaloMsg * max(len(recs), 1))(*recs)
+        self.h = capi.C.c_void_p()
+        capi.check(capi.load().pgpu_halo_create(grid.h, len(recs), arr, capi.C.byref(self.h)))
+        self.nphase = capi.load().pgpu_halo_phases(self.h)
+        self.bytes_per_exchange = 0
+        self.areas = {}         # (phase, side) -> (area index, offset in doubles)
+        for i, (ph, side, _) in enumerate(self.msgs):
+            off, cnt = capi.C.c_long(), capi.C.c_long()
+            capi.check(capi.load().pgpu_halo_area_offset(self.h, i, capi.C.byref(off), capi.C.byref(cnt)))
+            self.areas[(ph, side)] = (i, off.value)
+            self.bytes_per_exchange += 2 * 8 * cnt.value
+
+    # ---- wiring -------------------------------------------------------------------------------
+    def inbox_pointer(self):
+        p, n = self.capi.C.c_void_p(), self.capi.C.c_size_t()
+        self.capi.check(self.capi.load().pgpu_halo_inbox(self.h, self.capi.C.byref(p), self.capi.C.byref(n)))
+        return p.value
+
+    def _connect(self, pointer_of, areas_of):
+        lib, capi = self.capi.load(), self.capi
+        for i, (ph, side, peer) in enumerate(self.msgs):
+            area, off = areas_of(peer)[(ph, -side)]       # my +side message is the peer's -side arrival
+            capi.check(lib.pgpu_halo_connect(self.h, i, capi.C.c_void_p(pointer_of(peer)), area, off))
+
+    @staticmethod
+    def connect_local(exchanges):
+        """All boxes in this process (tests; several boxes per GPU): plain device pointers."""
+        by_rank = {e.rank: e for e in exchanges}
+        for e in exchanges:
+            e._connect(lambda r: by_rank[r].inbox_pointer(), lambda r: by_rank[r].areas)
+
+    def connect_ipc(self, comm):
+        """One process per box: all-gather the 64-byte CUDA IPC handle and the area table of every inbox,
+        open the neighbours' handles."""
+        import torch
+        capi, lib = self.capi, self.capi.load()
+        hbuf = (capi.C.c_ubyte * 64)()
+        capi.check(lib.pgpu_halo_ipc_handle(self.h, hbuf))
+        rec = np.zeros(8 + 1 + 4 * 16, dtype=np.int64)
+        rec[:8] = np.frombuffer(bytes(hbuf), dtype=np.int64)
+        rec[8] = len(self.msgs)
+        for i, ((ph, side), (area, off)) in enumerate(sorted(self.areas.items())):
+            rec[9 + 4 * i: 13 + 4 * i] = (ph, side, area, off)
+        device = torch.device("cuda", torch.cuda.current_device()) if comm.dist.get_backend() == "nccl" else "cpu"
+        allr = [x.numpy() for x in comm.all_gather(torch.as_tensor(rec).to(device))]
+        opened = {}
+
+        def pointer_of(r):
+            if r not in opened:
+                hb = (capi.C.c_ubyte * 64).from_buffer_copy(allr[r][:8].tobytes())
+                p = capi.C.c_void_p()
+                if r == self.rank:
+                    opened[r] = self.inbox_pointer()
+                else:
+                    capi.check(lib.pgpu_halo_ipc_open(self.h, hb, capi.C.byref(p)))
+                    opened[r] = p.value
+            return opened[r]
+
+        def areas_of(r):
+            n = int(allr[r][8])
+            return {(int(a[0]), int(a[1])): (int(a[2]), int(a[3])) for a in allr[r][9:9 + 4 * n].reshape(n, 4)}
+
+        self._connect(pointer_of, areas_of)
+
+    # ---- the exchange -------------------------------------------------------------------------
+    def begin(self):
+        self.capi.check(self.capi.load().pgpu_halo_begin(self.h))
+
+    def send(self, phase):
+        self.capi.check(self.capi.load().pgpu_halo_send(self.h, phase))
+
+    def recv_add(self, phase):
+        self.capi.check(self.capi.load().pgpu_halo_recv_add(self.h, phase))
+
+    def add_exchange(self):
+        """One process per box: the whole exchange (every rank calls this collectively)."""
+        self.begin()
+        for ph in range(self.nphase):
+            self.send(ph)
+            self.recv_add(ph)
+
+    def destroy(self):
+        if self.h:
+            self.capi.check(self.capi.load().pgpu_halo_destroy(self.h))
+            self.h = None
+
+
 # ------------------------------------------------------------------------------------------------
 # particle migration
 # ------------------------------------------------------------------------------------------------

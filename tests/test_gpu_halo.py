@@ -29,8 +29,12 @@ def _species(pgpu, grid, x, xo, v, w, ids):
     return sp
 
 
-@pytest.mark.parametrize("nbox", [(16, 16), (16, 8)])
-def test_add_exchange_matches_single_box(pgpu, nbox):
+@pytest.mark.parametrize("nbox,peer", [((16, 16), False), ((16, 8), False), ((16, 16), True), ((16, 8), True),
+                                       ((8, 16), True)])
+def test_add_exchange_matches_single_box(pgpu, nbox, peer):
+    """peer=False: pack / mailbox / unpack-add (the NCCL route's kernels); peer=True: the peer-memory
+    kernels (pgpu_halo_send / pgpu_halo_recv_add), three exchanges in a row so that both parity slots of
+    the inboxes and the sequence numbers are exercised."""
     import torch
     lay = halo.BoxLayout(2, NCELL, nbox, NG, (1, 1))
     x, xo, v, w = _particles(2)
@@ -55,12 +59,29 @@ def test_add_exchange_matches_single_box(pgpu, nbox):
         s.set_current_density(1.0)
         g.current_zero(); g.current_add(s)
         grids.append(g); sps.append(s)
-        hxs.append(halo.HaloExchange(lay, r, hub.view(r), halo.CapiGridBackend(g, torch.device("cuda", 0))))
-    for ph in range(hxs[0].n_phases()):
-        for h in hxs:
-            h.begin(ph)
-        for h in hxs:
-            h.end(ph)
+        if peer:
+            hxs.append(halo.PeerHaloExchange(lay, r, g))
+        else:
+            hxs.append(halo.HaloExchange(lay, r, hub.view(r), halo.CapiGridBackend(g, torch.device("cuda", 0))))
+    if peer:
+        halo.PeerHaloExchange.connect_local(hxs)
+        for rep in range(3):
+            if rep:                                   # same deposit again: the exchange must give the same sums
+                for g, s in zip(grids, sps):
+                    g.current_zero(); g.current_add(s)
+            for h in hxs:
+                h.begin()
+            for ph in range(hxs[0].nphase):
+                for h in hxs:
+                    h.send(ph)
+                for h in hxs:
+                    h.recv_add(ph)
+    else:
+        for ph in range(hxs[0].n_phases()):
+            for h in hxs:
+                h.begin(ph)
+            for h in hxs:
+                h.end(ph)
     worst = 0.0
     for r, g in enumerate(grids):
         g.current_finalize()          # folds the directions this box spans (none for 2x2 boxes)
@@ -71,6 +92,9 @@ def test_add_exchange_matches_single_box(pgpu, nbox):
             ii = np.mod(np.arange(lo[0], hi[0] + 1), NCELL[0]) - glo[0]
             jj = np.mod(np.arange(lo[1], hi[1] + 1), NCELL[1]) - glo[1]
             worst = max(worst, float(np.max(np.abs(a - ga[np.ix_(ii, jj)])) / np.max(np.abs(ga))))
+    if peer:
+        for h in hxs:
+            h.destroy()
     for s in sps:
         s.destroy()
     for g in grids:
