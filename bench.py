@@ -248,7 +248,7 @@ class Engine:
             return
         ev = self.torch.cuda.Event(enable_timing=True)
         ev.record(self.stream)
-        self.sections.append((name, ev))
+        self.sections.append((name, ev, time.perf_counter()))
 
     def sections_begin(self):
         self.sections = []
@@ -256,11 +256,12 @@ class Engine:
 
     def sections_end(self):
         """{section: total ms} of everything recorded since sections_begin (call after a synchronize)."""
-        out, marks = {}, self.sections
+        out, host, marks = {}, {}, self.sections
         self.sections = None
-        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+        for (_, e0, t0), (name, e1, t1) in zip(marks[:-1], marks[1:]):
             out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
-        return out
+            host[name] = host.get(name, 0.0) + (t1 - t0) * 1e3     # time the host spent issuing the section
+        return out, host
 
     def pre_rhs_op(self, j, host_io):
         """PicSpeciesInterface::preRHSOp (PicSpeciesInterface.cpp:899-994) for outer iteration j."""
@@ -432,7 +433,14 @@ def run_ours(args):
         barrier()
         if profile:
             capi.profile_enable(False)
-            region.sections = {k: round(v / nsteps, 4) for k, v in eng.sections_end().items()}
+            dev_s, host_s = eng.sections_end()
+            region.sections = {k: round(v / nsteps, 4) for k, v in dev_s.items()}
+            region.host_sections = {k: round(v / nsteps, 4) for k, v in host_s.items()}
+            if world > 1:      # slowest rank per section
+                names = sorted(dev_s)
+                t = torch.tensor([dev_s[k] / nsteps for k in names], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                region.sections_max = {k: round(float(v), 4) for k, v in zip(names, t.tolist())}
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -529,6 +537,8 @@ def run_ours(args):
                          "peak_source": peak_src},
             "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]},
             "section_ms_per_step": getattr(region, "sections", None),   # rank 0, CUDA events between the phases of a step
+            "section_ms_per_step_slowest_rank": getattr(region, "sections_max", None),
+            "host_issue_ms_per_step": getattr(region, "host_sections", None),
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

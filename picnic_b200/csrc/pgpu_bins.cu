@@ -437,6 +437,10 @@ int pgpu_bin_particles(pgpu_species_t s) {
     cub::DeviceRadixSort::SortPairs(nullptr, need, s->cell_key, s->key_sorted, iota, s->perm, (int)n, 0, nbits,
                                     c.stream);
     if (need > s->cub_bytes) {
+      // sized for the capacity, not for today's count: with migration n drifts from step to step and a
+      // cudaFree + cudaMalloc in the middle of a step stalls the whole device
+      cub::DeviceRadixSort::SortPairs(nullptr, need, s->cell_key, s->key_sorted, iota, s->perm, (int)s->cap, 0, nbits,
+                                      c.stream);
       if (s->cub_tmp) cudaFree(s->cub_tmp);
       PGPU_CUDA(cudaMalloc(&s->cub_tmp, need));
       s->cub_bytes = need;

@@ -313,7 +313,7 @@ int pgpu_species_pack_leavers_d(pgpu_species_t s, double *buf_d) {
   // scratch: holes and movers lists live in the second half of the key array / spare ints
   if (s->mig_list_cap < (size_t)(2 * L)) {
     if (s->mig_list) cudaFree(s->mig_list);
-    s->mig_list_cap = (size_t)(2 * L + 1024);
+    s->mig_list_cap = (size_t)(4 * L + 65536);   // generous: a reallocation stalls the device
     PGPU_CUDA(cudaMalloc(&s->mig_list, s->mig_list_cap * sizeof(int)));
   }
   int *holes = s->mig_list, *movers = s->mig_list + L;
