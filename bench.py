@@ -333,6 +333,9 @@ def collisions_leg(args, torch, capi, stream, peak):
     def one_step(prep):
         if prep:
             for sp in sps:
+                # a time step begins with updateOldParticlePositions/Velocities (flags only on the device)
+                sp.update_old_positions()
+                sp.update_old_velocities()
                 sp.bin_particles()
                 sp.set_moments()
         n = 0
@@ -365,6 +368,8 @@ def collisions_leg(args, torch, capi, stream, peak):
     capi.profile_enable(False)
     k_self, n_self = capi.profile_query("collide_ta_self")
     k_inter, n_inter = capi.profile_query("collide_ta_inter")
+    prep = {k: round(capi.profile_query(k)[0] / nsteps, 4)
+            for k in ("bin_key", "bin_sort", "bin_permute", "bin_starts", "cell_moments")}
     ms_k = timed(nsteps, False)
     n_total = sum(sp.n for sp in sps)
     for sp in sps:
@@ -380,6 +385,7 @@ def collisions_leg(args, torch, capi, stream, peak):
                         % (deck.ncell[0], deck.ncell[1]),
             "particles": n_total, "pairs_per_step": pairs, "steps": nsteps,
             "ms_per_step": ms_full / nsteps, "ms_per_step_kernels_only": ms_k / nsteps,
+            "prep_kernel_ms_per_step": prep,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "bytes_per_unit": 96.0,
                          "kernel": "collide_ta_self + collide_ta_inter (3 launches per step)",

@@ -378,18 +378,19 @@ static int gather_arrays(pgpu_species_s *s, std::vector<double **> &arrs, const 
   return 0;
 }
 
-int materialize_old(pgpu_species_s *s, bool keep_alias) {
-  if (!keep_alias && (s->xold_alias || s->vold_alias)) {
-    // the deferred copy of updateOldParticlePositions / Velocities (an aliased group has no pending gather)
-    if (s->xold_alias)
-      for (int d = 0; d < s->grid->desc.D; ++d)
-        PGPU_CUDA(cudaMemcpyAsync(s->xold[d], s->x[d], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
-    if (s->vold_alias)
-      for (int q = 0; q < 3; ++q)
-        PGPU_CUDA(cudaMemcpyAsync(s->vold[q], s->v[q], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
-    s->xold_alias = s->vold_alias = false;
+int materialize_old(pgpu_species_s *s, int keep) {
+  // the deferred copy of updateOldParticlePositions / Velocities (an aliased group has no pending gather)
+  if (s->xold_alias && !(keep & KEEP_XOLD_ALIAS)) {
+    for (int d = 0; d < s->grid->desc.D; ++d)
+      PGPU_CUDA(cudaMemcpyAsync(s->xold[d], s->x[d], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+    s->xold_alias = false;
   }
-  if (!s->pos_old_pending && !s->vel_old_pending) return 0;
+  if (s->vold_alias && !(keep & KEEP_VOLD_ALIAS)) {
+    for (int q = 0; q < 3; ++q)
+      PGPU_CUDA(cudaMemcpyAsync(s->vold[q], s->v[q], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+    s->vold_alias = false;
+  }
+  if ((keep & KEEP_PENDING) || (!s->pos_old_pending && !s->vel_old_pending)) return 0;
   std::vector<double **> arrs;
   if (s->pos_old_pending)
     for (int d = 0; d < s->grid->desc.D; ++d) arrs.push_back(&s->xold[d]);
@@ -456,7 +457,7 @@ int pgpu_bin_particles(pgpu_species_t s) {
   // gather the particle arrays into the sorted order, four arrays per launch (the old arrays
   // become the next spares); xold / vold are gathered lazily (materialize_old)
   // a still-pending gather of an earlier sort; an aliased old group stays aliased (x == xold in any order)
-  if (materialize_old(s, true)) return PGPU_ERR_CUDA;
+  if (materialize_old(s, KEEP_OLD_ALIASES)) return PGPU_ERR_CUDA;
   std::vector<double **> arrs;
   const int D = g->desc.D;
   for (int d = 0; d < D; ++d) arrs.push_back(&s->x[d]);

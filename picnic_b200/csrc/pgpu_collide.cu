@@ -52,9 +52,11 @@ __device__ __forceinline__ void scatter_delta_u(double ux, double uy, double uz,
     dU[1] = u * sinth * sinphi;
     dU[2] = u * costh - u;
   } else {
-    dU[0] = ux * uz / uperp * sinth * cosphi - uy * u / uperp * sinth * sinphi - ux * (1. - costh);
-    dU[1] = uy * uz / uperp * sinth * cosphi + ux * u / uperp * sinth * sinphi - uy * (1. - costh);
-    dU[2] = -uperp * sinth * cosphi - uz * (1. - costh);
+    // one reciprocal instead of the reference's four divisions by uperp (differs from it by rounding only)
+    const double iu = 1.0 / uperp, sc = sinth * cosphi, ss = sinth * sinphi, omc = 1. - costh;
+    dU[0] = ux * uz * iu * sc - uy * u * iu * ss - ux * omc;
+    dU[1] = uy * uz * iu * sc + ux * u * iu * ss - uy * omc;
+    dU[2] = -uperp * sc - uz * omc;
   }
 }
 
@@ -72,8 +74,9 @@ __device__ __forceinline__ void ta_delta_u(const double *vp1, double den1, const
   if (deltasq_var < 1.0) {
     const double delta = sqrt(deltasq_var) * gauss;
     const double deltasq = delta * delta;
-    sinth = 2.0 * delta / (1.0 + deltasq);
-    costh = 1.0 - 2.0 * deltasq / (1.0 + deltasq);
+    const double inv = 1.0 / (1.0 + deltasq);
+    sinth = 2.0 * delta * inv;
+    costh = 1.0 - 2.0 * deltasq * inv;
   } else {
     const double theta = PI * u_theta;
     sincos(theta, &sinth, &costh);
@@ -120,10 +123,69 @@ __device__ __forceinline__ unsigned global_cell(const TAParams &P, int cell) {
   return (unsigned)(i + j * P.ncell_glob0);
 }
 
+// Cells of up to 128 particles: bitonic network over R registers per lane and warp shuffles.  The sorted
+// word is (24 Philox bits << 7) | local index, so the sort needs no payload and the key is unique; two
+// particles whose 24 random bits collide (6e-5 per 64-particle cell) keep their storage order.
+template <int R>
+__device__ __forceinline__ void warp_bitonic_order(int s, int n, const uint64_t *id, const TAParams &P, unsigned salt,
+                                                   int *order, int lane) {
+  unsigned v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int k = lane + 32 * r;
+    v[r] = 0xffffffffu;
+    if (k < n) {
+      const uint64_t pid = id[s + k];
+      u4 c;
+      c.x = (unsigned)pid;
+      c.y = (unsigned)(pid >> 32);
+      c.z = P.step_lo;
+      c.w = P.step_hi ^ (STREAM_SHUFFLE << 16) ^ salt;
+      v[r] = ((philox4x32_10(c, P.seed_lo, P.seed_hi).x >> 1) & ~0x7fu) | (unsigned)k;
+    }
+  }
+  // element e = lane + 32 r; stage (k2, j): e and e ^ j are ordered ascending iff (e & k2) == 0
+#pragma unroll
+  for (int k2 = 2; k2 <= 32 * R; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int dr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r & dr) continue;
+          const bool up = (((lane + 32 * r) & k2) == 0);
+          const unsigned a = v[r], b = v[r | dr];
+          const unsigned lo = min(a, b), hi = max(a, b);
+          v[r] = up ? lo : hi;
+          v[r | dr] = up ? hi : lo;
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned o = __shfl_xor_sync(0xffffffffu, v[r], j);
+          const bool up = (((lane + 32 * r) & k2) == 0);
+          v[r] = (lower == up) ? min(v[r], o) : max(v[r], o);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int pos = lane + 32 * r;
+    if (pos < n) order[s + pos] = (int)(v[r] & 0x7fu);
+  }
+  __syncwarp();
+}
+
 // random order of the n particles of a cell: order[r] = local index of the particle
 // with the r-th smallest (key, id) where key = Philox(seed, step, id)
 __device__ __forceinline__ void warp_shuffle_order(int s, int n, const uint64_t *id, const TAParams &P,
                                                    unsigned salt, unsigned *key, int *order, int lane) {
+  if (n <= 64) return warp_bitonic_order<2>(s, n, id, P, salt, order, lane);
+  if (n <= 128) return warp_bitonic_order<4>(s, n, id, P, salt, order, lane);
+  // larger cells: rank of every key by counting, keys in global scratch
   for (int k = lane; k < n; k += 32) {
     const uint64_t pid = id[s + k];
     u4 c;
@@ -154,9 +216,11 @@ __device__ __forceinline__ void pair_randoms(const TAParams &P, unsigned gcell, 
   c.z = P.step_lo;
   c.w = P.step_hi ^ (STREAM_PAIR << 16) ^ salt;
   const u4 r = philox4x32_10(c, P.seed_lo, P.seed_hi);
-  // Box-Muller
-  const double TWOPI = 6.28318530717958647692;
-  gauss = sqrt(-2.0 * log(u01(r.x))) * cos(TWOPI * u01(r.y));
+  // Box-Muller in single precision: the two uniforms carry 32 random bits each, so an fp64 log / cos buys
+  // nothing for the N(0,1) draw (it only enters TakizukaAbe::computeDeltaU as a number)
+  const float f1 = ((float)(r.x >> 8) + 0.5f) * 5.9604644775390625e-8f;    // (0,1), 24 bits
+  const float f2 = ((float)(r.y >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  gauss = (double)(sqrtf(-2.0f * logf(f1)) * cospif(2.0f * f2));
   uth = u01(r.z);
   uphi = u01(r.w);
 }
@@ -985,8 +1049,8 @@ static int need_binned(pgpu_species_t sA, pgpu_species_t sB) {
     set_error("collisions need binned species: call pgpu_bin_particles + pgpu_set_moments_from_bins first");
     return PGPU_ERR_STATE;
   }
-  // collisions write v: a deferred vold = v copy has to happen first
-  if (materialize_old(sA) || materialize_old(sB)) return PGPU_ERR_CUDA;
+  // collisions write v: a deferred vold = v copy has to happen first (x is not touched: xold may stay aliased)
+  if (materialize_old(sA, KEEP_XOLD_ALIAS | KEEP_PENDING) || materialize_old(sB, KEEP_XOLD_ALIAS | KEEP_PENDING)) return PGPU_ERR_CUDA;
   return 0;
 }
 
@@ -1093,7 +1157,7 @@ int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt
     set_error("collisions need binned species: call pgpu_bin_particles + pgpu_set_moments_from_bins first");
     return PGPU_ERR_STATE;
   }
-  if (materialize_old(sA) || materialize_old(sB)) return PGPU_ERR_CUDA;
+  if (materialize_old(sA, KEEP_XOLD_ALIAS | KEEP_PENDING) || materialize_old(sB, KEEP_XOLD_ALIAS | KEEP_PENDING)) return PGPU_ERR_CUDA;
   Context &c = ctx();
   const pgpu_grid_s *g = sA->grid;
   // m_mu, m_b90_fact (TakizukaAbe.cpp:39-49); long double as in TakizukaAbe.H:137-139

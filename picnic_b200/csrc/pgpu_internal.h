@@ -219,7 +219,10 @@ int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f);
 int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi);
 
 // launchers implemented in the kernel translation units
-int materialize_old(pgpu_species_s *s, bool keep_alias = false);
+// keep: bit 0 = leave an aliased xold alone, bit 1 = leave an aliased vold alone 
+// bit 2 = leave the pending gathers of the last cell sort pending (the caller touches no old array)
+enum { KEEP_XOLD_ALIAS = 1, KEEP_VOLD_ALIAS = 2, KEEP_OLD_ALIASES = 3, KEEP_PENDING = 4 };
+int materialize_old(pgpu_species_s *s, int keep = 0);
 int grow_capacity(pgpu_species_s *s, long n);   // keeps the particles (pgpu_api.cu)
 int launch_gather(pgpu_species_s *s);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);

@@ -326,7 +326,7 @@ static int launch_advance_d(pgpu_species_s *s, const AdvanceParams &prm, bool fu
 // first; this generic visitor kernel then handles only the particles it deferred.
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit) {
   if (s->n == 0) return 0;
-  if (materialize_old(s, true)) return PGPU_ERR_CUDA;   // pending gathers; an aliased old group is left to the CC1 kernel
+  if (materialize_old(s, KEEP_OLD_ALIASES)) return PGPU_ERR_CUDA;   // pending gathers; an aliased old group is left to the CC1 kernel
   bool deferred = false;
   if (ctx().use_fast_cc1) {
     const int fr = launch_advance_cc1_fast(s, prm, fuse_deposit);
