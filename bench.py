@@ -55,7 +55,7 @@ EPS_OUTER = (0.0, 1.0e-3, 1.0e-6, 1.0e-9)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ncell", type=int, default=512, help="cells per direction of the per-GPU box")
@@ -127,7 +127,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -136,17 +136,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """Only the samples that arrived inside [t0, t1] (host clock around the timed region) count."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        for (ts, r) in self.rows:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.02):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -456,11 +462,14 @@ def run_ours(args):
 
     # warm-up (>= 3 steps), then the timed region.  The particle arrays (5 GB per GPU) are far
     # larger than the 126 MB L2, so every pass streams from HBM; no explicit flush is needed.
-    region(max(args.warmup, 1), False)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()           # nvidia-smi needs ~0.1 s to deliver its first sample: start before the warm-up
+    region(max(args.warmup, 3), False)
+    t_host0 = time.perf_counter()
     ms, launches = region(args.steps, False, profile=True)
+    if rank == 0:
+        sampler.window(t_host0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     prof = {}
     for name in ("advance_cc1_fused", "advance_deferred", "advance_deposit_fused", "advance", "deposit_current", "bin_", "finish_step", "second_half", "fold_periodic",
