@@ -152,3 +152,73 @@ def test_migration_on_device(pgpu):
         s.destroy()
     for g in grids:
         g.destroy()
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA IPC route: two PROCESSES (both on cuda:0 -- IPC does not care), handles over gloo
+# ------------------------------------------------------------------------------------------------
+def _ipc_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from picnic_b200 import capi
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        capi.load(); capi.init(0)
+        nbox = (16, 16)
+        lay = halo.BoxLayout(2, NCELL, nbox, NG, (1, 1))          # 2 x 1 boxes; y is folded locally
+        x, xo, v, w = _particles(2)
+        ids = np.arange(w.size, dtype=np.uint64)
+        own = np.floor((xo[0] - XMIN[0]) / (DX[0] * nbox[0])).astype(int)
+        lo, hi = lay.box(rank)
+        g = capi.Grid(2, NCELL, XMIN, DX, NG, (1, 1), box_lo=lo, box_hi=hi)
+        m = own == rank
+        s = _species(capi, g, x[:, m], xo[:, m], v[:, m], w[m], ids[m])
+        s.set_current_density(1.0)
+        hx = halo.PeerHaloExchange(lay, rank, g)
+        hx.connect_ipc(halo.DistComm(rank, world))
+        out = None
+        for rep in range(3):                                      # both parity slots, growing sequence numbers
+            g.current_zero(); g.current_add(s)
+            hx.add_exchange()
+            g.current_finalize()
+            out = [g.current_get(c) for c in range(3)]
+            dist.barrier()
+        bounds = [g.field_bounds(c) for c in range(3)]
+        dist.barrier()                                            # nobody tears its inbox down while a peer may write
+        hx.destroy(); s.destroy(); g.destroy(); capi.finalize()
+        q.put((rank, bounds, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_two_processes_ipc(pgpu):
+    import socket
+    import torch.multiprocessing as mp
+    x, xo, v, w = _particles(2)
+    ids = np.arange(w.size, dtype=np.uint64)
+    g1 = pgpu.Grid(2, NCELL, XMIN, DX, NG, (1, 1))
+    s1 = _species(pgpu, g1, x, xo, v, w, ids)
+    s1.set_current_density(1.0)
+    g1.current_zero(); g1.current_add(s1); g1.current_finalize()
+    Jg = [(g1.field_bounds(c), g1.current_get(c)) for c in range(3)]
+    s1.destroy(); g1.destroy()
+    sk = socket.socket(); sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]; sk.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ipc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for (rank, bounds, out) in res:
+        for c in range(3):
+            (lo, hi), a = bounds[c], out[c]
+            (glo, _), ga = Jg[c]
+            ii = np.mod(np.arange(lo[0], hi[0] + 1), NCELL[0]) - glo[0]
+            jj = np.mod(np.arange(lo[1], hi[1] + 1), NCELL[1]) - glo[1]
+            assert float(np.max(np.abs(a - ga[np.ix_(ii, jj)])) / np.max(np.abs(ga))) < 1e-13, (rank, c)
