@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="ghost-J add-exchange between boxes: the library's peer-memory kernels (default) or "
                          "pack + NCCL send/recv + unpack-add")
+    ap.add_argument("--migration", default="peer", choices=["peer", "nccl"],
+                    help="particle migration between boxes: peer-memory inboxes with device-side counts (default) or "
+                         "count all-gather + NCCL send/recv")
     ap.add_argument("--dt", type=float, default=0.1)
     ap.add_argument("--iter-max", type=int, default=21)
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles per species in the CPU sample (0 = auto)")
@@ -238,8 +241,16 @@ class Engine:
             else:
                 self.halo = halo.HaloExchange(lay, rank, comm,
                                               halo.CapiGridBackend(self.grid, dev, on_torch_stream=True))
-            self.migration = [halo.Migration(lay, rank, comm, halo.CapiSpeciesBackend(sp, dev, on_torch_stream=True))
-                              for sp in self.species]
+            if args.migration == "peer":
+                # leavers go straight into the neighbours' inboxes (peer stores), counts stay on the device
+                self.migration = [halo.PeerMigration(lay, rank, sp, capacity=max(16384, sp.n // 512))
+                                  for sp in self.species]
+                for m in self.migration:
+                    m.connect_ipc(comm)
+            else:
+                self.migration = [halo.Migration(lay, rank, comm,
+                                                 halo.CapiSpeciesBackend(sp, dev, on_torch_stream=True))
+                                  for sp in self.species]
         self.migrated = 0
         self.sections, self.stream = None, stream
 
@@ -304,7 +315,10 @@ class Engine:
         self._mark("finish_step")
         if self.migration:                             # remapOutcast: leavers to the owning box
             from picnic_b200 import halo
-            self.migrated += halo.migrate_all(self.migration)
+            if self.args.migration == "peer":
+                self.migrated += halo.migrate_all_peer(self.migration)
+            else:
+                self.migrated += halo.migrate_all(self.migration)
             self._mark("migration")
         self.step_no += 1
         if self.args.sort_every > 0 and self.step_no % self.args.sort_every == 0:
@@ -538,6 +552,8 @@ def run_ours(args):
                        "exchange": (None if world == 1 else
                                     {"ghost_J": "peer-memory kernels over NVLink (CUDA IPC inboxes)" if args.halo == "peer"
                                                 else "pack + NCCL send/recv + unpack-add",
+                                     "migration": "peer-memory inboxes, device-side counts, one host wait per step"
+                                                  if args.migration == "peer" else "count all-gather + NCCL send/recv",
                                      "ghost_J_bytes_per_evaluation": eng.halo.bytes_per_exchange,
                                      "migrated_particles_rank0": int(eng.migrated)}),
                        "mean_picard_passes": round(k_mean, 3), "unconverged_particles": int(unconv),

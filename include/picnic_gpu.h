@@ -249,6 +249,26 @@ int pgpu_halo_begin(pgpu_halo_t h);
 int pgpu_halo_send(pgpu_halo_t h, int phase);
 int pgpu_halo_recv_add(pgpu_halo_t h, int phase);
 
+/* Particle migration over peer memory: gatherOutcast + remapOutcast (ParticleDataI.H:405-547) without a
+ * message layer and with device-side counts.  Every species of every box owns an inbox of 9 areas (one per
+ * direction the particles arrive from) of capacity_records wire records, double buffered by step parity.
+ * send: marks the leavers, stores their records straight into the owning neighbours' inboxes (NVLink),
+ * fills the holes from the tail, posts counts + arrival flags.  recv: waits for the flags of all connected
+ * neighbours and appends what arrived.  finish: the step's only host synchronisation; updates the particle
+ * count.  With several species: send all, recv all, finish all (one wait).  More than capacity_records
+ * leavers towards one neighbour in one step is an error (PGPU_ERR_STATE at finish). */
+typedef struct pgpu_migrator_s *pgpu_migrator_t;
+int pgpu_migrator_create(pgpu_species_t s, long capacity_records, pgpu_migrator_t *out);
+int pgpu_migrator_destroy(pgpu_migrator_t m);
+int pgpu_migrator_inbox(pgpu_migrator_t m, void **inbox_d, size_t *bytes);
+int pgpu_migrator_ipc_handle(pgpu_migrator_t m, void *handle64);
+int pgpu_migrator_ipc_open(pgpu_migrator_t m, const void *handle64, void **inbox_d);
+/* the box in direction code = (d0+1) + 3 (d1+1) of this one owns inbox peer_inbox_d */
+int pgpu_migrator_connect(pgpu_migrator_t m, int code, void *peer_inbox_d);
+int pgpu_migrate_send(pgpu_migrator_t m);
+int pgpu_migrate_recv(pgpu_migrator_t m);
+int pgpu_migrate_finish(pgpu_migrator_t m, long *n_arrived, long *n_left, long *n_lost);
+
 /* reductions: setStableDt (:1869-1911), globalMoments (:4067-4130) */
 int pgpu_stable_dt(pgpu_species_t s, double *dt_out);
 int pgpu_global_moments(pgpu_species_t s, double *out /* [w, wux,wuy,wuz, wuu_x,wuu_y,wuu_z] */);

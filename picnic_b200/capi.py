@@ -113,6 +113,10 @@ def load():
         "pgpu_halo_ipc_handle": [vp, vp], "pgpu_halo_ipc_open": [vp, vp, vp],
         "pgpu_halo_connect": [vp, i32, vp, i32, lng], "pgpu_halo_begin": [vp], "pgpu_halo_send": [vp, i32],
         "pgpu_halo_recv_add": [vp, i32],
+        "pgpu_migrator_create": [vp, lng, vp], "pgpu_migrator_destroy": [vp], "pgpu_migrator_inbox": [vp, vp, vp],
+        "pgpu_migrator_ipc_handle": [vp, vp], "pgpu_migrator_ipc_open": [vp, vp, vp],
+        "pgpu_migrator_connect": [vp, i32, vp], "pgpu_migrate_send": [vp], "pgpu_migrate_recv": [vp],
+        "pgpu_migrate_finish": [vp, vp, vp, vp],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
         "pgpu_launch_count": [], "pgpu_picard_totals": [vp, vp, vp, i32], "pgpu_abi_version": [], "pgpu_last_error": [],
     }

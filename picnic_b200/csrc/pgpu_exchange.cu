@@ -13,6 +13,8 @@
 //     and arrivals are appended.
 #include "pgpu_internal.h"
 
+#include <vector>
+
 namespace pgpu {
 
 static inline unsigned nb(long n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
@@ -166,6 +168,146 @@ __global__ void k_append(WirePtrs P, long n0, long nadd, const double *buf) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nadd) return;
   wire_in(P, n0 + t, buf + (size_t)t * wire_len(P.D));
+}
+
+// ---- migration over peer memory (device-side counts) --------------------------------------
+// Inbox of one species of one box: [flags u64[16]] [counts u32 [2 parity][16]] pad to 1 KiB, then
+// [2 parity][9 areas][cap records] wire records.  Area a = direction code the particles ARRIVE from
+// (= 8 - the sender's code).
+constexpr size_t MIGBOX_HEADER = 1024;
+struct MigBoxView {
+  unsigned long long *flags;   // [16]
+  unsigned *counts;            // [2][16]
+  double *recs;                // [2][9][cap][nw]
+};
+__host__ __device__ inline MigBoxView migbox_view(void *base) {
+  MigBoxView v;
+  unsigned char *b = reinterpret_cast<unsigned char *>(base);
+  v.flags = reinterpret_cast<unsigned long long *>(b);
+  v.counts = reinterpret_cast<unsigned *>(b + 16 * sizeof(unsigned long long));
+  v.recs = reinterpret_cast<double *>(b + MIGBOX_HEADER);
+  return v;
+}
+struct MigPeers {
+  void *inbox[9];              // the neighbour's inbox per direction code (nullptr: no neighbour)
+};
+struct MigResult {             // written by the receiving kernel, read back by the host
+  long long n_final, n_arrived, n_left, n_lost;
+  unsigned overflow, pad;
+};
+
+// leavers -> the neighbours' inboxes (peer stores), holes below new_n = n - nleave
+__global__ void k_mig_pack_send(WirePtrs P, const int *list, const int *dead, MigCounters *mc, MigPeers peers,
+                                unsigned parity, long cap, long n, int *holes, long list_cap, unsigned *overflow) {
+  const unsigned nleave = mc->nleave;
+  const long new_n = n - (long)nleave;
+  const int nw = wire_len(P.D);
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nleave; t += gridDim.x * blockDim.x) {
+    const long i = list[t];
+    const int code = dead[i] - 1;
+    if (code < 9 && peers.inbox[code]) {
+      const unsigned pos = atomicAdd(&mc->cursor[code], 1u);
+      if (pos < (unsigned long)cap) {
+        const MigBoxView v = migbox_view(peers.inbox[code]);
+        wire_out(P, i, v.recs + (((size_t)parity * 9 + (8 - code)) * cap + pos) * nw);
+      } else {
+        *overflow = 1u;
+      }
+    }
+    if (i < new_n) {
+      const unsigned h = atomicAdd(&mc->nhole, 1u);
+      if ((long)h < list_cap) holes[h] = (int)i;
+      else *overflow = 1u;
+    }
+  }
+  __threadfence_system();
+}
+__global__ void k_mig_list_movers(const int *dead, long n, MigCounters *mc, int *movers, long list_cap) {
+  const unsigned nleave = mc->nleave;
+  const long new_n = n - (long)nleave;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nleave; t += gridDim.x * blockDim.x) {
+    const long i = new_n + t;
+    if (!dead[i]) {
+      const unsigned m = atomicAdd(&mc->nmove, 1u);
+      if ((long)m < list_cap) movers[m] = (int)i;
+    }
+  }
+}
+__global__ void k_mig_fill_holes(WirePtrs P, const int *holes, const int *movers, const MigCounters *mc, long list_cap) {
+  const unsigned nh = mc->nhole < (unsigned long)list_cap ? mc->nhole : (unsigned)list_cap;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < nh; t += gridDim.x * blockDim.x) {
+    const long dst = holes[t], src = movers[t];
+    for (int d = 0; d < P.D; ++d) {
+      P.x[d][dst] = P.x[d][src];
+      P.xold[d][dst] = P.xold[d][src];
+    }
+    for (int c = 0; c < 3; ++c) {
+      P.v[c][dst] = P.v[c][src];
+      P.vold[c][dst] = P.vold[c][src];
+    }
+    P.w[dst] = P.w[src];
+    P.id[dst] = P.id[src];
+  }
+}
+// counts + arrival flags to the neighbours (after k_mig_pack_send in stream order)
+__global__ void k_mig_post(const MigCounters *mc, MigPeers peers, unsigned parity, long cap, unsigned long long seq) {
+  const int code = threadIdx.x;
+  if (code >= 9 || code == 4 || !peers.inbox[code]) return;
+  const MigBoxView v = migbox_view(peers.inbox[code]);
+  const unsigned c = mc->cursor[code] < (unsigned long)cap ? mc->cursor[code] : (unsigned)cap;
+  v.counts[parity * 16 + (8 - code)] = c;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(v.flags + (8 - code)), "l"(seq) : "memory");
+}
+// wait for every neighbour, append what arrived behind the survivors
+__global__ void k_mig_recv_append(WirePtrs P, void *inbox, unsigned area_mask, unsigned parity, long cap, long n,
+                                  const MigCounters *mc, unsigned long long seq, MigResult *res, const unsigned *overflow) {
+  __shared__ unsigned cnt[9];
+  const MigBoxView v = migbox_view(inbox);
+  if (threadIdx.x < 9) {
+    const int a = threadIdx.x;
+    unsigned c = 0;
+    if (area_mask & (1u << a)) {
+      unsigned long long f;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(v.flags + a) : "memory");
+        if (f < seq) __nanosleep(64);
+      } while (f < seq);
+      c = __ldcg(v.counts + parity * 16 + a);
+    }
+    cnt[a] = c;
+  }
+  __syncthreads();
+  const long new_n = n - (long)mc->nleave;
+  const int nw = wire_len(P.D);
+  long base = new_n, total = 0;
+  for (int a = 0; a < 9; ++a) total += cnt[a];
+  for (int a = 0; a < 9; ++a) {
+    const long c = cnt[a];
+    const double *src = v.recs + ((size_t)parity * 9 + a) * cap * nw;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < c * nw; t += (long)gridDim.x * blockDim.x) {
+      // one double per thread: coalesced reads of the inbox (written by a peer: bypass L1)
+      const long j = t / nw;
+      const int k = (int)(t - j * nw);
+      const double val = __ldcg(src + t);
+      const long i = base + j;
+      const int D = P.D;
+      if (k < D) P.x[k][i] = val;
+      else if (k < 2 * D) P.xold[k - D][i] = val;
+      else if (k < 2 * D + 3) P.v[k - 2 * D][i] = val;
+      else if (k < 2 * D + 6) P.vold[k - 2 * D - 3][i] = val;
+      else if (k == 2 * D + 6) P.w[i] = val;
+      else P.id[i] = (uint64_t)__double_as_longlong(val);
+    }
+    base += c;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    res->n_final = new_n + total;
+    res->n_arrived = total;
+    res->n_left = mc->nleave;
+    res->n_lost = mc->count[9];
+    res->overflow = *overflow;
+  }
 }
 
 static WirePtrs wire_ptrs(pgpu_species_s *s) {
@@ -343,6 +485,165 @@ int pgpu_species_append_d(pgpu_species_t s, long n_add, const double *buf_d) {
   }
   s->n += n_add;
   s->binned = false;
+  return 0;
+}
+
+// ---- pgpu_migrator_*: migration over peer memory ---------------------------------------------
+struct pgpu_migrator_s {
+  pgpu_species_t s = nullptr;
+  long cap = 0;                 // records per inbox area
+  int nw = 0;
+  void *inbox = nullptr;
+  size_t inbox_bytes = 0;
+  pgpu::MigPeers peers;
+  unsigned area_mask = 0;       // areas (arrival codes) that have a neighbour
+  unsigned long long seq = 0;
+  pgpu::MigResult *d_res = nullptr, *h_res = nullptr;
+  unsigned *d_overflow = nullptr;
+  long n_at_send = 0;
+  bool sent = false, received = false;
+  std::vector<void *> opened;
+};
+
+int pgpu_migrator_create(pgpu_species_t s, long capacity_records, pgpu_migrator_t *out) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!s || !out || capacity_records < 1) return PGPU_ERR_ARG;
+  pgpu_migrator_s *m = new pgpu_migrator_s;
+  m->s = s;
+  m->cap = capacity_records;
+  m->nw = 2 * s->grid->desc.D + 8;
+  m->inbox_bytes = MIGBOX_HEADER + (size_t)2 * 9 * m->cap * m->nw * sizeof(double);
+  for (int k = 0; k < 9; ++k) m->peers.inbox[k] = nullptr;
+  PGPU_CUDA(cudaMalloc(&m->inbox, m->inbox_bytes));
+  PGPU_CUDA(cudaMemset(m->inbox, 0, MIGBOX_HEADER));
+  PGPU_CUDA(cudaMalloc(&m->d_res, sizeof(MigResult)));
+  PGPU_CUDA(cudaMallocHost(&m->h_res, sizeof(MigResult)));
+  PGPU_CUDA(cudaMalloc(&m->d_overflow, sizeof(unsigned)));
+  PGPU_CUDA(cudaMemset(m->d_overflow, 0, sizeof(unsigned)));
+  *out = m;
+  return 0;
+}
+
+int pgpu_migrator_destroy(pgpu_migrator_t m) {
+  if (!m) return 0;
+  cudaStreamSynchronize(ctx().stream);
+  for (void *p : m->opened) cudaIpcCloseMemHandle(p);
+  cudaFree(m->inbox);
+  cudaFree(m->d_res);
+  cudaFreeHost(m->h_res);
+  cudaFree(m->d_overflow);
+  delete m;
+  return 0;
+}
+
+int pgpu_migrator_inbox(pgpu_migrator_t m, void **inbox_d, size_t *bytes) {
+  if (!m || !inbox_d) return PGPU_ERR_ARG;
+  *inbox_d = m->inbox;
+  if (bytes) *bytes = m->inbox_bytes;
+  return 0;
+}
+
+int pgpu_migrator_ipc_handle(pgpu_migrator_t m, void *handle64) {
+  if (!m || !handle64) return PGPU_ERR_ARG;
+  cudaIpcMemHandle_t hd;
+  PGPU_CUDA(cudaIpcGetMemHandle(&hd, m->inbox));
+  memcpy(handle64, &hd, 64);
+  return 0;
+}
+
+int pgpu_migrator_ipc_open(pgpu_migrator_t m, const void *handle64, void **inbox_d) {
+  if (!m || !handle64 || !inbox_d) return PGPU_ERR_ARG;
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  void *p = nullptr;
+  PGPU_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+  m->opened.push_back(p);
+  *inbox_d = p;
+  return 0;
+}
+
+int pgpu_migrator_connect(pgpu_migrator_t m, int code, void *peer_inbox_d) {
+  if (!m || code < 0 || code > 8 || code == 4 || !peer_inbox_d) return PGPU_ERR_ARG;
+  m->peers.inbox[code] = peer_inbox_d;
+  // the neighbour in direction `code` sends me its leavers of direction 8 - code, which arrive from `code`
+  m->area_mask |= 1u << code;
+  return 0;
+}
+
+int pgpu_migrate_send(pgpu_migrator_t m) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!m || m->sent) return PGPU_ERR_ARG;
+  Context &c = ctx();
+  pgpu_species_s *s = m->s;
+  // room for everything that can arrive, before anything is in flight (a reallocation synchronises)
+  if (grow_capacity(s, s->n + 8 * m->cap)) return PGPU_ERR_CUDA;
+  int rc = mark_leavers_launch(s, nullptr);
+  if (rc) return rc;
+  m->seq += 1;
+  m->n_at_send = s->n;
+  m->sent = true;
+  const long list_cap = 8 * m->cap + 65536;
+  if (s->mig_list_cap < (size_t)(2 * list_cap)) {
+    if (s->mig_list) cudaFree(s->mig_list);
+    s->mig_list_cap = (size_t)(2 * list_cap);
+    PGPU_CUDA(cudaMalloc(&s->mig_list, s->mig_list_cap * sizeof(int)));
+  }
+  if (!s->mig) {   // n == 0 took the early exit of the marking pass
+    PGPU_CUDA(cudaMalloc(&s->mig, sizeof(MigCounters) + 16 * sizeof(unsigned)));
+    PGPU_CUDA(cudaMemsetAsync(s->mig, 0, sizeof(MigCounters) + 16 * sizeof(unsigned), c.stream));
+  }
+  int *holes = s->mig_list, *movers = s->mig_list + list_cap;
+  const WirePtrs P = wire_ptrs(s);
+  const unsigned parity = (unsigned)(m->seq & 1);
+  MigCounters *mc = (MigCounters *)s->mig;
+  const unsigned grid = (unsigned)(c.sm_count * 4);
+  {
+    KTimer t("mig_p2p_send");
+    if (s->n) {
+      k_mig_pack_send<<<grid, 256, 0, c.stream>>>(P, s->perm, s->cell_key, mc, m->peers, parity, m->cap, s->n, holes,
+                                                 list_cap, m->d_overflow);
+      k_mig_list_movers<<<grid, 256, 0, c.stream>>>(s->cell_key, s->n, mc, movers, list_cap);
+      k_mig_fill_holes<<<grid, 256, 0, c.stream>>>(P, holes, movers, mc, list_cap);
+    }
+    k_mig_post<<<1, 32, 0, c.stream>>>(mc, m->peers, parity, m->cap, m->seq);
+  }
+  return 0;
+}
+
+int pgpu_migrate_recv(pgpu_migrator_t m) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!m || !m->sent || m->received) return PGPU_ERR_ARG;
+  Context &c = ctx();
+  pgpu_species_s *s = m->s;
+  {
+    KTimer t("mig_p2p_recv");
+    k_mig_recv_append<<<(unsigned)c.sm_count, 256, 0, c.stream>>>(wire_ptrs(s), m->inbox, m->area_mask,
+                                                                 (unsigned)(m->seq & 1), m->cap, m->n_at_send,
+                                                                 (const MigCounters *)s->mig, m->seq, m->d_res,
+                                                                 m->d_overflow);
+  }
+  PGPU_CUDA(cudaMemcpyAsync(m->h_res, m->d_res, sizeof(MigResult), cudaMemcpyDeviceToHost, c.stream));
+  m->received = true;
+  return 0;
+}
+
+int pgpu_migrate_finish(pgpu_migrator_t m, long *n_arrived, long *n_left, long *n_lost) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!m || !m->received) return PGPU_ERR_ARG;
+  PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
+  m->sent = m->received = false;
+  pgpu_species_s *s = m->s;
+  if (m->h_res->overflow) {
+    set_error("migration inbox overflow: more than %ld particles left for one neighbour (raise the capacity of "
+              "pgpu_migrator_create)", m->cap);
+    return PGPU_ERR_STATE;
+  }
+  s->n = (long)m->h_res->n_final;
+  s->binned = false;
+  s->mig_marked = false;
+  if (n_arrived) *n_arrived = (long)m->h_res->n_arrived;
+  if (n_left) *n_left = (long)m->h_res->n_left;
+  if (n_lost) *n_lost = (long)m->h_res->n_lost;
   return 0;
 }
 

@@ -493,3 +493,89 @@ def migrate_all(migrations):
         m.begin_payload([allc[r][k][:9] for r in range(m.layout.world)])
         n_in += m.end()
     return n_in
+
+
+class PeerMigration:
+    """Migration of one species of one box over peer memory (pgpu_migrator_*, csrc/pgpu_exchange.cu):
+    leavers are stored straight into the owning neighbours' inboxes by the sending kernel, counts stay on
+    the device, the receiving kernel appends; the only host synchronisation is finish().  The CUDA IPC
+    handles of the inboxes are exchanged once (connect_ipc) -- nothing else goes through a message layer."""
+
+    def __init__(self, layout, rank, species, capacity):
+        from . import capi
+        self.capi, self.layout, self.rank, self.sp = capi, layout, rank, species
+        self.h = capi.C.c_void_p()
+        capi.check(capi.load().pgpu_migrator_create(species.h, int(capacity), capi.C.byref(self.h)))
+        self.capacity = int(capacity)
+        self.lost = 0
+
+    def neighbours(self):
+        """{direction code: rank} of the boxes that can own a leaver of this one."""
+        out = {}
+        for code in range(9):
+            if code == 4:
+                continue
+            peer = self.layout.neighbor_code(self.rank, code)
+            if peer is not None and peer != self.rank:
+                out[code] = peer
+        return out
+
+    def inbox_pointer(self):
+        p, n = self.capi.C.c_void_p(), self.capi.C.c_size_t()
+        self.capi.check(self.capi.load().pgpu_migrator_inbox(self.h, self.capi.C.byref(p), self.capi.C.byref(n)))
+        return p.value
+
+    @staticmethod
+    def connect_local(migrations):
+        by_rank = {m.rank: m for m in migrations}
+        for m in migrations:
+            for code, peer in m.neighbours().items():
+                m.capi.check(m.capi.load().pgpu_migrator_connect(m.h, code, m.capi.C.c_void_p(by_rank[peer].inbox_pointer())))
+
+    def connect_ipc(self, comm):
+        import torch
+        capi, lib = self.capi, self.capi.load()
+        hbuf = (capi.C.c_ubyte * 64)()
+        capi.check(lib.pgpu_migrator_ipc_handle(self.h, hbuf))
+        rec = np.zeros(9, dtype=np.int64)
+        rec[:8] = np.frombuffer(bytes(hbuf), dtype=np.int64)
+        rec[8] = self.capacity
+        device = torch.device("cuda", torch.cuda.current_device()) if comm.dist.get_backend() == "nccl" else "cpu"
+        allr = [x.numpy() for x in comm.all_gather(torch.as_tensor(rec).to(device))]
+        opened = {}
+        for code, peer in self.neighbours().items():
+            assert int(allr[peer][8]) == self.capacity, "migration inboxes must have one capacity"
+            if peer not in opened:
+                hb = (capi.C.c_ubyte * 64).from_buffer_copy(allr[peer][:8].tobytes())
+                p = capi.C.c_void_p()
+                capi.check(lib.pgpu_migrator_ipc_open(self.h, hb, capi.C.byref(p)))
+                opened[peer] = p.value
+            capi.check(lib.pgpu_migrator_connect(self.h, code, capi.C.c_void_p(opened[peer])))
+
+    def send(self):
+        self.capi.check(self.capi.load().pgpu_migrate_send(self.h))
+
+    def recv(self):
+        self.capi.check(self.capi.load().pgpu_migrate_recv(self.h))
+
+    def finish(self):
+        C = self.capi.C
+        a, l, x = C.c_long(), C.c_long(), C.c_long()
+        self.capi.check(self.capi.load().pgpu_migrate_finish(self.h, C.byref(a), C.byref(l), C.byref(x)))
+        self.lost = x.value
+        return a.value
+
+    def destroy(self):
+        if self.h:
+            self.capi.check(self.capi.load().pgpu_migrator_destroy(self.h))
+            self.h = None
+
+
+def migrate_all_peer(migrations):
+    """All species of this box (or all boxes of this process): send everything, then receive everything,
+    then ONE wait."""
+    for m in migrations:
+        m.send()
+    for m in migrations:
+        m.recv()
+    return sum(m.finish() for m in migrations)

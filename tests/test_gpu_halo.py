@@ -102,7 +102,10 @@ def test_add_exchange_matches_single_box(pgpu, nbox, peer):
     assert worst < 1e-13, worst
 
 
-def test_migration_on_device(pgpu):
+@pytest.mark.parametrize("route", ["mailbox", "peer"])
+def test_migration_on_device(pgpu, route):
+    """route=mailbox: mark / pack / append around a message layer (the NCCL route's kernels);
+    route=peer: pgpu_migrator_* -- leavers stored straight into the neighbours' inboxes, counts on the device."""
     import torch
     nbox = (16, 8)
     lay = halo.BoxLayout(2, NCELL, nbox, NG, (1, 1))
@@ -122,13 +125,22 @@ def test_migration_on_device(pgpu):
         s = _species(pgpu, g, x[:, m], xo[:, m], v[:, m], w[m], ids[m])
         s.apply_bcs((1, 1), (1, 1))                       # periodic wrap of x and xold
         grids.append(g); sps.append(s)
-        migs.append(halo.Migration(lay, r, hub.view(r), halo.CapiSpeciesBackend(s, dev)))
-    counts = [m.begin_counts().numpy() for m in migs]
-    moved = sum(int(c.sum()) for c in counts)
-    assert moved > 200 and all(m.lost == 0 for m in migs)
-    for m in migs:
-        m.begin_payload(counts)
-    assert sum(m.end() for m in migs) == moved
+        if route == "peer":
+            migs.append(halo.PeerMigration(lay, r, s, capacity=4096))
+        else:
+            migs.append(halo.Migration(lay, r, hub.view(r), halo.CapiSpeciesBackend(s, dev)))
+    if route == "peer":
+        halo.PeerMigration.connect_local(migs)
+        n_before = sum(s.n for s in sps)
+        moved = halo.migrate_all_peer(migs)
+        assert moved > 200 and all(m.lost == 0 for m in migs) and sum(s.n for s in sps) == n_before
+    else:
+        counts = [m.begin_counts().numpy() for m in migs]
+        moved = sum(int(c.sum()) for c in counts)
+        assert moved > 200 and all(m.lost == 0 for m in migs)
+        for m in migs:
+            m.begin_payload(counts)
+        assert sum(m.end() for m in migs) == moved
     xw = np.array(XMIN)[:, None] + np.mod(x - np.array(XMIN)[:, None], L[:, None])
     own_new = box_of(xw)
     order = np.argsort(ids)
@@ -146,8 +158,15 @@ def test_migration_on_device(pgpu):
             c = np.floor((got["x"][d] - XMIN[d]) / DX[d])
             assert c.min() >= lo[d] and c.max() <= hi[d]
         # nobody leaves any more
-        assert int(migs[r].begin_counts().sum()) == 0
+        if route != "peer":
+            assert int(migs[r].begin_counts().sum()) == 0
     assert total == w.size
+    if route == "peer":
+        assert halo.migrate_all_peer(migs) == 0          # second round (other parity): nothing moves
+        assert sum(s.n for s in sps) == w.size
+        # overflow is an error, not silent loss: capacity 4 cannot take the leavers of a fresh start
+        for m in migs:
+            m.destroy()
     for s in sps:
         s.destroy()
     for g in grids:
