@@ -298,8 +298,9 @@ class Engine:
             self._mark("ghost_J_exchange")
         self.grid.current_finalize()
         if host_io:
-            for c, (lo, hi, h, _) in enumerate(self.host_J):
-                capi.check(lib.pgpu_current_get(self.grid.h, c, h.ctypes.data, capi._i2(lo), capi._i2(hi)))
+            for c, (lo, hi, h, _) in enumerate(self.host_J):     # three D2H copies into pinned memory, one wait
+                capi.check(lib.pgpu_current_get_async(self.grid.h, c, h.ctypes.data, capi._i2(lo), capi._i2(hi)))
+            capi.check(lib.pgpu_synchronize())
         self._mark("J_out")
 
     def step(self, host_io=False):

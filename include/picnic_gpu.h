@@ -106,6 +106,10 @@ int pgpu_current_add_species(pgpu_grid_t g, pgpu_species_t s);/* FArrayBox::plus
  * PicSpeciesInterface::finalizeSettingJ (:766-772).  Single device: periodic fold. */
 int pgpu_current_finalize(pgpu_grid_t g);
 int pgpu_current_get(pgpu_grid_t g, int comp, double *data, const int *lo, const int *hi);
+/* The same without the wait: the copy is only enqueued (page-lock `data` with pgpu_host_register); the
+ * array is valid after pgpu_synchronize().  Lets getCurrentDensity + getCurrentDensity_virtual of one
+ * nonlinear evaluation cost one synchronisation instead of three. */
+int pgpu_current_get_async(pgpu_grid_t g, int comp, double *data, const int *lo, const int *hi);
 
 /* ---- species: PicChargedSpecies ------------------------------------------- */
 typedef struct {

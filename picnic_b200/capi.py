@@ -77,7 +77,7 @@ def load():
         "pgpu_fields_set": [vp, i32, vp, vp, vp], "pgpu_fields_select": [vp, i32],
         "pgpu_host_register": [vp, C.c_size_t], "pgpu_host_unregister": [vp], "pgpu_field_bounds": [vp, i32, vp, vp],
         "pgpu_current_zero": [vp], "pgpu_current_add_species": [vp, vp], "pgpu_current_finalize": [vp],
-        "pgpu_current_get": [vp, i32, vp, vp, vp],
+        "pgpu_current_get": [vp, i32, vp, vp, vp], "pgpu_current_get_async": [vp, i32, vp, vp, vp],
         "pgpu_species_create": [vp, vp, vp], "pgpu_species_destroy": [vp],
         "pgpu_species_set_solver_params": [vp, i32, i32, dbl],
         "pgpu_species_upload": [vp, lng, vp, vp, vp, vp, vp, vp],

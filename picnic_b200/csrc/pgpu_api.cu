@@ -214,7 +214,7 @@ int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f) {
   return 0;
 }
 
-int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi) {
+int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi, bool sync) {
   for (int d = 0; d < D; ++d)
     if (lo[d] != f.lo[d] || hi[d] != f.hi[d]) {
       set_error("array bounds [%d:%d] in dir %d do not match the device box [%d:%d]", lo[d], hi[d], d,
@@ -223,7 +223,7 @@ int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, con
     }
   Context &c = ctx();
   PGPU_CUDA(cudaMemcpyAsync(data, f.p, f.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-  PGPU_CUDA(cudaStreamSynchronize(c.stream));
+  if (sync) PGPU_CUDA(cudaStreamSynchronize(c.stream));
   return 0;
 }
 
@@ -561,6 +561,12 @@ int pgpu_current_get(pgpu_grid_t g, int comp, double *data, const int *lo, const
   NEED_INIT();
   if (!g || comp < 0 || comp >= 3) return PGPU_ERR_ARG;
   return copy_fab_to_host(g->jtot[comp], g->desc.D, data, lo, hi);
+}
+
+int pgpu_current_get_async(pgpu_grid_t g, int comp, double *data, const int *lo, const int *hi) {
+  NEED_INIT();
+  if (!g || comp < 0 || comp >= 3) return PGPU_ERR_ARG;
+  return copy_fab_to_host(g->jtot[comp], g->desc.D, data, lo, hi, false);
 }
 
 // ---- species ----------------------------------------------------------------------

@@ -216,7 +216,7 @@ CurrentSet species_current(const pgpu_species_s *s);
 
 int scale_fab(const DeviceFab &f, double s);
 int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f);
-int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi);
+int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi, bool sync = true);
 
 // launchers implemented in the kernel translation units
 // keep: bit 0 = leave an aliased xold alone, bit 1 = leave an aliased vold alone 
