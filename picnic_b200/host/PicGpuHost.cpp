@@ -27,7 +27,7 @@ void finalize() { pgpu_finalize(); }
 // ---- Mesh -----------------------------------------------------------------------------------
 Mesh::Mesh(int D, const int *num_cells, const Real *Xmin, const Real *dX, int num_ghosts, const int *is_periodic,
            const int *box_lo, const int *box_hi, Real volume_scale)
-    : m_h(nullptr), m_D(D) {
+    : m_h(nullptr), m_D(D), m_gx(nullptr) {
   pgpu_grid_desc d;
   std::memset(&d, 0, sizeof(d));
   d.D = D;
@@ -63,7 +63,10 @@ void Mesh::zeroCurrentDensity() { check(pgpu_current_zero(m_h), "Mesh::zeroCurre
 void Mesh::addSpeciesCurrentDensity(const PicChargedSpecies &sp) {
   check(pgpu_current_add_species(m_h, sp.handle()), "Mesh::addSpeciesCurrentDensity");
 }
-void Mesh::finalizeSettingJ() { check(pgpu_current_finalize(m_h), "Mesh::finalizeSettingJ"); }
+void Mesh::finalizeSettingJ() {
+  if (m_gx) m_gx->addExchange();
+  check(pgpu_current_finalize(m_h), "Mesh::finalizeSettingJ");
+}
 void Mesh::getCurrentDensity(int comp, const FabRef &out) const {
   check(pgpu_current_get(m_h, comp, out.data, out.lo, out.hi), "Mesh::getCurrentDensity");
 }
@@ -71,6 +74,192 @@ void Mesh::setDebyeLength(const std::vector<PicChargedSpecies *> &species, Real 
   std::vector<pgpu_species_t> h;
   for (size_t i = 0; i < species.size(); ++i) h.push_back(species[i]->handle());
   check(pgpu_debye_length(m_h, h.data(), (int)h.size(), LDe), "Mesh::setDebyeLength");
+}
+
+// ---- BoxLayout / GhostExchange / ParticleMigration ---------------------------------------------
+BoxLayout::BoxLayout(int a_D, const int *a_num_cells, const int *a_box_cells, int a_num_ghosts, const int *a_is_periodic)
+    : D(a_D), num_ghosts(a_num_ghosts) {
+  for (int d = 0; d < 2; ++d) {
+    num_cells[d] = d < D ? a_num_cells[d] : 1;
+    box_cells[d] = d < D ? a_box_cells[d] : 1;
+    is_periodic[d] = d < D ? a_is_periodic[d] : 0;
+    if (num_cells[d] % box_cells[d]) fatal("BoxLayout: boxes must tile the domain");
+    nb[d] = num_cells[d] / box_cells[d];
+    if (d < D && nb[d] > 1 && box_cells[d] < 2 * num_ghosts + 1) fatal("BoxLayout: box narrower than its ghost overlap");
+  }
+}
+void BoxLayout::box(int rank, int *lo, int *hi) const {
+  const int c[2] = {rank % nb[0], rank / nb[0]};
+  for (int d = 0; d < D; ++d) {
+    lo[d] = c[d] * box_cells[d];
+    hi[d] = lo[d] + box_cells[d] - 1;
+  }
+}
+int BoxLayout::neighborCode(int rank, int code) const {
+  int c[2] = {rank % nb[0], rank / nb[0]};
+  const int off[2] = {code % 3 - 1, code / 3 - 1};
+  for (int d = 0; d < D; ++d) {
+    c[d] += off[d];
+    if (c[d] < 0 || c[d] >= nb[d]) {
+      if (!is_periodic[d]) return -1;
+      c[d] = (c[d] + nb[d]) % nb[d];
+    }
+  }
+  return c[0] + (D == 2 ? c[1] * nb[0] : 0);
+}
+int BoxLayout::neighbor(int rank, int dir, int side) const {
+  return neighborCode(rank, 4 + side * (dir == 0 ? 1 : 3));
+}
+void BoxLayout::overlap(int rank, const int *stag, int dir, int side, int *lo, int *hi) const {
+  int blo[2] = {0, 0}, bhi[2] = {0, 0};
+  box(rank, blo, bhi);
+  const int g = num_ghosts;
+  for (int d = 0; d < D; ++d) {
+    lo[d] = blo[d] - g;
+    hi[d] = bhi[d] + g + stag[d];
+  }
+  if (side > 0) {
+    lo[dir] = bhi[dir] + 1 - g;
+    hi[dir] = bhi[dir] + g + stag[dir];
+  } else {
+    lo[dir] = blo[dir] - g;
+    hi[dir] = blo[dir] - 1 + g + stag[dir];
+  }
+}
+
+GhostExchange::GhostExchange(Mesh &mesh, const BoxLayout &layout, int rank)
+    : m_mesh(mesh), m_layout(layout), m_rank(rank), m_h(nullptr) {
+  static const int STAG_J[2][3][2] = {{{0, 0}, {1, 0}, {1, 0}}, {{0, 1}, {1, 0}, {1, 1}}};   // Jx, Jy, Jz centring
+  const int D = layout.D;
+  std::vector<pgpu_halo_msg> recs;
+  int phase = 0;
+  for (int d = 0; d < D; ++d) {
+    if (layout.nb[d] == 1) continue;      // spans the domain: folded locally by pgpu_current_finalize
+    for (int side = -1; side <= 1; side += 2) {
+      const int peer = layout.neighbor(rank, d, side);
+      if (peer < 0) continue;
+      pgpu_halo_msg m;
+      std::memset(&m, 0, sizeof(m));
+      m.phase = phase;
+      m.recv_area = (int)recs.size();
+      for (int c = 0; c < 3; ++c) layout.overlap(rank, STAG_J[D - 1][c], d, side, m.lo[c], m.hi[c]);
+      recs.push_back(m);
+      Msg q = {phase, side, peer, 0};
+      m_msgs.push_back(q);
+    }
+    ++phase;
+  }
+  check(pgpu_halo_create(mesh.handle(), (int)recs.size(), recs.data(), &m_h), "GhostExchange::GhostExchange");
+  for (size_t i = 0; i < m_msgs.size(); ++i)
+    check(pgpu_halo_area_offset(m_h, (int)i, &m_msgs[i].offset, nullptr), "GhostExchange::GhostExchange");
+}
+GhostExchange::~GhostExchange() {
+  m_mesh.setGhostExchange(nullptr);
+  pgpu_halo_destroy(m_h);
+}
+int GhostExchange::numPhases() const { return pgpu_halo_phases(m_h); }
+void GhostExchange::begin() { check(pgpu_halo_begin(m_h), "GhostExchange::begin"); }
+void GhostExchange::send(int phase) { check(pgpu_halo_send(m_h, phase), "GhostExchange::send"); }
+void GhostExchange::recvAdd(int phase) { check(pgpu_halo_recv_add(m_h, phase), "GhostExchange::recvAdd"); }
+void GhostExchange::addExchange() {
+  begin();
+  for (int ph = 0; ph < numPhases(); ++ph) {
+    send(ph);
+    recvAdd(ph);
+  }
+}
+std::vector<long> GhostExchange::areaTable() const {
+  std::vector<long> t;
+  for (size_t i = 0; i < m_msgs.size(); ++i) {
+    t.push_back(m_msgs[i].phase);
+    t.push_back(m_msgs[i].side);
+    t.push_back((long)i);
+    t.push_back(m_msgs[i].offset);
+  }
+  return t;
+}
+void GhostExchange::connectWith(const std::vector<void *> &inbox_of_rank,
+                                const std::vector<std::vector<long> > &table_of_rank) {
+  for (size_t i = 0; i < m_msgs.size(); ++i) {
+    const Msg &q = m_msgs[i];
+    const std::vector<long> &t = table_of_rank[q.peer];
+    bool found = false;
+    for (size_t k = 0; k + 3 < t.size(); k += 4)
+      if (t[k] == q.phase && t[k + 1] == -q.side) {      // my +side message is the peer's -side arrival
+        check(pgpu_halo_connect(m_h, (int)i, inbox_of_rank[q.peer], (int)t[k + 2], t[k + 3]), "GhostExchange::connect");
+        found = true;
+      }
+    if (!found) fatal("GhostExchange::connect: the neighbour has no matching message");
+  }
+}
+void GhostExchange::connectLocal(const std::vector<GhostExchange *> &all) {
+  std::vector<void *> inbox(all.size(), nullptr);
+  std::vector<std::vector<long> > table(all.size());
+  for (size_t k = 0; k < all.size(); ++k) {
+    const int r = all[k]->m_rank;
+    check(pgpu_halo_inbox(all[k]->m_h, &inbox[r], nullptr), "GhostExchange::connectLocal");
+    table[r] = all[k]->areaTable();
+  }
+  for (size_t k = 0; k < all.size(); ++k) all[k]->connectWith(inbox, table);
+}
+void GhostExchange::connect(AllGatherFn allgather, void *user) {
+  // record per rank: 64-byte IPC handle + message count + (phase, side, area, offset) of up to 16 messages
+  const int world = m_layout.numBoxes();
+  const size_t NREC = 8 + 1 + 4 * 16;
+  std::vector<long> mine(NREC, 0), all(NREC * world, 0);
+  check(pgpu_halo_ipc_handle(m_h, mine.data()), "GhostExchange::connect");
+  const std::vector<long> t = areaTable();
+  mine[8] = (long)m_msgs.size();
+  for (size_t k = 0; k < t.size(); ++k) mine[9 + k] = t[k];
+  allgather(mine.data(), all.data(), NREC * sizeof(long), user);
+  std::vector<void *> inbox(world, nullptr);
+  std::vector<std::vector<long> > table(world);
+  for (size_t i = 0; i < m_msgs.size(); ++i) {
+    const int r = m_msgs[i].peer;
+    if (inbox[r]) continue;
+    if (r == m_rank) check(pgpu_halo_inbox(m_h, &inbox[r], nullptr), "GhostExchange::connect");
+    else check(pgpu_halo_ipc_open(m_h, &all[NREC * r], &inbox[r]), "GhostExchange::connect");
+    table[r].assign(all.begin() + NREC * r + 9, all.begin() + NREC * r + 9 + 4 * all[NREC * r + 8]);
+  }
+  connectWith(inbox, table);
+}
+
+ParticleMigration::ParticleMigration(PicChargedSpecies &species, const BoxLayout &layout, int rank,
+                                     long capacity_records)
+    : m_layout(layout), m_rank(rank), m_h(nullptr), m_lost(0) {
+  check(pgpu_migrator_create(species.handle(), capacity_records, &m_h), "ParticleMigration::ParticleMigration");
+}
+ParticleMigration::~ParticleMigration() { pgpu_migrator_destroy(m_h); }
+void ParticleMigration::connectLocal(const std::vector<ParticleMigration *> &all) {
+  std::vector<void *> inbox(all.size(), nullptr);
+  for (size_t k = 0; k < all.size(); ++k)
+    check(pgpu_migrator_inbox(all[k]->m_h, &inbox[all[k]->m_rank], nullptr), "ParticleMigration::connectLocal");
+  for (size_t k = 0; k < all.size(); ++k)
+    for (int code = 0; code < 9; ++code) {
+      const int peer = code == 4 ? -1 : all[k]->m_layout.neighborCode(all[k]->m_rank, code);
+      if (peer >= 0 && peer != all[k]->m_rank)
+        check(pgpu_migrator_connect(all[k]->m_h, code, inbox[peer]), "ParticleMigration::connectLocal");
+    }
+}
+void ParticleMigration::connect(AllGatherFn allgather, void *user) {
+  const int world = m_layout.numBoxes();
+  std::vector<long> mine(8, 0), all(8 * world, 0);
+  check(pgpu_migrator_ipc_handle(m_h, mine.data()), "ParticleMigration::connect");
+  allgather(mine.data(), all.data(), 8 * sizeof(long), user);
+  std::vector<void *> inbox(world, nullptr);
+  for (int code = 0; code < 9; ++code) {
+    const int peer = code == 4 ? -1 : m_layout.neighborCode(m_rank, code);
+    if (peer < 0 || peer == m_rank) continue;
+    if (!inbox[peer]) check(pgpu_migrator_ipc_open(m_h, &all[8 * peer], &inbox[peer]), "ParticleMigration::connect");
+    check(pgpu_migrator_connect(m_h, code, inbox[peer]), "ParticleMigration::connect");
+  }
+}
+void ParticleMigration::send() { check(pgpu_migrate_send(m_h), "ParticleMigration::send"); }
+void ParticleMigration::recv() { check(pgpu_migrate_recv(m_h), "ParticleMigration::recv"); }
+long ParticleMigration::finish() {
+  long a = 0, l = 0;
+  check(pgpu_migrate_finish(m_h, &a, &l, &m_lost), "ParticleMigration::finish");
+  return a;
 }
 
 // ---- PicChargedSpecies ------------------------------------------------------------------------

@@ -100,3 +100,12 @@ def test_example_driver_matches_oracle(driver, tmp_path):
                        sdef.mass, sdef.mass, 3.0, True)
     assert abs(dt_scatter * nu - 1.0) < 1e-9
     assert int(line.split("pairs=")[1]) == sum((c // 2 if c % 2 == 0 else (c - 3) // 2 + 3) for c in np.bincount(cid, minlength=256) if c >= 2)
+
+
+@pytest.mark.gpu
+def test_example_two_boxes(driver):
+    """GhostExchange + ParticleMigration of the C++ shim: 2 x 2 boxes in one process against the single box
+    (picnic_b200/host/example_two_boxes.cpp checks J everywhere, ownership and the id sum itself)."""
+    r = subprocess.run([os.path.join(HOST, "example_two_boxes")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "misplaced 0" in r.stdout and "ids_ok 1" in r.stdout
