@@ -803,6 +803,196 @@ __device__ __forceinline__ bool push_tab(const FastArgs &A, const TabWindow &Wn,
   return true;
 }
 
+// ---- phase 1, NP particles of ONE dual cell in lockstep ------------------------------------------
+// The Picard pass is a chain of dependent fp64 instructions (8 cycles each on B200) and a warp issues in
+// order: with 4 warps per scheduler the chain latency, not the pipe, sets the pace.  Two particles of the same
+// dual cell (neighbours in the cell-sorted order) share the cell's table record and their chains are
+// independent, so interleaving them doubles the instructions in flight per warp.
+struct TabCell {
+  unsigned key;
+  int i0[2];
+  const double *td, *tn;
+  int nrow;
+};
+__device__ __forceinline__ bool locate_cell(const FastArgs &A, const TabWindow &Wn, const double (&xo)[2], TabCell &C,
+                                            double (&dO)[2]) {
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double xr = __dsub_rn(xo[d], A.le[d]);
+    C.i0[d] = floor_div_fast(__dsub_rn(xr, A.hdx[d]), A.dx[d], A.rdx[d]);
+    dO[d] = fma(xr, A.rdx[d], -(double)(C.i0[d] + 1));
+    if (C.i0[d] < A.i_lo[d] || C.i0[d] > A.i_hi[d]) ok = false;
+  }
+  if (!ok) return false;
+  C.key = ((unsigned)(C.i0[1] + 32768) << 16) | (unsigned)(C.i0[0] + 32768);
+  const unsigned wi = (unsigned)(C.i0[0] - Wn.i), wj = (unsigned)(C.i0[1] - Wn.j);
+  if (wi < (unsigned)Wn.ncol && wj < (unsigned)Wn.nrow) {
+    C.td = Wn.dual + (wi * TD + wj * Wn.drow);
+    C.tn = Wn.node + (wi * TN + wj * Wn.nrow_stride);
+    C.nrow = Wn.nrow_stride;
+  } else {
+    const int cidx = (C.i0[0] - A.tlo[0]) + (C.i0[1] - A.tlo[1]) * A.tn0;
+    C.td = A.tdual + (size_t)cidx * TD;
+    C.tn = A.tnode + (size_t)cidx * TN;
+    C.nrow = A.tn0 * TN;
+  }
+  return true;
+}
+__device__ __forceinline__ void load_record(DualRec &R, const TabCell &C) {
+  if (C.key != R.key) {
+    R.key = C.key;
+    R.x01 = ld2(C.td), R.x23 = ld2(C.td + 2), R.x45 = ld2(C.td + 4);
+    R.y01 = ld2(C.td + 6), R.y23 = ld2(C.td + 8), R.y45 = ld2(C.td + 10);
+    R.z01 = ld2(C.td + 12), R.z23 = ld2(C.td + 14);
+  }
+}
+
+// Same arithmetic and the same per-particle control flow as push_tab (pass order of advanceParticlesIteratively,
+// PicChargedSpecies.cpp:1614-1716).  ok[p]: in = particle present, out = false if it has to be deferred.
+template <int NP>
+__device__ __forceinline__ void picard_same_cell(const FastArgs &A, const TabCell (&CC)[NP],
+                                                 const double (&xo)[NP][2], double (&xb)[NP][2],
+                                                 const double (&uo)[NP][3], double (&ub)[NP][3],
+                                                 const double (&dO)[NP][2], bool (&ok)[NP], unsigned &apply,
+                                                 unsigned &unconv) {
+  double pO[NP][2][2];
+  bool live[NP], done[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const double a = 0.5 - dO[p][d], b = 0.5 + dO[p][d];
+      pO[p][d][0] = a * a;
+      pO[p][d][1] = b * b;
+    }
+    live[p] = ok[p];
+    done[p] = false;
+  }
+  int iter = 0;
+  unsigned napply[NP], nunconv[NP];   // counted only for particles that are not deferred (the generic kernel redoes those)
+  double dxp0[NP][2], dB[NP][2], dN[NP][2];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    napply[p] = nunconv[p] = 0;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) dxp0[p][d] = dB[p][d] = dN[p][d] = 0.0;
+  }
+  while (true) {
+    bool any = false;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      if (!live[p]) continue;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        dxp0[p][d] = xb[p][d] - xo[p][d];
+        dB[p][d] = fma(dxp0[p][d], A.rdx[d], dO[p][d]);
+        dN[p][d] = fma(2.0, dB[p][d], -dO[p][d]);
+      }
+      if (!(hi_abs(dN[p][0]) < HI_HALF_BAND && hi_abs(dN[p][1]) < HI_HALF_BAND)) {
+        bool same = true;   // near (or past) a dual-cell face: the reference's own floor decides
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const double xn = fma(2.0, xb[p][d], -xo[p][d]);
+          const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
+          if (in != CC[p].i0[d]) same = false;
+        }
+        if (!same) {
+          ok[p] = false;
+          live[p] = false;
+        }
+      }
+      if (live[p] && done[p]) live[p] = false;   // the final iterate's orbit stays in the cell: finished
+      any = any || live[p];
+    }
+    if (!any) break;
+    double un[NP][3];
+    asm volatile("" ::: "memory");   // keep the table loads inside the pass (hoisted they cost 32 registers a particle)
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      // a finished particle is recomputed from its last offsets; the result is dropped
+      const TabCell &C = CC[p];
+      DualRec R;
+      R.x01 = ld2(C.td), R.x23 = ld2(C.td + 2), R.x45 = ld2(C.td + 4);
+      R.y01 = ld2(C.td + 6), R.y23 = ld2(C.td + 8), R.y45 = ld2(C.td + 10);
+      R.z01 = ld2(C.td + 12), R.z23 = ld2(C.td + 14);
+      const double del0 = dB[p][0] + 0.5, del1 = dB[p][1] + 0.5;
+      double E[3], B[3];
+      {
+        const double a0 = 0.5 - dN[p][0], b0 = 0.5 + dN[p][0], a1 = 0.5 - dN[p][1], b1 = 0.5 + dN[p][1];
+        const double Wx0 = fma(a0, a0, pO[p][0][0]), Wx2 = fma(b0, b0, pO[p][0][1]);
+        const double Wy0 = fma(a1, a1, pO[p][1][0]), Wy2 = fma(b1, b1, pO[p][1][1]);
+        E[0] = fma(Wy0, fma(del0, R.x23.y, R.x23.x), fma(Wy2, fma(del0, R.x45.y, R.x45.x), fma(del0, R.x01.y, R.x01.x)));
+        E[1] = fma(Wx0, fma(del1, R.y23.y, R.y23.x), fma(Wx2, fma(del1, R.y45.y, R.y45.x), fma(del1, R.y01.y, R.y01.x)));
+      }
+      {
+        const bool sx = del0 >= 0.5, sy = del1 >= 0.5;
+        const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
+        const int ox = sx ? TN : 0, oy = sy ? C.nrow : 0;
+        const double2 ez01 = ld2(C.tn + ox + oy), ez23 = ld2(C.tn + ox + oy + 2);
+        const double2 bx01 = ld2(C.tn + ox + 4), bx23 = ld2(C.tn + ox + 6);
+        const double2 by01 = ld2(C.tn + oy + 8), by23 = ld2(C.tn + oy + 10);
+        E[2] = fma(fy, fma(fx, ez23.y, ez23.x), fma(fx, ez01.y, ez01.x));
+        B[0] = fma(del1, fma(fx, bx23.y, bx23.x), fma(fx, bx01.y, bx01.x));
+        B[1] = fma(fy, fma(del0, by23.y, by23.x), fma(del0, by01.y, by01.x));
+        B[2] = fma(del1, fma(del0, R.z23.y, R.z23.x), fma(del0, R.z01.y, R.z01.x));
+      }
+      {
+        const double vm0 = fma(A.alpha, E[0], uo[p][0]), vm1 = fma(A.alpha, E[1], uo[p][1]),
+                     vm2 = fma(A.alpha, E[2], uo[p][2]);
+        const double b0 = A.alpha * B[0], b1 = A.alpha * B[1], b2 = A.alpha * B[2];
+        const double den = fma(b2, b2, fma(b1, b1, fma(b0, b0, 1.0)));
+        const double p0 = fma(-vm2, b1, fma(vm1, b2, vm0));
+        const double p1 = fma(-vm0, b2, fma(vm2, b0, vm1));
+        const double p2 = fma(-vm1, b0, fma(vm0, b1, vm2));
+        const double rden = rcp_ge1(den);
+        const double r0 = b0 * rden, r1 = b1 * rden, r2 = b2 * rden;
+        un[p][0] = fma(-p2, r1, fma(p1, r2, vm0));
+        un[p][1] = fma(-p0, r2, fma(p2, r0, vm1));
+        un[p][2] = fma(-p1, r0, fma(p0, r1, vm2));
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      if (!live[p]) continue;
+      napply[p] += 1;
+      ub[p][0] = un[p][0], ub[p][1] = un[p][1], ub[p][2] = un[p][2];
+      if (A.iter_max < 0) {  // advanceParticles (:1594-1612), part_order_swap == false
+        xb[p][0] = fma(un[p][0], A.hdt, xo[p][0]);
+        xb[p][1] = fma(un[p][1], A.hdt, xo[p][1]);
+        done[p] = true;
+        continue;
+      }
+      // stepNormTransfer (:658-733)
+      const double dxp_0 = un[p][0] * A.hdt, dxp_1 = un[p][1] * A.hdt;
+      const double e0 = fabs(dxp0[p][0] - dxp_0), e1 = fabs(dxp0[p][1] - dxp_1);
+      if (iter == 0) {
+        xb[p][0] = xo[p][0] + dxp_0;
+        xb[p][1] = xo[p][1] + dxp_1;
+        if (!(e0 >= A.tol[0]) && !(e1 >= A.tol[1])) done[p] = true;
+      } else {
+        if (e0 < A.tol[0] && e1 < A.tol[1]) {   // reverse pass: xbar unchanged, its orbit was checked above
+          live[p] = false;
+          continue;
+        }
+        xb[p][0] = xo[p][0] + dxp_0;
+        xb[p][1] = xo[p][1] + dxp_1;
+      }
+      if (!done[p] && iter >= A.iter_max) {
+        nunconv[p] = 1;
+        done[p] = true;
+      }
+    }
+    iter += 1;
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+    if (ok[p]) {
+      apply += napply[p];
+      unconv += nunconv[p];
+    }
+}
+
 // Phase 2: add the 21 node contributions of one pushed particle into acc (FMA form).
 __device__ __forceinline__ void deposit_tab(const FastArgs &A, const double (&dO)[2], const double (&dB)[2],
                                             const double (&ub)[3], double wp, double (&acc)[NSLOT]) {
@@ -881,7 +1071,7 @@ __global__ void k_tile_boxes(const FastArgs A, int ntiles, int4 *box) {
   box[t] = b;
 }
 
-template <bool DEP, int RSTEPS, int MINB>
+template <bool DEP, int RSTEPS, int MINB, bool PAIR>
 __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastArgs A, int ntiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *st = reinterpret_cast<double *>(smem_raw);                 // [NTAB][TILE]
@@ -1019,32 +1209,85 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
     unsigned defer_mask = 0;
     DualRec R;
     R.key = NOKEY;   // the window is restaged per tile, so the cached record does not outlive it
+    (void)R;
+    if (PAIR) {
 #pragma unroll 1
-    for (int qq = 0; qq < TP; ++qq) {
-      const int q = (qq + (lane >> 2)) & (TP - 1);
-      const int k = tid * TP + q;
-      unsigned key = NOKEY;
-      if (k < nvalid) {
-        const double xo[2] = {st[0 * TILE + k], st[1 * TILE + k]};
-        double xb[2] = {st[2 * TILE + k], st[3 * TILE + k]};
-        const double uo[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
-        double ub[3] = {0.0, 0.0, 0.0}, dO[2], dB[2];
-        if (push_tab(A, Wn, R, xo, xb, uo, ub, key, dO, dB, apply, unconv)) {
-          st[0 * TILE + k] = dO[0];
-          st[1 * TILE + k] = dO[1];
-          st[2 * TILE + k] = xb[0];
-          st[3 * TILE + k] = xb[1];
-          st[4 * TILE + k] = ub[0];
-          st[5 * TILE + k] = ub[1];
-          st[6 * TILE + k] = ub[2];
-        } else {
-          // deferred: xbar stays as stored (the generic kernel restarts from it); the ubar slot
-          // keeps u_old, which that kernel overwrites
-          key = NOKEY;
-          defer_mask |= 1u << q;
+      for (int h = 0; h < TP / 2; ++h) {
+        int kk[2];
+        bool present[2], located[2];
+        double xo[2][2], xb[2][2], uo[2][3], ub[2][3], dO[2][2];
+        TabCell C[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const int q = (2 * h + p + (lane >> 2)) & (TP - 1);
+          kk[p] = tid * TP + q;
+          present[p] = kk[p] < nvalid;
+          located[p] = false;
+          C[p].key = NOKEY;
+          xo[p][0] = xo[p][1] = xb[p][0] = xb[p][1] = uo[p][0] = uo[p][1] = uo[p][2] = 0.0;
+          dO[p][0] = dO[p][1] = 0.0;
+          if (present[p]) {
+            const int k = kk[p];
+            xo[p][0] = st[0 * TILE + k], xo[p][1] = st[1 * TILE + k];
+            xb[p][0] = st[2 * TILE + k], xb[p][1] = st[3 * TILE + k];
+            uo[p][0] = st[4 * TILE + k], uo[p][1] = st[5 * TILE + k], uo[p][2] = st[6 * TILE + k];
+            located[p] = locate_cell(A, Wn, xo[p], C[p], dO[p]);
+          }
+          ub[p][0] = ub[p][1] = ub[p][2] = 0.0;
+        }
+        bool ok[2] = {located[0], located[1]};
+        if (!located[0]) C[0] = C[1];      // a missing particle is masked (ok = false) and only needs valid pointers
+        if (!located[1]) C[1] = C[0];
+        if (located[0] || located[1]) picard_same_cell<2>(A, C, xo, xb, uo, ub, dO, ok, apply, unconv);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const int k = kk[p];
+          unsigned key = NOKEY;
+          if (present[p]) {
+            if (ok[p]) {
+              key = C[p].key;
+              st[0 * TILE + k] = dO[p][0];
+              st[1 * TILE + k] = dO[p][1];
+              st[2 * TILE + k] = xb[p][0];
+              st[3 * TILE + k] = xb[p][1];
+              st[4 * TILE + k] = ub[p][0];
+              st[5 * TILE + k] = ub[p][1];
+              st[6 * TILE + k] = ub[p][2];
+            } else {
+              defer_mask |= 1u << (k - tid * TP);
+            }
+          }
+          skey[k] = key;
         }
       }
-      skey[k] = key;
+    } else {
+  #pragma unroll 1
+      for (int qq = 0; qq < TP; ++qq) {
+        const int q = (qq + (lane >> 2)) & (TP - 1);
+        const int k = tid * TP + q;
+        unsigned key = NOKEY;
+        if (k < nvalid) {
+          const double xo[2] = {st[0 * TILE + k], st[1 * TILE + k]};
+          double xb[2] = {st[2 * TILE + k], st[3 * TILE + k]};
+          const double uo[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
+          double ub[3] = {0.0, 0.0, 0.0}, dO[2], dB[2];
+          if (push_tab(A, Wn, R, xo, xb, uo, ub, key, dO, dB, apply, unconv)) {
+            st[0 * TILE + k] = dO[0];
+            st[1 * TILE + k] = dO[1];
+            st[2 * TILE + k] = xb[0];
+            st[3 * TILE + k] = xb[1];
+            st[4 * TILE + k] = ub[0];
+            st[5 * TILE + k] = ub[1];
+            st[6 * TILE + k] = ub[2];
+          } else {
+            // deferred: xbar stays as stored (the generic kernel restarts from it); the ubar slot
+            // keeps u_old, which that kernel overwrites
+            key = NOKEY;
+            defer_mask |= 1u << q;
+          }
+        }
+        skey[k] = key;
+      }
     }
 
     if (tid == 0) CK(3);
@@ -1293,24 +1536,33 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
       k_tile_boxes<<<(unsigned)((ntiles + 127) / 128), 128, 0, c.stream>>>(A, ntiles, (int4 *)s->tile_box);
     }
     KTimer t(deposit ? "advance_cc1_fused" : "advance_cc1");
-#define PGPU_TAB_LAUNCH(DEPV, RS, MB)                                                                     \
+#define PGPU_TAB_LAUNCH(DEPV, RS, MB, PR)                                                                 \
   do {                                                                                                    \
-    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tab<DEPV, RS, MB>,                                    \
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tab<DEPV, RS, MB, PR>,                                \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM));        \
-    k_advance_cc1_2d_tab<DEPV, RS, MB><<<gridm, BLOCK, TAB_SMEM, c.stream>>>(A, ntiles);                  \
+    k_advance_cc1_2d_tab<DEPV, RS, MB, PR><<<gridm, BLOCK, TAB_SMEM, c.stream>>>(A, ntiles);              \
   } while (0)
     const int mb = c.cc1_minblocks == 5 ? 5 : (c.cc1_minblocks == 3 ? 3 : 4);
     const int gridm = std::min(ntiles, c.sm_count * mb * c.cc1_waves);
-    if (!deposit) {
-      if (mb == 4) PGPU_TAB_LAUNCH(false, 0, 4);
-      else PGPU_TAB_LAUNCH(false, 0, 5);
+    if (c.cc1_pair) {
+      // two particles of a dual cell in lockstep through the Picard loop (PGPU_CC1_PAIR=1)
+      if (!deposit) {
+        if (mb == 3) PGPU_TAB_LAUNCH(false, 0, 3, true);
+        else PGPU_TAB_LAUNCH(false, 0, 4, true);
+      } else {
+        if (mb == 3) PGPU_TAB_LAUNCH(true, 3, 3, true);
+        else PGPU_TAB_LAUNCH(true, 3, 4, true);
+      }
+    } else if (!deposit) {
+      if (mb == 4) PGPU_TAB_LAUNCH(false, 0, 4, false);
+      else PGPU_TAB_LAUNCH(false, 0, 5, false);
     } else if (c.cc1_rsteps <= 2) {
-      if (mb == 4) PGPU_TAB_LAUNCH(true, 2, 4);
-      else PGPU_TAB_LAUNCH(true, 2, 5);
+      if (mb == 4) PGPU_TAB_LAUNCH(true, 2, 4, false);
+      else PGPU_TAB_LAUNCH(true, 2, 5, false);
     } else {
-      if (mb == 4) PGPU_TAB_LAUNCH(true, 3, 4);
-      else if (mb == 3) PGPU_TAB_LAUNCH(true, 3, 3);
-      else PGPU_TAB_LAUNCH(true, 3, 5);
+      if (mb == 4) PGPU_TAB_LAUNCH(true, 3, 4, false);
+      else if (mb == 3) PGPU_TAB_LAUNCH(true, 3, 3, false);
+      else PGPU_TAB_LAUNCH(true, 3, 5, false);
     }
     if (xa)
       for (int d = 0; d < 2; ++d) std::swap(s->x[d], s->xold[d]);

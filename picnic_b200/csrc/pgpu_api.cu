@@ -368,6 +368,7 @@ int pgpu_init(int device) {
   if (const char *e = getenv("PGPU_CC1_TMA")) c.cc1_tma = atoi(e);
   if (const char *e = getenv("PGPU_CC1_MINB")) c.cc1_minblocks = atoi(e);
   if (const char *e = getenv("PGPU_CC1_PREFETCH")) c.cc1_prefetch = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_PAIR")) c.cc1_pair = atoi(e);
   if (const char *e = getenv("PGPU_CC1_RSTEPS")) c.cc1_rsteps = atoi(e);
   if (const char *e = getenv("PGPU_CC1_WAVES")) c.cc1_waves = atoi(e) > 0 ? atoi(e) : 1;
   return 0;
