@@ -127,6 +127,13 @@ typedef struct {
   int bc_check_hi[2];
   int motion;          /* m_motion */
   int forces;          /* m_forces */
+  /* the reference's compile-time switch RELATIVISTIC_PARTICLES as a per-species flag: Boris with the
+   * time-centred gamma (PicSpeciesUtils.cpp:55-78; higuera_cary = pic_species.N.higuera_cary), positions and
+   * the Picard step norm with getImplicitGamma (PicChargedSpecies.cpp:496-498,548-553,693-708), current deposit
+   * with w/gamma (MeshInterpI.H:72-91), setStableDt and globalMoments (:1890-1893, 4095-4098).  Such species
+   * take the generic kernels; the collision models stay Galilean (LorentzScatter: SURVEY 8f). */
+  int relativistic;
+  int higuera_cary;
 } pgpu_species_desc;
 
 int pgpu_species_create(pgpu_grid_t g, const pgpu_species_desc *desc, pgpu_species_t *out);

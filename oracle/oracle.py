@@ -145,6 +145,32 @@ def deposit_current(g, interp, x, xold, v, w, cnormDt, J):
     return lib().orc_deposit_current(C.byref(g), interp, n, _ptr(x), _ptr(xold), _ptr(v), _ptr(w), cnormDt, _fabs3(J))
 
 
+def set_relativistic(relativistic, higuera_cary=False):
+    """Switch the push routines to the reference's RELATIVISTIC_PARTICLES build (global, test library)."""
+    lib().orc_set_relativistic(int(relativistic), int(higuera_cary))
+
+
+def implicit_gamma(upold, upbar):
+    f = lib().orc_implicit_gamma
+    f.restype = C.c_double
+    f.argtypes = [C.c_void_p, C.c_void_p]
+    a, b = np.ascontiguousarray(upold, dtype=np.float64), np.ascontiguousarray(upbar, dtype=np.float64)
+    return f(_ptr(a), _ptr(b))
+
+
+def advance_positions_implicit_rel(D, x, xold, v, vold, cnormDt):
+    f = lib().orc_advance_positions_implicit_rel
+    f.argtypes = [C.c_int, C.c_long] + [C.c_void_p] * 4 + [C.c_double]
+    f(D, x.shape[1], _ptr(x), _ptr(xold), _ptr(v), _ptr(vold), cnormDt)
+
+
+def deposit_current_rel(g, interp, x, xold, v, vold, w, cnormDt, J, from_explicit=False):
+    f = lib().orc_deposit_current_rel
+    f.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 5 + [C.c_double, C.c_int, C.c_void_p]
+    return f(C.byref(g), interp, x.shape[1], _ptr(x), _ptr(xold), _ptr(v), _ptr(vold), _ptr(w), cnormDt,
+             int(from_explicit), _fabs3(J))
+
+
 def deposit_rho(g, interp, x, w, stag, rho):
     st = (C.c_int * 2)(*(list(stag) + [0])[:2])
     f = rho.c()

@@ -12,6 +12,7 @@
  * the same places).  Build with -O2 -ffp-contract=off.
  */
 #include <cmath>
+#include <vector>
 #include <cstdlib>
 
 #include "picnic_oracle.h"
@@ -703,6 +704,29 @@ extern "C" int orc_gather(const orc_geom *gp, int interp, long n, const double *
  * Dispatch: MeshInterp::depositCurrent (MeshInterpI.H:48-228), non-relativistic
  * planar build: wpog = wp, up0 = up.
  * ======================================================================== */
+/* MeshInterp::depositCurrent of the RELATIVISTIC_PARTICLES build (MeshInterpI.H:72-91): the particle weight
+ * is divided by gamma -- of the stored velocity (explicit solvers) or the time-centred one of getImplicitGamma. */
+extern "C" double orc_implicit_gamma(const double *upold, const double *upbar);
+extern "C" int orc_deposit_current(const orc_geom *gp, int interp, long n, const double *x, const double *xold,
+                                   const double *v, const double *w, double cnormDt, orc_fab *Jf);
+extern "C" int orc_deposit_current_rel(const orc_geom *gp, int interp, long n, const double *x, const double *xold,
+                                       const double *v, const double *vold, const double *w, double cnormDt,
+                                       int from_explicit_solver, orc_fab *Jf) {
+  std::vector<double> wpog(n);
+  for (long p = 0; p < n; ++p) {
+    double gammap = 1.0;
+    if (from_explicit_solver) {
+      gammap += v[p] * v[p] + v[n + p] * v[n + p] + v[2 * n + p] * v[2 * n + p];
+      gammap = std::sqrt(gammap);
+    } else {
+      const double uo[3] = {vold[p], vold[n + p], vold[2 * n + p]}, ub[3] = {v[p], v[n + p], v[2 * n + p]};
+      gammap = orc_implicit_gamma(uo, ub);
+    }
+    wpog[p] = w[p] / gammap;
+  }
+  return orc_deposit_current(gp, interp, n, x, xold, v, wpog.data(), cnormDt, Jf);
+}
+
 extern "C" int orc_deposit_current(const orc_geom *gp, int interp, long n,
                                    const double *x, const double *xold,
                                    const double *v, const double *w,

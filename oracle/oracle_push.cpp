@@ -6,7 +6,8 @@
  *   src/species/pic/charged/PicChargedSpecies.cpp        (position updates,
  *       stepNormTransfer, advanceParticles[Iteratively], binning, moments, BCs)
  *   src/species/pic/PicSpeciesInterface.cpp:1627-1721    (Debye length)
- * Non-relativistic build (RELATIVISTIC_PARTICLES undefined), planar push.
+ * Planar push.  Default = the non-relativistic build; orc_set_relativistic(1, higuera_cary) switches every
+ * routine here (and orc_deposit_current_rel) to the code the reference compiles with -DRELATIVISTIC_PARTICLES.
  */
 #include <algorithm>
 #include <cmath>
@@ -29,6 +30,26 @@ const double kHBAR = kH / kTWOPI;
 const double kEV_PER_JOULE = 1.0 / kQE;
 }  // namespace
 
+static int g_rel = 0, g_hc = 0;
+extern "C" void orc_set_relativistic(int relativistic, int higuera_cary) {
+  g_rel = relativistic;
+  g_hc = higuera_cary;
+}
+extern "C" int orc_get_relativistic(void) { return g_rel; }
+
+/* PicSpeciesUtils::getImplicitGamma (PicSpeciesUtils.H:43-52) */
+extern "C" double orc_implicit_gamma(const double *upold, const double *upbar) {
+  double upnew[3];
+  for (int n = 0; n < 3; ++n) upnew[n] = 2.0 * upbar[n] - upold[n];
+  const double gbsq_old = upold[0] * upold[0] + upold[1] * upold[1] + upold[2] * upold[2];
+  const double gbsq_new = upnew[0] * upnew[0] + upnew[1] * upnew[1] + upnew[2] * upnew[2];
+  return 0.5 * (std::sqrt(1.0 + gbsq_old) + std::sqrt(1.0 + gbsq_new));
+}
+static double implicit_gamma_soa(long n, long p, const double *vold, const double *v) {
+  const double uo[3] = {vold[p], vold[n + p], vold[2 * n + p]}, ub[3] = {v[p], v[n + p], v[2 * n + p]};
+  return orc_implicit_gamma(uo, ub);
+}
+
 /* PicSpeciesUtils::applyForces (PicSpeciesUtils.cpp:8-101), dirp = {0,1,2}. */
 extern "C" void orc_boris(long n, double *v, const double *vold, const double *Ep,
                           const double *Bp, double fnorm, double cnormDt,
@@ -38,9 +59,26 @@ extern "C" void orc_boris(long n, double *v, const double *vold, const double *E
     const double vm0 = vold[p] + alpha * Ep[p];
     const double vm1 = vold[n + p] + alpha * Ep[n + p];
     const double vm2 = vold[2 * n + p] + alpha * Ep[2 * n + p];
-    const double bp0 = alpha * Bp[p];
-    const double bp1 = alpha * Bp[n + p];
-    const double bp2 = alpha * Bp[2 * n + p];
+    double bp0 = alpha * Bp[p];
+    double bp1 = alpha * Bp[n + p];
+    double bp2 = alpha * Bp[2 * n + p];
+    if (g_rel) { /* time-centred relativistic factor (:55-78) */
+      double root;
+      if (g_hc) {
+        const double vmsq = vm0 * vm0 + vm1 * vm1 + vm2 * vm2;
+        const double vmdbp = vm0 * bp0 + vm1 * bp1 + vm2 * bp2;
+        const double bpsq = bp0 * bp0 + bp1 * bp1 + bp2 * bp2;
+        const double c1 = 1.0 + vmsq - bpsq;
+        const double c2 = bpsq + vmdbp * vmdbp;
+        root = 0.5 * (c1 + std::sqrt(c1 * c1 + 4.0 * c2));
+      } else {
+        root = 1.0 + vm0 * vm0 + vm1 * vm1 + vm2 * vm2;
+      }
+      const double gammap = std::sqrt(root);
+      bp0 /= gammap;
+      bp1 /= gammap;
+      bp2 /= gammap;
+    }
     const double denom = 1.0 + bp0 * bp0 + bp1 * bp1 + bp2 * bp2;
     const double vpr0 = vm0 + vm1 * bp2 - vm2 * bp1;
     const double vpr1 = vm1 + vm2 * bp0 - vm0 * bp2;
@@ -63,8 +101,14 @@ extern "C" void orc_boris(long n, double *v, const double *vold, const double *E
 extern "C" void orc_advance_positions_explicit(int D, long n, double *x,
                                                const double *xold,
                                                const double *v, double cnormDt) {
-  for (long p = 0; p < n; ++p)
+  for (long p = 0; p < n; ++p) {
+    if (g_rel) { /* :496-498; v holds the 3 components of gamma*beta */
+      const double gammap = std::sqrt(1.0 + v[p] * v[p] + v[n + p] * v[n + p] + v[2 * n + p] * v[2 * n + p]);
+      for (int d = 0; d < D; ++d) x[d * n + p] = xold[d * n + p] + v[d * n + p] / gammap * cnormDt;
+      continue;
+    }
     for (int d = 0; d < D; ++d) x[d * n + p] = xold[d * n + p] + v[d * n + p] * cnormDt;
+  }
 }
 
 /* PicChargedSpecies::advancePositionsImplicit (PicChargedSpecies.cpp:523-561) */
@@ -74,6 +118,15 @@ extern "C" void orc_advance_positions_implicit(int D, long n, double *x,
   const double cnormHalfDt = cnormDt * 0.5;
   for (long p = 0; p < n; ++p)
     for (int d = 0; d < D; ++d) x[d * n + p] = xold[d * n + p] + v[d * n + p] * cnormHalfDt;
+}
+/* the RELATIVISTIC_PARTICLES build of the same (:548-553) needs the old velocity as well */
+extern "C" void orc_advance_positions_implicit_rel(int D, long n, double *x, const double *xold, const double *v,
+                                                   const double *vold, double cnormDt) {
+  const double cnormHalfDt = cnormDt * 0.5;
+  for (long p = 0; p < n; ++p) {
+    const double gammap = implicit_gamma_soa(n, p, vold, v);
+    for (int d = 0; d < D; ++d) x[d * n + p] = xold[d * n + p] + v[d * n + p] / gammap * cnormHalfDt;
+  }
 }
 
 /* PicChargedSpecies::advancePositions_2ndHalf (PicChargedSpecies.cpp:1015-1025) */
@@ -100,24 +153,29 @@ extern "C" int orc_advance_particles(const orc_geom *g, int interpE, long n,
                                      const orc_fab *B, double fnorm,
                                      double cnormDt, int order_swap) {
   std::vector<double> Ep(3 * n), Bp(3 * n);
-  if (order_swap) orc_advance_positions_implicit(g->D, n, x, xold, v, cnormDt);
+  auto move = [&]() {
+    if (g_rel) orc_advance_positions_implicit_rel(g->D, n, x, xold, v, vold, cnormDt);
+    else orc_advance_positions_implicit(g->D, n, x, xold, v, cnormDt);
+  };
+  if (order_swap) move();
   const int rc = orc_gather(g, interpE, n, x, xold, E, B, Ep.data(), Bp.data());
   orc_boris(n, v, vold, Ep.data(), Bp.data(), fnorm, cnormDt, 1);
-  if (!order_swap) orc_advance_positions_implicit(g->D, n, x, xold, v, cnormDt);
+  if (!order_swap) move();
   return rc;
 }
 
 /* stepNormTransfer (PicChargedSpecies.cpp:658-733) for one particle.
  * Returns true if the particle is converged; updates xbar as the reference does. */
 static bool step_norm(const orc_geom *g, long n, long p, double *x,
-                      const double *xold, const double *v, double cnormDt,
+                      const double *xold, const double *v, const double *vold, double cnormDt,
                       double rtol, bool reverse) {
   const double cnormHalfDt = 0.5 * cnormDt;
   double dxp[2] = {0.0, 0.0};
   double rel_diff_max = 0.0;
+  const double gammap = g_rel ? implicit_gamma_soa(n, p, vold, v) : 1.0;   /* :693-698 */
   for (int d = 0; d < g->D; ++d) {
     const double dxp0 = x[d * n + p] - xold[d * n + p];
-    dxp[d] = v[d * n + p] * cnormHalfDt;
+    dxp[d] = g_rel ? v[d * n + p] / gammap * cnormHalfDt : v[d * n + p] * cnormHalfDt;
     const double rel_diff_dir = std::fabs(dxp0 - dxp[d]) / g->dx[d];
     rel_diff_max = std::max(rel_diff_max, rel_diff_dir);
   }
@@ -147,7 +205,7 @@ extern "C" int orc_advance_particles_iteratively(
   std::vector<long> temp;
   for (long p = 0; p < n; ++p) {
     if (its_out) its_out[p] = 1;
-    if (!step_norm(g, n, p, x, xold, v, cnormDt, rtol, false)) temp.push_back(p);
+    if (!step_norm(g, n, p, x, xold, v, vold, cnormDt, rtol, false)) temp.push_back(p);
   }
   int iter = 1;
   double xp[2], xpo[2], vo[3], vn[3], ep[3], bp[3];
@@ -167,7 +225,7 @@ extern "C" int orc_advance_particles_iteratively(
     }
     apply_its += (long)temp.size();
     for (long p : temp)
-      if (!step_norm(g, n, p, x, xold, v, cnormDt, rtol, true)) still.push_back(p);
+      if (!step_norm(g, n, p, x, xold, v, vold, cnormDt, rtol, true)) still.push_back(p);
     temp.swap(still);
     if (temp.empty()) break;
     if (iter >= iter_max) break;

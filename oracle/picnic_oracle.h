@@ -60,6 +60,18 @@ typedef struct {
 } orc_fab;
 
 /* ---- push ------------------------------------------------------------- */
+/* 0 (default): the default build of the reference; 1: the code it compiles with -DRELATIVISTIC_PARTICLES
+ * (Boris with the time-centred gamma, optionally Higuera-Cary; positions and the Picard step norm with
+ * getImplicitGamma; see also orc_deposit_current_rel).  Global switch of this test library. */
+void orc_set_relativistic(int relativistic, int higuera_cary);
+int orc_get_relativistic(void);
+/* PicSpeciesUtils::getImplicitGamma (PicSpeciesUtils.H:43-52) */
+double orc_implicit_gamma(const double *upold, const double *upbar);
+void orc_advance_positions_implicit_rel(int D, long n, double *x, const double *xold, const double *v,
+                                        const double *vold, double cnormDt);
+int orc_deposit_current_rel(const orc_geom *g, int interp, long n, const double *x, const double *xold,
+                            const double *v, const double *vold, const double *w, double cnormDt,
+                            int from_explicit_solver, orc_fab *J);
 void orc_boris(long n, double *v, const double *vold, const double *Ep,
                const double *Bp, double fnorm, double cnormDt, int byHalfDt);
 void orc_advance_positions_explicit(int D, long n, double *x, const double *xold,

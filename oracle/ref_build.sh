@@ -20,3 +20,12 @@ g++ $FLAGS $INC -shared -o "$HERE/_ref/libpicnic_ref.so" \
   "$SRC/particle_tools/JustinsParticle.cpp" \
   "$SRC/particle_tools/BinItem.cpp"
 echo "built $HERE/_ref/libpicnic_ref.so"
+# the same sources as the reference compiles them with -DRELATIVISTIC_PARTICLES (Boris with gamma / Higuera-Cary,
+# getImplicitGamma): pins the relativistic branch of the oracle
+g++ $FLAGS -DRELATIVISTIC_PARTICLES $INC -shared -o "$HERE/_ref/libpicnic_ref_rel.so" \
+  "$HERE/ref_driver.cpp" \
+  "$SRC/species/pic/PicSpeciesUtils.cpp" \
+  "$SRC/scattering/ScatteringUtils.cpp" \
+  "$SRC/particle_tools/JustinsParticle.cpp" \
+  "$SRC/particle_tools/BinItem.cpp"
+echo "built $HERE/_ref/libpicnic_ref_rel.so"

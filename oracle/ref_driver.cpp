@@ -8,6 +8,7 @@
 //   ref_scattering_cos  -> ScatteringUtils::getScatteringCos   (src/scattering/ScatteringUtils.H:12-18)
 //   ref_mod_energy_pair -> ScatteringUtils::modEnergyPairwise  (src/scattering/ScatteringUtils.H:113-205)
 //   ref_particle_wire   -> JustinsParticle::linearOut          (src/particle_tools/JustinsParticle.cpp:339-383)
+//   ref_implicit_gamma  -> PicSpeciesUtils::getImplicitGamma   (src/species/pic/PicSpeciesUtils.H:43-52; -DRELATIVISTIC_PARTICLES)
 // This file contains no reference source; it only calls it.
 #include <array>
 #include <cstring>
@@ -18,6 +19,20 @@
 extern "C" {
 
 int ref_spacedim(void) { return SpaceDim; }
+
+// the RELATIVISTIC_PARTICLES build: pusher variant of ref_boris, and PicSpeciesUtils::getImplicitGamma
+static int g_higuera_cary = 0;
+void ref_set_higuera_cary(int on) { g_higuera_cary = on; }
+#ifdef RELATIVISTIC_PARTICLES
+int ref_is_relativistic(void) { return 1; }
+double ref_implicit_gamma(const double *upold, const double *upbar) {
+  std::array<Real, 3> uo = {upold[0], upold[1], upold[2]}, un;
+  for (int n = 0; n < 3; ++n) un[n] = 2.0 * upbar[n] - upold[n];
+  return PicSpeciesUtils::getImplicitGamma(uo, un);
+}
+#else
+int ref_is_relativistic(void) { return 0; }
+#endif
 
 // v[c*n+p] (out), vold/Ep/Bp[c*n+p] (in): SoA, component-major like the oracle
 void ref_boris(long n, double *v, const double *vold, const double *Ep, const double *Bp, double fnorm,
@@ -31,7 +46,11 @@ void ref_boris(long n, double *v, const double *vold, const double *Ep, const do
     q.setMagneticField({Bp[p], Bp[n + p], Bp[2 * n + p]});
     lst.add(q);
   }
+#ifdef RELATIVISTIC_PARTICLES
+  PicSpeciesUtils::applyForces(lst, fnorm, cnormDt, g_higuera_cary != 0, byHalfDt != 0, false);
+#else
   PicSpeciesUtils::applyForces(lst, fnorm, cnormDt, byHalfDt != 0, false);
+#endif
   long p = 0;
   for (ListIterator<JustinsParticle> lit(lst); lit.ok(); ++lit, ++p) {
     const std::array<Real, 3> &u = lit().velocity();

@@ -34,7 +34,7 @@ class SpeciesDesc(C.Structure):
                 ("cvac_norm", C.c_double), ("interp_N", C.c_int), ("interp_J", C.c_int),
                 ("interp_E", C.c_int), ("rtol", C.c_double), ("iter_max", C.c_int),
                 ("order_swap", C.c_int), ("bc_check_lo", C.c_int * 2), ("bc_check_hi", C.c_int * 2),
-                ("motion", C.c_int), ("forces", C.c_int)]
+                ("motion", C.c_int), ("forces", C.c_int), ("relativistic", C.c_int), ("higuera_cary", C.c_int)]
 
 
 class CoulombParams(C.Structure):
@@ -221,7 +221,7 @@ class Grid:
 class Species:
     def __init__(self, grid, mass, charge, fnorm_const, cvac_norm, interp_N=TSC, interp_J=CC1, interp_E=CC1,
                  rtol=1e-12, iter_max=21, order_swap=0, bc_check_lo=(0, 0), bc_check_hi=(0, 0),
-                 motion=1, forces=1):
+                 motion=1, forces=1, relativistic=False, higuera_cary=False):
         d = SpeciesDesc()
         d.mass, d.charge, d.fnorm_const, d.cvac_norm = mass, charge, fnorm_const, cvac_norm
         d.interp_N, d.interp_J, d.interp_E = interp_N, interp_J, interp_E
@@ -230,6 +230,7 @@ class Species:
             d.bc_check_lo[k] = bc_check_lo[k] if k < len(bc_check_lo) else 0
             d.bc_check_hi[k] = bc_check_hi[k] if k < len(bc_check_hi) else 0
         d.motion, d.forces = int(motion), int(forces)
+        d.relativistic, d.higuera_cary = int(relativistic), int(higuera_cary)
         self.desc = d
         self.grid = grid
         self.D = grid.D

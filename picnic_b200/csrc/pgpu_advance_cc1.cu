@@ -1408,7 +1408,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
 int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit) {
   Context &c = ctx();
   const pgpu_grid_s *g = s->grid;
-  if (c.exact || g->desc.D != 2 || s->desc.interp_E != CC1) return 0;
+  if (c.exact || g->desc.D != 2 || s->desc.interp_E != CC1 || s->desc.relativistic) return 0;
   if (deposit && s->desc.interp_J != CC1) return 0;
   if (prm.iter_max < 0 && prm.order_swap) return 0;
   for (int d = 0; d < 2; ++d)

@@ -145,7 +145,23 @@ __global__ void k_stream(double *out, const double *in1, const double *in2, long
   out[i] = r;
 }
 
-__global__ void k_boris_stored(PartPtrs p, long n, double alpha, int byHalfDt, int exact) {
+// advancePositionsExplicit / advancePositionsImplicit of the RELATIVISTIC_PARTICLES build
+// (PicChargedSpecies.cpp:496-498, 548-553): xp = xpold + up/gammap*a, gammap of up (explicit) or getImplicitGamma
+__global__ void k_positions_rel(PartPtrs p, long n, int D, double a, int implicit_gamma) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double u[3] = {p.v[0][i], p.v[1][i], p.v[2][i]};
+  double gammap;
+  if (implicit_gamma) {
+    const double uo[3] = {p.vold[0][i], p.vold[1][i], p.vold[2][i]};
+    gammap = gamma_implicit<true>(uo, u);
+  } else {
+    gammap = gamma_explicit<true>(u);
+  }
+  for (int d = 0; d < D; ++d) p.x[d][i] = __dadd_rn(p.xold[d][i], __dmul_rn(__ddiv_rn(u[d], gammap), a));
+}
+
+__global__ void k_boris_stored(PartPtrs p, long n, double alpha, int byHalfDt, int exact, int rel, int hc) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double uo[3], E[3], B[3], u[3];
@@ -155,8 +171,8 @@ __global__ void k_boris_stored(PartPtrs p, long n, double alpha, int byHalfDt, i
     E[c] = p.Ep[c][i];
     B[c] = p.Bp[c][i];
   }
-  if (exact) boris<true>(uo, E, B, alpha, byHalfDt != 0, u);
-  else boris<false>(uo, E, B, alpha, byHalfDt != 0, u);
+  if (exact) boris<true>(uo, E, B, alpha, byHalfDt != 0, u, rel, hc);
+  else boris<false>(uo, E, B, alpha, byHalfDt != 0, u, rel, hc);
 #pragma unroll
   for (int c = 0; c < 3; ++c) p.v[c][i] = u[c];
 }
@@ -738,6 +754,13 @@ int pgpu_advance_positions_explicit(pgpu_species_t s, double full_dt, int half_s
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   const double cnormDt = s->desc.cvac_norm * full_dt;
   const double dt_factor = half_step ? 0.5 : 1.0;
+  if (s->desc.relativistic) {
+    if (s->n == 0) return 0;
+    KTimer t("advance_positions");
+    k_positions_rel<<<nb(s->n), 256, 0, ctx().stream>>>(s->ptrs(), s->n, s->grid->desc.D, cnormDt * dt_factor, 0);
+    s->binned = false;
+    return 0;
+  }
   for (int d = 0; d < s->grid->desc.D; ++d)
     stream_pass("advance_positions", s->x[d], s->v[d], s->xold[d], s->n, cnormDt * dt_factor, 0);
   s->binned = false;
@@ -750,6 +773,13 @@ int pgpu_advance_positions_implicit(pgpu_species_t s, double full_dt) {
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   const double cnormDt = s->desc.cvac_norm * full_dt;
   const double cnormHalfDt = cnormDt * 0.5;
+  if (s->desc.relativistic) {
+    if (s->n == 0) return 0;
+    KTimer t("advance_positions");
+    k_positions_rel<<<nb(s->n), 256, 0, ctx().stream>>>(s->ptrs(), s->n, s->grid->desc.D, cnormHalfDt, 1);
+    s->binned = false;
+    return 0;
+  }
   for (int d = 0; d < s->grid->desc.D; ++d)
     stream_pass("advance_positions", s->x[d], s->v[d], s->xold[d], s->n, cnormHalfDt, 0);
   s->binned = false;
@@ -830,7 +860,8 @@ int pgpu_advance_velocities(pgpu_species_t s, double full_dt, int half_step) {
   const double cnormDt = full_dt * s->desc.cvac_norm;
   const double alpha = s->desc.fnorm_const * cnormDt / 2.0;
   KTimer t("boris");
-  k_boris_stored<<<nb(s->n), 256, 0, ctx().stream>>>(s->ptrs(), s->n, alpha, half_step, ctx().exact ? 1 : 0);
+  k_boris_stored<<<nb(s->n), 256, 0, ctx().stream>>>(s->ptrs(), s->n, alpha, half_step, ctx().exact ? 1 : 0,
+                                                     s->desc.relativistic, s->desc.higuera_cary);
   return 0;
 }
 
@@ -844,6 +875,8 @@ static AdvanceParams make_params(pgpu_species_t s, double dt, bool iterative) {
   const GeoAny &g = s->grid->geo;
   p.volume = (g.D == 1) ? g.dx[0] : g.dx[0] * g.dx[1];
   p.rvolume = 1.0 / p.volume;
+  p.rel = s->desc.relativistic;
+  p.hc = s->desc.higuera_cary;
   return p;
 }
 
@@ -910,8 +943,9 @@ int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_
   return 0;
 }
 
-int pgpu_set_current_density(pgpu_species_t s, double dt, int /*from_explicit_solver*/) {
+int pgpu_set_current_density(pgpu_species_t s, double dt, int from_explicit_solver) {
   NEED_INIT();
+  s->dep_from_explicit = from_explicit_solver ? 1 : 0;
   for (int c = 0; c < 3; ++c)
     PGPU_CUDA(cudaMemsetAsync(s->J[c].p, 0, s->J[c].size() * sizeof(double), ctx().stream));
   int rc = launch_deposit_current(s, dt * s->desc.cvac_norm);

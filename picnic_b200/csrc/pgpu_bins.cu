@@ -310,12 +310,17 @@ __global__ void k_bc_symmetry(double *x, double *xold, double *v, double *vold, 
 }
 
 // block reduction helpers for the global reductions
-__global__ void k_max_dtinv(const double *v0, const double *v1, long n, int D, double dx0, double dx1,
-                            unsigned long long *out_bits) {
+__global__ void k_max_dtinv(const double *v0, const double *v1, const double *v2, long n, int D, double dx0,
+                            double dx1, int rel, unsigned long long *out_bits) {
   double mx = 0.0;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    mx = fmax(mx, __ddiv_rn(fabs(v0[i]), dx0));
-    if (D == 2) mx = fmax(mx, __ddiv_rn(fabs(v1[i]), dx1));
+    double gammap = 1.0;
+    if (rel) {   // setStableDt :1890-1895: |up/gammap| / dX
+      const double u[3] = {v0[i], v1[i], v2[i]};
+      gammap = gamma_sum_first<true>(u);
+    }
+    mx = fmax(mx, __ddiv_rn(fabs(__ddiv_rn(v0[i], gammap)), dx0));
+    if (D == 2) mx = fmax(mx, __ddiv_rn(fabs(__ddiv_rn(v1[i], gammap)), dx1));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -324,7 +329,7 @@ __global__ void k_max_dtinv(const double *v0, const double *v1, long n, int D, d
 }
 
 __global__ void k_global_moments(const double *w, const double *v0, const double *v1, const double *v2,
-                                 long n, double *out7) {
+                                 long n, double *out7, int rel) {
   double a[7] = {0, 0, 0, 0, 0, 0, 0};
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const double wp = w[i], u0 = v0[i], u1 = v1[i], u2 = v2[i];
@@ -332,9 +337,12 @@ __global__ void k_global_moments(const double *w, const double *v0, const double
     a[1] += wp * u0;
     a[2] += wp * u1;
     a[3] += wp * u2;
-    a[4] += wp * u0 * u0;
-    a[5] += wp * u1 * u1;
-    a[6] += wp * u2 * u2;
+    // relativistic build (:4095-4098): energy = sum wp*gbsq*2/(gammap+1), split over the components here
+    double ke = 1.0;
+    if (rel) ke = 2.0 / (sqrt(1.0 + (u0 * u0 + u1 * u1 + u2 * u2)) + 1.0);
+    a[4] += wp * u0 * u0 * ke;
+    a[5] += wp * u1 * u1 * ke;
+    a[6] += wp * u2 * u2 * ke;
   }
 #pragma unroll
   for (int q = 0; q < 7; ++q) {
@@ -679,8 +687,9 @@ int pgpu_stable_dt(pgpu_species_t s, double *dt_out) {
   Counters k;
   if (s->n > 0) {
     KTimer t("stable_dt");
-    k_max_dtinv<<<c.sm_count * 4, 256, 0, c.stream>>>(s->v[0], s->v[1], s->n, s->grid->desc.D, s->grid->geo.dx[0],
-                                                       s->grid->geo.dx[1], d_bits);
+    k_max_dtinv<<<c.sm_count * 4, 256, 0, c.stream>>>(s->v[0], s->v[1], s->v[2], s->n, s->grid->desc.D,
+                                                       s->grid->geo.dx[0], s->grid->geo.dx[1], s->desc.relativistic,
+                                                       d_bits);
   }
   PGPU_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c.stream));
   PGPU_CUDA(cudaMemsetAsync(&c.d_counters->maxbits, 0, sizeof(unsigned long long), c.stream));
@@ -701,7 +710,8 @@ int pgpu_global_moments(pgpu_species_t s, double *out) {
   PGPU_CUDA(cudaMemsetAsync(d_out, 0, 7 * sizeof(double), c.stream));
   if (s->n > 0) {
     KTimer t("global_moments");
-    k_global_moments<<<c.sm_count * 4, 256, 0, c.stream>>>(s->w, s->v[0], s->v[1], s->v[2], s->n, d_out);
+    k_global_moments<<<c.sm_count * 4, 256, 0, c.stream>>>(s->w, s->v[0], s->v[1], s->v[2], s->n, d_out,
+                                                            s->desc.relativistic);
   }
   PGPU_CUDA(cudaMemcpyAsync(out, d_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   PGPU_CUDA(cudaStreamSynchronize(c.stream));

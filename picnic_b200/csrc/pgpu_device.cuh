@@ -560,17 +560,60 @@ __device__ __forceinline__ bool deposit_visit(const Geo<D> &g, const double *xp,
   return ok;
 }
 
-// PicSpeciesUtils::applyForces (PicSpeciesUtils.cpp:8-101), planar, non-relativistic.
+// gamma of a proper velocity as advancePositionsExplicit writes it (PicChargedSpecies.cpp:497):
+// sqrt(1 + u0 u0 + u1 u1 + u2 u2), summed left to right
+template <bool X>
+__device__ __forceinline__ double gamma_explicit(const double *u) {
+  typedef M<X> m;
+  return sqrt(m::mad(u[2], u[2], m::mad(u[1], u[1], m::mad(u[0], u[0], 1.0))));
+}
+// ... and as depositCurrent / setStableDt write it (MeshInterpI.H:74-76): gammap = 1; gammap += (u0 u0 + u1 u1 + u2 u2)
+template <bool X>
+__device__ __forceinline__ double gamma_sum_first(const double *u) {
+  typedef M<X> m;
+  return sqrt(m::add(1.0, m::mad(u[2], u[2], m::mad(u[1], u[1], m::mul(u[0], u[0])))));
+}
+// PicSpeciesUtils::getImplicitGamma (PicSpeciesUtils.H:43-52) of upold and upnew = 2 upbar - upold
+template <bool X>
+__device__ __forceinline__ double gamma_implicit(const double *upold, const double *upbar) {
+  typedef M<X> m;
+  double un[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) un[c] = m::sub(m::mul(2.0, upbar[c]), upold[c]);
+  const double go = m::mad(upold[2], upold[2], m::mad(upold[1], upold[1], m::mul(upold[0], upold[0])));
+  const double gn = m::mad(un[2], un[2], m::mad(un[1], un[1], m::mul(un[0], un[0])));
+  return m::mul(0.5, m::add(sqrt(m::add(1.0, go)), sqrt(m::add(1.0, gn))));
+}
+
+// PicSpeciesUtils::applyForces (PicSpeciesUtils.cpp:8-101), planar; rel = the RELATIVISTIC_PARTICLES build
+// (time-centred gamma of Boris or, hc, of Higuera-Cary, :55-78).
 template <bool X>
 __device__ __forceinline__ void boris(const double *upold, const double *Ep, const double *Bp,
-                                      double alpha, bool byHalfDt, double *up) {
+                                      double alpha, bool byHalfDt, double *up, int rel = 0, int hc = 0) {
   typedef M<X> m;
   const double vm0 = m::mad(alpha, Ep[0], upold[0]);
   const double vm1 = m::mad(alpha, Ep[1], upold[1]);
   const double vm2 = m::mad(alpha, Ep[2], upold[2]);
-  const double bp0 = m::mul(alpha, Bp[0]);
-  const double bp1 = m::mul(alpha, Bp[1]);
-  const double bp2 = m::mul(alpha, Bp[2]);
+  double bp0 = m::mul(alpha, Bp[0]);
+  double bp1 = m::mul(alpha, Bp[1]);
+  double bp2 = m::mul(alpha, Bp[2]);
+  if (rel) {
+    double root;
+    if (hc) {
+      const double vmsq = m::mad(vm2, vm2, m::mad(vm1, vm1, m::mul(vm0, vm0)));
+      const double vmdbp = m::mad(vm2, bp2, m::mad(vm1, bp1, m::mul(vm0, bp0)));
+      const double bpsq = m::mad(bp2, bp2, m::mad(bp1, bp1, m::mul(bp0, bp0)));
+      const double c1 = m::sub(m::add(1.0, vmsq), bpsq);
+      const double c2 = m::mad(vmdbp, vmdbp, bpsq);
+      root = m::mul(0.5, m::add(c1, sqrt(m::mad(4.0, c2, m::mul(c1, c1)))));
+    } else {
+      root = m::mad(vm2, vm2, m::mad(vm1, vm1, m::mad(vm0, vm0, 1.0)));
+    }
+    const double gammap = sqrt(root);
+    bp0 = __ddiv_rn(bp0, gammap);
+    bp1 = __ddiv_rn(bp1, gammap);
+    bp2 = __ddiv_rn(bp2, gammap);
+  }
   // denom = 1 + bp0*bp0 + bp1*bp1 + bp2*bp2 (left to right)
   const double denom = m::mad(bp2, bp2, m::mad(bp1, bp1, m::mad(bp0, bp0, 1.0)));
   // vpr = vm + vm x bp

@@ -54,6 +54,7 @@ struct AdvanceParams {
   int order_swap;
   double volume;    // cell volume prod(dx) (deposit)
   double rvolume;   // 1/volume
+  int rel, hc;      // RELATIVISTIC_PARTICLES build of the push; Higuera-Cary gamma
 };
 
 struct Counters {          // device-resident, 64-bit
@@ -176,6 +177,7 @@ struct pgpu_species_s {
   // stale old arrays, then the array pointers are swapped); everybody else gets the copy from
   // materialize_old before touching either array
   bool xold_alias = false, vold_alias = false;
+  int dep_from_explicit = 0;   // setCurrentDensity(a_from_explicit_solver): which gamma divides the weight (relativistic)
   int *key_sorted = nullptr;        // [n] sorted (4*cell+quadrant) keys of the last bin
   double *spare[4] = {nullptr, nullptr, nullptr, nullptr};  // gather targets of the cell sort
   size_t sort_cap = 0;

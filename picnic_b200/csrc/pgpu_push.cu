@@ -91,7 +91,8 @@ k_gather(PartPtrs p, long n, Geo<D> g, FieldSet F, Counters *cnt) {
 // ---- setCurrentDensity: deposit only ------------------------------------------------
 template <int D, int IJ, bool X>
 __global__ void __launch_bounds__(256)
-k_deposit(PartPtrs p, long n, Geo<D> g, CurrentSet J, double volume, double rvolume, Counters *cnt) {
+k_deposit(PartPtrs p, long n, Geo<D> g, CurrentSet J, double volume, double rvolume, Counters *cnt, int rel,
+          int from_explicit) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned err = 0;
   if (i < n) {
@@ -101,7 +102,19 @@ k_deposit(PartPtrs p, long n, Geo<D> g, CurrentSet J, double volume, double rvol
       xp[d] = p.x[d][i];
       xo[d] = p.xold[d][i];
     }
-    const double rhop = X ? __ddiv_rn(p.w[i], volume) : p.w[i] * rvolume;
+    double wp = p.w[i];
+    if (rel) {   // wpog = wp / gammap (MeshInterpI.H:72-91)
+      const double u[3] = {p.v[0][i], p.v[1][i], p.v[2][i]};
+      double gammap;
+      if (from_explicit) {
+        gammap = gamma_sum_first<X>(u);
+      } else {
+        const double uo[3] = {p.vold[0][i], p.vold[1][i], p.vold[2][i]};
+        gammap = gamma_implicit<X>(uo, u);
+      }
+      wp = __ddiv_rn(wp, gammap);
+    }
+    const double rhop = X ? __ddiv_rn(wp, volume) : wp * rvolume;
     DepositOpGlobal<D, X> op(J);
 #pragma unroll
     for (int c = 0; c < 3; ++c) op.val[c] = M<X>::mul(p.v[c][i], rhop);
@@ -141,17 +154,30 @@ k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
     if (prm.iter_max < 0) {
       // advanceParticles (PicChargedSpecies.cpp:1594-1612)
       if (prm.order_swap) {
+        if (prm.rel) {   // advancePositionsImplicit of the relativistic build (:548-553)
+          const double us[3] = {p.v[0][i], p.v[1][i], p.v[2][i]};
+          const double gammap = gamma_implicit<X>(uo, us);
 #pragma unroll
-        for (int d = 0; d < D; ++d) xb[d] = m::mad(p.v[d][i], hdt, xo[d]);
+          for (int d = 0; d < D; ++d) xb[d] = m::add(xo[d], m::mul(__ddiv_rn(us[d], gammap), hdt));
+        } else {
+#pragma unroll
+          for (int d = 0; d < D; ++d) xb[d] = m::mad(p.v[d][i], hdt, xo[d]);
+        }
       }
       GatherOp<D, X> op(F);
       if (!gather_visit<D, IE, X>(g, xb, xo, op)) err |= ERRBIT_SEGMENTS;
       if (op.oob) err |= ERRBIT_BOUNDS;
-      boris<X>(uo, op.acc, op.acc + 3, prm.alpha, true, ub);
+      boris<X>(uo, op.acc, op.acc + 3, prm.alpha, true, ub, prm.rel, prm.hc);
       apply += 1;
       if (!prm.order_swap) {
+        if (prm.rel) {
+          const double gammap = gamma_implicit<X>(uo, ub);
 #pragma unroll
-        for (int d = 0; d < D; ++d) xb[d] = m::mad(ub[d], hdt, xo[d]);
+          for (int d = 0; d < D; ++d) xb[d] = m::add(xo[d], m::mul(__ddiv_rn(ub[d], gammap), hdt));
+        } else {
+#pragma unroll
+          for (int d = 0; d < D; ++d) xb[d] = m::mad(ub[d], hdt, xo[d]);
+        }
       }
     } else {
       // advanceParticlesIteratively (:1614-1716) with stepNormTransfer (:658-733)
@@ -167,14 +193,15 @@ k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
           err |= ERRBIT_BOUNDS;
           break;
         }
-        boris<X>(uo, op.acc, op.acc + 3, prm.alpha, true, ub);
+        boris<X>(uo, op.acc, op.acc + 3, prm.alpha, true, ub, prm.rel, prm.hc);
         apply += 1;
         double dxp[D];
         double rel_diff_max = 0.0;
+        const double gammap = prm.rel ? gamma_implicit<X>(uo, ub) : 1.0;   // stepNormTransfer :693-708
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           const double dxp0 = m::sub(xb[d], xo[d]);
-          dxp[d] = m::mul(ub[d], hdt);
+          dxp[d] = prm.rel ? m::mul(__ddiv_rn(ub[d], gammap), hdt) : m::mul(ub[d], hdt);
           const double rel = __ddiv_rn(fabs(m::sub(dxp0, dxp[d])), g.dx[d]);
           rel_diff_max = fmax(rel_diff_max, rel);
         }
@@ -204,7 +231,9 @@ k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
     for (int c = 0; c < 3; ++c) p.v[c][i] = ub[c];
 
     if (DEP && !(err & (ERRBIT_SEGMENTS | ERRBIT_BOUNDS))) {
-      const double rhop = X ? __ddiv_rn(p.w[i], prm.volume) : p.w[i] * prm.rvolume;
+      double wp = p.w[i];
+      if (prm.rel) wp = __ddiv_rn(wp, gamma_implicit<X>(uo, ub));   // MeshInterpI.H:78-89
+      const double rhop = X ? __ddiv_rn(wp, prm.volume) : wp * prm.rvolume;
       DepositOpGlobal<D, X> dop(J);
 #pragma unroll
       for (int c = 0; c < 3; ++c) dop.val[c] = m::mul(ub[c], rhop);
@@ -259,11 +288,13 @@ static int launch_deposit_t(pgpu_species_s *s) {
   const double volume = (D == 1) ? ga.dx[0] : ga.dx[0] * ga.dx[1];
   KTimer t("deposit_current");
   if (c.exact)
-    k_deposit<D, IJ, true><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, J, volume,
-                                                                      1.0 / volume, c.d_counters);
+    k_deposit<D, IJ, true><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, J, volume, 1.0 / volume,
+                                                                      c.d_counters, s->desc.relativistic,
+                                                                      s->dep_from_explicit);
   else
-    k_deposit<D, IJ, false><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, J, volume,
-                                                                       1.0 / volume, c.d_counters);
+    k_deposit<D, IJ, false><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, J, volume, 1.0 / volume,
+                                                                       c.d_counters, s->desc.relativistic,
+                                                                       s->dep_from_explicit);
   return 0;
 }
 

@@ -265,7 +265,8 @@ long ParticleMigration::finish() {
 // ---- PicChargedSpecies ------------------------------------------------------------------------
 PicChargedSpecies::PicChargedSpecies(Mesh &a_mesh, const std::string &a_name, Real a_mass, Real a_charge,
                                      Real a_fnorm_const, Real a_cvac_norm, InterpType a_interpRhoToGrid,
-                                     InterpType a_interpJToGrid, InterpType a_interpEToParts)
+                                     InterpType a_interpJToGrid, InterpType a_interpEToParts, bool a_relativistic,
+                                     bool a_higuera_cary)
     : m_mesh(a_mesh), m_name(a_name), m_h(nullptr), m_stable_dt(DBL_MAX), m_num_parts_its(0), m_num_apply_its(0),
       m_num_unconverged(0) {
   std::memset(&m_desc, 0, sizeof(m_desc));
@@ -281,6 +282,8 @@ PicChargedSpecies::PicChargedSpecies(Mesh &a_mesh, const std::string &a_name, Re
   m_desc.order_swap = 0;
   m_desc.motion = 1;
   m_desc.forces = 1;
+  m_desc.relativistic = a_relativistic ? 1 : 0;
+  m_desc.higuera_cary = a_higuera_cary ? 1 : 0;
   check(pgpu_species_create(m_mesh.handle(), &m_desc, &m_h), "PicChargedSpecies::PicChargedSpecies");
 }
 PicChargedSpecies::~PicChargedSpecies() { pgpu_species_destroy(m_h); }

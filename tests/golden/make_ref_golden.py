@@ -82,7 +82,47 @@ def run_reference(d):
     return out
 
 
+def run_reference_relativistic(seed=20261018, n=96):
+    """The reference compiled with -DRELATIVISTIC_PARTICLES (oracle/_ref/libpicnic_ref_rel.so): applyForces with the
+    Boris and the Higuera-Cary gamma, both byHalfDt, and PicSpeciesUtils::getImplicitGamma, on velocities up to
+    gamma*beta ~ 3."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libpicnic_ref_rel.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["bash", os.path.join(ROOT, "oracle", "ref_build.sh")])
+    lib = C.CDLL(so)
+    dbl = C.c_double
+    lib.ref_boris.argtypes = [C.c_long] + [C.c_void_p] * 4 + [dbl, dbl, C.c_int]
+    lib.ref_implicit_gamma.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ref_implicit_gamma.restype = dbl
+    assert lib.ref_is_relativistic() == 1
+    rng = np.random.default_rng(seed)
+    d = {"vold": rng.standard_normal((3, n)) * 1.2, "Ep": rng.standard_normal((3, n)) * 3.0,
+         "Bp": rng.standard_normal((3, n)) * 2.0, "fnorm": -0.731, "cnormDt": 0.213,
+         "ubar": rng.standard_normal((3, n)) * 1.2}
+    d["Bp"][:, :4] = 0.0
+    d["vold"][:, 4:8] *= 1e-3                       # non-relativistic corner
+    p = lambda a: a.ctypes.data
+    out = {}
+    for hc in (0, 1):
+        lib.ref_set_higuera_cary(hc)
+        for half in (0, 1):
+            v = np.zeros((3, n))
+            lib.ref_boris(n, p(v), p(np.ascontiguousarray(d["vold"])), p(np.ascontiguousarray(d["Ep"])),
+                          p(np.ascontiguousarray(d["Bp"])), d["fnorm"], d["cnormDt"], half)
+            out["boris_hc%d_half%d" % (hc, half)] = v
+    g = np.zeros(n)
+    for i in range(n):
+        uo, ub = np.ascontiguousarray(d["vold"][:, i]), np.ascontiguousarray(d["ubar"][:, i])   # keep them alive
+        g[i] = lib.ref_implicit_gamma(p(uo), p(ub))
+    out["implicit_gamma"] = g
+    return d, out
+
+
 if __name__ == "__main__":
+    dr, outr = run_reference_relativistic()
+    np.savez(os.path.join(HERE, "ref_pins_rel.npz"), **{"in_" + k: np.asarray(v) for k, v in dr.items()},
+             **{"out_" + k: v for k, v in outr.items()})
+    print("wrote ref_pins_rel.npz:", {k: v.shape for k, v in outr.items()})
     d = inputs()
     out = run_reference(d)
     np.savez(os.path.join(HERE, "ref_pins.npz"), **{"in_" + k: np.asarray(v) for k, v in d.items()},

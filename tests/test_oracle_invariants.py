@@ -208,3 +208,30 @@ def test_ta_self_box_conserves_and_counts_pairs():
     assert npairs == expect
     assert np.max(np.abs(v.sum(axis=1) - p0)) < 1e-15
     assert abs((v ** 2).sum() - e0) / e0 < 1e-13
+
+
+@pytest.mark.parametrize("hc", [False, True])
+def test_relativistic_boris_invariants(hc):
+    """RELATIVISTIC_PARTICLES build of applyForces: with E = 0 the half-step rotation does no work
+    (|u_new| = |u_old| for u_new = 2 ubar - u_old), for the Boris and the Higuera-Cary gamma; for
+    |u| << 1 it reduces to the default build; getImplicitGamma -> sqrt(1 + u^2) for u_new = u_old."""
+    rng = np.random.default_rng(77)
+    n = 500
+    vold = rng.standard_normal((3, n)) * 1.5
+    Bp = rng.standard_normal((3, n)) * 3.0
+    Ep = np.zeros((3, n))
+    orc.set_relativistic(True, hc)
+    try:
+        v = orc.boris(np.zeros((3, n)), vold, Ep, Bp, -0.9, 0.4, False)
+        assert np.max(np.abs((v ** 2).sum(0) - (vold ** 2).sum(0)) / (vold ** 2).sum(0)) < 5e-15
+        small = vold * 1e-6
+        Es = rng.standard_normal((3, n)) * 1e-6
+        a = orc.boris(np.zeros((3, n)), small, Es, Bp, -0.9, 0.4, True)
+        orc.set_relativistic(False)
+        b = orc.boris(np.zeros((3, n)), small, Es, Bp, -0.9, 0.4, True)
+        assert np.max(np.abs(a - b)) < 1e-11 * np.max(np.abs(b))
+        for i in range(5):
+            g = orc.implicit_gamma(vold[:, i], vold[:, i])
+            assert abs(g - np.sqrt(1.0 + (vold[:, i] ** 2).sum())) < 1e-15 * g
+    finally:
+        orc.set_relativistic(False)

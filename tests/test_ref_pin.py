@@ -104,3 +104,42 @@ def test_gpu_delta_u_against_reference_vectors(pgpu):
     got = pgpu.scatter_delta_u(GOLD["in_u"], GOLD["in_costh"], GOLD["in_sinth"], GOLD["in_cosphi"], GOLD["in_sinphi"])
     want = GOLD["out_delta_u"].T
     assert np.max(np.abs(got - want)) <= 4e-15 * np.max(np.abs(GOLD["in_u"]))
+
+
+# ---- the RELATIVISTIC_PARTICLES build -------------------------------------------------------------
+GOLD_REL = np.load(os.path.join(ROOT, "tests", "golden", "ref_pins_rel.npz"))
+
+
+@pytest.mark.parametrize("hc", [0, 1])
+@pytest.mark.parametrize("half", [0, 1])
+def test_oracle_relativistic_boris_bit_equals_reference(hc, half):
+    """PicSpeciesUtils::applyForces compiled with -DRELATIVISTIC_PARTICLES (Boris gamma and Higuera-Cary)."""
+    n = GOLD_REL["in_vold"].shape[1]
+    v = np.zeros((3, n))
+    orc.set_relativistic(True, bool(hc))
+    try:
+        orc.lib().orc_boris(n, orc._ptr(v), orc._ptr(C(GOLD_REL["in_vold"])), orc._ptr(C(GOLD_REL["in_Ep"])),
+                            orc._ptr(C(GOLD_REL["in_Bp"])), float(GOLD_REL["in_fnorm"]), float(GOLD_REL["in_cnormDt"]),
+                            half)
+    finally:
+        orc.set_relativistic(False)
+    assert np.array_equal(v, GOLD_REL["out_boris_hc%d_half%d" % (hc, half)])
+    assert not np.array_equal(v, GOLD_REL["out_boris_hc%d_half%d" % (1 - hc, half)])   # the two pushers differ
+
+
+def test_oracle_implicit_gamma_bit_equals_reference():
+    n = GOLD_REL["in_vold"].shape[1]
+    got = np.array([orc.implicit_gamma(GOLD_REL["in_vold"][:, i], GOLD_REL["in_ubar"][:, i]) for i in range(n)])
+    assert np.array_equal(got, GOLD_REL["out_implicit_gamma"])
+
+
+def test_relativistic_golden_regenerates_from_reference():
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("no reference checkout on this box")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(ROOT, "tests", "golden", "make_ref_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    _, out = mk.run_reference_relativistic()
+    for k, v in out.items():
+        assert np.array_equal(v, GOLD_REL["out_" + k]), k
