@@ -296,6 +296,14 @@ int pgpu_ta_delta_u(long n, const double *vp1, const double *den1, const double 
                     const double *gauss, const double *u_theta, const double *u_phi,
                     double *dU);
 
+/* TakizukaAbe::LorentzScatter (:580-659) for explicit random numbers (test hook): the collision that
+ * pgpu_collide_ta applies when a species is relativistic (pgpu_species_desc.relativistic), through the
+ * centre-of-momentum frame.  up1/up2/out1/out2 are [3n] component-major; gauss is used where s12 < 2. */
+int pgpu_ta_lorentz_scatter(long n, const double *up1, const double *up2, double mass1, double mass2,
+                            const double *den2, double dt_sec, double b90_fact, double Clog,
+                            const double *gauss, const double *u_theta, const double *u_phi,
+                            double *out1, double *out2);
+
 /* Coulomb::applyScattering, PROBABILISTIC weight method (Coulomb.cpp:358-592, 919-1180): weighted
  * particles, lighter-weight particle always scatters, heavier with probability wmin/wmax; pairing
  * O(N) or all pairs (NxN / cells below NxN_Nthresh); sigma limited by the atomic spacing; b_max =

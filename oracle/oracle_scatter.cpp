@@ -101,12 +101,112 @@ extern "C" void orc_ta_delta_u(const double *vp1, double den1, const double *vp2
   orc_scatter_delta_u(ux, uy, uz, costh, sinth, cos(phi), sin(phi), dU);
 }
 
+/* ScatteringUtils::rotateVelocity (ScatteringUtils.H:49-75) */
+extern "C" void orc_rotate_velocity(double *a_u, double costh, double sinth, double cosphi, double sinphi) {
+  const double ux = a_u[0], uy = a_u[1], uz = a_u[2];
+  const double u = sqrt(ux * ux + uy * uy + uz * uz);
+  const double uperp = sqrt(ux * ux + uy * uy);
+  if (uperp == 0.0) {
+    a_u[0] = u * sinth * cosphi;
+    a_u[1] = u * sinth * sinphi;
+    a_u[2] = u * costh;
+  } else {
+    a_u[0] = ux * uz / uperp * sinth * cosphi - uy * u / uperp * sinth * sinphi + ux * costh;
+    a_u[1] = uy * uz / uperp * sinth * cosphi + ux * u / uperp * sinth * sinphi + uy * costh;
+    a_u[2] = -uperp * sinth * cosphi + uz * costh;
+  }
+}
+
+/* m_b90_fact of the RELATIVISTIC_PARTICLES build (TakizukaAbe.cpp:45-46, TakizukaAbe.H:27-28): no 1/mu, and
+ * twice the conversion factor */
+extern "C" double orc_ta_b90_fact_rel(double charge1, double charge2) {
+  const double b90_codeToPhys = kQE * kQE / (2.0 * kPI * kEP0 * kME);   /* TakizukaAbe.H:27-28: 2 pi, not 4 pi */
+  const double cvacSq = kCVAC * kCVAC;
+  const int q1 = (int)charge1, q2 = (int)charge2;
+  return abs(q1 * q2) / cvacSq * b90_codeToPhys;
+}
+
+/* TakizukaAbe::LorentzScatter (TakizukaAbe.cpp:580-659) with the three random draws made explicit
+ * (gauss is used if s12 < 2, u_theta otherwise).  long double intermediates as in the reference.
+ * Returns 1 if the small-angle (gaussian) branch was taken. */
+extern "C" int orc_ta_lorentz_scatter(double *a_up1, double *a_up2, double mass1, double mass2, double a_den2,
+                                      double a_dt_sec, double b90_fact, double Clog, double gauss, double u_theta,
+                                      double u_phi) {
+  const long double a_mass1 = mass1, a_mass2 = mass2;
+  long double gamma1, gamma2, Etot, gammacm, gamma1st, gamma2st;
+  long double vcmdotup, vrelst, s12, muRst, upst_fact, upstsq, denom;
+  double vcm[3], upst[3];
+  gamma1 = sqrt(1.0 + a_up1[0] * a_up1[0] + a_up1[1] * a_up1[1] + a_up1[2] * a_up1[2]);
+  gamma2 = sqrt(1.0 + a_up2[0] * a_up2[0] + a_up2[1] * a_up2[1] + a_up2[2] * a_up2[2]);
+  Etot = gamma1 * a_mass1 + gamma2 * a_mass2;
+  for (int n = 0; n < 3; n++) vcm[n] = (a_mass1 * a_up1[n] + a_mass2 * a_up2[n]) / Etot;
+  gammacm = 1.0 / sqrt(1.0 - vcm[0] * vcm[0] - vcm[1] * vcm[1] - vcm[2] * vcm[2]);
+  vcmdotup = vcm[0] * a_up2[0] + vcm[1] * a_up2[1] + vcm[2] * a_up2[2];
+  gamma2st = gammacm * (gamma2 - vcmdotup);
+  vcmdotup = vcm[0] * a_up1[0] + vcm[1] * a_up1[1] + vcm[2] * a_up1[2];
+  gamma1st = gammacm * (gamma1 - vcmdotup);
+  upst_fact = (gammacm / (1.0 + gammacm) * vcmdotup - gamma1) * gammacm;
+  for (int n = 0; n < 3; n++) upst[n] = a_up1[n] + upst_fact * vcm[n];
+  muRst = gamma1st * a_mass1 * gamma2st * a_mass2 / (a_mass2 * gamma2st + a_mass1 * gamma1st);
+  upstsq = upst[0] * upst[0] + upst[1] * upst[1] + upst[2] * upst[2];
+  denom = 1.0 + upstsq * a_mass1 / a_mass2 / gamma1st / gamma2st;
+  vrelst = sqrt(upstsq) * a_mass1 / muRst / denom;
+  s12 = kPI * b90_fact * b90_fact * a_den2 * Clog * vrelst * kCVAC * a_dt_sec;
+  s12 *= gamma1st * gamma2st / gamma1 / gamma2;
+  s12 /= pow(muRst * vrelst * vrelst, 2);
+  double costh, sinth;
+  int small = 0;
+  if (s12 < 2.0) {
+    const double delta = sqrt(s12 / 2.0) * gauss;
+    const double deltasq = delta * delta;
+    sinth = 2.0 * delta / (1.0 + deltasq);
+    costh = 1.0 - 2.0 * deltasq / (1.0 + deltasq);
+    small = 1;
+  } else {
+    const double theta = kPI * u_theta;
+    costh = cos(theta);
+    sinth = sin(theta);
+  }
+  const double phi = kTWOPI * u_phi;
+  orc_rotate_velocity(upst, costh, sinth, cos(phi), sin(phi));
+  vcmdotup = vcm[0] * upst[0] + vcm[1] * upst[1] + vcm[2] * upst[2];
+  upst_fact = (gammacm / (1.0 + gammacm) * vcmdotup + gamma1st) * gammacm;
+  for (int n = 0; n < 3; n++) a_up1[n] = upst[n] + upst_fact * vcm[n];
+  for (int n = 0; n < 3; n++) upst[n] *= -a_mass1 / a_mass2;
+  vcmdotup *= -a_mass1 / a_mass2;
+  upst_fact = (gammacm / (1.0 + gammacm) * vcmdotup + gamma2st) * gammacm;
+  for (int n = 0; n < 3; n++) a_up2[n] = upst[n] + upst_fact * vcm[n];
+  return small;
+}
+
+extern "C" int orc_get_relativistic(void);
+
 namespace {
 /* draws exactly what TakizukaAbe::computeDeltaU draws, in its order: randn only
  * in the small-angle branch, rand for theta only in the other, then rand for phi */
 void ta_pair(double *a, double *b, double den1, double den2, double b90_fact,
              double Clog, double dt_sec, long double mu, long double m1,
-             long double m2) {
+             long double m2, bool inter) {
+  if (orc_get_relativistic()) {
+    /* TakizukaAbe.cpp:336-337, 371-372, 503-505: LorentzScatter(up1, up2, m1, m2, den2); between species the one
+     * with the lower density goes second.  Draws in its order: randn in the small-angle branch or rand for
+     * theta, then rand for phi; the branch is found with a dry run (the draws do not enter s12). */
+    double *p1 = a, *p2 = b;
+    double ma = (double)m1, mb = (double)m2, den = den2;
+    if (inter && den1 <= den2) {
+      p1 = b, p2 = a;
+      ma = (double)m2, mb = (double)m1;
+      den = den1;
+    }
+    double t1[3] = {p1[0], p1[1], p1[2]}, t2[3] = {p2[0], p2[1], p2[2]};
+    const int small = orc_ta_lorentz_scatter(t1, t2, ma, mb, den, dt_sec, b90_fact, Clog, 0.0, 0.5, 0.5);
+    double gauss = 0.0, uth = 0.0;
+    if (small) gauss = mu_randn();
+    else uth = mu_rand();
+    const double uphi = mu_rand();
+    orc_ta_lorentz_scatter(p1, p2, ma, mb, den, dt_sec, b90_fact, Clog, gauss, uth, uphi);
+    return;
+  }
   const double ux = a[0] - b[0], uy = a[1] - b[1], uz = a[2] - b[2];
   const double u = sqrt(ux * ux + uy * uy + uz * uz);
   const double den = std::min(den1, den2);
@@ -132,7 +232,8 @@ extern "C" void orc_ta_self(long ncell, const long *cell_start, double *v, long 
                             double Clog, double dt_sec, long *npairs_out) {
   const long double m1 = mass, m2 = mass;
   const long double mu = m1 * m2 / (m1 + m2);
-  const double b90_fact = orc_ta_b90_fact(charge, charge, mass, mass);
+  const double b90_fact = orc_get_relativistic() ? orc_ta_b90_fact_rel(charge, charge)
+                                                 : orc_ta_b90_fact(charge, charge, mass, mass);
   long npairs = 0;
   std::vector<long> idx;
   for (long c = 0; c < ncell; ++c) {
@@ -148,7 +249,7 @@ extern "C" void orc_ta_self(long ncell, const long *cell_start, double *v, long 
     auto scatter = [&](long p1, long p2, double den) {
       double a[3] = {v[p1], v[n + p1], v[2 * n + p1]};
       double b[3] = {v[p2], v[n + p2], v[2 * n + p2]};
-      ta_pair(a, b, den, den, b90_fact, Clog, dt_sec, mu, m1, m2);
+      ta_pair(a, b, den, den, b90_fact, Clog, dt_sec, mu, m1, m2, false);
       for (int k = 0; k < 3; ++k) {
         v[k * n + p1] = a[k];
         v[k * n + p2] = b[k];
@@ -166,7 +267,8 @@ extern "C" void orc_ta_self(long ncell, const long *cell_start, double *v, long 
         const int q1 = p % 2;
         int q2 = 2;
         if (p == 0) q2 = 1;
-        scatter(idx[q1], idx[q2], numDen / 2.0);
+        /* the relativistic build passes the full density here (TakizukaAbe.cpp:372 vs :377) */
+        scatter(idx[q1], idx[q2], orc_get_relativistic() ? numDen : numDen / 2.0);
       }
     }
   }
@@ -182,7 +284,8 @@ extern "C" void orc_ta_inter(long ncell, const long *cell_start1, double *v1,
                              long *npairs_out) {
   const long double m1 = mass1, m2 = mass2;
   const long double mu = m1 * m2 / (m1 + m2);
-  const double b90_fact = orc_ta_b90_fact(charge1, charge2, mass1, mass2);
+  const double b90_fact = orc_get_relativistic() ? orc_ta_b90_fact_rel(charge1, charge2)
+                                                 : orc_ta_b90_fact(charge1, charge2, mass1, mass2);
   long npairs = 0;
   std::vector<long> idx1, idx2;
   for (long c = 0; c < ncell; ++c) {
@@ -211,7 +314,7 @@ extern "C" void orc_ta_inter(long ncell, const long *cell_start1, double *v1,
       const long i1 = idx1[p1], i2 = idx2[p2];
       double a[3] = {v1[i1], v1[n1 + i1], v1[2 * n1 + i1]};
       double b[3] = {v2[i2], v2[n2 + i2], v2[2 * n2 + i2]};
-      ta_pair(a, b, numDen1, numDen2, b90_fact, Clog, dt_sec, mu, m1, m2);
+      ta_pair(a, b, numDen1, numDen2, b90_fact, Clog, dt_sec, mu, m1, m2, true);
       for (int k = 0; k < 3; ++k) {
         v1[k * n1 + i1] = a[k];
         v2[k * n2 + i2] = b[k];

@@ -156,6 +156,13 @@ void orc_scatter_delta_u(double ux, double uy, double uz, double costh,
 void orc_ta_delta_u(const double *vp1, double den1, const double *vp2,
                     double den2, double b90_fact, double Clog, double dt_sec,
                     double gauss, double u_theta, double u_phi, double *dU);
+/* RELATIVISTIC_PARTICLES build of TakizukaAbe: m_b90_fact without 1/mu (TakizukaAbe.cpp:45-46), rotateVelocity
+ * (ScatteringUtils.H:49-75), LorentzScatter with explicit draws (TakizukaAbe.cpp:580-659; returns 1 if the
+ * gaussian branch was taken).  orc_ta_self / orc_ta_inter switch with orc_set_relativistic. */
+double orc_ta_b90_fact_rel(double charge1, double charge2);
+void orc_rotate_velocity(double *u, double costh, double sinth, double cosphi, double sinphi);
+int orc_ta_lorentz_scatter(double *up1, double *up2, double mass1, double mass2, double den2, double dt_sec,
+                           double b90_fact, double Clog, double gauss, double u_theta, double u_phi);
 double orc_ta_b90_fact(double charge1, double charge2, double mass1, double mass2);
 /* Whole-box TA scattering on cell-binned particles.  cell_start[ncell+1] are
  * offsets into the (cell-sorted) particle arrays of each species. */

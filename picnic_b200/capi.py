@@ -103,6 +103,7 @@ def load():
         "pgpu_apply_bcs": [vp, vp, vp], "pgpu_finish_implicit_step": [vp, vp, vp], "pgpu_stable_dt": [vp, vp], "pgpu_global_moments": [vp, vp],
         "pgpu_collide_ta": [vp, vp, dbl, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_ta_delta_u": [lng, vp, vp, vp, vp, dbl, dbl, dbl, vp, vp, vp, vp],
+        "pgpu_ta_lorentz_scatter": [lng, vp, vp, dbl, dbl, vp, dbl, dbl, dbl, vp, vp, vp, vp, vp],
         "pgpu_collide_coulomb": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_coulomb_delta_u": [lng, vp, vp, dbl, dbl, dbl, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "pgpu_collide_elastic": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],

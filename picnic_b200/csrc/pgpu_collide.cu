@@ -86,6 +86,92 @@ __device__ __forceinline__ void ta_delta_u(const double *vp1, double den1, const
   scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
 }
 
+// ScatteringUtils::rotateVelocity (ScatteringUtils.H:49-75)
+__device__ __forceinline__ void rotate_velocity(double *a_u, double costh, double sinth, double cosphi, double sinphi) {
+  const double ux = a_u[0], uy = a_u[1], uz = a_u[2];
+  const double u = sqrt(ux * ux + uy * uy + uz * uz);
+  const double uperp = sqrt(ux * ux + uy * uy);
+  if (uperp == 0.0) {
+    a_u[0] = u * sinth * cosphi;
+    a_u[1] = u * sinth * sinphi;
+    a_u[2] = u * costh;
+  } else {
+    const double iu = 1.0 / uperp, sc = sinth * cosphi, ss = sinth * sinphi;
+    a_u[0] = ux * uz * iu * sc - uy * u * iu * ss + ux * costh;
+    a_u[1] = uy * uz * iu * sc + ux * u * iu * ss + uy * costh;
+    a_u[2] = -uperp * sc + uz * costh;
+  }
+}
+
+// TakizukaAbe::LorentzScatter (TakizukaAbe.cpp:580-659): relativistic binary collision of two equal-weight
+// particles through the centre-of-momentum frame, draws made explicit.  The reference keeps the scalars in
+// long double; here they are doubles (differences at round-off).
+__device__ __forceinline__ void ta_lorentz_scatter(double *up1, double *up2, double m1, double m2, double den2,
+                                                   double dt_sec, double b90_fact, double Clog, double gauss,
+                                                   double u_theta, double u_phi) {
+  const double PI = 3.14159265358979323846, TWOPI = 2.0 * PI, CVAC = 2.99792458e+08;
+  const double gamma1 = sqrt(1.0 + up1[0] * up1[0] + up1[1] * up1[1] + up1[2] * up1[2]);
+  const double gamma2 = sqrt(1.0 + up2[0] * up2[0] + up2[1] * up2[1] + up2[2] * up2[2]);
+  const double Etot = gamma1 * m1 + gamma2 * m2;
+  double vcm[3], upst[3];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) vcm[n] = (m1 * up1[n] + m2 * up2[n]) / Etot;
+  const double gammacm = 1.0 / sqrt(1.0 - vcm[0] * vcm[0] - vcm[1] * vcm[1] - vcm[2] * vcm[2]);
+  double vcmdotup = vcm[0] * up2[0] + vcm[1] * up2[1] + vcm[2] * up2[2];
+  const double gamma2st = gammacm * (gamma2 - vcmdotup);
+  vcmdotup = vcm[0] * up1[0] + vcm[1] * up1[1] + vcm[2] * up1[2];
+  const double gamma1st = gammacm * (gamma1 - vcmdotup);
+  const double gfac = gammacm / (1.0 + gammacm);
+  double upst_fact = (gfac * vcmdotup - gamma1) * gammacm;
+#pragma unroll
+  for (int n = 0; n < 3; ++n) upst[n] = up1[n] + upst_fact * vcm[n];
+  const double muRst = gamma1st * m1 * gamma2st * m2 / (m2 * gamma2st + m1 * gamma1st);
+  const double upstsq = upst[0] * upst[0] + upst[1] * upst[1] + upst[2] * upst[2];
+  const double denom = 1.0 + upstsq * m1 / m2 / gamma1st / gamma2st;
+  const double vrelst = sqrt(upstsq) * m1 / muRst / denom;
+  double s12 = PI * b90_fact * b90_fact * den2 * Clog * vrelst * CVAC * dt_sec;
+  s12 *= gamma1st * gamma2st / gamma1 / gamma2;
+  const double mv2 = muRst * vrelst * vrelst;
+  s12 /= mv2 * mv2;
+  double sinth, costh;
+  if (s12 < 2.0) {
+    const double delta = sqrt(s12 / 2.0) * gauss;
+    const double deltasq = delta * delta;
+    const double inv = 1.0 / (1.0 + deltasq);
+    sinth = 2.0 * delta * inv;
+    costh = 1.0 - 2.0 * deltasq * inv;
+  } else {
+    sincos(PI * u_theta, &sinth, &costh);
+  }
+  double sinphi, cosphi;
+  sincos(TWOPI * u_phi, &sinphi, &cosphi);
+  rotate_velocity(upst, costh, sinth, cosphi, sinphi);
+  vcmdotup = vcm[0] * upst[0] + vcm[1] * upst[1] + vcm[2] * upst[2];
+  upst_fact = (gfac * vcmdotup + gamma1st) * gammacm;
+#pragma unroll
+  for (int n = 0; n < 3; ++n) up1[n] = upst[n] + upst_fact * vcm[n];
+  const double r = -m1 / m2;     // p2* = -p1*
+#pragma unroll
+  for (int n = 0; n < 3; ++n) upst[n] *= r;
+  vcmdotup *= r;
+  upst_fact = (gfac * vcmdotup + gamma2st) * gammacm;
+#pragma unroll
+  for (int n = 0; n < 3; ++n) up2[n] = upst[n] + upst_fact * vcm[n];
+}
+
+__global__ void k_ta_lorentz(long n, const double *u1, const double *u2, double m1, double m2, const double *den2,
+                             double dt_sec, double b90_fact, double Clog, const double *gauss, const double *uth,
+                             const double *uphi, double *o1, double *o2) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[3] = {u1[i], u1[n + i], u1[2 * n + i]}, b[3] = {u2[i], u2[n + i], u2[2 * n + i]};
+  ta_lorentz_scatter(a, b, m1, m2, den2[i], dt_sec, b90_fact, Clog, gauss[i], uth[i], uphi[i]);
+  for (int c = 0; c < 3; ++c) {
+    o1[c * n + i] = a[c];
+    o2[c * n + i] = b[c];
+  }
+}
+
 __global__ void k_ta_delta_u(long n, const double *vp1, const double *den1, const double *vp2,
                              const double *den2, double b90_fact, double Clog, double dt_sec,
                              const double *gauss, const double *uth, const double *uphi, double *dU) {
@@ -114,6 +200,8 @@ __global__ void k_scatter_delta_u(long n, const double *u, const double *ct, con
 struct TAParams {
   double b90_fact, Clog, dt_sec;
   double f1, f2;  // mu/m1, mu/m2
+  double m1, m2;  // masses (LorentzScatter)
+  int rel;        // RELATIVISTIC_PARTICLES build: LorentzScatter instead of computeDeltaU
   unsigned seed_lo, seed_hi, step_lo, step_hi;
   int box_lo0, box_lo1, nbox0, ncell_glob0;  // to form the global cell id
 };
@@ -227,9 +315,18 @@ __device__ __forceinline__ void pair_randoms(const TAParams &P, unsigned gcell, 
 
 __device__ __forceinline__ void scatter_pair(double *v0, double *v1, double *v2, int pa, double *w0,
                                              double *w1, double *w2, int pb, double dena, double denb,
-                                             const TAParams &P, double gauss, double uth, double uphi) {
+                                             const TAParams &P, double gauss, double uth, double uphi,
+                                             bool inter = false) {
   double a[3] = {v0[pa], v1[pa], v2[pa]};
   double b[3] = {w0[pb], w1[pb], w2[pb]};
+  if (P.rel) {
+    // TakizukaAbe.cpp:336-337 (self) and :503-505 (between species: the one with the lower density goes second)
+    if (inter && dena <= denb) ta_lorentz_scatter(b, a, P.m2, P.m1, dena, P.dt_sec, P.b90_fact, P.Clog, gauss, uth, uphi);
+    else ta_lorentz_scatter(a, b, P.m1, P.m2, denb, P.dt_sec, P.b90_fact, P.Clog, gauss, uth, uphi);
+    v0[pa] = a[0], v1[pa] = a[1], v2[pa] = a[2];
+    w0[pb] = b[0], w1[pb] = b[1], w2[pb] = b[2];
+    return;
+  }
   double dU[3];
   ta_delta_u(a, dena, b, denb, P.b90_fact, P.Clog, P.dt_sec, gauss, uth, uphi, dU);
   v0[pa] = a[0] + P.f1 * dU[0];
@@ -267,7 +364,9 @@ k_ta_self(const int *cell_start, int ncell, double *v0, double *v1, double *v2, 
     for (int p = 0; p < 3; ++p) {
       double g, ut, up;
       pair_randoms(P, gcell, (unsigned)p, 1u, g, ut, up);
-      scatter_pair(v0, v1, v2, t[p1[p]], v0, v1, v2, t[p2[p]], numDen / 2.0, numDen / 2.0, P, g, ut, up);
+      // the relativistic build passes the full density to the three pairs of an odd cell (:372 vs :377)
+      const double dh = P.rel ? numDen : numDen / 2.0;
+      scatter_pair(v0, v1, v2, t[p1[p]], v0, v1, v2, t[p2[p]], dh, dh, P, g, ut, up);
     }
   }
   if (lane == 0) atomicAdd(npairs, (unsigned long long)(nmain + (pstart == 3 ? 3 : 0)));
@@ -299,7 +398,7 @@ k_ta_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, do
       const int i2 = s2 + order2[s2 + (first_short ? p : r)];
       double g, ut, up;
       pair_randoms(P, gcell, (unsigned)p, 2u, g, ut, up);
-      scatter_pair(a0, a1, a2, i1, b0, b1, b2, i2, numDen1, numDen2, P, g, ut, up);
+      scatter_pair(a0, a1, a2, i1, b0, b1, b2, i2, numDen1, numDen2, P, g, ut, up, true);
     }
   }
   if (lane == 0) atomicAdd(npairs, (unsigned long long)pMax);
@@ -930,6 +1029,37 @@ int pgpu_ta_delta_u(long n, const double *vp1, const double *den1, const double 
   return 0;
 }
 
+int pgpu_ta_lorentz_scatter(long n, const double *up1, const double *up2, double mass1, double mass2,
+                            const double *den2, double dt_sec, double b90_fact, double Clog, const double *gauss,
+                            const double *u_theta, const double *u_phi, double *out1, double *out2) {
+  if (!ctx().inited) {
+    set_error("pgpu_init has not been called");
+    return PGPU_ERR_STATE;
+  }
+  cudaStream_t st = ctx().stream;
+  double *d = nullptr;
+  const size_t N = (size_t)n;
+  PGPU_CUDA(cudaMalloc(&d, 16 * N * sizeof(double)));
+  double *d_1 = d, *d_2 = d + 3 * N, *d_d = d + 6 * N, *d_g = d + 7 * N, *d_t = d + 8 * N, *d_p = d + 9 * N,
+         *d_o1 = d + 10 * N, *d_o2 = d + 13 * N;
+  PGPU_CUDA(cudaMemcpyAsync(d_1, up1, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(d_2, up2, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(d_d, den2, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(d_g, gauss, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(d_t, u_theta, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(d_p, u_phi, N * sizeof(double), cudaMemcpyHostToDevice, st));
+  {
+    KTimer t("ta_lorentz");
+    k_ta_lorentz<<<nb(n), 256, 0, st>>>(n, d_1, d_2, mass1, mass2, d_d, dt_sec, b90_fact, Clog, d_g, d_t, d_p, d_o1,
+                                        d_o2);
+  }
+  PGPU_CUDA(cudaMemcpyAsync(out1, d_o1, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaMemcpyAsync(out2, d_o2, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d);
+  return 0;
+}
+
 int pgpu_scatter_delta_u(long n, const double *u, const double *costh, const double *sinth, const double *cosphi,
                          const double *sinphi, double *dU) {
   if (!ctx().inited) {
@@ -1169,6 +1299,11 @@ int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt
   const int q1 = (int)sA->desc.charge, q2 = (int)sB->desc.charge;
   TAParams P;
   P.b90_fact = (double)(abs(q1 * q2) / (mu * (long double)(CVAC * CVAC)) * b90_codeToPhys);
+  P.rel = (sA->desc.relativistic || sB->desc.relativistic) ? 1 : 0;
+  P.m1 = sA->desc.mass;
+  P.m2 = sB->desc.mass;
+  // RELATIVISTIC_PARTICLES build: m_b90_codeToPhys has 2 pi (TakizukaAbe.H:27-28), m_b90_fact no 1/mu (.cpp:45-46)
+  if (P.rel) P.b90_fact = abs(q1 * q2) / (CVAC * CVAC) * (QE * QE / (2.0 * PI * EP0 * ME));
   P.Clog = Clog;
   P.dt_sec = dt_sec;
   P.f1 = (double)(mu / m1);

@@ -127,3 +127,89 @@ def test_deposit_from_explicit_solver_relativistic(pgpu):
     for c in range(3):
         assert rel_err(sp.current_get(c), J0[c].a * (-1.0)) <= 1e-12
     sp.destroy(); grid.destroy()
+
+
+# ---- TakizukaAbe::LorentzScatter (TakizukaAbe.cpp:580-659) ---------------------------------------------------
+def _orc_lorentz(u1, u2, m1, m2, den, dt, b90, clog, g, ut, up):
+    import ctypes as C
+    f = orc.lib().orc_ta_lorentz_scatter
+    f.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 9
+    a, b = np.ascontiguousarray(u1).copy(), np.ascontiguousarray(u2).copy()
+    f(orc._ptr(a), orc._ptr(b), m1, m2, den, dt, b90, clog, g, ut, up)
+    return a, b
+
+
+def test_lorentz_scatter_matches_oracle(pgpu):
+    import ctypes as C
+    lib = orc.lib()
+    lib.orc_ta_b90_fact_rel.restype = C.c_double
+    lib.orc_ta_b90_fact_rel.argtypes = [C.c_double, C.c_double]
+    rng = np.random.default_rng(61)
+    n = 3000
+    m1, m2 = 1.0, 1836.15
+    u1 = np.ascontiguousarray(rng.standard_normal((3, n)) * 0.8)
+    u2 = np.ascontiguousarray(rng.standard_normal((3, n)) * 0.02)
+    u1[:, :300] *= 1e-3; u2[:, :300] *= 1e-3          # slow pairs: s12 >= 2, isotropic branch
+    den = np.ascontiguousarray(10.0 ** rng.uniform(26, 31, n))
+    g, ut, up = rng.standard_normal(n), rng.random(n), rng.random(n)
+    b90 = lib.orc_ta_b90_fact_rel(-1.0, 1.0)
+    o1, o2 = np.zeros((3, n)), np.zeros((3, n))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    pgpu.check(pgpu.load().pgpu_ta_lorentz_scatter(n, p(u1), p(u2), m1, m2, p(den), 1.77e-18, b90, 10.0, p(g), p(ut),
+                                                   p(up), p(o1), p(o2)))
+    worst = 0.0
+    for i in range(n):
+        a, b = _orc_lorentz(u1[:, i], u2[:, i], m1, m2, den[i], 1.77e-18, b90, 10.0, g[i], ut[i], up[i])
+        s = max(np.linalg.norm(u1[:, i]), 1e-30)
+        worst = max(worst, np.max(np.abs(o1[:, i] - a)) / s, np.max(np.abs(o2[:, i] - b)) / s)
+    assert worst < 1e-12, worst        # long double scalars in the reference vs doubles on the device
+    gam = lambda u: np.sqrt(1.0 + (u ** 2).sum(axis=0))
+    e0, e1 = m1 * gam(u1) + m2 * gam(u2), m1 * gam(o1) + m2 * gam(o2)
+    assert np.max(np.abs(e1 - e0) / e0) < 1e-13
+    assert np.max(np.abs(m1 * o1 + m2 * o2 - m1 * u1 - m2 * u2)) < 1e-12 * m2
+
+
+def test_collide_ta_relativistic_conserves_four_momentum(pgpu):
+    """pgpu_collide_ta with relativistic species: LorentzScatter per pair -- total momentum and total energy
+    sum m*gamma of every cell conserved to round-off (self: odd and even cells; between species)."""
+    from picnic_b200 import decks
+    rng = np.random.default_rng(62)
+    ncell = 40
+    deck = decks.Deck(D=1, ncell=(ncell,), dx=(0.25,), xmin=(0.0,), nghost=2)
+    grid = pgpu.Grid(1, (ncell,), (0.0,), (0.25,), 2, (1,), volume_scale=deck.volume_scale)
+
+    def cells(counts):
+        return np.concatenate([(c + rng.random(k)) * 0.25 for c, k in enumerate(counts)])[None, :]
+
+    def species(mass, charge, x, scale):
+        sp = pgpu.Species(grid, mass, charge, 1.0, deck.units.cvac_norm, relativistic=True)
+        n = x.shape[1]
+        sp.upload(x, rng.standard_normal((3, n)) * scale, np.full(n, 1e28), ids=np.arange(n, dtype=np.uint64))
+        sp.bin_particles(); sp.set_moments()
+        return sp
+
+    xe = cells(rng.choice([7, 10, 21], size=ncell))
+    xi = cells(rng.choice([5, 12], size=ncell))
+    se, si = species(1.0, -1.0, xe, 0.6), species(1836.15, 1.0, xi, 0.01)
+
+    def totals(sp):
+        d = sp.download()
+        cell = np.floor(d["x"][0] / 0.25).astype(int)
+        g = np.sqrt(1.0 + (d["v"] ** 2).sum(axis=0))
+        P = np.stack([np.bincount(cell, d["v"][k], ncell) for k in range(3)])
+        return P, np.bincount(cell, g, ncell), d["v"]
+
+    Pe0, Ee0, ve0 = totals(se)
+    n1 = pgpu.collide_ta(se, se, 10.0, 1.77e-18, 11, 0)
+    Pe1, Ee1, ve1 = totals(se)
+    assert n1 > 0 and not np.array_equal(ve0, ve1)
+    assert np.max(np.abs(Pe1 - Pe0)) < 1e-12 and np.max(np.abs(Ee1 - Ee0) / Ee0) < 1e-13
+    Pi0, Ei0, _ = totals(si)
+    n2 = pgpu.collide_ta(se, si, 10.0, 1.77e-18, 11, 1)
+    Pe2, Ee2, _ = totals(se)
+    Pi2, Ei2, _ = totals(si)
+    assert n2 > 0
+    assert np.max(np.abs((Pe2 + 1836.15 * Pi2) - (Pe1 + 1836.15 * Pi0))) < 1e-10
+    tot0, tot2 = Ee1 + 1836.15 * Ei0, Ee2 + 1836.15 * Ei2
+    assert np.max(np.abs(tot2 - tot0) / tot0) < 1e-13
+    se.destroy(); si.destroy(); grid.destroy()

@@ -135,3 +135,45 @@ def test_elastic_probability_and_conservation():
     K0 = m1 * (v10 ** 2).sum() + m2 * (v20 ** 2).sum()
     K1 = m1 * (v1 ** 2).sum() + m2 * (v2 ** 2).sum()
     assert abs(K1 - K0) / K0 < 1e-12
+
+
+# ---- RELATIVISTIC_PARTICLES build of TakizukaAbe: LorentzScatter (TakizukaAbe.cpp:580-659) ---------------------
+def _lorentz(up1, up2, m1, m2, den, dt, b90, clog, g, ut, up):
+    import ctypes as C
+    f = orc.lib().orc_ta_lorentz_scatter
+    f.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 9
+    a, b = np.ascontiguousarray(up1, dtype=np.float64).copy(), np.ascontiguousarray(up2, dtype=np.float64).copy()
+    small = f(orc._ptr(a), orc._ptr(b), m1, m2, den, dt, b90, clog, g, ut, up)
+    return a, b, small
+
+
+def test_lorentz_scatter_conserves_four_momentum_and_has_the_galilean_limit():
+    import ctypes as C
+    lib = orc.lib()
+    lib.orc_ta_b90_fact_rel.restype = C.c_double
+    lib.orc_ta_b90_fact_rel.argtypes = [C.c_double, C.c_double]
+    lib.orc_ta_b90_fact.argtypes = [C.c_double] * 4
+    rng = np.random.default_rng(91)
+    m1, m2 = 1.0, 1836.15
+    b90r = lib.orc_ta_b90_fact_rel(-1.0, 1.0)
+    for scale in (2.0, 0.3):
+        for _ in range(200):
+            u1, u2 = rng.standard_normal(3) * scale, rng.standard_normal(3) * scale * 0.05
+            a, b, _ = _lorentz(u1, u2, m1, m2, 1e30, 1e-17, b90r, 10.0, rng.standard_normal(), rng.random(), rng.random())
+            g = lambda u: np.sqrt(1.0 + (u ** 2).sum())
+            p0, p1 = m1 * u1 + m2 * u2, m1 * a + m2 * b
+            e0, e1 = m1 * g(u1) + m2 * g(u2), m1 * g(a) + m2 * g(b)
+            assert np.max(np.abs(p1 - p0)) <= 2e-13 * max(np.max(np.abs(p0)), m2 * 1e-3)
+            assert abs(e1 - e0) <= 1e-14 * e0
+    # |u| << 1: the same kick as computeDeltaU + the mu/m updates of the default build, same random numbers
+    b90 = lib.orc_ta_b90_fact(-1.0, 1.0, m1, m2)
+    mu = m1 * m2 / (m1 + m2)
+    for _ in range(50):
+        u1, u2 = rng.standard_normal(3) * 1e-3, rng.standard_normal(3) * 1e-5
+        gss, ut, up = rng.standard_normal(), rng.random(), rng.random()
+        a, b, small = _lorentz(u1, u2, m1, m2, 1e19, 1e-16, b90r, 10.0, gss, ut, up)
+        dU = np.zeros(3)
+        lib.orc_ta_delta_u.argtypes = [C.c_void_p, C.c_double, C.c_void_p] + [C.c_double] * 7 + [C.c_void_p]
+        lib.orc_ta_delta_u(orc._ptr(u1), 1e19, orc._ptr(u2), 1e19, b90, 10.0, 1e-16, gss, ut, up, orc._ptr(dU))
+        assert small == 1
+        assert np.max(np.abs(a - (u1 + mu / m1 * dU))) <= 3e-6 * np.max(np.abs(dU)) + 1e-18

@@ -143,3 +143,18 @@ def test_relativistic_golden_regenerates_from_reference():
     _, out = mk.run_reference_relativistic()
     for k, v in out.items():
         assert np.array_equal(v, GOLD_REL["out_" + k]), k
+
+
+def test_oracle_rotate_velocity_bit_equals_reference():
+    """ScatteringUtils::rotateVelocity (the rotation inside TakizukaAbe::LorentzScatter)."""
+    import ctypes
+    lib = orc.lib()
+    lib.orc_rotate_velocity.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4
+    n = GOLD["in_u"].shape[1]
+    got = np.zeros((n, 3))
+    for i in range(n):
+        t = np.ascontiguousarray(GOLD["in_u"][:, i].copy())
+        lib.orc_rotate_velocity(orc._ptr(t), GOLD["in_costh"][i], GOLD["in_sinth"][i], GOLD["in_cosphi"][i],
+                                GOLD["in_sinphi"][i])
+        got[i] = t
+    assert np.array_equal(got, GOLD["out_rotate"])
