@@ -7,6 +7,8 @@
 
 #include "pgpu_internal.h"
 
+#include <algorithm>
+
 namespace pgpu {
 
 static char g_err[512] = "";
@@ -186,11 +188,33 @@ __global__ void k_add(double *a, const double *b, long n) {
   if (i < n) a[i] = __dadd_rn(a[i], b[i]);
 }
 
+// the three components of a current in one launch (blockIdx.y = component): these grid kernels are a few
+// microseconds each, so the launch count is what they cost
+struct Ptr3 {
+  double *a[3];
+  const double *b[3];
+  long n[3];
+};
+__global__ void k_scale3(Ptr3 P, double s) {
+  const int c = blockIdx.y;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n[c]) P.a[c][i] = __dmul_rn(P.a[c][i], s);
+}
+__global__ void k_add3(Ptr3 P) {
+  const int c = blockIdx.y;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n[c]) P.a[c][i] = __dadd_rn(P.a[c][i], P.b[c][i]);
+}
+struct Fab3 {
+  FabView f[3];
+};
+
 // Periodic ghost fold of one direction: pass 0 adds every non-owned entry onto its
 // owned image (atomics: several images can map to one entry), pass 1 refreshes the
 // images.  Owned index range in direction `dir` is own_lo..own_hi (cells; for nodal
 // data node own_hi+1 is the image of node own_lo).
-__global__ void k_fold(FabView f, int dir, int own_lo, int own_hi, int pass) {
+__global__ void k_fold(Fab3 F, int dir, int own_lo, int own_hi, int pass) {
+  const FabView f = F.f[blockIdx.y];
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)f.n0 * f.n1;
   if (t >= total) return;
@@ -214,20 +238,30 @@ int scale_fab(const DeviceFab &f, double s) {
   return 0;
 }
 
-int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f) {
+// nf arrays of one grid (same periodic directions; sizes may differ by the centring)
+static int fold_periodic_n(const pgpu_grid_s *g, const DeviceFab *const *f, int nf) {
   Context &c = ctx();
-  const FabView v = f.view();
-  const long total = (long)f.size();
+  Fab3 F;
+  long total = 0;
+  for (int k = 0; k < nf; ++k) {
+    F.f[k] = f[k]->view();
+    total = std::max(total, (long)f[k]->size());
+  }
+  for (int k = nf; k < 3; ++k) F.f[k] = F.f[0];
   for (int dir = 0; dir < g->desc.D; ++dir) {
     if (!g->desc.periodic[dir]) continue;
     // only a box spanning the whole periodic direction folds onto itself
     if (g->desc.box_lo[dir] != 0 || g->desc.box_hi[dir] != g->desc.ncell[dir] - 1) continue;
     for (int pass = 0; pass < 2; ++pass) {
       KTimer t("fold_periodic");
-      k_fold<<<nb(total), 256, 0, c.stream>>>(v, dir, g->desc.box_lo[dir], g->desc.box_hi[dir], pass);
+      k_fold<<<dim3(nb(total), nf), 256, 0, c.stream>>>(F, dir, g->desc.box_lo[dir], g->desc.box_hi[dir], pass);
     }
   }
   return 0;
+}
+int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f) {
+  const DeviceFab *one[1] = {&f};
+  return fold_periodic_n(g, one, 1);
 }
 
 int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi, bool sync) {
@@ -560,18 +594,23 @@ int pgpu_current_zero(pgpu_grid_t g) {
 
 int pgpu_current_add_species(pgpu_grid_t g, pgpu_species_t s) {
   NEED_INIT();
+  Ptr3 P;
+  long mx = 0;
   for (int c = 0; c < 3; ++c) {
-    KTimer t("current_add");
-    k_add<<<nb((long)g->jtot[c].size()), 256, 0, ctx().stream>>>(g->jtot[c].p, s->J[c].p, (long)g->jtot[c].size());
+    P.a[c] = g->jtot[c].p;
+    P.b[c] = s->J[c].p;
+    P.n[c] = (long)g->jtot[c].size();
+    mx = std::max(mx, P.n[c]);
   }
+  KTimer t("current_add");
+  k_add3<<<dim3(nb(mx), 3), 256, 0, ctx().stream>>>(P);
   return 0;
 }
 
 int pgpu_current_finalize(pgpu_grid_t g) {
   NEED_INIT();
-  for (int c = 0; c < 3; ++c)
-    if (fold_periodic(g, g->jtot[c])) return PGPU_ERR_CUDA;
-  return 0;
+  const DeviceFab *all[3] = {&g->jtot[0], &g->jtot[1], &g->jtot[2]};
+  return fold_periodic_n(g, all, 3);
 }
 
 int pgpu_current_get(pgpu_grid_t g, int comp, double *data, const int *lo, const int *hi) {
@@ -899,10 +938,16 @@ int pgpu_advance_particles(pgpu_species_t s, double dt) {
 
 static int scale_species_current(pgpu_species_t s) {
   const double f = s->desc.charge / s->grid->desc.volume_scale;
+  Ptr3 P;
+  long mx = 0;
   for (int c = 0; c < 3; ++c) {
-    KTimer t("current_scale");
-    k_scale<<<nb((long)s->J[c].size()), 256, 0, ctx().stream>>>(s->J[c].p, (long)s->J[c].size(), f);
+    P.a[c] = s->J[c].p;
+    P.b[c] = nullptr;
+    P.n[c] = (long)s->J[c].size();
+    mx = std::max(mx, P.n[c]);
   }
+  KTimer t("current_scale");
+  k_scale3<<<dim3(nb(mx), 3), 256, 0, ctx().stream>>>(P, f);
   return 0;
 }
 
