@@ -211,12 +211,14 @@ __device__ __forceinline__ unsigned global_cell(const TAParams &P, int cell) {
   return (unsigned)(i + j * P.ncell_glob0);
 }
 
-// Cells of up to 128 particles: bitonic network over R registers per lane and warp shuffles.  The sorted
-// word is (24 Philox bits << 7) | local index, so the sort needs no payload and the key is unique; two
-// particles whose 24 random bits collide (6e-5 per 64-particle cell) keep their storage order.
+// Cells of up to 32 R particles (R = 2, 4, 8): bitonic network over R registers per lane and warp shuffles.
+// The sorted word is (Philox bits << IB) | local index with IB = log2(32 R) index bits, so the sort needs no
+// payload and the key is unique; two particles whose 31 - IB random bits collide (6e-5 per 64-particle cell)
+// keep their storage order.
 template <int R>
 __device__ __forceinline__ void warp_bitonic_order(int s, int n, const uint64_t *id, const TAParams &P, unsigned salt,
                                                    int *order, int lane) {
+  constexpr unsigned IDX_MASK = 32u * R - 1u;
   unsigned v[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -229,7 +231,7 @@ __device__ __forceinline__ void warp_bitonic_order(int s, int n, const uint64_t 
       c.y = (unsigned)(pid >> 32);
       c.z = P.step_lo;
       c.w = P.step_hi ^ (STREAM_SHUFFLE << 16) ^ salt;
-      v[r] = ((philox4x32_10(c, P.seed_lo, P.seed_hi).x >> 1) & ~0x7fu) | (unsigned)k;
+      v[r] = ((philox4x32_10(c, P.seed_lo, P.seed_hi).x >> 1) & ~IDX_MASK) | (unsigned)k;
     }
   }
   // element e = lane + 32 r; stage (k2, j): e and e ^ j are ordered ascending iff (e & k2) == 0
@@ -262,7 +264,7 @@ __device__ __forceinline__ void warp_bitonic_order(int s, int n, const uint64_t 
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int pos = lane + 32 * r;
-    if (pos < n) order[s + pos] = (int)(v[r] & 0x7fu);
+    if (pos < n) order[s + pos] = (int)(v[r] & IDX_MASK);
   }
   __syncwarp();
 }
@@ -273,6 +275,7 @@ __device__ __forceinline__ void warp_shuffle_order(int s, int n, const uint64_t 
                                                    unsigned salt, unsigned *key, int *order, int lane) {
   if (n <= 64) return warp_bitonic_order<2>(s, n, id, P, salt, order, lane);
   if (n <= 128) return warp_bitonic_order<4>(s, n, id, P, salt, order, lane);
+  if (n <= 256) return warp_bitonic_order<8>(s, n, id, P, salt, order, lane);
   // larger cells: rank of every key by counting, keys in global scratch
   for (int k = lane; k < n; k += 32) {
     const uint64_t pid = id[s + k];
