@@ -231,4 +231,5 @@ int launch_gather(pgpu_species_s *s);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);
 int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit);
+int launch_advance_cc1_1d_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit);
 }  // namespace pgpu

@@ -395,7 +395,8 @@ int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposi
   if (materialize_old(s, KEEP_OLD_ALIASES)) return PGPU_ERR_CUDA;   // pending gathers; an aliased old group is left to the CC1 kernel
   bool deferred = false;
   if (ctx().use_fast_cc1) {
-    const int fr = launch_advance_cc1_fast(s, prm, fuse_deposit);
+    int fr = launch_advance_cc1_fast(s, prm, fuse_deposit);
+    if (fr == 0) fr = launch_advance_cc1_1d_fast(s, prm, fuse_deposit);
     if (fr < 0) return fr;
     deferred = fr == 1;
   }

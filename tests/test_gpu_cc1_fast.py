@@ -150,3 +150,105 @@ def test_fast_kernel_charge_continuity_large(pgpu):
     scale = np.max(np.abs(rho_old))
     assert np.max(np.abs(resid)) / scale < 1e-11
     sp.destroy(); grid.destroy()
+
+
+# ---- the 1D kernel (pgpu_advance_cc1_1d.cu) -------------------------------------------------------------------
+def _oracle_1d(prob, rtol=1e-12, itmax=21, charge=-1.0, vs=3.0):
+    x, v = prob.x.copy(), prob.v.copy()
+    rc, apply_its, unconv, its = orc.advance_particles_iteratively(
+        prob.geom, orc.CC1, x, prob.xold, v, prob.vold, prob.E, prob.B, FN, DT * CV, rtol, itmax)
+    assert rc == 0
+    J0 = prob.new_J()
+    assert orc.deposit_current(prob.geom, orc.CC1, x, prob.xold, v, prob.w, DT * CV, J0) == 0
+    for c in range(3):
+        orc.scale_fab(J0[c], 1, charge / vs)
+    return x, v, J0, apply_its, unconv
+
+
+def _run_1d(pgpu, prob, mode, deposit=True, itmax=21, alias=False):
+    pgpu.check(pgpu.load().pgpu_set_deposit_mode(mode))
+    grid, sp = make_gpu(pgpu, prob, INTERPS["CC1"], rtol=1e-12, iter_max=itmax, fnorm=FN, cvac_norm=CV,
+                        charge=-1.0, volume_scale=3.0)
+    if alias:
+        sp.update_old_positions(); sp.update_old_velocities()
+    pgpu.profile_reset(); pgpu.profile_enable(True)
+    st = sp.advance_iteratively(DT, deposit=deposit)
+    pgpu.profile_enable(False)
+    got = sp.download()
+    J = [sp.current_get(c) for c in range(3)] if deposit else None
+    nfast = pgpu.profile_query("advance_cc1_1d")[1]
+    sp.destroy(); grid.destroy()
+    pgpu.check(pgpu.load().pgpu_set_deposit_mode(1))
+    return got, J, st, nfast
+
+
+@pytest.mark.parametrize("order", ["sorted", "shuffled"])
+@pytest.mark.parametrize("max_disp", [0.02, 0.5, 1.6])
+@pytest.mark.parametrize("n", [20000, 4 * 777 + 3])
+def test_fast_kernel_1d_matches_oracle(pgpu, order, max_disp, n):
+    prob = Problem(1, (48,), (0.25,), (0.5,), 4, n, seed=25, max_disp=max_disp, E0=0.3, B0=0.8)
+    if order == "sorted":
+        perm = np.argsort(prob.xold[0], kind="stable")
+        for name in ("x", "xold", "v", "vold"):
+            setattr(prob, name, np.ascontiguousarray(getattr(prob, name)[:, perm]))
+        prob.w = np.ascontiguousarray(prob.w[perm])
+    x, v, J0, apply_its, unconv = _oracle_1d(prob)
+    got, J, st, nfast = _run_1d(pgpu, prob, 1)
+    assert nfast == 1
+    assert np.max(np.abs(got["x"] - x)) / prob.dx[0] <= 4e-12
+    assert rel_err(got["v"], v) <= 1e-11
+    for c in range(3):
+        assert rel_err(J[c], J0[c].a) <= 1e-11, c
+    assert st.num_parts_its == prob.n and st.num_unconverged == unconv
+    assert abs(st.num_apply_its - apply_its) <= max(3, prob.n // 100)
+    got0, J00, _, nfast0 = _run_1d(pgpu, prob, 0)
+    assert nfast0 == 0
+    for c in range(3):
+        assert rel_err(J[c], J00[c]) <= 1e-12
+
+
+def test_fast_kernel_1d_faces_alias_and_single_pass(pgpu):
+    """x_old on and next to dual-cell faces (cell centres) and primal faces, inside the ghost region too; then the
+    aliased update-old entry (out-of-place write + pointer swap) and advanceParticles (iter_max = 0, no deposit)."""
+    ncell, dx, xmin, ng, n = 40, 0.25, 0.5, 4, 9000
+    prob = Problem(1, (ncell,), (dx,), (xmin,), ng, n, seed=26, max_disp=0.05, E0=0.3, B0=0.8)
+    rng = np.random.default_rng(27)
+    k = rng.integers(-2 * (ng - 2), 2 * (ncell + ng - 2), size=n)
+    on_face = rng.random(n) < 0.5
+    xf = xmin + k * (0.5 * dx)
+    eps = rng.choice([-2, -1, 0, 0, 1, 2], size=n)
+    nudged = xf.copy()
+    for s in (-2, -1, 1, 2):
+        m = on_face & (eps == s)
+        t = xf[m]
+        for _ in range(abs(s)):
+            t = np.nextafter(t, np.inf if s > 0 else -np.inf)
+        nudged[m] = t
+    prob.xold[0] = np.where(on_face, nudged, prob.xold[0])
+    prob.x[0] = prob.xold[0] + (rng.random(n) * 2 - 1) * 0.02 * dx
+    prob.x[0] = np.where(rng.random(n) < 0.1, prob.xold[0], prob.x[0])
+    prob.vold[0] *= 0.05
+    prob.v[:] = prob.vold
+    x, v, J0, apply_its, unconv = _oracle_1d(prob)
+    got, J, st, nfast = _run_1d(pgpu, prob, 1)
+    assert nfast == 1
+    assert np.max(np.abs(got["x"] - x)) / dx <= 4e-12 and rel_err(got["v"], v) <= 1e-11
+    for c in range(3):
+        assert rel_err(J[c], J0[c].a) <= 1e-11, c
+    # aliased old arrays: the oracle starts from xold = x, vold = v
+    prob2 = Problem(1, (ncell,), (dx,), (xmin,), ng, 5001, seed=28, max_disp=0.3, E0=0.3, B0=0.8)
+    prob2.xold, prob2.vold = prob2.x.copy(), prob2.v.copy()
+    x, v, J0, _, _ = _oracle_1d(prob2)
+    got, J, st, nfast = _run_1d(pgpu, prob2, 1, alias=True)
+    assert nfast == 1
+    assert np.array_equal(got["xold"], prob2.xold) and np.array_equal(got["vold"], prob2.vold)
+    assert np.max(np.abs(got["x"] - x)) / dx <= 4e-12 and rel_err(got["v"], v) <= 1e-11
+    for c in range(3):
+        assert rel_err(J[c], J0[c].a) <= 1e-11, c
+    # advanceParticles
+    prob3 = Problem(1, (ncell,), (dx,), (xmin,), ng, 7000, seed=29, max_disp=0.1, E0=0.3, B0=0.8)
+    got, _, _, nfast = _run_1d(pgpu, prob3, 1, deposit=False, itmax=0)
+    assert nfast == 1
+    x, v = prob3.x.copy(), prob3.v.copy()
+    assert orc.advance_particles(prob3.geom, orc.CC1, x, prob3.xold, v, prob3.vold, prob3.E, prob3.B, FN, DT * CV, 0) == 0
+    assert rel_err(got["v"], v) <= 1e-12 and np.max(np.abs(got["x"] - x)) / dx <= 1e-11
