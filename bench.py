@@ -76,6 +76,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-collisions", action="store_true", help="skip the secondary C2 collision-pairs/s leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the secondary C4 leg (1D, 1e8 particles)")
     return ap.parse_args()
 
 
@@ -413,6 +414,88 @@ def collisions_leg(args, torch, capi, stream, peak):
                          "kernel_ms_per_step": kern_ms}}
 
 
+def c4_leg(args, torch, capi, stream, peak):
+    """Secondary line item: BASELINE.json configs[3] "C4" as a periodic stand-in -- 1D, 250 000 cells x 200 ppc x 2
+    species = 1e8 particles, CC1 gather/deposit, implicit push + deposit of one nonlinear evaluation per species
+    (1D fused kernel pgpu_advance_cc1_1d.cu), and the weighted Coulomb collisions (NANBU, Clog 10: e-e, i-i, e-i).
+    Device-resident; algorithmic bytes per advance in 1D = (2*1+7)*8 = 72."""
+    deck = decks.deck_c4()
+    deck.dt = 0.1
+    lo, hi = (0,), (deck.ncell[0] - 1,)
+    E, B = decks.analytic_fields(deck, lo, hi, E0=3.0e7, B0=5.0e8)
+    grid = capi.Grid(1, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1,), volume_scale=deck.volume_scale)
+    grid.set_fields(E, B)
+    rng = np.random.default_rng(3)
+    lib = capi.load()
+    sps = []
+    for sdef in deck.species:
+        p = decks.load_species(deck, sdef, lo, hi, rng)
+        sp = capi.Species(grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm,
+                          interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E, rtol=deck.rtol,
+                          iter_max=deck.iter_max)
+        sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
+        sp.bin_particles()
+        sps.append(sp)
+        del p
+    n = sum(sp.n for sp in sps)
+
+    def timed(fn, reps):
+        fn()
+        capi.check(lib.pgpu_synchronize())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        capi.check(lib.pgpu_synchronize())
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def adv():
+        for sp in sps:
+            capi.check(lib.pgpu_advance_particles_iteratively(sp.h, deck.dt, 1, None))
+    reps = max(args.steps // 4, 5)
+    capi.picard_totals(reset=True)
+    capi.profile_reset()
+    capi.profile_enable(True)
+    ms_adv = timed(adv, reps)
+    capi.profile_enable(False)
+    k_ms, k_n = capi.profile_query("advance_cc1_1d_fused")
+    padv, papp, _ = capi.picard_totals(reset=True)
+    for sp in sps:
+        sp.bin_particles()
+        sp.set_moments()
+    grid.debye_length(sps)
+    dt_sec = deck.dt * deck.units.time
+    state = {"k": 0}
+
+    def col():
+        for (a, b) in ((0, 0), (1, 1), (0, 1)):
+            capi.check(lib.pgpu_collide_coulomb(sps[a].h, sps[b].h, capi.C.byref(capi.CoulombParams(10.0, 1, 0, 11, 1)),
+                                                dt_sec, 1983, state["k"], None))
+        state["k"] += 1
+    ms_col = timed(col, 3)
+    pairs = sum(capi.collide_coulomb(sps[a], sps[b], 10.0, dt_sec, 1983, 99, angular=1)
+                for (a, b) in ((0, 0), (1, 1), (0, 1)))
+    for sp in sps:
+        sp.destroy()
+    grid.destroy()
+    kern = k_ms / max(k_n, 1)
+    achieved = 72.0 * (n / len(sps)) / (kern * 1e-3) / 1e9 if k_n else None
+    return {"metric": "particle-advances/s (implicit push + deposit, 1D)", "unit": "particle-advances/s",
+            "value": n / (ms_adv * 1e-3), "ms_per_evaluation": ms_adv, "particles": n,
+            "workload": "C4 stand-in: 1D periodic, %d cells x 200 ppc x 2 species, CC1, one nonlinear evaluation "
+                        "(fused advance+deposit of both species)" % deck.ncell[0],
+            "mean_picard_passes": round(papp / max(padv, 1), 3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "bytes_per_unit": 72.0,
+                         "kernel": "advance_cc1_1d_fused", "kernel_ms_per_launch": kern,
+                         "units_per_launch": n / len(sps)},
+            "coulomb": {"metric": "collision-pairs/s (weighted Coulomb, NANBU)", "value": pairs / (ms_col * 1e-3),
+                        "pairs_per_step": pairs, "ms_per_step": ms_col}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -580,6 +663,8 @@ def run_ours(args):
     eng.grid.destroy()
     if rank == 0 and world == 1 and not args.no_collisions:
         out["collisions"] = collisions_leg(args, torch, capi, stream, out["roofline"]["peak"])
+    if rank == 0 and world == 1 and not args.no_c4:
+        out["c4_1d"] = c4_leg(args, torch, capi, stream, out["roofline"]["peak"])
     capi.finalize()
     if world > 1:
         dist.barrier()

@@ -140,8 +140,11 @@ __device__ __forceinline__ bool push_1d(const Args1D &A, double xo, double &xb, 
   return true;
 }
 
+#ifndef PGPU_1D_MINB
+#define PGPU_1D_MINB 2
+#endif
 template <bool DEP>
-__global__ void __launch_bounds__(BLOCK1) k_advance_cc1_1d(const Args1D A) {
+__global__ void __launch_bounds__(BLOCK1, PGPU_1D_MINB) k_advance_cc1_1d(const Args1D A) {
   const int lane = threadIdx.x & 31;
   const long base = ((long)blockIdx.x * BLOCK1 + threadIdx.x) * TP1;
   unsigned apply = 0, unconv = 0, defer_mask = 0;
