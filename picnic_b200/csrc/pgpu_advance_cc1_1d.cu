@@ -22,7 +22,10 @@
 namespace pgpu {
 namespace {
 
-constexpr int TP1 = 4;          // consecutive particles per thread
+#ifndef PGPU_1D_TP
+#define PGPU_1D_TP 4
+#endif
+constexpr int TP1 = PGPU_1D_TP;   // consecutive particles per thread (even)
 constexpr int BLOCK1 = 256;
 constexpr int NS1 = 8;          // Jx(i0), Jx(i0+1), Jy(i0..i0+2), Jz(i0..i0+2)
 constexpr int NOCELL = 0x7fffffff;
