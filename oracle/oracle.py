@@ -29,6 +29,10 @@ class CFab(C.Structure):
     _fields_ = [("p", C.POINTER(C.c_double)), ("lo", C.c_int * 2), ("hi", C.c_int * 2)]
 
 
+class CMFab(C.Structure):
+    _fields_ = [("p", C.POINTER(C.c_double)), ("lo", C.c_int * 2), ("hi", C.c_int * 2), ("ncomp", C.c_int)]
+
+
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
@@ -389,3 +393,88 @@ def elastic_nu_max(m1, m2, mass1, mass2, const_sigma=0.0, E=None, Q=None, XI=Non
 def gammainc_3half(x):
     _coul_sigs()
     return lib().orc_gammainc_3half(float(x))
+
+
+# ---- mass matrices (oracle_massmatrix.cpp) ---------------------------------------------------
+SIGMA_NAMES = ["xx", "xy", "xz", "yx", "yy", "yz", "zx", "zy", "zz"]
+
+
+class MFab:
+    """ncomp components of one box in CHF_FRA layout (column major, component index slowest)."""
+
+    def __init__(self, lo, hi, ncomp):
+        self.lo = tuple(int(v) for v in lo)
+        self.hi = tuple(int(v) for v in hi)
+        self.ncomp = int(ncomp)
+        shape = tuple(h - l + 1 for l, h in zip(self.lo, self.hi)) + (self.ncomp,)
+        self.a = np.zeros(shape, dtype=np.float64, order="F")
+
+    def c(self):
+        f = CMFab()
+        f.p = self.a.ctypes.data_as(C.POINTER(C.c_double))
+        for d in range(2):
+            f.lo[d] = self.lo[d] if d < len(self.lo) else 0
+            f.hi[d] = self.hi[d] if d < len(self.hi) else 0
+        f.ncomp = self.ncomp
+        return f
+
+
+def mm_ncomp(D, interp, ghosts):
+    """(9, 2) int array: components per direction of sigma_xx .. sigma_zz."""
+    nc = np.zeros((9, 2), dtype=np.int32)
+    rc = lib().orc_mm_ncomp(D, interp, ghosts, _ptr(nc))
+    if rc:
+        raise ValueError("the reference asserts against this interp/ghosts/D combination")
+    return nc
+
+
+def j_stag(D):
+    """centring of Jx, Jy, Jz (= that of Ex, Ey, Ez)"""
+    return E_STAG[D]
+
+
+def mm_alloc(D, interp, ghosts, box_lo, box_hi):
+    """Nine zeroed sigma containers on the boxes of the J component of their row."""
+    nc = mm_ncomp(D, interp, ghosts)
+    out = []
+    for k in range(9):
+        stag = E_STAG[D][k // 3]
+        lo = [l - ghosts for l in box_lo]
+        hi = [h + ghosts + s for h, s in zip(box_hi, stag)]
+        out.append(MFab(lo, hi, int(nc[k, 0]) * int(nc[k, 1])))
+    return nc, out
+
+
+def _mfabs9(sig):
+    arr = (CMFab * 9)()
+    for i, f in enumerate(sig):
+        arr[i] = f.c()
+    return arr
+
+
+def mm_kernels(Bp, qp, alphas, volume, upold, upbar, anticyclic=1, relativistic=False):
+    out = np.zeros(12)
+    Bp = np.ascontiguousarray(Bp, dtype=np.float64)
+    upold = np.ascontiguousarray(upold, dtype=np.float64)
+    upbar = np.ascontiguousarray(upbar, dtype=np.float64)
+    f = lib().orc_mm_kernels
+    f.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    f(_ptr(Bp), qp, alphas, volume, _ptr(upold), _ptr(upbar), int(anticyclic), int(relativistic), _ptr(out))
+    return out[:3].copy(), out[3:].reshape(3, 3).copy()
+
+
+def deposit_mass_matrices(g, interp, x, xold, v, vold, w, qovs, alphas, cnormDt, B, J0, sigma, anticyclic=False,
+                          relativistic=False):
+    f = lib().orc_deposit_mass_matrices
+    f.argtypes = ([C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 5 + [C.c_double] * 3 + [C.c_int, C.c_int] +
+                  [C.c_void_p] * 3)
+    n = x.shape[1]
+    return f(C.byref(g), interp, n, _ptr(x), _ptr(xold), _ptr(v), _ptr(vold), _ptr(w), qovs, alphas, cnormDt,
+             int(anticyclic), int(relativistic), _fabs3(B), _fabs3(J0), _mfabs9(sigma))
+
+
+def compute_J_from_mass_matrices(D, ncomp, sigma, E0, E, J0, J):
+    f = lib().orc_compute_J_from_mass_matrices
+    f.argtypes = [C.c_int] + [C.c_void_p] * 6
+    nc = np.ascontiguousarray(ncomp, dtype=np.int32)
+    f(D, _ptr(nc), _mfabs9(sigma), _fabs3(E0), _fabs3(E), _fabs3(J0), _fabs3(J))

@@ -663,6 +663,12 @@ void cc_2d_virtual_deposit(const orc_geom &g, const double *xpbar,
  * Dispatch: MeshInterp::interpolateEMfieldsToPart (MeshInterpI.H:537-690).
  * Ep/Bp start from zero for every particle (:552-553).
  * ======================================================================== */
+/* truncate_boundaries for the mass-matrix restatement (oracle_massmatrix.cpp) */
+extern "C" void orc_truncate_boundaries_2d(const orc_geom *g, double *xpold, double *xpnew, double slope,
+                                           double slope_inv) {
+  truncate_boundaries_2d(*g, xpold, xpnew, slope, slope_inv);
+}
+
 extern "C" int orc_gather(const orc_geom *gp, int interp, long n, const double *x,
                           const double *xold, const orc_fab *Ef,
                           const orc_fab *Bf, double *Ep_out, double *Bp_out) {

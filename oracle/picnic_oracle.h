@@ -115,6 +115,30 @@ int orc_advance_particles_iteratively(const orc_geom *g, int interpE, long n,
                                       long *num_apply_its, long *num_unconverged,
                                       int *its_out);
 
+/* ---- mass matrices (oracle_massmatrix.cpp) --------------------------- */
+/* CHF_FRA: ncomp components of one box, component index slowest */
+typedef struct {
+  double *p;
+  int lo[2];
+  int hi[2];
+  int ncomp;
+} orc_mfab;
+/* PicSpeciesInterface::initializeMassMatrices (PicSpeciesInterface.cpp:256-350): ncomp[9][2], order
+ * xx xy xz yx yy yz zx zy zz. */
+int orc_mm_ncomp(int D, int interp, int ghosts, int *ncomp);
+/* compute_mm_kernals (MeshInterpMassMatrixF.ChF:1869-2076, planar): out = fp[3], f[3][3] */
+void orc_mm_kernels(const double *Bp, double qp, double alphas, double volume, const double *upold,
+                    const double *upbar, int anticyclic, int relativistic, double *out);
+/* PicChargedSpecies::accumulateMassMatrices for CC1 (PicChargedSpecies.cpp:3671-3761 ->
+ * cc1_{1,2}d_deposit_mass_matrix, MeshInterpMassMatrixF.ChF:835-1862).  Accumulates. */
+int orc_deposit_mass_matrices(const orc_geom *g, int interp, long n, const double *x, const double *xold,
+                              const double *v, const double *vold, const double *w, double qovs, double alphas,
+                              double cnormDt, int anticyclic, int relativistic, const orc_fab *B, orc_fab *J0,
+                              orc_mfab *sigma);
+/* compute_J{x,y,z}_from_mass_matrix (FieldsF.ChF:3-415): J = J0 + sigma (E - E0) */
+void orc_compute_J_from_mass_matrices(int D, const int *ncomp, const orc_mfab *sigma, const orc_fab *E0,
+                                      const orc_fab *E, const orc_fab *J0, orc_fab *J);
+
 /* ---- ghost handling of a deposited field (periodic, one box) -------------- */
 /* Adds every ghost entry onto its periodic image inside the valid region
  * (valid cells lo..hi; nodal directions own nodes lo..hi+1 with node hi+1 the
