@@ -284,6 +284,31 @@ int pgpu_migrate_finish(pgpu_migrator_t m, long *n_arrived, long *n_left, long *
 int pgpu_stable_dt(pgpu_species_t s, double *dt_out);
 int pgpu_global_moments(pgpu_species_t s, double *out /* [w, wux,wuy,wuz, wuu_x,wuu_y,wuu_z] */);
 
+/* ---- mass matrices (use_mass_matrices decks; CC1, planar push) -------------------------------
+ * The nine sigma containers and J0 / E0 of PicSpeciesInterface live on the device, on the boxes of the
+ * J component of their row (sigma_x*: Jx box, sigma_y*: Jy box, sigma_z*: Jz box), CHF_FRA layout
+ * (component index slowest).  Order everywhere: xx xy xz yx yy yz zx zy zz. */
+/* PicSpeciesInterface::initializeMassMatrices (PicSpeciesInterface.cpp:225-417): allocates; ncomp_or_null
+ * receives the components per direction [9][2] (m_ncomp_xx ... m_ncomp_zz). */
+int pgpu_mass_matrices_init(pgpu_grid_t g, int interp, int *ncomp_or_null);
+int pgpu_mass_matrices_ncomp(pgpu_grid_t g, int *ncomp /* [9][2] */);
+/* PicSpeciesInterface::setMassMatrices (:1038-1095) = zero, accumulate every species, save_E0. */
+int pgpu_mass_matrices_zero(pgpu_grid_t g);
+/* PicChargedSpecies::accumulateMassMatrices (PicChargedSpecies.cpp:3671-3761) ->
+ * cc1_{1,2}d_deposit_mass_matrix + compute_mm_kernals (MeshInterpMassMatrixF.ChF:835-2076); B = the
+ * selected field slot.  Asynchronous; a crossing / bounds error surfaces at the next *_get or
+ * pgpu_picard_totals. */
+int pgpu_accumulate_mass_matrices(pgpu_species_t s, double dt);
+/* m_E0 <- E of the selected field slot (:1076-1091) */
+int pgpu_mass_matrices_save_E0(pgpu_grid_t g);
+/* PicSpeciesInterface::computeJfromMassMatrices (:567-753) -> compute_J{x,y,z}_from_mass_matrix
+ * (src/fields/FieldsF.ChF:3-415): total J = J0 + sigma (E - E0) with E = the selected field slot, written
+ * over the whole ghosted box of the grid's total current (pgpu_current_finalize / pgpu_current_get follow,
+ * like finalizeSettingJ after it in the reference). */
+int pgpu_compute_J_from_mass_matrices(pgpu_grid_t g);
+int pgpu_mass_matrix_get(pgpu_grid_t g, int which, double *data, const int *lo, const int *hi, int ncomp);
+int pgpu_mass_matrix_J0_get(pgpu_grid_t g, int comp, double *data, const int *lo, const int *hi);
+
 /* ---- collisions: Scattering subclasses ------------------------------------- */
 /* TakizukaAbe::applyScattering (TakizukaAbe.cpp:240-536).  Species must be binned
  * and have number densities set.  sA == sB selects self-scattering.  The Philox

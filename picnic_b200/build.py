@@ -11,7 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpicnic_gpu.so")
-SOURCES = ["pgpu_api.cu", "pgpu_push.cu", "pgpu_advance_cc1.cu", "pgpu_advance_cc1_1d.cu", "pgpu_bins.cu", "pgpu_collide.cu", "pgpu_exchange.cu", "pgpu_halo_p2p.cu"]
+SOURCES = ["pgpu_api.cu", "pgpu_push.cu", "pgpu_advance_cc1.cu", "pgpu_advance_cc1_1d.cu", "pgpu_bins.cu", "pgpu_collide.cu", "pgpu_exchange.cu", "pgpu_halo_p2p.cu", "pgpu_massmatrix.cu"]
+# per-file flags: the mass-matrix deposit keeps every per-particle product an IEEE product (no contraction)
+EXTRA_FLAGS = {"pgpu_massmatrix.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -27,7 +29,7 @@ def _needs_build():
 
 def _compile(src, tag="", defines=()):
     obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
-    cmd = ["nvcc"] + NVCC_FLAGS + list(defines) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = ["nvcc"] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + list(defines) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

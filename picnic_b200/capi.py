@@ -118,6 +118,10 @@ def load():
         "pgpu_migrator_ipc_handle": [vp, vp], "pgpu_migrator_ipc_open": [vp, vp, vp],
         "pgpu_migrator_connect": [vp, i32, vp], "pgpu_migrate_send": [vp], "pgpu_migrate_recv": [vp],
         "pgpu_migrate_finish": [vp, vp, vp, vp],
+        "pgpu_mass_matrices_init": [vp, i32, vp], "pgpu_mass_matrices_ncomp": [vp, vp],
+        "pgpu_mass_matrices_zero": [vp], "pgpu_accumulate_mass_matrices": [vp, dbl],
+        "pgpu_mass_matrices_save_E0": [vp], "pgpu_compute_J_from_mass_matrices": [vp],
+        "pgpu_mass_matrix_get": [vp, i32, vp, vp, vp, i32], "pgpu_mass_matrix_J0_get": [vp, i32, vp, vp, vp],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
         "pgpu_launch_count": [], "pgpu_picard_totals": [vp, vp, vp, i32], "pgpu_abi_version": [], "pgpu_last_error": [],
     }
@@ -204,6 +208,37 @@ class Grid:
         shape = tuple(h - l + 1 for l, h in zip(lo, hi))
         out = np.zeros(shape, order="F")
         check(load().pgpu_current_get(self.h, comp, _p(out), _i2(lo), _i2(hi)))
+        return out
+
+    # ---- mass matrices (PicSpeciesInterface::initializeMassMatrices / setMassMatrices / computeJfromMassMatrices)
+    def mass_matrices_init(self, interp):
+        nc = np.zeros((9, 2), dtype=np.int32)
+        check(load().pgpu_mass_matrices_init(self.h, interp, _p(nc)))
+        self.mm_ncomp = nc
+        return nc
+
+    def mass_matrices_zero(self):
+        check(load().pgpu_mass_matrices_zero(self.h))
+
+    def mass_matrices_save_E0(self):
+        check(load().pgpu_mass_matrices_save_E0(self.h))
+
+    def compute_J_from_mass_matrices(self):
+        check(load().pgpu_compute_J_from_mass_matrices(self.h))
+
+    def mass_matrix_get(self, which):
+        """sigma `which` (0..8 = xx xy xz yx yy yz zx zy zz) as an array [box of the row's J component] + (ncomp,)"""
+        lo, hi = self.field_bounds(which // 3)
+        ncomp = int(self.mm_ncomp[which, 0]) * int(self.mm_ncomp[which, 1])
+        shape = tuple(h - l + 1 for l, h in zip(lo, hi)) + (ncomp,)
+        out = np.zeros(shape, order="F")
+        check(load().pgpu_mass_matrix_get(self.h, which, _p(out), _i2(lo), _i2(hi), ncomp))
+        return out
+
+    def mass_matrix_J0_get(self, comp):
+        lo, hi = self.field_bounds(comp)
+        out = np.zeros(tuple(h - l + 1 for l, h in zip(lo, hi)), order="F")
+        check(load().pgpu_mass_matrix_J0_get(self.h, comp, _p(out), _i2(lo), _i2(hi)))
         return out
 
     def debye_length(self, species):
@@ -306,6 +341,9 @@ class Species:
         st = PicardStats()
         check(load().pgpu_advance_particles_iteratively(self.h, dt, int(deposit), C.byref(st) if stats else None))
         return st if stats else None
+
+    def accumulate_mass_matrices(self, dt):
+        check(load().pgpu_accumulate_mass_matrices(self.h, dt))
 
     def set_current_density(self, dt, from_explicit=False):
         check(load().pgpu_set_current_density(self.h, dt, int(from_explicit)))

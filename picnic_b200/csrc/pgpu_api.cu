@@ -531,6 +531,7 @@ int pgpu_grid_destroy(pgpu_grid_t g) {
   }
   if (g->scratch_rho.p) cudaFree(g->scratch_rho.p);
   cudaFree(g->debye);
+  mm_destroy(g);
   delete g;
   return 0;
 }

@@ -36,6 +36,36 @@ struct Geo {
   int bc_lo[D], bc_hi[D];
 };
 
+// One fp64 reduction per distinct address of a converged warp instead of one per lane.  Cell-sorted particles
+// send all 32 lanes of a warp to one or two grid entries per stencil point, and same-address atomics
+// serialise in L2: on the 1D 1e8-particle deck (200 ppc) the plain version spent 3/4 of the fused kernel there.
+// Only fully converged warps aggregate (the stencil loops are uniform except at cell crossings); more than four
+// distinct addresses (unsorted input) fall back to one atomic per lane.
+__device__ __forceinline__ void warp_aggregated_add(double *base, long idx, double val) {
+  const unsigned act = __activemask();
+  if (act != 0xffffffffu) {
+    if (idx >= 0) atomicAdd(base + idx, val);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const unsigned grp = __match_any_sync(0xffffffffu, idx);
+  const bool leader = (__ffs(grp) - 1) == lane;
+  unsigned leaders = __ballot_sync(0xffffffffu, leader);
+  if (__popc(leaders) > 4) {
+    if (idx >= 0) atomicAdd(base + idx, val);
+    return;
+  }
+  while (leaders) {
+    const int src = __ffs(leaders) - 1;
+    leaders &= leaders - 1;
+    const unsigned g = __shfl_sync(0xffffffffu, grp, src);
+    double v = ((g >> lane) & 1u) ? val : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == src && idx >= 0) atomicAdd(base + idx, v);
+  }
+}
+
 // ---- arithmetic helpers ------------------------------------------------------
 template <bool X>
 struct M;

@@ -144,6 +144,7 @@ struct pgpu_grid_s {
   pgpu::DeviceFab jtot[3];
   pgpu::DeviceFab scratch_rho;  // reused by set_charge_density
   double *debye = nullptr;      // [ncell_box]
+  void *mm = nullptr;           // pgpu::MassMatrices (pgpu_massmatrix.cu), created by pgpu_mass_matrices_init
   long ncell_box = 0;
   int nbox[2] = {1, 1};
 };
@@ -232,4 +233,5 @@ int launch_deposit_current(pgpu_species_s *s, double cnormDt);
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);
 int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit);
 int launch_advance_cc1_1d_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit);
+void mm_destroy(pgpu_grid_s *g);   // pgpu_massmatrix.cu
 }  // namespace pgpu
