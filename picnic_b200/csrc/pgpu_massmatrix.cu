@@ -16,11 +16,12 @@
 // Two deposit kernels:
 //   k_mm<D>          one thread per particle, the reference's loops as they stand, one fp64 reduction per distinct
 //                    address of a converged warp.  Any D, any number of segments, any particle order.
-//   k_mm_cc1_2d_run  2D fast path for cell-sorted single-segment particles (the 95 % case): a warp stages the 15
-//                    weights and 12 kernel values of its 32 particles in shared memory, then every lane owns 8-9 of
-//                    the 272 (row point, column point) products of a particle and sums them over the run of
-//                    particles that share the dual cell and the node cell -- one RED per product and run instead
-//                    of one per product and particle, and no shuffles.  Other particles go to a list for k_mm.
+//   k_mm_cc1_2d_run  2D fast path for cell-sorted single-segment particles (the 95 % case): a warp stages the row
+//                    factors f*weight_J (64) and column weights (16) of its 32 particles in shared memory, then
+//                    every lane owns 8-9 of the 272 (row point, column point) products of a particle and sums
+//                    them in registers over the run of particles that share the dual cell and the node cell --
+//                    one RED per product and run instead of one per product and particle, and no shuffles.
+//                    Other particles go to a list for k_mm.
 //
 // This file is compiled with -fmad=false: every per-particle product is then the IEEE product the reference's
 // Fortran computes, and the index decisions (true divide + floor) are bit exact; only the summation order differs.
@@ -57,6 +58,8 @@ struct MassMatrices {
   int ncomp[9][2];
   int mX = 0;
   DeviceFab row_box[3];       // box of the J component of a row (sigma arrays share it)
+  double *arena = nullptr;     // J0[3] then sigma[9], one allocation (32-bit element offsets in the run kernel)
+  size_t arena_elems = 0;
   double *sigma[9] = {nullptr};
   DeviceFab J0[3];
   DeviceFab E0[3];
@@ -65,7 +68,8 @@ struct MassMatrices {
   int *defer_list = nullptr;
   unsigned *defer_count = nullptr;
   size_t defer_cap = 0;
-  void *table_d = nullptr;    // MMEntry[272]
+  void *table_d = nullptr;    // MMEntry[288]
+  void *flush_d = nullptr;    // MMFlush[288]
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -631,38 +635,73 @@ k_mm(PartPtrs p, long n, Geo<D> g, MMSet T, MMParams prm, Counters *cnt, const i
 }
 
 // ---- the 2D run kernel -------------------------------------------------------------------------------------------
-// One of the 272 (row point, column point) products of a single-segment particle:
-//   value   = F[fi] * W[a] * W[b] * W[c] * W[d]     (row weight W[a]*W[b], column weight W[c]*W[d])
-//   address = array arr, point base(row) + (di, dj), component nc0 + ncs0*shift0 + ncs1*shift1
-// W = { cicX0, cicX1, cicY0, cicY1, tscX0..2, tscY0..2, wsx0, wsx1, wsy0, wsy1, 1 }, F = { f[3][3], fp[3] }.
+// A single-segment particle makes 272 products  f * weight_J * weight_E  (256 into the sigmas, 16 into J0 with
+// weight_E = 1).  The weights come from three families of the particle's shape products,
+//   P[0..5]   cicX[i]*tscY[j]   (Jx / Ex points, i*3+j)
+//   P[6..11]  tscX[i]*cicY[j]   (Jy / Ey points, i*2+j)
+//   P[12..15] wsx[i]*wsy[j]     (Jz / Ez points, i*2+j)          P[16] = 1
+// and the row factor f * weight_J takes 64 values per particle,
+//   FJ[off(row) + col*npt(row) + point] = f[row][col] * P_row[point]    (x: 0..17, y: 18..35, z: 36..47)
+//   FJ[48..63] = fp[row] * P_row[point]                                  (J0)                FJ[64] = 0 (padding)
+// so product e of a particle is FJ[fj(e)] * P[pe(e)] -- the reference's (f * weight_J) * weight_E, bit for bit.
+// Phase 1: every lane writes the 65 + 17 values and the key (index, index_stag) of its particle to shared memory.
+// Phase 2: lane L owns products L, L+32, ... (9 register accumulators), walks the warp's 32 particles in order and
+// adds; when the key changes (warp-uniform) all lanes flush their accumulators with one RED each.
 struct MMEntry {
-  unsigned char arr;   // 0..8 sigma, 9..11 J0
-  unsigned char fi;    // 0..11
-  unsigned char a, b, c, d;
-  signed char di, dj;
-  short nc0;
-  signed char ncs0, ncs1;
+  unsigned char arr;   // 0..8 sigma, 9..11 J0, 255 = padding
+  unsigned char fj;    // index into FJ
+  unsigned char pe;    // index into P
   unsigned char base;  // 0: (index0, index1), 1: (index_stag0, index_stag1)
-  unsigned char pad[3];
+  signed char di, dj;  // point = base + (di, dj)
+  signed char ncs0, ncs1;
+  int nc0;             // component = nc0 + ncs0*shift0 + ncs1*shift1
 };
-enum { MM_NENT = 272, MM_NW = 15, MM_REC = 32 };   // record: 15 weights + 12 kernels + key (2 x int2) = 29 -> 32 doubles
-enum { W_CICX = 0, W_CICY = 2, W_TSCX = 4, W_TSCY = 7, W_WSX = 10, W_WSY = 12, W_ONE = 14 };
+// where product e of a run goes, as an element offset into the arena that holds J0 and the nine sigmas:
+//   off0 + bi + bj*n0(row) + (shift0*ncs0 + shift1*ncs1)*plane(row),  (bi, bj) = the run's index (base 0) or
+//   index_stag (base 1).  off0 folds in the array's place in the arena, the box origin, the point offset (di, dj) and
+//   the component nc0.  meta: bit 0 base, bits 1-2 row, bits 8-15 ncs0, bits 16-23 ncs1 (signed), < 0 = padding.
+//   Built on the host once per grid; every lane keeps its nine descriptors in registers.
+struct MMFlush {
+  unsigned off0;
+  int meta;
+};
+template <int IMM>
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+enum { MM_NENT = 272, MM_NFJ = 65, MM_NP = 17, MM_KEY = MM_NFJ + MM_NP, MM_REC = 85, MM_EPL = 9, MM_WARPS = 2 };
 
-__global__ void __launch_bounds__(128)
-k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEntry *__restrict__ table, Counters *cnt,
-                int *defer_list, unsigned *defer_count) {
-  __shared__ double rec[4][32][MM_REC + 1];   // +1: lanes of a warp write their records without bank conflicts
-  __shared__ MMEntry tab[MM_NENT];
-  for (int k = threadIdx.x; k < MM_NENT; k += blockDim.x) tab[k] = table[k];
-  __syncthreads();
+__global__ void __launch_bounds__(32 * MM_WARPS)
+k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEntry *__restrict__ table,
+                const MMFlush *__restrict__ flush, Counters *cnt, int *defer_list, unsigned *defer_count) {
+  extern __shared__ double mm_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const long nwarps = (long)gridDim.x * 4;
+  double *rec = mm_smem + (size_t)wid * 32 * MM_REC;
+  const long nwarps = (long)gridDim.x * MM_WARPS;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(rec);
+  // this lane's products: byte offsets into a record (packed) and where their run sums go
+  unsigned opk[MM_EPL], foff[MM_EPL];
+  int fmeta[MM_EPL];
+#pragma unroll
+  for (int e = 0; e < MM_EPL; ++e) {
+    const MMEntry en = table[e * 32 + lane];
+    opk[e] = (8u * en.fj) | ((8u * (MM_NFJ + en.pe)) << 16);
+    const MMFlush fl = flush[e * 32 + lane];
+    foff[e] = fl.off0;
+    fmeta[e] = fl.meta;
+  }
+  double *const arena = T.J[0].p;   // J0 of row x opens the arena
+  const long long rn0[3] = {T.J[0].n0, T.J[1].n0, T.J[2].n0};
+  const long long rplane[3] = {(long long)T.J[0].n0 * T.J[0].n1, (long long)T.J[1].n0 * T.J[1].n1,
+                               (long long)T.J[2].n0 * T.J[2].n1};
   unsigned err = 0;
-  for (long base = ((long)blockIdx.x * 4 + wid) * 32; base < n; base += nwarps * 32) {
+  for (long base = ((long)blockIdx.x * MM_WARPS + wid) * 32; base < n; base += nwarps * 32) {
     const long i = base + lane;
-    // ---- phase 1: every lane prepares its particle ----------------------------------------------------------
-    int key[4] = {INT_MIN, lane, 0, 0};   // a key no other lane has: the particle is not on the fast path
-    double *R = rec[wid][lane];
+    // ---- phase 1 -------------------------------------------------------------------------------------------------
+    double *R = rec + lane * MM_REC;
+    long long key01 = LLONG_MIN, key23 = lane;   // not on the fast path
     if (i < n) {
       const double xb[2] = {p.x[0][i], p.x[1][i]}, xo[2] = {p.xold[0][i], p.xold[1][i]};
       const double uo[3] = {p.vold[0][i], p.vold[1][i], p.vold[2][i]};
@@ -670,34 +709,26 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
       const double qp = p.w[i] * prm.qovs;
       MM2DHead h;
       bool fast = mm_2d_head(g, T, prm, uo, ub, qp, xb, h);
-      if (!fast) err |= ERRBIT_BOUNDS;
+      const bool oob = !fast;
+      if (oob) err |= ERRBIT_BOUNDS;
+      double cic[2][2], tsc[2][3];
       if (fast) {
         // single segment <=> xold and xnew lie in the dual cell of xbar (no boundary truncation on this path)
-        double xn[2];
-        bool one = !(g.bc_lo[0] | g.bc_hi[0] | g.bc_lo[1] | g.bc_hi[1]);
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          xn[d] = 2.0 * xb[d] - xo[d];
-          const int io = ifloor((xo[d] - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
-          const int in = ifloor((xn[d] - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
-          one = one && io == h.index[d] && in == h.index[d];
-        }
-        fast = one;
-      }
-      if (fast) {
-        // the weights of the only segment (:1517-1592 with nn = 0 = num_segments-1, seg_factor = 1 or dXp_sub/dXp = 1)
+        fast = !(g.bc_lo[0] | g.bc_hi[0] | g.bc_lo[1] | g.bc_hi[1]);
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
           const double xn = 2.0 * xb[d] - xo[d];
+          const int io = ifloor((xo[d] - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
+          const int in = ifloor((xn - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
+          // the weights of the only segment (:1517-1592 with nn = 0 = num_segments-1)
           const double dXp = xn - xo[d];
-          const double dXp_sub = xn - xo[d];
-          const double seg_factor = (dXp != 0.0) ? dXp_sub / dXp : 1.0;
+          const double seg_factor = (dXp != 0.0) ? dXp / dXp : 1.0;
           const double xpbar0 = 0.5 * (xo[d] + xn);
           const int index_start = ifloor((xpbar0 - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
-          if (index_start != h.index[d]) fast = false;   // midpoint rounding moved it: generic kernel
+          fast = fast && io == h.index[d] && in == h.index[d] && index_start == h.index[d];
           const double delta = (xpbar0 - (g.le[d] + (h.index[d] + 0.5) * g.dx[d])) / g.dx[d];
-          R[(d ? W_CICY : W_CICX) + 0] = (1.0 - delta) * seg_factor;
-          R[(d ? W_CICY : W_CICX) + 1] = delta * seg_factor;
+          cic[d][0] = (1.0 - delta) * seg_factor;
+          cic[d][1] = delta * seg_factor;
 #pragma unroll
           for (int b = 0; b < 3; ++b) {
             double l = (index_start + b) * g.dx[d] - xo[d] + g.le[d];
@@ -708,87 +739,105 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
             dl = fabs(l / g.dx[d]);
             t = 1.5 - dl;
             const double w_new = (b == 1) ? 0.75 - dl * dl : 0.5 * (t * t);
-            R[(d ? W_TSCY : W_TSCX) + b] = 0.5 * (w_old + w_new);
+            tsc[d][b] = 0.5 * (w_old + w_new);
           }
-          R[(d ? W_WSY : W_WSX) + 0] = h.wsv[d][0];
-          R[(d ? W_WSY : W_WSX) + 1] = h.wsv[d][1];
         }
-        R[W_ONE] = 1.0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-          for (int e = 0; e < 3; ++e) R[MM_NW + 3 * j + e] = h.f[j][e];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) R[MM_NW + 9 + c] = h.fp[c];
       }
       if (fast) {
-        key[0] = h.index[0];
-        key[1] = h.index[1];
-        key[2] = h.index_stag[0];
-        key[3] = h.index_stag[1];
-      } else if (!(err & ERRBIT_BOUNDS)) {
+        double *P = R + MM_NFJ;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            const double wx = cic[0][a] * tsc[1][b];    // Jx / Ex point (a, b)
+            const double wy = tsc[0][b] * cic[1][a];    // Jy / Ey point (b, a)
+            P[a * 3 + b] = wx;
+            P[6 + b * 2 + a] = wy;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              R[0 + c * 6 + a * 3 + b] = h.f[0][c] * wx;
+              R[18 + c * 6 + b * 2 + a] = h.f[1][c] * wy;
+            }
+            R[48 + a * 3 + b] = h.fp[0] * wx;
+            R[54 + b * 2 + a] = h.fp[1] * wy;
+          }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const double wz = h.wsv[0][a] * h.wsv[1][b];
+            P[12 + a * 2 + b] = wz;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) R[36 + c * 4 + a * 2 + b] = h.f[2][c] * wz;
+            R[60 + a * 2 + b] = h.fp[2] * wz;
+          }
+        P[16] = 1.0;
+        R[64] = 0.0;
+        key01 = ((long long)h.index[0] << 32) | (unsigned)h.index[1];
+        key23 = ((long long)h.index_stag[0] << 32) | (unsigned)h.index_stag[1];
+      } else if (!oob) {
         defer_list[atomicAdd(defer_count, 1u)] = (int)i;
       }
     }
-    int *K = reinterpret_cast<int *>(R + MM_NW + 12);
-    K[0] = key[0];
-    K[1] = key[1];
-    K[2] = key[2];
-    K[3] = key[3];
+    reinterpret_cast<long long *>(R + MM_KEY)[0] = key01;
+    reinterpret_cast<long long *>(R + MM_KEY)[1] = key23;
     __syncwarp();
-    // ---- phase 2: lane L owns products L, L+32, ...; it walks the warp's particles in order ------------------------
+    // ---- phase 2 -------------------------------------------------------------------------------------------------
+    // runs of the tile: maximal stretches of consecutive fast-path lanes with one key (warp-uniform bookkeeping)
+    const unsigned valid = __ballot_sync(0xffffffffu, key01 != LLONG_MIN);
+    const long long p01 = __shfl_up_sync(0xffffffffu, key01, 1), p23 = __shfl_up_sync(0xffffffffu, key23, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key01 != p01 || key23 != p23);
+    unsigned rem = valid;
 #pragma unroll 1
-    for (int e = lane; e < MM_NENT; e += 32) {
-      const MMEntry en = tab[e];
-      double acc = 0.0;
-      int k0 = INT_MIN, k1 = 0, k2 = 0, k3 = 0;
-      bool open = false;
+    while (rem) {
+      const int qs = __ffs(rem) - 1;
+      const unsigned stop = (heads | ~valid) & ~((2u << qs) - 1u);
+      const int qe = stop ? __ffs(stop) - 1 : 32;
+      rem &= (qe == 32) ? 0u : ~((1u << qe) - 1u);
+      double acc[MM_EPL];
+#pragma unroll
+      for (int e = 0; e < MM_EPL; ++e) acc[e] = 0.0;
+      int q = qs;
 #pragma unroll 1
-      for (int q = 0; q <= 32; ++q) {
-        int c0 = INT_MIN, c1 = 0, c2 = 0, c3 = 0;
-        const double *Q = rec[wid][q & 31];
-        if (q < 32) {
-          const int *KQ = reinterpret_cast<const int *>(Q + MM_NW + 12);
-          c0 = KQ[0];
-          c1 = KQ[1];
-          c2 = KQ[2];
-          c3 = KQ[3];
+      for (; q + 4 <= qe; q += 4) {
+        const unsigned qb = sbase + (unsigned)q * (MM_REC * 8);
+#pragma unroll
+        for (int e = 0; e < MM_EPL; ++e) {
+          const unsigned a1 = qb + (opk[e] & 0xffffu), a2 = qb + (opk[e] >> 16);
+          acc[e] += lds_f64<0>(a1) * lds_f64<0>(a2);
+          acc[e] += lds_f64<MM_REC * 8>(a1) * lds_f64<MM_REC * 8>(a2);
+          acc[e] += lds_f64<2 * MM_REC * 8>(a1) * lds_f64<2 * MM_REC * 8>(a2);
+          acc[e] += lds_f64<3 * MM_REC * 8>(a1) * lds_f64<3 * MM_REC * 8>(a2);
         }
-        const bool same = open && c0 == k0 && c1 == k1 && c2 == k2 && c3 == k3;
-        if (open && !same) {
-          // flush the run
-          const int bi = en.base ? k2 : k0, bj = en.base ? k3 : k1;
-          const int s0 = (k0 == k2) ? 0 : 1, s1 = (k1 == k3) ? 0 : 1;
-          const int ii = bi + en.di, jj = bj + en.dj;
-          if (en.arr < 9) {
-            const MMView &f = T.s[en.arr];
-            const int nc = en.nc0 + en.ncs0 * s0 + en.ncs1 * s1;
-            const unsigned a = (unsigned)(ii - f.lo0), b = (unsigned)(jj - f.lo1);
-            if (a < (unsigned)f.n0 && b < (unsigned)f.n1 && (unsigned)nc < (unsigned)f.ncomp)
-              atomicAdd(f.p + (a + (size_t)b * f.n0) + (long)nc * f.plane, acc);
-            else err |= ERRBIT_BOUNDS;
-          } else {
-            const FabView &f = T.J[en.arr - 9];
-            const unsigned a = (unsigned)(ii - f.lo0), b = (unsigned)(jj - f.lo1);
-            if (a < (unsigned)f.n0 && b < (unsigned)f.n1) atomicAdd(f.p + (a + (size_t)b * f.n0), acc);
-            else err |= ERRBIT_BOUNDS;
-          }
-          open = false;
-        }
-        if (q < 32 && c0 != INT_MIN) {
-          if (!open) {
-            open = true;
-            acc = 0.0;
-            k0 = c0;
-            k1 = c1;
-            k2 = c2;
-            k3 = c3;
-          }
-          // same association as the reference: f * weight_J * weight_E with weight_J = W[a]*W[b], weight_E = W[c]*W[d]
-          const double wJ = Q[en.a] * Q[en.b];
-          const double wE = Q[en.c] * Q[en.d];
-          acc += Q[MM_NW + en.fi] * wJ * wE;
-        }
+      }
+#pragma unroll 1
+      for (; q < qe; ++q) {
+        const unsigned qb = sbase + (unsigned)q * (MM_REC * 8);
+#pragma unroll
+        for (int e = 0; e < MM_EPL; ++e) acc[e] += lds_f64<0>(qb + (opk[e] & 0xffffu)) * lds_f64<0>(qb + (opk[e] >> 16));
+      }
+      // flush the run: one RED per product
+      const long long r01 = __shfl_sync(0xffffffffu, key01, qs), r23 = __shfl_sync(0xffffffffu, key23, qs);
+      const int k0 = (int)(r01 >> 32), k1 = (int)r01, k2 = (int)(r23 >> 32), k3 = (int)r23;
+      // every point of the stencils inside the arrays? (the row boxes are the J boxes; components are in range by
+      // construction of the table)
+      const bool in = fab_in(T.J[0], k0, k1) && fab_in(T.J[0], k0 + 1, k1 + 2) && fab_in(T.J[1], k0, k1) &&
+                      fab_in(T.J[1], k0 + 2, k1 + 1) && fab_in(T.J[2], k2, k3) && fab_in(T.J[2], k2 + 1, k3 + 1);
+      if (!in) {
+        err |= ERRBIT_BOUNDS;
+        continue;
+      }
+      const int s0 = (k0 == k2) ? 0 : 1, s1 = (k1 == k3) ? 0 : 1;
+#pragma unroll
+      for (int e = 0; e < MM_EPL; ++e) {
+        const int meta = fmeta[e];
+        if (meta < 0) continue;
+        const int row = (meta >> 1) & 3;
+        const long long bi = (meta & 1) ? k2 : k0, bj = (meta & 1) ? k3 : k1;
+        const int sh = s0 * (int)(signed char)(meta >> 8) + s1 * (int)(signed char)(meta >> 16);
+        const long long n0 = row == 0 ? rn0[0] : (row == 1 ? rn0[1] : rn0[2]);
+        const long long pl = row == 0 ? rplane[0] : (row == 1 ? rplane[1] : rplane[2]);
+        atomicAdd(arena + ((long long)foff[e] + bi + bj * n0 + sh * pl), acc[e]);
       }
     }
     __syncwarp();
@@ -871,83 +920,82 @@ static int mm_ncomp_table(int D, int interp, int ghosts, int nc[9][2]) {
   return -2;
 }
 
-// the 272 products of a single-segment 2D particle (llJ = mmJ = llE = mmE = 1), in the order of the reference's loops
-static void build_table(int mX, MMEntry *tab) {
+// the 272 products of a single-segment 2D particle (llJ = mmJ = llE = mmE = 1) following the reference's loops
+// (:1375-1411, :1603-1858), padded to 9 x 32 entries
+static int build_table(int mX, MMEntry *tab) {
   int n = 0;
-  auto put = [&](int arr, int fi, int a, int b, int c, int d, int di, int dj, int nc0, int ncs0, int ncs1, int base) {
+  auto put = [&](int arr, int fj, int pe, int di, int dj, int nc0, int ncs0, int ncs1, int base) {
     MMEntry e;
     memset(&e, 0, sizeof(e));
     e.arr = (unsigned char)arr;
-    e.fi = (unsigned char)fi;
-    e.a = (unsigned char)a;
-    e.b = (unsigned char)b;
-    e.c = (unsigned char)c;
-    e.d = (unsigned char)d;
+    e.fj = (unsigned char)fj;
+    e.pe = (unsigned char)pe;
+    e.base = (unsigned char)base;
     e.di = (signed char)di;
     e.dj = (signed char)dj;
-    e.nc0 = (short)nc0;
     e.ncs0 = (signed char)ncs0;
     e.ncs1 = (signed char)ncs1;
-    e.base = (unsigned char)base;
+    e.nc0 = nc0;
     tab[n++] = e;
   };
-  // Jz, sigma_zz
+  const int PX = 0, PY = 6, PZ = 12, ONE = 16;   // families of P
+  // Jz, sigma_zz (row z, column z)
   for (int iiJ = 0; iiJ < 2; ++iiJ)
     for (int jjJ = 0; jjJ < 2; ++jjJ) {
-      put(9 + 2, 9 + 2, W_WSX + iiJ, W_WSY + jjJ, W_ONE, W_ONE, iiJ, jjJ, 0, 0, 0, 1);
+      const int pt = iiJ * 2 + jjJ;
+      put(9 + 2, 60 + pt, ONE, iiJ, jjJ, 0, 0, 0, 1);
       for (int iiE = 0; iiE < 2; ++iiE)
         for (int jjE = 0; jjE < 2; ++jjE)
-          put(ZZ, 8, W_WSX + iiJ, W_WSY + jjJ, W_WSX + iiE, W_WSY + jjE, iiJ, jjJ, 1 + iiE - iiJ + 3 * (1 + jjE - jjJ),
-              0, 0, 1);
+          put(ZZ, 36 + 2 * 4 + pt, PZ + iiE * 2 + jjE, iiJ, jjJ, 1 + iiE - iiJ + 3 * (1 + jjE - jjJ), 0, 0, 1);
     }
   // Jx rows
   for (int iiJ = 0; iiJ < 2; ++iiJ)
     for (int jjJ = 0; jjJ < 3; ++jjJ) {
-      put(9 + 0, 9 + 0, W_CICX + iiJ, W_TSCY + jjJ, W_ONE, W_ONE, iiJ, jjJ, 0, 0, 0, 0);
+      const int pt = iiJ * 3 + jjJ;
+      put(9 + 0, 48 + pt, ONE, iiJ, jjJ, 0, 0, 0, 0);
       for (int iiE = 0; iiE < 2; ++iiE)
         for (int jjE = 0; jjE < 3; ++jjE)
-          put(XX, 0, W_CICX + iiJ, W_TSCY + jjJ, W_CICX + iiE, W_TSCY + jjE, iiJ, jjJ,
-              1 + mX + iiE - iiJ + (3 + 2 * mX) * (2 + mX + jjE - jjJ), 0, 0, 0);
+          put(XX, 0 + pt, PX + iiE * 3 + jjE, iiJ, jjJ, 1 + mX + iiE - iiJ + (3 + 2 * mX) * (2 + mX + jjE - jjJ), 0, 0, 0);
       for (int iiE = 0; iiE < 3; ++iiE)
         for (int jjE = 0; jjE < 2; ++jjE)
-          put(XY, 1, W_CICX + iiJ, W_TSCY + jjJ, W_TSCX + iiE, W_CICY + jjE, iiJ, jjJ,
-              1 + mX + iiE - iiJ + (4 + 2 * mX) * (2 + mX + jjE - jjJ), 0, 0, 0);
+          put(XY, 6 + pt, PY + iiE * 2 + jjE, iiJ, jjJ, 1 + mX + iiE - iiJ + (4 + 2 * mX) * (2 + mX + jjE - jjJ), 0, 0, 0);
       for (int iiE = 0; iiE < 2; ++iiE)
         for (int jjE = 0; jjE < 2; ++jjE)
-          put(XZ, 2, W_CICX + iiJ, W_TSCY + jjJ, W_WSX + iiE, W_WSY + jjE, iiJ, jjJ,
+          put(XZ, 12 + pt, PZ + iiE * 2 + jjE, iiJ, jjJ,
               1 + mX - 1 + iiE - iiJ + (2 + 2 * mX) * (2 + mX - 1 + jjE - jjJ), 1, 2 + 2 * mX, 0);
     }
   // Jy rows
   for (int iiJ = 0; iiJ < 3; ++iiJ)
     for (int jjJ = 0; jjJ < 2; ++jjJ) {
-      put(9 + 1, 9 + 1, W_TSCX + iiJ, W_CICY + jjJ, W_ONE, W_ONE, iiJ, jjJ, 0, 0, 0, 0);
+      const int pt = iiJ * 2 + jjJ;
+      put(9 + 1, 54 + pt, ONE, iiJ, jjJ, 0, 0, 0, 0);
       for (int iiE = 0; iiE < 2; ++iiE)
         for (int jjE = 0; jjE < 3; ++jjE)
-          put(YX, 3, W_TSCX + iiJ, W_CICY + jjJ, W_CICX + iiE, W_TSCY + jjE, iiJ, jjJ,
-              2 + mX + iiE - iiJ + (4 + 2 * mX) * (1 + mX + jjE - jjJ), 0, 0, 0);
+          put(YX, 18 + pt, PX + iiE * 3 + jjE, iiJ, jjJ, 2 + mX + iiE - iiJ + (4 + 2 * mX) * (1 + mX + jjE - jjJ), 0, 0, 0);
       for (int iiE = 0; iiE < 3; ++iiE)
         for (int jjE = 0; jjE < 2; ++jjE)
-          put(YY, 4, W_TSCX + iiJ, W_CICY + jjJ, W_TSCX + iiE, W_CICY + jjE, iiJ, jjJ,
-              2 + mX + iiE - iiJ + (5 + 2 * mX) * (1 + mX + jjE - jjJ), 0, 0, 0);
+          put(YY, 24 + pt, PY + iiE * 2 + jjE, iiJ, jjJ, 2 + mX + iiE - iiJ + (5 + 2 * mX) * (1 + mX + jjE - jjJ), 0, 0, 0);
       for (int iiE = 0; iiE < 2; ++iiE)
         for (int jjE = 0; jjE < 2; ++jjE)
-          put(YZ, 5, W_TSCX + iiJ, W_CICY + jjJ, W_WSX + iiE, W_WSY + jjE, iiJ, jjJ,
+          put(YZ, 30 + pt, PZ + iiE * 2 + jjE, iiJ, jjJ,
               2 + mX - 1 + iiE - iiJ + (3 + 2 * mX) * (1 + mX - 1 + jjE - jjJ), 1, 3 + 2 * mX, 0);
     }
   // Jz rows against Ex, Ey
   for (int iiJ = 0; iiJ < 2; ++iiJ)
     for (int jjJ = 0; jjJ < 2; ++jjJ) {
+      const int pt = iiJ * 2 + jjJ;
       for (int iiE = 0; iiE < 2; ++iiE)
         for (int jjE = 0; jjE < 3; ++jjE)
-          put(ZX, 6, W_WSX + iiJ, W_WSY + jjJ, W_CICX + iiE, W_TSCY + jjE, iiJ, jjJ,
-              mX + 1 + iiE - iiJ + (2 + 2 * mX) * (mX + 1 + jjE - jjJ), -1, -(2 + 2 * mX), 1);
+          put(ZX, 36 + pt, PX + iiE * 3 + jjE, iiJ, jjJ, mX + 1 + iiE - iiJ + (2 + 2 * mX) * (mX + 1 + jjE - jjJ), -1,
+              -(2 + 2 * mX), 1);
       for (int iiE = 0; iiE < 3; ++iiE)
         for (int jjE = 0; jjE < 2; ++jjE)
-          put(ZY, 7, W_WSX + iiJ, W_WSY + jjJ, W_TSCX + iiE, W_CICY + jjE, iiJ, jjJ,
-              mX + 1 + iiE - iiJ + (3 + 2 * mX) * (mX + 1 + jjE - jjJ), -1, -(3 + 2 * mX), 1);
+          put(ZY, 40 + pt, PY + iiE * 2 + jjE, iiJ, jjJ, mX + 1 + iiE - iiJ + (3 + 2 * mX) * (mX + 1 + jjE - jjJ), -1,
+              -(3 + 2 * mX), 1);
     }
-  // n == MM_NENT by construction (4*17 + 6*17 + 6*17 ... checked by the caller)
-  (void)n;
+  const int real = n;
+  while (n < MM_EPL * 32) put(255, 64, ONE, 0, 0, 0, 0, 0, 0);   // FJ[64] = 0
+  return real;
 }
 
 static MassMatrices *mm_of(pgpu_grid_s *g) { return static_cast<MassMatrices *>(g->mm); }
@@ -955,15 +1003,13 @@ static MassMatrices *mm_of(pgpu_grid_s *g) { return static_cast<MassMatrices *>(
 void mm_destroy(pgpu_grid_s *g) {
   MassMatrices *m = mm_of(g);
   if (!m) return;
-  for (int k = 0; k < 9; ++k)
-    if (m->sigma[k]) cudaFree(m->sigma[k]);
-  for (int c = 0; c < 3; ++c) {
-    if (m->J0[c].p) cudaFree(m->J0[c].p);
+  if (m->arena) cudaFree(m->arena);
+  for (int c = 0; c < 3; ++c)
     if (m->E0[c].p) cudaFree(m->E0[c].p);
-  }
   if (m->defer_list) cudaFree(m->defer_list);
   if (m->defer_count) cudaFree(m->defer_count);
   if (m->table_d) cudaFree(m->table_d);
+  if (m->flush_d) cudaFree(m->flush_d);
   delete m;
   g->mm = nullptr;
 }
@@ -1029,29 +1075,75 @@ int pgpu_mass_matrices_init(pgpu_grid_t g, int interp, int *ncomp_out) {
   memcpy(m->ncomp, nc, sizeof(nc));
   m->mX = g->desc.D == 1 ? g->desc.nghost - 1 : g->desc.nghost - 2;
   cudaStream_t st = ctx().stream;
+  size_t elems = 0;
   for (int c = 0; c < 3; ++c) {
     // the J component of the row: same box as the grid's total current
     m->row_box[c] = g->jtot[c];
     m->row_box[c].p = nullptr;
     m->J0[c] = g->jtot[c];
     m->E0[c] = g->jtot[c];
-    PGPU_CUDA(cudaMalloc(&m->J0[c].p, m->J0[c].size() * sizeof(double)));
     PGPU_CUDA(cudaMalloc(&m->E0[c].p, m->E0[c].size() * sizeof(double)));
-    PGPU_CUDA(cudaMemsetAsync(m->J0[c].p, 0, m->J0[c].size() * sizeof(double), st));
     PGPU_CUDA(cudaMemsetAsync(m->E0[c].p, 0, m->E0[c].size() * sizeof(double), st));
+    elems += m->J0[c].size();
   }
-  for (int k = 0; k < 9; ++k) {
-    const size_t bytes = m->row_box[k / 3].size() * (size_t)(nc[k][0] * nc[k][1]) * sizeof(double);
-    PGPU_CUDA(cudaMalloc(&m->sigma[k], bytes));
-    PGPU_CUDA(cudaMemsetAsync(m->sigma[k], 0, bytes, st));
+  for (int k = 0; k < 9; ++k) elems += m->row_box[k / 3].size() * (size_t)(nc[k][0] * nc[k][1]);
+  if (elems >= 0xffffffffull) {
+    set_error("mass matrices of this box need %zu doubles; the run kernel addresses them with 32 bits", elems);
+    return PGPU_ERR_ARG;
+  }
+  m->arena_elems = elems;
+  PGPU_CUDA(cudaMalloc(&m->arena, elems * sizeof(double)));
+  PGPU_CUDA(cudaMemsetAsync(m->arena, 0, elems * sizeof(double), st));
+  {
+    size_t at = 0;
+    for (int c = 0; c < 3; ++c) {
+      m->J0[c].p = m->arena + at;
+      at += m->J0[c].size();
+    }
+    for (int k = 0; k < 9; ++k) {
+      m->sigma[k] = m->arena + at;
+      at += m->row_box[k / 3].size() * (size_t)(nc[k][0] * nc[k][1]);
+    }
   }
   if (g->desc.D == 2) {
-    MMEntry tab[MM_NENT + 64];
-    memset(tab, 0, sizeof(tab));
-    build_table(m->mX, tab);
-    PGPU_CUDA(cudaMalloc(&m->table_d, sizeof(MMEntry) * MM_NENT));
-    PGPU_CUDA(cudaMemcpy(m->table_d, tab, sizeof(MMEntry) * MM_NENT, cudaMemcpyHostToDevice));
+    MMEntry tab[MM_EPL * 32];
+    if (build_table(m->mX, tab) != MM_NENT) {
+      set_error("internal: mass-matrix product table has the wrong length");
+      return PGPU_ERR_STATE;
+    }
+    PGPU_CUDA(cudaMalloc(&m->table_d, sizeof(tab)));
+    PGPU_CUDA(cudaMemcpy(m->table_d, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    {
+      const MMSet T = make_set(g, m);
+      MMFlush fl[MM_EPL * 32];
+      for (int e = 0; e < MM_EPL * 32; ++e) {
+        const MMEntry &en = tab[e];
+        MMFlush f;
+        f.off0 = 0;
+        f.meta = -1;
+        if (en.arr < 12) {
+          long off;
+          int row;
+          if (en.arr < 9) {
+            const MMView &v = T.s[en.arr];
+            row = en.arr / 3;
+            off = (v.p - m->arena) + (long)(en.di - v.lo0) + (long)(en.dj - v.lo1) * v.n0 + (long)en.nc0 * v.plane;
+          } else {
+            const FabView &v = T.J[en.arr - 9];
+            row = en.arr - 9;
+            off = (v.p - m->arena) + (long)(en.di - v.lo0) + (long)(en.dj - v.lo1) * v.n0;
+          }
+          f.off0 = (unsigned)off;
+          f.meta = (en.base & 1) | (row << 1) | ((int)(unsigned char)en.ncs0 << 8) | ((int)(unsigned char)en.ncs1 << 16);
+        }
+        fl[e] = f;
+      }
+      PGPU_CUDA(cudaMalloc(&m->flush_d, sizeof(fl)));
+      PGPU_CUDA(cudaMemcpy(m->flush_d, fl, sizeof(fl), cudaMemcpyHostToDevice));
+    }
     PGPU_CUDA(cudaMalloc(&m->defer_count, sizeof(unsigned)));
+    PGPU_CUDA(cudaFuncSetAttribute(k_mm_cc1_2d_run, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(MM_WARPS * 32 * MM_REC * sizeof(double))));
   }
   if (ncomp_out)
     for (int k = 0; k < 9; ++k) {
@@ -1065,11 +1157,7 @@ int pgpu_mass_matrices_zero(pgpu_grid_t g) {
   NEED_MM(g);
   MassMatrices *m = mm_of(g);
   cudaStream_t st = ctx().stream;
-  for (int c = 0; c < 3; ++c) PGPU_CUDA(cudaMemsetAsync(m->J0[c].p, 0, m->J0[c].size() * sizeof(double), st));
-  for (int k = 0; k < 9; ++k) {
-    const size_t bytes = m->row_box[k / 3].size() * (size_t)(m->ncomp[k][0] * m->ncomp[k][1]) * sizeof(double);
-    PGPU_CUDA(cudaMemsetAsync(m->sigma[k], 0, bytes, st));
-  }
+  PGPU_CUDA(cudaMemsetAsync(m->arena, 0, m->arena_elems * sizeof(double), st));
   return 0;
 }
 
@@ -1117,9 +1205,12 @@ int pgpu_accumulate_mass_matrices(pgpu_species_t s, double dt) {
   {
     KTimer t("mass_matrix_run");
     const long warps = (s->n + 31) / 32;
-    const unsigned nb = (unsigned)std::min<long>((warps + 3) / 4, (long)c.sm_count * 64);
-    k_mm_cc1_2d_run<<<nb, 128, 0, c.stream>>>(s->ptrs(), s->n, g2, T, prm, static_cast<const MMEntry *>(m->table_d),
-                                              c.d_counters, m->defer_list, m->defer_count);
+    const unsigned nb = (unsigned)std::min<long>((warps + MM_WARPS - 1) / MM_WARPS, (long)c.sm_count * 64);
+    const size_t smem = MM_WARPS * 32 * MM_REC * sizeof(double);
+    k_mm_cc1_2d_run<<<nb, 32 * MM_WARPS, smem, c.stream>>>(s->ptrs(), s->n, g2, T, prm,
+                                                           static_cast<const MMEntry *>(m->table_d),
+                                                           static_cast<const MMFlush *>(m->flush_d), c.d_counters,
+                                                           m->defer_list, m->defer_count);
   }
   {
     KTimer t("mass_matrix_deferred");
