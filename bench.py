@@ -77,6 +77,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-collisions", action="store_true", help="skip the secondary C2 collision-pairs/s leg")
     ap.add_argument("--no-c4", action="store_true", help="skip the secondary C4 leg (1D, 1e8 particles)")
+    ap.add_argument("--no-mass-matrix", action="store_true", help="skip the secondary mass-matrix leg")
     return ap.parse_args()
 
 
@@ -496,6 +497,81 @@ def c4_leg(args, torch, capi, stream, peak):
                         "pairs_per_step": pairs, "ms_per_step": ms_col}}
 
 
+def mass_matrix_leg(args, torch, capi, stream, peak):
+    """Secondary line item (SURVEY 8(f)1): PicSpeciesInterface::setMassMatrices + computeJfromMassMatrices on the C3 box
+    (2D 512x512, 2 species x 100 ppc, CC1, 3 ghost layers -> 231 sigma components = 0.5 GB).  Unit: one particle
+    through accumulateMassMatrices = 272 products f*weight_J*weight_E summed into J0 and the nine sigmas.  Algorithmic
+    bytes per particle: read xbar[2], xold[2], ubar[3], uold[3], w = 88 B (the sigma arrays stay L2 resident per
+    sweep row and cost 1 GB of DRAM traffic per 2.6e7 particles)."""
+    deck = decks.deck_c3(ncell=args.ncell, ppc=args.ppc, dt=args.dt, iter_max=args.iter_max)
+    lo, hi = (0, 0), (deck.ncell[0] - 1, deck.ncell[1] - 1)
+    E, B = decks.analytic_fields(deck, lo, hi, E0=3.0e7, B0=5.0e8)
+    grid = capi.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), volume_scale=deck.volume_scale)
+    grid.set_fields(E, B)
+    rng = np.random.default_rng(3)
+    lib = capi.load()
+    sps = []
+    for sdef in deck.species:
+        p = decks.load_species(deck, sdef, lo, hi, rng)
+        sp = capi.Species(grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm,
+                          interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E, rtol=deck.rtol,
+                          iter_max=deck.iter_max)
+        sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
+        sp.bin_particles()
+        sps.append(sp)
+        del p
+    n = sum(sp.n for sp in sps)
+    for sp in sps:      # converged orbits (xbar, ubar) of one implicit evaluation
+        capi.check(lib.pgpu_advance_particles_iteratively(sp.h, deck.dt, 1, None))
+    nc = grid.mass_matrices_init(3)
+    ncomp = int(sum(int(a) * int(b) for a, b in nc))
+
+    def timed(fn, reps):
+        fn()
+        capi.check(lib.pgpu_synchronize())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        capi.check(lib.pgpu_synchronize())
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def set_mm():
+        grid.mass_matrices_zero()
+        for sp in sps:
+            sp.accumulate_mass_matrices(deck.dt)
+        grid.mass_matrices_save_E0()
+
+    reps = max(args.steps // 8, 3)
+    capi.profile_reset()
+    capi.profile_enable(True)
+    ms_set = timed(set_mm, reps)
+    capi.profile_enable(False)
+    k_ms, k_n = capi.profile_query("mass_matrix_run")
+    d_ms, d_n = capi.profile_query("mass_matrix_deferred")
+    ms_J = timed(grid.compute_J_from_mass_matrices, reps)
+    capi.picard_totals(reset=True)      # raises on a crossing / bounds error of the deposit kernels
+    for sp in sps:
+        sp.destroy()
+    grid.destroy()
+    kern = k_ms / max(k_n, 1)
+    achieved = 88.0 * (n / len(sps)) / (kern * 1e-3) / 1e9 if k_n else None
+    return {"metric": "particles/s through setMassMatrices (accumulateMassMatrices of both species)",
+            "unit": "particles/s", "value": n / (ms_set * 1e-3), "ms_per_setMassMatrices": ms_set,
+            "ms_per_computeJfromMassMatrices": ms_J, "particles": n, "sigma_components": ncomp,
+            "workload": "C3 box: 2D %dx%d cells, 2 species x %d ppc, CC1, %d ghost layers; zero + accumulate both "
+                        "species + save E0, then J = J0 + sigma (E - E0)" % (deck.ncell[0], deck.ncell[1],
+                                                                              args.ppc * args.ppc, deck.nghost),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "bytes_per_unit": 88.0,
+                         "kernel": "mass_matrix_run (k_mm_cc1_2d_run)", "kernel_ms_per_launch": kern,
+                         "deferred_kernel_ms_per_launch": d_ms / max(d_n, 1), "units_per_launch": n / len(sps),
+                         "note": "272 fp64 products + run reductions per particle: instruction bound, not HBM bound"}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -665,6 +741,8 @@ def run_ours(args):
         out["collisions"] = collisions_leg(args, torch, capi, stream, out["roofline"]["peak"])
     if rank == 0 and world == 1 and not args.no_c4:
         out["c4_1d"] = c4_leg(args, torch, capi, stream, out["roofline"]["peak"])
+    if rank == 0 and world == 1 and not args.no_mass_matrix:
+        out["mass_matrices"] = mass_matrix_leg(args, torch, capi, stream, out["roofline"]["peak"])
     capi.finalize()
     if world > 1:
         dist.barrier()

@@ -334,6 +334,13 @@ __device__ bool mm_cc1_1d(const Geo<1> &g, MMTarget &T, const MMParams &prm, con
 }
 
 // ---- cc1_2d_deposit_mass_matrix (:1228-1862) ----------------------------------------------------------------
+// Shape arguments l/dx: a true divide like the reference's, or (-DMM_FASTDIV) l * (1/dx), which moves a weight
+// by at most one ulp; the index decisions always use the true divide.
+#ifdef MM_FASTDIV
+#define MM_DIVDX(a, d) ((a) * g.rdx[d])
+#else
+#define MM_DIVDX(a, d) ((a) / g.dx[d])
+#endif
 // Per-particle set-up shared by the two 2D kernels: indices, CIC weights at xbar, B gather, kernels.
 struct MM2DHead {
   int index[2], index_stag[2];
@@ -347,10 +354,10 @@ __device__ __forceinline__ bool mm_2d_head(const Geo<2> &g, const MMSet &T, cons
     h.index[d] = ifloor((xpbar[d] - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
     h.index_stag[d] = ifloor((xpbar[d] - g.le[d]) / g.dx[d]);
     const double l = xpbar[d] - ((h.index[d] + 0.5) * g.dx[d] + g.le[d]);
-    h.wv[d][1] = l / g.dx[d];
+    h.wv[d][1] = MM_DIVDX(l, d);
     h.wv[d][0] = 1.0 - h.wv[d][1];
     const double ls = xpbar[d] - (h.index_stag[d] * g.dx[d] + g.le[d]);
-    h.wsv[d][1] = ls / g.dx[d];
+    h.wsv[d][1] = MM_DIVDX(ls, d);
     h.wsv[d][0] = 1.0 - h.wsv[d][1];
   }
   double Bp[3] = {0.0, 0.0, 0.0};
@@ -722,21 +729,21 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
           const int in = ifloor((xn - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
           // the weights of the only segment (:1517-1592 with nn = 0 = num_segments-1)
           const double dXp = xn - xo[d];
-          const double seg_factor = (dXp != 0.0) ? dXp / dXp : 1.0;
+          const double seg_factor = (dXp != 0.0) ? dXp / dXp : 1.0;   // = 1 (folded by the compiler unless dXp is inf/nan)
           const double xpbar0 = 0.5 * (xo[d] + xn);
           const int index_start = ifloor((xpbar0 - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
           fast = fast && io == h.index[d] && in == h.index[d] && index_start == h.index[d];
-          const double delta = (xpbar0 - (g.le[d] + (h.index[d] + 0.5) * g.dx[d])) / g.dx[d];
+          const double delta = MM_DIVDX(xpbar0 - (g.le[d] + (h.index[d] + 0.5) * g.dx[d]), d);
           cic[d][0] = (1.0 - delta) * seg_factor;
           cic[d][1] = delta * seg_factor;
 #pragma unroll
           for (int b = 0; b < 3; ++b) {
             double l = (index_start + b) * g.dx[d] - xo[d] + g.le[d];
-            double dl = fabs(l / g.dx[d]);
+            double dl = fabs(MM_DIVDX(l, d));
             double t = 1.5 - dl;
             const double w_old = (b == 1) ? 0.75 - dl * dl : 0.5 * (t * t);
             l = (index_start + b) * g.dx[d] - xn + g.le[d];
-            dl = fabs(l / g.dx[d]);
+            dl = fabs(MM_DIVDX(l, d));
             t = 1.5 - dl;
             const double w_new = (b == 1) ? 0.75 - dl * dl : 0.5 * (t * t);
             tsc[d][b] = 0.5 * (w_old + w_new);

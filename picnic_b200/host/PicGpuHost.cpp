@@ -70,6 +70,23 @@ void Mesh::finalizeSettingJ() {
 void Mesh::getCurrentDensity(int comp, const FabRef &out) const {
   check(pgpu_current_get(m_h, comp, out.data, out.lo, out.hi), "Mesh::getCurrentDensity");
 }
+void Mesh::initializeMassMatrices(int a_interp_type, int *a_ncomp) {
+  check(pgpu_mass_matrices_init(m_h, a_interp_type, a_ncomp), "Mesh::initializeMassMatrices");
+}
+void Mesh::setMassMatrices(const std::vector<PicChargedSpecies *> &species, Real a_dt) {
+  check(pgpu_mass_matrices_zero(m_h), "Mesh::setMassMatrices");
+  for (size_t i = 0; i < species.size(); ++i) species[i]->accumulateMassMatrices(a_dt);
+  check(pgpu_mass_matrices_save_E0(m_h), "Mesh::setMassMatrices");
+}
+void Mesh::computeJfromMassMatrices() {
+  check(pgpu_compute_J_from_mass_matrices(m_h), "Mesh::computeJfromMassMatrices");
+}
+void Mesh::getMassMatrix(int a_which, const FabRef &out, int a_ncomp) const {
+  check(pgpu_mass_matrix_get(m_h, a_which, out.data, out.lo, out.hi, a_ncomp), "Mesh::getMassMatrix");
+}
+void Mesh::getJ0(int comp, const FabRef &out) const {
+  check(pgpu_mass_matrix_J0_get(m_h, comp, out.data, out.lo, out.hi), "Mesh::getJ0");
+}
 void Mesh::setDebyeLength(const std::vector<PicChargedSpecies *> &species, Real *LDe) {
   std::vector<pgpu_species_t> h;
   for (size_t i = 0; i < species.size(); ++i) h.push_back(species[i]->handle());
@@ -341,6 +358,9 @@ void PicChargedSpecies::advanceParticlesIteratively(Real a_dt, bool a_deposit_cu
 }
 void PicChargedSpecies::setCurrentDensity(Real a_dt, bool a_from_explicit_solver) {
   check(pgpu_set_current_density(m_h, a_dt, a_from_explicit_solver ? 1 : 0), "PicChargedSpecies::setCurrentDensity");
+}
+void PicChargedSpecies::accumulateMassMatrices(Real a_dt) {
+  check(pgpu_accumulate_mass_matrices(m_h, a_dt), "PicChargedSpecies::accumulateMassMatrices");
 }
 void PicChargedSpecies::getCurrentDensity(int comp, const FabRef &out) const {
   check(pgpu_species_current_get(m_h, comp, out.data, out.lo, out.hi), "PicChargedSpecies::getCurrentDensity");

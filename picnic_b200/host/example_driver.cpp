@@ -4,6 +4,7 @@
 // src/species/pic/PicSpeciesInterface.cpp:899-994).  Reads a problem written by
 // tests/test_host_shim.py, runs it on the GPU and writes J and the particles back.
 //   usage: example_driver <problem.bin> <result.bin>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -77,6 +78,30 @@ int main(int argc, char **argv) {
       FabRef out = R[c];
       out.data = J[c].data();
       mesh.getCurrentDensity(c, out);
+    }
+    // ---- mass matrices (use_mass_matrices decks): PicSpeciesInterface::setMassMatrices at the converged orbits,
+    // then computeJfromMassMatrices with E == E0 must give back the current just deposited (J0 is that current)
+    if (D == 2 && nghost >= 3) {
+      std::vector<PicChargedSpecies *> one(1, &sp);
+      int ncomp[18];
+      mesh.initializeMassMatrices(PGPU_CC1, ncomp);
+      mesh.setMassMatrices(one, dt);
+      mesh.computeJfromMassMatrices();
+      mesh.finalizeSettingJ();
+      double worst = 0.0;
+      for (int c = 0; c < 3; ++c) {
+        std::vector<double> Jm(F[c].size());
+        FabRef out = R[c];
+        out.data = Jm.data();
+        mesh.getCurrentDensity(c, out);
+        double scale = 0.0, diff = 0.0;
+        for (size_t k = 0; k < Jm.size(); ++k) {
+          scale = std::fmax(scale, std::fabs(J[c][k]));
+          diff = std::fmax(diff, std::fabs(Jm[k] - J[c][k]));
+        }
+        worst = std::fmax(worst, diff / scale);
+      }
+      std::printf("example_driver: mass matrices ncomp_xx=%dx%d, J(E0) vs deposited J: %.3e\n", ncomp[0], ncomp[1], worst);
     }
     const int bc[2] = {PGPU_BC_PERIODIC, PGPU_BC_PERIODIC};
     sp.advanceVelocities_2ndHalf();

@@ -58,6 +58,9 @@ def test_example_driver_matches_oracle(driver, tmp_path):
     r = subprocess.run([driver, str(prob), str(res)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     raw = np.fromfile(res, dtype=np.float64)
+    # Mesh::setMassMatrices / computeJfromMassMatrices at E == E0 give back the deposited current
+    mm = [l for l in r.stdout.splitlines() if "mass matrices" in l]
+    assert mm and "ncomp_xx=5x7" in mm[0] and float(mm[0].split()[-1]) < 1e-12, r.stdout
     # oracle, same call sequence
     geom = orc.make_geom(2, deck.xmin, deck.xmax, deck.dx, deck.nghost)
     Ef = [orc.Fab(l, h, a) for (l, h, a) in E]

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: tools/quick_bench.sh TAG [ENV=VAL ...] -- short device-resident bench of the C3 step, prints the headline numbers
 tag=$1; shift
-env "$@" python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --no-collisions --no-c4 ${SORT_EVERY:+--sort-every $SORT_EVERY} > gpurun_out/qb_$tag.json 2>gpurun_out/qb_$tag.err || tail -3 gpurun_out/qb_$tag.err
+env "$@" python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --no-collisions --no-c4 --no-mass-matrix ${SORT_EVERY:+--sort-every $SORT_EVERY} > gpurun_out/qb_$tag.json 2>gpurun_out/qb_$tag.err || tail -3 gpurun_out/qb_$tag.err
 python - <<PY
 import json
 try:
