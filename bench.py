@@ -546,6 +546,8 @@ def mass_matrix_leg(args, torch, capi, stream, peak):
         grid.mass_matrices_save_E0()
 
     reps = max(args.steps // 8, 3)
+    set_mm()                      # first launches (module load, local-memory reservation) stay out of the kernel timers
+    capi.check(lib.pgpu_synchronize())
     capi.profile_reset()
     capi.profile_enable(True)
     ms_set = timed(set_mm, reps)

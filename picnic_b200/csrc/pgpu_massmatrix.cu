@@ -334,13 +334,23 @@ __device__ bool mm_cc1_1d(const Geo<1> &g, MMTarget &T, const MMParams &prm, con
 }
 
 // ---- cc1_2d_deposit_mass_matrix (:1228-1862) ----------------------------------------------------------------
-// Shape arguments l/dx: a true divide like the reference's, or (-DMM_FASTDIV) l * (1/dx), which moves a weight
-// by at most one ulp; the index decisions always use the true divide.
+// a / dx[d] as the reference computes it (IEEE divide).  When dx is a power of two -- 0.25 in the reference's decks and
+// in every BASELINE configuration -- 1/dx is exact and a * (1/dx) is the same double bit for bit, without the ~15
+// instructions of a DDIV; the test is on the mantissa of dx and warp-uniform.  -DMM_FASTDIV takes the product for any dx
+// in the shape arguments (at most one ulp off in a weight); index decisions never do.
+__device__ __forceinline__ bool mm_pow2(double dx) {
+  return (__double_as_longlong(dx) & 0x000fffffffffffffLL) == 0;
+}
+template <class G>
+__device__ __forceinline__ double mm_div_exact(const G &g, double a, int d) {
+  return mm_pow2(g.dx[d]) ? a * g.rdx[d] : a / g.dx[d];
+}
 #ifdef MM_FASTDIV
 #define MM_DIVDX(a, d) ((a) * g.rdx[d])
 #else
-#define MM_DIVDX(a, d) ((a) / g.dx[d])
+#define MM_DIVDX(a, d) mm_div_exact(g, (a), (d))
 #endif
+#define MM_FLOORDX(a, d) ifloor(mm_div_exact(g, (a), (d)))
 // Per-particle set-up shared by the two 2D kernels: indices, CIC weights at xbar, B gather, kernels.
 struct MM2DHead {
   int index[2], index_stag[2];
@@ -351,8 +361,8 @@ __device__ __forceinline__ bool mm_2d_head(const Geo<2> &g, const MMSet &T, cons
                                            const double *upbar, double qp, const double *xpbar, MM2DHead &h) {
 #pragma unroll
   for (int d = 0; d < 2; ++d) {
-    h.index[d] = ifloor((xpbar[d] - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
-    h.index_stag[d] = ifloor((xpbar[d] - g.le[d]) / g.dx[d]);
+    h.index[d] = MM_FLOORDX(xpbar[d] - g.le[d] - 0.5 * g.dx[d], d);
+    h.index_stag[d] = MM_FLOORDX(xpbar[d] - g.le[d], d);
     const double l = xpbar[d] - ((h.index[d] + 0.5) * g.dx[d] + g.le[d]);
     h.wv[d][1] = MM_DIVDX(l, d);
     h.wv[d][0] = 1.0 - h.wv[d][1];
@@ -678,6 +688,22 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
   asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
   return v;
 }
+// one particle (record at byte offset IMM from the lane's base addresses) into the lane's nine accumulators
+template <int IMM>
+__device__ __forceinline__ void mm_accumulate(double *acc, unsigned a6, unsigned b6, unsigned a2, unsigned b2,
+                                              unsigned a1) {
+  const double f6 = lds_f64<IMM>(a6);
+  acc[0] += f6 * lds_f64<IMM>(b6);
+  acc[1] += f6 * lds_f64<IMM + 8>(b6);
+  acc[2] += f6 * lds_f64<IMM + 16>(b6);
+  acc[3] += f6 * lds_f64<IMM + 24>(b6);
+  acc[4] += f6 * lds_f64<IMM + 32>(b6);
+  acc[5] += f6 * lds_f64<IMM + 40>(b6);
+  const double f2 = lds_f64<IMM>(a2);
+  acc[6] += f2 * lds_f64<IMM>(b2);
+  acc[7] += f2 * lds_f64<IMM + 8>(b2);
+  acc[8] += lds_f64<IMM>(a1);   // J0: fp * weight_J, no column weight (padding lanes read FJ[64] = 0)
+}
 enum { MM_NENT = 272, MM_NFJ = 65, MM_NP = 17, MM_KEY = MM_NFJ + MM_NP, MM_REC = 85, MM_EPL = 9, MM_WARPS = 2 };
 
 __global__ void __launch_bounds__(32 * MM_WARPS)
@@ -688,21 +714,19 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
   double *rec = mm_smem + (size_t)wid * 32 * MM_REC;
   const long nwarps = (long)gridDim.x * MM_WARPS;
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(rec);
-  // this lane's products: byte offsets into a record (packed) and where their run sums go
-  unsigned opk[MM_EPL], foff[MM_EPL];
-  int fmeta[MM_EPL];
+  // this lane's products (build_table): slots 0..5 share the row factor FJ[fj6] and take six consecutive column
+  // weights, slots 6,7 share FJ[fj2] and take two, slot 8 is a J0 product (column weight 1).  Byte offsets into a
+  // record, and where the run sums go.
+  unsigned foff[MM_EPL];
 #pragma unroll
-  for (int e = 0; e < MM_EPL; ++e) {
-    const MMEntry en = table[e * 32 + lane];
-    opk[e] = (8u * en.fj) | ((8u * (MM_NFJ + en.pe)) << 16);
-    const MMFlush fl = flush[e * 32 + lane];
-    foff[e] = fl.off0;
-    fmeta[e] = fl.meta;
-  }
+  for (int e = 0; e < MM_EPL; ++e) foff[e] = flush[e * 32 + lane].off0;
+  const int fmeta6 = flush[lane].meta, fmeta2 = flush[6 * 32 + lane].meta, fmeta1 = flush[8 * 32 + lane].meta;
+  const unsigned ofj6 = 8u * table[lane].fj, opb6 = 8u * (MM_NFJ + table[lane].pe);
+  const unsigned ofj2 = 8u * table[6 * 32 + lane].fj, opb2 = 8u * (MM_NFJ + table[6 * 32 + lane].pe);
+  const unsigned ofj1 = 8u * table[8 * 32 + lane].fj;
   double *const arena = T.J[0].p;   // J0 of row x opens the arena
-  const long long rn0[3] = {T.J[0].n0, T.J[1].n0, T.J[2].n0};
-  const long long rplane[3] = {(long long)T.J[0].n0 * T.J[0].n1, (long long)T.J[1].n0 * T.J[1].n1,
-                               (long long)T.J[2].n0 * T.J[2].n1};
+  const int rn0[3] = {T.J[0].n0, T.J[1].n0, T.J[2].n0};
+  const int rplane[3] = {T.J[0].n0 * T.J[0].n1, T.J[1].n0 * T.J[1].n1, T.J[2].n0 * T.J[2].n1};
   unsigned err = 0;
   for (long base = ((long)blockIdx.x * MM_WARPS + wid) * 32; base < n; base += nwarps * 32) {
     const long i = base + lane;
@@ -725,13 +749,13 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
           const double xn = 2.0 * xb[d] - xo[d];
-          const int io = ifloor((xo[d] - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
-          const int in = ifloor((xn - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
+          const int io = MM_FLOORDX(xo[d] - g.le[d] - 0.5 * g.dx[d], d);
+          const int in = MM_FLOORDX(xn - g.le[d] - 0.5 * g.dx[d], d);
           // the weights of the only segment (:1517-1592 with nn = 0 = num_segments-1)
           const double dXp = xn - xo[d];
           const double seg_factor = (dXp != 0.0) ? dXp / dXp : 1.0;   // = 1 (folded by the compiler unless dXp is inf/nan)
           const double xpbar0 = 0.5 * (xo[d] + xn);
-          const int index_start = ifloor((xpbar0 - g.le[d] - 0.5 * g.dx[d]) / g.dx[d]);
+          const int index_start = MM_FLOORDX(xpbar0 - g.le[d] - 0.5 * g.dx[d], d);
           fast = fast && io == h.index[d] && in == h.index[d] && index_start == h.index[d];
           const double delta = MM_DIVDX(xpbar0 - (g.le[d] + (h.index[d] + 0.5) * g.dx[d]), d);
           cic[d][0] = (1.0 - delta) * seg_factor;
@@ -808,20 +832,15 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
 #pragma unroll 1
       for (; q + 4 <= qe; q += 4) {
         const unsigned qb = sbase + (unsigned)q * (MM_REC * 8);
-#pragma unroll
-        for (int e = 0; e < MM_EPL; ++e) {
-          const unsigned a1 = qb + (opk[e] & 0xffffu), a2 = qb + (opk[e] >> 16);
-          acc[e] += lds_f64<0>(a1) * lds_f64<0>(a2);
-          acc[e] += lds_f64<MM_REC * 8>(a1) * lds_f64<MM_REC * 8>(a2);
-          acc[e] += lds_f64<2 * MM_REC * 8>(a1) * lds_f64<2 * MM_REC * 8>(a2);
-          acc[e] += lds_f64<3 * MM_REC * 8>(a1) * lds_f64<3 * MM_REC * 8>(a2);
-        }
+        mm_accumulate<0>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
+        mm_accumulate<MM_REC * 8>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
+        mm_accumulate<2 * MM_REC * 8>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
+        mm_accumulate<3 * MM_REC * 8>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
       }
 #pragma unroll 1
       for (; q < qe; ++q) {
         const unsigned qb = sbase + (unsigned)q * (MM_REC * 8);
-#pragma unroll
-        for (int e = 0; e < MM_EPL; ++e) acc[e] += lds_f64<0>(qb + (opk[e] & 0xffffu)) * lds_f64<0>(qb + (opk[e] >> 16));
+        mm_accumulate<0>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
       }
       // flush the run: one RED per product
       const long long r01 = __shfl_sync(0xffffffffu, key01, qs), r23 = __shfl_sync(0xffffffffu, key23, qs);
@@ -835,17 +854,22 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
         continue;
       }
       const int s0 = (k0 == k2) ? 0 : 1, s1 = (k1 == k3) ? 0 : 1;
-#pragma unroll
-      for (int e = 0; e < MM_EPL; ++e) {
-        const int meta = fmeta[e];
-        if (meta < 0) continue;
+      // the products of a slot group go to one array: the run-dependent part of the address once per group (32-bit:
+      // the arena holds fewer than 2^32 doubles), the product-dependent part is foff[e]
+      auto dyn = [&](int meta) -> long long {
         const int row = (meta >> 1) & 3;
-        const long long bi = (meta & 1) ? k2 : k0, bj = (meta & 1) ? k3 : k1;
+        const int n0 = row == 0 ? rn0[0] : (row == 1 ? rn0[1] : rn0[2]);
+        const int pl = row == 0 ? rplane[0] : (row == 1 ? rplane[1] : rplane[2]);
+        const int bi = (meta & 1) ? k2 : k0, bj = (meta & 1) ? k3 : k1;
         const int sh = s0 * (int)(signed char)(meta >> 8) + s1 * (int)(signed char)(meta >> 16);
-        const long long n0 = row == 0 ? rn0[0] : (row == 1 ? rn0[1] : rn0[2]);
-        const long long pl = row == 0 ? rplane[0] : (row == 1 ? rplane[1] : rplane[2]);
-        atomicAdd(arena + ((long long)foff[e] + bi + bj * n0 + sh * pl), acc[e]);
-      }
+        return (long long)(bi + bj * n0 + sh * pl);
+      };
+      double *const t6 = arena + dyn(fmeta6), *const t2 = arena + dyn(fmeta2);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) atomicAdd(t6 + foff[e], acc[e]);
+      atomicAdd(t2 + foff[6], acc[6]);
+      atomicAdd(t2 + foff[7], acc[7]);
+      if (fmeta1 >= 0) atomicAdd(arena + dyn(fmeta1) + foff[8], acc[8]);
     }
     __syncwarp();
   }
@@ -928,8 +952,14 @@ static int mm_ncomp_table(int D, int interp, int ghosts, int nc[9][2]) {
 }
 
 // the 272 products of a single-segment 2D particle (llJ = mmJ = llE = mmE = 1) following the reference's loops
-// (:1375-1411, :1603-1858), padded to 9 x 32 entries
-static int build_table(int mX, MMEntry *tab) {
+// (:1375-1411, :1603-1858), then dealt to the lanes (9 slots x 32 lanes)
+static int build_table(int mX, MMEntry *tab_out) {
+  MMEntry tab_buf[MM_EPL * 32 + 32];
+  MMEntry *tab = tab_buf;
+  struct CopyBack {
+    MMEntry *from, *to;
+    ~CopyBack() { memcpy(to, from, sizeof(MMEntry) * MM_EPL * 32); }
+  } copy_back{tab_buf, tab_out};
   int n = 0;
   auto put = [&](int arr, int fj, int pe, int di, int dj, int nc0, int ncs0, int ncs1, int base) {
     MMEntry e;
@@ -1001,7 +1031,55 @@ static int build_table(int mX, MMEntry *tab) {
               -(3 + 2 * mX), 1);
     }
   const int real = n;
-  while (n < MM_EPL * 32) put(255, 64, ONE, 0, 0, 0, 0, 0, 0);   // FJ[64] = 0
+  if (real != MM_NENT) return real;
+  // Lane assignment: products that share the row factor FJ[fj] sit on one lane, so that a lane loads it once per
+  // particle.  32 groups of six column points (xx xy yx yy zx zy) -> slots 0..5 of lane L; 16 groups of four (xz yz zz)
+  // in halves -> slots 6,7; the 16 J0 products -> slot 8 of lanes 0..15 (padding elsewhere).
+  MMEntry flat[MM_NENT];
+  memcpy(flat, tab, sizeof(flat));
+  int first6[32], n6 = 0, first4[16], n4 = 0, j0[16], n1 = 0;
+  for (int k = 0; k < MM_NENT; ++k) {
+    if (flat[k].arr >= 9) {
+      if (n1 < 16) j0[n1] = k;
+      ++n1;
+      continue;
+    }
+    bool seen = false;
+    int cnt = 0;
+    for (int q = 0; q < MM_NENT; ++q)
+      if (flat[q].arr < 9 && flat[q].fj == flat[k].fj) {
+        if (q < k) seen = true;
+        ++cnt;
+      }
+    if (seen) continue;
+    if (cnt == 6 && n6 < 32) first6[n6++] = k;
+    else if (cnt == 4 && n4 < 16) first4[n4++] = k;
+    else return -1;
+  }
+  if (n6 != 32 || n4 != 16 || n1 != 16) return -1;
+  MMEntry pad;
+  memset(&pad, 0, sizeof(pad));
+  pad.arr = 255;
+  pad.fj = 64;   // FJ[64] = 0
+  pad.pe = ONE;
+  auto member = [&](int fj, int rank) -> int {   // the rank-th product (by column weight index) of group fj
+    int idx[6], m = 0;
+    for (int q = 0; q < MM_NENT; ++q)
+      if (flat[q].arr < 9 && flat[q].fj == fj) idx[m++] = q;
+    for (int a = 0; a < m; ++a)
+      for (int b = a + 1; b < m; ++b)
+        if (flat[idx[b]].pe < flat[idx[a]].pe) std::swap(idx[a], idx[b]);
+    return idx[rank];
+  };
+  for (int L = 0; L < 32; ++L) {
+    for (int e = 0; e < 6; ++e) tab[e * 32 + L] = flat[member(flat[first6[L]].fj, e)];
+    for (int e = 0; e < 2; ++e) tab[(6 + e) * 32 + L] = flat[member(flat[first4[L / 2]].fj, 2 * (L % 2) + e)];
+    tab[8 * 32 + L] = (L < 16) ? flat[j0[L]] : pad;
+    // the kernel relies on consecutive column weights within a slot group
+    for (int e = 1; e < 6; ++e)
+      if (tab[e * 32 + L].pe != tab[L].pe + e) return -1;
+    if (tab[7 * 32 + L].pe != tab[6 * 32 + L].pe + 1) return -1;
+  }
   return real;
 }
 

@@ -7,7 +7,9 @@ built on -- SURVEY.md 8c -- which the oracle satisfies at small size in test_ora
   C2  2D 256x256 cells, 64 ppc/species, Takizuka-Abe: exact pair counts, total momentum and energy of
       the whole plasma conserved to round-off, cell-locality (per-cell particle count unchanged);
   C4  1D 250 000 cells x 200 ppc x 2 species = 1e8 particles: 1D CC1 charge continuity and weighted
-      Coulomb (NANBU) momentum/energy conservation for equal weights."""
+      Coulomb (NANBU) momentum/energy conservation for equal weights;
+  C3  mass matrices: J0 equals the deposited current, and J0 + sigma (E - E0) equals the deposit of the Boris
+      response to a perturbed E at frozen orbits (what PicSpeciesInterface::computeJfromMassMatrices stands for)."""
 import numpy as np
 import pytest
 
@@ -168,6 +170,61 @@ def test_c4_full_size_1d_continuity_and_coulomb(pgpu):
     pscale = sum(mk * np.sqrt(mm[0] * mm[4:7].sum()) for mk, mm in zip(mass, m0))
     assert np.max(np.abs(P1 - P0)) <= 1e-12 * pscale          # equal weights: every pair conserves exactly
     assert abs(K1 - K0) <= 1e-12 * K0
+    for sp in sps:
+        sp.destroy()
+    grid.destroy()
+
+
+def test_c3_full_size_mass_matrices_reproduce_the_perturbed_current(pgpu):
+    deck = decks.deck_c3()
+    deck.dt = 0.1
+    n0 = deck.ncell[0]
+    lo, hi = (0, 0), (n0 - 1, n0 - 1)
+    E, B = decks.analytic_fields(deck, lo, hi, E0=3.0e7, B0=5.0e8)
+    grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), volume_scale=deck.volume_scale)
+    grid.set_fields(E, B)
+    rng = np.random.default_rng(12)
+    sps = []
+    for sdef in deck.species:
+        sp, n, _ = _upload(pgpu, grid, deck, sdef, lo, hi, rng)
+        sp.bin_particles()
+        st = sp.advance_iteratively(deck.dt, deposit=True)     # converged (xbar, ubar) + the species current
+        assert st.num_unconverged == 0
+        sps.append(sp)
+    grid.current_zero()
+    for sp in sps:
+        grid.current_add(sp)
+    Jdep = [grid.current_get(c) for c in range(3)]
+    nc = grid.mass_matrices_init(3)
+    assert nc.tolist() == [[5, 7], [6, 6], [4, 5], [6, 6], [7, 5], [5, 4], [4, 5], [5, 4], [3, 3]]
+    grid.mass_matrices_zero()
+    for sp in sps:
+        sp.accumulate_mass_matrices(deck.dt)
+    grid.mass_matrices_save_E0()
+    # (1) E == E0: the contraction returns J0, which is the current the fused kernel deposited
+    grid.compute_J_from_mass_matrices()
+    for c in range(3):
+        J = grid.current_get(c)
+        assert np.max(np.abs(J - Jdep[c])) <= 1e-12 * np.max(np.abs(Jdep[c])), c
+    # (2) perturbed E in field slot 1; frozen orbits: gather at the stored (xbar, xold), Boris half step, deposit
+    scale = (1.0 + 2.0e-2, 1.0 - 1.0e-2, 1.0 + 3.0e-2)
+    E1 = [(l, h, a * scale[c]) for c, (l, h, a) in enumerate(E)]
+    grid.fields_select(1)
+    grid.set_fields(E1, B)
+    grid.compute_J_from_mass_matrices()
+    Jmm = [grid.current_get(c) for c in range(3)]
+    grid.current_zero()
+    for sp in sps:
+        sp.interpolate_fields()
+        sp.advance_velocities(deck.dt, True)
+        sp.set_current_density(deck.dt)
+        grid.current_add(sp)
+    for c in range(3):
+        Jd = grid.current_get(c)
+        s = np.max(np.abs(Jd))
+        assert np.max(np.abs(Jd - Jdep[c])) > 1e-4 * s          # the perturbation is visible
+        assert np.max(np.abs(Jmm[c] - Jd)) <= 1e-10 * s, c
+    grid.fields_select(0)
     for sp in sps:
         sp.destroy()
     grid.destroy()

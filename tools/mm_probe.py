@@ -62,6 +62,7 @@ def set_mm():
 
 for mode, name in ((1, "run kernel"), (0, "generic kernel")):
     lib.pgpu_set_deposit_mode(mode)
+    set_mm(); capi.check(lib.pgpu_synchronize())      # first launches stay out of the kernel timers
     lib.pgpu_profile_enable(1)
     lib.pgpu_profile_reset()
     t = timed(set_mm, args.reps if mode else 1)
