@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "pgpu_internal.h"
@@ -652,23 +653,27 @@ k_mm(PartPtrs p, long n, Geo<D> g, MMSet T, MMParams prm, Counters *cnt, const i
 }
 
 // ---- the 2D run kernel -------------------------------------------------------------------------------------------
-// A single-segment particle makes 272 products  f * weight_J * weight_E  (256 into the sigmas, 16 into J0 with
-// weight_E = 1).  The weights come from three families of the particle's shape products,
+// A single-segment particle makes 272 products  f * weight_J * weight_E  (256 into the sigmas, 16 into J0 without
+// weight_E).  Both weights come from three families of the particle's shape products,
 //   P[0..5]   cicX[i]*tscY[j]   (Jx / Ex points, i*3+j)
 //   P[6..11]  tscX[i]*cicY[j]   (Jy / Ey points, i*2+j)
-//   P[12..15] wsx[i]*wsy[j]     (Jz / Ez points, i*2+j)          P[16] = 1
-// and the row factor f * weight_J takes 64 values per particle,
-//   FJ[off(row) + col*npt(row) + point] = f[row][col] * P_row[point]    (x: 0..17, y: 18..35, z: 36..47)
-//   FJ[48..63] = fp[row] * P_row[point]                                  (J0)                FJ[64] = 0 (padding)
-// so product e of a particle is FJ[fj(e)] * P[pe(e)] -- the reference's (f * weight_J) * weight_E, bit for bit.
-// Phase 1: every lane writes the 65 + 17 values and the key (index, index_stag) of its particle to shared memory.
-// Phase 2: lane L owns products L, L+32, ... (9 register accumulators), walks the warp's 32 particles in order and
-// adds; when the key changes (warp-uniform) all lanes flush their accumulators with one RED each.
+//   P[12..15] wsx[i]*wsy[j]     (Jz / Ez points, i*2+j)
+// and f from F[0..8] = f[row][col], F[9..11] = fp[row] (F[12] = 0 for padding), so a particle is a record of 13 + 16
+// doubles + its key (index, index_stag): 31 doubles.  Product e of a particle is (F[fi] * P[pj]) * P[pe] -- the
+// reference's f * weight_J * weight_E, bit for bit.
+// Phase 1: every lane writes the record of its particle to shared memory (7.9 KB per warp).
+// Phase 2: lane L owns nine products that share row factors (slots 0..5: one F[fi]*P[pj] and six consecutive column
+// weights; slots 6,7: one row factor and two column weights; slot 8: a J0 product), walks the runs of equal keys four
+// particles at a time and adds into nine register accumulators; at the end of a run (warp-uniform) every lane flushes
+// its accumulators with one RED each.
 struct MMEntry {
   unsigned char arr;   // 0..8 sigma, 9..11 J0, 255 = padding
-  unsigned char fj;    // index into FJ
-  unsigned char pe;    // index into P
+  unsigned char fj;    // group id: (array, row point)
+  unsigned char pe;    // column weight: index into P
   unsigned char base;  // 0: (index0, index1), 1: (index_stag0, index_stag1)
+  unsigned char fi;    // index into F
+  unsigned char pj;    // row weight: index into P
+  unsigned char pad[2];
   signed char di, dj;  // point = base + (di, dj)
   signed char ncs0, ncs1;
   int nc0;             // component = nc0 + ncs0*shift0 + ncs1*shift1
@@ -689,26 +694,34 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
   return v;
 }
 // one particle (record at byte offset IMM from the lane's base addresses) into the lane's nine accumulators
+struct MMLane {
+  unsigned f6, j6, e6, f2, j2, e2, f1, j1;   // byte offsets into a record
+};
 template <int IMM>
-__device__ __forceinline__ void mm_accumulate(double *acc, unsigned a6, unsigned b6, unsigned a2, unsigned b2,
-                                              unsigned a1) {
-  const double f6 = lds_f64<IMM>(a6);
-  acc[0] += f6 * lds_f64<IMM>(b6);
-  acc[1] += f6 * lds_f64<IMM + 8>(b6);
-  acc[2] += f6 * lds_f64<IMM + 16>(b6);
-  acc[3] += f6 * lds_f64<IMM + 24>(b6);
-  acc[4] += f6 * lds_f64<IMM + 32>(b6);
-  acc[5] += f6 * lds_f64<IMM + 40>(b6);
-  const double f2 = lds_f64<IMM>(a2);
-  acc[6] += f2 * lds_f64<IMM>(b2);
-  acc[7] += f2 * lds_f64<IMM + 8>(b2);
-  acc[8] += lds_f64<IMM>(a1);   // J0: fp * weight_J, no column weight (padding lanes read FJ[64] = 0)
+__device__ __forceinline__ void mm_accumulate(double *acc, unsigned qb, const MMLane &o) {
+  const double r6 = lds_f64<IMM>(qb + o.f6) * lds_f64<IMM>(qb + o.j6);
+  const unsigned b6 = qb + o.e6;
+  acc[0] += r6 * lds_f64<IMM>(b6);
+  acc[1] += r6 * lds_f64<IMM + 8>(b6);
+  acc[2] += r6 * lds_f64<IMM + 16>(b6);
+  acc[3] += r6 * lds_f64<IMM + 24>(b6);
+  acc[4] += r6 * lds_f64<IMM + 32>(b6);
+  acc[5] += r6 * lds_f64<IMM + 40>(b6);
+  const double r2 = lds_f64<IMM>(qb + o.f2) * lds_f64<IMM>(qb + o.j2);
+  const unsigned b2 = qb + o.e2;
+  acc[6] += r2 * lds_f64<IMM>(b2);
+  acc[7] += r2 * lds_f64<IMM + 8>(b2);
+  acc[8] += lds_f64<IMM>(qb + o.f1) * lds_f64<IMM>(qb + o.j1);   // J0: fp * weight_J (padding lanes read F[12] = 0)
 }
-enum { MM_NENT = 272, MM_NFJ = 65, MM_NP = 17, MM_KEY = MM_NFJ + MM_NP, MM_REC = 85, MM_EPL = 9, MM_WARPS = 2 };
+#ifndef MM_MINBLOCKS
+#define MM_MINBLOCKS 6
+#endif
+enum { MM_CHUNK_MAX = 32 };   // consecutive 32-particle tiles per warp and chunk (fewer on small problems)
+enum { MM_NENT = 272, MM_NF = 13, MM_NP = 16, MM_KEY = MM_NF + MM_NP, MM_REC = 31, MM_EPL = 9, MM_WARPS = 2 };
 
-__global__ void __launch_bounds__(32 * MM_WARPS)
+__global__ void __launch_bounds__(32 * MM_WARPS, MM_MINBLOCKS)
 k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEntry *__restrict__ table,
-                const MMFlush *__restrict__ flush, Counters *cnt, int *defer_list, unsigned *defer_count) {
+                const MMFlush *__restrict__ flush, Counters *cnt, int *defer_list, unsigned *defer_count, int chunk) {
   extern __shared__ double mm_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double *rec = mm_smem + (size_t)wid * 32 * MM_REC;
@@ -721,14 +734,61 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
 #pragma unroll
   for (int e = 0; e < MM_EPL; ++e) foff[e] = flush[e * 32 + lane].off0;
   const int fmeta6 = flush[lane].meta, fmeta2 = flush[6 * 32 + lane].meta, fmeta1 = flush[8 * 32 + lane].meta;
-  const unsigned ofj6 = 8u * table[lane].fj, opb6 = 8u * (MM_NFJ + table[lane].pe);
-  const unsigned ofj2 = 8u * table[6 * 32 + lane].fj, opb2 = 8u * (MM_NFJ + table[6 * 32 + lane].pe);
-  const unsigned ofj1 = 8u * table[8 * 32 + lane].fj;
+  MMLane o;
+  {
+    const MMEntry g6 = table[lane], g2 = table[6 * 32 + lane], g1 = table[8 * 32 + lane];
+    o.f6 = 8u * g6.fi;
+    o.j6 = 8u * (MM_NF + g6.pj);
+    o.e6 = 8u * (MM_NF + g6.pe);
+    o.f2 = 8u * g2.fi;
+    o.j2 = 8u * (MM_NF + g2.pj);
+    o.e2 = 8u * (MM_NF + g2.pe);
+    o.f1 = 8u * g1.fi;
+    o.j1 = 8u * (MM_NF + g1.pj);
+  }
   double *const arena = T.J[0].p;   // J0 of row x opens the arena
   const int rn0[3] = {T.J[0].n0, T.J[1].n0, T.J[2].n0};
   const int rplane[3] = {T.J[0].n0 * T.J[0].n1, T.J[1].n0 * T.J[1].n1, T.J[2].n0 * T.J[2].n1};
   unsigned err = 0;
-  for (long base = ((long)blockIdx.x * MM_WARPS + wid) * 32; base < n; base += nwarps * 32) {
+  // A warp takes chunks of `chunk` consecutive tiles and keeps a run open across tile boundaries (and across
+  // deferred particles): the reductions are what bounds this kernel (4.5e8 REDs = 3.6 of 6.1 ms when every tile
+  // flushed its own fragments), so a run is flushed only when the key changes or the chunk ends.
+  double acc[MM_EPL];
+  long long r01 = LLONG_MIN, r23 = 0;   // key of the open run (LLONG_MIN: none)
+  auto flush_run = [&]() {
+    const int k0 = (int)(r01 >> 32), k1 = (int)r01, k2 = (int)(r23 >> 32), k3 = (int)r23;
+    // every point of the stencils inside the arrays? (the row boxes are the J boxes; components are in range by
+    // construction of the table)
+    const bool in = fab_in(T.J[0], k0, k1) && fab_in(T.J[0], k0 + 1, k1 + 2) && fab_in(T.J[1], k0, k1) &&
+                    fab_in(T.J[1], k0 + 2, k1 + 1) && fab_in(T.J[2], k2, k3) && fab_in(T.J[2], k2 + 1, k3 + 1);
+    if (!in) {
+      err |= ERRBIT_BOUNDS;
+      return;
+    }
+    const int s0 = (k0 == k2) ? 0 : 1, s1 = (k1 == k3) ? 0 : 1;
+    // the products of a slot group go to one array: the run-dependent part of the address once per group (32-bit:
+    // the arena holds fewer than 2^32 doubles), the product-dependent part is foff[e]
+    auto dyn = [&](int meta) -> long long {
+      const int row = (meta >> 1) & 3;
+      const int n0 = row == 0 ? rn0[0] : (row == 1 ? rn0[1] : rn0[2]);
+      const int pl = row == 0 ? rplane[0] : (row == 1 ? rplane[1] : rplane[2]);
+      const int bi = (meta & 1) ? k2 : k0, bj = (meta & 1) ? k3 : k1;
+      const int sh = s0 * (int)(signed char)(meta >> 8) + s1 * (int)(signed char)(meta >> 16);
+      return (long long)(bi + bj * n0 + sh * pl);
+    };
+    double *const t6 = arena + dyn(fmeta6), *const t2 = arena + dyn(fmeta2);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) atomicAdd(t6 + foff[e], acc[e]);
+    atomicAdd(t2 + foff[6], acc[6]);
+    atomicAdd(t2 + foff[7], acc[7]);
+    if (fmeta1 >= 0) atomicAdd(arena + dyn(fmeta1) + foff[8], acc[8]);
+  };
+  const long ntiles = (n + 31) / 32;
+  for (long tile0 = ((long)blockIdx.x * MM_WARPS + wid) * chunk; tile0 < ntiles; tile0 += nwarps * chunk) {
+   const long tile1 = tile0 + chunk < ntiles ? tile0 + chunk : ntiles;
+#pragma unroll 1
+   for (long tile = tile0; tile < tile1; ++tile) {
+    const long base = tile * 32;
     const long i = base + lane;
     // ---- phase 1 -------------------------------------------------------------------------------------------------
     double *R = rec + lane * MM_REC;
@@ -775,35 +835,25 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
         }
       }
       if (fast) {
-        double *P = R + MM_NFJ;
+        double *P = R + MM_NF;
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
           for (int b = 0; b < 3; ++b) {
-            const double wx = cic[0][a] * tsc[1][b];    // Jx / Ex point (a, b)
-            const double wy = tsc[0][b] * cic[1][a];    // Jy / Ey point (b, a)
-            P[a * 3 + b] = wx;
-            P[6 + b * 2 + a] = wy;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              R[0 + c * 6 + a * 3 + b] = h.f[0][c] * wx;
-              R[18 + c * 6 + b * 2 + a] = h.f[1][c] * wy;
-            }
-            R[48 + a * 3 + b] = h.fp[0] * wx;
-            R[54 + b * 2 + a] = h.fp[1] * wy;
+            P[a * 3 + b] = cic[0][a] * tsc[1][b];       // Jx / Ex point (a, b)
+            P[6 + b * 2 + a] = tsc[0][b] * cic[1][a];   // Jy / Ey point (b, a)
           }
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const double wz = h.wsv[0][a] * h.wsv[1][b];
-            P[12 + a * 2 + b] = wz;
+          for (int b = 0; b < 2; ++b) P[12 + a * 2 + b] = h.wsv[0][a] * h.wsv[1][b];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) R[36 + c * 4 + a * 2 + b] = h.f[2][c] * wz;
-            R[60 + a * 2 + b] = h.fp[2] * wz;
-          }
-        P[16] = 1.0;
-        R[64] = 0.0;
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+          for (int e = 0; e < 3; ++e) R[3 * j + e] = h.f[j][e];
+          R[9 + j] = h.fp[j];
+        }
+        R[12] = 0.0;
         key01 = ((long long)h.index[0] << 32) | (unsigned)h.index[1];
         key23 = ((long long)h.index_stag[0] << 32) | (unsigned)h.index_stag[1];
       } else if (!oob) {
@@ -825,53 +875,30 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
       const unsigned stop = (heads | ~valid) & ~((2u << qs) - 1u);
       const int qe = stop ? __ffs(stop) - 1 : 32;
       rem &= (qe == 32) ? 0u : ~((1u << qe) - 1u);
-      double acc[MM_EPL];
+      const long long c01 = __shfl_sync(0xffffffffu, key01, qs), c23 = __shfl_sync(0xffffffffu, key23, qs);
+      if (c01 != r01 || c23 != r23) {     // warp-uniform
+        if (r01 != LLONG_MIN) flush_run();
+        r01 = c01;
+        r23 = c23;
 #pragma unroll
-      for (int e = 0; e < MM_EPL; ++e) acc[e] = 0.0;
+        for (int e = 0; e < MM_EPL; ++e) acc[e] = 0.0;
+      }
       int q = qs;
 #pragma unroll 1
       for (; q + 4 <= qe; q += 4) {
         const unsigned qb = sbase + (unsigned)q * (MM_REC * 8);
-        mm_accumulate<0>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
-        mm_accumulate<MM_REC * 8>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
-        mm_accumulate<2 * MM_REC * 8>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
-        mm_accumulate<3 * MM_REC * 8>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
+        mm_accumulate<0>(acc, qb, o);
+        mm_accumulate<MM_REC * 8>(acc, qb, o);
+        mm_accumulate<2 * MM_REC * 8>(acc, qb, o);
+        mm_accumulate<3 * MM_REC * 8>(acc, qb, o);
       }
 #pragma unroll 1
-      for (; q < qe; ++q) {
-        const unsigned qb = sbase + (unsigned)q * (MM_REC * 8);
-        mm_accumulate<0>(acc, qb + ofj6, qb + opb6, qb + ofj2, qb + opb2, qb + ofj1);
-      }
-      // flush the run: one RED per product
-      const long long r01 = __shfl_sync(0xffffffffu, key01, qs), r23 = __shfl_sync(0xffffffffu, key23, qs);
-      const int k0 = (int)(r01 >> 32), k1 = (int)r01, k2 = (int)(r23 >> 32), k3 = (int)r23;
-      // every point of the stencils inside the arrays? (the row boxes are the J boxes; components are in range by
-      // construction of the table)
-      const bool in = fab_in(T.J[0], k0, k1) && fab_in(T.J[0], k0 + 1, k1 + 2) && fab_in(T.J[1], k0, k1) &&
-                      fab_in(T.J[1], k0 + 2, k1 + 1) && fab_in(T.J[2], k2, k3) && fab_in(T.J[2], k2 + 1, k3 + 1);
-      if (!in) {
-        err |= ERRBIT_BOUNDS;
-        continue;
-      }
-      const int s0 = (k0 == k2) ? 0 : 1, s1 = (k1 == k3) ? 0 : 1;
-      // the products of a slot group go to one array: the run-dependent part of the address once per group (32-bit:
-      // the arena holds fewer than 2^32 doubles), the product-dependent part is foff[e]
-      auto dyn = [&](int meta) -> long long {
-        const int row = (meta >> 1) & 3;
-        const int n0 = row == 0 ? rn0[0] : (row == 1 ? rn0[1] : rn0[2]);
-        const int pl = row == 0 ? rplane[0] : (row == 1 ? rplane[1] : rplane[2]);
-        const int bi = (meta & 1) ? k2 : k0, bj = (meta & 1) ? k3 : k1;
-        const int sh = s0 * (int)(signed char)(meta >> 8) + s1 * (int)(signed char)(meta >> 16);
-        return (long long)(bi + bj * n0 + sh * pl);
-      };
-      double *const t6 = arena + dyn(fmeta6), *const t2 = arena + dyn(fmeta2);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) atomicAdd(t6 + foff[e], acc[e]);
-      atomicAdd(t2 + foff[6], acc[6]);
-      atomicAdd(t2 + foff[7], acc[7]);
-      if (fmeta1 >= 0) atomicAdd(arena + dyn(fmeta1) + foff[8], acc[8]);
+      for (; q < qe; ++q) mm_accumulate<0>(acc, sbase + (unsigned)q * (MM_REC * 8), o);
     }
     __syncwarp();
+   }
+   if (r01 != LLONG_MIN) flush_run();
+   r01 = LLONG_MIN;
   }
   if (err) atomicOr(&cnt->err, err);
 }
@@ -967,6 +994,13 @@ static int build_table(int mX, MMEntry *tab_out) {
     e.arr = (unsigned char)arr;
     e.fj = (unsigned char)fj;
     e.pe = (unsigned char)pe;
+    // row factor of group fj: F index and row-weight index (families PX = 0, PY = 6, PZ = 12)
+    if (fj < 18) { e.fi = (unsigned char)(0 + fj / 6); e.pj = (unsigned char)(0 + fj % 6); }
+    else if (fj < 36) { e.fi = (unsigned char)(3 + (fj - 18) / 6); e.pj = (unsigned char)(6 + (fj - 18) % 6); }
+    else if (fj < 48) { e.fi = (unsigned char)(6 + (fj - 36) / 4); e.pj = (unsigned char)(12 + (fj - 36) % 4); }
+    else if (fj < 54) { e.fi = 9; e.pj = (unsigned char)(0 + fj - 48); }
+    else if (fj < 60) { e.fi = 10; e.pj = (unsigned char)(6 + fj - 54); }
+    else { e.fi = 11; e.pj = (unsigned char)(12 + fj - 60); }
     e.base = (unsigned char)base;
     e.di = (signed char)di;
     e.dj = (signed char)dj;
@@ -1060,8 +1094,9 @@ static int build_table(int mX, MMEntry *tab_out) {
   MMEntry pad;
   memset(&pad, 0, sizeof(pad));
   pad.arr = 255;
-  pad.fj = 64;   // FJ[64] = 0
-  pad.pe = ONE;
+  pad.fi = 12;   // F[12] = 0
+  pad.pj = 0;
+  pad.pe = 0;
   auto member = [&](int fj, int rank) -> int {   // the rank-th product (by column weight index) of group fj
     int idx[6], m = 0;
     for (int q = 0; q < MM_NENT; ++q)
@@ -1289,13 +1324,19 @@ int pgpu_accumulate_mass_matrices(pgpu_species_t s, double dt) {
   PGPU_CUDA(cudaMemsetAsync(m->defer_count, 0, sizeof(unsigned), c.stream));
   {
     KTimer t("mass_matrix_run");
-    const long warps = (s->n + 31) / 32;
-    const unsigned nb = (unsigned)std::min<long>((warps + MM_WARPS - 1) / MM_WARPS, (long)c.sm_count * 64);
+    // chunk length: long enough that few runs are cut (a cut run costs 272 extra REDs), short enough that every SM
+    // gets several chunks per resident warp
+    const long ntiles = (s->n + 31) / 32;
+    const long resident = (long)c.sm_count * MM_MINBLOCKS * MM_WARPS;
+    int chunk = (int)std::max<long>(1, std::min<long>(MM_CHUNK_MAX, ntiles / (resident * 4)));
+    if (const char *e = getenv("PGPU_MM_CHUNK")) chunk = std::max(1, std::min((int)MM_CHUNK_MAX, atoi(e)));   // tests, tuning
+    const long chunks = (ntiles + chunk - 1) / chunk;
+    const unsigned nb = (unsigned)std::min<long>((chunks + MM_WARPS - 1) / MM_WARPS, (long)c.sm_count * 64);
     const size_t smem = MM_WARPS * 32 * MM_REC * sizeof(double);
     k_mm_cc1_2d_run<<<nb, 32 * MM_WARPS, smem, c.stream>>>(s->ptrs(), s->n, g2, T, prm,
                                                            static_cast<const MMEntry *>(m->table_d),
                                                            static_cast<const MMFlush *>(m->flush_d), c.d_counters,
-                                                           m->defer_list, m->defer_count);
+                                                           m->defer_list, m->defer_count, chunk);
   }
   {
     KTimer t("mass_matrix_deferred");

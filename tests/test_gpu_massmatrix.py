@@ -80,6 +80,22 @@ def test_accumulate_mass_matrices(pgpu, D, max_disp, nghost, mode):
         sp.destroy(); grid.destroy()
 
 
+@pytest.mark.parametrize("chunk", ["3", "32"])
+def test_runs_carried_across_tiles(pgpu, monkeypatch, chunk):
+    """Large problems give a warp several consecutive 32-particle tiles and keep a run open across them (and across
+    deferred particles); PGPU_MM_CHUNK forces that path on a problem the oracle can follow."""
+    monkeypatch.setenv("PGPU_MM_CHUNK", chunk)
+    prob = _sorted(_prob(2, 37, 9001, 0.95, 3))
+    grid, sp = make_gpu(pgpu, prob, CC1, charge=-1.0, fnorm=0.9)
+    try:
+        grid.mass_matrices_init(CC1)
+        nc, sigma, J0 = _oracle(prob, 3, -1.0, 1.0, 0.9, 1.0, 0.15)
+        sp.accumulate_mass_matrices(0.15)
+        _check(grid, nc, sigma, J0)
+    finally:
+        sp.destroy(); grid.destroy()
+
+
 def test_unsorted_particles_and_ragged_count(pgpu):
     """Any particle order is correct (runs of length one), also when n is not a multiple of the warp size."""
     prob = _prob(2, 32, 1237, 0.6, 3)
