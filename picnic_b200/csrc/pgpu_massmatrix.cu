@@ -16,12 +16,12 @@
 // Two deposit kernels:
 //   k_mm<D>          one thread per particle, the reference's loops as they stand, one fp64 reduction per distinct
 //                    address of a converged warp.  Any D, any number of segments, any particle order.
-//   k_mm_cc1_2d_run  2D fast path for cell-sorted single-segment particles (the 95 % case): a warp stages the row
-//                    factors f*weight_J (64) and column weights (16) of its 32 particles in shared memory, then
-//                    every lane owns 8-9 of the 272 (row point, column point) products of a particle and sums
-//                    them in registers over the run of particles that share the dual cell and the node cell --
-//                    one RED per product and run instead of one per product and particle, and no shuffles.
-//                    Other particles go to a list for k_mm.
+//   k_mm_cc1_2d_run  2D fast path for cell-sorted single-segment particles (the 95 % case): a warp stages the twelve
+//                    kernel values and sixteen shape products of its 32 particles in shared memory, then every lane
+//                    owns nine of the 272 (row point, column point) products of a particle and sums them in registers
+//                    over the run of particles that share the dual cell and the node cell -- across the consecutive
+//                    tiles of the warp's chunk -- with one RED per product and run instead of one per product and
+//                    particle, and no shuffles.  Other particles go to a list for k_mm.
 //
 // This file is compiled with -fmad=false: every per-particle product is then the IEEE product the reference's
 // Fortran computes, and the index decisions (true divide + floor) are bit exact; only the summation order differs.
