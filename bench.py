@@ -571,7 +571,7 @@ def mass_matrix_leg(args, torch, capi, stream, peak):
                          "frac": achieved / peak if achieved else None, "bytes_per_unit": 88.0,
                          "kernel": "mass_matrix_run (k_mm_cc1_2d_run)", "kernel_ms_per_launch": kern,
                          "deferred_kernel_ms_per_launch": d_ms / max(d_n, 1), "units_per_launch": n / len(sps),
-                         "note": "272 fp64 products + run reductions per particle: instruction bound, not HBM bound"}}
+                         "note": "bound by the fp64 reductions into L2 (272 per run of ~25 particles), not by HBM; see DESIGN.md 4.2"}}
 
 
 def run_ours(args):

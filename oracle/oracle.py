@@ -318,6 +318,19 @@ def coulomb_delta_u(vp1, vp2, q1, q2, m1, m2, EF_norm, Clog, angular, den12, bma
     return dU, s12.value
 
 
+def coulomb_lorentz_scatter(up1, up2, scatter2, q1, q2, m1, m2, EF_norm, Clog, angular, den12, bmax, sigma_max, dt_sec,
+                            gauss, upol, uphi):
+    """Coulomb::LorentzScatter for one pair; returns (up1', up2', live, s12)."""
+    f = lib().orc_coulomb_lorentz_scatter
+    f.argtypes = ([C.c_void_p, C.c_void_p, C.c_int] + [C.c_double] * 6 + [C.c_int] + [C.c_double] * 7 + [C.c_void_p])
+    a = np.array(up1, dtype=np.float64)
+    b = np.array(up2, dtype=np.float64)
+    s12 = C.c_double(0)
+    live = f(_ptr(a), _ptr(b), int(scatter2), q1, q2, m1, m2, EF_norm, Clog, angular, den12, bmax, sigma_max, dt_sec,
+             gauss, upol, uphi, C.byref(s12))
+    return a, b, live, s12.value
+
+
 def coulomb_intra(cell_start, v, w, dens, LDe, cellV_SI, mass, charge, Clog, angular, NxN, NxN_Nthresh, dt_sec):
     _coul_sigs()
     npairs = C.c_long(0)

@@ -433,6 +433,94 @@ extern "C" int orc_coulomb_delta_u(const double *vp1, const double *vp2, double 
   return 1;
 }
 
+/* Coulomb::LorentzScatter (Coulomb.cpp:1694-1793) + SetPolarScattering (:1795-1903, small-angle part) with the
+ * draws made explicit, long double scalars as in the reference.  Particle 1 always scatters, particle 2 only if
+ * scatter2 (its proper velocity then follows from momentum conservation).  Returns 0 when the reference returns
+ * early (vanishing relative velocity); s12_out receives m_s12. */
+extern "C" int orc_coulomb_lorentz_scatter(double *a_up1, double *a_up2, int a_scatter2, double charge1,
+                                           double charge2, double mass1, double mass2, double EF_norm, double Clog_in,
+                                           int angular, double a_den12, double a_bmax, double a_sigma_max,
+                                           double a_dt_sec, double gauss, double u_polar, double u_phi,
+                                           double *s12_out) {
+  const CoulombConsts k = coulomb_consts(charge1, charge2, mass1, mass2);
+  const long double a_mass1 = mass1, a_mass2 = mass2;
+  long double g1, g2, vcmsq, Etot, gcm, g1st, g2st;
+  long double ucmdotup, vrelst, vrelst_invar, muRst, upst_fact, upstsq, denom;
+  double ptot[3], vcm[3], upst[3];
+  if (s12_out) *s12_out = 0.0;
+  const double gb1sq = a_up1[0] * a_up1[0] + a_up1[1] * a_up1[1] + a_up1[2] * a_up1[2];
+  const double gb2sq = a_up2[0] * a_up2[0] + a_up2[1] * a_up2[1] + a_up2[2] * a_up2[2];
+  g1 = sqrt(1.0 + gb1sq);
+  g2 = sqrt(1.0 + gb2sq);
+  Etot = g1 * a_mass1 + g2 * a_mass2;
+  for (int n = 0; n < 3; n++) ptot[n] = a_mass1 * a_up1[n] + a_mass2 * a_up2[n];
+  for (int n = 0; n < 3; n++) vcm[n] = ptot[n] / Etot;
+  vcmsq = vcm[0] * vcm[0] + vcm[1] * vcm[1] + vcm[2] * vcm[2];
+  gcm = 1.0 / std::sqrt(1.0 - vcmsq);
+  ucmdotup = gcm * (vcm[0] * a_up2[0] + vcm[1] * a_up2[1] + vcm[2] * a_up2[2]);
+  g2st = gcm * g2 - ucmdotup;
+  ucmdotup = gcm * (vcm[0] * a_up1[0] + vcm[1] * a_up1[1] + vcm[2] * a_up1[2]);
+  g1st = gcm * g1 - ucmdotup;
+  upst_fact = gcm * (ucmdotup / (1.0 + gcm) - g1);
+  for (int n = 0; n < 3; n++) upst[n] = a_up1[n] + upst_fact * vcm[n];
+  muRst = g1st * a_mass1 * g2st * a_mass2 / (g1st * a_mass1 + g2st * a_mass2);
+  upstsq = upst[0] * upst[0] + upst[1] * upst[1] + upst[2] * upst[2];
+  vrelst = std::sqrt(upstsq) * a_mass1 / muRst;
+  if (vrelst <= std::numeric_limits<double>::min()) return 0;
+  const double vsum = std::sqrt(gb1sq) / g1 + std::sqrt(gb2sq) / g2;
+  if (vrelst <= 1.0e-14 * vsum) return 0;
+  denom = 1.0 + upstsq * a_mass1 / a_mass2 / g1st / g2st;
+  vrelst_invar = vrelst / denom;
+  double b0 = k.b90_fact / (muRst * vrelst * vrelst_invar + 2.0 * EF_norm);
+  const double bmin_qm = k.bqm_fact / (muRst * vrelst + std::sqrt(2.0 * EF_norm * muRst));
+  double Clog = Clog_in;
+  if (Clog == 0.0 && upstsq > 0.0) {
+    Clog = 0.5 * std::log((b0 * b0 / 4.0 + a_bmax * a_bmax) / (b0 * b0 / 4.0 + bmin_qm * bmin_qm));
+    Clog = std::max(2.0, Clog);
+  }
+  b0 = k.b90_fact / (muRst * vrelst * vrelst_invar);
+  double sigma_eff = kPI * b0 * b0 * Clog;
+  sigma_eff = std::min(sigma_eff, a_sigma_max);
+  double s12 = sigma_eff * a_den12 * vrelst * kCVAC * a_dt_sec;
+  s12 *= g1st * g2st / g1 / g2;
+  if (s12_out) *s12_out = s12;
+  double costh = 1.0, sinth = 0.0;
+  switch (angular) {
+    case 0:
+      if (s12 < 2.0) {
+        const double delta = sqrt(s12 / 2.0) * std::abs(gauss);
+        const double deltasq = delta * delta;
+        sinth = 2.0 * delta / (1.0 + deltasq);
+        costh = 1.0 - 2.0 * deltasq / (1.0 + deltasq);
+      } else {
+        const double theta = kPI * u_polar;
+        costh = std::cos(theta);
+        sinth = std::sin(theta);
+      }
+      break;
+    case 1:
+      orc_nanbu_costh_sinth(s12, u_polar, &costh, &sinth);
+      break;
+    case 2:
+      costh = 1.0 - std::min(s12, 2.0);
+      sinth = std::sin(std::acos(costh));
+      break;
+    default: {
+      const double theta = kPI * u_polar;
+      costh = std::cos(theta);
+      sinth = std::sin(theta);
+    }
+  }
+  const double phi = kTWOPI * u_phi;
+  orc_rotate_velocity(upst, costh, sinth, std::cos(phi), std::sin(phi));
+  ucmdotup = gcm * (vcm[0] * upst[0] + vcm[1] * upst[1] + vcm[2] * upst[2]);
+  upst_fact = gcm * (ucmdotup / (1.0 + gcm) + g1st);
+  for (int n = 0; n < 3; n++) a_up1[n] = upst[n] + upst_fact * vcm[n];
+  if (a_scatter2)
+    for (int n = 0; n < 3; n++) a_up2[n] = (ptot[n] - a_mass1 * a_up1[n]) / a_mass2;
+  return 1;
+}
+
 namespace {
 /* one pair with the reference's draw order: polar draw(s) inside SetPolarScattering, then phi,
  * then the weight-rejection uniform (only for unequal weights) */
@@ -443,6 +531,36 @@ struct PairCtx {
 };
 void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2, double den12, double f1,
                   double f2) {
+  if (orc_get_relativistic()) {
+    /* Coulomb.cpp:548-559 / 1139-1150: the weight-rejection draw comes first, then LorentzScatter with the
+     * lighter-weight particle in the first slot; draws inside it as in GalileanScatter (polar, then phi) */
+    double *p1 = b1, *p2 = b2;
+    double q1 = c.charge1, q2 = c.charge2, m1 = c.mass1, m2 = c.mass2;
+    bool scatter2 = true;
+    if ((float)w2 < (float)w1) {
+      if (mu_rand() > w2 / w1) scatter2 = false;
+      std::swap(p1, p2);
+      std::swap(q1, q2);
+      std::swap(m1, m2);
+    } else if ((float)w1 < (float)w2) {
+      if (mu_rand() > w1 / w2) scatter2 = false;
+    }
+    double t1[3] = {p1[0], p1[1], p1[2]}, t2[3] = {p2[0], p2[1], p2[2]}, s12 = 0.0;
+    const int live = orc_coulomb_lorentz_scatter(t1, t2, 0, q1, q2, m1, m2, c.EF_norm, c.Clog, 2, den12, c.bmax,
+                                                 c.sigma_max, c.dt_sec, 0.0, 0.0, 0.0, &s12);
+    if (!live) return;
+    double gauss = 0.0, upol = 0.0;
+    if (c.angular == 0) {
+      if (s12 < 2.0) gauss = mu_randn();
+      else upol = mu_rand();
+    } else if (c.angular != 2) {
+      upol = mu_rand();
+    }
+    const double uphi = mu_rand();
+    orc_coulomb_lorentz_scatter(p1, p2, scatter2 ? 1 : 0, q1, q2, m1, m2, c.EF_norm, c.Clog, c.angular, den12,
+                                c.bmax, c.sigma_max, c.dt_sec, gauss, upol, uphi, nullptr);
+    return;
+  }
   /* replicate which draws GalileanScatter makes: decide the branch from s12 first */
   double dU[3], s12 = 0.0;
   double probe[3];

@@ -205,6 +205,11 @@ int orc_coulomb_delta_u(const double *vp1, const double *vp2, double charge1, do
                         double mass1, double mass2, double EF_norm, double Clog_in, int angular,
                         double den12, double bmax, double sigma_max, double dt_sec, double gauss,
                         double u_polar, double u_phi, double *dU, double *s12_out);
+/* Coulomb::LorentzScatter (Coulomb.cpp:1694-1793), RELATIVISTIC_PARTICLES build; explicit draws */
+int orc_coulomb_lorentz_scatter(double *up1, double *up2, int scatter2, double charge1, double charge2, double mass1,
+                                double mass2, double EF_norm, double Clog, int angular, double den12, double bmax,
+                                double sigma_max, double dt_sec, double gauss, double u_polar, double u_phi,
+                                double *s12_out);
 void orc_coulomb_intra(long ncell, const long *cell_start, double *v, const double *w, long n,
                        const double *dens, const double *LDe, double cellV_SI, double mass,
                        double charge, double Clog, int angular, int NxN, int NxN_Nthresh,

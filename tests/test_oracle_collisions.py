@@ -177,3 +177,70 @@ def test_lorentz_scatter_conserves_four_momentum_and_has_the_galilean_limit():
         lib.orc_ta_delta_u(orc._ptr(u1), 1e19, orc._ptr(u2), 1e19, b90, 10.0, 1e-16, gss, ut, up, orc._ptr(dU))
         assert small == 1
         assert np.max(np.abs(a - (u1 + mu / m1 * dU))) <= 3e-6 * np.max(np.abs(dU)) + 1e-18
+
+
+def test_coulomb_lorentz_scatter_conserves_and_has_the_galilean_limit():
+    """Coulomb::LorentzScatter (Coulomb.cpp:1694-1793): total momentum exactly and total energy to round-off when
+    both particles scatter; particle 2 untouched when the weight rejection says so; for slow particles the update
+    is GalileanScatter's (mu/m1) deltaU with the same draws."""
+    rng = np.random.default_rng(9)
+    m1, m2 = 1.0, 1836.15
+    for angular in (0, 1, 2, 5):
+        for _ in range(50):
+            up1 = rng.standard_normal(3) * 0.8
+            up2 = rng.standard_normal(3) * 0.02
+            args = (-1.0, 1.0, m1, m2, 0.0, 10.0, angular, 1.0e28, 1.0e-8, 1.0e-18, 1.0e-16)
+            draws = (rng.standard_normal(), rng.random(), rng.random())
+            a, b, live, s12 = orc.coulomb_lorentz_scatter(up1, up2, 1, *args, *draws)
+            assert live == 1 and s12 > 0
+            p0 = m1 * up1 + m2 * up2
+            e0 = m1 * np.sqrt(1 + up1 @ up1) + m2 * np.sqrt(1 + up2 @ up2)
+            assert np.allclose(m1 * a + m2 * b, p0, rtol=0, atol=1e-13 * np.abs(p0).max())
+            e1 = m1 * np.sqrt(1 + a @ a) + m2 * np.sqrt(1 + b @ b)
+            assert abs(e1 - e0) < 1e-12 * e0
+            assert np.linalg.norm(a - up1) > 0
+            a2, b2, _, _ = orc.coulomb_lorentz_scatter(up1, up2, 0, *args, *draws)
+            assert np.array_equal(a2, a) and np.array_equal(b2, up2)
+    # Galilean limit
+    for angular in (0, 1, 5):
+        up1 = rng.standard_normal(3) * 1e-4
+        up2 = rng.standard_normal(3) * 1e-5
+        args = (-1.0, 1.0, m1, m2, 0.0, 10.0, angular, 1.0e20, 1.0e-8, 1.0e-18, 1.0e-16)
+        draws = (0.7, 0.3, 0.6)
+        a, b, live, s12 = orc.coulomb_lorentz_scatter(up1, up2, 1, *args, *draws)
+        dU, s12g = orc.coulomb_delta_u(up1, up2, *args, *draws)
+        mu = m1 * m2 / (m1 + m2)
+        assert abs(s12 - s12g) < 1e-6 * s12g
+        assert np.allclose(a - up1, mu / m1 * dU, rtol=0, atol=1e-6 * np.linalg.norm(dU))
+        assert np.allclose(b - up2, -mu / m2 * dU, rtol=0, atol=1e-6 * np.linalg.norm(dU) * mu / m2 + 1e-18)
+    # identical velocities: early return
+    _, _, live, _ = orc.coulomb_lorentz_scatter([0.1, 0, 0], [0.1, 0, 0], 1, -1.0, -1.0, 1.0, 1.0, 0.0, 10.0, 0, 1e28,
+                                                1e-8, 1e-18, 1e-16, 0.1, 0.2, 0.3)
+    assert live == 0
+
+
+def test_coulomb_intra_relativistic_build_conserves_for_equal_weights():
+    """applyIntraScattering_PROB of the RELATIVISTIC_PARTICLES build: every pair goes through LorentzScatter; with
+    equal weights both partners scatter, so the cell's momentum and energy (sum m gamma) are conserved."""
+    rng = np.random.default_rng(10)
+    ncell, npc = 6, 9
+    n = ncell * npc
+    cs = np.arange(0, n + 1, npc)
+    v = rng.standard_normal((3, n)) * 0.5
+    w = np.full(n, 2.0e10)
+    dens = np.full(ncell, 1.0e28)
+    LDe = np.full(ncell, 1.0e-8)
+    orc.set_relativistic(True)
+    try:
+        orc.lib().orc_rng_seed(5)
+        v1 = v.copy()
+        orc.coulomb_intra(cs, v1, w, dens, LDe, 1.0e-18, 1.0, -1.0, 10.0, 1, False, 11, 1.0e-16)
+    finally:
+        orc.set_relativistic(False)
+    assert np.max(np.abs(v1 - v)) > 1e-6
+    for c in range(ncell):
+        sl = slice(cs[c], cs[c + 1])
+        assert np.allclose(v1[:, sl].sum(1), v[:, sl].sum(1), rtol=0, atol=1e-12)
+        g0 = np.sqrt(1 + (v[:, sl] ** 2).sum(0)).sum()
+        g1 = np.sqrt(1 + (v1[:, sl] ** 2).sum(0)).sum()
+        assert abs(g1 - g0) < 1e-12 * g0
