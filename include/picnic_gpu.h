@@ -131,7 +131,8 @@ typedef struct {
    * time-centred gamma (PicSpeciesUtils.cpp:55-78; higuera_cary = pic_species.N.higuera_cary), positions and
    * the Picard step norm with getImplicitGamma (PicChargedSpecies.cpp:496-498,548-553,693-708), current deposit
    * with w/gamma (MeshInterpI.H:72-91), setStableDt and globalMoments (:1890-1893, 4095-4098).  Such species
-   * take the generic kernels; the collision models stay Galilean (LorentzScatter: SURVEY 8f). */
+   * take the generic kernels; pgpu_collide_ta and pgpu_collide_coulomb switch to their LorentzScatter
+   * (TakizukaAbe.cpp:580-659, Coulomb.cpp:1694-1793), Elastic stays Galilean. */
   int relativistic;
   int higuera_cary;
 } pgpu_species_desc;
@@ -349,6 +350,14 @@ int pgpu_coulomb_delta_u(long n, const double *vp1, const double *vp2, double ch
                          double mass1, double mass2, const pgpu_coulomb_params *prm, double dt_sec,
                          const double *EF_norm, const double *den12, const double *bmax, const double *sigma_max,
                          const double *gauss, const double *u_polar, const double *u_phi, double *dU, double *s12);
+/* Coulomb::LorentzScatter (Coulomb.cpp:1694-1793) for n pairs with explicit draws (test hook of the relativistic
+ * pair update that pgpu_collide_coulomb applies when a species is relativistic): particle 1 always scatters,
+ * particle 2 where scatter2[i] != 0. */
+int pgpu_coulomb_lorentz_scatter(long n, const double *up1, const double *up2, const int *scatter2, double charge1,
+                                 double charge2, double mass1, double mass2, const pgpu_coulomb_params *prm,
+                                 double dt_sec, const double *EF_norm, const double *den12, const double *bmax,
+                                 const double *sigma_max, const double *gauss, const double *u_polar,
+                                 const double *u_phi, double *out1, double *out2, double *s12);
 
 /* Elastic::electronImpact (Elastic.cpp:225-388), PROBABILISTIC weights: every particle of sA picks a
  * random partner of sB in its cell; sigma constant (ntab = 0) or tabulated (E [eV] ascending, Q, xi)

@@ -106,6 +106,7 @@ def load():
         "pgpu_ta_lorentz_scatter": [lng, vp, vp, dbl, dbl, vp, dbl, dbl, dbl, vp, vp, vp, vp, vp],
         "pgpu_collide_coulomb": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_coulomb_delta_u": [lng, vp, vp, dbl, dbl, dbl, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "pgpu_coulomb_lorentz_scatter": [lng, vp, vp, vp, dbl, dbl, dbl, dbl, vp, dbl] + [vp] * 10,
         "pgpu_collide_elastic": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_scatter_nu_max_ta": [vp, vp, dbl, vp], "pgpu_scatter_nu_max_coulomb": [vp, vp, vp, vp],
         "pgpu_scatter_nu_max_elastic": [vp, vp, vp, vp],
@@ -433,6 +434,20 @@ def collide_coulomb(sA, sB, Clog, dt_sec, seed, step, angular=0, NxN=False, NxN_
     np_ = C.c_long(0)
     check(load().pgpu_collide_coulomb(sA.h, sB.h, C.byref(prm), dt_sec, seed, step, C.byref(np_) if count else None))
     return np_.value
+
+
+def coulomb_lorentz_scatter(up1, up2, scatter2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, den12, bmax, sigma_max,
+                            gauss, upol, uphi):
+    """Coulomb::LorentzScatter for n pairs ([3][n] arrays): (up1', up2', s12)."""
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    n = np.asarray(den12).size
+    prm = CoulombParams(Clog, angular, 0, 11, 1)
+    a = [c(up1), c(up2), c(EF_norm), c(den12), c(bmax), c(sigma_max), c(gauss), c(upol), c(uphi)]
+    s2 = np.ascontiguousarray(scatter2, dtype=np.int32)
+    o1, o2, s12 = np.zeros((3, n)), np.zeros((3, n)), np.zeros(n)
+    check(load().pgpu_coulomb_lorentz_scatter(n, _p(a[0]), _p(a[1]), _p(s2), q1, q2, m1, m2, C.byref(prm), dt_sec,
+                                              *[_p(x) for x in a[2:]], _p(o1), _p(o2), _p(s12)))
+    return o1, o2, s12
 
 
 def coulomb_delta_u(vp1, vp2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, den12, bmax, sigma_max, gauss, upol, uphi):

@@ -427,6 +427,8 @@ struct CoulParams {
   int angular, NxN, NxN_Nthresh;
   unsigned seed_lo, seed_hi, step_lo, step_hi;
   int box_lo0, box_lo1, nbox0, ncell_glob0;
+  int rel;               // RELATIVISTIC_PARTICLES build: pairs go through LorentzScatter
+  double mass1, mass2;
 };
 __device__ __forceinline__ unsigned global_cell(const CoulParams &P, int cell) {
   const int i = cell % P.nbox0 + P.box_lo0, j = cell / P.nbox0 + P.box_lo1;
@@ -454,6 +456,35 @@ __device__ __forceinline__ void nanbu_costh_sinth(double s12, double U, double &
   sinth = sqrt(1.0 - c * c);
 }
 
+// Coulomb::SetPolarScattering (:1795-1903), small-angle part, with explicit draws
+__device__ __forceinline__ void coulomb_polar(int angular, double s12, double gauss, double upol, double &costh,
+                                              double &sinth) {
+  const double PI = 3.14159265358979323846;
+  costh = 1.0;
+  sinth = 0.0;
+  switch (angular) {
+    case ANG_TAKIZUKA:
+      if (s12 < 2.0) {
+        const double delta = sqrt(s12 / 2.0) * fabs(gauss);
+        const double deltasq = delta * delta;
+        sinth = 2.0 * delta / (1.0 + deltasq);
+        costh = 1.0 - 2.0 * deltasq / (1.0 + deltasq);
+      } else {
+        sincos(PI * upol, &sinth, &costh);
+      }
+      break;
+    case ANG_NANBU:
+      nanbu_costh_sinth(s12, upol, costh, sinth);
+      break;
+    case ANG_BOBYLEV:
+      costh = 1.0 - fmin(s12, 2.0);
+      sinth = sin(acos(costh));
+      break;
+    default:
+      sincos(PI * upol, &sinth, &costh);
+  }
+}
+
 // Coulomb::GalileanScatter (:1642-1692) + SetPolarScattering (:1795-1903) with explicit draws.
 // false (dU = 0) where the reference returns early.
 __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const double *vp1, const double *vp2,
@@ -479,32 +510,93 @@ __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const doubl
   sigma_eff = fmin(sigma_eff, sigma_max);
   const double s12 = sigma_eff * den12 * u * CVAC * P.dt_sec;
   if (s12o) *s12o = s12;
-  double costh = 1.0, sinth = 0.0;
-  switch (P.angular) {
-    case ANG_TAKIZUKA:
-      if (s12 < 2.0) {
-        const double delta = sqrt(s12 / 2.0) * fabs(gauss);
-        const double deltasq = delta * delta;
-        sinth = 2.0 * delta / (1.0 + deltasq);
-        costh = 1.0 - 2.0 * deltasq / (1.0 + deltasq);
-      } else {
-        sincos(PI * upol, &sinth, &costh);
-      }
-      break;
-    case ANG_NANBU:
-      nanbu_costh_sinth(s12, upol, costh, sinth);
-      break;
-    case ANG_BOBYLEV:
-      costh = 1.0 - fmin(s12, 2.0);
-      sinth = sin(acos(costh));
-      break;
-    default:
-      sincos(PI * upol, &sinth, &costh);
-  }
+  double costh, sinth;
+  coulomb_polar(P.angular, s12, gauss, upol, costh, sinth);
   double sinphi, cosphi;
   sincos(2.0 * PI * uphi, &sinphi, &cosphi);
   scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
   return true;
+}
+
+// Coulomb::LorentzScatter (:1694-1793): collision through the centre-of-momentum frame.  Particle 1 (mass m1)
+// always scatters, particle 2 only if scatter2 (momentum conservation then gives its proper velocity).  The reference
+// keeps the scalars in long double; fp64 here (parity with the oracle < 1e-12, tests/test_gpu_coulomb_elastic.py).
+__device__ __forceinline__ bool coulomb_lorentz_scatter(const CoulParams &P, double *up1, double *up2, bool scatter2,
+                                                        double m1, double m2, double EF_norm, double den12,
+                                                        double bmax, double sigma_max, double gauss, double upol,
+                                                        double uphi, double *s12o) {
+  const double PI = 3.14159265358979323846, CVAC = 2.99792458e+08;
+  if (s12o) *s12o = 0.0;
+  const double gb1sq = up1[0] * up1[0] + up1[1] * up1[1] + up1[2] * up1[2];
+  const double gb2sq = up2[0] * up2[0] + up2[1] * up2[1] + up2[2] * up2[2];
+  const double g1 = sqrt(1.0 + gb1sq), g2 = sqrt(1.0 + gb2sq);
+  const double Etot = g1 * m1 + g2 * m2;
+  double ptot[3], vcm[3], upst[3];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) {
+    ptot[n] = m1 * up1[n] + m2 * up2[n];
+    vcm[n] = ptot[n] / Etot;
+  }
+  const double vcmsq = vcm[0] * vcm[0] + vcm[1] * vcm[1] + vcm[2] * vcm[2];
+  const double gcm = 1.0 / sqrt(1.0 - vcmsq);
+  double ucmdotup = gcm * (vcm[0] * up2[0] + vcm[1] * up2[1] + vcm[2] * up2[2]);
+  const double g2st = gcm * g2 - ucmdotup;
+  ucmdotup = gcm * (vcm[0] * up1[0] + vcm[1] * up1[1] + vcm[2] * up1[2]);
+  const double g1st = gcm * g1 - ucmdotup;
+  double upst_fact = gcm * (ucmdotup / (1.0 + gcm) - g1);
+#pragma unroll
+  for (int n = 0; n < 3; ++n) upst[n] = up1[n] + upst_fact * vcm[n];
+  const double muRst = g1st * m1 * g2st * m2 / (g1st * m1 + g2st * m2);
+  const double upstsq = upst[0] * upst[0] + upst[1] * upst[1] + upst[2] * upst[2];
+  const double vrelst = sqrt(upstsq) * m1 / muRst;
+  if (vrelst <= 2.2250738585072014e-308) return false;
+  const double vsum = sqrt(gb1sq) / g1 + sqrt(gb2sq) / g2;
+  if (vrelst <= 1.0e-14 * vsum) return false;
+  const double denom = 1.0 + upstsq * m1 / m2 / g1st / g2st;
+  const double vrelst_invar = vrelst / denom;
+  double b0 = P.b90_fact / (muRst * vrelst * vrelst_invar + 2.0 * EF_norm);
+  const double bmin_qm = P.bqm_fact / (muRst * vrelst + sqrt(2.0 * EF_norm * muRst));
+  double Clog = P.Clog;
+  if (Clog == 0.0 && upstsq > 0.0) {
+    Clog = 0.5 * log((b0 * b0 / 4.0 + bmax * bmax) / (b0 * b0 / 4.0 + bmin_qm * bmin_qm));
+    Clog = fmax(2.0, Clog);
+  }
+  b0 = P.b90_fact / (muRst * vrelst * vrelst_invar);
+  double sigma_eff = PI * b0 * b0 * Clog;
+  sigma_eff = fmin(sigma_eff, sigma_max);
+  double s12 = sigma_eff * den12 * vrelst * CVAC * P.dt_sec;
+  s12 *= g1st * g2st / g1 / g2;
+  if (s12o) *s12o = s12;
+  double costh, sinth, sinphi, cosphi;
+  coulomb_polar(P.angular, s12, gauss, upol, costh, sinth);
+  sincos(2.0 * PI * uphi, &sinphi, &cosphi);
+  rotate_velocity(upst, costh, sinth, cosphi, sinphi);
+  ucmdotup = gcm * (vcm[0] * upst[0] + vcm[1] * upst[1] + vcm[2] * upst[2]);
+  upst_fact = gcm * (ucmdotup / (1.0 + gcm) + g1st);
+#pragma unroll
+  for (int n = 0; n < 3; ++n) up1[n] = upst[n] + upst_fact * vcm[n];
+  if (scatter2) {
+#pragma unroll
+    for (int n = 0; n < 3; ++n) up2[n] = (ptot[n] - m1 * up1[n]) / m2;
+  }
+  return true;
+}
+
+__global__ void k_coulomb_lorentz(long n, CoulParams P, const double *vp1, const double *vp2, const int *scatter2,
+                                  const double *EF, const double *den12, const double *bmax, const double *smax,
+                                  const double *gauss, const double *upol, const double *uphi, double *o1, double *o2,
+                                  double *s12) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[3] = {vp1[i], vp1[n + i], vp1[2 * n + i]}, b[3] = {vp2[i], vp2[n + i], vp2[2 * n + i]};
+  double s = 0.0;
+  coulomb_lorentz_scatter(P, a, b, scatter2[i] != 0, P.mass1, P.mass2, EF[i], den12[i], bmax[i], smax[i], gauss[i],
+                          upol[i], uphi[i], &s);
+  for (int c = 0; c < 3; ++c) {
+    o1[c * n + i] = a[c];
+    o2[c * n + i] = b[c];
+  }
+  s12[i] = s;
 }
 
 __global__ void k_coulomb_delta_u(long n, CoulParams P, const double *vp1, const double *vp2, const double *EF,
@@ -542,6 +634,29 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
   const double w1 = wa[pa], w2 = wb[pb];
   const double den12 = fmax(w1, w2) * den_fact;
   double va[3] = {a0[pa], a1[pa], a2[pa]}, vb[3] = {b0[pb], b1[pb], b2[pb]}, dU[3];
+  if (P.rel) {
+    // Coulomb.cpp:548-559 / 1139-1150: the lighter-weight particle goes first and always scatters, the other one
+    // with probability w_min / w_max
+    bool other = true;
+    if ((float)w1 != (float)w2) {
+      c.w = P.step_hi ^ (STREAM_WEIGHT << 16) ^ salt;
+      const double ur = u01(philox4x32_10(c, P.seed_lo, P.seed_hi).x);
+      other = !(ur > fmin(w1, w2) / fmax(w1, w2));
+    }
+    if ((float)w2 < (float)w1)
+      coulomb_lorentz_scatter(P, vb, va, other, P.mass2, P.mass1, C.EF_norm, den12, C.bmax, C.sigma_max, gauss,
+                              u01(r.z), u01(r.w), nullptr);
+    else
+      coulomb_lorentz_scatter(P, va, vb, other, P.mass1, P.mass2, C.EF_norm, den12, C.bmax, C.sigma_max, gauss,
+                              u01(r.z), u01(r.w), nullptr);
+    a0[pa] = va[0];
+    a1[pa] = va[1];
+    a2[pa] = va[2];
+    b0[pb] = vb[0];
+    b1[pb] = vb[1];
+    b2[pb] = vb[2];
+    return;
+  }
   coulomb_delta_u(P, va, vb, C.EF_norm, den12, C.bmax, C.sigma_max, gauss, u01(r.z), u01(r.w), dU, nullptr);
   bool s1 = true, s2 = true;
   if ((float)w1 != (float)w2) {
@@ -1112,6 +1227,9 @@ static int coulomb_consts(double charge1, double charge2, double mass1, double m
     P->EF_fact = HBAR * HBAR / (2.0 * ME * P->mu) * pow(3.0 * PI * PI, 2.0 / 3.0) / (ME * CVAC * CVAC);
   P->f1 = P->mu / mass1;
   P->f2 = P->mu / mass2;
+  P->mass1 = mass1;
+  P->mass2 = mass2;
+  P->rel = 0;
   P->Clog = prm->Clog;
   P->dt_sec = dt_sec;
   P->angular = a;
@@ -1159,6 +1277,48 @@ int pgpu_coulomb_delta_u(long n, const double *vp1, const double *vp2, double ch
   return 0;
 }
 
+int pgpu_coulomb_lorentz_scatter(long n, const double *up1, const double *up2, const int *scatter2, double charge1,
+                                 double charge2, double mass1, double mass2, const pgpu_coulomb_params *prm,
+                                 double dt_sec, const double *EF_norm, const double *den12, const double *bmax,
+                                 const double *sigma_max, const double *gauss, const double *u_polar,
+                                 const double *u_phi, double *out1, double *out2, double *s12) {
+  if (!ctx().inited) {
+    set_error("pgpu_init has not been called");
+    return PGPU_ERR_STATE;
+  }
+  CoulParams P;
+  const int rc = coulomb_consts(charge1, charge2, mass1, mass2, prm, dt_sec, &P);
+  if (rc) return rc;
+  P.rel = 1;
+  cudaStream_t st = ctx().stream;
+  const size_t N = (size_t)n;
+  double *d = nullptr;
+  int *ds = nullptr;
+  PGPU_CUDA(cudaMalloc(&d, 20 * N * sizeof(double)));   // v1[3] v2[3] EF den bmax smax g up uphi | o1[3] o2[3] s12
+  PGPU_CUDA(cudaMalloc(&ds, N * sizeof(int)));
+  PGPU_CUDA(cudaMemcpyAsync(ds, scatter2, N * sizeof(int), cudaMemcpyHostToDevice, st));
+  const double *src[9] = {up1, up2, EF_norm, den12, bmax, sigma_max, gauss, u_polar, u_phi};
+  const size_t len[9] = {3 * N, 3 * N, N, N, N, N, N, N, N};
+  size_t off[10] = {0};
+  for (int k = 0; k < 9; ++k) {
+    PGPU_CUDA(cudaMemcpyAsync(d + off[k], src[k], len[k] * sizeof(double), cudaMemcpyHostToDevice, st));
+    off[k + 1] = off[k] + len[k];
+  }
+  {
+    KTimer t("coulomb_lorentz");
+    k_coulomb_lorentz<<<nb(n), 256, 0, st>>>(n, P, d + off[0], d + off[1], ds, d + off[2], d + off[3], d + off[4],
+                                             d + off[5], d + off[6], d + off[7], d + off[8], d + off[9],
+                                             d + off[9] + 3 * N, d + off[9] + 6 * N);
+  }
+  PGPU_CUDA(cudaMemcpyAsync(out1, d + off[9], 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaMemcpyAsync(out2, d + off[9] + 3 * N, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaMemcpyAsync(s12, d + off[9] + 6 * N, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d);
+  cudaFree(ds);
+  return 0;
+}
+
 static int fetch_pairs(long *out) {
   Context &c = ctx();
   if (out) {
@@ -1198,6 +1358,7 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
   if (rc) return rc;
   const int nsub = prm->num_subcycles > 0 ? prm->num_subcycles : 1;
   P.dt_sec = dt_sec / (double)nsub;                                   // Coulomb.cpp:371
+  P.rel = (sA->desc.relativistic || sB->desc.relativistic) ? 1 : 0;   // the reference's compile-time switch
   const double dV = (g->desc.D == 1) ? g->geo.dx[0] : g->geo.dx[0] * g->geo.dx[1];
   P.cellV_SI = dV * g->desc.volume_scale;
   P.seed_lo = (unsigned)seed;

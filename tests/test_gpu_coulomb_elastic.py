@@ -333,3 +333,96 @@ def test_mean_free_time_matches_oracle(pgpu):
     got = pgpu.nu_max_elastic(spe, spi, E=E, Q=Q, xi=XI, angular=1, loglog=True)
     assert rel(got, orc.elastic_nu_max(me, me, se.mass, si.mass, E=E, Q=Q, XI=XI, angular=1, loglog=True)) < 1e-11
     spe.destroy(); spi.destroy(); grid.destroy()
+
+
+@pytest.mark.parametrize("angular", [0, 1, 2, 5])
+def test_coulomb_lorentz_scatter_matches_oracle(pgpu, angular):
+    """Coulomb::LorentzScatter (relativistic build of the weighted Coulomb model) per pair with explicit draws.  The
+    reference and the oracle keep the frame-change scalars in long double, the device in fp64: < 1e-12."""
+    rng = np.random.default_rng(61 + angular)
+    n = 4000
+    m1, m2 = 1.0, 1836.15
+    up1 = rng.standard_normal((3, n)) * np.where(rng.random(n) < 0.5, 1.5, 0.02)
+    up2 = rng.standard_normal((3, n)) * 0.01
+    scatter2 = (rng.random(n) < 0.6).astype(np.int32)
+    EF = np.zeros(n)
+    den12 = 10.0 ** rng.uniform(26, 30, n)
+    bmax = np.full(n, 1.0e-8)
+    smax = np.full(n, 1.0e-17)
+    gauss, upol, uphi = rng.standard_normal(n), rng.random(n), rng.random(n)
+    o1, o2, s12 = pgpu.coulomb_lorentz_scatter(up1, up2, scatter2, -1.0, 1.0, m1, m2, 10.0, angular, DT_SEC, EF, den12,
+                                               bmax, smax, gauss, upol, uphi)
+    worst = 0.0
+    for i in range(0, n, 7):
+        a, b, live, s = orc.coulomb_lorentz_scatter(up1[:, i], up2[:, i], scatter2[i], -1.0, 1.0, m1, m2, 0.0, 10.0,
+                                                    angular, den12[i], bmax[i], smax[i], DT_SEC, gauss[i], upol[i],
+                                                    uphi[i])
+        assert live == 1
+        assert abs(s12[i] - s) <= 1e-12 * s
+        scale = max(np.linalg.norm(up1[:, i]), 1e-3)
+        worst = max(worst, np.max(np.abs(o1[:, i] - a)) / scale, np.max(np.abs(o2[:, i] - b)) / scale)
+        if not scatter2[i]:
+            assert np.array_equal(o2[:, i], up2[:, i])
+    assert worst < 1e-12
+    # conservation where both scatter
+    both = scatter2 == 1
+    p0 = m1 * up1 + m2 * up2
+    p1 = m1 * o1 + m2 * o2
+    assert np.max(np.abs(p1 - p0)[:, both]) < 1e-12 * np.max(np.abs(p0))
+    e0 = m1 * np.sqrt(1 + (up1 ** 2).sum(0)) + m2 * np.sqrt(1 + (up2 ** 2).sum(0))
+    e1 = m1 * np.sqrt(1 + (o1 ** 2).sum(0)) + m2 * np.sqrt(1 + (o2 ** 2).sum(0))
+    assert np.max(np.abs(e1 - e0)[both] / e0[both]) < 1e-12
+
+
+def test_coulomb_relativistic_species_conserve_four_momentum_per_cell(pgpu):
+    """pgpu_collide_coulomb with relativistic species takes LorentzScatter for every pair: with equal weights both
+    partners scatter, so each cell keeps its momentum and its sum of m*gamma (e-e and e-i)."""
+    rng = np.random.default_rng(62)
+    ncell = 48
+    xe, ce = _ragged_cells(rng, ncell, [0, 1, 2, 5, 12, 16, 40])
+    xi, ci = _ragged_cells(rng, ncell, [0, 1, 3, 11, 17, 40])
+    deck = decks.Deck(D=1, ncell=(ncell,), dx=(0.25,), xmin=(0.0,), nghost=2)
+    grid = pgpu.Grid(1, (ncell,), (0.0,), (0.25,), 2, (1,), volume_scale=deck.volume_scale)
+    w0 = 1e30 * 0.25 * deck.volume_scale / 40.0
+
+    def make(sdef, x, vth):
+        n = x.shape[1]
+        sp = pgpu.Species(grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm,
+                          interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E, relativistic=1)
+        sp.upload(x, rng.standard_normal((3, n)) * vth, np.full(n, w0), ids=np.arange(n, dtype=np.uint64))
+        sp.bin_particles(); sp.set_moments()
+        return sp
+    se = make(decks.SpeciesDef("electron", 1.0, -1.0), xe, 0.6)
+    si = make(decks.SpeciesDef("proton", 1836.15, 1.0), xi, 0.01)
+    grid.debye_length([se, si])
+    be, bi = se.download(), si.download()
+    pgpu.collide_coulomb(se, se, 10.0, DT_SEC, 1983, 3, angular=1)
+    ae = se.download()
+    oe = se.cell_offsets()
+    moved = 0
+    for c in range(ncell):
+        a, b = oe[c], oe[c + 1]
+        if b - a < 2:
+            assert np.array_equal(ae["v"][:, a:b], be["v"][:, a:b])
+            continue
+        v0, v1 = be["v"][:, a:b], ae["v"][:, a:b]
+        assert np.max(np.abs(v1.sum(1) - v0.sum(1))) < 1e-13 * (b - a)
+        g0, g1 = np.sqrt(1 + (v0 ** 2).sum(0)).sum(), np.sqrt(1 + (v1 ** 2).sum(0)).sum()
+        assert abs(g1 - g0) < 1e-12 * g0
+        moved += int(np.any(v1 != v0))
+    assert moved > ncell // 3
+    # e-i: equal weights, so both partners of every pair scatter
+    pgpu.collide_coulomb(se, si, 10.0, DT_SEC, 1983, 4, angular=0)
+    ae2, ai2 = se.download(), si.download()
+    oi = si.cell_offsets()
+    for c in range(ncell):
+        a, b, p, q = oe[c], oe[c + 1], oi[c], oi[c + 1]
+        if b - a == 0 or q - p == 0:
+            continue
+        p0 = ae["v"][:, a:b].sum(1) + 1836.15 * bi["v"][:, p:q].sum(1)
+        p1 = ae2["v"][:, a:b].sum(1) + 1836.15 * ai2["v"][:, p:q].sum(1)
+        assert np.max(np.abs(p1 - p0)) < 1e-11 * max(np.max(np.abs(p0)), 1.0)
+        e0 = np.sqrt(1 + (ae["v"][:, a:b] ** 2).sum(0)).sum() + 1836.15 * np.sqrt(1 + (bi["v"][:, p:q] ** 2).sum(0)).sum()
+        e1 = np.sqrt(1 + (ae2["v"][:, a:b] ** 2).sum(0)).sum() + 1836.15 * np.sqrt(1 + (ai2["v"][:, p:q] ** 2).sum(0)).sum()
+        assert abs(e1 - e0) < 1e-12 * e0
+    se.destroy(); si.destroy(); grid.destroy()
