@@ -350,6 +350,14 @@ int pgpu_coulomb_delta_u(long n, const double *vp1, const double *vp2, double ch
                          double mass1, double mass2, const pgpu_coulomb_params *prm, double dt_sec,
                          const double *EF_norm, const double *den12, const double *bmax, const double *sigma_max,
                          const double *gauss, const double *u_polar, const double *u_phi, double *dU, double *s12);
+/* HardSphere::applySelfScattering / applyInterScattering, PROBABILISTIC weight method (HardSphere.cpp:223-665):
+ * no-time-counter pair selection with gmax = 5 thermal speeds of the cell, isotropic scattering.  sigmaT =
+ * pi (r1 + r2)^2 (HardSphere.cpp:52).  Species must be binned with their cell moments set.  The CONSERVATIVE
+ * weight method (collapseThreeToTwo) is not implemented. */
+int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double dt_sec, uint64_t seed,
+                             uint64_t step, long *ncollisions);
+/* HardSphere::setMeanFreeTime (HardSphere.cpp:65-194): box maximum of n sigmaT sqrt(Teff/m) */
+int pgpu_scatter_nu_max_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double *nu_max);
 /* Coulomb::LorentzScatter (Coulomb.cpp:1694-1793) for n pairs with explicit draws (test hook of the relativistic
  * pair update that pgpu_collide_coulomb applies when a species is relativistic): particle 1 always scatters,
  * particle 2 where scatter2[i] != 0. */

@@ -491,3 +491,38 @@ def compute_J_from_mass_matrices(D, ncomp, sigma, E0, E, J0, J):
     f.argtypes = [C.c_int] + [C.c_void_p] * 6
     nc = np.ascontiguousarray(ncomp, dtype=np.int32)
     f(D, _ptr(nc), _mfabs9(sigma), _fabs3(E0), _fabs3(E), _fabs3(J0), _fabs3(J))
+
+
+# ---- HardSphere (no-time-counter) -------------------------------------------------------------
+def hs_sigmaT(r1, r2):
+    f = lib().orc_hs_sigmaT
+    f.restype = C.c_double
+    f.argtypes = [C.c_double, C.c_double]
+    return f(r1, r2)
+
+
+def hs_self(cell_start, v, w, dens, ene, mass, sigmaT, dt_sec):
+    """HardSphere::applySelfScattering; v [3][n] is updated in place.  Returns (candidates, collisions)."""
+    f = lib().orc_hs_self
+    f.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p] + [C.c_double] * 3 + \
+                 [C.c_void_p] * 2
+    cs = np.ascontiguousarray(cell_start, dtype=np.int64)
+    ene = np.ascontiguousarray(ene, dtype=np.float64)
+    a, b = C.c_long(0), C.c_long(0)
+    f(cs.size - 1, _ptr(cs), _ptr(v), _ptr(w), v.shape[1], _ptr(dens), _ptr(ene), mass, sigmaT, dt_sec, C.byref(a),
+      C.byref(b))
+    return a.value, b.value
+
+
+def hs_inter(cs1, v1, w1, dens1, ene1, m1, cs2, v2, w2, dens2, ene2, m2, Vc, sigmaT, dt_sec):
+    f = lib().orc_hs_inter
+    f.argtypes = ([C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_double,
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p] + [C.c_double] * 4 +
+                  [C.c_void_p] * 2)
+    a1 = np.ascontiguousarray(cs1, dtype=np.int64)
+    a2 = np.ascontiguousarray(cs2, dtype=np.int64)
+    e1, e2 = np.ascontiguousarray(ene1, dtype=np.float64), np.ascontiguousarray(ene2, dtype=np.float64)
+    a, b = C.c_long(0), C.c_long(0)
+    f(a1.size - 1, _ptr(a1), _ptr(v1), _ptr(w1), v1.shape[1], _ptr(dens1), _ptr(e1), m1, _ptr(a2), _ptr(v2), _ptr(w2),
+      v2.shape[1], _ptr(dens2), _ptr(e2), m2, Vc, sigmaT, dt_sec, C.byref(a), C.byref(b))
+    return a.value, b.value

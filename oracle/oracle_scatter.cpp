@@ -874,6 +874,130 @@ extern "C" double orc_ta_nu_max(long ncell, const double *dens1, const double *e
   return box_nuMax;
 }
 
+/* ==========================================================================================
+ * HardSphere, PROBABILISTIC weight method (src/scattering/HardSphere.cpp:30-52, 223-418, 419-665):
+ * no-time-counter pair selection.  Per cell: gmax = 5 thermal speeds from the cell's energy density,
+ * Nmax candidate pairs (fractional part by a draw), each accepted with probability g12/gmax, isotropic
+ * scattering, velocity update with probability w_other/w_self.  ene = [3][ncell] energy densities as
+ * set{Energy}DensityFromBinFab leaves them.
+ * ======================================================================================== */
+namespace {
+int mu_randint(int a, int b) {   /* MathUtils::randInt */
+  std::uniform_int_distribution<int> dist(a, b);
+  return dist(global_rand_gen);
+}
+}  // namespace
+
+extern "C" double orc_hs_sigmaT(double r1, double r2) { return kPI * (r1 + r2) * (r1 + r2); }   /* HardSphere.cpp:52 */
+
+extern "C" void orc_hs_self(long ncell, const long *cs, double *v, const double *w, long n, const double *dens,
+                            const double *ene, double mass, double sigmaT, double dt_sec, long *ncand_out,
+                            long *ncoll_out) {
+  const double cvacSq = kCVAC * kCVAC;
+  long ncand = 0, ncoll = 0;
+  for (long c = 0; c < ncell; ++c) {
+    const double local_numberDensity = dens[c];
+    if (local_numberDensity == 0.0) continue;
+    double local_energyDensity = 0.0;
+    for (int dir = 0; dir < 3; dir++) local_energyDensity = local_energyDensity + ene[dir * ncell + c];
+    const double local_Teff = 2.0 / 3.0 * local_energyDensity / local_numberDensity * cvacSq;
+    const double local_gmax = 5.0 * sqrt(local_Teff / mass);
+    const double local_nuMaxDt = local_numberDensity * sigmaT * local_gmax * dt_sec;
+    const int local_numCell = (int)(cs[c + 1] - cs[c]);
+    if (local_numCell < 2) continue;
+    const double local_Nmax = 0.5 * (local_numCell - 1) * std::min(local_nuMaxDt, 1.0);
+    double local_Nmax_whole;
+    const double local_Nmax_remainder = modf(local_Nmax, &local_Nmax_whole);
+    const double rand_num = mu_rand();
+    int local_Nmax_integer = static_cast<int>(local_Nmax_whole);
+    if (rand_num <= local_Nmax_remainder) local_Nmax_integer = local_Nmax_integer + 1;
+    ncand += local_Nmax_integer;
+    for (int k = 0; k < local_Nmax_integer; k++) {
+      const int random_index1 = mu_randint(0, local_numCell - 1);
+      int random_index2 = mu_randint(0, local_numCell - 1);
+      while (random_index2 == random_index1) random_index2 = mu_randint(0, local_numCell - 1);
+      const long i1 = cs[c] + random_index1, i2 = cs[c] + random_index2;
+      double b1[3] = {v[i1], v[n + i1], v[2 * n + i1]}, b2[3] = {v[i2], v[n + i2], v[2 * n + i2]};
+      const double wp1 = w[i1], wp2 = w[i2];
+      double g12 = 0.0;
+      for (int dir = 0; dir < 3; dir++) g12 += pow(b1[dir] - b2[dir], 2);
+      g12 = sqrt(g12) * kCVAC;
+      const double q12 = g12 * sigmaT / (local_gmax * sigmaT);
+      if (mu_rand() > q12) continue;
+      ncoll += 1;
+      const double R = mu_rand();
+      const double costh = 1.0 - 2.0 * R;
+      const double sinth = sqrt(1.0 - costh * costh);
+      const double phi = kTWOPI * mu_rand();
+      double dU[3];
+      orc_scatter_delta_u(b1[0] - b2[0], b1[1] - b2[1], b1[2] - b2[2], costh, sinth, cos(phi), sin(phi), dU);
+      const double rand_num3 = mu_rand();
+      if (rand_num3 <= wp2 / wp1)
+        for (int dir = 0; dir < 3; dir++) v[dir * n + i1] = b1[dir] + 0.5 * dU[dir];
+      if (rand_num3 <= wp1 / wp2)
+        for (int dir = 0; dir < 3; dir++) v[dir * n + i2] = b2[dir] - 0.5 * dU[dir];
+    }
+  }
+  if (ncand_out) *ncand_out = ncand;
+  if (ncoll_out) *ncoll_out = ncoll;
+}
+
+extern "C" void orc_hs_inter(long ncell, const long *cs1, double *v1, const double *w1, long n1, const double *dens1,
+                             const double *ene1, double mass1, const long *cs2, double *v2, const double *w2, long n2,
+                             const double *dens2, const double *ene2, double mass2, double Vc, double sigmaT,
+                             double dt_sec, long *ncand_out, long *ncoll_out) {
+  const double cvacSq = kCVAC * kCVAC;
+  const double mu = mass1 * mass2 / (mass1 + mass2);
+  long ncand = 0, ncoll = 0;
+  for (long c = 0; c < ncell; ++c) {
+    const double nd1 = dens1[c], nd2 = dens2[c];
+    if (nd1 * nd2 == 0.0) continue;
+    double e1 = 0.0, e2 = 0.0;
+    for (int dir = 0; dir < 3; dir++) {
+      e1 = e1 + ene1[dir * ncell + c];
+      e2 = e2 + ene2[dir * ncell + c];
+    }
+    const double Teff1 = 2.0 / 3.0 * e1 / nd1 * cvacSq, Teff2 = 2.0 / 3.0 * e2 / nd2 * cvacSq;
+    const double local_gmax = 2.5 * sqrt(2.0 * std::max(Teff1, Teff2) / mu);
+    const int numCell1 = (int)(cs1[c + 1] - cs1[c]), numCell2 = (int)(cs2[c + 1] - cs2[c]);
+    if (numCell1 < 2 && numCell2 < 2) continue;
+    if (numCell1 < 1 || numCell2 < 1) continue;   /* randInt(0,-1) in the reference: no pair exists */
+    const double W1 = nd1 / numCell1 * Vc, W2 = nd2 / numCell2 * Vc;
+    const double Wmax = std::max(W1, W2);
+    const double local_Nmax = Wmax * numCell1 * numCell2 / Vc * sigmaT * local_gmax * dt_sec;
+    double whole;
+    const double rem = modf(local_Nmax, &whole);
+    const double rand_num = mu_rand();
+    int Nint = static_cast<int>(whole);
+    if (rand_num < rem) Nint = Nint + 1;
+    ncand += Nint;
+    for (int k = 0; k < Nint; k++) {
+      const long i1 = cs1[c] + mu_randint(0, numCell1 - 1), i2 = cs2[c] + mu_randint(0, numCell2 - 1);
+      double b1[3] = {v1[i1], v1[n1 + i1], v1[2 * n1 + i1]}, b2[3] = {v2[i2], v2[n2 + i2], v2[2 * n2 + i2]};
+      const double wp1 = w1[i1], wp2 = w2[i2];
+      double g12 = 0.0;
+      for (int dir = 0; dir < 3; dir++) g12 = g12 + pow(b1[dir] - b2[dir], 2);
+      g12 = sqrt(g12) * kCVAC;
+      const double q12 = g12 * sigmaT / (local_gmax * sigmaT);
+      if (mu_rand() > q12) continue;
+      ncoll += 1;
+      const double R = mu_rand();
+      const double costh = 1.0 - 2.0 * R;
+      const double sinth = sqrt(1.0 - costh * costh);
+      const double phi = kTWOPI * mu_rand();
+      double dU[3];
+      orc_scatter_delta_u(b1[0] - b2[0], b1[1] - b2[1], b1[2] - b2[2], costh, sinth, cos(phi), sin(phi), dU);
+      const double rand_num3 = mu_rand();
+      if (rand_num3 <= wp2 / wp1)
+        for (int dir = 0; dir < 3; dir++) v1[dir * n1 + i1] = b1[dir] + mu / mass1 * dU[dir];
+      if (rand_num3 <= wp1 / wp2)
+        for (int dir = 0; dir < 3; dir++) v2[dir * n2 + i2] = b2[dir] - mu / mass2 * dU[dir];
+    }
+  }
+  if (ncand_out) *ncand_out = ncand;
+  if (ncoll_out) *ncoll_out = ncoll;
+}
+
 /* Coulomb::setIntraMFT / setInterMFT (Coulomb.cpp:108-356) */
 extern "C" double orc_coulomb_nu_max(long ncell, const double *LDe, const double *dens1, const double *mom1,
                                      const double *ene1, const double *dens2, const double *mom2,

@@ -230,6 +230,14 @@ void orc_elastic(long ncell, const long *cs1, double *v1, const double *w1, long
 
 /* Scattering::setMeanFreeTime: box maximum of the per-cell collision frequency [Hz]
  * (TakizukaAbe.cpp:55-238, Coulomb.cpp:79-356, Elastic.cpp:122-202, MathUtils.cpp:65-95) */
+/* HardSphere, PROBABILISTIC (HardSphere.cpp:223-665): no-time-counter pairs; ene = [3][ncell] */
+double orc_hs_sigmaT(double r1, double r2);
+void orc_hs_self(long ncell, const long *cs, double *v, const double *w, long n, const double *dens,
+                 const double *ene, double mass, double sigmaT, double dt_sec, long *ncand, long *ncoll);
+void orc_hs_inter(long ncell, const long *cs1, double *v1, const double *w1, long n1, const double *dens1,
+                  const double *ene1, double mass1, const long *cs2, double *v2, const double *w2, long n2,
+                  const double *dens2, const double *ene2, double mass2, double Vc, double sigmaT, double dt_sec,
+                  long *ncand, long *ncoll);
 double orc_gammainc_3half(double x);
 double orc_ta_nu_max(long ncell, const double *dens1, const double *ene1, const double *dens2,
                      const double *ene2, double charge1, double charge2, double mass1, double mass2,

@@ -108,6 +108,8 @@ def load():
         "pgpu_coulomb_delta_u": [lng, vp, vp, dbl, dbl, dbl, dbl, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "pgpu_coulomb_lorentz_scatter": [lng, vp, vp, vp, dbl, dbl, dbl, dbl, vp, dbl] + [vp] * 10,
         "pgpu_collide_elastic": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
+        "pgpu_collide_hard_sphere": [vp, vp, dbl, dbl, C.c_uint64, C.c_uint64, vp],
+        "pgpu_scatter_nu_max_hard_sphere": [vp, vp, dbl, vp],
         "pgpu_scatter_nu_max_ta": [vp, vp, dbl, vp], "pgpu_scatter_nu_max_coulomb": [vp, vp, vp, vp],
         "pgpu_scatter_nu_max_elastic": [vp, vp, vp, vp],
         "pgpu_halo_create": [vp, i32, vp, vp], "pgpu_halo_destroy": [vp], "pgpu_halo_phases": [vp],
@@ -434,6 +436,18 @@ def collide_coulomb(sA, sB, Clog, dt_sec, seed, step, angular=0, NxN=False, NxN_
     np_ = C.c_long(0)
     check(load().pgpu_collide_coulomb(sA.h, sB.h, C.byref(prm), dt_sec, seed, step, C.byref(np_) if count else None))
     return np_.value
+
+
+def collide_hard_sphere(sA, sB, sigmaT, dt_sec, seed, step, count=True):
+    np_ = C.c_long(0)
+    check(load().pgpu_collide_hard_sphere(sA.h, sB.h, sigmaT, dt_sec, seed, step, C.byref(np_) if count else None))
+    return np_.value
+
+
+def nu_max_hard_sphere(sA, sB, sigmaT):
+    out = C.c_double(0)
+    check(load().pgpu_scatter_nu_max_hard_sphere(sA.h, sB.h, sigmaT, C.byref(out)))
+    return out.value
 
 
 def coulomb_lorentz_scatter(up1, up2, scatter2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, den12, bmax, sigma_max,

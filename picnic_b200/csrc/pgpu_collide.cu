@@ -10,6 +10,8 @@
 //
 // One warp owns one cell of the cell-sorted arrays: lanes build the random order
 // (rank of a per-particle Philox key), then each lane scatters pairs.
+#include <vector>
+
 #include "pgpu_internal.h"
 
 namespace pgpu {
@@ -817,6 +819,110 @@ k_coulomb_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a
 // same partner in one batch go one after the other (__match_any_sync), as the reference's
 // sequential loop would.
 // =============================================================================================
+// HardSphere, PROBABILISTIC weight method (src/scattering/HardSphere.cpp:223-418 self, 419-665 inter):
+// no-time-counter pairs.  The candidates of a cell are sequential by construction (a collision changes the
+// velocities the next candidate sees), so one thread owns a cell; the parallelism is the number of cells.
+// Draws: Philox keyed by (candidate, global cell, step); the reference's "redraw until different" for the
+// second index of a self pair is taken as a uniform pick among the other N-1 particles (same distribution).
+// =============================================================================================
+enum { STREAM_HS = 0x4853u };
+struct HSParams {
+  double sigmaT, dt_sec, mass1, mass2, mu, Vc;
+  unsigned seed_lo, seed_hi, step_lo, step_hi;
+  int box_lo0, box_lo1, nbox0, ncell_glob0;
+};
+__device__ __forceinline__ u4 hs_draw(const HSParams &P, unsigned k, unsigned gcell, unsigned sub) {
+  u4 c;
+  c.x = k;
+  c.y = gcell;
+  c.z = P.step_lo;
+  c.w = P.step_hi ^ (STREAM_HS << 16) ^ sub;
+  return philox4x32_10(c, P.seed_lo, P.seed_hi);
+}
+__global__ void __launch_bounds__(128)
+k_hard_sphere(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, double *a2, const double *wa,
+              const double *dens1, const double *ene1, double *b0, double *b1, double *b2, const double *wb,
+              const double *dens2, const double *ene2, HSParams P, int self, unsigned long long *ncoll) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned mine = 0;
+  if (cell < ncell) {
+    const double CVAC = 2.99792458e+08, TWOPI = 6.28318530717958647692, cvacSq = CVAC * CVAC;
+    const int s1 = cs1[cell], n1 = cs1[cell + 1] - s1, s2 = cs2[cell], n2 = cs2[cell + 1] - s2;
+    const double nd1 = dens1[cell], nd2 = dens2[cell];
+    const unsigned gcell = (unsigned)((cell % P.nbox0 + P.box_lo0) + (cell / P.nbox0 + P.box_lo1) * P.ncell_glob0);
+    double gmax = 0.0, Nmax = 0.0;
+    bool go;
+    if (self) {
+      go = nd1 != 0.0 && n1 >= 2;
+      if (go) {
+        double e = 0.0;
+        for (int d = 0; d < 3; ++d) e = e + ene1[(size_t)d * ncell + cell];
+        const double Teff = 2.0 / 3.0 * e / nd1 * cvacSq;
+        gmax = 5.0 * sqrt(Teff / P.mass1);
+        const double nuMaxDt = nd1 * P.sigmaT * gmax * P.dt_sec;
+        Nmax = 0.5 * (n1 - 1) * fmin(nuMaxDt, 1.0);
+      }
+    } else {
+      go = nd1 * nd2 != 0.0 && !(n1 < 2 && n2 < 2) && n1 >= 1 && n2 >= 1;
+      if (go) {
+        double e1 = 0.0, e2 = 0.0;
+        for (int d = 0; d < 3; ++d) {
+          e1 = e1 + ene1[(size_t)d * ncell + cell];
+          e2 = e2 + ene2[(size_t)d * ncell + cell];
+        }
+        const double Teff1 = 2.0 / 3.0 * e1 / nd1 * cvacSq, Teff2 = 2.0 / 3.0 * e2 / nd2 * cvacSq;
+        gmax = 2.5 * sqrt(2.0 * fmax(Teff1, Teff2) / P.mu);
+        const double W1 = nd1 / n1 * P.Vc, W2 = nd2 / n2 * P.Vc;
+        Nmax = fmax(W1, W2) * n1 * n2 / P.Vc * P.sigmaT * gmax * P.dt_sec;
+      }
+    }
+    if (go) {
+      const double whole = floor(Nmax), rem = Nmax - whole;
+      const double u0 = u01(hs_draw(P, 0xffffffffu, gcell, 2u).x);
+      int Nint = (int)whole;
+      if (self ? (u0 <= rem) : (u0 < rem)) Nint += 1;
+      const double f1 = self ? 0.5 : P.mu / P.mass1, f2 = self ? 0.5 : P.mu / P.mass2;
+      for (int k = 0; k < Nint; ++k) {
+        const u4 r0 = hs_draw(P, (unsigned)k, gcell, 0u);
+        int q1 = min(n1 - 1, (int)(u01(r0.x) * n1)), q2;
+        if (self) {
+          q2 = min(n1 - 2, (int)(u01(r0.y) * (n1 - 1)));
+          if (q2 >= q1) q2 += 1;
+        } else {
+          q2 = min(n2 - 1, (int)(u01(r0.y) * n2));
+        }
+        const int i1 = s1 + q1, i2 = s2 + q2;
+        const double v1[3] = {a0[i1], a1[i1], a2[i1]}, v2[3] = {b0[i2], b1[i2], b2[i2]};
+        const double ux = v1[0] - v2[0], uy = v1[1] - v2[1], uz = v1[2] - v2[2];
+        const double g12 = sqrt(ux * ux + uy * uy + uz * uz) * CVAC;
+        const double q12 = g12 * P.sigmaT / (gmax * P.sigmaT);
+        if (u01(r0.z) > q12) continue;
+        mine += 1;
+        const u4 r1 = hs_draw(P, (unsigned)k, gcell, 1u);
+        const double costh = 1.0 - 2.0 * u01(r0.w);
+        const double sinth = sqrt(1.0 - costh * costh);
+        double sinphi, cosphi, dU[3];
+        sincos(TWOPI * u01(r1.x), &sinphi, &cosphi);
+        scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
+        const double wp1 = wa[i1], wp2 = wb[i2], u3 = u01(r1.y);
+        if (u3 <= wp2 / wp1) {
+          a0[i1] = v1[0] + f1 * dU[0];
+          a1[i1] = v1[1] + f1 * dU[1];
+          a2[i1] = v1[2] + f1 * dU[2];
+        }
+        if (u3 <= wp1 / wp2) {
+          b0[i2] = v2[0] - f2 * dU[0];
+          b1[i2] = v2[1] - f2 * dU[1];
+          b2[i2] = v2[2] - f2 * dU[2];
+        }
+      }
+    }
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(ncoll, (unsigned long long)mine);
+}
+
+// =============================================================================================
 struct ElaParams {
   double mu, f1, f2, const_sigma, dt_sec, mcSq;
   int ntab, angular, loglog;
@@ -1438,6 +1544,87 @@ int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elasti
     cudaFree(d_tab);
   }
   return rc;
+}
+
+int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double dt_sec, uint64_t seed,
+                             uint64_t step, long *ncoll_out) {
+  int rc = need_binned(sA, sB);
+  if (rc) return rc;
+  if (!(sigmaT > 0.0)) {
+    set_error("HardSphere: sigmaT must be positive");
+    return PGPU_ERR_ARG;
+  }
+  if (!sA->dens || !sA->ene || !sB->dens || !sB->ene) {
+    set_error("HardSphere needs the cell moments: call pgpu_set_moments_from_bins first");
+    return PGPU_ERR_STATE;
+  }
+  Context &c = ctx();
+  const pgpu_grid_s *g = sA->grid;
+  HSParams P;
+  P.sigmaT = sigmaT;
+  P.dt_sec = dt_sec;
+  P.mass1 = sA->desc.mass;
+  P.mass2 = sB->desc.mass;
+  P.mu = P.mass1 * P.mass2 / (P.mass1 + P.mass2);
+  const double dV = (g->desc.D == 1) ? g->geo.dx[0] : g->geo.dx[0] * g->geo.dx[1];
+  P.Vc = dV * g->desc.volume_scale;      // DomainGrid::getMappedCellVolume in SI
+  P.seed_lo = (unsigned)seed;
+  P.seed_hi = (unsigned)(seed >> 32);
+  P.step_lo = (unsigned)step;
+  P.step_hi = (unsigned)(step >> 32) & 0xffffu;
+  P.box_lo0 = g->desc.box_lo[0];
+  P.box_lo1 = (g->desc.D == 2) ? g->desc.box_lo[1] : 0;
+  P.nbox0 = g->nbox[0];
+  P.ncell_glob0 = g->desc.ncell[0];
+  const int ncell = (int)g->ncell_box;
+  {
+    KTimer t("collide_hard_sphere");
+    k_hard_sphere<<<(unsigned)((ncell + 127) / 128), 128, 0, c.stream>>>(
+        sA->cell_start, sB->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->w, sA->dens, sA->ene, sB->v[0], sB->v[1],
+        sB->v[2], sB->w, sB->dens, sB->ene, P, sA == sB ? 1 : 0, &c.d_counters->npairs);
+  }
+  return fetch_pairs(ncoll_out);
+}
+
+// HardSphere::setIntraMFT / setInterMFT (HardSphere.cpp:84-194): nu_max = max over cells of n * sigmaT * sqrt(Teff/m).
+// The moments are ncell-sized: read back and reduced on the host (once per step, like the reference's loop).
+int pgpu_scatter_nu_max_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double *nu_max) {
+  if (!ctx().inited) {
+    set_error("pgpu_init has not been called");
+    return PGPU_ERR_STATE;
+  }
+  if (!sA || !sB || sA->grid != sB->grid || !nu_max) return PGPU_ERR_ARG;
+  if (!sA->dens || !sA->ene || !sB->dens || !sB->ene) {
+    set_error("HardSphere::setMeanFreeTime needs the cell moments: call pgpu_set_moments_from_bins first");
+    return PGPU_ERR_STATE;
+  }
+  const size_t ncell = (size_t)sA->grid->ncell_box;
+  std::vector<double> d1(ncell), e1(3 * ncell), d2(ncell), e2(3 * ncell);
+  cudaStream_t st = ctx().stream;
+  PGPU_CUDA(cudaMemcpyAsync(d1.data(), sA->dens, ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaMemcpyAsync(e1.data(), sA->ene, 3 * ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaMemcpyAsync(d2.data(), sB->dens, ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaMemcpyAsync(e2.data(), sB->ene, 3 * ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  const double CVAC = 2.99792458e+08, cvacSq = CVAC * CVAC;
+  const double m1 = sA->desc.mass, m2 = sB->desc.mass;
+  double box_nuMax = 0.0;
+  for (size_t c = 0; c < ncell; ++c) {
+    if (sA == sB) {
+      if (d1[c] == 0.0) continue;
+      const double e = e1[c] + e1[ncell + c] + e1[2 * ncell + c];
+      const double Teff = 2.0 / 3.0 * e / d1[c] * cvacSq;
+      box_nuMax = std::max(box_nuMax, d1[c] * sigmaT * sqrt(Teff / m1));
+    } else {
+      if (d1[c] * d2[c] == 0.0) continue;
+      const double ea = e1[c] + e1[ncell + c] + e1[2 * ncell + c], eb = e2[c] + e2[ncell + c] + e2[2 * ncell + c];
+      const double Teff1 = 2.0 / 3.0 * ea / d1[c] * cvacSq, Teff2 = 2.0 / 3.0 * eb / d2[c] * cvacSq;
+      box_nuMax = std::max(box_nuMax, d2[c] * sigmaT * sqrt(Teff1 / m1));
+      box_nuMax = std::max(box_nuMax, d1[c] * sigmaT * sqrt(Teff2 / m2));
+    }
+  }
+  *nu_max = box_nuMax;
+  return 0;
 }
 
 int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt_sec, uint64_t seed,

@@ -505,4 +505,28 @@ void Elastic::printParameters() const {
                  << (m_okhrimovskyy ? "OKHRIMOVSKYY" : "ISOTROPIC") << std::endl;
 }
 
+// ---- HardSphere (HardSphere.cpp:30-52, 65-194, 196-665) ------------------------------------------
+HardSphere::HardSphere(int a_sp1, int a_sp2, Real a_r1, Real a_r2)
+    : m_sp1(a_sp1), m_sp2(a_sp2), m_r1(a_r1), m_r2(a_r2), m_sigmaT(3.14159265358979323846 * (a_r1 + a_r2) * (a_r1 + a_r2)),
+      m_scatter_dt(DBL_MAX), m_ncoll(0) {}
+void HardSphere::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {
+  double nu = 0.0;
+  check(pgpu_scatter_nu_max_hard_sphere(a_species[m_sp1]->handle(), a_species[m_sp2]->handle(), m_sigmaT, &nu),
+        "HardSphere::setMeanFreeTime");
+  m_scatter_dt = nu > 0.0 ? 1.0 / nu : DBL_MAX;
+}
+void HardSphere::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real a_dt_sec) const {
+  PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
+  if (a->numParticles() == 0 || b->numParticles() == 0) return;
+  long nc = 0;
+  check(pgpu_collide_hard_sphere(a->handle(), b->handle(), m_sigmaT, a_dt_sec, s_seed, s_step, &nc),
+        "HardSphere::applyScattering");
+  m_ncoll = nc;
+}
+void HardSphere::printParameters() const {
+  std::cout << " HardSphere scattering parameters:" << std::endl;
+  std::cout << "  species A = " << m_sp1 << ", species B = " << m_sp2 << std::endl;
+  std::cout << "  r1 = " << m_r1 << " m, r2 = " << m_r2 << " m, sigmaT = " << m_sigmaT << " m^2" << std::endl;
+}
+
 }  // namespace picnic_gpu

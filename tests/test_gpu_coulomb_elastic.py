@@ -426,3 +426,90 @@ def test_coulomb_relativistic_species_conserve_four_momentum_per_cell(pgpu):
         e1 = np.sqrt(1 + (ae2["v"][:, a:b] ** 2).sum(0)).sum() + 1836.15 * np.sqrt(1 + (ai2["v"][:, p:q] ** 2).sum(0)).sum()
         assert abs(e1 - e0) < 1e-12 * e0
     se.destroy(); si.destroy(); grid.destroy()
+
+
+def test_hard_sphere_self_matches_oracle_statistics(pgpu):
+    """pgpu_collide_hard_sphere (HardSphere no-time-counter pairs): per-cell momentum and energy conserved for equal
+    weights, collision count and the decay of a temperature anisotropy within 3 % of the oracle on the same
+    cells (the RNG streams differ by construction)."""
+    deck = decks.Deck(D=2, ncell=(24, 24), dx=(0.25, 0.25), xmin=(0.0, 0.0), nghost=2)
+    sdef = decks.SpeciesDef("argon", 40.0 * 1836.15, 0.0, (3.0, 1.0, 1.0), 1.0e30, (7, 7))
+    rng = np.random.default_rng(1983)
+    p = decks.load_species(deck, sdef, (0, 0), (23, 23), rng)
+    grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, 2, (1, 1), volume_scale=deck.volume_scale)
+    sp = _species_on_grid(pgpu, grid, deck, sdef, p["x"], p["v"], p["w"], ids=p["id"])
+    s0 = sp.download()
+    dens, _, ene = sp.moments()
+    offs = sp.cell_offsets()
+    sig = orc.hs_sigmaT(1.9e-10, 1.9e-10)
+    gmax = 5.0 * np.sqrt(2.0 / 3.0 * ene.reshape(3, -1).sum(0) / dens / sdef.mass) * 2.99792458e8
+    dt_sec = 0.6 / float(np.max(dens * sig * gmax))
+
+    def aniso(v):
+        t = (v ** 2).mean(axis=1)
+        return (t[0] - 0.5 * (t[1] + t[2])) / t.mean()
+
+    a0 = aniso(s0["v"])
+    # HardSphere::setMeanFreeTime: box maximum of n sigmaT sqrt(Teff/m) = gmax/5 per cell
+    assert abs(pgpu.nu_max_hard_sphere(sp, sp, sig) - float(np.max(dens * sig * gmax / 5.0))) < 1e-12 * float(np.max(dens * sig * gmax))
+    nsteps, total_gpu = 6, 0
+    for step in range(nsteps):
+        sp.set_moments()
+        total_gpu += pgpu.collide_hard_sphere(sp, sp, sig, dt_sec, 1983, step)
+        if step == 0:
+            s1 = sp.download()
+            for c in range(0, offs.size - 1, 5):
+                a, b = offs[c], offs[c + 1]
+                v0, v1 = s0["v"][:, a:b], s1["v"][:, a:b]
+                assert np.max(np.abs(v1.sum(1) - v0.sum(1))) < 1e-15 * (b - a) * np.max(np.abs(v0))  + 1e-20
+                assert abs((v1 ** 2).sum() - (v0 ** 2).sum()) < 1e-12 * (v0 ** 2).sum()
+            assert np.mean(np.any(s1["v"] != s0["v"], axis=0)) > 0.1
+    a_gpu = aniso(sp.download()["v"])
+    sp.destroy(); grid.destroy()
+    # oracle on the same cells
+    v = s0["v"].copy()
+    Vc = 0.25 * 0.25 * deck.volume_scale
+    orc.lib().orc_rng_seed(1983)
+    total_cpu = 0
+    for step in range(nsteps):
+        e = np.zeros((3, offs.size - 1))
+        for c in range(offs.size - 1):
+            a, b = offs[c], offs[c + 1]
+            e[:, c] = 0.5 * sdef.mass * (s0["w"][a:b] * v[:, a:b] ** 2).sum(1) / Vc
+        total_cpu += orc.hs_self(offs, v, s0["w"], dens, e, sdef.mass, sig, dt_sec)[1]
+    a_cpu = aniso(v)
+    assert total_cpu > 10000
+    assert abs(total_gpu - total_cpu) < 0.03 * total_cpu, (total_gpu, total_cpu)
+    assert a_cpu / a0 < 0.8 and a_gpu / a0 < 0.8
+    assert abs(a_gpu - a_cpu) / a0 < 0.03
+
+
+def test_hard_sphere_inter_conserves_per_cell(pgpu):
+    deck = decks.Deck(D=1, ncell=(64,), dx=(0.25,), xmin=(0.0,), nghost=2)
+    rng = np.random.default_rng(71)
+    xa, ca = _ragged_cells(rng, 64, [0, 1, 2, 9, 30])
+    xb, cb = _ragged_cells(rng, 64, [0, 1, 3, 12, 25])
+    grid = pgpu.Grid(1, (64,), (0.0,), (0.25,), 2, (1,), volume_scale=deck.volume_scale)
+    w0 = 1e30 * 0.25 * deck.volume_scale / 30.0
+    sa_def, sb_def = decks.SpeciesDef("helium", 4.0 * 1836.15, 0.0), decks.SpeciesDef("argon", 40.0 * 1836.15, 0.0)
+    sa = _species_on_grid(pgpu, grid, deck, sa_def, xa, rng.standard_normal((3, xa.shape[1])) * 2e-3, np.full(xa.shape[1], w0))
+    sb = _species_on_grid(pgpu, grid, deck, sb_def, xb, rng.standard_normal((3, xb.shape[1])) * 5e-4, np.full(xb.shape[1], w0))
+    ba, bb = sa.download(), sb.download()
+    sig = orc.hs_sigmaT(1.2e-10, 1.8e-10)
+    ncoll = pgpu.collide_hard_sphere(sa, sb, sig, 2.0e-18, 7, 1)
+    assert ncoll > 50
+    aa, ab = sa.download(), sb.download()
+    oa, ob = sa.cell_offsets(), sb.cell_offsets()
+    m1, m2 = sa_def.mass, sb_def.mass
+    for c in range(64):
+        s1, s2 = slice(oa[c], oa[c + 1]), slice(ob[c], ob[c + 1])
+        if oa[c + 1] == oa[c] or ob[c + 1] == ob[c]:
+            assert np.array_equal(aa["v"][:, s1], ba["v"][:, s1]) and np.array_equal(ab["v"][:, s2], bb["v"][:, s2])
+            continue
+        p0 = m1 * ba["v"][:, s1].sum(1) + m2 * bb["v"][:, s2].sum(1)
+        p1 = m1 * aa["v"][:, s1].sum(1) + m2 * ab["v"][:, s2].sum(1)
+        assert np.max(np.abs(p1 - p0)) < 1e-12 * np.max(np.abs(p0)) + 1e-14
+        k0 = m1 * (ba["v"][:, s1] ** 2).sum() + m2 * (bb["v"][:, s2] ** 2).sum()
+        k1 = m1 * (aa["v"][:, s1] ** 2).sum() + m2 * (ab["v"][:, s2] ** 2).sum()
+        assert abs(k1 - k0) < 1e-12 * k0
+    sa.destroy(); sb.destroy(); grid.destroy()

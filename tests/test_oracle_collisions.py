@@ -244,3 +244,58 @@ def test_coulomb_intra_relativistic_build_conserves_for_equal_weights():
         g0 = np.sqrt(1 + (v[:, sl] ** 2).sum(0)).sum()
         g1 = np.sqrt(1 + (v1[:, sl] ** 2).sum(0)).sum()
         assert abs(g1 - g0) < 1e-12 * g0
+
+
+def _hs_cells(rng, ncell, npc, vth, mass, wgt, Vc):
+    n = ncell * npc
+    cs = np.arange(0, n + 1, npc)
+    v = rng.standard_normal((3, n)) * vth
+    w = np.full(n, wgt)
+    dens = np.full(ncell, npc * wgt / Vc)
+    ene = np.zeros((3, ncell))
+    for c in range(ncell):
+        ene[:, c] = 0.5 * mass * (w[cs[c]:cs[c + 1]] * v[:, cs[c]:cs[c + 1]] ** 2).sum(1) / Vc
+    return cs, v, w, dens, ene
+
+
+def test_hard_sphere_self_conserves_and_accepts_like_a_maxwellian():
+    """HardSphere::applySelfScattering (HardSphere.cpp:223-418): equal weights -> every accepted pair conserves
+    momentum and energy; acceptance = <g>/gmax = (4/sqrt(pi)) vth / (5 vth) ~ 0.45 for a Maxwellian."""
+    rng = np.random.default_rng(21)
+    ncell, npc, mass, Vc = 200, 40, 1836.0, 1.0e-9
+    cs, v, w, dens, ene = _hs_cells(rng, ncell, npc, 1.0e-3, mass, 1.0e20, Vc)
+    sig = orc.hs_sigmaT(1.0e-10, 1.0e-10)
+    assert abs(sig - np.pi * 4.0e-20) < 1e-30
+    gmax = 5.0 * 1.0e-3 * 2.99792458e8
+    dt = 0.8 / (dens[0] * sig * gmax)                      # nuMax*dt ~ 0.8
+    v0 = v.copy()
+    orc.lib().orc_rng_seed(3)
+    ncand, ncoll = orc.hs_self(cs, v, w, dens, ene, mass, sig, dt)
+    assert abs(ncand - ncell * 0.5 * (npc - 1) * 0.8) < 0.05 * ncand
+    assert 0.40 < ncoll / ncand < 0.50
+    dv = v.reshape(3, ncell, npc).sum(2) - v0.reshape(3, ncell, npc).sum(2)
+    assert np.max(np.abs(dv)) < 1e-16
+    e0, e1 = (v0 ** 2).reshape(3, ncell, npc).sum((0, 2)), (v ** 2).reshape(3, ncell, npc).sum((0, 2))
+    assert np.max(np.abs(e1 - e0) / e0) < 1e-13
+    assert np.mean(np.any(v != v0, axis=0)) > 0.2
+
+
+def test_hard_sphere_inter_conserves_total_momentum_and_energy():
+    rng = np.random.default_rng(22)
+    ncell, Vc = 120, 1.0e-9
+    m1, m2 = 4.0 * 1836.0, 40.0 * 1836.0
+    cs1, v1, w1, d1, e1 = _hs_cells(rng, ncell, 30, 2.0e-3, m1, 1.0e20, Vc)
+    cs2, v2, w2, d2, e2 = _hs_cells(rng, ncell, 20, 5.0e-4, m2, 1.0e20, Vc)
+    sig = orc.hs_sigmaT(1.2e-10, 1.8e-10)
+    a1, a2 = v1.copy(), v2.copy()
+    orc.lib().orc_rng_seed(4)
+    ncand, ncoll = orc.hs_inter(cs1, v1, w1, d1, e1, m1, cs2, v2, w2, d2, e2, m2, Vc, sig, 3.0e-18)
+    assert 1000 < ncand < 1000000 and 0.2 < ncoll / ncand < 0.7
+    for c in range(0, ncell, 7):
+        s1, s2 = slice(cs1[c], cs1[c + 1]), slice(cs2[c], cs2[c + 1])
+        p0 = m1 * a1[:, s1].sum(1) + m2 * a2[:, s2].sum(1)
+        p1 = m1 * v1[:, s1].sum(1) + m2 * v2[:, s2].sum(1)
+        assert np.max(np.abs(p1 - p0)) < 1e-12 * np.max(np.abs(p0)) + 1e-14
+        k0 = m1 * (a1[:, s1] ** 2).sum() + m2 * (a2[:, s2] ** 2).sum()
+        k1 = m1 * (v1[:, s1] ** 2).sum() + m2 * (v2[:, s2] ** 2).sum()
+        assert abs(k1 - k0) < 1e-12 * k0
