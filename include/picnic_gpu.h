@@ -356,6 +356,11 @@ int pgpu_coulomb_delta_u(long n, const double *vp1, const double *vp2, double ch
  * weight method (collapseThreeToTwo) is not implemented. */
 int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double dt_sec, uint64_t seed,
                              uint64_t step, long *ncollisions);
+/* VariableHardSphere::applySelfScattering (VariableHardSphere.cpp:217-412; the reference has no inter-species VHS):
+ * sigmaT(g) = 4 pi A g^(-4/alpha) with alpha = 4/(2 eta - 1) and A from the viscosity mu0 [Pa s] at T0 [K]
+ * (:28-47); both partners of an accepted pair scatter. */
+int pgpu_collide_vhs(pgpu_species_t s, double eta, double T0, double mu0, double dt_sec, uint64_t seed, uint64_t step,
+                     long *ncollisions);
 /* HardSphere::setMeanFreeTime (HardSphere.cpp:65-194): box maximum of n sigmaT sqrt(Teff/m) */
 int pgpu_scatter_nu_max_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double *nu_max);
 /* Coulomb::LorentzScatter (Coulomb.cpp:1694-1793) for n pairs with explicit draws (test hook of the relativistic

@@ -526,3 +526,23 @@ def hs_inter(cs1, v1, w1, dens1, ene1, m1, cs2, v2, w2, dens2, ene2, m2, Vc, sig
     f(a1.size - 1, _ptr(a1), _ptr(v1), _ptr(w1), v1.shape[1], _ptr(dens1), _ptr(e1), m1, _ptr(a2), _ptr(v2), _ptr(w2),
       v2.shape[1], _ptr(dens2), _ptr(e2), m2, Vc, sigmaT, dt_sec, C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+def vhs_consts(mass, eta, T0, mu0):
+    """(4 pi A, 4/alpha) of VariableHardSphere::initialize"""
+    a, b = C.c_double(0), C.c_double(0)
+    f = lib().orc_vhs_consts
+    f.argtypes = [C.c_double] * 4 + [C.c_void_p] * 2
+    f(mass, eta, T0, mu0, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def vhs_self(cell_start, v, dens, ene, mass, fourPiA, fourOverAlpha, dt_sec):
+    f = lib().orc_vhs_self
+    f.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p] + [C.c_double] * 4 + [C.c_void_p] * 2
+    cs = np.ascontiguousarray(cell_start, dtype=np.int64)
+    ene = np.ascontiguousarray(ene, dtype=np.float64)
+    a, b = C.c_long(0), C.c_long(0)
+    f(cs.size - 1, _ptr(cs), _ptr(v), v.shape[1], _ptr(dens), _ptr(ene), mass, fourPiA, fourOverAlpha, dt_sec, C.byref(a),
+      C.byref(b))
+    return a.value, b.value

@@ -942,6 +942,73 @@ extern "C" void orc_hs_self(long ncell, const long *cs, double *v, const double 
   if (ncoll_out) *ncoll_out = ncoll;
 }
 
+/* VariableHardSphere (src/scattering/VariableHardSphere.cpp:28-47 constants, 217-412 applySelfScattering; the
+ * reference implements self-scattering only): sigmaT(g) = 4 pi A g^(-4/alpha), alpha = 4/(2 eta - 1). */
+extern "C" void orc_vhs_consts(double mass, double eta, double T0, double mu0, double *fourPiA, double *fourOverAlpha) {
+  const double KB = 1.380649e-23;
+  const double alpha = 4. / (2. * eta - 1.);
+  const double Mass_kg = mass * kME;
+  const double VT0 = sqrt(KB * T0 / Mass_kg);
+  const double Gamma0 = tgamma(4. - 2. / alpha);
+  const double Aconst = 15. / 32. / Gamma0 / mu0 * Mass_kg / sqrt(kPI) * VT0 * pow(4. * VT0 * VT0, 2. / alpha);
+  *fourPiA = 4. * kPI * Aconst;
+  *fourOverAlpha = 4.0 / alpha;
+}
+
+extern "C" void orc_vhs_self(long ncell, const long *cs, double *v, long n, const double *dens, const double *ene,
+                             double mass, double fourPiA, double fourOverAlpha, double dt_sec, long *ncand_out,
+                             long *ncoll_out) {
+  const double cvacSq = kCVAC * kCVAC;
+  long ncand = 0, ncoll = 0;
+  for (long c = 0; c < ncell; ++c) {
+    const double local_numberDensity = dens[c];
+    if (local_numberDensity == 0.0) continue;
+    double local_energyDensity = 0.0;
+    for (int dir = 0; dir < 3; dir++) local_energyDensity = local_energyDensity + ene[dir * ncell + c];
+    const double local_Teff = 2.0 / 3.0 * local_energyDensity / local_numberDensity * cvacSq;
+    const double local_gmax = 5.0 * sqrt(local_Teff / mass);
+    const double local_sigmaTmax = fourPiA * pow(local_gmax, -fourOverAlpha);
+    const double local_nuMaxDt = local_numberDensity * local_sigmaTmax * local_gmax * dt_sec;
+    const int local_numCell = (int)(cs[c + 1] - cs[c]);
+    if (local_numCell < 2) continue;
+    const double local_Nmax = 0.5 * (local_numCell - 1) * local_nuMaxDt;
+    double whole;
+    const double rem = modf(local_Nmax, &whole);
+    double rand_num = mu_rand();
+    int Nint = static_cast<int>(whole);
+    if (rand_num < rem) Nint = Nint + 1;
+    ncand += Nint;
+    for (int k = 0; k < Nint; k++) {
+      const int r1 = mu_randint(0, local_numCell - 1);
+      int r2 = mu_randint(0, local_numCell - 1);
+      while (r2 == r1) r2 = mu_randint(0, local_numCell - 1);
+      const long i1 = cs[c] + r1, i2 = cs[c] + r2;
+      double b1[3] = {v[i1], v[n + i1], v[2 * n + i1]}, b2[3] = {v[i2], v[n + i2], v[2 * n + i2]};
+      double g12 = 0.0;
+      for (int dir = 0; dir < 3; dir++) g12 = g12 + pow(b1[dir] - b2[dir], 2);
+      g12 = sqrt(g12) * kCVAC;
+      const double local_sigmaT = fourPiA * pow(g12, -fourOverAlpha);
+      const double q12 = g12 * local_sigmaT / (local_gmax * local_sigmaTmax);
+      rand_num = mu_rand();
+      if (rand_num <= q12) {
+        ncoll += 1;
+        const double R = mu_rand();
+        const double costh = 1.0 - 2.0 * R;
+        const double sinth = sqrt(1.0 - costh * costh);
+        const double phi = kTWOPI * mu_rand();
+        double dU[3];
+        orc_scatter_delta_u(b1[0] - b2[0], b1[1] - b2[1], b1[2] - b2[2], costh, sinth, cos(phi), sin(phi), dU);
+        for (int dir = 0; dir < 3; dir++) {
+          v[dir * n + i1] = b1[dir] + 0.5 * dU[dir];
+          v[dir * n + i2] = b2[dir] - 0.5 * dU[dir];
+        }
+      }
+    }
+  }
+  if (ncand_out) *ncand_out = ncand;
+  if (ncoll_out) *ncoll_out = ncoll;
+}
+
 extern "C" void orc_hs_inter(long ncell, const long *cs1, double *v1, const double *w1, long n1, const double *dens1,
                              const double *ene1, double mass1, const long *cs2, double *v2, const double *w2, long n2,
                              const double *dens2, const double *ene2, double mass2, double Vc, double sigmaT,

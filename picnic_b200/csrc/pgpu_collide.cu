@@ -828,6 +828,8 @@ k_coulomb_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a
 enum { STREAM_HS = 0x4853u };
 struct HSParams {
   double sigmaT, dt_sec, mass1, mass2, mu, Vc;
+  int vhs;                          // VariableHardSphere: sigmaT(g) = fourPiA * g^(-fourOverAlpha), self only
+  double fourPiA, fourOverAlpha;
   unsigned seed_lo, seed_hi, step_lo, step_hi;
   int box_lo0, box_lo1, nbox0, ncell_glob0;
 };
@@ -850,7 +852,7 @@ k_hard_sphere(const int *cs1, const int *cs2, int ncell, double *a0, double *a1,
     const int s1 = cs1[cell], n1 = cs1[cell + 1] - s1, s2 = cs2[cell], n2 = cs2[cell + 1] - s2;
     const double nd1 = dens1[cell], nd2 = dens2[cell];
     const unsigned gcell = (unsigned)((cell % P.nbox0 + P.box_lo0) + (cell / P.nbox0 + P.box_lo1) * P.ncell_glob0);
-    double gmax = 0.0, Nmax = 0.0;
+    double gmax = 0.0, Nmax = 0.0, sigmaTmax = P.sigmaT;
     bool go;
     if (self) {
       go = nd1 != 0.0 && n1 >= 2;
@@ -859,8 +861,13 @@ k_hard_sphere(const int *cs1, const int *cs2, int ncell, double *a0, double *a1,
         for (int d = 0; d < 3; ++d) e = e + ene1[(size_t)d * ncell + cell];
         const double Teff = 2.0 / 3.0 * e / nd1 * cvacSq;
         gmax = 5.0 * sqrt(Teff / P.mass1);
-        const double nuMaxDt = nd1 * P.sigmaT * gmax * P.dt_sec;
-        Nmax = 0.5 * (n1 - 1) * fmin(nuMaxDt, 1.0);
+        if (P.vhs) {   // VariableHardSphere.cpp:279-289: sigmaT at gmax, no cap on nuMax*dt
+          sigmaTmax = P.fourPiA * pow(gmax, -P.fourOverAlpha);
+          Nmax = 0.5 * (n1 - 1) * (nd1 * sigmaTmax * gmax * P.dt_sec);
+        } else {
+          const double nuMaxDt = nd1 * P.sigmaT * gmax * P.dt_sec;
+          Nmax = 0.5 * (n1 - 1) * fmin(nuMaxDt, 1.0);
+        }
       }
     } else {
       go = nd1 * nd2 != 0.0 && !(n1 < 2 && n2 < 2) && n1 >= 1 && n2 >= 1;
@@ -880,7 +887,7 @@ k_hard_sphere(const int *cs1, const int *cs2, int ncell, double *a0, double *a1,
       const double whole = floor(Nmax), rem = Nmax - whole;
       const double u0 = u01(hs_draw(P, 0xffffffffu, gcell, 2u).x);
       int Nint = (int)whole;
-      if (self ? (u0 <= rem) : (u0 < rem)) Nint += 1;
+      if ((self && !P.vhs) ? (u0 <= rem) : (u0 < rem)) Nint += 1;
       const double f1 = self ? 0.5 : P.mu / P.mass1, f2 = self ? 0.5 : P.mu / P.mass2;
       for (int k = 0; k < Nint; ++k) {
         const u4 r0 = hs_draw(P, (unsigned)k, gcell, 0u);
@@ -895,7 +902,8 @@ k_hard_sphere(const int *cs1, const int *cs2, int ncell, double *a0, double *a1,
         const double v1[3] = {a0[i1], a1[i1], a2[i1]}, v2[3] = {b0[i2], b1[i2], b2[i2]};
         const double ux = v1[0] - v2[0], uy = v1[1] - v2[1], uz = v1[2] - v2[2];
         const double g12 = sqrt(ux * ux + uy * uy + uz * uz) * CVAC;
-        const double q12 = g12 * P.sigmaT / (gmax * P.sigmaT);
+        const double sigT = P.vhs ? P.fourPiA * pow(g12, -P.fourOverAlpha) : P.sigmaT;
+        const double q12 = g12 * sigT / (gmax * sigmaTmax);
         if (u01(r0.z) > q12) continue;
         mine += 1;
         const u4 r1 = hs_draw(P, (unsigned)k, gcell, 1u);
@@ -904,13 +912,13 @@ k_hard_sphere(const int *cs1, const int *cs2, int ncell, double *a0, double *a1,
         double sinphi, cosphi, dU[3];
         sincos(TWOPI * u01(r1.x), &sinphi, &cosphi);
         scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
-        const double wp1 = wa[i1], wp2 = wb[i2], u3 = u01(r1.y);
-        if (u3 <= wp2 / wp1) {
+        const double wp1 = wa[i1], wp2 = wb[i2], u3 = P.vhs ? 0.0 : u01(r1.y);   // VHS updates both partners
+        if (P.vhs || u3 <= wp2 / wp1) {
           a0[i1] = v1[0] + f1 * dU[0];
           a1[i1] = v1[1] + f1 * dU[1];
           a2[i1] = v1[2] + f1 * dU[2];
         }
-        if (u3 <= wp1 / wp2) {
+        if (P.vhs || u3 <= wp1 / wp2) {
           b0[i2] = v2[0] - f2 * dU[0];
           b1[i2] = v2[1] - f2 * dU[1];
           b2[i2] = v2[2] - f2 * dU[2];
@@ -1546,22 +1554,16 @@ int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elasti
   return rc;
 }
 
-int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double dt_sec, uint64_t seed,
-                             uint64_t step, long *ncoll_out) {
+static int launch_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, HSParams P, double dt_sec, uint64_t seed,
+                              uint64_t step, long *ncoll_out, const char *who) {
   int rc = need_binned(sA, sB);
   if (rc) return rc;
-  if (!(sigmaT > 0.0)) {
-    set_error("HardSphere: sigmaT must be positive");
-    return PGPU_ERR_ARG;
-  }
   if (!sA->dens || !sA->ene || !sB->dens || !sB->ene) {
-    set_error("HardSphere needs the cell moments: call pgpu_set_moments_from_bins first");
+    set_error("%s needs the cell moments: call pgpu_set_moments_from_bins first", who);
     return PGPU_ERR_STATE;
   }
   Context &c = ctx();
   const pgpu_grid_s *g = sA->grid;
-  HSParams P;
-  P.sigmaT = sigmaT;
   P.dt_sec = dt_sec;
   P.mass1 = sA->desc.mass;
   P.mass2 = sB->desc.mass;
@@ -1584,6 +1586,46 @@ int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT
         sB->v[2], sB->w, sB->dens, sB->ene, P, sA == sB ? 1 : 0, &c.d_counters->npairs);
   }
   return fetch_pairs(ncoll_out);
+}
+
+int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double dt_sec, uint64_t seed,
+                             uint64_t step, long *ncoll_out) {
+  if (!(sigmaT > 0.0)) {
+    set_error("HardSphere: sigmaT must be positive");
+    return PGPU_ERR_ARG;
+  }
+  HSParams P;
+  memset(&P, 0, sizeof(P));
+  P.sigmaT = sigmaT;
+  return launch_hard_sphere(sA, sB, P, dt_sec, seed, step, ncoll_out, "HardSphere");
+}
+
+// VariableHardSphere::initialize (VariableHardSphere.cpp:28-47): alpha = 4/(2 eta - 1), A from the reference
+// viscosity mu0 at T0
+static void vhs_consts(double mass, double eta, double T0, double mu0, double *fourPiA, double *fourOverAlpha) {
+  const double PI = 3.14159265358979323846, ME = 9.10938370e-31, KB = 1.380649e-23;
+  const double alpha = 4. / (2. * eta - 1.);
+  const double Mass_kg = mass * ME;
+  const double VT0 = sqrt(KB * T0 / Mass_kg);
+  const double Gamma0 = tgamma(4. - 2. / alpha);
+  const double Aconst = 15. / 32. / Gamma0 / mu0 * Mass_kg / sqrt(PI) * VT0 * pow(4. * VT0 * VT0, 2. / alpha);
+  *fourPiA = 4. * PI * Aconst;
+  *fourOverAlpha = 4.0 / alpha;
+}
+
+int pgpu_collide_vhs(pgpu_species_t s, double eta, double T0, double mu0, double dt_sec, uint64_t seed, uint64_t step,
+                     long *ncoll_out) {
+  if (!s) return PGPU_ERR_ARG;
+  if (!(eta > 0.5) || !(T0 > 0.0) || !(mu0 > 0.0)) {
+    set_error("VariableHardSphere: need eta > 1/2, T0 > 0, mu0 > 0");
+    return PGPU_ERR_ARG;
+  }
+  HSParams P;
+  memset(&P, 0, sizeof(P));
+  P.vhs = 1;
+  P.sigmaT = 1.0;
+  vhs_consts(s->desc.mass, eta, T0, mu0, &P.fourPiA, &P.fourOverAlpha);
+  return launch_hard_sphere(s, s, P, dt_sec, seed, step, ncoll_out, "VariableHardSphere");
 }
 
 // HardSphere::setIntraMFT / setInterMFT (HardSphere.cpp:84-194): nu_max = max over cells of n * sigmaT * sqrt(Teff/m).

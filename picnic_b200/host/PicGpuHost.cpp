@@ -529,4 +529,21 @@ void HardSphere::printParameters() const {
   std::cout << "  r1 = " << m_r1 << " m, r2 = " << m_r2 << " m, sigmaT = " << m_sigmaT << " m^2" << std::endl;
 }
 
+// ---- VariableHardSphere (VariableHardSphere.cpp:28-47, 217-412) ------------------------------------
+VariableHardSphere::VariableHardSphere(int a_sp, Real a_eta, Real a_T0, Real a_mu0)
+    : m_sp(a_sp), m_eta(a_eta), m_T0(a_T0), m_mu0(a_mu0), m_scatter_dt(DBL_MAX), m_ncoll(0) {}
+void VariableHardSphere::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real a_dt_sec) const {
+  PicChargedSpecies *a = a_species[m_sp];
+  if (a->numParticles() == 0) return;
+  long nc = 0;
+  check(pgpu_collide_vhs(a->handle(), m_eta, m_T0, m_mu0, a_dt_sec, s_seed, s_step, &nc),
+        "VariableHardSphere::applyScattering");
+  m_ncoll = nc;
+}
+void VariableHardSphere::printParameters() const {
+  std::cout << " VariableHardSphere scattering parameters:" << std::endl;
+  std::cout << "  species = " << m_sp << ", eta = " << m_eta << ", T0 = " << m_T0 << " K, mu0 = " << m_mu0 << " Pa s"
+            << std::endl;
+}
+
 }  // namespace picnic_gpu

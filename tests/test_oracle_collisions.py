@@ -299,3 +299,27 @@ def test_hard_sphere_inter_conserves_total_momentum_and_energy():
         k0 = m1 * (a1[:, s1] ** 2).sum() + m2 * (a2[:, s2] ** 2).sum()
         k1 = m1 * (v1[:, s1] ** 2).sum() + m2 * (v2[:, s2] ** 2).sum()
         assert abs(k1 - k0) < 1e-12 * k0
+
+
+def test_vhs_self_conserves_and_reduces_to_hard_sphere_for_eta_one_half_limit():
+    """VariableHardSphere::applySelfScattering (VariableHardSphere.cpp:217-412): both partners scatter, so every
+    cell conserves momentum and energy; acceptance = <g sigma(g)> / (gmax sigma(gmax)) in (0, 1)."""
+    rng = np.random.default_rng(23)
+    ncell, npc, Vc = 150, 40, 1.0e-9
+    mass = 39.948 * 1822.888
+    cs, v, w, dens, ene = _hs_cells(rng, ncell, npc, 5.0e-6, mass, 1.0e20, Vc)
+    fourPiA, fourOverAlpha = orc.vhs_consts(mass, 0.81, 273.0, 2.117e-5)
+    assert abs(fourOverAlpha - (2 * 0.81 - 1)) < 1e-15
+    gmax = 5.0 * 5.0e-6 * 2.99792458e8
+    sigmax = fourPiA * gmax ** (-fourOverAlpha)
+    assert 1e-20 < sigmax < 1e-17                          # a molecular cross section [m^2]
+    dt = 0.7 / (dens[0] * sigmax * gmax)
+    v0 = v.copy()
+    orc.lib().orc_rng_seed(6)
+    ncand, ncoll = orc.vhs_self(cs, v, dens, ene, mass, fourPiA, fourOverAlpha, dt)
+    assert abs(ncand - ncell * 0.5 * (npc - 1) * 0.7) < 0.06 * ncand
+    assert 0.3 < ncoll / ncand < 0.9
+    dv = v.reshape(3, ncell, npc).sum(2) - v0.reshape(3, ncell, npc).sum(2)
+    assert np.max(np.abs(dv)) < 1e-18
+    e0, e1 = (v0 ** 2).reshape(3, ncell, npc).sum((0, 2)), (v ** 2).reshape(3, ncell, npc).sum((0, 2))
+    assert np.max(np.abs(e1 - e0) / e0) < 1e-13
