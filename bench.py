@@ -497,6 +497,36 @@ def c4_leg(args, torch, capi, stream, peak):
                         "pairs_per_step": pairs, "ms_per_step": ms_col}}
 
 
+def mass_matrix_cpu_sample(deck, ncell=96):
+    """CPU leg of the mass-matrix item: the oracle's cc1_2d_deposit_mass_matrix restatement, one thread, on a bounded
+    sample of the same deck (ncell^2 cells x 100 ppc of the electron species, cell-ordered as the loader leaves them,
+    xbar half a step from xold)."""
+    from oracle import oracle as orc
+    import copy
+    d = copy.copy(deck)
+    d.ncell = (ncell, ncell)
+    lo, hi = (0, 0), (ncell - 1, ncell - 1)
+    _, B = decks.analytic_fields(d, lo, hi, E0=3.0e7, B0=5.0e8)
+    sdef = d.species[0]
+    p = decks.load_species(d, sdef, lo, hi, np.random.default_rng(3))
+    cn = d.dt * d.units.cvac_norm
+    xold = np.ascontiguousarray(p["x"])
+    x = np.ascontiguousarray(xold + 0.5 * cn * p["v"][:2])
+    v = np.ascontiguousarray(p["v"])
+    geom = orc.make_geom(2, d.xmin, d.xmax, d.dx, d.nghost)
+    Bf = [orc.Fab(l, h, a) for (l, h, a) in B]
+    nc, sigma = orc.mm_alloc(2, orc.CC1, d.nghost, lo, hi)
+    J0 = [orc.fab_for(lo, hi, d.nghost, st) for st in orc.E_STAG[2]]
+    t0 = time.perf_counter()
+    rc = orc.deposit_mass_matrices(geom, orc.CC1, x, xold, v, v, p["w"], sdef.charge / d.volume_scale,
+                                   sdef.fnorm_const(d.units) * cn / 2.0, cn, Bf, J0, sigma)
+    sec = time.perf_counter() - t0
+    n = int(p["w"].size)
+    return {"value": n / sec, "unit": "particles/s", "cores": 1, "kind": "port", "rc": int(rc), "seconds": sec,
+            "sample": "%d x %d cells x 100 ppc = %d particles of one species, oracle (g++ -O2 -ffp-contract=off), "
+                      "one thread" % (ncell, ncell, n)}
+
+
 def mass_matrix_leg(args, torch, capi, stream, peak):
     """Secondary line item (SURVEY 8(f)1): PicSpeciesInterface::setMassMatrices + computeJfromMassMatrices on the C3 box
     (2D 512x512, 2 species x 100 ppc, CC1, 3 ghost layers -> 231 sigma components = 0.5 GB).  Unit: one particle
@@ -561,7 +591,11 @@ def mass_matrix_leg(args, torch, capi, stream, peak):
     grid.destroy()
     kern = k_ms / max(k_n, 1)
     achieved = 88.0 * (n / len(sps)) / (kern * 1e-3) / 1e9 if k_n else None
-    return {"metric": "particles/s through setMassMatrices (accumulateMassMatrices of both species)",
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = mass_matrix_cpu_sample(deck)
+    return {"cpu_baseline": cpu,
+            "metric": "particles/s through setMassMatrices (accumulateMassMatrices of both species)",
             "unit": "particles/s", "value": n / (ms_set * 1e-3), "ms_per_setMassMatrices": ms_set,
             "ms_per_computeJfromMassMatrices": ms_J, "particles": n, "sigma_components": ncomp,
             "workload": "C3 box: 2D %dx%d cells, 2 species x %d ppc, CC1, %d ghost layers; zero + accumulate both "
