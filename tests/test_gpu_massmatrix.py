@@ -192,3 +192,83 @@ def test_needs_init_and_cc1(pgpu):
             grid.mass_matrices_init(orc.TSC)
     finally:
         sp.destroy(); grid.destroy()
+
+
+def test_two_boxes_J_from_mass_matrices_matches_single_box(pgpu):
+    """SURVEY 8(e) for the mass-matrix path: each box accumulates the matrices of its own particles and contracts them
+    over its ghosted box; the ghost add-exchange of J (peer-memory halo, as after a deposit) then gives the single-box
+    current.  The sigmas themselves are never exchanged -- as in PicSpeciesInterface::setMassMatrices."""
+    from picnic_b200 import halo
+    ncell, ng, dx, xmin = (32, 16), 3, (0.25, 0.5), (0.0, -1.0)
+    prob = Problem(2, ncell, dx, xmin, ng, 20000, seed=41, max_disp=0.8, B0=2.0)
+    rng = np.random.default_rng(42)
+    E1 = [f.copy() for f in prob.E]
+    for f, st in zip(E1, orc.E_STAG[2]):       # a periodic perturbation, so that ghosts stay images
+        core = rng.standard_normal(ncell) * 0.5
+        idx = [np.mod(np.arange(f.lo[d], f.hi[d] + 1), ncell[d]) for d in range(2)]
+        f.a += core[np.ix_(idx[0], idx[1])]
+    dt, charge, fnorm = 0.2, -1.0, 0.8
+
+    def sub(fabs, g):
+        out = []
+        for c, f in enumerate(fabs):
+            lo, hi = g.field_bounds(c if fabs is not prob.B else 3 + c)
+            ii = np.mod(np.arange(lo[0], hi[0] + 1), ncell[0]) - f.lo[0]
+            jj = np.mod(np.arange(lo[1], hi[1] + 1), ncell[1]) - f.lo[1]
+            out.append((lo, hi, np.asfortranarray(f.a[np.ix_(ii, jj)])))
+        return out
+
+    def run(g, m):
+        g.set_fields(sub(prob.E, g), sub(prob.B, g))
+        sp = pgpu.Species(g, 1.0, charge, fnorm, 1.0, interp_N=1, interp_J=CC1, interp_E=CC1)
+        sp.upload(prob.x[:, m], prob.v[:, m], prob.w[m], xold=prob.xold[:, m], vold=prob.vold[:, m],
+                  ids=np.arange(prob.n, dtype=np.uint64)[m])
+        g.mass_matrices_init(CC1)
+        g.mass_matrices_zero()
+        sp.accumulate_mass_matrices(dt)
+        g.mass_matrices_save_E0()
+        g.fields_select(1)
+        g.set_fields(sub(E1, g), sub(prob.B, g))
+        g.compute_J_from_mass_matrices()
+        return sp
+
+    g1 = pgpu.Grid(2, ncell, xmin, dx, ng, (1, 1))
+    s1 = run(g1, np.ones(prob.n, dtype=bool))
+    g1.current_finalize()
+    Jg = [(g1.field_bounds(c), g1.current_get(c)) for c in range(3)]
+    s1.destroy(); g1.destroy()
+
+    lay = halo.BoxLayout(2, ncell, (16, 16), ng, (1, 1))
+    own = np.floor((prob.xold[0] - xmin[0]) / (dx[0] * 16)).astype(int)
+    grids, sps, hxs = [], [], []
+    for r in range(lay.world):
+        lo, hi = lay.box(r)
+        g = pgpu.Grid(2, ncell, xmin, dx, ng, (1, 1), box_lo=lo, box_hi=hi)
+        sps.append(run(g, own == r))
+        grids.append(g)
+        hxs.append(halo.PeerHaloExchange(lay, r, g))
+    halo.PeerHaloExchange.connect_local(hxs)
+    for h in hxs:
+        h.begin()
+    for ph in range(hxs[0].nphase):
+        for h in hxs:
+            h.send(ph)
+        for h in hxs:
+            h.recv_add(ph)
+    worst = 0.0
+    for g in grids:
+        g.current_finalize()
+        for c in range(3):
+            lo, hi = g.field_bounds(c)
+            a = g.current_get(c)
+            (glo, _), ga = Jg[c]
+            ii = np.mod(np.arange(lo[0], hi[0] + 1), ncell[0]) - glo[0]
+            jj = np.mod(np.arange(lo[1], hi[1] + 1), ncell[1]) - glo[1]
+            worst = max(worst, float(np.max(np.abs(a - ga[np.ix_(ii, jj)])) / np.max(np.abs(ga))))
+    for h in hxs:
+        h.destroy()
+    for s in sps:
+        s.destroy()
+    for g in grids:
+        g.destroy()
+    assert worst < 1e-12, worst
