@@ -13,7 +13,7 @@
 // layers = 0.5 GB); they never travel to the host inside a solve: the contraction J = J0 + sigma (E - E0) runs here,
 // on the E of the selected field slot, into the grid's total current (pgpu_current_finalize / pgpu_current_get follow).
 //
-// Two deposit kernels:
+// Three deposit kernels:
 //   k_mm<D>          one thread per particle, the reference's loops as they stand, one fp64 reduction per distinct
 //                    address of a converged warp.  Any D, any number of segments, any particle order.
 //   k_mm_cc1_2d_run  2D fast path for cell-sorted single-segment particles (the 95 % case): a warp stages the twelve
@@ -22,6 +22,7 @@
 //                    over the run of particles that share the dual cell and the node cell -- across the consecutive
 //                    tiles of the warp's chunk -- with one RED per product and run instead of one per product and
 //                    particle, and no shuffles.  Other particles go to a list for k_mm.
+//   k_mm_cc1_1d_run  the same scheme in 1D (42 products, two per lane).
 //
 // This file is compiled with -fmad=false: every per-particle product is then the IEEE product the reference's
 // Fortran computes, and the index decisions (true divide + floor) are bit exact; only the summation order differs.
@@ -903,6 +904,183 @@ k_mm_cc1_2d_run(PartPtrs p, long n, Geo<2> g, MMSet T, MMParams prm, const MMEnt
   if (err) atomicOr(&cnt->err, err);
 }
 
+// ---- the 1D run kernel ---------------------------------------------------------------------------------------------
+// Same scheme as k_mm_cc1_2d_run for cc1_1d_deposit_mass_matrix (:835-1220) and one segment: 42 products per particle,
+// (F[fi] * P[pj]) * P[pe] with
+//   P[0..1] = Deltap_dn, Deltap_up (the CIC pair of the dual cell), P[2..3] = w0_stag of the two nodes (:966-967),
+//   P[4..5] = 1 - w0_stag (:976), P[6..7] = wx_dn_stag, wx_up_stag (:1053-1055), P[8] = 1 (J0 products).
+// The reference forms the node weights in two ways (1 - |l/dx| for the y/z rows, l/dx and its complement for the
+// mixed terms); both are kept so that every product is the reference's.  Lane L owns products L and L + 32.
+enum { MM1_NENT = 42, MM1_NP = 9, MM1_KEY = MM_NF + MM1_NP, MM1_REC = 23, MM1_EPL = 2 };
+
+__global__ void __launch_bounds__(32 * MM_WARPS)
+k_mm_cc1_1d_run(PartPtrs p, long n, Geo<1> g, MMSet T, MMParams prm, const MMEntry *__restrict__ table,
+                const MMFlush *__restrict__ flush, Counters *cnt, int *defer_list, unsigned *defer_count, int chunk) {
+  extern __shared__ double mm_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double *rec = mm_smem + (size_t)wid * 32 * MM1_REC;
+  const long nwarps = (long)gridDim.x * MM_WARPS;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(rec);
+  unsigned of[MM1_EPL], oj[MM1_EPL], oe[MM1_EPL], foff[MM1_EPL];
+  int fmeta[MM1_EPL];
+#pragma unroll
+  for (int e = 0; e < MM1_EPL; ++e) {
+    const MMEntry en = table[e * 32 + lane];
+    of[e] = 8u * en.fi;
+    oj[e] = 8u * (MM_NF + en.pj);
+    oe[e] = 8u * (MM_NF + en.pe);
+    const MMFlush fl = flush[e * 32 + lane];
+    foff[e] = fl.off0;
+    fmeta[e] = fl.meta;
+  }
+  double *const arena = T.J[0].p;
+  const int rplane[3] = {T.J[0].n0, T.J[1].n0, T.J[2].n0};
+  unsigned err = 0;
+  double acc[MM1_EPL];
+  long long rkey = LLONG_MIN;
+  auto flush_run = [&]() {
+    const int k0 = (int)(rkey >> 32), k2 = (int)rkey;
+    const bool in = fab_in(T.J[0], k0, 0) && fab_in(T.J[0], k0 + 1, 0) && fab_in(T.J[1], k2, 0) &&
+                    fab_in(T.J[1], k2 + 1, 0) && fab_in(T.J[2], k2, 0) && fab_in(T.J[2], k2 + 1, 0);
+    if (!in) {
+      err |= ERRBIT_BOUNDS;
+      return;
+    }
+    const int s0 = (k0 == k2) ? 0 : 1;
+#pragma unroll
+    for (int e = 0; e < MM1_EPL; ++e) {
+      const int meta = fmeta[e];
+      if (meta < 0) continue;
+      const int row = (meta >> 1) & 3;
+      const int pl = row == 0 ? rplane[0] : (row == 1 ? rplane[1] : rplane[2]);
+      const int bi = (meta & 1) ? k2 : k0;
+      const int sh = s0 * (int)(signed char)(meta >> 8);
+      atomicAdd(arena + ((long long)foff[e] + (long long)(bi + sh * pl)), acc[e]);
+    }
+  };
+  const long ntiles = (n + 31) / 32;
+  for (long tile0 = ((long)blockIdx.x * MM_WARPS + wid) * chunk; tile0 < ntiles; tile0 += nwarps * chunk) {
+   const long tile1 = tile0 + chunk < ntiles ? tile0 + chunk : ntiles;
+#pragma unroll 1
+   for (long tile = tile0; tile < tile1; ++tile) {
+    const long i = tile * 32 + lane;
+    double *R = rec + lane * MM1_REC;
+    long long key = LLONG_MIN;
+    if (i < n) {
+      const double xpbar = p.x[0][i], xpold = p.xold[0][i];
+      const double uo[3] = {p.vold[0][i], p.vold[1][i], p.vold[2][i]};
+      const double ub[3] = {p.v[0][i], p.v[1][i], p.v[2][i]};
+      const double qp = p.w[i] * prm.qovs;
+      const double dx = g.dx[0], le = g.le[0];
+      const int index = MM_FLOORDX(xpbar - le - 0.5 * dx, 0);
+      const int index_stag = MM_FLOORDX(xpbar - le, 0);
+      // magnetic field at the particle (:899-943) and the node weights of the y/z rows (:961-967)
+      double Bp[3] = {0.0, 0.0, 0.0}, wsa[2];
+      bool ok = true;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int ii = index + a, ii_stag = index_stag + a;
+        const double l0 = ii * dx + 0.5 * dx - xpbar + le;
+        const double l0_stag = ii_stag * dx - xpbar + le;
+        const double w0 = 1.0 - fabs(mm_div_exact(g, l0, 0));
+        const double w0_stag = 1.0 - fabs(mm_div_exact(g, l0_stag, 0));
+        wsa[a] = w0_stag;
+        if (!fab_in(T.B[0], ii_stag, 0) || !fab_in(T.B[1], ii, 0) || !fab_in(T.B[2], ii, 0)) {
+          ok = false;
+        } else {
+          Bp[0] = Bp[0] + w0_stag * fab_at(T.B[0], ii_stag, 0);
+          Bp[1] = Bp[1] + w0 * fab_at(T.B[1], ii, 0);
+          Bp[2] = Bp[2] + w0 * fab_at(T.B[2], ii, 0);
+        }
+      }
+      if (!ok) err |= ERRBIT_BOUNDS;
+      bool fast = ok && !(g.bc_lo[0] | g.bc_hi[0]);
+      if (fast) {
+        const double xpnew = 2.0 * xpbar - xpold;
+        const int index_old = MM_FLOORDX(xpold - le - 0.5 * dx, 0);
+        const int index_new = MM_FLOORDX(xpnew - le - 0.5 * dx, 0);
+        fast = index_old == index && index_new == index;   // one segment, in the dual cell of xbar
+      }
+      if (fast) {
+        double fp[3], f[3][3];
+        mm_kernels(fp, f, Bp, qp, prm, uo, ub);
+        // :1052-1058, :1099-1104 with bc_seg_factor = 1
+        const double l0_stag = xpbar - index_stag * dx - le;
+        const double wx_up_stag = mm_div_exact(g, l0_stag, 0);
+        const double wx_dn_stag = 1.0 - wx_up_stag;
+        const double l0 = xpbar - (index + 0.5) * dx - le;
+        const double wx_up = mm_div_exact(g, l0, 0);
+        const double wx_dn = 1.0 - wx_up;
+        double *P = R + MM_NF;
+        P[0] = wx_dn * 1.0;
+        P[1] = wx_up * 1.0;
+        P[2] = wsa[0];
+        P[3] = wsa[1];
+        P[4] = 1.0 - wsa[0];
+        P[5] = 1.0 - wsa[1];
+        P[6] = wx_dn_stag;
+        P[7] = wx_up_stag;
+        P[8] = 1.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+          for (int e = 0; e < 3; ++e) R[3 * j + e] = f[j][e];
+          R[9 + j] = fp[j];
+        }
+        R[12] = 0.0;
+        key = ((long long)index << 32) | (unsigned)index_stag;
+      } else if (ok) {
+        defer_list[atomicAdd(defer_count, 1u)] = (int)i;
+      }
+    }
+    reinterpret_cast<long long *>(R + MM1_KEY)[0] = key;
+    __syncwarp();
+    const unsigned valid = __ballot_sync(0xffffffffu, key != LLONG_MIN);
+    const long long pk = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != pk);
+    unsigned rem = valid;
+#pragma unroll 1
+    while (rem) {
+      const int qs = __ffs(rem) - 1;
+      const unsigned stop = (heads | ~valid) & ~((2u << qs) - 1u);
+      const int qe = stop ? __ffs(stop) - 1 : 32;
+      rem &= (qe == 32) ? 0u : ~((1u << qe) - 1u);
+      const long long ck = __shfl_sync(0xffffffffu, key, qs);
+      if (ck != rkey) {
+        if (rkey != LLONG_MIN) flush_run();
+        rkey = ck;
+#pragma unroll
+        for (int e = 0; e < MM1_EPL; ++e) acc[e] = 0.0;
+      }
+      int q = qs;
+#pragma unroll 1
+      for (; q + 4 <= qe; q += 4) {
+        const unsigned qb = sbase + (unsigned)q * (MM1_REC * 8);
+#pragma unroll
+        for (int e = 0; e < MM1_EPL; ++e) {
+          const unsigned a = qb + of[e], b = qb + oj[e], c = qb + oe[e];
+          acc[e] += (lds_f64<0>(a) * lds_f64<0>(b)) * lds_f64<0>(c);
+          acc[e] += (lds_f64<MM1_REC * 8>(a) * lds_f64<MM1_REC * 8>(b)) * lds_f64<MM1_REC * 8>(c);
+          acc[e] += (lds_f64<2 * MM1_REC * 8>(a) * lds_f64<2 * MM1_REC * 8>(b)) * lds_f64<2 * MM1_REC * 8>(c);
+          acc[e] += (lds_f64<3 * MM1_REC * 8>(a) * lds_f64<3 * MM1_REC * 8>(b)) * lds_f64<3 * MM1_REC * 8>(c);
+        }
+      }
+#pragma unroll 1
+      for (; q < qe; ++q) {
+        const unsigned qb = sbase + (unsigned)q * (MM1_REC * 8);
+#pragma unroll
+        for (int e = 0; e < MM1_EPL; ++e)
+          acc[e] += (lds_f64<0>(qb + of[e]) * lds_f64<0>(qb + oj[e])) * lds_f64<0>(qb + oe[e]);
+      }
+    }
+    __syncwarp();
+   }
+   if (rkey != LLONG_MIN) flush_run();
+   rkey = LLONG_MIN;
+  }
+  if (err) atomicOr(&cnt->err, err);
+}
+
 // ---- J = J0 + sigma (E - E0)  (FieldsF.ChF:3-415) ---------------------------------------------------------------
 struct ContractArgs {
   MMView s[3];            // the three sigma arrays of the row
@@ -1118,6 +1296,54 @@ static int build_table(int mX, MMEntry *tab_out) {
   return real;
 }
 
+// the 42 products of a single-segment 1D particle (cc1_1d_deposit_mass_matrix :961-1220 with llJ = llE = 1), 2 x 32 slots
+static int build_table_1d(int mX, MMEntry *tab) {
+  int n = 0;
+  MMEntry pad;
+  memset(&pad, 0, sizeof(pad));
+  pad.arr = 255;
+  pad.fi = 12;
+  for (int k = 0; k < MM1_EPL * 32; ++k) tab[k] = pad;
+  auto put = [&](int arr, int fi, int pj, int pe, int base, int di, int nc0, int ncs0) {
+    MMEntry e;
+    memset(&e, 0, sizeof(e));
+    e.arr = (unsigned char)arr;
+    e.fi = (unsigned char)fi;
+    e.pj = (unsigned char)pj;
+    e.pe = (unsigned char)pe;
+    e.base = (unsigned char)base;
+    e.di = (signed char)di;
+    e.nc0 = nc0;
+    e.ncs0 = (signed char)ncs0;
+    tab[n++] = e;
+  };
+  const int DN = 0, WSA = 2, WSC = 4, WSB = 6, ONE = 8;
+  for (int p = 0; p < 2; ++p) {                       // y and z rows against Ey, Ez (:961-1009)
+    const int off = (p == 0) ? 2 : 0;
+    const int arrs[4] = {YY, YZ, ZY, ZZ}, fis[4] = {4, 5, 7, 8};
+    for (int a = 0; a < 4; ++a) {
+      put(arrs[a], fis[a], WSA + p, WSA + p, 1, p, 1, 0);
+      put(arrs[a], fis[a], WSA + p, WSC + p, 1, p, off, 0);
+    }
+    put(9 + 1, 10, WSA + p, ONE, 1, p, 0, 0);
+    put(9 + 2, 11, WSA + p, ONE, 1, p, 0, 0);
+  }
+  for (int iiJ = 0; iiJ < 2; ++iiJ) {                 // x row (:1153-1195)
+    put(9 + 0, 9, DN + iiJ, ONE, 0, iiJ, 0, 0);
+    for (int iiE = 0; iiE < 2; ++iiE) put(XX, 0, DN + iiJ, DN + iiE, 0, iiJ, 1 + mX + iiE - iiJ, 0);
+    for (int iiE = 0; iiE < 2; ++iiE) {
+      put(XY, 1, DN + iiJ, WSB + iiE, 0, iiJ, 1 + mX + iiE - iiJ - 1, 1);
+      put(XZ, 2, DN + iiJ, WSB + iiE, 0, iiJ, 1 + mX + iiE - iiJ - 1, 1);
+    }
+  }
+  for (int iiJ = 0; iiJ < 2; ++iiJ)                   // y and z rows against Ex (:1200-1220)
+    for (int iiE = 0; iiE < 2; ++iiE) {
+      put(YX, 3, WSB + iiJ, DN + iiE, 1, iiJ, mX + iiE - iiJ + 1, -1);
+      put(ZX, 6, WSB + iiJ, DN + iiE, 1, iiJ, mX + iiE - iiJ + 1, -1);
+    }
+  return n;
+}
+
 static MassMatrices *mm_of(pgpu_grid_s *g) { return static_cast<MassMatrices *>(g->mm); }
 
 void mm_destroy(pgpu_grid_s *g) {
@@ -1225,18 +1451,20 @@ int pgpu_mass_matrices_init(pgpu_grid_t g, int interp, int *ncomp_out) {
       at += m->row_box[k / 3].size() * (size_t)(nc[k][0] * nc[k][1]);
     }
   }
-  if (g->desc.D == 2) {
+  {
+    const bool two = g->desc.D == 2;
+    const int nslot = (two ? (int)MM_EPL : (int)MM1_EPL) * 32;
     MMEntry tab[MM_EPL * 32];
-    if (build_table(m->mX, tab) != MM_NENT) {
+    if ((two ? build_table(m->mX, tab) : build_table_1d(m->mX, tab)) != (two ? (int)MM_NENT : (int)MM1_NENT)) {
       set_error("internal: mass-matrix product table has the wrong length");
       return PGPU_ERR_STATE;
     }
-    PGPU_CUDA(cudaMalloc(&m->table_d, sizeof(tab)));
-    PGPU_CUDA(cudaMemcpy(m->table_d, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    PGPU_CUDA(cudaMalloc(&m->table_d, sizeof(MMEntry) * nslot));
+    PGPU_CUDA(cudaMemcpy(m->table_d, tab, sizeof(MMEntry) * nslot, cudaMemcpyHostToDevice));
     {
       const MMSet T = make_set(g, m);
       MMFlush fl[MM_EPL * 32];
-      for (int e = 0; e < MM_EPL * 32; ++e) {
+      for (int e = 0; e < nslot; ++e) {
         const MMEntry &en = tab[e];
         MMFlush f;
         f.off0 = 0;
@@ -1258,12 +1486,13 @@ int pgpu_mass_matrices_init(pgpu_grid_t g, int interp, int *ncomp_out) {
         }
         fl[e] = f;
       }
-      PGPU_CUDA(cudaMalloc(&m->flush_d, sizeof(fl)));
-      PGPU_CUDA(cudaMemcpy(m->flush_d, fl, sizeof(fl), cudaMemcpyHostToDevice));
+      PGPU_CUDA(cudaMalloc(&m->flush_d, sizeof(MMFlush) * nslot));
+      PGPU_CUDA(cudaMemcpy(m->flush_d, fl, sizeof(MMFlush) * nslot, cudaMemcpyHostToDevice));
     }
     PGPU_CUDA(cudaMalloc(&m->defer_count, sizeof(unsigned)));
-    PGPU_CUDA(cudaFuncSetAttribute(k_mm_cc1_2d_run, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(MM_WARPS * 32 * MM_REC * sizeof(double))));
+    if (two)
+      PGPU_CUDA(cudaFuncSetAttribute(k_mm_cc1_2d_run, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(MM_WARPS * 32 * MM_REC * sizeof(double))));
   }
   if (ncomp_out)
     for (int k = 0; k < 9; ++k) {
@@ -1303,33 +1532,61 @@ int pgpu_accumulate_mass_matrices(pgpu_species_t s, double dt) {
   prm.rel = s->desc.relativistic;
   prm.mX = m->mX;
   const MMSet T = make_set(g, m);
+  const bool generic_only = c.deposit_mode == 0 || !c.use_fast_cc1;
+  auto chunk_for = [&](long ntiles, int minblocks) {
+    // chunk length: long enough that few runs are cut (a cut run costs a full set of REDs), short enough that every
+    // SM gets several chunks per resident warp
+    const long resident = (long)c.sm_count * minblocks * MM_WARPS;
+    int chunk = (int)std::max<long>(1, std::min<long>(MM_CHUNK_MAX, ntiles / (resident * 4)));
+    if (const char *e = getenv("PGPU_MM_CHUNK")) chunk = std::max(1, std::min((int)MM_CHUNK_MAX, atoi(e)));   // tests, tuning
+    return chunk;
+  };
+  if (!generic_only) {
+    if (m->defer_cap < (size_t)s->n) {
+      if (m->defer_list) cudaFree(m->defer_list);
+      m->defer_cap = s->cap ? s->cap : (size_t)s->n;
+      PGPU_CUDA(cudaMalloc(&m->defer_list, m->defer_cap * sizeof(int)));
+    }
+    PGPU_CUDA(cudaMemsetAsync(m->defer_count, 0, sizeof(unsigned), c.stream));
+  }
   if (g->desc.D == 1) {
-    KTimer t("mass_matrix_generic");
-    const unsigned nb = (unsigned)((s->n + 127) / 128);
-    k_mm<1><<<nb, 128, 0, c.stream>>>(s->ptrs(), s->n, make_geo<1>(ga), T, prm, c.d_counters, nullptr, nullptr);
+    const Geo<1> g1 = make_geo<1>(ga);
+    if (generic_only) {
+      KTimer t("mass_matrix_generic");
+      const unsigned nb = (unsigned)((s->n + 127) / 128);
+      k_mm<1><<<nb, 128, 0, c.stream>>>(s->ptrs(), s->n, g1, T, prm, c.d_counters, nullptr, nullptr);
+      return 0;
+    }
+    {
+      KTimer t("mass_matrix_run");
+      const long ntiles = (s->n + 31) / 32;
+      const int chunk = chunk_for(ntiles, 8);
+      const long chunks = (ntiles + chunk - 1) / chunk;
+      const unsigned nb = (unsigned)std::min<long>((chunks + MM_WARPS - 1) / MM_WARPS, (long)c.sm_count * 64);
+      const size_t smem = MM_WARPS * 32 * MM1_REC * sizeof(double);
+      k_mm_cc1_1d_run<<<nb, 32 * MM_WARPS, smem, c.stream>>>(s->ptrs(), s->n, g1, T, prm,
+                                                             static_cast<const MMEntry *>(m->table_d),
+                                                             static_cast<const MMFlush *>(m->flush_d), c.d_counters,
+                                                             m->defer_list, m->defer_count, chunk);
+    }
+    {
+      KTimer t("mass_matrix_deferred");
+      k_mm<1><<<(unsigned)(c.sm_count * 4), 128, 0, c.stream>>>(s->ptrs(), s->n, g1, T, prm, c.d_counters,
+                                                                  m->defer_list, m->defer_count);
+    }
     return 0;
   }
   const Geo<2> g2 = make_geo<2>(ga);
-  if (c.deposit_mode == 0 || !c.use_fast_cc1) {
+  if (generic_only) {
     KTimer t("mass_matrix_generic");
     const unsigned nb = (unsigned)((s->n + 127) / 128);
     k_mm<2><<<nb, 128, 0, c.stream>>>(s->ptrs(), s->n, g2, T, prm, c.d_counters, nullptr, nullptr);
     return 0;
   }
-  if (m->defer_cap < (size_t)s->n) {
-    if (m->defer_list) cudaFree(m->defer_list);
-    m->defer_cap = s->cap ? s->cap : (size_t)s->n;
-    PGPU_CUDA(cudaMalloc(&m->defer_list, m->defer_cap * sizeof(int)));
-  }
-  PGPU_CUDA(cudaMemsetAsync(m->defer_count, 0, sizeof(unsigned), c.stream));
   {
     KTimer t("mass_matrix_run");
-    // chunk length: long enough that few runs are cut (a cut run costs 272 extra REDs), short enough that every SM
-    // gets several chunks per resident warp
     const long ntiles = (s->n + 31) / 32;
-    const long resident = (long)c.sm_count * MM_MINBLOCKS * MM_WARPS;
-    int chunk = (int)std::max<long>(1, std::min<long>(MM_CHUNK_MAX, ntiles / (resident * 4)));
-    if (const char *e = getenv("PGPU_MM_CHUNK")) chunk = std::max(1, std::min((int)MM_CHUNK_MAX, atoi(e)));   // tests, tuning
+    const int chunk = chunk_for(ntiles, MM_MINBLOCKS);
     const long chunks = (ntiles + chunk - 1) / chunk;
     const unsigned nb = (unsigned)std::min<long>((chunks + MM_WARPS - 1) / MM_WARPS, (long)c.sm_count * 64);
     const size_t smem = MM_WARPS * 32 * MM_REC * sizeof(double);

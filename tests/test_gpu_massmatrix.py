@@ -80,12 +80,13 @@ def test_accumulate_mass_matrices(pgpu, D, max_disp, nghost, mode):
         sp.destroy(); grid.destroy()
 
 
+@pytest.mark.parametrize("D", [1, 2])
 @pytest.mark.parametrize("chunk", ["3", "32"])
-def test_runs_carried_across_tiles(pgpu, monkeypatch, chunk):
+def test_runs_carried_across_tiles(pgpu, monkeypatch, chunk, D):
     """Large problems give a warp several consecutive 32-particle tiles and keep a run open across them (and across
     deferred particles); PGPU_MM_CHUNK forces that path on a problem the oracle can follow."""
     monkeypatch.setenv("PGPU_MM_CHUNK", chunk)
-    prob = _sorted(_prob(2, 37, 9001, 0.95, 3))
+    prob = _sorted(_prob(D, 37, 9001, 0.95, 3))
     grid, sp = make_gpu(pgpu, prob, CC1, charge=-1.0, fnorm=0.9)
     try:
         grid.mass_matrices_init(CC1)
