@@ -479,6 +479,19 @@ def c4_leg(args, torch, capi, stream, peak):
     ms_col = timed(col, 3)
     pairs = sum(capi.collide_coulomb(sps[a], sps[b], 10.0, dt_sec, 1983, 99, angular=1)
                 for (a, b) in ((0, 0), (1, 1), (0, 1)))
+    # setMassMatrices on the same deck (1D run kernel, pgpu_massmatrix.cu); the orbits are the ones adv() left
+    for sp in sps:
+        sp.bin_particles()
+    adv()
+    grid.mass_matrices_init(3)
+
+    def set_mm():
+        grid.mass_matrices_zero()
+        for sp in sps:
+            sp.accumulate_mass_matrices(deck.dt)
+        grid.mass_matrices_save_E0()
+    ms_mm = timed(set_mm, 3)
+    capi.picard_totals(reset=True)
     for sp in sps:
         sp.destroy()
     grid.destroy()
@@ -494,7 +507,10 @@ def c4_leg(args, torch, capi, stream, peak):
                          "kernel": "advance_cc1_1d_fused", "kernel_ms_per_launch": kern,
                          "units_per_launch": n / len(sps)},
             "coulomb": {"metric": "collision-pairs/s (weighted Coulomb, NANBU)", "value": pairs / (ms_col * 1e-3),
-                        "pairs_per_step": pairs, "ms_per_step": ms_col}}
+                        "pairs_per_step": pairs, "ms_per_step": ms_col},
+            "mass_matrices": {"metric": "particles/s through setMassMatrices (1D run kernel)", "value": n / (ms_mm * 1e-3),
+                              "ms_per_setMassMatrices": ms_mm,
+                              "hbm_frac_at_72B": 72.0 * n / (ms_mm * 1e-3) / 1e9 / peak}}
 
 
 def mass_matrix_cpu_sample(deck, ncell=96):
