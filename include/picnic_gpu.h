@@ -361,6 +361,8 @@ int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT
  * (:28-47); both partners of an accepted pair scatter. */
 int pgpu_collide_vhs(pgpu_species_t s, double eta, double T0, double mu0, double dt_sec, uint64_t seed, uint64_t step,
                      long *ncollisions);
+/* VariableHardSphere::setMeanFreeTime (VariableHardSphere.cpp:50-125): box maximum of n sigmaT(VTeff) VTeff */
+int pgpu_scatter_nu_max_vhs(pgpu_species_t s, double eta, double T0, double mu0, double *nu_max);
 /* HardSphere::setMeanFreeTime (HardSphere.cpp:65-194): box maximum of n sigmaT sqrt(Teff/m) */
 int pgpu_scatter_nu_max_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double *nu_max);
 /* Coulomb::LorentzScatter (Coulomb.cpp:1694-1793) for n pairs with explicit draws (test hook of the relativistic

@@ -111,6 +111,7 @@ def load():
         "pgpu_collide_hard_sphere": [vp, vp, dbl, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_scatter_nu_max_hard_sphere": [vp, vp, dbl, vp],
         "pgpu_collide_vhs": [vp, dbl, dbl, dbl, dbl, C.c_uint64, C.c_uint64, vp],
+        "pgpu_scatter_nu_max_vhs": [vp, dbl, dbl, dbl, vp],
         "pgpu_scatter_nu_max_ta": [vp, vp, dbl, vp], "pgpu_scatter_nu_max_coulomb": [vp, vp, vp, vp],
         "pgpu_scatter_nu_max_elastic": [vp, vp, vp, vp],
         "pgpu_halo_create": [vp, i32, vp, vp], "pgpu_halo_destroy": [vp], "pgpu_halo_phases": [vp],
@@ -449,6 +450,12 @@ def collide_vhs(sp, eta, T0, mu0, dt_sec, seed, step, count=True):
     np_ = C.c_long(0)
     check(load().pgpu_collide_vhs(sp.h, eta, T0, mu0, dt_sec, seed, step, C.byref(np_) if count else None))
     return np_.value
+
+
+def nu_max_vhs(sp, eta, T0, mu0):
+    out = C.c_double(0)
+    check(load().pgpu_scatter_nu_max_vhs(sp.h, eta, T0, mu0, C.byref(out)))
+    return out.value
 
 
 def nu_max_hard_sphere(sA, sB, sigmaT):

@@ -1669,6 +1669,39 @@ int pgpu_scatter_nu_max_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double
   return 0;
 }
 
+// VariableHardSphere::setIntraMFT (VariableHardSphere.cpp:80-125): box maximum of n * sigmaT(VTeff) * VTeff
+int pgpu_scatter_nu_max_vhs(pgpu_species_t s, double eta, double T0, double mu0, double *nu_max) {
+  if (!ctx().inited) {
+    set_error("pgpu_init has not been called");
+    return PGPU_ERR_STATE;
+  }
+  if (!s || !nu_max || !(eta > 0.5) || !(T0 > 0.0) || !(mu0 > 0.0)) return PGPU_ERR_ARG;
+  if (!s->dens || !s->ene) {
+    set_error("VariableHardSphere::setMeanFreeTime needs the cell moments: call pgpu_set_moments_from_bins first");
+    return PGPU_ERR_STATE;
+  }
+  double fourPiA, fourOverAlpha;
+  vhs_consts(s->desc.mass, eta, T0, mu0, &fourPiA, &fourOverAlpha);
+  const size_t ncell = (size_t)s->grid->ncell_box;
+  std::vector<double> d(ncell), e(3 * ncell);
+  cudaStream_t st = ctx().stream;
+  PGPU_CUDA(cudaMemcpyAsync(d.data(), s->dens, ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaMemcpyAsync(e.data(), s->ene, 3 * ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  const double CVAC = 2.99792458e+08, cvacSq = CVAC * CVAC;
+  double box_nuMax = 0.0;
+  for (size_t c = 0; c < ncell; ++c) {
+    if (d[c] == 0.0) continue;
+    const double en = e[c] + e[ncell + c] + e[2 * ncell + c];
+    const double Teff = 2.0 / 3.0 * en / d[c] * cvacSq;
+    const double VTeff = sqrt(Teff / s->desc.mass);
+    const double sigmaTmax = fourPiA * pow(VTeff, -fourOverAlpha);
+    box_nuMax = std::max(box_nuMax, d[c] * sigmaTmax * VTeff);
+  }
+  *nu_max = box_nuMax;
+  return 0;
+}
+
 int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt_sec, uint64_t seed,
                     uint64_t step, long *npairs_out) {
   if (!ctx().inited) {

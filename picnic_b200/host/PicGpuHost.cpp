@@ -532,6 +532,11 @@ void HardSphere::printParameters() const {
 // ---- VariableHardSphere (VariableHardSphere.cpp:28-47, 217-412) ------------------------------------
 VariableHardSphere::VariableHardSphere(int a_sp, Real a_eta, Real a_T0, Real a_mu0)
     : m_sp(a_sp), m_eta(a_eta), m_T0(a_T0), m_mu0(a_mu0), m_scatter_dt(DBL_MAX), m_ncoll(0) {}
+void VariableHardSphere::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {
+  double nu = 0.0;
+  check(pgpu_scatter_nu_max_vhs(a_species[m_sp]->handle(), m_eta, m_T0, m_mu0, &nu), "VariableHardSphere::setMeanFreeTime");
+  m_scatter_dt = nu > 0.0 ? 1.0 / nu : DBL_MAX;
+}
 void VariableHardSphere::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real a_dt_sec) const {
   PicChargedSpecies *a = a_species[m_sp];
   if (a->numParticles() == 0) return;

@@ -538,6 +538,10 @@ def test_vhs_self_matches_oracle_statistics(pgpu):
         return (t[0] - 0.5 * (t[1] + t[2])) / t.mean()
 
     a0 = aniso(s0["v"])
+    # VariableHardSphere::setMeanFreeTime: box maximum of n sigmaT(VTeff) VTeff with VTeff = gmax / 5
+    vt = gmax / 5.0
+    nu_ref = float(np.max(dens * fourPiA * vt ** (-fourOverAlpha) * vt))
+    assert abs(pgpu.nu_max_vhs(sp, eta, T0, mu0) - nu_ref) < 1e-12 * nu_ref
     nsteps, total_gpu = 6, 0
     for step in range(nsteps):
         sp.set_moments()
