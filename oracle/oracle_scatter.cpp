@@ -44,6 +44,24 @@ double mu_randn() {
 
 extern "C" void orc_rng_seed(uint64_t seed) { global_rand_gen.seed((unsigned)seed); }
 
+/* ScatteringUtils::collapseThreeToTwo (ScatteringUtils.H:20-47): particles 2 (weight wp2 > wp2p), its scattered
+ * fraction 2p (weight wp2p) and 3 become two equally weighted particles with the same momentum and the same
+ * energy per direction.  PINNED bit for bit on the reference (tests/golden/ref_pins_collapse.npz). */
+extern "C" void orc_collapse_three_to_two(double *vp2, double *wp2, double *vp3, double *wp3, const double *vp2p,
+                                          double wp2p) {
+  const double wp23 = 0.5 * (*wp2 + *wp3);
+  for (int dir = 0; dir < 3; dir++) {
+    const double c23 = (wp2p * vp2p[dir] + (*wp2 - wp2p) * vp2[dir] + *wp3 * vp3[dir]) / wp23;
+    const double d23 =
+        (wp2p * vp2p[dir] * vp2p[dir] + (*wp2 - wp2p) * vp2[dir] * vp2[dir] + *wp3 * vp3[dir] * vp3[dir]) / wp23;
+    const double arg23 = 2.0 * d23 - c23 * c23;
+    vp2[dir] = 0.5 * (c23 + sqrt(arg23));
+    vp3[dir] = 0.5 * (c23 - sqrt(arg23));
+  }
+  *wp2 = wp23;
+  *wp3 = wp23;
+}
+
 /* ScatteringUtils::computeDeltaU (ScatteringUtils.H:78-105) */
 extern "C" void orc_scatter_delta_u(double ux, double uy, double uz, double costh,
                                     double sinth, double cosphi, double sinphi,

@@ -7,7 +7,7 @@
  * the product path may include, link or call it.
  *
  * PARITY STATUS
- *   pinned   : orc_boris, orc_scatter_delta_u -- bit-equal to the reference's own
+ *   pinned   : orc_boris, orc_scatter_delta_u, orc_rotate_velocity, orc_collapse_three_to_two -- bit-equal to the reference's own
  *              PicSpeciesUtils::applyForces / ScatteringUtils::computeDeltaU compiled
  *              from /root/reference behind oracle/chombo_mock (oracle/ref_build.sh ->
  *              oracle/_ref), vectors committed in tests/golden/ref_pins.npz
@@ -230,6 +230,8 @@ void orc_elastic(long ncell, const long *cs1, double *v1, const double *w1, long
 
 /* Scattering::setMeanFreeTime: box maximum of the per-cell collision frequency [Hz]
  * (TakizukaAbe.cpp:55-238, Coulomb.cpp:79-356, Elastic.cpp:122-202, MathUtils.cpp:65-95) */
+/* ScatteringUtils::collapseThreeToTwo (ScatteringUtils.H:20-47), pinned on the reference */
+void orc_collapse_three_to_two(double *vp2, double *wp2, double *vp3, double *wp3, const double *vp2p, double wp2p);
 /* HardSphere, PROBABILISTIC (HardSphere.cpp:223-665): no-time-counter pairs; ene = [3][ncell] */
 double orc_hs_sigmaT(double r1, double r2);
 void orc_hs_self(long ncell, const long *cs, double *v, const double *w, long n, const double *dens,

@@ -6,6 +6,7 @@
 //   ref_delta_u         -> ScatteringUtils::computeDeltaU      (src/scattering/ScatteringUtils.H:84-111)
 //   ref_rotate_velocity -> ScatteringUtils::rotateVelocity     (src/scattering/ScatteringUtils.H:51-82)
 //   ref_scattering_cos  -> ScatteringUtils::getScatteringCos   (src/scattering/ScatteringUtils.H:12-18)
+//   ref_collapse_three_to_two -> ScatteringUtils::collapseThreeToTwo (src/scattering/ScatteringUtils.H:20-47)
 //   ref_mod_energy_pair -> ScatteringUtils::modEnergyPairwise  (src/scattering/ScatteringUtils.H:113-205)
 //   ref_particle_wire   -> JustinsParticle::linearOut          (src/particle_tools/JustinsParticle.cpp:339-383)
 //   ref_implicit_gamma  -> PicSpeciesUtils::getImplicitGamma   (src/species/pic/PicSpeciesUtils.H:43-52; -DRELATIVISTIC_PARTICLES)
@@ -89,6 +90,17 @@ void ref_mod_energy_pair(double *b1, double *b2, double wpmp1, double wpmp2, dou
     b2[i] = b[i];
   }
   *deltaE = (double)dE;
+}
+
+// ScatteringUtils::collapseThreeToTwo (src/scattering/ScatteringUtils.H:20-47): vp2/wp2 and vp3/wp3 are updated
+void ref_collapse_three_to_two(double *vp2, double *wp2, double *vp3, double *wp3, const double *vp2p, double wp2p) {
+  std::array<Real, 3> a = {vp2[0], vp2[1], vp2[2]}, b = {vp3[0], vp3[1], vp3[2]};
+  const std::array<Real, 3> c = {vp2p[0], vp2p[1], vp2p[2]};
+  ScatteringUtils::collapseThreeToTwo(a, *wp2, b, *wp3, c, wp2p);
+  for (int i = 0; i < 3; ++i) {
+    vp2[i] = a[i];
+    vp3[i] = b[i];
+  }
 }
 
 // wire format of one particle (what MPI migration and checkpoints carry); returns bytes

@@ -158,3 +158,32 @@ def test_oracle_rotate_velocity_bit_equals_reference():
                                 GOLD["in_sinphi"][i])
         got[i] = t
     assert np.array_equal(got, GOLD["out_rotate"])
+
+
+def test_oracle_collapse_three_to_two_bit_equals_reference():
+    """ScatteringUtils::collapseThreeToTwo (the CONSERVATIVE weight method's 3 -> 2 merge): the oracle against the
+    committed outputs of the reference's own code, and live where /root/reference is present; and what it is for:
+    total weight, momentum and energy per direction are kept."""
+    import ctypes
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(ROOT, "tests", "golden", "make_ref_golden_collapse.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_pins_collapse.npz"))
+    d = {k[3:]: gold[k] for k in gold.files if k.startswith("in_")}
+    f = orc.lib().orc_collapse_three_to_two
+    f.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_double]
+    o2, o3, w2, w3 = mk.run(f, d)
+    for got, name in ((o2, "out_vp2"), (o3, "out_vp3"), (w2, "out_wp2"), (w3, "out_wp3")):
+        assert np.array_equal(got, gold[name]), name
+    if os.path.isdir("/root/reference"):
+        r2, r3, rw2, rw3 = mk.run(mk.ref_lib().ref_collapse_three_to_two, d)
+        assert np.array_equal(r2, o2) and np.array_equal(r3, o3) and np.array_equal(rw2, w2)
+    wsum0 = d["wp2"] + d["wp3"]
+    assert np.allclose(w2 + w3, wsum0, rtol=1e-15)
+    p0 = d["wp2p"][:, None] * d["vp2p"] + (d["wp2"] - d["wp2p"])[:, None] * d["vp2"] + d["wp3"][:, None] * d["vp3"]
+    p1 = w2[:, None] * o2 + w3[:, None] * o3
+    assert np.allclose(p1, p0, rtol=0, atol=1e-15 * np.abs(p0).max())
+    e0 = d["wp2p"][:, None] * d["vp2p"] ** 2 + (d["wp2"] - d["wp2p"])[:, None] * d["vp2"] ** 2 + d["wp3"][:, None] * d["vp3"] ** 2
+    e1 = w2[:, None] * o2 ** 2 + w3[:, None] * o3 ** 2
+    assert np.allclose(e1, e0, rtol=1e-12)
