@@ -352,10 +352,14 @@ int pgpu_coulomb_delta_u(long n, const double *vp1, const double *vp2, double ch
                          const double *gauss, const double *u_polar, const double *u_phi, double *dU, double *s12);
 /* HardSphere::applySelfScattering / applyInterScattering, PROBABILISTIC weight method (HardSphere.cpp:223-665):
  * no-time-counter pair selection with gmax = 5 thermal speeds of the cell, isotropic scattering.  sigmaT =
- * pi (r1 + r2)^2 (HardSphere.cpp:52).  Species must be binned with their cell moments set.  The CONSERVATIVE
- * weight method (collapseThreeToTwo) is not implemented. */
+ * pi (r1 + r2)^2 (HardSphere.cpp:52).  Species must be binned with their cell moments set. */
 int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double dt_sec, uint64_t seed,
                              uint64_t step, long *ncollisions);
+/* The same with the deck's weight_method: 0 = PROBABILISTIC, 1 = CONSERVATIVE (HardSphere.cpp:357-392: for unequal
+ * weights the heavier particle, its scattered fraction and a third particle of the cell are merged into two equally
+ * weighted ones by ScatteringUtils::collapseThreeToTwo; the weights change; self-scattering only). */
+int pgpu_collide_hard_sphere_wm(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, int weight_method, double dt_sec,
+                                uint64_t seed, uint64_t step, long *ncollisions);
 /* VariableHardSphere::applySelfScattering (VariableHardSphere.cpp:217-412; the reference has no inter-species VHS):
  * sigmaT(g) = 4 pi A g^(-4/alpha) with alpha = 4/(2 eta - 1) and A from the viscosity mu0 [Pa s] at T0 [K]
  * (:28-47); both partners of an accepted pair scatter. */

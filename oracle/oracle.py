@@ -514,6 +514,19 @@ def hs_self(cell_start, v, w, dens, ene, mass, sigmaT, dt_sec):
     return a.value, b.value
 
 
+def hs_self_conservative(cell_start, v, w, dens, ene, mass, sigmaT, dt_sec):
+    """HardSphere::applySelfScattering with weight_method = CONSERVATIVE; v and w are updated in place."""
+    f = lib().orc_hs_self_wm
+    f.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                  C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    cs = np.ascontiguousarray(cell_start, dtype=np.int64)
+    ene = np.ascontiguousarray(ene, dtype=np.float64)
+    a, b = C.c_long(0), C.c_long(0)
+    f(cs.size - 1, _ptr(cs), _ptr(v), _ptr(w), v.shape[1], _ptr(dens), _ptr(ene), mass, sigmaT, 1, dt_sec, C.byref(a),
+      C.byref(b))
+    return a.value, b.value
+
+
 def hs_inter(cs1, v1, w1, dens1, ene1, m1, cs2, v2, w2, dens2, ene2, m2, Vc, sigmaT, dt_sec):
     f = lib().orc_hs_inter
     f.argtypes = ([C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_double,

@@ -908,9 +908,20 @@ int mu_randint(int a, int b) {   /* MathUtils::randInt */
 
 extern "C" double orc_hs_sigmaT(double r1, double r2) { return kPI * (r1 + r2) * (r1 + r2); }   /* HardSphere.cpp:52 */
 
+extern "C" void orc_hs_self_wm(long ncell, const long *cs, double *v, double *w, long n, const double *dens,
+                               const double *ene, double mass, double sigmaT, int conservative, double dt_sec,
+                               long *ncand_out, long *ncoll_out);
 extern "C" void orc_hs_self(long ncell, const long *cs, double *v, const double *w, long n, const double *dens,
                             const double *ene, double mass, double sigmaT, double dt_sec, long *ncand_out,
                             long *ncoll_out) {
+  orc_hs_self_wm(ncell, cs, v, const_cast<double *>(w), n, dens, ene, mass, sigmaT, 0, dt_sec, ncand_out, ncoll_out);
+}
+/* conservative != 0: the CONSERVATIVE weight method (HardSphere.cpp:357-392): for unequal weights the lighter
+ * particle scatters and the heavier one, its scattered fraction and a third particle of the cell are merged into two
+ * equally weighted particles (collapseThreeToTwo); the weights w change. */
+extern "C" void orc_hs_self_wm(long ncell, const long *cs, double *v, double *w, long n, const double *dens,
+                               const double *ene, double mass, double sigmaT, int conservative, double dt_sec,
+                               long *ncand_out, long *ncoll_out) {
   const double cvacSq = kCVAC * kCVAC;
   long ncand = 0, ncoll = 0;
   for (long c = 0; c < ncell; ++c) {
@@ -949,6 +960,39 @@ extern "C" void orc_hs_self(long ncell, const long *cs, double *v, const double 
       const double phi = kTWOPI * mu_rand();
       double dU[3];
       orc_scatter_delta_u(b1[0] - b2[0], b1[1] - b2[1], b1[2] - b2[2], costh, sinth, cos(phi), sin(phi), dU);
+      if (conservative && wp1 != wp2) {
+        if (local_numCell < 3) continue;
+        int random_index3 = mu_randint(0, local_numCell - 1);
+        while (random_index3 == random_index2 || random_index3 == random_index1)
+          random_index3 = mu_randint(0, local_numCell - 1);
+        const long i3 = cs[c] + random_index3;
+        double b3[3] = {v[i3], v[n + i3], v[2 * n + i3]};
+        double wq3 = w[i3];
+        if (wp1 < wp2) {
+          double b2p[3], wq2 = wp2;
+          for (int dir = 0; dir < 3; dir++) {
+            b1[dir] += 0.5 * dU[dir];
+            b2p[dir] = b2[dir] - 0.5 * dU[dir];
+          }
+          orc_collapse_three_to_two(b2, &wq2, b3, &wq3, b2p, wp1);
+          w[i2] = wq2;
+        } else {
+          double b1p[3], wq1 = wp1;
+          for (int dir = 0; dir < 3; dir++) {
+            b1p[dir] = b1[dir] + 0.5 * dU[dir];
+            b2[dir] -= 0.5 * dU[dir];
+          }
+          orc_collapse_three_to_two(b1, &wq1, b3, &wq3, b1p, wp2);
+          w[i1] = wq1;
+        }
+        w[i3] = wq3;
+        for (int dir = 0; dir < 3; dir++) {
+          v[dir * n + i1] = b1[dir];
+          v[dir * n + i2] = b2[dir];
+          v[dir * n + i3] = b3[dir];
+        }
+        continue;
+      }
       const double rand_num3 = mu_rand();
       if (rand_num3 <= wp2 / wp1)
         for (int dir = 0; dir < 3; dir++) v[dir * n + i1] = b1[dir] + 0.5 * dU[dir];

@@ -110,6 +110,7 @@ def load():
         "pgpu_collide_elastic": [vp, vp, vp, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_collide_hard_sphere": [vp, vp, dbl, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_scatter_nu_max_hard_sphere": [vp, vp, dbl, vp],
+        "pgpu_collide_hard_sphere_wm": [vp, vp, dbl, i32, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_collide_vhs": [vp, dbl, dbl, dbl, dbl, C.c_uint64, C.c_uint64, vp],
         "pgpu_scatter_nu_max_vhs": [vp, dbl, dbl, dbl, vp],
         "pgpu_scatter_nu_max_ta": [vp, vp, dbl, vp], "pgpu_scatter_nu_max_coulomb": [vp, vp, vp, vp],
@@ -443,6 +444,12 @@ def collide_coulomb(sA, sB, Clog, dt_sec, seed, step, angular=0, NxN=False, NxN_
 def collide_hard_sphere(sA, sB, sigmaT, dt_sec, seed, step, count=True):
     np_ = C.c_long(0)
     check(load().pgpu_collide_hard_sphere(sA.h, sB.h, sigmaT, dt_sec, seed, step, C.byref(np_) if count else None))
+    return np_.value
+
+
+def collide_hard_sphere_conservative(sp, sigmaT, dt_sec, seed, step):
+    np_ = C.c_long(0)
+    check(load().pgpu_collide_hard_sphere_wm(sp.h, sp.h, sigmaT, 1, dt_sec, seed, step, C.byref(np_)))
     return np_.value
 
 

@@ -830,6 +830,8 @@ struct HSParams {
   double sigmaT, dt_sec, mass1, mass2, mu, Vc;
   int vhs;                          // VariableHardSphere: sigmaT(g) = fourPiA * g^(-fourOverAlpha), self only
   double fourPiA, fourOverAlpha;
+  int conservative;                 // HardSphere self, weight method CONSERVATIVE (collapseThreeToTwo), needs wmut
+  double *wmut;
   unsigned seed_lo, seed_hi, step_lo, step_hi;
   int box_lo0, box_lo1, nbox0, ncell_glob0;
 };
@@ -913,6 +915,49 @@ k_hard_sphere(const int *cs1, const int *cs2, int ncell, double *a0, double *a1,
         sincos(TWOPI * u01(r1.x), &sinphi, &cosphi);
         scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
         const double wp1 = wa[i1], wp2 = wb[i2], u3 = P.vhs ? 0.0 : u01(r1.y);   // VHS updates both partners
+        if (P.conservative && wp1 != wp2) {
+          // HardSphere.cpp:357-392: the lighter particle scatters; the heavier one, its scattered fraction and a third
+          // particle of the cell are merged into two equally weighted particles (ScatteringUtils::collapseThreeToTwo)
+          if (n1 < 3) continue;
+          int q3 = min(n1 - 3, (int)(u01(r1.z) * (n1 - 2)));
+          const int qlo = min(q1, q2), qhi = max(q1, q2);
+          if (q3 >= qlo) q3 += 1;
+          if (q3 >= qhi) q3 += 1;
+          const int i3 = s1 + q3;
+          const bool first_light = wp1 < wp2;
+          const int ih = first_light ? i2 : i1;                    // the heavier particle
+          const double wl = first_light ? wp1 : wp2;
+          double vh[3], vhp[3], vl[3], v3[3] = {a0[i3], a1[i3], a2[i3]};
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            if (first_light) {
+              vl[d] = v1[d] + 0.5 * dU[d];
+              vh[d] = v2[d];
+              vhp[d] = v2[d] - 0.5 * dU[d];
+            } else {
+              vh[d] = v1[d];
+              vhp[d] = v1[d] + 0.5 * dU[d];
+              vl[d] = v2[d] - 0.5 * dU[d];
+            }
+          }
+          const double wh = first_light ? wp2 : wp1, w3 = P.wmut[i3];
+          const double wp23 = 0.5 * (wh + w3);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double c23 = (wl * vhp[d] + (wh - wl) * vh[d] + w3 * v3[d]) / wp23;
+            const double d23 = (wl * vhp[d] * vhp[d] + (wh - wl) * vh[d] * vh[d] + w3 * v3[d] * v3[d]) / wp23;
+            const double root = sqrt(fmax(2.0 * d23 - c23 * c23, 0.0));   // the reference asserts arg >= 0
+            vh[d] = 0.5 * (c23 + root);
+            v3[d] = 0.5 * (c23 - root);
+          }
+          const int il = first_light ? i1 : i2;
+          a0[il] = vl[0]; a1[il] = vl[1]; a2[il] = vl[2];
+          a0[ih] = vh[0]; a1[ih] = vh[1]; a2[ih] = vh[2];
+          a0[i3] = v3[0]; a1[i3] = v3[1]; a2[i3] = v3[2];
+          P.wmut[ih] = wp23;
+          P.wmut[i3] = wp23;
+          continue;
+        }
         if (P.vhs || u3 <= wp2 / wp1) {
           a0[i1] = v1[0] + f1 * dU[0];
           a1[i1] = v1[1] + f1 * dU[1];
@@ -1597,6 +1642,26 @@ int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT
   HSParams P;
   memset(&P, 0, sizeof(P));
   P.sigmaT = sigmaT;
+  return launch_hard_sphere(sA, sB, P, dt_sec, seed, step, ncoll_out, "HardSphere");
+}
+
+// weight_method: 0 = PROBABILISTIC, 1 = CONSERVATIVE (self-scattering only here; the species' weights change)
+int pgpu_collide_hard_sphere_wm(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, int weight_method, double dt_sec,
+                                uint64_t seed, uint64_t step, long *ncoll_out) {
+  if (weight_method == 0) return pgpu_collide_hard_sphere(sA, sB, sigmaT, dt_sec, seed, step, ncoll_out);
+  if (weight_method != 1 || sA != sB) {
+    set_error("HardSphere: the CONSERVATIVE weight method is implemented for self-scattering only");
+    return PGPU_ERR_ARG;
+  }
+  if (!(sigmaT > 0.0)) {
+    set_error("HardSphere: sigmaT must be positive");
+    return PGPU_ERR_ARG;
+  }
+  HSParams P;
+  memset(&P, 0, sizeof(P));
+  P.sigmaT = sigmaT;
+  P.conservative = 1;
+  P.wmut = sA->w;
   return launch_hard_sphere(sA, sB, P, dt_sec, seed, step, ncoll_out, "HardSphere");
 }
 

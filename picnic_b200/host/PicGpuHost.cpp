@@ -506,9 +506,11 @@ void Elastic::printParameters() const {
 }
 
 // ---- HardSphere (HardSphere.cpp:30-52, 65-194, 196-665) ------------------------------------------
-HardSphere::HardSphere(int a_sp1, int a_sp2, Real a_r1, Real a_r2)
+HardSphere::HardSphere(int a_sp1, int a_sp2, Real a_r1, Real a_r2, bool a_conservative)
     : m_sp1(a_sp1), m_sp2(a_sp2), m_r1(a_r1), m_r2(a_r2), m_sigmaT(3.14159265358979323846 * (a_r1 + a_r2) * (a_r1 + a_r2)),
-      m_scatter_dt(DBL_MAX), m_ncoll(0) {}
+      m_conservative(a_conservative), m_scatter_dt(DBL_MAX), m_ncoll(0) {
+  if (a_conservative && a_sp1 != a_sp2) fatal("HardSphere: weight_method = CONSERVATIVE is implemented for self-scattering only");
+}
 void HardSphere::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {
   double nu = 0.0;
   check(pgpu_scatter_nu_max_hard_sphere(a_species[m_sp1]->handle(), a_species[m_sp2]->handle(), m_sigmaT, &nu),
@@ -519,7 +521,8 @@ void HardSphere::applyScattering(std::vector<PicChargedSpecies *> &a_species, Re
   PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
   if (a->numParticles() == 0 || b->numParticles() == 0) return;
   long nc = 0;
-  check(pgpu_collide_hard_sphere(a->handle(), b->handle(), m_sigmaT, a_dt_sec, s_seed, s_step, &nc),
+  check(pgpu_collide_hard_sphere_wm(a->handle(), b->handle(), m_sigmaT, m_conservative ? 1 : 0, a_dt_sec, s_seed, s_step,
+                                    &nc),
         "HardSphere::applyScattering");
   m_ncoll = nc;
 }

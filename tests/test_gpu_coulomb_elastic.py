@@ -576,3 +576,38 @@ def test_vhs_self_matches_oracle_statistics(pgpu):
     assert abs(total_gpu - total_cpu) < 0.03 * total_cpu, (total_gpu, total_cpu)
     assert a_cpu / a0 < 0.85 and a_gpu / a0 < 0.85
     assert abs(a_gpu - a_cpu) / a0 < 0.03
+
+
+def test_hard_sphere_conservative_weight_method(pgpu):
+    """pgpu_collide_hard_sphere_wm(weight_method = CONSERVATIVE): every cell keeps its total weight, weighted momentum
+    and weighted energy to round-off although the particle weights differ (collapseThreeToTwo, pinned on the
+    reference); the collision count stays within 10 % of the oracle on the same cells."""
+    deck = decks.Deck(D=2, ncell=(20, 20), dx=(0.25, 0.25), xmin=(0.0, 0.0), nghost=2)
+    sdef = decks.SpeciesDef("argon", 40.0 * 1836.15, 0.0, (1.0, 1.0, 1.0), 1.0e30, (6, 6))
+    rng = np.random.default_rng(81)
+    p = decks.load_species(deck, sdef, (0, 0), (19, 19), rng)
+    w = p["w"] * rng.choice([0.5, 1.0, 2.0], size=p["w"].size)
+    grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, 2, (1, 1), volume_scale=deck.volume_scale)
+    sp = _species_on_grid(pgpu, grid, deck, sdef, p["x"], p["v"], w, ids=p["id"])
+    s0 = sp.download()
+    dens, _, ene = sp.moments()
+    offs = sp.cell_offsets()
+    sig = orc.hs_sigmaT(1.9e-10, 1.9e-10)
+    gmax = 5.0 * np.sqrt(2.0 / 3.0 * ene.reshape(3, -1).sum(0) / dens / sdef.mass) * 2.99792458e8
+    dt_sec = 0.7 / float(np.max(dens * sig * gmax))
+    ncoll = pgpu.collide_hard_sphere_conservative(sp, sig, dt_sec, 1983, 0)
+    s1 = sp.download()
+    sp.destroy(); grid.destroy()
+    assert ncoll > 1000 and not np.isnan(s1["v"]).any()
+    assert np.array_equal(s1["id"], s0["id"])
+    assert np.mean(s1["w"] != s0["w"]) > 0.05
+    for c in range(offs.size - 1):
+        a, b = offs[c], offs[c + 1]
+        w0, w1, v0, v1 = s0["w"][a:b], s1["w"][a:b], s0["v"][:, a:b], s1["v"][:, a:b]
+        assert abs(w1.sum() - w0.sum()) < 1e-13 * w0.sum()
+        assert np.max(np.abs((w1 * v1).sum(1) - (w0 * v0).sum(1))) < 1e-12 * np.abs(w0 * v0).sum(1).max()
+        assert abs((w1 * v1 ** 2).sum() - (w0 * v0 ** 2).sum()) < 1e-12 * (w0 * v0 ** 2).sum()
+    v, wc = s0["v"].copy(), s0["w"].copy()
+    orc.lib().orc_rng_seed(5)
+    n_cpu = orc.hs_self_conservative(offs, v, wc, dens, ene, sdef.mass, sig, dt_sec)[1]
+    assert abs(ncoll - n_cpu) < 0.10 * n_cpu, (ncoll, n_cpu)

@@ -323,3 +323,39 @@ def test_vhs_self_conserves_and_reduces_to_hard_sphere_for_eta_one_half_limit():
     assert np.max(np.abs(dv)) < 1e-18
     e0, e1 = (v0 ** 2).reshape(3, ncell, npc).sum((0, 2)), (v ** 2).reshape(3, ncell, npc).sum((0, 2))
     assert np.max(np.abs(e1 - e0) / e0) < 1e-13
+
+
+def test_hard_sphere_conservative_weight_method_keeps_weight_momentum_and_energy():
+    """HardSphere::applySelfScattering with weight_method = CONSERVATIVE (HardSphere.cpp:357-392): unequal-weight
+    pairs go through ScatteringUtils::collapseThreeToTwo (pinned on the reference in test_ref_pin.py); every cell keeps
+    its total weight, its weighted momentum and its weighted energy to round-off -- which the PROBABILISTIC method
+    only does on average."""
+    rng = np.random.default_rng(31)
+    ncell, npc, mass, Vc = 100, 30, 1836.0, 1.0e-9
+    cs, v, w, dens, ene = _hs_cells(rng, ncell, npc, 1.0e-3, mass, 1.0e20, Vc)
+    w *= rng.choice([0.5, 1.0, 2.0], size=w.size)
+    for c in range(ncell):
+        sl = slice(cs[c], cs[c + 1])
+        dens[c] = w[sl].sum() / Vc
+        ene[:, c] = 0.5 * mass * (w[sl] * v[:, sl] ** 2).sum(1) / Vc
+    sig = orc.hs_sigmaT(1.0e-10, 1.0e-10)
+    dt = 0.8 / (dens.max() * sig * 5.0e-3 * 2.99792458e8)
+    v0, w0 = v.copy(), w.copy()
+    orc.lib().orc_rng_seed(3)
+    ncand, ncoll = orc.hs_self_conservative(cs, v, w, dens, ene, mass, sig, dt)
+    assert ncoll > 200 and not np.isnan(v).any()
+    assert np.mean(w != w0) > 0.05
+    for c in range(ncell):
+        sl = slice(cs[c], cs[c + 1])
+        assert abs(w[sl].sum() - w0[sl].sum()) < 1e-14 * w0[sl].sum()
+        p0, p1 = (w0[sl] * v0[:, sl]).sum(1), (w[sl] * v[:, sl]).sum(1)
+        assert np.max(np.abs(p1 - p0)) < 1e-13 * np.abs(w0[sl] * v0[:, sl]).sum(1).max()
+        e0, e1 = (w0[sl] * v0[:, sl] ** 2).sum(), (w[sl] * v[:, sl] ** 2).sum()
+        assert abs(e1 - e0) < 1e-13 * e0
+    # the PROBABILISTIC method on the same cells does not conserve per cell
+    v2, w2 = v0.copy(), w0.copy()
+    orc.lib().orc_rng_seed(3)
+    orc.hs_self(cs, v2, w2, dens, ene, mass, sig, dt)
+    drift = max(abs((w0[cs[c]:cs[c + 1]] * v2[:, cs[c]:cs[c + 1]] ** 2).sum() - (w0[cs[c]:cs[c + 1]] * v0[:, cs[c]:cs[c + 1]] ** 2).sum())
+                / (w0[cs[c]:cs[c + 1]] * v0[:, cs[c]:cs[c + 1]] ** 2).sum() for c in range(ncell))
+    assert drift > 1e-6
