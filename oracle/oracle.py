@@ -376,6 +376,20 @@ def elastic(cs1, v1, w1, m1, cs2, v2, w2, dens2, m2, dt_sec, const_sigma=0.0, E=
     return ncoll.value
 
 
+def elastic_conservative(cs1, v1, w1, m1, cs2, v2, w2, dens2, m2, dt_sec, const_sigma):
+    """Elastic::electronImpact with weight_method = CONSERVATIVE, constant cross section; v1, v2 and w2 change."""
+    f = lib().orc_elastic_wm
+    f.argtypes = ([C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_long, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                   C.c_int, C.c_int, C.c_double, C.c_void_p])
+    ncoll = C.c_long(0)
+    a1 = np.ascontiguousarray(cs1, dtype=np.int64)
+    a2 = np.ascontiguousarray(cs2, dtype=np.int64)
+    f(a1.size - 1, _ptr(a1), _ptr(v1), _ptr(w1), v1.shape[1], m1, _ptr(a2), _ptr(v2), _ptr(w2), v2.shape[1], _ptr(dens2),
+      m2, const_sigma, 0, None, None, None, 0, 0, 1, dt_sec, C.byref(ncoll))
+    return ncoll.value
+
+
 def ta_nu_max(m1, m2, q1, q2, mass1, mass2, Clog, intra):
     """TakizukaAbe::setMeanFreeTime: m = (dens[ncell], mom[3, ncell], ene[3, ncell]) per species."""
     _coul_sigs()

@@ -772,10 +772,24 @@ extern "C" double orc_elastic_sigma(double g12, double mu, double const_sigma, i
 }
 
 /* Elastic::electronImpact (Elastic.cpp:225-388), PROBABILISTIC weight method */
+extern "C" void orc_elastic_wm(long ncell, const long *cs1, double *v1, const double *w1, long n1, double mass1,
+                               const long *cs2, double *v2, double *w2, long n2, const double *dens2, double mass2,
+                               double const_sigma, int ntab, const double *E, const double *Q, const double *XI,
+                               int angular, int loglog, int conservative, double dt_sec, long *ncoll_out);
 extern "C" void orc_elastic(long ncell, const long *cs1, double *v1, const double *w1, long n1, double mass1,
                             const long *cs2, double *v2, const double *w2, long n2, const double *dens2,
                             double mass2, double const_sigma, int ntab, const double *E, const double *Q,
                             const double *XI, int angular, int loglog, double dt_sec, long *ncoll_out) {
+  orc_elastic_wm(ncell, cs1, v1, w1, n1, mass1, cs2, v2, const_cast<double *>(w2), n2, dens2, mass2, const_sigma, ntab, E,
+                 Q, XI, angular, loglog, 0, dt_sec, ncoll_out);
+}
+/* conservative != 0: weight_method = CONSERVATIVE (Elastic.cpp:333-358): when the projectile is the lighter one
+ * (wp1 < wp2) it scatters, and the target, its scattered fraction and a second target of the cell are merged into two
+ * equally weighted particles (collapseThreeToTwo); w2 changes.  Oracle only: the device has no such branch yet. */
+extern "C" void orc_elastic_wm(long ncell, const long *cs1, double *v1, const double *w1, long n1, double mass1,
+                               const long *cs2, double *v2, double *w2, long n2, const double *dens2, double mass2,
+                               double const_sigma, int ntab, const double *E, const double *Q, const double *XI,
+                               int angular, int loglog, int conservative, double dt_sec, long *ncoll_out) {
   const double mu = mass1 * mass2 / (mass1 + mass2);
   long ncoll = 0;
   for (long c = 0; c < ncell; ++c) {
@@ -802,6 +816,27 @@ extern "C" void orc_elastic(long ncell, const long *cs1, double *v1, const doubl
         const double sinth = sqrt(1.0 - costh * costh);
         double dU[3];
         orc_scatter_delta_u(a[0] - b[0], a[1] - b[1], a[2] - b[2], costh, sinth, cos(phi), sin(phi), dU);
+        if (conservative && w1[i1] < w2[i2]) {
+          if (numCell2 < 2) continue;
+          double b2p[3];
+          for (int d = 0; d < 3; ++d) {
+            a[d] += mu / mass1 * dU[d];
+            b2p[d] = b[d] - mu / mass2 * dU[d];
+          }
+          long i3 = cs2[c] + pick(global_rand_gen);
+          while (i3 == i2) i3 = cs2[c] + pick(global_rand_gen);
+          double b3[3] = {v2[i3], v2[n2 + i3], v2[2 * n2 + i3]};
+          double wq2 = w2[i2], wq3 = w2[i3];
+          orc_collapse_three_to_two(b, &wq2, b3, &wq3, b2p, w1[i1]);
+          w2[i2] = wq2;
+          w2[i3] = wq3;
+          for (int d = 0; d < 3; ++d) {
+            v1[d * n1 + i1] = a[d];
+            v2[d * n2 + i2] = b[d];
+            v2[d * n2 + i3] = b3[d];
+          }
+          continue;
+        }
         const double r2 = mu_rand();
         if (r2 <= w2[i2] / w1[i1])
           for (int d = 0; d < 3; ++d) v1[d * n1 + i1] = a[d] + mu / mass1 * dU[d];

@@ -230,6 +230,11 @@ void orc_elastic(long ncell, const long *cs1, double *v1, const double *w1, long
 
 /* Scattering::setMeanFreeTime: box maximum of the per-cell collision frequency [Hz]
  * (TakizukaAbe.cpp:55-238, Coulomb.cpp:79-356, Elastic.cpp:122-202, MathUtils.cpp:65-95) */
+/* Elastic::electronImpact with weight_method = CONSERVATIVE (Elastic.cpp:333-358); oracle only so far */
+void orc_elastic_wm(long ncell, const long *cs1, double *v1, const double *w1, long n1, double mass1, const long *cs2,
+                    double *v2, double *w2, long n2, const double *dens2, double mass2, double const_sigma, int ntab,
+                    const double *E, const double *Q, const double *XI, int angular, int loglog, int conservative,
+                    double dt_sec, long *ncoll_out);
 /* ScatteringUtils::collapseThreeToTwo (ScatteringUtils.H:20-47), pinned on the reference */
 void orc_collapse_three_to_two(double *vp2, double *wp2, double *vp3, double *wp3, const double *vp2p, double wp2p);
 /* HardSphere, PROBABILISTIC (HardSphere.cpp:223-665): no-time-counter pairs; ene = [3][ncell] */

@@ -359,3 +359,31 @@ def test_hard_sphere_conservative_weight_method_keeps_weight_momentum_and_energy
     drift = max(abs((w0[cs[c]:cs[c + 1]] * v2[:, cs[c]:cs[c + 1]] ** 2).sum() - (w0[cs[c]:cs[c + 1]] * v0[:, cs[c]:cs[c + 1]] ** 2).sum())
                 / (w0[cs[c]:cs[c + 1]] * v0[:, cs[c]:cs[c + 1]] ** 2).sum() for c in range(ncell))
     assert drift > 1e-6
+
+
+def test_elastic_conservative_weight_method_keeps_weight_momentum_and_energy():
+    """Elastic::electronImpact with weight_method = CONSERVATIVE (Elastic.cpp:333-358), oracle only so far: light
+    projectiles (electrons, small weights) on heavier-weight targets; every cell keeps the targets' total weight and the
+    pair's weighted momentum m1 w1 v1 + m2 w2 v2 and weighted energy to round-off."""
+    rng = np.random.default_rng(41)
+    ncell, Vc = 60, 1.0e-9
+    m1, m2 = 1.0, 40.0 * 1836.0
+    cs1, v1, w1, d1, _ = _hs_cells(rng, ncell, 25, 2.0e-2, m1, 0.25e20, Vc)
+    cs2, v2, w2, d2, _ = _hs_cells(rng, ncell, 15, 2.0e-5, m2, 1.0e20, Vc)
+    w2 *= rng.choice([1.0, 2.0], size=w2.size)             # the targets' weights differ, so the merges change them
+    d2 = np.array([w2[cs2[c]:cs2[c + 1]].sum() / Vc for c in range(ncell)])
+    a1, a2, u2 = v1.copy(), v2.copy(), w2.copy()
+    orc.lib().orc_rng_seed(8)
+    ncoll = orc.elastic_conservative(cs1, v1, w1, m1, cs2, v2, w2, d2, m2, 2.0e-11, 1.0e-19)
+    assert ncoll > 100 and not np.isnan(v2).any()
+    assert np.mean(w2 != u2) > 0.02
+    for c in range(ncell):
+        s1, s2 = slice(cs1[c], cs1[c + 1]), slice(cs2[c], cs2[c + 1])
+        assert abs(w2[s2].sum() - u2[s2].sum()) < 1e-14 * u2[s2].sum()
+        p0 = m1 * (w1[s1] * a1[:, s1]).sum(1) + m2 * (u2[s2] * a2[:, s2]).sum(1)
+        p1 = m1 * (w1[s1] * v1[:, s1]).sum(1) + m2 * (w2[s2] * v2[:, s2]).sum(1)
+        scale = m1 * np.abs(w1[s1] * a1[:, s1]).sum() + m2 * np.abs(u2[s2] * a2[:, s2]).sum()
+        assert np.max(np.abs(p1 - p0)) < 1e-13 * scale
+        e0 = m1 * (w1[s1] * a1[:, s1] ** 2).sum() + m2 * (u2[s2] * a2[:, s2] ** 2).sum()
+        e1 = m1 * (w1[s1] * v1[:, s1] ** 2).sum() + m2 * (w2[s2] * v2[:, s2] ** 2).sum()
+        assert abs(e1 - e0) < 1e-12 * e0
