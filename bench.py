@@ -885,8 +885,45 @@ def cpu_arm(args, steps, warmup):
             "seconds": dt}, dt / max(steps, 1)
 
 
+def cpu_layout_sample(args, n_sample=400000):
+    """One host thread, one nonlinear evaluation of one species on a strip of the C3 box, twice: the SoA oracle (what
+    `cpu_baseline.value` runs on every core) and the same arithmetic on 176-byte particle objects in a doubly linked
+    list with one kernel call per particle (oracle_aos.cpp) -- the reference's memory behaviour; "scattered"
+    places consecutive particles' nodes at random heap addresses, as after many steps of list transfers."""
+    orc, deck, geom, Ef, Bf, parts, rows = cpu_sample_problem(args, 1)
+    lo, hi = (0, 0), (args.ncell - 1, args.ncell - 1)
+    p, sdef = parts[0], deck.species[0]
+    n = min(n_sample, p["w"].size)
+    x = np.ascontiguousarray(p["x"][:, :n]); v = np.ascontiguousarray(p["v"][:, :n]); w = np.ascontiguousarray(p["w"][:n])
+    fn = sdef.fnorm_const(deck.units)
+    out = {}
+    for name in ("soa", "aos_list", "aos_list_scattered"):
+        J = [orc.fab_for(lo, hi, deck.nghost, st) for st in orc.E_STAG[2]]
+        if name == "soa":
+            xa, va = x.copy(), v.copy()
+            t0 = time.perf_counter()
+            rc, _, _, _ = orc.advance_particles_iteratively(geom, deck.interp_E, xa, x, va, v, Ef, Bf, fn, deck.cnorm_dt,
+                                                            deck.rtol, deck.iter_max)
+            orc.deposit_current(geom, deck.interp_J, xa, x, va, w, deck.cnorm_dt, J)
+            sec = time.perf_counter() - t0
+        else:
+            aos = orc.AosList(2, x, x, v, v, w, scattered=name.endswith("scattered"))
+            t0 = time.perf_counter()
+            rc, _, _ = aos.advance_deposit(geom, deck.interp_E, Ef, Bf, fn, deck.cnorm_dt, deck.rtol, deck.iter_max, J)
+            sec = time.perf_counter() - t0
+            aos.destroy()
+        out[name] = {"value": n / sec, "seconds": sec, "rc": int(rc)}
+    out["unit"] = "particle-advances/s on one thread"
+    out["sample"] = "%d particles of one species, one evaluation" % n
+    return out
+
+
 def cpu_baseline(args, steps=1):
     res, _ = cpu_arm(args, steps=steps, warmup=0)
+    try:
+        res["layout"] = cpu_layout_sample(args)
+    except Exception as e:      # the layout comparison is an extra; never lose the baseline over it
+        res["layout"] = {"error": repr(e)}
     return res
 
 

@@ -573,3 +573,38 @@ def vhs_self(cell_start, v, dens, ene, mass, fourPiA, fourOverAlpha, dt_sec):
     f(cs.size - 1, _ptr(cs), _ptr(v), v.shape[1], _ptr(dens), _ptr(ene), mass, fourPiA, fourOverAlpha, dt_sec, C.byref(a),
       C.byref(b))
     return a.value, b.value
+
+
+# ---- AoS + linked-list driver of the same arithmetic (oracle_aos.cpp) ---------------------------
+class AosList:
+    """Particles as 176-byte objects in a doubly linked list, advanced and deposited with one kernel call per
+    particle -- the reference's memory behaviour (bench.py's faithful CPU number)."""
+
+    def __init__(self, D, x, xold, v, vold, w, scattered=False):
+        L = lib()
+        L.orc_aos_create_ex.restype = C.c_void_p
+        L.orc_aos_create_ex.argtypes = [C.c_int, C.c_long] + [C.c_void_p] * 5 + [C.c_int]
+        L.orc_aos_destroy.argtypes = [C.c_void_p]
+        L.orc_aos_advance_deposit.argtypes = ([C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_double] * 3 +
+                                              [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
+        L.orc_aos_read.argtypes = [C.c_void_p] * 3
+        self.D, self.n = D, x.shape[1]
+        self.h = L.orc_aos_create_ex(D, self.n, _ptr(x), _ptr(xold), _ptr(v), _ptr(vold), _ptr(w), int(scattered))
+        if not self.h:
+            raise RuntimeError("orc_aos_create failed (relativistic build is not supported)")
+
+    def advance_deposit(self, g, interp, E, B, fnorm, cnormDt, rtol, iter_max, J):
+        a, b = C.c_long(0), C.c_long(0)
+        rc = lib().orc_aos_advance_deposit(self.h, C.byref(g), interp, _fabs3(E), _fabs3(B), fnorm, cnormDt, rtol, iter_max,
+                                           _fabs3(J), C.byref(a), C.byref(b))
+        return rc, a.value, b.value
+
+    def read(self):
+        x, v = np.zeros((self.D, self.n)), np.zeros((3, self.n))
+        lib().orc_aos_read(self.h, _ptr(x), _ptr(v))
+        return x, v
+
+    def destroy(self):
+        if self.h:
+            lib().orc_aos_destroy(self.h)
+            self.h = None

@@ -139,6 +139,18 @@ int orc_deposit_mass_matrices(const orc_geom *g, int interp, long n, const doubl
 void orc_compute_J_from_mass_matrices(int D, const int *ncomp, const orc_mfab *sigma, const orc_fab *E0,
                                       const orc_fab *E, const orc_fab *J0, orc_fab *J);
 
+/* ---- the same advance + deposit on 176-byte particle objects in a doubly linked list, one kernel call per particle
+ * (oracle_aos.cpp): the reference's memory behaviour, for the "faithful" CPU number of bench.py ---------------- */
+void *orc_aos_create(int D, long n, const double *x, const double *xold, const double *v, const double *vold,
+                     const double *w);
+void *orc_aos_create_ex(int D, long n, const double *x, const double *xold, const double *v, const double *vold,
+                        const double *w, int scattered);
+void orc_aos_destroy(void *h);
+int orc_aos_advance_deposit(void *h, const orc_geom *g, int interp, const orc_fab *E, const orc_fab *B, double fnorm,
+                            double cnormDt, double rtol, int iter_max, orc_fab *J, long *num_apply_its,
+                            long *num_unconverged);
+void orc_aos_read(void *h, double *x, double *v);
+
 /* ---- ghost handling of a deposited field (periodic, one box) -------------- */
 /* Adds every ghost entry onto its periodic image inside the valid region
  * (valid cells lo..hi; nodal directions own nodes lo..hi+1 with node hi+1 the

@@ -235,3 +235,28 @@ def test_relativistic_boris_invariants(hc):
             assert abs(g - np.sqrt(1.0 + (vold[:, i] ** 2).sum())) < 1e-15 * g
     finally:
         orc.set_relativistic(False)
+
+
+@pytest.mark.parametrize("D", [1, 2])
+def test_aos_linked_list_driver_equals_the_soa_oracle(D):
+    """oracle_aos.cpp drives the same per-particle kernels the way the reference does in memory (176-byte objects
+    in a doubly linked list, one gather / Boris / deposit call per particle, stepNormTransfer between lists): per
+    particle it must be bit-identical to orc_advance_particles_iteratively; J only differs by the order of the sums."""
+    prob = Problem(D, (16,) if D == 1 else (10, 8), (0.25,) if D == 1 else (0.25, 0.3), (0.0,) if D == 1 else (0.0, -1.0),
+                   3, 3000, seed=5, max_disp=0.6, E0=0.3, B0=1.0)
+    fnorm, cnormDt, rtol, itmax = -0.7, 0.4, 1e-12, 21
+    x, v = prob.x.copy(), prob.v.copy()
+    rc, apply_its, unconv, _ = orc.advance_particles_iteratively(prob.geom, orc.CC1, x, prob.xold, v, prob.vold, prob.E,
+                                                                 prob.B, fnorm, cnormDt, rtol, itmax)
+    assert rc == 0
+    J = prob.new_J()
+    assert orc.deposit_current(prob.geom, orc.CC1, x, prob.xold, v, prob.w, cnormDt, J) == 0
+    aos = orc.AosList(D, prob.x, prob.xold, prob.v, prob.vold, prob.w, scattered=(D == 2))
+    Ja = prob.new_J()
+    rc2, apply2, unconv2 = aos.advance_deposit(prob.geom, orc.CC1, prob.E, prob.B, fnorm, cnormDt, rtol, itmax, Ja)
+    xa, va = aos.read()
+    aos.destroy()
+    assert rc2 == 0 and apply2 == apply_its and unconv2 == unconv
+    assert np.array_equal(xa, x) and np.array_equal(va, v)
+    for c in range(3):
+        assert np.max(np.abs(Ja[c].a - J[c].a)) <= 1e-13 * np.max(np.abs(J[c].a))
