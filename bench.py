@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--sort-every", type=int, default=4,
                     help="cell-sort period in steps (the reference never sorts a collisionless deck; the sort only "
                          "keeps the fused kernel on its fast path: measured 11.6 / 10.5 / 9.9 / 9.5 ms per step at 1/2/4/8)")
+    ap.add_argument("--sort", default="dual", choices=["dual", "cell"],
+                    help="locality sort of the collisionless step: by dual cell (pgpu_sort_for_locality, default) or by "
+                         "primal cell + quadrant (pgpu_bin_particles, what the collision step needs)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="ghost-J add-exchange between boxes: the library's peer-memory kernels (default) or "
                          "pack + NCCL send/recv + unpack-add")
@@ -220,7 +223,7 @@ class Engine:
                               interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E,
                               rtol=deck.rtol, iter_max=deck.iter_max)
             sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
-            sp.bin_particles()
+            self._sort(sp)
             self.species.append(sp)
             self.n_particles += sp.n
             del p
@@ -255,6 +258,12 @@ class Engine:
                                   for sp in self.species]
         self.migrated = 0
         self.sections, self.stream = None, stream
+
+    def _sort(self, sp):
+        if self.args.sort == "dual":
+            sp.sort_for_locality()
+        else:
+            sp.bin_particles()
 
     def _upload_fields(self, j):
         lib, capi = self.capi.load(), self.capi
@@ -326,7 +335,7 @@ class Engine:
         self.step_no += 1
         if self.args.sort_every > 0 and self.step_no % self.args.sort_every == 0:
             for sp in self.species:
-                sp.bin_particles()
+                self._sort(sp)
             self._mark("cell_sort")
 
     def sync(self):

@@ -191,6 +191,12 @@ int pgpu_set_charge_density(pgpu_species_t s, const int *stag, double *data, con
 /* cell sort + cell moments: binTheParticles (:1913-1947), set*DensityFromBinFab
  * (:2881-3047), PicSpeciesInterface::setDebyeLength (PicSpeciesInterface.cpp:1627-1721) */
 int pgpu_bin_particles(pgpu_species_t s);
+/* The engine's own locality sort for collisionless steps (no reference counterpart: PICNIC bins only for
+ * scattering): orders the particles by the cell of the half-shifted grid that the CC1 deposit of
+ * MeshInterpChargeConservingF.ChF:1517-1625 segments on, so that all particles that touch the same 21 nodes
+ * are contiguous.  Any particle order is correct; this one is the fast one for the fused advance + deposit
+ * and for the mass-matrix deposit.  Invalidates the per-cell lists of pgpu_bin_particles. */
+int pgpu_sort_for_locality(pgpu_species_t s);
 int pgpu_species_cell_index(pgpu_species_t s, int *cell /* [D][n] */);
 int pgpu_species_cell_offsets(pgpu_species_t s, long *offsets /* ncell+1 */);
 int pgpu_set_moments_from_bins(pgpu_species_t s);

@@ -12,7 +12,18 @@
  *              from /root/reference behind oracle/chombo_mock (oracle/ref_build.sh ->
  *              oracle/_ref), vectors committed in tests/golden/ref_pins.npz
  *              (tests/test_ref_pin.py).
- *   "parity unpinned": everything else (CIC/TSC/CC0/CC1 gather and deposit, the
+ *   pinned (round 2): orc_gather for CIC and TSC in 1D and 2D (all six components), the CIC gather of B and of the
+ *              out-of-plane E under CC0/CC1, the CC0 segment walk and weights in 1D and 2D and the CC1 walk and
+ *              weights in 1D -- against the reference's own C++ gathers (MeshInterp::interpolateEMfieldsToPart_testing,
+ *              MeshInterpI.H:1013-1850, compiled from /root/reference by oracle/ref_build.sh; vectors in
+ *              tests/golden/ref_pins_gather.npz; tests/test_ref_pin_gather.py): 1D CC0/CC1 in-plane E bit-equal, the
+ *              rest within 4 ulp of the stencil scale (the C++ routines order the same operations differently from
+ *              the Fortran the oracle follows).  The deposit of every shape uses the identical indices and weights
+ *              (adjointness to round-off, tests/test_oracle_invariants.py), so these pins carry over to
+ *              orc_deposit_current.  NOT pinned by them: the 2D CC1 in-plane weights (the reference's 2D C++ CC1
+ *              routine is "just a copy of _CC0 in 2D" and never dispatched) -- they rest on the pinned 1D CC1
+ *              weights, the pinned 2D CC0 walk (the same walk on the half-shifted grid) and the invariants below.
+ *   "parity unpinned": everything else (the 2D CC1 weights as said, the
  *              Picard loop, binning, moments, TA/Coulomb/Elastic pairing).  The
  *              reference ships no golden vectors for this path (SURVEY.md section
  *              4 / 8c) and those parts cannot be built here (Chombo proper, chfpp,

@@ -29,3 +29,12 @@ g++ $FLAGS -DRELATIVISTIC_PARTICLES $INC -shared -o "$HERE/_ref/libpicnic_ref_re
   "$SRC/particle_tools/JustinsParticle.cpp" \
   "$SRC/particle_tools/BinItem.cpp"
 echo "built $HERE/_ref/libpicnic_ref_rel.so"
+# the reference's C++ gathers (MeshInterpI.H:1013-1850, the NEW_EM_INTERP_METHOD path) in 1D and 2D: pins the gather
+# restatement of the oracle (tests/test_ref_pin_gather.py)
+for D in 1 2; do
+  g++ -O2 -ffp-contract=off -fPIC -std=c++17 -DCH_SPACEDIM=$D -DCH_LANG_CC -w -DREFMI_DEFINE_REALVECT_ZERO \
+    -I"$HERE/chombo_mock" -I"$SRC/particle_tools" -I"$SRC/species/pic" -I"$SRC/core" \
+    -shared -o "$HERE/_ref/libpicnic_ref_mi${D}d.so" \
+    "$HERE/ref_meshinterp.cpp" "$SRC/particle_tools/JustinsParticle.cpp" "$SRC/particle_tools/BinItem.cpp"
+  echo "built $HERE/_ref/libpicnic_ref_mi${D}d.so"
+done

@@ -97,7 +97,7 @@ def load():
         "pgpu_advance_particles": [vp, dbl], "pgpu_advance_particles_iteratively": [vp, dbl, i32, vp],
         "pgpu_set_current_density": [vp, dbl, i32], "pgpu_species_current_get": [vp, i32, vp, vp, vp],
         "pgpu_set_charge_density": [vp, vp, vp, vp, vp],
-        "pgpu_bin_particles": [vp], "pgpu_species_cell_index": [vp, vp],
+        "pgpu_bin_particles": [vp], "pgpu_sort_for_locality": [vp], "pgpu_species_cell_index": [vp, vp],
         "pgpu_species_cell_offsets": [vp, vp], "pgpu_set_moments_from_bins": [vp],
         "pgpu_species_moments_get": [vp, vp, vp, vp], "pgpu_debye_length": [vp, vp, i32, vp],
         "pgpu_apply_bcs": [vp, vp, vp], "pgpu_finish_implicit_step": [vp, vp, vp], "pgpu_stable_dt": [vp, vp], "pgpu_global_moments": [vp, vp],
@@ -371,6 +371,9 @@ class Species:
 
     def bin_particles(self):
         check(load().pgpu_bin_particles(self.h))
+
+    def sort_for_locality(self):
+        check(load().pgpu_sort_for_locality(self.h))
 
     def cell_index(self):
         out = np.zeros((self.D, self.n), dtype=np.int32)

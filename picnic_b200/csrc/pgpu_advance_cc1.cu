@@ -665,8 +665,12 @@ struct TabWindow {
 struct DualRec {
   unsigned key;
   double2 x01, x23, x45, y01, y23, y45, z01, z23;
+  // NODECACHE: the node records of the last (dual cell, half-cell of xbar) this thread gathered from
+  unsigned nkey, nsel;
+  double2 ez01, ez23, bx01, bx23, by01, by23;
 };
 
+template <bool NODECACHE>
 __device__ __forceinline__ bool push_tab(const FastArgs &A, const TabWindow &Wn, DualRec &R, const double (&xo)[2],
                                          double (&xb)[2], const double (&uo)[3], double (&ub)[3],
                                          unsigned &key, double (&dO)[2], double (&dB)[2], unsigned &apply,
@@ -750,9 +754,22 @@ __device__ __forceinline__ bool push_tab(const FastArgs &A, const TabWindow &Wn,
       const bool sx = del0 >= 0.5, sy = del1 >= 0.5;
       const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
       const int ox = sx ? TN : 0, oy = sy ? nrow : 0;
-      const double2 ez01 = ld2(tn + ox + oy), ez23 = ld2(tn + ox + oy + 2);
-      const double2 bx01 = ld2(tn + ox + 4), bx23 = ld2(tn + ox + 6);
-      const double2 by01 = ld2(tn + oy + 8), by23 = ld2(tn + oy + 10);
+      double2 ez01, ez23, bx01, bx23, by01, by23;
+      if (NODECACHE) {
+        const unsigned sel = (sx ? 1u : 0u) | (sy ? 2u : 0u);
+        if (R.nkey != key || R.nsel != sel) {
+          R.nkey = key;
+          R.nsel = sel;
+          R.ez01 = ld2(tn + ox + oy), R.ez23 = ld2(tn + ox + oy + 2);
+          R.bx01 = ld2(tn + ox + 4), R.bx23 = ld2(tn + ox + 6);
+          R.by01 = ld2(tn + oy + 8), R.by23 = ld2(tn + oy + 10);
+        }
+        ez01 = R.ez01, ez23 = R.ez23, bx01 = R.bx01, bx23 = R.bx23, by01 = R.by01, by23 = R.by23;
+      } else {
+        ez01 = ld2(tn + ox + oy), ez23 = ld2(tn + ox + oy + 2);
+        bx01 = ld2(tn + ox + 4), bx23 = ld2(tn + ox + 6);
+        by01 = ld2(tn + oy + 8), by23 = ld2(tn + oy + 10);
+      }
       E[2] = fma(fy, fma(fx, ez23.y, ez23.x), fma(fx, ez01.y, ez01.x));
       B[0] = fma(del1, fma(fx, bx23.y, bx23.x), fma(fx, bx01.y, bx01.x));
       B[1] = fma(fy, fma(del0, by23.y, by23.x), fma(del0, by01.y, by01.x));
@@ -1041,6 +1058,14 @@ constexpr int NTAB = 8;    // xo0->dO0 xo1->dO1 xb0 xb1 u0 u1 u2 w
 constexpr int WMAX = 16;   // widest dual-cell window staged in shared memory (2 rows; node records: 3 rows, +1 column)
 constexpr int DROW = WMAX * TD + 8;   // doubles between the two rows of the staged dual records
 constexpr int SDUAL = 2 * DROW, SNODE = 3 * (WMAX + 1) * TN;
+// the same storage as a window of THREE dual rows (four node rows) of up to W3 columns: tiles of particles sorted by
+// dual cell (pgpu_sort_for_locality) sit in one dual row, and the rows above and below catch the particles that
+// drifted since the sort
+constexpr int W3 = 10;
+constexpr int DROW3 = W3 * TD + 8, NROW3 = (W3 + 1) * TN;
+static_assert(3 * DROW3 <= SDUAL && 4 * NROW3 <= SNODE, "three-row window does not fit");
+__device__ __forceinline__ int win_drow(int rows) { return rows == 3 ? DROW3 : DROW; }
+__device__ __forceinline__ int win_nstride(int rows) { return rows == 3 ? NROW3 : (WMAX + 1) * TN; }
 constexpr size_t TAB_SMEM =
     (size_t)(NTAB * TILE + SDUAL + SNODE) * sizeof(double) + TILE * sizeof(unsigned) + 64;
 
@@ -1062,6 +1087,26 @@ __global__ void k_tile_boxes(const FastArgs A, int ntiles, int4 *box) {
       c[e][d] = __double2int_rd(__ddiv_rn(__dsub_rn(A.xo[d][p], A.le[d]), A.dx[d]));
   }
   int4 b = make_int4(0, 0, 0, 0);
+  // dual cells of the first and last particle: floor((x - le - dx/2)/dx)
+  int dc[2][2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const long p = e ? last : first;
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+      dc[e][d] = __double2int_rd(__ddiv_rn(__dsub_rn(__dsub_rn(A.xo[d][p], A.le[d]), A.hdx[d]), A.dx[d]));
+  }
+  if (dc[0][1] == dc[1][1] && dc[1][0] >= dc[0][0] && dc[1][0] - dc[0][0] + 3 <= W3) {
+    // one dual row (tile sorted by dual cell, or a stretch of one half-row of primal cells): three rows, +-1 column
+    const int i0 = max(dc[0][0] - 1, A.i_lo[0]), i1 = min(dc[1][0] + 1, A.i_hi[0]);
+    const int j0 = max(dc[0][1] - 1, A.i_lo[1]), j1 = min(dc[0][1] + 1, A.i_hi[1]);
+    if (i1 >= i0 && j1 >= j0) b = make_int4(i0, j0, i1 - i0 + 1, j1 - j0 + 1);
+    if (b.w == 3 || b.z == 0) {
+      box[t] = b;
+      return;
+    }
+    b = make_int4(0, 0, 0, 0);   // clipped to fewer rows at the table edge: the two-row layout below handles it
+  }
   if (c[0][1] == c[1][1] && c[1][0] >= c[0][0]) {
     // dual columns i-1 .. i_last, dual rows j-1 .. j, clipped to the table
     const int i0 = max(c[0][0] - 1, A.i_lo[0]), i1 = min(c[1][0], A.i_hi[0]);
@@ -1071,7 +1116,7 @@ __global__ void k_tile_boxes(const FastArgs A, int ntiles, int4 *box) {
   box[t] = b;
 }
 
-template <bool DEP, int RSTEPS, int MINB, bool PAIR>
+template <bool DEP, int RSTEPS, int MINB, bool PAIR, bool NODECACHE = false, bool ALIAS = false>
 __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastArgs A, int ntiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *st = reinterpret_cast<double *>(smem_raw);                 // [NTAB][TILE]
@@ -1123,8 +1168,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
         bulk_g2s(st + 0 * TILE, A.xo[0] + tbase, BYTES, bar);
         bulk_g2s(st + 1 * TILE, A.xo[1] + tbase, BYTES, bar);
       } else if (wp == 1) {
-        bulk_g2s(st + 2 * TILE, A.xb[0] + tbase, BYTES, bar);
-        bulk_g2s(st + 3 * TILE, A.xb[1] + tbase, BYTES, bar);
+        if (!ALIAS) {   // first evaluation of a step: xbar == x_old, nothing to load
+          bulk_g2s(st + 2 * TILE, A.xb[0] + tbase, BYTES, bar);
+          bulk_g2s(st + 3 * TILE, A.xb[1] + tbase, BYTES, bar);
+        }
       } else if (wp == 2) {
         bulk_g2s(st + 4 * TILE, A.uo[0] + tbase, BYTES, bar);
         bulk_g2s(st + 5 * TILE, A.uo[1] + tbase, BYTES, bar);
@@ -1142,7 +1189,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
         sbox = box;
         if (box.z) {
           for (int r = 0; r < box.w; ++r)
-            bulk_g2s(sdual + r * DROW, A.tdual + (cw0 + (size_t)r * A.tn0) * TD, dbytes, bar);
+            bulk_g2s(sdual + r * win_drow(box.w), A.tdual + (cw0 + (size_t)r * A.tn0) * TD, dbytes, bar);
+          if (box.w == 3)   // fourth node row of the three-row window (warps 1..3 load node rows 0..2)
+            bulk_g2s(snode + 3 * win_nstride(3), A.tnode + (cw0 + (size_t)3 * A.tn0) * TN, nbytes, bar);
         }
         // the one arrival of the phase, posted after this thread's copies (a copy that completes first only
         // drives the transaction count negative for a while; the phase cannot end before this arrival)
@@ -1150,12 +1199,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
 #if PGPU_TAB_LDGSTS
         mbar_expect_tx(bar, tabbytes);
 #else
-        mbar_expect_tx(bar, NIN * TILE * (unsigned)sizeof(double) + tabbytes);
+        mbar_expect_tx(bar, (ALIAS ? NIN - 2 : NIN) * TILE * (unsigned)sizeof(double) + tabbytes);
 #endif
       } else {
         const int r = wp - 1;   // node-record row of the window
-        if (box.z && r <= box.w)
-          bulk_g2s(snode + r * ((WMAX + 1) * TN), A.tnode + (cw0 + (size_t)r * A.tn0) * TN, nbytes, bar);
+        if (box.z && r <= box.w && r < 3)
+          bulk_g2s(snode + r * win_nstride(box.w), A.tnode + (cw0 + (size_t)r * A.tn0) * TN, nbytes, bar);
       }
       if (tid == 0) CK(7);
       if (tile + (int)gridDim.x < ntiles) {
@@ -1201,14 +1250,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
       Wn.j = box.y;
       Wn.ncol = box.z;
       Wn.nrow = box.w;
-      Wn.drow = DROW;
-      Wn.nrow_stride = (WMAX + 1) * TN;
+      Wn.drow = win_drow(box.w);
+      Wn.nrow_stride = win_nstride(box.w);
     }
 
     // ---- phase 1: push ------------------------------------------------------------------
     unsigned defer_mask = 0;
     DualRec R;
-    R.key = NOKEY;   // the window is restaged per tile, so the cached record does not outlive it
+    R.key = R.nkey = NOKEY;   // the window is restaged per tile, so the cached records do not outlive it
+    R.nsel = 0;
     (void)R;
     if (PAIR) {
 #pragma unroll 1
@@ -1268,10 +1318,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
         unsigned key = NOKEY;
         if (k < nvalid) {
           const double xo[2] = {st[0 * TILE + k], st[1 * TILE + k]};
-          double xb[2] = {st[2 * TILE + k], st[3 * TILE + k]};
+          double xb[2];
+          if (ALIAS) {
+            xb[0] = xo[0];
+            xb[1] = xo[1];
+          } else {
+            xb[0] = st[2 * TILE + k];
+            xb[1] = st[3 * TILE + k];
+          }
           const double uo[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
           double ub[3] = {0.0, 0.0, 0.0}, dO[2], dB[2];
-          if (push_tab(A, Wn, R, xo, xb, uo, ub, key, dO, dB, apply, unconv)) {
+          if (push_tab<NODECACHE>(A, Wn, R, xo, xb, uo, ub, key, dO, dB, apply, unconv)) {
             st[0 * TILE + k] = dO[0];
             st[1 * TILE + k] = dO[1];
             st[2 * TILE + k] = xb[0];
@@ -1282,6 +1339,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
           } else {
             // deferred: xbar stays as stored (the generic kernel restarts from it); the ubar slot
             // keeps u_old, which that kernel overwrites
+            if (ALIAS) {
+              st[2 * TILE + k] = xo[0];
+              st[3 * TILE + k] = xo[1];
+            }
             key = NOKEY;
             defer_mask |= 1u << q;
           }
@@ -1392,6 +1453,386 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_tab(const FastAr
            blockIdx.x, it, ck[0] / it, (ck[6] + ck[7] + ck[1]) / it, ck[6] / it, ck[7] / it, ck[2] / it, ck[3] / it, ck[4] / it,
            ck[5] / it);
 #endif
+
+  apply = __reduce_add_sync(0xffffffffu, apply);
+  unconv = __reduce_add_sync(0xffffffffu, unconv);
+  if (lane == 0) {
+    if (apply) atomicAdd(&A.cnt->apply_its, (unsigned long long)apply);
+    if (unconv) atomicAdd(&A.cnt->unconverged, (unsigned long long)unconv);
+  }
+}
+
+
+// =============================================================================================
+// v2 of the table-driven tile kernel (round 2).  ncu of v1 put the shared-memory data pipe at 66 % of its
+// peak (above the fp64 pipe, 43 %, and the issue slots, 57 %): with v1's map of four CONSECUTIVE particles
+// per thread a warp's 32 lanes sit in five or six different dual cells at any time, so every 128-bit table
+// load is replayed ~3 times, and a third of the RED instructions run with one or two active lanes.
+//   * Phase 1 (push) maps LANES to consecutive particles (particle = warp base + 32 r + lane): the lanes of
+//     a warp then sit in one to three dual cells, the table loads are near-broadcasts, and every access to
+//     the particle tile is a conflict-free 64-bit access.  The per-thread record cache of v1 is gone (its
+//     hit rate would be nil with this map) and with it 32 registers.
+//   * Phase 2 (deposit) keeps v1's map (four consecutive particles per thread: the register accumulators
+//     need runs of equal keys per THREAD).  A warp only ever touches its own 128 particles of the tile, so
+//     the phases are separated by __syncwarp(), not by a block barrier.
+//   * ALIAS: the first evaluation of a step has xbar == x_old (updateOldParticlePositions recorded as an
+//     alias): the two xbar arrays are then not loaded at all (-16 B per particle of HBM traffic).
+// =============================================================================================
+template <bool REC_PER_PASS>
+__device__ __forceinline__ bool push_v2(const FastArgs &A, const TabWindow &Wn, const double (&xo)[2], double (&xb)[2],
+                                        const double (&uo)[3], double (&ub)[3], unsigned &key, double (&dO)[2],
+                                        unsigned &apply, unsigned &unconv) {
+  int i0[2];
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double xr = __dsub_rn(xo[d], A.le[d]);
+    i0[d] = floor_div_fast(__dsub_rn(xr, A.hdx[d]), A.dx[d], A.rdx[d]);
+    dO[d] = fma(xr, A.rdx[d], -(double)(i0[d] + 1));
+    if (i0[d] < A.i_lo[d] || i0[d] > A.i_hi[d]) ok = false;
+  }
+  if (!ok) return false;
+  key = ((unsigned)(i0[1] + 32768) << 16) | (unsigned)(i0[0] + 32768);
+  const double *td, *tn;
+  int nrow;
+  {
+    const unsigned wi = (unsigned)(i0[0] - Wn.i), wj = (unsigned)(i0[1] - Wn.j);
+    if (wi < (unsigned)Wn.ncol && wj < (unsigned)Wn.nrow) {
+      td = Wn.dual + (wi * TD + wj * Wn.drow);
+      tn = Wn.node + (wi * TN + wj * Wn.nrow_stride);
+      nrow = Wn.nrow_stride;
+    } else {
+      const int cidx = (i0[0] - A.tlo[0]) + (i0[1] - A.tlo[1]) * A.tn0;
+      td = A.tdual + (size_t)cidx * TD;
+      tn = A.tnode + (size_t)cidx * TN;
+      nrow = A.tn0 * TN;
+    }
+  }
+  double2 x01, x23, x45, y01, y23, y45, z01, z23;
+  if (!REC_PER_PASS) {
+    x01 = ld2(td), x23 = ld2(td + 2), x45 = ld2(td + 4);       // Ex: e1 d1 | P0 Q0 | P2 Q2
+    y01 = ld2(td + 6), y23 = ld2(td + 8), y45 = ld2(td + 10);   // Ey
+    z01 = ld2(td + 12), z23 = ld2(td + 14);                      // Bz c0 c1 | c2 c3
+  }
+  double pO[2][2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double a = 0.5 - dO[d], b = 0.5 + dO[d];
+    pO[d][0] = a * a;
+    pO[d][1] = b * b;
+  }
+
+  int iter = 0;
+  bool done = false;
+  unsigned napply = 0, nunconv = 0;
+  while (true) {
+    double dxp0[2], dB[2], dN[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      dxp0[d] = xb[d] - xo[d];
+      dB[d] = fma(dxp0[d], A.rdx[d], dO[d]);
+      dN[d] = fma(2.0, dB[d], -dO[d]);
+    }
+    if (!(hi_abs(dN[0]) < HI_HALF_BAND && hi_abs(dN[1]) < HI_HALF_BAND)) {
+      // near (or past) a dual-cell face: the reference's own floor decides
+      bool same = true;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const double xn = fma(2.0, xb[d], -xo[d]);
+        const int in = floor_div_exact(__dsub_rn(__dsub_rn(xn, A.le[d]), A.hdx[d]), A.dx[d]);
+        if (in != i0[d]) same = false;
+      }
+      if (!same) return false;
+    }
+    if (done) break;
+    if (REC_PER_PASS) {
+      asm volatile("" ::: "memory");   // keep the record loads inside the pass
+      x01 = ld2(td), x23 = ld2(td + 2), x45 = ld2(td + 4);
+      y01 = ld2(td + 6), y23 = ld2(td + 8), y45 = ld2(td + 10);
+      z01 = ld2(td + 12), z23 = ld2(td + 14);
+    }
+    const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
+    double E[3], B[3];
+    {
+      const double a0 = 0.5 - dN[0], b0 = 0.5 + dN[0], a1 = 0.5 - dN[1], b1 = 0.5 + dN[1];
+      const double Wx0 = fma(a0, a0, pO[0][0]), Wx2 = fma(b0, b0, pO[0][1]);   // 4 W
+      const double Wy0 = fma(a1, a1, pO[1][0]), Wy2 = fma(b1, b1, pO[1][1]);
+      E[0] = fma(Wy0, fma(del0, x23.y, x23.x), fma(Wy2, fma(del0, x45.y, x45.x), fma(del0, x01.y, x01.x)));
+      E[1] = fma(Wx0, fma(del1, y23.y, y23.x), fma(Wx2, fma(del1, y45.y, y45.x), fma(del1, y01.y, y01.x)));
+    }
+    {
+      // nodal CIC at xbar: node pair (i0+s, i0+s+1), fraction f
+      const bool sx = del0 >= 0.5, sy = del1 >= 0.5;
+      const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
+      const int ox = sx ? TN : 0, oy = sy ? nrow : 0;
+      const double2 ez01 = ld2(tn + ox + oy), ez23 = ld2(tn + ox + oy + 2);
+      const double2 bx01 = ld2(tn + ox + 4), bx23 = ld2(tn + ox + 6);
+      const double2 by01 = ld2(tn + oy + 8), by23 = ld2(tn + oy + 10);
+      E[2] = fma(fy, fma(fx, ez23.y, ez23.x), fma(fx, ez01.y, ez01.x));
+      B[0] = fma(del1, fma(fx, bx23.y, bx23.x), fma(fx, bx01.y, bx01.x));
+      B[1] = fma(fy, fma(del0, by23.y, by23.x), fma(del0, by01.y, by01.x));
+      B[2] = fma(del1, fma(del0, z23.y, z23.x), fma(del0, z01.y, z01.x));
+    }
+    // Boris half step (PicSpeciesUtils.cpp:8-101)
+    {
+      const double vm0 = fma(A.alpha, E[0], uo[0]), vm1 = fma(A.alpha, E[1], uo[1]),
+                   vm2 = fma(A.alpha, E[2], uo[2]);
+      const double b0 = A.alpha * B[0], b1 = A.alpha * B[1], b2 = A.alpha * B[2];
+      const double den = fma(b2, b2, fma(b1, b1, fma(b0, b0, 1.0)));
+      const double p0 = fma(-vm2, b1, fma(vm1, b2, vm0));
+      const double p1 = fma(-vm0, b2, fma(vm2, b0, vm1));
+      const double p2 = fma(-vm1, b0, fma(vm0, b1, vm2));
+      const double rden = rcp_ge1(den);
+      const double r0 = b0 * rden, r1 = b1 * rden, r2 = b2 * rden;
+      ub[0] = fma(-p2, r1, fma(p1, r2, vm0));
+      ub[1] = fma(-p0, r2, fma(p2, r0, vm1));
+      ub[2] = fma(-p1, r0, fma(p0, r1, vm2));
+    }
+    napply += 1;
+    if (A.iter_max < 0) {  // advanceParticles (:1594-1612), part_order_swap == false
+      xb[0] = fma(ub[0], A.hdt, xo[0]);
+      xb[1] = fma(ub[1], A.hdt, xo[1]);
+      done = true;
+      continue;
+    }
+    // stepNormTransfer (:658-733): |dxp0 - dxp| / dX against rtol, as |dxp0 - dxp| against rtol*dX
+    const double dxp_0 = ub[0] * A.hdt, dxp_1 = ub[1] * A.hdt;
+    const double e0 = fabs(dxp0[0] - dxp_0), e1 = fabs(dxp0[1] - dxp_1);
+    if (iter == 0) {
+      xb[0] = xo[0] + dxp_0;
+      xb[1] = xo[1] + dxp_1;
+      if (!(e0 >= A.tol[0]) && !(e1 >= A.tol[1])) done = true;
+    } else {
+      if (e0 < A.tol[0] && e1 < A.tol[1]) break;  // reverse pass: xbar unchanged, its orbit was checked above
+      xb[0] = xo[0] + dxp_0;
+      xb[1] = xo[1] + dxp_1;
+    }
+    if (!done && iter >= A.iter_max) {
+      nunconv = 1;
+      done = true;
+    }
+    iter += 1;
+  }
+  apply += napply;
+  unconv += nunconv;
+  return true;
+}
+
+template <bool DEP, int RSTEPS, int MINB, bool ALIAS, bool REC_PER_PASS>
+__global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_v2(const FastArgs A, int ntiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *st = reinterpret_cast<double *>(smem_raw);                 // [NTAB][TILE]
+  double *sdual = st + NTAB * TILE;                                   // [2][WMAX][TD]
+  double *snode = sdual + SDUAL;                                      // [3][WMAX+1][TN]
+  unsigned *skey = reinterpret_cast<unsigned *>(snode + SNODE);      // [TILE]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(skey + TILE);
+  __shared__ int4 sbox;
+  const int tid = threadIdx.x, lane = tid & 31, wbase = (tid >> 5) * (32 * TP);
+  constexpr unsigned NLOAD = ALIAS ? NIN - 2 : NIN;
+
+  int nbx = 0, nby = 0, nbz = 0, nbw = 0;
+  auto fetch_box = [&](int t) {
+    const int4 b = __ldg(A.tile_box + t);
+    nbx = b.x;
+    nby = b.y;
+    nbz = b.z;
+    nbw = b.w;
+  };
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (lane == 0 && (int)blockIdx.x < ntiles) fetch_box(blockIdx.x);
+  __syncthreads();
+
+  unsigned apply = 0, unconv = 0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const long tbase = (long)tile * TILE;
+    if (lane == 0) {
+      const int wp = tid >> 5;
+      if (wp) bulk_wait_read0();   // this thread's stores of the previous tile have read their buffers
+      constexpr unsigned BYTES = TILE * (unsigned)sizeof(double);
+      if (wp == 0) {
+        bulk_g2s(st + 0 * TILE, A.xo[0] + tbase, BYTES, bar);
+        bulk_g2s(st + 1 * TILE, A.xo[1] + tbase, BYTES, bar);
+      } else if (wp == 1) {
+        if (!ALIAS) {
+          bulk_g2s(st + 2 * TILE, A.xb[0] + tbase, BYTES, bar);
+          bulk_g2s(st + 3 * TILE, A.xb[1] + tbase, BYTES, bar);
+        }
+      } else if (wp == 2) {
+        bulk_g2s(st + 4 * TILE, A.uo[0] + tbase, BYTES, bar);
+        bulk_g2s(st + 5 * TILE, A.uo[1] + tbase, BYTES, bar);
+      } else {
+        bulk_g2s(st + 6 * TILE, A.uo[2] + tbase, BYTES, bar);
+        bulk_g2s(st + 7 * TILE, A.w + tbase, BYTES, bar);
+      }
+      const int4 box = make_int4(nbx, nby, nbz, nbw);
+      const unsigned dbytes = (unsigned)box.z * TD * (unsigned)sizeof(double);
+      const unsigned nbytes = (unsigned)(box.z + 1) * TN * (unsigned)sizeof(double);
+      const size_t cw0 = (size_t)(box.x - A.tlo[0]) + (size_t)(box.y - A.tlo[1]) * A.tn0;
+      if (wp == 0) {
+        sbox = box;
+        if (box.z) {
+          for (int r = 0; r < box.w; ++r)
+            bulk_g2s(sdual + r * win_drow(box.w), A.tdual + (cw0 + (size_t)r * A.tn0) * TD, dbytes, bar);
+          if (box.w == 3)   // fourth node row of the three-row window (warps 1..3 load node rows 0..2)
+            bulk_g2s(snode + 3 * win_nstride(3), A.tnode + (cw0 + (size_t)3 * A.tn0) * TN, nbytes, bar);
+        }
+        const unsigned tabbytes = box.z ? box.w * dbytes + (box.w + 1) * nbytes : 0u;
+        mbar_expect_tx(bar, NLOAD * TILE * (unsigned)sizeof(double) + tabbytes);
+      } else {
+        const int r = wp - 1;   // node-record row of the window
+        if (box.z && r <= box.w && r < 3)
+          bulk_g2s(snode + r * win_nstride(box.w), A.tnode + (cw0 + (size_t)r * A.tn0) * TN, nbytes, bar);
+      }
+      if (tile + (int)gridDim.x < ntiles) fetch_box(tile + gridDim.x);
+    }
+    __syncthreads();       // sbox written (and the previous tile's shared-memory reads are over)
+    mbar_wait(bar, (unsigned)(it & 1));
+    const int nvalid = (A.n - tbase) < TILE ? (int)(A.n - tbase) : TILE;
+    TabWindow Wn;
+    {
+      const int4 box = sbox;
+      Wn.dual = sdual;
+      Wn.node = snode;
+      Wn.i = box.x;
+      Wn.j = box.y;
+      Wn.ncol = box.z;
+      Wn.nrow = box.w;
+      Wn.drow = win_drow(box.w);
+      Wn.nrow_stride = win_nstride(box.w);
+    }
+
+    // ---- phase 1: push; lane <-> consecutive particles ---------------------------------------
+    unsigned defer_mask = 0;
+#pragma unroll 1
+    for (int r = 0; r < TP; ++r) {
+      const int k = wbase + 32 * r + lane;
+      unsigned key = NOKEY;
+      if (k < nvalid) {
+        const double xo[2] = {st[0 * TILE + k], st[1 * TILE + k]};
+        double xb[2];
+        if (ALIAS) {
+          xb[0] = xo[0];
+          xb[1] = xo[1];
+        } else {
+          xb[0] = st[2 * TILE + k];
+          xb[1] = st[3 * TILE + k];
+        }
+        const double uo[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
+        double ub[3] = {0.0, 0.0, 0.0}, dO[2];
+        if (push_v2<REC_PER_PASS>(A, Wn, xo, xb, uo, ub, key, dO, apply, unconv)) {
+          st[0 * TILE + k] = dO[0];
+          st[1 * TILE + k] = dO[1];
+          st[2 * TILE + k] = xb[0];
+          st[3 * TILE + k] = xb[1];
+          st[4 * TILE + k] = ub[0];
+          st[5 * TILE + k] = ub[1];
+          st[6 * TILE + k] = ub[2];
+        } else {
+          // deferred: xbar stays as stored (the generic kernel restarts from it); the ubar slot keeps
+          // u_old, which that kernel overwrites
+          if (ALIAS) {
+            st[2 * TILE + k] = xo[0];
+            st[3 * TILE + k] = xo[1];
+          }
+          key = NOKEY;
+          defer_mask |= 1u << r;
+        }
+      }
+      skey[k] = key;
+    }
+    __syncwarp();
+
+    // ---- phase 2: deposit; thread <-> four consecutive particles of its own warp -------------
+    if (DEP) {
+      unsigned acc_key = NOKEY;
+      double acc[NSLOT];
+#pragma unroll
+      for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
+#pragma unroll 1
+      for (int qq = 0; qq < TP; ++qq) {
+        const int q = (qq + (lane >> 2)) & (TP - 1);
+        const int k = tid * TP + q;
+        const unsigned key = skey[k];
+        if (key == NOKEY) continue;
+        if (key != acc_key) {
+          if (acc_key != NOKEY) {
+            flush_direct(A, acc_key, acc);
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
+          }
+          acc_key = key;
+        }
+        const double dO[2] = {st[0 * TILE + k], st[1 * TILE + k]};
+        const double dB[2] = {
+            fma(st[2 * TILE + k] - A.le[0], A.rdx[0], -(double)((int)(key & 0xffffu) - 32767)),
+            fma(st[3 * TILE + k] - A.le[1], A.rdx[1], -(double)((int)(key >> 16) - 32767))};
+        const double ub[3] = {st[4 * TILE + k], st[5 * TILE + k], st[6 * TILE + k]};
+        deposit_tab(A, dO, dB, ub, st[7 * TILE + k], acc);
+      }
+      const unsigned any = __ballot_sync(0xffffffffu, acc_key != NOKEY);
+      if (any) {
+        const unsigned prev = __shfl_up_sync(0xffffffffu, acc_key, 1);
+        const bool head = (lane == 0) || (prev != acc_key);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const unsigned above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+        const int run_end = above ? (__ffs(above) - 1) : 32;
+        const int run_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+        for (int sidx = 0; sidx < RSTEPS; ++sidx) {
+          const int off = 1 << sidx;
+          const double take = (lane + off < run_end) ? 1.0 : 0.0;
+#pragma unroll
+          for (int j = 0; j < NSLOT; ++j) acc[j] = fma(__shfl_down_sync(0xffffffffu, acc[j], off), take, acc[j]);
+        }
+        if (acc_key != NOKEY && (((lane - run_start) & ((1 << RSTEPS) - 1)) == 0)) flush_direct(A, acc_key, acc);
+      }
+    }
+
+    // ---- results -> global ----------------------------------------------------------------
+    if (nvalid == TILE) {
+      fence_proxy_async();
+      __syncthreads();
+      if (lane == 0 && tid) {
+        constexpr unsigned BYTES = TILE * (unsigned)sizeof(double);
+        const int wp = tid >> 5;
+        if (wp == 1) {
+          bulk_s2g(A.xbo[0] + tbase, st + 2 * TILE, BYTES);
+          bulk_s2g(A.xbo[1] + tbase, st + 3 * TILE, BYTES);
+        } else if (wp == 2) {
+          bulk_s2g(A.ub[0] + tbase, st + 4 * TILE, BYTES);
+          bulk_s2g(A.ub[1] + tbase, st + 5 * TILE, BYTES);
+        } else {
+          bulk_s2g(A.ub[2] + tbase, st + 6 * TILE, BYTES);
+        }
+        bulk_commit();
+      }
+    } else {
+      __syncthreads();
+#pragma unroll 1
+      for (int q = 0; q < TP; ++q) {
+        const int k = tid * TP + q;
+        if (k < nvalid) {
+          A.xbo[0][tbase + k] = st[2 * TILE + k];
+          A.xbo[1][tbase + k] = st[3 * TILE + k];
+          A.ub[0][tbase + k] = st[4 * TILE + k];
+          A.ub[1][tbase + k] = st[5 * TILE + k];
+          A.ub[2][tbase + k] = st[6 * TILE + k];
+        }
+      }
+      __syncthreads();
+    }
+    if (defer_mask) {
+      unsigned slot = atomicAdd(A.list_count, (unsigned)__popc(defer_mask));
+#pragma unroll
+      for (int r = 0; r < TP; ++r)
+        if (defer_mask & (1u << r)) A.list[slot++] = (int)(tbase + wbase + 32 * r + lane);
+    }
+  }
+  if (lane == 0 && tid) bulk_wait0();
 
   apply = __reduce_add_sync(0xffffffffu, apply);
   unconv = __reduce_add_sync(0xffffffffu, unconv);
@@ -1540,10 +1981,45 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   do {                                                                                                    \
     PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tab<DEPV, RS, MB, PR>,                                \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM));        \
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tab<DEPV, RS, MB, PR>,                                \
+                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));                \
     k_advance_cc1_2d_tab<DEPV, RS, MB, PR><<<gridm, BLOCK, TAB_SMEM, c.stream>>>(A, ntiles);              \
   } while (0)
     const int mb = c.cc1_minblocks == 5 ? 5 : (c.cc1_minblocks == 3 ? 3 : 4);
     const int gridm = std::min(ntiles, c.sm_count * mb * c.cc1_waves);
+    if (c.cc1_version >= 2) {
+#define PGPU_V2_LAUNCH(DEPV, RS, MB, AL, RP)                                                              \
+  do {                                                                                                    \
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_v2<DEPV, RS, MB, AL, RP>,                             \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM));        \
+    /* the driver's default carve-out (196 KB) holds four 45.7 KB blocks; five need the full 228 KB */   \
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_v2<DEPV, RS, MB, AL, RP>,                             \
+                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));                \
+    k_advance_cc1_2d_v2<DEPV, RS, MB, AL, RP><<<gridm, BLOCK, TAB_SMEM, c.stream>>>(A, ntiles);           \
+  } while (0)
+#define PGPU_V2_PICK(DEPV, RS)                                                                            \
+  do {                                                                                                    \
+    const int sel = (mb == 5 ? 4 : 0) | (xa ? 2 : 0) | (c.cc1_rec_per_pass ? 1 : 0);                      \
+    switch (sel) {                                                                                        \
+      case 0: PGPU_V2_LAUNCH(DEPV, RS, 4, false, false); break;                                           \
+      case 1: PGPU_V2_LAUNCH(DEPV, RS, 4, false, true); break;                                            \
+      case 2: PGPU_V2_LAUNCH(DEPV, RS, 4, true, false); break;                                            \
+      case 3: PGPU_V2_LAUNCH(DEPV, RS, 4, true, true); break;                                             \
+      case 4: PGPU_V2_LAUNCH(DEPV, RS, 5, false, false); break;                                           \
+      case 5: PGPU_V2_LAUNCH(DEPV, RS, 5, false, true); break;                                            \
+      case 6: PGPU_V2_LAUNCH(DEPV, RS, 5, true, false); break;                                            \
+      default: PGPU_V2_LAUNCH(DEPV, RS, 5, true, true); break;                                            \
+    }                                                                                                     \
+  } while (0)
+      if (deposit) PGPU_V2_PICK(true, 3);
+      else PGPU_V2_PICK(false, 0);
+      if (xa)
+        for (int d = 0; d < 2; ++d) std::swap(s->x[d], s->xold[d]);
+      if (va)
+        for (int k = 0; k < 3; ++k) std::swap(s->v[k], s->vold[k]);
+      s->xold_alias = s->vold_alias = false;
+      return 1;
+    }
     if (c.cc1_pair) {
       // two particles of a dual cell in lockstep through the Picard loop (PGPU_CC1_PAIR=1)
       if (!deposit) {
@@ -1559,6 +2035,30 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
     } else if (c.cc1_rsteps <= 2) {
       if (mb == 4) PGPU_TAB_LAUNCH(true, 2, 4, false);
       else PGPU_TAB_LAUNCH(true, 2, 5, false);
+    } else if (c.cc1_nodecache || xa) {
+#define PGPU_TAB_LAUNCH6(MB, NC, AL)                                                                      \
+  do {                                                                                                    \
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tab<true, 3, MB, false, NC, AL>,                      \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM));        \
+    PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tab<true, 3, MB, false, NC, AL>,                      \
+                                   cudaFuncAttributePreferredSharedMemoryCarveout, 100));                \
+    k_advance_cc1_2d_tab<true, 3, MB, false, NC, AL><<<gridm, BLOCK, TAB_SMEM, c.stream>>>(A, ntiles);    \
+  } while (0)
+      const int sel = (mb == 3 ? 0 : (mb == 4 ? 4 : 8)) | (c.cc1_nodecache ? 2 : 0) | (xa ? 1 : 0);
+      switch (sel) {
+        case 0: PGPU_TAB_LAUNCH6(3, false, false); break;
+        case 1: PGPU_TAB_LAUNCH6(3, false, true); break;
+        case 2: PGPU_TAB_LAUNCH6(3, true, false); break;
+        case 3: PGPU_TAB_LAUNCH6(3, true, true); break;
+        case 4: PGPU_TAB_LAUNCH6(4, false, false); break;
+        case 5: PGPU_TAB_LAUNCH6(4, false, true); break;
+        case 6: PGPU_TAB_LAUNCH6(4, true, false); break;
+        case 7: PGPU_TAB_LAUNCH6(4, true, true); break;
+        case 8: PGPU_TAB_LAUNCH6(5, false, false); break;
+        case 9: PGPU_TAB_LAUNCH6(5, false, true); break;
+        case 10: PGPU_TAB_LAUNCH6(5, true, false); break;
+        default: PGPU_TAB_LAUNCH6(5, true, true); break;
+      }
     } else {
       if (mb == 4) PGPU_TAB_LAUNCH(true, 3, 4, false);
       else if (mb == 3) PGPU_TAB_LAUNCH(true, 3, 3, false);

@@ -420,6 +420,9 @@ int pgpu_init(int device) {
   if (const char *e = getenv("PGPU_CC1_PREFETCH")) c.cc1_prefetch = atoi(e);
   if (const char *e = getenv("PGPU_CC1_PAIR")) c.cc1_pair = atoi(e);
   if (const char *e = getenv("PGPU_CC1_RSTEPS")) c.cc1_rsteps = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_V")) c.cc1_version = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_NODECACHE")) c.cc1_nodecache = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_REC")) c.cc1_rec_per_pass = atoi(e);
   if (const char *e = getenv("PGPU_CC1_WAVES")) c.cc1_waves = atoi(e) > 0 ? atoi(e) : 1;
   return 0;
 }

@@ -49,7 +49,10 @@ __device__ __forceinline__ int locate_bin(double x, double le, double dx) {
 // contiguous (what the collision and moment kernels need) and, inside the cell, particles
 // that deposit onto the same node set are contiguous too (what pgpu_advance_cc1.cu sums
 // over).  Outcasts (outside the box) get the last key.
-__global__ void k_cell_key(const double *x0, const double *x1, long n, BoxInfo b, int *key, int *iota) {
+// dual != 0: key = index of the DUAL cell (the cell of the half-shifted grid CC1 segments on) = (c0 + q0) + (c1 + q1)
+// (n0 + 1): all particles that share the 21 deposit nodes are then ONE run (four times longer than the runs of
+// 4*cell + quadrant, where they sit in four primal cells); pgpu_sort_for_locality
+__global__ void k_cell_key(const double *x0, const double *x1, long n, BoxInfo b, int *key, int *iota, int dual) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double xa = x0[i];
@@ -64,6 +67,11 @@ __global__ void k_cell_key(const double *x0, const double *x1, long n, BoxInfo b
   }
   int k = 4 * b.ncell;  // outcast bin
   if (c0 >= 0 && c0 < b.n[0] && c1 >= 0 && c1 < b.n[1]) k = 4 * (c0 + c1 * b.n[0]) + q;
+  if (dual) {
+    const int m0 = b.n[0] + 1, m1 = (b.D == 2) ? b.n[1] + 1 : 1;
+    k = m0 * m1;
+    if (c0 >= 0 && c0 < b.n[0] && c1 >= 0 && c1 < b.n[1]) k = (c0 + (q & 1)) + (c1 + (q >> 1)) * m0;
+  }
   key[i] = k;
   iota[i] = (int)i;
 }
@@ -412,7 +420,11 @@ int materialize_old(pgpu_species_s *s, int keep) {
 
 extern "C" {
 
-int pgpu_bin_particles(pgpu_species_t s) {
+static int bin_impl(pgpu_species_t s, bool dual);
+int pgpu_bin_particles(pgpu_species_t s) { return bin_impl(s, false); }
+int pgpu_sort_for_locality(pgpu_species_t s) { return bin_impl(s, true); }
+
+static int bin_impl(pgpu_species_t s, bool dual) {
   NEED_INIT();
   if (!s) return PGPU_ERR_ARG;
   Context &c = ctx();
@@ -422,7 +434,7 @@ int pgpu_bin_particles(pgpu_species_t s) {
   const int nbins = b.ncell + 1;  // + outcast bin
   if (n == 0) {
     PGPU_CUDA(cudaMemsetAsync(s->cell_start, 0, (nbins + 1) * sizeof(int), c.stream));
-    s->binned = true;
+    s->binned = !dual;
     return 0;
   }
   // scratch: sorted keys + the pool of spare particle arrays the gather writes into
@@ -437,10 +449,11 @@ int pgpu_bin_particles(pgpu_species_t s) {
   int *iota = reinterpret_cast<int *>(s->tmp);  // tmp holds >= n doubles
   {
     KTimer t("bin_key");
-    k_cell_key<<<nb(n), 256, 0, c.stream>>>(s->x[0], s->x[1], n, b, s->cell_key, iota);
+    k_cell_key<<<nb(n), 256, 0, c.stream>>>(s->x[0], s->x[1], n, b, s->cell_key, iota, dual ? 1 : 0);
   }
   int nbits = 1;
-  while ((1L << nbits) <= 4L * b.ncell) ++nbits;
+  const long maxkey = dual ? (long)(b.n[0] + 1) * (b.D == 2 ? b.n[1] + 1 : 1) : 4L * b.ncell;
+  while ((1L << nbits) <= maxkey) ++nbits;
   {
     size_t need = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, s->cell_key, s->key_sorted, iota, s->perm, (int)n, 0, nbits,
@@ -458,7 +471,7 @@ int pgpu_bin_particles(pgpu_species_t s) {
     PGPU_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_tmp, need, s->cell_key, s->key_sorted, iota, s->perm, (int)n, 0,
                                               nbits, c.stream));
   }
-  {
+  if (!dual) {
     KTimer t("bin_starts");
     k_cell_starts<<<nb(n + 1), 256, 0, c.stream>>>(s->key_sorted, n, nbins, s->cell_start);
   }
@@ -481,7 +494,7 @@ int pgpu_bin_particles(pgpu_species_t s) {
   std::swap(s->perm, s->old_perm);
   s->pos_old_pending = !s->xold_alias;
   s->vel_old_pending = !s->vold_alias;
-  s->binned = true;
+  s->binned = !dual;   // the per-cell lists (collisions, moments) exist only after the primal-cell sort
   return 0;
 }
 

@@ -90,9 +90,12 @@ struct Context {
   int deposit_mode = 1;
   int cc1_tma = 3;           // CC1 kernel: 3 = table-driven two-phase TMA tile kernel, 2 = the same reading the raw field arrays (env PGPU_CC1_TMA)
   int cc1_rsteps = 3;        // shuffle-reduction steps before the REDs: 2, 3 or 4 (env PGPU_CC1_RSTEPS)
-  int cc1_minblocks = 4;     // blocks of 128 threads per SM the table kernel is compiled for: 4 (128 regs) or 5 (96 regs); env PGPU_CC1_MINB
+  int cc1_minblocks = 5;     // blocks of 128 threads per SM the table kernel is compiled for: 4 (128 regs) or 5 (96 regs, needs the 228 KB carve-out); env PGPU_CC1_MINB
   int cc1_pair = 0;          // CC1 kernel: two particles of a dual cell in lockstep through the Picard loop (env PGPU_CC1_PAIR)
   int cc1_prefetch = 0;      // L2 prefetch of a block's next particle tile (env PGPU_CC1_PREFETCH)
+  int cc1_version = 2;       // table kernel generation: 1 = round-1 map (4 consecutive particles per thread in both phases), 2 = lane map in the push phase (env PGPU_CC1_V)
+  int cc1_rec_per_pass = 1;  // v2: reload the dual-cell record every Picard pass instead of holding it in 32 registers (env PGPU_CC1_REC)
+  int cc1_nodecache = 0;     // v1: keep the node records of the last (dual cell, half cell) in registers too (env PGPU_CC1_NODECACHE)
   int cc1_waves = 64;        // tile kernel grid = min(tiles, SMs*4*waves) (env PGPU_CC1_WAVES)
   bool use_fast_cc1 = true;  // pgpu_set_deposit_mode(0) turns the specialised CC1 kernel off
   Counters *d_counters = nullptr;
