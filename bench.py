@@ -64,6 +64,11 @@ def parse():
     ap.add_argument("--sort-every", type=int, default=4,
                     help="cell-sort period in steps (the reference never sorts a collisionless deck; the sort only "
                          "keeps the fused kernel on its fast path: measured 11.6 / 10.5 / 9.9 / 9.5 ms per step at 1/2/4/8)")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c5"],
+                    help="c3: BASELINE configs[2], one 512^2 box x 2 species x 100 ppc per GPU (the deck the single-GPU "
+                         "roofline target is quoted on); c5: the per-GPU shard of BASELINE configs[4] (2048^2 cells x 256 ppc "
+                         "over 8 GPUs = sixteen 512^2 boxes, two per GPU, 2 species x 128 ppc); auto = c3 at 1 GPU, c5 above")
+    ap.add_argument("--boxes-per-gpu", type=int, default=0, help="0 = from the workload (c3: 1, c5: 2)")
     ap.add_argument("--sort", default="dual", choices=["dual", "cell"],
                     help="locality sort of the collisionless step: by dual cell (pgpu_sort_for_locality, default) or by "
                          "primal cell + quadrant (pgpu_bin_particles, what the collision step needs)")
@@ -81,7 +86,15 @@ def parse():
     ap.add_argument("--no-collisions", action="store_true", help="skip the secondary C2 collision-pairs/s leg")
     ap.add_argument("--no-c4", action="store_true", help="skip the secondary C4 leg (1D, 1e8 particles)")
     ap.add_argument("--no-mass-matrix", action="store_true", help="skip the secondary mass-matrix leg")
-    return ap.parse_args()
+    ap.add_argument("--no-c5-shard", action="store_true", help="skip the one-GPU run of the C5 per-GPU shard")
+    a = ap.parse_args()
+    if a.workload == "auto":
+        a.workload = "c3" if a.gpus == 1 else "c5"
+    if a.boxes_per_gpu == 0:
+        a.boxes_per_gpu = 2 if a.workload == "c5" else 1
+    # particles per cell per species as a lattice (ppc0, ppc1): c3 10 x 10 (or --ppc squared), c5 16 x 8 = 128
+    a.ppc2 = (16, 8) if a.workload == "c5" else (a.ppc, a.ppc)
+    return a
 
 
 # ------------------------------------------------------------------------------------------
@@ -98,8 +111,10 @@ def box_layout(world):
 
 
 def make_deck(args, world):
-    px, py = box_layout(world)
+    """The periodic domain of world * boxes_per_gpu square boxes of ncell^2 cells."""
+    px, py = box_layout(world * args.boxes_per_gpu)
     d = decks.deck_c3(ncell=args.ncell, ppc=args.ppc, dt=args.dt, iter_max=args.iter_max)
+    d.species = decks.electron_proton(tuple(args.ppc2))
     d.ncell = (args.ncell * px, args.ncell * py)
     return d, (px, py)
 
@@ -178,8 +193,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # the GPU arm
 # ------------------------------------------------------------------------------------------
+class Box:
+    """One Chombo box of this process: its grid, its species and its exchanges."""
+    pass
+
+
 class Engine:
-    """The particle side of the implicit step, driven through the C ABI (capi)."""
+    """The particle side of the implicit step, driven through the C ABI (capi).  A process owns `boxes_per_rank`
+    boxes of the square equal-box decomposition (System.cpp:169-245); box b = bi + bj * px lives in process
+    b // boxes_per_rank."""
 
     def __init__(self, args, rank, world, device, stream=None):
         import torch
@@ -187,75 +209,100 @@ class Engine:
         self.torch, self.capi, self.args, self.rank, self.world = torch, capi, args, rank, world
         self.deck, self.layout = make_deck(args, world)
         deck = self.deck
-        self.lo, self.hi = rank_box(args, rank, self.layout)
-        self.grid = capi.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), box_lo=self.lo,
-                              box_hi=self.hi, volume_scale=deck.volume_scale)
+        B = args.boxes_per_gpu
+        self.nboxes = world * B
         E0, B0 = field_amplitudes(deck)
-        E, B = decks.analytic_fields(deck, self.lo, self.hi, E0=E0, B0=B0)
         self.n_outer = args.n_outer
-        # pinned host copies of the field sets of each outer iteration + pinned J read-back
-        self.host_fields = []
-        for j in range(self.n_outer):
-            comps = []
-            for (lo, hi, a) in list(E) + list(B):
-                t = torch.empty(a.size, dtype=torch.float64).pin_memory()
-                h = t.numpy().reshape(a.shape, order="F")
-                h[...] = a * (1.0 + EPS_OUTER[j % len(EPS_OUTER)])
-                comps.append((lo, hi, h, t))
-            self.host_fields.append(comps)
-        self.host_J = []
-        for c in range(3):
-            lo, hi = self.grid.field_bounds(c)
-            shape = tuple(h - l + 1 for l, h in zip(lo, hi))
-            t = torch.empty(int(np.prod(shape)), dtype=torch.float64).pin_memory()
-            self.host_J.append((lo, hi, t.numpy().reshape(shape, order="F"), t))
-        for j in range(self.n_outer):           # resident field slots for the device-timed arm
-            self.grid.fields_select(j)
-            self._upload_fields(j)
-        self.grid.fields_select(0)
-        capi.check(capi.load().pgpu_synchronize())
-        rng = np.random.default_rng(deck.seed + 1000 * rank)
-        self.species = []
+        self.boxes = []
         self.n_particles = 0
-        for sdef in deck.species:
-            p = decks.load_species(deck, sdef, self.lo, self.hi, rng)
-            sp = capi.Species(self.grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm,
-                              interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E,
-                              rtol=deck.rtol, iter_max=deck.iter_max)
-            sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
-            self._sort(sp)
-            self.species.append(sp)
-            self.n_particles += sp.n
-            del p
-        self.h2d = sum(h.nbytes for (_, _, h, _) in self.host_fields[0]) * self.n_outer
-        self.d2h = sum(h.nbytes for (_, _, h, _) in self.host_J) * self.n_outer
+        self.h2d = self.d2h = 0
+        for k in range(B):
+            bx = Box()
+            bx.id = rank * B + k
+            bx.lo, bx.hi = rank_box(args, bx.id, self.layout)
+            bx.grid = capi.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), box_lo=bx.lo,
+                                box_hi=bx.hi, volume_scale=deck.volume_scale)
+            E, Bf = decks.analytic_fields(deck, bx.lo, bx.hi, E0=E0, B0=B0)
+            # pinned host copies of the field sets of each outer iteration + pinned J read-back: ONE contiguous
+            # buffer per direction of transfer (components back to back in the C ABI's packed order)
+            nfield = bx.grid.fields_packed_size()
+            nJ = bx.grid.current_packed_size()
+            bx.host_fields = []
+            for j in range(self.n_outer):
+                t = torch.empty(nfield, dtype=torch.float64).pin_memory()
+                h = t.numpy()
+                off = 0
+                for (lo, hi, a) in list(E) + list(Bf):
+                    h[off:off + a.size] = (a * (1.0 + EPS_OUTER[j % len(EPS_OUTER)])).ravel(order="F")
+                    off += a.size
+                assert off == nfield
+                bx.host_fields.append((h, t))
+            tJ = torch.empty(nJ, dtype=torch.float64).pin_memory()
+            bx.host_J = (tJ.numpy(), tJ)
+            for j in range(self.n_outer):           # resident field slots for the device-timed arm
+                bx.grid.fields_select(j)
+                self._upload_fields(bx, j)
+            bx.grid.fields_select(0)
+            capi.check(capi.load().pgpu_synchronize())
+            rng = np.random.default_rng(deck.seed + 1000 * bx.id)
+            bx.species = []
+            for sdef in deck.species:
+                p = decks.load_species(deck, sdef, bx.lo, bx.hi, rng)
+                sp = capi.Species(bx.grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm,
+                                  interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E,
+                                  rtol=deck.rtol, iter_max=deck.iter_max)
+                sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
+                self._sort(sp)
+                bx.species.append(sp)
+                self.n_particles += sp.n
+                del p
+            self.h2d += nfield * 8 * self.n_outer
+            self.d2h += nJ * 8 * self.n_outer
+            bx.halo, bx.migration = None, []
+            self.boxes.append(bx)
+        self.species = [sp for bx in self.boxes for sp in bx.species]
+        self.grid = self.boxes[0].grid
         self.step_no = 0
-        self.halo, self.migration = None, []
-        if world > 1:
-            # one box per GPU: ghost add-exchange of J after every deposit and particle migration
-            # once per step, on device buffers over NCCL (picnic_b200/halo.py)
+        self.halo_bytes = 0
+        if self.nboxes > 1:
+            # ghost add-exchange of J after every deposit and particle migration once per step, between the boxes of
+            # this process (plain device pointers) and of the other processes (CUDA IPC), picnic_b200/halo.py
             from picnic_b200 import halo
             dev = torch.device("cuda", device)
             lay = halo.BoxLayout(2, deck.ncell, (args.ncell, args.ncell), deck.nghost, (1, 1))
-            assert lay.world == world and lay.box(rank) == (tuple(self.lo), tuple(self.hi))
-            comm = halo.DistComm(rank, world, stream=stream)
+            assert lay.world == self.nboxes
+            for bx in self.boxes:
+                assert lay.box(bx.id) == (tuple(bx.lo), tuple(bx.hi))
+            comm = halo.DistComm(rank, world, stream=stream) if world > 1 else None
             if args.halo == "peer":
-                # ghost-J exchange by the library's own kernels over peer memory (NVLink): CUDA IPC inboxes
-                self.halo = halo.PeerHaloExchange(lay, rank, self.grid)
-                self.halo.connect_ipc(comm)
+                for bx in self.boxes:
+                    bx.halo = halo.PeerHaloExchange(lay, bx.id, bx.grid)
+                hs = [bx.halo for bx in self.boxes]
+                if world == 1:
+                    halo.PeerHaloExchange.connect_local(hs)
+                else:
+                    halo.PeerHaloExchange.connect_mixed(hs, comm, B)
             else:
-                self.halo = halo.HaloExchange(lay, rank, comm,
-                                              halo.CapiGridBackend(self.grid, dev, on_torch_stream=True))
+                assert B == 1, "--halo nccl is the one-box-per-process route"
+                self.boxes[0].halo = halo.HaloExchange(lay, rank, comm,
+                                                       halo.CapiGridBackend(self.grid, dev, on_torch_stream=True))
+            self.halo_bytes = sum(bx.halo.bytes_per_exchange for bx in self.boxes)
             if args.migration == "peer":
                 # leavers go straight into the neighbours' inboxes (peer stores), counts stay on the device
-                self.migration = [halo.PeerMigration(lay, rank, sp, capacity=max(16384, sp.n // 512))
-                                  for sp in self.species]
-                for m in self.migration:
-                    m.connect_ipc(comm)
+                for bx in self.boxes:
+                    bx.migration = [halo.PeerMigration(lay, bx.id, sp, capacity=max(16384, sp.n // 512))
+                                    for sp in bx.species]
+                for k in range(len(deck.species)):
+                    ms = [bx.migration[k] for bx in self.boxes]
+                    if world == 1:
+                        halo.PeerMigration.connect_local(ms)
+                    else:
+                        halo.PeerMigration.connect_mixed(ms, comm, B)
             else:
-                self.migration = [halo.Migration(lay, rank, comm,
-                                                 halo.CapiSpeciesBackend(sp, dev, on_torch_stream=True))
-                                  for sp in self.species]
+                assert B == 1, "--migration nccl is the one-box-per-process route"
+                self.boxes[0].migration = [halo.Migration(lay, rank, comm,
+                                                          halo.CapiSpeciesBackend(sp, dev, on_torch_stream=True))
+                                           for sp in self.boxes[0].species]
         self.migrated = 0
         self.sections, self.stream = None, stream
 
@@ -265,10 +312,10 @@ class Engine:
         else:
             sp.bin_particles()
 
-    def _upload_fields(self, j):
-        lib, capi = self.capi.load(), self.capi
-        for c, (lo, hi, h, _) in enumerate(self.host_fields[j]):
-            capi.check(lib.pgpu_fields_set(self.grid.h, c, h.ctypes.data, capi._i2(lo), capi._i2(hi)))
+    def _upload_fields(self, bx, j):
+        """One H2D copy of the six field components from pinned memory (pgpu_fields_set_packed)."""
+        capi = self.capi
+        capi.check(capi.load().pgpu_fields_set_packed(bx.grid.h, bx.host_fields[j][0].ctypes.data))
 
     # device-side section timers: pairs of events on the engine stream, resolved after the region
     def _mark(self, name):
@@ -292,26 +339,40 @@ class Engine:
         return out, host
 
     def pre_rhs_op(self, j, host_io):
-        """PicSpeciesInterface::preRHSOp (PicSpeciesInterface.cpp:899-994) for outer iteration j."""
+        """PicSpeciesInterface::preRHSOp (PicSpeciesInterface.cpp:899-994) for outer iteration j, all boxes."""
         capi, lib = self.capi, self.capi.load()
-        if host_io:
-            self._upload_fields(j)                  # async H2D from pinned memory on the engine stream
-        else:
-            self.grid.fields_select(j)
-        self.grid.current_zero()
+        for bx in self.boxes:
+            if host_io:
+                self._upload_fields(bx, j)          # async H2D from pinned memory on the engine stream
+            else:
+                bx.grid.fields_select(j)
+            bx.grid.current_zero()
         self._mark("fields_in")
-        for sp in self.species:
-            capi.check(lib.pgpu_advance_particles_iteratively(sp.h, self.deck.dt, 1, None))
-            self.grid.current_add(sp)
+        for bx in self.boxes:
+            for sp in bx.species:
+                capi.check(lib.pgpu_advance_particles_iteratively(sp.h, self.deck.dt, 1, None))
+                bx.grid.current_add(sp)
         self._mark("advance_deposit")
-        if self.halo is not None:
-            self.halo.add_exchange()
+        if self.nboxes > 1:
+            if self.args.halo == "peer":
+                # every send of a phase is enqueued before any receive of that phase: a receive spins on its
+                # neighbours' arrival flags, and the boxes of one process share one stream
+                for bx in self.boxes:
+                    bx.halo.begin()
+                for ph in range(self.boxes[0].halo.nphase):
+                    for bx in self.boxes:
+                        bx.halo.send(ph)
+                    for bx in self.boxes:
+                        bx.halo.recv_add(ph)
+            else:
+                self.boxes[0].halo.add_exchange()
             self._mark("ghost_J_exchange")
-        self.grid.current_finalize()
+        for bx in self.boxes:
+            bx.grid.current_finalize()
+            if host_io:                             # ONE D2H copy of the three J components into pinned memory
+                capi.check(lib.pgpu_current_get_packed_async(bx.grid.h, bx.host_J[0].ctypes.data))
         if host_io:
-            for c, (lo, hi, h, _) in enumerate(self.host_J):     # three D2H copies into pinned memory, one wait
-                capi.check(lib.pgpu_current_get_async(self.grid.h, c, h.ctypes.data, capi._i2(lo), capi._i2(hi)))
-            capi.check(lib.pgpu_synchronize())
+            capi.check(lib.pgpu_synchronize())      # the host reads J here (the field solve's residual)
         self._mark("J_out")
 
     def step(self, host_io=False):
@@ -319,18 +380,20 @@ class Engine:
             sp.update_old_positions()
             sp.update_old_velocities()
         if host_io:
-            self.grid.fields_select(0)
+            for bx in self.boxes:
+                bx.grid.fields_select(0)
         for j in range(self.n_outer):
             self.pre_rhs_op(j, host_io)
         for sp in self.species:
             sp.finish_implicit_step((1, 1), (1, 1))   # 2nd-half v, 2nd-half x, periodic applyBCs
         self._mark("finish_step")
-        if self.migration:                             # remapOutcast: leavers to the owning box
+        if self.nboxes > 1:                            # remapOutcast: leavers to the owning box
             from picnic_b200 import halo
+            ms = [m for bx in self.boxes for m in bx.migration]
             if self.args.migration == "peer":
-                self.migrated += halo.migrate_all_peer(self.migration)
+                self.migrated += halo.migrate_all_peer(ms)
             else:
-                self.migrated += halo.migrate_all(self.migration)
+                self.migrated += halo.migrate_all(ms)
             self._mark("migration")
         self.step_no += 1
         if self.args.sort_every > 0 and self.step_no % self.args.sort_every == 0:
@@ -340,6 +403,17 @@ class Engine:
 
     def sync(self):
         self.capi.check(self.capi.load().pgpu_synchronize())
+
+    def destroy(self):
+        for bx in self.boxes:
+            for m in bx.migration:
+                if hasattr(m, "destroy"):
+                    m.destroy()
+            if bx.halo is not None and hasattr(bx.halo, "destroy"):
+                bx.halo.destroy()
+            for sp in bx.species:
+                sp.destroy()
+            bx.grid.destroy()
 
 
 def collisions_leg(args, torch, capi, stream, peak):
@@ -633,6 +707,45 @@ def mass_matrix_leg(args, torch, capi, stream, peak):
                          "note": "bound by the fp64 reductions into L2 (272 per run of ~25 particles), not by HBM; see DESIGN.md 4.2"}}
 
 
+def workload_name(args, world):
+    ppc = args.ppc2[0] * args.ppc2[1]
+    if args.workload == "c5":
+        return ("C5 shard: BASELINE configs[4] (2D 2048x2048 cells x 256 ppc over 8 GPUs, sixteen 512^2 boxes) at %d GPU(s): "
+                "%d boxes of %dx%d cells per GPU, 2 species x %d ppc, CC1 gather/deposit, Picard particle loop (rtol 1e-12, "
+                "iter_max %d), %d nonlinear evaluations per step, ghost-J add-exchange + particle migration between all boxes"
+                % (world, args.boxes_per_gpu, args.ncell, args.ncell, ppc, args.iter_max, args.n_outer))
+    return ("C3: 2D implicit energy-conserving PIC, %dx%d cells per GPU box, 2 species x %d ppc, CC1 gather/deposit, Picard "
+            "particle loop (rtol 1e-12, iter_max %d), %d nonlinear evaluations per step"
+            % (args.ncell, args.ncell, ppc, args.iter_max, args.n_outer))
+
+
+def c5_shard_leg(args, rank, local, stream, region, capi):
+    """The per-GPU shard of C5 on ONE GPU (two 512^2 boxes x 2 species x 128 ppc = 1.34e8 particles, periodic, with the
+    box-to-box ghost-J exchange and migration): the like-for-like base of the weak-scaling numbers `--gpus N` reports for
+    N > 1, which run this shard on every GPU."""
+    import copy
+    a = copy.copy(args)
+    a.workload, a.boxes_per_gpu, a.ppc2 = "c5", 2, (16, 8)
+    a.steps, a.warmup = max(4, min(args.steps, 8)), 3
+    eng = Engine(a, rank, 1, local, stream=stream)
+    region(a.warmup, False, eng=eng)
+    ms, _ = region(a.steps, False, profile=True, eng=eng)
+    k_ms, k_n = capi.profile_query("advance_cc1_fused")
+    adv, app, unconv = capi.picard_totals(reset=True)
+    n = eng.n_particles
+    units = float(n) * a.n_outer * a.steps
+    per_launch = n / len(eng.species)
+    out = {"metric": "particle-advances/s (implicit push + deposit)", "value": units / (ms * 1e-3),
+           "unit": "particle-advances/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+           "workload": workload_name(a, 1), "particles_per_gpu": n, "mean_picard_passes": round(app / max(adv, 1), 3),
+           "kernel_ms_per_launch": k_ms / max(k_n, 1), "units_per_launch": per_launch,
+           "roofline_frac_kernel": (BYTES_PER_ADVANCE_2D * per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9
+                                    / region.peak) if k_n else None,
+           "section_ms_per_step": getattr(region, "sections", None)}
+    eng.destroy()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -657,13 +770,14 @@ def run_ours(args):
     eng = Engine(args, rank, world, local, stream=stream)
 
     def barrier():
-        eng.sync()
+        capi.check(capi.load().pgpu_synchronize())
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def region(nsteps, host_io, profile=False):
+    def region(nsteps, host_io, profile=False, eng=None):
+        eng = eng or region.eng
         barrier()
         if profile:
             capi.profile_reset()
@@ -695,6 +809,7 @@ def run_ours(args):
             ms = float(t.item())
         return ms, capi.load().pgpu_launch_count() - launches0
 
+    region.eng = eng
     # warm-up (>= 3 steps), then the timed region.  The particle arrays (5 GB per GPU) are far
     # larger than the 126 MB L2, so every pass streams from HBM; no explicit flush is needed.
     sampler = ClockSampler(local)
@@ -743,6 +858,7 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        region.peak = peak
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         k_name = "advance_cc1_fused"
         k_ms, k_n = prof[k_name]
@@ -764,18 +880,16 @@ def run_ours(args):
             "metric": "particle-advances/s (implicit push + deposit)", "value": value, "unit": "particle-advances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3: 2D implicit energy-conserving PIC, %dx%d cells per GPU box, 2 species x %d ppc, "
-                                   "CC1 gather/deposit, Picard particle loop (rtol 1e-12, iter_max %d), %d nonlinear "
-                                   "evaluations per step" % (args.ncell, args.ncell, args.ppc ** 2, args.iter_max,
-                                                             args.n_outer),
-                       "particles_per_gpu": eng.n_particles, "boxes": "%dx%d" % eng.layout, "dt": args.dt,
+            "config": {"workload": workload_name(args, world),
+                       "particles_per_gpu": eng.n_particles, "particles_total": n_total,
+                       "boxes": "%dx%d" % eng.layout, "boxes_per_gpu": args.boxes_per_gpu, "dt": args.dt,
                        "n_outer": args.n_outer, "sort_every": args.sort_every,
                        "exchange": (None if world == 1 else
                                     {"ghost_J": "peer-memory kernels over NVLink (CUDA IPC inboxes)" if args.halo == "peer"
                                                 else "pack + NCCL send/recv + unpack-add",
                                      "migration": "peer-memory inboxes, device-side counts, one host wait per step"
                                                   if args.migration == "peer" else "count all-gather + NCCL send/recv",
-                                     "ghost_J_bytes_per_evaluation": eng.halo.bytes_per_exchange,
+                                     "ghost_J_bytes_per_evaluation": eng.halo_bytes,
                                      "migrated_particles_rank0": int(eng.migrated)}),
                        "mean_picard_passes": round(k_mean, 3), "unconverged_particles": int(unconv),
                        "l2_policy": "inputs (%.1f GB particle SoA per GPU) exceed the 126 MB L2; no flush needed"
@@ -795,9 +909,9 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, steps=5)
-    for sp in eng.species:
-        sp.destroy()
-    eng.grid.destroy()
+    eng.destroy()
+    if rank == 0 and world == 1 and args.workload == "c3" and not args.no_c5_shard:
+        out["c5_shard"] = c5_shard_leg(args, rank, local, stream, region, capi)
     if rank == 0 and world == 1 and not args.no_collisions:
         out["collisions"] = collisions_leg(args, torch, capi, stream, out["roofline"]["peak"])
     if rank == 0 and world == 1 and not args.no_c4:

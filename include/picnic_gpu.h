@@ -93,6 +93,14 @@ int pgpu_fields_set(pgpu_grid_t g, int comp, const double *data, const int *lo, 
  * the next nonlinear iteration (preRHSOp, PicSpeciesInterface.cpp:899-994) behind the
  * particle work of the current one.  Slot 0 is selected at creation. */
 int pgpu_fields_select(pgpu_grid_t g, int slot);
+/* One transfer per preRHSOp each way (PicSpeciesInterface.cpp:899-994 hands the particles six field arrays and takes three
+ * current arrays back): the six components Ex Ey Ez Bx By Bz back to back in one host buffer, each in the layout
+ * pgpu_fields_set takes; and Jx Jy Jz of pgpu_current_finalize likewise.  pgpu_current_get_packed_async returns before the
+ * copy has finished: read the buffer after pgpu_synchronize. */
+int pgpu_fields_packed_size(pgpu_grid_t g, long *ndoubles);
+int pgpu_fields_set_packed(pgpu_grid_t g, const double *data);
+int pgpu_current_packed_size(pgpu_grid_t g, long *ndoubles);
+int pgpu_current_get_packed_async(pgpu_grid_t g, double *data);
 /* Page-lock a caller-owned host array (e.g. a Chombo FArrayBox dataPtr) so that the
  * H2D/D2H copies of pgpu_fields_set / pgpu_current_get run at full PCIe/C2C rate. */
 int pgpu_host_register(void *ptr, size_t bytes);

@@ -97,6 +97,8 @@ def load():
         "pgpu_advance_particles": [vp, dbl], "pgpu_advance_particles_iteratively": [vp, dbl, i32, vp],
         "pgpu_set_current_density": [vp, dbl, i32], "pgpu_species_current_get": [vp, i32, vp, vp, vp],
         "pgpu_set_charge_density": [vp, vp, vp, vp, vp],
+        "pgpu_fields_packed_size": [vp, vp], "pgpu_fields_set_packed": [vp, vp],
+        "pgpu_current_packed_size": [vp, vp], "pgpu_current_get_packed_async": [vp, vp],
         "pgpu_bin_particles": [vp], "pgpu_sort_for_locality": [vp], "pgpu_species_cell_index": [vp, vp],
         "pgpu_species_cell_offsets": [vp, vp], "pgpu_set_moments_from_bins": [vp],
         "pgpu_species_moments_get": [vp, vp, vp, vp], "pgpu_debye_length": [vp, vp, i32, vp],
@@ -188,6 +190,16 @@ class Grid:
         a = np.asfortranarray(arr, dtype=np.float64)
         check(load().pgpu_fields_set(self.h, comp, _p(a), _i2(lo), _i2(hi)))
         self._keep = a  # async H2D: keep the host buffer alive until the next sync
+
+    def fields_packed_size(self):
+        n = C.c_long()
+        check(load().pgpu_fields_packed_size(self.h, C.byref(n)))
+        return n.value
+
+    def current_packed_size(self):
+        n = C.c_long()
+        check(load().pgpu_current_packed_size(self.h, C.byref(n)))
+        return n.value
 
     def set_fields(self, E, B):
         keep = []

@@ -1892,6 +1892,7 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
       hi[d] = hi[d] < f.hi[d] - 2 ? hi[d] : f.hi[d] - 2;
     }
   };
+  if (fields_wait(g)) return PGPU_ERR_CUDA;
   for (int k = 0; k < 6; ++k) {
     const DeviceFab &f = g->field[k];
     clamp(f);

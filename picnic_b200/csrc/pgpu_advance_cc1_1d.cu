@@ -317,6 +317,7 @@ int launch_advance_cc1_1d_fast(pgpu_species_s *s, const AdvanceParams &prm, bool
   A.rdx = g->geo.rdx[0];
   A.hdx = 0.5 * g->geo.dx[0];
   int lo = -(1 << 30), hi = 1 << 30;
+  if (fields_wait(g)) return PGPU_ERR_CUDA;
   for (int k = 0; k < 6; ++k) {
     const DeviceFab &f = g->field[k];
     lo = std::max(lo, f.lo[0]);

@@ -66,7 +66,16 @@ GeoAny species_geo(const pgpu_species_s *s) {
   }
   return g;
 }
+int fields_wait(const pgpu_grid_s *g) {
+  if (g->upload_pending) {
+    PGPU_CUDA(cudaStreamWaitEvent(ctx().stream, g->upload_done, 0));
+    g->upload_pending = false;
+  }
+  return 0;
+}
+
 FieldSet grid_fields(const pgpu_grid_s *g) {
+  fields_wait(g);
   FieldSet F;
   for (int c = 0; c < 6; ++c) F.f[c] = g->field[c].view();
   return F;
@@ -102,6 +111,38 @@ static int alloc_fab(const pgpu_grid_desc &d, const int *stag, DeviceFab *f) {
   f->n1 = f->hi[1] - f->lo[1] + 1;
   PGPU_CUDA(cudaMalloc(&f->p, f->size() * sizeof(double)));
   PGPU_CUDA(cudaMemsetAsync(f->p, 0, f->size() * sizeof(double), ctx().stream));
+  return 0;
+}
+
+// n arrays of one centring set in ONE allocation, back to back: a packed host buffer in the same order moves with a
+// single cudaMemcpyAsync (pgpu_fields_set_packed / pgpu_current_get_packed_async)
+static int alloc_fab_arena(const pgpu_grid_desc &d, int first_comp, int n, DeviceFab *f) {
+  size_t total = 0;
+  for (int c = 0; c < n; ++c) {
+    int stag[2];
+    comp_stag(d.D, first_comp + c, stag);
+    DeviceFab &o = f[c];
+    for (int k = 0; k < 2; ++k) {
+      if (k < d.D) {
+        o.lo[k] = d.box_lo[k] - d.nghost;
+        o.hi[k] = d.box_hi[k] + d.nghost + stag[k];
+      } else {
+        o.lo[k] = o.hi[k] = 0;
+      }
+      o.stag[k] = (k < d.D) ? stag[k] : 0;
+    }
+    o.n0 = o.hi[0] - o.lo[0] + 1;
+    o.n1 = o.hi[1] - o.lo[1] + 1;
+    total += o.size();
+  }
+  double *base = nullptr;
+  PGPU_CUDA(cudaMalloc(&base, total * sizeof(double)));
+  PGPU_CUDA(cudaMemsetAsync(base, 0, total * sizeof(double), ctx().stream));
+  size_t off = 0;
+  for (int c = 0; c < n; ++c) {
+    f[c].p = base + off;
+    off += f[c].size();
+  }
   return 0;
 }
 
@@ -420,6 +461,7 @@ int pgpu_init(int device) {
   if (const char *e = getenv("PGPU_CC1_PREFETCH")) c.cc1_prefetch = atoi(e);
   if (const char *e = getenv("PGPU_CC1_PAIR")) c.cc1_pair = atoi(e);
   if (const char *e = getenv("PGPU_CC1_RSTEPS")) c.cc1_rsteps = atoi(e);
+  if (const char *e = getenv("PGPU_COPY_STREAM")) c.use_copy_stream = atoi(e);
   if (const char *e = getenv("PGPU_CC1_V")) c.cc1_version = atoi(e);
   if (const char *e = getenv("PGPU_CC1_NODECACHE")) c.cc1_nodecache = atoi(e);
   if (const char *e = getenv("PGPU_CC1_REC")) c.cc1_rec_per_pass = atoi(e);
@@ -430,6 +472,11 @@ int pgpu_init(int device) {
 int pgpu_finalize(void) {
   Context &c = ctx();
   if (!c.inited) return 0;
+  if (c.copy_stream) {
+    cudaStreamSynchronize(c.copy_stream);
+    cudaStreamDestroy(c.copy_stream);
+    cudaEventDestroy(c.copy_fence);
+  }
   cudaStreamSynchronize(c.stream);
   profile_drain();
   if (c.own_stream) cudaStreamDestroy(c.stream);
@@ -459,6 +506,7 @@ int pgpu_set_stream(void *cuda_stream) {
 int pgpu_synchronize(void) {
   NEED_INIT();
   Context &c = ctx();
+  if (c.copy_stream) PGPU_CUDA(cudaStreamSynchronize(c.copy_stream));
   Counters k;
   if (fetch_counters(&k)) return PGPU_ERR_CUDA;
   int rc = check_err_bits(k.err);
@@ -505,17 +553,9 @@ int pgpu_grid_create(const pgpu_grid_desc *d, pgpu_grid_t *out) {
   }
   g->geo.ghosts = d->nghost;
   g->ncell_box = (long)g->nbox[0] * g->nbox[1];
-  for (int c = 0; c < 6; ++c) {
-    int stag[2];
-    comp_stag(d->D, c, stag);
-    if (alloc_fab(*d, stag, &g->field[c])) return PGPU_ERR_CUDA;
-    g->field_slot[0][c] = g->field[c];
-  }
-  for (int c = 0; c < 3; ++c) {
-    int stag[2];
-    comp_stag(d->D, c, stag);
-    if (alloc_fab(*d, stag, &g->jtot[c])) return PGPU_ERR_CUDA;
-  }
+  if (alloc_fab_arena(*d, 0, 6, g->field)) return PGPU_ERR_CUDA;
+  for (int c = 0; c < 6; ++c) g->field_slot[0][c] = g->field[c];
+  if (alloc_fab_arena(*d, 0, 3, g->jtot)) return PGPU_ERR_CUDA;   // J has the centring of E
   PGPU_CUDA(cudaMalloc(&g->debye, g->ncell_box * sizeof(double)));
   *out = g;
   return 0;
@@ -523,11 +563,12 @@ int pgpu_grid_create(const pgpu_grid_desc *d, pgpu_grid_t *out) {
 
 int pgpu_grid_destroy(pgpu_grid_t g) {
   if (!g) return 0;
+  if (ctx().copy_stream) cudaStreamSynchronize(ctx().copy_stream);
   cudaStreamSynchronize(ctx().stream);
+  if (g->upload_done) cudaEventDestroy(g->upload_done);
   for (int k = 0; k < 4; ++k)
-    for (int c = 0; c < 6; ++c)
-      if (g->field_slot[k][c].p) cudaFree(g->field_slot[k][c].p);
-  for (int c = 0; c < 3; ++c) cudaFree(g->jtot[c].p);
+    if (g->field_slot[k][0].p) cudaFree(g->field_slot[k][0].p);   // one arena per slot (alloc_fab_arena)
+  cudaFree(g->jtot[0].p);
   for (int k = 0; k < 4; ++k) {
     if (g->tab_dual[k]) cudaFree(g->tab_dual[k]);
     if (g->tab_node[k]) cudaFree(g->tab_node[k]);
@@ -558,6 +599,7 @@ int pgpu_fields_set(pgpu_grid_t g, int comp, const double *data, const int *lo, 
                 d, f.lo[d], f.hi[d]);
       return PGPU_ERR_ARG;
     }
+  if (fields_wait(g)) return PGPU_ERR_CUDA;
   PGPU_CUDA(cudaMemcpyAsync(f.p, data, f.size() * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
   g->tab_dirty[g->cur_slot] = true;
   return 0;
@@ -566,15 +608,60 @@ int pgpu_fields_set(pgpu_grid_t g, int comp, const double *data, const int *lo, 
 int pgpu_fields_select(pgpu_grid_t g, int slot) {
   NEED_INIT();
   if (!g || slot < 0 || slot >= 4) return PGPU_ERR_ARG;
-  for (int c = 0; c < 6; ++c) {
-    if (!g->field_slot[slot][c].p) {
-      int stag[2];
-      comp_stag(g->desc.D, c, stag);
-      if (alloc_fab(g->desc, stag, &g->field_slot[slot][c])) return PGPU_ERR_CUDA;
-    }
-    g->field[c] = g->field_slot[slot][c];
-  }
+  if (!g->field_slot[slot][0].p && alloc_fab_arena(g->desc, 0, 6, g->field_slot[slot])) return PGPU_ERR_CUDA;
+  for (int c = 0; c < 6; ++c) g->field[c] = g->field_slot[slot][c];
   g->cur_slot = slot;
+  return 0;
+}
+
+// The six field components in one host buffer, back to back in the order Ex Ey Ez Bx By Bz, each in the layout
+// pgpu_fields_set takes (ghosted box of the component, column major): one H2D copy per preRHSOp instead of six.
+int pgpu_fields_packed_size(pgpu_grid_t g, long *ndoubles) {
+  if (!g || !ndoubles) return PGPU_ERR_ARG;
+  long n = 0;
+  for (int c = 0; c < 6; ++c) n += (long)g->field[c].size();
+  *ndoubles = n;
+  return 0;
+}
+int pgpu_fields_set_packed(pgpu_grid_t g, const double *data) {
+  NEED_INIT();
+  if (!g || !data) return PGPU_ERR_ARG;
+  long n = 0;
+  for (int c = 0; c < 6; ++c) n += (long)g->field[c].size();
+  Context &c = ctx();
+  if (c.use_copy_stream) {
+    // the copy is ordered behind everything already enqueued on the library stream (earlier readers of this slot) but
+    // not behind what is enqueued after this call: box B's fields move while box A's particles run
+    if (!c.copy_stream) {
+      PGPU_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+      PGPU_CUDA(cudaEventCreateWithFlags(&c.copy_fence, cudaEventDisableTiming));
+    }
+    if (!g->upload_done) PGPU_CUDA(cudaEventCreateWithFlags(&g->upload_done, cudaEventDisableTiming));
+    PGPU_CUDA(cudaEventRecord(c.copy_fence, c.stream));
+    PGPU_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_fence, 0));
+    PGPU_CUDA(cudaMemcpyAsync(g->field[0].p, data, n * sizeof(double), cudaMemcpyHostToDevice, c.copy_stream));
+    PGPU_CUDA(cudaEventRecord(g->upload_done, c.copy_stream));
+    g->upload_pending = true;
+  } else {
+    PGPU_CUDA(cudaMemcpyAsync(g->field[0].p, data, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  }
+  g->tab_dirty[g->cur_slot] = true;
+  return 0;
+}
+// Jx Jy Jz of pgpu_current_finalize likewise in one buffer; asynchronous: the data is valid after pgpu_synchronize
+int pgpu_current_packed_size(pgpu_grid_t g, long *ndoubles) {
+  if (!g || !ndoubles) return PGPU_ERR_ARG;
+  long n = 0;
+  for (int c = 0; c < 3; ++c) n += (long)g->jtot[c].size();
+  *ndoubles = n;
+  return 0;
+}
+int pgpu_current_get_packed_async(pgpu_grid_t g, double *data) {
+  NEED_INIT();
+  if (!g || !data) return PGPU_ERR_ARG;
+  long n = 0;
+  for (int c = 0; c < 3; ++c) n += (long)g->jtot[c].size();
+  PGPU_CUDA(cudaMemcpyAsync(data, g->jtot[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
   return 0;
 }
 
@@ -591,8 +678,9 @@ int pgpu_host_unregister(void *ptr) {
 
 int pgpu_current_zero(pgpu_grid_t g) {
   NEED_INIT();
-  for (int c = 0; c < 3; ++c)
-    PGPU_CUDA(cudaMemsetAsync(g->jtot[c].p, 0, g->jtot[c].size() * sizeof(double), ctx().stream));
+  size_t n = 0;
+  for (int c = 0; c < 3; ++c) n += g->jtot[c].size();
+  PGPU_CUDA(cudaMemsetAsync(g->jtot[0].p, 0, n * sizeof(double), ctx().stream));   // one arena (alloc_fab_arena)
   return 0;
 }
 

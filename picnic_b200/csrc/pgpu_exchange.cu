@@ -37,7 +37,10 @@ __global__ void k_fab_unpack(FabView f, int lo0, int lo1, int m0, int m1, const 
 static const DeviceFab *pick_fab(pgpu_grid_t g, int kind, int comp) {
   if (!g) return nullptr;
   if (kind == PGPU_FAB_JTOTAL && comp >= 0 && comp < 3) return &g->jtot[comp];
-  if (kind == PGPU_FAB_FIELD && comp >= 0 && comp < 6) return &g->field[comp];
+  if (kind == PGPU_FAB_FIELD && comp >= 0 && comp < 6) {
+    fields_wait(g);
+    return &g->field[comp];
+  }
   return nullptr;
 }
 

@@ -86,6 +86,9 @@ struct Context {
   bool inited = false;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;   // H2D of packed field sets (env PGPU_COPY_STREAM=0 puts them on `stream`)
+  cudaEvent_t copy_fence = nullptr;     // "everything enqueued on `stream` so far", waited on by the copy stream
+  int use_copy_stream = 1;
   bool exact = false;
   int deposit_mode = 1;
   int cc1_tma = 3;           // CC1 kernel: 3 = table-driven two-phase TMA tile kernel, 2 = the same reading the raw field arrays (env PGPU_CC1_TMA)
@@ -139,6 +142,10 @@ struct pgpu_grid_s {
   pgpu::DeviceFab field[6];             // the selected slot (aliases field_slot[cur_slot])
   pgpu::DeviceFab field_slot[4][6];     // resident field sets (slot 0 always allocated)
   int cur_slot = 0;
+  // pgpu_fields_set_packed copies on the library's copy stream (so that the upload of one box overlaps the particle
+  // kernels of another); every reader of the field arrays orders itself behind it with fields_wait()
+  cudaEvent_t upload_done = nullptr;
+  mutable bool upload_pending = false;
   // per-cell coefficient tables of each field slot for the 2D CC1 kernel (pgpu_advance_cc1.cu)
   double *tab_dual[4] = {nullptr, nullptr, nullptr, nullptr};
   double *tab_node[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -218,7 +225,8 @@ struct pgpu_species_s {
 
 namespace pgpu {
 GeoAny species_geo(const pgpu_species_s *s);
-FieldSet grid_fields(const pgpu_grid_s *g);
+FieldSet grid_fields(const pgpu_grid_s *g);   // waits for a pending packed upload (fields_wait)
+int fields_wait(const pgpu_grid_s *g);        // order the library stream behind a pending pgpu_fields_set_packed
 CurrentSet species_current(const pgpu_species_s *s);
 
 int scale_fab(const DeviceFab &f, double s);

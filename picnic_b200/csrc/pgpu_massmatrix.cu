@@ -1376,7 +1376,7 @@ static MMSet make_set(pgpu_grid_s *g, MassMatrices *m) {
   }
   for (int c = 0; c < 3; ++c) {
     T.J[c] = m->J0[c].view();
-    T.B[c] = g->field[3 + c].view();
+    T.B[c] = g->field[3 + c].view();   // callers have run fields_wait(g)
   }
   return T;
 }
@@ -1393,7 +1393,8 @@ using namespace pgpu;
   if (!(g) || !(g)->mm) {                                                       \
     set_error("mass matrices are not initialised (pgpu_mass_matrices_init)");   \
     return PGPU_ERR_STATE;                                                      \
-  }
+  }                                                                             \
+  if (fields_wait(g)) return PGPU_ERR_CUDA;
 
 extern "C" {
 
@@ -1606,6 +1607,7 @@ int pgpu_accumulate_mass_matrices(pgpu_species_t s, double dt) {
 int pgpu_mass_matrices_save_E0(pgpu_grid_t g) {
   NEED_MM(g);
   MassMatrices *m = mm_of(g);
+  if (fields_wait(g)) return PGPU_ERR_CUDA;
   for (int c = 0; c < 3; ++c)
     PGPU_CUDA(cudaMemcpyAsync(m->E0[c].p, g->field[c].p, m->E0[c].size() * sizeof(double), cudaMemcpyDeviceToDevice,
                               ctx().stream));

@@ -1,4 +1,4 @@
-"""Multi-box exchanges of the particle engine: one process per GPU, one Chombo box per process.
+"""Multi-box exchanges of the particle engine: one process per GPU, one or several Chombo boxes per process.
 
 What the reference does with MPI inside Chombo -- `LevelData::exchange` with an add op on the
 ghost cells of J (PicSpeciesInterface::finalizeSettingJ, PicSpeciesInterface.cpp:766-772) and
@@ -335,6 +335,47 @@ class PeerHaloExchange:
 
         self._connect(pointer_of, areas_of)
 
+    @staticmethod
+    def connect_mixed(exchanges, comm, boxes_per_rank):
+        """Several boxes per process, several processes (C5: sixteen boxes, two per GPU): boxes of this process are wired
+        with plain device pointers, the others through their CUDA IPC handles.  `exchanges` = this process's
+        PeerHaloExchange objects in box order; box b lives in process b // boxes_per_rank."""
+        import torch
+        e0 = exchanges[0]
+        capi, lib = e0.capi, e0.capi.load()
+        B = boxes_per_rank
+        assert len(exchanges) == B
+        nrec = 8 + 1 + 4 * 16
+        rec = np.zeros((B, nrec), dtype=np.int64)
+        for k, e in enumerate(exchanges):
+            hbuf = (capi.C.c_ubyte * 64)()
+            capi.check(lib.pgpu_halo_ipc_handle(e.h, hbuf))
+            rec[k, :8] = np.frombuffer(bytes(hbuf), dtype=np.int64)
+            rec[k, 8] = len(e.msgs)
+            for i, ((ph, side), (area, off)) in enumerate(sorted(e.areas.items())):
+                rec[k, 9 + 4 * i: 13 + 4 * i] = (ph, side, area, off)
+        device = torch.device("cuda", torch.cuda.current_device()) if comm.dist.get_backend() == "nccl" else "cpu"
+        allr = [x.numpy() for x in comm.all_gather(torch.as_tensor(rec).to(device))]     # [process][box, nrec]
+        local = {e.rank: e for e in exchanges}
+        opened = {}
+
+        def areas_of(b):
+            r = allr[b // B][b % B]
+            n = int(r[8])
+            return {(int(a[0]), int(a[1])): (int(a[2]), int(a[3])) for a in r[9:9 + 4 * n].reshape(n, 4)}
+
+        for e in exchanges:
+            def pointer_of(b, e=e):
+                if b in local:
+                    return local[b].inbox_pointer()
+                if b not in opened:
+                    hb = (capi.C.c_ubyte * 64).from_buffer_copy(allr[b // B][b % B][:8].tobytes())
+                    ptr = capi.C.c_void_p()
+                    capi.check(lib.pgpu_halo_ipc_open(e.h, hb, capi.C.byref(ptr)))
+                    opened[b] = ptr.value
+                return opened[b]
+            e._connect(pointer_of, areas_of)
+
     # ---- the exchange -------------------------------------------------------------------------
     def begin(self):
         self.capi.check(self.capi.load().pgpu_halo_begin(self.h))
@@ -551,6 +592,39 @@ class PeerMigration:
                 capi.check(lib.pgpu_migrator_ipc_open(self.h, hb, capi.C.byref(p)))
                 opened[peer] = p.value
             capi.check(lib.pgpu_migrator_connect(self.h, code, capi.C.c_void_p(opened[peer])))
+
+    @staticmethod
+    def connect_mixed(migrations, comm, boxes_per_rank):
+        """Several boxes per process, several processes: `migrations` = the PeerMigration objects of ONE species for
+        this process's boxes, in box order (box b lives in process b // boxes_per_rank)."""
+        import torch
+        m0 = migrations[0]
+        capi, lib = m0.capi, m0.capi.load()
+        B = boxes_per_rank
+        assert len(migrations) == B
+        rec = np.zeros((B, 9), dtype=np.int64)
+        for k, m in enumerate(migrations):
+            hbuf = (capi.C.c_ubyte * 64)()
+            capi.check(lib.pgpu_migrator_ipc_handle(m.h, hbuf))
+            rec[k, :8] = np.frombuffer(bytes(hbuf), dtype=np.int64)
+            rec[k, 8] = m.capacity
+        device = torch.device("cuda", torch.cuda.current_device()) if comm.dist.get_backend() == "nccl" else "cpu"
+        allr = [x.numpy() for x in comm.all_gather(torch.as_tensor(rec).to(device))]
+        local = {m.rank: m for m in migrations}
+        opened = {}
+        for m in migrations:
+            for code, peer in m.neighbours().items():
+                assert int(allr[peer // B][peer % B][8]) == m.capacity, "migration inboxes must have one capacity"
+                if peer in local:
+                    ptr = local[peer].inbox_pointer()
+                else:
+                    if peer not in opened:
+                        hb = (capi.C.c_ubyte * 64).from_buffer_copy(allr[peer // B][peer % B][:8].tobytes())
+                        q = capi.C.c_void_p()
+                        capi.check(lib.pgpu_migrator_ipc_open(m.h, hb, capi.C.byref(q)))
+                        opened[peer] = q.value
+                    ptr = opened[peer]
+                capi.check(lib.pgpu_migrator_connect(m.h, code, capi.C.c_void_p(ptr)))
 
     def send(self):
         self.capi.check(self.capi.load().pgpu_migrate_send(self.h))
