@@ -61,9 +61,10 @@ def parse():
     ap.add_argument("--ncell", type=int, default=512, help="cells per direction of the per-GPU box")
     ap.add_argument("--ppc", type=int, default=10, help="particles per cell per direction per species")
     ap.add_argument("--n-outer", type=int, default=3)
-    ap.add_argument("--sort-every", type=int, default=4,
-                    help="cell-sort period in steps (the reference never sorts a collisionless deck; the sort only "
-                         "keeps the fused kernel on its fast path: measured 11.6 / 10.5 / 9.9 / 9.5 ms per step at 1/2/4/8)")
+    ap.add_argument("--sort-every", type=int, default=8,
+                    help="locality-sort period in steps (the reference never sorts a collisionless deck; the sort only "
+                         "keeps the fused kernel on its fast path: measured 8.31 / 8.07 / 8.16 ms per step at 4 / 8 / 16, "
+                         "round 2, C3)")
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c5"],
                     help="c3: BASELINE configs[2], one 512^2 box x 2 species x 100 ppc per GPU (the deck the single-GPU "
                          "roofline target is quoted on); c5: the per-GPU shard of BASELINE configs[4] (2048^2 cells x 256 ppc "
