@@ -162,6 +162,23 @@ long pgpu_species_count(pgpu_species_t s);            /* numParticles() */
 int pgpu_advance_positions_explicit(pgpu_species_t s, double full_dt, int half_step); /* :463-504 */
 int pgpu_advance_positions_implicit(pgpu_species_t s, double full_dt);               /* :506-561 */
 int pgpu_advance_positions_2nd_half(pgpu_species_t s);                               /* :997-1025 */
+/* External fields: EMFields::getExternalE/B (src/fields/EMFields.H:176-198) evaluate six GridFunction objects at the
+ * particle position (x_bar during the implicit solve); PicChargedSpecies::addExternalFieldsToParticles
+ * (PicChargedSpecies.cpp:3948-3996) adds them to E_p, B_p after every gather of the particle loop (:1606, :1652, :1669).
+ * Supported here: Constant (ibc/grid_functions/Constant.H), Cosine (Cosine.H:31-45), Heavyside (Heavyside.H:40-54). */
+enum { PGPU_EXT_NONE = 0, PGPU_EXT_CONSTANT = 1, PGPU_EXT_COSINE = 2, PGPU_EXT_HEAVYSIDE = 3 };
+typedef struct {
+  int type;                        /* PGPU_EXT_* */
+  double value;                    /* Constant: value; Cosine: amplitude */
+  double constant;                 /* Cosine: constant */
+  double L[2], mode[2], phase[2];  /* Cosine: value = amplitude * prod_d cos(fmod(2 pi mode_d x_d / L_d + phase_d pi, 2 pi)) + constant */
+  double C[2], A[2], X0[2], eps[2];/* Heavyside: prod_d (C_d + A_d H(x_d - X0_d)), H = 1/2 within eps_d */
+} pgpu_ext_fn;
+/* six functions in the order Ex Ey Ez Bx By Bz; NULL switches the external fields off (the default) */
+int pgpu_grid_set_external_fields(pgpu_grid_t g, const pgpu_ext_fn *six_or_null);
+/* addExternalFieldsToParticles on the stored E_p, B_p of pgpu_interpolate_fields_to_particles; the fused advance
+ * entry points add them by themselves */
+int pgpu_add_external_fields_to_particles(pgpu_species_t s);
 int pgpu_interpolate_fields_to_particles(pgpu_species_t s);                          /* :3814-3917 */
 int pgpu_advance_velocities(pgpu_species_t s, double full_dt, int half_step);        /* :1116-1134 */
 int pgpu_advance_velocities_2nd_half(pgpu_species_t s);                              /* :1136-1244 */
@@ -187,6 +204,14 @@ int pgpu_advance_particles(pgpu_species_t s, double dt);
  * setCurrentDensity(dt,false) (:3184-3253) into the same kernel. */
 int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_J,
                                        pgpu_picard_stats *stats);
+
+/* PIC_EM_EXPLICIT: the particle side of one leap-frog step (PICTimeIntegrator_EM_Explicit::timeStep,
+ * src/time/PICTimeIntegrator_EM_Explicit.cpp:92-170, default branch) as ONE pass over the particles:
+ * interpolateFieldsToParticles + addExternalFieldsToParticles + advanceVelocities(dt, false) (:94-111),
+ * advancePositionsExplicit(dt/2) + applyBCs (:126-128), setCurrentDensity(dt, true) (:137) into the species current and,
+ * if second_half != 0, advancePositions_2ndHalf + applyBCs (:166-168; only legal to fuse when no scattering runs between
+ * the deposit and the second half).  Expects x_old == x and u_old == u (updateOldParticle*), like the separate calls. */
+int pgpu_explicit_step(pgpu_species_t s, double dt, const int *bc_lo, const int *bc_hi, int second_half);
 
 /* deposit */
 int pgpu_set_current_density(pgpu_species_t s, double dt, int from_explicit_solver); /* :3184-3253 */

@@ -53,6 +53,7 @@ def lib():
         _LIB.orc_advance_positions_2nd_half.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_void_p]
         _LIB.orc_advance_velocities_2nd_half.argtypes = [C.c_long, C.c_void_p, C.c_void_p]
         _LIB.orc_average_velocities.argtypes = [C.c_long, C.c_void_p, C.c_void_p]
+        _LIB.orc_set_external_fields.argtypes = [C.c_void_p]
         _LIB.orc_gather.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 6
         _LIB.orc_deposit_current.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 4 + [dbl, C.c_void_p]
         _LIB.orc_deposit_rho.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 4
@@ -128,6 +129,39 @@ def _fabs3(fabs):
     for i, f in enumerate(fabs):
         arr[i] = f.c()
     return arr
+
+
+class ExtFn(C.Structure):
+    _fields_ = [("type", C.c_int), ("value", C.c_double), ("constant", C.c_double),
+                ("L", C.c_double * 2), ("mode", C.c_double * 2), ("phase", C.c_double * 2),
+                ("C", C.c_double * 2), ("A", C.c_double * 2), ("X0", C.c_double * 2), ("eps", C.c_double * 2)]
+
+
+class ExtFields(C.Structure):
+    _fields_ = [("on", C.c_int), ("f", ExtFn * 6)]
+
+
+def set_external_fields(six):
+    """six: list of 6 dicts (keys of orc_ext_fn) or None.  Global, like the reference's EMFields object."""
+    if six is None:
+        lib().orc_set_external_fields(None)
+        return
+    e = ExtFields()
+    e.on = 1
+    for c, d in enumerate(six):
+        f = e.f[c]
+        f.type = int(d.get("type", 0))
+        f.value = float(d.get("value", 0.0))
+        f.constant = float(d.get("constant", 0.0))
+        for k in ("L", "mode", "phase", "C", "A", "X0", "eps"):
+            v = d.get(k, (0.0, 0.0))
+            getattr(f, k)[0], getattr(f, k)[1] = float(v[0]), float(v[1] if len(v) > 1 else 0.0)
+    lib().orc_set_external_fields(C.byref(e))
+
+
+def add_external_fields(D, x, Ep, Bp):
+    lib().orc_add_external_fields.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib().orc_add_external_fields(D, x.shape[1], _ptr(x), _ptr(Ep), _ptr(Bp))
 
 
 def gather(g, interp, x, xold, E, B):

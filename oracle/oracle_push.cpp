@@ -146,6 +146,54 @@ extern "C" void orc_average_velocities(long n, double *v, const double *vold) {
   for (long i = 0; i < 3 * n; ++i) v[i] = (v[i] + vold[i]) / 2.0;
 }
 
+/* ---- external fields ------------------------------------------------------------------------------------------- */
+static orc_ext_fields g_ext = {};
+extern "C" void orc_set_external_fields(const orc_ext_fields *ext) {
+  if (ext) g_ext = *ext;
+  else g_ext.on = 0;
+}
+extern "C" double orc_ext_value(const orc_ext_fn *f, int D, const double *x) {
+  const double PI = M_PI, TWOPI = 2.0 * M_PI;   /* PicnicConstants.H:15-17 */
+  switch (f->type) {
+    case 1: return f->value;                     /* Constant.H:30-32 */
+    case 2: {                                    /* Cosine.H:31-45 */
+      double value = f->value;
+      for (int dir = 0; dir < D; ++dir) {
+        const double X0 = x[dir], L0 = f->L[dir];
+        double arg = TWOPI * f->mode[dir] * X0 / L0 + f->phase[dir] * PI;
+        arg = std::fmod(arg, TWOPI);
+        value = value * std::cos(arg);
+      }
+      value = value + f->constant;
+      return value;
+    }
+    case 3: {                                    /* Heavyside.H:40-54 */
+      double prod = 1.0;
+      for (int dir = 0; dir < D; ++dir) {
+        const double arg = x[dir] - f->X0[dir];
+        double H = (arg < 0.0) ? 0.0 : 1.0;
+        if (std::fabs(arg) < f->eps[dir]) H = 0.5;
+        const double v = f->C[dir] + f->A[dir] * H;
+        prod = (dir == 0) ? v : prod * v;        /* RealVect::product() */
+      }
+      return prod;
+    }
+    default: return 0.0;
+  }
+}
+/* PicChargedSpecies::addExternalFieldsToParticles (PicChargedSpecies.cpp:3967-3996) */
+extern "C" void orc_add_external_fields(int D, long n, const double *x, double *Ep, double *Bp) {
+  if (!g_ext.on) return;
+  for (long p = 0; p < n; ++p) {
+    double xp[2] = {0.0, 0.0};
+    for (int d = 0; d < D; ++d) xp[d] = x[d * n + p];
+    for (int c = 0; c < 3; ++c) {
+      Ep[c * n + p] += orc_ext_value(&g_ext.f[c], D, xp);
+      Bp[c * n + p] += orc_ext_value(&g_ext.f[3 + c], D, xp);
+    }
+  }
+}
+
 /* PicChargedSpecies::advanceParticles (PicChargedSpecies.cpp:1594-1612) */
 extern "C" int orc_advance_particles(const orc_geom *g, int interpE, long n,
                                      double *x, const double *xold, double *v,
@@ -159,6 +207,7 @@ extern "C" int orc_advance_particles(const orc_geom *g, int interpE, long n,
   };
   if (order_swap) move();
   const int rc = orc_gather(g, interpE, n, x, xold, E, B, Ep.data(), Bp.data());
+  orc_add_external_fields(g->D, n, x, Ep.data(), Bp.data());   /* :1606 */
   orc_boris(n, v, vold, Ep.data(), Bp.data(), fnorm, cnormDt, 1);
   if (!order_swap) move();
   return rc;
@@ -200,6 +249,7 @@ extern "C" int orc_advance_particles_iteratively(
   long apply_its = 0;
   std::vector<double> Ep(3 * n), Bp(3 * n);
   if (orc_gather(g, interpE, n, x, xold, E, B, Ep.data(), Bp.data())) rc = -1;
+  orc_add_external_fields(g->D, n, x, Ep.data(), Bp.data());   /* :1652 */
   orc_boris(n, v, vold, Ep.data(), Bp.data(), fnorm, cnormDt, 1);
   apply_its += n;
   std::vector<long> temp;
@@ -219,6 +269,7 @@ extern "C" int orc_advance_particles_iteratively(
       }
       for (int c = 0; c < 3; ++c) vo[c] = vold[c * n + p];
       if (orc_gather(g, interpE, 1, xp, xpo, E, B, ep, bp)) rc = -1;
+      orc_add_external_fields(g->D, 1, xp, ep, bp);              /* :1669 */
       orc_boris(1, vn, vo, ep, bp, fnorm, cnormDt, 1);
       for (int c = 0; c < 3; ++c) v[c * n + p] = vn[c];
       if (its_out) its_out[p] += 1;

@@ -64,6 +64,27 @@ typedef struct {
   int bc_hi[2];    /* m_bc_check_hi */
 } orc_geom;
 
+/* External fields (EMFields::getExternalE/B, src/fields/EMFields.H:176-198): six GridFunction objects evaluated at the
+ * particle position.  Restated: Constant (ibc/grid_functions/Constant.H:30-32), Cosine (Cosine.H:31-45), Heavyside
+ * (Heavyside.H:40-54).  type: 0 = absent (value 0), 1 = Constant, 2 = Cosine, 3 = Heavyside. */
+typedef struct {
+  int type;
+  double value;                               /* Constant: m_value; Cosine: m_amplitude */
+  double constant;                            /* Cosine: m_constant */
+  double L[2], mode[2], phase[2];             /* Cosine */
+  double C[2], A[2], X0[2], eps[2];           /* Heavyside */
+} orc_ext_fn;
+typedef struct {
+  int on;                                     /* EMFields::externalFields() */
+  orc_ext_fn f[6];                            /* Ex Ey Ez Bx By Bz */
+} orc_ext_fields;
+/* set (or clear with NULL) the external fields the advance routines add after every gather
+ * (PicChargedSpecies.cpp:1606, 1652, 1669) */
+void orc_set_external_fields(const orc_ext_fields *ext);
+double orc_ext_value(const orc_ext_fn *f, int D, const double *x);
+/* PicChargedSpecies::addExternalFieldsToParticles (PicChargedSpecies.cpp:3948-3996) on stored Ep, Bp */
+void orc_add_external_fields(int D, long n, const double *x, double *Ep, double *Bp);
+
 typedef struct {
   double *p;       /* first element (lo0,lo1) of ONE component */
   int lo[2];

@@ -23,6 +23,13 @@ class PgpuError(RuntimeError):
         self.code = code
 
 
+class ExtFn(C.Structure):
+    """pgpu_ext_fn (include/picnic_gpu.h): one external-field grid function."""
+    _fields_ = [("type", C.c_int), ("value", C.c_double), ("constant", C.c_double),
+                ("L", C.c_double * 2), ("mode", C.c_double * 2), ("phase", C.c_double * 2),
+                ("C", C.c_double * 2), ("A", C.c_double * 2), ("X0", C.c_double * 2), ("eps", C.c_double * 2)]
+
+
 class GridDesc(C.Structure):
     _fields_ = [("D", C.c_int), ("ncell", C.c_int * 2), ("xmin", C.c_double * 2), ("dx", C.c_double * 2),
                 ("nghost", C.c_int), ("periodic", C.c_int * 2), ("box_lo", C.c_int * 2),
@@ -97,6 +104,8 @@ def load():
         "pgpu_advance_particles": [vp, dbl], "pgpu_advance_particles_iteratively": [vp, dbl, i32, vp],
         "pgpu_set_current_density": [vp, dbl, i32], "pgpu_species_current_get": [vp, i32, vp, vp, vp],
         "pgpu_set_charge_density": [vp, vp, vp, vp, vp],
+        "pgpu_explicit_step": [vp, C.c_double, vp, vp, C.c_int],
+        "pgpu_grid_set_external_fields": [vp, vp], "pgpu_add_external_fields_to_particles": [vp],
         "pgpu_fields_packed_size": [vp, vp], "pgpu_fields_set_packed": [vp, vp],
         "pgpu_current_packed_size": [vp, vp], "pgpu_current_get_packed_async": [vp, vp],
         "pgpu_bin_particles": [vp], "pgpu_sort_for_locality": [vp], "pgpu_species_cell_index": [vp, vp],
@@ -190,6 +199,14 @@ class Grid:
         a = np.asfortranarray(arr, dtype=np.float64)
         check(load().pgpu_fields_set(self.h, comp, _p(a), _i2(lo), _i2(hi)))
         self._keep = a  # async H2D: keep the host buffer alive until the next sync
+
+    def set_external_fields(self, six):
+        """six: list of 6 ExtFn (Ex Ey Ez Bx By Bz) or None to switch them off."""
+        if six is None:
+            check(load().pgpu_grid_set_external_fields(self.h, None))
+        else:
+            arr = (ExtFn * 6)(*six)
+            check(load().pgpu_grid_set_external_fields(self.h, arr))
 
     def fields_packed_size(self):
         n = C.c_long()
@@ -319,6 +336,12 @@ class Species:
 
     def advance_positions_2nd_half(self):
         check(load().pgpu_advance_positions_2nd_half(self.h))
+
+    def explicit_step(self, dt, bc_lo, bc_hi, second_half=False):
+        check(load().pgpu_explicit_step(self.h, dt, _i2(bc_lo), _i2(bc_hi), int(second_half)))
+
+    def add_external_fields(self):
+        check(load().pgpu_add_external_fields_to_particles(self.h))
 
     def interpolate_fields(self):
         check(load().pgpu_interpolate_fields_to_particles(self.h))

@@ -678,6 +678,7 @@ int pgpu_host_unregister(void *ptr) {
 
 int pgpu_current_zero(pgpu_grid_t g) {
   NEED_INIT();
+  if (!g) return PGPU_ERR_ARG;
   size_t n = 0;
   for (int c = 0; c < 3; ++c) n += g->jtot[c].size();
   PGPU_CUDA(cudaMemsetAsync(g->jtot[0].p, 0, n * sizeof(double), ctx().stream));   // one arena (alloc_fab_arena)
@@ -686,6 +687,7 @@ int pgpu_current_zero(pgpu_grid_t g) {
 
 int pgpu_current_add_species(pgpu_grid_t g, pgpu_species_t s) {
   NEED_INIT();
+  if (!g || !s) return PGPU_ERR_ARG;
   Ptr3 P;
   long mx = 0;
   for (int c = 0; c < 3; ++c) {
@@ -701,6 +703,7 @@ int pgpu_current_add_species(pgpu_grid_t g, pgpu_species_t s) {
 
 int pgpu_current_finalize(pgpu_grid_t g) {
   NEED_INIT();
+  if (!g) return PGPU_ERR_ARG;
   const DeviceFab *all[3] = {&g->jtot[0], &g->jtot[1], &g->jtot[2]};
   return fold_periodic_n(g, all, 3);
 }
@@ -727,6 +730,8 @@ int pgpu_species_create(pgpu_grid_t g, const pgpu_species_desc *d, pgpu_species_
     return PGPU_ERR_ARG;
   }
   pgpu_species_s *s = new pgpu_species_s();
+  static unsigned next_serial = 1;
+  s->serial = next_serial++;
   s->grid = g;
   s->desc = *d;
   for (int c = 0; c < 3; ++c) {
@@ -790,6 +795,11 @@ int pgpu_species_destroy(pgpu_species_t s) {
 
 long pgpu_species_count(pgpu_species_t s) { return s ? s->n : -1; }
 
+static __global__ void k_iota_ids(uint64_t *id, long n, uint64_t base) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) id[i] = base + (uint64_t)i;
+}
+
 int pgpu_species_upload(pgpu_species_t s, long n, const double *x, const double *xold, const double *v,
                         const double *vold, const double *w, const uint64_t *id) {
   NEED_INIT();
@@ -808,7 +818,12 @@ int pgpu_species_upload(pgpu_species_t s, long n, const double *x, const double 
   }
   PGPU_CUDA(cudaMemcpyAsync(s->w, w, nb8, cudaMemcpyHostToDevice, st));
   if (id) PGPU_CUDA(cudaMemcpyAsync(s->id, id, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  else PGPU_CUDA(cudaMemsetAsync(s->id, 0, (size_t)n * sizeof(uint64_t), st));
+  else {
+    // no ids given: unique ones are made up (serial of the species in the high bits, index below).  The collision
+    // kernels key their per-particle draws (shuffle order, weight rejection, partner pick) on the id: identical ids
+    // would give every particle of a cell identical draws
+    if (n > 0) k_iota_ids<<<nb(n), 256, 0, st>>>(s->id, n, (uint64_t)s->serial << 40);
+  }
   PGPU_CUDA(cudaStreamSynchronize(st));
   s->n = n;
   s->binned = false;
@@ -961,6 +976,7 @@ int pgpu_update_old_particle_velocities(pgpu_species_t s) {
 
 int pgpu_reset_particles(pgpu_species_t s) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   for (int d = 0; d < s->grid->desc.D; ++d)
     PGPU_CUDA(cudaMemcpyAsync(s->x[d], s->xold[d], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
@@ -968,6 +984,47 @@ int pgpu_reset_particles(pgpu_species_t s) {
     PGPU_CUDA(cudaMemcpyAsync(s->v[c], s->vold[c], s->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
   s->binned = false;
   return 0;
+}
+
+int pgpu_grid_set_external_fields(pgpu_grid_t g, const pgpu_ext_fn *six) {
+  NEED_INIT();
+  if (!g) return PGPU_ERR_ARG;
+  memset(&g->ext, 0, sizeof(g->ext));
+  if (!six) return 0;
+  for (int c = 0; c < 6; ++c) {
+    const pgpu_ext_fn &f = six[c];
+    if (f.type < PGPU_EXT_NONE || f.type > PGPU_EXT_HEAVYSIDE) {
+      set_error("external field %d: unknown grid function type %d", c, f.type);
+      return PGPU_ERR_ARG;
+    }
+    ExtFn &o = g->ext.f[c];
+    o.type = f.type;
+    o.value = f.value;
+    o.constant = f.constant;
+    for (int d = 0; d < 2; ++d) {
+      o.L[d] = f.L[d]; o.mode[d] = f.mode[d]; o.phase[d] = f.phase[d];
+      o.C[d] = f.C[d]; o.A[d] = f.A[d]; o.X0[d] = f.X0[d]; o.eps[d] = f.eps[d];
+    }
+    if (f.type == PGPU_EXT_COSINE)
+      for (int d = 0; d < g->desc.D; ++d)
+        if (!(f.L[d] != 0.0)) {
+          set_error("external field %d: Cosine needs L[%d] != 0", c, d);
+          return PGPU_ERR_ARG;
+        }
+  }
+  g->ext.on = 1;   // EMFields::externalFields(): components of type NONE contribute zero
+  return 0;
+}
+
+int pgpu_add_external_fields_to_particles(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  if (!s->desc.forces || s->desc.charge == 0.0 || !s->grid->ext.on) return 0;   // PicChargedSpecies.cpp:3950-3952
+  if (!s->Ep[0]) {
+    set_error("addExternalFieldsToParticles needs particle fields: call pgpu_interpolate_fields_to_particles first");
+    return PGPU_ERR_STATE;
+  }
+  return launch_add_external(s);
 }
 
 int pgpu_interpolate_fields_to_particles(pgpu_species_t s) {
@@ -1008,6 +1065,7 @@ static AdvanceParams make_params(pgpu_species_t s, double dt, bool iterative) {
   p.rvolume = 1.0 / p.volume;
   p.rel = s->desc.relativistic;
   p.hc = s->desc.higuera_cary;
+  p.ext = s->grid->ext;
   return p;
 }
 
@@ -1082,10 +1140,48 @@ int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_
 
 int pgpu_set_current_density(pgpu_species_t s, double dt, int from_explicit_solver) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   s->dep_from_explicit = from_explicit_solver ? 1 : 0;
   for (int c = 0; c < 3; ++c)
     PGPU_CUDA(cudaMemsetAsync(s->J[c].p, 0, s->J[c].size() * sizeof(double), ctx().stream));
   int rc = launch_deposit_current(s, dt * s->desc.cvac_norm);
+  if (rc) return rc;
+  return scale_species_current(s);
+}
+
+// The particle side of one PIC_EM_EXPLICIT leap-frog step (PICTimeIntegrator_EM_Explicit.cpp:92-170) in one pass:
+// see k_explicit_step (pgpu_push.cu).  Composes the separate calls where the fused kernel does not apply (relativistic
+// species, non-periodic particle BCs, switched-off motion or forces).
+int pgpu_explicit_step(pgpu_species_t s, double dt, const int *bc_lo, const int *bc_hi, int second_half) {
+  NEED_INIT();
+  if (!s || !bc_lo || !bc_hi) return PGPU_ERR_ARG;
+  const int D = s->grid->desc.D;
+  bool fused = !s->desc.relativistic && s->desc.motion && s->desc.forces && s->desc.charge != 0.0;
+  int periodic[2] = {0, 0};
+  for (int d = 0; d < D; ++d) {
+    if (bc_lo[d] != bc_hi[d] || (bc_lo[d] != PGPU_BC_PERIODIC && bc_lo[d] != PGPU_BC_NONE)) fused = false;
+    periodic[d] = bc_lo[d] == PGPU_BC_PERIODIC;
+  }
+  for (int d = 0; d < D; ++d)
+    if (s->desc.bc_check_lo[d] || s->desc.bc_check_hi[d]) fused = false;
+  if (!fused) {
+    int rc = pgpu_interpolate_fields_to_particles(s);
+    if (!rc) rc = pgpu_add_external_fields_to_particles(s);
+    if (!rc) rc = pgpu_advance_velocities(s, dt, 0);
+    if (!rc) rc = pgpu_advance_positions_explicit(s, dt, 1);
+    if (!rc) rc = pgpu_apply_bcs(s, bc_lo, bc_hi);
+    if (!rc) rc = pgpu_set_current_density(s, dt, 1);
+    if (!rc && second_half) {
+      rc = pgpu_advance_positions_2nd_half(s);
+      if (!rc) rc = pgpu_apply_bcs(s, bc_lo, bc_hi);
+    }
+    return rc;
+  }
+  s->binned = false;
+  s->dep_from_explicit = 1;
+  for (int c = 0; c < 3; ++c)
+    PGPU_CUDA(cudaMemsetAsync(s->J[c].p, 0, s->J[c].size() * sizeof(double), ctx().stream));
+  int rc = launch_explicit_step(s, make_params(s, dt, false), periodic, second_half != 0);
   if (rc) return rc;
   return scale_species_current(s);
 }

@@ -547,6 +547,7 @@ int pgpu_set_moments_from_bins(pgpu_species_t s) {
 
 int pgpu_species_moments_get(pgpu_species_t s, double *dens, double *mom, double *ene) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   const long nc = s->grid->ncell_box;
   cudaStream_t st = ctx().stream;
   if (dens) PGPU_CUDA(cudaMemcpyAsync(dens, s->dens, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -558,6 +559,7 @@ int pgpu_species_moments_get(pgpu_species_t s, double *dens, double *mom, double
 
 int pgpu_debye_length(pgpu_grid_t g, pgpu_species_t *species, int nspecies, double *LDe) {
   NEED_INIT();
+  if (!g) return PGPU_ERR_ARG;
   const int nc = (int)g->ncell_box;
   cudaStream_t st = ctx().stream;
   PGPU_CUDA(cudaMemsetAsync(g->debye, 0, nc * sizeof(double), st));
@@ -580,6 +582,7 @@ int pgpu_debye_length(pgpu_grid_t g, pgpu_species_t *species, int nspecies, doub
 
 int pgpu_set_charge_density(pgpu_species_t s, const int *stag, double *data, const int *lo, const int *hi) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   pgpu_grid_s *g = s->grid;
   const int D = g->desc.D;
   Context &c = ctx();
@@ -695,6 +698,7 @@ int pgpu_finish_implicit_step(pgpu_species_t s, const int *bc_lo, const int *bc_
 
 int pgpu_stable_dt(pgpu_species_t s, double *dt_out) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   Context &c = ctx();
   unsigned long long *d_bits = &c.d_counters->maxbits;  // zero between calls
   Counters k;
@@ -717,6 +721,7 @@ int pgpu_stable_dt(pgpu_species_t s, double *dt_out) {
 
 int pgpu_global_moments(pgpu_species_t s, double *out) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   Context &c = ctx();
   double *d_out = nullptr;
   PGPU_CUDA(cudaMalloc(&d_out, 7 * sizeof(double)));

@@ -1491,6 +1491,26 @@ static int fetch_pairs(long *out) {
   return 0;
 }
 
+// Every scattering operator draws from its own Philox stream: the caller's seed is mixed with the identity of the two
+// species (mass and charge: stable when a species object is re-created, e.g. at a restart) and a per-model salt
+// (splitmix64 finaliser), so that e-e and i-i self-scattering, or e-i1 and e-i2, of one step do not replay each other's
+// draws when a driver hands every operator the same (seed, step).  Two species with identical mass and charge are told
+// apart by the caller's seed (the C++ shim gives every operator object its own).
+static uint64_t species_tag(const pgpu_species_s *s) {
+  if (!s) return 0;
+  uint64_t a, b;
+  memcpy(&a, &s->desc.mass, 8);
+  memcpy(&b, &s->desc.charge, 8);
+  return a * 0x9e3779b97f4a7c15ull ^ (b + 0x7f4a7c15ull) * 0xc2b2ae3d27d4eb4full;
+}
+static uint64_t stream_seed(uint64_t seed, const pgpu_species_s *sA, const pgpu_species_s *sB, uint64_t salt) {
+  uint64_t z = seed ^ species_tag(sA) ^ (species_tag(sB) << 1 | species_tag(sB) >> 63) ^ (salt << 8);
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
 static int need_binned(pgpu_species_t sA, pgpu_species_t sB) {
   if (!ctx().inited) {
     set_error("pgpu_init has not been called");
@@ -1520,6 +1540,7 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
   P.rel = (sA->desc.relativistic || sB->desc.relativistic) ? 1 : 0;   // the reference's compile-time switch
   const double dV = (g->desc.D == 1) ? g->geo.dx[0] : g->geo.dx[0] * g->geo.dx[1];
   P.cellV_SI = dV * g->desc.volume_scale;
+  seed = stream_seed(seed, sA, sB, 1);
   P.seed_lo = (unsigned)seed;
   P.seed_hi = (unsigned)(seed >> 32);
   P.step_lo = (unsigned)step;
@@ -1568,18 +1589,35 @@ int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elasti
   P.angular = prm->angular_scattering;
   P.loglog = prm->use_loglog_interp;
   P.E = P.Q = P.XI = nullptr;
-  double *d_tab = nullptr;
   if (prm->ntab) {
+    // the cross-section table lives on the device between calls (no cudaMalloc / cudaFree in the middle of a step):
+    // re-uploaded only when its contents change
+    static double *d_tab = nullptr;
+    static size_t d_cap = 0;
+    static std::vector<double> h_tab;
     const size_t N = (size_t)prm->ntab;
-    PGPU_CUDA(cudaMalloc(&d_tab, 3 * N * sizeof(double)));
-    PGPU_CUDA(cudaMemcpyAsync(d_tab, prm->E, N * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    PGPU_CUDA(cudaMemcpyAsync(d_tab + N, prm->Q, N * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    if (prm->xi) PGPU_CUDA(cudaMemcpyAsync(d_tab + 2 * N, prm->xi, N * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    else PGPU_CUDA(cudaMemsetAsync(d_tab + 2 * N, 0, N * sizeof(double), c.stream));
+    std::vector<double> cur(3 * N, 0.0);
+    memcpy(cur.data(), prm->E, N * sizeof(double));
+    memcpy(cur.data() + N, prm->Q, N * sizeof(double));
+    if (prm->xi) memcpy(cur.data() + 2 * N, prm->xi, N * sizeof(double));
+    if (cur != h_tab) {
+      if (3 * N > d_cap) {
+        if (d_tab) {
+          cudaStreamSynchronize(c.stream);
+          cudaFree(d_tab);
+        }
+        PGPU_CUDA(cudaMalloc(&d_tab, 3 * N * sizeof(double)));
+        d_cap = 3 * N;
+      }
+      PGPU_CUDA(cudaStreamSynchronize(c.stream));   // an earlier launch may still read the old table
+      PGPU_CUDA(cudaMemcpy(d_tab, cur.data(), 3 * N * sizeof(double), cudaMemcpyHostToDevice));
+      h_tab.swap(cur);
+    }
     P.E = d_tab;
     P.Q = d_tab + N;
     P.XI = d_tab + 2 * N;
   }
+  seed = stream_seed(seed, sA, sB, 3);
   P.seed_lo = (unsigned)seed;
   P.seed_hi = (unsigned)(seed >> 32);
   P.step_lo = (unsigned)step;
@@ -1591,12 +1629,7 @@ int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elasti
                                                           sA->v[2], sA->w, sA->id, sB->v[0], sB->v[1], sB->v[2], sB->w,
                                                           sB->dens, P, &c.d_counters->npairs);
   }
-  rc = fetch_pairs(ncoll_out);
-  if (d_tab) {
-    cudaStreamSynchronize(c.stream);
-    cudaFree(d_tab);
-  }
-  return rc;
+  return fetch_pairs(ncoll_out);
 }
 
 static int launch_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, HSParams P, double dt_sec, uint64_t seed,
@@ -1615,6 +1648,7 @@ static int launch_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, HSParams P, 
   P.mu = P.mass1 * P.mass2 / (P.mass1 + P.mass2);
   const double dV = (g->desc.D == 1) ? g->geo.dx[0] : g->geo.dx[0] * g->geo.dx[1];
   P.Vc = dV * g->desc.volume_scale;      // DomainGrid::getMappedCellVolume in SI
+  seed = stream_seed(seed, sA, sB, 5);
   P.seed_lo = (unsigned)seed;
   P.seed_hi = (unsigned)(seed >> 32);
   P.step_lo = (unsigned)step;
@@ -1649,6 +1683,7 @@ int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT
 int pgpu_collide_hard_sphere_wm(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, int weight_method, double dt_sec,
                                 uint64_t seed, uint64_t step, long *ncoll_out) {
   if (weight_method == 0) return pgpu_collide_hard_sphere(sA, sB, sigmaT, dt_sec, seed, step, ncoll_out);
+  if (!sA || !sB) return PGPU_ERR_ARG;
   if (weight_method != 1 || sA != sB) {
     set_error("HardSphere: the CONSERVATIVE weight method is implemented for self-scattering only");
     return PGPU_ERR_ARG;
@@ -1689,6 +1724,7 @@ int pgpu_collide_vhs(pgpu_species_t s, double eta, double T0, double mu0, double
   memset(&P, 0, sizeof(P));
   P.vhs = 1;
   P.sigmaT = 1.0;
+  if (!s) return PGPU_ERR_ARG;
   vhs_consts(s->desc.mass, eta, T0, mu0, &P.fourPiA, &P.fourOverAlpha);
   return launch_hard_sphere(s, s, P, dt_sec, seed, step, ncoll_out, "VariableHardSphere");
 }
@@ -1799,6 +1835,7 @@ int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt
   P.dt_sec = dt_sec;
   P.f1 = (double)(mu / m1);
   P.f2 = (double)(mu / m2);
+  seed = stream_seed(seed, sA, sB, 7);
   P.seed_lo = (unsigned)seed;
   P.seed_hi = (unsigned)(seed >> 32);
   P.step_lo = (unsigned)step;

@@ -66,6 +66,53 @@ __device__ __forceinline__ void warp_aggregated_add(double *base, long idx, doub
   }
 }
 
+// ---- external fields (EMFields::getExternalE/B; Constant.H, Cosine.H:31-45, Heavyside.H:40-54) -------------------
+struct ExtFn {
+  int type;
+  double value, constant;
+  double L[2], mode[2], phase[2];
+  double C[2], A[2], X0[2], eps[2];
+};
+struct ExtFields {
+  int on;
+  ExtFn f[6];
+};
+template <int D>
+__device__ __forceinline__ double ext_value(const ExtFn &f, const double *x) {
+  if (f.type == 1) return f.value;
+  if (f.type == 2) {
+    const double PI = 3.14159265358979323846, TWOPI = 2.0 * PI;   // PicnicConstants.H:15-17
+    double value = f.value;
+#pragma unroll
+    for (int dir = 0; dir < D; ++dir) {
+      double arg = __dadd_rn(__ddiv_rn(__dmul_rn(__dmul_rn(TWOPI, f.mode[dir]), x[dir]), f.L[dir]), __dmul_rn(f.phase[dir], PI));
+      arg = fmod(arg, TWOPI);
+      value = __dmul_rn(value, cos(arg));
+    }
+    return __dadd_rn(value, f.constant);
+  }
+  if (f.type == 3) {
+    double prod = 1.0;
+#pragma unroll
+    for (int dir = 0; dir < D; ++dir) {
+      const double arg = __dsub_rn(x[dir], f.X0[dir]);
+      double H = (arg < 0.0) ? 0.0 : 1.0;
+      if (fabs(arg) < f.eps[dir]) H = 0.5;
+      const double v = __dadd_rn(f.C[dir], __dmul_rn(f.A[dir], H));
+      prod = (dir == 0) ? v : __dmul_rn(prod, v);
+    }
+    return prod;
+  }
+  return 0.0;
+}
+// E_p += extE(x), B_p += extB(x) (PicChargedSpecies.cpp:3984-3991); acc = E_p[3], B_p[3]
+template <int D>
+__device__ __forceinline__ void add_external(const ExtFields &ext, const double *x, double *acc) {
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+    if (ext.f[c].type) acc[c] = __dadd_rn(acc[c], ext_value<D>(ext.f[c], x));
+}
+
 // ---- arithmetic helpers ------------------------------------------------------
 template <bool X>
 struct M;

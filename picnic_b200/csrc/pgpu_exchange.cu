@@ -196,7 +196,7 @@ struct MigPeers {
 };
 struct MigResult {             // written by the receiving kernel, read back by the host
   long long n_final, n_arrived, n_left, n_lost;
-  unsigned overflow, pad;
+  unsigned overflow, pad;      // leavers that did not fit a neighbour's inbox area (dropped; reported as an error)
 };
 
 // leavers -> the neighbours' inboxes (peer stores), holes below new_n = n - nleave
@@ -214,13 +214,15 @@ __global__ void k_mig_pack_send(WirePtrs P, const int *list, const int *dead, Mi
         const MigBoxView v = migbox_view(peers.inbox[code]);
         wire_out(P, i, v.recs + (((size_t)parity * 9 + (8 - code)) * cap + pos) * nw);
       } else {
-        *overflow = 1u;
+        atomicAdd(overflow, 1u);        // dropped: counted, reported by pgpu_migrate_finish as an error
       }
+    } else if (code < 9 && code != 4) {
+      atomicAdd(&mc->count[9], 1u);     // a leaver towards a direction without a connected box is lost, not sent
     }
     if (i < new_n) {
       const unsigned h = atomicAdd(&mc->nhole, 1u);
       if ((long)h < list_cap) holes[h] = (int)i;
-      else *overflow = 1u;
+      else atomicAdd(overflow, 1u);
     }
   }
   __threadfence_system();
@@ -636,17 +638,19 @@ int pgpu_migrate_finish(pgpu_migrator_t m, long *n_arrived, long *n_left, long *
   PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
   m->sent = m->received = false;
   pgpu_species_s *s = m->s;
-  if (m->h_res->overflow) {
-    set_error("migration inbox overflow: more than %ld particles left for one neighbour (raise the capacity of "
-              "pgpu_migrator_create)", m->cap);
-    return PGPU_ERR_STATE;
-  }
+  // the species is left consistent in every case: the leavers are gone, the arrivals appended, the count updated
   s->n = (long)m->h_res->n_final;
   s->binned = false;
   s->mig_marked = false;
   if (n_arrived) *n_arrived = (long)m->h_res->n_arrived;
   if (n_left) *n_left = (long)m->h_res->n_left;
-  if (n_lost) *n_lost = (long)m->h_res->n_lost;
+  if (n_lost) *n_lost = (long)m->h_res->n_lost + (long)m->h_res->overflow;
+  if (m->h_res->overflow) {
+    PGPU_CUDA(cudaMemsetAsync(m->d_overflow, 0, sizeof(unsigned), ctx().stream));
+    set_error("migration inbox overflow: %u leavers did not fit an inbox area of %ld particles and were dropped (raise "
+              "the capacity of pgpu_migrator_create)", m->h_res->overflow, m->cap);
+    return PGPU_ERR_STATE;
+  }
   return 0;
 }
 

@@ -55,6 +55,7 @@ struct AdvanceParams {
   double volume;    // cell volume prod(dx) (deposit)
   double rvolume;   // 1/volume
   int rel, hc;      // RELATIVISTIC_PARTICLES build of the push; Higuera-Cary gamma
+  ExtFields ext;    // external fields added after every gather (addExternalFieldsToParticles)
 };
 
 struct Counters {          // device-resident, 64-bit
@@ -142,6 +143,7 @@ struct pgpu_grid_s {
   pgpu::DeviceFab field[6];             // the selected slot (aliases field_slot[cur_slot])
   pgpu::DeviceFab field_slot[4][6];     // resident field sets (slot 0 always allocated)
   int cur_slot = 0;
+  pgpu::ExtFields ext = {};             // pgpu_grid_set_external_fields
   // pgpu_fields_set_packed copies on the library's copy stream (so that the upload of one box overlaps the particle
   // kernels of another); every reader of the field arrays orders itself behind it with fields_wait()
   cudaEvent_t upload_done = nullptr;
@@ -162,6 +164,7 @@ struct pgpu_grid_s {
 struct pgpu_species_s {
   pgpu_grid_t grid = nullptr;
   pgpu_species_desc desc;
+  unsigned serial = 0;   // creation order of the species in this process (random-stream separation, default particle ids)
   long n = 0;
   size_t cap = 0;
   double *x[2] = {nullptr, nullptr}, *xold[2] = {nullptr, nullptr};
@@ -240,6 +243,8 @@ enum { KEEP_XOLD_ALIAS = 1, KEEP_VOLD_ALIAS = 2, KEEP_OLD_ALIASES = 3, KEEP_PEND
 int materialize_old(pgpu_species_s *s, int keep = 0);
 int grow_capacity(pgpu_species_s *s, long n);   // keeps the particles (pgpu_api.cu)
 int launch_gather(pgpu_species_s *s);
+int launch_add_external(pgpu_species_s *s);
+int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int *periodic, bool second_half);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);
 int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit);

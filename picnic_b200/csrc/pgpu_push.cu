@@ -93,6 +93,35 @@ k_gather(PartPtrs p, long n, Geo<D> g, FieldSet F, Counters *cnt) {
   flush_counters(cnt, 0, 0, err);
 }
 
+// ---- addExternalFieldsToParticles on the stored Ep, Bp (PicChargedSpecies.cpp:3967-3996) ----------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_add_external(PartPtrs p, long n, ExtFields ext) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x[D], acc[6];
+#pragma unroll
+  for (int d = 0; d < D; ++d) x[d] = p.x[d][i];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    acc[c] = p.Ep[c][i];
+    acc[3 + c] = p.Bp[c][i];
+  }
+  add_external<D>(ext, x, acc);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    p.Ep[c][i] = acc[c];
+    p.Bp[c][i] = acc[3 + c];
+  }
+}
+int launch_add_external(pgpu_species_s *s) {
+  if (s->n == 0 || !s->grid->ext.on) return 0;
+  KTimer t("add_external");
+  const unsigned nb = (unsigned)((s->n + 255) / 256);
+  if (s->grid->desc.D == 1) k_add_external<1><<<nb, 256, 0, ctx().stream>>>(s->ptrs(), s->n, s->grid->ext);
+  else k_add_external<2><<<nb, 256, 0, ctx().stream>>>(s->ptrs(), s->n, s->grid->ext);
+  return 0;
+}
+
 // ---- setCurrentDensity: deposit only ------------------------------------------------
 template <int D, int IJ, bool X>
 __global__ void __launch_bounds__(256)
@@ -172,6 +201,7 @@ k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
       GatherOp<D, X> op(F);
       if (!gather_visit<D, IE, X>(g, xb, xo, op)) err |= ERRBIT_SEGMENTS;
       if (op.oob) err |= ERRBIT_BOUNDS;
+      if (prm.ext.on) add_external<D>(prm.ext, xb, op.acc);   // :1606
       boris<X>(uo, op.acc, op.acc + 3, prm.alpha, true, ub, prm.rel, prm.hc);
       apply += 1;
       if (!prm.order_swap) {
@@ -198,6 +228,7 @@ k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
           err |= ERRBIT_BOUNDS;
           break;
         }
+        if (prm.ext.on) add_external<D>(prm.ext, xb, op.acc);   // :1652, :1669
         boris<X>(uo, op.acc, op.acc + 3, prm.alpha, true, ub, prm.rel, prm.hc);
         apply += 1;
         double dxp[D];
@@ -360,11 +391,137 @@ static int launch_advance_d(pgpu_species_s *s, const AdvanceParams &prm, bool fu
 // fuse_deposit requires interp_J == interp_E (the fused kernel reuses one visitor type).
 // 2D CC1 species in fast arithmetic take the specialised kernel (pgpu_advance_cc1.cu)
 // first; this generic visitor kernel then handles only the particles it deferred.
+// ---- PIC_EM_EXPLICIT: the particle side of one leap-frog step in ONE pass ----------------------------------------------
+// PICTimeIntegrator_EM_Explicit::timeStep (src/time/PICTimeIntegrator_EM_Explicit.cpp:92-170), default branch (no Strang
+// splitting, no averaged-v deposit, no scattering between the calls):
+//   interpolateFieldsToParticles + addExternalFieldsToParticles + advanceVelocities(dt, false)        (:94-111)
+//   advancePositionsExplicit(dt/2) + applyBCs                                                        (:126-128)
+//   setCurrentDensity(dt, from_explicit = true)                                                      (:137)
+//   advancePositions_2ndHalf + applyBCs  (optional: `second_half`)                                    (:166-168)
+// The separate calls move 48 B of stored E_p, B_p per particle out and back in and read the particle arrays four times;
+// here a particle is read once (x, x_old, u_old, w) and written once (x, u).  Same arithmetic, same order per particle.
+struct ExplicitArgs {
+  int periodic[2];
+  double left[2], right[2];
+  int second_half;
+};
+template <int D>
+__device__ __forceinline__ void wrap_periodic(const ExplicitArgs &e, double *xp, double *xo) {
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    if (!e.periodic[d]) continue;
+    const double Lbox = __dsub_rn(e.right[d], e.left[d]);   // PicChargedSpeciesBC::enforcePeriodic (:738-765)
+    if (xp[d] < e.left[d]) {
+      xp[d] = __dadd_rn(xp[d], Lbox);
+      xo[d] = __dadd_rn(xo[d], Lbox);
+    }
+    if (xp[d] >= e.right[d]) {
+      xp[d] = __dsub_rn(xp[d], Lbox);
+      xo[d] = __dsub_rn(xo[d], Lbox);
+    }
+  }
+}
+template <int D, int IE, int IJ, bool X>
+__global__ void __launch_bounds__(256)
+k_explicit_step(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams prm, ExplicitArgs e, Counters *cnt) {
+  typedef M<X> m;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned err = 0;
+  if (i < n) {
+    double xp[D], xo[D], uo[3], u[3];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      xp[d] = p.x[d][i];
+      xo[d] = p.xold[d][i];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) uo[c] = p.vold[c][i];
+    GatherOp<D, X> op(F);
+    if (!gather_visit<D, IE, X>(g, xp, xo, op)) err |= ERRBIT_SEGMENTS;
+    if (op.oob) err |= ERRBIT_BOUNDS;
+    if (prm.ext.on) add_external<D>(prm.ext, xp, op.acc);
+    boris<X>(uo, op.acc, op.acc + 3, prm.alpha, false, u, 0, 0);   // advanceVelocities(dt, byHalfDt = false)
+    const double hdt = m::mul(prm.cnormDt, 0.5);
+#pragma unroll
+    for (int d = 0; d < D; ++d) xp[d] = m::mad(u[d], hdt, xo[d]);   // advancePositionsExplicit(dt/2): x = x_old + u cnormHalfDt
+    wrap_periodic<D>(e, xp, xo);
+    if (!(err & (ERRBIT_SEGMENTS | ERRBIT_BOUNDS))) {
+      const double rhop = X ? __ddiv_rn(p.w[i], prm.volume) : p.w[i] * prm.rvolume;
+      DepositOpGlobal<D, X> dop(J);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dop.val[c] = m::mul(u[c], rhop);
+      if (!deposit_visit<D, IJ, X>(g, xp, xo, dop)) err |= ERRBIT_SEGMENTS;
+      if (dop.oob) err |= ERRBIT_BOUNDS;
+    }
+    if (e.second_half) {   // advancePositions_2ndHalf: x = 2 x - x_old, then applyBCs
+#pragma unroll
+      for (int d = 0; d < D; ++d) xp[d] = m::sub(m::mul(2.0, xp[d]), xo[d]);
+      wrap_periodic<D>(e, xp, xo);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      p.x[d][i] = xp[d];
+      p.xold[d][i] = xo[d];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p.v[c][i] = u[c];
+  }
+  flush_counters(cnt, 0, 0, err);
+}
+
+template <int D, int IE, int IJ>
+static int launch_explicit_t(pgpu_species_s *s, const AdvanceParams &prm, const ExplicitArgs &e) {
+  Context &c = ctx();
+  const Geo<D> g = make_geo<D>(species_geo(s));
+  const FieldSet F = grid_fields(s->grid);
+  const CurrentSet J = species_current(s);
+  KTimer t("explicit_step_fused");
+  if (c.exact)
+    k_explicit_step<D, IE, IJ, true><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, e, c.d_counters);
+  else
+    k_explicit_step<D, IE, IJ, false><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, e, c.d_counters);
+  return 0;
+}
+template <int D, int IE>
+static int launch_explicit_e(pgpu_species_s *s, const AdvanceParams &prm, const ExplicitArgs &e) {
+  switch (s->desc.interp_J) {
+    case CIC: return launch_explicit_t<D, IE, CIC>(s, prm, e);
+    case TSC: return launch_explicit_t<D, IE, TSC>(s, prm, e);
+    case CC0: return launch_explicit_t<D, IE, CC0>(s, prm, e);
+    case CC1: return launch_explicit_t<D, IE, CC1>(s, prm, e);
+  }
+  return PGPU_ERR_ARG;
+}
+template <int D>
+static int launch_explicit_d(pgpu_species_s *s, const AdvanceParams &prm, const ExplicitArgs &e) {
+  switch (s->desc.interp_E) {
+    case CIC: return launch_explicit_e<D, CIC>(s, prm, e);
+    case TSC: return launch_explicit_e<D, TSC>(s, prm, e);
+    case CC0: return launch_explicit_e<D, CC0>(s, prm, e);
+    case CC1: return launch_explicit_e<D, CC1>(s, prm, e);
+  }
+  return PGPU_ERR_ARG;
+}
+// bc: 1 = periodic in that direction (the only particle BC the fused pass applies)
+int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int *periodic, bool second_half) {
+  if (s->n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  ExplicitArgs e;
+  const GeoAny &ga = s->grid->geo;
+  for (int d = 0; d < 2; ++d) {
+    e.periodic[d] = (d < ga.D) ? periodic[d] : 0;
+    e.left[d] = ga.le[d];
+    e.right[d] = ga.re[d];
+  }
+  e.second_half = second_half ? 1 : 0;
+  return ga.D == 1 ? launch_explicit_d<1>(s, prm, e) : launch_explicit_d<2>(s, prm, e);
+}
+
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit) {
   if (s->n == 0) return 0;
   if (materialize_old(s, KEEP_OLD_ALIASES)) return PGPU_ERR_CUDA;   // pending gathers; an aliased old group is left to the CC1 kernel
   bool deferred = false;
-  if (ctx().use_fast_cc1) {
+  if (ctx().use_fast_cc1 && !prm.ext.on) {   // the specialised CC1 kernels gather from the grid arrays only
     int fr = launch_advance_cc1_fast(s, prm, fuse_deposit);
     if (fr == 0) fr = launch_advance_cc1_1d_fast(s, prm, fuse_deposit);
     if (fr < 0) return fr;

@@ -396,7 +396,7 @@ void PicChargedSpecies::picardParams(uint64_t &a_num_parts_its, uint64_t &a_num_
 }
 
 // ---- scattering --------------------------------------------------------------------------------
-uint64_t Scattering::s_seed = 1983, Scattering::s_step = 0;
+uint64_t Scattering::s_seed = 1983, Scattering::s_step = 0, Scattering::s_next_stream = 0;
 void Scattering::setRandomState(uint64_t a_seed, uint64_t a_step) {
   s_seed = a_seed;
   s_step = a_step;
@@ -420,7 +420,7 @@ void TakizukaAbe::applyScattering(std::vector<PicChargedSpecies *> &a_species, R
   if (a->numParticles() == 0 || b->numParticles() == 0) return;
   long np = 0;
   // prepForScatter (PicSpeciesInterface.cpp:1593-1625) binned the particles and set the moments
-  check(pgpu_collide_ta(a->handle(), b->handle(), m_Clog, a_dt_sec, s_seed, s_step, &np), "TakizukaAbe::applyScattering");
+  check(pgpu_collide_ta(a->handle(), b->handle(), m_Clog, a_dt_sec, streamSeed(), nextStep(), &np), "TakizukaAbe::applyScattering");
   m_npairs = np;
 }
 void TakizukaAbe::printParameters() const {
@@ -450,7 +450,7 @@ void Coulomb::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real 
   PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
   if (a->numParticles() == 0 || b->numParticles() == 0) return;
   long np = 0;
-  check(pgpu_collide_coulomb(a->handle(), b->handle(), &m_prm, a_dt_sec, s_seed, s_step, &np), "Coulomb::applyScattering");
+  check(pgpu_collide_coulomb(a->handle(), b->handle(), &m_prm, a_dt_sec, streamSeed(), nextStep(), &np), "Coulomb::applyScattering");
   m_npairs = np;
 }
 void Coulomb::printParameters() const {
@@ -494,7 +494,7 @@ void Elastic::applyScattering(std::vector<PicChargedSpecies *> &a_species, Real 
   if (a->numParticles() == 0 || b->numParticles() == 0) return;
   const pgpu_elastic_params prm = params();
   long nc = 0;
-  check(pgpu_collide_elastic(a->handle(), b->handle(), &prm, a_dt_sec, s_seed, s_step, &nc), "Elastic::applyScattering");
+  check(pgpu_collide_elastic(a->handle(), b->handle(), &prm, a_dt_sec, streamSeed(), nextStep(), &nc), "Elastic::applyScattering");
   m_ncoll = nc;
 }
 void Elastic::printParameters() const {
@@ -521,7 +521,7 @@ void HardSphere::applyScattering(std::vector<PicChargedSpecies *> &a_species, Re
   PicChargedSpecies *a = a_species[m_sp1], *b = a_species[m_sp2];
   if (a->numParticles() == 0 || b->numParticles() == 0) return;
   long nc = 0;
-  check(pgpu_collide_hard_sphere_wm(a->handle(), b->handle(), m_sigmaT, m_conservative ? 1 : 0, a_dt_sec, s_seed, s_step,
+  check(pgpu_collide_hard_sphere_wm(a->handle(), b->handle(), m_sigmaT, m_conservative ? 1 : 0, a_dt_sec, streamSeed(), nextStep(),
                                     &nc),
         "HardSphere::applyScattering");
   m_ncoll = nc;
@@ -544,7 +544,7 @@ void VariableHardSphere::applyScattering(std::vector<PicChargedSpecies *> &a_spe
   PicChargedSpecies *a = a_species[m_sp];
   if (a->numParticles() == 0) return;
   long nc = 0;
-  check(pgpu_collide_vhs(a->handle(), m_eta, m_T0, m_mu0, a_dt_sec, s_seed, s_step, &nc),
+  check(pgpu_collide_vhs(a->handle(), m_eta, m_T0, m_mu0, a_dt_sec, streamSeed(), nextStep(), &nc),
         "VariableHardSphere::applyScattering");
   m_ncoll = nc;
 }

@@ -430,58 +430,69 @@ def test_coulomb_relativistic_species_conserve_four_momentum_per_cell(pgpu):
 
 def test_hard_sphere_self_matches_oracle_statistics(pgpu):
     """pgpu_collide_hard_sphere (HardSphere no-time-counter pairs): per-cell momentum and energy conserved for equal
-    weights, collision count and the decay of a temperature anisotropy within 3 % of the oracle on the same
-    cells (the RNG streams differ by construction)."""
+    weights; collision count and the decay of a temperature anisotropy within 2 % of the oracle on the same cells.  The
+    RNG streams differ by construction, so both sides are means over SEEDS runs from the same initial state (one run
+    carries ~1 % of sampling noise in either quantity)."""
+    SEEDS = range(1983, 1989)
     deck = decks.Deck(D=2, ncell=(24, 24), dx=(0.25, 0.25), xmin=(0.0, 0.0), nghost=2)
     sdef = decks.SpeciesDef("argon", 40.0 * 1836.15, 0.0, (3.0, 1.0, 1.0), 1.0e30, (7, 7))
     rng = np.random.default_rng(1983)
     p = decks.load_species(deck, sdef, (0, 0), (23, 23), rng)
     grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, 2, (1, 1), volume_scale=deck.volume_scale)
-    sp = _species_on_grid(pgpu, grid, deck, sdef, p["x"], p["v"], p["w"], ids=p["id"])
-    s0 = sp.download()
-    dens, _, ene = sp.moments()
-    offs = sp.cell_offsets()
     sig = orc.hs_sigmaT(1.9e-10, 1.9e-10)
-    gmax = 5.0 * np.sqrt(2.0 / 3.0 * ene.reshape(3, -1).sum(0) / dens / sdef.mass) * 2.99792458e8
-    dt_sec = 0.6 / float(np.max(dens * sig * gmax))
 
     def aniso(v):
         t = (v ** 2).mean(axis=1)
         return (t[0] - 0.5 * (t[1] + t[2])) / t.mean()
 
-    a0 = aniso(s0["v"])
-    # HardSphere::setMeanFreeTime: box maximum of n sigmaT sqrt(Teff/m) = gmax/5 per cell
-    assert abs(pgpu.nu_max_hard_sphere(sp, sp, sig) - float(np.max(dens * sig * gmax / 5.0))) < 1e-12 * float(np.max(dens * sig * gmax))
-    nsteps, total_gpu = 6, 0
-    for step in range(nsteps):
-        sp.set_moments()
-        total_gpu += pgpu.collide_hard_sphere(sp, sp, sig, dt_sec, 1983, step)
-        if step == 0:
-            s1 = sp.download()
-            for c in range(0, offs.size - 1, 5):
-                a, b = offs[c], offs[c + 1]
-                v0, v1 = s0["v"][:, a:b], s1["v"][:, a:b]
-                assert np.max(np.abs(v1.sum(1) - v0.sum(1))) < 1e-15 * (b - a) * np.max(np.abs(v0))  + 1e-20
-                assert abs((v1 ** 2).sum() - (v0 ** 2).sum()) < 1e-12 * (v0 ** 2).sum()
-            assert np.mean(np.any(s1["v"] != s0["v"], axis=0)) > 0.1
-    a_gpu = aniso(sp.download()["v"])
-    sp.destroy(); grid.destroy()
+    nsteps = 6
+    gpu_runs = []
+    for seed in SEEDS:
+        sp = _species_on_grid(pgpu, grid, deck, sdef, p["x"], p["v"], p["w"], ids=p["id"])
+        if seed == SEEDS[0]:
+            s0 = sp.download()
+            dens, _, ene = sp.moments()
+            offs = sp.cell_offsets()
+            gmax = 5.0 * np.sqrt(2.0 / 3.0 * ene.reshape(3, -1).sum(0) / dens / sdef.mass) * 2.99792458e8
+            dt_sec = 0.6 / float(np.max(dens * sig * gmax))
+            a0 = aniso(s0["v"])
+            # HardSphere::setMeanFreeTime: box maximum of n sigmaT sqrt(Teff/m) = gmax/5 per cell
+            assert abs(pgpu.nu_max_hard_sphere(sp, sp, sig) - float(np.max(dens * sig * gmax / 5.0))) < 1e-12 * float(np.max(dens * sig * gmax))
+        tot = 0
+        for step in range(nsteps):
+            sp.set_moments()
+            tot += pgpu.collide_hard_sphere(sp, sp, sig, dt_sec, seed, step)
+            if step == 0 and seed == SEEDS[0]:
+                s1 = sp.download()
+                for c in range(0, offs.size - 1, 5):
+                    a, b = offs[c], offs[c + 1]
+                    v0, v1 = s0["v"][:, a:b], s1["v"][:, a:b]
+                    assert np.max(np.abs(v1.sum(1) - v0.sum(1))) < 1e-15 * (b - a) * np.max(np.abs(v0)) + 1e-20
+                    assert abs((v1 ** 2).sum() - (v0 ** 2).sum()) < 1e-12 * (v0 ** 2).sum()
+                assert np.mean(np.any(s1["v"] != s0["v"], axis=0)) > 0.1
+        gpu_runs.append((tot, aniso(sp.download()["v"])))
+        sp.destroy()
+    grid.destroy()
     # oracle on the same cells
-    v = s0["v"].copy()
     Vc = 0.25 * 0.25 * deck.volume_scale
-    orc.lib().orc_rng_seed(1983)
-    total_cpu = 0
-    for step in range(nsteps):
-        e = np.zeros((3, offs.size - 1))
-        for c in range(offs.size - 1):
-            a, b = offs[c], offs[c + 1]
-            e[:, c] = 0.5 * sdef.mass * (s0["w"][a:b] * v[:, a:b] ** 2).sum(1) / Vc
-        total_cpu += orc.hs_self(offs, v, s0["w"], dens, e, sdef.mass, sig, dt_sec)[1]
-    a_cpu = aniso(v)
+    cpu_runs = []
+    for seed in SEEDS:
+        v = s0["v"].copy()
+        orc.lib().orc_rng_seed(seed)
+        tot = 0
+        for step in range(nsteps):
+            e = np.zeros((3, offs.size - 1))
+            for c in range(offs.size - 1):
+                a, b = offs[c], offs[c + 1]
+                e[:, c] = 0.5 * sdef.mass * (s0["w"][a:b] * v[:, a:b] ** 2).sum(1) / Vc
+            tot += orc.hs_self(offs, v, s0["w"], dens, e, sdef.mass, sig, dt_sec)[1]
+        cpu_runs.append((tot, aniso(v)))
+    total_gpu, a_gpu = (float(np.mean([r[k] for r in gpu_runs])) for k in (0, 1))
+    total_cpu, a_cpu = (float(np.mean([r[k] for r in cpu_runs])) for k in (0, 1))
     assert total_cpu > 10000
-    assert abs(total_gpu - total_cpu) < 0.03 * total_cpu, (total_gpu, total_cpu)
+    assert abs(total_gpu - total_cpu) < 0.02 * total_cpu, (total_gpu, total_cpu)
     assert a_cpu / a0 < 0.8 and a_gpu / a0 < 0.8
-    assert abs(a_gpu - a_cpu) / a0 < 0.03
+    assert abs(a_gpu - a_cpu) / a0 < 0.02, (a_gpu / a0, a_cpu / a0)
 
 
 def test_hard_sphere_inter_conserves_per_cell(pgpu):
@@ -516,50 +527,54 @@ def test_hard_sphere_inter_conserves_per_cell(pgpu):
 
 
 def test_vhs_self_matches_oracle_statistics(pgpu):
-    """pgpu_collide_vhs (VariableHardSphere, argon viscosity law): per-cell conservation, collision count and
-    anisotropy decay within 3 % of the oracle."""
+    """pgpu_collide_vhs (VariableHardSphere, argon viscosity law): per-cell conservation; collision count and anisotropy
+    decay within 2 % of the oracle, both as means over SEEDS runs from the same initial state."""
+    SEEDS = range(1984, 1990)
     deck = decks.Deck(D=2, ncell=(24, 24), dx=(0.25, 0.25), xmin=(0.0, 0.0), nghost=2)
     mass = 39.948 * 1822.888
     sdef = decks.SpeciesDef("argon", mass, 0.0, (3.0, 1.0, 1.0), 1.0e30, (7, 7))
     rng = np.random.default_rng(1984)
     p = decks.load_species(deck, sdef, (0, 0), (23, 23), rng)
     grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, 2, (1, 1), volume_scale=deck.volume_scale)
-    sp = _species_on_grid(pgpu, grid, deck, sdef, p["x"], p["v"], p["w"], ids=p["id"])
-    s0 = sp.download()
-    dens, _, ene = sp.moments()
-    offs = sp.cell_offsets()
     eta, T0, mu0 = 0.81, 273.0, 2.117e-5
     fourPiA, fourOverAlpha = orc.vhs_consts(mass, eta, T0, mu0)
-    gmax = 5.0 * np.sqrt(2.0 / 3.0 * ene.reshape(3, -1).sum(0) / dens / mass) * 2.99792458e8
-    dt_sec = 0.6 / float(np.max(dens * fourPiA * gmax ** (-fourOverAlpha) * gmax))
 
     def aniso(v):
         t = (v ** 2).mean(axis=1)
         return (t[0] - 0.5 * (t[1] + t[2])) / t.mean()
 
-    a0 = aniso(s0["v"])
-    # VariableHardSphere::setMeanFreeTime: box maximum of n sigmaT(VTeff) VTeff with VTeff = gmax / 5
-    vt = gmax / 5.0
-    nu_ref = float(np.max(dens * fourPiA * vt ** (-fourOverAlpha) * vt))
-    assert abs(pgpu.nu_max_vhs(sp, eta, T0, mu0) - nu_ref) < 1e-12 * nu_ref
-    nsteps, total_gpu = 6, 0
-    for step in range(nsteps):
-        sp.set_moments()
-        total_gpu += pgpu.collide_vhs(sp, eta, T0, mu0, dt_sec, 1984, step)
-        if step == 0:
-            s1 = sp.download()
-            for c in range(0, offs.size - 1, 5):
-                a, b = offs[c], offs[c + 1]
-                v0, v1 = s0["v"][:, a:b], s1["v"][:, a:b]
-                assert np.max(np.abs(v1.sum(1) - v0.sum(1))) < 1e-15 * (b - a) * np.max(np.abs(v0)) + 1e-20
-                assert abs((v1 ** 2).sum() - (v0 ** 2).sum()) < 1e-12 * (v0 ** 2).sum()
-    a_gpu = aniso(sp.download()["v"])
-    sp.destroy(); grid.destroy()
-    # oracle on the same cells; the anisotropy of 2.8e4 particles carries ~1 % of a0 of sampling noise per run, so the
-    # reference value is the mean over a few seeds of the reference's own generator
+    nsteps = 6
+    gpu_runs = []
+    for seed in SEEDS:
+        sp = _species_on_grid(pgpu, grid, deck, sdef, p["x"], p["v"], p["w"], ids=p["id"])
+        if seed == SEEDS[0]:
+            s0 = sp.download()
+            dens, _, ene = sp.moments()
+            offs = sp.cell_offsets()
+            gmax = 5.0 * np.sqrt(2.0 / 3.0 * ene.reshape(3, -1).sum(0) / dens / mass) * 2.99792458e8
+            dt_sec = 0.6 / float(np.max(dens * fourPiA * gmax ** (-fourOverAlpha) * gmax))
+            a0 = aniso(s0["v"])
+            # VariableHardSphere::setMeanFreeTime: box maximum of n sigmaT(VTeff) VTeff with VTeff = gmax / 5
+            vt = gmax / 5.0
+            nu_ref = float(np.max(dens * fourPiA * vt ** (-fourOverAlpha) * vt))
+            assert abs(pgpu.nu_max_vhs(sp, eta, T0, mu0) - nu_ref) < 1e-12 * nu_ref
+        tot = 0
+        for step in range(nsteps):
+            sp.set_moments()
+            tot += pgpu.collide_vhs(sp, eta, T0, mu0, dt_sec, seed, step)
+            if step == 0 and seed == SEEDS[0]:
+                s1 = sp.download()
+                for c in range(0, offs.size - 1, 5):
+                    a, b = offs[c], offs[c + 1]
+                    v0, v1 = s0["v"][:, a:b], s1["v"][:, a:b]
+                    assert np.max(np.abs(v1.sum(1) - v0.sum(1))) < 1e-15 * (b - a) * np.max(np.abs(v0)) + 1e-20
+                    assert abs((v1 ** 2).sum() - (v0 ** 2).sum()) < 1e-12 * (v0 ** 2).sum()
+        gpu_runs.append((tot, aniso(sp.download()["v"])))
+        sp.destroy()
+    grid.destroy()
     Vc = 0.25 * 0.25 * deck.volume_scale
-    runs = []
-    for seed in (1984, 1985, 1986, 1987):
+    cpu_runs = []
+    for seed in SEEDS:
         v = s0["v"].copy()
         orc.lib().orc_rng_seed(seed)
         tot = 0
@@ -569,19 +584,19 @@ def test_vhs_self_matches_oracle_statistics(pgpu):
                 a, b = offs[c], offs[c + 1]
                 e[:, c] = 0.5 * mass * (s0["w"][a:b] * v[:, a:b] ** 2).sum(1) / Vc
             tot += orc.vhs_self(offs, v, dens, e, mass, fourPiA, fourOverAlpha, dt_sec)[1]
-        runs.append((tot, aniso(v)))
-    total_cpu = float(np.mean([r[0] for r in runs]))
-    a_cpu = float(np.mean([r[1] for r in runs]))
+        cpu_runs.append((tot, aniso(v)))
+    total_gpu, a_gpu = (float(np.mean([r[k] for r in gpu_runs])) for k in (0, 1))
+    total_cpu, a_cpu = (float(np.mean([r[k] for r in cpu_runs])) for k in (0, 1))
     assert total_cpu > 10000
-    assert abs(total_gpu - total_cpu) < 0.03 * total_cpu, (total_gpu, total_cpu)
+    assert abs(total_gpu - total_cpu) < 0.02 * total_cpu, (total_gpu, total_cpu)
     assert a_cpu / a0 < 0.85 and a_gpu / a0 < 0.85
-    assert abs(a_gpu - a_cpu) / a0 < 0.03
+    assert abs(a_gpu - a_cpu) / a0 < 0.02, (a_gpu / a0, a_cpu / a0)
 
 
 def test_hard_sphere_conservative_weight_method(pgpu):
     """pgpu_collide_hard_sphere_wm(weight_method = CONSERVATIVE): every cell keeps its total weight, weighted momentum
     and weighted energy to round-off although the particle weights differ (collapseThreeToTwo, pinned on the
-    reference); the collision count stays within 10 % of the oracle on the same cells."""
+    reference); the collision count (mean over 16 seeds) stays within 3 % of the oracle on the same cells."""
     deck = decks.Deck(D=2, ncell=(20, 20), dx=(0.25, 0.25), xmin=(0.0, 0.0), nghost=2)
     sdef = decks.SpeciesDef("argon", 40.0 * 1836.15, 0.0, (1.0, 1.0, 1.0), 1.0e30, (6, 6))
     rng = np.random.default_rng(81)
@@ -607,7 +622,17 @@ def test_hard_sphere_conservative_weight_method(pgpu):
         assert abs(w1.sum() - w0.sum()) < 1e-13 * w0.sum()
         assert np.max(np.abs((w1 * v1).sum(1) - (w0 * v0).sum(1))) < 1e-12 * np.abs(w0 * v0).sum(1).max()
         assert abs((w1 * v1 ** 2).sum() - (w0 * v0 ** 2).sum()) < 1e-12 * (w0 * v0 ** 2).sum()
-    v, wc = s0["v"].copy(), s0["w"].copy()
-    orc.lib().orc_rng_seed(5)
-    n_cpu = orc.hs_self_conservative(offs, v, wc, dens, ene, sdef.mass, sig, dt_sec)[1]
-    assert abs(ncoll - n_cpu) < 0.10 * n_cpu, (ncoll, n_cpu)
+    # collision count: means over 16 seeds on either side (one run of ~1.4e3 collisions carries ~3 % of Poisson noise)
+    grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, 2, (1, 1), volume_scale=deck.volume_scale)
+    n_gpu = []
+    for seed in range(100, 116):
+        spk = _species_on_grid(pgpu, grid, deck, sdef, p["x"], p["v"], w, ids=p["id"])
+        n_gpu.append(pgpu.collide_hard_sphere_conservative(spk, sig, dt_sec, seed, 0))
+        spk.destroy()
+    grid.destroy()
+    n_cpu = []
+    for seed in range(200, 216):
+        v, wc = s0["v"].copy(), s0["w"].copy()
+        orc.lib().orc_rng_seed(seed)
+        n_cpu.append(orc.hs_self_conservative(offs, v, wc, dens, ene, sdef.mass, sig, dt_sec)[1])
+    assert abs(np.mean(n_gpu) - np.mean(n_cpu)) < 0.03 * np.mean(n_cpu), (np.mean(n_gpu), np.mean(n_cpu))
