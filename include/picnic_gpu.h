@@ -417,15 +417,19 @@ int pgpu_coulomb_lorentz_scatter(long n, const double *up1, const double *up2, c
                                  const double *sigma_max, const double *gauss, const double *u_polar,
                                  const double *u_phi, double *out1, double *out2, double *s12);
 
-/* Elastic::electronImpact (Elastic.cpp:225-388), PROBABILISTIC weights: every particle of sA picks a
- * random partner of sB in its cell; sigma constant (ntab = 0) or tabulated (E [eV] ascending, Q, xi)
- * with the reference's interpolation; angular 0 = ISOTROPIC (Q = momentum-transfer), 1 = OKHRIMOVSKYY. */
+/* Elastic::electronImpact (Elastic.cpp:225-388): every particle of sA picks a random partner of sB in its cell; sigma
+ * constant (ntab = 0) or tabulated (E [eV] ascending, Q, xi) with the reference's interpolation; angular 0 = ISOTROPIC
+ * (Q = momentum-transfer), 1 = OKHRIMOVSKYY.  weight_method 0 = PROBABILISTIC (:361-369: each partner is updated with
+ * probability w_other / w_self), 1 = CONSERVATIVE (:334-356: where the projectile is the lighter one it scatters and the
+ * target, its scattered fraction and a second target of the cell are merged by ScatteringUtils::collapseThreeToTwo into
+ * two equally weighted particles -- the weights of sB change). */
 typedef struct {
   double const_sigma;     /* [m^2] */
   int ntab;
   const double *E, *Q, *xi;   /* host arrays of length ntab */
   int angular_scattering;
   int use_loglog_interp;
+  int weight_method;
 } pgpu_elastic_params;
 int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elastic_params *prm, double dt_sec,
                          uint64_t seed, uint64_t step, long *ncollisions);

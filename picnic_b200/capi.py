@@ -51,7 +51,8 @@ class CoulombParams(C.Structure):
 
 class ElasticParams(C.Structure):
     _fields_ = [("const_sigma", C.c_double), ("ntab", C.c_int), ("E", C.c_void_p), ("Q", C.c_void_p),
-                ("xi", C.c_void_p), ("angular_scattering", C.c_int), ("use_loglog_interp", C.c_int)]
+                ("xi", C.c_void_p), ("angular_scattering", C.c_int), ("use_loglog_interp", C.c_int),
+                ("weight_method", C.c_int)]
 
 
 class PicardStats(C.Structure):
@@ -535,10 +536,11 @@ def coulomb_delta_u(vp1, vp2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, de
 
 
 def collide_elastic(sA, sB, dt_sec, seed, step, const_sigma=0.0, E=None, Q=None, xi=None, angular=0, loglog=False,
-                    count=True):
+                    count=True, conservative=False):
     c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
     E, Q, xi = c(E), c(Q), c(xi)
-    prm = ElasticParams(const_sigma, 0 if E is None else E.size, _p(E), _p(Q), _p(xi), angular, int(loglog))
+    prm = ElasticParams(const_sigma, 0 if E is None else E.size, _p(E), _p(Q), _p(xi), angular, int(loglog),
+                        int(conservative))
     nc = C.c_long(0)
     check(load().pgpu_collide_elastic(sA.h, sB.h, C.byref(prm), dt_sec, seed, step, C.byref(nc) if count else None))
     return nc.value

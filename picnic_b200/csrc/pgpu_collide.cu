@@ -979,6 +979,8 @@ k_hard_sphere(const int *cs1, const int *cs2, int ncell, double *a0, double *a1,
 struct ElaParams {
   double mu, f1, f2, const_sigma, dt_sec, mcSq;
   int ntab, angular, loglog;
+  int conservative;   // weight_method = CONSERVATIVE (Elastic.cpp:334-356): wmut = the weights of species 2, rewritten
+  double *wmut;
   const double *E, *Q, *XI;
   unsigned seed_lo, seed_hi, step_lo, step_hi;
 };
@@ -1045,8 +1047,15 @@ k_elastic(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, dou
     }
     bool pending = have;
     while (__any_sync(0xffffffffu, pending)) {
-      const unsigned same = __match_any_sync(0xffffffffu, pending ? i2 : -1 - lane);
-      const bool turn = pending && (__ffs(same) - 1 == lane);
+      bool turn;
+      if (P.conservative) {
+        // a merge also rewrites a third particle of species 2: the projectiles of a cell go one at a time
+        const unsigned pend = __ballot_sync(0xffffffffu, pending);
+        turn = pending && (__ffs(pend) - 1 == lane);
+      } else {
+        const unsigned same = __match_any_sync(0xffffffffu, pending ? i2 : -1 - lane);
+        turn = pending && (__ffs(same) - 1 == lane);
+      }
       if (turn) {
         const double va[3] = {a0[i1], a1[i1], a2[i1]}, vb[3] = {b0[i2], b1[i2], b2[i2]};
         const double ux = va[0] - vb[0], uy = va[1] - vb[1], uz = va[2] - vb[2];
@@ -1064,7 +1073,36 @@ k_elastic(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, dou
             const double sinth = sqrt(1.0 - costh * costh);
             double dU[3];
             scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
-            const double r2 = u01(r1.x), w1 = wa[i1], w2 = wb[i2];
+            const double r2 = u01(r1.x), w1 = wa[i1], w2 = P.conservative ? P.wmut[i2] : wb[i2];
+            if (P.conservative && w1 < w2) {
+              // Elastic.cpp:334-356: the lighter projectile scatters; the target, its scattered fraction w1 and a second
+              // target of the cell become two equally weighted particles (ScatteringUtils::collapseThreeToTwo, :20-47)
+              if (n2 >= 2) {
+                const int q2 = i2 - s2;
+                int q3 = min(n2 - 2, (int)(u01(r1.y) * (n2 - 1)));   // uniform over the other n2 - 1 (the reference redraws)
+                if (q3 >= q2) q3 += 1;
+                const int i3 = s2 + q3;
+                const double w3 = P.wmut[i3], wp23 = 0.5 * (w2 + w3);
+                const double v3[3] = {b0[i3], b1[i3], b2[i3]};
+                double nh[3], n3[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                  const double vhp = vb[d] - P.f2 * dU[d];
+                  const double c23 = (w1 * vhp + (w2 - w1) * vb[d] + w3 * v3[d]) / wp23;
+                  const double d23 = (w1 * vhp * vhp + (w2 - w1) * vb[d] * vb[d] + w3 * v3[d] * v3[d]) / wp23;
+                  const double root = sqrt(fmax(2.0 * d23 - c23 * c23, 0.0));   // the reference asserts arg >= 0
+                  nh[d] = 0.5 * (c23 + root);
+                  n3[d] = 0.5 * (c23 - root);
+                }
+                a0[i1] = va[0] + P.f1 * dU[0];
+                a1[i1] = va[1] + P.f1 * dU[1];
+                a2[i1] = va[2] + P.f1 * dU[2];
+                b0[i2] = nh[0]; b1[i2] = nh[1]; b2[i2] = nh[2];
+                b0[i3] = n3[0]; b1[i3] = n3[1]; b2[i3] = n3[2];
+                P.wmut[i2] = wp23;
+                P.wmut[i3] = wp23;
+              }
+            } else {
             if (r2 <= w2 / w1) {
               a0[i1] = va[0] + P.f1 * dU[0];
               a1[i1] = va[1] + P.f1 * dU[1];
@@ -1074,6 +1112,7 @@ k_elastic(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, dou
               b0[i2] = vb[0] - P.f2 * dU[0];
               b1[i2] = vb[1] - P.f2 * dU[1];
               b2[i2] = vb[2] - P.f2 * dU[2];
+            }
             }
           }
         }
@@ -1588,6 +1627,9 @@ int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elasti
   P.ntab = prm->ntab;
   P.angular = prm->angular_scattering;
   P.loglog = prm->use_loglog_interp;
+  if (prm->weight_method != 0 && prm->weight_method != 1) return PGPU_ERR_ARG;
+  P.conservative = prm->weight_method;
+  P.wmut = sB->w;
   P.E = P.Q = P.XI = nullptr;
   if (prm->ntab) {
     // the cross-section table lives on the device between calls (no cudaMalloc / cudaFree in the middle of a step):

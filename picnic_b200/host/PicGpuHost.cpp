@@ -462,11 +462,11 @@ void Coulomb::printParameters() const {
 }
 
 Elastic::Elastic(int a_sp1, int a_sp2, Real a_const_sigma)
-    : m_sp1(a_sp1), m_sp2(a_sp2), m_const_sigma(a_const_sigma), m_okhrimovskyy(false), m_loglog(false), m_scatter_dt(DBL_MAX), m_ncoll(0) {}
+    : m_sp1(a_sp1), m_sp2(a_sp2), m_const_sigma(a_const_sigma), m_okhrimovskyy(false), m_loglog(false), m_conservative(false), m_scatter_dt(DBL_MAX), m_ncoll(0) {}
 Elastic::Elastic(int a_sp1, int a_sp2, const std::vector<Real> &a_E_eV, const std::vector<Real> &a_Q,
                  const std::vector<Real> &a_xi, bool a_okhrimovskyy, bool a_use_loglog_interp)
     : m_sp1(a_sp1), m_sp2(a_sp2), m_const_sigma(0.0), m_E(a_E_eV), m_Q(a_Q), m_xi(a_xi),
-      m_okhrimovskyy(a_okhrimovskyy), m_loglog(a_use_loglog_interp), m_scatter_dt(DBL_MAX), m_ncoll(0) {
+      m_okhrimovskyy(a_okhrimovskyy), m_loglog(a_use_loglog_interp), m_conservative(false), m_scatter_dt(DBL_MAX), m_ncoll(0) {
   if (m_E.size() < 2 || m_Q.size() != m_E.size() || (a_okhrimovskyy && m_xi.size() != m_E.size()))
     fatal("Elastic: cross-section table columns differ in length");
 }
@@ -479,6 +479,7 @@ pgpu_elastic_params Elastic::params() const {
   prm.xi = m_xi.empty() ? nullptr : m_xi.data();
   prm.angular_scattering = m_okhrimovskyy ? 1 : 0;
   prm.use_loglog_interp = m_loglog ? 1 : 0;
+  prm.weight_method = m_conservative ? 1 : 0;
   return prm;
 }
 void Elastic::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {

@@ -259,6 +259,72 @@ def test_elastic_collision_count_and_conservation(pgpu):
     spe.destroy(); spn.destroy(); grid.destroy()
 
 
+def test_elastic_conservative_weight_method(pgpu):
+    """pgpu_collide_elastic with weight_method = CONSERVATIVE (Elastic.cpp:334-356, collapseThreeToTwo pinned on the
+    reference): light projectiles on heavier-weight targets.  Every cell keeps the targets' total weight and the pair's
+    weighted momentum m1 w1 v1 + m2 w2 v2 and weighted energy to round-off; the collision count is the binomial sum of
+    the per-projectile probabilities and agrees with the oracle's mean over seeds within 2 %."""
+    rng = np.random.default_rng(62)
+    ncell = 240
+    deck = decks.Deck(D=1, ncell=(ncell,), dx=(0.25,), xmin=(0.0,), nghost=2)
+    se = decks.SpeciesDef("electron", 1.0, -1.0)
+    sn = decks.SpeciesDef("argon", 40.0 * 1836.0, 0.0)
+    grid = pgpu.Grid(1, (ncell,), (0.0,), (0.25,), 2, (1,), volume_scale=deck.volume_scale)
+    xe, ce = _ragged_cells(rng, ncell, [0, 5, 20, 33, 64])
+    xn, cn = _ragged_cells(rng, ncell, [0, 1, 2, 10, 40])
+    ve = rng.standard_normal((3, xe.shape[1])) * 0.02
+    vn = rng.standard_normal((3, xn.shape[1])) * 2.0e-5
+    cellV = 0.25 * deck.volume_scale
+    we = np.full(xe.shape[1], 0.25e22 * cellV / 20.0)
+    wn = np.full(xn.shape[1], 1.0e22 * cellV / 10.0) * rng.choice([1.0, 2.0], size=xn.shape[1])
+    spe = _species_on_grid(pgpu, grid, deck, se, xe, ve, we)
+    spn = _species_on_grid(pgpu, grid, deck, sn, xn, vn, wn)
+    be, bn = spe.download(), spn.download()
+    dens_n = spn.moments()[0]
+    oe, on = spe.cell_offsets(), spn.cell_offsets()
+    sigma, dt = 1.0e-19, 2.0e-11
+    ncoll = pgpu.collide_elastic(spe, spn, dt, 77, 5, const_sigma=sigma, conservative=True)
+    ae, an = spe.download(), spn.download()
+    assert ncoll > 500 and not np.isnan(an["v"]).any() and not np.isnan(ae["v"]).any()
+    assert np.mean(an["w"] != bn["w"]) > 0.02 and np.array_equal(ae["w"], be["w"])
+    m1, m2 = se.mass, sn.mass
+    for c in range(ncell):
+        s1, s2 = slice(oe[c], oe[c + 1]), slice(on[c], on[c + 1])
+        if ce[c] < 1 or cn[c] < 2:
+            # a lone target cannot be merged (Elastic.cpp:336): nothing may change for the targets
+            assert np.array_equal(bn["w"][s2], an["w"][s2])
+            if cn[c] < 1:
+                assert np.array_equal(be["v"][:, s1], ae["v"][:, s1])
+            continue
+        assert abs(an["w"][s2].sum() - bn["w"][s2].sum()) < 1e-13 * bn["w"][s2].sum()
+        p0 = m1 * (be["w"][s1] * be["v"][:, s1]).sum(1) + m2 * (bn["w"][s2] * bn["v"][:, s2]).sum(1)
+        p1 = m1 * (ae["w"][s1] * ae["v"][:, s1]).sum(1) + m2 * (an["w"][s2] * an["v"][:, s2]).sum(1)
+        scale = m1 * np.abs(be["w"][s1] * be["v"][:, s1]).sum() + m2 * np.abs(bn["w"][s2] * bn["v"][:, s2]).sum()
+        assert np.max(np.abs(p1 - p0)) < 1e-12 * scale
+        e0 = m1 * (be["w"][s1] * be["v"][:, s1] ** 2).sum() + m2 * (bn["w"][s2] * bn["v"][:, s2] ** 2).sum()
+        e1 = m1 * (ae["w"][s1] * ae["v"][:, s1] ** 2).sum() + m2 * (an["w"][s2] * an["v"][:, s2] ** 2).sum()
+        assert abs(e1 - e0) < 1e-11 * e0
+    # collision count: expectation from the initial state, and the oracle's mean over seeds on the same cells
+    expect = 0.0
+    for c in range(ncell):
+        if cn[c] >= 1 and ce[c] >= 1:
+            g = np.linalg.norm(be["v"][:, oe[c]:oe[c + 1]], axis=0)
+            expect += (1.0 - np.exp(-g * 2.99792458e8 * sigma * dens_n[c] * dt)).sum()
+    assert abs(ncoll - expect) < 4.5 * np.sqrt(expect)
+    n_cpu = []
+    for seed in range(8):
+        v1, v2, w2 = be["v"].copy(), bn["v"].copy(), bn["w"].copy()
+        orc.lib().orc_rng_seed(seed)
+        n_cpu.append(orc.elastic_conservative(oe, v1, be["w"], m1, on, v2, w2, dens_n, m2, dt, sigma))
+    n_gpu = [ncoll]
+    for seed in range(1, 8):
+        spe.upload(be["x"], be["v"], be["w"], ids=be["id"]); spe.bin_particles(); spe.set_moments()
+        spn.upload(bn["x"], bn["v"], bn["w"], ids=bn["id"]); spn.bin_particles(); spn.set_moments()
+        n_gpu.append(pgpu.collide_elastic(spe, spn, dt, 77 + seed, 5, const_sigma=sigma, conservative=True))
+    assert abs(np.mean(n_gpu) - np.mean(n_cpu)) < 0.02 * np.mean(n_cpu), (np.mean(n_gpu), np.mean(n_cpu))
+    spe.destroy(); spn.destroy(); grid.destroy()
+
+
 def test_elastic_table_lookup_matches_oracle_statistics(pgpu):
     """Tabulated cross section (OKHRIMOVSKYY): collision counts of GPU and oracle agree within noise."""
     rng = np.random.default_rng(63)
