@@ -380,6 +380,15 @@ typedef struct {
   int NxN;                /* Coulomb.NxN */
   int NxN_Nthresh;        /* Coulomb.NxN_Nthresh (11) */
   int num_subcycles;      /* Coulomb.num_subcycles (1) */
+  /* scattering.coulomb.enforce_conservations and companions (Coulomb.H:286-293; Coulomb.cpp:596-714, 1182-1430): after
+   * the weight-rejection update the cell's momentum change is taken back out of every particle and the energy change is
+   * absorbed by ScatteringUtils::modEnergyPairwise sweeps.  0 = off (the remaining fields are then ignored). */
+  int enforce_conservations;
+  double energy_fraction;       /* 0.05 */
+  double energy_fraction_max;   /* 0.5 */
+  int beta_weight_exponent;     /* 1 */
+  int sort_weighted_particles;  /* must be 0: the sweeps pair particles in storage order */
+  int conservation_Nmin_save;   /* 100000 (0 = that default) */
 } pgpu_coulomb_params;
 int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm, double dt_sec,
                          uint64_t seed, uint64_t step, long *npairs);

@@ -365,6 +365,14 @@ def coulomb_lorentz_scatter(up1, up2, scatter2, q1, q2, m1, m2, EF_norm, Clog, a
     return a, b, live, s12.value
 
 
+def coulomb_set_enforce(on, energy_fraction=0.05, energy_fraction_max=0.5, beta_weight_exponent=1, sort_weighted=False,
+                        nmin_save=100000):
+    """scattering.coulomb.enforce_conservations and companions (Coulomb.H:286-293); global like the deck keys."""
+    f = lib().orc_coulomb_set_enforce
+    f.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
+    f(int(on), energy_fraction, energy_fraction_max, int(beta_weight_exponent), int(sort_weighted), int(nmin_save))
+
+
 def coulomb_intra(cell_start, v, w, dens, LDe, cellV_SI, mass, charge, Clog, angular, NxN, NxN_Nthresh, dt_sec):
     _coul_sigs()
     npairs = C.c_long(0)

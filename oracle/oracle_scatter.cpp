@@ -613,7 +613,147 @@ void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2
 }
 }  // namespace
 
-/* Coulomb::applyIntraScattering_PROB (Coulomb.cpp:400-592), enforce_conservations = false */
+/* ScatteringUtils::modEnergyPairwise (ScatteringUtils.H:113-205): zero-angle inelastic "collision" of a pair that removes
+ * (a_deltaE > 0) or adds (< 0) up to Erel_frac of the pair's relative energy without touching its momentum.  The scalars
+ * are long double as in the reference.  rel selects the RELATIVISTIC_PARTICLES branch. */
+static void mod_energy_pairwise(double *b1, double *b2, double wpmp1, double wpmp2, double Erel_frac, double &Erel_cumm,
+                                long double &a_deltaE, int rel) {
+  int sign = 1;
+  if (a_deltaE < 0.0) sign = -1;
+  const double ux = b1[0] - b2[0], uy = b1[1] - b2[1], uz = b1[2] - b2[2];
+  const long double usq = ux * ux + uy * uy + uz * uz;
+  long double Erel, muR = 0.0, E1 = 0.0, E2 = 0.0, Etot = 0.0, pxtot = 0.0, pytot = 0.0, pztot = 0.0;
+  if (rel) {
+    long double gbsq1 = 0.0, gbsq2 = 0.0;
+    for (int n = 0; n < 3; n++) gbsq1 += b1[n] * b1[n];
+    for (int n = 0; n < 3; n++) gbsq2 += b2[n] * b2[n];
+    const long double gamma1 = std::sqrt(1.0 + gbsq1), gamma2 = std::sqrt(1.0 + gbsq2);
+    E1 = wpmp1 * gamma1;
+    E2 = wpmp2 * gamma2;
+    Etot = E1 + E2;
+    pxtot = wpmp1 * b1[0] + wpmp2 * b2[0];
+    pytot = wpmp1 * b1[1] + wpmp2 * b2[1];
+    pztot = wpmp1 * b1[2] + wpmp2 * b2[2];
+    const long double Ecm = std::sqrt(Etot * Etot - pxtot * pxtot - pytot * pytot - pztot * pztot);
+    Erel = Ecm - wpmp1 - wpmp2;
+  } else {
+    muR = wpmp1 * wpmp2 / (wpmp1 + wpmp2);
+    Erel = muR / 2.0 * usq;
+  }
+  if (Erel <= 0.0) return;
+  long double deltaE = sign * Erel_frac * Erel;
+  if (std::abs(deltaE) > std::abs(a_deltaE)) {
+    deltaE = a_deltaE;
+    a_deltaE = 0.0;
+  } else {
+    a_deltaE -= deltaE;
+  }
+  Erel_cumm += Erel - deltaE;
+  if (rel) {
+    const long double A = Etot - deltaE;
+    const long double D = A * A + E2 * E2 - E1 * E1;
+    const long double p2dotu = wpmp2 * (b2[0] * ux + b2[1] * uy + b2[2] * uz);
+    const long double ptdotu = pxtot * ux + pytot * uy + pztot * uz;
+    const long double a = A * A * usq - ptdotu * ptdotu;
+    const long double b = D * ptdotu - 2 * A * A * p2dotu;
+    const long double c = A * A * E2 * E2 - D * D / 4.0;
+    const long double root = b * b - 4.0 * a * c;
+    if (root < 0.0 || a == 0.0) return;
+    const long double alpha = (-b + std::sqrt(root)) / (2.0 * a);
+    const long double ratio1 = alpha / wpmp1, ratio2 = alpha / wpmp2;
+    b1[0] += ratio1 * ux; b1[1] += ratio1 * uy; b1[2] += ratio1 * uz;
+    b2[0] -= ratio2 * ux; b2[1] -= ratio2 * uy; b2[2] -= ratio2 * uz;
+  } else {
+    const long double uprime_over_u = std::sqrt(1.0 - deltaE / Erel);
+    double deltaU[3];
+    deltaU[0] = uprime_over_u * ux - ux;
+    deltaU[1] = uprime_over_u * uy - uy;
+    deltaU[2] = uprime_over_u * uz - uz;
+    for (int n = 0; n < 3; n++) {
+      b1[n] += muR / wpmp1 * deltaU[n];
+      b2[n] -= muR / wpmp2 * deltaU[n];
+    }
+  }
+}
+extern "C" void orc_mod_energy_pairwise(double *b1, double *b2, double wpmp1, double wpmp2, double Erel_frac,
+                                        double *Erel_cumm, double *deltaE, int rel) {
+  long double dE = *deltaE;
+  mod_energy_pairwise(b1, b2, wpmp1, wpmp2, Erel_frac, *Erel_cumm, dE, rel);
+  *deltaE = (double)dE;
+}
+
+/* scattering.coulomb.enforce_conservations and its companions (Coulomb.H:286-293, defaults :32-33, :325-333) */
+struct EnforcePrm {
+  int on;
+  double energy_fraction, energy_fraction_max;
+  int beta_weight_exponent, sort_weighted, nmin_save;
+};
+static EnforcePrm g_enf = {0, 0.05, 0.5, 1, 0, 100000};
+extern "C" void orc_coulomb_set_enforce(int on, double energy_fraction, double energy_fraction_max, int beta_weight_exponent,
+                                        int sort_weighted, int nmin_save) {
+  g_enf = {on, energy_fraction, energy_fraction_max, beta_weight_exponent, sort_weighted, nmin_save};
+}
+namespace {
+struct CellSums {
+  double W;
+  double p[3];
+  long double E;
+};
+/* Wtot0 / ptot0 / Etot0 of a cell list (Coulomb.cpp:486-512; the Galilean Efact = 1/2) */
+CellSums cell_sums(const std::vector<long> &idx, const double *v, const double *w, long n) {
+  CellSums s = {0.0, {0.0, 0.0, 0.0}, 0.0};
+  for (long i : idx) {
+    s.W += std::pow(w[i], g_enf.beta_weight_exponent);
+    double gbsq = 0.0;
+    for (int q = 0; q < 3; ++q) {
+      s.p[q] += w[i] * v[q * n + i];
+      gbsq += v[q * n + i] * v[q * n + i];
+    }
+    s.E += w[i] * 0.5 * gbsq;
+  }
+  return s;
+}
+/* the pair sweep that absorbs deltaE inside one list (Coulomb.cpp:643-706 and :1257-1300): returns false if the
+ * correction failed (energy_frac_eff > energy_fraction_max or more than ten sweeps) */
+bool absorb_energy(std::vector<long> order, double *v, const double *w, long n, double mass, long double &deltaE,
+                   long *count) {
+  if (g_enf.sort_weighted)
+    std::sort(order.begin(), order.end(), [&](long a, long b) { return w[a] > w[b]; });
+  const int N = (int)order.size();
+  int loop_count = 0;
+  double Erel_cumm = 0.0, fmult_fact = 1.0;
+  for (int p = 0; p < N; p++) {
+    if (deltaE == 0.0) break;
+    const int p1 = p;
+    p++;
+    if (p == N) {
+      loop_count++;
+      p = 0;
+    }
+    const int p2 = p;
+    const long i1 = order[p1], i2 = order[p2];
+    double a[3] = {v[i1], v[n + i1], v[2 * n + i1]}, b[3] = {v[i2], v[n + i2], v[2 * n + i2]};
+    mod_energy_pairwise(a, b, mass * w[i1], mass * w[i2], g_enf.energy_fraction * fmult_fact, Erel_cumm, deltaE, 0);
+    for (int q = 0; q < 3; ++q) {
+      v[q * n + i1] = a[q];
+      v[q * n + i2] = b[q];
+    }
+    if (count) ++*count;
+    if (deltaE == 0.0) break;
+    if (p == N - 1) {
+      loop_count++;
+      const double energy_frac_eff = (double)std::abs(deltaE) / Erel_cumm;
+      if (energy_frac_eff > g_enf.energy_fraction_max || loop_count > 10) return false;
+      else if (energy_frac_eff > g_enf.energy_fraction) fmult_fact = energy_frac_eff / g_enf.energy_fraction;
+      Erel_cumm = 0.0;
+      p = -1;
+    }
+  }
+  return true;
+}
+}  // namespace
+
+/* Coulomb::applyIntraScattering_PROB (Coulomb.cpp:400-728); enforce_conservations per orc_coulomb_set_enforce */
 extern "C" void orc_coulomb_intra(long ncell, const long *cell_start, double *v, const double *w, long n,
                                   const double *dens, const double *LDe, double cellV_SI, double mass, double charge,
                                   double Clog, int angular, int NxN_in, int NxN_Nthresh, double dt_sec,
@@ -637,6 +777,14 @@ extern "C" void orc_coulomb_intra(long ncell, const long *cell_start, double *v,
     idx.resize(numCell);
     for (long q = 0; q < numCell; ++q) idx[q] = cell_start[c] + q;
     std::shuffle(idx.begin(), idx.end(), global_rand_gen);
+    CellSums s0 = {0.0, {0.0, 0.0, 0.0}, 0.0};
+    std::vector<double> vsave;
+    if (g_enf.on) {   /* :490-512 */
+      s0 = cell_sums(idx, v, w, n);
+      if (numCell <= g_enf.nmin_save)
+        for (long i : idx)
+          for (int q = 0; q < 3; ++q) vsave.push_back(v[q * n + i]);
+    }
     const long p1_max = numCell - 2;
     for (long p1 = 0; p1 <= p1_max; p1++) {
       long p2_max = p1 + 1;
@@ -660,11 +808,38 @@ extern "C" void orc_coulomb_intra(long ncell, const long *cell_start, double *v,
       if (odd_NxN && p1 == 1) odd_NxN = false;
       if (!odd_NxN && !NxN) ++p1;
     }
+    if (g_enf.on) {   /* :611-711.  dBetaAvg = the cell's weighted momentum change, taken from the sums as the
+                         RELATIVISTIC_PARTICLES build does (:596-609); the Galilean build accumulates the same number pair by pair */
+      const CellSums s1 = cell_sums(idx, v, w, n);
+      double dBetaAvg[3], dBetaSq = 0.0;
+      for (int q = 0; q < 3; ++q) {
+        dBetaAvg[q] = s1.p[q] - s0.p[q];
+        dBetaSq += dBetaAvg[q] * dBetaAvg[q];
+      }
+      if (dBetaSq > 0.0) {
+        for (int q = 0; q < 3; ++q) dBetaAvg[q] /= s0.W;
+        long double Etot1 = 0.0;
+        for (long i : idx) {
+          double gbsq = 0.0;
+          for (int q = 0; q < 3; ++q) {
+            v[q * n + i] -= std::pow(w[i], g_enf.beta_weight_exponent - 1) * dBetaAvg[q];
+            gbsq += v[q * n + i] * v[q * n + i];
+          }
+          Etot1 += w[i] * 0.5 * gbsq;
+        }
+        long double deltaE = mass * (Etot1 - s0.E);
+        if (!absorb_energy(idx, v, w, n, mass, deltaE, nullptr) && numCell <= g_enf.nmin_save) {
+          long k = 0;
+          for (long i : idx)
+            for (int q = 0; q < 3; ++q) v[q * n + i] = vsave[k++];
+        }
+      }
+    }
   }
   if (npairs_out) *npairs_out = npairs;
 }
 
-/* Coulomb::applyInterScattering_PROB (Coulomb.cpp:919-1180), enforce_conservations = false */
+/* Coulomb::applyInterScattering_PROB (Coulomb.cpp:919-1438); enforce_conservations per orc_coulomb_set_enforce */
 extern "C" void orc_coulomb_inter(long ncell, const long *cs1, double *v1, const double *w1, long n1,
                                   const double *dens1, double mass1, double charge1, const long *cs2, double *v2,
                                   const double *w2, long n2, const double *dens2, double mass2, double charge2,
@@ -691,6 +866,23 @@ extern "C" void orc_coulomb_inter(long ncell, const long *cs1, double *v1, const
     idx2.resize(numCell2);
     for (long q = 0; q < numCell2; ++q) idx2[q] = cs2[c] + q;
     std::shuffle(idx2.begin(), idx2.end(), global_rand_gen);
+    CellSums s01 = {0.0, {0.0, 0.0, 0.0}, 0.0}, s02 = s01;
+    double wp1_mean = 0.0, wp2_mean = 0.0;
+    std::vector<double> vsave1, vsave2;
+    if (g_enf.on) {   /* :1024-1083 */
+      s01 = cell_sums(idx1, v1, w1, n1);
+      s02 = cell_sums(idx2, v2, w2, n2);
+      for (long i : idx1) wp1_mean += w1[i];
+      for (long i : idx2) wp2_mean += w2[i];
+      wp1_mean /= numCell1;
+      wp2_mean /= numCell2;
+      if (numCell1 <= g_enf.nmin_save || numCell2 <= g_enf.nmin_save) {
+        for (long i : idx1)
+          for (int q = 0; q < 3; ++q) vsave1.push_back(v1[q * n1 + i]);
+        for (long i : idx2)
+          for (int q = 0; q < 3; ++q) vsave2.push_back(v2[q * n2 + i]);
+      }
+    }
     for (long p = 0; p < Nmax; p++) {
       long p1, p2, pmin_start;
       if (Nmin == numCell1) {
@@ -722,6 +914,61 @@ extern "C" void orc_coulomb_inter(long ncell, const long *cs1, double *v1, const
           v2[q * n2 + i2] = b[q];
         }
         ++npairs;
+      }
+    }
+    if (g_enf.on) {   /* :1182-1430 */
+      const double Wtot0 = mass1 * s01.W + mass2 * s02.W;
+      const long double Etot0 = mass1 * s01.E + mass2 * s02.E;
+      const CellSums s11 = cell_sums(idx1, v1, w1, n1), s12 = cell_sums(idx2, v2, w2, n2);
+      double dBetaAvg[3], dBetaSq = 0.0;
+      for (int q = 0; q < 3; ++q) {
+        dBetaAvg[q] = (mass1 * s11.p[q] + mass2 * s12.p[q]) - (mass1 * s01.p[q] + mass2 * s02.p[q]);
+        dBetaSq += dBetaAvg[q] * dBetaAvg[q];
+      }
+      if (dBetaSq > 0.0) {
+        for (int q = 0; q < 3; ++q) dBetaAvg[q] /= Wtot0;
+        long double Etot11 = 0.0, Etot12 = 0.0;
+        for (long i : idx1) {
+          double gbsq = 0.0;
+          for (int q = 0; q < 3; ++q) {
+            v1[q * n1 + i] -= std::pow(w1[i], g_enf.beta_weight_exponent - 1) * dBetaAvg[q];
+            gbsq += v1[q * n1 + i] * v1[q * n1 + i];
+          }
+          Etot11 += w1[i] * 0.5 * gbsq;
+        }
+        Etot11 *= mass1;
+        for (long i : idx2) {
+          double gbsq = 0.0;
+          for (int q = 0; q < 3; ++q) {
+            v2[q * n2 + i] -= std::pow(w2[i], g_enf.beta_weight_exponent - 1) * dBetaAvg[q];
+            gbsq += v2[q * n2 + i] * v2[q * n2 + i];
+          }
+          Etot12 += w2[i] * 0.5 * gbsq;
+        }
+        Etot12 *= mass2;
+        const long double deltaE = (Etot11 + Etot12) - Etot0;
+        const long double Etotdenom = wp1_mean * Etot11 + wp2_mean * Etot12;
+        long double deltaEp1, deltaEp2;
+        if (numCell1 == 1) {
+          deltaEp1 = 0.0;
+          deltaEp2 = deltaE;
+        } else if (numCell2 == 1) {
+          deltaEp1 = deltaE;
+          deltaEp2 = 0.0;
+        } else {
+          deltaEp1 = wp1_mean * Etot11 / Etotdenom * deltaE;
+          deltaEp2 = wp2_mean * Etot12 / Etotdenom * deltaE;
+        }
+        bool ok = absorb_energy(idx1, v1, w1, n1, mass1, deltaEp1, nullptr);
+        if (ok) ok = absorb_energy(idx2, v2, w2, n2, mass2, deltaEp2, nullptr);
+        if (!ok && (numCell1 <= g_enf.nmin_save || numCell2 <= g_enf.nmin_save)) {
+          long k = 0;
+          for (long i : idx1)
+            for (int q = 0; q < 3; ++q) v1[q * n1 + i] = vsave1[k++];
+          k = 0;
+          for (long i : idx2)
+            for (int q = 0; q < 3; ++q) v2[q * n2 + i] = vsave2[k++];
+        }
       }
     }
   }

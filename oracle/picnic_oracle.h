@@ -279,6 +279,13 @@ void orc_elastic_wm(long ncell, const long *cs1, double *v1, const double *w1, l
                     double *v2, double *w2, long n2, const double *dens2, double mass2, double const_sigma, int ntab,
                     const double *E, const double *Q, const double *XI, int angular, int loglog, int conservative,
                     double dt_sec, long *ncoll_out);
+/* ScatteringUtils::modEnergyPairwise (ScatteringUtils.H:113-205), pinned on the reference (tests/test_ref_pin.py);
+ * scattering.coulomb.enforce_conservations for orc_coulomb_intra / orc_coulomb_inter (Coulomb.cpp:486-512, 596-714,
+ * 1024-1083, 1182-1430) */
+void orc_mod_energy_pairwise(double *b1, double *b2, double wpmp1, double wpmp2, double Erel_frac, double *Erel_cumm,
+                             double *deltaE, int rel);
+void orc_coulomb_set_enforce(int on, double energy_fraction, double energy_fraction_max, int beta_weight_exponent,
+                             int sort_weighted, int nmin_save);
 /* ScatteringUtils::collapseThreeToTwo (ScatteringUtils.H:20-47), pinned on the reference */
 void orc_collapse_three_to_two(double *vp2, double *wp2, double *vp3, double *wp3, const double *vp2p, double wp2p);
 /* HardSphere, PROBABILISTIC (HardSphere.cpp:223-665): no-time-counter pairs; ene = [3][ncell] */

@@ -779,6 +779,7 @@ int pgpu_species_destroy(pgpu_species_t s) {
   cudaFree(s->cub_tmp);
   for (int k = 0; k < 4; ++k) cudaFree(s->spare[k]);
   cudaFree(s->defer_list);
+  cudaFree(s->enf_save);
   cudaFree(s->tile_box);
   cudaFree(s->mig);
   cudaFree(s->mig_list);

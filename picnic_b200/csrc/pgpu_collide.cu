@@ -1530,6 +1530,228 @@ static int fetch_pairs(long *out) {
   return 0;
 }
 
+// =============================================================================================
+// scattering.coulomb.enforce_conservations (Coulomb.cpp:486-512, 596-714 intra; 1024-1083, 1182-1430 inter): the
+// weight-rejection update of unequal-weight pairs conserves momentum and energy only on average; afterwards the cell's
+// weighted momentum change is taken back out of every particle and the energy change is absorbed by zero-angle inelastic
+// "collisions" of neighbouring particles of one list (ScatteringUtils::modEnergyPairwise, ScatteringUtils.H:113-205).
+// One warp per cell: the sums are warp reductions; the pair sweeps are sequential in the reference (each pair sees what
+// the previous one left of deltaE) and run on lane 0.
+// =============================================================================================
+struct EnfParams {
+  double energy_fraction, energy_fraction_max;
+  int wexp, nmin_save, rel;
+  double mass1, mass2;
+};
+struct EnfList {
+  const int *cs;
+  double *v0, *v1, *v2;
+  const double *w;
+  double *save;      // [3][cap] copy of the velocities before the collisions (restored if the fix-up fails)
+  long cap;
+};
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double ipow(double w, int e) {
+  double r = 1.0;
+  for (int k = 0; k < e; ++k) r *= w;
+  return r;
+}
+// W = sum w^exp, p = sum w v, E = sum w Efact |v|^2 (Efact = 1/2, or 1/(gamma+1) in the relativistic build), wsum = sum w
+__device__ __forceinline__ void cell_sums_dev(const EnfList &L, int s, int n, const EnfParams &P, int lane, double &W,
+                                              double (&p)[3], double &E, double &wsum) {
+  W = E = wsum = 0.0;
+  p[0] = p[1] = p[2] = 0.0;
+  for (int q = lane; q < n; q += 32) {
+    const int i = s + q;
+    const double w = L.w[i], a = L.v0[i], b = L.v1[i], c = L.v2[i];
+    const double gbsq = a * a + b * b + c * c;
+    const double Efact = P.rel ? 1.0 / (sqrt(1.0 + gbsq) + 1.0) : 0.5;
+    W += ipow(w, P.wexp);
+    wsum += w;
+    p[0] += w * a;
+    p[1] += w * b;
+    p[2] += w * c;
+    E += w * Efact * gbsq;
+  }
+  W = warp_sum(W);
+  wsum = warp_sum(wsum);
+  E = warp_sum(E);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[k] = warp_sum(p[k]);
+}
+// before the collisions: sums of the cell list -> buf[6] = W p0 p1 p2 E wsum, and the velocities -> save
+__global__ void __launch_bounds__(256) k_coul_enf_pre(EnfList L, int ncell, EnfParams P, int which, double *buf) {
+  const int cell = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (cell >= ncell) return;
+  const int s = L.cs[cell], n = L.cs[cell + 1] - s;
+  double W, p[3], E, wsum;
+  cell_sums_dev(L, s, n, P, lane, W, p, E, wsum);
+  if (lane == 0) {
+    double *b = buf + ((size_t)cell * 2 + which) * 6;
+    b[0] = W, b[1] = p[0], b[2] = p[1], b[3] = p[2], b[4] = E, b[5] = wsum;
+  }
+  for (int q = lane; q < n; q += 32) {
+    const int i = s + q;
+    L.save[i] = L.v0[i];
+    L.save[L.cap + i] = L.v1[i];
+    L.save[2 * L.cap + i] = L.v2[i];
+  }
+}
+// ScatteringUtils::modEnergyPairwise in fp64 (the reference keeps the scalars in long double)
+__device__ void mod_energy_pairwise_dev(double *b1, double *b2, double wpmp1, double wpmp2, double Erel_frac,
+                                        double &Erel_cumm, double &a_deltaE, int rel) {
+  const double sign = a_deltaE < 0.0 ? -1.0 : 1.0;
+  const double ux = b1[0] - b2[0], uy = b1[1] - b2[1], uz = b1[2] - b2[2];
+  const double usq = ux * ux + uy * uy + uz * uz;
+  double Erel, muR = 0.0, E1 = 0.0, E2 = 0.0, Etot = 0.0, px = 0.0, py = 0.0, pz = 0.0;
+  if (rel) {
+    const double g1 = sqrt(1.0 + b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+    const double g2 = sqrt(1.0 + b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2]);
+    E1 = wpmp1 * g1;
+    E2 = wpmp2 * g2;
+    Etot = E1 + E2;
+    px = wpmp1 * b1[0] + wpmp2 * b2[0];
+    py = wpmp1 * b1[1] + wpmp2 * b2[1];
+    pz = wpmp1 * b1[2] + wpmp2 * b2[2];
+    Erel = sqrt(Etot * Etot - px * px - py * py - pz * pz) - wpmp1 - wpmp2;
+  } else {
+    muR = wpmp1 * wpmp2 / (wpmp1 + wpmp2);
+    Erel = muR / 2.0 * usq;
+  }
+  if (!(Erel > 0.0)) return;
+  double deltaE = sign * Erel_frac * Erel;
+  if (fabs(deltaE) > fabs(a_deltaE)) {
+    deltaE = a_deltaE;
+    a_deltaE = 0.0;
+  } else {
+    a_deltaE -= deltaE;
+  }
+  Erel_cumm += Erel - deltaE;
+  if (rel) {
+    const double A = Etot - deltaE, D = A * A + E2 * E2 - E1 * E1;
+    const double p2dotu = wpmp2 * (b2[0] * ux + b2[1] * uy + b2[2] * uz), ptdotu = px * ux + py * uy + pz * uz;
+    const double a = A * A * usq - ptdotu * ptdotu, b = D * ptdotu - 2.0 * A * A * p2dotu, c = A * A * E2 * E2 - D * D / 4.0;
+    const double root = b * b - 4.0 * a * c;
+    if (root < 0.0 || a == 0.0) return;
+    const double alpha = (-b + sqrt(root)) / (2.0 * a), r1 = alpha / wpmp1, r2 = alpha / wpmp2;
+    b1[0] += r1 * ux, b1[1] += r1 * uy, b1[2] += r1 * uz;
+    b2[0] -= r2 * ux, b2[1] -= r2 * uy, b2[2] -= r2 * uz;
+  } else {
+    const double k = sqrt(1.0 - deltaE / Erel) - 1.0;   // u'/u - 1
+    const double f1 = muR / wpmp1 * k, f2 = muR / wpmp2 * k;
+    b1[0] += f1 * ux, b1[1] += f1 * uy, b1[2] += f1 * uz;
+    b2[0] -= f2 * ux, b2[1] -= f2 * uy, b2[2] -= f2 * uz;
+  }
+}
+// the pair sweeps over one list in storage order (Coulomb.cpp:643-706 / 1257-1341); false = the correction failed
+__device__ bool absorb_energy_dev(const EnfList &L, int s, int N, double mass, const EnfParams &P, double &deltaE) {
+  int loop_count = 0;
+  double Erel_cumm = 0.0, fmult = 1.0;
+  for (int p = 0; p < N; p++) {
+    if (deltaE == 0.0) break;
+    const int p1 = p;
+    p++;
+    if (p == N) {
+      loop_count++;
+      p = 0;
+    }
+    const int i1 = s + p1, i2 = s + p;
+    double a[3] = {L.v0[i1], L.v1[i1], L.v2[i1]}, b[3] = {L.v0[i2], L.v1[i2], L.v2[i2]};
+    mod_energy_pairwise_dev(a, b, mass * L.w[i1], mass * L.w[i2], P.energy_fraction * fmult, Erel_cumm, deltaE, P.rel);
+    L.v0[i1] = a[0], L.v1[i1] = a[1], L.v2[i1] = a[2];
+    L.v0[i2] = b[0], L.v1[i2] = b[1], L.v2[i2] = b[2];
+    if (deltaE == 0.0) break;
+    if (p == N - 1) {
+      loop_count++;
+      const double eff = fabs(deltaE) / Erel_cumm;
+      if (eff > P.energy_fraction_max || loop_count > 10) return false;
+      if (eff > P.energy_fraction) fmult = eff / P.energy_fraction;
+      Erel_cumm = 0.0;
+      p = -1;
+    }
+  }
+  return true;
+}
+// after the collisions.  inter != 0: two lists (L1 with mass1, L2 with mass2); else L1 only
+__global__ void __launch_bounds__(256)
+k_coul_enf_post(EnfList L1, EnfList L2, int inter, int ncell, EnfParams P, const double *buf, unsigned *nfailed) {
+  const int cell = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (cell >= ncell) return;
+  const int s1 = L1.cs[cell], n1 = L1.cs[cell + 1] - s1;
+  const int s2 = inter ? L2.cs[cell] : 0, n2 = inter ? L2.cs[cell + 1] - s2 : 0;
+  if (inter ? (n1 < 1 || n2 < 1 || (long)n1 * n2 < 2) : (n1 < 2)) return;   // cells the collision kernels skip
+  const double *b1 = buf + ((size_t)cell * 2 + 0) * 6, *b2 = buf + ((size_t)cell * 2 + 1) * 6;
+  double W, p[3], E, wsum, W2 = 0.0, p2[3] = {0.0, 0.0, 0.0}, E2 = 0.0, wsum2 = 0.0;
+  cell_sums_dev(L1, s1, n1, P, lane, W, p, E, wsum);
+  if (inter) cell_sums_dev(L2, s2, n2, P, lane, W2, p2, E2, wsum2);
+  const double m1 = inter ? P.mass1 : 1.0, m2 = P.mass2;
+  const double Wtot0 = inter ? m1 * b1[0] + m2 * b2[0] : b1[0];
+  double dB[3], dBsq = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    dB[k] = inter ? (m1 * p[k] + m2 * p2[k]) - (m1 * b1[1 + k] + m2 * b2[1 + k]) : p[k] - b1[1 + k];
+    dBsq += dB[k] * dB[k];
+  }
+  if (!(dBsq > 0.0)) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) dB[k] /= Wtot0;
+  // take the momentum change back out, and sum the energies of the shifted velocities
+  double Et1 = 0.0, Et2 = 0.0;
+  for (int q = lane; q < n1; q += 32) {
+    const int i = s1 + q;
+    const double f = ipow(L1.w[i], P.wexp - 1);
+    const double a = L1.v0[i] - f * dB[0], b = L1.v1[i] - f * dB[1], c = L1.v2[i] - f * dB[2];
+    L1.v0[i] = a, L1.v1[i] = b, L1.v2[i] = c;
+    const double gbsq = a * a + b * b + c * c;
+    Et1 += L1.w[i] * (P.rel ? 1.0 / (sqrt(1.0 + gbsq) + 1.0) : 0.5) * gbsq;
+  }
+  for (int q = lane; q < n2; q += 32) {
+    const int i = s2 + q;
+    const double f = ipow(L2.w[i], P.wexp - 1);
+    const double a = L2.v0[i] - f * dB[0], b = L2.v1[i] - f * dB[1], c = L2.v2[i] - f * dB[2];
+    L2.v0[i] = a, L2.v1[i] = b, L2.v2[i] = c;
+    const double gbsq = a * a + b * b + c * c;
+    Et2 += L2.w[i] * (P.rel ? 1.0 / (sqrt(1.0 + gbsq) + 1.0) : 0.5) * gbsq;
+  }
+  Et1 = warp_sum(Et1);
+  Et2 = warp_sum(Et2);
+  __syncwarp();
+  int ok = 1;
+  if (lane == 0) {
+    if (!inter) {
+      double deltaE = P.mass1 * (Et1 - b1[4]);
+      ok = absorb_energy_dev(L1, s1, n1, P.mass1, P, deltaE) ? 1 : 0;
+    } else {
+      Et1 *= m1;
+      Et2 *= m2;
+      const double deltaE = (Et1 + Et2) - (m1 * b1[4] + m2 * b2[4]);
+      const double wm1 = b1[5] / n1, wm2 = b2[5] / n2, den = wm1 * Et1 + wm2 * Et2;
+      double d1, d2;
+      if (n1 == 1) d1 = 0.0, d2 = deltaE;
+      else if (n2 == 1) d1 = deltaE, d2 = 0.0;
+      else d1 = wm1 * Et1 / den * deltaE, d2 = wm2 * Et2 / den * deltaE;
+      ok = absorb_energy_dev(L1, s1, n1, m1, P, d1) ? 1 : 0;
+      if (ok) ok = absorb_energy_dev(L2, s2, n2, m2, P, d2) ? 1 : 0;
+    }
+    if (!ok) atomicAdd(nfailed, 1u);
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (!ok && (n1 <= P.nmin_save || (inter && n2 <= P.nmin_save))) {   // Coulomb.cpp:689-696 / 1409-1426
+    for (int q = lane; q < n1; q += 32) {
+      const int i = s1 + q;
+      L1.v0[i] = L1.save[i], L1.v1[i] = L1.save[L1.cap + i], L1.v2[i] = L1.save[2 * L1.cap + i];
+    }
+    for (int q = lane; q < n2; q += 32) {
+      const int i = s2 + q;
+      L2.v0[i] = L2.save[i], L2.v1[i] = L2.save[L2.cap + i], L2.v2[i] = L2.save[2 * L2.cap + i];
+    }
+  }
+}
+
 // Every scattering operator draws from its own Philox stream: the caller's seed is mixed with the identity of the two
 // species (mass and charge: stable when a species object is re-created, e.g. at a restart) and a per-model salt
 // (splitmix64 finaliser), so that e-e and i-i self-scattering, or e-i1 and e-i2, of one step do not replay each other's
@@ -1589,8 +1811,60 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
   P.ncell_glob0 = g->desc.ncell[0];
   const int ncell = (int)g->ncell_box;
   unsigned long long *d_np = &c.d_counters->npairs;
+  // scattering.coulomb.enforce_conservations (Coulomb.H:286-293)
+  const bool enforce = prm->enforce_conservations != 0;
+  EnfParams EP;
+  EnfList L1, L2;
+  static double *enf_buf = nullptr;
+  static size_t enf_buf_cells = 0;
+  static unsigned *enf_failed = nullptr;
+  if (enforce) {
+    if (prm->sort_weighted_particles) {
+      set_error("Coulomb: sort_weighted_particles is not implemented (the energy fix-up pairs particles in storage order)");
+      return PGPU_ERR_ARG;
+    }
+    if (!(prm->energy_fraction > 0.0) || !(prm->energy_fraction_max > 0.0) || prm->beta_weight_exponent < 1) {
+      set_error("Coulomb: enforce_conservations needs energy_fraction > 0, energy_fraction_max > 0, beta_weight_exponent >= 1");
+      return PGPU_ERR_ARG;
+    }
+    EP.energy_fraction = prm->energy_fraction;
+    EP.energy_fraction_max = prm->energy_fraction_max;
+    EP.wexp = prm->beta_weight_exponent;
+    EP.nmin_save = prm->conservation_Nmin_save > 0 ? prm->conservation_Nmin_save : 100000;
+    EP.rel = P.rel;
+    EP.mass1 = sA->desc.mass;
+    EP.mass2 = sB->desc.mass;
+    if ((size_t)ncell > enf_buf_cells) {
+      if (enf_buf) cudaFree(enf_buf);
+      PGPU_CUDA(cudaMalloc(&enf_buf, (size_t)ncell * 12 * sizeof(double)));
+      enf_buf_cells = (size_t)ncell;
+    }
+    if (!enf_failed) {
+      PGPU_CUDA(cudaMalloc(&enf_failed, sizeof(unsigned)));
+      PGPU_CUDA(cudaMemsetAsync(enf_failed, 0, sizeof(unsigned), c.stream));
+    }
+    auto mk = [&](pgpu_species_s *sp, EnfList &L) -> int {
+      if (!sp->enf_save || sp->enf_cap < sp->cap) {
+        if (sp->enf_save) cudaFree(sp->enf_save);
+        if (cudaMalloc(&sp->enf_save, 3 * sp->cap * sizeof(double)) != cudaSuccess) return PGPU_ERR_CUDA;
+        sp->enf_cap = sp->cap;
+      }
+      L.cs = sp->cell_start;
+      L.v0 = sp->v[0], L.v1 = sp->v[1], L.v2 = sp->v[2];
+      L.w = sp->w;
+      L.save = sp->enf_save;
+      L.cap = (long)sp->enf_cap;
+      return 0;
+    };
+    if (mk(sA, L1) || mk(sB, L2)) return PGPU_ERR_CUDA;
+  }
   for (int sub = 0; sub < nsub; ++sub) {
     P.step_hi = ((unsigned)(step >> 32) & 0xffu) | ((unsigned)sub << 8);
+    if (enforce) {
+      KTimer t("collide_coulomb_enforce");
+      k_coul_enf_pre<<<nb((long)ncell * 32), 256, 0, c.stream>>>(L1, ncell, EP, 0, enf_buf);
+      if (sA != sB) k_coul_enf_pre<<<nb((long)ncell * 32), 256, 0, c.stream>>>(L2, ncell, EP, 1, enf_buf);
+    }
     if (sA == sB) {
       KTimer t("collide_coulomb_intra");
       k_coulomb_intra<<<nb((long)ncell * 32), 256, 0, c.stream>>>(sA->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2],
@@ -1602,6 +1876,10 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
           sA->cell_start, sB->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->w, sA->id, sA->dens, sB->v[0],
           sB->v[1], sB->v[2], sB->w, sB->id, sB->dens, g->debye, P, (unsigned *)sA->cell_key, sA->perm,
           (unsigned *)sB->cell_key, sB->perm, d_np);
+    }
+    if (enforce) {
+      KTimer t("collide_coulomb_enforce");
+      k_coul_enf_post<<<nb((long)ncell * 32), 256, 0, c.stream>>>(L1, L2, sA != sB ? 1 : 0, ncell, EP, enf_buf, enf_failed);
     }
   }
   return fetch_pairs(npairs_out);

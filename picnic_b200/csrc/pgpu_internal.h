@@ -197,6 +197,8 @@ struct pgpu_species_s {
   size_t sort_cap = 0;
   void *cub_tmp = nullptr;
   size_t cub_bytes = 0;
+  double *enf_save = nullptr;       // Coulomb enforce_conservations: velocities before the collisions [3][enf_cap]
+  size_t enf_cap = 0;
   int *defer_list = nullptr;        // particles the CC1 fast kernel left to the generic one
   unsigned *defer_count = nullptr;
   size_t defer_cap = 0;

@@ -437,6 +437,12 @@ Coulomb::Coulomb(int a_sp1, int a_sp2, Real a_Clog, AngularScattering a_angular,
   m_prm.NxN = a_NxN ? 1 : 0;
   m_prm.NxN_Nthresh = a_NxN_Nthresh;
   m_prm.num_subcycles = a_num_subcycles;
+  m_prm.enforce_conservations = 0;        // Coulomb.H:325-333 defaults; setEnforceConservations switches it on
+  m_prm.energy_fraction = 0.05;
+  m_prm.energy_fraction_max = 0.5;
+  m_prm.beta_weight_exponent = 1;
+  m_prm.sort_weighted_particles = 0;
+  m_prm.conservation_Nmin_save = 100000;
   if (a_Clog != 0.0 && a_Clog < 2.0) fatal("Coulomb: coulomb_logarithm must be 0 (computed) or >= 2");   // Coulomb.H:224
 }
 void Coulomb::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {

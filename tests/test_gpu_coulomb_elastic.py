@@ -13,8 +13,9 @@ pytestmark = pytest.mark.gpu
 DT_SEC = 0.1 * 1.77e-17
 
 
-def _species_on_grid(pgpu, grid, deck, sdef, x, v, w, ids=None):
-    sp = pgpu.Species(grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm)
+def _species_on_grid(pgpu, grid, deck, sdef, x, v, w, ids=None, relativistic=False):
+    sp = pgpu.Species(grid, sdef.mass, sdef.charge, sdef.fnorm_const(deck.units), deck.units.cvac_norm,
+                      relativistic=relativistic)
     sp.upload(x, v, w, ids=np.arange(w.size, dtype=np.uint64) if ids is None else ids)
     sp.bin_particles()
     sp.set_moments()
@@ -132,6 +133,63 @@ def test_coulomb_inter_counts_and_conservation(pgpu):
         k1 = me * (e1 ** 2).sum() + mi * (i1 ** 2).sum()
         assert abs(k1 - k0) / k0 < 1e-11
     spe.destroy(); spi.destroy(); grid.destroy()
+
+
+@pytest.mark.parametrize("relativistic", [False, True])
+def test_coulomb_enforce_conservations(pgpu, relativistic):
+    """scattering.coulomb.enforce_conservations on the device (Coulomb.cpp:596-714, 1182-1430): weighted electrons and
+    ions, e-e then e-i.  Without the fix-up every cell's weighted momentum and energy drift; with it both are conserved
+    per cell to round-off (kinetic energy m w (gamma - 1) in the relativistic build), and the drift relaxation keeps the
+    oracle's rate."""
+    deck = decks.Deck(D=2, ncell=(10, 10), dx=(0.25, 0.25), xmin=(0.0, 0.0), nghost=2)
+    se, si = decks.electron_proton((8, 8))
+    rng = np.random.default_rng(19)
+    pe = decks.load_species(deck, se, (0, 0), (9, 9), rng)
+    pi = decks.load_species(deck, si, (0, 0), (9, 9), rng)
+    pe["v"][0] += 0.01
+    pe["w"] = pe["w"] * np.where(rng.random(pe["w"].size) < 0.5, 0.5, 1.5)
+    pi["w"] = pi["w"] * np.where(rng.random(pi["w"].size) < 0.5, 2.0, 0.5)
+    dt_sec = 0.3 * deck.units.time
+    me, mi = se.mass, si.mass
+
+    def energy(v):
+        u2 = (v ** 2).sum(0)
+        return u2 / (np.sqrt(1.0 + u2) + 1.0) if relativistic else 0.5 * u2
+
+    res = {}
+    for enforce in (False, True):
+        grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, 2, (1, 1), volume_scale=deck.volume_scale)
+        spe = _species_on_grid(pgpu, grid, deck, se, pe["x"], pe["v"], pe["w"], ids=pe["id"], relativistic=relativistic)
+        spi = _species_on_grid(pgpu, grid, deck, si, pi["x"], pi["v"], pi["w"], ids=pi["id"], relativistic=relativistic)
+        grid.debye_length([spe, spi])
+        e0, i0 = spe.download(), spi.download()
+        oe, oi = spe.cell_offsets(), spi.cell_offsets()
+        pgpu.collide_coulomb(spe, spe, 10.0, dt_sec, 11, 0, angular=1, enforce=enforce)
+        e1 = spe.download()
+        pgpu.collide_coulomb(spe, spi, 10.0, dt_sec, 11, 1, angular=1, enforce=enforce)
+        e2, i2 = spe.download(), spi.download()
+        spe.destroy(); spi.destroy(); grid.destroy()
+        worst = 0.0
+        for c in range(oe.size - 1):
+            a, b, p, q = oe[c], oe[c + 1], oi[c], oi[c + 1]
+            w, u = e0["w"][a:b], i0["w"][p:q]
+            scaleP = me * np.abs(w * e0["v"][:, a:b]).sum() + 1e-300
+            dP = np.abs((w * e1["v"][:, a:b]).sum(1) - (w * e0["v"][:, a:b]).sum(1)).max() * me / scaleP
+            dK = abs((w * energy(e1["v"][:, a:b])).sum() - (w * energy(e0["v"][:, a:b])).sum()) / (w * energy(e0["v"][:, a:b])).sum()
+            P1 = me * (w * e1["v"][:, a:b]).sum(1) + mi * (u * i0["v"][:, p:q]).sum(1)
+            P2 = me * (w * e2["v"][:, a:b]).sum(1) + mi * (u * i2["v"][:, p:q]).sum(1)
+            K1 = me * (w * energy(e1["v"][:, a:b])).sum() + mi * (u * energy(i0["v"][:, p:q])).sum()
+            K2 = me * (w * energy(e2["v"][:, a:b])).sum() + mi * (u * energy(i2["v"][:, p:q])).sum()
+            scaleP2 = me * np.abs(w * e1["v"][:, a:b]).sum() + mi * np.abs(u * i0["v"][:, p:q]).sum()
+            worst = max(worst, dP, dK, np.abs(P2 - P1).max() / scaleP2, abs(K2 - K1) / K1)
+        res[enforce] = (worst, (e2["w"] * e2["v"][0]).sum() / e2["w"].sum())
+        assert np.any(e1["v"] != e0["v"]) and np.any(i2["v"] != i0["v"])
+    # the relativistic form of modEnergyPairwise (E_rel = E_cm - m1 - m2, a quadratic for the momentum exchange) cancels
+    # ten digits at these speeds; the reference carries it in long double, the device in fp64
+    assert res[True][0] < (1e-9 if relativistic else 1e-11), res
+    assert res[False][0] > 1e-6, res
+    d0 = (pe["w"] * pe["v"][0]).sum() / pe["w"].sum()
+    assert abs(res[True][1] - res[False][1]) < 0.05 * abs(d0 - res[False][1]) + 1e-3 * abs(d0)
 
 
 def test_coulomb_weighted_drift_relaxation_matches_oracle(pgpu):

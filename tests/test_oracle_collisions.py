@@ -88,6 +88,58 @@ def test_coulomb_inter_weighted_conserves_on_average():
     assert abs(K1 - K0) / K0 < 0.02
 
 
+def test_coulomb_enforce_conservations_intra_and_inter():
+    """scattering.coulomb.enforce_conservations (Coulomb.cpp:596-714, 1182-1430): with unequal weights the weight-rejection
+    update conserves momentum and energy only on average; the fix-up (shift by the weighted mean momentum change, then
+    modEnergyPairwise sweeps) restores both per cell to round-off."""
+    rng = np.random.default_rng(9)
+    ncell, n1c, n2c = 120, 30, 18
+    cs1 = np.arange(ncell + 1, dtype=np.int64) * n1c
+    cs2 = np.arange(ncell + 1, dtype=np.int64) * n2c
+    cellV = 1.0e-3
+    LDe = np.full(ncell, 5.0e-10)
+    m1, m2 = 1.0, 1836.15
+
+    def make():
+        r = np.random.default_rng(10)
+        v1 = r.standard_normal((3, ncell * n1c)) * 0.02
+        v2 = r.standard_normal((3, ncell * n2c)) * 0.0008
+        w1 = np.where(r.random(ncell * n1c) < 0.5, 1.0e27, 3.0e27)
+        w2 = np.where(r.random(ncell * n2c) < 0.5, 2.0e27, 0.5e27)
+        return v1, v2, w1, w2
+
+    def cell_P_K(v, w, cs, m):
+        P = np.stack([np.add.reduceat(m * w * v[q], cs[:-1]) for q in range(3)])
+        K = np.add.reduceat(m * w * (v ** 2).sum(0), cs[:-1])
+        return P, K
+
+    for on in (False, True):
+        v1, v2, w1, w2 = make()
+        dens1 = np.add.reduceat(w1, cs1[:-1]) / cellV
+        dens2 = np.add.reduceat(w2, cs2[:-1]) / cellV
+        Pa0, Ka0 = cell_P_K(v1, w1, cs1, m1)
+        orc.lib().orc_rng_seed(4)
+        orc.coulomb_set_enforce(on)
+        try:
+            orc.coulomb_intra(cs1, v1, w1, dens1, LDe, cellV, m1, -1.0, 10.0, 1, False, 11, 40 * DT_SEC)
+            Pa1, Ka1 = cell_P_K(v1, w1, cs1, m1)
+            Pb0 = Pa1 + cell_P_K(v2, w2, cs2, m2)[0]
+            Kb0 = Ka1 + cell_P_K(v2, w2, cs2, m2)[1]
+            orc.coulomb_inter(cs1, v1, w1, dens1, m1, -1.0, cs2, v2, w2, dens2, m2, 1.0, LDe, cellV, 10.0, 1, False, 11,
+                              40 * DT_SEC)
+            Pb1 = cell_P_K(v1, w1, cs1, m1)[0] + cell_P_K(v2, w2, cs2, m2)[0]
+            Kb1 = cell_P_K(v1, w1, cs1, m1)[1] + cell_P_K(v2, w2, cs2, m2)[1]
+        finally:
+            orc.coulomb_set_enforce(False)
+        scaleP = m1 * 3.0e27 * 0.02 * n1c
+        errs = (np.abs(Pa1 - Pa0).max() / scaleP, np.abs(Ka1 - Ka0).max() / Ka0.max(),
+                np.abs(Pb1 - Pb0).max() / scaleP, np.abs(Kb1 - Kb0).max() / Kb0.max())
+        if on:
+            assert max(errs) < 1e-12, errs
+        else:
+            assert min(errs) > 1e-6, errs      # without the fix-up every cell drifts
+
+
 def test_elastic_sigma_lookup():
     E = np.array([0.01, 0.1, 1.0, 10.0, 100.0])
     Q = np.array([1.0e-19, 2.0e-19, 5.0e-20, 2.0e-20, 1.0e-20])
