@@ -389,6 +389,11 @@ typedef struct {
   int beta_weight_exponent;     /* 1 */
   int sort_weighted_particles;  /* must be 0: the sweeps pair particles in storage order */
   int conservation_Nmin_save;   /* 100000 (0 = that default) */
+  /* weight_method: 0 = PROBABILISTIC (above), 1 = CONSERVATIVE = Coulomb::applyIntra/InterScattering_SK08
+   * (Coulomb.cpp:730-917, 1439-1640; Sentoku & Kemp 2008): O(N) pairs; the lighter-weight particle scatters, the heavier
+   * one takes the fraction w_min / w_max of its scattered change plus a transverse kick that conserves the pair's
+   * weighted energy exactly (Coulomb::enforceEnergyConservation, Coulomb.H:796-823).  Galilean build only. */
+  int weight_method;
 } pgpu_coulomb_params;
 int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm, double dt_sec,
                          uint64_t seed, uint64_t step, long *npairs);

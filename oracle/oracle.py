@@ -373,6 +373,13 @@ def coulomb_set_enforce(on, energy_fraction=0.05, energy_fraction_max=0.5, beta_
     f(int(on), energy_fraction, energy_fraction_max, int(beta_weight_exponent), int(sort_weighted), int(nmin_save))
 
 
+def coulomb_set_weight_method(conservative):
+    """Coulomb weight_method: False PROBABILISTIC, True CONSERVATIVE (Sentoku-Kemp, Coulomb.cpp:730-917, 1439-1640)."""
+    f = lib().orc_coulomb_set_weight_method
+    f.argtypes = [C.c_int]
+    f(int(conservative))
+
+
 def coulomb_intra(cell_start, v, w, dens, LDe, cellV_SI, mass, charge, Clog, angular, NxN, NxN_Nthresh, dt_sec):
     _coul_sigs()
     npairs = C.c_long(0)

@@ -539,6 +539,10 @@ extern "C" int orc_coulomb_lorentz_scatter(double *a_up1, double *a_up2, int a_s
   return 1;
 }
 
+/* Coulomb weight_method: 0 PROBABILISTIC, 1 CONSERVATIVE (the Sentoku-Kemp update of applyIntra/InterScattering_SK08;
+ * O(N) pairs only) */
+static int g_sk08 = 0;
+extern "C" void orc_coulomb_set_weight_method(int conservative) { g_sk08 = conservative ? 1 : 0; }
 namespace {
 /* one pair with the reference's draw order: polar draw(s) inside SetPolarScattering, then phi,
  * then the weight-rejection uniform (only for unequal weights) */
@@ -597,6 +601,37 @@ void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2
                         c.bmax, c.sigma_max, c.dt_sec, gauss, upol, uphi, dU, nullptr);
   } else {
     dU[0] = dU[1] = dU[2] = 0.0;
+  }
+  if (g_sk08 && (float)w1 != (float)w2) {
+    /* weight_method = CONSERVATIVE: Coulomb::applyIntra/InterScattering_SK08 (Coulomb.cpp:849-897, 1575-1621) with
+     * Coulomb::enforceEnergyConservation (Coulomb.H:796-823) */
+    const bool first_light = (float)w1 < (float)w2;
+    double *vl = first_light ? b1 : b2, *vh = first_light ? b2 : b1;
+    const double fl = first_light ? f1 : -f2, fh = first_light ? -f2 : f1;
+    const double mh = first_light ? c.mass2 : c.mass1;
+    const long double ratio = first_light ? w1 / w2 : w2 / w1;
+    double before[3] = {vh[0], vh[1], vh[2]}, vhp[3];
+    const double Ebefore = mh * (vh[0] * vh[0] + vh[1] * vh[1] + vh[2] * vh[2]) / 2.0;
+    for (int n = 0; n < 3; n++) vl[n] += fl * dU[n];
+    for (int n = 0; n < 3; n++) vhp[n] = vh[n] + fh * dU[n];
+    const double Escatter = mh * (vhp[0] * vhp[0] + vhp[1] * vhp[1] + vhp[2] * vhp[2]) / 2.0;
+    const double Eafter = Ebefore + ratio * (Escatter - Ebefore);
+    for (int n = 0; n < 3; n++) vh[n] = before[n] + ratio * (vhp[n] - before[n]);
+    double betap_r = vh[0] * vh[0] + vh[1] * vh[1];
+    double betap_mag = betap_r + vh[2] * vh[2];
+    const double Eafter2 = mh / 2.0 * betap_mag;
+    betap_mag = std::sqrt(betap_mag);
+    betap_r = std::sqrt(betap_r);
+    if (Eafter < Eafter2) return;
+    const double dmag = std::sqrt(2.0 / mh * (Eafter - Eafter2));
+    const double phi = kTWOPI * mu_rand();
+    const double cosphi = cos(phi), sinphi = sin(phi);
+    double d[3];
+    d[0] = (vh[2] * vh[0] * cosphi - betap_mag * vh[1] * sinphi) / betap_r * dmag / betap_mag;
+    d[1] = (vh[2] * vh[1] * cosphi + betap_mag * vh[0] * sinphi) / betap_r * dmag / betap_mag;
+    d[2] = -betap_r * cosphi * dmag / betap_mag;
+    for (int n = 0; n < 3; n++) vh[n] += d[n];
+    return;
   }
   if ((float)w1 == (float)w2) {
     for (int n = 0; n < 3; n++) b1[n] += f1 * dU[n];
@@ -771,6 +806,7 @@ extern "C" void orc_coulomb_intra(long ncell, const long *cell_start, double *v,
     if (numCell < 2) continue;
     bool NxN = NxN_in != 0;
     if (numCell < NxN_Nthresh) NxN = true;
+    if (g_sk08) NxN = false;   /* _SK08 pairs in O(N) only (its first three pairs of an odd cell are the same three) */
     bool odd_NxN = false;
     if (!NxN && numCell % 2 == 1) odd_NxN = true;
     const long Naa = numCell - 1;
@@ -860,6 +896,7 @@ extern "C" void orc_coulomb_inter(long ncell, const long *cs1, double *v1, const
     const long Nmin = std::min(numCell1, numCell2), Nmax = std::max(numCell1, numCell2);
     bool NxN = NxN_in != 0;
     if (Nmin < NxN_Nthresh) NxN = true;
+    if (g_sk08) NxN = false;
     idx1.resize(numCell1);
     for (long q = 0; q < numCell1; ++q) idx1[q] = cs1[c] + q;
     std::shuffle(idx1.begin(), idx1.end(), global_rand_gen);

@@ -48,7 +48,7 @@ class CoulombParams(C.Structure):
     _fields_ = [("Clog", C.c_double), ("angular_scattering", C.c_int), ("NxN", C.c_int), ("NxN_Nthresh", C.c_int),
                 ("num_subcycles", C.c_int), ("enforce_conservations", C.c_int), ("energy_fraction", C.c_double),
                 ("energy_fraction_max", C.c_double), ("beta_weight_exponent", C.c_int),
-                ("sort_weighted_particles", C.c_int), ("conservation_Nmin_save", C.c_int)]
+                ("sort_weighted_particles", C.c_int), ("conservation_Nmin_save", C.c_int), ("weight_method", C.c_int)]
 
 
 class ElasticParams(C.Structure):
@@ -475,9 +475,10 @@ def ta_delta_u(vp1, den1, vp2, den2, b90_fact, Clog, dt_sec, gauss, u_theta, u_p
 
 
 def collide_coulomb(sA, sB, Clog, dt_sec, seed, step, angular=0, NxN=False, NxN_Nthresh=11, num_subcycles=1,
-                    count=True, enforce=False, energy_fraction=0.05, energy_fraction_max=0.5, beta_weight_exponent=1):
+                    count=True, enforce=False, energy_fraction=0.05, energy_fraction_max=0.5, beta_weight_exponent=1,
+                    conservative=False):
     prm = CoulombParams(Clog, angular, int(NxN), NxN_Nthresh, num_subcycles, int(enforce), energy_fraction,
-                        energy_fraction_max, beta_weight_exponent, 0, 0)
+                        energy_fraction_max, beta_weight_exponent, 0, 0, int(conservative))
     np_ = C.c_long(0)
     check(load().pgpu_collide_coulomb(sA.h, sB.h, C.byref(prm), dt_sec, seed, step, C.byref(np_) if count else None))
     return np_.value

@@ -430,6 +430,7 @@ struct CoulParams {
   unsigned seed_lo, seed_hi, step_lo, step_hi;
   int box_lo0, box_lo1, nbox0, ncell_glob0;
   int rel;               // RELATIVISTIC_PARTICLES build: pairs go through LorentzScatter
+  int sk08;              // weight_method = CONSERVATIVE (Sentoku-Kemp 2008 update of the heavier-weight particle)
   double mass1, mass2;
 };
 __device__ __forceinline__ unsigned global_cell(const CoulParams &P, int cell) {
@@ -660,6 +661,47 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
     return;
   }
   coulomb_delta_u(P, va, vb, C.EF_norm, den12, C.bmax, C.sigma_max, gauss, u01(r.z), u01(r.w), dU, nullptr);
+  if (P.sk08 && (float)w1 != (float)w2) {
+    // weight_method = CONSERVATIVE: Sentoku & Kemp, JCP 227 (2008) (Coulomb.cpp:849-897 / 1575-1621).  The lighter
+    // particle scatters; the heavier one moves by the fraction w_min / w_max of its scattered change, and a kick normal to
+    // its velocity (random azimuth) makes up the energy E_before + ratio (E_scattered - E_before) exactly
+    // (Coulomb::enforceEnergyConservation, Coulomb.H:796-823)
+    c.w = P.step_hi ^ (STREAM_WEIGHT << 16) ^ salt;
+    const double phi = TWOPI * u01(philox4x32_10(c, P.seed_lo, P.seed_hi).x);
+    const bool first_light = (float)w1 < (float)w2;
+    double *vl = first_light ? va : vb, *vh = first_light ? vb : va;
+    const double fl = first_light ? P.f1 : -P.f2, fh = first_light ? -P.f2 : P.f1;
+    const double mh = first_light ? P.mass2 : P.mass1;
+    const double ratio = first_light ? w1 / w2 : w2 / w1;
+    double vhp[3], nb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      vl[k] += fl * dU[k];
+      vhp[k] = vh[k] + fh * dU[k];
+    }
+    const double Ebefore = mh * (vh[0] * vh[0] + vh[1] * vh[1] + vh[2] * vh[2]) / 2.0;
+    const double Escatter = mh * (vhp[0] * vhp[0] + vhp[1] * vhp[1] + vhp[2] * vhp[2]) / 2.0;
+    const double Eafter = Ebefore + ratio * (Escatter - Ebefore);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nb[k] = vh[k] + ratio * (vhp[k] - vh[k]);
+    double br = nb[0] * nb[0] + nb[1] * nb[1], bm = br + nb[2] * nb[2];
+    const double Eafter2 = mh / 2.0 * bm;
+    bm = sqrt(bm);
+    br = sqrt(br);
+    if (!(Eafter < Eafter2)) {
+      const double dmag = sqrt(2.0 / mh * (Eafter - Eafter2));
+      double sphi, cphi;
+      sincos(phi, &sphi, &cphi);
+      const double d0 = (nb[2] * nb[0] * cphi - bm * nb[1] * sphi) / br * dmag / bm;
+      const double d1 = (nb[2] * nb[1] * cphi + bm * nb[0] * sphi) / br * dmag / bm;
+      const double d2 = -br * cphi * dmag / bm;
+      nb[0] += d0, nb[1] += d1, nb[2] += d2;
+    }
+    vh[0] = nb[0], vh[1] = nb[1], vh[2] = nb[2];
+    a0[pa] = va[0], a1[pa] = va[1], a2[pa] = va[2];
+    b0[pb] = vb[0], b1[pb] = vb[1], b2[pb] = vb[2];
+    return;
+  }
   bool s1 = true, s2 = true;
   if ((float)w1 != (float)w2) {
     c.w = P.step_hi ^ (STREAM_WEIGHT << 16) ^ salt;
@@ -1428,6 +1470,11 @@ static int coulomb_consts(double charge1, double charge2, double mass1, double m
   P->mass1 = mass1;
   P->mass2 = mass2;
   P->rel = 0;
+  if (prm->weight_method != 0 && prm->weight_method != 1) {
+    set_error("Coulomb: weight_method must be 0 (PROBABILISTIC) or 1 (CONSERVATIVE, Sentoku-Kemp)");
+    return PGPU_ERR_ARG;
+  }
+  P->sk08 = prm->weight_method;
   P->Clog = prm->Clog;
   P->dt_sec = dt_sec;
   P->angular = a;
@@ -1799,6 +1846,12 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
   const int nsub = prm->num_subcycles > 0 ? prm->num_subcycles : 1;
   P.dt_sec = dt_sec / (double)nsub;                                   // Coulomb.cpp:371
   P.rel = (sA->desc.relativistic || sB->desc.relativistic) ? 1 : 0;   // the reference's compile-time switch
+  if (P.sk08 && (P.rel || prm->enforce_conservations)) {
+    set_error("Coulomb: weight_method CONSERVATIVE is the Galilean SK08 update (Coulomb.cpp:730-917, 1439-1640); it has no "
+              "relativistic form and is not combined with enforce_conservations");
+    return PGPU_ERR_ARG;
+  }
+  if (P.sk08) P.NxN = 0, P.NxN_Nthresh = 0;   // applyIntra/InterScattering_SK08 pair in O(N) only
   const double dV = (g->desc.D == 1) ? g->geo.dx[0] : g->geo.dx[0] * g->geo.dx[1];
   P.cellV_SI = dV * g->desc.volume_scale;
   seed = stream_seed(seed, sA, sB, 1);

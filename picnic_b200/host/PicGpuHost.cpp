@@ -443,6 +443,7 @@ Coulomb::Coulomb(int a_sp1, int a_sp2, Real a_Clog, AngularScattering a_angular,
   m_prm.beta_weight_exponent = 1;
   m_prm.sort_weighted_particles = 0;
   m_prm.conservation_Nmin_save = 100000;
+  m_prm.weight_method = 0;
   if (a_Clog != 0.0 && a_Clog < 2.0) fatal("Coulomb: coulomb_logarithm must be 0 (computed) or >= 2");   // Coulomb.H:224
 }
 void Coulomb::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {

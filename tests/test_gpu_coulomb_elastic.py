@@ -192,6 +192,60 @@ def test_coulomb_enforce_conservations(pgpu, relativistic):
     assert abs(res[True][1] - res[False][1]) < 0.05 * abs(d0 - res[False][1]) + 1e-3 * abs(d0)
 
 
+def test_coulomb_sk08_conservative_weight_method(pgpu):
+    """pgpu_collide_coulomb with weight_method = CONSERVATIVE (Sentoku-Kemp, Coulomb.cpp:730-917, 1439-1640): weighted
+    electrons on weighted ions.  Every cell keeps its weighted energy to round-off (e-e and e-i); the electron drift relaxes
+    at the oracle's rate (2 % of the initial drift)."""
+    deck = decks.Deck(D=2, ncell=(12, 12), dx=(0.25, 0.25), xmin=(0.0, 0.0), nghost=2)
+    se, si = decks.electron_proton((16, 16))
+    rng = np.random.default_rng(23)
+    pe = decks.load_species(deck, se, (0, 0), (11, 11), rng)
+    pi = decks.load_species(deck, si, (0, 0), (11, 11), rng)
+    pe["v"][0] += 0.01
+    pe["w"] = pe["w"] * np.where(rng.random(pe["w"].size) < 0.5, 0.5, 1.5)
+    pi["w"] = pi["w"] * np.where(rng.random(pi["w"].size) < 0.5, 2.0, 0.5)
+    nsteps, Clog = 25, 10.0
+    dt_sec = 0.3 * deck.units.time
+    grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, 2, (1, 1), volume_scale=deck.volume_scale)
+    spe = _species_on_grid(pgpu, grid, deck, se, pe["x"], pe["v"], pe["w"], ids=pe["id"])
+    spi = _species_on_grid(pgpu, grid, deck, si, pi["x"], pi["v"], pi["w"], ids=pi["id"])
+    LDe = grid.debye_length([spe, spi])
+    e0, i0 = spe.download(), spi.download()
+    oe, oi = spe.cell_offsets(), spi.cell_offsets()
+    me, mi = se.mass, si.mass
+    Kc = lambda d, o, m: np.add.reduceat(m * d["w"] * (d["v"] ** 2).sum(0), o[:-1])
+    pgpu.collide_coulomb(spe, spe, Clog, dt_sec, 11, 1000, angular=1, conservative=True)
+    e1 = spe.download()
+    assert np.abs(Kc(e1, oe, me) - Kc(e0, oe, me)).max() < 1e-12 * Kc(e0, oe, me).max()
+    assert np.mean(np.any(e1["v"] != e0["v"], axis=0)) > 0.9
+    pgpu.collide_coulomb(spe, spi, Clog, dt_sec, 11, 1001, angular=1, conservative=True)
+    e2, i2 = spe.download(), spi.download()
+    assert np.abs((Kc(e2, oe, me) + Kc(i2, oi, mi)) - (Kc(e1, oe, me) + Kc(i0, oi, mi))).max() < 1e-12 * Kc(e1, oe, me).max()
+    # drift relaxation over nsteps of e-i collisions from the original state, against the oracle's SK08
+    spe.upload(e0["x"], e0["v"], e0["w"], ids=e0["id"]); spe.bin_particles(); spe.set_moments()
+    spi.upload(i0["x"], i0["v"], i0["w"], ids=i0["id"]); spi.bin_particles(); spi.set_moments()
+    d0 = (e0["w"] * e0["v"][0]).sum() / e0["w"].sum()
+    for step in range(nsteps):
+        pgpu.collide_coulomb(spe, spi, Clog, dt_sec, 11, step, angular=1, count=False, conservative=True)
+    ef = spe.download()
+    d_gpu = (ef["w"] * ef["v"][0]).sum() / ef["w"].sum()
+    de, di = spe.moments()[0], spi.moments()[0]
+    spe.destroy(); spi.destroy(); grid.destroy()
+    ve, vi = e0["v"].copy(), i0["v"].copy()
+    cellV = 0.25 * 0.25 * deck.volume_scale
+    orc.lib().orc_rng_seed(11)
+    orc.coulomb_set_weight_method(True)
+    try:
+        for step in range(nsteps):
+            orc.coulomb_inter(oe, ve, e0["w"], de, me, se.charge, oi, vi, i0["w"], di, mi, si.charge, LDe, cellV, Clog, 1,
+                              False, 11, dt_sec)
+    finally:
+        orc.coulomb_set_weight_method(False)
+    d_cpu = (e0["w"] * ve[0]).sum() / e0["w"].sum()
+    assert d_cpu / d0 < 0.9
+    assert abs(d_gpu - d_cpu) / d0 < 0.02
+
+
 def test_coulomb_weighted_drift_relaxation_matches_oracle(pgpu):
     """Electrons with two weight classes slowing down on protons: NANBU, Clog = 10; the momentum
     exchange of the GPU path (Philox) and of the oracle (mt19937, as the reference) agree."""

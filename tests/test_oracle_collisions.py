@@ -140,6 +140,45 @@ def test_coulomb_enforce_conservations_intra_and_inter():
             assert min(errs) > 1e-6, errs      # without the fix-up every cell drifts
 
 
+def test_coulomb_sk08_conserves_weighted_energy_per_cell():
+    """Coulomb weight_method = CONSERVATIVE (Sentoku-Kemp 2008, Coulomb.cpp:730-917, 1439-1640): unequal weights, every
+    pair keeps its weighted energy exactly (the heavier particle's transverse kick, Coulomb.H:796-823) and its weighted
+    momentum on average."""
+    ncell, n1c, n2c = 150, 30, 18
+    cs1 = np.arange(ncell + 1, dtype=np.int64) * n1c
+    cs2 = np.arange(ncell + 1, dtype=np.int64) * n2c
+    cellV, LDe, m1, m2 = 1.0e-3, np.full(ncell, 5.0e-10), 1.0, 1836.15
+    r = np.random.default_rng(12)
+    v1 = r.standard_normal((3, ncell * n1c)) * 0.02
+    v2 = r.standard_normal((3, ncell * n2c)) * 0.0008
+    v1[0] += 0.01
+    w1 = np.where(r.random(ncell * n1c) < 0.5, 1.0e27, 3.0e27)
+    w2 = np.where(r.random(ncell * n2c) < 0.5, 2.0e27, 0.5e27)
+    dens1 = np.add.reduceat(w1, cs1[:-1]) / cellV
+    dens2 = np.add.reduceat(w2, cs2[:-1]) / cellV
+    K = lambda v, w, cs, m: np.add.reduceat(m * w * (v ** 2).sum(0), cs[:-1])
+    a0 = v1.copy()
+    K0 = K(v1, w1, cs1, m1)
+    orc.lib().orc_rng_seed(6)
+    orc.coulomb_set_weight_method(True)
+    try:
+        orc.coulomb_intra(cs1, v1, w1, dens1, LDe, cellV, m1, -1.0, 10.0, 1, False, 11, 40 * DT_SEC)
+        K1 = K(v1, w1, cs1, m1)
+        Kb0 = K1 + K(v2, w2, cs2, m2)
+        P0 = m1 * (w1 * v1).sum(1) + m2 * (w2 * v2).sum(1)
+        d0 = m1 * (w1 * v1[0]).sum()
+        orc.coulomb_inter(cs1, v1, w1, dens1, m1, -1.0, cs2, v2, w2, dens2, m2, 1.0, LDe, cellV, 10.0, 1, False, 11,
+                          40 * DT_SEC)
+    finally:
+        orc.coulomb_set_weight_method(False)
+    Kb1 = K(v1, w1, cs1, m1) + K(v2, w2, cs2, m2)
+    assert np.abs(K1 - K0).max() < 1e-13 * K0.max() and np.abs(Kb1 - Kb0).max() < 1e-13 * Kb0.max()
+    assert np.mean(np.any(v1 != a0, axis=0)) > 0.9
+    P1 = m1 * (w1 * v1).sum(1) + m2 * (w2 * v2).sum(1)
+    exchanged = abs(m1 * (w1 * v1[0]).sum() - d0)
+    assert exchanged > 0.02 * abs(d0) and abs(P1[0] - P0[0]) < 0.2 * exchanged
+
+
 def test_elastic_sigma_lookup():
     E = np.array([0.01, 0.1, 1.0, 10.0, 100.0])
     Q = np.array([1.0e-19, 2.0e-19, 5.0e-20, 2.0e-20, 1.0e-20])
