@@ -213,6 +213,28 @@ int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_
  * the deposit and the second half).  Expects x_old == x and u_old == u (updateOldParticle*), like the separate calls. */
 int pgpu_explicit_step(pgpu_species_t s, double dt, const int *bc_lo, const int *bc_hi, int second_half);
 
+/* Sub-orbit model (pic_species.N.use_suborbit_model, .suborbit_fast_particles): a second particle container per species
+ * (m_data_suborbit) for the particles the particle Picard loop leaves unconverged at iter_max_particles
+ * (PicChargedSpecies.cpp:1699-1706: moved there by pgpu_advance_particles_iteratively, with two sub-orbits, depositing
+ * nothing in that call) and for "fast" particles (transferFastParticles, :894-956).
+ * pgpu_advance_suborbit_particles_and_set_J = advanceSubOrbitParticlesAndSetJ (:3324-3669), bulk container, PLANAR push:
+ * every sub-orbit particle takes the step in nsub equal implicit sub-steps (one more whenever a sub-step does not
+ * converge), ends at the NEW-time x, u with x_old, u_old of the step start, and the species' sub-orbit current
+ * (m_suborbitJ) = sum over particles of (sum over sub-orbits of the deposit) / nsub, x charge / volume_scale.
+ * pgpu_current_add_suborbit = PicSpeciesInterface::addSubOrbitJ (PicSpeciesInterface.cpp:1538-1590);
+ * pgpu_merge_suborbit_particles = mergeSubOrbitParticles (:1718-1747), to be called after the second half-step of the
+ * main container, as PICTimeIntegrator_EM_ThetaImplicit.cpp:313-318 does. */
+int pgpu_species_set_suborbit_model(pgpu_species_t s, int use_suborbit_model, int suborbit_fast_particles);
+long pgpu_species_suborbit_count(pgpu_species_t s);
+int pgpu_transfer_fast_particles(pgpu_species_t s);
+int pgpu_advance_suborbit_particles_and_set_J(pgpu_species_t s, double dt, int from_emjacobian);
+int pgpu_species_suborbit_current_get(pgpu_species_t s, int comp, double *data, const int *lo, const int *hi);
+int pgpu_current_add_suborbit(pgpu_grid_t g, pgpu_species_t s);
+int pgpu_merge_suborbit_particles(pgpu_species_t s);
+/* test / I-O hook: the sub-orbit container (component-major arrays of pgpu_species_suborbit_count entries) */
+int pgpu_species_suborbit_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
+                                   uint64_t *id, int *nsub);
+
 /* deposit */
 int pgpu_set_current_density(pgpu_species_t s, double dt, int from_explicit_solver); /* :3184-3253 */
 int pgpu_species_current_get(pgpu_species_t s, int comp, double *data, const int *lo, const int *hi);

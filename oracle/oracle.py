@@ -243,6 +243,27 @@ def advance_particles_iteratively(g, interpE, x, xold, v, vold, E, B, fnorm, cno
     return rc, apply_its.value, unconv.value, its
 
 
+def advance_suborbit_and_set_J(g, interpE, interpJ, x, xold, v, vold, w, nsub, E, B, fnorm, cnormDt, rtol, iter_max, J,
+                               from_emjacobian=False, max_suborbits=512):
+    """advanceSubOrbitParticlesAndSetJ (bulk container): x, xold, v, vold, nsub are updated in place; J accumulates."""
+    f = lib().orc_advance_suborbit_particles_and_set_J
+    f.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_long] + [C.c_void_p] * 8 + [C.c_double] * 3 + [C.c_int] * 3
+                  + [C.c_void_p])
+    nsub_c = np.ascontiguousarray(nsub, dtype=np.int32)
+    rc = f(C.byref(g), interpE, interpJ, x.shape[1], _ptr(x), _ptr(xold), _ptr(v), _ptr(vold), _ptr(w), _ptr(nsub_c),
+           _fabs3(E), _fabs3(B), fnorm, cnormDt, rtol, iter_max, int(from_emjacobian), max_suborbits, _fabs3(J))
+    nsub[...] = nsub_c
+    return rc
+
+
+def fast_particles(g, x, xold):
+    flag = np.zeros(x.shape[1], dtype=np.int32)
+    f = lib().orc_fast_particles
+    f.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(C.byref(g), x.shape[1], _ptr(x), _ptr(xold), _ptr(flag))
+    return flag
+
+
 def bin_cells(g, x):
     n = x.shape[1]
     cell = np.zeros((g.D, n), dtype=np.int32)

@@ -287,6 +287,134 @@ extern "C" int orc_advance_particles_iteratively(
   return rc;
 }
 
+/* PicChargedSpecies::advanceSubOrbitParticlesAndSetJ (PicChargedSpecies.cpp:3376-3669) for the bulk sub-orbit container
+ * (is_inflow_list = false), PLANAR push, no interp_bc_check.  Each particle -- one that the particle Picard loop left
+ * unconverged (:1699-1706) or a "fast" one (transferFastParticles, :894-956) -- is advanced through nsub[p] equal
+ * sub-steps of the time step, each an implicit push of its own (gather at the sub-orbit's x_bar, Boris half step over
+ * cnormDt/nsub, stepNormTransfer in reverse mode until converged), deposits each sub-orbit's current and ends at the
+ * NEW-time position and velocity with x_old, u_old restored to the start of the step.  A sub-orbit that does not
+ * converge in iter_max passes restarts the particle with one more sub-orbit (unless from_emjacobian: then iter_max is
+ * doubled and the unconverged state is deposited as it is).  J (three arrays, zeroed by the caller) receives the sum
+ * over particles of (sum over sub-orbits of the deposit)/nsub, un-scaled (the caller multiplies by charge/volume_scale).
+ * Returns 0, -1 on a gather/deposit failure, -2 if a particle needed more than max_suborbits. */
+extern "C" int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int interpE, int interpJ, long n, double *x,
+                                                        double *xold, double *v, double *vold, const double *w, int *nsub,
+                                                        const orc_fab *E, const orc_fab *B, double fnorm, double cnormDt,
+                                                        double rtol, int iter_max_in, int from_emjacobian,
+                                                        int max_suborbits, orc_fab *J) {
+  const int D = g->D;
+  int rc = 0;
+  int iter_max = iter_max_in;
+  if (from_emjacobian) iter_max += iter_max;   /* :3400 */
+  /* per-particle current, as the reference's this_Jp / this_Jpv: same boxes as J */
+  std::vector<std::vector<double>> Jp(3);
+  orc_fab Jpf[3];
+  for (int c = 0; c < 3; ++c) {
+    long sz = 1;
+    for (int d = 0; d < D; ++d) sz *= (J[c].hi[d] - J[c].lo[d] + 1);
+    Jp[c].assign(sz, 0.0);
+    Jpf[c] = J[c];
+    Jpf[c].p = Jp[c].data();
+  }
+  for (long p = 0; p < n; ++p) {
+    int num_suborbits = nsub[p];
+    double cnormDt_sub = cnormDt / num_suborbits;
+    for (int c = 0; c < 3; ++c) std::fill(Jp[c].begin(), Jp[c].end(), 0.0);
+    double xpold0_save[2], vpold0[3];
+    for (int d = 0; d < D; ++d) xpold0_save[d] = xold[d * n + p];
+    for (int c = 0; c < 3; ++c) vpold0[c] = vold[c * n + p];
+    double xp[2] = {0.0, 0.0}, xo[2] = {0.0, 0.0}, vp[3], vo[3];
+    for (int d = 0; d < D; ++d) xp[d] = xo[d] = xpold0_save[d];   /* x_bar guess = x_old (:3443) */
+    for (int c = 0; c < 3; ++c) vp[c] = vo[c] = vpold0[c];
+    bool failed = false;
+    for (int nv = 0; nv < num_suborbits; nv++) {
+      int iter = 0;
+      bool restart = false;
+      while (true) {
+        double ep[3], bp[3];
+        if (orc_gather(g, interpE, 1, xp, xo, E, B, ep, bp)) rc = -1;
+        orc_add_external_fields(D, 1, xp, ep, bp);
+        orc_boris(1, vp, vo, ep, bp, fnorm, cnormDt_sub, 1);
+        /* stepNormTransfer(single, temp, cnormDt_sub, reverse = true) (:658-733; iter_min = 0) */
+        const double cnormHalfDt = 0.5 * cnormDt_sub;
+        double dxp[2] = {0.0, 0.0}, rel_diff_max = 0.0;
+        for (int d = 0; d < D; ++d) {
+          const double dxp0 = xp[d] - xo[d];
+          dxp[d] = vp[d] * cnormHalfDt;
+          rel_diff_max = std::max(rel_diff_max, std::fabs(dxp0 - dxp[d]) / g->dx[d]);
+        }
+        if (rel_diff_max < rtol) break;
+        for (int d = 0; d < D; ++d) xp[d] = xo[d] + dxp[d];
+        iter += 1;
+        if (iter >= iter_max) {
+          if (!from_emjacobian) {   /* :3521-3541: one more sub-orbit, start again */
+            num_suborbits++;
+            if (num_suborbits > max_suborbits) {
+              failed = true;
+              break;
+            }
+            for (int d = 0; d < D; ++d) xp[d] = xo[d] = xpold0_save[d];
+            for (int c = 0; c < 3; ++c) vp[c] = vo[c] = vpold0[c];
+            cnormDt_sub = cnormDt / num_suborbits;
+            for (int c = 0; c < 3; ++c) std::fill(Jp[c].begin(), Jp[c].end(), 0.0);
+            restart = true;
+          }
+          break;   /* from_emjacobian: deposit the unconverged state (:3543-3548) */
+        }
+      }
+      if (failed) break;
+      if (restart) {
+        nv = -1;
+        continue;
+      }
+      /* 3) deposit this sub-orbit's current (:3557-3574) */
+      const double wp = w[p];
+      if (orc_deposit_current(g, interpJ, 1, xp, xo, vp, &wp, cnormDt_sub, Jpf)) rc = -1;
+      /* 4) time-centred -> new (:3591-3594) */
+      for (int c = 0; c < 3; ++c) vp[c] = 2.0 * vp[c] - vo[c];
+      for (int d = 0; d < D; ++d) xp[d] = 2.0 * xp[d] - xo[d];
+      /* 5) next sub-orbit starts from here (:3634-3640); the last one keeps the new values (:3603-3618) */
+      if (nv < num_suborbits - 1) {
+        for (int d = 0; d < D; ++d) xo[d] = xp[d];
+        for (int c = 0; c < 3; ++c) vo[c] = vp[c];
+      }
+    }
+    if (failed) {
+      rc = -2;
+      continue;
+    }
+    nsub[p] = num_suborbits;
+    for (int d = 0; d < D; ++d) {
+      x[d * n + p] = xp[d];
+      xold[d * n + p] = xpold0_save[d];
+    }
+    for (int c = 0; c < 3; ++c) {
+      v[c * n + p] = vp[c];
+      vold[c * n + p] = vpold0[c];
+    }
+    /* divide the particle's J by its number of sub-orbits and add it to the total (:3647-3654) */
+    for (int c = 0; c < 3; ++c)
+      for (size_t k = 0; k < Jp[c].size(); ++k) J[c].p[k] += Jp[c][k] / num_suborbits;
+  }
+  return rc;
+}
+
+/* PicChargedSpecies::transferFastParticles (PicChargedSpecies.cpp:894-956): flag[p] = 1 if the orbit x_old -> 2 x_bar -
+ * x_old crosses more than ghosts - D faces of the half-shifted grid in any direction (CC1 only) */
+extern "C" void orc_fast_particles(const orc_geom *g, long n, const double *x, const double *xold, int *flag) {
+  const int D = g->D, max_crossings = g->ghosts - D;
+  for (long p = 0; p < n; ++p) {
+    flag[p] = 0;
+    for (int dir = 0; dir < D; ++dir) {
+      const double xpnew = 2.0 * x[dir * n + p] - xold[dir * n + p];
+      /* the reference leaves out the domain's left edge here (:930-931): kept, it matters only for Xmin != 0 */
+      const int index_old = (int)std::floor((xold[dir * n + p] - 0.5 * g->dx[dir]) / g->dx[dir]);
+      const int index_new = (int)std::floor((xpnew - 0.5 * g->dx[dir]) / g->dx[dir]);
+      if (std::abs(index_new - index_old) > max_crossings) flag[p] = 1;
+    }
+  }
+}
+
 /* BinFab::locateBin (BinFabImplem.H:582-594): (int)floor((x-origin)/dx). */
 extern "C" void orc_bin(const orc_geom *g, long n, const double *x, int *cell) {
   for (long p = 0; p < n; ++p)

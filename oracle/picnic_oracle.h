@@ -279,6 +279,13 @@ void orc_elastic_wm(long ncell, const long *cs1, double *v1, const double *w1, l
                     double *v2, double *w2, long n2, const double *dens2, double mass2, double const_sigma, int ntab,
                     const double *E, const double *Q, const double *XI, int angular, int loglog, int conservative,
                     double dt_sec, long *ncoll_out);
+/* sub-orbit model: advanceSubOrbitParticlesAndSetJ (PicChargedSpecies.cpp:3376-3669) and
+ * transferFastParticles (:894-956); see oracle_push.cpp */
+int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int interpE, int interpJ, long n, double *x, double *xold,
+                                             double *v, double *vold, const double *w, int *nsub, const orc_fab *E,
+                                             const orc_fab *B, double fnorm, double cnormDt, double rtol, int iter_max,
+                                             int from_emjacobian, int max_suborbits, orc_fab *J);
+void orc_fast_particles(const orc_geom *g, long n, const double *x, const double *xold, int *flag);
 /* ScatteringUtils::modEnergyPairwise (ScatteringUtils.H:113-205), pinned on the reference (tests/test_ref_pin.py);
  * scattering.coulomb.enforce_conservations for orc_coulomb_intra / orc_coulomb_inter (Coulomb.cpp:486-512, 596-714,
  * 1024-1083, 1182-1430) */

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpicnic_gpu.so")
-SOURCES = ["pgpu_api.cu", "pgpu_push.cu", "pgpu_advance_cc1.cu", "pgpu_advance_cc1_1d.cu", "pgpu_bins.cu", "pgpu_collide.cu", "pgpu_exchange.cu", "pgpu_halo_p2p.cu", "pgpu_massmatrix.cu"]
+SOURCES = ["pgpu_api.cu", "pgpu_push.cu", "pgpu_advance_cc1.cu", "pgpu_advance_cc1_1d.cu", "pgpu_bins.cu", "pgpu_collide.cu", "pgpu_exchange.cu", "pgpu_halo_p2p.cu", "pgpu_massmatrix.cu", "pgpu_suborbit.cu"]
 # per-file flags: the mass-matrix deposit keeps every per-particle product an IEEE product (no contraction)
 EXTRA_FLAGS = {"pgpu_massmatrix.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

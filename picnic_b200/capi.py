@@ -108,6 +108,10 @@ def load():
         "pgpu_set_current_density": [vp, dbl, i32], "pgpu_species_current_get": [vp, i32, vp, vp, vp],
         "pgpu_set_charge_density": [vp, vp, vp, vp, vp],
         "pgpu_explicit_step": [vp, C.c_double, vp, vp, C.c_int],
+        "pgpu_species_set_suborbit_model": [vp, C.c_int, C.c_int], "pgpu_transfer_fast_particles": [vp],
+        "pgpu_advance_suborbit_particles_and_set_J": [vp, C.c_double, C.c_int],
+        "pgpu_species_suborbit_current_get": [vp, C.c_int, vp, vp, vp], "pgpu_current_add_suborbit": [vp, vp],
+        "pgpu_merge_suborbit_particles": [vp], "pgpu_species_suborbit_download": [vp] * 8,
         "pgpu_grid_set_external_fields": [vp, vp], "pgpu_add_external_fields_to_particles": [vp],
         "pgpu_fields_packed_size": [vp, vp], "pgpu_fields_set_packed": [vp, vp],
         "pgpu_current_packed_size": [vp, vp], "pgpu_current_get_packed_async": [vp, vp],
@@ -339,6 +343,41 @@ class Species:
 
     def advance_positions_2nd_half(self):
         check(load().pgpu_advance_positions_2nd_half(self.h))
+
+    # ---- sub-orbit model --------------------------------------------------------------------------
+    def set_suborbit_model(self, use=True, fast_particles=False):
+        check(load().pgpu_species_set_suborbit_model(self.h, int(use), int(fast_particles)))
+
+    @property
+    def n_suborbit(self):
+        f = load().pgpu_species_suborbit_count
+        f.restype = C.c_long
+        f.argtypes = [C.c_void_p]
+        return f(self.h)
+
+    def transfer_fast_particles(self):
+        check(load().pgpu_transfer_fast_particles(self.h))
+
+    def advance_suborbit_and_set_J(self, dt, from_emjacobian=False):
+        check(load().pgpu_advance_suborbit_particles_and_set_J(self.h, dt, int(from_emjacobian)))
+
+    def suborbit_current_get(self, comp):
+        lo, hi = self.grid.field_bounds(comp)
+        out = np.zeros(tuple(h - l + 1 for l, h in zip(lo, hi)), order="F")
+        check(load().pgpu_species_suborbit_current_get(self.h, comp, _p(out), _i2(lo), _i2(hi)))
+        return out
+
+    def merge_suborbit(self):
+        check(load().pgpu_merge_suborbit_particles(self.h))
+
+    def suborbit_download(self):
+        n = self.n_suborbit
+        out = {"x": np.zeros((self.D, n)), "xold": np.zeros((self.D, n)), "v": np.zeros((3, n)), "vold": np.zeros((3, n)),
+               "w": np.zeros(n), "id": np.zeros(n, dtype=np.uint64), "nsub": np.zeros(n, dtype=np.int32)}
+        if n:
+            check(load().pgpu_species_suborbit_download(self.h, _p(out["x"]), _p(out["xold"]), _p(out["v"]), _p(out["vold"]),
+                                                        _p(out["w"]), _p(out["id"]), _p(out["nsub"])))
+        return out
 
     def explicit_step(self, dt, bc_lo, bc_hi, second_half=False):
         check(load().pgpu_explicit_step(self.h, dt, _i2(bc_lo), _i2(bc_hi), int(second_half)))

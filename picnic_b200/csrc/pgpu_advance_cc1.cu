@@ -67,6 +67,7 @@ struct FastArgs {
   double tol[2];            // rtol * dx
   const int4 *tile_box;     // per tile: dual-cell window (i, j, columns, rows) staged in shared memory
   int prefetch;             // persistent grid: pull the block's next tile into L2 while this one is computed
+  int suborbit;             // m_use_suborbit_model: a particle that hits iter_max is deferred, not counted
 };
 
 // 21 fp64 REDs of one accumulator set into the J arrays at dual cell `key` (one pointer per grid row:
@@ -317,6 +318,7 @@ __device__ __forceinline__ bool push_one(const FastArgs &A, const double (&xo)[2
       xb[1] = xo[1] + dxp_1;
     }
     if (!done && iter >= A.iter_max) {
+      if (A.suborbit) return false;   // sub-orbit model: the generic kernel redoes it and lists it for the sub-orbit container
       nunconv = 1;
       done = true;
     }
@@ -810,6 +812,7 @@ __device__ __forceinline__ bool push_tab(const FastArgs &A, const TabWindow &Wn,
       xb[1] = xo[1] + dxp_1;
     }
     if (!done && iter >= A.iter_max) {
+      if (A.suborbit) return false;   // sub-orbit model: the generic kernel redoes it and lists it for the sub-orbit container
       nunconv = 1;
       done = true;
     }
@@ -1608,6 +1611,7 @@ __device__ __forceinline__ bool push_v2(const FastArgs &A, const TabWindow &Wn, 
       xb[1] = xo[1] + dxp_1;
     }
     if (!done && iter >= A.iter_max) {
+      if (A.suborbit) return false;   // sub-orbit model: the generic kernel redoes it and lists it for the sub-orbit container
       nunconv = 1;
       done = true;
     }
@@ -1914,6 +1918,7 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   A.rtol = prm.rtol;
   A.rvolume = prm.rvolume;
   A.iter_max = prm.iter_max;
+  A.suborbit = prm.suborbit;
   A.list = s->defer_list;
   A.list_count = s->defer_count;
   A.cnt = c.d_counters;
@@ -2021,7 +2026,7 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
       s->xold_alias = s->vold_alias = false;
       return 1;
     }
-    if (c.cc1_pair) {
+    if (c.cc1_pair && !prm.suborbit) {
       // two particles of a dual cell in lockstep through the Picard loop (PGPU_CC1_PAIR=1)
       if (!deposit) {
         if (mb == 3) PGPU_TAB_LAUNCH(false, 0, 3, true);

@@ -40,6 +40,7 @@ struct Args1D {
   double *J[3];
   double alpha, hdt, tol, rvolume;
   int iter_max;
+  int suborbit;
   int *list;
   unsigned *list_count;
   Counters *cnt;
@@ -131,6 +132,7 @@ __device__ __forceinline__ bool push_1d(const Args1D &A, double xo, double &xb, 
       xb = xo + dxp;
     }
     if (!done && iter >= A.iter_max) {
+      if (A.suborbit) return false;   // sub-orbit model: left to the generic kernel, which lists it
       nunconv = 1;
       done = true;
     }
@@ -338,6 +340,7 @@ int launch_advance_cc1_1d_fast(pgpu_species_s *s, const AdvanceParams &prm, bool
   A.tol = prm.rtol * A.dx;
   A.rvolume = prm.rvolume;
   A.iter_max = prm.iter_max;
+  A.suborbit = prm.suborbit;
   A.list = s->defer_list;
   A.list_count = s->defer_count;
   A.cnt = c.d_counters;

@@ -780,6 +780,13 @@ int pgpu_species_destroy(pgpu_species_t s) {
   for (int k = 0; k < 4; ++k) cudaFree(s->spare[k]);
   cudaFree(s->defer_list);
   cudaFree(s->enf_save);
+  for (int k = 0; k < 10; ++k) cudaFree(s->sub[k]);
+  cudaFree(s->sub_w);
+  cudaFree(s->sub_id);
+  cudaFree(s->sub_nsub);
+  for (int c = 0; c < 3; ++c) cudaFree(s->Jsub[c].p);
+  cudaFree(s->unconv_list);
+  cudaFree(s->unconv_count);
   cudaFree(s->tile_box);
   cudaFree(s->mig);
   cudaFree(s->mig_list);
@@ -1067,6 +1074,10 @@ static AdvanceParams make_params(pgpu_species_t s, double dt, bool iterative) {
   p.rel = s->desc.relativistic;
   p.hc = s->desc.higuera_cary;
   p.ext = s->grid->ext;
+  p.fnorm = s->desc.fnorm_const;
+  p.suborbit = 0;
+  p.unconv_list = nullptr;
+  p.unconv_count = nullptr;
   return p;
 }
 
@@ -1119,8 +1130,29 @@ int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_
   if (deposit_J)
     for (int c = 0; c < 3; ++c)
       PGPU_CUDA(cudaMemsetAsync(s->J[c].p, 0, s->J[c].size() * sizeof(double), ctx().stream));
-  rc = launch_advance(s, make_params(s, dt, iterative), fuse);
+  AdvanceParams prm = make_params(s, dt, iterative);
+  const bool sub = iterative && s->use_suborbit_model;
+  if (sub) {
+    // m_use_suborbit_model (:1699-1706): particles the loop leaves unconverged are listed, deposit nothing here and move
+    // to the sub-orbit container
+    if (ensure_unconv_list(s)) return PGPU_ERR_CUDA;
+    PGPU_CUDA(cudaMemsetAsync(s->unconv_count, 0, sizeof(unsigned), ctx().stream));
+    prm.suborbit = 1;
+    prm.unconv_list = s->unconv_list;
+    prm.unconv_count = s->unconv_count;
+  }
+  rc = launch_advance(s, prm, fuse);
   if (rc) return rc;
+  if (sub) {
+    unsigned count = 0;
+    PGPU_CUDA(cudaMemcpyAsync(&count, s->unconv_count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
+    PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (count && !fuse && deposit_J) {
+      set_error("sub-orbit model: the separate deposit pass would include the particles that moved to the sub-orbit container");
+    }
+    rc = transfer_listed_to_suborbit(s, count);
+    if (rc) return rc;
+  }
   if (deposit_J) {
     if (!fuse) {
       rc = launch_deposit_current(s, dt * s->desc.cvac_norm);

@@ -56,6 +56,10 @@ struct AdvanceParams {
   double rvolume;   // 1/volume
   int rel, hc;      // RELATIVISTIC_PARTICLES build of the push; Higuera-Cary gamma
   ExtFields ext;    // external fields added after every gather (addExternalFieldsToParticles)
+  double fnorm;     // m_fnorm_const (the sub-orbit model forms its own alpha per sub-step)
+  int suborbit;     // m_use_suborbit_model: particles left unconverged are listed (unconv_list) and deposit nothing
+  int *unconv_list;
+  unsigned *unconv_count;
 };
 
 struct Counters {          // device-resident, 64-bit
@@ -197,6 +201,18 @@ struct pgpu_species_s {
   size_t sort_cap = 0;
   void *cub_tmp = nullptr;
   size_t cub_bytes = 0;
+  // sub-orbit model (PicChargedSpecies m_data_suborbit, m_suborbitJ): a second, small particle container
+  int use_suborbit_model = 0, suborbit_fast_particles = 0;
+  double *sub[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double *sub_w = nullptr;
+  uint64_t *sub_id = nullptr;
+  int *sub_nsub = nullptr;
+  long n_sub = 0;
+  size_t sub_cap = 0;
+  pgpu::DeviceFab Jsub[3];
+  int *unconv_list = nullptr;       // particles the last advance left unconverged (suborbit model)
+  unsigned *unconv_count = nullptr;
+  size_t unconv_cap = 0;
   double *enf_save = nullptr;       // Coulomb enforce_conservations: velocities before the collisions [3][enf_cap]
   size_t enf_cap = 0;
   int *defer_list = nullptr;        // particles the CC1 fast kernel left to the generic one
@@ -246,6 +262,9 @@ int materialize_old(pgpu_species_s *s, int keep = 0);
 int grow_capacity(pgpu_species_s *s, long n);   // keeps the particles (pgpu_api.cu)
 int launch_gather(pgpu_species_s *s);
 int launch_add_external(pgpu_species_s *s);
+int ensure_unconv_list(pgpu_species_s *s);                               // pgpu_suborbit.cu
+int transfer_listed_to_suborbit(pgpu_species_s *s, unsigned count);      // pgpu_suborbit.cu
+int launch_suborbit(pgpu_species_s *s, const AdvanceParams &prm, int from_jac, const DeviceFab *Jsub, unsigned *nfail);
 int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int *periodic, bool second_half);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);

@@ -184,6 +184,7 @@ k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
       ub[c] = uo[c];  // only survives if the first gather fails
     }
     const double hdt = m::mul(prm.cnormDt, 0.5);  // cnormHalfDt
+    bool left_unconverged = false;
 
     if (prm.iter_max < 0) {
       // advanceParticles (PicChargedSpecies.cpp:1594-1612)
@@ -256,17 +257,23 @@ k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
         if (iter >= prm.iter_max) {
           // iter counts reverse passes done; cap reached (:1678-1693)
           unconv += 1;
+          left_unconverged = true;
           break;
         }
         iter += 1;
       }
+    }
+    if (left_unconverged && prm.suborbit) {
+      // m_use_suborbit_model (:1699-1706): off to the sub-orbit container with two sub-orbits; it deposits there
+      const unsigned slot = atomicAdd(prm.unconv_count, 1u);
+      prm.unconv_list[slot] = (int)i;
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) p.x[d][i] = xb[d];
 #pragma unroll
     for (int c = 0; c < 3; ++c) p.v[c][i] = ub[c];
 
-    if (DEP && !(err & (ERRBIT_SEGMENTS | ERRBIT_BOUNDS))) {
+    if (DEP && !(err & (ERRBIT_SEGMENTS | ERRBIT_BOUNDS)) && !(left_unconverged && prm.suborbit)) {
       double wp = p.w[i];
       if (prm.rel) wp = __ddiv_rn(wp, gamma_implicit<X>(uo, ub));   // MeshInterpI.H:78-89
       const double rhop = X ? __ddiv_rn(wp, prm.volume) : wp * prm.rvolume;
@@ -515,6 +522,182 @@ int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int 
   }
   e.second_half = second_half ? 1 : 0;
   return ga.D == 1 ? launch_explicit_d<1>(s, prm, e) : launch_explicit_d<2>(s, prm, e);
+}
+
+// ---- sub-orbit model ------------------------------------------------------------------------------------
+// PicChargedSpecies::advanceSubOrbitParticlesAndSetJ (PicChargedSpecies.cpp:3376-3669), bulk container (no inflow list),
+// PLANAR push: one thread per sub-orbit particle.  The reference accumulates a particle's current in a private array
+// and divides it by the final number of sub-orbits; atomics cannot be taken back, so the thread first runs the
+// sub-orbit loop WITHOUT depositing until it has the number of sub-orbits that converges, then runs that (deterministic)
+// sequence again depositing value/nsub.
+struct SubPtrs {
+  double *x[2], *xold[2], *v[3], *vold[3], *w;
+  int *nsub;
+};
+template <int D, int IE, int IJ, bool X, bool DEP>
+__device__ bool suborbit_run(const Geo<D> &g, const FieldSet &F, const CurrentSet &J, const AdvanceParams &prm,
+                             int iter_max, bool from_jac, int max_sub, const double (&x0)[D], const double (&u0)[3],
+                             double wp, int &nsub, double (&xp)[D], double (&vp)[3], unsigned &err, unsigned &apply) {
+  typedef M<X> m;
+  double xo[D], vo[3];
+  int num = nsub;
+  double cdt = __ddiv_rn(prm.cnormDt, (double)num);
+#pragma unroll
+  for (int d = 0; d < D; ++d) xp[d] = xo[d] = x0[d];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) vp[c] = vo[c] = u0[c];
+  for (int nv = 0; nv < num; nv++) {
+    int iter = 0;
+    bool restart = false;
+    while (true) {
+      GatherOp<D, X> op(F);
+      if (!gather_visit<D, IE, X>(g, xp, xo, op)) {
+        err |= ERRBIT_SEGMENTS;
+        return false;
+      }
+      if (op.oob) {
+        err |= ERRBIT_BOUNDS;
+        return false;
+      }
+      if (prm.ext.on) add_external<D>(prm.ext, xp, op.acc);
+      // alpha = fnorm * cnormDt_sub / 2 (PicSpeciesUtils.cpp:20)
+      boris<X>(vo, op.acc, op.acc + 3, __ddiv_rn(__dmul_rn(prm.fnorm, cdt), 2.0), true, vp, 0, 0);
+      apply += 1;
+      const double hdt = m::mul(cdt, 0.5);
+      double dxp[D], rel_max = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double dxp0 = m::sub(xp[d], xo[d]);
+        dxp[d] = m::mul(vp[d], hdt);
+        rel_max = fmax(rel_max, __ddiv_rn(fabs(m::sub(dxp0, dxp[d])), g.dx[d]));
+      }
+      if (rel_max < prm.rtol) break;
+#pragma unroll
+      for (int d = 0; d < D; ++d) xp[d] = m::add(xo[d], dxp[d]);
+      iter += 1;
+      if (iter >= iter_max) {
+        if (!from_jac) {
+          num++;
+          if (num > max_sub) return false;
+#pragma unroll
+          for (int d = 0; d < D; ++d) xp[d] = xo[d] = x0[d];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) vp[c] = vo[c] = u0[c];
+          cdt = __ddiv_rn(prm.cnormDt, (double)num);
+          restart = true;
+        }
+        break;
+      }
+    }
+    if (restart) {
+      if (DEP) return false;   // the depositing run starts from the converged count: cannot happen
+      nv = -1;
+      continue;
+    }
+    if (DEP) {
+      const double rhop = X ? __ddiv_rn(wp, prm.volume) : wp * prm.rvolume;
+      DepositOpGlobal<D, X> dop(J, false);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dop.val[c] = __ddiv_rn(m::mul(vp[c], rhop), (double)num);
+      if (!deposit_visit<D, IJ, X>(g, xp, xo, dop)) err |= ERRBIT_SEGMENTS;
+      if (dop.oob) err |= ERRBIT_BOUNDS;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vp[c] = m::sub(m::mul(2.0, vp[c]), vo[c]);
+#pragma unroll
+    for (int d = 0; d < D; ++d) xp[d] = m::sub(m::mul(2.0, xp[d]), xo[d]);
+    if (nv < num - 1) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) xo[d] = xp[d];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) vo[c] = vp[c];
+    }
+  }
+  nsub = num;
+  return true;
+}
+template <int D, int IE, int IJ, bool X>
+__global__ void __launch_bounds__(128)
+k_suborbit(SubPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams prm, int iter_max, int from_jac, int max_sub,
+           Counters *cnt, unsigned *nfail) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned err = 0, apply = 0;
+  if (i < n) {
+    double x0[D], u0[3], xp[D], vp[3];
+#pragma unroll
+    for (int d = 0; d < D; ++d) x0[d] = p.xold[d][i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) u0[c] = p.vold[c][i];
+    int nsub = p.nsub[i];
+    const double wp = p.w[i];
+    bool ok = suborbit_run<D, IE, IJ, X, false>(g, F, J, prm, iter_max, from_jac != 0, max_sub, x0, u0, wp, nsub, xp, vp, err, apply);
+    if (ok) ok = suborbit_run<D, IE, IJ, X, true>(g, F, J, prm, iter_max, from_jac != 0, max_sub, x0, u0, wp, nsub, xp, vp, err, apply);
+    if (ok) {
+      p.nsub[i] = nsub;
+#pragma unroll
+      for (int d = 0; d < D; ++d) p.x[d][i] = xp[d];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) p.v[c][i] = vp[c];
+    } else {
+      atomicAdd(nfail, 1u);
+    }
+  }
+  flush_counters(cnt, 0, 0, err);
+}
+template <int D, int IE, int IJ>
+static int launch_suborbit_t(pgpu_species_s *s, const SubPtrs &P, long n, const CurrentSet &J, const AdvanceParams &prm,
+                             int iter_max, int from_jac, unsigned *nfail) {
+  Context &c = ctx();
+  const Geo<D> g = make_geo<D>(species_geo(s));
+  const FieldSet F = grid_fields(s->grid);
+  KTimer t("suborbit");
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  if (c.exact) k_suborbit<D, IE, IJ, true><<<nb, 128, 0, c.stream>>>(P, n, g, F, J, prm, iter_max, from_jac, 512, c.d_counters, nfail);
+  else k_suborbit<D, IE, IJ, false><<<nb, 128, 0, c.stream>>>(P, n, g, F, J, prm, iter_max, from_jac, 512, c.d_counters, nfail);
+  return 0;
+}
+template <int D, int IE>
+static int launch_suborbit_e(pgpu_species_s *s, const SubPtrs &P, long n, const CurrentSet &J, const AdvanceParams &prm,
+                             int iter_max, int from_jac, unsigned *nfail) {
+  switch (s->desc.interp_J) {
+    case CIC: return launch_suborbit_t<D, IE, CIC>(s, P, n, J, prm, iter_max, from_jac, nfail);
+    case TSC: return launch_suborbit_t<D, IE, TSC>(s, P, n, J, prm, iter_max, from_jac, nfail);
+    case CC0: return launch_suborbit_t<D, IE, CC0>(s, P, n, J, prm, iter_max, from_jac, nfail);
+    case CC1: return launch_suborbit_t<D, IE, CC1>(s, P, n, J, prm, iter_max, from_jac, nfail);
+  }
+  return PGPU_ERR_ARG;
+}
+template <int D>
+static int launch_suborbit_d(pgpu_species_s *s, const SubPtrs &P, long n, const CurrentSet &J, const AdvanceParams &prm,
+                             int iter_max, int from_jac, unsigned *nfail) {
+  switch (s->desc.interp_E) {
+    case CIC: return launch_suborbit_e<D, CIC>(s, P, n, J, prm, iter_max, from_jac, nfail);
+    case TSC: return launch_suborbit_e<D, TSC>(s, P, n, J, prm, iter_max, from_jac, nfail);
+    case CC0: return launch_suborbit_e<D, CC0>(s, P, n, J, prm, iter_max, from_jac, nfail);
+    case CC1: return launch_suborbit_e<D, CC1>(s, P, n, J, prm, iter_max, from_jac, nfail);
+  }
+  return PGPU_ERR_ARG;
+}
+// the sub-orbit container of s: arrays sub[0..9] = x0 x1 xold0 xold1 v0 v1 v2 vold0 vold1 vold2, sub_w, sub_nsub
+int launch_suborbit(pgpu_species_s *s, const AdvanceParams &prm, int from_jac, const DeviceFab *Jsub, unsigned *nfail) {
+  if (s->n_sub == 0) return 0;
+  SubPtrs P;
+  for (int d = 0; d < 2; ++d) {
+    P.x[d] = s->sub[d];
+    P.xold[d] = s->sub[2 + d];
+  }
+  for (int c = 0; c < 3; ++c) {
+    P.v[c] = s->sub[4 + c];
+    P.vold[c] = s->sub[7 + c];
+  }
+  P.w = s->sub_w;
+  P.nsub = s->sub_nsub;
+  CurrentSet J;
+  for (int c = 0; c < 3; ++c) J.j[c] = Jsub[c].view();
+  int iter_max = s->desc.iter_max;
+  if (from_jac) iter_max += iter_max;
+  return s->grid->desc.D == 1 ? launch_suborbit_d<1>(s, P, s->n_sub, J, prm, iter_max, from_jac, nfail)
+                              : launch_suborbit_d<2>(s, P, s->n_sub, J, prm, iter_max, from_jac, nfail);
 }
 
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit) {

@@ -1,0 +1,317 @@
+// pgpu_suborbit.cu -- the sub-orbit model of the implicit particle advance.
+//
+// PICNIC keeps a second particle container per species, m_data_suborbit, for the particles the particle Picard loop
+// cannot converge (PicChargedSpecies::advanceParticlesIteratively, PicChargedSpecies.cpp:1699-1706) and for "fast"
+// particles that cross more cell faces than the CC1 mass matrices allow (transferFastParticles, :894-956).  Those
+// particles take the time step in 2, 3, ... equal sub-steps (advanceSubOrbitParticlesAndSetJ, :3324-3669, the kernel is in
+// pgpu_push.cu), deposit into their own current m_suborbitJ, which PicSpeciesInterface::addSubOrbitJ adds to the total
+// (PicSpeciesInterface.cpp:1538-1590), and return to the main container at the end of the step (mergeSubOrbitParticles,
+// :1718-1747).  Here the container is a second, small SoA next to the species' main arrays; moving particles between
+// the two is a gather into the tail of one and a hole fill from the tail of the other.
+#include <algorithm>
+
+#include "pgpu_internal.h"
+
+using namespace pgpu;
+
+#define NEED_INIT()                                  \
+  if (!ctx().inited) {                               \
+    set_error("pgpu_init has not been called");      \
+    return PGPU_ERR_STATE;                           \
+  }
+
+namespace {
+inline unsigned nb(long n) { return (unsigned)((n + 255) / 256); }
+
+struct MainPtrs {
+  double *a[10];   // x0 x1 xold0 xold1 v0 v1 v2 vold0 vold1 vold2 (entries of unused directions are null)
+  double *w;
+  uint64_t *id;
+};
+MainPtrs main_ptrs(pgpu_species_s *s) {
+  MainPtrs P;
+  for (int d = 0; d < 2; ++d) {
+    P.a[d] = s->x[d];
+    P.a[2 + d] = s->xold[d];
+  }
+  for (int c = 0; c < 3; ++c) {
+    P.a[4 + c] = s->v[c];
+    P.a[7 + c] = s->vold[c];
+  }
+  P.w = s->w;
+  P.id = s->id;
+  return P;
+}
+MainPtrs sub_ptrs(pgpu_species_s *s) {
+  MainPtrs P;
+  for (int k = 0; k < 10; ++k) P.a[k] = s->sub[k];
+  P.w = s->sub_w;
+  P.id = s->sub_id;
+  return P;
+}
+
+// listed particles of `from` -> positions base .. base+count-1 of `to`
+__global__ void k_copy_listed(MainPtrs from, MainPtrs to, const int *list, unsigned count, long base, int *nsub, int D,
+                              int *dead) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const long i = list[t], o = base + t;
+  for (int k = 0; k < 10; ++k) {
+    if ((k < 4) && ((k & 1) >= D)) continue;   // x1 / xold1 in 1D
+    to.a[k][o] = from.a[k][i];
+  }
+  to.w[o] = from.w[i];
+  to.id[o] = from.id[i];
+  if (nsub) nsub[o] = 2;           // setNumSubOrbits(2)
+  if (dead) dead[i] = 1;
+}
+// the usual hole fill: survivors of the tail [new_n, n) move into the holes below new_n
+__global__ void k_list_holes_movers(const int *dead, long n, long new_n, const int *list, unsigned count, int *holes,
+                                    int *movers, unsigned *nh, unsigned *nm) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const long i = list[t];
+  if (i < new_n) holes[atomicAdd(nh, 1u)] = (int)i;
+  const long j = new_n + t;
+  if (j < n && !dead[j]) movers[atomicAdd(nm, 1u)] = (int)j;
+}
+__global__ void k_fill(MainPtrs P, const int *holes, const int *movers, const unsigned *nh, int D) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *nh) return;
+  const long dst = holes[t], src = movers[t];
+  for (int k = 0; k < 10; ++k) {
+    if ((k < 4) && ((k & 1) >= D)) continue;
+    P.a[k][dst] = P.a[k][src];
+  }
+  P.w[dst] = P.w[src];
+  P.id[dst] = P.id[src];
+}
+__global__ void k_clear_dead(int *dead, const int *list, unsigned count) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count) dead[list[t]] = 0;
+}
+// PicChargedSpecies::transferFastParticles (:894-956): more than ghosts - D face crossings of the half-shifted grid
+__global__ void k_flag_fast(const double *x0, const double *x1, const double *xo0, const double *xo1, long n, int D,
+                            double dx0, double dx1, int max_crossings, int *list, unsigned *count) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool fast = false;
+  for (int d = 0; d < D; ++d) {
+    const double xb = d ? x1[i] : x0[i], xo = d ? xo1[i] : xo0[i], dx = d ? dx1 : dx0;
+    const double xn = __dsub_rn(__dmul_rn(2.0, xb), xo);
+    // as the reference writes it (:930-931): no domain left edge in the index
+    const int io = __double2int_rd(__ddiv_rn(__dsub_rn(xo, __dmul_rn(0.5, dx)), dx));
+    const int in = __double2int_rd(__ddiv_rn(__dsub_rn(xn, __dmul_rn(0.5, dx)), dx));
+    if (abs(in - io) > max_crossings) fast = true;
+  }
+  if (fast) list[atomicAdd(count, 1u)] = (int)i;
+}
+
+int ensure_sub_cap(pgpu_species_s *s, long need) {
+  if ((size_t)need <= s->sub_cap) return 0;
+  const size_t cap = (size_t)(need + need / 4 + 4096);
+  cudaStream_t st = ctx().stream;
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  auto re = [&](void **p, size_t elem) -> int {
+    void *q = nullptr;
+    if (cudaMalloc(&q, cap * elem) != cudaSuccess) return PGPU_ERR_CUDA;
+    if (*p) {
+      cudaMemcpy(q, *p, (size_t)s->n_sub * elem, cudaMemcpyDeviceToDevice);
+      cudaFree(*p);
+    }
+    *p = q;
+    return 0;
+  };
+  for (int k = 0; k < 10; ++k)
+    if (re(reinterpret_cast<void **>(&s->sub[k]), sizeof(double))) return PGPU_ERR_CUDA;
+  if (re(reinterpret_cast<void **>(&s->sub_w), sizeof(double))) return PGPU_ERR_CUDA;
+  if (re(reinterpret_cast<void **>(&s->sub_id), sizeof(uint64_t))) return PGPU_ERR_CUDA;
+  if (re(reinterpret_cast<void **>(&s->sub_nsub), sizeof(int))) return PGPU_ERR_CUDA;
+  s->sub_cap = cap;
+  return 0;
+}
+}  // namespace
+
+namespace pgpu {
+// scratch of the unconverged / fast list: list [cap] + holes [cap] + movers [cap] ints, two counters behind the count
+int ensure_unconv_list(pgpu_species_s *s) {
+  if (s->unconv_list && s->unconv_cap >= s->cap) return 0;
+  if (s->unconv_list) cudaFree(s->unconv_list);
+  if (!s->unconv_count) PGPU_CUDA(cudaMalloc(&s->unconv_count, 4 * sizeof(unsigned)));
+  PGPU_CUDA(cudaMalloc(&s->unconv_list, 3 * s->cap * sizeof(int)));
+  s->unconv_cap = s->cap;
+  return 0;
+}
+
+// move the particles listed in s->unconv_list[0 .. count) from the main container to the sub-orbit container
+int transfer_listed_to_suborbit(pgpu_species_s *s, unsigned count) {
+  if (count == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  if (ensure_sub_cap(s, s->n_sub + (long)count)) return PGPU_ERR_CUDA;
+  cudaStream_t st = ctx().stream;
+  const int D = s->grid->desc.D;
+  int *dead = s->cell_key;   // [cap] ints, free between cell sorts (the sort is invalidated below)
+  int *list = s->unconv_list, *holes = list + s->unconv_cap, *movers = holes + s->unconv_cap;
+  unsigned *nh = s->unconv_count + 1, *nm = s->unconv_count + 2;
+  const long new_n = s->n - (long)count;
+  // only the tail [new_n, n) is ever tested for "dead": clear just that
+  PGPU_CUDA(cudaMemsetAsync(dead + new_n, 0, (size_t)count * sizeof(int), st));
+  PGPU_CUDA(cudaMemsetAsync(nh, 0, 2 * sizeof(unsigned), st));
+  KTimer t("suborbit_transfer");
+  k_copy_listed<<<nb(count), 256, 0, st>>>(main_ptrs(s), sub_ptrs(s), list, count, s->n_sub, s->sub_nsub, D, dead);
+  k_list_holes_movers<<<nb(count), 256, 0, st>>>(dead, s->n, new_n, list, count, holes, movers, nh, nm);
+  k_fill<<<nb(count), 256, 0, st>>>(main_ptrs(s), holes, movers, nh, D);
+  s->n = new_n;
+  s->n_sub += (long)count;
+  s->binned = false;
+  return 0;
+}
+}  // namespace pgpu
+
+extern "C" {
+
+int pgpu_species_set_suborbit_model(pgpu_species_t s, int use_suborbit_model, int suborbit_fast_particles) {
+  if (!s) return PGPU_ERR_ARG;
+  s->use_suborbit_model = use_suborbit_model ? 1 : 0;
+  s->suborbit_fast_particles = suborbit_fast_particles ? 1 : 0;
+  return 0;
+}
+
+long pgpu_species_suborbit_count(pgpu_species_t s) { return s ? s->n_sub : -1; }
+
+int pgpu_transfer_fast_particles(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  if (!s->suborbit_fast_particles || s->desc.interp_J != CC1 || s->n == 0) return 0;   // :896-897
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  if (ensure_unconv_list(s)) return PGPU_ERR_CUDA;
+  cudaStream_t st = ctx().stream;
+  const pgpu_grid_s *g = s->grid;
+  PGPU_CUDA(cudaMemsetAsync(s->unconv_count, 0, sizeof(unsigned), st));
+  k_flag_fast<<<nb(s->n), 256, 0, st>>>(s->x[0], s->x[1], s->xold[0], s->xold[1], s->n, g->desc.D, g->geo.dx[0], g->geo.dx[1],
+                                        g->desc.nghost - g->desc.D, s->unconv_list, s->unconv_count);
+  unsigned count = 0;
+  PGPU_CUDA(cudaMemcpyAsync(&count, s->unconv_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  return transfer_listed_to_suborbit(s, count);
+}
+
+int pgpu_advance_suborbit_particles_and_set_J(pgpu_species_t s, double dt, int from_emjacobian) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  if (s->desc.relativistic) {
+    set_error("the sub-orbit model is implemented for the non-relativistic planar push");
+    return PGPU_ERR_STATE;
+  }
+  cudaStream_t st = ctx().stream;
+  for (int c = 0; c < 3; ++c) {
+    if (!s->Jsub[c].p) {
+      s->Jsub[c] = s->J[c];
+      s->Jsub[c].p = nullptr;
+      PGPU_CUDA(cudaMalloc(&s->Jsub[c].p, s->J[c].size() * sizeof(double)));
+    }
+    PGPU_CUDA(cudaMemsetAsync(s->Jsub[c].p, 0, s->Jsub[c].size() * sizeof(double), st));   // SpaceUtils::zero (:3330-3331)
+  }
+  if (s->n_sub == 0) return 0;
+  if (!s->unconv_count) PGPU_CUDA(cudaMalloc(&s->unconv_count, 4 * sizeof(unsigned)));
+  unsigned *nfail = s->unconv_count + 3;
+  PGPU_CUDA(cudaMemsetAsync(nfail, 0, sizeof(unsigned), st));
+  AdvanceParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.cnormDt = dt * s->desc.cvac_norm;
+  prm.fnorm = s->desc.fnorm_const;
+  prm.alpha = s->desc.fnorm_const * prm.cnormDt / 2.0;
+  prm.rtol = s->desc.rtol;
+  prm.iter_max = s->desc.iter_max;
+  const GeoAny &g = s->grid->geo;
+  prm.volume = (g.D == 1) ? g.dx[0] : g.dx[0] * g.dx[1];
+  prm.rvolume = 1.0 / prm.volume;
+  prm.ext = s->grid->ext;
+  int rc = launch_suborbit(s, prm, from_emjacobian ? 1 : 0, s->Jsub, nfail);
+  if (rc) return rc;
+  // multiply by charge / volume_scale (:3366-3372)
+  const double f = s->desc.charge / s->grid->desc.volume_scale;
+  for (int c = 0; c < 3; ++c) {
+    rc = scale_fab(s->Jsub[c], f);
+    if (rc) return rc;
+  }
+  unsigned failed = 0;
+  PGPU_CUDA(cudaMemcpyAsync(&failed, nfail, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  if (failed) {
+    set_error("sub-orbit model: %u particles did not converge with 512 sub-orbits or left the ghosted arrays", failed);
+    return PGPU_ERR_STATE;
+  }
+  return 0;
+}
+
+int pgpu_species_suborbit_current_get(pgpu_species_t s, int comp, double *data, const int *lo, const int *hi) {
+  NEED_INIT();
+  if (!s || comp < 0 || comp >= 3 || !s->Jsub[comp].p) return PGPU_ERR_ARG;
+  int rc = copy_fab_to_host(s->Jsub[comp], s->grid->desc.D, data, lo, hi);
+  if (rc) return rc;
+  return pgpu_synchronize();
+}
+
+// PicSpeciesInterface::addSubOrbitJ (PicSpeciesInterface.cpp:1538-1590): total J += this species' sub-orbit J
+__global__ void k_add_arr(double *a, const double *b, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = __dadd_rn(a[i], b[i]);
+}
+int pgpu_current_add_suborbit(pgpu_grid_t g, pgpu_species_t s) {
+  NEED_INIT();
+  if (!g || !s) return PGPU_ERR_ARG;
+  if (!s->use_suborbit_model || s->desc.charge == 0.0 || !s->Jsub[0].p) return 0;
+  for (int c = 0; c < 3; ++c) {
+    const long n = (long)g->jtot[c].size();
+    k_add_arr<<<nb(n), 256, 0, ctx().stream>>>(g->jtot[c].p, s->Jsub[c].p, n);
+  }
+  return 0;
+}
+
+int pgpu_merge_suborbit_particles(pgpu_species_t s) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  if (!s->use_suborbit_model || s->n_sub == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  int rc = grow_capacity(s, s->n + s->n_sub);
+  if (rc) return rc;
+  cudaStream_t st = ctx().stream;
+  const int D = s->grid->desc.D;
+  const MainPtrs M = main_ptrs(s), S = sub_ptrs(s);
+  for (int k = 0; k < 10; ++k) {
+    if ((k < 4) && ((k & 1) >= D)) continue;
+    PGPU_CUDA(cudaMemcpyAsync(M.a[k] + s->n, S.a[k], (size_t)s->n_sub * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  PGPU_CUDA(cudaMemcpyAsync(M.w + s->n, S.w, (size_t)s->n_sub * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  PGPU_CUDA(cudaMemcpyAsync(M.id + s->n, S.id, (size_t)s->n_sub * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+  s->n += s->n_sub;
+  s->n_sub = 0;
+  s->binned = false;
+  return 0;
+}
+
+int pgpu_species_suborbit_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
+                                   uint64_t *id, int *nsub) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  const long n = s->n_sub;
+  if (n == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  const int D = s->grid->desc.D;
+  for (int d = 0; d < D; ++d) {
+    if (x) PGPU_CUDA(cudaMemcpyAsync(x + d * n, s->sub[d], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (xold) PGPU_CUDA(cudaMemcpyAsync(xold + d * n, s->sub[2 + d], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (v) PGPU_CUDA(cudaMemcpyAsync(v + c * n, s->sub[4 + c], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (vold) PGPU_CUDA(cudaMemcpyAsync(vold + c * n, s->sub[7 + c], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  if (w) PGPU_CUDA(cudaMemcpyAsync(w, s->sub_w, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (id) PGPU_CUDA(cudaMemcpyAsync(id, s->sub_id, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (nsub) PGPU_CUDA(cudaMemcpyAsync(nsub, s->sub_nsub, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"
