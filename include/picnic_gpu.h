@@ -38,7 +38,7 @@ typedef struct pgpu_species_s *pgpu_species_t;
 enum { PGPU_CIC = 0, PGPU_TSC = 1, PGPU_CC0 = 2, PGPU_CC1 = 3 }; /* InterpType */
 enum { PGPU_EX = 0, PGPU_EY, PGPU_EZ, PGPU_BX, PGPU_BY, PGPU_BZ, PGPU_NFIELD };
 enum { PGPU_JX = 0, PGPU_JY, PGPU_JZ };
-enum { PGPU_BC_NONE = 0, PGPU_BC_PERIODIC = 1, PGPU_BC_SYMMETRY = 2 };
+enum { PGPU_BC_NONE = 0, PGPU_BC_PERIODIC = 1, PGPU_BC_SYMMETRY = 2, PGPU_BC_OUTFLOW = 3, PGPU_BC_INFLOW_OUTFLOW = 4 };
 enum {
   PGPU_OK = 0,
   PGPU_ERR_ARG = -1,
@@ -234,6 +234,23 @@ int pgpu_merge_suborbit_particles(pgpu_species_t s);
 /* test / I-O hook: the sub-orbit container (component-major arrays of pgpu_species_suborbit_count entries) */
 int pgpu_species_suborbit_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
                                    uint64_t *id, int *nsub);
+
+/* Outflow and inflow boundaries (PicChargedSpeciesBC, species BC types "outflow" and "inflow_outflow"):
+ * pgpu_apply_bcs with PGPU_BC_OUTFLOW / PGPU_BC_INFLOW_OUTFLOW moves the particles beyond that boundary (x < Xmin,
+ * x >= Xmax; outflow_Lo/Hi, PicChargedSpeciesBC.cpp:872-918) from the species into its outflow lists, kept on the device
+ * and tagged boundary = 2 dir + side.  pgpu_set_current_density(.., from_explicit_solver = 1) adds their current
+ * (depositInflowOutflowJ, :667-736).  The host reads them for the surface charge it keeps (pgpu_species_outflow_download),
+ * takes the flux diagnostics m_delta_{Mass,MomX,MomY,MomZ,Energy}Out per boundary (flux[boundary * 5 + k]) and empties the
+ * lists (removeOutflowParticles, :508-545).  Inflow particles are made by the host's InflowBC objects
+ * (createInflowParticles, :467-506) and enter through pgpu_species_append (injectInflowParticles, :563-665; x_old / u_old
+ * NULL = same as x / u; id NULL = made up). */
+long pgpu_species_outflow_count(pgpu_species_t s);
+int pgpu_species_outflow_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
+                                  uint64_t *id, int *boundary);
+int pgpu_species_outflow_fluxes(pgpu_species_t s, double *flux20);
+int pgpu_remove_outflow_particles(pgpu_species_t s);
+int pgpu_species_append(pgpu_species_t s, long n, const double *x, const double *xold, const double *v, const double *vold,
+                        const double *w, const uint64_t *id);
 
 /* deposit */
 int pgpu_set_current_density(pgpu_species_t s, double dt, int from_explicit_solver); /* :3184-3253 */

@@ -108,6 +108,8 @@ def load():
         "pgpu_set_current_density": [vp, dbl, i32], "pgpu_species_current_get": [vp, i32, vp, vp, vp],
         "pgpu_set_charge_density": [vp, vp, vp, vp, vp],
         "pgpu_explicit_step": [vp, C.c_double, vp, vp, C.c_int],
+        "pgpu_species_outflow_download": [vp] * 8, "pgpu_species_outflow_fluxes": [vp, vp],
+        "pgpu_remove_outflow_particles": [vp], "pgpu_species_append": [vp, C.c_long] + [vp] * 6,
         "pgpu_species_set_suborbit_model": [vp, C.c_int, C.c_int], "pgpu_transfer_fast_particles": [vp],
         "pgpu_advance_suborbit_particles_and_set_J": [vp, C.c_double, C.c_int],
         "pgpu_species_suborbit_current_get": [vp, C.c_int, vp, vp, vp], "pgpu_current_add_suborbit": [vp, vp],
@@ -343,6 +345,37 @@ class Species:
 
     def advance_positions_2nd_half(self):
         check(load().pgpu_advance_positions_2nd_half(self.h))
+
+    # ---- outflow lists / inflow injection ---------------------------------------------------------------
+    @property
+    def n_outflow(self):
+        f = load().pgpu_species_outflow_count
+        f.restype = C.c_long
+        f.argtypes = [C.c_void_p]
+        return f(self.h)
+
+    def outflow_download(self):
+        n = self.n_outflow
+        out = {"x": np.zeros((self.D, n)), "xold": np.zeros((self.D, n)), "v": np.zeros((3, n)), "vold": np.zeros((3, n)),
+               "w": np.zeros(n), "id": np.zeros(n, dtype=np.uint64), "boundary": np.zeros(n, dtype=np.int32)}
+        if n:
+            check(load().pgpu_species_outflow_download(self.h, _p(out["x"]), _p(out["xold"]), _p(out["v"]), _p(out["vold"]),
+                                                       _p(out["w"]), _p(out["id"]), _p(out["boundary"])))
+        return out
+
+    def outflow_fluxes(self):
+        out = np.zeros((4, 5))
+        check(load().pgpu_species_outflow_fluxes(self.h, _p(out)))
+        return out
+
+    def remove_outflow(self):
+        check(load().pgpu_remove_outflow_particles(self.h))
+
+    def append(self, x, v, w, xold=None, vold=None, ids=None):
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        x, v, w, xold, vold = c(x), c(v), c(w), c(xold), c(vold)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+        check(load().pgpu_species_append(self.h, w.size, _p(x), _p(xold), _p(v), _p(vold), _p(w), _p(ids)))
 
     # ---- sub-orbit model --------------------------------------------------------------------------
     def set_suborbit_model(self, use=True, fast_particles=False):

@@ -780,6 +780,11 @@ int pgpu_species_destroy(pgpu_species_t s) {
   for (int k = 0; k < 4; ++k) cudaFree(s->spare[k]);
   cudaFree(s->defer_list);
   cudaFree(s->enf_save);
+  for (int k = 0; k < 10; ++k) cudaFree(s->out[k]);
+  cudaFree(s->out_w);
+  cudaFree(s->out_id);
+  cudaFree(s->out_tag);
+  cudaFree(s->out_listtag);
   for (int k = 0; k < 10; ++k) cudaFree(s->sub[k]);
   cudaFree(s->sub_w);
   cudaFree(s->sub_id);
@@ -1179,6 +1184,10 @@ int pgpu_set_current_density(pgpu_species_t s, double dt, int from_explicit_solv
     PGPU_CUDA(cudaMemsetAsync(s->J[c].p, 0, s->J[c].size() * sizeof(double), ctx().stream));
   int rc = launch_deposit_current(s, dt * s->desc.cvac_norm);
   if (rc) return rc;
+  if (from_explicit_solver && s->n_out > 0) {   // depositInflowOutflowJ (PicChargedSpecies.cpp:3232-3235)
+    rc = launch_deposit_outflow(s);
+    if (rc) return rc;
+  }
   return scale_species_current(s);
 }
 

@@ -641,12 +641,9 @@ int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi) {
   if (n == 0) return 0;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   cudaStream_t st = ctx().stream;
+  // the order of PicChargedSpeciesBC::apply (:161-239): symmetry, then outflow / inflow_outflow, then periodic
   for (int d = 0; d < g->desc.D; ++d) {
     const double left = g->geo.le[d], right = g->geo.re[d];
-    if (bc_lo[d] == PGPU_BC_PERIODIC || bc_hi[d] == PGPU_BC_PERIODIC) {
-      KTimer t("bc_periodic");
-      k_bc_periodic<<<nb(n), 256, 0, st>>>(s->x[d], s->xold[d], n, left, right);
-    }
     const int do_lo = bc_lo[d] == PGPU_BC_SYMMETRY, do_hi = bc_hi[d] == PGPU_BC_SYMMETRY;
     if (do_lo || do_hi) {
       KTimer t("bc_symmetry");
@@ -654,6 +651,16 @@ int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi) {
     }
   }
   s->binned = false;
+  // the leavers of outflow boundaries move to the outflow lists (:187-224)
+  int rc = transfer_outflow(s, bc_lo, bc_hi);
+  if (rc) return rc;
+  if (s->n == 0) return 0;
+  for (int d = 0; d < g->desc.D; ++d) {
+    if (bc_lo[d] == PGPU_BC_PERIODIC || bc_hi[d] == PGPU_BC_PERIODIC) {
+      KTimer t("bc_periodic");
+      k_bc_periodic<<<nb(s->n), 256, 0, st>>>(s->x[d], s->xold[d], s->n, g->geo.le[d], g->geo.re[d]);
+    }
+  }
   return 0;
 }
 

@@ -210,6 +210,16 @@ struct pgpu_species_s {
   long n_sub = 0;
   size_t sub_cap = 0;
   pgpu::DeviceFab Jsub[3];
+  // outflow lists of PicChargedSpeciesBC (m_outflow_list_vector): one container, tag = 2 dir + side
+  double *out[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double *out_w = nullptr;
+  uint64_t *out_id = nullptr;
+  int *out_tag = nullptr;
+  long n_out = 0;
+  size_t out_cap = 0;
+  int *out_listtag = nullptr;
+  size_t out_listtag_cap = 0;
+  unsigned long next_id = 0;        // ids made up by pgpu_species_append
   int *unconv_list = nullptr;       // particles the last advance left unconverged (suborbit model)
   unsigned *unconv_count = nullptr;
   size_t unconv_cap = 0;
@@ -264,9 +274,12 @@ int launch_gather(pgpu_species_s *s);
 int launch_add_external(pgpu_species_s *s);
 int ensure_unconv_list(pgpu_species_s *s);                               // pgpu_suborbit.cu
 int transfer_listed_to_suborbit(pgpu_species_s *s, unsigned count);      // pgpu_suborbit.cu
+int transfer_outflow(pgpu_species_s *s, const int *bc_lo, const int *bc_hi);   // pgpu_suborbit.cu
+PartPtrs outflow_part_ptrs(pgpu_species_s *s);
 int launch_suborbit(pgpu_species_s *s, const AdvanceParams &prm, int from_jac, const DeviceFab *Jsub, unsigned *nfail);
 int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int *periodic, bool second_half);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);
+int launch_deposit_outflow(pgpu_species_s *s);   // the outflow lists into s->J (explicit solver)
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);
 int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit);
 int launch_advance_cc1_1d_fast(pgpu_species_s *s, const AdvanceParams &prm, bool deposit);

@@ -341,6 +341,37 @@ static int launch_deposit_t(pgpu_species_s *s) {
   return 0;
 }
 
+template <int D, int IJ>
+static int launch_deposit_out_t(pgpu_species_s *s) {
+  Context &c = ctx();
+  const GeoAny ga = species_geo(s);
+  const Geo<D> g = make_geo<D>(ga);
+  const CurrentSet J = species_current(s);
+  const double volume = (D == 1) ? ga.dx[0] : ga.dx[0] * ga.dx[1];
+  KTimer t("deposit_outflow");
+  if (c.exact)
+    k_deposit<D, IJ, true><<<nblocks(s->n_out, 256), 256, 0, c.stream>>>(outflow_part_ptrs(s), s->n_out, g, J, volume,
+                                                                          1.0 / volume, c.d_counters, s->desc.relativistic, 1);
+  else
+    k_deposit<D, IJ, false><<<nblocks(s->n_out, 256), 256, 0, c.stream>>>(outflow_part_ptrs(s), s->n_out, g, J, volume,
+                                                                           1.0 / volume, c.d_counters, s->desc.relativistic, 1);
+  return 0;
+}
+template <int D>
+static int launch_deposit_out_d(pgpu_species_s *s) {
+  switch (s->desc.interp_J) {
+    case CIC: return launch_deposit_out_t<D, CIC>(s);
+    case TSC: return launch_deposit_out_t<D, TSC>(s);
+    case CC0: return launch_deposit_out_t<D, CC0>(s);
+    case CC1: return launch_deposit_out_t<D, CC1>(s);
+  }
+  return PGPU_ERR_ARG;
+}
+int launch_deposit_outflow(pgpu_species_s *s) {
+  if (s->n_out == 0) return 0;
+  return s->grid->desc.D == 1 ? launch_deposit_out_d<1>(s) : launch_deposit_out_d<2>(s);
+}
+
 template <int D>
 static int launch_deposit_d(pgpu_species_s *s) {
   switch (s->desc.interp_J) {

@@ -9,6 +9,7 @@
 // :1718-1747).  Here the container is a second, small SoA next to the species' main arrays; moving particles between
 // the two is a gather into the tail of one and a hole fill from the tail of the other.
 #include <algorithm>
+#include <vector>
 
 #include "pgpu_internal.h"
 
@@ -49,10 +50,28 @@ MainPtrs sub_ptrs(pgpu_species_s *s) {
   P.id = s->sub_id;
   return P;
 }
+MainPtrs out_ptrs(pgpu_species_s *s) {
+  MainPtrs P;
+  for (int k = 0; k < 10; ++k) P.a[k] = s->out[k];
+  P.w = s->out_w;
+  P.id = s->out_id;
+  return P;
+}
+// a side container of a species: the sub-orbit container, or the outflow lists of PicChargedSpeciesBC
+struct Aux {
+  double **a;
+  double **w;
+  uint64_t **id;
+  int **tag;
+  long *n;
+  size_t *cap;
+};
+Aux sub_aux(pgpu_species_s *s) { return Aux{s->sub, &s->sub_w, &s->sub_id, &s->sub_nsub, &s->n_sub, &s->sub_cap}; }
+Aux out_aux(pgpu_species_s *s) { return Aux{s->out, &s->out_w, &s->out_id, &s->out_tag, &s->n_out, &s->out_cap}; }
 
 // listed particles of `from` -> positions base .. base+count-1 of `to`
 __global__ void k_copy_listed(MainPtrs from, MainPtrs to, const int *list, unsigned count, long base, int *nsub, int D,
-                              int *dead) {
+                              int *dead, const int *listtag) {
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
   const long i = list[t], o = base + t;
@@ -62,7 +81,7 @@ __global__ void k_copy_listed(MainPtrs from, MainPtrs to, const int *list, unsig
   }
   to.w[o] = from.w[i];
   to.id[o] = from.id[i];
-  if (nsub) nsub[o] = 2;           // setNumSubOrbits(2)
+  if (nsub) nsub[o] = listtag ? listtag[t] : 2;   // setNumSubOrbits(2); outflow lists: 2 dir + side
   if (dead) dead[i] = 1;
 }
 // the usual hole fill: survivors of the tail [new_n, n) move into the holes below new_n
@@ -107,28 +126,64 @@ __global__ void k_flag_fast(const double *x0, const double *x1, const double *xo
   if (fast) list[atomicAdd(count, 1u)] = (int)i;
 }
 
-int ensure_sub_cap(pgpu_species_s *s, long need) {
-  if ((size_t)need <= s->sub_cap) return 0;
+int ensure_aux_cap(const Aux &A, long need) {
+  if ((size_t)need <= *A.cap) return 0;
   const size_t cap = (size_t)(need + need / 4 + 4096);
   cudaStream_t st = ctx().stream;
   PGPU_CUDA(cudaStreamSynchronize(st));
+  const long have = *A.n;
   auto re = [&](void **p, size_t elem) -> int {
     void *q = nullptr;
     if (cudaMalloc(&q, cap * elem) != cudaSuccess) return PGPU_ERR_CUDA;
     if (*p) {
-      cudaMemcpy(q, *p, (size_t)s->n_sub * elem, cudaMemcpyDeviceToDevice);
+      cudaMemcpy(q, *p, (size_t)have * elem, cudaMemcpyDeviceToDevice);
       cudaFree(*p);
     }
     *p = q;
     return 0;
   };
   for (int k = 0; k < 10; ++k)
-    if (re(reinterpret_cast<void **>(&s->sub[k]), sizeof(double))) return PGPU_ERR_CUDA;
-  if (re(reinterpret_cast<void **>(&s->sub_w), sizeof(double))) return PGPU_ERR_CUDA;
-  if (re(reinterpret_cast<void **>(&s->sub_id), sizeof(uint64_t))) return PGPU_ERR_CUDA;
-  if (re(reinterpret_cast<void **>(&s->sub_nsub), sizeof(int))) return PGPU_ERR_CUDA;
-  s->sub_cap = cap;
+    if (re(reinterpret_cast<void **>(&A.a[k]), sizeof(double))) return PGPU_ERR_CUDA;
+  if (re(reinterpret_cast<void **>(A.w), sizeof(double))) return PGPU_ERR_CUDA;
+  if (re(reinterpret_cast<void **>(A.id), sizeof(uint64_t))) return PGPU_ERR_CUDA;
+  if (re(reinterpret_cast<void **>(A.tag), sizeof(int))) return PGPU_ERR_CUDA;
+  *A.cap = cap;
   return 0;
+}
+// first boundary (dir 0 lo, dir 0 hi, dir 1 lo, dir 1 hi) with an outflow BC the particle is beyond:
+// PicChargedSpeciesBC::outflow_Lo / outflow_Hi (PicChargedSpeciesBC.cpp:872-918): x < Xmin, x >= Xmax
+__global__ void k_flag_outflow(const double *x0, const double *x1, long n, int D, double l0, double r0, double l1, double r1,
+                               int lo0, int hi0, int lo1, int hi1, int *list, int *listtag, unsigned *count) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int tag = -1;
+  const double a = x0[i];
+  if (lo0 && a < l0) tag = 0;
+  else if (hi0 && a >= r0) tag = 1;
+  else if (D == 2) {
+    const double b = x1[i];
+    if (lo1 && b < l1) tag = 2;
+    else if (hi1 && b >= r1) tag = 3;
+  }
+  if (tag >= 0) {
+    const unsigned slot = atomicAdd(count, 1u);
+    list[slot] = (int)i;
+    listtag[slot] = tag;
+  }
+}
+// PicChargedSpeciesBC::outflow / inflow flux diagnostics (:935-947 pattern): sums of w, w u_old, w |u_old|^2 / (gamma + 1) per tag
+__global__ void k_aux_flux(MainPtrs P, const int *tag, long n, int rel, double *out /* [4][5] */) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = tag[i];
+  if (t < 0 || t > 3) return;
+  const double w = P.w[i], a = P.a[7][i], b = P.a[8][i], c = P.a[9][i];
+  const double gbsq = a * a + b * b + c * c, gamma = rel ? sqrt(1.0 + gbsq) : 1.0;
+  atomicAdd(out + t * 5 + 0, w);
+  atomicAdd(out + t * 5 + 1, w * a);
+  atomicAdd(out + t * 5 + 2, w * b);
+  atomicAdd(out + t * 5 + 3, w * c);
+  atomicAdd(out + t * 5 + 4, w * gbsq / (gamma + 1.0));
 }
 }  // namespace
 
@@ -143,11 +198,11 @@ int ensure_unconv_list(pgpu_species_s *s) {
   return 0;
 }
 
-// move the particles listed in s->unconv_list[0 .. count) from the main container to the sub-orbit container
-int transfer_listed_to_suborbit(pgpu_species_s *s, unsigned count) {
+// move the particles listed in s->unconv_list[0 .. count) from the main container to a side container
+static int transfer_listed(pgpu_species_s *s, const Aux &A, const MainPtrs &to, unsigned count, const int *listtag) {
   if (count == 0) return 0;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
-  if (ensure_sub_cap(s, s->n_sub + (long)count)) return PGPU_ERR_CUDA;
+  if (ensure_aux_cap(A, *A.n + (long)count)) return PGPU_ERR_CUDA;
   cudaStream_t st = ctx().stream;
   const int D = s->grid->desc.D;
   int *dead = s->cell_key;   // [cap] ints, free between cell sorts (the sort is invalidated below)
@@ -158,13 +213,66 @@ int transfer_listed_to_suborbit(pgpu_species_s *s, unsigned count) {
   PGPU_CUDA(cudaMemsetAsync(dead + new_n, 0, (size_t)count * sizeof(int), st));
   PGPU_CUDA(cudaMemsetAsync(nh, 0, 2 * sizeof(unsigned), st));
   KTimer t("suborbit_transfer");
-  k_copy_listed<<<nb(count), 256, 0, st>>>(main_ptrs(s), sub_ptrs(s), list, count, s->n_sub, s->sub_nsub, D, dead);
+  MainPtrs dst = to;   // the arrays may just have been re-allocated
+  for (int k = 0; k < 10; ++k) dst.a[k] = A.a[k];
+  dst.w = *A.w;
+  dst.id = *A.id;
+  k_copy_listed<<<nb(count), 256, 0, st>>>(main_ptrs(s), dst, list, count, *A.n, *A.tag, D, dead, listtag);
   k_list_holes_movers<<<nb(count), 256, 0, st>>>(dead, s->n, new_n, list, count, holes, movers, nh, nm);
   k_fill<<<nb(count), 256, 0, st>>>(main_ptrs(s), holes, movers, nh, D);
   s->n = new_n;
-  s->n_sub += (long)count;
+  *A.n += (long)count;
   s->binned = false;
   return 0;
+}
+int transfer_listed_to_suborbit(pgpu_species_s *s, unsigned count) {
+  return transfer_listed(s, sub_aux(s), sub_ptrs(s), count, nullptr);
+}
+// PicChargedSpeciesBC::apply, the outflow part (:187-224): particles beyond an outflow (or inflow_outflow) boundary leave
+// the main container for the outflow lists (one container, tagged 2 dir + side)
+int transfer_outflow(pgpu_species_s *s, const int *bc_lo, const int *bc_hi) {
+  const pgpu_grid_s *g = s->grid;
+  const int D = g->desc.D;
+  auto is_out = [](int bc) { return bc == PGPU_BC_OUTFLOW || bc == PGPU_BC_INFLOW_OUTFLOW; };
+  const int lo0 = is_out(bc_lo[0]), hi0 = is_out(bc_hi[0]);
+  const int lo1 = D == 2 && is_out(bc_lo[1]), hi1 = D == 2 && is_out(bc_hi[1]);
+  if (!(lo0 || hi0 || lo1 || hi1) || s->n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  if (ensure_unconv_list(s)) return PGPU_ERR_CUDA;
+  cudaStream_t st = ctx().stream;
+  int *listtag = s->unconv_list + 2 * s->unconv_cap;   // the "movers" third of the scratch is free until the transfer
+  if (!s->out_listtag || s->out_listtag_cap < s->cap) {
+    if (s->out_listtag) cudaFree(s->out_listtag);
+    PGPU_CUDA(cudaMalloc(&s->out_listtag, s->cap * sizeof(int)));
+    s->out_listtag_cap = s->cap;
+  }
+  listtag = s->out_listtag;
+  PGPU_CUDA(cudaMemsetAsync(s->unconv_count, 0, sizeof(unsigned), st));
+  {
+    KTimer t("bc_outflow");
+    k_flag_outflow<<<nb(s->n), 256, 0, st>>>(s->x[0], s->x[1], s->n, D, g->geo.le[0], g->geo.re[0], g->geo.le[1], g->geo.re[1],
+                                             lo0, hi0, lo1, hi1, s->unconv_list, listtag, s->unconv_count);
+  }
+  unsigned count = 0;
+  PGPU_CUDA(cudaMemcpyAsync(&count, s->unconv_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  return transfer_listed(s, out_aux(s), out_ptrs(s), count, listtag);
+}
+// setCurrentDensity(dt, from_explicit_solver = true) adds the current of the outflow lists before the scaling
+// (PicChargedSpecies.cpp:3232-3235 -> PicChargedSpeciesBC::depositInflowOutflowJ, PicChargedSpeciesBC.cpp:667-736)
+PartPtrs outflow_part_ptrs(pgpu_species_s *s) {
+  PartPtrs p;
+  for (int d = 0; d < 2; ++d) {
+    p.x[d] = s->out[d];
+    p.xold[d] = s->out[2 + d];
+  }
+  for (int c = 0; c < 3; ++c) {
+    p.v[c] = s->out[4 + c];
+    p.vold[c] = s->out[7 + c];
+    p.Ep[c] = p.Bp[c] = nullptr;
+  }
+  p.w = s->out_w;
+  return p;
 }
 }  // namespace pgpu
 
@@ -291,26 +399,95 @@ int pgpu_merge_suborbit_particles(pgpu_species_t s) {
   return 0;
 }
 
-int pgpu_species_suborbit_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
-                                   uint64_t *id, int *nsub) {
-  NEED_INIT();
-  if (!s) return PGPU_ERR_ARG;
-  const long n = s->n_sub;
+static int aux_download(pgpu_species_t s, const Aux &A, double *x, double *xold, double *v, double *vold, double *w,
+                        uint64_t *id, int *tag) {
+  const long n = *A.n;
   if (n == 0) return 0;
   cudaStream_t st = ctx().stream;
   const int D = s->grid->desc.D;
   for (int d = 0; d < D; ++d) {
-    if (x) PGPU_CUDA(cudaMemcpyAsync(x + d * n, s->sub[d], n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (xold) PGPU_CUDA(cudaMemcpyAsync(xold + d * n, s->sub[2 + d], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (x) PGPU_CUDA(cudaMemcpyAsync(x + d * n, A.a[d], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (xold) PGPU_CUDA(cudaMemcpyAsync(xold + d * n, A.a[2 + d], n * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
   for (int c = 0; c < 3; ++c) {
-    if (v) PGPU_CUDA(cudaMemcpyAsync(v + c * n, s->sub[4 + c], n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (vold) PGPU_CUDA(cudaMemcpyAsync(vold + c * n, s->sub[7 + c], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (v) PGPU_CUDA(cudaMemcpyAsync(v + c * n, A.a[4 + c], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (vold) PGPU_CUDA(cudaMemcpyAsync(vold + c * n, A.a[7 + c], n * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
-  if (w) PGPU_CUDA(cudaMemcpyAsync(w, s->sub_w, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (id) PGPU_CUDA(cudaMemcpyAsync(id, s->sub_id, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  if (nsub) PGPU_CUDA(cudaMemcpyAsync(nsub, s->sub_nsub, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (w) PGPU_CUDA(cudaMemcpyAsync(w, *A.w, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (id) PGPU_CUDA(cudaMemcpyAsync(id, *A.id, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (tag) PGPU_CUDA(cudaMemcpyAsync(tag, *A.tag, n * sizeof(int), cudaMemcpyDeviceToHost, st));
   PGPU_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+int pgpu_species_suborbit_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
+                                   uint64_t *id, int *nsub) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  return aux_download(s, sub_aux(s), x, xold, v, vold, w, id, nsub);
+}
+
+// ---- outflow lists (PicChargedSpeciesBC m_outflow_list_vector) ------------------------------------------------------
+long pgpu_species_outflow_count(pgpu_species_t s) { return s ? s->n_out : -1; }
+int pgpu_species_outflow_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
+                                  uint64_t *id, int *boundary) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  return aux_download(s, out_aux(s), x, xold, v, vold, w, id, boundary);
+}
+// m_delta_{Mass,MomX,MomY,MomZ,Energy}Out per boundary (2 dir + side): sums of w, w u_old, w |u_old|^2 / (gamma + 1)
+int pgpu_species_outflow_fluxes(pgpu_species_t s, double *flux20) {
+  NEED_INIT();
+  if (!s || !flux20) return PGPU_ERR_ARG;
+  for (int k = 0; k < 20; ++k) flux20[k] = 0.0;
+  if (s->n_out == 0) return 0;
+  double *d = nullptr;
+  PGPU_CUDA(cudaMalloc(&d, 20 * sizeof(double)));
+  PGPU_CUDA(cudaMemsetAsync(d, 0, 20 * sizeof(double), ctx().stream));
+  k_aux_flux<<<nb(s->n_out), 256, 0, ctx().stream>>>(out_ptrs(s), s->out_tag, s->n_out, s->desc.relativistic, d);
+  PGPU_CUDA(cudaMemcpyAsync(flux20, d, 20 * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+  PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
+  cudaFree(d);
+  return 0;
+}
+// PicChargedSpeciesBC::removeOutflowParticles (:508-545): the lists are emptied (the surface charge they leave behind is
+// the host's: download the lists first)
+int pgpu_remove_outflow_particles(pgpu_species_t s) {
+  if (!s) return PGPU_ERR_ARG;
+  s->n_out = 0;
+  return 0;
+}
+// inflow: the host's InflowBC objects create the particles (PicChargedSpeciesBC::createInflowParticles, :467-506, host
+// logic with the reference's own generator); injectInflowParticles (:563-665) puts them into the main container
+int pgpu_species_append(pgpu_species_t s, long n, const double *x, const double *xold, const double *v, const double *vold,
+                        const double *w, const uint64_t *id) {
+  NEED_INIT();
+  if (!s || n < 0 || (n && (!x || !v || !w))) return PGPU_ERR_ARG;
+  if (n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  int rc = grow_capacity(s, s->n + n);
+  if (rc) return rc;
+  cudaStream_t st = ctx().stream;
+  const int D = s->grid->desc.D;
+  const long o = s->n;
+  for (int d = 0; d < D; ++d) {
+    PGPU_CUDA(cudaMemcpyAsync(s->x[d] + o, x + d * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    PGPU_CUDA(cudaMemcpyAsync(s->xold[d] + o, (xold ? xold : x) + d * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  for (int c = 0; c < 3; ++c) {
+    PGPU_CUDA(cudaMemcpyAsync(s->v[c] + o, v + c * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    PGPU_CUDA(cudaMemcpyAsync(s->vold[c] + o, (vold ? vold : v) + c * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  PGPU_CUDA(cudaMemcpyAsync(s->w + o, w, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (id) PGPU_CUDA(cudaMemcpyAsync(s->id + o, id, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  else {
+    std::vector<uint64_t> tmp((size_t)n);
+    for (long k = 0; k < n; ++k) tmp[k] = ((uint64_t)s->serial << 40) + (uint64_t)(s->next_id++) + (1ull << 39);
+    PGPU_CUDA(cudaMemcpyAsync(s->id + o, tmp.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGPU_CUDA(cudaStreamSynchronize(st));
+  }
+  PGPU_CUDA(cudaStreamSynchronize(st));   // the host buffers are borrowed for the call only
+  s->n += n;
+  s->binned = false;
   return 0;
 }
 
