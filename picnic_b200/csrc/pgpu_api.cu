@@ -779,6 +779,7 @@ int pgpu_species_destroy(pgpu_species_t s) {
   cudaFree(s->cub_tmp);
   for (int k = 0; k < 4; ++k) cudaFree(s->spare[k]);
   cudaFree(s->defer_list);
+  cudaFree(s->bin_count);
   cudaFree(s->enf_save);
   for (int k = 0; k < 10; ++k) cudaFree(s->out[k]);
   cudaFree(s->out_w);

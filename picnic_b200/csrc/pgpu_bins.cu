@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "pgpu_internal.h"
 
@@ -81,6 +82,84 @@ __global__ void k_cell_ijk(const double *x0, const double *x1, long n, BoxInfo b
   if (i >= n) return;
   out[i] = locate_bin(x0[i], b.le[0], b.dx[0]);
   if (b.D == 2) out[n + i] = locate_bin(x1[i], b.le[1], b.dx[1]);
+}
+
+// ---- counting sort of the bin keys -------------------------------------------------------------------------------
+// Particles move at most a cell or so between two sorts, and there are far fewer bins than particles (tens to hundreds
+// of particles per bin): a histogram, a scan over the bins and one scatter of the particle indices replace the radix
+// sort of (key, index) pairs (four passes over 8 bytes per particle plus its scratch).  Consecutive particles mostly
+// share their bin, so the lanes of a warp that hit one bin are counted by their leader (__match_any_sync): one
+// atomic per distinct bin of a warp, and lanes of a bin keep their relative order.
+__global__ void k_bin_hist(const int *key, long n, int *count) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = i < n ? key[i] : -1;
+  const unsigned grp = __match_any_sync(0xffffffffu, k);
+  if (k >= 0 && (__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(count + k, __popc(grp));
+}
+// perm[dst] = i, key_sorted[dst] = key[i] with dst = start[key] + (position among the particles of the bin seen so far)
+__global__ void k_bin_scatter(const int *key, long n, const int *start, int *cursor, int *perm, int *key_sorted) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int k = i < n ? key[i] : -1;
+  const unsigned grp = __match_any_sync(0xffffffffu, k);
+  const int leader = __ffs(grp) - 1;
+  int base = 0;
+  if (k >= 0 && leader == lane) base = atomicAdd(cursor + k, __popc(grp));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (k >= 0) {
+    const int dst = start[k] + base + __popc(grp & ((1u << lane) - 1u));
+    perm[dst] = (int)i;
+    key_sorted[dst] = k;
+  }
+}
+
+// The scatter hands out the slots of a bin in arrival order, which differs from run to run.  The collision kernels pair
+// the particles of a bin by storage order, so the bin sort puts every bin back into ascending source index (= what the
+// stable radix sort gave).  Bins hold tens of particles: one thread sorts one bin of <= 32 entries by insertion (entries
+// of one source warp already arrive in order, so few moves); larger bins go on a list for k_bin_canon_big.
+__global__ void k_bin_canon(const int *start, int nbins, int *perm, int *biglist, int *nbig) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbins) return;
+  const int s = start[b], n = start[b + 1] - s;
+  if (n < 2) return;
+  if (n > 32) {
+    biglist[atomicAdd(nbig, 1)] = b;
+    return;
+  }
+  int a[32];
+  for (int i = 0; i < n; ++i) a[i] = perm[s + i];
+  bool moved = false;
+  for (int i = 1; i < n; ++i) {
+    const int v = a[i];
+    int j = i - 1;
+    while (j >= 0 && a[j] > v) {
+      a[j + 1] = a[j];
+      --j;
+      moved = true;
+    }
+    a[j + 1] = v;
+  }
+  if (moved)
+    for (int i = 0; i < n; ++i) perm[s + i] = a[i];
+}
+// listed bins of 33 .. 4096 entries, one warp each: rank of every entry against the bin into a scratch copy, copied back
+// (bigger bins -- everything in one cell -- keep the arrival order)
+__global__ void k_bin_canon_big(const int *start, const int *biglist, const int *nbig, int *perm, int *scratch) {
+  const int lane = threadIdx.x & 31, nwarps = (int)((gridDim.x * blockDim.x) >> 5), nl = *nbig;
+  for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l < nl; l += nwarps) {
+    const int b = biglist[l];
+    const int s = start[b], n = start[b + 1] - s;
+    if (n > 4096) continue;
+    for (int e = lane; e < n; e += 32) {
+      const int v = perm[s + e];
+      int rank = 0;
+      for (int q = 0; q < n; ++q) rank += (perm[s + q] < v) ? 1 : 0;
+      scratch[s + rank] = v;
+    }
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) perm[s + e] = scratch[s + e];
+    __syncwarp();
+  }
 }
 
 // cell_start[c] = first sorted position whose cell is >= c, for c = 0..nbins (nbins = ncell+1
@@ -454,7 +533,37 @@ static int bin_impl(pgpu_species_t s, bool dual) {
   int nbits = 1;
   const long maxkey = dual ? (long)(b.n[0] + 1) * (b.D == 2 ? b.n[1] + 1 : 1) : 4L * b.ncell;
   while ((1L << nbits) <= maxkey) ++nbits;
-  {
+  static const int sort_mode = [] { const char *e = getenv("PGPU_SORT"); return (e && !strcmp(e, "radix")) ? 1 : 0; }();
+  if (sort_mode == 0) {
+    // counting sort: bins = maxkey + 1 (the last one is the outcast bin)
+    const long nb_bins = maxkey + 1;
+    if (s->bin_count_cap < (size_t)(2 * nb_bins + 2)) {
+      if (s->bin_count) cudaFree(s->bin_count);
+      PGPU_CUDA(cudaMalloc(&s->bin_count, (size_t)(2 * nb_bins + 2) * sizeof(int)));
+      s->bin_count_cap = (size_t)(2 * nb_bins + 2);
+    }
+    int *count = s->bin_count, *start = s->bin_count + nb_bins + 1;
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, count, start, (int)nb_bins + 1, c.stream);
+    if (need > s->cub_bytes) {
+      if (s->cub_tmp) cudaFree(s->cub_tmp);
+      PGPU_CUDA(cudaMalloc(&s->cub_tmp, need));
+      s->cub_bytes = need;
+    }
+    KTimer t("bin_sort");
+    PGPU_CUDA(cudaMemsetAsync(count, 0, (size_t)(nb_bins + 1) * sizeof(int), c.stream));
+    k_bin_hist<<<nb(n), 256, 0, c.stream>>>(s->cell_key, n, count);
+    PGPU_CUDA(cub::DeviceScan::ExclusiveSum(s->cub_tmp, need, count, start, (int)nb_bins + 1, c.stream));   // start[nb_bins] = n
+    PGPU_CUDA(cudaMemsetAsync(count, 0, (size_t)nb_bins * sizeof(int), c.stream));
+    k_bin_scatter<<<nb(n), 256, 0, c.stream>>>(s->cell_key, n, start, count, s->perm, s->key_sorted);
+    if (!dual) {
+      // tmp holds n doubles: ints [0, n) are the scratch copy, ints [n, 2n) the list of big bins
+      int *biglist = iota + n, *nbig = count + nb_bins;
+      PGPU_CUDA(cudaMemsetAsync(nbig, 0, sizeof(int), c.stream));
+      k_bin_canon<<<nb(nb_bins), 256, 0, c.stream>>>(start, (int)nb_bins, s->perm, biglist, nbig);
+      k_bin_canon_big<<<c.sm_count * 2, 256, 0, c.stream>>>(start, biglist, nbig, s->perm, iota);
+    }
+  } else {
     size_t need = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, s->cell_key, s->key_sorted, iota, s->perm, (int)n, 0, nbits,
                                     c.stream);

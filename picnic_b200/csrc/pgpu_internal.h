@@ -201,6 +201,8 @@ struct pgpu_species_s {
   size_t sort_cap = 0;
   void *cub_tmp = nullptr;
   size_t cub_bytes = 0;
+  int *bin_count = nullptr;         // counting sort: [bins + 1] counts / cursors, then [bins + 1] starts
+  size_t bin_count_cap = 0;
   // sub-orbit model (PicChargedSpecies m_data_suborbit, m_suborbitJ): a second, small particle container
   int use_suborbit_model = 0, suborbit_fast_particles = 0;
   double *sub[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -89,10 +89,13 @@ def test_ta_self_conservation_and_pair_counts(pgpu):
     # deterministic in (seed, step); a different step gives different angles
     sp.upload(before["x"], before["v"], before["w"], ids=before["id"]); sp.bin_particles(); sp.set_moments()
     pgpu.collide_ta(sp, sp, 3.0, DT_SEC, 1983, 7)
-    assert np.array_equal(sp.download()["v"], after["v"])
+    # (the order of the particles inside a cell is the sort's business -- the counting sort does not fix it -- so
+    # results are compared particle by particle, by id)
+    by_id = lambda d: d["v"][:, np.argsort(d["id"])]
+    assert np.array_equal(by_id(sp.download()), by_id(after))
     sp.upload(before["x"], before["v"], before["w"], ids=before["id"]); sp.bin_particles(); sp.set_moments()
     pgpu.collide_ta(sp, sp, 3.0, DT_SEC, 1983, 8)
-    assert not np.array_equal(sp.download()["v"], after["v"])
+    assert not np.array_equal(by_id(sp.download()), by_id(after))
     sp.destroy(); grid.destroy()
 
 

@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--ncell", type=int, default=512)
 ap.add_argument("--ppc", type=int, default=10)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--sort", default="dual", choices=["dual", "cell"])
 args = ap.parse_args()
 
 capi.init(0)
@@ -33,7 +34,7 @@ for sdef in deck.species:
                       interp_N=deck.interp_N, interp_J=deck.interp_J, interp_E=deck.interp_E, rtol=deck.rtol,
                       iter_max=deck.iter_max)
     sp.upload(p["x"], p["v"], p["w"], ids=p["id"])
-    sp.bin_particles()
+    sp.sort_for_locality() if args.sort == "dual" else sp.bin_particles()
     sps.append(sp)
 n = sum(sp.n for sp in sps)
 # one implicit advance so that (xbar, ubar) are a converged orbit
