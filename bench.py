@@ -81,6 +81,14 @@ def parse():
                          "count all-gather + NCCL send/recv")
     ap.add_argument("--dt", type=float, default=0.1)
     ap.add_argument("--iter-max", type=int, default=21)
+    ap.add_argument("--field-scale", type=float, default=1.0,
+                    help="multiplies the amplitudes of the synthetic E, B (1 = a thermal electron's velocity changes by "
+                         "~5 %% per step from E and turns by ~0.05 rad from B: mean Picard passes k = 2.2; 8 gives k >= 4)")
+    ap.add_argument("--field-kmul", type=int, default=1,
+                    help="multiplies the wave numbers of the synthetic fields (1: wavelengths of 512, 256 and 171 cells; "
+                         "32: 16, 8 and 5.3 cells)")
+    ap.add_argument("--no-variants", action="store_true",
+                    help="skip the secondary C3 variants (iter_max 0, harder fields, explicit leap-frog)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles per species in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -128,14 +136,14 @@ def rank_box(args, rank, layout):
     return lo, hi
 
 
-def field_amplitudes(deck):
+def field_amplitudes(deck, scale=1.0):
     """E0, B0 such that omega_pe*dt ~ omega_ce*dt ~ 0.1-like kicks: a thermal electron's
     velocity changes by ~10 % per step from E and rotates by ~0.1 rad from B."""
     sp = deck.species[0]
     fn = abs(sp.fnorm_const(deck.units))
     vth = np.sqrt(decks.QE / decks.ME * sp.temperature_eV[0] / sp.mass) / decks.CVAC
     alpha = fn * deck.cnorm_dt / 2.0
-    return 0.05 * vth / alpha, 0.05 / alpha
+    return scale * 0.05 * vth / alpha, scale * 0.05 / alpha
 
 
 # ------------------------------------------------------------------------------------------
@@ -212,7 +220,7 @@ class Engine:
         deck = self.deck
         B = args.boxes_per_gpu
         self.nboxes = world * B
-        E0, B0 = field_amplitudes(deck)
+        E0, B0 = field_amplitudes(deck, args.field_scale)
         self.n_outer = args.n_outer
         self.boxes = []
         self.n_particles = 0
@@ -223,7 +231,7 @@ class Engine:
             bx.lo, bx.hi = rank_box(args, bx.id, self.layout)
             bx.grid = capi.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), box_lo=bx.lo,
                                 box_hi=bx.hi, volume_scale=deck.volume_scale)
-            E, Bf = decks.analytic_fields(deck, bx.lo, bx.hi, E0=E0, B0=B0)
+            E, Bf = decks.analytic_fields(deck, bx.lo, bx.hi, E0=E0, B0=B0, kmul=args.field_kmul)
             # pinned host copies of the field sets of each outer iteration + pinned J read-back: ONE contiguous
             # buffer per direction of transfer (components back to back in the C ABI's packed order)
             nfield = bx.grid.fields_packed_size()
@@ -560,7 +568,11 @@ def c4_leg(args, torch, capi, stream, peak):
             capi.check(lib.pgpu_collide_coulomb(sps[a].h, sps[b].h, capi.C.byref(capi.CoulombParams(10.0, 1, 0, 11, 1)),
                                                 dt_sec, 1983, state["k"], None))
         state["k"] += 1
+    capi.profile_reset()
+    capi.profile_enable(True)
     ms_col = timed(col, 3)
+    capi.profile_enable(False)
+    kc_ms = (capi.profile_query("collide_coulomb_intra")[0] + capi.profile_query("collide_coulomb_inter")[0]) / 4.0
     pairs = sum(capi.collide_coulomb(sps[a], sps[b], 10.0, dt_sec, 1983, 99, angular=1)
                 for (a, b) in ((0, 0), (1, 1), (0, 1)))
     # setMassMatrices on the same deck (1D run kernel, pgpu_massmatrix.cu); the orbits are the ones adv() left
@@ -591,7 +603,15 @@ def c4_leg(args, torch, capi, stream, peak):
                          "kernel": "advance_cc1_1d_fused", "kernel_ms_per_launch": kern,
                          "units_per_launch": n / len(sps)},
             "coulomb": {"metric": "collision-pairs/s (weighted Coulomb, NANBU)", "value": pairs / (ms_col * 1e-3),
-                        "pairs_per_step": pairs, "ms_per_step": ms_col},
+                        "pairs_per_step": pairs, "ms_per_step": ms_col,
+                        # a weighted pair reads and writes 3 velocity doubles of both partners and reads
+                        # their weights: 112 B
+                        "roofline": {"bound": "hbm", "achieved": 112.0 * pairs / (kc_ms * 1e-3) / 1e9 if kc_ms else None,
+                                     "peak": peak, "unit": "GB/s",
+                                     "frac": 112.0 * pairs / (kc_ms * 1e-3) / 1e9 / peak if kc_ms else None,
+                                     "bytes_per_unit": 112.0,
+                                     "kernel": "collide_coulomb_intra x2 + collide_coulomb_inter (3 launches per step)",
+                                     "kernel_ms_per_step": kc_ms}},
             "mass_matrices": {"metric": "particles/s through setMassMatrices (1D run kernel)", "value": n / (ms_mm * 1e-3),
                               "ms_per_setMassMatrices": ms_mm,
                               "hbm_frac_at_72B": 72.0 * n / (ms_mm * 1e-3) / 1e9 / peak}}
@@ -743,6 +763,85 @@ def c5_shard_leg(args, rank, local, stream, region, capi):
            "roofline_frac_kernel": (BYTES_PER_ADVANCE_2D * per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9
                                     / region.peak) if k_n else None,
            "section_ms_per_step": getattr(region, "sections", None)}
+    eng.destroy()
+    return out
+
+
+def variants_leg(args, rank, local, stream, region, capi):
+    """The C3 box under other particle-Picard workloads, so that the headline fraction cannot be read as tuned to one
+    k (mean passes per advance): iter_max_particles = 0 (BASELINE configs[2] lists {0, 21}: one pass, k = 1), fields
+    150x stronger with 64x shorter wavelengths (8, 4 and 2.7 cells: k ~ 4, and four times as many particles cross a
+    dual-cell face and take the deferred kernel; measured on the way: amplitude x8 -> k 2.54, x300 -> 3.2, x100 with the
+    short waves -> 3.9), and the explicit leap-frog step (PIC_EM_EXPLICIT: gather + Boris + move + deposit + second half in
+    ONE kernel, pgpu_explicit_step).  Device-timed like `value`, fewer steps."""
+    import copy
+    out = {}
+    nsteps, nwarm = max(4, min(args.steps, 6)), 3
+    for label, over in (("iter_max_0", {"iter_max": 0}), ("hard_fields", {"field_scale": 150.0 * args.field_scale, "field_kmul": 64})):
+        a = copy.copy(args)
+        for k, v in over.items():
+            setattr(a, k, v)
+        a.steps, a.warmup = nsteps, nwarm
+        eng = Engine(a, rank, 1, local, stream=stream)
+        region(a.warmup, False, eng=eng)
+        ms, _ = region(a.steps, False, profile=True, eng=eng)
+        k_ms, k_n = capi.profile_query("advance_cc1_fused")
+        d_ms, _ = capi.profile_query("advance_deferred")
+        adv, app, unconv = capi.picard_totals(reset=True)
+        n = eng.n_particles
+        per_launch = n / len(eng.species)
+        out[label] = {"value": float(n) * a.n_outer * a.steps / (ms * 1e-3), "unit": "particle-advances/s",
+                      "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+                      "mean_picard_passes": round(app / max(adv, 1), 3), "unconverged_particles": int(unconv),
+                      "kernel_ms_per_launch": k_ms / max(k_n, 1), "deferred_ms_per_step": d_ms / a.steps,
+                      "roofline_frac_kernel": (BYTES_PER_ADVANCE_2D * per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9
+                                               / region.peak) if k_n else None,
+                      "overrides": over}
+        eng.destroy()
+    # explicit leap-frog: one advance = one particle through one fused step
+    a = copy.copy(args)
+    eng = Engine(a, rank, 1, local, stream=stream)
+    torch = eng.torch
+    bc = (1, 1)
+
+    def estep():
+        for bx in eng.boxes:
+            bx.grid.current_zero()
+            for sp in bx.species:
+                sp.update_old_positions()
+                sp.update_old_velocities()
+                sp.explicit_step(eng.deck.dt, bc, bc, True)
+                bx.grid.current_add(sp)
+            bx.grid.current_finalize()
+        eng.step_no += 1
+        if a.sort_every > 0 and eng.step_no % a.sort_every == 0:
+            for sp in eng.species:
+                eng._sort(sp)
+
+    for _ in range(nwarm):
+        estep()
+    eng.sync()
+    capi.profile_reset()
+    capi.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(nsteps):
+        estep()
+    e1.record(stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    capi.profile_enable(False)
+    ms = e0.elapsed_time(e1)
+    k_ms, k_n = capi.profile_query("explicit_step")
+    n = eng.n_particles
+    per_launch = n / len(eng.species)
+    out["explicit_leapfrog"] = {
+        "value": float(n) * nsteps / (ms * 1e-3), "unit": "particle-advances/s (explicit: gather + Boris + move + deposit)",
+        "steps": nsteps, "warmup": nwarm, "ms_per_step": ms / nsteps,
+        "kernel": "explicit_step (k_explicit_step, generic CC1 visitor)", "kernel_ms_per_launch": k_ms / max(k_n, 1),
+        "roofline_frac_kernel": (BYTES_PER_ADVANCE_2D * per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9 / region.peak)
+                                if k_n else None,
+        "bytes_per_unit": BYTES_PER_ADVANCE_2D}
     eng.destroy()
     return out
 
@@ -909,10 +1008,12 @@ def run_ours(args):
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(args, steps=5)
+            out["cpu_baseline"] = cpu_baseline(args)
     eng.destroy()
     if rank == 0 and world == 1 and args.workload == "c3" and not args.no_c5_shard:
         out["c5_shard"] = c5_shard_leg(args, rank, local, stream, region, capi)
+    if rank == 0 and world == 1 and args.workload == "c3" and not args.no_variants:
+        out["variants"] = variants_leg(args, rank, local, stream, region, capi)
     if rank == 0 and world == 1 and not args.no_collisions:
         out["collisions"] = collisions_leg(args, torch, capi, stream, out["roofline"]["peak"])
     if rank == 0 and world == 1 and not args.no_c4:
@@ -931,8 +1032,7 @@ def run_ours(args):
 # the CPU arm: the oracle (restatement of the reference algorithm) on the host cores
 # ------------------------------------------------------------------------------------------
 def cpu_sample_problem(args, nthreads):
-    """A bounded sample of the C3 workload: a strip of the same box (full 512 cells wide, a few
-    rows), same ppc, same fields, same dt -- particle density and field sampling are identical."""
+    """A strip of the C3 box on one thread (the layout comparison below)."""
     from oracle import oracle as orc
     deck, _ = make_deck(args, 1)
     target = args.cpu_sample or 1000000 * max(nthreads, 1)          # particles per species
@@ -949,64 +1049,40 @@ def cpu_sample_problem(args, nthreads):
     return orc, deck, geom, Ef, Bf, parts, rows
 
 
-def cpu_step(orc, deck, geom, Ef, Bf, parts, args, nthreads, pool):
-    """Same step as Engine.step on the sample; threads own contiguous particle slices and
-    private J arrays (the reference's MPI ranks own boxes the same way)."""
-    n_adv = 0
-    lo, hi = (0, 0), (args.ncell - 1, args.ncell - 1)
-
-    def work(sdef, sl):
-        x, xold, v, vold, w = sl
-        fn = sdef.fnorm_const(deck.units)
-        J = [orc.fab_for(lo, hi, deck.nghost, s) for s in orc.E_STAG[2]]
-        for j in range(args.n_outer):
-            # (the eps-scaled field sets only change k slightly; the CPU arm reuses one set)
-            rc, _, _, _ = orc.advance_particles_iteratively(geom, deck.interp_E, x, xold, v, vold, Ef, Bf, fn,
-                                                            deck.cnorm_dt, deck.rtol, deck.iter_max)
-            assert rc == 0
-            for f in J:
-                f.a[...] = 0.0
-            orc.deposit_current(geom, deck.interp_J, x, xold, v, w, deck.cnorm_dt, J)
-        orc.lib().orc_advance_velocities_2nd_half(v.shape[1], orc._ptr(v), orc._ptr(vold))
-        orc.lib().orc_advance_positions_2nd_half(2, x.shape[1], orc._ptr(x), orc._ptr(xold))
-        xold[...] = x
-        vold[...] = v
-        return x.shape[1] * args.n_outer
-
-    futs = []
-    for sdef, p in zip(deck.species, parts):
-        for sl in p["slices"]:
-            futs.append(pool.submit(work, sdef, sl))
-    for f in futs:
-        n_adv += f.result()
-    return n_adv
-
-
-def cpu_arm(args, steps, warmup):
-    import concurrent.futures as cf
+def cpu_arm(args, steps, warmup, seconds):
+    """The reference's CPU path (oracle port) as R box-owning workers (oracle/cpu_boxes.py): one square box per host
+    thread, the same species / ppc / dx / dt / field amplitudes / Picard tolerances / evaluations per step as the GPU
+    arm, ghost-J add-exchange after every deposit and particle migration once per step through shared memory.  The
+    box edge is sized from a one-thread probe so that warmup + steps take about `seconds`."""
+    from oracle import cpu_boxes
     nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    orc, deck, geom, Ef, Bf, parts, rows = cpu_sample_problem(args, nthreads)
-    for p in parts:
-        n = p["w"].size
-        edges = np.linspace(0, n, nthreads + 1).astype(np.int64)
-        p["slices"] = []
-        for a, b in zip(edges[:-1], edges[1:]):
-            x = np.ascontiguousarray(p["x"][:, a:b]); v = np.ascontiguousarray(p["v"][:, a:b])
-            p["slices"].append((x, x.copy(), v, v.copy(), np.ascontiguousarray(p["w"][a:b])))
-    n_sample = sum(p["w"].size for p in parts)
-    with cf.ThreadPoolExecutor(max_workers=nthreads) as pool:
-        for _ in range(warmup):
-            cpu_step(orc, deck, geom, Ef, Bf, parts, args, nthreads, pool)
-        t0 = time.perf_counter()
-        units = 0
-        for _ in range(steps):
-            units += cpu_step(orc, deck, geom, Ef, Bf, parts, args, nthreads, pool)
-        dt = time.perf_counter() - t0
-    return {"value": units / dt, "unit": "particle-advances/s", "cores": nthreads, "kind": "port",
-            "sample": "%d rows x %d cells x 2 species x %d ppc = %d particles of the C3 box, %d step(s) x %d "
-                      "evaluations, oracle (g++ -O2 -ffp-contract=off) on %d threads"
-                      % (rows, args.ncell, args.ppc ** 2, n_sample, steps, args.n_outer, nthreads),
-            "seconds": dt}, dt / max(steps, 1)
+
+    def deck_fn(ncell):
+        d = decks.deck_c3(ncell=args.ncell, ppc=args.ppc, dt=args.dt, iter_max=args.iter_max)
+        d.species = decks.electron_proton(tuple(args.ppc2))
+        d.ncell = tuple(ncell)
+        return d
+
+    def amps(deck):
+        return field_amplitudes(deck, args.field_scale)
+
+    ppc_tot = 2 * args.ppc2[0] * args.ppc2[1]
+    if args.cpu_sample:
+        bn = max(8, int(round((args.cpu_sample * 2.0 / ppc_tot / max(nthreads, 1)) ** 0.5)))
+    else:
+        rate1 = cpu_boxes.probe_rate(deck_fn, amps, args.n_outer, EPS_OUTER)
+        per_worker = rate1 * seconds / ((steps + warmup) * args.n_outer)      # particles a worker can own
+        bn = int(max(8, min(args.ncell, (per_worker / ppc_tot) ** 0.5)))
+    r = cpu_boxes.run(deck_fn, amps, nthreads, steps, warmup, args.n_outer, EPS_OUTER, bn)
+    res = {"value": r["units"] / r["seconds"], "unit": "particle-advances/s", "cores": r["workers"], "kind": "port",
+           "sample": "%s boxes of %d^2 cells (periodic), 2 species x %d ppc = %d particles, one box-owning worker "
+                     "thread per box with ghost-J add-exchange per evaluation and migration per step (%d moved), "
+                     "%d step(s) + %d warm-up x %d evaluations, oracle (g++ -O2 -ffp-contract=off)"
+                     % (r["boxes"], r["box_cells"], ppc_tot // 2, r["particles"], r["migrated"], steps, warmup,
+                        args.n_outer),
+           "mean_picard_passes": round(r["mean_picard_passes"], 3),
+           "host_threads_visible": nthreads, "seconds": r["seconds"]}
+    return res, r["seconds"] / max(steps, 1)
 
 
 def cpu_layout_sample(args, n_sample=400000):
@@ -1042,8 +1118,8 @@ def cpu_layout_sample(args, n_sample=400000):
     return out
 
 
-def cpu_baseline(args, steps=1):
-    res, _ = cpu_arm(args, steps=steps, warmup=0)
+def cpu_baseline(args, steps=2):
+    res, _ = cpu_arm(args, steps=steps, warmup=1, seconds=15.0)
     try:
         res["layout"] = cpu_layout_sample(args)
     except Exception as e:      # the layout comparison is an extra; never lose the baseline over it
@@ -1055,13 +1131,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    res, sec_per_step = cpu_arm(args, steps=steps, warmup=min(args.warmup, 1))
+    # the same --steps / --warmup as the GPU arm; the sample (box edge) shrinks so that the run takes ~90 s
+    res, sec_per_step = cpu_arm(args, steps=args.steps, warmup=args.warmup, seconds=90.0)
     out = {"impl": "reference", "metric": "particle-advances/s (implicit push + deposit)", "value": res["value"],
-           "unit": "particle-advances/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+           "unit": "particle-advances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "C3 (bounded sample): " + res["sample"]},
+           "config": {"workload": "C3 (bounded sample): " + res["sample"], "dt": args.dt, "n_outer": args.n_outer,
+                      "mean_picard_passes": res["mean_picard_passes"]},
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": "particle-advances/s", "h2d_bytes_per_step": 0,
                    "d2h_bytes_per_step": 0},

@@ -147,10 +147,11 @@ def load_species(deck, sp, box_lo, box_hi, rng, dtype=np.float64):
     return {"x": x, "v": v, "w": w, "id": ids}
 
 
-def analytic_fields(deck, box_lo, box_hi, E0=2.0e7, B0=4.0e8, modes=3):
+def analytic_fields(deck, box_lo, box_hi, E0=2.0e7, B0=4.0e8, modes=3, kmul=1):
     """Six field components on the ghosted arrays of the box, Yee-staggered.
 
-    Smooth periodic sums of `modes` low-k modes.  Returns (E, B, meta) with
+    Smooth periodic sums of `modes` low-k modes (wave numbers kmul * 2 pi (m+1) / L: kmul > 1 shortens the
+    wavelengths, the Picard particle loop then needs more passes).  Returns (E, B, meta) with
     E[c], B[c] = (lo, hi, array(F-order))."""
     D = deck.D
     L = [n * h for n, h in zip(deck.ncell, deck.dx)]
@@ -168,14 +169,14 @@ def analytic_fields(deck, box_lo, box_hi, E0=2.0e7, B0=4.0e8, modes=3):
         if D == 1:
             a = np.zeros(X.shape)
             for m in range(modes):
-                k = 2 * PI * (m + 1) / L[0]
+                k = 2 * PI * kmul * (m + 1) / L[0]
                 a += amp[ci, m] * np.sin(k * (X - deck.xmin[0]) + ph[ci, m, 0])
         else:
             Y = coords(stag[1], 1, lo[1], hi[1])
             a = np.zeros((X.size, Y.size))
             for m in range(modes):
-                kx = 2 * PI * (m + 1) / L[0]
-                ky = 2 * PI * (modes - m) / L[1]
+                kx = 2 * PI * kmul * (m + 1) / L[0]
+                ky = 2 * PI * kmul * (modes - m) / L[1]
                 a += amp[ci, m] * np.outer(np.sin(kx * (X - deck.xmin[0]) + ph[ci, m, 0]),
                                            np.cos(ky * (Y - deck.xmin[1]) + ph[ci, m, 1]))
         return lo, hi, np.asfortranarray(scale * a / modes)

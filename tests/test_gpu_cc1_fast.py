@@ -71,6 +71,22 @@ def test_fast_kernel_matches_oracle(pgpu, order, max_disp):
         assert rel_err(J[c], J00[c]) <= 1e-12
 
 
+@pytest.mark.parametrize("passes", [1, 3, 6])
+def test_fast_kernel_fixed_pass_count_at_1e12(pgpu, passes):
+    """The tolerances above (4e-12 dx, 1e-11) are the error budget of an rtol-limited loop: a particle whose last
+    step norm lands within round-off of rtol = 1e-12 stops one pass earlier in one implementation than in the other,
+    and the two answers then differ by ~rtol.  With the pass count FIXED (rtol = 0: no particle ever converges, every
+    particle does iter_max + 1 field applications in both) only the arithmetic differs, and the north_star bar of
+    1e-12 applies -- with room to spare."""
+    prob = Problem(2, (24, 20), (0.25, 0.3), (0.5, -1.0), 4, 20000, seed=31, max_disp=0.3, E0=0.3, B0=0.8)
+    x, v, J0, apply_its, unconv = _oracle(prob, rtol=0.0, itmax=passes)
+    got, J, st, nfast = _run(pgpu, prob, 1, rtol=0.0, itmax=passes)
+    assert nfast == 1
+    _check(prob, got, J, x, v, J0, tol_x=1e-12, tol_v=1e-12, tol_j=1e-12)
+    assert st.num_apply_its == apply_its
+    assert st.num_unconverged == unconv == prob.n
+
+
 def test_fast_kernel_faces_and_ghost_region(pgpu):
     """x_old exactly on dual-cell faces (cell centres), on primal faces, and up to ghosts-1 cells
     outside the box: the same-cell decision must be the reference's, and edge stencils defer."""
