@@ -832,13 +832,16 @@ def variants_leg(args, rank, local, stream, region, capi):
     torch.cuda.synchronize()
     capi.profile_enable(False)
     ms = e0.elapsed_time(e1)
-    k_ms, k_n = capi.profile_query("explicit_step")
+    k_ms, k_n = capi.profile_query("explicit_step_cc1")
+    d_ms, _ = capi.profile_query("explicit_step_deferred")
     n = eng.n_particles
     per_launch = n / len(eng.species)
     out["explicit_leapfrog"] = {
         "value": float(n) * nsteps / (ms * 1e-3), "unit": "particle-advances/s (explicit: gather + Boris + move + deposit)",
         "steps": nsteps, "warmup": nwarm, "ms_per_step": ms / nsteps,
-        "kernel": "explicit_step (k_explicit_step, generic CC1 visitor)", "kernel_ms_per_launch": k_ms / max(k_n, 1),
+        "kernel": "explicit_step_cc1 (the CC1 tile kernel in its one-pass explicit mode; particles that cross a dual-cell "
+                  "face go to k_explicit_step)",
+        "kernel_ms_per_launch": k_ms / max(k_n, 1), "deferred_ms_per_step": d_ms / nsteps,
         "roofline_frac_kernel": (BYTES_PER_ADVANCE_2D * per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9 / region.peak)
                                 if k_n else None,
         "bytes_per_unit": BYTES_PER_ADVANCE_2D}

@@ -42,6 +42,8 @@ constexpr int BLOCK = 128;
 constexpr double BAND = 1.0e-9;
 constexpr unsigned NOKEY = 0xffffffffu;
 
+constexpr int ITER_EXPLICIT = -2;   // FastArgs::iter_max of the explicit leap-frog step (v2 kernel only)
+
 struct FastArgs {
   const double *xo[2];
   double *xb[2];
@@ -1593,6 +1595,14 @@ __device__ __forceinline__ bool push_v2(const FastArgs &A, const TabWindow &Wn, 
     }
     napply += 1;
     if (A.iter_max < 0) {  // advanceParticles (:1594-1612), part_order_swap == false
+      if (A.iter_max == ITER_EXPLICIT) {
+        // PIC_EM_EXPLICIT (pgpu_explicit_step): advanceVelocities(dt, byHalfDt = false) leaves u_new = 2 ubar - u_old,
+        // advancePositionsExplicit(dt/2) moves with it, and setCurrentDensity(dt, true) deposits u_new over the orbit
+        // x_old -> 2 x - x_old: the same closed forms with u_new in the place of ubar
+        ub[0] = fma(2.0, ub[0], -uo[0]);
+        ub[1] = fma(2.0, ub[1], -uo[1]);
+        ub[2] = fma(2.0, ub[2], -uo[2]);
+      }
       xb[0] = fma(ub[0], A.hdt, xo[0]);
       xb[1] = fma(ub[1], A.hdt, xo[1]);
       done = true;
@@ -1856,6 +1866,7 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   if (c.exact || g->desc.D != 2 || s->desc.interp_E != CC1 || s->desc.relativistic) return 0;
   if (deposit && s->desc.interp_J != CC1) return 0;
   if (prm.iter_max < 0 && prm.order_swap) return 0;
+  if (prm.explicit_step && (c.cc1_tma != 3 || c.cc1_version < 2 || !deposit || prm.iter_max >= 0)) return 0;
   for (int d = 0; d < 2; ++d)
     if (s->desc.bc_check_lo[d] || s->desc.bc_check_hi[d]) return 0;
   if (g->nbox[0] + 2 * g->desc.nghost >= 32768 || g->nbox[1] + 2 * g->desc.nghost >= 32768) return 0;
@@ -1917,7 +1928,7 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   A.hdt = prm.cnormDt * 0.5;
   A.rtol = prm.rtol;
   A.rvolume = prm.rvolume;
-  A.iter_max = prm.iter_max;
+  A.iter_max = prm.explicit_step ? ITER_EXPLICIT : prm.iter_max;
   A.suborbit = prm.suborbit;
   A.list = s->defer_list;
   A.list_count = s->defer_count;
@@ -1982,7 +1993,7 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
       KTimer t("tile_boxes");
       k_tile_boxes<<<(unsigned)((ntiles + 127) / 128), 128, 0, c.stream>>>(A, ntiles, (int4 *)s->tile_box);
     }
-    KTimer t(deposit ? "advance_cc1_fused" : "advance_cc1");
+    KTimer t(prm.explicit_step ? "explicit_step_cc1" : (deposit ? "advance_cc1_fused" : "advance_cc1"));
 #define PGPU_TAB_LAUNCH(DEPV, RS, MB, PR)                                                                 \
   do {                                                                                                    \
     PGPU_CUDA(cudaFuncSetAttribute(k_advance_cc1_2d_tab<DEPV, RS, MB, PR>,                                \

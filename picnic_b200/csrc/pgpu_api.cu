@@ -1082,6 +1082,7 @@ static AdvanceParams make_params(pgpu_species_t s, double dt, bool iterative) {
   p.ext = s->grid->ext;
   p.fnorm = s->desc.fnorm_const;
   p.suborbit = 0;
+  p.explicit_step = 0;
   p.unconv_list = nullptr;
   p.unconv_count = nullptr;
   return p;
@@ -1224,7 +1225,29 @@ int pgpu_explicit_step(pgpu_species_t s, double dt, const int *bc_lo, const int 
   s->dep_from_explicit = 1;
   for (int c = 0; c < 3; ++c)
     PGPU_CUDA(cudaMemsetAsync(s->J[c].p, 0, s->J[c].size() * sizeof(double), ctx().stream));
-  int rc = launch_explicit_step(s, make_params(s, dt, false), periodic, second_half != 0);
+  AdvanceParams prm = make_params(s, dt, false);
+  if (D == 2 && s->desc.interp_E == CC1 && s->desc.interp_J == CC1 && !prm.ext.on && !ctx().exact && periodic[0] &&
+      periodic[1]) {
+    // 2D CC1: the tile kernel of the implicit advance does the step for the particles whose orbit stays in one dual
+    // cell (single pass, u_new = 2 ubar - u_old, deposit of u_new); the one-pass visitor kernel redoes the ones it lists.
+    // The periodic wrap and the second half then run as the streaming passes of the separate calls.
+    prm.explicit_step = 1;
+    prm.order_swap = 0;
+    const int fast = launch_advance_cc1_fast(s, prm, true);
+    if (fast < 0) return fast;
+    if (fast > 0) {
+      int rc = launch_explicit_step(s, prm, periodic, false, true);
+      if (!rc) rc = scale_species_current(s);
+      if (!rc) rc = pgpu_apply_bcs(s, bc_lo, bc_hi);
+      if (!rc && second_half) {
+        rc = pgpu_advance_positions_2nd_half(s);
+        if (!rc) rc = pgpu_apply_bcs(s, bc_lo, bc_hi);
+      }
+      return rc;
+    }
+    prm.explicit_step = 0;
+  }
+  int rc = launch_explicit_step(s, prm, periodic, second_half != 0);
   if (rc) return rc;
   return scale_species_current(s);
 }

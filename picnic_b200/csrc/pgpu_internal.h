@@ -58,6 +58,7 @@ struct AdvanceParams {
   ExtFields ext;    // external fields added after every gather (addExternalFieldsToParticles)
   double fnorm;     // m_fnorm_const (the sub-orbit model forms its own alpha per sub-step)
   int suborbit;     // m_use_suborbit_model: particles left unconverged are listed (unconv_list) and deposit nothing
+  int explicit_step;   // PIC_EM_EXPLICIT leap-frog step through the CC1 tile kernel (iter_max < 0, u_new = 2 ubar - u_old)
   int *unconv_list;
   unsigned *unconv_count;
 };
@@ -279,7 +280,8 @@ int transfer_listed_to_suborbit(pgpu_species_s *s, unsigned count);      // pgpu
 int transfer_outflow(pgpu_species_s *s, const int *bc_lo, const int *bc_hi);   // pgpu_suborbit.cu
 PartPtrs outflow_part_ptrs(pgpu_species_s *s);
 int launch_suborbit(pgpu_species_s *s, const AdvanceParams &prm, int from_jac, const DeviceFab *Jsub, unsigned *nfail);
-int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int *periodic, bool second_half);
+int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int *periodic, bool second_half,
+                         bool deferred = false);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);
 int launch_deposit_outflow(pgpu_species_s *s);   // the outflow lists into s->J (explicit solver)
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit);

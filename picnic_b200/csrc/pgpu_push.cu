@@ -442,6 +442,7 @@ struct ExplicitArgs {
   int periodic[2];
   double left[2], right[2];
   int second_half;
+  int deferred;   // host side only: walk the species' deferred list
 };
 template <int D>
 __device__ __forceinline__ void wrap_periodic(const ExplicitArgs &e, double *xp, double *xo) {
@@ -461,11 +462,15 @@ __device__ __forceinline__ void wrap_periodic(const ExplicitArgs &e, double *xp,
 }
 template <int D, int IE, int IJ, bool X>
 __global__ void __launch_bounds__(256)
-k_explicit_step(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams prm, ExplicitArgs e, Counters *cnt) {
+k_explicit_step(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams prm, ExplicitArgs e, Counters *cnt,
+                const int *list, const unsigned *list_count) {
   typedef M<X> m;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  // list != nullptr: the particles the CC1 tile kernel deferred (grid stride over list[0 .. *list_count))
+  const long total = list ? (long)*list_count : n;
+  const long stride = (long)gridDim.x * blockDim.x;
   unsigned err = 0;
-  if (i < n) {
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long i = list ? (long)list[t] : t;
     double xp[D], xo[D], uo[3], u[3];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -513,11 +518,15 @@ static int launch_explicit_t(pgpu_species_s *s, const AdvanceParams &prm, const 
   const Geo<D> g = make_geo<D>(species_geo(s));
   const FieldSet F = grid_fields(s->grid);
   const CurrentSet J = species_current(s);
-  KTimer t("explicit_step_fused");
+  const bool deferred = e.deferred != 0;
+  const unsigned nb = deferred ? (unsigned)(c.sm_count * 4) : nblocks(s->n, 256);
+  const int *list = deferred ? s->defer_list : nullptr;
+  const unsigned *cnt = deferred ? s->defer_count : nullptr;
+  KTimer t(deferred ? "explicit_step_deferred" : "explicit_step_fused");
   if (c.exact)
-    k_explicit_step<D, IE, IJ, true><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, e, c.d_counters);
+    k_explicit_step<D, IE, IJ, true><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, e, c.d_counters, list, cnt);
   else
-    k_explicit_step<D, IE, IJ, false><<<nblocks(s->n, 256), 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, e, c.d_counters);
+    k_explicit_step<D, IE, IJ, false><<<nb, 256, 0, c.stream>>>(s->ptrs(), s->n, g, F, J, prm, e, c.d_counters, list, cnt);
   return 0;
 }
 template <int D, int IE>
@@ -541,7 +550,7 @@ static int launch_explicit_d(pgpu_species_s *s, const AdvanceParams &prm, const 
   return PGPU_ERR_ARG;
 }
 // bc: 1 = periodic in that direction (the only particle BC the fused pass applies)
-int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int *periodic, bool second_half) {
+int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int *periodic, bool second_half, bool deferred) {
   if (s->n == 0) return 0;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   ExplicitArgs e;
@@ -552,6 +561,7 @@ int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int 
     e.right[d] = ga.re[d];
   }
   e.second_half = second_half ? 1 : 0;
+  e.deferred = deferred ? 1 : 0;
   return ga.D == 1 ? launch_explicit_d<1>(s, prm, e) : launch_explicit_d<2>(s, prm, e);
 }
 

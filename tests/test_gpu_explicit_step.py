@@ -90,3 +90,61 @@ def test_fused_explicit_step_matches_oracle(pgpu, D, interp):
         orc.scale_fab(J0[c], D, -1.0 / 2.0)
         assert rel_err(J[c], J0[c].a) < 1e-12
     sp.destroy(); grid.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("second_half", [False, True])
+@pytest.mark.parametrize("order", ["sorted", "shuffled"])
+def test_explicit_step_cc1_tile_kernel_matches_oracle(pgpu, order, second_half):
+    """2D CC1/CC1 in fast arithmetic: the step goes through the tile kernel of the implicit advance (single pass,
+    u_new = 2 ubar - u_old) and the one-pass visitor kernel for the particles it defers.  Against the oracle's restatement
+    of the separate reference calls.  The tile kernel deposits before the periodic wrap (the generic kernel after it), so
+    the currents are compared after the ghost fold, which is what the field solve sees."""
+    D, it = 2, INTERPS["CC1"]
+    prob = Problem(2, (24, 20), (0.25, 0.3), (0.5, -1.0), 4, 20000, seed=41, max_disp=0.0)
+    prob.x = prob.xold.copy()
+    prob.v = prob.vold.copy()
+    if order == "sorted":
+        cells = orc.bin_cells(prob.geom, prob.xold)
+        perm = np.argsort(cells[0] + cells[1] * prob.ncell[0], kind="stable")
+        for name in ("x", "xold", "v", "vold"):
+            setattr(prob, name, np.ascontiguousarray(getattr(prob, name)[:, perm]))
+        prob.w = np.ascontiguousarray(prob.w[perm])
+    fn, dt, cv = 0.08, 0.9, 1.0
+    grid, sp = make_gpu(pgpu, prob, it, fnorm=fn, cvac_norm=cv, charge=-1.0, volume_scale=2.0)
+    pgpu.profile_reset(); pgpu.profile_enable(True)
+    sp.explicit_step(dt, (1, 1), (1, 1), second_half)
+    pgpu.profile_enable(False)
+    assert pgpu.profile_query("explicit_step_cc1")[1] == 1          # the tile kernel ran
+    assert pgpu.profile_query("explicit_step_deferred")[1] == 1     # and the visitor kernel took its list
+    assert pgpu.profile_query("explicit_step_fused")[1] == 0
+    got = sp.download()
+    J = [sp.current_get(c) for c in range(3)]
+    n = prob.n
+    rc, Ep, Bp = orc.gather(prob.geom, it, prob.x, prob.xold, prob.E, prob.B)
+    assert rc == 0
+    v = np.ascontiguousarray(orc.boris(np.zeros((3, n)), prob.vold, Ep, Bp, fn, dt * cv, 0))
+    x = prob.x.copy()
+    xold = prob.xold.copy()
+    orc.lib().orc_advance_positions_explicit(D, n, orc._ptr(x), orc._ptr(xold), orc._ptr(v), cv * dt * 0.5)
+    for d in range(D):
+        orc.lib().orc_bc_periodic(n, x[d].ctypes.data, xold[d].ctypes.data, prob.xmin[d], prob.xmax[d])
+    J0 = prob.new_J()
+    assert orc.deposit_current(prob.geom, it, x, xold, v, prob.w, dt * cv, J0) == 0
+    if second_half:
+        orc.lib().orc_advance_positions_2nd_half(D, n, orc._ptr(x), orc._ptr(xold))
+        for d in range(D):
+            orc.lib().orc_bc_periodic(n, x[d].ctypes.data, xold[d].ctypes.data, prob.xmin[d], prob.xmax[d])
+    assert rel_err(got["v"], v) < 1e-12
+    assert np.abs(got["x"] - x).max() < 1e-12 * max(prob.xmax)
+    assert np.abs(got["xold"] - xold).max() < 1e-12 * max(prob.xmax)
+    assert np.abs(got["x"] - prob.x).max() > 1e-3                   # particles did move
+    lo, hi = (0, 0), tuple(nc - 1 for nc in prob.ncell)
+    for c, stag in enumerate(orc.E_STAG[2]):
+        orc.scale_fab(J0[c], D, -1.0 / 2.0)
+        Jg = orc.Fab(J0[c].lo, J0[c].hi, np.asfortranarray(J[c]))
+        orc.fold_periodic(J0[c], D, stag, lo, hi, (1, 1))
+        orc.fold_periodic(Jg, D, stag, lo, hi, (1, 1))
+        assert np.abs(J0[c].a).max() > 0
+        assert rel_err(Jg.a, J0[c].a) < 1e-12
+    sp.destroy(); grid.destroy()
