@@ -862,6 +862,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from picnic_b200 import capi
     capi.load()
@@ -931,6 +934,8 @@ def run_ours(args):
         prof[name] = capi.profile_query(name)
     adv, app, unconv = capi.picard_totals(reset=True)
     k_mean = app / max(adv, 1)
+    # share of the particles the tile kernel handed to the generic kernel in the last evaluation (diagnostic read-back)
+    deferred_frac = sum(sp.deferred_count() for sp in eng.species) / max(eng.n_particles, 1)
 
     # weak scaling: every rank loads the same number of particles and migration conserves the sum
     n_total = eng.n_particles * world
@@ -995,6 +1000,7 @@ def run_ours(args):
                                      "ghost_J_bytes_per_evaluation": eng.halo_bytes,
                                      "migrated_particles_rank0": int(eng.migrated)}),
                        "mean_picard_passes": round(k_mean, 3), "unconverged_particles": int(unconv),
+                       "deferred_fraction_rank0": round(deferred_frac, 5),
                        "l2_policy": "inputs (%.1f GB particle SoA per GPU) exceed the 126 MB L2; no flush needed"
                                     % (eng.n_particles * 96 / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches),

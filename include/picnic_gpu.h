@@ -515,6 +515,10 @@ long pgpu_launch_count(void);
  * particles advanced, Boris applications (m_num_apply_its) and particles left
  * unconverged -- picardParams / avg_picard_its (PicChargedSpecies.cpp:4280-4337). */
 int pgpu_picard_totals(long *advances, long *apply_its, long *unconverged, int reset);
+/* How many particles of `s` the specialised kernel of its last advance (or explicit step) handed to the generic
+ * kernel (orbits that cross a face of the half-shifted grid, stencils at the array edge); 0 if it did not run.
+ * Diagnostic: synchronises. */
+int pgpu_species_deferred_count(pgpu_species_t s, long *count);
 
 #ifdef __cplusplus
 }

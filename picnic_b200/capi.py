@@ -149,6 +149,7 @@ def load():
         "pgpu_mass_matrices_save_E0": [vp], "pgpu_compute_J_from_mass_matrices": [vp],
         "pgpu_mass_matrix_get": [vp, i32, vp, vp, vp, i32], "pgpu_mass_matrix_J0_get": [vp, i32, vp, vp, vp],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
+        "pgpu_species_deferred_count": [vp, vp],
         "pgpu_launch_count": [], "pgpu_picard_totals": [vp, vp, vp, i32], "pgpu_abi_version": [], "pgpu_last_error": [],
     }
     for name, args in sig.items():
@@ -411,6 +412,11 @@ class Species:
             check(load().pgpu_species_suborbit_download(self.h, _p(out["x"]), _p(out["xold"]), _p(out["v"]), _p(out["vold"]),
                                                         _p(out["w"]), _p(out["id"]), _p(out["nsub"])))
         return out
+
+    def deferred_count(self):
+        n = C.c_long(0)
+        check(load().pgpu_species_deferred_count(self.h, C.byref(n)))
+        return n.value
 
     def explicit_step(self, dt, bc_lo, bc_hi, second_half=False):
         check(load().pgpu_explicit_step(self.h, dt, _i2(bc_lo), _i2(bc_hi), int(second_half)))

@@ -1273,6 +1273,18 @@ int pgpu_picard_totals(long *advances, long *apply_its, long *unconverged, int r
   return check_err_bits(k.err);
 }
 
+int pgpu_species_deferred_count(pgpu_species_t s, long *count) {
+  NEED_INIT();
+  if (!s || !count) return PGPU_ERR_ARG;
+  unsigned n = 0;
+  if (s->defer_count) {
+    PGPU_CUDA(cudaMemcpyAsync(&n, s->defer_count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
+    PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
+  }
+  *count = (long)n;
+  return 0;
+}
+
 int pgpu_profile_enable(int on) {
   ctx().profile = on != 0;
   return 0;
