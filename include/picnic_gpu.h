@@ -415,7 +415,7 @@ int pgpu_ta_lorentz_scatter(long n, const double *up1, const double *up2, double
 enum { PGPU_ANG_TAKIZUKA = 0, PGPU_ANG_NANBU = 1, PGPU_ANG_BOBYLEV = 2, PGPU_ANG_ISOTROPIC = 5 };
 typedef struct {
   double Clog;            /* coulomb_logarithm; 0 = per pair from b_max / b_min (Coulomb.cpp:1664-1672) */
-  int angular_scattering; /* PGPU_ANG_*  (NANBU_FAS*, large-angle events: not implemented -> PGPU_ERR_ARG) */
+  int angular_scattering; /* PGPU_ANG_*  (NANBU_FAS, NANBU_FAS_v2: not implemented -> PGPU_ERR_ARG) */
   int NxN;                /* Coulomb.NxN */
   int NxN_Nthresh;        /* Coulomb.NxN_Nthresh (11) */
   int num_subcycles;      /* Coulomb.num_subcycles (1) */
@@ -433,6 +433,13 @@ typedef struct {
    * one takes the fraction w_min / w_max of its scattered change plus a transverse kick that conserves the pair's
    * weighted energy exactly (Coulomb::enforceEnergyConservation, Coulomb.H:796-823).  Galilean build only. */
   int weight_method;
+  /* scattering.coulomb.include_large_angle_scattering (Coulomb::SetPolarScattering, Coulomb.cpp:1801-1863): single
+   * Rutherford events below a cutoff impact parameter on top of the cumulative small-angle model.  The host applies
+   * exclude_electron_fas (Coulomb.cpp:69-71: off when one of the species is the electron).  test_large_angle_draw is
+   * the event's uniform draw in the explicit-draw test entry points (pgpu_coulomb_delta_u, _lorentz_scatter); the
+   * collision kernels draw it from Philox. */
+  int include_large_angle_scattering;
+  double test_large_angle_draw;
 } pgpu_coulomb_params;
 int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm, double dt_sec,
                          uint64_t seed, uint64_t step, long *npairs);

@@ -394,6 +394,14 @@ def coulomb_set_enforce(on, energy_fraction=0.05, energy_fraction_max=0.5, beta_
     f(int(on), energy_fraction, energy_fraction_max, int(beta_weight_exponent), int(sort_weighted), int(nmin_save))
 
 
+def coulomb_set_large_angle(on, test_draw=0.5):
+    """scattering.coulomb.include_large_angle_scattering; test_draw = the RL of the explicit-draw entry points"""
+    f = lib().orc_coulomb_set_large_angle
+    f.argtypes = [C.c_int, C.c_double]
+    f.restype = None
+    f(int(on), float(test_draw))
+
+
 def coulomb_set_weight_method(conservative):
     """Coulomb weight_method: False PROBABILISTIC, True CONSERVATIVE (Sentoku-Kemp, Coulomb.cpp:730-917, 1439-1640)."""
     f = lib().orc_coulomb_set_weight_method

@@ -391,6 +391,54 @@ extern "C" void orc_nanbu_costh_sinth(double s12, double U, double *costh, doubl
   *sinth = std::sqrt(1.0 - c * c);
 }
 
+/* scattering.coulomb.include_large_angle_scattering: the first half of Coulomb::SetPolarScattering (Coulomb.cpp:1801-1863).
+ * A pair makes one Rutherford scattering event with an impact parameter below the cutoff b_c with probability SL, and the
+ * variance of the cumulative small-angle part is reduced so that the total stays s12.  RL is the reference's one uniform
+ * draw; returns true when the small-angle part is skipped (costh/sinth are then final).  The test value of RL used by the
+ * explicit-draw entry points (orc_coulomb_delta_u, orc_coulomb_lorentz_scatter) comes from orc_coulomb_set_large_angle. */
+static int g_large_angle = 0;
+static double g_large_angle_draw = 0.5;
+extern "C" void orc_coulomb_set_large_angle(int on, double test_draw) {
+  g_large_angle = on ? 1 : 0;
+  g_large_angle_draw = test_draw;
+}
+static bool large_angle_part(double &s12, double Clog, double b0, double bmin_qm, double sigma_eff, double RL,
+                             double &costh, double &sinth) {
+  double N12, N12_min, N12_tr;
+  double bperp_sq, bmin_sq, bmax_sq, bc_sq, SL, ClogM;
+  bperp_sq = b0 * b0 / 4.0;
+  bmin_sq = bmin_qm * bmin_qm;
+  bmax_sq = std::exp(2.0 * Clog) * (bperp_sq + bmin_sq) - bperp_sq;
+  N12 = s12 / sigma_eff * kPI * (bmax_sq - bmin_sq);
+  bc_sq = bperp_sq + bmin_sq;
+  N12_min = 0.1;
+  N12_tr = 80.0;
+  const double N12_tr0 = N12_min / 2.0 * (bmax_sq - bmin_sq) / (bc_sq - bmin_sq);
+  if (N12_tr0 < N12_tr) N12_tr = N12_tr0;
+  if (N12 <= N12_min) {
+    SL = N12;
+  } else if (N12 <= N12_tr) {
+    const double SL_tr = N12_tr * (bc_sq - bmin_sq) / (bmax_sq - bmin_sq);
+    const double SL_min = N12_min;
+    SL = (N12 - N12_min) / (N12_tr - N12_min) * SL_tr + (N12_tr - N12) / (N12_tr - N12_min) * SL_min;
+  } else {
+    SL = std::min(0.1, N12 * (bc_sq - bmin_sq) / (bmax_sq - bmin_sq));
+  }
+  bc_sq = bmin_sq + SL / N12 * (bmax_sq - bmin_sq);
+  ClogM = 0.5 * std::log((bperp_sq + bmax_sq) / (bperp_sq + bc_sq));
+  s12 *= ClogM / Clog / (1.0 - SL);
+  costh = 1.0;
+  sinth = 0.0;
+  if (RL < SL) {
+    const double bsq = bc_sq - RL / SL * (bc_sq - bmin_sq);
+    costh = (bsq - bperp_sq) / (bsq + bperp_sq);
+    sinth = std::sqrt(1.0 - costh * costh);
+    return true;
+  }
+  if (N12 <= N12_min) return true;
+  return false;
+}
+
 /* Coulomb::GalileanScatter + SetPolarScattering (TAKIZUKA=0, NANBU=1, BOBYLEV=2, ISOTROPIC=5)
  * with explicit draws: r_polar = |randn| for TAKIZUKA's small-angle branch, else a uniform;
  * u_phi uniform.  Returns 0 and leaves dU = 0 when the reference returns early (Appendix B:
@@ -417,10 +465,12 @@ extern "C" int orc_coulomb_delta_u(const double *vp1, const double *vp2, double 
   b0 = k.b90_fact / (k.mu * u * u);
   double sigma_eff = kPI * b0 * b0 * Clog;
   sigma_eff = std::min(sigma_eff, sigma_max);
-  const double s12 = sigma_eff * den12 * u * kCVAC * dt_sec;
-  if (s12_out) *s12_out = s12;
+  double s12 = sigma_eff * den12 * u * kCVAC * dt_sec;
   double costh = 1.0, sinth = 0.0;
-  switch (angular) {
+  bool skip_small = false;
+  if (g_large_angle) skip_small = large_angle_part(s12, Clog, b0, bmin_qm, sigma_eff, g_large_angle_draw, costh, sinth);
+  if (s12_out) *s12_out = skip_small ? -1.0 : s12;   /* -1: no polar draw follows */
+  if (!skip_small) switch (angular) {
     case 0:
       if (s12 < 2.0) {
         const double delta = sqrt(s12 / 2.0) * std::abs(gauss);
@@ -501,9 +551,11 @@ extern "C" int orc_coulomb_lorentz_scatter(double *a_up1, double *a_up2, int a_s
   sigma_eff = std::min(sigma_eff, a_sigma_max);
   double s12 = sigma_eff * a_den12 * vrelst * kCVAC * a_dt_sec;
   s12 *= g1st * g2st / g1 / g2;
-  if (s12_out) *s12_out = s12;
   double costh = 1.0, sinth = 0.0;
-  switch (angular) {
+  bool skip_small = false;
+  if (g_large_angle) skip_small = large_angle_part(s12, Clog, b0, bmin_qm, sigma_eff, g_large_angle_draw, costh, sinth);
+  if (s12_out) *s12_out = skip_small ? -1.0 : s12;
+  if (!skip_small) switch (angular) {
     case 0:
       if (s12 < 2.0) {
         const double delta = sqrt(s12 / 2.0) * std::abs(gauss);
@@ -571,8 +623,17 @@ void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2
     const int live = orc_coulomb_lorentz_scatter(t1, t2, 0, q1, q2, m1, m2, c.EF_norm, c.Clog, 2, den12, c.bmax,
                                                  c.sigma_max, c.dt_sec, 0.0, 0.0, 0.0, &s12);
     if (!live) return;
+    const double saved_draw = g_large_angle_draw;
+    if (g_large_angle) {   /* SetPolarScattering draws RL first; it decides whether a polar draw follows */
+      g_large_angle_draw = mu_rand();
+      double u1[3] = {p1[0], p1[1], p1[2]}, u2[3] = {p2[0], p2[1], p2[2]};
+      orc_coulomb_lorentz_scatter(u1, u2, 0, q1, q2, m1, m2, c.EF_norm, c.Clog, 2, den12, c.bmax, c.sigma_max, c.dt_sec,
+                                  0.0, 0.0, 0.0, &s12);
+    }
     double gauss = 0.0, upol = 0.0;
-    if (c.angular == 0) {
+    if (s12 < 0.0) {
+      /* large-angle event (or too few collisions): no polar draw */
+    } else if (c.angular == 0) {
       if (s12 < 2.0) gauss = mu_randn();
       else upol = mu_rand();
     } else if (c.angular != 2) {
@@ -581,6 +642,7 @@ void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2
     const double uphi = mu_rand();
     orc_coulomb_lorentz_scatter(p1, p2, scatter2 ? 1 : 0, q1, q2, m1, m2, c.EF_norm, c.Clog, c.angular, den12,
                                 c.bmax, c.sigma_max, c.dt_sec, gauss, upol, uphi, nullptr);
+    g_large_angle_draw = saved_draw;
     return;
   }
   /* replicate which draws GalileanScatter makes: decide the branch from s12 first */
@@ -589,8 +651,16 @@ void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2
   const int live = orc_coulomb_delta_u(b1, b2, c.charge1, c.charge2, c.mass1, c.mass2, c.EF_norm, c.Clog, 2,
                                        den12, c.bmax, c.sigma_max, c.dt_sec, 0.0, 0.0, 0.0, probe, &s12);
   if (live) {
+    const double saved_draw = g_large_angle_draw;
+    if (g_large_angle) {
+      g_large_angle_draw = mu_rand();
+      orc_coulomb_delta_u(b1, b2, c.charge1, c.charge2, c.mass1, c.mass2, c.EF_norm, c.Clog, 2, den12, c.bmax,
+                          c.sigma_max, c.dt_sec, 0.0, 0.0, 0.0, probe, &s12);
+    }
     double gauss = 0.0, upol = 0.0;
-    if (c.angular == 0) {
+    if (s12 < 0.0) {
+      /* large-angle event (or too few collisions): no polar draw */
+    } else if (c.angular == 0) {
       if (s12 < 2.0) gauss = mu_randn();
       else upol = mu_rand();
     } else if (c.angular != 2) {
@@ -599,6 +669,7 @@ void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2
     const double uphi = mu_rand();
     orc_coulomb_delta_u(b1, b2, c.charge1, c.charge2, c.mass1, c.mass2, c.EF_norm, c.Clog, c.angular, den12,
                         c.bmax, c.sigma_max, c.dt_sec, gauss, upol, uphi, dU, nullptr);
+    g_large_angle_draw = saved_draw;
   } else {
     dU[0] = dU[1] = dU[2] = 0.0;
   }

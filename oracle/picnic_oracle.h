@@ -291,6 +291,9 @@ void orc_fast_particles(const orc_geom *g, long n, const double *x, const double
  * 1024-1083, 1182-1430) */
 void orc_mod_energy_pairwise(double *b1, double *b2, double wpmp1, double wpmp2, double Erel_frac, double *Erel_cumm,
                              double *deltaE, int rel);
+/* scattering.coulomb.include_large_angle_scattering (Coulomb::SetPolarScattering, Coulomb.cpp:1801-1863); test_draw is the
+ * uniform RL the explicit-draw entry points use (the cell drivers draw it from the stream). */
+void orc_coulomb_set_large_angle(int on, double test_draw);
 void orc_coulomb_set_enforce(int on, double energy_fraction, double energy_fraction_max, int beta_weight_exponent,
                              int sort_weighted, int nmin_save);
 /* ScatteringUtils::collapseThreeToTwo (ScatteringUtils.H:20-47), pinned on the reference */

@@ -48,7 +48,8 @@ class CoulombParams(C.Structure):
     _fields_ = [("Clog", C.c_double), ("angular_scattering", C.c_int), ("NxN", C.c_int), ("NxN_Nthresh", C.c_int),
                 ("num_subcycles", C.c_int), ("enforce_conservations", C.c_int), ("energy_fraction", C.c_double),
                 ("energy_fraction_max", C.c_double), ("beta_weight_exponent", C.c_int),
-                ("sort_weighted_particles", C.c_int), ("conservation_Nmin_save", C.c_int), ("weight_method", C.c_int)]
+                ("sort_weighted_particles", C.c_int), ("conservation_Nmin_save", C.c_int), ("weight_method", C.c_int),
+                ("include_large_angle_scattering", C.c_int), ("test_large_angle_draw", C.c_double)]
 
 
 class ElasticParams(C.Structure):
@@ -554,9 +555,9 @@ def ta_delta_u(vp1, den1, vp2, den2, b90_fact, Clog, dt_sec, gauss, u_theta, u_p
 
 def collide_coulomb(sA, sB, Clog, dt_sec, seed, step, angular=0, NxN=False, NxN_Nthresh=11, num_subcycles=1,
                     count=True, enforce=False, energy_fraction=0.05, energy_fraction_max=0.5, beta_weight_exponent=1,
-                    conservative=False):
+                    conservative=False, large_angle=False):
     prm = CoulombParams(Clog, angular, int(NxN), NxN_Nthresh, num_subcycles, int(enforce), energy_fraction,
-                        energy_fraction_max, beta_weight_exponent, 0, 0, int(conservative))
+                        energy_fraction_max, beta_weight_exponent, 0, 0, int(conservative), int(large_angle), 0.5)
     np_ = C.c_long(0)
     check(load().pgpu_collide_coulomb(sA.h, sB.h, C.byref(prm), dt_sec, seed, step, C.byref(np_) if count else None))
     return np_.value
@@ -593,11 +594,14 @@ def nu_max_hard_sphere(sA, sB, sigmaT):
 
 
 def coulomb_lorentz_scatter(up1, up2, scatter2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, den12, bmax, sigma_max,
-                            gauss, upol, uphi):
-    """Coulomb::LorentzScatter for n pairs ([3][n] arrays): (up1', up2', s12)."""
+                            gauss, upol, uphi, large_angle=None):
+    """Coulomb::LorentzScatter for n pairs ([3][n] arrays): (up1', up2', s12).  large_angle = the uniform draw of the
+    large-angle event (include_large_angle_scattering on), None = off."""
     c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     n = np.asarray(den12).size
     prm = CoulombParams(Clog, angular, 0, 11, 1)
+    if large_angle is not None:
+        prm.include_large_angle_scattering, prm.test_large_angle_draw = 1, float(large_angle)
     a = [c(up1), c(up2), c(EF_norm), c(den12), c(bmax), c(sigma_max), c(gauss), c(upol), c(uphi)]
     s2 = np.ascontiguousarray(scatter2, dtype=np.int32)
     o1, o2, s12 = np.zeros((3, n)), np.zeros((3, n)), np.zeros(n)
@@ -606,10 +610,13 @@ def coulomb_lorentz_scatter(up1, up2, scatter2, q1, q2, m1, m2, Clog, angular, d
     return o1, o2, s12
 
 
-def coulomb_delta_u(vp1, vp2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, den12, bmax, sigma_max, gauss, upol, uphi):
+def coulomb_delta_u(vp1, vp2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, den12, bmax, sigma_max, gauss, upol, uphi,
+                    large_angle=None):
     c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     n = np.asarray(den12).size
     prm = CoulombParams(Clog, angular, 0, 11, 1)
+    if large_angle is not None:
+        prm.include_large_angle_scattering, prm.test_large_angle_draw = 1, float(large_angle)
     a = [c(vp1), c(vp2), c(EF_norm), c(den12), c(bmax), c(sigma_max), c(gauss), c(upol), c(uphi)]
     dU, s12 = np.zeros((3, n)), np.zeros(n)
     check(load().pgpu_coulomb_delta_u(n, _p(a[0]), _p(a[1]), q1, q2, m1, m2, C.byref(prm), dt_sec, *[_p(x) for x in a[2:]],

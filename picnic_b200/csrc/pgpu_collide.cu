@@ -432,6 +432,8 @@ struct CoulParams {
   int rel;               // RELATIVISTIC_PARTICLES build: pairs go through LorentzScatter
   int sk08;              // weight_method = CONSERVATIVE (Sentoku-Kemp 2008 update of the heavier-weight particle)
   double mass1, mass2;
+  int large_angle;       // include_large_angle_scattering (Coulomb::SetPolarScattering, first half)
+  double large_draw;     // its uniform RL in the explicit-draw test entry points
 };
 __device__ __forceinline__ unsigned global_cell(const CoulParams &P, int cell) {
   const int i = cell % P.nbox0 + P.box_lo0, j = cell / P.nbox0 + P.box_lo1;
@@ -488,11 +490,49 @@ __device__ __forceinline__ void coulomb_polar(int angular, double s12, double ga
   }
 }
 
+// scattering.coulomb.include_large_angle_scattering, Coulomb::SetPolarScattering (:1801-1863): with probability SL the pair
+// makes ONE Rutherford event with an impact parameter below the cutoff b_c; the variance of the cumulative small-angle part
+// shrinks so that the total stays s12.  RL = the reference's uniform draw.  true = no small-angle part follows.
+__device__ __forceinline__ bool coulomb_large_angle(double &s12, double Clog, double b0, double bmin_qm, double sigma_eff,
+                                                    double RL, double &costh, double &sinth) {
+  const double PI = 3.14159265358979323846;
+  const double bperp_sq = b0 * b0 / 4.0, bmin_sq = bmin_qm * bmin_qm;
+  const double bmax_sq = exp(2.0 * Clog) * (bperp_sq + bmin_sq) - bperp_sq;
+  const double N12 = s12 / sigma_eff * PI * (bmax_sq - bmin_sq);
+  double bc_sq = bperp_sq + bmin_sq;
+  const double N12_min = 0.1;
+  double N12_tr = 80.0;
+  const double N12_tr0 = N12_min / 2.0 * (bmax_sq - bmin_sq) / (bc_sq - bmin_sq);
+  if (N12_tr0 < N12_tr) N12_tr = N12_tr0;
+  double SL;
+  if (N12 <= N12_min) {
+    SL = N12;
+  } else if (N12 <= N12_tr) {
+    const double SL_tr = N12_tr * (bc_sq - bmin_sq) / (bmax_sq - bmin_sq);
+    SL = (N12 - N12_min) / (N12_tr - N12_min) * SL_tr + (N12_tr - N12) / (N12_tr - N12_min) * N12_min;
+  } else {
+    SL = fmin(0.1, N12 * (bc_sq - bmin_sq) / (bmax_sq - bmin_sq));
+  }
+  bc_sq = bmin_sq + SL / N12 * (bmax_sq - bmin_sq);
+  const double ClogM = 0.5 * log((bperp_sq + bmax_sq) / (bperp_sq + bc_sq));
+  s12 *= ClogM / Clog / (1.0 - SL);
+  costh = 1.0;
+  sinth = 0.0;
+  if (RL < SL) {
+    const double bsq = bc_sq - RL / SL * (bc_sq - bmin_sq);
+    costh = (bsq - bperp_sq) / (bsq + bperp_sq);
+    sinth = sqrt(1.0 - costh * costh);
+    return true;
+  }
+  return N12 <= N12_min;
+}
+
 // Coulomb::GalileanScatter (:1642-1692) + SetPolarScattering (:1795-1903) with explicit draws.
 // false (dU = 0) where the reference returns early.
 __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const double *vp1, const double *vp2,
                                                 double EF_norm, double den12, double bmax, double sigma_max,
-                                                double gauss, double upol, double uphi, double *dU, double *s12o) {
+                                                double gauss, double upol, double uphi, double *dU, double *s12o,
+                                                double ularge = 0.5) {
   const double PI = 3.14159265358979323846, CVAC = 2.99792458e+08;
   dU[0] = dU[1] = dU[2] = 0.0;
   const double ux = vp1[0] - vp2[0], uy = vp1[1] - vp2[1], uz = vp1[2] - vp2[2];
@@ -511,10 +551,12 @@ __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const doubl
   b0 = P.b90_fact / (P.mu * u * u);
   double sigma_eff = PI * b0 * b0 * Clog;
   sigma_eff = fmin(sigma_eff, sigma_max);
-  const double s12 = sigma_eff * den12 * u * CVAC * P.dt_sec;
-  if (s12o) *s12o = s12;
+  double s12 = sigma_eff * den12 * u * CVAC * P.dt_sec;
   double costh, sinth;
-  coulomb_polar(P.angular, s12, gauss, upol, costh, sinth);
+  bool skip_small = false;
+  if (P.large_angle) skip_small = coulomb_large_angle(s12, Clog, b0, bmin_qm, sigma_eff, ularge, costh, sinth);
+  if (s12o) *s12o = skip_small ? -1.0 : s12;
+  if (!skip_small) coulomb_polar(P.angular, s12, gauss, upol, costh, sinth);
   double sinphi, cosphi;
   sincos(2.0 * PI * uphi, &sinphi, &cosphi);
   scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
@@ -527,7 +569,7 @@ __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const doubl
 __device__ __forceinline__ bool coulomb_lorentz_scatter(const CoulParams &P, double *up1, double *up2, bool scatter2,
                                                         double m1, double m2, double EF_norm, double den12,
                                                         double bmax, double sigma_max, double gauss, double upol,
-                                                        double uphi, double *s12o) {
+                                                        double uphi, double *s12o, double ularge = 0.5) {
   const double PI = 3.14159265358979323846, CVAC = 2.99792458e+08;
   if (s12o) *s12o = 0.0;
   const double gb1sq = up1[0] * up1[0] + up1[1] * up1[1] + up1[2] * up1[2];
@@ -569,9 +611,11 @@ __device__ __forceinline__ bool coulomb_lorentz_scatter(const CoulParams &P, dou
   sigma_eff = fmin(sigma_eff, sigma_max);
   double s12 = sigma_eff * den12 * vrelst * CVAC * P.dt_sec;
   s12 *= g1st * g2st / g1 / g2;
-  if (s12o) *s12o = s12;
   double costh, sinth, sinphi, cosphi;
-  coulomb_polar(P.angular, s12, gauss, upol, costh, sinth);
+  bool skip_small = false;
+  if (P.large_angle) skip_small = coulomb_large_angle(s12, Clog, b0, bmin_qm, sigma_eff, ularge, costh, sinth);
+  if (s12o) *s12o = skip_small ? -1.0 : s12;
+  if (!skip_small) coulomb_polar(P.angular, s12, gauss, upol, costh, sinth);
   sincos(2.0 * PI * uphi, &sinphi, &cosphi);
   rotate_velocity(upst, costh, sinth, cosphi, sinphi);
   ucmdotup = gcm * (vcm[0] * upst[0] + vcm[1] * upst[1] + vcm[2] * upst[2]);
@@ -594,7 +638,7 @@ __global__ void k_coulomb_lorentz(long n, CoulParams P, const double *vp1, const
   double a[3] = {vp1[i], vp1[n + i], vp1[2 * n + i]}, b[3] = {vp2[i], vp2[n + i], vp2[2 * n + i]};
   double s = 0.0;
   coulomb_lorentz_scatter(P, a, b, scatter2[i] != 0, P.mass1, P.mass2, EF[i], den12[i], bmax[i], smax[i], gauss[i],
-                          upol[i], uphi[i], &s);
+                          upol[i], uphi[i], &s, P.large_draw);
   for (int c = 0; c < 3; ++c) {
     o1[c * n + i] = a[c];
     o2[c * n + i] = b[c];
@@ -609,7 +653,7 @@ __global__ void k_coulomb_delta_u(long n, CoulParams P, const double *vp1, const
   if (i >= n) return;
   const double a[3] = {vp1[i], vp1[n + i], vp1[2 * n + i]}, b[3] = {vp2[i], vp2[n + i], vp2[2 * n + i]};
   double d[3], s = 0.0;
-  coulomb_delta_u(P, a, b, EF[i], den12[i], bmax[i], smax[i], gauss[i], upol[i], uphi[i], d, &s);
+  coulomb_delta_u(P, a, b, EF[i], den12[i], bmax[i], smax[i], gauss[i], upol[i], uphi[i], d, &s, P.large_draw);
   dU[i] = d[0];
   dU[n + i] = d[1];
   dU[2 * n + i] = d[2];
@@ -637,6 +681,11 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
   const double w1 = wa[pa], w2 = wb[pb];
   const double den12 = fmax(w1, w2) * den_fact;
   double va[3] = {a0[pa], a1[pa], a2[pa]}, vb[3] = {b0[pb], b1[pb], b2[pb]}, dU[3];
+  double ularge = 0.5;
+  if (P.large_angle) {   // the one extra uniform of SetPolarScattering: second word of the pair's weight stream
+    c.w = P.step_hi ^ (STREAM_WEIGHT << 16) ^ salt;
+    ularge = u01(philox4x32_10(c, P.seed_lo, P.seed_hi).y);
+  }
   if (P.rel) {
     // Coulomb.cpp:548-559 / 1139-1150: the lighter-weight particle goes first and always scatters, the other one
     // with probability w_min / w_max
@@ -648,10 +697,10 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
     }
     if ((float)w2 < (float)w1)
       coulomb_lorentz_scatter(P, vb, va, other, P.mass2, P.mass1, C.EF_norm, den12, C.bmax, C.sigma_max, gauss,
-                              u01(r.z), u01(r.w), nullptr);
+                              u01(r.z), u01(r.w), nullptr, ularge);
     else
       coulomb_lorentz_scatter(P, va, vb, other, P.mass1, P.mass2, C.EF_norm, den12, C.bmax, C.sigma_max, gauss,
-                              u01(r.z), u01(r.w), nullptr);
+                              u01(r.z), u01(r.w), nullptr, ularge);
     a0[pa] = va[0];
     a1[pa] = va[1];
     a2[pa] = va[2];
@@ -660,7 +709,7 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
     b2[pb] = vb[2];
     return;
   }
-  coulomb_delta_u(P, va, vb, C.EF_norm, den12, C.bmax, C.sigma_max, gauss, u01(r.z), u01(r.w), dU, nullptr);
+  coulomb_delta_u(P, va, vb, C.EF_norm, den12, C.bmax, C.sigma_max, gauss, u01(r.z), u01(r.w), dU, nullptr, ularge);
   if (P.sk08 && (float)w1 != (float)w2) {
     // weight_method = CONSERVATIVE: Sentoku & Kemp, JCP 227 (2008) (Coulomb.cpp:849-897 / 1575-1621).  The lighter
     // particle scatters; the heavier one moves by the fraction w_min / w_max of its scattered change, and a kick normal to
@@ -1475,6 +1524,8 @@ static int coulomb_consts(double charge1, double charge2, double mass1, double m
     return PGPU_ERR_ARG;
   }
   P->sk08 = prm->weight_method;
+  P->large_angle = prm->include_large_angle_scattering ? 1 : 0;
+  P->large_draw = prm->test_large_angle_draw;
   P->Clog = prm->Clog;
   P->dt_sec = dt_sec;
   P->angular = a;

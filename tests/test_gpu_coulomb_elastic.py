@@ -282,7 +282,60 @@ def test_coulomb_weighted_drift_relaxation_matches_oracle(pgpu):
     assert abs(d_gpu - d_cpu) / d0 < 0.02
 
 
-def test_coulomb_intra_isotropisation_matches_oracle(pgpu):
+@pytest.mark.parametrize("Clog", [0.0, 6.0])
+@pytest.mark.parametrize("relativistic", [False, True])
+def test_coulomb_large_angle_scattering_matches_oracle_per_pair(pgpu, relativistic, Clog):
+    """scattering.coulomb.include_large_angle_scattering (Coulomb::SetPolarScattering, Coulomb.cpp:1801-1863) with the event's
+    uniform draw made explicit: small draws give Rutherford events (no small-angle part: s12 reported as -1), large ones the
+    cumulative model with the reduced variance.  Galilean and Lorentz pair updates against the oracle."""
+    rng = np.random.default_rng(77)
+    n = 4000
+    v1 = rng.standard_normal((3, n)) * 0.02
+    v2 = rng.standard_normal((3, n)) * 0.02
+    EF = 10.0 ** rng.uniform(-8, -5, n)
+    den12 = 10.0 ** rng.uniform(24, 31, n)      # spans N12 << 0.1 (pure Rutherford) to N12 >> 80
+    bmax = 10.0 ** rng.uniform(-10, -8, n)
+    smax = 10.0 ** rng.uniform(-20, -17, n)
+    g, up, uph = rng.standard_normal(n), rng.random(n), rng.random(n)
+    m1, m2 = 1.0, 1836.15
+    events = 0
+    try:
+        for RL in (1.0e-4, 0.02, 0.08, 0.6):
+            orc.coulomb_set_large_angle(True, RL)
+            if relativistic:
+                s2 = (rng.random(n) < 0.5).astype(np.int32)
+                o1, o2, s12 = pgpu.coulomb_lorentz_scatter(v1, v2, s2, -1.0, 1.0, m1, m2, Clog, 1, DT_SEC, EF, den12, bmax,
+                                                           smax, g, up, uph, large_angle=RL)
+                for i in range(0, n, 7):
+                    a, b, live, ws = orc.coulomb_lorentz_scatter(v1[:, i], v2[:, i], int(s2[i]), -1.0, 1.0, m1, m2, EF[i], Clog,
+                                                                 1, den12[i], bmax[i], smax[i], DT_SEC, g[i], up[i], uph[i])
+                    assert live
+                    assert (ws < 0) == (s12[i] < 0)
+                    if ws > 0:
+                        assert abs(s12[i] - ws) / ws < 1e-11
+                    scale = np.linalg.norm(v1[:, i]) + np.linalg.norm(v2[:, i])
+                    assert np.max(np.abs(o1[:, i] - a)) / scale < 1e-9 and np.max(np.abs(o2[:, i] - b)) / scale < 1e-9
+                    events += ws < 0
+            else:
+                got, s12 = pgpu.coulomb_delta_u(v1, v2, -1.0, 1.0, m1, m2, Clog, 1, DT_SEC, EF, den12, bmax, smax, g, up, uph,
+                                                large_angle=RL)
+                u = np.linalg.norm(v1 - v2, axis=0)
+                for i in range(0, n, 3):
+                    want, ws = orc.coulomb_delta_u(v1[:, i], v2[:, i], -1.0, 1.0, m1, m2, EF[i], Clog, 1, den12[i], bmax[i],
+                                                   smax[i], DT_SEC, g[i], up[i], uph[i])
+                    assert (ws < 0) == (s12[i] < 0)
+                    if ws > 0:
+                        assert abs(s12[i] - ws) / ws < 1e-11
+                    assert np.max(np.abs(got[:, i] - want)) / u[i] < 1e-9
+                    events += ws < 0
+                assert np.max(np.abs(np.linalg.norm(v1 - v2 + got, axis=0) - u) / u) < 1e-10     # a rotation of u
+    finally:
+        orc.coulomb_set_large_angle(False)
+    assert events > 50           # both branches were exercised
+
+
+@pytest.mark.parametrize("large_angle", [False, True])
+def test_coulomb_intra_isotropisation_matches_oracle(pgpu, large_angle):
     deck = decks.Deck(D=2, ncell=(12, 12), dx=(0.25, 0.25), xmin=(0.0, 0.0), nghost=2)
     sdef = decks.SpeciesDef("electron", 1.0, -1.0, (300.0, 100.0, 100.0), 1.0e30, (20, 20))
     rng = np.random.default_rng(1983)
@@ -300,15 +353,19 @@ def test_coulomb_intra_isotropisation_matches_oracle(pgpu):
     s0 = sp.download()
     a0 = aniso(s0["v"])
     for step in range(nsteps):
-        pgpu.collide_coulomb(sp, sp, Clog, dt_sec, 1983, step, angular=0, count=False)
+        pgpu.collide_coulomb(sp, sp, Clog, dt_sec, 1983, step, angular=0, count=False, large_angle=large_angle)
     a_gpu = aniso(sp.download()["v"])
     dens, offs = sp.moments()[0], sp.cell_offsets()
     sp.destroy(); grid.destroy()
     v = s0["v"].copy()
     orc.lib().orc_rng_seed(1983)
-    for step in range(nsteps):
-        orc.coulomb_intra(offs, v, s0["w"], dens, LDe, 0.25 * 0.25 * deck.volume_scale, sdef.mass, sdef.charge, Clog, 0,
-                          False, 11, dt_sec)
+    orc.coulomb_set_large_angle(large_angle)
+    try:
+        for step in range(nsteps):
+            orc.coulomb_intra(offs, v, s0["w"], dens, LDe, 0.25 * 0.25 * deck.volume_scale, sdef.mass, sdef.charge, Clog, 0,
+                              False, 11, dt_sec)
+    finally:
+        orc.coulomb_set_large_angle(False)
     a_cpu = aniso(v)
     assert a_cpu / a0 < 0.7 and a_gpu / a0 < 0.7
     assert abs(a_gpu - a_cpu) / a0 < 0.02

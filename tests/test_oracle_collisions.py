@@ -56,6 +56,51 @@ def test_coulomb_intra_equal_weights_conserve_and_count(angular):
         assert abs((v[:, a:b] ** 2).sum() - (v0[:, a:b] ** 2).sum()) / (v0[:, a:b] ** 2).sum() < 1e-13
 
 
+def test_coulomb_large_angle_scattering_keeps_the_variance_and_conserves():
+    """include_large_angle_scattering (Coulomb.cpp:1801-1863): single Rutherford events below a cutoff impact parameter, the
+    small-angle s12 reduced "in order to keep total variance equal to s12".  (a) every pair update is a rotation of the
+    relative velocity; (b) the mean of 1 - cos(theta) over the event draw and the polar draw stays within a few per cent of
+    the small-angle model's; (c) the cell driver draws the extra uniform and still conserves momentum and energy."""
+    rng = np.random.default_rng(11)
+    v1, v2 = np.array([0.03, -0.01, 0.02]), np.array([-0.02, 0.015, 0.0])
+    u = np.linalg.norm(v1 - v2)
+    args = dict(EF=1.0e-7, Clog=3.0, den=1.0e30, bmax=1.0e-9, smax=1.0e-15)   # N12 ~ 10: one pair in ten makes an event
+
+    def mean_one_minus_cos(on, ndraw=20000):
+        acc, events = 0.0, 0
+        for _ in range(ndraw):
+            orc.coulomb_set_large_angle(on, rng.random())
+            dU, s12 = orc.coulomb_delta_u(v1, v2, -1.0, 1.0, 1.0, 1.0, args["EF"], args["Clog"], 1, args["den"], args["bmax"],
+                                          args["smax"], 4.0 * DT_SEC, 0.0, rng.random(), rng.random())
+            un = v1 - v2 + dU
+            assert abs(np.linalg.norm(un) - u) / u < 1e-12
+            acc += 1.0 - np.dot(un, v1 - v2) / u ** 2
+            events += s12 < 0
+        return acc / ndraw, events
+    try:
+        m_off, e_off = mean_one_minus_cos(False)
+        m_on, e_on = mean_one_minus_cos(True)
+        assert e_off == 0 and e_on > 100
+        assert abs(m_on - m_off) / m_off < 0.08
+        counts = np.array([0, 1, 2, 5, 11, 12, 13, 40])
+        cs, v = _cells(rng, counts)
+        w = np.full(v.shape[1], 2.0e27)
+        cellV = 1.0e-3
+        v0 = v.copy()
+        orc.coulomb_set_large_angle(True)
+        orc.lib().orc_rng_seed(5)
+        orc.coulomb_intra(cs, v, w, counts * 2.0e27 / cellV, np.full(counts.size, 1.0e-9), cellV, 1.0, -1.0, 0.0, 1, False, 11,
+                          DT_SEC)
+        assert np.abs(v - v0).max() > 0
+        for k, c in enumerate(counts):
+            a, b = cs[k], cs[k + 1]
+            if c >= 2:
+                assert np.max(np.abs(v[:, a:b].sum(axis=1) - v0[:, a:b].sum(axis=1))) < 1e-15 * c
+                assert abs((v[:, a:b] ** 2).sum() - (v0[:, a:b] ** 2).sum()) / (v0[:, a:b] ** 2).sum() < 1e-13
+    finally:
+        orc.coulomb_set_large_angle(False)
+
+
 def test_coulomb_inter_weighted_conserves_on_average():
     """Unequal weights: the lighter-weight particle always scatters, the heavier with probability
     wmin/wmax, so momentum and energy are conserved in expectation (Coulomb.cpp:1149-1172)."""
