@@ -13,6 +13,7 @@ built on -- SURVEY.md 8c -- which the oracle satisfies at small size in test_ora
 import numpy as np
 import pytest
 
+from common import orc
 from picnic_b200 import decks
 
 pytestmark = pytest.mark.gpu
@@ -228,3 +229,77 @@ def test_c3_full_size_mass_matrices_reproduce_the_perturbed_current(pgpu):
     for sp in sps:
         sp.destroy()
     grid.destroy()
+
+
+def test_c2_thermalization_rate_matches_oracle(pgpu):
+    """SURVEY 8(c) invariant 5 on the C2 plasma (n = 1e30 m^-3, T_e = 150 eV, T_i = 50 eV, Clog 3, 64 particles per cell and
+    species): the rate at which Takizuka-Abe e-e + i-i + e-i collisions close the temperature gap, device against the oracle
+    on the SAME particles (128 x 128 cells = 1.05e6 per species; the rate estimator is dominated by the slow electrons of the
+    sample, so both sides must start from the same sample), averaged over three collision seeds each; bar 2 % of the
+    change.  Then the full 256 x 256 deck on the device against that rate, and the order of magnitude against the NRL
+    equilibration rate nu_eq = 1.8e-19 sqrt(m_e m_i) Z^2 n lambda / (m_e T_i + m_i T_e)^1.5 (cgs, eV), which TA approaches
+    from below as nu dt -> 0 (here nu_ei dt ~ 0.03)."""
+    Clog, dtf, nsteps = 3.0, 4.0, 60
+    seeds = (1983, 7, 21)
+
+    def gap_closed(T0, T1):
+        return ((T0[0] - T0[1]) - (T1[0] - T1[1])) / (T0[0] - T0[1])
+
+    def device(ncell, seed):
+        deck = decks.deck_c2(ncell=ncell)
+        lo, hi = (0, 0), (ncell - 1, ncell - 1)
+        grid = pgpu.Grid(2, deck.ncell, deck.xmin, deck.dx, deck.nghost, (1, 1), volume_scale=deck.volume_scale)
+        rng = np.random.default_rng(12)
+        sps = [_upload(pgpu, grid, deck, sdef, lo, hi, rng)[0] for sdef in deck.species]
+        mass = [s.mass for s in deck.species]
+        dt_sec = dtf * deck.dt * deck.units.time
+
+        def temps():
+            return [mk * sp.global_moments()[4:7].sum() / sp.global_moments()[0] for mk, sp in zip(mass, sps)]
+        T0 = temps()
+        for step in range(nsteps):
+            for sp in sps:
+                sp.bin_particles()
+                sp.set_moments()
+            for (a, b) in ((0, 0), (1, 1), (0, 1)):
+                pgpu.collide_ta(sps[a], sps[b], Clog, dt_sec, seed, step, count=False)
+        T1 = temps()
+        for sp in sps:
+            sp.destroy()
+        grid.destroy()
+        return gap_closed(T0, T1), dt_sec
+
+    def oracle(ncell, seed):
+        deck = decks.deck_c2(ncell=ncell)
+        lo, hi = (0, 0), (ncell - 1, ncell - 1)
+        rng = np.random.default_rng(12)
+        ps = [decks.load_species(deck, sdef, lo, hi, rng) for sdef in deck.species]
+        nc = ncell * ncell
+        cs = np.arange(nc + 1, dtype=np.int64) * 64
+        cellV = deck.dx[0] * deck.dx[1] * deck.volume_scale
+        dens = [np.full(nc, p["w"][:64].sum() / cellV) for p in ps]
+        mass = [s.mass for s in deck.species]
+        q = [s.charge for s in deck.species]
+        v = [p["v"].copy() for p in ps]
+        dt_sec = dtf * deck.dt * deck.units.time
+
+        def temps():
+            return [m * (vv ** 2).sum() / vv.shape[1] for m, vv in zip(mass, v)]
+        T0 = temps()
+        orc.lib().orc_rng_seed(seed)
+        for step in range(nsteps):
+            orc.ta_self(cs, v[0], dens[0], mass[0], q[0], Clog, dt_sec)
+            orc.ta_self(cs, v[1], dens[1], mass[1], q[1], Clog, dt_sec)
+            orc.ta_inter(cs, v[0], dens[0], mass[0], q[0], cs, v[1], dens[1], mass[1], q[1], Clog, dt_sec)
+        return gap_closed(T0, temps())
+
+    g = [device(128, s)[0] for s in seeds]
+    c = [oracle(128, s) for s in seeds]
+    assert min(g + c) > 0                                        # the gap closes in every run
+    assert abs(np.mean(g) / np.mean(c) - 1.0) < 0.02, (g, c)
+    full, dt_sec = device(256, seeds[0])
+    assert abs(full / np.mean(c) - 1.0) < 0.04, (full, c)      # another sample of initial velocities: twice the bar
+    me, mi = 9.1093837e-28, 1.67262192e-24
+    nu_eq = 1.8e-19 * np.sqrt(me * mi) * 1.0e24 * Clog / (me * 50.0 + mi * 150.0) ** 1.5
+    nrl = 2.0 * nu_eq * nsteps * dt_sec
+    assert 0.6 < np.mean(g) / nrl < 1.1, (np.mean(g), nrl)
