@@ -849,6 +849,26 @@ def variants_leg(args, rank, local, stream, region, capi):
     return out
 
 
+def bind_to_gpu_cpus(device):
+    """Pin this rank (and the pinned host buffers it first-touches afterwards) to the CPUs NVML reports as local to its GPU:
+    with eight ranks on one host the field uploads / J downloads of the e2e arm otherwise cross the socket interconnect."""
+    if os.environ.get("PGPU_BENCH_NO_AFFINITY"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[device]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else device
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        bind_to_gpu_cpus.original = os.sched_getaffinity(0)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        return {"cpus_before": before, "cpus_bound": len(after), "first": after[0], "last": after[-1]}
+    except Exception as e:      # no NVML, container without the sysfs topology, ...: run unbound
+        return {"error": repr(e)[:120]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -861,6 +881,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_cpus(local)
     if world > 1:
         # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -991,7 +1012,7 @@ def run_ours(args):
             "config": {"workload": workload_name(args, world),
                        "particles_per_gpu": eng.n_particles, "particles_total": n_total,
                        "boxes": "%dx%d" % eng.layout, "boxes_per_gpu": args.boxes_per_gpu, "dt": args.dt,
-                       "n_outer": args.n_outer, "sort_every": args.sort_every,
+                       "n_outer": args.n_outer, "sort_every": args.sort_every, "cpu_affinity_rank0": numa,
                        "exchange": (None if world == 1 else
                                     {"ghost_J": "peer-memory kernels over NVLink (CUDA IPC inboxes)" if args.halo == "peer"
                                                 else "pack + NCCL send/recv + unpack-add",
@@ -1128,6 +1149,9 @@ def cpu_layout_sample(args, n_sample=400000):
 
 
 def cpu_baseline(args, steps=2):
+    orig = getattr(bind_to_gpu_cpus, "original", None)
+    if orig:                      # the CPU arm runs on every core the process started with
+        os.sched_setaffinity(0, orig)
     res, _ = cpu_arm(args, steps=steps, warmup=1, seconds=15.0)
     try:
         res["layout"] = cpu_layout_sample(args)

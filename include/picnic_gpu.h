@@ -157,6 +157,15 @@ int pgpu_species_upload(pgpu_species_t s, long n, const double *x, const double 
 int pgpu_species_download(pgpu_species_t s, double *x, double *xold, double *v,
                           double *vold, double *w, uint64_t *id);
 long pgpu_species_count(pgpu_species_t s);            /* numParticles() */
+/* The same through the particle object's own linear record, for hosts that keep a List<JustinsParticle> (partData()
+ * users: I/O, Piston, out-of-scope scattering models): JustinsParticle::linearOut / linearIn
+ * (src/particle_tools/JustinsParticle.cpp:339-378, 410-450), per particle
+ *   [ w | x[D] | x_old[D] | pos_virt[2] | v[3] | v_old[3] | (Real) ID ],  pgpu_particle_linear_size() = (2 D + 10) * 8 bytes
+ * (JustinsParticle::size()); pos_virt is written as zero and ignored on input (planar push).  `records` holds
+ * pgpu_species_count() resp. n records back to back, i.e. what ListBox::linearOut / linearIn move for a box. */
+long pgpu_particle_linear_size(pgpu_species_t s);
+int pgpu_species_download_linear(pgpu_species_t s, void *records);
+int pgpu_species_upload_linear(pgpu_species_t s, long n, const void *records);
 
 /* push: same-named PicChargedSpecies methods */
 int pgpu_advance_positions_explicit(pgpu_species_t s, double full_dt, int half_step); /* :463-504 */

@@ -151,6 +151,8 @@ def load():
         "pgpu_mass_matrix_get": [vp, i32, vp, vp, vp, i32], "pgpu_mass_matrix_J0_get": [vp, i32, vp, vp, vp],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
         "pgpu_species_deferred_count": [vp, vp],
+        "pgpu_particle_linear_size": [vp], "pgpu_species_download_linear": [vp, vp],
+        "pgpu_species_upload_linear": [vp, lng, vp],
         "pgpu_launch_count": [], "pgpu_picard_totals": [vp, vp, vp, i32], "pgpu_abi_version": [], "pgpu_last_error": [],
     }
     for name, args in sig.items():
@@ -413,6 +415,19 @@ class Species:
             check(load().pgpu_species_suborbit_download(self.h, _p(out["x"]), _p(out["xold"]), _p(out["v"]), _p(out["vold"]),
                                                         _p(out["w"]), _p(out["id"]), _p(out["nsub"])))
         return out
+
+    def download_linear(self):
+        """[n, 2 D + 10] array of JustinsParticle::linearOut records"""
+        lib = load()
+        lib.pgpu_particle_linear_size.restype = C.c_long
+        nw = lib.pgpu_particle_linear_size(self.h) // 8
+        rec = np.zeros((self.n, nw))
+        check(lib.pgpu_species_download_linear(self.h, _p(rec)))
+        return rec
+
+    def upload_linear(self, rec):
+        rec = np.ascontiguousarray(rec, dtype=np.float64)
+        check(load().pgpu_species_upload_linear(self.h, rec.shape[0], _p(rec)))
 
     def deferred_count(self):
         n = C.c_long(0)

@@ -869,6 +869,79 @@ int pgpu_species_download(pgpu_species_t s, double *x, double *xold, double *v, 
   return 0;
 }
 
+// ---- List<JustinsParticle> adapter: the particle object's own linear record ---------------------------------------------
+// JustinsParticle::linearOut / linearIn (src/particle_tools/JustinsParticle.cpp:339-378, 410-450) for CH_SPACEDIM = D < 3:
+//   [ w | x[D] | x_old[D] | pos_virt[2] | v[3] | v_old[3] | (Real) ID ]   = 2 D + 10 doubles per particle
+// (pos_virt: out-of-plane coordinates of the curvilinear pushes; zero in the planar path this library covers).  The
+// transpose runs on the device, the record array crosses the bus in one copy.
+static __global__ void k_linear_out(PartPtrs p, const uint64_t *id, long n, int D, double *rec) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *r = rec + (size_t)i * (2 * D + 10);
+  *r++ = p.w[i];
+  for (int d = 0; d < D; ++d) *r++ = p.x[d][i];
+  for (int d = 0; d < D; ++d) *r++ = p.xold[d][i];
+  *r++ = 0.0;
+  *r++ = 0.0;
+  for (int c = 0; c < 3; ++c) *r++ = p.v[c][i];
+  for (int c = 0; c < 3; ++c) *r++ = p.vold[c][i];
+  *r = (double)id[i];
+}
+static __global__ void k_linear_in(PartPtrs p, uint64_t *id, long n, int D, const double *rec) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *r = rec + (size_t)i * (2 * D + 10);
+  p.w[i] = *r++;
+  for (int d = 0; d < D; ++d) p.x[d][i] = *r++;
+  for (int d = 0; d < D; ++d) p.xold[d][i] = *r++;
+  r += 2;
+  for (int c = 0; c < 3; ++c) p.v[c][i] = *r++;
+  for (int c = 0; c < 3; ++c) p.vold[c][i] = *r++;
+  id[i] = (uint64_t)*r;
+}
+
+long pgpu_particle_linear_size(pgpu_species_t s) {
+  return s ? (long)((2 * s->grid->desc.D + 10) * sizeof(double)) : -1;
+}
+
+int pgpu_species_download_linear(pgpu_species_t s, void *records) {
+  NEED_INIT();
+  if (!s || (s->n > 0 && !records)) return PGPU_ERR_ARG;
+  if (s->n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  const int D = s->grid->desc.D;
+  const size_t bytes = (size_t)s->n * (2 * D + 10) * sizeof(double);
+  double *d = nullptr;
+  PGPU_CUDA(cudaMalloc(&d, bytes));
+  cudaStream_t st = ctx().stream;
+  k_linear_out<<<nb(s->n), 256, 0, st>>>(s->ptrs(), s->id, s->n, D, d);
+  PGPU_CUDA(cudaMemcpyAsync(records, d, bytes, cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d);
+  return 0;
+}
+
+int pgpu_species_upload_linear(pgpu_species_t s, long n, const void *records) {
+  NEED_INIT();
+  if (!s || n < 0 || (n > 0 && !records)) return PGPU_ERR_ARG;
+  if (ensure_capacity(s, n)) return PGPU_ERR_CUDA;
+  const int D = s->grid->desc.D;
+  s->n = n;
+  s->binned = false;
+  s->pos_old_pending = s->vel_old_pending = false;
+  s->xold_alias = s->vold_alias = false;
+  if (n == 0) return 0;
+  const size_t bytes = (size_t)n * (2 * D + 10) * sizeof(double);
+  double *d = nullptr;
+  PGPU_CUDA(cudaMalloc(&d, bytes));
+  cudaStream_t st = ctx().stream;
+  PGPU_CUDA(cudaMemcpyAsync(d, records, bytes, cudaMemcpyHostToDevice, st));
+  k_linear_in<<<nb(n), 256, 0, st>>>(s->ptrs(), s->id, n, D, d);
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d);
+  return 0;
+}
+
 int pgpu_species_download_fields(pgpu_species_t s, double *Ep, double *Bp) {
   NEED_INIT();
   if (!s || !s->Ep[0]) {

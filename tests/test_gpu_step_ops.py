@@ -148,3 +148,43 @@ def test_update_old_without_copy(pgpu, user):
             ref = J0[c].a * (-1.0)               # charge / volume_scale
             assert np.max(np.abs(J[c] - ref)) <= 1e-11 * np.max(np.abs(ref))
     sp.destroy(); grid.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D", [1, 2])
+def test_linear_record_adapter_matches_reference_wire_format(pgpu, D):
+    """pgpu_species_download_linear / upload_linear speak JustinsParticle::linearOut / linearIn: the field order is the
+    one pinned on the reference's own compiled JustinsParticle.cpp (tests/golden/ref_pins.npz: out_wire, 2D), and the
+    round trip through the records is the identity."""
+    import os
+    rng = np.random.default_rng(5)
+    ncell = (16,) * D
+    grid = pgpu.Grid(D, ncell, (0.0,) * D, (0.25,) * D, 2, (1,) * D)
+    sp = pgpu.Species(grid, 1.0, -1.0, 1.0, 1.0)
+    n = 1000
+    x = rng.random((D, n)) * 4.0
+    xold = rng.random((D, n)) * 4.0
+    v, vold, w = rng.standard_normal((3, n)), rng.standard_normal((3, n)), rng.random(n) + 0.5
+    ids = rng.integers(1, 2 ** 40, n).astype(np.uint64)
+    if D == 2:
+        gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pins.npz"))["out_wire"]
+        # the particle the reference vector was made from (make_ref_golden.py)
+        w[0], x[:, 0], xold[:, 0] = gold[0], gold[1:3], gold[3:5]
+        v[:, 0], vold[:, 0], ids[0] = gold[7:10], gold[10:13], np.uint64(gold[13])
+    sp.upload(x, v, w, xold=xold, vold=vold, ids=ids)
+    rec = sp.download_linear()
+    assert rec.shape == (n, 2 * D + 10)
+    want = np.concatenate([w[None], x, xold, np.zeros((2, n)), v, vold, ids.astype(np.float64)[None]]).T
+    assert np.array_equal(rec, want)
+    if D == 2:
+        assert np.array_equal(rec[0], gold)                      # bit for bit the reference's record
+    sp2 = pgpu.Species(grid, 1.0, -1.0, 1.0, 1.0)
+    sp2.upload_linear(rec[::-1])
+    got = sp2.download()
+    assert sp2.n == n
+    for k, a in (("x", x), ("xold", xold), ("v", v), ("vold", vold)):
+        assert np.array_equal(got[k], a[:, ::-1]), k
+    assert np.array_equal(got["w"], w[::-1]) and np.array_equal(got["id"], ids[::-1])
+    sp2.upload_linear(np.zeros((0, 2 * D + 10)))
+    assert sp2.n == 0
+    sp.destroy(); sp2.destroy(); grid.destroy()
