@@ -261,6 +261,32 @@ int pgpu_remove_outflow_particles(pgpu_species_t s);
 int pgpu_species_append(pgpu_species_t s, long n, const double *x, const double *xold, const double *v, const double *vold,
                         const double *w, const uint64_t *id);
 
+/* Inflow lists with pic_species.N.suborbit_inflow_J = true (the implicit shock decks): the particles the host's
+ * createInflowParticles made for boundary (bdry_dir, bdry_side) -- positions OUTSIDE the domain, moving in -- are not
+ * injected at once (PicChargedSpecies::injectInflowParticles returns, PicChargedSpecies.cpp:1787) but wait in the
+ * boundary's inflow list (PicChargedSpeciesBC::m_inflow_list_vector): pgpu_species_inflow_append (x_old = x, u_old = u,
+ * one sub-orbit).  Every nonlinear evaluation then calls pgpu_advance_inflow_particles_and_set_J =
+ * PicChargedSpecies::advanceInflowParticlesAndSetJ (:3255-3322): free streaming to the boundary plane
+ * (advanceInflowPartToBdry, :958-995), the rest of the step as sub-orbits (advanceSubOrbitParticlesAndSetJ with
+ * is_inflow_list, :3376-3669), current into the species' inflow J (x charge / volume_scale), which
+ * pgpu_current_add_inflow adds to the total (PicSpeciesInterface::addInflowJ, PicSpeciesInterface.cpp:1499-1536).  The
+ * particles stay in the list, time-centred against their original old state; pgpu_apply_bcs with
+ * PGPU_BC_INFLOW_OUTFLOW on that side then does PicChargedSpeciesBC::inflow_Lo / inflow_Hi
+ * (PicChargedSpeciesBC.cpp:961-1001, 1047-1086): 2 x - x_old inside the boundary joins the species, anything else (a
+ * particle the fields turned around) is dropped, and the m_delta_*In probes accumulate (pgpu_species_inflow_fluxes:
+ * [2 dir + side][w, w ux, w uy, w uz, w |u|^2 / (gamma + 1)] of u_old; reading resets). */
+int pgpu_species_inflow_append(pgpu_species_t s, long n, const double *x, const double *v, const double *w,
+                               const uint64_t *id, int bdry_dir, int bdry_side);
+long pgpu_species_inflow_count(pgpu_species_t s);
+/* nsub_boundary[i] = 8 * numSubOrbits + (2 dir + side) */
+int pgpu_species_inflow_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
+                                 uint64_t *id, int *nsub_boundary);
+int pgpu_species_inflow_clear(pgpu_species_t s);
+int pgpu_advance_inflow_particles_and_set_J(pgpu_species_t s, double dt, int from_emjacobian);
+int pgpu_species_inflow_current_get(pgpu_species_t s, int comp, double *data, const int *lo, const int *hi);
+int pgpu_current_add_inflow(pgpu_grid_t g, pgpu_species_t s);
+int pgpu_species_inflow_fluxes(pgpu_species_t s, double *flux20);
+
 /* deposit */
 int pgpu_set_current_density(pgpu_species_t s, double dt, int from_explicit_solver); /* :3184-3253 */
 int pgpu_species_current_get(pgpu_species_t s, int comp, double *data, const int *lo, const int *hi);

@@ -256,6 +256,20 @@ def advance_suborbit_and_set_J(g, interpE, interpJ, x, xold, v, vold, w, nsub, E
     return rc
 
 
+def advance_inflow_and_set_J(g, interpE, interpJ, x, xold, v, vold, w, nsub, E, B, fnorm, cnormDt, rtol, iter_max, J,
+                             bdry_dir, bdry_side, from_emjacobian=False, max_suborbits=512):
+    """advanceInflowParticlesAndSetJ for the inflow list of boundary (bdry_dir, bdry_side); in place like the above."""
+    f = lib().orc_advance_inflow_particles_and_set_J
+    f.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_long] + [C.c_void_p] * 8 + [C.c_double] * 3 + [C.c_int] * 3
+                  + [C.c_void_p, C.c_int, C.c_int])
+    nsub_c = np.ascontiguousarray(nsub, dtype=np.int32)
+    rc = f(C.byref(g), interpE, interpJ, x.shape[1], _ptr(x), _ptr(xold), _ptr(v), _ptr(vold), _ptr(w), _ptr(nsub_c),
+           _fabs3(E), _fabs3(B), fnorm, cnormDt, rtol, iter_max, int(from_emjacobian), max_suborbits, _fabs3(J),
+           bdry_dir, bdry_side)
+    nsub[...] = nsub_c
+    return rc
+
+
 def fast_particles(g, x, xold):
     flag = np.zeros(x.shape[1], dtype=np.int32)
     f = lib().orc_fast_particles

@@ -297,12 +297,12 @@ extern "C" int orc_advance_particles_iteratively(
  * doubled and the unconverged state is deposited as it is).  J (three arrays, zeroed by the caller) receives the sum
  * over particles of (sum over sub-orbits of the deposit)/nsub, un-scaled (the caller multiplies by charge/volume_scale).
  * Returns 0, -1 on a gather/deposit failure, -2 if a particle needed more than max_suborbits. */
-extern "C" int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int interpE, int interpJ, long n, double *x,
-                                                        double *xold, double *v, double *vold, const double *w, int *nsub,
-                                                        const orc_fab *E, const orc_fab *B, double fnorm, double cnormDt,
-                                                        double rtol, int iter_max_in, int from_emjacobian,
-                                                        int max_suborbits, orc_fab *J) {
+static int suborbit_core(const orc_geom *g, int interpE, int interpJ, long n, double *x, double *xold, double *v,
+                         double *vold, const double *w, int *nsub, const orc_fab *E, const orc_fab *B, double fnorm,
+                         double cnormDt, double rtol, int iter_max_in, int from_emjacobian, int max_suborbits, orc_fab *J,
+                         int bdry_dir, int bdry_side) {
   const int D = g->D;
+  const bool is_inflow_list = (bdry_dir >= 0 && bdry_side >= 0);   /* :3401-3402 */
   int rc = 0;
   int iter_max = iter_max_in;
   if (from_emjacobian) iter_max += iter_max;   /* :3400 */
@@ -320,13 +320,25 @@ extern "C" int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int i
     int num_suborbits = nsub[p];
     double cnormDt_sub = cnormDt / num_suborbits;
     for (int c = 0; c < 3; ++c) std::fill(Jp[c].begin(), Jp[c].end(), 0.0);
-    double xpold0_save[2], vpold0[3];
-    for (int d = 0; d < D; ++d) xpold0_save[d] = xold[d * n + p];
+    double xpold0_save[2], xpold0[2] = {0.0, 0.0}, vpold0[3];
+    for (int d = 0; d < D; ++d) xpold0[d] = xpold0_save[d] = xold[d * n + p];
     for (int c = 0; c < 3; ++c) vpold0[c] = vold[c * n + p];
+    if (is_inflow_list) {
+      /* advanceInflowPartToBdry (:958-995): free streaming from where createInflowParticles put the particle (outside
+       * the domain) to the boundary plane; the rest of the step is what the sub-orbits share (:3437-3442) */
+      const double X0 = bdry_side == 0 ? g->le[bdry_dir] : g->re[bdry_dir];
+      const double cnormDt0 = (X0 - xpold0[bdry_dir]) / (vpold0[bdry_dir] / 1.0);
+      for (int d = 0; d < D; ++d) {
+        if (d == bdry_dir) xpold0[d] = X0;
+        else xpold0[d] = xpold0[d] + vpold0[d] / 1.0 * cnormDt0;
+      }
+      cnormDt_sub = cnormDt - cnormDt0;
+      cnormDt_sub /= num_suborbits;
+    }
     double xp[2] = {0.0, 0.0}, xo[2] = {0.0, 0.0}, vp[3], vo[3];
-    for (int d = 0; d < D; ++d) xp[d] = xo[d] = xpold0_save[d];   /* x_bar guess = x_old (:3443) */
+    for (int d = 0; d < D; ++d) xp[d] = xo[d] = xpold0[d];   /* x_bar guess = x_old (:3443) */
     for (int c = 0; c < 3; ++c) vp[c] = vo[c] = vpold0[c];
-    bool failed = false;
+    bool failed = false, reflected = false;
     for (int nv = 0; nv < num_suborbits; nv++) {
       int iter = 0;
       bool restart = false;
@@ -345,6 +357,15 @@ extern "C" int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int i
         }
         if (rel_diff_max < rtol) break;
         for (int d = 0; d < D; ++d) xp[d] = xo[d] + dxp[d];
+        if (is_inflow_list) {
+          /* a particle the fields turn around before it is inside (:3486-3509): it ends the call at rest normal to the
+           * boundary, where it started, as a one-sub-orbit particle that deposited nothing */
+          const double xpnew0 = xo[bdry_dir] + vp[bdry_dir] * cnormDt_sub;
+          if ((bdry_side == 0 && xpnew0 < g->le[bdry_dir]) || (bdry_side == 1 && xpnew0 > g->re[bdry_dir])) {
+            reflected = true;
+            break;
+          }
+        }
         iter += 1;
         if (iter >= iter_max) {
           if (!from_emjacobian) {   /* :3521-3541: one more sub-orbit, start again */
@@ -353,8 +374,10 @@ extern "C" int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int i
               failed = true;
               break;
             }
-            for (int d = 0; d < D; ++d) xp[d] = xo[d] = xpold0_save[d];
+            for (int d = 0; d < D; ++d) xp[d] = xo[d] = xpold0[d];
             for (int c = 0; c < 3; ++c) vp[c] = vo[c] = vpold0[c];
+            /* :3532-3534: the inflow branch's own value (the remaining time split once more) is overwritten by the
+             * bulk formula on the next line of the reference; restated as it stands */
             cnormDt_sub = cnormDt / num_suborbits;
             for (int c = 0; c < 3; ++c) std::fill(Jp[c].begin(), Jp[c].end(), 0.0);
             restart = true;
@@ -362,7 +385,7 @@ extern "C" int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int i
           break;   /* from_emjacobian: deposit the unconverged state (:3543-3548) */
         }
       }
-      if (failed) break;
+      if (failed || reflected) break;
       if (restart) {
         nv = -1;
         continue;
@@ -383,20 +406,58 @@ extern "C" int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int i
       rc = -2;
       continue;
     }
+    if (reflected) {
+      nsub[p] = 1;
+      for (int d = 0; d < D; ++d) x[d * n + p] = xold[d * n + p] = xpold0_save[d];
+      for (int c = 0; c < 3; ++c) v[c * n + p] = vold[c * n + p] = vpold0[c];
+      v[bdry_dir * n + p] = 0.0;
+      continue;   /* this_Jp zeroed: nothing is added */
+    }
     nsub[p] = num_suborbits;
     for (int d = 0; d < D; ++d) {
-      x[d * n + p] = xp[d];
+      /* inflow particles are handed back time-centred against their ORIGINAL old state (:3608-3617) */
+      x[d * n + p] = is_inflow_list ? (xp[d] + xpold0_save[d]) / 2.0 : xp[d];
       xold[d * n + p] = xpold0_save[d];
     }
     for (int c = 0; c < 3; ++c) {
-      v[c * n + p] = vp[c];
+      v[c * n + p] = is_inflow_list ? (vp[c] + vpold0[c]) / 2.0 : vp[c];
       vold[c * n + p] = vpold0[c];
     }
-    /* divide the particle's J by its number of sub-orbits and add it to the total (:3647-3654) */
+    /* divide the particle's J by its number of sub-orbits (inflow: scale by the sub-step over the step) and add it to
+     * the total (:3647-3654) */
     for (int c = 0; c < 3; ++c)
-      for (size_t k = 0; k < Jp[c].size(); ++k) J[c].p[k] += Jp[c][k] / num_suborbits;
+      for (size_t k = 0; k < Jp[c].size(); ++k) {
+        if (is_inflow_list) J[c].p[k] += Jp[c][k] * (cnormDt_sub / cnormDt);
+        else J[c].p[k] += Jp[c][k] / num_suborbits;
+      }
   }
   return rc;
+}
+
+extern "C" int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int interpE, int interpJ, long n, double *x,
+                                                        double *xold, double *v, double *vold, const double *w, int *nsub,
+                                                        const orc_fab *E, const orc_fab *B, double fnorm, double cnormDt,
+                                                        double rtol, int iter_max_in, int from_emjacobian,
+                                                        int max_suborbits, orc_fab *J) {
+  return suborbit_core(g, interpE, interpJ, n, x, xold, v, vold, w, nsub, E, B, fnorm, cnormDt, rtol, iter_max_in,
+                       from_emjacobian, max_suborbits, J, -1, -1);
+}
+
+/* PicChargedSpecies::advanceInflowParticlesAndSetJ (PicChargedSpecies.cpp:3255-3322; pic_species.N.suborbit_inflow_J): the
+ * particles createInflowParticles left in the inflow list of boundary (bdry_dir, bdry_side) -- x_old outside the domain,
+ * moving in -- stream freely to the boundary plane and take the REST of the step as nsub[p] sub-orbits of the same kind
+ * as above (advanceSubOrbitParticlesAndSetJ with is_inflow_list, :3376-3669).  On return x, v are time-centred against
+ * the original x_old, u_old (which are kept), so that PicChargedSpeciesBC::inflow_Lo/Hi (2 x - x_old, :965-972) finds the
+ * new-time state; a particle turned around before it is inside comes back with x = x_old, zero normal velocity and no
+ * current.  J receives sum over sub-orbits of the deposit times cnormDt_sub / cnormDt, un-scaled. */
+extern "C" int orc_advance_inflow_particles_and_set_J(const orc_geom *g, int interpE, int interpJ, long n, double *x,
+                                                      double *xold, double *v, double *vold, const double *w, int *nsub,
+                                                      const orc_fab *E, const orc_fab *B, double fnorm, double cnormDt,
+                                                      double rtol, int iter_max_in, int from_emjacobian, int max_suborbits,
+                                                      orc_fab *J, int bdry_dir, int bdry_side) {
+  if (bdry_dir < 0 || bdry_dir >= g->D || bdry_side < 0 || bdry_side > 1) return -3;
+  return suborbit_core(g, interpE, interpJ, n, x, xold, v, vold, w, nsub, E, B, fnorm, cnormDt, rtol, iter_max_in,
+                       from_emjacobian, max_suborbits, J, bdry_dir, bdry_side);
 }
 
 /* PicChargedSpecies::transferFastParticles (PicChargedSpecies.cpp:894-956): flag[p] = 1 if the orbit x_old -> 2 x_bar -

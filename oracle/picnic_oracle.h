@@ -285,6 +285,11 @@ int orc_advance_suborbit_particles_and_set_J(const orc_geom *g, int interpE, int
                                              double *v, double *vold, const double *w, int *nsub, const orc_fab *E,
                                              const orc_fab *B, double fnorm, double cnormDt, double rtol, int iter_max,
                                              int from_emjacobian, int max_suborbits, orc_fab *J);
+/* advanceInflowParticlesAndSetJ (PicChargedSpecies.cpp:3255-3322): the same loop for the inflow list of one boundary */
+int orc_advance_inflow_particles_and_set_J(const orc_geom *g, int interpE, int interpJ, long n, double *x, double *xold,
+                                           double *v, double *vold, const double *w, int *nsub, const orc_fab *E,
+                                           const orc_fab *B, double fnorm, double cnormDt, double rtol, int iter_max,
+                                           int from_emjacobian, int max_suborbits, orc_fab *J, int bdry_dir, int bdry_side);
 void orc_fast_particles(const orc_geom *g, long n, const double *x, const double *xold, int *flag);
 /* ScatteringUtils::modEnergyPairwise (ScatteringUtils.H:113-205), pinned on the reference (tests/test_ref_pin.py);
  * scattering.coulomb.enforce_conservations for orc_coulomb_intra / orc_coulomb_inter (Coulomb.cpp:486-512, 596-714,

@@ -44,6 +44,10 @@ class SpeciesDesc(C.Structure):
                 ("motion", C.c_int), ("forces", C.c_int), ("relativistic", C.c_int), ("higuera_cary", C.c_int)]
 
 
+# particle boundary conditions of pgpu_apply_bcs (PGPU_BC_*)
+BC_NONE, BC_PERIODIC, BC_SYMMETRY, BC_OUTFLOW, BC_INFLOW_OUTFLOW = 0, 1, 2, 3, 4
+
+
 class CoulombParams(C.Structure):
     _fields_ = [("Clog", C.c_double), ("angular_scattering", C.c_int), ("NxN", C.c_int), ("NxN_Nthresh", C.c_int),
                 ("num_subcycles", C.c_int), ("enforce_conservations", C.c_int), ("energy_fraction", C.c_double),
@@ -111,6 +115,11 @@ def load():
         "pgpu_explicit_step": [vp, C.c_double, vp, vp, C.c_int],
         "pgpu_species_outflow_download": [vp] * 8, "pgpu_species_outflow_fluxes": [vp, vp],
         "pgpu_remove_outflow_particles": [vp], "pgpu_species_append": [vp, C.c_long] + [vp] * 6,
+        "pgpu_species_inflow_append": [vp, C.c_long] + [vp] * 4 + [i32, i32], "pgpu_species_inflow_count": [vp],
+        "pgpu_species_inflow_download": [vp] * 8, "pgpu_species_inflow_clear": [vp],
+        "pgpu_advance_inflow_particles_and_set_J": [vp, dbl, i32],
+        "pgpu_species_inflow_current_get": [vp, i32, vp, vp, vp], "pgpu_current_add_inflow": [vp, vp],
+        "pgpu_species_inflow_fluxes": [vp, vp],
         "pgpu_species_set_suborbit_model": [vp, C.c_int, C.c_int], "pgpu_transfer_fast_particles": [vp],
         "pgpu_advance_suborbit_particles_and_set_J": [vp, C.c_double, C.c_int],
         "pgpu_species_suborbit_current_get": [vp, C.c_int, vp, vp, vp], "pgpu_current_add_suborbit": [vp, vp],
@@ -248,6 +257,9 @@ class Grid:
     def current_add(self, sp):
         check(load().pgpu_current_add_species(self.h, sp.h))
 
+    def current_add_inflow(self, sp):
+        check(load().pgpu_current_add_inflow(self.h, sp.h))
+
     def current_finalize(self):
         check(load().pgpu_current_finalize(self.h))
 
@@ -380,6 +392,43 @@ class Species:
         x, v, w, xold, vold = c(x), c(v), c(w), c(xold), c(vold)
         ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
         check(load().pgpu_species_append(self.h, w.size, _p(x), _p(xold), _p(v), _p(vold), _p(w), _p(ids)))
+
+    # ---- inflow lists (suborbit_inflow_J) -------------------------------------------------------------
+    def inflow_append(self, x, v, w, bdry_dir, bdry_side, ids=None):
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        x, v, w = c(x), c(v), c(w)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+        check(load().pgpu_species_inflow_append(self.h, w.size, _p(x), _p(v), _p(w), _p(ids), bdry_dir, bdry_side))
+
+    @property
+    def n_inflow(self):
+        f = load().pgpu_species_inflow_count
+        f.restype = C.c_long
+        return f(self.h)
+
+    def inflow_download(self):
+        n = self.n_inflow
+        out = {"x": np.zeros((self.D, n)), "xold": np.zeros((self.D, n)), "v": np.zeros((3, n)), "vold": np.zeros((3, n)),
+               "w": np.zeros(n), "id": np.zeros(n, dtype=np.uint64), "code": np.zeros(n, dtype=np.int32)}
+        if n:
+            check(load().pgpu_species_inflow_download(self.h, _p(out["x"]), _p(out["xold"]), _p(out["v"]), _p(out["vold"]),
+                                                      _p(out["w"]), _p(out["id"]), _p(out["code"])))
+        out["nsub"], out["boundary"] = out["code"] >> 3, out["code"] & 7
+        return out
+
+    def advance_inflow_and_set_J(self, dt, from_emjacobian=False):
+        check(load().pgpu_advance_inflow_particles_and_set_J(self.h, dt, int(from_emjacobian)))
+
+    def inflow_current_get(self, comp):
+        lo, hi = self.grid.field_bounds(comp)
+        out = np.zeros(tuple(h - l + 1 for l, h in zip(lo, hi)), order="F")
+        check(load().pgpu_species_inflow_current_get(self.h, comp, _p(out), _i2(lo), _i2(hi)))
+        return out
+
+    def inflow_fluxes(self):
+        out = np.zeros(20)
+        check(load().pgpu_species_inflow_fluxes(self.h, _p(out)))
+        return out.reshape(4, 5)
 
     # ---- sub-orbit model --------------------------------------------------------------------------
     def set_suborbit_model(self, use=True, fast_particles=False):

@@ -786,6 +786,11 @@ int pgpu_species_destroy(pgpu_species_t s) {
   cudaFree(s->out_id);
   cudaFree(s->out_tag);
   cudaFree(s->out_listtag);
+  for (int k = 0; k < 10; ++k) cudaFree(s->inf[k]);
+  cudaFree(s->inf_w);
+  cudaFree(s->inf_id);
+  cudaFree(s->inf_code);
+  for (int c = 0; c < 3; ++c) cudaFree(s->Jinf[c].p);
   for (int k = 0; k < 10; ++k) cudaFree(s->sub[k]);
   cudaFree(s->sub_w);
   cudaFree(s->sub_id);

@@ -747,21 +747,24 @@ int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi) {
   if (!s->desc.motion) return 0;
   const pgpu_grid_s *g = s->grid;
   const long n = s->n;
-  if (n == 0) return 0;
+  if (n == 0 && s->n_inf == 0) return 0;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   cudaStream_t st = ctx().stream;
   // the order of PicChargedSpeciesBC::apply (:161-239): symmetry, then outflow / inflow_outflow, then periodic
   for (int d = 0; d < g->desc.D; ++d) {
     const double left = g->geo.le[d], right = g->geo.re[d];
     const int do_lo = bc_lo[d] == PGPU_BC_SYMMETRY, do_hi = bc_hi[d] == PGPU_BC_SYMMETRY;
-    if (do_lo || do_hi) {
+    if ((do_lo || do_hi) && n > 0) {
       KTimer t("bc_symmetry");
       k_bc_symmetry<<<nb(n), 256, 0, st>>>(s->x[d], s->xold[d], s->v[d], s->vold[d], n, left, right, do_lo, do_hi);
     }
   }
   s->binned = false;
   // the leavers of outflow boundaries move to the outflow lists (:187-224)
-  int rc = transfer_outflow(s, bc_lo, bc_hi);
+  int rc = s->n > 0 ? transfer_outflow(s, bc_lo, bc_hi) : 0;
+  if (rc) return rc;
+  // the inflow lists of inflow_outflow boundaries join the species (inflow_Lo / inflow_Hi, :199-224)
+  rc = inject_inflow(s, bc_lo, bc_hi);
   if (rc) return rc;
   if (s->n == 0) return 0;
   for (int d = 0; d < g->desc.D; ++d) {
@@ -781,6 +784,10 @@ int pgpu_finish_implicit_step(pgpu_species_t s, const int *bc_lo, const int *bc_
   for (int d = 0; d < g->desc.D; ++d) {
     if (bc_lo[d] == PGPU_BC_SYMMETRY || bc_hi[d] == PGPU_BC_SYMMETRY) fusable = false;
     if ((bc_lo[d] == PGPU_BC_PERIODIC) != (bc_hi[d] == PGPU_BC_PERIODIC)) fusable = false;
+    // outflow / inflow_outflow boundaries move particles between the species and its side lists: the separate calls
+    if (bc_lo[d] == PGPU_BC_OUTFLOW || bc_hi[d] == PGPU_BC_OUTFLOW || bc_lo[d] == PGPU_BC_INFLOW_OUTFLOW ||
+        bc_hi[d] == PGPU_BC_INFLOW_OUTFLOW)
+      fusable = false;
   }
   if (!fusable) {
     int rc = pgpu_advance_velocities_2nd_half(s);

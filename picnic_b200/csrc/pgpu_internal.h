@@ -222,6 +222,15 @@ struct pgpu_species_s {
   size_t out_cap = 0;
   int *out_listtag = nullptr;
   size_t out_listtag_cap = 0;
+  // inflow lists of PicChargedSpeciesBC (m_inflow_list_vector): one container; inf_code = 8 * numSubOrbits + (2 dir + side)
+  double *inf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double *inf_w = nullptr;
+  uint64_t *inf_id = nullptr;
+  int *inf_code = nullptr;
+  long n_inf = 0;
+  size_t inf_cap = 0;
+  pgpu::DeviceFab Jinf[3];          // m_inflowJ / m_inflowJ_virtual
+  double flux_in[20] = {0};         // m_delta_{Mass,MomX,MomY,MomZ,Energy}In per boundary since the last read
   unsigned long next_id = 0;        // ids made up by pgpu_species_append
   int *unconv_list = nullptr;       // particles the last advance left unconverged (suborbit model)
   unsigned *unconv_count = nullptr;
@@ -277,9 +286,11 @@ int launch_gather(pgpu_species_s *s);
 int launch_add_external(pgpu_species_s *s);
 int ensure_unconv_list(pgpu_species_s *s);                               // pgpu_suborbit.cu
 int transfer_listed_to_suborbit(pgpu_species_s *s, unsigned count);      // pgpu_suborbit.cu
+int inject_inflow(pgpu_species_s *s, const int *bc_lo, const int *bc_hi);
 int transfer_outflow(pgpu_species_s *s, const int *bc_lo, const int *bc_hi);   // pgpu_suborbit.cu
 PartPtrs outflow_part_ptrs(pgpu_species_s *s);
-int launch_suborbit(pgpu_species_s *s, const AdvanceParams &prm, int from_jac, const DeviceFab *Jsub, unsigned *nfail);
+int launch_suborbit(pgpu_species_s *s, const AdvanceParams &prm, int from_jac, const DeviceFab *Jsub, unsigned *nfail,
+                    int inflow = 0);
 int launch_explicit_step(pgpu_species_s *s, const AdvanceParams &prm, const int *periodic, bool second_half,
                          bool deferred = false);
 int launch_deposit_current(pgpu_species_s *s, double cnormDt);

@@ -575,16 +575,38 @@ struct SubPtrs {
   double *x[2], *xold[2], *v[3], *vold[3], *w;
   int *nsub;
 };
+// Inflow lists (advanceInflowParticlesAndSetJ, :3255-3322 = the same loop with is_inflow_list): the particle first streams
+// freely from where createInflowParticles put it, outside the domain, to the boundary plane (advanceInflowPartToBdry,
+// :958-995) and takes the REST of the step in sub-orbits; one the fields turn around before it is inside is handed back
+// at rest normal to the boundary (:3486-3509).  bdry < 0: the bulk sub-orbit container.
+struct SubRun {
+  int bdry;          // 2 * dir + side of the inflow boundary, -1 for the bulk container
+  bool restarted;    // in: the sub-orbit count was raised in this call (the reference then uses cnormDt / num, :3534)
+  bool reflected;    // out
+};
 template <int D, int IE, int IJ, bool X, bool DEP>
 __device__ bool suborbit_run(const Geo<D> &g, const FieldSet &F, const CurrentSet &J, const AdvanceParams &prm,
                              int iter_max, bool from_jac, int max_sub, const double (&x0)[D], const double (&u0)[3],
-                             double wp, int &nsub, double (&xp)[D], double (&vp)[3], unsigned &err, unsigned &apply) {
+                             double wp, int &nsub, double (&xp)[D], double (&vp)[3], unsigned &err, unsigned &apply,
+                             SubRun &R) {
   typedef M<X> m;
-  double xo[D], vo[3];
+  double xo[D], vo[3], xs[D];
   int num = nsub;
   double cdt = __ddiv_rn(prm.cnormDt, (double)num);
+  const bool inflow = R.bdry >= 0;
+  const int bdir = inflow ? (R.bdry >> 1) : 0, bside = R.bdry & 1;
 #pragma unroll
-  for (int d = 0; d < D; ++d) xp[d] = xo[d] = x0[d];
+  for (int d = 0; d < D; ++d) xs[d] = x0[d];
+  if (inflow) {
+    const double X0 = bside == 0 ? g.le[bdir] : g.re[bdir];
+    const double cdt0 = __ddiv_rn(__dsub_rn(X0, x0[bdir]), u0[bdir]);
+#pragma unroll
+    for (int d = 0; d < D; ++d) xs[d] = (d == bdir) ? X0 : __dadd_rn(x0[d], __dmul_rn(u0[d], cdt0));
+    cdt = R.restarted ? __ddiv_rn(prm.cnormDt, (double)num) : __ddiv_rn(__dsub_rn(prm.cnormDt, cdt0), (double)num);
+  }
+  R.reflected = false;
+#pragma unroll
+  for (int d = 0; d < D; ++d) xp[d] = xo[d] = xs[d];
 #pragma unroll
   for (int c = 0; c < 3; ++c) vp[c] = vo[c] = u0[c];
   for (int nv = 0; nv < num; nv++) {
@@ -615,13 +637,20 @@ __device__ bool suborbit_run(const Geo<D> &g, const FieldSet &F, const CurrentSe
       if (rel_max < prm.rtol) break;
 #pragma unroll
       for (int d = 0; d < D; ++d) xp[d] = m::add(xo[d], dxp[d]);
+      if (inflow) {
+        const double xn = __dadd_rn(xo[bdir], __dmul_rn(vp[bdir], cdt));
+        if ((bside == 0 && xn < g.le[bdir]) || (bside == 1 && xn > g.re[bdir])) {
+          R.reflected = true;
+          return true;
+        }
+      }
       iter += 1;
       if (iter >= iter_max) {
         if (!from_jac) {
           num++;
           if (num > max_sub) return false;
 #pragma unroll
-          for (int d = 0; d < D; ++d) xp[d] = xo[d] = x0[d];
+          for (int d = 0; d < D; ++d) xp[d] = xo[d] = xs[d];
 #pragma unroll
           for (int c = 0; c < 3; ++c) vp[c] = vo[c] = u0[c];
           cdt = __ddiv_rn(prm.cnormDt, (double)num);
@@ -632,14 +661,18 @@ __device__ bool suborbit_run(const Geo<D> &g, const FieldSet &F, const CurrentSe
     }
     if (restart) {
       if (DEP) return false;   // the depositing run starts from the converged count: cannot happen
+      R.restarted = true;
       nv = -1;
       continue;
     }
     if (DEP) {
       const double rhop = X ? __ddiv_rn(wp, prm.volume) : wp * prm.rvolume;
       DepositOpGlobal<D, X> dop(J, false);
+      // bulk: the particle's current over its number of sub-orbits; inflow: times cnormDt_sub / cnormDt (:3647-3654)
+      const double scale = inflow ? __ddiv_rn(cdt, prm.cnormDt) : 0.0;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) dop.val[c] = __ddiv_rn(m::mul(vp[c], rhop), (double)num);
+      for (int c = 0; c < 3; ++c)
+        dop.val[c] = inflow ? m::mul(m::mul(vp[c], rhop), scale) : __ddiv_rn(m::mul(vp[c], rhop), (double)num);
       if (!deposit_visit<D, IJ, X>(g, xp, xo, dop)) err |= ERRBIT_SEGMENTS;
       if (dop.oob) err |= ERRBIT_BOUNDS;
     }
@@ -657,10 +690,11 @@ __device__ bool suborbit_run(const Geo<D> &g, const FieldSet &F, const CurrentSe
   nsub = num;
   return true;
 }
+// p.nsub[i]: the particle's number of sub-orbits; for the inflow container 8 * nsub + (2 * dir + side)
 template <int D, int IE, int IJ, bool X>
 __global__ void __launch_bounds__(128)
 k_suborbit(SubPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams prm, int iter_max, int from_jac, int max_sub,
-           Counters *cnt, unsigned *nfail) {
+           Counters *cnt, unsigned *nfail, int inflow) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned err = 0, apply = 0;
   if (i < n) {
@@ -669,76 +703,95 @@ k_suborbit(SubPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams 
     for (int d = 0; d < D; ++d) x0[d] = p.xold[d][i];
 #pragma unroll
     for (int c = 0; c < 3; ++c) u0[c] = p.vold[c][i];
-    int nsub = p.nsub[i];
+    const int code = p.nsub[i];
+    int nsub = inflow ? (code >> 3) : code;
+    SubRun R;
+    R.bdry = inflow ? (code & 7) : -1;
+    R.restarted = false;
+    R.reflected = false;
     const double wp = p.w[i];
-    bool ok = suborbit_run<D, IE, IJ, X, false>(g, F, J, prm, iter_max, from_jac != 0, max_sub, x0, u0, wp, nsub, xp, vp, err, apply);
-    if (ok) ok = suborbit_run<D, IE, IJ, X, true>(g, F, J, prm, iter_max, from_jac != 0, max_sub, x0, u0, wp, nsub, xp, vp, err, apply);
-    if (ok) {
-      p.nsub[i] = nsub;
+    bool ok = suborbit_run<D, IE, IJ, X, false>(g, F, J, prm, iter_max, from_jac != 0, max_sub, x0, u0, wp, nsub, xp, vp, err, apply, R);
+    if (ok && R.reflected) {
+      // x = x_old as created, u = u_old with no normal component, one sub-orbit, no current (:3497-3506)
+      p.nsub[i] = 8 + R.bdry;
 #pragma unroll
-      for (int d = 0; d < D; ++d) p.x[d][i] = xp[d];
+      for (int d = 0; d < D; ++d) p.x[d][i] = x0[d];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) p.v[c][i] = vp[c];
+      for (int c = 0; c < 3; ++c) p.v[c][i] = (c == (R.bdry >> 1)) ? 0.0 : u0[c];
     } else {
-      atomicAdd(nfail, 1u);
+      if (ok) ok = suborbit_run<D, IE, IJ, X, true>(g, F, J, prm, iter_max, from_jac != 0, max_sub, x0, u0, wp, nsub, xp, vp, err, apply, R);
+      if (ok && !R.reflected) {
+        p.nsub[i] = inflow ? (nsub * 8 + R.bdry) : nsub;
+        // inflow particles go back time-centred against their original old state (:3608-3617): inflow_Lo/Hi form 2 x - x_old
+#pragma unroll
+        for (int d = 0; d < D; ++d) p.x[d][i] = inflow ? __ddiv_rn(__dadd_rn(xp[d], x0[d]), 2.0) : xp[d];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p.v[c][i] = inflow ? __ddiv_rn(__dadd_rn(vp[c], u0[c]), 2.0) : vp[c];
+      } else {
+        atomicAdd(nfail, 1u);
+      }
     }
   }
   flush_counters(cnt, 0, 0, err);
 }
 template <int D, int IE, int IJ>
 static int launch_suborbit_t(pgpu_species_s *s, const SubPtrs &P, long n, const CurrentSet &J, const AdvanceParams &prm,
-                             int iter_max, int from_jac, unsigned *nfail) {
+                             int iter_max, int from_jac, unsigned *nfail, int inflow) {
   Context &c = ctx();
   const Geo<D> g = make_geo<D>(species_geo(s));
   const FieldSet F = grid_fields(s->grid);
   KTimer t("suborbit");
   const unsigned nb = (unsigned)((n + 127) / 128);
-  if (c.exact) k_suborbit<D, IE, IJ, true><<<nb, 128, 0, c.stream>>>(P, n, g, F, J, prm, iter_max, from_jac, 512, c.d_counters, nfail);
-  else k_suborbit<D, IE, IJ, false><<<nb, 128, 0, c.stream>>>(P, n, g, F, J, prm, iter_max, from_jac, 512, c.d_counters, nfail);
+  if (c.exact) k_suborbit<D, IE, IJ, true><<<nb, 128, 0, c.stream>>>(P, n, g, F, J, prm, iter_max, from_jac, 512, c.d_counters, nfail, inflow);
+  else k_suborbit<D, IE, IJ, false><<<nb, 128, 0, c.stream>>>(P, n, g, F, J, prm, iter_max, from_jac, 512, c.d_counters, nfail, inflow);
   return 0;
 }
 template <int D, int IE>
 static int launch_suborbit_e(pgpu_species_s *s, const SubPtrs &P, long n, const CurrentSet &J, const AdvanceParams &prm,
-                             int iter_max, int from_jac, unsigned *nfail) {
+                             int iter_max, int from_jac, unsigned *nfail, int inflow) {
   switch (s->desc.interp_J) {
-    case CIC: return launch_suborbit_t<D, IE, CIC>(s, P, n, J, prm, iter_max, from_jac, nfail);
-    case TSC: return launch_suborbit_t<D, IE, TSC>(s, P, n, J, prm, iter_max, from_jac, nfail);
-    case CC0: return launch_suborbit_t<D, IE, CC0>(s, P, n, J, prm, iter_max, from_jac, nfail);
-    case CC1: return launch_suborbit_t<D, IE, CC1>(s, P, n, J, prm, iter_max, from_jac, nfail);
+    case CIC: return launch_suborbit_t<D, IE, CIC>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow);
+    case TSC: return launch_suborbit_t<D, IE, TSC>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow);
+    case CC0: return launch_suborbit_t<D, IE, CC0>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow);
+    case CC1: return launch_suborbit_t<D, IE, CC1>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow);
   }
   return PGPU_ERR_ARG;
 }
 template <int D>
 static int launch_suborbit_d(pgpu_species_s *s, const SubPtrs &P, long n, const CurrentSet &J, const AdvanceParams &prm,
-                             int iter_max, int from_jac, unsigned *nfail) {
+                             int iter_max, int from_jac, unsigned *nfail, int inflow) {
   switch (s->desc.interp_E) {
-    case CIC: return launch_suborbit_e<D, CIC>(s, P, n, J, prm, iter_max, from_jac, nfail);
-    case TSC: return launch_suborbit_e<D, TSC>(s, P, n, J, prm, iter_max, from_jac, nfail);
-    case CC0: return launch_suborbit_e<D, CC0>(s, P, n, J, prm, iter_max, from_jac, nfail);
-    case CC1: return launch_suborbit_e<D, CC1>(s, P, n, J, prm, iter_max, from_jac, nfail);
+    case CIC: return launch_suborbit_e<D, CIC>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow);
+    case TSC: return launch_suborbit_e<D, TSC>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow);
+    case CC0: return launch_suborbit_e<D, CC0>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow);
+    case CC1: return launch_suborbit_e<D, CC1>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow);
   }
   return PGPU_ERR_ARG;
 }
-// the sub-orbit container of s: arrays sub[0..9] = x0 x1 xold0 xold1 v0 v1 v2 vold0 vold1 vold2, sub_w, sub_nsub
-int launch_suborbit(pgpu_species_s *s, const AdvanceParams &prm, int from_jac, const DeviceFab *Jsub, unsigned *nfail) {
-  if (s->n_sub == 0) return 0;
+// the sub-orbit container of s: arrays sub[0..9] = x0 x1 xold0 xold1 v0 v1 v2 vold0 vold1 vold2, sub_w, sub_nsub; with
+// inflow != 0 the inflow container inf[0..9], inf_w, inf_code instead
+int launch_suborbit(pgpu_species_s *s, const AdvanceParams &prm, int from_jac, const DeviceFab *Jsub, unsigned *nfail,
+                    int inflow) {
+  const long n = inflow ? s->n_inf : s->n_sub;
+  if (n == 0) return 0;
+  double **a = inflow ? s->inf : s->sub;
   SubPtrs P;
   for (int d = 0; d < 2; ++d) {
-    P.x[d] = s->sub[d];
-    P.xold[d] = s->sub[2 + d];
+    P.x[d] = a[d];
+    P.xold[d] = a[2 + d];
   }
   for (int c = 0; c < 3; ++c) {
-    P.v[c] = s->sub[4 + c];
-    P.vold[c] = s->sub[7 + c];
+    P.v[c] = a[4 + c];
+    P.vold[c] = a[7 + c];
   }
-  P.w = s->sub_w;
-  P.nsub = s->sub_nsub;
+  P.w = inflow ? s->inf_w : s->sub_w;
+  P.nsub = inflow ? s->inf_code : s->sub_nsub;
   CurrentSet J;
   for (int c = 0; c < 3; ++c) J.j[c] = Jsub[c].view();
   int iter_max = s->desc.iter_max;
   if (from_jac) iter_max += iter_max;
-  return s->grid->desc.D == 1 ? launch_suborbit_d<1>(s, P, s->n_sub, J, prm, iter_max, from_jac, nfail)
-                              : launch_suborbit_d<2>(s, P, s->n_sub, J, prm, iter_max, from_jac, nfail);
+  return s->grid->desc.D == 1 ? launch_suborbit_d<1>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow)
+                              : launch_suborbit_d<2>(s, P, n, J, prm, iter_max, from_jac, nfail, inflow);
 }
 
 int launch_advance(pgpu_species_s *s, const AdvanceParams &prm, bool fuse_deposit) {

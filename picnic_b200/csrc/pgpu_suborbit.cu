@@ -68,6 +68,54 @@ struct Aux {
 };
 Aux sub_aux(pgpu_species_s *s) { return Aux{s->sub, &s->sub_w, &s->sub_id, &s->sub_nsub, &s->n_sub, &s->sub_cap}; }
 Aux out_aux(pgpu_species_s *s) { return Aux{s->out, &s->out_w, &s->out_id, &s->out_tag, &s->n_out, &s->out_cap}; }
+Aux inf_aux(pgpu_species_s *s) { return Aux{s->inf, &s->inf_w, &s->inf_id, &s->inf_code, &s->n_inf, &s->inf_cap}; }
+MainPtrs inf_ptrs(pgpu_species_s *s) {
+  MainPtrs P;
+  for (int k = 0; k < 10; ++k) P.a[k] = s->inf[k];
+  P.w = s->inf_w;
+  P.id = s->inf_id;
+  return P;
+}
+// PicChargedSpeciesBC::inflow_Lo / inflow_Hi, final (not intermediate) advance (:961-1001, 1047-1086): the inflow-list
+// particle is time-centred; its new-time state 2 x - x_old, 2 u - u_old decides: inside the boundary plane it joins the
+// species (slot base + rank in `to`), otherwise (turned around) it is dropped.  Flux probes m_delta_*In from u_old.
+__global__ void k_inflow_inject(MainPtrs from, const int *code, long n, MainPtrs to, long base, int D, double l0, double r0,
+                                double l1, double r1, unsigned mask /* bit (2 dir + side): boundary is inflow_outflow */,
+                                int rel, unsigned *count, double *flux /* [4][5] */) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int tag = code[i] & 7, dir = tag >> 1, side = tag & 1;
+  if (!((mask >> tag) & 1u)) return;   // not an inflow boundary in this call: dropped with the rest of the list
+  double xn[2] = {0.0, 0.0}, un[3];
+  for (int d = 0; d < D; ++d) xn[d] = __dsub_rn(__dmul_rn(2.0, from.a[d][i]), from.a[2 + d][i]);
+  for (int c = 0; c < 3; ++c) un[c] = __dsub_rn(__dmul_rn(2.0, from.a[4 + c][i]), from.a[7 + c][i]);
+  const double edge = dir == 0 ? (side == 0 ? l0 : r0) : (side == 0 ? l1 : r1);
+  const bool inside = side == 0 ? (xn[dir] >= edge) : (xn[dir] < edge);
+  if (!inside) return;
+  const long o = base + atomicAdd(count, 1u);
+  for (int d = 0; d < D; ++d) {
+    to.a[d][o] = xn[d];
+    to.a[2 + d][o] = from.a[2 + d][i];
+  }
+  for (int c = 0; c < 3; ++c) {
+    to.a[4 + c][o] = un[c];
+    to.a[7 + c][o] = from.a[7 + c][i];
+  }
+  const double w = from.w[i];
+  to.w[o] = w;
+  to.id[o] = from.id[i];
+  const double a = from.a[7][i], b = from.a[8][i], c = from.a[9][i];
+  const double gbsq = a * a + b * b + c * c, gamma = rel ? sqrt(1.0 + gbsq) : 1.0;
+  atomicAdd(flux + tag * 5 + 0, w);
+  atomicAdd(flux + tag * 5 + 1, w * a);
+  atomicAdd(flux + tag * 5 + 2, w * b);
+  atomicAdd(flux + tag * 5 + 3, w * c);
+  atomicAdd(flux + tag * 5 + 4, w * gbsq / (gamma + 1.0));
+}
+__global__ void k_fill_int(int *p, long n, int v) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
 
 // listed particles of `from` -> positions base .. base+count-1 of `to`
 __global__ void k_copy_listed(MainPtrs from, MainPtrs to, const int *list, unsigned count, long base, int *nsub, int D,
@@ -188,6 +236,43 @@ __global__ void k_aux_flux(MainPtrs P, const int *tag, long n, int rel, double *
 }  // namespace
 
 namespace pgpu {
+// the inflow-list part of PicChargedSpeciesBC::apply (:199-224), final advance: see k_inflow_inject.  The list is emptied
+// (joined or dropped), as the reference leaves it.  The order of the injected particles among themselves is the order of
+// the atomics, i.e. not reproducible; the next cell sort removes it.
+int inject_inflow(pgpu_species_s *s, const int *bc_lo, const int *bc_hi) {
+  if (s->n_inf == 0) return 0;
+  const pgpu_grid_s *g = s->grid;
+  const int D = g->desc.D;
+  unsigned mask = 0;
+  for (int d = 0; d < D; ++d) {
+    if (bc_lo[d] == PGPU_BC_INFLOW_OUTFLOW) mask |= 1u << (2 * d);
+    if (bc_hi[d] == PGPU_BC_INFLOW_OUTFLOW) mask |= 1u << (2 * d + 1);
+  }
+  if (!mask) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  int rc = grow_capacity(s, s->n + s->n_inf);
+  if (rc) return rc;
+  cudaStream_t st = ctx().stream;
+  double *dflux = nullptr;
+  PGPU_CUDA(cudaMalloc(&dflux, 20 * sizeof(double) + sizeof(unsigned)));
+  PGPU_CUDA(cudaMemsetAsync(dflux, 0, 20 * sizeof(double) + sizeof(unsigned), st));
+  unsigned *dcount = reinterpret_cast<unsigned *>(dflux + 20);
+  k_inflow_inject<<<nb(s->n_inf), 256, 0, st>>>(inf_ptrs(s), s->inf_code, s->n_inf, main_ptrs(s), s->n, D, g->geo.le[0],
+                                                g->geo.re[0], g->geo.le[1], g->geo.re[1], mask, s->desc.relativistic, dcount,
+                                                dflux);
+  double hflux[20];
+  unsigned joined = 0;
+  PGPU_CUDA(cudaMemcpyAsync(hflux, dflux, sizeof(hflux), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaMemcpyAsync(&joined, dcount, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  cudaFree(dflux);
+  for (int k = 0; k < 20; ++k) s->flux_in[k] += hflux[k];
+  s->n += joined;
+  s->n_inf = 0;
+  s->binned = false;
+  return 0;
+}
+
 // scratch of the unconverged / fast list: list [cap] + holes [cap] + movers [cap] ints, two counters behind the count
 int ensure_unconv_list(pgpu_species_s *s) {
   if (s->unconv_list && s->unconv_cap >= s->cap) return 0;
@@ -488,6 +573,134 @@ int pgpu_species_append(pgpu_species_t s, long n, const double *x, const double 
   PGPU_CUDA(cudaStreamSynchronize(st));   // the host buffers are borrowed for the call only
   s->n += n;
   s->binned = false;
+  return 0;
+}
+
+// ---- inflow lists with pic_species.N.suborbit_inflow_J (PicChargedSpeciesBC m_inflow_list_vector) --------------------
+// createInflowParticles (:467-506) stays on the host (it draws from the host generator); with suborbit_inflow_J the
+// particles are NOT injected at once (PicChargedSpecies::injectInflowParticles returns, :1787): they wait in the inflow list
+// of their boundary, every nonlinear evaluation advances them from there (advanceInflowParticlesAndSetJ), and the applyBCs
+// at the end of the step lets them join the species (inflow_Lo / inflow_Hi).
+int pgpu_species_inflow_append(pgpu_species_t s, long n, const double *x, const double *v, const double *w,
+                               const uint64_t *id, int bdry_dir, int bdry_side) {
+  NEED_INIT();
+  if (!s || n < 0 || (n && (!x || !v || !w))) return PGPU_ERR_ARG;
+  const int D = s->grid->desc.D;
+  if (bdry_dir < 0 || bdry_dir >= D || bdry_side < 0 || bdry_side > 1) return PGPU_ERR_ARG;
+  if (n == 0) return 0;
+  const Aux A = inf_aux(s);
+  int rc = ensure_aux_cap(A, s->n_inf + n);
+  if (rc) return rc;
+  cudaStream_t st = ctx().stream;
+  const long o = s->n_inf;
+  for (int d = 0; d < D; ++d) {
+    PGPU_CUDA(cudaMemcpyAsync(s->inf[d] + o, x + d * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    PGPU_CUDA(cudaMemcpyAsync(s->inf[2 + d] + o, x + d * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  for (int c = 0; c < 3; ++c) {
+    PGPU_CUDA(cudaMemcpyAsync(s->inf[4 + c] + o, v + c * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    PGPU_CUDA(cudaMemcpyAsync(s->inf[7 + c] + o, v + c * n, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  PGPU_CUDA(cudaMemcpyAsync(s->inf_w + o, w, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  std::vector<uint64_t> tmp;
+  if (!id) {
+    tmp.resize((size_t)n);
+    for (long k = 0; k < n; ++k) tmp[k] = ((uint64_t)s->serial << 40) + (uint64_t)(s->next_id++) + (1ull << 39);
+    id = tmp.data();
+  }
+  PGPU_CUDA(cudaMemcpyAsync(s->inf_id + o, id, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  k_fill_int<<<nb(n), 256, 0, st>>>(s->inf_code + o, n, 8 + 2 * bdry_dir + bdry_side);   // one sub-orbit
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  s->n_inf += n;
+  return 0;
+}
+long pgpu_species_inflow_count(pgpu_species_t s) { return s ? s->n_inf : -1; }
+// nsub_boundary[i] = 8 * numSubOrbits + (2 dir + side)
+int pgpu_species_inflow_download(pgpu_species_t s, double *x, double *xold, double *v, double *vold, double *w,
+                                 uint64_t *id, int *nsub_boundary) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  return aux_download(s, inf_aux(s), x, xold, v, vold, w, id, nsub_boundary);
+}
+int pgpu_species_inflow_clear(pgpu_species_t s) {
+  if (!s) return PGPU_ERR_ARG;
+  s->n_inf = 0;
+  return 0;
+}
+
+int pgpu_advance_inflow_particles_and_set_J(pgpu_species_t s, double dt, int from_emjacobian) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  if (s->desc.relativistic) {
+    set_error("the inflow sub-orbit path is implemented for the non-relativistic planar push");
+    return PGPU_ERR_STATE;
+  }
+  cudaStream_t st = ctx().stream;
+  for (int c = 0; c < 3; ++c) {
+    if (!s->Jinf[c].p) {
+      s->Jinf[c] = s->J[c];
+      s->Jinf[c].p = nullptr;
+      PGPU_CUDA(cudaMalloc(&s->Jinf[c].p, s->J[c].size() * sizeof(double)));
+    }
+    PGPU_CUDA(cudaMemsetAsync(s->Jinf[c].p, 0, s->Jinf[c].size() * sizeof(double), st));   // SpaceUtils::zero (:3262-3263)
+  }
+  if (s->n_inf == 0) return 0;
+  if (!s->unconv_count) PGPU_CUDA(cudaMalloc(&s->unconv_count, 4 * sizeof(unsigned)));
+  unsigned *nfail = s->unconv_count + 3;
+  PGPU_CUDA(cudaMemsetAsync(nfail, 0, sizeof(unsigned), st));
+  AdvanceParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.cnormDt = dt * s->desc.cvac_norm;
+  prm.fnorm = s->desc.fnorm_const;
+  prm.alpha = s->desc.fnorm_const * prm.cnormDt / 2.0;
+  prm.rtol = s->desc.rtol;
+  prm.iter_max = s->desc.iter_max;
+  const GeoAny &g = s->grid->geo;
+  prm.volume = (g.D == 1) ? g.dx[0] : g.dx[0] * g.dx[1];
+  prm.rvolume = 1.0 / prm.volume;
+  prm.ext = s->grid->ext;
+  int rc = launch_suborbit(s, prm, from_emjacobian ? 1 : 0, s->Jinf, nfail, 1);
+  if (rc) return rc;
+  const double f = s->desc.charge / s->grid->desc.volume_scale;   // :3308-3315
+  for (int c = 0; c < 3; ++c) {
+    rc = scale_fab(s->Jinf[c], f);
+    if (rc) return rc;
+  }
+  unsigned failed = 0;
+  PGPU_CUDA(cudaMemcpyAsync(&failed, nfail, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  PGPU_CUDA(cudaStreamSynchronize(st));
+  if (failed) {
+    set_error("inflow sub-orbits: %u particles did not converge with 512 sub-orbits or left the ghosted arrays", failed);
+    return PGPU_ERR_STATE;
+  }
+  return 0;
+}
+int pgpu_species_inflow_current_get(pgpu_species_t s, int comp, double *data, const int *lo, const int *hi) {
+  NEED_INIT();
+  if (!s || comp < 0 || comp >= 3 || !s->Jinf[comp].p) return PGPU_ERR_ARG;
+  int rc = copy_fab_to_host(s->Jinf[comp], s->grid->desc.D, data, lo, hi);
+  if (rc) return rc;
+  return pgpu_synchronize();
+}
+// PicSpeciesInterface::addInflowJ (PicSpeciesInterface.cpp:1499-1536): total J += this species' inflow J
+int pgpu_current_add_inflow(pgpu_grid_t g, pgpu_species_t s) {
+  NEED_INIT();
+  if (!g || !s) return PGPU_ERR_ARG;
+  if (s->desc.charge == 0.0 || !s->Jinf[0].p) return 0;
+  for (int c = 0; c < 3; ++c) {
+    const long n = (long)g->jtot[c].size();
+    k_add_arr<<<nb(n), 256, 0, ctx().stream>>>(g->jtot[c].p, s->Jinf[c].p, n);
+  }
+  return 0;
+}
+// m_delta_{Mass,MomX,MomY,MomZ,Energy}In per boundary (2 dir + side), accumulated by the inflow part of pgpu_apply_bcs
+// since the last call; reading resets them (PicChargedSpeciesBC::zeroDeltas)
+int pgpu_species_inflow_fluxes(pgpu_species_t s, double *flux20) {
+  if (!s || !flux20) return PGPU_ERR_ARG;
+  for (int k = 0; k < 20; ++k) {
+    flux20[k] = s->flux_in[k];
+    s->flux_in[k] = 0.0;
+  }
   return 0;
 }
 
