@@ -179,3 +179,78 @@ def test_gpu_inflow_advance_and_injection_match_oracle(pgpu, D, interp, exact):
     assert np.all(sp.inflow_fluxes() == 0.0)                       # reading resets
     sp.destroy(); grid.destroy()
     pgpu.load().pgpu_set_exact_math(0)
+
+
+@pytest.mark.gpu
+def test_gpu_flow_through_with_inflow_and_outflow_boundaries(pgpu):
+    """The life cycle of the shock decks (BASELINE configs[3]) at reduced size, field free: every step the host makes a
+    batch of inflow particles outside the left boundary (as createInflowParticles does: where they would be one step
+    before they enter), the implicit step advances bulk and inflow lists, the final applyBCs lets the inflow particles
+    join and moves the leavers of the right boundary to the outflow list, which the next step removes.
+    Checked: exact bookkeeping (injected = inside + left), the steady-state content against the transit times, and --
+    the point of the inflow current's cnormDt_sub / cnormDt weight -- a time-averaged J_x that is the same on every
+    edge of the domain, the two next to the inflow boundary included."""
+    D, ncell, dx, ng = 1, 32, 0.25, 4
+    prob = Problem(1, (ncell,), (dx,), (0.0,), ng, 1, seed=3, max_disp=0.0, E0=0.0, B0=0.0)
+    for f in prob.E + prob.B:
+        f.a[...] = 0.0
+    it = INTERPS["CC1"]
+    dt, cv = 0.5, 0.9986
+    cdt = dt * cv
+    grid, sp = make_gpu(pgpu, prob, it, rtol=RTOL, iter_max=ITMAX, fnorm=FN, cvac_norm=cv, charge=-1.0, volume_scale=2.0,
+                        periodic=[0])
+    sp.upload(np.zeros((1, 0)), np.zeros((3, 0)), np.zeros(0))                  # start empty
+    rng = np.random.default_rng(8)
+    ud = 0.4 * dx / cdt                                                          # 0.4 cells per step
+    bc_lo, bc_hi = (pgpu.BC_INFLOW_OUTFLOW,), (pgpu.BC_OUTFLOW,)
+    nsteps, nin, L = 400, 40, ncell * dx
+    injected = left = 0.0
+    Jsum, nacc, next_id = None, 0, 1
+    for step in range(nsteps):
+        sp.remove_outflow()
+        v = np.zeros((3, nin))
+        v[0] = ud * (1.0 + 0.1 * rng.standard_normal(nin)).clip(0.5, 1.5)
+        v[1:] = 0.01 * rng.standard_normal((2, nin))
+        x = (0.0 - v[0] * cdt * rng.random(nin))[None, :]
+        w = np.ones(nin)
+        sp.inflow_append(x, v, w, 0, 0, ids=np.arange(next_id, next_id + nin, dtype=np.uint64))
+        next_id += nin
+        sp.update_old_positions(); sp.update_old_velocities()
+        grid.current_zero()
+        sp.advance_iteratively(dt, deposit=True, stats=False)
+        grid.current_add(sp)
+        sp.advance_inflow_and_set_J(dt)
+        grid.current_add_inflow(sp)
+        grid.current_finalize()
+        if step >= nsteps - 150:
+            Jx = grid.current_get(0)
+            Jsum = Jx.copy() if Jsum is None else Jsum + Jx
+            nacc += 1
+        sp.advance_velocities_2nd_half(); sp.advance_positions_2nd_half()
+        sp.apply_bcs(bc_lo, bc_hi)
+        assert sp.n_inflow == 0
+        injected += sp.inflow_fluxes()[0, 0]
+        left += sp.outflow_fluxes()[1, 0]
+    assert injected == nsteps * nin                                              # nothing is turned around without fields
+    assert injected == sp.n + left                                               # exact bookkeeping
+    # steady state: a particle stays L / (v cdt) steps; <1/v> over the clipped normal factor
+    f = (1.0 + 0.1 * np.random.default_rng(1).standard_normal(400000)).clip(0.5, 1.5)
+    transit = L / (ud * cdt) * np.mean(1.0 / f)
+    assert abs(sp.n / (nin * transit) - 1.0) < 0.03
+    all_p = sp.download()
+    assert np.all((all_p["x"][0] >= 0.0) & (all_p["x"][0] < L))
+    # J_x on the cell-centred edges 0 .. ncell-1 of the domain (array index ng + k)
+    J = Jsum[ng:ng + ncell] / nacc
+    assert np.all(J < 0.0)                                                       # electrons moving to +x
+    interior = J[4:-4].mean()
+    # every edge but the two boundary ones carries the same current ...
+    assert np.abs(J[1:-1] / interior - 1.0).max() < 0.01, J / interior
+    # ... and at the inflow face the CC1 shape puts 1/8 of it on the ghost edge outside (a particle in the first half
+    # cell shares its current between edges -1 and 0): together they carry all of it.  A wrong time weight of the inflow
+    # current (the particles spend only part of the step inside) would show here at the 50 % level.
+    Jm1 = Jsum[ng - 1] / nacc
+    assert abs((Jm1 + J[0]) / interior - 1.0) < 0.005 and abs(Jm1 / interior - 0.125) < 0.005
+    assert Jsum[ng - 2] == 0.0
+    # and its value: charge * (weight per step) / (cnormDt * volume_scale) through every face
+    assert abs(interior / (-1.0 * nin / cdt / 2.0) - 1.0) < 0.02
+    sp.destroy(); grid.destroy()
