@@ -51,6 +51,31 @@ void Mesh::setEMfields(const FabRef &Ex, const FabRef &Ey, const FabRef &Ez, con
   for (int c = 0; c < 6; ++c) check(pgpu_fields_set(m_h, c, f[c]->data, f[c]->lo, f[c]->hi), "Mesh::setEMfields");
   check(pgpu_synchronize(), "Mesh::setEMfields");   // the host arrays may change after this returns
 }
+long Mesh::packedFieldSize() const {
+  long n = 0;
+  check(pgpu_fields_packed_size(m_h, &n), "Mesh::packedFieldSize");
+  return n;
+}
+long Mesh::packedCurrentSize() const {
+  long n = 0;
+  check(pgpu_current_packed_size(m_h, &n), "Mesh::packedCurrentSize");
+  return n;
+}
+void Mesh::setEMfieldsPacked(const Real *six_components) {
+  check(pgpu_fields_set_packed(m_h, six_components), "Mesh::setEMfieldsPacked");
+}
+void Mesh::getCurrentDensityPacked(Real *three_components) const {
+  check(pgpu_current_get_packed_async(m_h, three_components), "Mesh::getCurrentDensityPacked");
+}
+void Mesh::setExternalFields(const pgpu_ext_fn *six_or_null) {
+  check(pgpu_grid_set_external_fields(m_h, six_or_null), "Mesh::setExternalFields");
+}
+void Mesh::addSubOrbitJ(const PicChargedSpecies &sp) {
+  check(pgpu_current_add_suborbit(m_h, sp.handle()), "Mesh::addSubOrbitJ");
+}
+void Mesh::addInflowJ(const PicChargedSpecies &sp) {
+  check(pgpu_current_add_inflow(m_h, sp.handle()), "Mesh::addInflowJ");
+}
 void Mesh::fieldBounds(int comp, int *lo, int *hi) const {
   int l[2], h[2];
   check(pgpu_field_bounds(m_h, comp, l, h), "Mesh::fieldBounds");
@@ -380,6 +405,56 @@ void PicChargedSpecies::setChargeDensityOnNodes(const FabRef &out) {
 void PicChargedSpecies::getMomentsFromBinFab(Real *dens, Real *mom, Real *ene) const {
   check(pgpu_species_moments_get(m_h, dens, mom, ene), "PicChargedSpecies::getMomentsFromBinFab");
 }
+void PicChargedSpecies::explicitStep(Real a_dt, const int *bc_lo, const int *bc_hi, bool a_second_half) {
+  check(pgpu_explicit_step(m_h, a_dt, bc_lo, bc_hi, a_second_half ? 1 : 0), "PicChargedSpecies::explicitStep");
+}
+void PicChargedSpecies::addExternalFieldsToParticles() {
+  check(pgpu_add_external_fields_to_particles(m_h), "PicChargedSpecies::addExternalFieldsToParticles");
+}
+void PicChargedSpecies::setSubOrbitModel(bool a_use_suborbit_model, bool a_suborbit_fast_particles) {
+  check(pgpu_species_set_suborbit_model(m_h, a_use_suborbit_model ? 1 : 0, a_suborbit_fast_particles ? 1 : 0),
+        "PicChargedSpecies::setSubOrbitModel");
+}
+void PicChargedSpecies::transferFastParticles() {
+  check(pgpu_transfer_fast_particles(m_h), "PicChargedSpecies::transferFastParticles");
+}
+void PicChargedSpecies::advanceSubOrbitParticlesAndSetJ(Real a_dt, bool a_from_emjacobian) {
+  check(pgpu_advance_suborbit_particles_and_set_J(m_h, a_dt, a_from_emjacobian ? 1 : 0),
+        "PicChargedSpecies::advanceSubOrbitParticlesAndSetJ");
+}
+void PicChargedSpecies::mergeSubOrbitParticles() {
+  check(pgpu_merge_suborbit_particles(m_h), "PicChargedSpecies::mergeSubOrbitParticles");
+}
+long PicChargedSpecies::numSubOrbitParticles() const { return pgpu_species_suborbit_count(m_h); }
+void PicChargedSpecies::removeOutflowParticles() {
+  check(pgpu_remove_outflow_particles(m_h), "PicChargedSpecies::removeOutflowParticles");
+}
+void PicChargedSpecies::outflowProbes(Real *a_flux20) const {
+  check(pgpu_species_outflow_fluxes(m_h, a_flux20), "PicChargedSpecies::outflowProbes");
+}
+void PicChargedSpecies::injectInflowParticles(long n, const Real *x, const Real *v, const Real *w, const uint64_t *id) {
+  check(pgpu_species_append(m_h, n, x, nullptr, v, nullptr, w, id), "PicChargedSpecies::injectInflowParticles");
+}
+void PicChargedSpecies::addToInflowList(long n, const Real *x, const Real *v, const Real *w, const uint64_t *id,
+                                        int a_bdry_dir, int a_bdry_side) {
+  check(pgpu_species_inflow_append(m_h, n, x, v, w, id, a_bdry_dir, a_bdry_side), "PicChargedSpecies::addToInflowList");
+}
+void PicChargedSpecies::advanceInflowParticlesAndSetJ(Real a_dt, bool a_from_emjacobian) {
+  check(pgpu_advance_inflow_particles_and_set_J(m_h, a_dt, a_from_emjacobian ? 1 : 0),
+        "PicChargedSpecies::advanceInflowParticlesAndSetJ");
+}
+void PicChargedSpecies::inflowProbes(Real *a_flux20) {
+  check(pgpu_species_inflow_fluxes(m_h, a_flux20), "PicChargedSpecies::inflowProbes");
+}
+long PicChargedSpecies::numInflowParticles() const { return pgpu_species_inflow_count(m_h); }
+long PicChargedSpecies::linearSize() const { return pgpu_particle_linear_size(m_h); }
+void PicChargedSpecies::getParticlesLinear(void *a_records) const {
+  check(pgpu_species_download_linear(m_h, a_records), "PicChargedSpecies::getParticlesLinear");
+}
+void PicChargedSpecies::setParticlesLinear(long n, const void *a_records) {
+  check(pgpu_species_upload_linear(m_h, n, a_records), "PicChargedSpecies::setParticlesLinear");
+}
+void PicChargedSpecies::sortForLocality() { check(pgpu_sort_for_locality(m_h), "PicChargedSpecies::sortForLocality"); }
 void PicChargedSpecies::applyBCs(const int *bc_lo, const int *bc_hi) {
   check(pgpu_apply_bcs(m_h, bc_lo, bc_hi), "PicChargedSpecies::applyBCs");
 }

@@ -112,3 +112,15 @@ def test_example_two_boxes(driver):
     r = subprocess.run([os.path.join(HOST, "example_two_boxes")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "misplaced 0" in r.stdout and "ids_ok 1" in r.stdout
+
+
+@pytest.mark.gpu
+def test_example_shock_1d_life_cycle_through_the_shim(driver):
+    """picnic_b200/host/example_shock_1d.cpp: the implicit shock decks' particle side (inflow list with
+    suborbit_inflow_J, outflow list, packed host I/O, List<JustinsParticle> records, the fused explicit step) driven through
+    the C++ host classes; the program checks itself and exits non-zero on any failed check."""
+    exe = os.path.join(HOST, "example_shock_1d")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, "150"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout and "injected=4500" in r.stdout
