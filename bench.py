@@ -756,7 +756,13 @@ def c5_shard_leg(args, rank, local, stream, region, capi):
     n = eng.n_particles
     units = float(n) * a.n_outer * a.steps
     per_launch = n / len(eng.species)
-    out = {"metric": "particle-advances/s (implicit push + deposit)", "value": units / (ms * 1e-3),
+    e2e = None
+    if not args.no_e2e:      # the same shard through host field / J buffers: the base of the e2e scaling numbers
+        region(1, True, eng=eng)
+        ms_e, _ = region(a.steps, True, eng=eng)
+        e2e = {"value": units / (ms_e * 1e-3), "unit": "particle-advances/s", "ms_per_step": ms_e / a.steps,
+               "h2d_bytes_per_step": int(eng.h2d), "d2h_bytes_per_step": int(eng.d2h)}
+    out = {"metric": "particle-advances/s (implicit push + deposit)", "value": units / (ms * 1e-3), "e2e": e2e,
            "unit": "particle-advances/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
            "workload": workload_name(a, 1), "particles_per_gpu": n, "mean_picard_passes": round(app / max(adv, 1), 3),
            "kernel_ms_per_launch": k_ms / max(k_n, 1), "units_per_launch": per_launch,
