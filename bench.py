@@ -955,7 +955,7 @@ def run_ours(args):
         sampler.window(t_host0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     prof = {}
-    for name in ("advance_cc1_fused", "advance_deferred", "advance_deposit_fused", "advance", "deposit_current", "bin_", "finish_step", "second_half", "fold_periodic",
+    for name in ("advance_cc1_fused", "advance_multiseg", "advance_deferred", "advance_deposit_fused", "advance", "deposit_current", "bin_", "finish_step", "second_half", "fold_periodic",
                  "current_add", "current_scale", "bc_periodic", "halo_", "mig_", "build_tables", "tile_boxes",
                  "bin_key", "bin_sort", "bin_permute", "bin_starts"):
         prof[name] = capi.profile_query(name)

@@ -1856,6 +1856,339 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_advance_cc1_2d_v2(const FastArg
   }
 }
 
+// =============================================================================================
+// Multi-segment orbits (the particles the tile kernel defers), table driven.
+//
+// CC1 splits the orbit x_old -> x_new at the faces of the half-shifted grid; per segment the in-plane weights are the
+// single-segment closed forms with the SEGMENT's end points, times seg_factor = segment length / orbit length per direction
+// (cc1_2d_interpolate_fields / cc1_2d_deposit_current, MeshInterpChargeConservingF.ChF:1885-1960, 1616-1709), and Ez, B
+// and Jz use nodal CIC at the orbit's x_bar (no segments).  So a crossing particle needs the same table records as a
+// single-segment one, of the two or three dual cells it visits: this kernel walks the reference's segments
+// (walk_cc1_2d = the walker of cc_2d_inplane_visit, pgpu_device.cuh, decision for decision) and evaluates every segment
+// from the global coefficient tables -- ~2.5x fewer instructions than the visitor kernel's per-point loads with bounds
+// checks.  One thread per listed particle.  Anything it cannot do (a visited cell whose stencil leaves the arrays, more
+// segments than ghosts + 1, a particle bound for the sub-orbit container) goes, untouched, to a second list for the visitor
+// kernel, which keeps the reference's error behaviour.
+// =============================================================================================
+struct DeferPtrs {
+  double *x[2];            // in: the stored x_bar (Picard starting guess); out: x_bar
+  const double *xold[2];
+  double *v[3];            // out: u_bar
+  const double *vold[3];
+  const double *w;
+  const int *list;
+  const unsigned *count;
+  int *list2;              // rejects, for the visitor kernel
+  unsigned *count2;
+  int max_segments;        // ghosts + 1
+};
+
+// fn(ii, jj, x_start, x_end, seg_factor) per segment; returns 0, 1 (fn refused a cell) or 2 (too many segments)
+template <class Fn>
+__device__ __forceinline__ int walk_cc1_2d(const FastArgs &A, int max_segments, const double (&xo)[2],
+                                           const double (&xb)[2], Fn &&fn) {
+  double xpnew[2], dXp[2];
+  int sign[2] = {1, 1}, index_old[2], cell_crossings[2], num_segments = 1;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    xpnew[d] = 2.0 * xb[d] - xo[d];
+    dXp[d] = xpnew[d] - xo[d];
+  }
+  // the reference divides (slope = dXp1 / dXp0, its inverse, one seg_factor per segment and direction); two reciprocals
+  // serve them all within an ulp, which only matters for the tie of an orbit through a cell corner (either order of the
+  // two zero-length-apart crossings gives the same sums)
+  const double rd0 = __ddiv_rn(1.0, dXp[0]), rd1 = __ddiv_rn(1.0, dXp[1]);
+  const double slope = dXp[1] * rd0;
+  const double slope_inv = dXp[0] * rd1;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    index_old[d] = floor_div_fast(__dsub_rn(__dsub_rn(xo[d], A.le[d]), A.hdx[d]), A.dx[d], A.rdx[d]);
+    const int index_new = floor_div_fast(__dsub_rn(__dsub_rn(xpnew[d], A.le[d]), A.hdx[d]), A.dx[d], A.rdx[d]);
+    if (index_new < index_old[d]) sign[d] = -1;
+    cell_crossings[d] = abs(index_new - index_old[d]);
+    num_segments += cell_crossings[d];
+  }
+  if (num_segments > max_segments) return 2;
+  double Xcell[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    double cidx = __dadd_rn((double)index_old[d], 0.5 * (double)(1 - sign[d]));
+    cidx = __dadd_rn(cidx, 0.5);
+    Xcell[d] = A.le[d] + cidx * A.dx[d];
+  }
+  double xpold0[2] = {xo[0], xo[1]};
+  double xpnew0[2] = {0.0, 0.0}, dXp_sub[2] = {0.0, 0.0};
+  int ii_next = index_old[0], jj_next = index_old[1];
+  for (int nn = 0; nn < num_segments; ++nn) {
+    const int ii = ii_next, jj = jj_next;
+    if (nn == num_segments - 1) {
+      xpnew0[0] = xpnew[0];
+      xpnew0[1] = xpnew[1];
+      dXp_sub[0] = xpnew0[0] - xpold0[0];
+      dXp_sub[1] = xpnew0[1] - xpold0[1];
+    } else if (cell_crossings[0] == 0) {
+      jj_next = jj + sign[1];
+      Xcell[1] = Xcell[1] + (double)sign[1] * A.dx[1];
+      xpnew0[1] = Xcell[1];
+      dXp_sub[1] = xpnew0[1] - xpold0[1];
+      dXp_sub[0] = __dmul_rn(slope_inv, dXp_sub[1]);
+      xpnew0[0] = xpold0[0] + dXp_sub[0];
+    } else if (cell_crossings[1] == 0) {
+      ii_next = ii + sign[0];
+      Xcell[0] = Xcell[0] + (double)sign[0] * A.dx[0];
+      xpnew0[0] = Xcell[0];
+      dXp_sub[0] = xpnew0[0] - xpold0[0];
+      dXp_sub[1] = __dmul_rn(slope, dXp_sub[0]);
+      xpnew0[1] = xpold0[1] + dXp_sub[1];
+    } else {
+      xpnew0[0] = Xcell[0] + (double)sign[0] * A.dx[0];
+      xpnew0[1] = Xcell[1] + (double)sign[1] * A.dx[1];
+      dXp_sub[0] = xpnew0[0] - xpold0[0];
+      dXp_sub[1] = xpnew0[1] - xpold0[1];
+      const double dXp_sub02 = __dmul_rn(slope_inv, dXp_sub[1]);
+      if (fabs(dXp_sub[0]) < fabs(dXp_sub02)) {
+        dXp_sub[1] = __dmul_rn(slope, dXp_sub[0]);
+        xpnew0[1] = xpold0[1] + dXp_sub[1];
+        Xcell[0] = xpnew0[0];
+        ii_next = ii + sign[0];
+        cell_crossings[0] -= 1;
+      } else {
+        dXp_sub[0] = __dmul_rn(slope_inv, dXp_sub[1]);
+        xpnew0[0] = xpold0[0] + dXp_sub[0];
+        Xcell[1] = xpnew0[1];
+        jj_next = jj + sign[1];
+        cell_crossings[1] -= 1;
+      }
+    }
+    const double seg_factor[2] = {(dXp[0] != 0.0) ? dXp_sub[0] * rd0 : 1.0, (dXp[1] != 0.0) ? dXp_sub[1] * rd1 : 1.0};
+    if (!fn(ii, jj, xpold0, xpnew0, seg_factor)) return 1;
+    xpold0[0] = xpnew0[0];
+    xpold0[1] = xpnew0[1];
+  }
+  return 0;
+}
+
+__device__ __forceinline__ bool tab_cell_ok(const FastArgs &A, int i, int j) {
+  return i >= A.i_lo[0] && i <= A.i_hi[0] && j >= A.i_lo[1] && j <= A.i_hi[1];
+}
+// offsets of a point from the centre node of dual cell (i, j), in cells
+__device__ __forceinline__ double cell_offset(const FastArgs &A, int d, double x, int idx) {
+  return fma(__dsub_rn(x, A.le[d]), A.rdx[d], -(double)(idx + 1));
+}
+
+// the segments of the orbit gathered last: the deposit of a converged particle reuses them instead of walking again
+constexpr int MAXSEG = 4;
+struct SegStore {
+  int n;
+  int ii[MAXSEG], jj[MAXSEG];
+  double dS[MAXSEG][2], dE[MAXSEG][2], sf[MAXSEG][2];
+  int ib[2];        // dual cell of x_bar and its offsets there (nodal part)
+  double dB[2];
+};
+
+// E and B at the orbit (x_old, x_bar); false = hand the particle to the visitor kernel
+__device__ __forceinline__ bool gather_multiseg(const FastArgs &A, int max_segments, const double (&xo)[2],
+                                                const double (&xb)[2], double (&E)[3], double (&B)[3], SegStore &S) {
+  double e0 = 0.0, e1 = 0.0;
+  S.n = 0;
+  const int rc = walk_cc1_2d(A, max_segments < MAXSEG ? max_segments : MAXSEG, xo, xb,
+                             [&](int ii, int jj, const double *xs, const double *xe, const double *sf) {
+    if (!tab_cell_ok(A, ii, jj)) return false;
+    const double *td = A.tdual + (size_t)((ii - A.tlo[0]) + (jj - A.tlo[1]) * A.tn0) * TD;
+    const double dS0 = cell_offset(A, 0, xs[0], ii), dS1 = cell_offset(A, 1, xs[1], jj);
+    const double dE0 = cell_offset(A, 0, xe[0], ii), dE1 = cell_offset(A, 1, xe[1], jj);
+    {
+      const int k = S.n++;
+      S.ii[k] = ii, S.jj[k] = jj;
+      S.dS[k][0] = dS0, S.dS[k][1] = dS1, S.dE[k][0] = dE0, S.dE[k][1] = dE1;
+      S.sf[k][0] = sf[0], S.sf[k][1] = sf[1];
+    }
+    const double del0 = 0.5 * (dS0 + dE0) + 0.5, del1 = 0.5 * (dS1 + dE1) + 0.5;
+    const double a0 = 0.5 - dE0, b0 = 0.5 + dE0, c0 = 0.5 - dS0, g0 = 0.5 + dS0;
+    const double a1 = 0.5 - dE1, b1 = 0.5 + dE1, c1 = 0.5 - dS1, g1 = 0.5 + dS1;
+    const double Wx0 = fma(a0, a0, c0 * c0), Wx2 = fma(b0, b0, g0 * g0);   // 4 W
+    const double Wy0 = fma(a1, a1, c1 * c1), Wy2 = fma(b1, b1, g1 * g1);
+    const double2 x01 = ld2(td), x23 = ld2(td + 2), x45 = ld2(td + 4);
+    const double2 y01 = ld2(td + 6), y23 = ld2(td + 8), y45 = ld2(td + 10);
+    const double ex = fma(Wy0, fma(del0, x23.y, x23.x), fma(Wy2, fma(del0, x45.y, x45.x), fma(del0, x01.y, x01.x)));
+    const double ey = fma(Wx0, fma(del1, y23.y, y23.x), fma(Wx2, fma(del1, y45.y, y45.x), fma(del1, y01.y, y01.x)));
+    e0 = fma(sf[0], ex, e0);
+    e1 = fma(sf[1], ey, e1);
+    return true;
+  });
+  if (rc) return false;
+  E[0] = e0;
+  E[1] = e1;
+  // nodal CIC at x_bar, from the records of x_bar's own dual cell
+  int ib[2];
+  double dB[2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const double xr = __dsub_rn(xb[d], A.le[d]);
+    ib[d] = floor_div_fast(__dsub_rn(xr, A.hdx[d]), A.dx[d], A.rdx[d]);
+    dB[d] = fma(xr, A.rdx[d], -(double)(ib[d] + 1));
+  }
+  if (!tab_cell_ok(A, ib[0], ib[1])) return false;
+  S.ib[0] = ib[0], S.ib[1] = ib[1], S.dB[0] = dB[0], S.dB[1] = dB[1];
+  const size_t cidx = (size_t)((ib[0] - A.tlo[0]) + (ib[1] - A.tlo[1]) * A.tn0);
+  const double *td = A.tdual + cidx * TD, *tn = A.tnode + cidx * TN;
+  const int nrow = A.tn0 * TN;
+  const double del0 = dB[0] + 0.5, del1 = dB[1] + 0.5;
+  const bool sx = del0 >= 0.5, sy = del1 >= 0.5;
+  const double fx = del0 + (sx ? -0.5 : 0.5), fy = del1 + (sy ? -0.5 : 0.5);
+  const int ox = sx ? TN : 0, oy = sy ? nrow : 0;
+  const double2 ez01 = ld2(tn + ox + oy), ez23 = ld2(tn + ox + oy + 2);
+  const double2 bx01 = ld2(tn + ox + 4), bx23 = ld2(tn + ox + 6);
+  const double2 by01 = ld2(tn + oy + 8), by23 = ld2(tn + oy + 10);
+  const double2 z01 = ld2(td + 12), z23 = ld2(td + 14);
+  E[2] = fma(fy, fma(fx, ez23.y, ez23.x), fma(fx, ez01.y, ez01.x));
+  B[0] = fma(del1, fma(fx, bx23.y, bx23.x), fma(fx, bx01.y, bx01.x));
+  B[1] = fma(fy, fma(del0, by23.y, by23.x), fma(del0, by01.y, by01.x));
+  B[2] = fma(del1, fma(del0, z23.y, z23.x), fma(del0, z01.y, z01.x));
+  return true;
+}
+
+__device__ __forceinline__ void boris_half(const FastArgs &A, const double (&uo)[3], const double (&E)[3],
+                                           const double (&B)[3], double (&ub)[3]) {
+  const double vm0 = fma(A.alpha, E[0], uo[0]), vm1 = fma(A.alpha, E[1], uo[1]), vm2 = fma(A.alpha, E[2], uo[2]);
+  const double b0 = A.alpha * B[0], b1 = A.alpha * B[1], b2 = A.alpha * B[2];
+  const double den = fma(b2, b2, fma(b1, b1, fma(b0, b0, 1.0)));
+  const double p0 = fma(-vm2, b1, fma(vm1, b2, vm0));
+  const double p1 = fma(-vm0, b2, fma(vm2, b0, vm1));
+  const double p2 = fma(-vm1, b0, fma(vm0, b1, vm2));
+  const double rden = rcp_ge1(den);
+  const double r0 = b0 * rden, r1 = b1 * rden, r2 = b2 * rden;
+  ub[0] = fma(-p2, r1, fma(p1, r2, vm0));
+  ub[1] = fma(-p0, r2, fma(p2, r0, vm1));
+  ub[2] = fma(-p1, r0, fma(p0, r1, vm2));
+}
+
+template <bool DEP>
+__global__ void __launch_bounds__(128) k_advance_cc1_2d_multiseg(const FastArgs A, const DeferPtrs P) {
+  const long total = (long)*P.count;
+  const long stride = (long)gridDim.x * blockDim.x;
+  unsigned apply = 0, unconv = 0;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long i = (long)P.list[t];
+    const double xo[2] = {P.xold[0][i], P.xold[1][i]};
+    double xb[2] = {P.x[0][i], P.x[1][i]};
+    const double uo[3] = {P.vold[0][i], P.vold[1][i], P.vold[2][i]};
+    double ub[3] = {uo[0], uo[1], uo[2]}, E[3], B[3];
+    unsigned napply = 0;
+    bool ok = true, left_unconverged = false;
+    SegStore S;
+    bool segs_current = false;   // S describes the orbit (x_old, x_bar as it stands)
+    if (A.iter_max < 0) {   // advanceParticles (:1594-1612), part_order_swap == false
+      ok = gather_multiseg(A, P.max_segments, xo, xb, E, B, S);
+      if (ok) {
+        boris_half(A, uo, E, B, ub);
+        napply = 1;
+        xb[0] = fma(ub[0], A.hdt, xo[0]);
+        xb[1] = fma(ub[1], A.hdt, xo[1]);
+      }
+    } else {                // advanceParticlesIteratively (:1614-1716) with stepNormTransfer (:658-733)
+      int iter = 0;
+      while (true) {
+        if (!gather_multiseg(A, P.max_segments, xo, xb, E, B, S)) {
+          ok = false;
+          break;
+        }
+        segs_current = true;
+        boris_half(A, uo, E, B, ub);
+        napply += 1;
+        const double dxp_0 = ub[0] * A.hdt, dxp_1 = ub[1] * A.hdt;
+        const double e0 = fabs((xb[0] - xo[0]) - dxp_0), e1 = fabs((xb[1] - xo[1]) - dxp_1);
+        bool converged;
+        if (iter == 0) {
+          xb[0] = xo[0] + dxp_0;
+          xb[1] = xo[1] + dxp_1;
+          segs_current = false;
+          converged = !(e0 >= A.tol[0]) && !(e1 >= A.tol[1]);
+        } else {
+          converged = e0 < A.tol[0] && e1 < A.tol[1];
+          if (!converged) {
+            xb[0] = xo[0] + dxp_0;
+            xb[1] = xo[1] + dxp_1;
+            segs_current = false;
+          }
+        }
+        if (converged) break;
+        if (iter >= A.iter_max) {
+          left_unconverged = true;
+          break;
+        }
+        iter += 1;
+      }
+    }
+    if (ok && left_unconverged && A.suborbit) ok = false;   // the visitor kernel lists it for the sub-orbit container
+    if (ok && DEP && !segs_current) {
+      // the orbit moved after its last gather (converged in the first pass, or left unconverged): its segments, and
+      // that every cell of them is depositable, before the first atomic goes out
+      double Ed[3], Bd[3];
+      ok = gather_multiseg(A, P.max_segments, xo, xb, Ed, Bd, S);
+    }
+    if (!ok) {
+      P.list2[atomicAdd(P.count2, 1u)] = (int)i;
+      continue;
+    }
+    apply += napply;
+    unconv += left_unconverged ? 1u : 0u;
+    P.x[0][i] = xb[0];
+    P.x[1][i] = xb[1];
+    P.v[0][i] = ub[0];
+    P.v[1][i] = ub[1];
+    P.v[2][i] = ub[2];
+    if (DEP) {
+      const double wp = P.w[i];
+      for (int k = 0; k < S.n; ++k) {
+        const int ii = S.ii[k], jj = S.jj[k];
+        const double dO[2] = {S.dS[k][0], S.dS[k][1]};
+        const double dM[2] = {0.5 * (S.dS[k][0] + S.dE[k][0]), 0.5 * (S.dS[k][1] + S.dE[k][1])};
+        const double us[3] = {ub[0] * S.sf[k][0], ub[1] * S.sf[k][1], 0.0};
+        double c[NSLOT];
+#pragma unroll
+        for (int j = 0; j < NSLOT; ++j) c[j] = 0.0;
+        deposit_tab(A, dO, dM, us, wp, c);
+        {
+          double *p0 = A.J[0] + (ii + jj * A.jn0[0]);
+          double *p1 = p0 + A.jn0[0];
+          double *p2 = p1 + A.jn0[0];
+          atomicAdd(p0, c[0]), atomicAdd(p0 + 1, c[1]);
+          atomicAdd(p1, c[2]), atomicAdd(p1 + 1, c[3]);
+          atomicAdd(p2, c[4]), atomicAdd(p2 + 1, c[5]);
+        }
+        {
+          double *p0 = A.J[1] + (ii + jj * A.jn0[1]);
+          double *p1 = p0 + A.jn0[1];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) atomicAdd(p0 + a, c[6 + a]), atomicAdd(p1 + a, c[9 + a]);
+        }
+      }
+      // Jz: nodal CIC at x_bar (cc1_2d_deposit_current :1720-1740)
+      const double dB[2] = {S.dB[0], S.dB[1]};
+      const double uz[3] = {0.0, 0.0, ub[2]};
+      double c[NSLOT];
+#pragma unroll
+      for (int j = 0; j < NSLOT; ++j) c[j] = 0.0;
+      deposit_tab(A, dB, dB, uz, wp, c);
+      double *p0 = A.J[2] + (S.ib[0] + S.ib[1] * A.jn0[2]);
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double val = c[12 + a + 3 * b];
+          if (val != 0.0) atomicAdd(p0 + a + b * A.jn0[2], val);
+        }
+    }
+  }
+  apply = __reduce_add_sync(0xffffffffu, apply);
+  unconv = __reduce_add_sync(0xffffffffu, unconv);
+  if ((threadIdx.x & 31) == 0) {
+    if (apply) atomicAdd(&A.cnt->apply_its, (unsigned long long)apply);
+    if (unconv) atomicAdd(&A.cnt->unconverged, (unsigned long long)unconv);
+  }
+}
+
 }  // namespace
 
 // Returns 1 if the fast kernel was launched (deferred particles are then in s->defer_list),
@@ -2030,11 +2363,48 @@ int launch_advance_cc1_fast(pgpu_species_s *s, const AdvanceParams &prm, bool de
   } while (0)
       if (deposit) PGPU_V2_PICK(true, 3);
       else PGPU_V2_PICK(false, 0);
+      t.stop();
       if (xa)
         for (int d = 0; d < 2; ++d) std::swap(s->x[d], s->xold[d]);
       if (va)
         for (int k = 0; k < 3; ++k) std::swap(s->v[k], s->vold[k]);
       s->xold_alias = s->vold_alias = false;
+      s->defer_count_first = s->defer_count;
+      if (c.cc1_multiseg && !prm.explicit_step) {
+        // the listed (crossing) particles from the tables; what it cannot do lands on the second list, which becomes
+        // THE list of the visitor kernel
+        if (!s->defer_list2 || s->defer_cap2 < s->defer_cap) {
+          if (s->defer_list2) cudaFree(s->defer_list2);
+          if (!s->defer_count2) PGPU_CUDA(cudaMalloc(&s->defer_count2, sizeof(unsigned)));
+          PGPU_CUDA(cudaMalloc(&s->defer_list2, s->defer_cap * sizeof(int)));
+          s->defer_cap2 = s->defer_cap;
+        }
+        PGPU_CUDA(cudaMemsetAsync(s->defer_count2, 0, sizeof(unsigned), c.stream));
+        DeferPtrs P;
+        for (int d = 0; d < 2; ++d) {
+          P.x[d] = s->x[d];
+          P.xold[d] = s->xold[d];
+        }
+        for (int k = 0; k < 3; ++k) {
+          P.v[k] = s->v[k];
+          P.vold[k] = s->vold[k];
+        }
+        P.w = s->w;
+        P.list = s->defer_list;
+        P.count = s->defer_count;
+        P.list2 = s->defer_list2;
+        P.count2 = s->defer_count2;
+        P.max_segments = g->desc.nghost + 1;
+        {
+          KTimer t2(deposit ? "advance_multiseg_fused" : "advance_multiseg");
+          const unsigned gridd = (unsigned)(c.sm_count * 8);
+          if (deposit) k_advance_cc1_2d_multiseg<true><<<gridd, 128, 0, c.stream>>>(A, P);
+          else k_advance_cc1_2d_multiseg<false><<<gridd, 128, 0, c.stream>>>(A, P);
+        }
+        std::swap(s->defer_list, s->defer_list2);
+        std::swap(s->defer_count, s->defer_count2);
+        std::swap(s->defer_cap, s->defer_cap2);
+      }
       return 1;
     }
     if (c.cc1_pair && !prm.suborbit) {

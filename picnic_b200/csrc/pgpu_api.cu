@@ -35,13 +35,15 @@ KTimer::KTimer(const char *n) : name(n) {
     cudaEventRecord(a, c.stream);
   }
 }
-KTimer::~KTimer() {
+void KTimer::stop() {
   Context &c = ctx();
   if (a) {
     cudaEventRecord(b, c.stream);
     c.recs.push_back(Context::Rec{std::string(name), a, b});
+    a = b = nullptr;
   }
 }
+KTimer::~KTimer() { stop(); }
 
 static void profile_drain() {
   Context &c = ctx();
@@ -464,6 +466,7 @@ int pgpu_init(int device) {
   if (const char *e = getenv("PGPU_COPY_STREAM")) c.use_copy_stream = atoi(e);
   if (const char *e = getenv("PGPU_CC1_V")) c.cc1_version = atoi(e);
   if (const char *e = getenv("PGPU_CC1_NODECACHE")) c.cc1_nodecache = atoi(e);
+  if (const char *e = getenv("PGPU_CC1_MULTISEG")) c.cc1_multiseg = atoi(e);
   if (const char *e = getenv("PGPU_CC1_REC")) c.cc1_rec_per_pass = atoi(e);
   if (const char *e = getenv("PGPU_CC1_WAVES")) c.cc1_waves = atoi(e) > 0 ? atoi(e) : 1;
   return 0;
@@ -779,6 +782,8 @@ int pgpu_species_destroy(pgpu_species_t s) {
   cudaFree(s->cub_tmp);
   for (int k = 0; k < 4; ++k) cudaFree(s->spare[k]);
   cudaFree(s->defer_list);
+  cudaFree(s->defer_list2);
+  cudaFree(s->defer_count2);
   cudaFree(s->bin_count);
   cudaFree(s->enf_save);
   for (int k = 0; k < 10; ++k) cudaFree(s->out[k]);
@@ -1355,8 +1360,9 @@ int pgpu_species_deferred_count(pgpu_species_t s, long *count) {
   NEED_INIT();
   if (!s || !count) return PGPU_ERR_ARG;
   unsigned n = 0;
-  if (s->defer_count) {
-    PGPU_CUDA(cudaMemcpyAsync(&n, s->defer_count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
+  const unsigned *src = s->defer_count_first ? s->defer_count_first : s->defer_count;
+  if (src) {
+    PGPU_CUDA(cudaMemcpyAsync(&n, src, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx().stream));
     PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
   }
   *count = (long)n;

@@ -104,6 +104,7 @@ struct Context {
   int cc1_prefetch = 0;      // L2 prefetch of a block's next particle tile (env PGPU_CC1_PREFETCH)
   int cc1_version = 2;       // table kernel generation: 1 = round-1 map (4 consecutive particles per thread in both phases), 2 = lane map in the push phase (env PGPU_CC1_V)
   int cc1_rec_per_pass = 1;  // v2: reload the dual-cell record every Picard pass instead of holding it in 32 registers (env PGPU_CC1_REC)
+  int cc1_multiseg = 1;      // crossing particles of the tile kernel through the table-driven multi-segment kernel (env PGPU_CC1_MULTISEG)
   int cc1_nodecache = 0;     // v1: keep the node records of the last (dual cell, half cell) in registers too (env PGPU_CC1_NODECACHE)
   int cc1_waves = 64;        // tile kernel grid = min(tiles, SMs*4*waves) (env PGPU_CC1_WAVES)
   bool use_fast_cc1 = true;  // pgpu_set_deposit_mode(0) turns the specialised CC1 kernel off
@@ -137,6 +138,7 @@ struct KTimer {
   const char *name;
   cudaEvent_t a = nullptr, b = nullptr;
   explicit KTimer(const char *n);
+  void stop();     // close the interval now (the destructor then does nothing)
   ~KTimer();
 };
 
@@ -240,6 +242,10 @@ struct pgpu_species_s {
   int *defer_list = nullptr;        // particles the CC1 fast kernel left to the generic one
   unsigned *defer_count = nullptr;
   size_t defer_cap = 0;
+  int *defer_list2 = nullptr;       // second list: what the table-driven multi-segment kernel hands on (the two swap roles)
+  unsigned *defer_count2 = nullptr;
+  size_t defer_cap2 = 0;
+  unsigned *defer_count_first = nullptr;   // the count the tile kernel of the last advance wrote (diagnostic)
   // migration scratch (pgpu_exchange.cu)
   void *mig = nullptr;
   bool mig_marked = false;

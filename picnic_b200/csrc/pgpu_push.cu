@@ -159,8 +159,11 @@ k_deposit(PartPtrs p, long n, Geo<D> g, CurrentSet J, double volume, double rvol
 }
 
 // ---- advanceParticles / advanceParticlesIteratively (+ optional fused deposit) ------
+#ifndef PGPU_ADV_MINB
+#define PGPU_ADV_MINB 2
+#endif
 template <int D, int IE, bool X, bool DEP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PGPU_ADV_MINB)
 k_advance(PartPtrs p, long n, Geo<D> g, FieldSet F, CurrentSet J, AdvanceParams prm, Counters *cnt,
           const int *list, const unsigned *list_count) {
   typedef M<X> m;
