@@ -793,13 +793,15 @@ def variants_leg(args, rank, local, stream, region, capi):
         ms, _ = region(a.steps, False, profile=True, eng=eng)
         k_ms, k_n = capi.profile_query("advance_cc1_fused")
         d_ms, _ = capi.profile_query("advance_deferred")
+        m_ms, _ = capi.profile_query("advance_multiseg")
         adv, app, unconv = capi.picard_totals(reset=True)
         n = eng.n_particles
         per_launch = n / len(eng.species)
         out[label] = {"value": float(n) * a.n_outer * a.steps / (ms * 1e-3), "unit": "particle-advances/s",
                       "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
                       "mean_picard_passes": round(app / max(adv, 1), 3), "unconverged_particles": int(unconv),
-                      "kernel_ms_per_launch": k_ms / max(k_n, 1), "deferred_ms_per_step": d_ms / a.steps,
+                      "kernel_ms_per_launch": k_ms / max(k_n, 1), "multiseg_ms_per_step": m_ms / a.steps,
+                      "deferred_ms_per_step": d_ms / a.steps,
                       "roofline_frac_kernel": (BYTES_PER_ADVANCE_2D * per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9
                                                / region.peak) if k_n else None,
                       "overrides": over}

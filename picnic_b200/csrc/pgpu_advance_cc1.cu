@@ -2063,8 +2063,11 @@ __device__ __forceinline__ void boris_half(const FastArgs &A, const double (&uo)
   ub[2] = fma(-p1, r0, fma(p0, r1, vm2));
 }
 
+#ifndef PGPU_MS_MINB
+#define PGPU_MS_MINB 4
+#endif
 template <bool DEP>
-__global__ void __launch_bounds__(128) k_advance_cc1_2d_multiseg(const FastArgs A, const DeferPtrs P) {
+__global__ void __launch_bounds__(128, PGPU_MS_MINB) k_advance_cc1_2d_multiseg(const FastArgs A, const DeferPtrs P) {
   const long total = (long)*P.count;
   const long stride = (long)gridDim.x * blockDim.x;
   unsigned apply = 0, unconv = 0;
