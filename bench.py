@@ -891,9 +891,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     numa = bind_to_gpu_cpus(local)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0 prints ONE JSON line on stdout: the image exports NCCL_DEBUG=VERSION, whose only effect is a
+        # "NCCL version ..." banner on stdout (WARN prints it too); INFO etc. set by a user are left alone
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from picnic_b200 import capi
     capi.load()
