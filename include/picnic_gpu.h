@@ -214,6 +214,19 @@ int pgpu_advance_particles(pgpu_species_t s, double dt);
 int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_J,
                                        pgpu_picard_stats *stats);
 
+/* The curvilinear velocity pushes PicChargedSpecies::applyForces dispatches to (PicChargedSpecies.cpp:341-355):
+ * PicSpeciesUtils::applyForces_CYL_CYL / _SPH_SPH / _CYL_HYB / _SPH_HYB (src/species/pic/PicSpeciesUtils.cpp:103-473), on
+ * the stored particle fields (pgpu_interpolate_fields_to_particles) like pgpu_advance_velocities.  r_old is x_old[0];
+ * the particle's position_virt (dtheta, dphi) lives in two device arrays ([2][n] on the host side): zero selects the
+ * predictor-corrector branch of CYL_CYL / SPH_SPH, which stores the corrected angle.  anticyclic: components stored
+ * {X, Z, Y} (cyl_RZ).  The HYB types return the time-centred velocity (the reference has no byHalfDt there).  Only the
+ * velocity update of the curvilinear geometries is covered: their position advance, virtual-position re-basing and
+ * Jacobian-weighted deposits are not. */
+enum { PGPU_PUSH_CYL_CYL = 1, PGPU_PUSH_SPH_SPH = 2, PGPU_PUSH_CYL_HYB = 3, PGPU_PUSH_SPH_HYB = 4 };
+int pgpu_apply_forces_curvilinear(pgpu_species_t s, int push_type, double full_dt, int by_half_dt, int anticyclic);
+int pgpu_species_virtual_positions_set(pgpu_species_t s, const double *virt /* [2][n] */);
+int pgpu_species_virtual_positions_get(pgpu_species_t s, double *virt /* [2][n] */);
+
 /* PIC_EM_EXPLICIT: the particle side of one leap-frog step (PICTimeIntegrator_EM_Explicit::timeStep,
  * src/time/PICTimeIntegrator_EM_Explicit.cpp:92-170, default branch) as ONE pass over the particles:
  * interpolateFieldsToParticles + addExternalFieldsToParticles + advanceVelocities(dt, false) (:94-111),

@@ -178,6 +178,20 @@ def boris(v, vold, Ep, Bp, fnorm, cnormDt, by_half):
     return out
 
 
+PUSH_CYL_CYL, PUSH_SPH_SPH, PUSH_CYL_HYB, PUSH_SPH_HYB = 1, 2, 3, 4
+
+
+def boris_curvilinear(push_type, vold, Ep, Bp, r_old, virt, fnorm, cnormDt, by_half, anticyclic=False):
+    """applyForces_CYL_CYL / SPH_SPH / CYL_HYB / SPH_HYB; virt [2, n] is updated in place (types 1, 2)."""
+    f = lib().orc_boris_curvilinear
+    f.argtypes = [C.c_int, C.c_long] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_int, C.c_int]
+    out = np.zeros_like(vold)
+    rc = f(push_type, vold.shape[1], _ptr(out), _ptr(vold), _ptr(Ep), _ptr(Bp), _ptr(r_old), _ptr(virt), fnorm, cnormDt,
+           int(by_half), int(anticyclic))
+    assert rc == 0
+    return out
+
+
 def deposit_current(g, interp, x, xold, v, w, cnormDt, J):
     n = x.shape[1]
     return lib().orc_deposit_current(C.byref(g), interp, n, _ptr(x), _ptr(xold), _ptr(v), _ptr(w), cnormDt, _fabs3(J))

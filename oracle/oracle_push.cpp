@@ -50,6 +50,140 @@ static double implicit_gamma_soa(long n, long p, const double *vold, const doubl
   return orc_implicit_gamma(uo, ub);
 }
 
+/* The curvilinear velocity pushes of PicChargedSpecies::applyForces (PicChargedSpecies.cpp:341-355):
+ *   type 1 CYL_CYL  PicSpeciesUtils::applyForces_CYL_CYL (PicSpeciesUtils.cpp:103-206): Boris with the inertia term as an
+ *                   extra B_z = sin(dtheta); dtheta (pos_virt[0]) is predicted from u_old and r_old when it is zero and
+ *                   then corrected with the new velocity and stored (the caller iterates);
+ *   type 2 SPH_SPH  applyForces_SPH_SPH (:208-309): the same with dtheta, dphi (pos_virt[0], [1]), sines of the angles;
+ *   type 3 CYL_HYB  applyForces_CYL_HYB (:311-383): Cartesian Boris on u_old rotated by the time-centred angle pos_virt[0];
+ *   type 4 SPH_HYB  applyForces_SPH_HYB (:385-473): the same with two angles.
+ * r_old = x_old[0] (types 1, 2).  virt[k*n+p], k < 2, is read and (types 1, 2) written.  anticyclic: particle arrays are
+ * stored {X, Z, Y} (cyl_RZ).  HYB types always return the time-centred velocity (the reference has no byHalfDt there).
+ * The relativistic build divides the scaled B by gamma = sqrt(1 + |vm|^2) (no Higuera-Cary variant in these pushes). */
+extern "C" int orc_boris_curvilinear(int type, long n, double *v, const double *vold, const double *Ep, const double *Bp,
+                                     const double *r_old, double *virt, double fnorm, double cnormDt, int byHalfDt,
+                                     int anticyclic) {
+  if (type < 1 || type > 4) return -1;
+  const double alpha = fnorm * cnormDt / 2.0;
+  int dirp[3] = {0, 1, 2};
+  if (anticyclic && (type == 1 || type == 3)) {
+    dirp[1] = 2;
+    dirp[2] = 1;
+  }
+  for (long p = 0; p < n; ++p) {
+    const double uo[3] = {vold[dirp[0] * n + p], vold[dirp[1] * n + p], vold[dirp[2] * n + p]};
+    const double E[3] = {Ep[dirp[0] * n + p], Ep[dirp[1] * n + p], Ep[dirp[2] * n + p]};
+    const double B[3] = {Bp[dirp[0] * n + p], Bp[dirp[1] * n + p], Bp[dirp[2] * n + p]};
+    double vm0 = uo[0] + alpha * E[0];
+    double vm1 = uo[1] + alpha * E[1];
+    double vm2 = uo[2] + alpha * E[2];
+    double bp0, bp1, bp2, gammap = 1.0, up[3];
+    if (type == 1) {
+      bp0 = alpha * B[0];
+      bp1 = alpha * B[1];
+      if (g_rel) {
+        gammap = std::sqrt(1.0 + vm0 * vm0 + vm1 * vm1 + vm2 * vm2);
+        bp0 /= gammap;
+        bp1 /= gammap;
+      }
+      double dtheta = virt[p];
+      bool set_dtheta = false;
+      if (dtheta == 0.0) {
+        dtheta = cnormDt / 2.0 * uo[1] / r_old[p] / gammap;
+        set_dtheta = true;
+      }
+      bp2 = alpha * B[2] / gammap + std::sin(dtheta);
+      const double denom = 1.0 + bp0 * bp0 + bp1 * bp1 + bp2 * bp2;
+      const double vpr0 = vm0 + vm1 * bp2 - vm2 * bp1;
+      const double vpr1 = vm1 + vm2 * bp0 - vm0 * bp2;
+      const double vpr2 = vm2 + vm0 * bp1 - vm1 * bp0;
+      up[0] = vm0 + (vpr1 * bp2 - vpr2 * bp1) / denom;
+      up[1] = vm1 + (vpr2 * bp0 - vpr0 * bp2) / denom;
+      up[2] = vm2 + (vpr0 * bp1 - vpr1 * bp0) / denom;
+      if (set_dtheta) {
+        const double rpbar = r_old[p] + cnormDt / 2.0 * up[0];
+        dtheta = cnormDt / 2.0 * up[1] / rpbar / gammap;
+        virt[p] = dtheta;
+      }
+      if (!byHalfDt)
+        for (int k = 0; k < 3; ++k) up[k] = 2.0 * up[k] - uo[k];
+    } else if (type == 2) {
+      if (g_rel) gammap = std::sqrt(1.0 + vm0 * vm0 + vm1 * vm1 + vm2 * vm2);
+      bp0 = alpha * B[0] / gammap;
+      bp1 = alpha * B[1] / gammap;
+      bp2 = alpha * B[2] / gammap;
+      double dtheta = virt[p], dphi = virt[n + p];
+      bool set_dtheta = false;
+      if (dtheta == 0.0) {
+        dtheta = cnormDt / 2.0 * uo[1] / r_old[p] / gammap;
+        dphi = cnormDt / 2.0 * uo[2] / r_old[p] / gammap;
+        dtheta = std::sin(dtheta);
+        dphi = std::sin(dphi);
+        set_dtheta = true;
+      }
+      bp0 += std::sin(dphi) * dtheta;
+      bp1 -= dphi;
+      bp2 += std::cos(dphi) * dtheta;
+      const double denom = 1.0 + bp0 * bp0 + bp1 * bp1 + bp2 * bp2;
+      const double vpr0 = vm0 + vm1 * bp2 - vm2 * bp1;
+      const double vpr1 = vm1 + vm2 * bp0 - vm0 * bp2;
+      const double vpr2 = vm2 + vm0 * bp1 - vm1 * bp0;
+      up[0] = vm0 + (vpr1 * bp2 - vpr2 * bp1) / denom;
+      up[1] = vm1 + (vpr2 * bp0 - vpr0 * bp2) / denom;
+      up[2] = vm2 + (vpr0 * bp1 - vpr1 * bp0) / denom;
+      if (set_dtheta) {
+        const double rpbar = r_old[p] + cnormDt / 2.0 * up[0];
+        dphi = cnormDt / 2.0 * up[2] / rpbar / gammap;
+        dphi = std::sin(dphi);
+        dtheta = cnormDt / 2.0 * up[1] / rpbar / gammap / std::cos(dphi);
+        dtheta = std::sin(dtheta);
+        virt[p] = dtheta;
+        virt[n + p] = dphi;
+      }
+      if (!byHalfDt)
+        for (int k = 0; k < 3; ++k) up[k] = 2.0 * up[k] - uo[k];
+    } else {
+      bp0 = alpha * B[0];
+      bp1 = alpha * B[1];
+      bp2 = alpha * B[2];
+      if (g_rel) {
+        gammap = std::sqrt(1.0 + vm0 * vm0 + vm1 * vm1 + vm2 * vm2);
+        bp0 /= gammap;
+        bp1 /= gammap;
+        bp2 /= gammap;
+      }
+      const double denom = 1.0 + bp0 * bp0 + bp1 * bp1 + bp2 * bp2;
+      if (type == 3) {
+        const double dthp = virt[p];
+        const double costhp = std::cos(dthp), sinthp = std::sin(dthp);
+        const double upoldr_2 = costhp * uo[0] + sinthp * uo[1];
+        const double upoldth_2 = -sinthp * uo[0] + costhp * uo[1];
+        vm0 = upoldr_2 + alpha * E[0];
+        vm1 = upoldth_2 + alpha * E[1];
+      } else {
+        const double thp = virt[p], php = virt[n + p];
+        const double costhp = std::cos(thp), sinthp = std::sin(thp), cosphp = std::cos(php), sinphp = std::sin(php);
+        const double upoldr_2 = cosphp * (costhp * uo[0] + sinthp * uo[1]) + sinphp * uo[2];
+        const double upoldth_2 = -sinthp * uo[0] + costhp * uo[1];
+        const double upoldph_2 = -sinphp * (costhp * uo[0] + sinthp * uo[1]) + cosphp * uo[2];
+        vm0 = upoldr_2 + alpha * E[0];
+        vm1 = upoldth_2 + alpha * E[1];
+        vm2 = upoldph_2 + alpha * E[2];
+      }
+      const double vpr0 = vm0 + vm1 * bp2 - vm2 * bp1;
+      const double vpr1 = vm1 + vm2 * bp0 - vm0 * bp2;
+      const double vpr2 = vm2 + vm0 * bp1 - vm1 * bp0;
+      up[0] = vm0 + (vpr1 * bp2 - vpr2 * bp1) / denom;
+      up[1] = vm1 + (vpr2 * bp0 - vpr0 * bp2) / denom;
+      up[2] = vm2 + (vpr0 * bp1 - vpr1 * bp0) / denom;
+    }
+    v[dirp[0] * n + p] = up[0];
+    v[dirp[1] * n + p] = up[1];
+    v[dirp[2] * n + p] = up[2];
+  }
+  return 0;
+}
+
 /* PicSpeciesUtils::applyForces (PicSpeciesUtils.cpp:8-101), dirp = {0,1,2}. */
 extern "C" void orc_boris(long n, double *v, const double *vold, const double *Ep,
                           const double *Bp, double fnorm, double cnormDt,

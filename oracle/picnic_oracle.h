@@ -104,6 +104,10 @@ void orc_advance_positions_implicit_rel(int D, long n, double *x, const double *
 int orc_deposit_current_rel(const orc_geom *g, int interp, long n, const double *x, const double *xold,
                             const double *v, const double *vold, const double *w, double cnormDt,
                             int from_explicit_solver, orc_fab *J);
+/* curvilinear velocity pushes (applyForces_CYL_CYL / SPH_SPH / CYL_HYB / SPH_HYB, PicSpeciesUtils.cpp:103-473): type 1..4;
+ * pinned bit for bit on the reference's compiled code (tests/test_ref_pin_curvilinear.py) */
+int orc_boris_curvilinear(int type, long n, double *v, const double *vold, const double *Ep, const double *Bp,
+                          const double *r_old, double *virt, double fnorm, double cnormDt, int byHalfDt, int anticyclic);
 void orc_boris(long n, double *v, const double *vold, const double *Ep,
                const double *Bp, double fnorm, double cnormDt, int byHalfDt);
 void orc_advance_positions_explicit(int D, long n, double *x, const double *xold,

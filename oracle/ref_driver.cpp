@@ -3,6 +3,7 @@
 // oracle/ref_build.sh against oracle/chombo_mock/) on plain arrays, so that the oracle restatement
 // can be pinned against the real thing:
 //   ref_boris           -> PicSpeciesUtils::applyForces        (src/species/pic/PicSpeciesUtils.cpp:8-101)
+//   ref_boris_curvilinear -> PicSpeciesUtils::applyForces_CYL_CYL/_SPH_SPH/_CYL_HYB/_SPH_HYB (PicSpeciesUtils.cpp:103-473)
 //   ref_delta_u         -> ScatteringUtils::computeDeltaU      (src/scattering/ScatteringUtils.H:84-111)
 //   ref_rotate_velocity -> ScatteringUtils::rotateVelocity     (src/scattering/ScatteringUtils.H:51-82)
 //   ref_scattering_cos  -> ScatteringUtils::getScatteringCos   (src/scattering/ScatteringUtils.H:12-18)
@@ -58,6 +59,41 @@ void ref_boris(long n, double *v, const double *vold, const double *Ep, const do
     v[p] = u[0];
     v[n + p] = u[1];
     v[2 * n + p] = u[2];
+  }
+}
+
+// PicSpeciesUtils::applyForces_CYL_CYL / _SPH_SPH / _CYL_HYB / _SPH_HYB (src/species/pic/PicSpeciesUtils.cpp:103-473),
+// type 1..4; r_old -> position_old()[0]; virt[k*n+p] <-> position_virt()[k]
+void ref_boris_curvilinear(int type, long n, double *v, const double *vold, const double *Ep, const double *Bp,
+                           const double *r_old, double *virt, double fnorm, double cnormDt, int byHalfDt,
+                           int anticyclic) {
+  List<JustinsParticle> lst;
+  for (long p = 0; p < n; ++p) {
+    JustinsParticle q;
+    q.setOldVelocity({vold[p], vold[n + p], vold[2 * n + p]});
+    q.setVelocity({0.0, 0.0, 0.0});
+    q.setElectricField({Ep[p], Ep[n + p], Ep[2 * n + p]});
+    q.setMagneticField({Bp[p], Bp[n + p], Bp[2 * n + p]});
+    RealVect xo;
+    for (int d = 0; d < SpaceDim; ++d) xo[d] = 0.0;
+    xo[0] = r_old[p];
+    q.setOldPosition(xo);
+    std::array<Real, 4 - CH_SPACEDIM> &pv = q.position_virt();
+    for (int k = 0; k < 4 - CH_SPACEDIM && k < 2; ++k) pv[k] = virt[k * n + p];
+    lst.add(q);
+  }
+  if (type == 1) PicSpeciesUtils::applyForces_CYL_CYL(lst, fnorm, cnormDt, byHalfDt != 0, anticyclic != 0);
+  else if (type == 2) PicSpeciesUtils::applyForces_SPH_SPH(lst, fnorm, cnormDt, byHalfDt != 0);
+  else if (type == 3) PicSpeciesUtils::applyForces_CYL_HYB(lst, fnorm, cnormDt, anticyclic != 0);
+  else PicSpeciesUtils::applyForces_SPH_HYB(lst, fnorm, cnormDt);
+  long p = 0;
+  for (ListIterator<JustinsParticle> lit(lst); lit.ok(); ++lit, ++p) {
+    const std::array<Real, 3> &u = lit().velocity();
+    v[p] = u[0];
+    v[n + p] = u[1];
+    v[2 * n + p] = u[2];
+    const std::array<Real, 4 - CH_SPACEDIM> &pv = lit().position_virt();
+    for (int k = 0; k < 4 - CH_SPACEDIM && k < 2; ++k) virt[k * n + p] = pv[k];
   }
 }
 

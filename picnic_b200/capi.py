@@ -160,6 +160,8 @@ def load():
         "pgpu_mass_matrix_get": [vp, i32, vp, vp, vp, i32], "pgpu_mass_matrix_J0_get": [vp, i32, vp, vp, vp],
         "pgpu_profile_enable": [i32], "pgpu_profile_reset": [], "pgpu_profile_query": [C.c_char_p, vp, vp],
         "pgpu_species_deferred_count": [vp, vp],
+        "pgpu_apply_forces_curvilinear": [vp, i32, dbl, i32, i32],
+        "pgpu_species_virtual_positions_set": [vp, vp], "pgpu_species_virtual_positions_get": [vp, vp],
         "pgpu_particle_linear_size": [vp], "pgpu_species_download_linear": [vp, vp],
         "pgpu_species_upload_linear": [vp, lng, vp],
         "pgpu_launch_count": [], "pgpu_picard_totals": [vp, vp, vp, i32], "pgpu_abi_version": [], "pgpu_last_error": [],
@@ -477,6 +479,19 @@ class Species:
     def upload_linear(self, rec):
         rec = np.ascontiguousarray(rec, dtype=np.float64)
         check(load().pgpu_species_upload_linear(self.h, rec.shape[0], _p(rec)))
+
+    def apply_forces_curvilinear(self, push_type, dt, by_half, anticyclic=False):
+        check(load().pgpu_apply_forces_curvilinear(self.h, push_type, dt, int(by_half), int(anticyclic)))
+
+    def set_virtual_positions(self, virt):
+        virt = np.ascontiguousarray(virt, dtype=np.float64)
+        assert virt.shape == (2, self.n)
+        check(load().pgpu_species_virtual_positions_set(self.h, _p(virt)))
+
+    def virtual_positions(self):
+        out = np.zeros((2, self.n))
+        check(load().pgpu_species_virtual_positions_get(self.h, _p(out)))
+        return out
 
     def deferred_count(self):
         n = C.c_long(0)

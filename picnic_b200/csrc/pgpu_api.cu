@@ -222,6 +222,118 @@ __global__ void k_boris_stored(PartPtrs p, long n, double alpha, int byHalfDt, i
   for (int c = 0; c < 3; ++c) p.v[c][i] = u[c];
 }
 
+// The curvilinear velocity pushes of PicChargedSpecies::applyForces (PicChargedSpecies.cpp:341-355) on the stored particle
+// fields: type 1 applyForces_CYL_CYL, 2 _SPH_SPH, 3 _CYL_HYB, 4 _SPH_HYB (PicSpeciesUtils.cpp:103-473).  A streaming pass:
+// every operation is the reference's, individually rounded (no contraction), so the result differs from the reference's only
+// through sin / cos (1-2 ulp against glibc).  r_old = x_old[0]; virt0 / virt1 = position_virt (dtheta, dphi).
+__global__ void k_boris_curvilinear(PartPtrs p, const double *r_old, double *virt0, double *virt1, long n, int type,
+                                    double alpha, double cnormDt, int byHalfDt, int anticyclic, int rel) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto A = [](double a, double b) { return __dadd_rn(a, b); };
+  auto S = [](double a, double b) { return __dsub_rn(a, b); };
+  auto M_ = [](double a, double b) { return __dmul_rn(a, b); };
+  auto D_ = [](double a, double b) { return __ddiv_rn(a, b); };
+  int dirp[3] = {0, 1, 2};
+  if (anticyclic && (type == 1 || type == 3)) {
+    dirp[1] = 2;
+    dirp[2] = 1;
+  }
+  const double uo[3] = {p.vold[dirp[0]][i], p.vold[dirp[1]][i], p.vold[dirp[2]][i]};
+  const double E[3] = {p.Ep[dirp[0]][i], p.Ep[dirp[1]][i], p.Ep[dirp[2]][i]};
+  const double B[3] = {p.Bp[dirp[0]][i], p.Bp[dirp[1]][i], p.Bp[dirp[2]][i]};
+  double vm0 = A(uo[0], M_(alpha, E[0])), vm1 = A(uo[1], M_(alpha, E[1])), vm2 = A(uo[2], M_(alpha, E[2]));
+  double bp0, bp1, bp2, gammap = 1.0, up[3];
+  const double hdt = D_(cnormDt, 2.0);
+  auto rotate = [&]() {
+    const double denom = A(A(A(1.0, M_(bp0, bp0)), M_(bp1, bp1)), M_(bp2, bp2));
+    const double vpr0 = S(A(vm0, M_(vm1, bp2)), M_(vm2, bp1));
+    const double vpr1 = S(A(vm1, M_(vm2, bp0)), M_(vm0, bp2));
+    const double vpr2 = S(A(vm2, M_(vm0, bp1)), M_(vm1, bp0));
+    up[0] = A(vm0, D_(S(M_(vpr1, bp2), M_(vpr2, bp1)), denom));
+    up[1] = A(vm1, D_(S(M_(vpr2, bp0), M_(vpr0, bp2)), denom));
+    up[2] = A(vm2, D_(S(M_(vpr0, bp1), M_(vpr1, bp0)), denom));
+  };
+  auto gamma_vm = [&]() { return __dsqrt_rn(A(A(A(1.0, M_(vm0, vm0)), M_(vm1, vm1)), M_(vm2, vm2))); };
+  if (type == 1) {
+    bp0 = M_(alpha, B[0]);
+    bp1 = M_(alpha, B[1]);
+    if (rel) {
+      gammap = gamma_vm();
+      bp0 = D_(bp0, gammap);
+      bp1 = D_(bp1, gammap);
+    }
+    const double r = r_old[i];
+    double dtheta = virt0[i];
+    bool set_dtheta = false;
+    if (dtheta == 0.0) {
+      dtheta = D_(D_(M_(hdt, uo[1]), r), gammap);
+      set_dtheta = true;
+    }
+    bp2 = A(D_(M_(alpha, B[2]), gammap), sin(dtheta));
+    rotate();
+    if (set_dtheta) {
+      const double rpbar = A(r, M_(hdt, up[0]));
+      virt0[i] = D_(D_(M_(hdt, up[1]), rpbar), gammap);
+    }
+    if (!byHalfDt)
+      for (int k = 0; k < 3; ++k) up[k] = S(M_(2.0, up[k]), uo[k]);
+  } else if (type == 2) {
+    if (rel) gammap = gamma_vm();
+    bp0 = D_(M_(alpha, B[0]), gammap);
+    bp1 = D_(M_(alpha, B[1]), gammap);
+    bp2 = D_(M_(alpha, B[2]), gammap);
+    const double r = r_old[i];
+    double dtheta = virt0[i], dphi = virt1[i];
+    bool set_dtheta = false;
+    if (dtheta == 0.0) {
+      dtheta = sin(D_(D_(M_(hdt, uo[1]), r), gammap));
+      dphi = sin(D_(D_(M_(hdt, uo[2]), r), gammap));
+      set_dtheta = true;
+    }
+    bp0 = A(bp0, M_(sin(dphi), dtheta));
+    bp1 = S(bp1, dphi);
+    bp2 = A(bp2, M_(cos(dphi), dtheta));
+    rotate();
+    if (set_dtheta) {
+      const double rpbar = A(r, M_(hdt, up[0]));
+      dphi = sin(D_(D_(M_(hdt, up[2]), rpbar), gammap));
+      dtheta = sin(D_(D_(D_(M_(hdt, up[1]), rpbar), gammap), cos(dphi)));
+      virt0[i] = dtheta;
+      virt1[i] = dphi;
+    }
+    if (!byHalfDt)
+      for (int k = 0; k < 3; ++k) up[k] = S(M_(2.0, up[k]), uo[k]);
+  } else {
+    bp0 = M_(alpha, B[0]);
+    bp1 = M_(alpha, B[1]);
+    bp2 = M_(alpha, B[2]);
+    if (rel) {
+      gammap = gamma_vm();
+      bp0 = D_(bp0, gammap);
+      bp1 = D_(bp1, gammap);
+      bp2 = D_(bp2, gammap);
+    }
+    const double thp = virt0[i];
+    const double costhp = cos(thp), sinthp = sin(thp);
+    if (type == 3) {
+      vm0 = A(A(M_(costhp, uo[0]), M_(sinthp, uo[1])), M_(alpha, E[0]));
+      vm1 = A(A(M_(-sinthp, uo[0]), M_(costhp, uo[1])), M_(alpha, E[1]));
+    } else {
+      const double php = virt1[i];
+      const double cosphp = cos(php), sinphp = sin(php);
+      const double h = A(M_(costhp, uo[0]), M_(sinthp, uo[1]));
+      vm0 = A(A(M_(cosphp, h), M_(sinphp, uo[2])), M_(alpha, E[0]));
+      vm1 = A(A(M_(-sinthp, uo[0]), M_(costhp, uo[1])), M_(alpha, E[1]));
+      vm2 = A(A(M_(-sinphp, h), M_(cosphp, uo[2])), M_(alpha, E[2]));
+    }
+    rotate();
+  }
+  p.v[dirp[0]][i] = up[0];
+  p.v[dirp[1]][i] = up[1];
+  p.v[dirp[2]][i] = up[2];
+}
+
 __global__ void k_scale(double *a, long n, double s) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = __dmul_rn(a[i], s);
@@ -791,6 +903,7 @@ int pgpu_species_destroy(pgpu_species_t s) {
   cudaFree(s->out_id);
   cudaFree(s->out_tag);
   cudaFree(s->out_listtag);
+  for (int k = 0; k < 2; ++k) cudaFree(s->virt[k]);
   for (int k = 0; k < 10; ++k) cudaFree(s->inf[k]);
   cudaFree(s->inf_w);
   cudaFree(s->inf_id);
@@ -1147,6 +1260,67 @@ int pgpu_advance_velocities(pgpu_species_t s, double full_dt, int half_step) {
   KTimer t("boris");
   k_boris_stored<<<nb(s->n), 256, 0, ctx().stream>>>(s->ptrs(), s->n, alpha, half_step, ctx().exact ? 1 : 0,
                                                      s->desc.relativistic, s->desc.higuera_cary);
+  return 0;
+}
+
+static int ensure_virt(pgpu_species_t s) {
+  if (s->virt[0] && s->virt_cap >= s->cap) return 0;
+  for (int k = 0; k < 2; ++k) {
+    double *q = nullptr;
+    PGPU_CUDA(cudaMalloc(&q, s->cap * sizeof(double)));
+    PGPU_CUDA(cudaMemsetAsync(q, 0, s->cap * sizeof(double), ctx().stream));
+    if (s->virt[k]) {
+      PGPU_CUDA(cudaMemcpyAsync(q, s->virt[k], (size_t)std::min<size_t>(s->virt_cap, s->cap) * sizeof(double),
+                                cudaMemcpyDeviceToDevice, ctx().stream));
+      PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
+      cudaFree(s->virt[k]);
+    }
+    s->virt[k] = q;
+  }
+  s->virt_cap = s->cap;
+  return 0;
+}
+
+int pgpu_apply_forces_curvilinear(pgpu_species_t s, int push_type, double full_dt, int by_half_dt, int anticyclic) {
+  NEED_INIT();
+  if (!s || push_type < PGPU_PUSH_CYL_CYL || push_type > PGPU_PUSH_SPH_HYB) return PGPU_ERR_ARG;
+  if (!s->desc.forces) return 0;
+  if (!s->Ep[0]) {
+    set_error("applyForces needs particle fields: call pgpu_interpolate_fields_to_particles first");
+    return PGPU_ERR_STATE;
+  }
+  if (s->n == 0) return 0;
+  if (materialize_old(s)) return PGPU_ERR_CUDA;
+  if (ensure_virt(s)) return PGPU_ERR_CUDA;
+  const double cnormDt = full_dt * s->desc.cvac_norm;
+  const double alpha = s->desc.fnorm_const * cnormDt / 2.0;
+  KTimer t("boris_curvilinear");
+  k_boris_curvilinear<<<nb(s->n), 256, 0, ctx().stream>>>(s->ptrs(), s->xold[0], s->virt[0], s->virt[1], s->n, push_type,
+                                                          alpha, cnormDt, by_half_dt, anticyclic, s->desc.relativistic);
+  return 0;
+}
+
+int pgpu_species_virtual_positions_set(pgpu_species_t s, const double *virt) {
+  NEED_INIT();
+  if (!s || (s->n > 0 && !virt)) return PGPU_ERR_ARG;
+  if (s->n == 0) return 0;
+  if (ensure_virt(s)) return PGPU_ERR_CUDA;
+  for (int k = 0; k < 2; ++k)
+    PGPU_CUDA(cudaMemcpyAsync(s->virt[k], virt + (size_t)k * s->n, (size_t)s->n * sizeof(double), cudaMemcpyHostToDevice,
+                              ctx().stream));
+  PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+int pgpu_species_virtual_positions_get(pgpu_species_t s, double *virt) {
+  NEED_INIT();
+  if (!s || (s->n > 0 && !virt)) return PGPU_ERR_ARG;
+  if (s->n == 0) return 0;
+  if (ensure_virt(s)) return PGPU_ERR_CUDA;
+  for (int k = 0; k < 2; ++k)
+    PGPU_CUDA(cudaMemcpyAsync(virt + (size_t)k * s->n, s->virt[k], (size_t)s->n * sizeof(double), cudaMemcpyDeviceToHost,
+                              ctx().stream));
+  PGPU_CUDA(cudaStreamSynchronize(ctx().stream));
   return 0;
 }
 

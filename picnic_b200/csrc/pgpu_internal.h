@@ -224,6 +224,10 @@ struct pgpu_species_s {
   size_t out_cap = 0;
   int *out_listtag = nullptr;
   size_t out_listtag_cap = 0;
+  // JustinsParticle::m_pos_virt of the curvilinear pushes (dtheta, dphi); allocated by the first curvilinear call.  The
+  // cell sort and the migration do not carry them: the reference re-bases them every step (rebaseVirtualPositions)
+  double *virt[2] = {nullptr, nullptr};
+  size_t virt_cap = 0;
   // inflow lists of PicChargedSpeciesBC (m_inflow_list_vector): one container; inf_code = 8 * numSubOrbits + (2 dir + side)
   double *inf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double *inf_w = nullptr;

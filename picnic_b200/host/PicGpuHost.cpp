@@ -411,6 +411,16 @@ void PicChargedSpecies::explicitStep(Real a_dt, const int *bc_lo, const int *bc_
 void PicChargedSpecies::addExternalFieldsToParticles() {
   check(pgpu_add_external_fields_to_particles(m_h), "PicChargedSpecies::addExternalFieldsToParticles");
 }
+void PicChargedSpecies::applyForcesCurvilinear(int a_push_type, Real a_full_dt, bool a_byHalfDt, bool a_anticyclic) {
+  check(pgpu_apply_forces_curvilinear(m_h, a_push_type, a_full_dt, a_byHalfDt ? 1 : 0, a_anticyclic ? 1 : 0),
+        "PicChargedSpecies::applyForcesCurvilinear");
+}
+void PicChargedSpecies::setVirtualPositions(const Real *a_virt) {
+  check(pgpu_species_virtual_positions_set(m_h, a_virt), "PicChargedSpecies::setVirtualPositions");
+}
+void PicChargedSpecies::getVirtualPositions(Real *a_virt) const {
+  check(pgpu_species_virtual_positions_get(m_h, a_virt), "PicChargedSpecies::getVirtualPositions");
+}
 void PicChargedSpecies::setSubOrbitModel(bool a_use_suborbit_model, bool a_suborbit_fast_particles) {
   check(pgpu_species_set_suborbit_model(m_h, a_use_suborbit_model ? 1 : 0, a_suborbit_fast_particles ? 1 : 0),
         "PicChargedSpecies::setSubOrbitModel");
