@@ -504,7 +504,9 @@ int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT
                              uint64_t step, long *ncollisions);
 /* The same with the deck's weight_method: 0 = PROBABILISTIC, 1 = CONSERVATIVE (HardSphere.cpp:357-392: for unequal
  * weights the heavier particle, its scattered fraction and a third particle of the cell are merged into two equally
- * weighted ones by ScatteringUtils::collapseThreeToTwo; the weights change; self-scattering only). */
+ * weighted ones by ScatteringUtils::collapseThreeToTwo; the weights change).  Between two species (:594-636) the third
+ * particle comes from the heavier particle's species, and -- as in the reference -- the partners move by 0.5 deltaU, not
+ * mu/m deltaU: the pair's momentum is conserved only for equal masses. */
 int pgpu_collide_hard_sphere_wm(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, int weight_method, double dt_sec,
                                 uint64_t seed, uint64_t step, long *ncollisions);
 /* VariableHardSphere::applySelfScattering (VariableHardSphere.cpp:217-412; the reference has no inter-species VHS):

@@ -661,6 +661,21 @@ def hs_inter(cs1, v1, w1, dens1, ene1, m1, cs2, v2, w2, dens2, ene2, m2, Vc, sig
     return a.value, b.value
 
 
+def hs_inter_conservative(cs1, v1, w1, dens1, ene1, m1, cs2, v2, w2, dens2, ene2, m2, Vc, sigmaT, dt_sec):
+    """HardSphere between species, weight_method CONSERVATIVE: v1, w1, v2, w2 change in place"""
+    f = lib().orc_hs_inter_wm
+    f.argtypes = ([C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_double,
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p] + [C.c_double] * 3 + [C.c_int] +
+                  [C.c_double] + [C.c_void_p] * 2)
+    a1 = np.ascontiguousarray(cs1, dtype=np.int64)
+    a2 = np.ascontiguousarray(cs2, dtype=np.int64)
+    e1, e2 = np.ascontiguousarray(ene1, dtype=np.float64), np.ascontiguousarray(ene2, dtype=np.float64)
+    a, b = C.c_long(0), C.c_long(0)
+    f(a1.size - 1, _ptr(a1), _ptr(v1), _ptr(w1), v1.shape[1], _ptr(dens1), _ptr(e1), m1, _ptr(a2), _ptr(v2), _ptr(w2),
+      v2.shape[1], _ptr(dens2), _ptr(e2), m2, Vc, sigmaT, 1, dt_sec, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
 def vhs_consts(mass, eta, T0, mu0):
     """(4 pi A, 4/alpha) of VariableHardSphere::initialize"""
     a, b = C.c_double(0), C.c_double(0)

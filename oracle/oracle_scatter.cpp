@@ -1461,10 +1461,26 @@ extern "C" void orc_vhs_self(long ncell, const long *cs, double *v, long n, cons
   if (ncoll_out) *ncoll_out = ncoll;
 }
 
+extern "C" void orc_hs_inter_wm(long ncell, const long *cs1, double *v1, double *w1, long n1, const double *dens1,
+                                const double *ene1, double mass1, const long *cs2, double *v2, double *w2, long n2,
+                                const double *dens2, const double *ene2, double mass2, double Vc, double sigmaT,
+                                int conservative, double dt_sec, long *ncand_out, long *ncoll_out);
 extern "C" void orc_hs_inter(long ncell, const long *cs1, double *v1, const double *w1, long n1, const double *dens1,
                              const double *ene1, double mass1, const long *cs2, double *v2, const double *w2, long n2,
                              const double *dens2, const double *ene2, double mass2, double Vc, double sigmaT,
                              double dt_sec, long *ncand_out, long *ncoll_out) {
+  orc_hs_inter_wm(ncell, cs1, v1, const_cast<double *>(w1), n1, dens1, ene1, mass1, cs2, v2, const_cast<double *>(w2), n2,
+                  dens2, ene2, mass2, Vc, sigmaT, 0, dt_sec, ncand_out, ncoll_out);
+}
+/* conservative != 0: the CONSERVATIVE weight method between species (HardSphere.cpp:594-636).  For unequal weights the
+ * lighter particle moves by 0.5 deltaU and the heavier one's scattered copy by -0.5 deltaU -- NOT mu/m deltaU, as the
+ * PROBABILISTIC branch below and the self-scattering code do: the reference conserves the pair's momentum here only
+ * for equal masses (SURVEY App. B style quirk, restated as it stands) -- then the heavier particle, its scattered
+ * fraction and a third particle of the heavier particle's species are merged (collapseThreeToTwo); weights change. */
+extern "C" void orc_hs_inter_wm(long ncell, const long *cs1, double *v1, double *w1, long n1, const double *dens1,
+                                const double *ene1, double mass1, const long *cs2, double *v2, double *w2, long n2,
+                                const double *dens2, const double *ene2, double mass2, double Vc, double sigmaT,
+                                int conservative, double dt_sec, long *ncand_out, long *ncoll_out) {
   const double cvacSq = kCVAC * kCVAC;
   const double mu = mass1 * mass2 / (mass1 + mass2);
   long ncand = 0, ncoll = 0;
@@ -1506,6 +1522,50 @@ extern "C" void orc_hs_inter(long ncell, const long *cs1, double *v1, const doub
       const double phi = kTWOPI * mu_rand();
       double dU[3];
       orc_scatter_delta_u(b1[0] - b2[0], b1[1] - b2[1], b1[2] - b2[2], costh, sinth, cos(phi), sin(phi), dU);
+      if (conservative && wp1 != wp2) {
+        if (wp1 < wp2) {
+          if (numCell2 < 2) continue;
+          double b2p[3], wq2 = wp2;
+          for (int dir = 0; dir < 3; dir++) {
+            b1[dir] += 0.5 * dU[dir];
+            b2p[dir] = b2[dir] - 0.5 * dU[dir];
+          }
+          const int q2 = (int)(i2 - cs2[c]);
+          int q3 = mu_randint(0, numCell2 - 1);
+          while (q3 == q2) q3 = mu_randint(0, numCell2 - 1);
+          const long i3 = cs2[c] + q3;
+          double b3[3] = {v2[i3], v2[n2 + i3], v2[2 * n2 + i3]}, wq3 = w2[i3];
+          orc_collapse_three_to_two(b2, &wq2, b3, &wq3, b2p, wp1);
+          w2[i2] = wq2;
+          w2[i3] = wq3;
+          for (int dir = 0; dir < 3; dir++) {
+            v1[dir * n1 + i1] = b1[dir];
+            v2[dir * n2 + i2] = b2[dir];
+            v2[dir * n2 + i3] = b3[dir];
+          }
+        } else {
+          if (numCell1 < 2) continue;
+          double b1p[3], wq1 = wp1;
+          for (int dir = 0; dir < 3; dir++) {
+            b1p[dir] = b1[dir] + 0.5 * dU[dir];
+            b2[dir] -= 0.5 * dU[dir];
+          }
+          const int q1 = (int)(i1 - cs1[c]);
+          int q3 = mu_randint(0, numCell1 - 1);
+          while (q3 == q1) q3 = mu_randint(0, numCell1 - 1);
+          const long i3 = cs1[c] + q3;
+          double b3[3] = {v1[i3], v1[n1 + i3], v1[2 * n1 + i3]}, wq3 = w1[i3];
+          orc_collapse_three_to_two(b1, &wq1, b3, &wq3, b1p, wp2);
+          w1[i1] = wq1;
+          w1[i3] = wq3;
+          for (int dir = 0; dir < 3; dir++) {
+            v1[dir * n1 + i1] = b1[dir];
+            v1[dir * n1 + i3] = b3[dir];
+            v2[dir * n2 + i2] = b2[dir];
+          }
+        }
+        continue;
+      }
       const double rand_num3 = mu_rand();
       if (rand_num3 <= wp2 / wp1)
         for (int dir = 0; dir < 3; dir++) v1[dir * n1 + i1] = b1[dir] + mu / mass1 * dU[dir];

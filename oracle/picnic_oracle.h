@@ -318,6 +318,11 @@ void orc_vhs_self(long ncell, const long *cs, double *v, long n, const double *d
 /* weight method CONSERVATIVE (HardSphere.cpp:357-392): w is updated by the 3 -> 2 merges */
 void orc_hs_self_wm(long ncell, const long *cs, double *v, double *w, long n, const double *dens, const double *ene,
                     double mass, double sigmaT, int conservative, double dt_sec, long *ncand, long *ncoll);
+/* HardSphere inter-species with weight_method CONSERVATIVE (HardSphere.cpp:594-636); w1, w2 change */
+void orc_hs_inter_wm(long ncell, const long *cs1, double *v1, double *w1, long n1, const double *dens1, const double *ene1,
+                     double mass1, const long *cs2, double *v2, double *w2, long n2, const double *dens2,
+                     const double *ene2, double mass2, double Vc, double sigmaT, int conservative, double dt_sec,
+                     long *ncand_out, long *ncoll_out);
 void orc_hs_inter(long ncell, const long *cs1, double *v1, const double *w1, long n1, const double *dens1,
                   const double *ene1, double mass1, const long *cs2, double *v2, const double *w2, long n2,
                   const double *dens2, const double *ene2, double mass2, double Vc, double sigmaT, double dt_sec,

@@ -648,9 +648,10 @@ def collide_hard_sphere(sA, sB, sigmaT, dt_sec, seed, step, count=True):
     return np_.value
 
 
-def collide_hard_sphere_conservative(sp, sigmaT, dt_sec, seed, step):
+def collide_hard_sphere_conservative(sp, sigmaT, dt_sec, seed, step, sp2=None):
+    """weight_method CONSERVATIVE: self-scattering of sp, or sp against sp2"""
     np_ = C.c_long(0)
-    check(load().pgpu_collide_hard_sphere_wm(sp.h, sp.h, sigmaT, 1, dt_sec, seed, step, C.byref(np_)))
+    check(load().pgpu_collide_hard_sphere_wm(sp.h, (sp2 or sp).h, sigmaT, 1, dt_sec, seed, step, C.byref(np_)))
     return np_.value
 
 

@@ -921,8 +921,9 @@ struct HSParams {
   double sigmaT, dt_sec, mass1, mass2, mu, Vc;
   int vhs;                          // VariableHardSphere: sigmaT(g) = fourPiA * g^(-fourOverAlpha), self only
   double fourPiA, fourOverAlpha;
-  int conservative;                 // HardSphere self, weight method CONSERVATIVE (collapseThreeToTwo), needs wmut
+  int conservative;                 // HardSphere weight method CONSERVATIVE (collapseThreeToTwo), needs wmut (species 1)
   double *wmut;
+  double *wmut2;                    // species 2 (inter-species CONSERVATIVE)
   unsigned seed_lo, seed_hi, step_lo, step_hi;
   int box_lo0, box_lo1, nbox0, ncell_glob0;
 };
@@ -1006,6 +1007,45 @@ k_hard_sphere(const int *cs1, const int *cs2, int ncell, double *a0, double *a1,
         sincos(TWOPI * u01(r1.x), &sinphi, &cosphi);
         scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
         const double wp1 = wa[i1], wp2 = wb[i2], u3 = P.vhs ? 0.0 : u01(r1.y);   // VHS updates both partners
+        if (P.conservative && wp1 != wp2 && !self) {
+          // HardSphere.cpp:594-636, between species: the lighter particle moves by 0.5 deltaU (the reference's factor
+          // here, not mu/m: its quirk, kept), the heavier one's scattered copy by -0.5 deltaU; the heavier particle,
+          // that copy and a third particle of the heavier particle's species are merged (collapseThreeToTwo)
+          const bool first_light = wp1 < wp2;
+          const int nh = first_light ? n2 : n1, sh = first_light ? s2 : s1, qh = first_light ? q2 : q1;
+          if (nh < 2) continue;
+          int q3 = min(nh - 2, (int)(u01(r1.z) * (nh - 1)));
+          if (q3 >= qh) q3 += 1;
+          double *h0 = first_light ? b0 : a0, *h1 = first_light ? b1 : a1, *h2 = first_light ? b2 : a2;
+          double *hw = first_light ? P.wmut2 : P.wmut;
+          const int ih = sh + qh, i3 = sh + q3;
+          const double wl = first_light ? wp1 : wp2, wh = first_light ? wp2 : wp1, w3 = hw[i3];
+          double vh[3], vhp[3], v3[3] = {h0[i3], h1[i3], h2[i3]};
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            vh[d] = first_light ? v2[d] : v1[d];
+            vhp[d] = first_light ? v2[d] - 0.5 * dU[d] : v1[d] + 0.5 * dU[d];
+          }
+          const double wp23 = 0.5 * (wh + w3);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double c23 = (wl * vhp[d] + (wh - wl) * vh[d] + w3 * v3[d]) / wp23;
+            const double d23 = (wl * vhp[d] * vhp[d] + (wh - wl) * vh[d] * vh[d] + w3 * v3[d] * v3[d]) / wp23;
+            const double root = sqrt(fmax(2.0 * d23 - c23 * c23, 0.0));
+            vh[d] = 0.5 * (c23 + root);
+            v3[d] = 0.5 * (c23 - root);
+          }
+          if (first_light) {
+            a0[i1] = v1[0] + 0.5 * dU[0]; a1[i1] = v1[1] + 0.5 * dU[1]; a2[i1] = v1[2] + 0.5 * dU[2];
+          } else {
+            b0[i2] = v2[0] - 0.5 * dU[0]; b1[i2] = v2[1] - 0.5 * dU[1]; b2[i2] = v2[2] - 0.5 * dU[2];
+          }
+          h0[ih] = vh[0]; h1[ih] = vh[1]; h2[ih] = vh[2];
+          h0[i3] = v3[0]; h1[i3] = v3[1]; h2[i3] = v3[2];
+          hw[ih] = wp23;
+          hw[i3] = wp23;
+          continue;
+        }
         if (P.conservative && wp1 != wp2) {
           // HardSphere.cpp:357-392: the lighter particle scatters; the heavier one, its scattered fraction and a third
           // particle of the cell are merged into two equally weighted particles (ScatteringUtils::collapseThreeToTwo)
@@ -2103,13 +2143,13 @@ int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT
   return launch_hard_sphere(sA, sB, P, dt_sec, seed, step, ncoll_out, "HardSphere");
 }
 
-// weight_method: 0 = PROBABILISTIC, 1 = CONSERVATIVE (self-scattering only here; the species' weights change)
+// weight_method: 0 = PROBABILISTIC, 1 = CONSERVATIVE (self and inter-species; the species' weights change)
 int pgpu_collide_hard_sphere_wm(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, int weight_method, double dt_sec,
                                 uint64_t seed, uint64_t step, long *ncoll_out) {
   if (weight_method == 0) return pgpu_collide_hard_sphere(sA, sB, sigmaT, dt_sec, seed, step, ncoll_out);
   if (!sA || !sB) return PGPU_ERR_ARG;
-  if (weight_method != 1 || sA != sB) {
-    set_error("HardSphere: the CONSERVATIVE weight method is implemented for self-scattering only");
+  if (weight_method != 1) {
+    set_error("HardSphere: weight_method must be 0 (PROBABILISTIC) or 1 (CONSERVATIVE)");
     return PGPU_ERR_ARG;
   }
   if (!(sigmaT > 0.0)) {
@@ -2121,6 +2161,7 @@ int pgpu_collide_hard_sphere_wm(pgpu_species_t sA, pgpu_species_t sB, double sig
   P.sigmaT = sigmaT;
   P.conservative = 1;
   P.wmut = sA->w;
+  P.wmut2 = sB->w;
   return launch_hard_sphere(sA, sB, P, dt_sec, seed, step, ncoll_out, "HardSphere");
 }
 

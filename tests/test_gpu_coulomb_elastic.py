@@ -871,3 +871,54 @@ def test_hard_sphere_conservative_weight_method(pgpu):
         orc.lib().orc_rng_seed(seed)
         n_cpu.append(orc.hs_self_conservative(offs, v, wc, dens, ene, sdef.mass, sig, dt_sec)[1])
     assert abs(np.mean(n_gpu) - np.mean(n_cpu)) < 0.03 * np.mean(n_cpu), (np.mean(n_gpu), np.mean(n_cpu))
+
+
+def test_hard_sphere_inter_conservative_weight_method(pgpu):
+    """pgpu_collide_hard_sphere_wm between two species (HardSphere.cpp:594-636): the weights of either species are kept cell
+    by cell, and for equal masses so are the weighted momentum and energy of the pair of species; collision counts (means
+    over 12 seeds) within 3 % of the oracle on the same cells."""
+    deck = decks.Deck(D=1, ncell=(64,), dx=(0.25,), xmin=(0.0,), nghost=2)
+    rng = np.random.default_rng(91)
+    xa, ca = _ragged_cells(rng, 64, [0, 1, 2, 9, 30])
+    xb, cb = _ragged_cells(rng, 64, [0, 1, 3, 12, 25])
+    w0 = 1e30 * 0.25 * deck.volume_scale / 30.0
+    m = 4.0 * 1836.15
+    sa_def, sb_def = decks.SpeciesDef("helium", m, 0.0), decks.SpeciesDef("helium2", m, 0.0)
+    va, vb = rng.standard_normal((3, xa.shape[1])) * 2e-3, rng.standard_normal((3, xb.shape[1])) * 1e-3
+    wa = w0 * rng.choice([0.5, 1.0], size=xa.shape[1])
+    wb = w0 * rng.choice([1.0, 2.0], size=xb.shape[1])
+    sig = orc.hs_sigmaT(1.2e-10, 1.8e-10)
+    dt_sec = 2.0e-17
+
+    def run(seed):
+        grid = pgpu.Grid(1, (64,), (0.0,), (0.25,), 2, (1,), volume_scale=deck.volume_scale)
+        sa = _species_on_grid(pgpu, grid, deck, sa_def, xa, va, wa)
+        sb = _species_on_grid(pgpu, grid, deck, sb_def, xb, vb, wb)
+        before = (sa.download(), sb.download(), sa.cell_offsets(), sb.cell_offsets(), sa.moments(), sb.moments())
+        n = pgpu.collide_hard_sphere_conservative(sa, sig, dt_sec, seed, 0, sp2=sb)
+        after = (sa.download(), sb.download())
+        sa.destroy(); sb.destroy(); grid.destroy()
+        return n, before, after
+
+    ncoll, (ba, bb, oa, ob, ma, mb), (aa, ab) = run(7)
+    assert ncoll > 100 and not np.isnan(aa["v"]).any() and not np.isnan(ab["v"]).any()
+    assert np.mean(ab["w"] != bb["w"]) > 0.02 or np.mean(aa["w"] != ba["w"]) > 0.02
+    for c in range(64):
+        s1, s2 = slice(oa[c], oa[c + 1]), slice(ob[c], ob[c + 1])
+        assert abs(aa["w"][s1].sum() - ba["w"][s1].sum()) <= 1e-13 * max(ba["w"][s1].sum(), 1.0)
+        assert abs(ab["w"][s2].sum() - bb["w"][s2].sum()) <= 1e-13 * max(bb["w"][s2].sum(), 1.0)
+        p0 = (ba["w"][s1] * ba["v"][:, s1]).sum(1) + (bb["w"][s2] * bb["v"][:, s2]).sum(1)
+        p1 = (aa["w"][s1] * aa["v"][:, s1]).sum(1) + (ab["w"][s2] * ab["v"][:, s2]).sum(1)
+        k0 = (ba["w"][s1] * ba["v"][:, s1] ** 2).sum() + (bb["w"][s2] * bb["v"][:, s2] ** 2).sum()
+        k1 = (aa["w"][s1] * aa["v"][:, s1] ** 2).sum() + (ab["w"][s2] * ab["v"][:, s2] ** 2).sum()
+        if k0 > 0:
+            assert np.max(np.abs(p1 - p0)) < 1e-11 * np.sqrt(k0 * (ba["w"][s1].sum() + bb["w"][s2].sum()))
+            assert abs(k1 - k0) < 1e-11 * k0
+    n_gpu = [run(seed)[0] for seed in range(300, 312)]
+    Vc = 0.25 * deck.volume_scale
+    n_cpu = []
+    for seed in range(400, 412):
+        v1, v2, w1, w2 = ba["v"].copy(), bb["v"].copy(), ba["w"].copy(), bb["w"].copy()
+        orc.lib().orc_rng_seed(seed)
+        n_cpu.append(orc.hs_inter_conservative(oa, v1, w1, ma[0], ma[2], m, ob, v2, w2, mb[0], mb[2], m, Vc, sig, dt_sec)[1])
+    assert abs(np.mean(n_gpu) - np.mean(n_cpu)) < 0.03 * np.mean(n_cpu), (np.mean(n_gpu), np.mean(n_cpu))

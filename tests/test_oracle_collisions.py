@@ -523,3 +523,46 @@ def test_elastic_conservative_weight_method_keeps_weight_momentum_and_energy():
         e0 = m1 * (w1[s1] * a1[:, s1] ** 2).sum() + m2 * (u2[s2] * a2[:, s2] ** 2).sum()
         e1 = m1 * (w1[s1] * v1[:, s1] ** 2).sum() + m2 * (w2[s2] * v2[:, s2] ** 2).sum()
         assert abs(e1 - e0) < 1e-12 * e0
+
+
+def test_hard_sphere_inter_conservative_weight_method():
+    """HardSphere between species with weight_method CONSERVATIVE (HardSphere.cpp:594-636): every cell keeps the total weight
+    of either species; with EQUAL masses (where the reference's 0.5 deltaU equals mu/m deltaU) it also keeps the weighted
+    momentum and the weighted energy of the two species together, per direction-summed, to round-off."""
+    rng = np.random.default_rng(17)
+    ncell = 40
+    c1 = rng.choice([0, 1, 2, 9, 30], size=ncell)
+    c2 = rng.choice([0, 1, 3, 12, 25], size=ncell)
+    cs1 = np.concatenate([[0], np.cumsum(c1)]).astype(np.int64)
+    cs2 = np.concatenate([[0], np.cumsum(c2)]).astype(np.int64)
+    n1, n2 = int(cs1[-1]), int(cs2[-1])
+    v1, v2 = rng.standard_normal((3, n1)) * 2e-3, rng.standard_normal((3, n2)) * 1e-3
+    w1 = 1.0e27 * rng.choice([0.5, 1.0], size=n1)
+    w2 = 1.0e27 * rng.choice([1.0, 2.0], size=n2)
+    Vc = 1.0e-3
+    m = 4.0 * 1836.15
+
+    def moments(cs, v, w, mass):
+        dens = np.array([w[cs[c]:cs[c + 1]].sum() / Vc for c in range(ncell)])
+        ene = np.array([[0.5 * mass * (w[cs[c]:cs[c + 1]] * v[d, cs[c]:cs[c + 1]] ** 2).sum() / Vc for c in range(ncell)]
+                        for d in range(3)])
+        return dens, ene
+    d1, e1 = moments(cs1, v1, w1, m)
+    d2, e2 = moments(cs2, v2, w2, m)
+    sig = orc.hs_sigmaT(1.2e-10, 1.8e-10)
+    a1, a2, b1, b2 = v1.copy(), v2.copy(), w1.copy(), w2.copy()
+    orc.lib().orc_rng_seed(9)
+    ncand, ncoll = orc.hs_inter_conservative(cs1, a1, b1, d1, e1, m, cs2, a2, b2, d2, e2, m, Vc, sig, 3.0e-15)
+    assert ncoll > 100 and not np.isnan(a1).any() and not np.isnan(a2).any()
+    assert np.mean(b2 != w2) > 0.02 or np.mean(b1 != w1) > 0.02          # merges happened
+    for c in range(ncell):
+        s1, s2 = slice(cs1[c], cs1[c + 1]), slice(cs2[c], cs2[c + 1])
+        assert abs(b1[s1].sum() - w1[s1].sum()) <= 1e-13 * max(w1[s1].sum(), 1.0)
+        assert abs(b2[s2].sum() - w2[s2].sum()) <= 1e-13 * max(w2[s2].sum(), 1.0)
+        p0 = (w1[s1] * v1[:, s1]).sum(1) + (w2[s2] * v2[:, s2]).sum(1)
+        p1 = (b1[s1] * a1[:, s1]).sum(1) + (b2[s2] * a2[:, s2]).sum(1)
+        k0 = (w1[s1] * v1[:, s1] ** 2).sum() + (w2[s2] * v2[:, s2] ** 2).sum()
+        k1 = (b1[s1] * a1[:, s1] ** 2).sum() + (b2[s2] * a2[:, s2] ** 2).sum()
+        if k0 > 0:
+            assert np.max(np.abs(p1 - p0)) < 1e-11 * np.sqrt(k0 * (w1[s1].sum() + w2[s2].sum()))
+            assert abs(k1 - k0) < 1e-11 * k0
