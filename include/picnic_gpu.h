@@ -307,6 +307,22 @@ int pgpu_species_current_get(pgpu_species_t s, int comp, double *data, const int
  * stag = 0,0) and one face direction (:3088-3132): deposit, x charge/volume_scale,
  * ghost add-exchange.  Result returned in data (bounds for that centring). */
 int pgpu_set_charge_density(pgpu_species_t s, const int *stag, double *data, const int *lo, const int *hi);
+/* The two halves of pgpu_set_charge_density for a domain of several boxes: _deposit leaves the species' scaled charge
+ * density in the grid's resident array of that centring, self-periodic directions folded; a pgpu_halo_create_rho
+ * plan adds the ghost layers of neighbouring boxes into each other on the device; pgpu_charge_density_filter
+ * optionally smooths it; _get copies the array out (bounds = the ghosted box of the centring). */
+/* SpaceUtils::applyBinomialFilter (SpaceUtils.cpp:9-112) on the device arrays: the [1 2 1]/4 (1D) or
+ * [1 2 1; 2 4 2; 1 2 1]/16 (2D) smoothing over the box's own edges / nodes, same operation order as the reference.
+ * pgpu_current_filter is the filter step of PicSpeciesInterface::filterJ (PicSpeciesInterface.cpp:996-1012;
+ * in_plane = filterE_inPlane, virtual_comps = filterE_virtual) and runs after pgpu_current_finalize / the halo
+ * add-exchange, which leave the neighbour sums in the first ghost layer; pgpu_charge_density_filter is the
+ * a_use_filtering tail of setChargeDensityOnNodes (PicChargedSpecies.cpp:3176-3180), between the exchange and
+ * pgpu_charge_density_get.  Ghosts at a physical (non-periodic) boundary are used as they are in the device array:
+ * the field-BC fill the reference does there (applyEdgeBC / applyNodeBC / applyToRhoInGhosts) is host-side grid work. */
+int pgpu_current_filter(pgpu_grid_t g, int in_plane, int virtual_comps);
+int pgpu_charge_density_filter(pgpu_grid_t g, const int *stag);
+int pgpu_charge_density_deposit(pgpu_species_t s, const int *stag);
+int pgpu_charge_density_get(pgpu_grid_t g, const int *stag, double *data, const int *lo, const int *hi);
 
 /* cell sort + cell moments: binTheParticles (:1913-1947), set*DensityFromBinFab
  * (:2881-3047), PicSpeciesInterface::setDebyeLength (PicSpeciesInterface.cpp:1627-1721) */
@@ -374,6 +390,11 @@ typedef struct {
   int lo[3][2], hi[3][2];
 } pgpu_halo_msg;
 int pgpu_halo_create(pgpu_grid_t g, int nmsg, const pgpu_halo_msg *msgs, pgpu_halo_t *out);
+/* The same plan for one resident charge-density array (the centring `stag`, see pgpu_charge_density_deposit): only
+ * lo[0]/hi[0] of each message are read.  It replaces the rho.exchange / addGhosts pass at the end of
+ * PicChargedSpecies::setChargeDensity, setChargeDensityOnFaces and setChargeDensityOnNodes
+ * (PicChargedSpecies.cpp:3083, :3120 and :3141-3143, the reverseCopier add-exchanges). */
+int pgpu_halo_create_rho(pgpu_grid_t g, const int *stag, int nmsg, const pgpu_halo_msg *msgs, pgpu_halo_t *out);
 int pgpu_halo_destroy(pgpu_halo_t h);
 int pgpu_halo_phases(pgpu_halo_t h);
 /* inbox area of message msg: offset in doubles behind the flag block, and its length */

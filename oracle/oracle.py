@@ -240,6 +240,26 @@ def fold_periodic(f, D, stag, valid_lo, valid_hi, periodic):
     lib().orc_fold_periodic(C.byref(cf), D, i2(stag), i2(valid_lo), i2(valid_hi), i2(periodic))
 
 
+def binomial_filter(f, D, box_lo, box_hi, stag):
+    """SpaceUtils::applyBinomialFilter(FArrayBox&, const Box&) (SpaceUtils.cpp:54-112) on a Fab, numpy restatement:
+    Q2 = neighbour sum over the grid box (box_lo .. box_hi + stag), then Q = (2^D Q + Q2) / 4^D in the reference's
+    operation order.  The reference's update also touches the ghosts with an uninitialised Q2; here they are left
+    as they are."""
+    a = f.a
+    sl = [slice(box_lo[d] - f.lo[d], box_hi[d] + stag[d] - f.lo[d] + 1) for d in range(D)]
+    sh = lambda d, k: slice(sl[d].start + k, sl[d].stop + k)
+    if D == 1:
+        q2 = a[sh(0, 1)] + a[sh(0, -1)]
+        a[sl[0]] = (a[sl[0]] * 2.0 + q2) / 4.0
+        return
+    q2 = 2.0 * (a[sh(0, 1), sl[1]] + a[sh(0, -1), sl[1]]) + 2.0 * (a[sl[0], sh(1, 1)] + a[sl[0], sh(1, -1)])
+    q2 = q2 + a[sh(0, 1), sh(1, 1)]
+    q2 = q2 + a[sh(0, 1), sh(1, -1)]
+    q2 = q2 + a[sh(0, -1), sh(1, 1)]
+    q2 = q2 + a[sh(0, -1), sh(1, -1)]
+    a[sl[0], sl[1]] = (a[sl[0], sl[1]] * 4.0 + q2) / 16.0
+
+
 def advance_particles(g, interpE, x, xold, v, vold, E, B, fnorm, cnormDt, order_swap):
     n = x.shape[1]
     return lib().orc_advance_particles(C.byref(g), interpE, n, _ptr(x), _ptr(xold), _ptr(v), _ptr(vold),

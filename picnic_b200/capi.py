@@ -145,7 +145,9 @@ def load():
         "pgpu_scatter_nu_max_vhs": [vp, dbl, dbl, dbl, vp],
         "pgpu_scatter_nu_max_ta": [vp, vp, dbl, vp], "pgpu_scatter_nu_max_coulomb": [vp, vp, vp, vp],
         "pgpu_scatter_nu_max_elastic": [vp, vp, vp, vp],
-        "pgpu_halo_create": [vp, i32, vp, vp], "pgpu_halo_destroy": [vp], "pgpu_halo_phases": [vp],
+        "pgpu_halo_create": [vp, i32, vp, vp], "pgpu_halo_create_rho": [vp, vp, i32, vp, vp],
+        "pgpu_current_filter": [vp, i32, i32], "pgpu_charge_density_filter": [vp, vp],
+        "pgpu_charge_density_deposit": [vp, vp], "pgpu_charge_density_get": [vp, vp, vp, vp, vp], "pgpu_halo_destroy": [vp], "pgpu_halo_phases": [vp],
         "pgpu_halo_area_offset": [vp, i32, vp, vp], "pgpu_halo_inbox": [vp, vp, vp],
         "pgpu_halo_ipc_handle": [vp, vp], "pgpu_halo_ipc_open": [vp, vp, vp],
         "pgpu_halo_connect": [vp, i32, vp, i32, lng], "pgpu_halo_begin": [vp], "pgpu_halo_send": [vp, i32],
@@ -231,6 +233,24 @@ class Grid:
         else:
             arr = (ExtFn * 6)(*six)
             check(load().pgpu_grid_set_external_fields(self.h, arr))
+
+    def current_filter(self, in_plane=True, virtual=True):
+        """PicSpeciesInterface::filterJ's binomial filter on the summed J (after current_finalize / the halo)."""
+        check(load().pgpu_current_filter(self.h, int(in_plane), int(virtual)))
+
+    def charge_density_filter(self, stag):
+        check(load().pgpu_charge_density_filter(self.h, _i2(stag)))
+
+    def charge_density_get(self, stag):
+        """The grid's resident charge-density array of one centring (after Species.charge_density_deposit and the
+        ghost add-exchange) -> (array, lo, hi)."""
+        g = self.desc
+        D = g.D
+        lo = [g.box_lo[k] - g.nghost for k in range(D)]
+        hi = [g.box_hi[k] + g.nghost + stag[k] for k in range(D)]
+        out = np.zeros(tuple(h - l + 1 for l, h in zip(lo, hi)), order="F")
+        check(load().pgpu_charge_density_get(self.h, _i2(stag), _p(out), _i2(lo), _i2(hi)))
+        return out, lo, hi
 
     def fields_packed_size(self):
         n = C.c_long()
@@ -564,6 +584,12 @@ class Species:
         out = np.zeros(tuple(h - l + 1 for l, h in zip(lo, hi)), order="F")
         check(load().pgpu_set_charge_density(self.h, _i2(stag), _p(out), _i2(lo), _i2(hi)))
         return out, lo, hi
+
+    def charge_density_deposit(self, stag):
+        """First half of charge_density for a domain of several boxes: the scaled deposit stays in the grid's
+        resident array of this centring; a PeerHaloExchange(..., rho_stag=stag) then adds the ghost layers of
+        neighbouring boxes, and Grid.charge_density_get reads the array."""
+        check(load().pgpu_charge_density_deposit(self.h, _i2(stag)))
 
     def bin_particles(self):
         check(load().pgpu_bin_particles(self.h))

@@ -414,6 +414,91 @@ static int fold_periodic_n(const pgpu_grid_s *g, const DeviceFab *const *f, int 
   }
   return 0;
 }
+// SpaceUtils::applyBinomialFilter(FArrayBox&, const Box&) (SpaceUtils.cpp:54-112): Q2 = the [1 2 1] (x) [1 2 1] sum of
+// the neighbours over the box's own edges / nodes, then Q = (2^D Q + Q2) / 4^D -- in that operation order.  Two
+// passes (Q2 from the unmodified array, then the update); entries outside the grid box keep their values.
+__global__ void k_binomial_q2(FabView f, double *q2, int D, int lo0, int hi0, int lo1, int hi1) {
+  const int m0 = hi0 - lo0 + 1, m1 = hi1 - lo1 + 1;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)m0 * m1) return;
+  const int i = lo0 + (int)(t % m0), j = lo1 + (int)(t / m0);
+  const double *p = f.p + (i - f.lo0) + (long)(j - f.lo1) * f.n0;
+  if (D == 1) {
+    q2[t] = __dadd_rn(p[1], p[-1]);
+    return;
+  }
+  const long n0 = f.n0;
+  double a = __dmul_rn(2.0, __dadd_rn(p[1], p[-1]));
+  a = __dadd_rn(a, __dmul_rn(2.0, __dadd_rn(p[n0], p[-n0])));
+  a = __dadd_rn(a, p[1 + n0]);
+  a = __dadd_rn(a, p[1 - n0]);
+  a = __dadd_rn(a, p[-1 + n0]);
+  a = __dadd_rn(a, p[-1 - n0]);
+  q2[t] = a;
+}
+__global__ void k_binomial_apply(FabView f, const double *q2, int D, int lo0, int hi0, int lo1, int hi1) {
+  const int m0 = hi0 - lo0 + 1, m1 = hi1 - lo1 + 1;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)m0 * m1) return;
+  const int i = lo0 + (int)(t % m0), j = lo1 + (int)(t / m0);
+  double *p = f.p + (i - f.lo0) + (long)(j - f.lo1) * f.n0;
+  const double f0 = D == 1 ? 2.0 : 4.0, f1 = D == 1 ? 4.0 : 16.0;
+  *p = __ddiv_rn(__dadd_rn(__dmul_rn(*p, f0), q2[t]), f1);
+}
+
+int binomial_filter(pgpu_grid_s *g, const DeviceFab &f) {
+  Context &c = ctx();
+  const int D = g->desc.D;
+  if (g->desc.nghost < 1) {
+    set_error("the binomial filter needs one ghost layer");
+    return PGPU_ERR_STATE;
+  }
+  int lo[2] = {0, 0}, hi[2] = {0, 0};
+  for (int k = 0; k < D; ++k) lo[k] = g->desc.box_lo[k], hi[k] = g->desc.box_hi[k] + f.stag[k];
+  const long n = (long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1);
+  if (g->filter_cap < (size_t)n) {
+    if (g->filter_tmp) cudaFree(g->filter_tmp);
+    g->filter_tmp = nullptr;
+    PGPU_CUDA(cudaMalloc(&g->filter_tmp, n * sizeof(double)));
+    g->filter_cap = n;
+  }
+  {
+    KTimer t("binomial_filter");
+    k_binomial_q2<<<nb(n), 256, 0, c.stream>>>(f.view(), g->filter_tmp, D, lo[0], hi[0], lo[1], hi[1]);
+    k_binomial_apply<<<nb(n), 256, 0, c.stream>>>(f.view(), g->filter_tmp, D, lo[0], hi[0], lo[1], hi[1]);
+  }
+  // keep the periodic images of a self-periodic direction equal to their owners
+  Fab3 F;
+  F.f[0] = F.f[1] = F.f[2] = f.view();
+  for (int dir = 0; dir < D; ++dir) {
+    if (!g->desc.periodic[dir]) continue;
+    if (g->desc.box_lo[dir] != 0 || g->desc.box_hi[dir] != g->desc.ncell[dir] - 1) continue;
+    k_fold<<<dim3(nb((long)f.size()), 1), 256, 0, c.stream>>>(F, dir, g->desc.box_lo[dir], g->desc.box_hi[dir], 1);
+  }
+  return 0;
+}
+
+int grid_rho_fab(pgpu_grid_s *g, const int *stag, DeviceFab **out) {
+  const int D = g->desc.D;
+  const int st2[2] = {stag[0] ? 1 : 0, (D == 2 && stag[1]) ? 1 : 0};
+  DeviceFab &f = g->rho[st2[0] + 2 * st2[1]];
+  if (!f.p) {
+    for (int k = 0; k < 2; ++k) {
+      if (k < D) {
+        f.lo[k] = g->desc.box_lo[k] - g->desc.nghost;
+        f.hi[k] = g->desc.box_hi[k] + g->desc.nghost + st2[k];
+      }
+      f.stag[k] = st2[k];
+    }
+    f.n0 = f.hi[0] - f.lo[0] + 1;
+    f.n1 = f.hi[1] - f.lo[1] + 1;
+    PGPU_CUDA(cudaMalloc(&f.p, f.size() * sizeof(double)));
+    PGPU_CUDA(cudaMemsetAsync(f.p, 0, f.size() * sizeof(double), ctx().stream));
+  }
+  *out = &f;
+  return 0;
+}
+
 int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f) {
   const DeviceFab *one[1] = {&f};
   return fold_periodic_n(g, one, 1);
@@ -689,6 +774,9 @@ int pgpu_grid_destroy(pgpu_grid_t g) {
     if (g->tab_node[k]) cudaFree(g->tab_node[k]);
   }
   if (g->scratch_rho.p) cudaFree(g->scratch_rho.p);
+  for (auto &f : g->rho)
+    if (f.p) cudaFree(f.p);
+  if (g->filter_tmp) cudaFree(g->filter_tmp);
   cudaFree(g->debye);
   mm_destroy(g);
   delete g;
@@ -821,6 +909,28 @@ int pgpu_current_finalize(pgpu_grid_t g) {
   if (!g) return PGPU_ERR_ARG;
   const DeviceFab *all[3] = {&g->jtot[0], &g->jtot[1], &g->jtot[2]};
   return fold_periodic_n(g, all, 3);
+}
+
+int pgpu_current_filter(pgpu_grid_t g, int in_plane, int virtual_comps) {
+  NEED_INIT();
+  if (!g) return PGPU_ERR_ARG;
+  const int D = g->desc.D;
+  for (int c = 0; c < 3; ++c) {
+    const bool virt = c >= D;
+    if (virt ? !virtual_comps : !in_plane) continue;
+    int rc = binomial_filter(g, g->jtot[c]);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int pgpu_charge_density_filter(pgpu_grid_t g, const int *stag) {
+  NEED_INIT();
+  if (!g || !stag) return PGPU_ERR_ARG;
+  DeviceFab *f = nullptr;
+  int rc = grid_rho_fab(g, stag, &f);
+  if (rc) return rc;
+  return binomial_filter(g, *f);
 }
 
 int pgpu_current_get(pgpu_grid_t g, int comp, double *data, const int *lo, const int *hi) {

@@ -689,34 +689,17 @@ int pgpu_debye_length(pgpu_grid_t g, pgpu_species_t *species, int nspecies, doub
   return 0;
 }
 
-int pgpu_set_charge_density(pgpu_species_t s, const int *stag, double *data, const int *lo, const int *hi) {
+int pgpu_charge_density_deposit(pgpu_species_t s, const int *stag) {
   NEED_INIT();
-  if (!s) return PGPU_ERR_ARG;
+  if (!s || !stag) return PGPU_ERR_ARG;
   pgpu_grid_s *g = s->grid;
   const int D = g->desc.D;
   Context &c = ctx();
-  DeviceFab f;
-  int st2[2] = {stag[0], D == 2 ? stag[1] : 0};
-  for (int k = 0; k < 2; ++k) {
-    if (k < D) {
-      f.lo[k] = g->desc.box_lo[k] - g->desc.nghost;
-      f.hi[k] = g->desc.box_hi[k] + g->desc.nghost + st2[k];
-    }
-    f.stag[k] = st2[k];
-  }
-  f.n0 = f.hi[0] - f.lo[0] + 1;
-  f.n1 = f.hi[1] - f.lo[1] + 1;
-  for (int k = 0; k < D; ++k)
-    if (lo[k] != f.lo[k] || hi[k] != f.hi[k]) {
-      set_error("charge density bounds do not match the ghosted box for this centring");
-      return PGPU_ERR_ARG;
-    }
-  // scratch sized for the all-nodal array, the largest centring
-  if (!g->scratch_rho.p) {
-    size_t mx = (size_t)(g->nbox[0] + 2 * g->desc.nghost + 1) * (size_t)(D == 2 ? g->nbox[1] + 2 * g->desc.nghost + 1 : 1);
-    PGPU_CUDA(cudaMalloc(&g->scratch_rho.p, mx * sizeof(double)));
-  }
-  f.p = g->scratch_rho.p;
+  DeviceFab *fp = nullptr;
+  int rc = grid_rho_fab(g, stag, &fp);
+  if (rc) return rc;
+  const DeviceFab &f = *fp;
+  const int st2[2] = {f.stag[0], f.stag[1]};
   PGPU_CUDA(cudaMemsetAsync(f.p, 0, f.size() * sizeof(double), c.stream));
   const GeoAny ga = species_geo(s);
   const double volume = (D == 1) ? ga.dx[0] : ga.dx[0] * ga.dx[1];
@@ -734,12 +717,44 @@ int pgpu_set_charge_density(pgpu_species_t s, const int *stag, double *data, con
         k_deposit_rho<2, false><<<nb(s->n), 256, 0, c.stream>>>(s->x[0], s->x[1], s->w, s->n, make_geo<2>(ga), s->desc.interp_N, st2[0], st2[1], f.view(), volume, c.d_counters);
     }
   }
-  // this_rho.mult(m_charge/volume_scale); ghost add-exchange; (cartesian Jacobian == 1)
+  // this_rho.mult(m_charge/volume_scale); (cartesian Jacobian == 1)
   scale_fab(f, s->desc.charge / g->desc.volume_scale);
+  // the ghost add-exchange of a box that is its own periodic neighbour; between boxes it is the halo plan's job
   if (fold_periodic(g, f)) return PGPU_ERR_CUDA;
-  int rc = copy_fab_to_host(f, D, data, lo, hi);
+  return 0;
+}
+
+int pgpu_charge_density_get(pgpu_grid_t g, const int *stag, double *data, const int *lo, const int *hi) {
+  NEED_INIT();
+  if (!g || !stag || !data || !lo || !hi) return PGPU_ERR_ARG;
+  const int D = g->desc.D;
+  DeviceFab *fp = nullptr;
+  int rc = grid_rho_fab(g, stag, &fp);
+  if (rc) return rc;
+  for (int k = 0; k < D; ++k)
+    if (lo[k] != fp->lo[k] || hi[k] != fp->hi[k]) {
+      set_error("charge density bounds do not match the ghosted box for this centring");
+      return PGPU_ERR_ARG;
+    }
+  rc = copy_fab_to_host(*fp, D, data, lo, hi);
   if (rc) return rc;
   return pgpu_synchronize();
+}
+
+int pgpu_set_charge_density(pgpu_species_t s, const int *stag, double *data, const int *lo, const int *hi) {
+  NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
+  DeviceFab *fp = nullptr;
+  int rc = grid_rho_fab(s->grid, stag, &fp);
+  if (rc) return rc;
+  for (int k = 0; k < s->grid->desc.D; ++k)
+    if (lo[k] != fp->lo[k] || hi[k] != fp->hi[k]) {
+      set_error("charge density bounds do not match the ghosted box for this centring");
+      return PGPU_ERR_ARG;
+    }
+  rc = pgpu_charge_density_deposit(s, stag);
+  if (rc) return rc;
+  return pgpu_charge_density_get(s->grid, stag, data, lo, hi);
 }
 
 int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi) {

@@ -108,6 +108,10 @@ using namespace pgpu;
 
 struct pgpu_halo_s {
   pgpu_grid_t grid = nullptr;
+  // the device arrays the plan adds into: the three J components (pgpu_halo_create) or one resident charge-density
+  // array (pgpu_halo_create_rho, nparts == 1)
+  const DeviceFab *target[3] = {nullptr, nullptr, nullptr};
+  int nparts = 3;
   std::vector<pgpu_halo_msg> msgs;
   std::vector<long> count, area_off;     // per message: doubles, offset of its area in an inbox (doubles)
   std::vector<double *> remote_base;     // per message: the peer's inbox (nullptr until connected),
@@ -122,9 +126,9 @@ struct pgpu_halo_s {
   std::vector<void *> opened;            // IPC mappings to close
 };
 
-static long msg_count(pgpu_grid_t g, const pgpu_halo_msg &m) {
+static long msg_count(pgpu_grid_t g, const pgpu_halo_msg &m, int nparts) {
   long n = 0;
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < nparts; ++c) {
     long k = 1;
     for (int d = 0; d < g->desc.D; ++d) k *= (m.hi[c][d] - m.lo[c][d] + 1);
     n += k;
@@ -134,11 +138,12 @@ static long msg_count(pgpu_grid_t g, const pgpu_halo_msg &m) {
 
 extern "C" {
 
-int pgpu_halo_create(pgpu_grid_t g, int nmsg, const pgpu_halo_msg *msgs, pgpu_halo_t *out) {
-  if (!ctx().inited) return PGPU_ERR_STATE;
-  if (!g || !out || nmsg < 0 || (nmsg && !msgs)) return PGPU_ERR_ARG;
+static int halo_create(pgpu_grid_t g, const DeviceFab *const *target, int nparts, int nmsg, const pgpu_halo_msg *msgs,
+                       pgpu_halo_t *out) {
   pgpu_halo_s *h = new pgpu_halo_s;
   h->grid = g;
+  h->nparts = nparts;
+  for (int c = 0; c < nparts; ++c) h->target[c] = target[c];
   std::vector<int> per_phase;
   long off = 0;
   for (int i = 0; i < nmsg; ++i) {
@@ -147,10 +152,10 @@ int pgpu_halo_create(pgpu_grid_t g, int nmsg, const pgpu_halo_msg *msgs, pgpu_ha
       delete h;
       return PGPU_ERR_ARG;
     }
-    for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < nparts; ++c)
       for (int d = 0; d < g->desc.D; ++d)
-        if (m.lo[c][d] < g->jtot[c].lo[d] || m.hi[c][d] > g->jtot[c].hi[d] || m.hi[c][d] < m.lo[c][d]) {
-          set_error("halo message %d: index box of J component %d is not inside the device array", i, c);
+        if (m.lo[c][d] < target[c]->lo[d] || m.hi[c][d] > target[c]->hi[d] || m.hi[c][d] < m.lo[c][d]) {
+          set_error("halo message %d: index box of component %d is not inside the device array", i, c);
           delete h;
           return PGPU_ERR_ARG;
         }
@@ -161,7 +166,7 @@ int pgpu_halo_create(pgpu_grid_t g, int nmsg, const pgpu_halo_msg *msgs, pgpu_ha
       return PGPU_ERR_ARG;
     }
     h->msgs.push_back(m);
-    h->count.push_back(msg_count(g, m));
+    h->count.push_back(msg_count(g, m, nparts));
   }
   // inbox areas in recv_area order, so that a peer with the mirrored plan knows where to write
   h->area_off.assign(nmsg, 0);
@@ -190,6 +195,23 @@ int pgpu_halo_create(pgpu_grid_t g, int nmsg, const pgpu_halo_msg *msgs, pgpu_ha
   h->remote_off.assign(nmsg, 0);
   *out = h;
   return 0;
+}
+
+int pgpu_halo_create(pgpu_grid_t g, int nmsg, const pgpu_halo_msg *msgs, pgpu_halo_t *out) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!g || !out || nmsg < 0 || (nmsg && !msgs)) return PGPU_ERR_ARG;
+  const DeviceFab *target[3] = {&g->jtot[0], &g->jtot[1], &g->jtot[2]};
+  return halo_create(g, target, 3, nmsg, msgs, out);
+}
+
+int pgpu_halo_create_rho(pgpu_grid_t g, const int *stag, int nmsg, const pgpu_halo_msg *msgs, pgpu_halo_t *out) {
+  if (!ctx().inited) return PGPU_ERR_STATE;
+  if (!g || !stag || !out || nmsg < 0 || (nmsg && !msgs)) return PGPU_ERR_ARG;
+  DeviceFab *f = nullptr;
+  int rc = grid_rho_fab(g, stag, &f);
+  if (rc) return rc;
+  const DeviceFab *target[1] = {f};
+  return halo_create(g, target, 1, nmsg, msgs, out);
 }
 
 int pgpu_halo_destroy(pgpu_halo_t h) {
@@ -261,8 +283,12 @@ static int fill_phase(pgpu_halo_s *h, int phase, HaloPhase *P) {
     HaloMsg &M = P->msg[P->nmsg++];
     long off = 0;
     for (int c = 0; c < 3; ++c) {
-      const DeviceFab &f = g->jtot[c];
       HaloPart &Q = M.part[c];
+      if (c >= h->nparts) {               // an empty part: the kernels' part search never selects it
+        Q.n0 = 1, Q.m0 = 0, Q.m1 = 0, Q.p = nullptr, Q.off = off;
+        continue;
+      }
+      const DeviceFab &f = *h->target[c];
       Q.n0 = f.n0;
       Q.m0 = m.hi[c][0] - m.lo[c][0] + 1;
       Q.m1 = D == 2 ? m.hi[c][1] - m.lo[c][1] + 1 : 1;

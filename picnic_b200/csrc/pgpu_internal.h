@@ -161,7 +161,12 @@ struct pgpu_grid_s {
   bool tab_dirty[4] = {true, true, true, true};
   size_t tab_cells = 0;
   pgpu::DeviceFab jtot[3];
-  pgpu::DeviceFab scratch_rho;  // reused by set_charge_density
+  pgpu::DeviceFab scratch_rho;  // (unused since the resident rho arrays; kept for pgpu_grid_destroy)
+  // resident charge-density arrays, one per centring (index stag0 + 2*stag1), filled by pgpu_charge_density_deposit
+  // and exchanged between boxes by a halo plan made with pgpu_halo_create_rho
+  pgpu::DeviceFab rho[4];
+  double *filter_tmp = nullptr;   // Q2 of the binomial filter
+  size_t filter_cap = 0;
   double *debye = nullptr;      // [ncell_box]
   void *mm = nullptr;           // pgpu::MassMatrices (pgpu_massmatrix.cu), created by pgpu_mass_matrices_init
   long ncell_box = 0;
@@ -284,6 +289,8 @@ CurrentSet species_current(const pgpu_species_s *s);
 
 int scale_fab(const DeviceFab &f, double s);
 int fold_periodic(const pgpu_grid_s *g, const DeviceFab &f);
+// the grid's resident charge-density array of one centring (allocated on first use)
+int grid_rho_fab(pgpu_grid_s *g, const int *stag, DeviceFab **out);
 int copy_fab_to_host(const DeviceFab &f, int D, double *data, const int *lo, const int *hi, bool sync = true);
 
 // launchers implemented in the kernel translation units

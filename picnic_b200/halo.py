@@ -248,10 +248,13 @@ class PeerHaloExchange:
     own flags and adds what arrived.  No NCCL call and no host synchronisation on the data path; the
     only collective is the one-off exchange of the CUDA IPC handles of the inboxes (connect_*)."""
 
-    def __init__(self, layout, rank, grid):
+    def __init__(self, layout, rank, grid, rho_stag=None):
+        """rho_stag = None: the plan for the three J components; a centring tuple: the plan for the grid's resident
+        charge-density array of that centring (pgpu_halo_create_rho, PicChargedSpecies.cpp:3083/:3120/:3141)."""
         from . import capi
         self.capi, self.layout, self.rank, self.grid = capi, layout, rank, grid
         D = layout.D
+        stags = STAG_J[D] if rho_stag is None else [tuple(int(v) for v in rho_stag[:D])]
         self.msgs = []          # (phase, side, peer)
         recs = []
         phase = 0
@@ -264,7 +267,7 @@ class PeerHaloExchange:
                     continue
                 m = capi.HaloMsg()
                 m.phase, m.recv_area = phase, len(recs)
-                for comp, stag in enumerate(STAG_J[D]):
+                for comp, stag in enumerate(stags):
                     lo, hi = layout.overlap(rank, stag, d, side)
                     for k in range(D):
                         m.lo[comp][k], m.hi[comp][k] = lo[k], hi[k]
@@ -273,7 +276,11 @@ class PeerHaloExchange:
             phase += 1
         arr = (capi.HaloMsg * max(len(recs), 1))(*recs)
         self.h = capi.C.c_void_p()
-        capi.check(capi.load().pgpu_halo_create(grid.h, len(recs), arr, capi.C.byref(self.h)))
+        if rho_stag is None:
+            capi.check(capi.load().pgpu_halo_create(grid.h, len(recs), arr, capi.C.byref(self.h)))
+        else:
+            st = (capi.C.c_int * 2)(int(rho_stag[0]), int(rho_stag[1]) if D == 2 else 0)
+            capi.check(capi.load().pgpu_halo_create_rho(grid.h, st, len(recs), arr, capi.C.byref(self.h)))
         self.nphase = capi.load().pgpu_halo_phases(self.h)
         self.bytes_per_exchange = 0
         self.areas = {}         # (phase, side) -> (area index, offset in doubles)

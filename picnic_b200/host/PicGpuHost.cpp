@@ -76,6 +76,9 @@ void Mesh::addSubOrbitJ(const PicChargedSpecies &sp) {
 void Mesh::addInflowJ(const PicChargedSpecies &sp) {
   check(pgpu_current_add_inflow(m_h, sp.handle()), "Mesh::addInflowJ");
 }
+void Mesh::filterJ(bool filterE_inPlane, bool filterE_virtual) {
+  check(pgpu_current_filter(m_h, filterE_inPlane ? 1 : 0, filterE_virtual ? 1 : 0), "PicSpeciesInterface::filterJ");
+}
 void Mesh::fieldBounds(int comp, int *lo, int *hi) const {
   int l[2], h[2];
   check(pgpu_field_bounds(m_h, comp, l, h), "Mesh::fieldBounds");
@@ -401,6 +404,12 @@ void PicChargedSpecies::setChargeDensityOnFaces(int dir, const FabRef &out) {
 void PicChargedSpecies::setChargeDensityOnNodes(const FabRef &out) {
   const int stag[2] = {1, 1};
   check(pgpu_set_charge_density(m_h, stag, out.data, out.lo, out.hi), "PicChargedSpecies::setChargeDensityOnNodes");
+}
+void PicChargedSpecies::depositChargeDensity(const int *stag) {
+  check(pgpu_charge_density_deposit(m_h, stag), "PicChargedSpecies::depositChargeDensity");
+}
+void PicChargedSpecies::getChargeDensity(const int *stag, const FabRef &out) const {
+  check(pgpu_charge_density_get(m_mesh.handle(), stag, out.data, out.lo, out.hi), "PicChargedSpecies::getChargeDensity");
 }
 void PicChargedSpecies::getMomentsFromBinFab(Real *dens, Real *mom, Real *ene) const {
   check(pgpu_species_moments_get(m_h, dens, mom, ene), "PicChargedSpecies::getMomentsFromBinFab");

@@ -102,6 +102,137 @@ def test_add_exchange_matches_single_box(pgpu, nbox, peer):
     assert worst < 1e-13, worst
 
 
+@pytest.mark.parametrize("stag", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("nbox", [(16, 16), (8, 16)])
+def test_charge_density_add_exchange_matches_single_box(pgpu, nbox, stag):
+    """setChargeDensity / OnFaces / OnNodes over several boxes (PicChargedSpecies.cpp:3083, :3120, :3141): deposit
+    per box into the resident array, add-exchange of the ghost layers on the device, read -- against the same
+    particles in one box spanning the (periodic) domain.  Twice, for both inbox slots."""
+    lay = halo.BoxLayout(2, NCELL, nbox, NG, (1, 1))
+    x, xo, v, w = _particles(2)
+    ids = np.arange(w.size, dtype=np.uint64)
+    g1 = pgpu.Grid(2, NCELL, XMIN, DX, NG, (1, 1))
+    s1 = _species(pgpu, g1, x, xo, v, w, ids)
+    ref, glo, _ = s1.charge_density(stag)
+    s1.destroy(); g1.destroy()
+    # owner by the old position (inside the domain); x is within half a cell of it, i.e. inside the owner's ghosts
+    own = sum(np.floor((xo[d] - XMIN[d]) / (DX[d] * nbox[d])).astype(int) * (1 if d == 0 else lay.nb[0])
+              for d in range(2))
+    grids, sps, hxs = [], [], []
+    for r in range(lay.world):
+        lo, hi = lay.box(r)
+        g = pgpu.Grid(2, NCELL, XMIN, DX, NG, (1, 1), box_lo=lo, box_hi=hi)
+        m = own == r
+        grids.append(g)
+        sps.append(_species(pgpu, g, x[:, m], xo[:, m], v[:, m], w[m], ids[m]))
+        hxs.append(halo.PeerHaloExchange(lay, r, g, rho_stag=stag))
+    halo.PeerHaloExchange.connect_local(hxs)
+    worst = 0.0
+    for rep in range(2):
+        for s in sps:
+            s.charge_density_deposit(stag)
+        for h in hxs:
+            h.begin()
+        for ph in range(hxs[0].nphase):
+            for h in hxs:
+                h.send(ph)
+            for h in hxs:
+                h.recv_add(ph)
+        for g in grids:
+            a, lo, hi = g.charge_density_get(stag)
+            ii = np.mod(np.arange(lo[0], hi[0] + 1), NCELL[0]) - glo[0]
+            jj = np.mod(np.arange(lo[1], hi[1] + 1), NCELL[1]) - glo[1]
+            worst = max(worst, float(np.max(np.abs(a - ref[np.ix_(ii, jj)])) / np.max(np.abs(ref))))
+    for h in hxs:
+        h.destroy()
+    for s in sps:
+        s.destroy()
+    for g in grids:
+        g.destroy()
+    assert worst < 1e-13, worst
+
+
+def test_binomial_filter_of_J_and_rho(pgpu):
+    """PicSpeciesInterface::filterJ / setChargeDensityOnNodes(use_filtering) (SpaceUtils.cpp:54-112): the device
+    filter against the oracle's restatement bit for bit on one periodic box, and two boxes with the add-exchange
+    in front of it against the one box."""
+    from common import orc
+    x, xo, v, w = _particles(5)
+    ids = np.arange(w.size, dtype=np.uint64)
+    g1 = pgpu.Grid(2, NCELL, XMIN, DX, NG, (1, 1))
+    s1 = _species(pgpu, g1, x, xo, v, w, ids)
+    s1.set_current_density(1.0)
+    g1.current_zero(); g1.current_add(s1); g1.current_finalize()
+    before = [g1.current_get(c) for c in range(3)]
+    g1.current_filter(True, True)
+    after = [g1.current_get(c) for c in range(3)]
+    blo, bhi = (0, 0), (NCELL[0] - 1, NCELL[1] - 1)
+    own = lambda a, st: a[NG:NG + NCELL[0] + st[0], NG:NG + NCELL[1] + st[1]]
+    for c in range(3):
+        lo, hi = g1.field_bounds(c)
+        st = orc.E_STAG[2][c]
+        f = orc.Fab(lo, hi, before[c].copy(order="F"))
+        orc.binomial_filter(f, 2, blo, bhi, st)
+        assert np.array_equal(own(after[c], st), own(f.a, st)), c
+        # the periodic images follow their owners
+        assert np.array_equal(after[c][NG - 1, NG:NG + NCELL[1]], after[c][NG + NCELL[0] - 1, NG:NG + NCELL[1]])
+    # only the in-plane components
+    g1.current_zero(); g1.current_add(s1); g1.current_finalize()
+    g1.current_filter(True, False)
+    assert np.array_equal(g1.current_get(2), before[2]) and np.array_equal(g1.current_get(0), after[0])
+    # rho on nodes
+    st = (1, 1)
+    s1.charge_density_deposit(st)
+    rho0, lo, hi = g1.charge_density_get(st)          # the same deposit (atomics: a second one may differ in the last bit)
+    g1.charge_density_filter(st)
+    rho1, _, _ = g1.charge_density_get(st)
+    f = orc.Fab(lo, hi, rho0.copy(order="F"))
+    orc.binomial_filter(f, 2, blo, bhi, st)
+    assert np.array_equal(own(rho1, st), own(f.a, st))
+    s1.destroy(); g1.destroy()
+    # two boxes in x
+    nbox = (16, 16)
+    lay = halo.BoxLayout(2, NCELL, nbox, NG, (1, 1))
+    ownr = np.floor((xo[0] - XMIN[0]) / (DX[0] * nbox[0])).astype(int)
+    grids, sps, hxs = [], [], []
+    for r in range(lay.world):
+        lo, hi = lay.box(r)
+        g = pgpu.Grid(2, NCELL, XMIN, DX, NG, (1, 1), box_lo=lo, box_hi=hi)
+        m = ownr == r
+        s = _species(pgpu, g, x[:, m], xo[:, m], v[:, m], w[m], ids[m])
+        s.set_current_density(1.0)
+        g.current_zero(); g.current_add(s)
+        grids.append(g); sps.append(s); hxs.append(halo.PeerHaloExchange(lay, r, g))
+    halo.PeerHaloExchange.connect_local(hxs)
+    for h in hxs:
+        h.begin()
+    for ph in range(hxs[0].nphase):
+        for h in hxs:
+            h.send(ph)
+        for h in hxs:
+            h.recv_add(ph)
+    worst = 0.0
+    for r, g in enumerate(grids):
+        g.current_finalize()
+        g.current_filter(True, True)
+        blo_r, bhi_r = lay.box(r)
+        for c in range(3):
+            lo, hi = g.field_bounds(c)
+            st = orc.E_STAG[2][c]
+            a = g.current_get(c)
+            sl = (slice(blo_r[0] - lo[0], bhi_r[0] + st[0] - lo[0] + 1), slice(blo_r[1] - lo[1], bhi_r[1] + st[1] - lo[1] + 1))
+            ii = np.mod(np.arange(blo_r[0], bhi_r[0] + st[0] + 1), NCELL[0]) + NG
+            jj = np.mod(np.arange(blo_r[1], bhi_r[1] + st[1] + 1), NCELL[1]) + NG
+            worst = max(worst, float(np.max(np.abs(a[sl] - after[c][np.ix_(ii, jj)])) / np.max(np.abs(after[c]))))
+    for h in hxs:
+        h.destroy()
+    for s in sps:
+        s.destroy()
+    for g in grids:
+        g.destroy()
+    assert worst < 1e-13, worst
+
+
 @pytest.mark.parametrize("route", ["mailbox", "peer"])
 def test_migration_on_device(pgpu, route):
     """route=mailbox: mark / pack / append around a message layer (the NCCL route's kernels);

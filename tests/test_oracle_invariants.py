@@ -173,6 +173,50 @@ def test_periodic_fold_conserves_total():
         assert np.array_equal(f.a[g + 6, g:g + 5], f.a[g, g:g + 5])
 
 
+@pytest.mark.parametrize("D", [1, 2])
+def test_binomial_filter_restatement(D):
+    """SpaceUtils::applyBinomialFilter (SpaceUtils.cpp:54-112): against a literal loop over the grid box, and the
+    properties of the [1 2 1] stencil on a periodic box: constants kept, the Nyquist mode removed, total kept."""
+    rng = np.random.default_rng(3)
+    n, g = (8, 6)[:D], 2
+    stag = (1, 0)[:D]
+    lo, hi = [0] * D, [k - 1 for k in n]
+    f = orc.fab_for(lo, hi, g, stag)
+    f.a[...] = rng.standard_normal(f.a.shape)
+    want = f.a.copy()
+    if D == 1:
+        for i in range(lo[0], hi[0] + stag[0] + 1):
+            q2 = f.a[i + 1 + g] + f.a[i - 1 + g]
+            want[i + g] = (f.a[i + g] * 2.0 + q2) / 4.0
+    else:
+        A = lambda i, j: f.a[i + g, j + g]
+        for i in range(lo[0], hi[0] + stag[0] + 1):
+            for j in range(lo[1], hi[1] + stag[1] + 1):
+                q2 = (2.0 * (A(i + 1, j) + A(i - 1, j)) + 2.0 * (A(i, j + 1) + A(i, j - 1)) + A(i + 1, j + 1)
+                      + A(i + 1, j - 1) + A(i - 1, j + 1) + A(i - 1, j - 1))
+                want[i + g, j + g] = (A(i, j) * 4.0 + q2) / 16.0
+    orc.binomial_filter(f, D, lo, hi, stag)
+    assert np.array_equal(f.a, want)
+    # periodic properties on cell-centred data
+    st0 = (0,) * D
+    idx = np.indices(tuple(k + 2 * g for k in n)) - g
+    for mode, check in (("const", lambda own, own0: np.allclose(own, 1.0, atol=1e-15)),
+                        ("nyquist", lambda own, own0: np.max(np.abs(own)) < 1e-15),
+                        ("random", lambda own, own0: abs(own.sum() - own0.sum()) < 1e-12)):
+        q = orc.fab_for(lo, hi, g, st0)
+        if mode == "const":
+            q.a[...] = 1.0
+        elif mode == "nyquist":
+            q.a[...] = (-1.0) ** idx[0]
+        else:
+            base = rng.standard_normal(n)
+            q.a[...] = base[tuple(np.mod(idx[d], n[d]) for d in range(D))]
+        own_sl = tuple(slice(g, g + k) for k in n)
+        own0 = q.a[own_sl].copy()
+        orc.binomial_filter(q, D, lo, hi, st0)
+        assert check(q.a[own_sl], own0), mode
+
+
 def test_ta_pair_conservation():
     rng = np.random.default_rng(8)
     m1, m2 = 1.0, 1836.15
