@@ -664,6 +664,7 @@ int pgpu_init(int device) {
   if (const char *e = getenv("PGPU_CC1_V")) c.cc1_version = atoi(e);
   if (const char *e = getenv("PGPU_CC1_NODECACHE")) c.cc1_nodecache = atoi(e);
   if (const char *e = getenv("PGPU_CC1_MULTISEG")) c.cc1_multiseg = atoi(e);
+  if (const char *e = getenv("PGPU_TA_STAGED")) c.ta_staged = atoi(e);
   if (const char *e = getenv("PGPU_CC1_REC")) c.cc1_rec_per_pass = atoi(e);
   if (const char *e = getenv("PGPU_CC1_WAVES")) c.cc1_waves = atoi(e) > 0 ? atoi(e) : 1;
   return 0;
@@ -681,6 +682,7 @@ int pgpu_finalize(void) {
   profile_drain();
   if (c.own_stream) cudaStreamDestroy(c.stream);
   cudaFree(c.d_counters);
+  if (c.ta_list) cudaFree(c.ta_list);
   cudaFreeHost(c.h_counters);
   c = Context();
   return 0;

@@ -53,28 +53,36 @@ __device__ __forceinline__ int locate_bin(double x, double le, double dx) {
 // dual != 0: key = index of the DUAL cell (the cell of the half-shifted grid CC1 segments on) = (c0 + q0) + (c1 + q1)
 // (n0 + 1): all particles that share the 21 deposit nodes are then ONE run (four times longer than the runs of
 // 4*cell + quadrant, where they sit in four primal cells); pgpu_sort_for_locality
-__global__ void k_cell_key(const double *x0, const double *x1, long n, BoxInfo b, int *key, int *iota, int dual) {
+// count != nullptr: the histogram of the counting sort in the same pass (warp-aggregated); iota may be nullptr
+__global__ void k_cell_key(const double *x0, const double *x1, long n, BoxInfo b, int *key, int *iota, int dual,
+                           int *count) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double xa = x0[i];
-  const int g0 = locate_bin(xa, b.le[0], b.dx[0]);
-  int q = (__dsub_rn(xa, b.le[0]) - ((double)g0 + 0.5) * b.dx[0]) >= 0.0 ? 1 : 0;
-  int c0 = g0 - b.lo[0], c1 = 0;
-  if (b.D == 2) {
-    const double xc = x1[i];
-    const int g1 = locate_bin(xc, b.le[1], b.dx[1]);
-    q |= (__dsub_rn(xc, b.le[1]) - ((double)g1 + 0.5) * b.dx[1]) >= 0.0 ? 2 : 0;
-    c1 = g1 - b.lo[1];
+  int k = -1;
+  if (i < n) {
+    const double xa = x0[i];
+    const int g0 = locate_bin(xa, b.le[0], b.dx[0]);
+    int q = (__dsub_rn(xa, b.le[0]) - ((double)g0 + 0.5) * b.dx[0]) >= 0.0 ? 1 : 0;
+    int c0 = g0 - b.lo[0], c1 = 0;
+    if (b.D == 2) {
+      const double xc = x1[i];
+      const int g1 = locate_bin(xc, b.le[1], b.dx[1]);
+      q |= (__dsub_rn(xc, b.le[1]) - ((double)g1 + 0.5) * b.dx[1]) >= 0.0 ? 2 : 0;
+      c1 = g1 - b.lo[1];
+    }
+    const bool inside = c0 >= 0 && c0 < b.n[0] && c1 >= 0 && c1 < b.n[1];
+    if (dual) {
+      const int m0 = b.n[0] + 1, m1 = (b.D == 2) ? b.n[1] + 1 : 1;
+      k = inside ? (c0 + (q & 1)) + (c1 + (q >> 1)) * m0 : m0 * m1;
+    } else {
+      k = inside ? 4 * (c0 + c1 * b.n[0]) + q : 4 * b.ncell;   // else the outcast bin
+    }
+    key[i] = k;
+    if (iota) iota[i] = (int)i;
   }
-  int k = 4 * b.ncell;  // outcast bin
-  if (c0 >= 0 && c0 < b.n[0] && c1 >= 0 && c1 < b.n[1]) k = 4 * (c0 + c1 * b.n[0]) + q;
-  if (dual) {
-    const int m0 = b.n[0] + 1, m1 = (b.D == 2) ? b.n[1] + 1 : 1;
-    k = m0 * m1;
-    if (c0 >= 0 && c0 < b.n[0] && c1 >= 0 && c1 < b.n[1]) k = (c0 + (q & 1)) + (c1 + (q >> 1)) * m0;
+  if (count) {
+    const unsigned grp = __match_any_sync(0xffffffffu, k);
+    if (k >= 0 && (__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(count + k, __popc(grp));
   }
-  key[i] = k;
-  iota[i] = (int)i;
 }
 
 __global__ void k_cell_ijk(const double *x0, const double *x1, long n, BoxInfo b, int *out) {
@@ -90,12 +98,6 @@ __global__ void k_cell_ijk(const double *x0, const double *x1, long n, BoxInfo b
 // sort of (key, index) pairs (four passes over 8 bytes per particle plus its scratch).  Consecutive particles mostly
 // share their bin, so the lanes of a warp that hit one bin are counted by their leader (__match_any_sync): one
 // atomic per distinct bin of a warp, and lanes of a bin keep their relative order.
-__global__ void k_bin_hist(const int *key, long n, int *count) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = i < n ? key[i] : -1;
-  const unsigned grp = __match_any_sync(0xffffffffu, k);
-  if (k >= 0 && (__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(count + k, __popc(grp));
-}
 // perm[dst] = i, key_sorted[dst] = key[i] with dst = start[key] + (position among the particles of the bin seen so far)
 __global__ void k_bin_scatter(const int *key, long n, const int *start, int *cursor, int *perm, int *key_sorted) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,7 +111,7 @@ __global__ void k_bin_scatter(const int *key, long n, const int *start, int *cur
   if (k >= 0) {
     const int dst = start[k] + base + __popc(grp & ((1u << lane) - 1u));
     perm[dst] = (int)i;
-    key_sorted[dst] = k;
+    if (key_sorted) key_sorted[dst] = k;
   }
 }
 
@@ -171,6 +173,12 @@ __global__ void k_cell_starts(const int *sorted_key, long n, int nbins, int *cel
   const int cur = (i < n) ? (sorted_key[i] >> 2) : nbins;
   const int prev = (i > 0) ? (sorted_key[i - 1] >> 2) : -1;
   for (int c = prev + 1; c <= cur; ++c) cell_start[c] = (int)i;
+}
+
+// the same from the bin starts of the counting sort (bins = 4 quadrants per cell + the outcast bin; start[nb_bins] = n)
+__global__ void k_cell_starts_from_bins(const int *start, int nb_bins, int nbins, int *cell_start) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c <= nbins) cell_start[c] = start[min(4 * c, nb_bins)];
 }
 
 // out[a][i] = in[a][perm[i]] for up to 4 arrays per launch (perm is read once per particle)
@@ -526,14 +534,14 @@ static int bin_impl(pgpu_species_t s, bool dual) {
     s->sort_cap = s->cap;
   }
   int *iota = reinterpret_cast<int *>(s->tmp);  // tmp holds >= n doubles
-  {
-    KTimer t("bin_key");
-    k_cell_key<<<nb(n), 256, 0, c.stream>>>(s->x[0], s->x[1], n, b, s->cell_key, iota, dual ? 1 : 0);
-  }
   int nbits = 1;
   const long maxkey = dual ? (long)(b.n[0] + 1) * (b.D == 2 ? b.n[1] + 1 : 1) : 4L * b.ncell;
   while ((1L << nbits) <= maxkey) ++nbits;
   static const int sort_mode = [] { const char *e = getenv("PGPU_SORT"); return (e && !strcmp(e, "radix")) ? 1 : 0; }();
+  if (sort_mode != 0) {
+    KTimer t("bin_key");
+    k_cell_key<<<nb(n), 256, 0, c.stream>>>(s->x[0], s->x[1], n, b, s->cell_key, iota, dual ? 1 : 0, nullptr);
+  }
   if (sort_mode == 0) {
     // counting sort: bins = maxkey + 1 (the last one is the outcast bin)
     const long nb_bins = maxkey + 1;
@@ -550,13 +558,17 @@ static int bin_impl(pgpu_species_t s, bool dual) {
       PGPU_CUDA(cudaMalloc(&s->cub_tmp, need));
       s->cub_bytes = need;
     }
-    KTimer t("bin_sort");
     PGPU_CUDA(cudaMemsetAsync(count, 0, (size_t)(nb_bins + 1) * sizeof(int), c.stream));
-    k_bin_hist<<<nb(n), 256, 0, c.stream>>>(s->cell_key, n, count);
+    {
+      KTimer t("bin_key");     // keys + histogram in one pass
+      k_cell_key<<<nb(n), 256, 0, c.stream>>>(s->x[0], s->x[1], n, b, s->cell_key, nullptr, dual ? 1 : 0, count);
+    }
+    KTimer t("bin_sort");
     PGPU_CUDA(cub::DeviceScan::ExclusiveSum(s->cub_tmp, need, count, start, (int)nb_bins + 1, c.stream));   // start[nb_bins] = n
     PGPU_CUDA(cudaMemsetAsync(count, 0, (size_t)nb_bins * sizeof(int), c.stream));
-    k_bin_scatter<<<nb(n), 256, 0, c.stream>>>(s->cell_key, n, start, count, s->perm, s->key_sorted);
+    k_bin_scatter<<<nb(n), 256, 0, c.stream>>>(s->cell_key, n, start, count, s->perm, nullptr);
     if (!dual) {
+      k_cell_starts_from_bins<<<nb(nbins + 1), 256, 0, c.stream>>>(start, (int)nb_bins, nbins, s->cell_start);
       // tmp holds n doubles: ints [0, n) are the scratch copy, ints [n, 2n) the list of big bins
       int *biglist = iota + n, *nbig = count + nb_bins;
       PGPU_CUDA(cudaMemsetAsync(nbig, 0, sizeof(int), c.stream));
@@ -580,7 +592,7 @@ static int bin_impl(pgpu_species_t s, bool dual) {
     PGPU_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_tmp, need, s->cell_key, s->key_sorted, iota, s->perm, (int)n, 0,
                                               nbits, c.stream));
   }
-  if (!dual) {
+  if (!dual && sort_mode != 0) {
     KTimer t("bin_starts");
     k_cell_starts<<<nb(n + 1), 256, 0, c.stream>>>(s->key_sorted, n, nbins, s->cell_start);
   }

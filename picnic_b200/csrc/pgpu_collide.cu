@@ -80,11 +80,10 @@ __device__ __forceinline__ void ta_delta_u(const double *vp1, double den1, const
     sinth = 2.0 * delta * inv;
     costh = 1.0 - 2.0 * deltasq * inv;
   } else {
-    const double theta = PI * u_theta;
-    sincos(theta, &sinth, &costh);
+    sincospi(u_theta, &sinth, &costh);          // theta = pi u_theta
   }
   double sinphi, cosphi;
-  sincos(TWOPI * u_phi, &sinphi, &cosphi);
+  sincospi(2.0 * u_phi, &sinphi, &cosphi);      // phi = 2 pi u_phi
   scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
 }
 
@@ -219,7 +218,7 @@ __device__ __forceinline__ unsigned global_cell(const TAParams &P, int cell) {
 // keep their storage order.
 template <int R>
 __device__ __forceinline__ void warp_bitonic_order(int s, int n, const uint64_t *id, const TAParams &P, unsigned salt,
-                                                   int *order, int lane) {
+                                                   int *out, int lane) {   // out[pos], pos = 0..n-1 (global or shared)
   constexpr unsigned IDX_MASK = 32u * R - 1u;
   unsigned v[R];
 #pragma unroll
@@ -266,7 +265,7 @@ __device__ __forceinline__ void warp_bitonic_order(int s, int n, const uint64_t 
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int pos = lane + 32 * r;
-    if (pos < n) order[s + pos] = (int)(v[r] & IDX_MASK);
+    if (pos < n) out[pos] = (int)(v[r] & IDX_MASK);
   }
   __syncwarp();
 }
@@ -275,9 +274,9 @@ __device__ __forceinline__ void warp_bitonic_order(int s, int n, const uint64_t 
 // with the r-th smallest (key, id) where key = Philox(seed, step, id)
 __device__ __forceinline__ void warp_shuffle_order(int s, int n, const uint64_t *id, const TAParams &P,
                                                    unsigned salt, unsigned *key, int *order, int lane) {
-  if (n <= 64) return warp_bitonic_order<2>(s, n, id, P, salt, order, lane);
-  if (n <= 128) return warp_bitonic_order<4>(s, n, id, P, salt, order, lane);
-  if (n <= 256) return warp_bitonic_order<8>(s, n, id, P, salt, order, lane);
+  if (n <= 64) return warp_bitonic_order<2>(s, n, id, P, salt, order + s, lane);
+  if (n <= 128) return warp_bitonic_order<4>(s, n, id, P, salt, order + s, lane);
+  if (n <= 256) return warp_bitonic_order<8>(s, n, id, P, salt, order + s, lane);
   // larger cells: rank of every key by counting, keys in global scratch
   for (int k = lane; k < n; k += 32) {
     const uint64_t pid = id[s + k];
@@ -318,13 +317,14 @@ __device__ __forceinline__ void pair_randoms(const TAParams &P, unsigned gcell, 
   uphi = u01(r.w);
 }
 
+template <int REL = -1>   // -1: P.rel decides at run time; 0 / 1: compiled for one build
 __device__ __forceinline__ void scatter_pair(double *v0, double *v1, double *v2, int pa, double *w0,
                                              double *w1, double *w2, int pb, double dena, double denb,
                                              const TAParams &P, double gauss, double uth, double uphi,
                                              bool inter = false) {
   double a[3] = {v0[pa], v1[pa], v2[pa]};
   double b[3] = {w0[pb], w1[pb], w2[pb]};
-  if (P.rel) {
+  if (REL < 0 ? P.rel != 0 : REL != 0) {
     // TakizukaAbe.cpp:336-337 (self) and :503-505 (between species: the one with the lower density goes second)
     if (inter && dena <= denb) ta_lorentz_scatter(b, a, P.m2, P.m1, dena, P.dt_sec, P.b90_fact, P.Clog, gauss, uth, uphi);
     else ta_lorentz_scatter(a, b, P.m1, P.m2, denb, P.dt_sec, P.b90_fact, P.Clog, gauss, uth, uphi);
@@ -342,16 +342,14 @@ __device__ __forceinline__ void scatter_pair(double *v0, double *v1, double *v2,
   w2[pb] = b[2] - P.f2 * dU[2];
 }
 
-// TakizukaAbe::applySelfScattering (TakizukaAbe.cpp:263-402)
-__global__ void __launch_bounds__(256)
-k_ta_self(const int *cell_start, int ncell, double *v0, double *v1, double *v2, const uint64_t *id,
-          const double *dens, TAParams P, unsigned *key, int *order, unsigned long long *npairs) {
-  const int cell = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (cell >= ncell) return;
-  const double numDen = dens[cell];
+// TakizukaAbe::applySelfScattering (TakizukaAbe.cpp:263-402), one cell by one warp
+__device__ __forceinline__ void ta_self_cell(int cell, int lane, const int *cell_start, double *v0, double *v1, double *v2,
+                                             const uint64_t *id, const double *dens, const TAParams &P, unsigned *key,
+                                             int *order, unsigned long long *npairs) {
   const int s = cell_start[cell], n = cell_start[cell + 1] - s;
-  if (numDen == 0.0 || n < 2) return;
+  if (n < 2) return;
+  const double numDen = dens[cell];
+  if (numDen == 0.0) return;
   warp_shuffle_order(s, n, id, P, 0u, key, order, lane);
   const unsigned gcell = global_cell(P, cell);
   const int pstart = (n % 2 == 0) ? 0 : 3;
@@ -377,21 +375,30 @@ k_ta_self(const int *cell_start, int ncell, double *v0, double *v1, double *v2, 
   if (lane == 0) atomicAdd(npairs, (unsigned long long)(nmain + (pstart == 3 ? 3 : 0)));
 }
 
+// every cell (list == nullptr), or the cells the staged kernel left in `list` (list[0] = how many, then the cells)
+__global__ void __launch_bounds__(256)
+k_ta_self(const int *cell_start, int ncell, double *v0, double *v1, double *v2, const uint64_t *id,
+          const double *dens, TAParams P, unsigned *key, int *order, unsigned long long *npairs, const int *list) {
+  const int gw = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)(((long)gridDim.x * blockDim.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const int count = list ? list[0] : ncell;
+  for (int i = gw; i < count; i += nw)
+    ta_self_cell(list ? list[1 + i] : i, lane, cell_start, v0, v1, v2, id, dens, P, key, order, npairs);
+}
+
 // TakizukaAbe::applyInterScattering (TakizukaAbe.cpp:404-536).  Pair p couples
 // particle p%n1 with p (or p with p%n2): the particle of the shorter list collides
 // repeatedly, in order of p, so one lane owns it and walks its partners.
-__global__ void __launch_bounds__(256)
-k_ta_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, double *a2, const uint64_t *id1,
-           const double *dens1, double *b0, double *b1, double *b2, const uint64_t *id2, const double *dens2,
-           TAParams P, unsigned *key1, int *order1, unsigned *key2, int *order2, unsigned long long *npairs) {
-  const int cell = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (cell >= ncell) return;
-  const double numDen1 = dens1[cell], numDen2 = dens2[cell];
-  if (numDen1 * numDen2 == 0.0) return;
+__device__ __forceinline__ void ta_inter_cell(int cell, int lane, const int *cs1, const int *cs2, double *a0, double *a1,
+                                              double *a2, const uint64_t *id1, const double *dens1, double *b0, double *b1,
+                                              double *b2, const uint64_t *id2, const double *dens2, const TAParams &P,
+                                              unsigned *key1, int *order1, unsigned *key2, int *order2,
+                                              unsigned long long *npairs) {
   const int s1 = cs1[cell], n1 = cs1[cell + 1] - s1;
   const int s2 = cs2[cell], n2 = cs2[cell + 1] - s2;
   if ((long)n1 * n2 < 2) return;
+  const double numDen1 = dens1[cell], numDen2 = dens2[cell];
+  if (numDen1 * numDen2 == 0.0) return;
   warp_shuffle_order(s1, n1, id1, P, 2u, key1, order1, lane);
   warp_shuffle_order(s2, n2, id2, P, 3u, key2, order2, lane);
   const unsigned gcell = global_cell(P, cell);
@@ -407,6 +414,167 @@ k_ta_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, do
     }
   }
   if (lane == 0) atomicAdd(npairs, (unsigned long long)pMax);
+}
+
+__global__ void __launch_bounds__(256)
+k_ta_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, double *a2, const uint64_t *id1,
+           const double *dens1, double *b0, double *b1, double *b2, const uint64_t *id2, const double *dens2,
+           TAParams P, unsigned *key1, int *order1, unsigned *key2, int *order2, unsigned long long *npairs,
+           const int *list) {
+  const int gw = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)(((long)gridDim.x * blockDim.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const int count = list ? list[0] : ncell;
+  for (int i = gw; i < count; i += nw)
+    ta_inter_cell(list ? list[1 + i] : i, lane, cs1, cs2, a0, a1, a2, id1, dens1, b0, b1, b2, id2, dens2, P, key1, order1,
+                  key2, order2, npairs);
+}
+
+
+// ---- the staged Takizuka-Abe kernels ------------------------------------------------------------------------------
+// Cells of up to TA_NMAX particles per species (the usual case: decks run 16 - 200 per cell): the warp copies the
+// cell's velocities into shared memory with cp.async while it draws and sorts the shuffle keys, pairs the particles
+// there, and writes the velocities back in storage order.  Same keys, same pair draws, same arithmetic as
+// k_ta_self / k_ta_inter, which keep the larger cells: what changes is that the three dependent global round trips of
+// a cell (ids -> order -> velocities) become one.
+constexpr int TA_NMAX = 128;
+constexpr int TA_SPECIES_BYTES = TA_NMAX * (3 * 8 + 4);     // v[3][TA_NMAX] doubles + order[TA_NMAX]
+constexpr int TA_SELF_WARPS = 8, TA_INTER_WARPS = 4;
+#ifndef PGPU_TA_SELF_MINB
+#define PGPU_TA_SELF_MINB 3
+#endif
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *g) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void ta_stage_in(double *sv, const double *v0, const double *v1, const double *v2, int s, int n,
+                                            int lane) {
+  for (int k = lane; k < n; k += 32) {
+    cp_async8(sv + k, v0 + s + k);
+    cp_async8(sv + TA_NMAX + k, v1 + s + k);
+    cp_async8(sv + 2 * TA_NMAX + k, v2 + s + k);
+  }
+}
+__device__ __forceinline__ void ta_stage_out(const double *sv, double *v0, double *v1, double *v2, int s, int n, int lane) {
+  for (int k = lane; k < n; k += 32) {
+    v0[s + k] = sv[k];
+    v1[s + k] = sv[TA_NMAX + k];
+    v2[s + k] = sv[2 * TA_NMAX + k];
+  }
+}
+__device__ __forceinline__ void ta_staged_order(int s, int n, const uint64_t *id, const TAParams &P, unsigned salt, int *so,
+                                                int lane) {
+  if (n <= 64) warp_bitonic_order<2>(s, n, id, P, salt, so, lane);
+  else warp_bitonic_order<4>(s, n, id, P, salt, so, lane);
+}
+
+template <int REL>
+__global__ void __launch_bounds__(32 * TA_SELF_WARPS, PGPU_TA_SELF_MINB)
+k_ta_self_staged(const int *cell_start, int ncell, double *v0, double *v1, double *v2, const uint64_t *id,
+                 const double *dens, TAParams P, unsigned long long *npairs, int *list) {
+  extern __shared__ __align__(16) unsigned char ta_smem[];
+  __shared__ unsigned block_pairs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) block_pairs = 0;
+  __syncthreads();
+  const int cell = blockIdx.x * TA_SELF_WARPS + warp;
+  int s = 0, n = 0;
+  double numDen = 0.0;
+  if (cell < ncell) {
+    s = cell_start[cell];
+    n = cell_start[cell + 1] - s;
+    numDen = dens[cell];
+  }
+  if (numDen != 0.0 && n >= 2 && n <= TA_NMAX) {
+    double *sv = reinterpret_cast<double *>(ta_smem + warp * TA_SPECIES_BYTES);
+    int *so = reinterpret_cast<int *>(sv + 3 * TA_NMAX);
+    ta_stage_in(sv, v0, v1, v2, s, n, lane);
+    ta_staged_order(s, n, id, P, 0u, so, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    const unsigned gcell = global_cell(P, cell);
+    const int pstart = (n % 2 == 0) ? 0 : 3;
+    const int nmain = (n - pstart) / 2;
+    double *w0 = sv, *w1 = sv + TA_NMAX, *w2 = sv + 2 * TA_NMAX;
+    for (int q = lane; q < nmain; q += 32) {
+      const int pa = so[pstart + 2 * q], pb = so[pstart + 2 * q + 1];
+      double g, ut, up;
+      pair_randoms(P, gcell, (unsigned)(pstart + 2 * q), 0u, g, ut, up);
+      scatter_pair<REL>(w0, w1, w2, pa, w0, w1, w2, pb, numDen, numDen, P, g, ut, up);
+    }
+    if (pstart == 3 && lane == 0) {
+      // particles 0,1,2 scatter as (0,1), (1,2), (0,2) with half the density (TakizukaAbe.cpp:353-388)
+      const int t[3] = {so[0], so[1], so[2]};
+      const int p1[3] = {0, 1, 0}, p2[3] = {1, 2, 2};
+      for (int p = 0; p < 3; ++p) {
+        double g, ut, up;
+        pair_randoms(P, gcell, (unsigned)p, 1u, g, ut, up);
+        const double dh = REL ? numDen : numDen / 2.0;
+        scatter_pair<REL>(w0, w1, w2, t[p1[p]], w0, w1, w2, t[p2[p]], dh, dh, P, g, ut, up);
+      }
+    }
+    __syncwarp();
+    ta_stage_out(sv, v0, v1, v2, s, n, lane);
+    if (lane == 0) atomicAdd(&block_pairs, (unsigned)(nmain + (pstart == 3 ? 3 : 0)));
+  } else if (n > TA_NMAX && lane == 0) {
+    list[1 + atomicAdd(list, 1)] = cell;       // left to k_ta_self
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && block_pairs) atomicAdd(npairs, (unsigned long long)block_pairs);
+}
+
+template <int REL>
+__global__ void __launch_bounds__(32 * TA_INTER_WARPS, 6)
+k_ta_inter_staged(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, double *a2, const uint64_t *id1,
+                  const double *dens1, double *b0, double *b1, double *b2, const uint64_t *id2, const double *dens2,
+                  TAParams P, unsigned long long *npairs, int *list) {
+  extern __shared__ __align__(16) unsigned char ta_smem[];
+  __shared__ unsigned block_pairs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) block_pairs = 0;
+  __syncthreads();
+  const int cell = blockIdx.x * TA_INTER_WARPS + warp;
+  int s1 = 0, n1 = 0, s2 = 0, n2 = 0;
+  double numDen1 = 0.0, numDen2 = 0.0;
+  if (cell < ncell) {
+    s1 = cs1[cell], n1 = cs1[cell + 1] - s1;
+    s2 = cs2[cell], n2 = cs2[cell + 1] - s2;
+    numDen1 = dens1[cell], numDen2 = dens2[cell];
+  }
+  if (numDen1 * numDen2 != 0.0 && (long)n1 * n2 >= 2 && max(n1, n2) <= TA_NMAX) {
+    double *sa = reinterpret_cast<double *>(ta_smem + warp * 2 * TA_SPECIES_BYTES);
+    int *oa = reinterpret_cast<int *>(sa + 3 * TA_NMAX);
+    double *sb = reinterpret_cast<double *>(ta_smem + warp * 2 * TA_SPECIES_BYTES + TA_SPECIES_BYTES);
+    int *ob = reinterpret_cast<int *>(sb + 3 * TA_NMAX);
+    ta_stage_in(sa, a0, a1, a2, s1, n1, lane);
+    ta_stage_in(sb, b0, b1, b2, s2, n2, lane);
+    ta_staged_order(s1, n1, id1, P, 2u, oa, lane);
+    ta_staged_order(s2, n2, id2, P, 3u, ob, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    const unsigned gcell = global_cell(P, cell);
+    const int pMin = min(n1, n2), pMax = max(n1, n2);
+    const bool first_short = (pMin == n1);
+    for (int r = lane; r < pMin; r += 32) {
+      for (int p = r; p < pMax; p += pMin) {
+        const int i1 = oa[first_short ? r : p], i2 = ob[first_short ? p : r];
+        double g, ut, up;
+        pair_randoms(P, gcell, (unsigned)p, 2u, g, ut, up);
+        scatter_pair<REL>(sa, sa + TA_NMAX, sa + 2 * TA_NMAX, i1, sb, sb + TA_NMAX, sb + 2 * TA_NMAX, i2, numDen1, numDen2, P, g,
+                     ut, up, true);
+      }
+    }
+    __syncwarp();
+    ta_stage_out(sa, a0, a1, a2, s1, n1, lane);
+    ta_stage_out(sb, b0, b1, b2, s2, n2, lane);
+    if (lane == 0) atomicAdd(&block_pairs, (unsigned)pMax);
+  } else if (max(n1, n2) > TA_NMAX && lane == 0) {
+    list[1 + atomicAdd(list, 1)] = cell;       // left to k_ta_inter
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && block_pairs) atomicAdd(npairs, (unsigned long long)block_pairs);
 }
 
 
@@ -2311,17 +2479,45 @@ int pgpu_collide_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double dt
   P.ncell_glob0 = g->desc.ncell[0];
   const int ncell = (int)g->ncell_box;
   unsigned long long *d_np = &c.d_counters->npairs;  // zero between calls
+  // cells of up to TA_NMAX particles per species go through the staged kernels, which leave the others in a list for
+  // the general ones
+  int *list = nullptr;
+  if (c.ta_staged) {
+    if (c.ta_list_cap < ncell + 1) {
+      if (c.ta_list) cudaFree(c.ta_list);
+      c.ta_list = nullptr;
+      PGPU_CUDA(cudaMalloc(&c.ta_list, (size_t)(ncell + 1) * sizeof(int)));
+      c.ta_list_cap = ncell + 1;
+      cudaFuncSetAttribute(k_ta_self_staged<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(k_ta_self_staged<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(k_ta_inter_staged<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(k_ta_inter_staged<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    list = c.ta_list;
+    PGPU_CUDA(cudaMemsetAsync(list, 0, sizeof(int), c.stream));
+  }
+  const unsigned tail_blocks = list ? (unsigned)(2 * c.sm_count) : nb((long)ncell * 32);
   if (sA == sB) {
     KTimer t("collide_ta_self");
-    k_ta_self<<<nb((long)ncell * 32), 256, 0, c.stream>>>(sA->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2],
-                                                          sA->id, sA->dens, P, (unsigned *)sA->cell_key, sA->perm,
-                                                          d_np);
+    if (list) {
+      auto k = P.rel ? k_ta_self_staged<1> : k_ta_self_staged<0>;
+      k<<<(ncell + TA_SELF_WARPS - 1) / TA_SELF_WARPS, 32 * TA_SELF_WARPS, TA_SELF_WARPS * TA_SPECIES_BYTES, c.stream>>>(
+          sA->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->id, sA->dens, P, d_np, list);
+    }
+    k_ta_self<<<tail_blocks, 256, 0, c.stream>>>(sA->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->id, sA->dens, P,
+                                                 (unsigned *)sA->cell_key, sA->perm, d_np, list);
   } else {
     KTimer t("collide_ta_inter");
-    k_ta_inter<<<nb((long)ncell * 32), 256, 0, c.stream>>>(
+    if (list) {
+      auto k = P.rel ? k_ta_inter_staged<1> : k_ta_inter_staged<0>;
+      k<<<(ncell + TA_INTER_WARPS - 1) / TA_INTER_WARPS, 32 * TA_INTER_WARPS, TA_INTER_WARPS * 2 * TA_SPECIES_BYTES,
+          c.stream>>>(sA->cell_start, sB->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->id, sA->dens, sB->v[0],
+                      sB->v[1], sB->v[2], sB->id, sB->dens, P, d_np, list);
+    }
+    k_ta_inter<<<tail_blocks, 256, 0, c.stream>>>(
         sA->cell_start, sB->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->id, sA->dens, sB->v[0],
         sB->v[1], sB->v[2], sB->id, sB->dens, P, (unsigned *)sA->cell_key, sA->perm, (unsigned *)sB->cell_key,
-        sB->perm, d_np);
+        sB->perm, d_np, list);
   }
   if (npairs_out) {
     PGPU_CUDA(cudaMemcpyAsync(c.h_counters, c.d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c.stream));

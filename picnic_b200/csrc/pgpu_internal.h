@@ -100,6 +100,7 @@ struct Context {
   int cc1_tma = 3;           // CC1 kernel: 3 = table-driven two-phase TMA tile kernel, 2 = the same reading the raw field arrays (env PGPU_CC1_TMA)
   int cc1_rsteps = 3;        // shuffle-reduction steps before the REDs: 2, 3 or 4 (env PGPU_CC1_RSTEPS)
   int cc1_minblocks = 5;     // blocks of 128 threads per SM the table kernel is compiled for: 4 (128 regs) or 5 (96 regs, needs the 228 KB carve-out); env PGPU_CC1_MINB
+  int ta_staged = 1;         // Takizuka-Abe: cells of <= 128 particles per species through the shared-memory kernels (env PGPU_TA_STAGED)
   int cc1_pair = 0;          // CC1 kernel: two particles of a dual cell in lockstep through the Picard loop (env PGPU_CC1_PAIR)
   int cc1_prefetch = 0;      // L2 prefetch of a block's next particle tile (env PGPU_CC1_PREFETCH)
   int cc1_version = 2;       // table kernel generation: 1 = round-1 map (4 consecutive particles per thread in both phases), 2 = lane map in the push phase (env PGPU_CC1_V)
@@ -109,6 +110,8 @@ struct Context {
   int cc1_waves = 64;        // tile kernel grid = min(tiles, SMs*4*waves) (env PGPU_CC1_WAVES)
   bool use_fast_cc1 = true;  // pgpu_set_deposit_mode(0) turns the specialised CC1 kernel off
   Counters *d_counters = nullptr;
+  int *ta_list = nullptr;    // cells the staged Takizuka-Abe kernels left to the general ones: [count, cells...]
+  int ta_list_cap = 0;
   Counters *h_counters = nullptr;  // pinned
   int sticky_error = 0;
   int sm_count = 148;
