@@ -503,8 +503,13 @@ def collisions_leg(args, torch, capi, stream, peak):
             "prep_kernel_ms_per_step": prep,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "bytes_per_unit": 96.0,
-                         "kernel": "collide_ta_self + collide_ta_inter (3 launches per step)",
-                         "kernel_ms_per_step": kern_ms}}
+                         "kernel": "collide_ta_self + collide_ta_inter (per step 3 staged launches, cells <= 128 "
+                                   "particles/species in shared memory, + 3 launches for the larger cells)",
+                         "kernel_ms_per_step": kern_ms,
+                         "note": "instruction-issue bound, not HBM bound: per pair two Philox4x32-10 blocks, a share of "
+                                 "the warp's bitonic sort of the shuffle keys and fp64 sqrt/div/sincospi; ncu "
+                                 "(profiles/r02_f_ncu_k_ta.txt) has issue-active 57-60 % at 12-15 % fp64 pipe and "
+                                 "<= 30 % DRAM throughput"}}
 
 
 def c4_leg(args, torch, capi, stream, peak):

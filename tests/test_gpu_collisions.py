@@ -63,7 +63,8 @@ def _ragged_cells(rng, ncell, counts_choice):
 def test_ta_self_conservation_and_pair_counts(pgpu):
     rng = np.random.default_rng(32)
     ncell = 64
-    x, counts = _ragged_cells(rng, ncell, [0, 1, 2, 3, 4, 5, 7, 32, 33, 65])
+    # 65..128: the staged kernel's four-register sort; above 128 the cell list handed to the general kernel
+    x, counts = _ragged_cells(rng, ncell, [0, 1, 2, 3, 4, 5, 7, 32, 33, 65, 127, 128, 129, 200, 301])
     n = x.shape[1]
     deck = decks.Deck(D=1, ncell=(ncell,), dx=(0.25,), xmin=(0.0,), nghost=2)
     sdef = decks.SpeciesDef("electron", 1.0, -1.0)
@@ -126,8 +127,8 @@ def test_ta_shuffle_independent_of_storage_order(pgpu):
 def test_ta_inter_conservation_and_pair_counts(pgpu):
     rng = np.random.default_rng(34)
     ncell = 48
-    xe, ce = _ragged_cells(rng, ncell, [0, 1, 2, 5, 16, 40])
-    xi, ci = _ragged_cells(rng, ncell, [0, 1, 3, 16, 17, 70])
+    xe, ce = _ragged_cells(rng, ncell, [0, 1, 2, 5, 16, 40, 128, 131])
+    xi, ci = _ragged_cells(rng, ncell, [0, 1, 3, 16, 17, 70, 129, 260])
     deck = decks.Deck(D=1, ncell=(ncell,), dx=(0.25,), xmin=(0.0,), nghost=2)
     se, si = decks.electron_proton((1,))
     grid = pgpu.Grid(1, (ncell,), (0.0,), (0.25,), 2, (1,), volume_scale=deck.volume_scale)
