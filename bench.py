@@ -616,7 +616,11 @@ def c4_leg(args, torch, capi, stream, peak):
                                      "frac": 112.0 * pairs / (kc_ms * 1e-3) / 1e9 / peak if kc_ms else None,
                                      "bytes_per_unit": 112.0,
                                      "kernel": "collide_coulomb_intra x2 + collide_coulomb_inter (3 launches per step)",
-                                     "kernel_ms_per_step": kc_ms}},
+                                     "kernel_ms_per_step": kc_ms,
+                                     "note": "instruction-issue bound: ~1700 warp instructions per pair slot (fp64 sqrt x4, "
+                                             "div x5, Nanbu's exp/log inversion, sincos, two Philox blocks); ncu "
+                                             "(profiles/r02_f_ncu_k_coulomb.txt): issue-active 49-52 %, fp64 pipe 24-29 %, "
+                                             "DRAM 16-20 %, 128 registers"}},
             "mass_matrices": {"metric": "particles/s through setMassMatrices (1D run kernel)", "value": n / (ms_mm * 1e-3),
                               "ms_per_setMassMatrices": ms_mm,
                               "hbm_frac_at_72B": 72.0 * n / (ms_mm * 1e-3) / 1e9 / peak}}
