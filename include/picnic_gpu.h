@@ -481,10 +481,12 @@ int pgpu_ta_lorentz_scatter(long n, const double *up1, const double *up2, double
  * particles, lighter-weight particle always scatters, heavier with probability wmin/wmax; pairing
  * O(N) or all pairs (NxN / cells below NxN_Nthresh); sigma limited by the atomic spacing; b_max =
  * the Debye length set by pgpu_debye_length.  Species must be binned with moments set. */
-enum { PGPU_ANG_TAKIZUKA = 0, PGPU_ANG_NANBU = 1, PGPU_ANG_BOBYLEV = 2, PGPU_ANG_ISOTROPIC = 5 };
+enum { PGPU_ANG_TAKIZUKA = 0, PGPU_ANG_NANBU = 1, PGPU_ANG_BOBYLEV = 2, PGPU_ANG_NANBU_FAS = 3, PGPU_ANG_NANBU_FAS_V2 = 4,
+       PGPU_ANG_ISOTROPIC = 5 };   /* the reference's enum order (Coulomb.H:132-139) */
 typedef struct {
   double Clog;            /* coulomb_logarithm; 0 = per pair from b_max / b_min (Coulomb.cpp:1664-1672) */
-  int angular_scattering; /* PGPU_ANG_*  (NANBU_FAS, NANBU_FAS_v2: not implemented -> PGPU_ERR_ARG) */
+  int angular_scattering; /* PGPU_ANG_*; the host applies exclude_electron_fas (Coulomb.cpp:65-68: NANBU_FAS(_v2) -> NANBU
+                           * when one of the species is the electron) */
   int NxN;                /* Coulomb.NxN */
   int NxN_Nthresh;        /* Coulomb.NxN_Nthresh (11) */
   int num_subcycles;      /* Coulomb.num_subcycles (1) */
@@ -509,6 +511,10 @@ typedef struct {
    * collision kernels draw it from Philox. */
   int include_large_angle_scattering;
   double test_large_angle_draw;
+  /* NANBU_FAS / NANBU_FAS_v2 (Coulomb.H:365-718, full-angle scattering after Higginson JCP 2017) draw up to three uniforms
+   * per pair, one after the other: u_polar and these two in the explicit-draw test entry points; the collision kernels
+   * take them from Philox. */
+  double test_fas_draw2, test_fas_draw3;
 } pgpu_coulomb_params;
 int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm, double dt_sec,
                          uint64_t seed, uint64_t step, long *npairs);

@@ -450,6 +450,24 @@ def coulomb_set_large_angle(on, test_draw=0.5):
     f(int(on), float(test_draw))
 
 
+def coulomb_set_fas_draws(second=0.5, third=0.5):
+    """the second and third uniform of NANBU_FAS / NANBU_FAS_v2 in the explicit-draw entry points (the first is u_polar)"""
+    f = lib().orc_coulomb_set_fas_draws
+    f.argtypes = [C.c_double, C.c_double]
+    f.restype = None
+    f(float(second), float(third))
+
+
+def nanbu_fas_costh_sinth(variant, s12, Clog, b0, bmin_qm, sigma_eff, u1, u2, u3):
+    """Coulomb::setNANBUFAScosthsinth (variant 3) / setNANBUFAS_v2_costhsinth (variant 4) with explicit draws"""
+    f = lib().orc_nanbu_fas_costh_sinth
+    f.argtypes = [C.c_int] + [C.c_double] * 8 + [C.c_void_p, C.c_void_p]
+    f.restype = None
+    c, sn = C.c_double(), C.c_double()
+    f(int(variant), s12, Clog, b0, bmin_qm, sigma_eff, u1, u2, u3, C.byref(c), C.byref(sn))
+    return c.value, sn.value
+
+
 def coulomb_set_weight_method(conservative):
     """Coulomb weight_method: False PROBABILISTIC, True CONSERVATIVE (Sentoku-Kemp, Coulomb.cpp:730-917, 1439-1640)."""
     f = lib().orc_coulomb_set_weight_method

@@ -439,7 +439,238 @@ static bool large_angle_part(double &s12, double Clog, double b0, double bmin_qm
   return false;
 }
 
+/* Coulomb angular_scattering = NANBU_FAS (3) and NANBU_FAS_v2 (4): Coulomb::setNANBUFAScosthsinth (Coulomb.H:365-428),
+ * setNANBUFAS_v2_costhsinth (:430-571), setFAScoefficients (:573-618), setFAS_v2_coefficients (:620-678) and
+ * getTransitionX_NANBU (:680-718).  Full-angle scattering after Higginson, JCP 2017: Nanbu's cumulative small-angle
+ * distribution joined to single Rutherford events, the coefficients from a fixed-point solve per pair.
+ * The reference draws its uniforms one after the other, and only those a branch needs; FasDraws hands them out in
+ * that order -- from the explicit test values (u_polar, then the two of orc_coulomb_set_fas_draws) or, inside the pair
+ * driver, live from the generator (the azimuth then follows the polar draws, as in GalileanScatter).
+ * Where the reference prints a message and exits on a failed v2 solve, this falls back to setNANBUcosthsinth. */
+static double g_fas_draw2 = 0.5, g_fas_draw3 = 0.5;
+static int g_fas_live = 0;
+extern "C" void orc_coulomb_set_fas_draws(double second, double third) {
+  g_fas_draw2 = second;
+  g_fas_draw3 = third;
+}
+namespace {
+struct FasDraws {
+  double u[3];
+  int pos;
+  double next() {
+    if (g_fas_live) return mu_rand();
+    const double v = u[pos < 3 ? pos : 2];
+    ++pos;
+    return v;
+  }
+};
+double transition_x_nanbu(double Clog, double s12, double alpha_g, double sA) {
+  double xc = 2.0;
+  const double C0 = s12 / (8.0 * Clog * alpha_g * sA);
+  if (C0 > std::exp(-2.0)) return 1.0;
+  double error = 1.0;
+  int iter = 0;
+  while (error > 1.0e-4) {
+    const double xold = xc;
+    const double y0 = xc * xc * std::exp(-2.0 * xc) - C0;
+    const double dy0dx = 2.0 * xc * (1.0 - xc) * std::exp(-2.0 * xc);
+    xc = xc - y0 / dy0dx;
+    error = std::abs(1.0 - xold / xc);
+    iter += 1;
+    if (iter > 20) break;
+  }
+  if (sA * xc > 1.0) xc = 1.0 / sA;
+  return xc;
+}
+int fas_coefficients(double &alpha_g, double &sA, double &muc, double Clog, double s12, double mu_max) {
+  alpha_g = 1.0;
+  sA = s12 / 2.0;
+  double Xc = transition_x_nanbu(Clog, s12, alpha_g, sA);
+  muc = sA * Xc;
+  int iter = 0, success = 1;
+  double error = 1.0;
+  while (error > 1.0e-4) {
+    const double sAold = sA;
+    const double f1 = 1.0 - std::exp(-s12) + s12 / Clog * 0.5 * std::log(Xc * sAold / mu_max);
+    const double f2 = (1.0 - std::exp(-2.0 * Xc)) / (1.0 - (1.0 + Xc) * std::exp(-2.0 * Xc));
+    sA = (4.0 * mu_max * Clog / (4.0 * mu_max * Clog + s12)) * (s12 / (4.0 * Xc * Clog) + f1 * f2);
+    Xc = transition_x_nanbu(Clog, s12, alpha_g, sA);
+    muc = sA * Xc;
+    alpha_g = (1.0 - s12 / (4.0 * Clog) * (mu_max - muc) / mu_max / muc) / (1.0 - std::exp(-2.0 * muc / sA));
+    error = std::abs(1.0 - sAold / sA);
+    iter += 1;
+    if (iter > 20) {
+      success = -1;
+      break;
+    }
+  }
+  return success;
+}
+int fas_v2_coefficients(double &alpha_g, double &sA, double Clog, double s12, double mu_max, double mu_tr) {
+  const double S_L = s12 / (4.0 * Clog) * mu_max / mu_tr / (mu_max + mu_tr);
+  const double mu_L = s12 / (2.0 * Clog) * std::log((mu_max + mu_tr) / mu_tr);
+  const double mu_N97 = 1.0 - std::exp(-s12);
+  if (mu_L > mu_N97 || S_L > 1.0) {
+    alpha_g = 0.0;
+    sA = mu_tr;
+    return -1;
+  }
+  sA = s12 / 2.0;
+  alpha_g = std::max(0.0, (1.0 - S_L) / (1.0 - std::exp(-2.0 * mu_max / sA)));
+  int iter = 0, success = 1;
+  double error = 1.0;
+  while (error > 1.0e-4) {
+    const double sAold = sA;
+    const double f1 = mu_N97 - mu_L + alpha_g * mu_max * std::exp(-2.0 * mu_max / sAold);
+    const double f2 = 1.0 - S_L;
+    sA = f1 / f2;
+    alpha_g = std::max(0.0, (1.0 - S_L) / (1.0 - std::exp(-2.0 * mu_max / sA)));
+    error = std::abs(1.0 - sAold / sA);
+    iter += 1;
+    if (iter > 20) {
+      success = -1;
+      break;
+    }
+  }
+  return success;
+}
+void nanbu_fas(double s12, double Clog, double b0, double bmin_qm, double sigma_eff, FasDraws &D, double &costh,
+               double &sinth) {
+  const double bperp_sq = b0 * b0 / 4.0, bmin_sq = bmin_qm * bmin_qm;
+  const double bmax_sq = std::exp(2.0 * Clog) * (bperp_sq + bmin_sq) - bperp_sq;
+  const double s12_min = 1.33 * 4.0 * Clog / (std::exp(2.0 * Clog) - 1.0);
+  costh = 1.0;
+  sinth = 0.0;
+  if (s12 < s12_min) {
+    const double N12 = s12 / sigma_eff * kPI * (bmax_sq - bmin_sq);
+    const double PL = 1.0 - std::exp(-N12);
+    if (D.next() < PL) {
+      const double RL = D.next();
+      const double bsq = bmax_sq - RL * (bmax_sq - bmin_sq);
+      costh = (bsq - bperp_sq) / (bsq + bperp_sq);
+      sinth = std::sqrt(1.0 - costh * costh);
+    }
+  } else if (s12 < 0.5) {
+    double alpha_g, sA, muc;
+    const double costhmax = (bmin_sq - bperp_sq) / (bmin_sq + bperp_sq);
+    const double mu_max = (1.0 - costhmax) / 2.0;
+    const int success = fas_coefficients(alpha_g, sA, muc, Clog, s12, mu_max);
+    if (success < 0 || muc != muc) {
+      orc_nanbu_costh_sinth(s12, D.next(), &costh, &sinth);
+    } else {
+      const double Uc = 1.0 - s12 / (4.0 * Clog) * (mu_max - muc) / (mu_max * muc);
+      const double R = D.next();
+      if (R < Uc) {
+        costh = 1.0 + sA * std::log(1.0 - R / Uc * (1.0 - std::exp(-2.0 * muc / sA)));
+        sinth = std::sqrt(1.0 - costh * costh);
+      } else {
+        const double costhc = 1.0 - 2.0 * muc;
+        const double R2 = D.next();
+        const double numer = R2 * (costhc - costhmax) - costhc * (1.0 - costhmax);
+        const double denom = R2 * (costhc - costhmax) - (1.0 - costhmax);
+        costh = numer / denom;
+        sinth = std::sqrt(1.0 - costh * costh);
+      }
+    }
+  } else {
+    orc_nanbu_costh_sinth(s12, D.next(), &costh, &sinth);
+  }
+}
+void nanbu_fas_v2(double s12, double Clog, double b0, double bmin_qm, double /*sigma_eff*/, FasDraws &D, double &costh,
+                  double &sinth) {
+  const double bperp_sq = b0 * b0 / 4.0, bmin_sq = bmin_qm * bmin_qm;
+  const double bmax_sq = std::exp(2.0 * Clog) * (bperp_sq + bmin_sq) - bperp_sq;
+  const double costhmax = (bmin_sq - bperp_sq) / (bmin_sq + bperp_sq);
+  const double mu_max = (1.0 - costhmax) / 2.0;
+  if (s12 > 0.6) {
+    orc_nanbu_costh_sinth(s12, D.next(), &costh, &sinth);
+    return;
+  }
+  double Nmax = 2.0 * Clog;
+  const double mutr_factor = Clog;
+  const double sig_ratio = bperp_sq / (bmax_sq - bmin_sq);
+  const double s12_Nmin = 4.0 * Clog * sig_ratio;
+  double s12_Nmax = Nmax * s12_Nmin;
+  const double Nmax_min = 2.0 * mutr_factor * mu_max / (std::exp(2.0 * Clog) - 1.0) / s12_Nmin;
+  if (Nmax < Nmax_min) {
+    Nmax = Nmax_min;
+    s12_Nmax = Nmax * s12_Nmin;
+  }
+  if (s12 < s12_Nmax) {
+    const double Ntot = s12 / s12_Nmin;
+    const double Pscatter = 1.0 - std::exp(-Ntot);
+    if (D.next() > Pscatter) {
+      costh = 1.0;
+      sinth = 0.0;
+      return;
+    }
+    double alpha_g, sA;
+    double mu_tr = s12_Nmax / mutr_factor;
+    const int success = fas_v2_coefficients(alpha_g, sA, Clog, s12_Nmax, mu_max, mu_tr);
+    if (success < 0 || sA != sA) {
+      orc_nanbu_costh_sinth(s12, D.next(), &costh, &sinth);
+      return;
+    }
+    alpha_g = std::max(0.0, alpha_g * (s12 - s12_Nmin) / (s12_Nmax - s12_Nmin));
+    if (alpha_g == 0.0) sA = mu_max;
+    else sA *= s12 / s12_Nmax;
+    double mu0;
+    const double coefc = 4.0 * sig_ratio / mu_max;
+    if (coefc < 1.0e-10) mu0 = sig_ratio;
+    else mu0 = mu_max * (-1.0 + std::sqrt(1.0 + coefc)) / 2.0;
+    const double S_N97 = alpha_g * (1.0 - std::exp(-2.0 * mu_max / sA));
+    if (s12 <= s12_Nmin) {
+      mu_tr = mu0;
+    } else {
+      const double C0 = (1.0 - S_N97) * 4.0 * Clog / s12;
+      const double coef = 4.0 / mu_max / C0;
+      if (coef < 1.0e-10) mu_tr = 1.0 / C0;
+      else mu_tr = mu_max * (-1.0 + std::sqrt(1.0 + coef)) / 2.0;
+      mu_tr = std::max(mu_tr, mu0);
+    }
+    const double R = D.next();
+    if (R < S_N97) {
+      costh = 1.0 + sA * std::log(1.0 - R / S_N97 * (1.0 - std::exp(-2.0 * mu_max / sA)));
+    } else {
+      const double RL = D.next();
+      costh = 1.0 - 2.0 * RL * mu_tr * mu_max / (mu_max * (1.0 - RL) + mu_tr);
+    }
+    sinth = std::sqrt(1.0 - costh * costh);
+  } else {
+    double alpha_g, sA;
+    const double mu_tr = s12 / mutr_factor;
+    const int success = fas_v2_coefficients(alpha_g, sA, Clog, s12, mu_max, mu_tr);
+    if (success < 0 || sA != sA) {
+      orc_nanbu_costh_sinth(s12, D.next(), &costh, &sinth);
+      return;
+    }
+    const double S_L = s12 / (4.0 * Clog) * mu_max / mu_tr / (mu_max + mu_tr);
+    const double S_N97 = 1.0 - S_L;
+    const double R = D.next();
+    if (R < S_N97) {
+      costh = 1.0 + sA * std::log(1.0 - R / S_N97 * (1.0 - std::exp(-2.0 * mu_max / sA)));
+    } else {
+      const double RL = D.next();
+      costh = 1.0 - 2.0 * RL * mu_tr * mu_max / (mu_max * (1.0 - RL) + mu_tr);
+    }
+    sinth = std::sqrt(1.0 - costh * costh);
+  }
+}
+}  // namespace
+
+/* the polar part alone, for the parity tests of the device kernels (variant 3 NANBU_FAS, 4 NANBU_FAS_v2) */
+extern "C" void orc_nanbu_fas_costh_sinth(int variant, double s12, double Clog, double b0, double bmin_qm, double sigma_eff,
+                                          double u1, double u2, double u3, double *costh, double *sinth) {
+  FasDraws D = {{u1, u2, u3}, 0};
+  const int live = g_fas_live;
+  g_fas_live = 0;
+  if (variant == 3) nanbu_fas(s12, Clog, b0, bmin_qm, sigma_eff, D, *costh, *sinth);
+  else nanbu_fas_v2(s12, Clog, b0, bmin_qm, sigma_eff, D, *costh, *sinth);
+  g_fas_live = live;
+}
+
 /* Coulomb::GalileanScatter + SetPolarScattering (TAKIZUKA=0, NANBU=1, BOBYLEV=2, ISOTROPIC=5)
+ * and NANBU_FAS=3, NANBU_FAS_v2=4 (their second and third uniforms: orc_coulomb_set_fas_draws)
  * with explicit draws: r_polar = |randn| for TAKIZUKA's small-angle branch, else a uniform;
  * u_phi uniform.  Returns 0 and leaves dU = 0 when the reference returns early (Appendix B:
  * the reference then uses an uninitialised deltaU; treated as zero). */
@@ -490,13 +721,20 @@ extern "C" int orc_coulomb_delta_u(const double *vp1, const double *vp2, double 
       costh = 1.0 - std::min(s12, 2.0);
       sinth = std::sin(std::acos(costh));
       break;
+    case 3:
+    case 4: {
+      FasDraws D = {{u_polar, g_fas_draw2, g_fas_draw3}, 0};
+      if (angular == 3) nanbu_fas(s12, Clog, b0, bmin_qm, sigma_eff, D, costh, sinth);
+      else nanbu_fas_v2(s12, Clog, b0, bmin_qm, sigma_eff, D, costh, sinth);
+      break;
+    }
     default: {
       const double theta = kPI * u_polar;
       costh = std::cos(theta);
       sinth = std::sin(theta);
     }
   }
-  const double phi = kTWOPI * u_phi;
+  const double phi = kTWOPI * (g_fas_live ? mu_rand() : u_phi);   /* live: the azimuth follows the polar draws */
   orc_scatter_delta_u(ux, uy, uz, costh, sinth, std::cos(phi), std::sin(phi), dU);
   return 1;
 }
@@ -575,13 +813,20 @@ extern "C" int orc_coulomb_lorentz_scatter(double *a_up1, double *a_up2, int a_s
       costh = 1.0 - std::min(s12, 2.0);
       sinth = std::sin(std::acos(costh));
       break;
+    case 3:
+    case 4: {
+      FasDraws D = {{u_polar, g_fas_draw2, g_fas_draw3}, 0};
+      if (angular == 3) nanbu_fas(s12, Clog, b0, bmin_qm, sigma_eff, D, costh, sinth);
+      else nanbu_fas_v2(s12, Clog, b0, bmin_qm, sigma_eff, D, costh, sinth);
+      break;
+    }
     default: {
       const double theta = kPI * u_polar;
       costh = std::cos(theta);
       sinth = std::sin(theta);
     }
   }
-  const double phi = kTWOPI * u_phi;
+  const double phi = kTWOPI * (g_fas_live ? mu_rand() : u_phi);   /* live: the azimuth follows the polar draws */
   orc_rotate_velocity(upst, costh, sinth, std::cos(phi), std::sin(phi));
   ucmdotup = gcm * (vcm[0] * upst[0] + vcm[1] * upst[1] + vcm[2] * upst[2]);
   upst_fact = gcm * (ucmdotup / (1.0 + gcm) + g1st);
@@ -636,12 +881,15 @@ void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2
     } else if (c.angular == 0) {
       if (s12 < 2.0) gauss = mu_randn();
       else upol = mu_rand();
+    } else if (c.angular == 3 || c.angular == 4) {
+      g_fas_live = 1;          /* the polar uniforms and then the azimuth are drawn inside, in the reference's order */
     } else if (c.angular != 2) {
       upol = mu_rand();
     }
-    const double uphi = mu_rand();
+    const double uphi = g_fas_live ? 0.0 : mu_rand();
     orc_coulomb_lorentz_scatter(p1, p2, scatter2 ? 1 : 0, q1, q2, m1, m2, c.EF_norm, c.Clog, c.angular, den12,
                                 c.bmax, c.sigma_max, c.dt_sec, gauss, upol, uphi, nullptr);
+    g_fas_live = 0;
     g_large_angle_draw = saved_draw;
     return;
   }
@@ -663,12 +911,15 @@ void coulomb_pair(const PairCtx &c, double *b1, double w1, double *b2, double w2
     } else if (c.angular == 0) {
       if (s12 < 2.0) gauss = mu_randn();
       else upol = mu_rand();
+    } else if (c.angular == 3 || c.angular == 4) {
+      g_fas_live = 1;          /* the polar uniforms and then the azimuth are drawn inside, in the reference's order */
     } else if (c.angular != 2) {
       upol = mu_rand();
     }
-    const double uphi = mu_rand();
+    const double uphi = g_fas_live ? 0.0 : mu_rand();
     orc_coulomb_delta_u(b1, b2, c.charge1, c.charge2, c.mass1, c.mass2, c.EF_norm, c.Clog, c.angular, den12,
                         c.bmax, c.sigma_max, c.dt_sec, gauss, upol, uphi, dU, nullptr);
+    g_fas_live = 0;
     g_large_angle_draw = saved_draw;
   } else {
     dU[0] = dU[1] = dU[2] = 0.0;

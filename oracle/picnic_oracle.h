@@ -303,6 +303,15 @@ void orc_mod_energy_pairwise(double *b1, double *b2, double wpmp1, double wpmp2,
 /* scattering.coulomb.include_large_angle_scattering (Coulomb::SetPolarScattering, Coulomb.cpp:1801-1863); test_draw is the
  * uniform RL the explicit-draw entry points use (the cell drivers draw it from the stream). */
 void orc_coulomb_set_large_angle(int on, double test_draw);
+/* angular_scattering = NANBU_FAS (variant 3, Coulomb.H:365-428, 573-618, 680-718) and NANBU_FAS_v2 (variant 4,
+ * Coulomb.H:430-571, 620-678): orc_coulomb_delta_u / orc_coulomb_lorentz_scatter and the cell drivers take them as
+ * angular = 3 / 4.  The reference draws up to three uniforms, one after the other and only those a branch needs:
+ * u1..u3 here; the explicit-draw entry points use u_polar, then the two set by orc_coulomb_set_fas_draws.
+ * parity unpinned: Coulomb.H does not compile outside the reference's build; pinned by its own properties
+ * (tests/test_oracle_collisions.py). */
+void orc_coulomb_set_fas_draws(double second, double third);
+void orc_nanbu_fas_costh_sinth(int variant, double s12, double Clog, double b0, double bmin_qm, double sigma_eff, double u1,
+                               double u2, double u3, double *costh, double *sinth);
 void orc_coulomb_set_enforce(int on, double energy_fraction, double energy_fraction_max, int beta_weight_exponent,
                              int sort_weighted, int nmin_save);
 /* ScatteringUtils::collapseThreeToTwo (ScatteringUtils.H:20-47), pinned on the reference */

@@ -53,7 +53,11 @@ class CoulombParams(C.Structure):
                 ("num_subcycles", C.c_int), ("enforce_conservations", C.c_int), ("energy_fraction", C.c_double),
                 ("energy_fraction_max", C.c_double), ("beta_weight_exponent", C.c_int),
                 ("sort_weighted_particles", C.c_int), ("conservation_Nmin_save", C.c_int), ("weight_method", C.c_int),
-                ("include_large_angle_scattering", C.c_int), ("test_large_angle_draw", C.c_double)]
+                ("include_large_angle_scattering", C.c_int), ("test_large_angle_draw", C.c_double),
+                ("test_fas_draw2", C.c_double), ("test_fas_draw3", C.c_double)]
+
+
+ANG_TAKIZUKA, ANG_NANBU, ANG_BOBYLEV, ANG_NANBU_FAS, ANG_NANBU_FAS_V2, ANG_ISOTROPIC = 0, 1, 2, 3, 4, 5
 
 
 class ElasticParams(C.Structure):
@@ -700,12 +704,14 @@ def nu_max_hard_sphere(sA, sB, sigmaT):
 
 
 def coulomb_lorentz_scatter(up1, up2, scatter2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, den12, bmax, sigma_max,
-                            gauss, upol, uphi, large_angle=None):
+                            gauss, upol, uphi, large_angle=None, fas_draws=(0.5, 0.5)):
     """Coulomb::LorentzScatter for n pairs ([3][n] arrays): (up1', up2', s12).  large_angle = the uniform draw of the
-    large-angle event (include_large_angle_scattering on), None = off."""
+    large-angle event (include_large_angle_scattering on), None = off; fas_draws = the second and third uniform of
+    NANBU_FAS(_v2)."""
     c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     n = np.asarray(den12).size
     prm = CoulombParams(Clog, angular, 0, 11, 1)
+    prm.test_fas_draw2, prm.test_fas_draw3 = float(fas_draws[0]), float(fas_draws[1])
     if large_angle is not None:
         prm.include_large_angle_scattering, prm.test_large_angle_draw = 1, float(large_angle)
     a = [c(up1), c(up2), c(EF_norm), c(den12), c(bmax), c(sigma_max), c(gauss), c(upol), c(uphi)]
@@ -717,10 +723,11 @@ def coulomb_lorentz_scatter(up1, up2, scatter2, q1, q2, m1, m2, Clog, angular, d
 
 
 def coulomb_delta_u(vp1, vp2, q1, q2, m1, m2, Clog, angular, dt_sec, EF_norm, den12, bmax, sigma_max, gauss, upol, uphi,
-                    large_angle=None):
+                    large_angle=None, fas_draws=(0.5, 0.5)):
     c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     n = np.asarray(den12).size
     prm = CoulombParams(Clog, angular, 0, 11, 1)
+    prm.test_fas_draw2, prm.test_fas_draw3 = float(fas_draws[0]), float(fas_draws[1])
     if large_angle is not None:
         prm.include_large_angle_scattering, prm.test_large_angle_draw = 1, float(large_angle)
     a = [c(vp1), c(vp2), c(EF_norm), c(den12), c(bmax), c(sigma_max), c(gauss), c(upol), c(uphi)]

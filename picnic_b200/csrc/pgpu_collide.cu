@@ -590,7 +590,7 @@ k_ta_inter_staged(const int *cs1, const int *cs2, int ncell, double *a0, double 
 //  * inter-species: a lane owns one particle of the shorter list and walks its partners.
 // =============================================================================================
 enum { STREAM_WEIGHT = 0x5754u, STREAM_ELA = 0x454cu };
-enum { ANG_TAKIZUKA = 0, ANG_NANBU = 1, ANG_BOBYLEV = 2, ANG_ISOTROPIC = 5 };
+enum { ANG_TAKIZUKA = 0, ANG_NANBU = 1, ANG_BOBYLEV = 2, ANG_NANBU_FAS = 3, ANG_NANBU_FAS_V2 = 4, ANG_ISOTROPIC = 5 };
 
 struct CoulParams {
   double b90_fact, bqm_fact, EF_fact, mu, f1, f2, Clog, dt_sec, cellV_SI;
@@ -602,6 +602,7 @@ struct CoulParams {
   double mass1, mass2;
   int large_angle;       // include_large_angle_scattering (Coulomb::SetPolarScattering, first half)
   double large_draw;     // its uniform RL in the explicit-draw test entry points
+  double fas_draw2, fas_draw3;   // second / third uniform of NANBU_FAS(_v2) in the explicit-draw test entry points
 };
 __device__ __forceinline__ unsigned global_cell(const CoulParams &P, int cell) {
   const int i = cell % P.nbox0 + P.box_lo0, j = cell / P.nbox0 + P.box_lo1;
@@ -629,9 +630,211 @@ __device__ __forceinline__ void nanbu_costh_sinth(double s12, double U, double &
   sinth = sqrt(1.0 - c * c);
 }
 
+// angular_scattering = NANBU_FAS / NANBU_FAS_v2 (Higginson, JCP 2017): Coulomb::setNANBUFAScosthsinth (Coulomb.H:365-428),
+// setNANBUFAS_v2_costhsinth (:430-571), setFAScoefficients (:573-618), setFAS_v2_coefficients (:620-678),
+// getTransitionX_NANBU (:680-718).  The reference draws its uniforms one after the other and only those a branch takes;
+// u[0..2] are handed out in that order.  A failed v2 solve (the reference exits) falls back to Nanbu's model.
+struct FasDraws {
+  double u[3];
+  int pos;
+  __device__ __forceinline__ double next() {
+    const double v = pos == 0 ? u[0] : (pos == 1 ? u[1] : u[2]);
+    ++pos;
+    return v;
+  }
+};
+__device__ __noinline__ double fas_transition_x(double Clog, double s12, double alpha_g, double sA) {
+  double xc = 2.0;
+  const double C0 = s12 / (8.0 * Clog * alpha_g * sA);
+  if (C0 > exp(-2.0)) return 1.0;
+  double error = 1.0;
+  int iter = 0;
+  while (error > 1.0e-4) {
+    const double xold = xc;
+    const double y0 = xc * xc * exp(-2.0 * xc) - C0;
+    const double dy0dx = 2.0 * xc * (1.0 - xc) * exp(-2.0 * xc);
+    xc = xc - y0 / dy0dx;
+    error = fabs(1.0 - xold / xc);
+    iter += 1;
+    if (iter > 20) break;
+  }
+  if (sA * xc > 1.0) xc = 1.0 / sA;
+  return xc;
+}
+__device__ __noinline__ int fas_coefficients(double &alpha_g, double &sA, double &muc, double Clog, double s12,
+                                             double mu_max) {
+  alpha_g = 1.0;
+  sA = s12 / 2.0;
+  double Xc = fas_transition_x(Clog, s12, alpha_g, sA);
+  muc = sA * Xc;
+  int iter = 0, success = 1;
+  double error = 1.0;
+  while (error > 1.0e-4) {
+    const double sAold = sA;
+    const double f1 = 1.0 - exp(-s12) + s12 / Clog * 0.5 * log(Xc * sAold / mu_max);
+    const double f2 = (1.0 - exp(-2.0 * Xc)) / (1.0 - (1.0 + Xc) * exp(-2.0 * Xc));
+    sA = (4.0 * mu_max * Clog / (4.0 * mu_max * Clog + s12)) * (s12 / (4.0 * Xc * Clog) + f1 * f2);
+    Xc = fas_transition_x(Clog, s12, alpha_g, sA);
+    muc = sA * Xc;
+    alpha_g = (1.0 - s12 / (4.0 * Clog) * (mu_max - muc) / mu_max / muc) / (1.0 - exp(-2.0 * muc / sA));
+    error = fabs(1.0 - sAold / sA);
+    iter += 1;
+    if (iter > 20) {
+      success = -1;
+      break;
+    }
+  }
+  return success;
+}
+__device__ __noinline__ int fas_v2_coefficients(double &alpha_g, double &sA, double Clog, double s12, double mu_max,
+                                                double mu_tr) {
+  const double S_L = s12 / (4.0 * Clog) * mu_max / mu_tr / (mu_max + mu_tr);
+  const double mu_L = s12 / (2.0 * Clog) * log((mu_max + mu_tr) / mu_tr);
+  const double mu_N97 = 1.0 - exp(-s12);
+  if (mu_L > mu_N97 || S_L > 1.0) {
+    alpha_g = 0.0;
+    sA = mu_tr;
+    return -1;
+  }
+  sA = s12 / 2.0;
+  alpha_g = fmax(0.0, (1.0 - S_L) / (1.0 - exp(-2.0 * mu_max / sA)));
+  int iter = 0, success = 1;
+  double error = 1.0;
+  while (error > 1.0e-4) {
+    const double sAold = sA;
+    const double f1 = mu_N97 - mu_L + alpha_g * mu_max * exp(-2.0 * mu_max / sAold);
+    const double f2 = 1.0 - S_L;
+    sA = f1 / f2;
+    alpha_g = fmax(0.0, (1.0 - S_L) / (1.0 - exp(-2.0 * mu_max / sA)));
+    error = fabs(1.0 - sAold / sA);
+    iter += 1;
+    if (iter > 20) {
+      success = -1;
+      break;
+    }
+  }
+  return success;
+}
+__device__ __noinline__ void nanbu_fas(double s12, double Clog, double b0, double bmin_qm, double sigma_eff, FasDraws D,
+                                       double &costh, double &sinth) {
+  const double PI = 3.14159265358979323846;
+  const double bperp_sq = b0 * b0 / 4.0, bmin_sq = bmin_qm * bmin_qm;
+  const double bmax_sq = exp(2.0 * Clog) * (bperp_sq + bmin_sq) - bperp_sq;
+  const double s12_min = 1.33 * 4.0 * Clog / (exp(2.0 * Clog) - 1.0);
+  costh = 1.0;
+  sinth = 0.0;
+  if (s12 < s12_min) {
+    const double N12 = s12 / sigma_eff * PI * (bmax_sq - bmin_sq);
+    const double PL = 1.0 - exp(-N12);
+    if (D.next() < PL) {
+      const double RL = D.next();
+      const double bsq = bmax_sq - RL * (bmax_sq - bmin_sq);
+      costh = (bsq - bperp_sq) / (bsq + bperp_sq);
+      sinth = sqrt(1.0 - costh * costh);
+    }
+  } else if (s12 < 0.5) {
+    double alpha_g, sA, muc;
+    const double costhmax = (bmin_sq - bperp_sq) / (bmin_sq + bperp_sq);
+    const double mu_max = (1.0 - costhmax) / 2.0;
+    const int success = fas_coefficients(alpha_g, sA, muc, Clog, s12, mu_max);
+    if (success < 0 || muc != muc) {
+      nanbu_costh_sinth(s12, D.next(), costh, sinth);
+    } else {
+      const double Uc = 1.0 - s12 / (4.0 * Clog) * (mu_max - muc) / (mu_max * muc);
+      const double R = D.next();
+      if (R < Uc) {
+        costh = 1.0 + sA * log(1.0 - R / Uc * (1.0 - exp(-2.0 * muc / sA)));
+        sinth = sqrt(1.0 - costh * costh);
+      } else {
+        const double costhc = 1.0 - 2.0 * muc;
+        const double R2 = D.next();
+        const double numer = R2 * (costhc - costhmax) - costhc * (1.0 - costhmax);
+        const double denom = R2 * (costhc - costhmax) - (1.0 - costhmax);
+        costh = numer / denom;
+        sinth = sqrt(1.0 - costh * costh);
+      }
+    }
+  } else {
+    nanbu_costh_sinth(s12, D.next(), costh, sinth);
+  }
+}
+__device__ __noinline__ void nanbu_fas_v2(double s12, double Clog, double b0, double bmin_qm, FasDraws D, double &costh,
+                                          double &sinth) {
+  const double bperp_sq = b0 * b0 / 4.0, bmin_sq = bmin_qm * bmin_qm;
+  const double bmax_sq = exp(2.0 * Clog) * (bperp_sq + bmin_sq) - bperp_sq;
+  const double costhmax = (bmin_sq - bperp_sq) / (bmin_sq + bperp_sq);
+  const double mu_max = (1.0 - costhmax) / 2.0;
+  if (s12 > 0.6) {
+    nanbu_costh_sinth(s12, D.next(), costh, sinth);
+    return;
+  }
+  double Nmax = 2.0 * Clog;
+  const double mutr_factor = Clog;
+  const double sig_ratio = bperp_sq / (bmax_sq - bmin_sq);
+  const double s12_Nmin = 4.0 * Clog * sig_ratio;
+  double s12_Nmax = Nmax * s12_Nmin;
+  const double Nmax_min = 2.0 * mutr_factor * mu_max / (exp(2.0 * Clog) - 1.0) / s12_Nmin;
+  if (Nmax < Nmax_min) {
+    Nmax = Nmax_min;
+    s12_Nmax = Nmax * s12_Nmin;
+  }
+  double alpha_g, sA, S_N97, mu_tr;
+  if (s12 < s12_Nmax) {
+    const double Ntot = s12 / s12_Nmin;
+    const double Pscatter = 1.0 - exp(-Ntot);
+    if (D.next() > Pscatter) {
+      costh = 1.0;
+      sinth = 0.0;
+      return;
+    }
+    mu_tr = s12_Nmax / mutr_factor;
+    const int success = fas_v2_coefficients(alpha_g, sA, Clog, s12_Nmax, mu_max, mu_tr);
+    if (success < 0 || sA != sA) {
+      nanbu_costh_sinth(s12, D.next(), costh, sinth);
+      return;
+    }
+    alpha_g = fmax(0.0, alpha_g * (s12 - s12_Nmin) / (s12_Nmax - s12_Nmin));
+    if (alpha_g == 0.0) sA = mu_max;
+    else sA *= s12 / s12_Nmax;
+    double mu0;
+    const double coefc = 4.0 * sig_ratio / mu_max;
+    if (coefc < 1.0e-10) mu0 = sig_ratio;
+    else mu0 = mu_max * (-1.0 + sqrt(1.0 + coefc)) / 2.0;
+    S_N97 = alpha_g * (1.0 - exp(-2.0 * mu_max / sA));
+    if (s12 <= s12_Nmin) {
+      mu_tr = mu0;
+    } else {
+      const double C0 = (1.0 - S_N97) * 4.0 * Clog / s12;
+      const double coef = 4.0 / mu_max / C0;
+      if (coef < 1.0e-10) mu_tr = 1.0 / C0;
+      else mu_tr = mu_max * (-1.0 + sqrt(1.0 + coef)) / 2.0;
+      mu_tr = fmax(mu_tr, mu0);
+    }
+  } else {
+    mu_tr = s12 / mutr_factor;
+    const int success = fas_v2_coefficients(alpha_g, sA, Clog, s12, mu_max, mu_tr);
+    if (success < 0 || sA != sA) {
+      nanbu_costh_sinth(s12, D.next(), costh, sinth);
+      return;
+    }
+    const double S_L = s12 / (4.0 * Clog) * mu_max / mu_tr / (mu_max + mu_tr);
+    S_N97 = 1.0 - S_L;
+  }
+  const double R = D.next();
+  if (R < S_N97) {
+    costh = 1.0 + sA * log(1.0 - R / S_N97 * (1.0 - exp(-2.0 * mu_max / sA)));
+  } else {
+    const double RL = D.next();
+    costh = 1.0 - 2.0 * RL * mu_tr * mu_max / (mu_max * (1.0 - RL) + mu_tr);
+  }
+  sinth = sqrt(1.0 - costh * costh);
+}
+
 // Coulomb::SetPolarScattering (:1795-1903), small-angle part, with explicit draws
 __device__ __forceinline__ void coulomb_polar(int angular, double s12, double gauss, double upol, double &costh,
-                                              double &sinth) {
+                                              double &sinth, double Clog = 0.0, double b0 = 0.0, double bmin_qm = 0.0,
+                                              double sigma_eff = 0.0, double ufas2 = 0.5, double ufas3 = 0.5,
+                                              const bool fas = true) {   // fas = false: compiled without the full-angle models
   const double PI = 3.14159265358979323846;
   costh = 1.0;
   sinth = 0.0;
@@ -652,6 +855,18 @@ __device__ __forceinline__ void coulomb_polar(int angular, double s12, double ga
     case ANG_BOBYLEV:
       costh = 1.0 - fmin(s12, 2.0);
       sinth = sin(acos(costh));
+      break;
+    case ANG_NANBU_FAS:
+      if (fas) {
+        FasDraws D = {{upol, ufas2, ufas3}, 0};
+        nanbu_fas(s12, Clog, b0, bmin_qm, sigma_eff, D, costh, sinth);
+      }
+      break;
+    case ANG_NANBU_FAS_V2:
+      if (fas) {
+        FasDraws D = {{upol, ufas2, ufas3}, 0};
+        nanbu_fas_v2(s12, Clog, b0, bmin_qm, D, costh, sinth);
+      }
       break;
     default:
       sincos(PI * upol, &sinth, &costh);
@@ -700,7 +915,8 @@ __device__ __forceinline__ bool coulomb_large_angle(double &s12, double Clog, do
 __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const double *vp1, const double *vp2,
                                                 double EF_norm, double den12, double bmax, double sigma_max,
                                                 double gauss, double upol, double uphi, double *dU, double *s12o,
-                                                double ularge = 0.5) {
+                                                double ularge = 0.5, double ufas2 = 0.5, double ufas3 = 0.5,
+                                                const bool fas = true) {
   const double PI = 3.14159265358979323846, CVAC = 2.99792458e+08;
   dU[0] = dU[1] = dU[2] = 0.0;
   const double ux = vp1[0] - vp2[0], uy = vp1[1] - vp2[1], uz = vp1[2] - vp2[2];
@@ -724,7 +940,7 @@ __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const doubl
   bool skip_small = false;
   if (P.large_angle) skip_small = coulomb_large_angle(s12, Clog, b0, bmin_qm, sigma_eff, ularge, costh, sinth);
   if (s12o) *s12o = skip_small ? -1.0 : s12;
-  if (!skip_small) coulomb_polar(P.angular, s12, gauss, upol, costh, sinth);
+  if (!skip_small) coulomb_polar(P.angular, s12, gauss, upol, costh, sinth, Clog, b0, bmin_qm, sigma_eff, ufas2, ufas3, fas);
   double sinphi, cosphi;
   sincos(2.0 * PI * uphi, &sinphi, &cosphi);
   scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
@@ -737,7 +953,8 @@ __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const doubl
 __device__ __forceinline__ bool coulomb_lorentz_scatter(const CoulParams &P, double *up1, double *up2, bool scatter2,
                                                         double m1, double m2, double EF_norm, double den12,
                                                         double bmax, double sigma_max, double gauss, double upol,
-                                                        double uphi, double *s12o, double ularge = 0.5) {
+                                                        double uphi, double *s12o, double ularge = 0.5,
+                                                        double ufas2 = 0.5, double ufas3 = 0.5, const bool fas = true) {
   const double PI = 3.14159265358979323846, CVAC = 2.99792458e+08;
   if (s12o) *s12o = 0.0;
   const double gb1sq = up1[0] * up1[0] + up1[1] * up1[1] + up1[2] * up1[2];
@@ -783,7 +1000,7 @@ __device__ __forceinline__ bool coulomb_lorentz_scatter(const CoulParams &P, dou
   bool skip_small = false;
   if (P.large_angle) skip_small = coulomb_large_angle(s12, Clog, b0, bmin_qm, sigma_eff, ularge, costh, sinth);
   if (s12o) *s12o = skip_small ? -1.0 : s12;
-  if (!skip_small) coulomb_polar(P.angular, s12, gauss, upol, costh, sinth);
+  if (!skip_small) coulomb_polar(P.angular, s12, gauss, upol, costh, sinth, Clog, b0, bmin_qm, sigma_eff, ufas2, ufas3, fas);
   sincos(2.0 * PI * uphi, &sinphi, &cosphi);
   rotate_velocity(upst, costh, sinth, cosphi, sinphi);
   ucmdotup = gcm * (vcm[0] * upst[0] + vcm[1] * upst[1] + vcm[2] * upst[2]);
@@ -806,7 +1023,7 @@ __global__ void k_coulomb_lorentz(long n, CoulParams P, const double *vp1, const
   double a[3] = {vp1[i], vp1[n + i], vp1[2 * n + i]}, b[3] = {vp2[i], vp2[n + i], vp2[2 * n + i]};
   double s = 0.0;
   coulomb_lorentz_scatter(P, a, b, scatter2[i] != 0, P.mass1, P.mass2, EF[i], den12[i], bmax[i], smax[i], gauss[i],
-                          upol[i], uphi[i], &s, P.large_draw);
+                          upol[i], uphi[i], &s, P.large_draw, P.fas_draw2, P.fas_draw3);
   for (int c = 0; c < 3; ++c) {
     o1[c * n + i] = a[c];
     o2[c * n + i] = b[c];
@@ -821,7 +1038,8 @@ __global__ void k_coulomb_delta_u(long n, CoulParams P, const double *vp1, const
   if (i >= n) return;
   const double a[3] = {vp1[i], vp1[n + i], vp1[2 * n + i]}, b[3] = {vp2[i], vp2[n + i], vp2[2 * n + i]};
   double d[3], s = 0.0;
-  coulomb_delta_u(P, a, b, EF[i], den12[i], bmax[i], smax[i], gauss[i], upol[i], uphi[i], d, &s, P.large_draw);
+  coulomb_delta_u(P, a, b, EF[i], den12[i], bmax[i], smax[i], gauss[i], upol[i], uphi[i], d, &s, P.large_draw, P.fas_draw2,
+                  P.fas_draw3);
   dU[i] = d[0];
   dU[n + i] = d[1];
   dU[2 * n + i] = d[2];
@@ -834,6 +1052,7 @@ struct CellCtx {
 };
 
 // one pair: draws from Philox(cell, pair), weight rejection as Coulomb.cpp:561-584 / 1149-1172
+template <bool FAS>
 __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx &C, double *a0, double *a1, double *a2,
                                              const double *wa, int pa, double *b0, double *b1, double *b2,
                                              const double *wb, int pb, double den_fact, unsigned pair_id,
@@ -849,10 +1068,15 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
   const double w1 = wa[pa], w2 = wb[pb];
   const double den12 = fmax(w1, w2) * den_fact;
   double va[3] = {a0[pa], a1[pa], a2[pa]}, vb[3] = {b0[pb], b1[pb], b2[pb]}, dU[3];
-  double ularge = 0.5;
-  if (P.large_angle) {   // the one extra uniform of SetPolarScattering: second word of the pair's weight stream
+  double ularge = 0.5, ufas2 = 0.5, ufas3 = 0.5;
+  if (P.large_angle || (FAS && (P.angular == ANG_NANBU_FAS || P.angular == ANG_NANBU_FAS_V2))) {
+    // the extra uniforms of SetPolarScattering come from the pair's weight stream: word 1 the large-angle event, words 2
+    // and 3 the second and third draw of the full-angle models
     c.w = P.step_hi ^ (STREAM_WEIGHT << 16) ^ salt;
-    ularge = u01(philox4x32_10(c, P.seed_lo, P.seed_hi).y);
+    const u4 wr = philox4x32_10(c, P.seed_lo, P.seed_hi);
+    ularge = u01(wr.y);
+    ufas2 = u01(wr.z);
+    ufas3 = u01(wr.w);
   }
   if (P.rel) {
     // Coulomb.cpp:548-559 / 1139-1150: the lighter-weight particle goes first and always scatters, the other one
@@ -865,10 +1089,10 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
     }
     if ((float)w2 < (float)w1)
       coulomb_lorentz_scatter(P, vb, va, other, P.mass2, P.mass1, C.EF_norm, den12, C.bmax, C.sigma_max, gauss,
-                              u01(r.z), u01(r.w), nullptr, ularge);
+                              u01(r.z), u01(r.w), nullptr, ularge, ufas2, ufas3, FAS);
     else
       coulomb_lorentz_scatter(P, va, vb, other, P.mass1, P.mass2, C.EF_norm, den12, C.bmax, C.sigma_max, gauss,
-                              u01(r.z), u01(r.w), nullptr, ularge);
+                              u01(r.z), u01(r.w), nullptr, ularge, ufas2, ufas3, FAS);
     a0[pa] = va[0];
     a1[pa] = va[1];
     a2[pa] = va[2];
@@ -877,7 +1101,8 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
     b2[pb] = vb[2];
     return;
   }
-  coulomb_delta_u(P, va, vb, C.EF_norm, den12, C.bmax, C.sigma_max, gauss, u01(r.z), u01(r.w), dU, nullptr, ularge);
+  coulomb_delta_u(P, va, vb, C.EF_norm, den12, C.bmax, C.sigma_max, gauss, u01(r.z), u01(r.w), dU, nullptr, ularge, ufas2,
+                  ufas3, FAS);
   if (P.sk08 && (float)w1 != (float)w2) {
     // weight_method = CONSERVATIVE: Sentoku & Kemp, JCP 227 (2008) (Coulomb.cpp:849-897 / 1575-1621).  The lighter
     // particle scatters; the heavier one moves by the fraction w_min / w_max of its scattered change, and a kick normal to
@@ -946,6 +1171,7 @@ __device__ __forceinline__ void ta_from_coul(const CoulParams &P, TAParams &T) {
 }
 
 // Coulomb::applyIntraScattering_PROB (:400-592)
+template <bool FAS>
 __global__ void __launch_bounds__(256)
 k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double *v2, const double *w,
                 const uint64_t *id, const double *dens, const double *LDe, CoulParams P, unsigned *key, int *order,
@@ -982,7 +1208,7 @@ k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double
             pa = pb;
             pb = t;
           }
-          coulomb_pair(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], den_fact,
+          coulomb_pair<FAS>(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], den_fact,
                        (unsigned)(pa * 65536 + pb), 0u);
           ++mine;
         }
@@ -995,7 +1221,7 @@ k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double
       // odd cell: (0,1), (0,2), (1,2) with half the density (:468-470, 536-538)
       const int p1[3] = {0, 0, 1}, p2[3] = {1, 2, 2};
       for (int q = 0; q < 3; ++q) {
-        coulomb_pair(P, C, v0, v1, v2, w, s + order[s + p1[q]], v0, v1, v2, w, s + order[s + p2[q]],
+        coulomb_pair<FAS>(P, C, v0, v1, v2, w, s + order[s + p1[q]], v0, v1, v2, w, s + order[s + p2[q]],
                      Naa / P.cellV_SI / 2.0, (unsigned)(p1[q] * 65536 + p2[q]), 1u);
         ++mine;
       }
@@ -1003,7 +1229,7 @@ k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double
     const int nmain = (n - pstart) / 2;
     for (int q = lane; q < nmain; q += 32) {
       const int pa = pstart + 2 * q, pb = pa + 1;
-      coulomb_pair(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], Naa / P.cellV_SI,
+      coulomb_pair<FAS>(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], Naa / P.cellV_SI,
                    (unsigned)(pa * 65536 + pb), 0u);
       ++mine;
     }
@@ -1013,6 +1239,7 @@ k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double
 }
 
 // Coulomb::applyInterScattering_PROB (:919-1180)
+template <bool FAS>
 __global__ void __launch_bounds__(256)
 k_coulomb_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, double *a2, const double *wa,
                 const uint64_t *id1, const double *dens1, double *b0, double *b1, double *b2, const double *wb,
@@ -1051,7 +1278,7 @@ k_coulomb_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a
           const int pl = cb + t, ps = (t + rr) % Nmin;
           const int i1 = s1 + order1[s1 + (first_short ? ps : pl)];
           const int i2 = s2 + order2[s2 + (first_short ? pl : ps)];
-          coulomb_pair(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)(pl * 65536 + ps), 2u);
+          coulomb_pair<FAS>(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)(pl * 65536 + ps), 2u);
           ++mine;
         }
         __syncwarp();
@@ -1063,7 +1290,7 @@ k_coulomb_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a
       for (int p = r; p < Nmax; p += Nmin) {
         const int i1 = s1 + order1[s1 + (first_short ? r : p)];
         const int i2 = s2 + order2[s2 + (first_short ? p : r)];
-        coulomb_pair(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)p, 2u);
+        coulomb_pair<FAS>(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)p, 2u);
         ++mine;
       }
     }
@@ -1705,8 +1932,8 @@ static int coulomb_consts(double charge1, double charge2, double mass1, double m
                           double dt_sec, CoulParams *P) {
   if (!prm) return PGPU_ERR_ARG;
   const int a = prm->angular_scattering;
-  if (a != PGPU_ANG_TAKIZUKA && a != PGPU_ANG_NANBU && a != PGPU_ANG_BOBYLEV && a != PGPU_ANG_ISOTROPIC) {
-    set_error("Coulomb: angular_scattering %d is not implemented (TAKIZUKA, NANBU, BOBYLEV, ISOTROPIC are)", a);
+  if (a < PGPU_ANG_TAKIZUKA || a > PGPU_ANG_ISOTROPIC) {
+    set_error("Coulomb: angular_scattering %d is not one of TAKIZUKA, NANBU, BOBYLEV, NANBU_FAS, NANBU_FAS_v2, ISOTROPIC", a);
     return PGPU_ERR_ARG;
   }
   if (charge1 == 0.0 || charge2 == 0.0) {
@@ -1734,6 +1961,8 @@ static int coulomb_consts(double charge1, double charge2, double mass1, double m
   P->sk08 = prm->weight_method;
   P->large_angle = prm->include_large_angle_scattering ? 1 : 0;
   P->large_draw = prm->test_large_angle_draw;
+  P->fas_draw2 = prm->test_fas_draw2;
+  P->fas_draw3 = prm->test_fas_draw3;
   P->Clog = prm->Clog;
   P->dt_sec = dt_sec;
   P->angular = a;
@@ -2170,6 +2399,8 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
     };
     if (mk(sA, L1) || mk(sB, L2)) return PGPU_ERR_CUDA;
   }
+  // the full-angle models live in their own instantiation: their solver calls cost the others registers
+  const bool fas = P.angular == ANG_NANBU_FAS || P.angular == ANG_NANBU_FAS_V2;
   for (int sub = 0; sub < nsub; ++sub) {
     P.step_hi = ((unsigned)(step >> 32) & 0xffu) | ((unsigned)sub << 8);
     if (enforce) {
@@ -2179,12 +2410,13 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
     }
     if (sA == sB) {
       KTimer t("collide_coulomb_intra");
-      k_coulomb_intra<<<nb((long)ncell * 32), 256, 0, c.stream>>>(sA->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2],
-                                                                  sA->w, sA->id, sA->dens, g->debye, P,
-                                                                  (unsigned *)sA->cell_key, sA->perm, d_np);
+      auto k = fas ? k_coulomb_intra<true> : k_coulomb_intra<false>;
+      k<<<nb((long)ncell * 32), 256, 0, c.stream>>>(sA->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->w, sA->id,
+                                                    sA->dens, g->debye, P, (unsigned *)sA->cell_key, sA->perm, d_np);
     } else {
       KTimer t("collide_coulomb_inter");
-      k_coulomb_inter<<<nb((long)ncell * 32), 256, 0, c.stream>>>(
+      auto k = fas ? k_coulomb_inter<true> : k_coulomb_inter<false>;
+      k<<<nb((long)ncell * 32), 256, 0, c.stream>>>(
           sA->cell_start, sB->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->w, sA->id, sA->dens, sB->v[0],
           sB->v[1], sB->v[2], sB->w, sB->id, sB->dens, g->debye, P, (unsigned *)sA->cell_key, sA->perm,
           (unsigned *)sB->cell_key, sB->perm, d_np);

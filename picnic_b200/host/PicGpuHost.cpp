@@ -540,6 +540,7 @@ Coulomb::Coulomb(int a_sp1, int a_sp2, Real a_Clog, AngularScattering a_angular,
   m_prm.weight_method = 0;
   m_prm.include_large_angle_scattering = 0;   // Coulomb.H:329; setLargeAngleScattering switches it on
   m_prm.test_large_angle_draw = 0.5;
+  m_prm.test_fas_draw2 = m_prm.test_fas_draw3 = 0.5;
   if (a_Clog != 0.0 && a_Clog < 2.0) fatal("Coulomb: coulomb_logarithm must be 0 (computed) or >= 2");   // Coulomb.H:224
 }
 void Coulomb::setMeanFreeTime(const std::vector<PicChargedSpecies *> &a_species) const {

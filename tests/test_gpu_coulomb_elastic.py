@@ -57,7 +57,41 @@ def test_coulomb_delta_u_matches_oracle(pgpu, angular, Clog):
     assert np.max(np.abs(np.linalg.norm(v1 - v2 + got, axis=0) - u)[live] / u[live]) < 1e-10
 
 
-@pytest.mark.parametrize("angular", [0, 1])
+@pytest.mark.parametrize("angular", [3, 4])
+@pytest.mark.parametrize("draws", [(0.3, 0.7), (0.97, 0.02)])
+def test_coulomb_full_angle_scattering_matches_oracle(pgpu, angular, draws):
+    """NANBU_FAS / NANBU_FAS_v2 (Coulomb.H:365-718) pair by pair on explicit draws: the device's fixed-point solves
+    against the oracle's, over pairs on both sides of every switch-over of the two models."""
+    rng = np.random.default_rng(70 + angular)
+    n = 4000
+    v1 = rng.standard_normal((3, n)) * 0.02
+    v2 = rng.standard_normal((3, n)) * 0.02
+    v1[:, :400] *= 1e-2; v2[:, :400] *= 1e-2          # slow pairs: s12 above the switch-over (plain Nanbu)
+    EF = 10.0 ** rng.uniform(-8, -5, n)
+    den12 = 10.0 ** rng.uniform(30, 39, n)            # s12 from far below the switch-overs to beyond 1
+    bmax = 10.0 ** rng.uniform(-10, -8, n)
+    smax = 10.0 ** rng.uniform(-20, -17, n)
+    g, up, uph = rng.standard_normal(n), rng.random(n), rng.random(n)
+    m1, m2 = 1836.15, 3672.3                          # ions: the reference keeps the electrons out of FAS by default
+    Clog = 5.0
+    got, s12 = pgpu.coulomb_delta_u(v1, v2, 1.0, 1.0, m1, m2, Clog, angular, DT_SEC, EF, den12, bmax, smax, g, up, uph,
+                                    fas_draws=draws)
+    orc.coulomb_set_fas_draws(*draws)
+    want = np.zeros((3, n)); ws = np.zeros(n)
+    for i in range(n):
+        want[:, i], ws[i] = orc.coulomb_delta_u(v1[:, i], v2[:, i], 1.0, 1.0, m1, m2, EF[i], Clog, angular, den12[i],
+                                                bmax[i], smax[i], DT_SEC, g[i], up[i], uph[i])
+    orc.coulomb_set_fas_draws()
+    u = np.linalg.norm(v1 - v2, axis=0)
+    assert np.max(np.abs(s12 - ws) / ws) < 1e-12
+    # the regimes are all there
+    assert (ws < 1e-4).sum() > 100 and ((ws > 1e-3) & (ws < 0.5)).sum() > 100 and (ws > 0.6).sum() > 100
+    assert np.max(np.abs(got - want) / u) < 1e-10
+    assert np.max(np.abs(np.linalg.norm(v1 - v2 + got, axis=0) - u) / u) < 1e-10
+    assert np.any(np.all(got == 0.0, axis=0))         # pairs without an event keep their velocities
+
+
+@pytest.mark.parametrize("angular", [0, 1, 3, 4])
 def test_coulomb_intra_counts_and_conservation(pgpu, angular):
     rng = np.random.default_rng(52)
     ncell = 96
@@ -90,7 +124,8 @@ def test_coulomb_intra_counts_and_conservation(pgpu, angular):
             continue
         assert np.max(np.abs(v1.sum(axis=1) - v0.sum(axis=1))) < 2e-15 * (b - a)
         assert abs((v1 ** 2).sum() - (v0 ** 2).sum()) / (v0 ** 2).sum() < 1e-12
-        assert np.all(np.any(v1 != v0, axis=0))
+        if angular < 3:                               # the full-angle models leave pairs without an event alone
+            assert np.all(np.any(v1 != v0, axis=0))
     # NxN = true: every pair of every cell
     sp.upload(before["x"], before["v"], before["w"], ids=before["id"]); sp.bin_particles(); sp.set_moments()
     npairs = pgpu.collide_coulomb(sp, sp, 0.0, DT_SEC, 1983, 7, angular=angular, NxN=True)

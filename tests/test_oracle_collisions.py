@@ -26,7 +26,45 @@ def _cells(rng, counts):
     return cs, v
 
 
-@pytest.mark.parametrize("angular", [0, 1, 2, 5])
+@pytest.mark.parametrize("variant", [3, 4])
+def test_nanbu_full_angle_scattering_restatement(variant):
+    """NANBU_FAS / NANBU_FAS_v2 (Coulomb.H:365-718): the cumulative branch above the switch-over is Nanbu's model with the
+    same draw; the mean of 1 - cos(theta) follows what the model is built for -- Nanbu's 1 - exp(-s12) for FAS; for v2
+    the same minus the part of the Rutherford tail its sampling formula leaves out,
+    s12/(2 Clog) mu_max/(mu_max + mu_tr) with mu_tr = s12/Clog; draws are consumed in order and only when needed."""
+    rng = np.random.default_rng(17 + variant)
+    Clog, b0 = 5.0, 1.0e-9
+    bmin = 0.15 * b0
+    sigma_eff = np.pi * b0 * b0 * Clog
+    above = 0.5 if variant == 3 else 0.6000001
+    for s12 in (above, 1.0, 4.0, 7.0):
+        for u in rng.random(20):
+            c, sn = orc.nanbu_fas_costh_sinth(variant, s12, Clog, b0, bmin, sigma_eff, u, 0.123, 0.987)
+            assert (c, sn) == orc.nanbu_costh_sinth(s12, u)
+    bperp_sq, bmin_sq = b0 * b0 / 4.0, bmin * bmin
+    mu_max = bperp_sq / (bmin_sq + bperp_sq)
+    for s12 in (0.05, 0.2, 0.45):
+        U = rng.random((40000, 3))
+        c = np.array([orc.nanbu_fas_costh_sinth(variant, s12, Clog, b0, bmin, sigma_eff, *u)[0] for u in U])
+        assert np.all(np.abs(c) <= 1.0)
+        want = 1.0 - np.exp(-s12)
+        if variant == 4:
+            mu_tr = s12 / Clog
+            want -= s12 / (2.0 * Clog) * mu_max / (mu_max + mu_tr)
+        assert abs(np.mean(1.0 - c) - want) / want < 0.03, (s12, np.mean(1.0 - c), want)
+    # far below the switch-over: at most one Rutherford event, probability ~ N12, else no deflection
+    s12 = 1.0e-6
+    U = rng.random((20000, 3))
+    c = np.array([orc.nanbu_fas_costh_sinth(variant, s12, Clog, b0, bmin, sigma_eff, *u)[0] for u in U])
+    assert 0.0 < np.mean(c != 1.0) < 0.05
+    # the second draw is only looked at when the first one asks for it
+    c1 = orc.nanbu_fas_costh_sinth(variant, s12, Clog, b0, bmin, sigma_eff, 0.999999, 0.1, 0.2)
+    c2 = orc.nanbu_fas_costh_sinth(variant, s12, Clog, b0, bmin, sigma_eff, 0.999999, 0.9, 0.8)
+    if variant == 3:
+        assert c1 == c2 == (1.0, 0.0)          # rand() < PL fails: no event, RL never drawn
+
+
+@pytest.mark.parametrize("angular", [0, 1, 2, 3, 4, 5])
 def test_coulomb_intra_equal_weights_conserve_and_count(angular):
     rng = np.random.default_rng(3)
     counts = np.array([0, 1, 2, 3, 5, 10, 11, 12, 13, 40, 41])
