@@ -846,7 +846,7 @@ __device__ __forceinline__ void coulomb_polar(int angular, double s12, double ga
         sinth = 2.0 * delta / (1.0 + deltasq);
         costh = 1.0 - 2.0 * deltasq / (1.0 + deltasq);
       } else {
-        sincos(PI * upol, &sinth, &costh);
+        sincospi(upol, &sinth, &costh);        // theta = pi upol
       }
       break;
     case ANG_NANBU:
@@ -869,7 +869,7 @@ __device__ __forceinline__ void coulomb_polar(int angular, double s12, double ga
       }
       break;
     default:
-      sincos(PI * upol, &sinth, &costh);
+      sincospi(upol, &sinth, &costh);        // theta = pi upol
   }
 }
 
@@ -916,7 +916,7 @@ __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const doubl
                                                 double EF_norm, double den12, double bmax, double sigma_max,
                                                 double gauss, double upol, double uphi, double *dU, double *s12o,
                                                 double ularge = 0.5, double ufas2 = 0.5, double ufas3 = 0.5,
-                                                const bool fas = true) {
+                                                const bool fas = true, const bool lean = false) {
   const double PI = 3.14159265358979323846, CVAC = 2.99792458e+08;
   dU[0] = dU[1] = dU[2] = 0.0;
   const double ux = vp1[0] - vp2[0], uy = vp1[1] - vp2[1], uz = vp1[2] - vp2[2];
@@ -938,11 +938,11 @@ __device__ __forceinline__ bool coulomb_delta_u(const CoulParams &P, const doubl
   double s12 = sigma_eff * den12 * u * CVAC * P.dt_sec;
   double costh, sinth;
   bool skip_small = false;
-  if (P.large_angle) skip_small = coulomb_large_angle(s12, Clog, b0, bmin_qm, sigma_eff, ularge, costh, sinth);
+  if (!lean && P.large_angle) skip_small = coulomb_large_angle(s12, Clog, b0, bmin_qm, sigma_eff, ularge, costh, sinth);
   if (s12o) *s12o = skip_small ? -1.0 : s12;
   if (!skip_small) coulomb_polar(P.angular, s12, gauss, upol, costh, sinth, Clog, b0, bmin_qm, sigma_eff, ufas2, ufas3, fas);
   double sinphi, cosphi;
-  sincos(2.0 * PI * uphi, &sinphi, &cosphi);
+  sincospi(2.0 * uphi, &sinphi, &cosphi);       // phi = 2 pi uphi
   scatter_delta_u(ux, uy, uz, costh, sinth, cosphi, sinphi, dU);
   return true;
 }
@@ -1052,7 +1052,8 @@ struct CellCtx {
 };
 
 // one pair: draws from Philox(cell, pair), weight rejection as Coulomb.cpp:561-584 / 1149-1172
-template <bool FAS>
+// LEAN: compiled for the plain case (Galilean build, PROBABILISTIC weights, no large-angle events): fewer registers
+template <bool FAS, bool LEAN = false>
 __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx &C, double *a0, double *a1, double *a2,
                                              const double *wa, int pa, double *b0, double *b1, double *b2,
                                              const double *wb, int pb, double den_fact, unsigned pair_id,
@@ -1064,12 +1065,13 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
   c.w = P.step_hi ^ (STREAM_PAIR << 16) ^ salt;
   const u4 r = philox4x32_10(c, P.seed_lo, P.seed_hi);
   const double TWOPI = 6.28318530717958647692;
-  const double gauss = sqrt(-2.0 * log(u01(r.x))) * cos(TWOPI * u01(r.y));
+  // the N(0,1) draw only enters TAKIZUKA's small-angle branch (SetPolarScattering :1868-1874)
+  const double gauss = (P.angular == ANG_TAKIZUKA) ? sqrt(-2.0 * log(u01(r.x))) * cos(TWOPI * u01(r.y)) : 0.0;
   const double w1 = wa[pa], w2 = wb[pb];
   const double den12 = fmax(w1, w2) * den_fact;
   double va[3] = {a0[pa], a1[pa], a2[pa]}, vb[3] = {b0[pb], b1[pb], b2[pb]}, dU[3];
   double ularge = 0.5, ufas2 = 0.5, ufas3 = 0.5;
-  if (P.large_angle || (FAS && (P.angular == ANG_NANBU_FAS || P.angular == ANG_NANBU_FAS_V2))) {
+  if ((!LEAN && P.large_angle) || (FAS && (P.angular == ANG_NANBU_FAS || P.angular == ANG_NANBU_FAS_V2))) {
     // the extra uniforms of SetPolarScattering come from the pair's weight stream: word 1 the large-angle event, words 2
     // and 3 the second and third draw of the full-angle models
     c.w = P.step_hi ^ (STREAM_WEIGHT << 16) ^ salt;
@@ -1078,7 +1080,7 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
     ufas2 = u01(wr.z);
     ufas3 = u01(wr.w);
   }
-  if (P.rel) {
+  if (!LEAN && P.rel) {
     // Coulomb.cpp:548-559 / 1139-1150: the lighter-weight particle goes first and always scatters, the other one
     // with probability w_min / w_max
     bool other = true;
@@ -1102,14 +1104,14 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
     return;
   }
   coulomb_delta_u(P, va, vb, C.EF_norm, den12, C.bmax, C.sigma_max, gauss, u01(r.z), u01(r.w), dU, nullptr, ularge, ufas2,
-                  ufas3, FAS);
-  if (P.sk08 && (float)w1 != (float)w2) {
+                  ufas3, FAS, LEAN);
+  if (!LEAN && P.sk08 && (float)w1 != (float)w2) {
     // weight_method = CONSERVATIVE: Sentoku & Kemp, JCP 227 (2008) (Coulomb.cpp:849-897 / 1575-1621).  The lighter
     // particle scatters; the heavier one moves by the fraction w_min / w_max of its scattered change, and a kick normal to
     // its velocity (random azimuth) makes up the energy E_before + ratio (E_scattered - E_before) exactly
     // (Coulomb::enforceEnergyConservation, Coulomb.H:796-823)
     c.w = P.step_hi ^ (STREAM_WEIGHT << 16) ^ salt;
-    const double phi = TWOPI * u01(philox4x32_10(c, P.seed_lo, P.seed_hi).x);
+    const double phi2 = 2.0 * u01(philox4x32_10(c, P.seed_lo, P.seed_hi).x);   // phi / pi
     const bool first_light = (float)w1 < (float)w2;
     double *vl = first_light ? va : vb, *vh = first_light ? vb : va;
     const double fl = first_light ? P.f1 : -P.f2, fh = first_light ? -P.f2 : P.f1;
@@ -1133,7 +1135,7 @@ __device__ __forceinline__ void coulomb_pair(const CoulParams &P, const CellCtx 
     if (!(Eafter < Eafter2)) {
       const double dmag = sqrt(2.0 / mh * (Eafter - Eafter2));
       double sphi, cphi;
-      sincos(phi, &sphi, &cphi);
+      sincospi(phi2, &sphi, &cphi);
       const double d0 = (nb[2] * nb[0] * cphi - bm * nb[1] * sphi) / br * dmag / bm;
       const double d1 = (nb[2] * nb[1] * cphi + bm * nb[0] * sphi) / br * dmag / bm;
       const double d2 = -br * cphi * dmag / bm;
@@ -1170,9 +1172,12 @@ __device__ __forceinline__ void ta_from_coul(const CoulParams &P, TAParams &T) {
   T.step_hi = P.step_hi;
 }
 
+#ifndef PGPU_COUL_LEAN_MINB
+#define PGPU_COUL_LEAN_MINB 5
+#endif
 // Coulomb::applyIntraScattering_PROB (:400-592)
-template <bool FAS>
-__global__ void __launch_bounds__(256)
+template <bool FAS, bool LEAN>
+__global__ void __launch_bounds__(LEAN ? 128 : 256, LEAN ? PGPU_COUL_LEAN_MINB : 1)
 k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double *v2, const double *w,
                 const uint64_t *id, const double *dens, const double *LDe, CoulParams P, unsigned *key, int *order,
                 unsigned long long *npairs) {
@@ -1208,7 +1213,7 @@ k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double
             pa = pb;
             pb = t;
           }
-          coulomb_pair<FAS>(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], den_fact,
+          coulomb_pair<FAS, LEAN>(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], den_fact,
                        (unsigned)(pa * 65536 + pb), 0u);
           ++mine;
         }
@@ -1221,7 +1226,7 @@ k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double
       // odd cell: (0,1), (0,2), (1,2) with half the density (:468-470, 536-538)
       const int p1[3] = {0, 0, 1}, p2[3] = {1, 2, 2};
       for (int q = 0; q < 3; ++q) {
-        coulomb_pair<FAS>(P, C, v0, v1, v2, w, s + order[s + p1[q]], v0, v1, v2, w, s + order[s + p2[q]],
+        coulomb_pair<FAS, LEAN>(P, C, v0, v1, v2, w, s + order[s + p1[q]], v0, v1, v2, w, s + order[s + p2[q]],
                      Naa / P.cellV_SI / 2.0, (unsigned)(p1[q] * 65536 + p2[q]), 1u);
         ++mine;
       }
@@ -1229,7 +1234,7 @@ k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double
     const int nmain = (n - pstart) / 2;
     for (int q = lane; q < nmain; q += 32) {
       const int pa = pstart + 2 * q, pb = pa + 1;
-      coulomb_pair<FAS>(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], Naa / P.cellV_SI,
+      coulomb_pair<FAS, LEAN>(P, C, v0, v1, v2, w, s + order[s + pa], v0, v1, v2, w, s + order[s + pb], Naa / P.cellV_SI,
                    (unsigned)(pa * 65536 + pb), 0u);
       ++mine;
     }
@@ -1239,8 +1244,8 @@ k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double
 }
 
 // Coulomb::applyInterScattering_PROB (:919-1180)
-template <bool FAS>
-__global__ void __launch_bounds__(256)
+template <bool FAS, bool LEAN>
+__global__ void __launch_bounds__(LEAN ? 128 : 256, LEAN ? PGPU_COUL_LEAN_MINB : 1)
 k_coulomb_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, double *a2, const double *wa,
                 const uint64_t *id1, const double *dens1, double *b0, double *b1, double *b2, const double *wb,
                 const uint64_t *id2, const double *dens2, const double *LDe, CoulParams P, unsigned *key1, int *order1,
@@ -1278,7 +1283,7 @@ k_coulomb_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a
           const int pl = cb + t, ps = (t + rr) % Nmin;
           const int i1 = s1 + order1[s1 + (first_short ? ps : pl)];
           const int i2 = s2 + order2[s2 + (first_short ? pl : ps)];
-          coulomb_pair<FAS>(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)(pl * 65536 + ps), 2u);
+          coulomb_pair<FAS, LEAN>(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)(pl * 65536 + ps), 2u);
           ++mine;
         }
         __syncwarp();
@@ -1290,7 +1295,7 @@ k_coulomb_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a
       for (int p = r; p < Nmax; p += Nmin) {
         const int i1 = s1 + order1[s1 + (first_short ? r : p)];
         const int i2 = s2 + order2[s2 + (first_short ? p : r)];
-        coulomb_pair<FAS>(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)p, 2u);
+        coulomb_pair<FAS, LEAN>(P, C, a0, a1, a2, wa, i1, b0, b1, b2, wb, i2, den_fact, (unsigned)p, 2u);
         ++mine;
       }
     }
@@ -2401,6 +2406,9 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
   }
   // the full-angle models live in their own instantiation: their solver calls cost the others registers
   const bool fas = P.angular == ANG_NANBU_FAS || P.angular == ANG_NANBU_FAS_V2;
+  // the plain case (Galilean, PROBABILISTIC weights, no large-angle events) has a leaner instantiation in smaller blocks
+  const bool lean = !fas && !P.rel && !P.sk08 && !P.large_angle;
+  const int tpb = lean ? 128 : 256;
   for (int sub = 0; sub < nsub; ++sub) {
     P.step_hi = ((unsigned)(step >> 32) & 0xffu) | ((unsigned)sub << 8);
     if (enforce) {
@@ -2410,13 +2418,13 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
     }
     if (sA == sB) {
       KTimer t("collide_coulomb_intra");
-      auto k = fas ? k_coulomb_intra<true> : k_coulomb_intra<false>;
-      k<<<nb((long)ncell * 32), 256, 0, c.stream>>>(sA->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->w, sA->id,
+      auto k = fas ? k_coulomb_intra<true, false> : (lean ? k_coulomb_intra<false, true> : k_coulomb_intra<false, false>);
+      k<<<nb((long)ncell * 32, tpb), tpb, 0, c.stream>>>(sA->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->w, sA->id,
                                                     sA->dens, g->debye, P, (unsigned *)sA->cell_key, sA->perm, d_np);
     } else {
       KTimer t("collide_coulomb_inter");
-      auto k = fas ? k_coulomb_inter<true> : k_coulomb_inter<false>;
-      k<<<nb((long)ncell * 32), 256, 0, c.stream>>>(
+      auto k = fas ? k_coulomb_inter<true, false> : (lean ? k_coulomb_inter<false, true> : k_coulomb_inter<false, false>);
+      k<<<nb((long)ncell * 32, tpb), tpb, 0, c.stream>>>(
           sA->cell_start, sB->cell_start, ncell, sA->v[0], sA->v[1], sA->v[2], sA->w, sA->id, sA->dens, sB->v[0],
           sB->v[1], sB->v[2], sB->w, sB->id, sB->dens, g->debye, P, (unsigned *)sA->cell_key, sA->perm,
           (unsigned *)sB->cell_key, sB->perm, d_np);
