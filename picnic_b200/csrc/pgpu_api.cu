@@ -1218,6 +1218,7 @@ static int stream_pass(const char *name, double *out, const double *a, const dou
 
 int pgpu_advance_positions_explicit(pgpu_species_t s, double full_dt, int half_step) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.motion) return 0;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   const double cnormDt = s->desc.cvac_norm * full_dt;
@@ -1237,6 +1238,7 @@ int pgpu_advance_positions_explicit(pgpu_species_t s, double full_dt, int half_s
 
 int pgpu_advance_positions_implicit(pgpu_species_t s, double full_dt) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.motion) return 0;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   const double cnormDt = s->desc.cvac_norm * full_dt;
@@ -1256,6 +1258,7 @@ int pgpu_advance_positions_implicit(pgpu_species_t s, double full_dt) {
 
 int pgpu_advance_positions_2nd_half(pgpu_species_t s) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.motion) return 0;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   for (int d = 0; d < s->grid->desc.D; ++d)
@@ -1266,6 +1269,7 @@ int pgpu_advance_positions_2nd_half(pgpu_species_t s) {
 
 int pgpu_advance_velocities_2nd_half(pgpu_species_t s) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.forces) return 0;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   for (int c = 0; c < 3; ++c) stream_pass("second_half", s->v[c], s->v[c], s->vold[c], s->n, 0.0, 1);
@@ -1274,6 +1278,7 @@ int pgpu_advance_velocities_2nd_half(pgpu_species_t s) {
 
 int pgpu_average_velocities(pgpu_species_t s) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.forces) return 0;
   if (materialize_old(s)) return PGPU_ERR_CUDA;
   for (int c = 0; c < 3; ++c) stream_pass("average_velocities", s->v[c], s->v[c], s->vold[c], s->n, 0.0, 2);
@@ -1282,6 +1287,7 @@ int pgpu_average_velocities(pgpu_species_t s) {
 
 int pgpu_update_old_particle_positions(pgpu_species_t s) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.motion) return 0;
   s->pos_old_pending = false;   // every xold entry is overwritten: a pending gather is moot
   s->xold_alias = true;         // the copy itself is deferred (materialize_old) or never happens (CC1 tile kernel)
@@ -1290,6 +1296,7 @@ int pgpu_update_old_particle_positions(pgpu_species_t s) {
 
 int pgpu_update_old_particle_velocities(pgpu_species_t s) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.forces) return 0;
   s->vel_old_pending = false;
   s->vold_alias = true;
@@ -1351,6 +1358,7 @@ int pgpu_add_external_fields_to_particles(pgpu_species_t s) {
 
 int pgpu_interpolate_fields_to_particles(pgpu_species_t s) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.forces || s->desc.charge == 0.0) return 0;
   if (ensure_epbp(s)) return PGPU_ERR_CUDA;
   int rc = launch_gather(s);
@@ -1360,6 +1368,7 @@ int pgpu_interpolate_fields_to_particles(pgpu_species_t s) {
 
 int pgpu_advance_velocities(pgpu_species_t s, double full_dt, int half_step) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.forces) return 0;
   if (!s->Ep[0]) {
     set_error("advanceVelocities needs particle fields: call pgpu_interpolate_fields_to_particles first");
@@ -1459,6 +1468,7 @@ static AdvanceParams make_params(pgpu_species_t s, double dt, bool iterative) {
 
 int pgpu_advance_particles(pgpu_species_t s, double dt) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.motion || !s->desc.forces || s->desc.charge == 0.0) {
     // degenerate switches: compose the reference sequence from the separate passes
     if (s->desc.order_swap) pgpu_advance_positions_implicit(s, dt);
@@ -1491,6 +1501,7 @@ static int scale_species_current(pgpu_species_t s) {
 
 int pgpu_advance_particles_iteratively(pgpu_species_t s, double dt, int deposit_J, pgpu_picard_stats *stats) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   const bool iterative = !(s->desc.iter_max == 0 || !s->desc.motion || !s->desc.forces || s->desc.charge == 0.0);
   int rc = 0;
   if (!iterative && (!s->desc.motion || !s->desc.forces || s->desc.charge == 0.0)) {

@@ -651,6 +651,7 @@ int pgpu_species_cell_offsets(pgpu_species_t s, long *offsets) {
 
 int pgpu_set_moments_from_bins(pgpu_species_t s) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->binned) {
     set_error("species is not binned; call pgpu_bin_particles first");
     return PGPU_ERR_STATE;
@@ -771,6 +772,7 @@ int pgpu_set_charge_density(pgpu_species_t s, const int *stag, double *data, con
 
 int pgpu_apply_bcs(pgpu_species_t s, const int *bc_lo, const int *bc_hi) {
   NEED_INIT();
+  if (!s) return PGPU_ERR_ARG;
   if (!s->desc.motion) return 0;
   const pgpu_grid_s *g = s->grid;
   const long n = s->n;

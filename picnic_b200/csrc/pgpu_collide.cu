@@ -2329,6 +2329,7 @@ static int need_binned(pgpu_species_t sA, pgpu_species_t sB) {
 
 int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm, double dt_sec,
                          uint64_t seed, uint64_t step, long *npairs_out) {
+  if (!sA) return PGPU_ERR_ARG;
   int rc = need_binned(sA, sB);
   if (rc) return rc;
   Context &c = ctx();
@@ -2439,6 +2440,7 @@ int pgpu_collide_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulom
 
 int pgpu_collide_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elastic_params *prm, double dt_sec,
                          uint64_t seed, uint64_t step, long *ncoll_out) {
+  if (!sA) return PGPU_ERR_ARG;
   int rc = need_binned(sA, sB);
   if (rc) return rc;
   if (!prm || sA == sB || (prm->ntab && (!prm->E || !prm->Q || prm->ntab < 2))) return PGPU_ERR_ARG;
@@ -2541,6 +2543,7 @@ static int launch_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, HSParams P, 
 
 int pgpu_collide_hard_sphere(pgpu_species_t sA, pgpu_species_t sB, double sigmaT, double dt_sec, uint64_t seed,
                              uint64_t step, long *ncoll_out) {
+  if (!sA) return PGPU_ERR_ARG;
   if (!(sigmaT > 0.0)) {
     set_error("HardSphere: sigmaT must be positive");
     return PGPU_ERR_ARG;
@@ -2795,6 +2798,7 @@ static int fetch_nu_max(double *nu_max) {
 }
 
 int pgpu_scatter_nu_max_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, double *nu_max) {
+  if (!sA) return PGPU_ERR_ARG;
   int rc = need_moments(sA, sB);
   if (rc) return rc;
   if (!nu_max) return PGPU_ERR_ARG;
@@ -2811,6 +2815,7 @@ int pgpu_scatter_nu_max_ta(pgpu_species_t sA, pgpu_species_t sB, double Clog, do
 
 int pgpu_scatter_nu_max_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu_coulomb_params *prm,
                                 double *nu_max) {
+  if (!sA) return PGPU_ERR_ARG;
   int rc = need_moments(sA, sB);
   if (rc) return rc;
   if (!nu_max || !prm) return PGPU_ERR_ARG;
@@ -2835,6 +2840,7 @@ int pgpu_scatter_nu_max_coulomb(pgpu_species_t sA, pgpu_species_t sB, const pgpu
 
 int pgpu_scatter_nu_max_elastic(pgpu_species_t sA, pgpu_species_t sB, const pgpu_elastic_params *prm,
                                 double *nu_max) {
+  if (!sA) return PGPU_ERR_ARG;
   int rc = need_moments(sA, sB);
   if (rc) return rc;
   if (!nu_max || !prm || (prm->ntab && (!prm->E || !prm->Q || prm->ntab < 2))) return PGPU_ERR_ARG;

@@ -338,6 +338,7 @@ using namespace pgpu;
 extern "C" {
 
 int pgpu_fab_pack_d(pgpu_grid_t g, int kind, int comp, const int *lo, const int *hi, double *buf_d) {
+  if (!g) return PGPU_ERR_ARG;
   if (!ctx().inited) return PGPU_ERR_STATE;
   const DeviceFab *f = pick_fab(g, kind, comp);
   if (!f || !buf_d) return PGPU_ERR_ARG;
@@ -350,6 +351,7 @@ int pgpu_fab_pack_d(pgpu_grid_t g, int kind, int comp, const int *lo, const int 
 }
 
 int pgpu_fab_unpack_d(pgpu_grid_t g, int kind, int comp, const int *lo, const int *hi, const double *buf_d, int add) {
+  if (!g) return PGPU_ERR_ARG;
   if (!ctx().inited) return PGPU_ERR_STATE;
   const DeviceFab *f = pick_fab(g, kind, comp);
   if (!f || !buf_d) return PGPU_ERR_ARG;

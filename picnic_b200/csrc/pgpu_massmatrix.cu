@@ -1605,6 +1605,7 @@ int pgpu_accumulate_mass_matrices(pgpu_species_t s, double dt) {
 }
 
 int pgpu_mass_matrices_save_E0(pgpu_grid_t g) {
+  if (!g) return PGPU_ERR_ARG;
   NEED_MM(g);
   MassMatrices *m = mm_of(g);
   if (fields_wait(g)) return PGPU_ERR_CUDA;
@@ -1664,6 +1665,7 @@ int pgpu_mass_matrices_ncomp(pgpu_grid_t g, int *ncomp_out) {
 }
 
 int pgpu_mass_matrix_get(pgpu_grid_t g, int which, double *data, const int *lo, const int *hi, int ncomp) {
+  if (!g) return PGPU_ERR_ARG;
   NEED_MM(g);
   MassMatrices *m = mm_of(g);
   if (which < 0 || which >= 9 || !data) return PGPU_ERR_ARG;
@@ -1685,6 +1687,7 @@ int pgpu_mass_matrix_get(pgpu_grid_t g, int which, double *data, const int *lo, 
 }
 
 int pgpu_mass_matrix_J0_get(pgpu_grid_t g, int comp, double *data, const int *lo, const int *hi) {
+  if (!g) return PGPU_ERR_ARG;
   NEED_MM(g);
   if (comp < 0 || comp >= 3) return PGPU_ERR_ARG;
   int rc = copy_fab_to_host(mm_of(g)->J0[comp], g->desc.D, data, lo, hi);
