@@ -144,13 +144,81 @@ __global__ void k_bin_canon(const int *start, int nbins, int *perm, int *biglist
   if (moved)
     for (int i = 0; i < n; ++i) perm[s + i] = a[i];
 }
-// listed bins of 33 .. 4096 entries, one warp each: rank of every entry against the bin into a scratch copy, copied back
-// (bigger bins -- everything in one cell -- keep the arrival order)
+// ascending bitonic sort of up to 32 R distinct ints held R per lane (element e = lane + 32 r), padded with INT_MAX
+template <int R>
+__device__ __forceinline__ void warp_sort_ints(int *p, int n, int lane) {
+  int v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int k = lane + 32 * r;
+    v[r] = k < n ? p[k] : 0x7fffffff;
+  }
+  // already ascending (particles that did not change bin since the last sort mostly are): nothing to do
+  bool sorted = true;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int nxt = __shfl_down_sync(0xffffffffu, v[r], 1);
+    if (lane == 31) nxt = 0x7fffffff;
+    sorted = sorted && v[r] <= nxt;
+  }
+#pragma unroll
+  for (int r = 0; r + 1 < R; ++r) {
+    const int first_next = __shfl_sync(0xffffffffu, v[r + 1], 0);
+    if (lane == 31) sorted = sorted && v[r] <= first_next;
+  }
+  if (__all_sync(0xffffffffu, sorted)) return;
+#pragma unroll
+  for (int k2 = 2; k2 <= 32 * R; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int dr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r & dr) continue;
+          const bool up = (((lane + 32 * r) & k2) == 0);
+          const int x = v[r], y = v[r | dr];
+          const int lo = min(x, y), hi = max(x, y);
+          v[r] = up ? lo : hi;
+          v[r | dr] = up ? hi : lo;
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int o = __shfl_xor_sync(0xffffffffu, v[r], j);
+          const bool up = (((lane + 32 * r) & k2) == 0);
+          v[r] = (lower == up) ? min(v[r], o) : max(v[r], o);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int k = lane + 32 * r;
+    if (k < n) p[k] = v[r];
+  }
+}
+// listed bins of 33 .. 4096 entries, one warp each: up to 256 entries in registers through a bitonic network, beyond that
+// the rank of every entry against the bin into a scratch copy, copied back (bigger bins -- everything in one cell -- keep
+// the arrival order)
 __global__ void k_bin_canon_big(const int *start, const int *biglist, const int *nbig, int *perm, int *scratch) {
   const int lane = threadIdx.x & 31, nwarps = (int)((gridDim.x * blockDim.x) >> 5), nl = *nbig;
   for (int l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l < nl; l += nwarps) {
     const int b = biglist[l];
     const int s = start[b], n = start[b + 1] - s;
+    if (n <= 64) {
+      warp_sort_ints<2>(perm + s, n, lane);
+      continue;
+    }
+    if (n <= 128) {
+      warp_sort_ints<4>(perm + s, n, lane);
+      continue;
+    }
+    if (n <= 256) {
+      warp_sort_ints<8>(perm + s, n, lane);
+      continue;
+    }
     if (n > 4096) continue;
     for (int e = lane; e < n; e += 32) {
       const int v = perm[s + e];
@@ -187,13 +255,31 @@ struct PermuteSet {
   double *out[4];
   int count;
 };
-__global__ void k_permute(PermuteSet ps, const int *perm, long n) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int src = perm[i];
+// four particles per thread, a block-width apart: all the loads of a thread are in flight before its first store
+constexpr int PERMUTE_UNROLL = 4;
+__global__ void __launch_bounds__(256) k_permute(PermuteSet ps, const int *perm, long n) {
+  const long base = (long)blockIdx.x * (256 * PERMUTE_UNROLL) + threadIdx.x;
+  int src[PERMUTE_UNROLL];
+#pragma unroll
+  for (int u = 0; u < PERMUTE_UNROLL; ++u) {
+    const long i = base + u * 256;
+    src[u] = i < n ? perm[i] : -1;
+  }
+  double val[4][PERMUTE_UNROLL];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
-    if (a < ps.count) ps.out[a][i] = ps.in[a][src];
+    if (a < ps.count) {
+#pragma unroll
+      for (int u = 0; u < PERMUTE_UNROLL; ++u)
+        if (src[u] >= 0) val[a][u] = ps.in[a][src[u]];
+    }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    if (a < ps.count) {
+#pragma unroll
+      for (int u = 0; u < PERMUTE_UNROLL; ++u)
+        if (src[u] >= 0) __stcs(ps.out[a] + base + u * 256, val[a][u]);
+    }
 }
 
 // set{Number,Momentum,Energy}DensityFromBinFab (PicChargedSpecies.cpp:2881-3047):
@@ -471,7 +557,7 @@ static int gather_arrays(pgpu_species_s *s, std::vector<double **> &arrs, const 
       ps.out[a] = s->spare[a];
     }
     KTimer t("bin_permute");
-    k_permute<<<nb(n), 256, 0, ctx().stream>>>(ps, perm, n);
+    k_permute<<<nb(n, 256 * PERMUTE_UNROLL), 256, 0, ctx().stream>>>(ps, perm, n);
     for (int a = 0; a < ps.count; ++a) {
       double *old = *arrs[a0 + a];
       *arrs[a0 + a] = s->spare[a];
@@ -573,7 +659,7 @@ static int bin_impl(pgpu_species_t s, bool dual) {
       int *biglist = iota + n, *nbig = count + nb_bins;
       PGPU_CUDA(cudaMemsetAsync(nbig, 0, sizeof(int), c.stream));
       k_bin_canon<<<nb(nb_bins), 256, 0, c.stream>>>(start, (int)nb_bins, s->perm, biglist, nbig);
-      k_bin_canon_big<<<c.sm_count * 2, 256, 0, c.stream>>>(start, biglist, nbig, s->perm, iota);
+      k_bin_canon_big<<<c.sm_count * 8, 256, 0, c.stream>>>(start, biglist, nbig, s->perm, iota);
     }
   } else {
     size_t need = 0;

@@ -45,6 +45,11 @@ def run(deck, name, ncell_scale=1):
         for sp in sps:
             sp.bin_particles(); sp.set_moments()
     t_sort = timed(srt)
+    capi.profile_reset(); capi.profile_enable(True)
+    srt(); capi.check(lib.pgpu_synchronize())
+    capi.profile_enable(False)
+    print("  sort breakdown (ms): " + ", ".join("%s %.3f" % (k, capi.profile_query(k)[0])
+                                                for k in ("bin_key", "bin_sort", "bin_permute", "bin_starts", "cell_moments")))
     grid.debye_length(sps)
     dt_sec = deck.dt * deck.units.time
     state = {"k": 0}
