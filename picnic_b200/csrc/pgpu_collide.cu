@@ -362,14 +362,14 @@ __device__ __forceinline__ void ta_self_cell(int cell, int lane, const int *cell
   }
   if (pstart == 3 && lane == 0) {
     // particles 0,1,2 scatter as (0,1), (1,2), (0,2) with half the density (:353-388)
-    const int t[3] = {s + order[s], s + order[s + 1], s + order[s + 2]};
-    const int p1[3] = {0, 1, 0}, p2[3] = {1, 2, 2};
+    const int t0 = s + order[s], t1 = s + order[s + 1], t2 = s + order[s + 2];
     for (int p = 0; p < 3; ++p) {
       double g, ut, up;
       pair_randoms(P, gcell, (unsigned)p, 1u, g, ut, up);
       // the relativistic build passes the full density to the three pairs of an odd cell (:372 vs :377)
       const double dh = P.rel ? numDen : numDen / 2.0;
-      scatter_pair(v0, v1, v2, t[p1[p]], v0, v1, v2, t[p2[p]], dh, dh, P, g, ut, up);
+      // (no small arrays here: indexed by the loop counter they would live in local memory)
+      scatter_pair(v0, v1, v2, p == 1 ? t1 : t0, v0, v1, v2, p == 0 ? t1 : t2, dh, dh, P, g, ut, up);
     }
   }
   if (lane == 0) atomicAdd(npairs, (unsigned long long)(nmain + (pstart == 3 ? 3 : 0)));
@@ -506,13 +506,12 @@ k_ta_self_staged(const int *cell_start, int ncell, double *v0, double *v1, doubl
     }
     if (pstart == 3 && lane == 0) {
       // particles 0,1,2 scatter as (0,1), (1,2), (0,2) with half the density (TakizukaAbe.cpp:353-388)
-      const int t[3] = {so[0], so[1], so[2]};
-      const int p1[3] = {0, 1, 0}, p2[3] = {1, 2, 2};
+      const int t0 = so[0], t1 = so[1], t2 = so[2];
       for (int p = 0; p < 3; ++p) {
         double g, ut, up;
         pair_randoms(P, gcell, (unsigned)p, 1u, g, ut, up);
         const double dh = REL ? numDen : numDen / 2.0;
-        scatter_pair<REL>(w0, w1, w2, t[p1[p]], w0, w1, w2, t[p2[p]], dh, dh, P, g, ut, up);
+        scatter_pair<REL>(w0, w1, w2, p == 1 ? t1 : t0, w0, w1, w2, p == 0 ? t1 : t2, dh, dh, P, g, ut, up);
       }
     }
     __syncwarp();
@@ -1224,10 +1223,10 @@ k_coulomb_intra(const int *cell_start, int ncell, double *v0, double *v1, double
     const int pstart = (n & 1) ? 3 : 0;
     if (pstart == 3 && lane == 0) {
       // odd cell: (0,1), (0,2), (1,2) with half the density (:468-470, 536-538)
-      const int p1[3] = {0, 0, 1}, p2[3] = {1, 2, 2};
       for (int q = 0; q < 3; ++q) {
-        coulomb_pair<FAS, LEAN>(P, C, v0, v1, v2, w, s + order[s + p1[q]], v0, v1, v2, w, s + order[s + p2[q]],
-                     Naa / P.cellV_SI / 2.0, (unsigned)(p1[q] * 65536 + p2[q]), 1u);
+        const int p1 = q == 2 ? 1 : 0, p2 = q == 0 ? 1 : 2;
+        coulomb_pair<FAS, LEAN>(P, C, v0, v1, v2, w, s + order[s + p1], v0, v1, v2, w, s + order[s + p2],
+                                Naa / P.cellV_SI / 2.0, (unsigned)(p1 * 65536 + p2), 1u);
         ++mine;
       }
     }
