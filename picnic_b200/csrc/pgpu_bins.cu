@@ -651,13 +651,13 @@ static int bin_impl(pgpu_species_t s, bool dual) {
     }
     KTimer t("bin_sort");
     PGPU_CUDA(cub::DeviceScan::ExclusiveSum(s->cub_tmp, need, count, start, (int)nb_bins + 1, c.stream));   // start[nb_bins] = n
-    PGPU_CUDA(cudaMemsetAsync(count, 0, (size_t)nb_bins * sizeof(int), c.stream));
+    // the cursors of the scatter, and in the slot behind them the counter of the big-bin list
+    PGPU_CUDA(cudaMemsetAsync(count, 0, (size_t)(nb_bins + 1) * sizeof(int), c.stream));
     k_bin_scatter<<<nb(n), 256, 0, c.stream>>>(s->cell_key, n, start, count, s->perm, nullptr);
     if (!dual) {
       k_cell_starts_from_bins<<<nb(nbins + 1), 256, 0, c.stream>>>(start, (int)nb_bins, nbins, s->cell_start);
       // tmp holds n doubles: ints [0, n) are the scratch copy, ints [n, 2n) the list of big bins
       int *biglist = iota + n, *nbig = count + nb_bins;
-      PGPU_CUDA(cudaMemsetAsync(nbig, 0, sizeof(int), c.stream));
       k_bin_canon<<<nb(nb_bins), 256, 0, c.stream>>>(start, (int)nb_bins, s->perm, biglist, nbig);
       k_bin_canon_big<<<c.sm_count * 8, 256, 0, c.stream>>>(start, biglist, nbig, s->perm, iota);
     }
