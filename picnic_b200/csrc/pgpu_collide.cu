@@ -439,8 +439,13 @@ k_ta_inter(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, do
 constexpr int TA_NMAX = 128;
 constexpr int TA_SPECIES_BYTES = TA_NMAX * (3 * 8 + 4);     // v[3][TA_NMAX] doubles + order[TA_NMAX]
 constexpr int TA_SELF_WARPS = 8, TA_INTER_WARPS = 4;
+// blocks per SM the staged kernels are compiled for: 4 x 8 warps at 64 registers (self), 7 x 4 warps at 72 (inter; 201 KB of
+// shared memory) -- measured against 3 / 6: kernels of a C2 step 0.396 -> 0.366 ms
 #ifndef PGPU_TA_SELF_MINB
-#define PGPU_TA_SELF_MINB 3
+#define PGPU_TA_SELF_MINB 4
+#endif
+#ifndef PGPU_TA_INTER_MINB
+#define PGPU_TA_INTER_MINB 7
 #endif
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *g) {
@@ -525,7 +530,7 @@ k_ta_self_staged(const int *cell_start, int ncell, double *v0, double *v1, doubl
 }
 
 template <int REL>
-__global__ void __launch_bounds__(32 * TA_INTER_WARPS, 6)
+__global__ void __launch_bounds__(32 * TA_INTER_WARPS, PGPU_TA_INTER_MINB)
 k_ta_inter_staged(const int *cs1, const int *cs2, int ncell, double *a0, double *a1, double *a2, const uint64_t *id1,
                   const double *dens1, double *b0, double *b1, double *b2, const uint64_t *id2, const double *dens2,
                   TAParams P, unsigned long long *npairs, int *list) {
