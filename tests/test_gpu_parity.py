@@ -269,6 +269,39 @@ def test_explicit_boris_from_stored_fields(pgpu):
     pgpu.load().pgpu_set_exact_math(0)
 
 
+def test_bin_sort_restores_source_order_in_bins_of_every_size(pgpu):
+    """The counting sort hands out slots in arrival order; the canonicalisation (thread per bin up to 32 entries, a warp's
+    bitonic network up to 256, rank pass up to 4096) must give back what a stable sort gives: ids ascending in every
+    (cell, half-cell) bin."""
+    rng = np.random.default_rng(77)
+    counts = np.array([1, 2, 31, 32, 33, 40, 64, 65, 100, 128, 129, 200, 256, 257, 300, 700, 0, 5] * 3)
+    ncell = counts.size
+    dx = 0.25
+    xs = [(c + rng.random(k)) * dx for c, k in enumerate(counts)]
+    x = np.concatenate(xs)
+    perm = rng.permutation(x.size)                     # storage order unrelated to the cells
+    x = np.ascontiguousarray(x[perm][None, :])
+    n = x.shape[1]
+    grid = pgpu.Grid(1, (ncell,), (0.0,), (dx,), 2, (1,))
+    sp = pgpu.Species(grid, 1.0, -1.0, 1.0, 1.0)
+    sp.upload(x, np.zeros((3, n)), np.ones(n), ids=np.arange(n, dtype=np.uint64))
+    for rep in range(2):                               # second time: already sorted input (the early-out)
+        sp.bin_particles()
+        got = sp.download()
+        ids = got["id"].astype(np.int64)
+        cell = np.floor(got["x"][0] / dx).astype(int)
+        quad = (got["x"][0] / dx - cell >= 0.5).astype(int)
+        key = 2 * cell + quad
+        assert np.all(np.diff(key) >= 0)
+        same = np.diff(key) == 0
+        assert np.all(np.diff(ids)[same] > 0) or rep == 1
+        if rep == 1:                                   # ids were re-ordered by the first sort: source order = storage order
+            assert np.array_equal(ids, first)
+        first = ids
+        assert np.array_equal(np.sort(ids), np.arange(n))
+    sp.destroy(); grid.destroy()
+
+
 @pytest.mark.parametrize("D", [1, 2])
 def test_bin_sort_and_moments(pgpu, D):
     prob = _prob(D, seed=19, n=5000)
