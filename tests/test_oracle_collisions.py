@@ -171,6 +171,44 @@ def test_coulomb_inter_weighted_conserves_on_average():
     assert abs(K1 - K0) / K0 < 0.02
 
 
+@pytest.mark.parametrize("angular", [3, 4])
+@pytest.mark.parametrize("relativistic", [False, True])
+def test_coulomb_inter_full_angle_models_conserve_for_equal_weights(angular, relativistic):
+    """NANBU_FAS / NANBU_FAS_v2 through the inter-species cell driver, Galilean and LorentzScatter builds: with equal
+    weights every pair conserves momentum and energy, whatever branch of the full-angle model it took."""
+    rng = np.random.default_rng(23)
+    ncell, n1c, n2c = 40, 24, 16
+    cs1 = np.arange(ncell + 1, dtype=np.int64) * n1c
+    cs2 = np.arange(ncell + 1, dtype=np.int64) * n2c
+    m1, m2 = 3672.3, 5508.0                              # two ion species (the reference keeps electrons out by default)
+    v1 = rng.standard_normal((3, ncell * n1c)) * 4.0e-4
+    v2 = rng.standard_normal((3, ncell * n2c)) * 3.0e-4
+    w1 = np.full(ncell * n1c, 2.0e27); w2 = np.full(ncell * n2c, 2.0e27)
+    cellV = 1.0e-3
+    dens1 = np.add.reduceat(w1, cs1[:-1]) / cellV
+    dens2 = np.add.reduceat(w2, cs2[:-1]) / cellV
+    LDe = np.full(ncell, 5.0e-10)
+    orc.set_relativistic(relativistic)
+    try:
+        gam = (lambda v: np.sqrt(1.0 + (v ** 2).sum(axis=0))) if relativistic else (lambda v: 0.5 * (v ** 2).sum(axis=0))
+        P0 = [m1 * v1[:, cs1[c]:cs1[c + 1]].sum(axis=1) + m2 * v2[:, cs2[c]:cs2[c + 1]].sum(axis=1) for c in range(ncell)]
+        E0 = [m1 * gam(v1[:, cs1[c]:cs1[c + 1]]).sum() + m2 * gam(v2[:, cs2[c]:cs2[c + 1]]).sum() for c in range(ncell)]
+        v1_0 = v1.copy()
+        orc.lib().orc_rng_seed(4)
+        npairs = orc.coulomb_inter(cs1, v1, w1, dens1, m1, 1.0, cs2, v2, w2, dens2, m2, 1.0, LDe, cellV, 5.0, angular, False,
+                                   11, 2000 * DT_SEC)
+        assert npairs == ncell * max(n1c, n2c)
+        assert np.any(v1 != v1_0)
+        for c in range(ncell):
+            P1 = m1 * v1[:, cs1[c]:cs1[c + 1]].sum(axis=1) + m2 * v2[:, cs2[c]:cs2[c + 1]].sum(axis=1)
+            E1 = m1 * gam(v1[:, cs1[c]:cs1[c + 1]]).sum() + m2 * gam(v2[:, cs2[c]:cs2[c + 1]]).sum()
+            scale = m1 * np.abs(v1[:, cs1[c]:cs1[c + 1]]).sum() + m2 * np.abs(v2[:, cs2[c]:cs2[c + 1]]).sum()
+            assert np.max(np.abs(P1 - P0[c])) / scale < 1e-13
+            assert abs(E1 - E0[c]) / abs(E0[c]) < 1e-12
+    finally:
+        orc.set_relativistic(False)
+
+
 def test_coulomb_enforce_conservations_intra_and_inter():
     """scattering.coulomb.enforce_conservations (Coulomb.cpp:596-714, 1182-1430): with unequal weights the weight-rejection
     update conserves momentum and energy only on average; the fix-up (shift by the weighted mean momentum change, then
