@@ -133,6 +133,50 @@ def test_coulomb_intra_counts_and_conservation(pgpu, angular):
     sp.destroy(); grid.destroy()
 
 
+@pytest.mark.parametrize("angular", [3, 4])
+@pytest.mark.parametrize("relativistic", [False, True])
+def test_coulomb_inter_full_angle_models_conserve_per_cell(pgpu, angular, relativistic):
+    """NANBU_FAS / NANBU_FAS_v2 through the inter-species kernel (their own instantiation), Galilean pairs and
+    LorentzScatter pairs: equal weights, so momentum and energy of every cell are kept to round-off."""
+    rng = np.random.default_rng(61)
+    ncell = 48
+    x1, c1 = _ragged_cells(rng, ncell, [0, 1, 2, 5, 12, 16, 40, 70])
+    x2, c2 = _ragged_cells(rng, ncell, [0, 1, 3, 11, 17, 30])
+    deck = decks.Deck(D=1, ncell=(ncell,), dx=(0.25,), xmin=(0.0,), nghost=2)
+    sd1 = decks.SpeciesDef("deuteron", 3672.3, 1.0)
+    sd2 = decks.SpeciesDef("triton", 5508.0, 1.0)
+    grid = pgpu.Grid(1, (ncell,), (0.0,), (0.25,), 2, (1,), volume_scale=deck.volume_scale)
+    v1 = rng.standard_normal((3, x1.shape[1])) * 4.0e-4
+    v2 = rng.standard_normal((3, x2.shape[1])) * 3.0e-4
+    w1 = np.full(x1.shape[1], 1e28); w2 = np.full(x2.shape[1], 1e28)
+    sp1 = _species_on_grid(pgpu, grid, deck, sd1, x1, v1, w1, relativistic=relativistic)
+    sp2 = _species_on_grid(pgpu, grid, deck, sd2, x2, v2, w2, relativistic=relativistic)
+    grid.debye_length([sp1, sp2])
+    b1, b2 = sp1.download(), sp2.download()
+    npairs = pgpu.collide_coulomb(sp1, sp2, 5.0, 2000 * DT_SEC, 1983, 3, angular=angular)
+    assert npairs == sum((a * b if min(a, b) < 11 else max(a, b)) for a, b in zip(c1, c2) if a * b >= 2)
+    a1, a2 = sp1.download(), sp2.download()
+    o1, o2 = sp1.cell_offsets(), sp2.cell_offsets()
+    m1, m2 = sd1.mass, sd2.mass
+    en = (lambda v: np.sqrt(1.0 + (v ** 2).sum(axis=0)).sum()) if relativistic else (lambda v: 0.5 * (v ** 2).sum())
+    moved = 0
+    for c in range(ncell):
+        p0, p1 = b1["v"][:, o1[c]:o1[c + 1]], a1["v"][:, o1[c]:o1[c + 1]]
+        q0, q1 = b2["v"][:, o2[c]:o2[c + 1]], a2["v"][:, o2[c]:o2[c + 1]]
+        if c1[c] * c2[c] < 2:
+            assert np.array_equal(p0, p1) and np.array_equal(q0, q1)
+            continue
+        moved += int(np.any(p0 != p1))
+        P0 = m1 * p0.sum(axis=1) + m2 * q0.sum(axis=1)
+        P1 = m1 * p1.sum(axis=1) + m2 * q1.sum(axis=1)
+        scale = m1 * np.abs(p0).sum() + m2 * np.abs(q0).sum()
+        assert np.max(np.abs(P1 - P0)) / scale < 1e-13
+        E0, E1 = m1 * en(p0) + m2 * en(q0), m1 * en(p1) + m2 * en(q1)
+        assert abs(E1 - E0) / abs(E0) < 1e-11
+    assert moved > 10
+    sp1.destroy(); sp2.destroy(); grid.destroy()
+
+
 def test_coulomb_inter_counts_and_conservation(pgpu):
     rng = np.random.default_rng(54)
     ncell = 64
