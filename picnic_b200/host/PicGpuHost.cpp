@@ -172,8 +172,8 @@ void BoxLayout::overlap(int rank, const int *stag, int dir, int side, int *lo, i
   }
 }
 
-GhostExchange::GhostExchange(Mesh &mesh, const BoxLayout &layout, int rank)
-    : m_mesh(mesh), m_layout(layout), m_rank(rank), m_h(nullptr) {
+GhostExchange::GhostExchange(Mesh &mesh, const BoxLayout &layout, int rank, const int *a_rho_stag)
+    : m_mesh(mesh), m_layout(layout), m_rank(rank), m_h(nullptr), m_for_rho(a_rho_stag != nullptr) {
   static const int STAG_J[2][3][2] = {{{0, 0}, {1, 0}, {1, 0}}, {{0, 1}, {1, 0}, {1, 1}}};   // Jx, Jy, Jz centring
   const int D = layout.D;
   std::vector<pgpu_halo_msg> recs;
@@ -187,19 +187,25 @@ GhostExchange::GhostExchange(Mesh &mesh, const BoxLayout &layout, int rank)
       std::memset(&m, 0, sizeof(m));
       m.phase = phase;
       m.recv_area = (int)recs.size();
-      for (int c = 0; c < 3; ++c) layout.overlap(rank, STAG_J[D - 1][c], d, side, m.lo[c], m.hi[c]);
+      if (a_rho_stag) layout.overlap(rank, a_rho_stag, d, side, m.lo[0], m.hi[0]);
+      else for (int c = 0; c < 3; ++c) layout.overlap(rank, STAG_J[D - 1][c], d, side, m.lo[c], m.hi[c]);
       recs.push_back(m);
       Msg q = {phase, side, peer, 0};
       m_msgs.push_back(q);
     }
     ++phase;
   }
-  check(pgpu_halo_create(mesh.handle(), (int)recs.size(), recs.data(), &m_h), "GhostExchange::GhostExchange");
+  if (a_rho_stag) {
+    const int st[2] = {a_rho_stag[0], D == 2 ? a_rho_stag[1] : 0};
+    check(pgpu_halo_create_rho(mesh.handle(), st, (int)recs.size(), recs.data(), &m_h), "GhostExchange::GhostExchange");
+  } else {
+    check(pgpu_halo_create(mesh.handle(), (int)recs.size(), recs.data(), &m_h), "GhostExchange::GhostExchange");
+  }
   for (size_t i = 0; i < m_msgs.size(); ++i)
     check(pgpu_halo_area_offset(m_h, (int)i, &m_msgs[i].offset, nullptr), "GhostExchange::GhostExchange");
 }
 GhostExchange::~GhostExchange() {
-  m_mesh.setGhostExchange(nullptr);
+  if (!m_for_rho) m_mesh.setGhostExchange(nullptr);
   pgpu_halo_destroy(m_h);
 }
 int GhostExchange::numPhases() const { return pgpu_halo_phases(m_h); }

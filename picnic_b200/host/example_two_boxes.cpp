@@ -53,6 +53,7 @@ int main() {
   }
   // one box spanning the domain
   std::vector<Fab> Jg;
+  Fab rho_g;
   {
     const int lo[2] = {0, 0}, hi[2] = {NC[0] - 1, NC[1] - 1};
     Mesh mesh(2, NC, XMIN, DX, NG, PER, lo, hi, 1.0);
@@ -63,13 +64,20 @@ int main() {
     mesh.addSpeciesCurrentDensity(sp);
     mesh.finalizeSettingJ();
     for (int c = 0; c < 3; ++c) Jg.push_back(fetchJ(mesh, c));
+    // charge density on the nodes of the one box (setChargeDensityOnNodes)
+    rho_g.lo[0] = rho_g.lo[1] = -NG;
+    rho_g.hi[0] = NC[0] - 1 + NG + 1;
+    rho_g.hi[1] = NC[1] - 1 + NG + 1;
+    rho_g.a.assign((size_t)(rho_g.hi[0] - rho_g.lo[0] + 1) * (rho_g.hi[1] - rho_g.lo[1] + 1), 0.0);
+    sp.setChargeDensityOnNodes(rho_g.ref());
   }
   // 2 x 2 boxes in this process
   BoxLayout lay(2, NC, NB, NG, PER);
   const int world = lay.numBoxes();
   std::vector<Mesh *> mesh(world);
   std::vector<PicChargedSpecies *> sp(world);
-  std::vector<GhostExchange *> gx(world);
+  std::vector<GhostExchange *> gx(world), gxr(world);
+  const int NODES[2] = {1, 1};
   std::vector<ParticleMigration *> mg(world);
   for (int r = 0; r < world; ++r) {
     int lo[2], hi[2];
@@ -95,9 +103,11 @@ int main() {
     mesh[r]->zeroCurrentDensity();
     mesh[r]->addSpeciesCurrentDensity(*sp[r]);
     gx[r] = new GhostExchange(*mesh[r], lay, r);
+    gxr[r] = new GhostExchange(*mesh[r], lay, r, NODES);
     mg[r] = new ParticleMigration(*sp[r], lay, r, 4096);
   }
   GhostExchange::connectLocal(gx);
+  GhostExchange::connectLocal(gxr);
   ParticleMigration::connectLocal(mg);
   // several boxes per process: every box sends before any box receives
   for (int r = 0; r < world; ++r) gx[r]->begin();
@@ -118,6 +128,28 @@ int main() {
           worst = std::fmax(worst, std::fabs(f.at(i, j) - Jg[c].at(gi, gj)) / scale);
         }
     }
+  }
+  // the same for the nodal charge density: deposit per box, add-exchange of the ghost layers, read
+  double worst_rho = 0.0, scale_rho = 0.0;
+  for (size_t k = 0; k < rho_g.a.size(); ++k) scale_rho = std::fmax(scale_rho, std::fabs(rho_g.a[k]));
+  for (int r = 0; r < world; ++r) sp[r]->depositChargeDensity(NODES);
+  for (int r = 0; r < world; ++r) gxr[r]->begin();
+  for (int ph = 0; ph < gxr[0]->numPhases(); ++ph) {
+    for (int r = 0; r < world; ++r) gxr[r]->send(ph);
+    for (int r = 0; r < world; ++r) gxr[r]->recvAdd(ph);
+  }
+  for (int r = 0; r < world; ++r) {
+    int lo[2], hi[2];
+    lay.box(r, lo, hi);
+    Fab f;
+    for (int d = 0; d < 2; ++d) { f.lo[d] = lo[d] - NG; f.hi[d] = hi[d] + NG + 1; }
+    f.a.assign((size_t)(f.hi[0] - f.lo[0] + 1) * (f.hi[1] - f.lo[1] + 1), 0.0);
+    sp[r]->getChargeDensity(NODES, f.ref());
+    for (int j = f.lo[1]; j <= f.hi[1]; ++j)
+      for (int i = f.lo[0]; i <= f.hi[0]; ++i) {
+        const int gi = ((i % NC[0]) + NC[0]) % NC[0], gj = ((j % NC[1]) + NC[1]) % NC[1];
+        worst_rho = std::fmax(worst_rho, std::fabs(f.at(i, j) - rho_g.at(gi, gj)) / scale_rho);
+      }
   }
   // migration: periodic wrap of the new positions, then every leaver to the box that owns it
   const int bc[2] = {PGPU_BC_PERIODIC, PGPU_BC_PERIODIC};
@@ -144,14 +176,15 @@ int main() {
     }
     total += m;
   }
-  std::printf("max_rel_err_J %.3e moved %ld total %ld misplaced %ld ids_ok %d\n", worst, moved, total, misplaced,
-              (int)(idsum == idsum0));
+  std::printf("max_rel_err_J %.3e max_rel_err_rho %.3e moved %ld total %ld misplaced %ld ids_ok %d\n", worst, worst_rho, moved,
+              total, misplaced, (int)(idsum == idsum0));
   for (int r = 0; r < world; ++r) {
     delete mg[r];
     delete gx[r];
+    delete gxr[r];
     delete sp[r];
     delete mesh[r];
   }
   finalize();
-  return (worst < 1e-13 && total == n && misplaced == 0 && moved > 100 && idsum == idsum0) ? 0 : 1;
+  return (worst < 1e-13 && worst_rho < 1e-13 && total == n && misplaced == 0 && moved > 100 && idsum == idsum0) ? 0 : 1;
 }
