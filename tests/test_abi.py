@@ -62,3 +62,33 @@ def test_product_does_not_import_oracle():
                 if re.search(r"\boracle\b", s) and "liboracle" in s or re.search(r"^\s*(from|import)\s+oracle", s, re.M):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_ctypes_structures_match_the_header(tmp_path):
+    """The Python binding mirrors the header's structs by hand: sizes and the offset of every struct's last field must
+    agree with what a C compiler makes of include/picnic_gpu.h (a silent mismatch would shift every later parameter)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from picnic_b200 import capi
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    pairs = [("pgpu_grid_desc", capi.GridDesc), ("pgpu_species_desc", capi.SpeciesDesc), ("pgpu_ext_fn", capi.ExtFn),
+             ("pgpu_picard_stats", capi.PicardStats), ("pgpu_halo_msg", capi.HaloMsg),
+             ("pgpu_coulomb_params", capi.CoulombParams), ("pgpu_elastic_params", capi.ElasticParams)]
+    src = tmp_path / "sizes.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "picnic_gpu.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        last = cls._fields_[-1][0]
+        lines.append('  printf("%s %%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));' % (cname, cname, cname, last))
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "sizes"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run([cc, "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = {l.split()[0]: (int(l.split()[1]), int(l.split()[2])) for l in out if l.strip()}
+    for cname, cls in pairs:
+        last = cls._fields_[-1][0]
+        assert got[cname] == (C.sizeof(cls), getattr(cls, last).offset), (cname, got[cname], C.sizeof(cls))
